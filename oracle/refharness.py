@@ -1,0 +1,192 @@
+"""TEST INFRASTRUCTURE (oracle) -- ctypes access to oracle/_ref/libnairnmpm_ref.so.
+
+The library is the reference NairnMPM, unmodified, plus oracle/ref_harness.cpp.  The reference keeps all
+state in process globals, so one process can open ONE input: use `run_reference()` (spawns a worker
+process per input) from tests, or `RefRun` directly inside a dedicated process.
+
+Only tests/, __graft_entry__.smoke() and bench.py's reference/cpu_baseline arm may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libnairnmpm_ref.so")
+BIN = os.path.join(HERE, "_ref", "NairnMPM")
+
+INT_KEYS = ["np", "is3D", "nmpms", "nmpmsNR", "nmpmsRB", "nmpmsRC", "nnodes", "nelems", "horiz", "vert",
+            "depth", "mpmApproach", "useGimp", "skipPostExtrapolation", "XPICOrder", "usingFMPM", "mstep",
+            "nmat", "maxShapeNodes", "incrementalDefGradTerms", "adiabatic", "conduction", "numPatches",
+            "hasGravity", "useDamping", "usePDamping"]
+DBL_KEYS = ["xmin", "ymin", "zmin", "gridx", "gridy", "gridz", "timestep", "strainTimestepFirst",
+            "strainTimestepLast", "fractionUSF", "mtime", "damping", "pdamping", "gx", "gy", "gz", "rcrit",
+            "thickness", "maxtime"]
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+class RefRun:
+    """One reference run in THIS process (cannot be reopened)."""
+
+    def __init__(self, xml_path, nprocs=1, log=None):
+        self.lib = C.CDLL(LIB)
+        self.lib.ref_last_error.restype = C.c_char_p
+        self.lib.ref_task_name.restype = C.c_char_p
+        rv = self.lib.ref_open(xml_path.encode(), int(nprocs), (log or "").encode())
+        if rv != 0:
+            raise RuntimeError("ref_open failed: %s" % self.lib.ref_last_error().decode())
+        self.info = self.get_info()
+
+    def get_info(self):
+        iv = np.zeros(32, dtype=np.int32)
+        dv = np.zeros(32, dtype=np.float64)
+        self.lib.ref_info(_ip(iv), _dp(dv))
+        d = {k: int(iv[i]) for i, k in enumerate(INT_KEYS)}
+        d.update({k: float(dv[i]) for i, k in enumerate(DBL_KEYS)})
+        return d
+
+    def step(self, n=1):
+        if self.lib.ref_step(int(n)) != 0:
+            raise RuntimeError("ref_step failed: %s" % self.lib.ref_last_error().decode())
+
+    def task_names(self):
+        return [self.lib.ref_task_name(i).decode() for i in range(self.lib.ref_num_tasks())]
+
+    def run_task(self, i):
+        if self.lib.ref_run_task(int(i)) != 0:
+            raise RuntimeError("ref_run_task failed: %s" % self.lib.ref_last_error().decode())
+
+    def particles(self, nhist=4):
+        n = self.info["nmpms"]
+        out = dict(pos=np.zeros((3, n)), vel=np.zeros((3, n)), mp=np.zeros(n), lp=np.zeros((3, n)),
+                   inElem=np.zeros(n, np.int32), matnum=np.zeros(n, np.int32), sp=np.zeros((6, n)),
+                   pressure=np.zeros(n), ep=np.zeros((6, n)), wrot=np.zeros((3, n)), eplast=np.zeros((6, n)),
+                   energies=np.zeros((6, n)), hist=np.zeros((nhist, n)), pFext=np.zeros((3, n)),
+                   origpos=np.zeros((3, n)), crossings=np.zeros(n, np.int32), ncpos=np.zeros((3, n)),
+                   acc=np.zeros((3, n)))
+        o = out
+        self.lib.ref_get_particles(_dp(o["pos"]), _dp(o["vel"]), _dp(o["mp"]), _dp(o["lp"]), _ip(o["inElem"]),
+                                   _ip(o["matnum"]), _dp(o["sp"]), _dp(o["pressure"]), _dp(o["ep"]),
+                                   _dp(o["wrot"]), _dp(o["eplast"]), _dp(o["energies"]), _dp(o["hist"]),
+                                   C.c_int(nhist), _dp(o["pFext"]), _dp(o["origpos"]), _ip(o["crossings"]),
+                                   _dp(o["ncpos"]), _dp(o["acc"]))
+        return out
+
+    def nodes(self):
+        n = self.info["nnodes"]
+        o = dict(numberPoints=np.zeros(n, np.int32), mass=np.zeros(n), pk=np.zeros((3, n)),
+                 ftot=np.zeros((3, n)), vk0=np.zeros((3, n)), pkcopy=np.zeros((3, n)),
+                 fixedDirection=np.zeros(n, np.int32))
+        self.lib.ref_get_nodes(_ip(o["numberPoints"]), _dp(o["mass"]), _dp(o["pk"]), _dp(o["ftot"]),
+                               _dp(o["vk0"]), _dp(o["pkcopy"]), _ip(o["fixedDirection"]))
+        return o
+
+    def node_coords(self):
+        xyz = np.zeros((self.info["nnodes"], 3))
+        self.lib.ref_get_node_coords(_dp(xyz))
+        return xyz
+
+    def element_extents(self):
+        ext = np.zeros((self.info["nelems"], 6))
+        self.lib.ref_get_element_extents(_dp(ext))
+        return ext
+
+    def velbcs(self):
+        n = self.lib.ref_num_velbcs()
+        o = dict(node=np.zeros(n, np.int32), dir=np.zeros(n, np.int32), style=np.zeros(n, np.int32),
+                 norm=np.zeros((n, 3)), value=np.zeros(n), ftime=np.zeros(n), offset=np.zeros(n),
+                 currentValue=np.zeros(n))
+        if n:
+            self.lib.ref_get_velbcs(_ip(o["node"]), _ip(o["dir"]), _ip(o["style"]), _dp(o["norm"]),
+                                    _dp(o["value"]), _dp(o["ftime"]), _dp(o["offset"]), _dp(o["currentValue"]))
+        return o
+
+    def materials(self):
+        nm = self.info["nmat"]
+        ids = np.zeros(nm, np.int32)
+        par = np.zeros((nm, 32))
+        self.lib.ref_get_materials(_ip(ids), _dp(par))
+        return ids, par
+
+    def close(self):
+        self.lib.ref_close()
+
+
+def _flatten(prefix, d, out):
+    for k, v in d.items():
+        out["%s/%s" % (prefix, k)] = np.asarray(v)
+
+
+def _worker(xml, out_npz, nprocs, snaps, per_task_steps):
+    """snaps: sorted step counts at which to snapshot particles (+nodes); per_task_steps: number of
+    initial steps run task-by-task with node+particle dumps after every task."""
+    r = RefRun(xml, nprocs)
+    out = {}
+    _flatten("info", r.info, out)
+    out["node_coords"] = r.node_coords()
+    out["element_extents"] = r.element_extents()
+    _flatten("velbcs", r.velbcs(), out)
+    ids, par = r.materials()
+    out["mat_ids"], out["mat_params"] = ids, par
+    names = r.task_names()
+    out["task_names"] = np.array(names)
+    _flatten("p0", r.particles(), out)
+    done = 0
+    for s in range(per_task_steps):
+        for i, nm in enumerate(names):
+            r.run_task(i)
+            _flatten("s%d/t%d/nodes" % (s + 1, i), r.nodes(), out)
+            _flatten("s%d/t%d/p" % (s + 1, i), r.particles(), out)
+        done += 1
+        if done in snaps:
+            _flatten("p%d" % done, r.particles(), out)
+            _flatten("n%d" % done, r.nodes(), out)
+    for s in snaps:
+        if s > done:
+            r.step(s - done)
+            done = s
+            _flatten("p%d" % done, r.particles(), out)
+            _flatten("n%d" % done, r.nodes(), out)
+    _flatten("info_end", r.get_info(), out)
+    r.close()
+    np.savez_compressed(out_npz, **out)
+
+
+def run_reference(xml_text_or_path, snaps=(1,), per_task_steps=0, nprocs=1, workdir=None):
+    """Run the reference on an XML input in a fresh process; returns dict of arrays (see _worker)."""
+    if not available():
+        raise RuntimeError("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
+    tmp = workdir or tempfile.mkdtemp(prefix="mpmref_")
+    if os.path.exists(xml_text_or_path):
+        xml = os.path.abspath(xml_text_or_path)
+    else:
+        xml = os.path.join(tmp, "input.fmcmd")
+        with open(xml, "w") as f:
+            f.write(xml_text_or_path)
+    out = os.path.join(tmp, "ref_out.npz")
+    cmd = [sys.executable, os.path.abspath(__file__), xml, out, str(nprocs),
+           ",".join(str(s) for s in sorted(snaps)), str(per_task_steps)]
+    p = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("reference worker failed:\n%s\n%s" % (p.stdout[-2000:], p.stderr[-2000:]))
+    with np.load(out) as z:
+        return {k: z[k] for k in z.files}
+
+
+if __name__ == "__main__":
+    _xml, _out, _np, _snaps, _pt = sys.argv[1:6]
+    _worker(_xml, _out, int(_np), [int(s) for s in _snaps.split(",") if s], int(_pt))

@@ -1,0 +1,62 @@
+"""XML inputs (NairnMPM.dtd format) for the parity tests and the bench.
+
+These are the synthetic cases SURVEY.md section 8(d) names, written in the reference's own input
+format so the same text drives the reference (oracle/_ref) and the GPU path (via xml_input.read_xml).
+"""
+
+
+def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy=0.0, cfl=0.4,
+            method=2, gimp="uGIMP", maxtime=1.0, material=None, extra_header="", bc=True,
+            gravity=None, damping=None, pdamping=None, ppc=None, custom_tasks=""):
+    """3D block of ncell^3 cells (8 particles per cell) inside a (ncell+2*margin)^3 grid, 1 mm cells.
+
+    Config 2 of BASELINE.json is block3d(ncell=50, margin=7).  The bottom plane z<=margin is held
+    with a zero z-velocity grid BC.
+    """
+    n = ncell + 2 * margin
+    lo, hi = margin, margin + ncell
+    mat = material or ('<Material Type="1" Name="Blk"><rho>%r</rho><E>%r</E><nu>%r</nu><alpha>0</alpha></Material>'
+                       % (rho, E, nu))
+    gimp_tag = '<GIMP type="%s"/>' % gimp if gimp else ""
+    ppc_tag = "<MatlPtsPerElement>%d</MatlPtsPerElement>" % ppc if ppc else ""
+    bcs = ""
+    if bc:
+        bcs = ('<GridBCs><BCBox xmin="-1" xmax="%d" ymin="-1" ymax="%d" zmin="-1" zmax="%g">'
+               '<DisBC dir="3" vel="0"/></BCBox></GridBCs>' % (n + 1, n + 1, lo + 0.01))
+    grav = ""
+    if gravity:
+        grav = '<Gravity><BodyXForce>%r</BodyXForce><BodyYForce>%r</BodyYForce><BodyZForce>%r</BodyZForce></Gravity>' % tuple(gravity)
+    damp = ""
+    if damping is not None:
+        damp += "<Damping>%r</Damping>" % damping
+    if pdamping is not None:
+        damp += "<PDamping>%r</PDamping>" % pdamping
+    return """<?xml version='1.0'?>
+<!DOCTYPE JANFEAInput SYSTEM "NairnMPM.dtd">
+<JANFEAInput version='3'>
+  <Header><Description>3D block</Description><Analysis>12</Analysis></Header>
+  <MPMHeader>
+    <MPMMethod>%d</MPMMethod>
+    <Timing step="1e-3" max="%r" CFL="%r" units="ms"/>
+    <ArchiveTime units="ms">1000</ArchiveTime>
+    <ArchiveRoot>res/blk.</ArchiveRoot>
+    <MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>
+    %s %s %s %s
+  </MPMHeader>
+  <Mesh output="file">
+    <Grid xmin="0" xmax="%d" ymin="0" ymax="%d" zmin="0" zmax="%d">
+      <Horiz cellsize="1"/><Vert cellsize="1"/><Depth cellsize="1"/>
+    </Grid>
+  </Mesh>
+  <MaterialPoints>
+    <Body matname="Blk" vx="%r" vy="%r" vz="%r">
+      <Box xmin="%d" xmax="%d" ymin="%d" ymax="%d" zmin="%d" zmax="%d"/>
+    </Body>
+  </MaterialPoints>
+  %s
+  %s
+  %s
+  %s
+</JANFEAInput>
+""" % (method, maxtime, cfl, gimp_tag, ppc_tag, damp, extra_header, n, n, n, vx, vy, vz,
+       lo, hi, lo, hi, lo, hi, mat, bcs, grav, custom_tasks)
