@@ -1,0 +1,229 @@
+/*
+ * mpmgpu.h -- C ABI of libmpmgpu: NairnMPM's explicit MPM time step on one B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's MPMTask pipeline
+ * (NairnMPM/src/NairnMPM_Class/NairnMPM.cpp:870-1110 CreateTasks, :284-335 MPMStep).  The host
+ * driver (the reference's own C++ driver through nairn_mpm_fea_b200/host/GpuTasks.cpp, or the Python
+ * host in nairn_mpm_fea_b200/) owns input parsing, materials objects, BC lists and archiving; this
+ * library owns device-resident structure-of-arrays copies of the particle state (MPMBase,
+ * MPM_Classes/MPMBase.hpp:34-264) and node state (MatVelocityField, Nodes/MatVelocityField.hpp:44-48)
+ * and runs tasks 1-9 and 11 of the step on them.
+ *
+ * Conventions
+ *  - every entry point returns 0 on success, a negative MPMGPU_E* code on failure; the text is
+ *    available from mpmgpu_last_error().  No C++ exception crosses this boundary: the C++ task
+ *    wrapper turns a failure into the reference's CommonException (Common/Exceptions/CommonException.hpp).
+ *  - plain pointers and sizes only; all floating point is IEEE double; all host arrays are
+ *    structure-of-arrays, component-major ( v[c*n + p] ), in the caller's particle order
+ *    (the reference's mpm[] order).  The device may keep particles in cell-sorted order internally;
+ *    uploads/downloads always use the caller's order.
+ *  - units are whatever the host uses consistently (the reference's internal mm-g-s units).
+ *  - node numbers are the reference's 1-based numbers (Read_MPM/Generators.cpp:1910); element numbers
+ *    are the reference's 1-based MPMBase::inElem (MPM_Classes/MPMBase.cpp:456-472).
+ *  - one context is bound to one CUDA device and is used from one host thread at a time.
+ *  - there is NO CPU fallback: without a CUDA device mpmgpu_create fails with MPMGPU_ENODEVICE.
+ */
+#ifndef MPMGPU_H
+#define MPMGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPMGPU_ABI_VERSION 1
+
+/* error codes */
+#define MPMGPU_OK            0
+#define MPMGPU_EINVAL       -1   /* bad argument / unsupported option (message says which) */
+#define MPMGPU_ENODEVICE    -2   /* no usable CUDA device */
+#define MPMGPU_ECUDA        -3   /* CUDA runtime error */
+#define MPMGPU_ELEFTGRID    -4   /* a particle left the grid (ResetElementsTask.cpp:71-95) and could not be returned */
+#define MPMGPU_ENAN         -5   /* particle position became NaN (ResetElementsTask.cpp:200-203) */
+#define MPMGPU_ESTATE       -6   /* call out of order (e.g. step before upload) */
+#define MPMGPU_ECPDI        -7   /* CPDI corner left the grid (MPM_Classes/MatPoint3D.cpp:596-601) */
+
+/* analysis type: reference codes, System/MPMPrefix.hpp:114-115 */
+#define MPMGPU_PLANE_STRAIN_MPM 10
+#define MPMGPU_PLANE_STRESS_MPM 11
+#define MPMGPU_THREED_MPM       12
+
+/* update method: reference codes, System/MPMPrefix.hpp:110 */
+#define MPMGPU_USF   0
+#define MPMGPU_USAVG 2
+#define MPMGPU_USL   3
+
+/* shape functions: reference ElementBase::useGimp codes, System/MPMPrefix.hpp:127-140 */
+#define MPMGPU_POINT_GIMP     0   /* "Classic": linear element shape functions */
+#define MPMGPU_UNIFORM_GIMP   1   /* uGIMP */
+#define MPMGPU_LINEAR_CPDI   10   /* lCPDI (2D and 3D) */
+#define MPMGPU_QUADRATIC_CPDI 11  /* qCPDI (2D only, as in the reference) */
+
+/* material kinds: reference MaterialID() values, Common/Read_XML/MaterialController.cpp:105-232 */
+#define MPMGPU_MAT_ISOTROPIC      1   /* IsotropicMat, small-rotation hypoelastic */
+#define MPMGPU_MAT_ISOPLASTICITY  9   /* IsoPlasticity + LinearHardening */
+#define MPMGPU_MAT_RIGIDBC       11   /* RigidMaterial used as moving velocity BC */
+#define MPMGPU_MAT_NEOHOOKEAN    28   /* Neohookean */
+
+#define MPMGPU_MAT_NPARAMS 32
+#define MPMGPU_MAX_HISTORY 4
+
+typedef struct mpmgpu_ctx mpmgpu_ctx;
+
+/* Grid, method and global constants: everything CreateTasks/MPMStep read from fmobj, mpmgrid,
+ * bodyFrc and ElementBase statics. */
+typedef struct mpmgpu_config {
+    int abi_version;        /* MPMGPU_ABI_VERSION */
+    int device;             /* CUDA device ordinal */
+    int np;                 /* analysis type (MPMGPU_*_MPM) */
+    int horiz, vert, depth; /* cells per axis INCLUDING the automatic border cell on each side
+                               (Read_MPM/Generators.cpp:1769-1785); depth = 0 in 2D */
+    const double *xpts;     /* node coordinates per axis exactly as the host generated them, */
+    const double *ypts;     /*   horiz+1 / vert+1 / depth+1 long (Generators.cpp:1823-1833);  */
+    const double *zpts;     /*   zpts NULL in 2D.  Element extents are taken from these.      */
+    double gridx, gridy, gridz; /* mpmgrid.grid (MeshInfo::SetCartesian); gridz = 0 in 2D */
+    double thickness;       /* 2D grid thickness (unused by the step, kept for archives) */
+    int shape;              /* MPMGPU_POINT_GIMP | _UNIFORM_GIMP | _LINEAR_CPDI | _QUADRATIC_CPDI */
+    double cpdi_rcrit;      /* ElementBase::rcrit, <0 for none (MatPoint3D.cpp:436-442) */
+    int method;             /* MPMGPU_USF | _USAVG | _USL */
+    int skip_post_extrapolation; /* <SkipPostExtrapolation/>: USL-/USAVG- (NairnMPM.cpp:1076-1087) */
+    double fraction_usf;    /* fractionUSF (NairnMPM.cpp:78), 0.5 default */
+    int xpic_order;         /* bodyFrc.GetXPICOrder(): 0 FLIP, 1 PIC, k>1 XPIC(k)/FMPM(k) */
+    int using_fmpm;         /* bodyFrc.UsingFMPM() */
+    double grid_damping;    /* bodyFrc.GetGridDamping(mtime) (constant part) */
+    double particle_damping;/* bodyFrc.GetParticleDamping(mtime) */
+    double gravity[3];      /* bodyFrc.gforce (zero vector if no gravity) */
+    int max_particles;      /* capacity; 0 = size to the first upload */
+    int sort_interval;      /* re-sort particles by cell every this many steps (0 = library default) */
+    int kernel_path;        /* 0 = auto (tiled fast path when eligible), 1 = force reference-order
+                               per-task kernels, 2 = force tiled path (error if not eligible) */
+} mpmgpu_config;
+
+/* One material: kind + POD parameter block harvested from the host's MaterialBase object
+ * (what GetCopyOfMechanicalProps would hand to MPMConstitutiveLaw, MaterialBase.hpp:143-165).
+ * Parameter slots by kind (all stiffness-like values are SPECIFIC, i.e. divided by rho):
+ *  all kinds:  [0] rho   [1] heat capacity Cv   [2] particle damping override or -1
+ *  ISOTROPIC (3D):  [8] C11 [9] C12 [10] C13 [11] C22 [12] C23 [13] C33 [14] C44 [15] C55 [16] C66
+ *                   [17] CTE1 [18] CTE2 [19] CTE3 [20] gamma0
+ *  ISOTROPIC (2D, ElasticProperties 2D slots, Common/Materials/Elastic.cpp:90-140):
+ *                   [8] C[1][1] [9] C[1][2] [11] C[2][2] [16] C[3][3] [21] C[4][1] [22] C[4][2]
+ *                   [23] C[4][4] [24] C[5][1]  (+CTE/gamma0 as above)
+ *  NEOHOOKEAN:      [8] Gsp [9] Ksp [10] Lamesp [11] UofJOption [12] CTE1 [13] gamma0-related Ka2sp
+ *  ISOPLASTICITY:   [8] Gred [9] Kred [10] yldred [11] Epred [12] CTE(1 or 3) [13] gamma0
+ *                   [14] psRed [15] psLr2G [16] psKred  (plane stress only)
+ *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)
+ */
+typedef struct mpmgpu_material {
+    int kind;
+    int n_history;          /* doubles of history per particle (MaterialBase::NumberOfHistoryDoubles) */
+    double p[MPMGPU_MAT_NPARAMS];
+} mpmgpu_material;
+
+/* Host structure-of-arrays view of the particles.  Any pointer may be NULL: on upload the field is
+ * then zero (or 1 for temperature-like defaults noted below); on download it is skipped.
+ * n particles; nonrigid particles first, rigid-BC particles last (NairnMPM::ReorderParticles,
+ * NairnMPM.cpp:1117-1194); n_nonrigid of them are nonrigid. */
+typedef struct mpmgpu_particles {
+    int n;
+    int n_nonrigid;
+    double *pos;        /* [3][n]  MPMBase::pos */
+    double *vel;        /* [3][n]  MPMBase::vel */
+    double *mp;         /* [n]     MPMBase::mp */
+    double *lp;         /* [3][n]  MPMBase::mpm_lp (dimensionless semi-size) */
+    int    *in_elem;    /* [n]     MPMBase::inElem (1-based) */
+    int    *matnum;     /* [n]     MPMBase::matnum (1-based index into the materials array) */
+    double *sp;         /* [6][n]  xx,yy,zz,yz,xz,xy  MPMBase::sp (specific stress) */
+    double *pressure;   /* [n]     MPMBase::pressure */
+    double *ep;         /* [6][n]  MPMBase::ep  } together the deformation gradient,           */
+    double *wrot;       /* [3][n]  xy,xz,yz     } MatPoint3D.cpp:320-336,363-376                */
+    double *eplast;     /* [6][n]  MPMBase::eplast (plastic strain, or elastic B for hyperelastic) */
+    double *energies;   /* [6][n]  workEnergy,resEnergy,heatEnergy,entropy,plastEnergy,pPreviousTemperature */
+    double *history;    /* [MPMGPU_MAX_HISTORY][n] material history doubles */
+    double *pfext;      /* [3][n]  MPMBase::pFext (external particle force, MatPtLoadBC) */
+    int    *crossings;  /* [n]     MPMBase::elementCrossings */
+    double *acc;        /* [3][n]  MPMBase::acc (download only) */
+} mpmgpu_particles;
+
+/* download masks */
+#define MPMGPU_F_POS      0x001
+#define MPMGPU_F_VEL      0x002
+#define MPMGPU_F_STRESS   0x004   /* sp + pressure */
+#define MPMGPU_F_STRAIN   0x008   /* ep + wrot */
+#define MPMGPU_F_EPLAST   0x010
+#define MPMGPU_F_ENERGY   0x020
+#define MPMGPU_F_HISTORY  0x040
+#define MPMGPU_F_ELEM     0x080   /* in_elem + crossings */
+#define MPMGPU_F_ACC      0x100
+#define MPMGPU_F_ALL      0x1ff
+
+/* Host view of the node accumulators (debug / global quantities / parity tests).
+ * Arrays are nnodes long (vectors [3][nnodes]), reference node order; NULL = skip. */
+typedef struct mpmgpu_nodes {
+    int nnodes;
+    int    *number_points;  /* MatVelocityField::numberPoints */
+    double *mass;           /* MatVelocityField::mass */
+    double *pk;             /* [3][nnodes] momentum */
+    double *ftot;           /* [3][nnodes] force */
+    double *vk;             /* [3][nnodes] vk[0] */
+    double *pk_copy;        /* [3][nnodes] vk[pkCopy] */
+} mpmgpu_nodes;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+int mpmgpu_abi_version(void);
+int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out);
+int mpmgpu_destroy(mpmgpu_ctx *ctx);
+const char *mpmgpu_last_error(const mpmgpu_ctx *ctx);   /* ctx may be NULL for create() failures */
+
+/* ---- set-up (host -> device) ------------------------------------------------------------- */
+int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_material *mats);
+int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
+/* timestep, strainTimestepFirst, strainTimestepLast (NairnMPM.cpp:1207-1240) */
+int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dt_strain_first, double dt_strain_last);
+/* XPIC/FMPM order can change per step (Custom_Tasks/PeriodicXPIC.cpp:161-240) */
+int mpmgpu_set_xpic(mpmgpu_ctx *ctx, int order, int using_fmpm);
+/* Grid velocity BCs in the host's list order (firstVelocityBC..., Boundary_Conditions/NodalVelBC.cpp:321-400):
+ * node[i] 1-based, norm[3*i..] unit direction, value[i] = currentValue at this step's mtime
+ * (BoundaryCondition::BCValue), active[i] = GetNodeNum(mtime)>0, symdir[i] = the node's
+ * fixedDirection symmetry-plane bits (32|64|128, ADJUST_COPIED_PK) or 0.  Call again whenever values change. */
+int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *norm,
+                            const double *value, const int *active, const int *symdir);
+/* update only the values/active flags of the BC list set above (same n, same order) */
+int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const double *value, const int *active);
+
+/* ---- the step ---------------------------------------------------------------------------- */
+/* nsteps full MPMSteps (tasks 1-9, 11) with the configured method; mtime advances by dt each step */
+int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps);
+
+/* The same step as separate entry points named after the reference's tasks, so that the
+ * reference's per-task timing report (MPMTask.cpp:106-121) stays meaningful and each task can be
+ * checked in isolation.  Call in pipeline order. */
+int mpmgpu_task_initialization(mpmgpu_ctx *ctx);        /* InitializationTask.cpp:43-103 */
+int mpmgpu_task_mass_and_momentum(mpmgpu_ctx *ctx);     /* MassAndMomentumTask.cpp:48-127 (+ProjectRigidBCsTask) */
+int mpmgpu_task_post_extrapolation(mpmgpu_ctx *ctx);    /* PostExtrapolationTask.cpp:46-165 */
+int mpmgpu_task_update_strains_first(mpmgpu_ctx *ctx);  /* UpdateStrainsFirstTask.cpp:52-168 */
+int mpmgpu_task_grid_forces(mpmgpu_ctx *ctx);           /* GridForcesTask.cpp:40-153 */
+int mpmgpu_task_post_forces(mpmgpu_ctx *ctx);           /* PostForcesTask.cpp:43-111 */
+int mpmgpu_task_update_momenta(mpmgpu_ctx *ctx);        /* UpdateMomentaTask.cpp:44-64 */
+int mpmgpu_task_update_particles(mpmgpu_ctx *ctx);      /* UpdateParticlesTask.cpp:44-298 */
+int mpmgpu_task_update_strains_last(mpmgpu_ctx *ctx);   /* UpdateStrainsLast(Contact)Task.cpp */
+int mpmgpu_task_reset_elements(mpmgpu_ctx *ctx);        /* ResetElementsTask.cpp:44-265 */
+
+/* ---- device -> host ---------------------------------------------------------------------- */
+int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *host, unsigned mask);
+int mpmgpu_download_nodes(mpmgpu_ctx *ctx, mpmgpu_nodes *host);
+int mpmgpu_synchronize(mpmgpu_ctx *ctx);
+/* step counter, simulated time, particles that crossed an element boundary / left the grid so far */
+int mpmgpu_get_status(mpmgpu_ctx *ctx, long long *mstep, double *mtime, long long *crossings, long long *left_grid);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long mpmgpu_launch_count(const mpmgpu_ctx *ctx);
+/* CUDA stream the context launches on (as a cudaStream_t cast to void*), for event timing */
+void *mpmgpu_stream(mpmgpu_ctx *ctx);
+/* per-task device time (the reference's task timing report, MPMTask.cpp:100-121): when profiling is
+ * on every task is bracketed by CUDA events (this serialises the stream; leave it off when timing
+ * whole steps).  mpmgpu_task_times fills ms[10] (accumulated) and calls[10] in task order above. */
+int mpmgpu_set_profiling(mpmgpu_ctx *ctx, int on);
+int mpmgpu_task_times(mpmgpu_ctx *ctx, double *ms, long long *calls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPMGPU_H */

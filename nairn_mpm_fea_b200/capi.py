@@ -1,0 +1,286 @@
+"""ctypes binding of libmpmgpu (include/mpmgpu.h) -- the call a Python user makes.
+
+`MpmGpu` mirrors the life cycle of the reference driver around its MPMTask list
+(NairnMPM_Class/NairnMPM.cpp:135-200): create from a `Problem`, upload, step (whole steps or task by
+task), download.  There is no CPU path: if the library or a CUDA device is missing this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpmgpu.so")
+
+ABI_VERSION = 1
+MAT_NPARAMS = 32
+MAX_HISTORY = 4
+
+F_POS, F_VEL, F_STRESS, F_STRAIN, F_EPLAST, F_ENERGY, F_HISTORY, F_ELEM, F_ACC = (
+    0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040, 0x080, 0x100)
+F_ALL = 0x1FF
+
+TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_strains_first", "grid_forces",
+         "post_forces", "update_momenta", "update_particles", "update_strains_last", "reset_elements"]
+
+# every symbol include/mpmgpu.h declares (tests check the library exports all of them)
+EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
+           "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
+           "mpmgpu_update_velocity_bc_values", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
+    "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
+    "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times"]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_int), ("device", C.c_int), ("np", C.c_int),
+                ("horiz", C.c_int), ("vert", C.c_int), ("depth", C.c_int),
+                ("xpts", _dp), ("ypts", _dp), ("zpts", _dp),
+                ("gridx", C.c_double), ("gridy", C.c_double), ("gridz", C.c_double),
+                ("thickness", C.c_double), ("shape", C.c_int), ("cpdi_rcrit", C.c_double),
+                ("method", C.c_int), ("skip_post_extrapolation", C.c_int), ("fraction_usf", C.c_double),
+                ("xpic_order", C.c_int), ("using_fmpm", C.c_int),
+                ("grid_damping", C.c_double), ("particle_damping", C.c_double), ("gravity", C.c_double * 3),
+                ("max_particles", C.c_int), ("sort_interval", C.c_int), ("kernel_path", C.c_int)]
+
+
+class Material(C.Structure):
+    _fields_ = [("kind", C.c_int), ("n_history", C.c_int), ("p", C.c_double * MAT_NPARAMS)]
+
+
+class ParticlesView(C.Structure):
+    _fields_ = [("n", C.c_int), ("n_nonrigid", C.c_int),
+                ("pos", _dp), ("vel", _dp), ("mp", _dp), ("lp", _dp), ("in_elem", _ip), ("matnum", _ip),
+                ("sp", _dp), ("pressure", _dp), ("ep", _dp), ("wrot", _dp), ("eplast", _dp),
+                ("energies", _dp), ("history", _dp), ("pfext", _dp), ("crossings", _ip), ("acc", _dp)]
+
+
+class NodesView(C.Structure):
+    _fields_ = [("nnodes", C.c_int), ("number_points", _ip), ("mass", _dp), ("pk", _dp), ("ftot", _dp),
+                ("vk", _dp), ("pk_copy", _dp)]
+
+
+class MpmGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libmpmgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libmpmgpu.so and declare prototypes.  Fails loudly if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise MpmGpuError(-2, "%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.mpmgpu_abi_version.restype = C.c_int
+    lib.mpmgpu_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.mpmgpu_destroy.argtypes = [vp]
+    lib.mpmgpu_last_error.argtypes = [vp]
+    lib.mpmgpu_last_error.restype = C.c_char_p
+    lib.mpmgpu_set_materials.argtypes = [vp, C.c_int, C.POINTER(Material)]
+    lib.mpmgpu_upload_particles.argtypes = [vp, C.POINTER(ParticlesView)]
+    lib.mpmgpu_set_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    lib.mpmgpu_set_xpic.argtypes = [vp, C.c_int, C.c_int]
+    lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
+    lib.mpmgpu_update_velocity_bc_values.argtypes = [vp, C.c_int, _dp, _ip]
+    lib.mpmgpu_step.argtypes = [vp, C.c_int]
+    for t in TASKS:
+        getattr(lib, "mpmgpu_task_" + t).argtypes = [vp]
+    lib.mpmgpu_download_particles.argtypes = [vp, C.POINTER(ParticlesView), C.c_uint]
+    lib.mpmgpu_download_nodes.argtypes = [vp, C.POINTER(NodesView)]
+    lib.mpmgpu_synchronize.argtypes = [vp]
+    lib.mpmgpu_get_status.argtypes = [vp, C.POINTER(C.c_longlong), _dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    lib.mpmgpu_launch_count.argtypes = [vp]
+    lib.mpmgpu_launch_count.restype = C.c_longlong
+    lib.mpmgpu_stream.argtypes = [vp]
+    lib.mpmgpu_stream.restype = vp
+    lib.mpmgpu_set_profiling.argtypes = [vp, C.c_int]
+    lib.mpmgpu_task_times.argtypes = [vp, _dp, C.POINTER(C.c_longlong)]
+    if lib.mpmgpu_abi_version() != ABI_VERSION:
+        raise MpmGpuError(-1, "libmpmgpu ABI %d, binding expects %d" % (lib.mpmgpu_abi_version(), ABI_VERSION))
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _c64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _c32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class MpmGpu:
+    """One libmpmgpu context bound to one GPU, created from a `problem.Problem`."""
+
+    def __init__(self, prob, device=0, kernel_path=0, max_particles=0, sort_interval=0, upload=True):
+        self.lib = load_library()
+        self.prob = prob
+        self._keep = []
+        cfg = Config()
+        cfg.abi_version = ABI_VERSION
+        cfg.device = device
+        cfg.np = prob.np
+        cfg.horiz, cfg.vert, cfg.depth = prob.horiz, prob.vert, prob.depth
+        xp, yp = _c64(prob.xpts), _c64(prob.ypts)
+        zp = _c64(prob.zpts) if prob.is3d else None
+        self._keep += [xp, yp, zp]
+        cfg.xpts, cfg.ypts, cfg.zpts = _d(xp), _d(yp), _d(zp)
+        cfg.gridx, cfg.gridy, cfg.gridz = prob.grid
+        cfg.thickness = prob.thickness
+        cfg.shape = prob.shape
+        cfg.cpdi_rcrit = prob.rcrit
+        cfg.method = prob.method
+        cfg.skip_post_extrapolation = int(prob.skip_post_extrapolation)
+        cfg.fraction_usf = prob.fraction_usf
+        cfg.xpic_order = prob.xpic_order
+        cfg.using_fmpm = int(prob.using_fmpm)
+        cfg.grid_damping = prob.grid_damping
+        cfg.particle_damping = prob.particle_damping
+        cfg.gravity = (C.c_double * 3)(*prob.gravity)
+        cfg.max_particles = max_particles
+        cfg.sort_interval = sort_interval
+        cfg.kernel_path = kernel_path
+        self.ctx = C.c_void_p()
+        rc = self.lib.mpmgpu_create(C.byref(cfg), C.byref(self.ctx))
+        if rc != 0:
+            msg = self.lib.mpmgpu_last_error(None).decode()
+            self.ctx = None
+            raise MpmGpuError(rc, msg)
+        self.nnodes = prob.nnodes
+        mats = (Material * len(prob.materials))()
+        for k, m in enumerate(prob.materials):
+            mats[k].kind = m["kind"]
+            mats[k].n_history = m.get("n_history", 0)
+            for j, v in enumerate(m["p"]):
+                mats[k].p[j] = v
+        self._check(self.lib.mpmgpu_set_materials(self.ctx, len(prob.materials), mats))
+        self._check(self.lib.mpmgpu_set_time_step(self.ctx, prob.dt, prob.dt_strain_first, prob.dt_strain_last))
+        self.set_velocity_bcs(prob.bc_node, prob.bc_norm, prob.bc_value, prob.bc_active, prob.bc_symdir)
+        if upload:
+            self.upload(prob.particles)
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise MpmGpuError(rc, self.lib.mpmgpu_last_error(self.ctx).decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.mpmgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- host -> device -----------------------------------------------------------------------
+    def upload(self, pt):
+        """pt: dict of host arrays in the layout of mpmgpu_particles (component-major)."""
+        v = ParticlesView()
+        n = int(np.asarray(pt["mp"]).shape[0])
+        v.n = n
+        v.n_nonrigid = int(pt.get("n_nonrigid", n))
+        keep = {}
+        for k in ("pos", "vel", "mp", "lp", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "pfext"):
+            keep[k] = _c64(pt.get(k))
+            setattr(v, k, _d(keep[k]))
+        for k in ("in_elem", "matnum", "crossings"):
+            keep[k] = _c32(pt.get(k))
+            setattr(v, k, _i(keep[k]))
+        self.n = n
+        self._check(self.lib.mpmgpu_upload_particles(self.ctx, C.byref(v)))
+
+    def set_velocity_bcs(self, node, norm, value, active=None, symdir=None):
+        n = 0 if node is None else len(node)
+        node, norm, value = _c32(node), _c64(norm), _c64(value)
+        active, symdir = _c32(active), _c32(symdir)
+        self._check(self.lib.mpmgpu_set_velocity_bcs(self.ctx, n, _i(node), _d(norm), _d(value), _i(active), _i(symdir)))
+
+    def update_velocity_bc_values(self, value, active=None):
+        value, active = _c64(value), _c32(active)
+        self._check(self.lib.mpmgpu_update_velocity_bc_values(self.ctx, len(value), _d(value), _i(active)))
+
+    def set_time_step(self, dt, dt_first, dt_last):
+        self._check(self.lib.mpmgpu_set_time_step(self.ctx, dt, dt_first, dt_last))
+
+    def set_xpic(self, order, using_fmpm):
+        self._check(self.lib.mpmgpu_set_xpic(self.ctx, order, int(using_fmpm)))
+
+    # -- the step -----------------------------------------------------------------------------
+    def step(self, nsteps=1):
+        self._check(self.lib.mpmgpu_step(self.ctx, int(nsteps)))
+
+    def run_task(self, name_or_index):
+        name = TASKS[name_or_index] if isinstance(name_or_index, int) else name_or_index
+        self._check(getattr(self.lib, "mpmgpu_task_" + name)(self.ctx))
+
+    def synchronize(self):
+        self._check(self.lib.mpmgpu_synchronize(self.ctx))
+
+    # -- device -> host -----------------------------------------------------------------------
+    def download(self, mask=F_ALL):
+        n = self.n
+        out = dict(pos=np.zeros((3, n)), vel=np.zeros((3, n)), sp=np.zeros((6, n)), pressure=np.zeros(n),
+                   ep=np.zeros((6, n)), wrot=np.zeros((3, n)), eplast=np.zeros((6, n)), energies=np.zeros((6, n)),
+                   history=np.zeros((MAX_HISTORY, n)), acc=np.zeros((3, n)),
+                   in_elem=np.zeros(n, np.int32), crossings=np.zeros(n, np.int32))
+        v = ParticlesView()
+        for k in ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "acc"):
+            setattr(v, k, _d(out[k]))
+        v.in_elem, v.crossings = _i(out["in_elem"]), _i(out["crossings"])
+        self._check(self.lib.mpmgpu_download_particles(self.ctx, C.byref(v), mask))
+        return out
+
+    def download_nodes(self):
+        n = self.nnodes
+        out = dict(number_points=np.zeros(n, np.int32), mass=np.zeros(n), pk=np.zeros((3, n)), ftot=np.zeros((3, n)),
+                   vk=np.zeros((3, n)), pk_copy=np.zeros((3, n)))
+        v = NodesView()
+        v.number_points = _i(out["number_points"])
+        for k in ("mass", "pk", "ftot", "vk", "pk_copy"):
+            setattr(v, k, _d(out[k]))
+        self._check(self.lib.mpmgpu_download_nodes(self.ctx, C.byref(v)))
+        return out
+
+    def status(self):
+        ms, cr, lg = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        mt = C.c_double()
+        self._check(self.lib.mpmgpu_get_status(self.ctx, C.byref(ms), C.byref(mt), C.byref(cr), C.byref(lg)))
+        return dict(mstep=ms.value, mtime=mt.value, crossings=cr.value, left_grid=lg.value)
+
+    def launch_count(self):
+        return int(self.lib.mpmgpu_launch_count(self.ctx))
+
+    def stream(self):
+        return self.lib.mpmgpu_stream(self.ctx)
+
+    def set_profiling(self, on):
+        self._check(self.lib.mpmgpu_set_profiling(self.ctx, int(on)))
+
+    def task_times(self):
+        ms = np.zeros(len(TASKS))
+        calls = np.zeros(len(TASKS), np.int64)
+        self._check(self.lib.mpmgpu_task_times(self.ctx, _d(ms), calls.ctypes.data_as(C.POINTER(C.c_longlong))))
+        return {t: (float(ms[i]), int(calls[i])) for i, t in enumerate(TASKS)}

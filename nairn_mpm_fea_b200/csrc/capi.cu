@@ -1,0 +1,773 @@
+// libmpmgpu: C ABI implementation (include/mpmgpu.h).  Owns the device-resident SoA particle and
+// node state and sequences the kernels of one MPM step in the reference's task order
+// (NairnMPM_Class/NairnMPM.cpp:870-1110, :284-335).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpmgpu.h"
+#include "mpm_types.cuh"
+#include "shape.cuh"
+#include "materials.cuh"
+#include "kernels_task.cuh"
+#include "kernels_tiled.cuh"
+
+static std::string g_create_error;
+
+enum { T_INIT = 0, T_MASSMOM, T_POSTEXTRAP, T_USF, T_FORCES, T_POSTFORCES, T_MOMENTA, T_PARTICLES, T_USL, T_RESET, T_NTASKS };
+
+struct mpmgpu_ctx {
+    mpmgpu_config cfg;
+    int dim;
+    Grid g;
+    Particles P;
+    Nodes N;
+    StepParams sp;
+    VelBCs B;
+    int nBCEntries;
+    std::vector<int> bcOrder;           // entry e on device = host list index bcOrder[e]
+    Material *dMats;
+    int nmat;
+    std::vector<Material> hMats;
+    StatusFlags *dFlags;
+    StatusFlags hFlags;
+    cudaStream_t stream;
+    std::vector<void *> allocs;         // everything cudaMalloc'd, for destroy
+    double *particlePool;               // one slab for all particle doubles
+    int *particleIntPool;
+    double *nodePool;
+    size_t cap;                         // particle capacity
+    long long mstep;
+    double mtime;
+    long long launches;
+    bool uploaded, hasFext, hasBCs;
+    std::string err;
+    // profiling
+    bool profiling;
+    cudaEvent_t ev0, ev1;
+    double taskMs[T_NTASKS];
+    long long taskCalls[T_NTASKS];
+    // staging
+    double *hStage; size_t hStageBytes;
+    TiledState tiled;
+};
+
+static int fail(mpmgpu_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(ctx, MPMGPU_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <class T>
+static cudaError_t dalloc(mpmgpu_ctx *ctx, T **p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) ctx->allocs.push_back((void *)*p);
+    return e;
+}
+
+static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
+
+#define LAUNCH(kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int mpmgpu_abi_version(void) { return MPMGPU_ABI_VERSION; }
+
+extern "C" const char *mpmgpu_last_error(const mpmgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
+{
+    mpmgpu_ctx *ctx = NULL;
+    if (!cfg || !out) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: null argument");
+    *out = NULL;
+    if (cfg->abi_version != MPMGPU_ABI_VERSION) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: ABI version %d, library is %d", cfg->abi_version, MPMGPU_ABI_VERSION);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(NULL, MPMGPU_ENODEVICE, "mpmgpu_create: no CUDA device (libmpmgpu has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: device %d of %d", cfg->device, ndev);
+    if (cfg->np != MPMGPU_THREED_MPM && cfg->np != MPMGPU_PLANE_STRAIN_MPM && cfg->np != MPMGPU_PLANE_STRESS_MPM)
+        return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: analysis type %d not supported (10, 11, 12)", cfg->np);
+    const bool is3D = cfg->np == MPMGPU_THREED_MPM;
+    if (cfg->horiz < 3 || cfg->vert < 3 || (is3D && cfg->depth < 3)) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: grid needs >=3 cells per axis incl. border");
+    if (!cfg->xpts || !cfg->ypts || (is3D && !cfg->zpts)) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: node coordinate arrays missing");
+    if (cfg->shape != MPMGPU_POINT_GIMP && cfg->shape != MPMGPU_UNIFORM_GIMP && cfg->shape != MPMGPU_LINEAR_CPDI && cfg->shape != MPMGPU_QUADRATIC_CPDI)
+        return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: shape function code %d not supported", cfg->shape);
+    if (cfg->shape == MPMGPU_QUADRATIC_CPDI && is3D) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: qCPDI is 2D only (as in the reference)");
+    if (cfg->method != MPMGPU_USF && cfg->method != MPMGPU_USAVG && cfg->method != MPMGPU_USL)
+        return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: MPM method %d not supported", cfg->method);
+    if (cfg->shape == MPMGPU_LINEAR_CPDI || cfg->shape == MPMGPU_QUADRATIC_CPDI)
+        return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: CPDI shape functions are not built yet in this round");
+    if (cfg->xpic_order > 1) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: XPIC/FMPM order>1 is not built yet in this round");
+
+    ctx = new mpmgpu_ctx();
+    ctx->cfg = *cfg;
+    ctx->dim = is3D ? 3 : 2;
+    ctx->dMats = NULL; ctx->nmat = 0; ctx->dFlags = NULL;
+    ctx->cap = 0; ctx->mstep = 0; ctx->mtime = 0.; ctx->launches = 0;
+    ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->profiling = false;
+    ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
+    ctx->hStage = NULL; ctx->hStageBytes = 0; ctx->nBCEntries = 0;
+    memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B);
+    memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
+    memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
+    tiled_state_init(ctx->tiled);
+
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { int rc = fail(NULL, MPMGPU_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); delete ctx; return rc; }
+    cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+
+    Grid &g = ctx->g;
+    g.dim = ctx->dim; g.np = cfg->np;
+    g.horiz = cfg->horiz; g.vert = cfg->vert; g.depth = is3D ? cfg->depth : 1;
+    g.yplane = g.horiz + 1; g.zplane = (g.horiz + 1) * (g.vert + 1);
+    g.nnodes = is3D ? (g.horiz + 1) * (g.vert + 1) * (g.depth + 1) : (g.horiz + 1) * (g.vert + 1);
+    g.nelems = g.horiz * g.vert * g.depth;
+    g.gx = cfg->gridx; g.gy = cfg->gridy; g.gz = is3D ? cfg->gridz : 0.;
+    g.xmin = cfg->xpts[0]; g.ymin = cfg->ypts[0]; g.zmin = is3D ? cfg->zpts[0] : 0.;
+    g.rcrit = cfg->cpdi_rcrit;
+    double *dx = NULL, *dy = NULL, *dz = NULL;
+    int rc = MPMGPU_OK;
+    do {
+        if (dalloc(ctx, &dx, g.horiz + 1) != cudaSuccess || dalloc(ctx, &dy, g.vert + 1) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+        cudaMemcpy(dx, cfg->xpts, (g.horiz + 1) * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(dy, cfg->ypts, (g.vert + 1) * sizeof(double), cudaMemcpyHostToDevice);
+        if (is3D) {
+            if (dalloc(ctx, &dz, g.depth + 1) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+            cudaMemcpy(dz, cfg->zpts, (g.depth + 1) * sizeof(double), cudaMemcpyHostToDevice);
+        }
+        g.xpts = dx; g.ypts = dy; g.zpts = dz;
+        // node arrays: mass + 7 vectors, one pool
+        size_t nn = (size_t)g.nnodes;
+        size_t nnPad = (nn + 31) & ~(size_t)31;
+        if (dalloc(ctx, &ctx->nodePool, nnPad * 22) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+        cudaMemset(ctx->nodePool, 0, nnPad * 22 * sizeof(double));
+        double *q = ctx->nodePool;
+        ctx->N.mass = q; q += nnPad;
+        for (int c = 0; c < 3; c++) { ctx->N.pk[c] = q; q += nnPad; }
+        for (int c = 0; c < 3; c++) { ctx->N.ftot[c] = q; q += nnPad; }
+        for (int c = 0; c < 3; c++) { ctx->N.vk[c] = q; q += nnPad; }
+        for (int c = 0; c < 3; c++) { ctx->N.pkc[c] = q; q += nnPad; }
+        for (int c = 0; c < 3; c++) { ctx->N.vsp[c] = q; q += nnPad; }
+        for (int c = 0; c < 3; c++) { ctx->N.vsn[c] = q; q += nnPad; }
+        if (dalloc(ctx, &ctx->N.cnt, nnPad) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+        cudaMemset(ctx->N.cnt, 0, nnPad * sizeof(int));
+        if (dalloc(ctx, &ctx->dFlags, 1) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+        cudaMemset(ctx->dFlags, 0, sizeof(StatusFlags));
+        if (dalloc(ctx, &ctx->dMats, MPM_MAX_MATERIALS) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+    } while (0);
+    if (rc != MPMGPU_OK) { fail(NULL, rc, "mpmgpu_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); mpmgpu_destroy(ctx); return rc; }
+
+    StepParams &sp = ctx->sp;
+    memset(&sp, 0, sizeof sp);
+    sp.method = cfg->method; sp.skipPost = cfg->skip_post_extrapolation;
+    sp.fractionUSF = cfg->fraction_usf > 0. ? cfg->fraction_usf : 0.5;
+    sp.xpicOrder = cfg->xpic_order; sp.usingFMPM = cfg->using_fmpm;
+    sp.gridAlpha = cfg->grid_damping; sp.particleAlpha = cfg->particle_damping;
+    for (int c = 0; c < 3; c++) sp.grav[c] = cfg->gravity[c];
+    sp.hasGravity = (sp.grav[0] != 0. || sp.grav[1] != 0. || sp.grav[2] != 0.);
+    *out = ctx;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_destroy(mpmgpu_ctx *ctx)
+{
+    if (!ctx) return MPMGPU_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    tiled_state_free(ctx->tiled);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_material *mats)
+{
+    if (!ctx || !mats || nmat < 1 || nmat > MPM_MAX_MATERIALS) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: need 1..%d materials", MPM_MAX_MATERIALS);
+    ctx->hMats.resize(nmat);
+    for (int i = 0; i < nmat; i++) {
+        int k = mats[i].kind;
+        if (k != MAT_ISOTROPIC && k != MAT_RIGIDBC)
+            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d is not built yet in this round (have %d IsotropicMat, %d rigid BC)", k, MAT_ISOTROPIC, MAT_RIGIDBC);
+        if (mats[i].n_history < 0 || mats[i].n_history > MPM_MAX_HISTORY) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: %d history doubles (max %d)", mats[i].n_history, MPM_MAX_HISTORY);
+        ctx->hMats[i].kind = k; ctx->hMats[i].nhist = mats[i].n_history;
+        memcpy(ctx->hMats[i].p, mats[i].p, sizeof(double) * MPM_MAT_NPARAMS);
+    }
+    ctx->nmat = nmat;
+    CK(cudaMemcpyAsync(ctx->dMats, ctx->hMats.data(), nmat * sizeof(Material), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+// number of double arrays per particle in the pool
+#define NPD (3 + 3 + 1 + 3 + 3 + 9 + 6 + 1 + 6 + 6 + MPM_MAX_HISTORY + 3 + 3)
+#define NPI 4
+
+static int alloc_particles(mpmgpu_ctx *ctx, size_t cap)
+{
+    if (ctx->cap >= cap) return MPMGPU_OK;
+    if (ctx->cap != 0) return fail(ctx, MPMGPU_EINVAL, "particle capacity %zu exceeded (%zu); set max_particles", ctx->cap, cap);
+    size_t capPad = (cap + 31) & ~(size_t)31;
+    CK(dalloc(ctx, &ctx->particlePool, capPad * NPD));
+    CK(dalloc(ctx, &ctx->particleIntPool, capPad * NPI));
+    CK(cudaMemsetAsync(ctx->particlePool, 0, capPad * NPD * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->particleIntPool, 0, capPad * NPI * sizeof(int), ctx->stream));
+    Particles &P = ctx->P;
+    double *q = ctx->particlePool;
+    auto take = [&]() { double *r = q; q += capPad; return r; };
+    for (int c = 0; c < 3; c++) P.pos[c] = take();
+    for (int c = 0; c < 3; c++) P.vel[c] = take();
+    P.mp = take();
+    for (int c = 0; c < 3; c++) P.lp[c] = take();
+    for (int c = 0; c < 3; c++) P.ncpos[c] = take();
+    for (int c = 0; c < 9; c++) P.F[c] = take();
+    for (int c = 0; c < 6; c++) P.sp[c] = take();
+    P.pressure = take();
+    for (int c = 0; c < 6; c++) P.eplast[c] = take();
+    P.work = take(); P.res = take(); P.heat = take(); P.entropy = take(); P.plast = take(); P.prevT = take();
+    for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c] = take();
+    for (int c = 0; c < 3; c++) P.pfext[c] = take();
+    for (int c = 0; c < 3; c++) P.acc[c] = take();
+    int *qi = ctx->particleIntPool;
+    P.elem = qi; qi += capPad; P.mat = qi; qi += capPad; P.cross = qi; qi += capPad; P.orig = qi;
+    ctx->cap = capPad;
+    return MPMGPU_OK;
+}
+
+static int ensure_stage(mpmgpu_ctx *ctx, size_t bytes)
+{
+    if (ctx->hStageBytes >= bytes) return MPMGPU_OK;
+    if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    ctx->hStage = NULL; ctx->hStageBytes = 0;
+    CK(cudaMallocHost((void **)&ctx->hStage, bytes));
+    ctx->hStageBytes = bytes;
+    return MPMGPU_OK;
+}
+
+// copy a host [ncomp][n] array to device component arrays (zero-fill when host is NULL)
+static int up_field(mpmgpu_ctx *ctx, double *const *dev, const double *host, int ncomp, int n)
+{
+    for (int c = 0; c < ncomp; c++) {
+        if (host) CK(cudaMemcpyAsync(dev[c], host + (size_t)c * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(dev[c], 0, (size_t)n * sizeof(double), ctx->stream));
+    }
+    return MPMGPU_OK;
+}
+
+__global__ void k_epwrot_to_F(int n, int dim, const double *ep, const double *wrot, Particles P)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    // MatPoint3D::GetDeformationGradient (MatPoint3D.cpp:363-376), 2D: MatPoint2D.cpp:369-377
+    double exx = ep ? ep[p] : 0., eyy = ep ? ep[n + p] : 0., ezz = ep ? ep[2 * n + p] : 0.;
+    double eyz = ep ? ep[3 * n + p] : 0., exz = ep ? ep[4 * n + p] : 0., exy = ep ? ep[5 * n + p] : 0.;
+    double wxy = wrot ? wrot[p] : 0., wxz = wrot ? wrot[n + p] : 0., wyz = wrot ? wrot[2 * n + p] : 0.;
+    P.F[0][p] = 1. + exx; P.F[4][p] = 1. + eyy; P.F[8][p] = 1. + ezz;
+    P.F[1][p] = 0.5 * (exy - wxy); P.F[3][p] = 0.5 * (exy + wxy);
+    if (dim == 3) {
+        P.F[2][p] = 0.5 * (exz - wxz); P.F[6][p] = 0.5 * (exz + wxz);
+        P.F[5][p] = 0.5 * (eyz - wyz); P.F[7][p] = 0.5 * (eyz + wyz);
+    } else {
+        P.F[2][p] = 0.; P.F[6][p] = 0.; P.F[5][p] = 0.; P.F[7][p] = 0.;
+    }
+}
+
+__global__ void k_F_to_epwrot(int n, int dim, Particles P, const int *slot, double *ep, double *wrot)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int o = slot[p];        // caller's index
+    // MatPoint3D::SetDeformationGradientMatrix (MatPoint3D.cpp:320-336)
+    double F0 = P.F[0][p], F1 = P.F[1][p], F2 = P.F[2][p], F3 = P.F[3][p], F4 = P.F[4][p], F5 = P.F[5][p], F6 = P.F[6][p], F7 = P.F[7][p], F8 = P.F[8][p];
+    ep[o] = F0 - 1.; ep[n + o] = F4 - 1.; ep[2 * n + o] = F8 - 1.;
+    ep[5 * n + o] = F3 + F1; wrot[o] = F3 - F1;
+    if (dim == 3) {
+        ep[4 * n + o] = F6 + F2; ep[3 * n + o] = F7 + F5;
+        wrot[n + o] = F6 - F2; wrot[2 * n + o] = F7 - F5;
+    } else {
+        ep[4 * n + o] = 0.; ep[3 * n + o] = 0.; wrot[n + o] = 0.; wrot[2 * n + o] = 0.;
+    }
+}
+
+__global__ void k_iota(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+__global__ void k_fill(int n, double *a, double v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = v; }
+__global__ void k_dec(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] -= 1; }
+
+// scatter device (internal order) -> staging buffer in the caller's order
+__global__ void k_unpermute(int n, const double *src, const int *slot, double *dst)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[slot[p]] = src[p];
+}
+__global__ void k_unpermute_int(int n, const int *src, const int *slot, int *dst, int add)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[slot[p]] = src[p] + add;
+}
+
+extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *h)
+{
+    if (!ctx || !h) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: null argument");
+    if (ctx->nmat == 0) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_upload_particles: call mpmgpu_set_materials first");
+    const int n = h->n;
+    if (n < 1 || h->n_nonrigid < 0 || h->n_nonrigid > n) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: bad counts n=%d nonrigid=%d", n, h->n_nonrigid);
+    if (!h->pos || !h->mp || !h->in_elem || !h->lp) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: pos, mp, lp and in_elem are required");
+    cudaSetDevice(ctx->cfg.device);
+    size_t want = ctx->cfg.max_particles > n ? (size_t)ctx->cfg.max_particles : (size_t)n;
+    int rc = alloc_particles(ctx, want);
+    if (rc) return rc;
+    // validate on the host: materials and elements in range
+    for (int p = 0; p < n; p++) {
+        int m = h->matnum ? h->matnum[p] : 1;
+        if (m < 1 || m > ctx->nmat) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d has material %d of %d", p, m, ctx->nmat);
+        int e = h->in_elem[p];
+        if (e < 1 || e > ctx->g.nelems) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d in element %d of %d", p, e, ctx->g.nelems);
+    }
+    Particles &P = ctx->P;
+    P.n = n; P.nNR = h->n_nonrigid;
+    const int T = 256;
+    if ((rc = up_field(ctx, P.pos, h->pos, 3, n))) return rc;
+    if ((rc = up_field(ctx, P.vel, h->vel, 3, n))) return rc;
+    if ((rc = up_field(ctx, &P.mp, h->mp, 1, n))) return rc;
+    if ((rc = up_field(ctx, P.lp, h->lp, 3, n))) return rc;
+    if ((rc = up_field(ctx, P.sp, h->sp, 6, n))) return rc;
+    if ((rc = up_field(ctx, &P.pressure, h->pressure, 1, n))) return rc;
+    if ((rc = up_field(ctx, P.eplast, h->eplast, 6, n))) return rc;
+    if (h->energies) {
+        double *const e5[6] = {P.work, P.res, P.heat, P.entropy, P.plast, P.prevT};
+        if ((rc = up_field(ctx, e5, h->energies, 6, n))) return rc;
+    } else {
+        double *const e5[5] = {P.work, P.res, P.heat, P.entropy, P.plast};
+        if ((rc = up_field(ctx, e5, NULL, 5, n))) return rc;
+        LAUNCH(k_fill, nblocks(n, T), T, n, P.prevT, 1.);
+    }
+    if ((rc = up_field(ctx, P.hist, h->history, MPM_MAX_HISTORY, n))) return rc;
+    if ((rc = up_field(ctx, P.pfext, h->pfext, 3, n))) return rc;
+    ctx->hasFext = h->pfext != NULL;
+    if ((rc = up_field(ctx, P.acc, NULL, 3, n))) return rc;
+    if ((rc = up_field(ctx, P.ncpos, NULL, 3, n))) return rc;
+    CK(cudaMemcpyAsync(P.elem, h->in_elem, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (h->matnum) {
+        CK(cudaMemcpyAsync(P.mat, h->matnum, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_dec, nblocks(n, T), T, n, P.mat);
+    } else CK(cudaMemsetAsync(P.mat, 0, (size_t)n * sizeof(int), ctx->stream));
+    if (h->crossings) CK(cudaMemcpyAsync(P.cross, h->crossings, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(P.cross, 0, (size_t)n * sizeof(int), ctx->stream));
+    LAUNCH(k_iota, nblocks(n, T), T, n, P.orig);
+    // strain + rotation -> deformation gradient (staged through a temporary device buffer)
+    {
+        double *tmp = NULL;
+        CK(cudaMalloc((void **)&tmp, (size_t)n * 9 * sizeof(double)));
+        const double *dep = NULL, *dw = NULL;
+        if (h->ep) { CK(cudaMemcpyAsync(tmp, h->ep, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); dep = tmp; }
+        if (h->wrot) { CK(cudaMemcpyAsync(tmp + (size_t)6 * n, h->wrot, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); dw = tmp + (size_t)6 * n; }
+        LAUNCH(k_epwrot_to_F, nblocks(n, T), T, n, ctx->dim, dep, dw, P);
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(StatusFlags), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->uploaded = true;
+    tiled_on_upload(ctx->tiled);
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dtFirst, double dtLast)
+{
+    if (!ctx || !(dt > 0.)) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_time_step: dt must be > 0");
+    ctx->sp.dt = dt; ctx->sp.dtStrainFirst = dtFirst; ctx->sp.dtStrainLast = dtLast;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_set_xpic(mpmgpu_ctx *ctx, int order, int usingFMPM)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (order > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: order>1 is not built yet in this round");
+    ctx->sp.xpicOrder = order; ctx->sp.usingFMPM = usingFMPM;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *norm,
+                                       const double *value, const int *active, const int *symdir)
+{
+    if (!ctx || n < 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    ctx->hasBCs = n > 0;
+    ctx->nBCEntries = n;
+    if (n == 0) { ctx->B.nUnique = 0; return MPMGPU_OK; }
+    if (!node || !norm || !value) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: null arrays");
+    for (int i = 0; i < n; i++)
+        if (node[i] < 1 || node[i] > ctx->g.nnodes) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: BC %d on node %d of %d", i, node[i], ctx->g.nnodes);
+    // group by node, keeping list order inside a node
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return node[a] < node[b]; });
+    std::vector<int> un, st, sd, ac(n);
+    std::vector<double> nm(3 * (size_t)n), va(n);
+    for (int e = 0; e < n; e++) {
+        int i = order[e];
+        if (e == 0 || node[i] != node[order[e - 1]]) { un.push_back(node[i] - 1); st.push_back(e); sd.push_back(0); }
+        if (symdir) sd.back() |= symdir[i];
+        nm[3 * e] = norm[3 * i]; nm[3 * e + 1] = norm[3 * i + 1]; nm[3 * e + 2] = norm[3 * i + 2];
+        va[e] = value[i]; ac[e] = active ? active[i] : 1;
+    }
+    st.push_back(n);
+    ctx->bcOrder = order;
+    int nu = (int)un.size();
+    int *dn, *ds, *dsd, *da; double *dnm, *dva;
+    CK(dalloc(ctx, &dn, nu)); CK(dalloc(ctx, &ds, nu + 1)); CK(dalloc(ctx, &dsd, nu)); CK(dalloc(ctx, &da, n));
+    CK(dalloc(ctx, &dnm, 3 * (size_t)n)); CK(dalloc(ctx, &dva, n));
+    CK(cudaMemcpy(dn, un.data(), nu * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ds, st.data(), (nu + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsd, sd.data(), nu * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(da, ac.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dnm, nm.data(), 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dva, va.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->B.nUnique = nu; ctx->B.node = dn; ctx->B.start = ds; ctx->B.symdir = dsd; ctx->B.active = da; ctx->B.norm = dnm; ctx->B.value = dva;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const double *value, const int *active)
+{
+    if (!ctx || n != ctx->nBCEntries) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_velocity_bc_values: n=%d but %d BCs are set", n, ctx ? ctx->nBCEntries : 0);
+    if (n == 0) return MPMGPU_OK;
+    cudaSetDevice(ctx->cfg.device);
+    std::vector<double> va(n); std::vector<int> ac(n);
+    for (int e = 0; e < n; e++) { int i = ctx->bcOrder[e]; va[e] = value[i]; ac[e] = active ? active[i] : 1; }
+    CK(cudaMemcpyAsync((void *)ctx->B.value, va.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((void *)ctx->B.active, ac.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// task bodies
+#define DISPATCH_DIM_SHAPE(KERNEL, n, ...) do { \
+    const int grid_ = nblocks((n), TASK_THREADS); \
+    if (grid_ > 0) { \
+        if (ctx->dim == 3) { \
+            if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<3, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else LAUNCH((KERNEL<3, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
+        } else { \
+            if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<2, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else LAUNCH((KERNEL<2, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
+        } } } while (0)
+
+static int check_ready(mpmgpu_ctx *ctx, const char *who)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "%s: no particles uploaded", who);
+    if (!(ctx->sp.dt > 0.)) return fail(ctx, MPMGPU_ESTATE, "%s: time step not set", who);
+    cudaSetDevice(ctx->cfg.device);
+    return MPMGPU_OK;
+}
+
+static void prof_begin(mpmgpu_ctx *ctx) { if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream); }
+static void prof_end(mpmgpu_ctx *ctx, int task)
+{
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->taskMs[task] += ms; ctx->taskCalls[task]++;
+}
+
+static int apply_bcs(mpmgpu_ctx *ctx, int pass, int adjustSym)
+{
+    if (!ctx->hasBCs || ctx->B.nUnique == 0) return MPMGPU_OK;
+    LAUNCH(k_velocity_bcs, nblocks(ctx->B.nUnique, 128), 128, ctx->B, ctx->N, pass, ctx->sp.dt, adjustSym);
+    return MPMGPU_OK;
+}
+
+static int t_initialization(mpmgpu_ctx *ctx)
+{
+    const Grid &g = ctx->g;
+    size_t nnPad = ((size_t)g.nnodes + 31) & ~(size_t)31;
+    // MatVelocityField::Zero: mass, pk, ftot, vk[0], vk[pkCopy] (+XPIC vectors), numberPoints
+    CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 22 * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
+    ctx->launches += 2;
+    const int n = ctx->P.n;
+    if (ctx->dim == 3) LAUNCH(k_init_particles<3>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P);
+    else LAUNCH(k_init_particles<2>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P);
+    return MPMGPU_OK;
+}
+
+static int t_mass_and_momentum(mpmgpu_ctx *ctx)
+{
+    DISPATCH_DIM_SHAPE(k_p2g_mass_momentum, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
+    return MPMGPU_OK;
+}
+
+static int t_post_extrapolation(mpmgpu_ctx *ctx)
+{
+    LAUNCH(k_copy_momenta, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+    // MASS_MOMENTUM_CALL: symmetry adjust always, BC loop only when a USF task exists (NodalVelBC.cpp:339-361)
+    const bool hasUSF = ctx->sp.method == METHOD_USF || ctx->sp.method == METHOD_USAVG;
+    return apply_bcs(ctx, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
+}
+
+static int strain_update(mpmgpu_ctx *ctx, double strainTime)
+{
+    LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+    DISPATCH_DIM_SHAPE(k_update_strains, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
+    return MPMGPU_OK;
+}
+
+static int t_update_strains_first(mpmgpu_ctx *ctx)
+{
+    if (ctx->sp.method == METHOD_USL) return MPMGPU_OK;       // no USF task in the list (NairnMPM.cpp:1004-1010)
+    double st = ctx->sp.method == METHOD_USAVG ? ctx->sp.dtStrainFirst : ctx->sp.dt;
+    return strain_update(ctx, st);
+}
+
+static int t_grid_forces(mpmgpu_ctx *ctx)
+{
+    DISPATCH_DIM_SHAPE(k_p2g_forces, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->hasFext ? 1 : 0);
+    return MPMGPU_OK;
+}
+
+static int t_post_forces(mpmgpu_ctx *ctx)
+{
+    LAUNCH(k_post_forces, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N, ctx->sp);
+    return apply_bcs(ctx, PASS_GRID_FORCES, 0);
+}
+
+static int t_update_momenta(mpmgpu_ctx *ctx)
+{
+    LAUNCH(k_update_momenta, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N, ctx->sp.dt);
+    if (ctx->sp.xpicOrder <= 1) return apply_bcs(ctx, PASS_UPDATE_MOMENTUM, 0);      // NodalVelBC.cpp:367-375
+    return MPMGPU_OK;
+}
+
+static int t_update_particles(mpmgpu_ctx *ctx)
+{
+    LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+    int m = ctx->sp.xpicOrder;
+    if (!ctx->sp.usingFMPM) m = -m;
+    DISPATCH_DIM_SHAPE(k_update_particles, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, ctx->sp, m);
+    return MPMGPU_OK;
+}
+
+static int t_update_strains_last(mpmgpu_ctx *ctx)
+{
+    if (ctx->sp.method == METHOD_USF) return MPMGPU_OK;
+    if (!ctx->sp.skipPost) {
+        LAUNCH(k_rezero_momenta, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+        DISPATCH_DIM_SHAPE(k_p2g_momentum_last, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
+        int rc = apply_bcs(ctx, PASS_UPDATE_STRAINS_LAST, 0);
+        if (rc) return rc;
+    }
+    double st = ctx->sp.method == METHOD_USAVG ? ctx->sp.dtStrainLast : ctx->sp.dt;
+    return strain_update(ctx, st);
+}
+
+static int t_reset_elements(mpmgpu_ctx *ctx)
+{
+    const int n = ctx->P.n;
+    if (ctx->dim == 3) LAUNCH(k_reset_elements<3>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->dFlags, ctx->sp.dt);
+    else LAUNCH(k_reset_elements<2>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->dFlags, ctx->sp.dt);
+    return MPMGPU_OK;
+}
+
+static int poll_flags(mpmgpu_ctx *ctx)
+{
+    CK(cudaMemcpyAsync(&ctx->hFlags, ctx->dFlags, sizeof(StatusFlags), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (ctx->hFlags.nanParticle) return fail(ctx, MPMGPU_ENAN, "particle %d left grid with position nan (ResetElementsTask)", ctx->hFlags.nanParticle - 1);
+    if (ctx->hFlags.cpdiLeft) return fail(ctx, MPMGPU_ECPDI, "a CPDI corner of particle %d has left the grid", ctx->hFlags.cpdiLeft - 1);
+    return MPMGPU_OK;
+}
+
+#define TASK_ENTRY(NAME, BODY, TASKID) \
+extern "C" int NAME(mpmgpu_ctx *ctx) \
+{ \
+    int rc = check_ready(ctx, #NAME); if (rc) return rc; \
+    prof_begin(ctx); rc = BODY(ctx); prof_end(ctx, TASKID); \
+    if (rc) return rc; \
+    CK(cudaGetLastError()); \
+    return MPMGPU_OK; \
+}
+
+TASK_ENTRY(mpmgpu_task_initialization, t_initialization, T_INIT)
+TASK_ENTRY(mpmgpu_task_mass_and_momentum, t_mass_and_momentum, T_MASSMOM)
+TASK_ENTRY(mpmgpu_task_post_extrapolation, t_post_extrapolation, T_POSTEXTRAP)
+TASK_ENTRY(mpmgpu_task_update_strains_first, t_update_strains_first, T_USF)
+TASK_ENTRY(mpmgpu_task_grid_forces, t_grid_forces, T_FORCES)
+TASK_ENTRY(mpmgpu_task_post_forces, t_post_forces, T_POSTFORCES)
+TASK_ENTRY(mpmgpu_task_update_momenta, t_update_momenta, T_MOMENTA)
+TASK_ENTRY(mpmgpu_task_update_particles, t_update_particles, T_PARTICLES)
+TASK_ENTRY(mpmgpu_task_update_strains_last, t_update_strains_last, T_USL)
+
+extern "C" int mpmgpu_task_reset_elements(mpmgpu_ctx *ctx)
+{
+    int rc = check_ready(ctx, "mpmgpu_task_reset_elements"); if (rc) return rc;
+    prof_begin(ctx); rc = t_reset_elements(ctx); prof_end(ctx, T_RESET);
+    if (rc) return rc;
+    ctx->mstep++; ctx->mtime += ctx->sp.dt;
+    return poll_flags(ctx);
+}
+
+static int step_by_tasks(mpmgpu_ctx *ctx)
+{
+    int rc;
+    typedef int (*taskfn)(mpmgpu_ctx *);
+    static const taskfn seq[T_NTASKS] = {t_initialization, t_mass_and_momentum, t_post_extrapolation, t_update_strains_first,
+                                         t_grid_forces, t_post_forces, t_update_momenta, t_update_particles,
+                                         t_update_strains_last, t_reset_elements};
+    for (int t = 0; t < T_NTASKS; t++) {
+        prof_begin(ctx);
+        rc = seq[t](ctx);
+        prof_end(ctx, t);
+        if (rc) return rc;
+    }
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
+{
+    int rc = check_ready(ctx, "mpmgpu_step"); if (rc) return rc;
+    for (int s = 0; s < nsteps; s++) {
+        rc = step_by_tasks(ctx);
+        if (rc) return rc;
+        ctx->mstep++; ctx->mtime += ctx->sp.dt;
+    }
+    return poll_flags(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int down_field(mpmgpu_ctx *ctx, double *const *dev, double *host, int ncomp, int n, double *dtmp)
+{
+    if (!host) return MPMGPU_OK;
+    const int T = 256;
+    for (int c = 0; c < ncomp; c++) {
+        LAUNCH(k_unpermute, nblocks(n, T), T, n, dev[c], ctx->P.orig, dtmp);
+        CK(cudaMemcpyAsync(host + (size_t)c * n, dtmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, unsigned mask)
+{
+    if (!ctx || !h) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_download_particles: null argument");
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_download_particles: nothing uploaded");
+    cudaSetDevice(ctx->cfg.device);
+    Particles &P = ctx->P;
+    const int n = P.n;
+    h->n = n; h->n_nonrigid = P.nNR;
+    double *dtmp = NULL;
+    CK(cudaMalloc((void **)&dtmp, (size_t)n * 9 * sizeof(double)));
+    int rc = MPMGPU_OK;
+    const int T = 256;
+    do {
+        if ((mask & MPMGPU_F_POS) && (rc = down_field(ctx, P.pos, h->pos, 3, n, dtmp))) break;
+        if ((mask & MPMGPU_F_VEL) && (rc = down_field(ctx, P.vel, h->vel, 3, n, dtmp))) break;
+        if (mask & MPMGPU_F_STRESS) {
+            if ((rc = down_field(ctx, P.sp, h->sp, 6, n, dtmp))) break;
+            if ((rc = down_field(ctx, &P.pressure, h->pressure, 1, n, dtmp))) break;
+        }
+        if ((mask & MPMGPU_F_STRAIN) && h->ep && h->wrot) {
+            LAUNCH(k_F_to_epwrot, nblocks(n, T), T, n, ctx->dim, P, P.orig, dtmp, dtmp + (size_t)6 * n);
+            CK(cudaMemcpyAsync(h->ep, dtmp, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h->wrot, dtmp + (size_t)6 * n, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if ((mask & MPMGPU_F_EPLAST) && (rc = down_field(ctx, P.eplast, h->eplast, 6, n, dtmp))) break;
+        if ((mask & MPMGPU_F_ENERGY) && h->energies) {
+            double *const e6[6] = {P.work, P.res, P.heat, P.entropy, P.plast, P.prevT};
+            if ((rc = down_field(ctx, e6, h->energies, 6, n, dtmp))) break;
+        }
+        if ((mask & MPMGPU_F_HISTORY) && (rc = down_field(ctx, P.hist, h->history, MPM_MAX_HISTORY, n, dtmp))) break;
+        if ((mask & MPMGPU_F_ACC) && (rc = down_field(ctx, P.acc, h->acc, 3, n, dtmp))) break;
+        if (mask & MPMGPU_F_ELEM) {
+            int *itmp = (int *)dtmp;
+            if (h->in_elem) {
+                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.elem, P.orig, itmp, 0);
+                CK(cudaMemcpyAsync(h->in_elem, itmp, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            if (h->crossings) {
+                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.cross, P.orig, itmp + n, 0);
+                CK(cudaMemcpyAsync(h->crossings, itmp + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        }
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dtmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, MPMGPU_ECUDA, "mpmgpu_download_particles: %s", cudaGetErrorString(e));
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_download_nodes(mpmgpu_ctx *ctx, mpmgpu_nodes *h)
+{
+    if (!ctx || !h) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_download_nodes: null argument");
+    cudaSetDevice(ctx->cfg.device);
+    const size_t nn = ctx->g.nnodes;
+    h->nnodes = (int)nn;
+    if (h->number_points) CK(cudaMemcpyAsync(h->number_points, ctx->N.cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (h->mass) CK(cudaMemcpyAsync(h->mass, ctx->N.mass, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int c = 0; c < 3; c++) {
+        if (h->pk) CK(cudaMemcpyAsync(h->pk + c * nn, ctx->N.pk[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h->ftot) CK(cudaMemcpyAsync(h->ftot + c * nn, ctx->N.ftot[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h->vk) CK(cudaMemcpyAsync(h->vk + c * nn, ctx->N.vk[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h->pk_copy) CK(cudaMemcpyAsync(h->pk_copy + c * nn, ctx->N.pkc[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_synchronize(mpmgpu_ctx *ctx)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    cudaSetDevice(ctx->cfg.device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_get_status(mpmgpu_ctx *ctx, long long *mstep, double *mtime, long long *crossings, long long *leftGrid)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    cudaSetDevice(ctx->cfg.device);
+    CK(cudaMemcpyAsync(&ctx->hFlags, ctx->dFlags, sizeof(StatusFlags), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (mstep) *mstep = ctx->mstep;
+    if (mtime) *mtime = ctx->mtime;
+    if (crossings) *crossings = (long long)ctx->hFlags.crossings;
+    if (leftGrid) *leftGrid = (long long)ctx->hFlags.leftGrid;
+    return MPMGPU_OK;
+}
+
+extern "C" long long mpmgpu_launch_count(const mpmgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void *mpmgpu_stream(mpmgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : NULL; }
+
+extern "C" int mpmgpu_set_profiling(mpmgpu_ctx *ctx, int on)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    ctx->profiling = on != 0;
+    memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_task_times(mpmgpu_ctx *ctx, double *ms, long long *calls)
+{
+    if (!ctx || !ms) return MPMGPU_EINVAL;
+    for (int t = 0; t < T_NTASKS; t++) { ms[t] = ctx->taskMs[t]; if (calls) calls[t] = ctx->taskCalls[t]; }
+    return MPMGPU_OK;
+}

@@ -1,0 +1,365 @@
+// Per-task kernels: one kernel (or a node sweep) per reference MPMTask, particles in any order,
+// node accumulation by global FP64 atomics.  This is the general path (every shape function,
+// 2D and 3D, every material); the cell-sorted tiled kernels in kernels_tiled.cuh replace the
+// particle<->grid transfers of the 3D uGIMP step when the configuration is eligible.
+#pragma once
+#include "mpm_types.cuh"
+#include "shape.cuh"
+#include "materials.cuh"
+
+#define TASK_THREADS 128
+
+__device__ __forceinline__ void load_xi_lp(const Particles &P, int p, double xi[3], double lp[3])
+{
+    xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
+    lp[0] = P.lp[0][p]; lp[1] = P.lp[1][p]; lp[2] = P.lp[2][p];
+}
+
+// ---- task 1: InitializationTask (InitializationTask.cpp:49-85) ------------------------------
+// node zeroing is a memset; this is the particle half: ncpos = GetXiPos(pos) in the current element
+template <int DIM>
+__global__ void __launch_bounds__(TASK_THREADS) k_init_particles(Grid g, Particles P)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    int e = P.elem[p];
+    if (e <= 1 && false) return;
+    double pos[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
+    double xi[3];
+    get_xipos<DIM>(g, e, pos, xi);
+    P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
+}
+
+// ---- task 2: MassAndMomentumTask (MassAndMomentumTask.cpp:62-98, NodalPointMPM.cpp:419-453) ---
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_p2g_mass_momentum(Grid g, Particles P, Nodes N)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double xi[3], lp[3];
+    load_xi_lp(P, p, xi, lp);
+    const double mp = P.mp[p];
+    const double vx = P.vel[0][p], vy = P.vel[1][p], vz = DIM == 3 ? P.vel[2][p] : 0.;
+    for_each_node<DIM, SHAPE, false>(g, P.elem[p], xi, lp, [&](int nd, double S, double, double, double) {
+        const double fnmp = S * mp;
+        atomAdd(&N.pk[0][nd], vx * fnmp);
+        atomAdd(&N.pk[1][nd], vy * fnmp);
+        if (DIM == 3) atomAdd(&N.pk[2][nd], vz * fnmp);
+        atomAdd(&N.mass[nd], fnmp);
+        atomicAdd(&N.cnt[nd], 1);
+    });
+}
+
+// ---- task 3: PostExtrapolationTask node pass (MatVelocityField.cpp:158-164) ------------------
+__global__ void k_copy_momenta(int nnodes, Nodes N)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    N.pkc[0][i] = N.pk[0][i]; N.pkc[1][i] = N.pk[1][i]; N.pkc[2][i] = N.pk[2][i];
+}
+
+// ---- grid velocity BCs (NodalVelBC.cpp:321-400, MatVelocityField.cpp:490-575) ----------------
+// One thread per node that has BCs; its entries are walked in list order, first the zero pass
+// over all of them, then the add pass (VelocityBCLoop).  BCs act only on active fields
+// (numberPoints>0, NodalPointMPM.cpp:1849-1862).
+__global__ void k_velocity_bcs(VelBCs B, Nodes N, int pass, double dt, int adjustSym)
+{
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= B.nUnique) return;
+    const int nd = B.node[u];
+    if (N.cnt[nd] <= 0) return;
+    if (adjustSym) {        // ADJUST_COPIED_PK==1 (NodalVelBC.cpp:339-353, MatVelocityField.cpp:579-586)
+        int sd = B.symdir[u];
+        if (sd & 32) N.pkc[0][nd] = 0.;
+        if (sd & 64) N.pkc[1][nd] = 0.;
+        if (sd & 128) N.pkc[2][nd] = 0.;
+        if (adjustSym == 2) return;      // symmetry adjust only (no USF task: NodalVelBC.cpp:356)
+    }
+    double pk[3] = {N.pk[0][nd], N.pk[1][nd], N.pk[2][nd]};
+    double ft[3] = {N.ftot[0][nd], N.ftot[1][nd], N.ftot[2][nd]};
+    const double mass = N.mass[nd];
+    const int e0 = B.start[u], e1 = B.start[u + 1];
+    for (int e = e0; e < e1; e++) {
+        if (!B.active[e]) continue;
+        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
+        if (pass == PASS_GRID_FORCES) {
+            double dotf = ft[0] * nx + ft[1] * ny + ft[2] * nz;
+            double dotp = pk[0] * nx + pk[1] * ny + pk[2] * nz;
+            double s = -dotf - dotp / dt;
+            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        } else {
+            double dotn = pk[0] * nx + pk[1] * ny + pk[2] * nz;
+            pk[0] += nx * (-dotn); pk[1] += ny * (-dotn); pk[2] += nz * (-dotn);
+            if (pass == PASS_UPDATE_MOMENTUM) {
+                double s = -dotn / dt;
+                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+            }
+        }
+    }
+    for (int e = e0; e < e1; e++) {
+        if (!B.active[e]) continue;
+        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
+        const double vel = B.value[e];
+        if (pass == PASS_GRID_FORCES) {
+            double s = mass * vel / dt;
+            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        } else {
+            double pvel = mass * vel;
+            pk[0] += nx * pvel; pk[1] += ny * pvel; pk[2] += nz * pvel;
+            if (pass == PASS_UPDATE_MOMENTUM) {
+                double s = pvel / dt;
+                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+            }
+        }
+    }
+    N.pk[0][nd] = pk[0]; N.pk[1][nd] = pk[1]; N.pk[2][nd] = pk[2];
+    N.ftot[0][nd] = ft[0]; N.ftot[1][nd] = ft[1]; N.ftot[2][nd] = ft[2];
+}
+
+// ---- grid velocity for strain / particle update (MatVelocityField.cpp:239-251) ---------------
+__global__ void k_grid_velocity(int nnodes, Nodes N)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    const double m = N.mass[i];
+    if (N.cnt[i] == 0 || m == 0.) return;
+    const double rm = 1. / m;
+    N.vk[0][i] = N.pk[0][i] * rm; N.vk[1][i] = N.pk[1][i] * rm; N.vk[2][i] = N.pk[2][i] * rm;
+}
+
+// ---- particle state <-> registers -------------------------------------------------------------
+__device__ __forceinline__ void load_pstate(const Particles &P, int p, PState &s)
+{
+#pragma unroll
+    for (int i = 0; i < 9; i++) s.F[i] = P.F[i][p];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { s.sp[i] = P.sp[i][p]; s.eplast[i] = P.eplast[i][p]; }
+    s.pressure = P.pressure[p];
+    s.work = P.work[p]; s.res = P.res[p]; s.heat = P.heat[p]; s.entropy = P.entropy[p]; s.plast = P.plast[p];
+    s.prevT = P.prevT[p];
+#pragma unroll
+    for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = P.hist[i][p];
+}
+
+__device__ __forceinline__ void store_pstate(const Particles &P, int p, const PState &s)
+{
+#pragma unroll
+    for (int i = 0; i < 9; i++) P.F[i][p] = s.F[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { P.sp[i][p] = s.sp[i]; P.eplast[i][p] = s.eplast[i]; }
+    P.pressure[p] = s.pressure;
+    P.work[p] = s.work; P.res[p] = s.res; P.heat[p] = s.heat; P.entropy[p] = s.entropy; P.plast[p] = s.plast;
+#pragma unroll
+    for (int i = 0; i < MPM_MAX_HISTORY; i++) P.hist[i][p] = s.hist[i];
+}
+
+// ---- tasks 4 and 9b: FullStrainUpdate (UpdateStrainsFirstTask.cpp:101-168, MatPoint3D.cpp:45-93) ----
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_update_strains(Grid g, Particles P, Nodes N, const Material *mats,
+                                                                 double strainTime)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double xi[3], lp[3];
+    load_xi_lp(P, p, xi, lp);
+    double dv[9] = {0., 0., 0., 0., 0., 0., 0., 0., 0.};
+    for_each_node<DIM, SHAPE, true>(g, P.elem[p], xi, lp, [&](int nd, double S, double gx, double gy, double gz) {
+        const double vx = N.vk[0][nd], vy = N.vk[1][nd];
+        dv[0] += vx * gx; dv[1] += vx * gy;
+        dv[3] += vy * gx; dv[4] += vy * gy;
+        if (DIM == 3) {
+            const double vz = N.vk[2][nd];
+            dv[2] += vx * gz; dv[5] += vy * gz;
+            dv[6] += vz * gx; dv[7] += vz * gy; dv[8] += vz * gz;
+        }
+    });
+#pragma unroll
+    for (int i = 0; i < 9; i++) dv[i] *= strainTime;
+    PState s;
+    load_pstate(P, p, s);
+    constitutive_law<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+    store_pstate(P, p, s);
+}
+
+// ---- task 5: GridForcesTask (GridForcesTask.cpp:55-117, MatPoint3D.cpp:248-252) ---------------
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_p2g_forces(Grid g, Particles P, Nodes N, int hasFext)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double xi[3], lp[3];
+    load_xi_lp(P, p, xi, lp);
+    const double mp = P.mp[p], pr = P.pressure[p];
+    const double sxx = P.sp[XX][p] - pr, syy = P.sp[YY][p] - pr, sxy = P.sp[XY][p];
+    double szz = 0., syz = 0., sxz = 0.;
+    if (DIM == 3) { szz = P.sp[ZZ][p] - pr; syz = P.sp[YZ][p]; sxz = P.sp[XZ][p]; }
+    double fx = 0., fy = 0., fz = 0.;
+    if (hasFext) { fx = P.pfext[0][p]; fy = P.pfext[1][p]; fz = P.pfext[2][p]; }
+    for_each_node<DIM, SHAPE, true>(g, P.elem[p], xi, lp, [&](int nd, double S, double gx, double gy, double gz) {
+        if (DIM == 3) {
+            atomAdd(&N.ftot[0][nd], -mp * (sxx * gx + sxy * gy + sxz * gz) + S * fx);
+            atomAdd(&N.ftot[1][nd], -mp * (sxy * gx + syy * gy + syz * gz) + S * fy);
+            atomAdd(&N.ftot[2][nd], -mp * (sxz * gx + syz * gy + szz * gz) + S * fz);
+        } else {
+            atomAdd(&N.ftot[0][nd], -mp * (sxx * gx + sxy * gy) + S * fx);
+            atomAdd(&N.ftot[1][nd], -mp * (sxy * gx + syy * gy) + S * fy);
+        }
+    });
+}
+
+// ---- task 6: PostForcesTask node pass (PostForcesTask.cpp:46-94) -------------------------------
+__global__ void k_post_forces(int nnodes, Nodes N, StepParams sp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    if (N.cnt[i] == 0) return;
+    N.pk[0][i] = N.pkc[0][i]; N.pk[1][i] = N.pkc[1][i]; N.pk[2][i] = N.pkc[2][i];     // RestoreMomenta
+    if (sp.hasGravity) {                                                                  // AddGravityAndBodyForceTask3
+        const double m = N.mass[i];
+        N.ftot[0][i] += m * sp.grav[0]; N.ftot[1][i] += m * sp.grav[1]; N.ftot[2][i] += m * sp.grav[2];
+    }
+}
+
+// ---- task 7: UpdateMomentaTask node pass (MatVelocityField.cpp:301-304) ------------------------
+__global__ void k_update_momenta(int nnodes, Nodes N, double dt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    if (N.cnt[i] == 0) return;
+    N.pk[0][i] += N.ftot[0][i] * dt; N.pk[1][i] += N.ftot[1][i] * dt; N.pk[2][i] += N.ftot[2][i] * dt;
+}
+
+// ---- task 8: UpdateParticlesTask (UpdateParticlesTask.cpp:99-286, MatPoint3D.cpp:104-194) ------
+// m: 0 FLIP, >0 FMPM(m), <0 XPIC(-m)
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_update_particles(Grid g, Particles P, Nodes N, const Material *mats,
+                                                                   StepParams sp, int m)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double xi[3], lp[3];
+    load_xi_lp(P, p, xi, lp);
+    double Svk[3] = {0., 0., 0.}, Sacc[3] = {0., 0., 0.};
+    for_each_node<DIM, SHAPE, false>(g, P.elem[p], xi, lp, [&](int nd, double S, double, double, double) {
+        Svk[0] += N.vk[0][nd] * S; Svk[1] += N.vk[1][nd] * S; Svk[2] += N.vk[2][nd] * S;
+        if (m <= 0) {
+            const double mnode = S / N.mass[nd];
+            Sacc[0] += N.ftot[0][nd] * mnode; Sacc[1] += N.ftot[1][nd] * mnode; Sacc[2] += N.ftot[2][nd] * mnode;
+        }
+    });
+    const double dt = sp.dt;
+    const double matDamp = mats[P.mat[p]].p[2];
+    const double pAlpha = matDamp >= 0. ? matDamp : sp.particleAlpha;      // MaterialBase::GetMaterialDamping
+    double vel[3] = {P.vel[0][p], P.vel[1][p], P.vel[2][p]};
+    double pos[3] = {P.pos[0][p], P.pos[1][p], P.pos[2][p]};
+    double vm[3], delV[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        vm[c] = Svk[c];
+        if (m == 0) vm[c] += Sacc[c] * (-dt);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (DIM == 2 && c == 2) { delV[c] = 0.; continue; }
+        double Adamp0 = vel[c] * pAlpha;
+        Adamp0 += vm[c] * sp.gridAlpha;
+        if (m > 0) {
+            double delXRate = vel[c];
+            vel[c] = vm[c];
+            vel[c] += Adamp0 * (-dt);
+            delV[c] = vel[c] - delXRate;
+            delXRate += vel[c];
+            pos[c] += delXRate * (0.5 * dt);
+        } else if (m == 0) {
+            delV[c] = (Sacc[c] - Adamp0) * dt;
+            vel[c] += delV[c];
+            double delXRate = vm[c] + 0.5 * delV[c];
+            pos[c] += delXRate * dt;
+        } else {
+            double delXRate = vel[c];
+            vel[c] = Svk[c] - Adamp0 * dt;
+            delV[c] = vel[c] - delXRate;
+            delXRate = vm[c] + 0.5 * delV[c];
+            pos[c] += delXRate * dt;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < DIM; c++) {
+        P.vel[c][p] = vel[c];
+        P.pos[c][p] = pos[c];
+        P.acc[c][p] = delV[c] / dt;
+    }
+}
+
+// ---- task 9a: UpdateStrainsLastContactTask re-extrapolation (UpdateStrainsLastContactTask.cpp:71-149) ----
+__global__ void k_rezero_momenta(int nnodes, Nodes N)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    N.pk[0][i] = 0.; N.pk[1][i] = 0.; N.pk[2][i] = 0.;
+}
+
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_p2g_momentum_last(Grid g, Particles P, Nodes N)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double xi[3], lp[3];
+    load_xi_lp(P, p, xi, lp);
+    const double mp = P.mp[p];
+    const double vx = P.vel[0][p], vy = P.vel[1][p], vz = DIM == 3 ? P.vel[2][p] : 0.;
+    for_each_node<DIM, SHAPE, false>(g, P.elem[p], xi, lp, [&](int nd, double S, double, double, double) {
+        const double fnmp = S * mp;
+        atomAdd(&N.pk[0][nd], vx * fnmp);
+        atomAdd(&N.pk[1][nd], vy * fnmp);
+        if (DIM == 3) atomAdd(&N.pk[2][nd], vz * fnmp);
+    });
+}
+
+// ---- task 11: ResetElementsTask (ResetElementsTask.cpp:196-265) ---------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(TASK_THREADS) k_reset_elements(Grid g, Particles P, StatusFlags *flags, double dt)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    double pos[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
+    if (pos[0] != pos[0] || pos[1] != pos[1] || pos[2] != pos[2]) {
+        atomicCAS(&flags->nanParticle, 0, P.orig[p] + 1);
+        return;
+    }
+    const int e = P.elem[p];
+    if (pt_in_element<DIM>(g, e, pos)) return;                 // SAME_ELEMENT
+    int ne = find_element_from_point<DIM>(g, pos);
+    if (ne > 0 && !edge_element<DIM>(g, ne)) {                 // NEW_ELEMENT (MPMBase::ChangeElemID)
+        P.elem[p] = ne;
+        int c = P.cross[p];
+        P.cross[p] = c >= 0 ? c + 1 : c - 1;
+        atomicAdd(&flags->crossings, 1ull);
+        return;
+    }
+    // LEFT_GRID: count it (IncrementElementCrossings flips the sign on the first exit) and push the
+    // particle back into its element by bisection (ReturnToElement, ResetElementsTask.cpp:232-265)
+    {
+        int c = P.cross[p];
+        P.cross[p] = c > 0 ? -(c + 1) : c - 1;
+        atomicAdd(&flags->leftGrid, 1ull);
+    }
+    double outside[3] = {pos[0], pos[1], pos[2]};
+    double inside[3];
+    inside[0] = outside[0] - dt * P.vel[0][p];
+    inside[1] = outside[1] - dt * P.vel[1][p];
+    inside[2] = DIM == 3 ? outside[2] - dt * P.vel[2][p] : 0.;
+    if (!pt_in_element<DIM>(g, e, inside)) {
+        ElemIJK c = elem_ijk(g, e);
+        inside[0] = (g.xpts[c.i] + g.xpts[c.i + 1]) / 2.;
+        inside[1] = (g.ypts[c.j] + g.ypts[c.j + 1]) / 2.;
+        inside[2] = DIM == 3 ? (g.zpts[c.k] + g.zpts[c.k + 1]) / 2. : 0.;
+    }
+    for (int pass = 1; pass <= 10; pass++) {
+        double middle[3] = {(outside[0] + inside[0]) / 2., (outside[1] + inside[1]) / 2., (outside[2] + inside[2]) / 2.};
+        if (pt_in_element<DIM>(g, e, middle)) { inside[0] = middle[0]; inside[1] = middle[1]; inside[2] = middle[2]; }
+        else { outside[0] = middle[0]; outside[1] = middle[1]; outside[2] = middle[2]; }
+    }
+    P.pos[0][p] = inside[0]; P.pos[1][p] = inside[1];
+    if (DIM == 3) P.pos[2][p] = inside[2];
+}

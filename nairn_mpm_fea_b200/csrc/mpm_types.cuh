@@ -1,0 +1,100 @@
+// Device-side data layout of libmpmgpu (structure-of-arrays, FP64) and small helpers.
+//
+// Particle fields mirror MPMBase (reference MPM_Classes/MPMBase.hpp:34-264); node fields mirror the
+// single material velocity field cvf[0]->mvf[0] (reference Nodes/MatVelocityField.hpp:44-48).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MPM_MAX_HISTORY 4
+#define MPM_MAT_NPARAMS 32
+#define MPM_MAX_MATERIALS 16
+
+// reference codes (System/MPMPrefix.hpp:110-140)
+enum { NP_PLANE_STRAIN = 10, NP_PLANE_STRESS = 11, NP_THREED = 12 };
+enum { METHOD_USF = 0, METHOD_USAVG = 2, METHOD_USL = 3 };
+enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_LCPDI = 10, SHAPE_QCPDI = 11 };
+enum { MAT_ISOTROPIC = 1, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28 };
+
+// BC pass types (reference NodalVelBC.cpp:321-380)
+enum { PASS_MASS_MOMENTUM = 0, PASS_GRID_FORCES = 1, PASS_UPDATE_MOMENTUM = 2, PASS_UPDATE_STRAINS_LAST = 3,
+       PASS_XPIC = 4 };
+
+struct Grid {
+    int dim;                 // 2 or 3
+    int np;                  // analysis type
+    int horiz, vert, depth;  // cells per axis incl. border (depth>=1; 1 in 2D)
+    int yplane, zplane;      // node strides (xplane = 1): MeshInfo.cpp:1510-1512
+    int nnodes, nelems;
+    const double *xpts, *ypts, *zpts;   // node coordinates per axis (device)
+    double gx, gy, gz;       // mpmgrid.grid
+    double xmin, ymin, zmin; // mpmgrid.xmin... (= xpts[0]...)
+    double rcrit;            // CPDI critical radius or <0
+};
+
+// one velocity field per node, component-major
+struct Nodes {
+    double *mass;            // [nnodes]
+    double *pk[3];           // momentum
+    double *ftot[3];         // force
+    double *vk[3];           // vk[0] (velocity for strain update / particle update)
+    double *pkc[3];          // vk[pkCopy]: momentum saved after the first extrapolation
+    double *vsp[3];          // XPIC/FMPM: vk[VSTARPREV]
+    double *vsn[3];          // XPIC/FMPM: vk[VSTARNEXT]
+    int *cnt;                // numberPoints
+};
+
+struct Particles {
+    int n;                   // particles resident
+    int nNR;                 // nonrigid particles come first
+    double *pos[3], *vel[3], *mp, *lp[3];
+    double *ncpos[3];        // natural coordinates fixed for the step (MPMBase::ncpos)
+    double *F[9];            // deformation gradient, row-major (reference stores ep + wrot)
+    double *sp[6];           // xx,yy,zz,yz,xz,xy
+    double *pressure;
+    double *eplast[6];       // xx,yy,zz,yz,xz,xy
+    double *work, *res, *heat, *entropy, *plast, *prevT;
+    double *hist[MPM_MAX_HISTORY];
+    double *pfext[3];
+    double *acc[3];
+    int *elem;               // 1-based inElem
+    int *mat;                // 0-based material index
+    int *cross;              // elementCrossings
+    int *orig;               // caller's index of this particle
+};
+
+struct Material {
+    int kind;
+    int nhist;
+    double p[MPM_MAT_NPARAMS];
+};
+
+struct StepParams {
+    double dt, dtStrainFirst, dtStrainLast;
+    double fractionUSF;
+    double gridAlpha, particleAlpha;
+    double grav[3];
+    int method, skipPost;
+    int xpicOrder, usingFMPM;
+    int hasGravity;
+};
+
+// velocity BCs grouped by node (entries keep the host's list order within a node)
+struct VelBCs {
+    int nUnique;             // nodes with at least one BC
+    const int *node;         // [nUnique] 0-based node index
+    const int *start;        // [nUnique+1] range into the entry arrays
+    const int *symdir;       // [nUnique] symmetry-plane bits of the node
+    const double *norm;      // [3*nEntries]
+    const double *value;     // [nEntries]
+    const int *active;       // [nEntries]
+};
+
+struct StatusFlags {         // device -> host error reporting (ResetElementsTask.cpp:71-151)
+    unsigned long long crossings;
+    unsigned long long leftGrid;
+    int nanParticle;         // 1 + index of a particle with NaN position
+    int cpdiLeft;            // 1 + index of a particle whose CPDI corner left the grid
+};
+
+__device__ __forceinline__ void atomAdd(double *a, double v) { atomicAdd(a, v); }

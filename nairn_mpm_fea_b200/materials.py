@@ -1,0 +1,117 @@
+"""Material parameter blocks for libmpmgpu (mpmgpu_material in include/mpmgpu.h).
+
+Host-side mirror of what the reference's material classes compute in VerifyAndLoadProperties and hand to
+MPMConstitutiveLaw through GetCopyOfMechanicalProps.  Inputs are in the reference's INTERNAL units
+(Legacy units after UnitsController::ScaledPtr: modulus MPa*1e6, rho g/cm^3*1e-3, CTE ppm/K*1e-6,
+Cv J/(kg-K)*1e6).  `from_xml_units` converts from the numbers written in an XML file.
+"""
+import numpy as np
+
+NPARAMS = 32
+ISOTROPIC, ISOPLASTICITY, RIGIDBC, NEOHOOKEAN = 1, 9, 11, 28
+PLANE_STRAIN_MPM, PLANE_STRESS_MPM, THREED_MPM = 10, 11, 12
+
+DEFAULT_CV = 1.0e6          # MaterialBase.cpp:74 heatCapacity = Scaling(1.e6)
+
+
+def xml_units(E=None, rho=None, alpha=None, Cv=None, G=None, K=None, yld=None, Ep=None):
+    """Scale XML (Legacy) numbers to internal units.  Returns dict of the ones given."""
+    out = {}
+    if E is not None:
+        out["E"] = E * 1.0e6            # Common/Materials/IsotropicMat.cpp:38-46
+    if G is not None:
+        out["G"] = G * 1.0e6
+    if K is not None:
+        out["K"] = K * 1.0e6
+    if rho is not None:
+        out["rho"] = rho * 1.0e-3       # MaterialBaseMPM.cpp (rho scaled 1e-3)
+    if alpha is not None:
+        out["alpha"] = alpha            # aI kept in ppm/K; 1e-6 applied in VerifyAndLoadProperties
+    if Cv is not None:
+        out["Cv"] = Cv * 1.0e6
+    if yld is not None:
+        out["yld"] = yld * 1.0e6
+    if Ep is not None:
+        out["Ep"] = Ep * 1.0e6
+    return out
+
+
+def _base(rho, Cv, pdamping):
+    p = np.zeros(NPARAMS)
+    p[0] = rho
+    p[1] = Cv
+    p[2] = -1.0 if pdamping is None else pdamping
+    return p
+
+
+def isotropic(E, nu, rho, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None):
+    """IsotropicMat (MaterialID 1).  aI in ppm/K as in the XML <alpha>.
+
+    Follows IsotropicMat::VerifyAndLoadProperties (Common/Materials/IsotropicMat.cpp:93-168) ->
+    Elastic::SetAnalysisProps (Common/Materials/Elastic.cpp:194-329) ->
+    Elastic::FillUnrotatedElasticProperties (Common/Materials/Elastic.cpp:43-140).
+    """
+    G = E / (2.0 * (1.0 + nu))
+    alphaV = 3.0e-6 * aI
+    Kbulk = E / (3.0 * (1 - 2 * nu))
+    gamma0 = Kbulk * alphaV / (rho * Cv)
+    e1 = e2 = e3 = E
+    v12 = v13 = v23 = nu
+    a1 = a2 = a3 = 1.0e-6 * aI
+    v32 = v23 * e3 / e2
+    v31 = v13 * e3 / e1
+    v21 = v12 * e2 / e1
+    p = _base(rho, Cv, pdamping)
+    rrho = 1.0 / rho
+    if np_ == THREED_MPM:
+        xx = 1.0 - v13 * v31 - v23 * v32 - v12 * v21 - 2.0 * v13 * v32 * v21
+        C11 = e1 * (1.0 - v23 * v32) / xx
+        C12 = e2 * (v12 + v13 * v32) / xx
+        C13 = e3 * (v13 + v12 * v23) / xx
+        C22 = e2 * (1.0 - v13 * v31) / xx
+        C23 = e3 * (v23 + v21 * v13) / xx
+        C33 = e3 * (1.0 - v21 * v12) / xx
+        C66 = C44 = C55 = G
+        p[8:17] = [C11 * rrho, C12 * rrho, C13 * rrho, C22 * rrho, C23 * rrho, C33 * rrho,
+                   C44 * rrho, C55 * rrho, C66 * rrho]
+        p[17:20] = [a1, a2, a3]
+    elif np_ == PLANE_STRAIN_MPM:
+        xx = 1.0 - v13 * v31 - v23 * v32 - v12 * v21 - 2.0 * v12 * v23 * v31
+        C11 = e1 * (1.0 - v23 * v32) / xx
+        C12 = e2 * (v12 + v13 * v32) / xx
+        C22 = e2 * (1.0 - v13 * v31) / xx
+        C66 = G
+        C13 = e3 * (v13 + v12 * v23) / xx
+        C23 = e3 * (v23 + v21 * v13) / xx
+        C33 = e3 * (1.0 - v21 * v12) / xx
+        S13, S23, S33 = -v13 / e1, -v23 / e2, 1.0 / e3
+        p[8], p[9], p[11], p[16] = C11 * rrho, C12 * rrho, C22 * rrho, C66 * rrho
+        p[21], p[22], p[23] = C13 * rrho, C23 * rrho, C33 * rrho
+        p[24] = S13 / S33
+        p[17:20] = [a1 + v31 * a3, a2 + v32 * a3, a3]
+    elif np_ == PLANE_STRESS_MPM:
+        xx = 1.0 - v12 * v21
+        C11 = e1 / xx
+        C12 = e2 * v12 / xx
+        C22 = e2 / xx
+        C66 = G
+        xx3 = 1.0 - v13 * v31 - v23 * v32 - v12 * v21 - 2.0 * v13 * v32 * v21
+        C13 = -(v13 + v12 * v23) / (1.0 - v21 * v12)
+        C23 = -(v23 + v21 * v13) / (1.0 - v21 * v12)
+        C33 = e3 * (1.0 - v21 * v12) / xx3
+        S13 = -v13 / e1
+        p[8], p[9], p[11], p[16] = C11 * rrho, C12 * rrho, C22 * rrho, C66 * rrho
+        p[21], p[22], p[23] = C13, C23, C33 * rrho
+        p[24] = S13 * rho
+        p[17:20] = [a1, a2, a3]
+    else:
+        raise ValueError("analysis type %r not supported" % np_)
+    p[20] = gamma0
+    return dict(kind=ISOTROPIC, n_history=0, p=p, rho=rho, wave_speed=float(np.sqrt(2.0 * G * (1.0 - nu) / (rho * (1.0 - 2.0 * nu)))))
+
+
+def rigid_bc(direction_bits):
+    """RigidMaterial as moving velocity BC (MaterialID 11, Materials/RigidMaterial.hpp)."""
+    p = _base(1.0, DEFAULT_CV, None)
+    p[8] = float(direction_bits)
+    return dict(kind=RIGIDBC, n_history=0, p=p, rho=1.0, wave_speed=0.0)

@@ -1,0 +1,248 @@
+"""Host-side problem description: what the reference driver holds after ReadFile + CMPreparations
+(grid, particle lattice, materials, BC list, time step) in the flat form libmpmgpu takes.
+
+Generators here reproduce the reference's own set-up arithmetic so the same XML gives the same
+numbers:  grid + border cells  Read_MPM/Generators.cpp:1760-1935;  particle lattice
+Elements/MoreMPMElementBase.cpp:348-441 (MPMPoints) in element-major order Generators.cpp:1486-1588;
+mass and time step  NairnMPM_Class/NairnMPM.cpp:589-730, :1207-1240.
+"""
+import numpy as np
+
+from . import materials as M
+
+USF, USAVG, USL = 0, 2, 3
+POINT_GIMP, UNIFORM_GIMP, LINEAR_CPDI, QUADRATIC_CPDI = 0, 1, 10, 11
+X_DIRECTION, Y_DIRECTION, Z_DIRECTION = 1, 2, 4
+
+
+class Problem:
+    """Plain data; see capi.MpmGpu for how it is handed to the library."""
+
+    def __init__(self):
+        self.np = M.THREED_MPM
+        self.horiz = self.vert = self.depth = 0
+        self.xpts = self.ypts = self.zpts = None
+        self.grid = (0.0, 0.0, 0.0)
+        self.thickness = 1.0
+        self.shape = UNIFORM_GIMP
+        self.rcrit = -1.0
+        self.method = USAVG
+        self.skip_post_extrapolation = False
+        self.fraction_usf = 0.5
+        self.xpic_order = 0
+        self.using_fmpm = False
+        self.grid_damping = 0.0
+        self.particle_damping = 0.0
+        self.gravity = (0.0, 0.0, 0.0)
+        self.materials = []
+        self.dt = self.dt_strain_first = self.dt_strain_last = 0.0
+        self.maxtime = 0.0
+        self.bc_node = np.zeros(0, np.int32)
+        self.bc_norm = np.zeros((0, 3))
+        self.bc_value = np.zeros(0)
+        self.bc_active = np.zeros(0, np.int32)
+        self.bc_symdir = np.zeros(0, np.int32)
+        self.particles = {}
+
+    @property
+    def is3d(self):
+        return self.np == M.THREED_MPM
+
+    @property
+    def nnodes(self):
+        n = (self.horiz + 1) * (self.vert + 1)
+        return n * (self.depth + 1) if self.is3d else n
+
+    @property
+    def nelems(self):
+        return self.horiz * self.vert * (self.depth if self.is3d else 1)
+
+    @property
+    def nparticles(self):
+        return int(np.asarray(self.particles["mp"]).shape[0])
+
+    def set_time_step(self, dt):
+        """CFLTimeStep tail (NairnMPM.cpp:1228-1236)."""
+        self.dt = dt
+        if self.method == USAVG:
+            self.dt_strain_first = self.fraction_usf * dt
+            self.dt_strain_last = dt - self.dt_strain_first
+        else:
+            self.dt_strain_first = self.dt_strain_last = dt
+
+
+def structured_axis(lo, hi, cell):
+    """One axis of <Grid>: returns (ncells incl. border, node coordinates) as Generators.cpp:1769-1833."""
+    n = int((hi - lo) / cell + 0.5)          # Nhoriz from cellsize (MPMReadHandler Horiz cellsize)
+    c = (hi - lo) / float(n)
+    n += 2
+    lo2 = lo - c
+    hi2 = hi + c
+    delta = (hi2 - lo2) / float(n)
+    pts = np.array([lo2 + float(i) * delta for i in range(n + 1)])
+    return n, pts, delta
+
+
+def lattice_points(xpts, ypts, zpts, elems_ijk, pts_per_side=2):
+    """Particle positions of ElementBase::MPMPoints for the listed elements, in the reference's
+    order (z slowest, x fastest within an element) -- positions come from the element's linear
+    shape functions applied to its node coordinates, summed in node order."""
+    is3d = zpts is not None
+    n = pts_per_side
+    gap = 1.0 / float(n)
+    xi1 = np.array([-1.0 + (2.0 * j + 1.0) * gap for j in range(n)])
+    if is3d:
+        zz, yy, xx = np.meshgrid(xi1, xi1, xi1, indexing="ij")
+        nat = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1)          # (n^3, 3)
+        sx = np.array([-1., 1., 1., -1., -1., 1., 1., -1.])
+        sy = np.array([-1., -1., 1., 1., -1., -1., 1., 1.])
+        sz = np.array([-1., -1., -1., -1., 1., 1., 1., 1.])
+    else:
+        yy, xx = np.meshgrid(xi1, xi1, indexing="ij")
+        nat = np.stack([xx.ravel(), yy.ravel(), 0.0 * xx.ravel()], axis=1)
+        sx = np.array([-1., 1., 1., -1.])
+        sy = np.array([-1., -1., 1., 1.])
+        sz = None
+    ei, ej, ek = elems_ijk
+    ne = len(ei)
+    npp = nat.shape[0]
+    pos = np.zeros((3, ne, npp))
+    for a in range(len(sx)):
+        if is3d:
+            fxn = 0.125 * (1.0 + sx[a] * nat[:, 0]) * (1.0 + sy[a] * nat[:, 1]) * (1.0 + sz[a] * nat[:, 2])
+            nz = zpts[ek + (1 if sz[a] > 0 else 0)]
+        else:
+            fxn = 0.25 * (1.0 + sx[a] * nat[:, 0]) * (1.0 + sy[a] * nat[:, 1])
+        nx = xpts[ei + (1 if sx[a] > 0 else 0)]
+        ny = ypts[ej + (1 if sy[a] > 0 else 0)]
+        pos[0] += nx[:, None] * fxn[None, :]
+        pos[1] += ny[:, None] * fxn[None, :]
+        if is3d:
+            pos[2] += nz[:, None] * fxn[None, :]
+    return pos.reshape(3, ne * npp), gap
+
+
+def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0.0, 0.0, -1000.0), cfl=0.4,
+            step_ms=1e-3, method=USAVG, shape=UNIFORM_GIMP, bottom_bc=True, gravity=None, velocity_fn=None,
+            pts_per_side=2, ncell_xyz=None):
+    """BASELINE.json config 2 family: block of ncell^3 cells (pts_per_side^3 particles per cell) of
+    IsotropicMat inside a (ncell+2*margin)^3-cell grid (+1 border cell per side), initial velocity,
+    bottom plane z<=margin held in z.  Numbers are XML (Legacy) units: mm, MPa, g/cm^3, mm/s, ms.
+    Same problem as tests/inputs.py::block3d(ncell, margin) fed to the reference."""
+    pr = Problem()
+    pr.np = M.THREED_MPM
+    pr.method = method
+    pr.shape = shape
+    ncx, ncy, ncz = ncell_xyz or (ncell, ncell, ncell)
+    ext = [n + 2 * margin for n in (ncx, ncy, ncz)]
+    pr.horiz, pr.xpts, gx = structured_axis(0.0, ext[0] * cell, cell)
+    pr.vert, pr.ypts, gy = structured_axis(0.0, ext[1] * cell, cell)
+    pr.depth, pr.zpts, gz = structured_axis(0.0, ext[2] * cell, cell)
+    pr.grid = (gx, gy, gz)
+    u = M.xml_units(E=E, rho=rho)
+    mat = M.isotropic(u["E"], nu, u["rho"], 0.0, M.DEFAULT_CV, M.THREED_MPM)
+    pr.materials = [mat]
+    # filled elements: cells [margin, margin+nc) of the user grid = element index +1 (border) per axis
+    ii = np.arange(margin + 1, margin + 1 + ncx)
+    jj = np.arange(margin + 1, margin + 1 + ncy)
+    kk = np.arange(margin + 1, margin + 1 + ncz)
+    K, J, I = np.meshgrid(kk, jj, ii, indexing="ij")
+    ei, ej, ek = I.ravel(), J.ravel(), K.ravel()
+    pos, gap = lattice_points(pr.xpts, pr.ypts, pr.zpts, (ei, ej, ek), pts_per_side)
+    npp = pts_per_side ** 3
+    n = pos.shape[1]
+    elem = (pr.horiz * (ek * pr.vert + ej) + ei + 1).astype(np.int32)
+    in_elem = np.repeat(elem, npp)
+    lp = np.full((3, n), gap)
+    # mp = rho * 8 * psize.x*psize.y*psize.z, psize = 0.5*lp*cell extent (NairnMPM.cpp:624-637, MatPoint3D.cpp:219-225)
+    dxe = (pr.xpts[ei + 1] - pr.xpts[ei])
+    dye = (pr.ypts[ej + 1] - pr.ypts[ej])
+    dze = (pr.zpts[ek + 1] - pr.zpts[ek])
+    psx, psy, psz = dxe * (0.5 * gap), dye * (0.5 * gap), dze * (0.5 * gap)
+    mp = np.repeat(u["rho"] * (8.0 * psx * psy * psz), npp)
+    vel = np.zeros((3, n))
+    if velocity_fn is not None:
+        vel[:] = velocity_fn(pos)
+    else:
+        for c in range(3):
+            vel[c] = velocity[c]
+    energies = np.zeros((6, n))
+    energies[5] = 1.0            # pPreviousTemperature: thermal.reference default... set by caller if needed
+    pr.particles = dict(pos=pos, vel=vel, mp=mp, lp=lp, in_elem=in_elem, matnum=np.ones(n, np.int32),
+                        n_nonrigid=n, energies=energies)
+    # time step (NairnMPM.cpp:695-699, :1207-1227): dcell = grid.x (cubic grid, MeshInfo.cpp:1555-1563)
+    dt_cfl = cfl * (gx / mat["wave_speed"])
+    pr.set_time_step(min(step_ms * 1.0e-3, dt_cfl))
+    if bottom_bc:
+        # BCBox zmax = margin + 0.01: every node with z <= that, in node order, dir 3 (z), value 0
+        zsel = np.nonzero(pr.zpts <= margin * cell + 0.01)[0]
+        nx1, ny1 = pr.horiz + 1, pr.vert + 1
+        nodes = (zsel[:, None] * (nx1 * ny1) + np.arange(nx1 * ny1)[None, :] + 1).ravel()
+        nb = len(nodes)
+        pr.bc_node = nodes.astype(np.int32)
+        pr.bc_norm = np.tile(np.array([0.0, 0.0, 1.0]), (nb, 1))
+        pr.bc_value = np.zeros(nb)
+        pr.bc_active = np.ones(nb, np.int32)
+        pr.bc_symdir = np.zeros(nb, np.int32)
+    if gravity is not None:
+        pr.gravity = tuple(gravity)
+    return pr
+
+
+def from_reference_dump(z, snapshot="p0"):
+    """Problem from an oracle/refharness.py dump: the state the reference itself holds after
+    ReadFile + CMPreparations.  Used by the parity tests (same inputs on both sides)."""
+    info = {k[5:]: z[k].item() for k in z if k.startswith("info/")}
+    pr = Problem()
+    pr.np = int(info["np"])
+    pr.horiz, pr.vert, pr.depth = int(info["horiz"]), int(info["vert"]), int(info["depth"])
+    xyz = z["node_coords"]
+    nx1, ny1 = pr.horiz + 1, pr.vert + 1
+    pr.xpts = xyz[:nx1, 0].copy()
+    pr.ypts = xyz[0:nx1 * ny1:nx1, 1].copy()
+    if pr.is3d:
+        pr.zpts = xyz[0::nx1 * ny1, 2].copy()
+    else:
+        pr.depth = 0
+    pr.grid = (info["gridx"], info["gridy"], info["gridz"])
+    pr.thickness = info["thickness"]
+    pr.shape = int(info["useGimp"])
+    pr.rcrit = info["rcrit"]
+    pr.method = int(info["mpmApproach"])
+    pr.skip_post_extrapolation = bool(info["skipPostExtrapolation"])
+    pr.fraction_usf = info["fractionUSF"]
+    pr.xpic_order = int(info["XPICOrder"])
+    pr.using_fmpm = bool(info["usingFMPM"])
+    pr.grid_damping = info["damping"]
+    pr.particle_damping = info["pdamping"]
+    pr.gravity = (info["gx"], info["gy"], info["gz"]) if info["hasGravity"] else (0.0, 0.0, 0.0)
+    pr.dt = info["timestep"]
+    pr.dt_strain_first = info["strainTimestepFirst"]
+    pr.dt_strain_last = info["strainTimestepLast"]
+    pr.maxtime = info["maxtime"]
+    pr.materials = []
+    for mid, q in zip(z["mat_ids"], z["mat_params"]):
+        pd = None if q[3] < 0 else q[3]
+        if mid == M.ISOTROPIC:
+            m = M.isotropic(q[8], q[9], q[0], q[11] * 1.0e6, q[1], pr.np, pd)
+        else:
+            raise NotImplementedError("material id %d" % mid)
+        pr.materials.append(m)
+    s = snapshot
+    n = z[s + "/mp"].shape[0]
+    pr.particles = dict(pos=z[s + "/pos"], vel=z[s + "/vel"], mp=z[s + "/mp"], lp=z[s + "/lp"],
+                        in_elem=z[s + "/inElem"], matnum=z[s + "/matnum"], sp=z[s + "/sp"],
+                        pressure=z[s + "/pressure"], ep=z[s + "/ep"], wrot=z[s + "/wrot"], eplast=z[s + "/eplast"],
+                        energies=z[s + "/energies"], history=z[s + "/hist"], crossings=z[s + "/crossings"],
+                        n_nonrigid=int(info["nmpmsNR"]))
+    if np.any(z[s + "/pFext"] != 0.0):
+        pr.particles["pfext"] = z[s + "/pFext"]
+    nb = z["velbcs/node"].shape[0]
+    pr.bc_node = z["velbcs/node"].astype(np.int32)
+    pr.bc_norm = z["velbcs/norm"]
+    pr.bc_value = z["velbcs/value"].copy()            # constant-style BCs: value; others evaluated by the host
+    pr.bc_active = np.ones(nb, np.int32)
+    pr.bc_symdir = np.zeros(nb, np.int32)
+    pr.bc_style = z["velbcs/style"]
+    pr.bc_ftime = z["velbcs/ftime"]
+    return pr

@@ -1,0 +1,59 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference (oracle/_ref,
+built by oracle/build_ref.sh from /root/reference) on the XML inputs of tests/inputs.py.
+
+    python tests/golden/make_golden.py            # regenerates every *.npz here
+
+Each fixture holds: the reference's state after set-up (particles p0, grid, BC list, materials),
+node + particle dumps after EVERY task of step 1, and particle/node snapshots after N steps.
+Only this script and the reference produce these files; the tests only read them.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.refharness import run_reference  # noqa: E402
+from tests import inputs  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (xml text, snapshots, per-task steps)
+    "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
+    "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
+    "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),
+                                               damping=50.0, pdamping=20.0), (1, 50), 1),
+    "block3d_linear_usl": (inputs.block3d(ncell=3, margin=2, gimp=None, method=3), (1, 50), 1),
+    "block3d_ugimp_usf": (inputs.block3d(ncell=3, margin=2, method=0), (1, 50), 1),
+}
+
+KEEP_P = ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "hist", "inElem", "crossings", "ncpos", "acc")
+
+
+def slim(z):
+    out = {}
+    for k, v in z.items():
+        parts = k.split("/")
+        if parts[0].startswith("s") and parts[1].startswith("t") and parts[2] == "p":
+            if parts[3] not in KEEP_P:
+                continue
+        out[k] = v
+    return out
+
+
+def main(names=None):
+    for name, (xml, snaps, pts) in CASES.items():
+        if names and name not in names:
+            continue
+        z = run_reference(xml, snaps=snaps, per_task_steps=pts, nprocs=1)
+        z = slim(z)
+        z["xml"] = np.array(xml)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **z)
+        print(name, "%.1f KB" % (os.path.getsize(path) / 1024.0), "tasks:", list(z["task_names"]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,77 @@
+"""Shared helpers for the parity tests: compare libmpmgpu output with reference dumps."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# reference task name -> libmpmgpu task entry point
+TASK_MAP = {
+    "Initialize": "initialization",
+    "Extrapolate Mass and Momentum": "mass_and_momentum",
+    "Post Extrapolation Tasks": "post_extrapolation",
+    "Update Strains First": "update_strains_first",
+    "Extrapolate Grid Forces": "grid_forces",
+    "Post Force Extrapolation Tasks": "post_forces",
+    "Update Momenta": "update_momenta",
+    "Update Particles": "update_particles",
+    "Update Strains Last with Extrapolation": "update_strains_last",
+    "Update Strains Last": "update_strains_last",
+    "Reset Elements": "reset_elements",
+}
+
+TOL_1STEP = 1.0e-10      # BASELINE.json north_star: relative 1e-10 after 1 step
+TOL_100STEP = 1.0e-7     # and 1e-7 after 100 steps (FP64), relative to the field's max magnitude
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| over the whole field; NaN must match NaN (the reference's entropy is
+    0/0 when the reference temperature is 0)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return np.inf
+    if a.size == 0:
+        return 0.0
+    d = np.where(nb, 0.0, np.abs(a - b))
+    scale = np.max(np.where(nb, 0.0, np.abs(b)))
+    if scale == 0.0:
+        return float(np.max(d))          # reference field identically zero: absolute error
+    return float(np.max(d) / scale)
+
+
+def compare_particles(got, ref, prefix, tol, fields=None):
+    """got: MpmGpu.download() dict; ref: golden dict with keys prefix/<field>.  Returns {field: err}."""
+    pairs = [("pos", "pos"), ("vel", "vel"), ("sp", "sp"), ("pressure", "pressure"), ("ep", "ep"), ("wrot", "wrot"),
+             ("eplast", "eplast")]
+    errs = {}
+    for g, r in pairs:
+        if fields and g not in fields:
+            continue
+        errs[g] = rel_err(got[g], ref[prefix + "/" + r])
+    e = ref[prefix + "/energies"]
+    names = ["work", "res", "heat", "entropy", "plast"]
+    for i, nm in enumerate(names):
+        errs[nm] = rel_err(got["energies"][i], e[i])
+    nh = min(got["history"].shape[0], ref[prefix + "/hist"].shape[0])
+    errs["history"] = rel_err(got["history"][:nh], ref[prefix + "/hist"][:nh])
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    return errs, bad
+
+
+def compare_nodes(got, ref, prefix, tol):
+    errs = {}
+    errs["mass"] = rel_err(got["mass"], ref[prefix + "/mass"])
+    errs["pk"] = rel_err(got["pk"], ref[prefix + "/pk"])
+    errs["ftot"] = rel_err(got["ftot"], ref[prefix + "/ftot"])
+    errs["vk"] = rel_err(got["vk"], ref[prefix + "/vk0"])
+    errs["pk_copy"] = rel_err(got["pk_copy"], ref[prefix + "/pkcopy"])
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    return errs, bad

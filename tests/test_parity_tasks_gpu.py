@@ -1,0 +1,66 @@
+"""GPU parity, through the C ABI, against golden dumps of the UNMODIFIED reference
+(tests/golden/*.npz, made by tests/golden/make_golden.py with oracle/_ref).
+
+1. every task of step 1 in isolation: node fields after each grid task, particle fields after each
+   particle task, to 1e-10 of the field's max; element ids bit-exact;
+2. whole steps: 1 step to 1e-10, N<=100 steps to 1e-7 (BASELINE.json north_star tolerances).
+"""
+import numpy as np
+import pytest
+
+from tests.parity import TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compare_particles, load_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
+         "block3d_ugimp_usf"]
+
+
+def make_sim(z, kernel_path=1):
+    from nairn_mpm_fea_b200 import MpmGpu
+    from nairn_mpm_fea_b200.problem import from_reference_dump
+    prob = from_reference_dump(z)
+    return MpmGpu(prob, device=0, kernel_path=kernel_path), prob
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_each_task_of_step_one(case):
+    z = load_golden(case)
+    sim, prob = make_sim(z)
+    names = [str(s) for s in z["task_names"]]
+    for i, nm in enumerate(names):
+        sim.run_task(TASK_MAP[nm])
+        pre = "s1/t%d" % i
+        nodes = sim.download_nodes()
+        errs, bad = compare_nodes(nodes, z, pre + "/nodes", TOL_1STEP)
+        assert not bad, "%s after task %d (%s): node fields %s" % (case, i, nm, bad)
+        assert np.array_equal(nodes["number_points"] > 0, z[pre + "/nodes/numberPoints"] > 0), "active node set differs"
+        got = sim.download()
+        errs, bad = compare_particles(got, z, pre + "/p", TOL_1STEP)
+        assert not bad, "%s after task %d (%s): particle fields %s" % (case, i, nm, bad)
+        assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"]), "element ids differ after %s" % nm
+        assert np.array_equal(got["crossings"], z[pre + "/p/crossings"])
+    sim.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_whole_steps(case):
+    z = load_golden(case)
+    sim, prob = make_sim(z)
+    snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
+    done = 0
+    for s in snaps:
+        sim.step(s - done)
+        done = s
+        tol = TOL_1STEP if s == 1 else TOL_100STEP
+        got = sim.download()
+        errs, bad = compare_particles(got, z, "p%d" % s, tol)
+        assert not bad, "%s after %d steps: %s (all: %s)" % (case, s, bad, errs)
+        assert np.array_equal(got["in_elem"], z["p%d/inElem" % s]), "%s: element ids differ after %d steps" % (case, s)
+        assert np.array_equal(got["crossings"], z["p%d/crossings" % s])
+        nodes = sim.download_nodes()
+        errs, bad = compare_nodes(nodes, z, "n%d" % s, tol)
+        assert not bad, "%s after %d steps: nodes %s" % (case, s, bad)
+    st = sim.status()
+    assert st["mstep"] == snaps[-1]
+    sim.close()
