@@ -29,9 +29,10 @@ def load_golden(name):
         return {k: z[k] for k in z.files}
 
 
-def rel_err(a, b):
+def rel_err(a, b, scale_with=None):
     """max |a-b| / max |b| over the whole field; NaN must match NaN (the reference's entropy is
-    0/0 when the reference temperature is 0)."""
+    0/0 when the reference temperature is 0).  scale_with: another reference array that belongs to
+    the same physical quantity (wrot and ep are the two halves of the deformation gradient)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (a.shape, b.shape)
@@ -42,6 +43,8 @@ def rel_err(a, b):
         return 0.0
     d = np.where(nb, 0.0, np.abs(a - b))
     scale = np.max(np.where(nb, 0.0, np.abs(b)))
+    if scale_with is not None:
+        scale = max(scale, float(np.nanmax(np.abs(scale_with))))
     if scale == 0.0:
         return float(np.max(d))          # reference field identically zero: absolute error
     return float(np.max(d) / scale)
@@ -55,7 +58,7 @@ def compare_particles(got, ref, prefix, tol, fields=None):
     for g, r in pairs:
         if fields and g not in fields:
             continue
-        errs[g] = rel_err(got[g], ref[prefix + "/" + r])
+        errs[g] = rel_err(got[g], ref[prefix + "/" + r], ref[prefix + "/ep"] if g == "wrot" else None)
     e = ref[prefix + "/energies"]
     names = ["work", "res", "heat", "entropy", "plast"]
     for i, nm in enumerate(names):
