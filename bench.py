@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/sec of the explicit MPM step (3D uGIMP, isotropic elastic, FLIP, USAVG+).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path (default arm)
+    python bench.py --impl reference --steps 3 --warmup 1      # the reference's own CPU path (oracle/_ref)
+
+One "step" = one full MPMStep (tasks 1-9, 11) over the resident particle block.  Workloads
+(BASELINE.json configs, synthetic lattice blocks exactly as the reference's generator makes them):
+  block8m  (default)  100^3 cells x 8 particles = 8,000,000 particles per GPU: config 5 at N GPUs
+                      (and the size the north_star target is quoted on at N=1)
+  block1m             50^3 cells = 1,000,000 particles: config 2
+Prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (3D uGIMP) at 1/2/4/8 B200; % of HBM roofline"
+UNIT = "particle-steps/s"
+ALGO_BYTES_PER_PARTICLE_STEP = 504.0        # elastic uGIMP 3D FLIP USAVG+
+
+# algorithmic (compulsory) bytes per particle of each task's kernels, 3D uGIMP elastic, FP64 SoA
+# (DESIGN.md "kernels and their algorithmic bytes"): fields each kernel must read + write once.
+TASK_ALGO_BYTES = {
+    "initialization": 3 * 8 + 4 + 3 * 8,                       # pos, elem -> ncpos
+    "mass_and_momentum": (3 + 3 + 3 + 1) * 8 + 4 + 5,          # ncpos, lp, vel, mp, elem; grid 4.5 B/particle
+    "post_extrapolation": 6,                                   # node sweep: 2x3 doubles per node / 8 ppc
+    "update_strains_first": (3 + 3) * 8 + 4 + 2 * (9 + 6 + 4) * 8 + 3,   # ncpos, lp, elem; F, sp, energies r+w; grid vk
+    "grid_forces": (3 + 3 + 1 + 6 + 1) * 8 + 4 + 3,
+    "post_forces": 6,
+    "update_momenta": 6,
+    "update_particles": (3 + 3) * 8 + 4 + 2 * (3 + 3) * 8 + 3 * 8 + 6,   # ncpos, lp; pos, vel r+w; acc w; grid vk+ftot+mass
+    "update_strains_last": (3 + 3 + 3 + 1) * 8 + 4 + 2 * (9 + 6 + 4) * 8 + 6,
+    "reset_elements": 3 * 8 + 4,
+}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_problem(workload, ncell_override=None, rank=0, world=1):
+    from nairn_mpm_fea_b200 import problem
+    ncell = {"block8m": 100, "block1m": 50}[workload]
+    if ncell_override:
+        ncell = ncell_override
+    # small uniform compression velocity + sinusoidal perturbation along z so particles cross cells
+    L = float(ncell)
+
+    def vel(pos):
+        v = np.zeros_like(pos)
+        v[2] = -1000.0 + 200.0 * np.sin(2.0 * np.pi * (pos[2] - 7.0) / L)
+        v[0] = 100.0 * np.sin(2.0 * np.pi * (pos[1] - 7.0) / L)
+        return v
+
+    pr = problem.block3d(ncell=ncell, margin=7, velocity_fn=vel, jitter_amp=0.4)
+    return pr, ncell
+
+
+def host_state_bytes(pt):
+    n = 0
+    for k, v in pt.items():
+        if isinstance(v, np.ndarray):
+            n += v.nbytes
+    return n
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nairn_mpm_fea_b200 import MpmGpu, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmpmgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = read_peaks()
+
+    prob, ncell = make_problem(args.workload, args.ncell, rank, world)
+    n = prob.nparticles
+    sim = MpmGpu(prob, device=local, kernel_path=args.kernel_path)
+    stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        sim.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput: inputs already in HBM -------------------------------------
+    for _ in range(args.warmup):
+        sim.step(1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = sim.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sim.step(1)
+    ev1.record(stream)
+    barrier()
+    launches = sim.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    total_particles = n * world
+    value = total_particles * args.steps / (ms_total * 1e-3)
+
+    # ---- per-task device times (events around every task; serialises, so done OUTSIDE the timed region)
+    sim.set_profiling(True)
+    psteps = max(2, min(5, args.steps))
+    for _ in range(psteps):
+        sim.step(1)
+    tt = sim.task_times()
+    sim.set_profiling(False)
+    task_ms = {k: v[0] / max(1, v[1]) for k, v in tt.items()}
+    dom = max(task_ms, key=lambda k: task_ms[k])
+    dom_bytes = TASK_ALGO_BYTES[dom] * n
+    dom_gbs = dom_bytes / (task_ms[dom] * 1e-3) / 1e9
+    step_gbs = ALGO_BYTES_PER_PARTICLE_STEP * n / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": task_ms[dom], "kernel_share_of_step": task_ms[dom] / sum(task_ms.values()),
+                "whole_step": {"algorithmic_bytes_per_particle_step": ALGO_BYTES_PER_PARTICLE_STEP,
+                               "achieved": step_gbs, "frac": step_gbs / hbm_peak},
+                "task_ms": task_ms}
+
+    # ---- end to end through the public API with HOST buffers ------------------------------------
+    # One archive interval: upload the full particle state from pinned host memory, run K steps with
+    # the per-step BC values going H2D and the status word coming D2H, download the full state.
+    pt = prob.particles
+    pinned = {}
+    for k, v in pt.items():
+        if isinstance(v, np.ndarray):
+            tt_ = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+            pinned[k] = tt_.numpy()
+        else:
+            pinned[k] = v
+    nb = len(prob.bc_value)
+    bcv = np.zeros(nb)
+    barrier()
+    t0 = time.perf_counter()
+    sim.upload(pinned)
+    for _ in range(args.steps):
+        sim.update_velocity_bc_values(bcv, prob.bc_active)
+        sim.step(1)
+        st = sim.status()
+    out = sim.download()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    up_bytes = host_state_bytes(pinned)
+    down_bytes = sum(v.nbytes for v in out.values())
+    e2e = {"value": total_particles * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": (up_bytes / args.steps + nb * 12) * world,
+           "d2h_bytes_per_step": (down_bytes / args.steps + 32) * world,
+           "what": "upload full particle state (pinned host) + %d steps with per-step BC values H2D and status D2H "
+                   "+ download full particle state, wall clock" % args.steps}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: 3D uGIMP isotropic-elastic block, %d^3 cells x 8 = %d particles per GPU, FLIP, USAVG+, "
+                                   "grid %d^3 cells, particle positions hash-jittered +-0.2 cell off the lattice" % (args.workload, ncell, n, prob.horiz),
+                       "particles_per_gpu": n, "nodes": prob.nnodes, "l2_policy": "inputs larger than L2 (%.0f MB state)" % (n * 460 / 1e6),
+                       "kernel_path": sim_kernel_path_name(args.kernel_path),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent slabs (halo exchange not built yet)" % world},
+            "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_ncell, args.cpu_steps)
+    sim.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def sim_kernel_path_name(k):
+    return {0: "auto", 1: "per-task kernels (global atomics)", 2: "tiled"}[k]
+
+
+_REF_WORKER = r"""
+import sys, time, json
+sys.path.insert(0, %(root)r)
+from oracle.refharness import RefRun
+from tests.inputs import block3d
+import tempfile, os
+d = tempfile.mkdtemp(prefix="mpmbench_")
+xml = os.path.join(d, "in.fmcmd")
+open(xml, "w").write(block3d(ncell=%(ncell)d, margin=7, maxtime=1.0))
+os.chdir(d)
+t0 = time.perf_counter()
+r = RefRun(xml, nprocs=%(nprocs)d)
+t1 = time.perf_counter()
+r.step(%(warm)d)
+t2 = time.perf_counter()
+r.step(%(steps)d)
+t3 = time.perf_counter()
+print(json.dumps({"n": r.info["nmpms"], "setup_s": t1 - t0, "warm_s": t2 - t1, "run_s": t3 - t2, "patches": r.info["numPatches"]}))
+"""
+
+
+def time_reference(ncell, steps, warm=1, nprocs=None):
+    """Time the UNMODIFIED reference (oracle/_ref/libnairnmpm_ref.so) on the host cores."""
+    from oracle import refharness
+    if not refharness.available():
+        return None
+    nprocs = nprocs or os.cpu_count() or 1
+    code = _REF_WORKER % dict(root=ROOT, ncell=ncell, nprocs=nprocs, warm=warm, steps=steps)
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(nprocs)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    if p.returncode != 0:
+        return {"error": (p.stderr or p.stdout)[-400:]}
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    d["cores"] = nprocs
+    d["steps"] = steps
+    return d
+
+
+def cpu_baseline(ncell, steps):
+    d = time_reference(ncell, steps)
+    if d is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    if "error" in d:
+        return {"value": None, "unit": UNIT, "cores": d.get("cores", 0), "kind": "reference", "sample": d["error"]}
+    return {"value": d["n"] * d["steps"] / d["run_s"], "unit": UNIT, "cores": d["cores"], "kind": "reference",
+            "sample": "reference NairnMPM (oracle/_ref, -O3 -fopenmp) on the same block input at %d^3 cells = %d particles, "
+                      "%d steps after 1 warm-up, %d OpenMP threads, %.1f s" % (ncell, d["n"], d["steps"], d["cores"], d["run_s"])}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = time_reference(args.cpu_ncell, args.steps, warm=args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if d is None or "error" in d:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built or failed: %s" % (d or {}).get("error", "")}))
+        return
+    v = d["n"] * d["steps"] / d["run_s"]
+    sample = ("reference NairnMPM (oracle/_ref) on the bench block input at %d^3 cells = %d particles (bounded sample of the "
+              "%s workload), %d steps, %d OpenMP threads" % (args.cpu_ncell, d["n"], args.workload, d["steps"], d["cores"]))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * d["run_s"] / d["steps"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s (CPU sample: %d^3 cells)" % (args.workload, args.cpu_ncell)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": d["cores"], "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m"])
+    ap.add_argument("--ncell", type=int, default=0, help="override block edge in cells (testing)")
+    ap.add_argument("--kernel-path", type=int, default=0)
+    ap.add_argument("--cpu-ncell", type=int, default=50, help="block edge of the CPU sample (50 -> 1M particles)")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@
 #include "shape.cuh"
 #include "materials.cuh"
 #include "kernels_task.cuh"
-#include "kernels_tiled.cuh"
+#include "kernels_fused.cuh"
 
 static std::string g_create_error;
 
@@ -168,6 +168,10 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
         if (dalloc(ctx, &ctx->dFlags, 1) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
         cudaMemset(ctx->dFlags, 0, sizeof(StatusFlags));
         if (dalloc(ctx, &ctx->dMats, MPM_MAX_MATERIALS) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+        if (is3D) {
+            if (dalloc(ctx, &ctx->tiled.FN.V, nnPad) != cudaSuccess || dalloc(ctx, &ctx->tiled.FN.A, nnPad) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+            cudaMemset(ctx->tiled.FN.V, 0, nnPad * sizeof(double4)); cudaMemset(ctx->tiled.FN.A, 0, nnPad * sizeof(double4));
+        }
     } while (0);
     if (rc != MPMGPU_OK) { fail(NULL, rc, "mpmgpu_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); mpmgpu_destroy(ctx); return rc; }
 
@@ -219,6 +223,8 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
 #define NPD (3 + 3 + 1 + 3 + 3 + 9 + 6 + 1 + 6 + 6 + MPM_MAX_HISTORY + 3 + 3)
 #define NPI 4
 
+static void bind_particles(Particles &P, double *pool, int *ipool, size_t capPad);
+
 static int alloc_particles(mpmgpu_ctx *ctx, size_t cap)
 {
     if (ctx->cap >= cap) return MPMGPU_OK;
@@ -228,8 +234,14 @@ static int alloc_particles(mpmgpu_ctx *ctx, size_t cap)
     CK(dalloc(ctx, &ctx->particleIntPool, capPad * NPI));
     CK(cudaMemsetAsync(ctx->particlePool, 0, capPad * NPD * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->particleIntPool, 0, capPad * NPI * sizeof(int), ctx->stream));
-    Particles &P = ctx->P;
-    double *q = ctx->particlePool;
+    bind_particles(ctx->P, ctx->particlePool, ctx->particleIntPool, capPad);
+    ctx->cap = capPad;
+    return MPMGPU_OK;
+}
+
+static void bind_particles(Particles &P, double *pool, int *ipool, size_t capPad)
+{
+    double *q = pool;
     auto take = [&]() { double *r = q; q += capPad; return r; };
     for (int c = 0; c < 3; c++) P.pos[c] = take();
     for (int c = 0; c < 3; c++) P.vel[c] = take();
@@ -244,10 +256,8 @@ static int alloc_particles(mpmgpu_ctx *ctx, size_t cap)
     for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c] = take();
     for (int c = 0; c < 3; c++) P.pfext[c] = take();
     for (int c = 0; c < 3; c++) P.acc[c] = take();
-    int *qi = ctx->particleIntPool;
+    int *qi = ipool;
     P.elem = qi; qi += capPad; P.mat = qi; qi += capPad; P.cross = qi; qi += capPad; P.orig = qi;
-    ctx->cap = capPad;
-    return MPMGPU_OK;
 }
 
 static int ensure_stage(mpmgpu_ctx *ctx, size_t bytes)
@@ -385,6 +395,15 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
     tiled_on_upload(ctx->tiled);
+    {   // the fused path needs 3D uGIMP, particles no larger than a cell, FLIP/PIC, no rigid particles
+        bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && ctx->sp.xpicOrder <= 1 && h->n_nonrigid == n;
+        if (ok) for (size_t i = 0; i < (size_t)3 * n; i++) if (!(h->lp[i] <= 1.0)) { ok = false; break; }
+        if (ctx->cfg.kernel_path == 1) ok = false;
+        if (ctx->cfg.kernel_path == 2 && !ok)
+            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, XPIC order<=1 and no rigid particles");
+        ctx->tiled.enabled = ok ? 1 : 0;
+        ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 25;
+    }
     return MPMGPU_OK;
 }
 
@@ -410,7 +429,7 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
     cudaSetDevice(ctx->cfg.device);
     ctx->hasBCs = n > 0;
     ctx->nBCEntries = n;
-    if (n == 0) { ctx->B.nUnique = 0; return MPMGPU_OK; }
+    if (n == 0) { ctx->B.nUnique = 0; ctx->tiled.FN.bcOfNode = NULL; return MPMGPU_OK; }
     if (!node || !norm || !value) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: null arrays");
     for (int i = 0; i < n; i++)
         if (node[i] < 1 || node[i] > ctx->g.nnodes) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: BC %d on node %d of %d", i, node[i], ctx->g.nnodes);
@@ -440,6 +459,14 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
     CK(cudaMemcpy(dnm, nm.data(), 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dva, va.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     ctx->B.nUnique = nu; ctx->B.node = dn; ctx->B.start = ds; ctx->B.symdir = dsd; ctx->B.active = da; ctx->B.norm = dnm; ctx->B.value = dva;
+    {   // node -> BC group lookup for the fused node sweeps
+        std::vector<int> of(ctx->g.nnodes, -1);
+        for (int u = 0; u < nu; u++) of[un[u]] = u;
+        int *dof;
+        CK(dalloc(ctx, &dof, (size_t)ctx->g.nnodes));
+        CK(cudaMemcpy(dof, of.data(), (size_t)ctx->g.nnodes * sizeof(int), cudaMemcpyHostToDevice));
+        ctx->tiled.FN.bcOfNode = dof;
+    }
     return MPMGPU_OK;
 }
 
@@ -642,11 +669,92 @@ static int step_by_tasks(mpmgpu_ctx *ctx)
     return MPMGPU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused fast path (kernels_fused.cuh)
+static int sort_particles(mpmgpu_ctx *ctx)
+{
+    TiledState &t = ctx->tiled;
+    const int n = ctx->P.n;
+    if (t.cap < ctx->cap) {
+        if (t.cap != 0) return fail(ctx, MPMGPU_EINVAL, "sort workspace capacity changed");
+        CK(dalloc(ctx, &t.keysIn, ctx->cap)); CK(dalloc(ctx, &t.keysOut, ctx->cap));
+        CK(dalloc(ctx, &t.idxIn, ctx->cap)); CK(dalloc(ctx, &t.idxOut, ctx->cap));
+        CK(dalloc(ctx, &t.altPool, ctx->cap * NPD)); CK(dalloc(ctx, &t.altIntPool, ctx->cap * NPI));
+        CK(cudaMemsetAsync(t.altPool, 0, ctx->cap * NPD * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(t.altIntPool, 0, ctx->cap * NPI * sizeof(int), ctx->stream));
+        t.cubTempBytes = 0;
+        cub::DeviceRadixSort::SortPairs(NULL, t.cubTempBytes, t.keysIn, t.keysOut, t.idxIn, t.idxOut, (int)ctx->cap, 0, 32, ctx->stream);
+        CK(dalloc(ctx, (char **)&t.cubTemp, t.cubTempBytes));
+        t.cap = ctx->cap;
+    }
+    LAUNCH(k_sort_keys, nblocks(n, 256), 256, ctx->g, ctx->P, t.keysIn, t.idxIn);
+    int bits = 1;
+    while ((1ll << bits) < (long long)ctx->g.nnodes + (n - ctx->P.nNR) + 1) bits++;
+    CK(cub::DeviceRadixSort::SortPairs(t.cubTemp, t.cubTempBytes, t.keysIn, t.keysOut, t.idxIn, t.idxOut, n, 0, bits, ctx->stream));
+    ctx->launches += 4;
+    LAUNCH(k_permute_pool, nblocks(n, 256), 256, n, ctx->cap, NPD, ctx->particlePool, t.altPool, NPI, ctx->particleIntPool, t.altIntPool, t.idxOut);
+    std::swap(ctx->particlePool, t.altPool);
+    std::swap(ctx->particleIntPool, t.altIntPool);
+    int nn = ctx->P.n, nnr = ctx->P.nNR;
+    bind_particles(ctx->P, ctx->particlePool, ctx->particleIntPool, ctx->cap);
+    ctx->P.n = nn; ctx->P.nNR = nnr;
+    t.stepsSinceSort = 0;
+    return MPMGPU_OK;
+}
+
+static int fused_step(mpmgpu_ctx *ctx)
+{
+    TiledState &t = ctx->tiled;
+    const Grid &g = ctx->g;
+    const StepParams &sp = ctx->sp;
+    int rc;
+    if (t.stepsSinceSort >= t.sortInterval) { if ((rc = sort_particles(ctx))) return rc; }
+    t.stepsSinceSort++;
+    const size_t nnPad = ((size_t)g.nnodes + 31) & ~(size_t)31;
+    const int n = ctx->P.n, nNR = ctx->P.nNR;
+    const int pgrid = nblocks(nNR, FUSED_THREADS), ngrid = nblocks(g.nnodes, 256);
+    const bool hasUSF = sp.method == METHOD_USF || sp.method == METHOD_USAVG;
+    const bool hasUSL = sp.method == METHOD_USL || sp.method == METHOD_USAVG;
+    const bool reextrap = hasUSL && !sp.skipPost;
+    const double stFirst = sp.method == METHOD_USAVG ? sp.dtStrainFirst : sp.dt;
+    const double stLast = sp.method == METHOD_USAVG ? sp.dtStrainLast : sp.dt;
+    int m = sp.xpicOrder;
+    if (!sp.usingFMPM) m = -m;
+
+    prof_begin(ctx);
+    CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 13 * sizeof(double), ctx->stream));      // mass, pk, ftot, vk, pkc
+    CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
+    ctx->launches += 2;
+    prof_end(ctx, T_INIT);
+    prof_begin(ctx);
+    LAUNCH(k_f1_mass_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N);
+    prof_end(ctx, T_MASSMOM);
+    prof_begin(ctx);
+    LAUNCH(k_n1_post_extrapolation, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp, hasUSF ? 1 : 0);
+    prof_end(ctx, T_POSTEXTRAP);
+    prof_begin(ctx);
+    if (ctx->hasFext) LAUNCH(k_f2_strain_forces<true>, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+    else LAUNCH(k_f2_strain_forces<false>, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+    prof_end(ctx, T_USF);
+    prof_begin(ctx);
+    LAUNCH(k_n2_forces_momenta, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp, reextrap ? 1 : 0);
+    prof_end(ctx, T_POSTFORCES);
+    prof_begin(ctx);
+    LAUNCH(k_f3_update_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, sp, m, reextrap ? 1 : 0);
+    prof_end(ctx, T_PARTICLES);
+    prof_begin(ctx);
+    if (reextrap) LAUNCH(k_n3_strains_last, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp);
+    LAUNCH(k_f4_strain_reset, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt);
+    prof_end(ctx, T_USL);
+    return MPMGPU_OK;
+}
+
 extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
 {
     int rc = check_ready(ctx, "mpmgpu_step"); if (rc) return rc;
     for (int s = 0; s < nsteps; s++) {
-        rc = step_by_tasks(ctx);
+        rc = ctx->tiled.enabled ? fused_step(ctx) : step_by_tasks(ctx);
         if (rc) return rc;
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
     }

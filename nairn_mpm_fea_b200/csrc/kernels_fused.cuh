@@ -1,0 +1,571 @@
+// Fused fast path for the 3D uGIMP step (USAVG/USF/USL, FLIP/PIC, any material in materials.cuh).
+//
+// Four particle kernels + three node sweeps per step replace the ten per-task kernels:
+//   F1  ncpos + P2G mass/momentum                       (tasks 1,2)
+//   N1  save momenta, velocity BCs, v = p/m              (tasks 3, 4a)
+//   F2  G2P grad v + constitutive law + P2G forces       (tasks 4b, 5)
+//   N2  restore p, gravity, BCs, p += f dt, BCs, v, a    (tasks 6, 7, 8a) + zero p for the re-extrapolation
+//   F3  G2P particle update + P2G momentum (new v)       (tasks 8b, 9a)
+//   N3  velocity BCs, v = p/m                            (task 9b)
+//   F4  G2P grad v + constitutive law + element reset    (tasks 9c, 11)
+//
+// Particle -> grid transfers use the DUAL CELL of a particle: the node nearest to it.  With a
+// particle no larger than a cell (lp <= 1) the uGIMP stencil is exactly the 3x3x3 nodes around that
+// node (shape.cuh explains why this is the reference's node set).  Particles are kept physically
+// sorted by dual cell (integer radix key = centre node index, re-sorted every few steps), so the
+// ~8 particles of a dual cell sit in neighbouring lanes.  A warp takes 32 consecutive particles,
+// each lane computes its particle's 1-D weights and payload into shared memory, then the warp
+// walks the groups of equal key (__match_any_sync): lanes 0..26 BECOME the 27 nodes of that dual
+// cell and accumulate the group's particles in registers; one FP64 RED per node and component
+// leaves the warp.  That cuts global atomics ~8x relative to one atomic per particle-node pair and
+// never depends on the sort being exact (an out-of-place particle just forms its own group).
+//
+// Grid -> particle transfers are one thread per particle reading 32-byte node records
+// {vx,vy,vz,pad} / {ax,ay,az,pad} that the node sweeps write; the records of a whole 8M-particle
+// grid fit in the 126 MB L2.
+#pragma once
+#include <cub/device/device_radix_sort.cuh>
+#include "mpm_types.cuh"
+#include "shape.cuh"
+#include "materials.cuh"
+#include "kernels_task.cuh"
+
+#define FUSED_THREADS 128
+#define FUSED_WARPS (FUSED_THREADS / 32)
+
+struct FusedNodes {
+    double4 *V;          // [nnodes] {vx,vy,vz,0}: vk[0]
+    double4 *A;          // [nnodes] {ax,ay,az,0}: ftot/mass
+    const int *bcOfNode; // [nnodes] index into VelBCs unique list or -1
+};
+
+struct TiledState {
+    int enabled;         // fast path usable for this context
+    int sortInterval;
+    long long stepsSinceSort;
+    FusedNodes FN;
+    // sorting workspace
+    int *keysIn, *keysOut, *idxIn, *idxOut;
+    void *cubTemp; size_t cubTempBytes;
+    double *altPool; int *altIntPool;       // second particle pool for the physical reorder
+    size_t cap;
+};
+
+static inline void tiled_state_init(TiledState &t) { memset(&t, 0, sizeof t); }
+static inline void tiled_state_free(TiledState &t) {}
+static inline void tiled_on_upload(TiledState &t) { t.stepsSinceSort = 1 << 30; }
+
+// 32-byte node record through the read-only path
+__device__ __forceinline__ double4 ldg4(const double4 *p)
+{
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// ---- 3-node uGIMP weights around the dual-cell centre -------------------------------------------
+// base = -1 (xi<0: nodes at -3,-1,1) or 0 (xi>=0: nodes at -1,1,3); returns S[3], dS[3] (signed, not
+// yet scaled by 2/dx) and a 3-bit validity mask (xp < 2+lp).
+template <bool GRAD>
+__device__ __forceinline__ int gimp3(double xi, double lp, double inv_size, double lpd, double S[3], double dS[3], unsigned &ok)
+{
+    const int base = xi < 0. ? -1 : 0;
+    const double q1 = 2. - lp, q2 = 2. + lp;
+    ok = 0;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        const double xn = (double)(2 * (base + t) - 1);
+        const double xp = fabs(xi - xn);
+        double s = 0., d = 0.;
+        if (xp < q2) {
+            ok |= 1u << t;
+            if (xp < lp) {
+                s = ((4. - lp) * lp - xp * xp) * inv_size;
+                if (GRAD) d = -xp / (2. * lpd);
+            } else if (xp <= q1) {
+                s = 0.5 * (2. - xp);
+                if (GRAD) d = -0.5;
+            } else {
+                double arg = (q2 - xp) * inv_size;
+                s = 2. * lp * arg * arg;
+                if (GRAD) d = -arg;
+            }
+            if (GRAD && !(xi > xn)) d = -d;
+        }
+        S[t] = s;
+        if (GRAD) dS[t] = d;
+    }
+    return base;
+}
+
+struct Weights3 {
+    double S[3][3];      // [axis][t]
+    double dS[3][3];     // gradient factors, already multiplied by 2/delta of the element
+    unsigned ok;         // 9 bits: axis*3+t
+    int center;          // 0-based node index of the dual-cell centre
+};
+
+template <bool GRAD>
+__device__ __forceinline__ void particle_weights(const Grid &g, int inElem, const double xi[3], const double lp[3], Weights3 &w)
+{
+    const ElemIJK c = elem_ijk(g, inElem);
+    unsigned okx, oky, okz;
+    // inv_size and the branch-1 derivative divisor follow EightNodeIsoparamBrick.cpp:296-303,:365-387
+    const int bx = gimp3<GRAD>(xi[0], lp[0], 1. / (4. * lp[0]), lp[0], w.S[0], w.dS[0], okx);
+    const int by = gimp3<GRAD>(xi[1], lp[1], 1. / (4. * lp[1]), lp[1], w.S[1], w.dS[1], oky);
+    const int bz = gimp3<GRAD>(xi[2], lp[2], 1. / (4. * lp[1]), lp[2], w.S[2], w.dS[2], okz);
+    w.ok = okx | (oky << 3) | (okz << 6);
+    w.center = elem_node0(g, c) + (bx + 1) + (by + 1) * g.yplane + (bz + 1) * g.zplane;
+    if (GRAD) {
+        const double ix = 2.0 / (g.xpts[c.i + 1] - g.xpts[c.i]);
+        const double iy = 2.0 / (g.ypts[c.j + 1] - g.ypts[c.j]);
+        const double iz = 2.0 / (g.zpts[c.k + 1] - g.zpts[c.k]);
+#pragma unroll
+        for (int t = 0; t < 3; t++) { w.dS[0][t] *= ix; w.dS[1][t] *= iy; w.dS[2][t] *= iz; }
+    }
+}
+
+// per-warp shared staging: component-major so that a lane-as-node reads W[comp][srcLane]
+template <int NW, int NP>
+struct WarpStage {
+    double W[NW][32];    // weights: 0..8 S[axis*3+t], 9..17 dS[axis*3+t]
+    double Q[NP][32];    // payload
+    unsigned ok[32];
+};
+
+// ---- the warp-cooperative scatter ----------------------------------------------------------------
+// NV values per node.  contrib(src, i, j, k, acc[]) adds particle `src`'s contribution for node
+// (i,j,k) of its stencil into acc.  Groups = lanes with equal key.
+template <int NV, bool COUNT, class Stage, class Contrib>
+__device__ __forceinline__ void warp_scatter(const Grid &g, const Stage &st, int key, bool active, double *const *dst, int *cnt, Contrib contrib)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned mymask = __match_any_sync(full, active ? key : (-1 - lane));
+    unsigned remaining = __ballot_sync(full, active);
+    const int li = lane % 3, lj = (lane / 3) % 3, lk = lane / 9;        // node of this lane (lane < 27)
+    const int okbit = (1 << li) | (1 << (3 + lj)) | (1 << (6 + lk));
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const unsigned grp = __shfl_sync(full, mymask, leader);
+        const int center = __shfl_sync(full, key, leader);
+        remaining &= ~grp;
+        if (lane < 27) {
+            double acc[NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++) acc[v] = 0.;
+            int n = 0;
+            for (unsigned mm = grp; mm; mm &= mm - 1) {
+                const int src = __ffs(mm) - 1;
+                if ((st.ok[src] & okbit) == okbit) {
+                    contrib(src, li, lj, lk, acc);
+                    n++;
+                }
+            }
+            if (n) {
+                const int nd = center + (li - 1) + (lj - 1) * g.yplane + (lk - 1) * g.zplane;
+#pragma unroll
+                for (int v = 0; v < NV; v++) atomAdd(&dst[v][nd], acc[v]);
+                if (COUNT) atomicAdd(&cnt[nd], n);
+            }
+        }
+    }
+}
+
+// ---- F1: ncpos + P2G mass and momentum ------------------------------------------------------------
+__global__ void __launch_bounds__(FUSED_THREADS) k_f1_mass_momentum(Grid g, Particles P, Nodes N)
+{
+    __shared__ WarpStage<9, 4> stage[FUSED_WARPS];
+    WarpStage<9, 4> &st = stage[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = p < P.nNR;
+    int key = 0;
+    if (active) {
+        const int e = P.elem[p];
+        double pos[3] = {P.pos[0][p], P.pos[1][p], P.pos[2][p]};
+        double xi[3], lp[3] = {P.lp[0][p], P.lp[1][p], P.lp[2][p]};
+        get_xipos<3>(g, e, pos, xi);
+        P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
+        Weights3 w;
+        particle_weights<false>(g, e, xi, lp, w);
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int t = 0; t < 3; t++) st.W[a * 3 + t][lane] = w.S[a][t];
+        st.ok[lane] = w.ok;
+        st.Q[0][lane] = P.mp[p];
+        st.Q[1][lane] = P.vel[0][p]; st.Q[2][lane] = P.vel[1][p]; st.Q[3][lane] = P.vel[2][p];
+        key = w.center;
+    }
+    __syncwarp();
+    double *dst[4] = {N.mass, N.pk[0], N.pk[1], N.pk[2]};
+    warp_scatter<4, true>(g, st, key, active, dst, N.cnt, [&](int src, int i, int j, int k, double *acc) {
+        const double S = st.W[i][src] * st.W[3 + j][src] * st.W[6 + k][src];
+        const double fnmp = S * st.Q[0][src];
+        acc[0] += fnmp;
+        acc[1] += st.Q[1][src] * fnmp; acc[2] += st.Q[2][src] * fnmp; acc[3] += st.Q[3][src] * fnmp;
+    });
+}
+
+// ---- gather of grad v from the V records -----------------------------------------------------------
+__device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, const double4 *__restrict__ V, double dv[9])
+{
+#pragma unroll
+    for (int i = 0; i < 9; i++) dv[i] = 0.;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double syz = w.S[1][j] * w.S[2][k];
+            const int row = w.center + (j - 1) * g.yplane + (k - 1) * g.zplane - 1;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double4 v = ldg4(&V[row + i]);
+                const double gx = w.dS[0][i] * w.S[1][j] * w.S[2][k];
+                const double gy = w.S[0][i] * w.dS[1][j] * w.S[2][k];
+                const double gz = w.S[0][i] * w.S[1][j] * w.dS[2][k];
+                (void)syz;
+                dv[0] += v.x * gx; dv[1] += v.x * gy; dv[2] += v.x * gz;
+                dv[3] += v.y * gx; dv[4] += v.y * gy; dv[5] += v.y * gz;
+                dv[6] += v.z * gx; dv[7] += v.z * gy; dv[8] += v.z * gz;
+            }
+        }
+    }
+}
+
+// ---- F2: grad v + constitutive law + P2G forces ------------------------------------------------------
+template <bool FEXT>
+__global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
+                                                                    double strainTime, int doStrain)
+{
+    __shared__ WarpStage<18, FEXT ? 10 : 7> stage[FUSED_WARPS];
+    WarpStage<18, FEXT ? 10 : 7> &st = stage[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = p < P.nNR;
+    int key = 0;
+    if (active) {
+        const int e = P.elem[p];
+        double xi[3], lp[3];
+        load_xi_lp(P, p, xi, lp);
+        Weights3 w;
+        particle_weights<true>(g, e, xi, lp, w);
+        key = w.center;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int t = 0; t < 3; t++) { st.W[a * 3 + t][lane] = w.S[a][t]; st.W[9 + a * 3 + t][lane] = w.dS[a][t]; }
+        st.ok[lane] = w.ok;
+        double sp[6], pr;
+        if (doStrain) {
+            double dv[9];
+            gather_gradv(g, w, FN.V, dv);
+#pragma unroll
+            for (int i = 0; i < 9; i++) dv[i] *= strainTime;
+            PState s;
+            load_pstate(P, p, s);
+            constitutive_law<3>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+            store_pstate(P, p, s);
+#pragma unroll
+            for (int i = 0; i < 6; i++) sp[i] = s.sp[i];
+            pr = s.pressure;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; i++) sp[i] = P.sp[i][p];
+            pr = P.pressure[p];
+        }
+        st.Q[0][lane] = P.mp[p];
+        st.Q[1][lane] = sp[XX] - pr; st.Q[2][lane] = sp[YY] - pr; st.Q[3][lane] = sp[ZZ] - pr;
+        st.Q[4][lane] = sp[YZ]; st.Q[5][lane] = sp[XZ]; st.Q[6][lane] = sp[XY];
+        if (FEXT) { st.Q[7][lane] = P.pfext[0][p]; st.Q[8][lane] = P.pfext[1][p]; st.Q[9][lane] = P.pfext[2][p]; }
+    }
+    __syncwarp();
+    double *dst[3] = {N.ftot[0], N.ftot[1], N.ftot[2]};
+    warp_scatter<3, false>(g, st, key, active, dst, (int *)0, [&](int src, int i, int j, int k, double *acc) {
+        const double Sx = st.W[i][src], Sy = st.W[3 + j][src], Sz = st.W[6 + k][src];
+        const double gx = st.W[9 + i][src] * Sy * Sz;
+        const double gy = Sx * st.W[12 + j][src] * Sz;
+        const double gz = Sx * Sy * st.W[15 + k][src];
+        const double mp = st.Q[0][src];
+        const double sxx = st.Q[1][src], syy = st.Q[2][src], szz = st.Q[3][src];
+        const double syz = st.Q[4][src], sxz = st.Q[5][src], sxy = st.Q[6][src];
+        double fx = -mp * (sxx * gx + sxy * gy + sxz * gz);
+        double fy = -mp * (sxy * gx + syy * gy + syz * gz);
+        double fz = -mp * (sxz * gx + syz * gy + szz * gz);
+        if (FEXT) {
+            const double S = Sx * Sy * Sz;
+            fx += S * st.Q[7][src]; fy += S * st.Q[8][src]; fz += S * st.Q[9][src];
+        }
+        acc[0] += fx; acc[1] += fy; acc[2] += fz;
+    });
+}
+
+// ---- F3: particle update + P2G momentum with the new velocity ------------------------------------------
+__global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
+                                                                      StepParams sp, int m, int doScatter)
+{
+    __shared__ WarpStage<9, 4> stage[FUSED_WARPS];
+    WarpStage<9, 4> &st = stage[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = p < P.nNR;
+    int key = 0;
+    if (active) {
+        const int e = P.elem[p];
+        double xi[3], lp[3];
+        load_xi_lp(P, p, xi, lp);
+        Weights3 w;
+        particle_weights<false>(g, e, xi, lp, w);
+        key = w.center;
+        double Svk[3] = {0., 0., 0.}, Sacc[3] = {0., 0., 0.};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int row = w.center + (j - 1) * g.yplane + (k - 1) * g.zplane - 1;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double S = w.S[0][i] * w.S[1][j] * w.S[2][k];
+                    const double4 v = ldg4(&FN.V[row + i]);
+                    Svk[0] += v.x * S; Svk[1] += v.y * S; Svk[2] += v.z * S;
+                    if (m <= 0) {
+                        const double4 a = ldg4(&FN.A[row + i]);
+                        Sacc[0] += a.x * S; Sacc[1] += a.y * S; Sacc[2] += a.z * S;
+                    }
+                }
+            }
+        }
+        const double dt = sp.dt;
+        const double matDamp = mats[P.mat[p]].p[2];
+        const double pAlpha = matDamp >= 0. ? matDamp : sp.particleAlpha;
+        double vel[3] = {P.vel[0][p], P.vel[1][p], P.vel[2][p]};
+        double pos[3] = {P.pos[0][p], P.pos[1][p], P.pos[2][p]};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double vm = Svk[c];
+            if (m == 0) vm += Sacc[c] * (-dt);
+            double Adamp0 = vel[c] * pAlpha;
+            Adamp0 += vm * sp.gridAlpha;
+            double delV;
+            if (m > 0) {
+                double delXRate = vel[c];
+                vel[c] = vm;
+                vel[c] += Adamp0 * (-dt);
+                delV = vel[c] - delXRate;
+                delXRate += vel[c];
+                pos[c] += delXRate * (0.5 * dt);
+            } else if (m == 0) {
+                delV = (Sacc[c] - Adamp0) * dt;
+                vel[c] += delV;
+                double delXRate = vm + 0.5 * delV;
+                pos[c] += delXRate * dt;
+            } else {
+                double delXRate = vel[c];
+                vel[c] = Svk[c] - Adamp0 * dt;
+                delV = vel[c] - delXRate;
+                delXRate = vm + 0.5 * delV;
+                pos[c] += delXRate * dt;
+            }
+            P.vel[c][p] = vel[c];
+            P.pos[c][p] = pos[c];
+            P.acc[c][p] = delV / dt;
+        }
+        if (doScatter) {
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int t = 0; t < 3; t++) st.W[a * 3 + t][lane] = w.S[a][t];
+            st.ok[lane] = w.ok;
+            st.Q[0][lane] = P.mp[p];
+            st.Q[1][lane] = vel[0]; st.Q[2][lane] = vel[1]; st.Q[3][lane] = vel[2];
+        }
+    }
+    if (!doScatter) return;
+    __syncwarp();
+    double *dst[3] = {N.pk[0], N.pk[1], N.pk[2]};
+    warp_scatter<3, false>(g, st, key, active, dst, (int *)0, [&](int src, int i, int j, int k, double *acc) {
+        const double S = st.W[i][src] * st.W[3 + j][src] * st.W[6 + k][src];
+        const double fnmp = S * st.Q[0][src];
+        acc[0] += st.Q[1][src] * fnmp; acc[1] += st.Q[2][src] * fnmp; acc[2] += st.Q[3][src] * fnmp;
+    });
+}
+
+// ---- F4: second strain update + element reset --------------------------------------------------------
+__global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Particles P, FusedNodes FN, const Material *mats,
+                                                                   double strainTime, int doStrain, StatusFlags *flags, double dt)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    if (doStrain && p < P.nNR) {
+        double xi[3], lp[3];
+        load_xi_lp(P, p, xi, lp);
+        Weights3 w;
+        particle_weights<true>(g, P.elem[p], xi, lp, w);
+        double dv[9];
+        gather_gradv(g, w, FN.V, dv);
+#pragma unroll
+        for (int i = 0; i < 9; i++) dv[i] *= strainTime;
+        PState s;
+        load_pstate(P, p, s);
+        constitutive_law<3>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+        store_pstate(P, p, s);
+    }
+    reset_element_one<3>(g, P, p, flags, dt);
+}
+
+// ---- node sweeps -------------------------------------------------------------------------------------
+// BC application for one node inside a sweep: same arithmetic as k_velocity_bcs
+__device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3])
+{
+    const int e0 = B.start[u], e1 = B.start[u + 1];
+    for (int e = e0; e < e1; e++) {
+        if (!B.active[e]) continue;
+        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
+        if (pass == PASS_GRID_FORCES) {
+            double dotf = ft[0] * nx + ft[1] * ny + ft[2] * nz;
+            double dotp = pk[0] * nx + pk[1] * ny + pk[2] * nz;
+            double s = -dotf - dotp / dt;
+            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        } else {
+            double dotn = pk[0] * nx + pk[1] * ny + pk[2] * nz;
+            pk[0] += nx * (-dotn); pk[1] += ny * (-dotn); pk[2] += nz * (-dotn);
+            if (pass == PASS_UPDATE_MOMENTUM) {
+                double s = -dotn / dt;
+                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+            }
+        }
+    }
+    for (int e = e0; e < e1; e++) {
+        if (!B.active[e]) continue;
+        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
+        const double vel = B.value[e];
+        if (pass == PASS_GRID_FORCES) {
+            double s = mass * vel / dt;
+            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        } else {
+            double pvel = mass * vel;
+            pk[0] += nx * pvel; pk[1] += ny * pvel; pk[2] += nz * pvel;
+            if (pass == PASS_UPDATE_MOMENTUM) {
+                double s = pvel / dt;
+                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+            }
+        }
+    }
+}
+
+// N1: tasks 3 + 4a.  pkc = pk; symmetry adjust; BCs(MASS_MOMENTUM) if a USF task exists; V = pk/mass
+__global__ void k_n1_post_extrapolation(int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp, int hasUSF)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    double4 v = make_double4(0., 0., 0., 0.);
+    if (N.cnt[i] > 0) {
+        double pk[3] = {N.pk[0][i], N.pk[1][i], N.pk[2][i]};
+        double pkc[3] = {pk[0], pk[1], pk[2]};
+        const double mass = N.mass[i];
+        const int u = FN.bcOfNode ? FN.bcOfNode[i] : -1;
+        if (u >= 0) {
+            const int sd = B.symdir[u];
+            if (sd & 32) pkc[0] = 0.;
+            if (sd & 64) pkc[1] = 0.;
+            if (sd & 128) pkc[2] = 0.;
+            if (hasUSF) {
+                double ft[3] = {0., 0., 0.};
+                node_bcs(B, u, PASS_MASS_MOMENTUM, sp.dt, mass, pk, ft);
+                N.pk[0][i] = pk[0]; N.pk[1][i] = pk[1]; N.pk[2][i] = pk[2];
+            }
+        }
+        N.pkc[0][i] = pkc[0]; N.pkc[1][i] = pkc[1]; N.pkc[2][i] = pkc[2];
+        if (mass != 0.) {
+            const double rm = 1. / mass;
+            v = make_double4(pk[0] * rm, pk[1] * rm, pk[2] * rm, 0.);
+            N.vk[0][i] = v.x; N.vk[1][i] = v.y; N.vk[2][i] = v.z;
+        }
+    }
+    FN.V[i] = v;
+}
+
+// N2: tasks 6 + 7 + 8a.  pk = pkc; ftot += m g; BCs(GRID_FORCES); pk += ftot dt; BCs(UPDATE_MOMENTUM);
+// V = pk/mass; A = ftot/mass; then (when a re-extrapolation follows) pk = 0 for task 9a.
+__global__ void k_n2_forces_momenta(int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp, int rezero)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    double4 v = make_double4(0., 0., 0., 0.), a = make_double4(0., 0., 0., 0.);
+    if (N.cnt[i] > 0) {
+        double pk[3] = {N.pkc[0][i], N.pkc[1][i], N.pkc[2][i]};
+        double ft[3] = {N.ftot[0][i], N.ftot[1][i], N.ftot[2][i]};
+        const double mass = N.mass[i];
+        if (sp.hasGravity) { ft[0] += mass * sp.grav[0]; ft[1] += mass * sp.grav[1]; ft[2] += mass * sp.grav[2]; }
+        const int u = FN.bcOfNode ? FN.bcOfNode[i] : -1;
+        if (u >= 0) node_bcs(B, u, PASS_GRID_FORCES, sp.dt, mass, pk, ft);
+        pk[0] += ft[0] * sp.dt; pk[1] += ft[1] * sp.dt; pk[2] += ft[2] * sp.dt;
+        if (u >= 0 && sp.xpicOrder <= 1) node_bcs(B, u, PASS_UPDATE_MOMENTUM, sp.dt, mass, pk, ft);
+        N.ftot[0][i] = ft[0]; N.ftot[1][i] = ft[1]; N.ftot[2][i] = ft[2];
+        if (mass != 0.) {
+            const double rm = 1. / mass;
+            v = make_double4(pk[0] * rm, pk[1] * rm, pk[2] * rm, 0.);
+            a = make_double4(ft[0] / mass, ft[1] / mass, ft[2] / mass, 0.);
+            N.vk[0][i] = v.x; N.vk[1][i] = v.y; N.vk[2][i] = v.z;
+        }
+        if (rezero) { pk[0] = 0.; pk[1] = 0.; pk[2] = 0.; }
+        N.pk[0][i] = pk[0]; N.pk[1][i] = pk[1]; N.pk[2][i] = pk[2];
+    }
+    FN.V[i] = v;
+    FN.A[i] = a;
+}
+
+// N3: task 9b.  BCs(UPDATE_STRAINS_LAST); V = pk/mass
+__global__ void k_n3_strains_last(int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    double4 v = make_double4(0., 0., 0., 0.);
+    if (N.cnt[i] > 0) {
+        double pk[3] = {N.pk[0][i], N.pk[1][i], N.pk[2][i]};
+        const double mass = N.mass[i];
+        const int u = FN.bcOfNode ? FN.bcOfNode[i] : -1;
+        if (u >= 0) {
+            double ft[3] = {0., 0., 0.};
+            node_bcs(B, u, PASS_UPDATE_STRAINS_LAST, sp.dt, mass, pk, ft);
+            N.pk[0][i] = pk[0]; N.pk[1][i] = pk[1]; N.pk[2][i] = pk[2];
+        }
+        if (mass != 0.) {
+            const double rm = 1. / mass;
+            v = make_double4(pk[0] * rm, pk[1] * rm, pk[2] * rm, 0.);
+            N.vk[0][i] = v.x; N.vk[1][i] = v.y; N.vk[2][i] = v.z;
+        }
+    }
+    FN.V[i] = v;
+}
+
+// ---- physical sort by dual cell -----------------------------------------------------------------------
+__global__ void k_sort_keys(Grid g, Particles P, int *keys, int *idx)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    int key;
+    if (p < P.nNR) {
+        const int e = P.elem[p];
+        double pos[3] = {P.pos[0][p], P.pos[1][p], P.pos[2][p]};
+        double xi[3];
+        get_xipos<3>(g, e, pos, xi);
+        const ElemIJK c = elem_ijk(g, e);
+        key = elem_node0(g, c) + (xi[0] < 0. ? 0 : 1) + (xi[1] < 0. ? 0 : 1) * g.yplane + (xi[2] < 0. ? 0 : 1) * g.zplane;
+    } else {
+        key = g.nnodes + (p - P.nNR);        // rigid particles keep their place after the nonrigid block
+    }
+    keys[p] = key;
+    idx[p] = p;
+}
+
+__global__ void k_permute_pool(int n, size_t stride, int nd, const double *__restrict__ src, double *__restrict__ dst,
+                               int ni, const int *__restrict__ isrc, int *__restrict__ idst, const int *__restrict__ perm)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int q = perm[p];
+    for (int f = 0; f < nd; f++) dst[(size_t)f * stride + p] = src[(size_t)f * stride + q];
+    for (int f = 0; f < ni; f++) idst[(size_t)f * stride + p] = isrc[(size_t)f * stride + q];
+}

@@ -318,10 +318,8 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_momentum_last(Grid g, Part
 
 // ---- task 11: ResetElementsTask (ResetElementsTask.cpp:196-265) ---------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(TASK_THREADS) k_reset_elements(Grid g, Particles P, StatusFlags *flags, double dt)
+__device__ __forceinline__ void reset_element_one(const Grid &g, const Particles &P, int p, StatusFlags *flags, double dt)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
     double pos[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
     if (pos[0] != pos[0] || pos[1] != pos[1] || pos[2] != pos[2]) {
         atomicCAS(&flags->nanParticle, 0, P.orig[p] + 1);
@@ -362,4 +360,12 @@ __global__ void __launch_bounds__(TASK_THREADS) k_reset_elements(Grid g, Particl
     }
     P.pos[0][p] = inside[0]; P.pos[1][p] = inside[1];
     if (DIM == 3) P.pos[2][p] = inside[2];
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(TASK_THREADS) k_reset_elements(Grid g, Particles P, StatusFlags *flags, double dt)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    reset_element_one<DIM>(g, P, p, flags, dt);
 }

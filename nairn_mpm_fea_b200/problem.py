@@ -71,6 +71,23 @@ class Problem:
             self.dt_strain_first = self.dt_strain_last = dt
 
 
+def jitter(arr, amplitude, seed=12345):
+    """Deterministic integer-hash jitter (same on every platform):
+    arr[c][p] += amplitude * (hash(p, c) / 2^32 - 0.5)."""
+    arr = np.array(arr, dtype=np.float64, copy=True)
+    n = arr.shape[1]
+    idx = np.arange(n, dtype=np.uint64)
+    for c in range(arr.shape[0]):
+        h = (idx * np.uint64(2654435761) + np.uint64(seed + 7919 * c)) & np.uint64(0xFFFFFFFF)
+        h ^= h >> np.uint64(16)
+        h = (h * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+        h ^= h >> np.uint64(13)
+        h = (h * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+        h ^= h >> np.uint64(16)
+        arr[c] += amplitude * (h.astype(np.float64) / 4294967296.0 - 0.5)
+    return arr
+
+
 def structured_axis(lo, hi, cell):
     """One axis of <Grid>: returns (ncells incl. border, node coordinates) as Generators.cpp:1769-1833."""
     n = int((hi - lo) / cell + 0.5)          # Nhoriz from cellsize (MPMReadHandler Horiz cellsize)
@@ -124,7 +141,7 @@ def lattice_points(xpts, ypts, zpts, elems_ijk, pts_per_side=2):
 
 def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0.0, 0.0, -1000.0), cfl=0.4,
             step_ms=1e-3, method=USAVG, shape=UNIFORM_GIMP, bottom_bc=True, gravity=None, velocity_fn=None,
-            pts_per_side=2, ncell_xyz=None):
+            pts_per_side=2, ncell_xyz=None, jitter_amp=0.0):
     """BASELINE.json config 2 family: block of ncell^3 cells (pts_per_side^3 particles per cell) of
     IsotropicMat inside a (ncell+2*margin)^3-cell grid (+1 border cell per side), initial velocity,
     bottom plane z<=margin held in z.  Numbers are XML (Legacy) units: mm, MPa, g/cm^3, mm/s, ms.
@@ -154,6 +171,14 @@ def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0
     elem = (pr.horiz * (ek * pr.vert + ej) + ei + 1).astype(np.int32)
     in_elem = np.repeat(elem, npp)
     lp = np.full((3, n), gap)
+    if jitter_amp > 0.0:
+        # off-lattice start (so the uGIMP stencils are the generic 27-node ones); elements re-found as
+        # MeshInfo::FindElementFromPoint does (MeshInfo.cpp:593-633)
+        pos = jitter(pos, jitter_amp * cell, 12345)
+        col = ((pos[0] - pr.xpts[0]) / gx).astype(np.int64)
+        row = ((pos[1] - pr.ypts[0]) / gy).astype(np.int64)
+        zrow = ((pos[2] - pr.zpts[0]) / gz).astype(np.int64)
+        in_elem = (pr.horiz * (zrow * pr.vert + row) + col + 1).astype(np.int32)
     # mp = rho * 8 * psize.x*psize.y*psize.z, psize = 0.5*lp*cell extent (NairnMPM.cpp:624-637, MatPoint3D.cpp:219-225)
     dxe = (pr.xpts[ei + 1] - pr.xpts[ei])
     dye = (pr.ypts[ej + 1] - pr.ypts[ej])

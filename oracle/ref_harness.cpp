@@ -23,6 +23,7 @@
 #include "NairnMPM_Class/NairnMPM.hpp"
 #include "NairnMPM_Class/MPMTask.hpp"
 #include "NairnMPM_Class/MeshInfo.hpp"
+#include "NairnMPM_Class/ResetElementsTask.hpp"
 #include "MPM_Classes/MPMBase.hpp"
 #include "Nodes/NodalPoint.hpp"
 #include "Nodes/CrackVelocityField.hpp"
@@ -331,6 +332,30 @@ int ref_get_materials(int *ids, double *params)
         }
     }
     return nmat;
+}
+
+// Overwrite particle positions / velocities (arrays [3][nmpms]) before stepping, so that tests and the
+// bench can give the reference exactly the (jittered, non-lattice) state they give the GPU path.
+// Each particle's element is re-found with the reference's own ResetElementsTask::ResetElement.
+int ref_set_particles(const double *pos, const double *vel)
+{
+    int n = nmpms, bad = 0;
+    for (int p = 0; p < n; p++) {
+        MPMBase *m = mpm[p];
+        if (pos) {
+            Vector x = MakeVector(pos[p], pos[n + p], pos[2 * n + p]);
+            m->SetPosition(&x);
+            m->SetOrigin(&x);
+            int status = ResetElementsTask::ResetElement(m);
+            if (status != SAME_ELEMENT && status != NEW_ELEMENT) bad++;
+            m->SetElementCrossings(0);
+        }
+        if (vel) {
+            Vector v = MakeVector(vel[p], vel[n + p], vel[2 * n + p]);
+            m->SetVelocity(&v);
+        }
+    }
+    return bad;
 }
 
 void ref_close(void)

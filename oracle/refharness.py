@@ -14,6 +14,8 @@ import tempfile
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libnairnmpm_ref.so")
 BIN = os.path.join(HERE, "_ref", "NairnMPM")
@@ -58,6 +60,14 @@ class RefRun:
         d = {k: int(iv[i]) for i, k in enumerate(INT_KEYS)}
         d.update({k: float(dv[i]) for i, k in enumerate(DBL_KEYS)})
         return d
+
+    def set_particles(self, pos=None, vel=None):
+        """Overwrite positions/velocities ([3][n] arrays); returns number of particles off the grid."""
+        pos = None if pos is None else np.ascontiguousarray(pos, dtype=np.float64)
+        vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64)
+        bad = self.lib.ref_set_particles(_dp(pos), _dp(vel))
+        self.info = self.get_info()
+        return bad
 
     def step(self, n=1):
         if self.lib.ref_step(int(n)) != 0:
@@ -131,10 +141,20 @@ def _flatten(prefix, d, out):
         out["%s/%s" % (prefix, k)] = np.asarray(v)
 
 
-def _worker(xml, out_npz, nprocs, snaps, per_task_steps):
+from nairn_mpm_fea_b200.problem import jitter  # noqa: E402  (test infrastructure may import the product)
+
+
+def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp=0.0):
     """snaps: sorted step counts at which to snapshot particles (+nodes); per_task_steps: number of
-    initial steps run task-by-task with node+particle dumps after every task."""
+    initial steps run task-by-task with node+particle dumps after every task.  jitter_amp/vel_amp:
+    hash-jitter the initial positions (length units) and velocities before the first step."""
     r = RefRun(xml, nprocs)
+    if jitter_amp > 0.0 or vel_amp > 0.0:
+        p0 = r.particles()
+        newpos = jitter(p0["pos"], jitter_amp, 12345) if jitter_amp > 0.0 else None
+        newvel = jitter(p0["vel"], vel_amp, 777) if vel_amp > 0.0 else None
+        bad = r.set_particles(newpos, newvel)
+        assert bad == 0, "jitter pushed %d particles off the grid" % bad
     out = {}
     _flatten("info", r.info, out)
     out["node_coords"] = r.node_coords()
@@ -166,7 +186,7 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps):
     np.savez_compressed(out_npz, **out)
 
 
-def run_reference(xml_text_or_path, snaps=(1,), per_task_steps=0, nprocs=1, workdir=None):
+def run_reference(xml_text_or_path, snaps=(1,), per_task_steps=0, nprocs=1, workdir=None, jitter_amp=0.0, vel_amp=0.0):
     """Run the reference on an XML input in a fresh process; returns dict of arrays (see _worker)."""
     if not available():
         raise RuntimeError("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
@@ -179,7 +199,7 @@ def run_reference(xml_text_or_path, snaps=(1,), per_task_steps=0, nprocs=1, work
             f.write(xml_text_or_path)
     out = os.path.join(tmp, "ref_out.npz")
     cmd = [sys.executable, os.path.abspath(__file__), xml, out, str(nprocs),
-           ",".join(str(s) for s in sorted(snaps)), str(per_task_steps)]
+           ",".join(str(s) for s in sorted(snaps)), str(per_task_steps), repr(jitter_amp), repr(vel_amp)]
     p = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("reference worker failed:\n%s\n%s" % (p.stdout[-2000:], p.stderr[-2000:]))
@@ -189,4 +209,6 @@ def run_reference(xml_text_or_path, snaps=(1,), per_task_steps=0, nprocs=1, work
 
 if __name__ == "__main__":
     _xml, _out, _np, _snaps, _pt = sys.argv[1:6]
-    _worker(_xml, _out, int(_np), [int(s) for s in _snaps.split(",") if s], int(_pt))
+    _ja = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
+    _va = float(sys.argv[7]) if len(sys.argv) > 7 else 0.0
+    _worker(_xml, _out, int(_np), [int(s) for s in _snaps.split(",") if s], int(_pt), _ja, _va)

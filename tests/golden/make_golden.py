@@ -20,7 +20,8 @@ from tests import inputs  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 CASES = {
-    # name: (xml text, snapshots, per-task steps)
+    # name: (xml text, snapshots, per-task steps[, position jitter, velocity jitter])
+    "block3d_jitter": (inputs.block3d(ncell=5, margin=3, E=100.0, vx=3.0e3, vy=-2.0e3, vz=-6.0e3), (1, 20, 60), 1, 0.35, 4000.0),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),
@@ -44,10 +45,12 @@ def slim(z):
 
 
 def main(names=None):
-    for name, (xml, snaps, pts) in CASES.items():
+    for name, spec in CASES.items():
         if names and name not in names:
             continue
-        z = run_reference(xml, snaps=snaps, per_task_steps=pts, nprocs=1)
+        xml, snaps, pts = spec[:3]
+        ja, va = (spec[3], spec[4]) if len(spec) > 3 else (0.0, 0.0)
+        z = run_reference(xml, snaps=snaps, per_task_steps=pts, nprocs=1, jitter_amp=ja, vel_amp=va)
         z = slim(z)
         z["xml"] = np.array(xml)
         path = os.path.join(HERE, name + ".npz")

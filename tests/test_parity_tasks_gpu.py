@@ -12,15 +12,18 @@ from tests.parity import TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compar
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
+CASES = ["block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
          "block3d_ugimp_usf"]
 
 
-def make_sim(z, kernel_path=1):
+FUSED_CASES = [c for c in CASES if "linear" not in c]
+
+
+def make_sim(z, kernel_path=1, sort_interval=0):
     from nairn_mpm_fea_b200 import MpmGpu
     from nairn_mpm_fea_b200.problem import from_reference_dump
     prob = from_reference_dump(z)
-    return MpmGpu(prob, device=0, kernel_path=kernel_path), prob
+    return MpmGpu(prob, device=0, kernel_path=kernel_path, sort_interval=sort_interval), prob
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -43,10 +46,13 @@ def test_each_task_of_step_one(case):
     sim.close()
 
 
-@pytest.mark.parametrize("case", CASES)
-def test_whole_steps(case):
+@pytest.mark.parametrize("case,kernel_path,sort_interval",
+                         [(c, 1, 0) for c in CASES] + [(c, 2, 0) for c in FUSED_CASES] +
+                         [("block3d_jitter", 2, 1), ("block3d_fast_crossings", 2, 3)])
+def test_whole_steps(case, kernel_path, sort_interval):
+    """kernel_path 1 = per-task kernels, 2 = fused dual-cell path (with its periodic physical sort)."""
     z = load_golden(case)
-    sim, prob = make_sim(z)
+    sim, prob = make_sim(z, kernel_path, sort_interval)
     snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
     done = 0
     for s in snaps:
