@@ -139,6 +139,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     g.gx = cfg->gridx; g.gy = cfg->gridy; g.gz = is3D ? cfg->gridz : 0.;
     g.xmin = cfg->xpts[0]; g.ymin = cfg->ypts[0]; g.zmin = is3D ? cfg->zpts[0] : 0.;
     g.rcrit = cfg->cpdi_rcrit;
+    g.lpUniform = 0; g.lpU[0] = g.lpU[1] = g.lpU[2] = 0.;
     double *dx = NULL, *dy = NULL, *dz = NULL;
     int rc = MPMGPU_OK;
     do {
@@ -398,6 +399,12 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     {   // the fused path needs 3D uGIMP, particles no larger than a cell, FLIP/PIC, no rigid particles
         bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && ctx->sp.xpicOrder <= 1 && h->n_nonrigid == n;
         if (ok) for (size_t i = 0; i < (size_t)3 * n; i++) if (!(h->lp[i] <= 1.0)) { ok = false; break; }
+        bool uni = true;
+        for (int c = 0; c < 3 && uni; c++) for (int q = 1; q < n; q++) if (h->lp[(size_t)c * n + q] != h->lp[(size_t)c * n]) { uni = false; break; }
+        ctx->g.lpUniform = uni ? 1 : 0;
+        for (int c = 0; c < 3; c++) ctx->g.lpU[c] = h->lp[(size_t)c * n];
+        ctx->tiled.stateKind = SK_ELASTIC;
+        for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC) ctx->tiled.stateKind = SK_FULL;
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
             return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, XPIC order<=1 and no rigid particles");
@@ -734,8 +741,13 @@ static int fused_step(mpmgpu_ctx *ctx)
     LAUNCH(k_n1_post_extrapolation, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp, hasUSF ? 1 : 0);
     prof_end(ctx, T_POSTEXTRAP);
     prof_begin(ctx);
-    if (ctx->hasFext) LAUNCH(k_f2_strain_forces<true>, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
-    else LAUNCH(k_f2_strain_forces<false>, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+    if (t.stateKind == SK_ELASTIC) {
+        if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_ELASTIC, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+        else LAUNCH((k_f2_strain_forces<SK_ELASTIC, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+    } else {
+        if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_FULL, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+        else LAUNCH((k_f2_strain_forces<SK_FULL, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+    }
     prof_end(ctx, T_USF);
     prof_begin(ctx);
     LAUNCH(k_n2_forces_momenta, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp, reextrap ? 1 : 0);
@@ -745,7 +757,8 @@ static int fused_step(mpmgpu_ctx *ctx)
     prof_end(ctx, T_PARTICLES);
     prof_begin(ctx);
     if (reextrap) LAUNCH(k_n3_strains_last, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp);
-    LAUNCH(k_f4_strain_reset, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt);
+    if (t.stateKind == SK_ELASTIC) LAUNCH(k_f4_strain_reset<SK_ELASTIC>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt);
+    else LAUNCH(k_f4_strain_reset<SK_FULL>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt);
     prof_end(ctx, T_USL);
     return MPMGPU_OK;
 }

@@ -41,6 +41,7 @@ struct FusedNodes {
 
 struct TiledState {
     int enabled;         // fast path usable for this context
+    int stateKind;       // SK_ELASTIC / SK_FULL: which particle fields the materials in use touch
     int sortInterval;
     long long stepsSinceSort;
     FusedNodes FN;
@@ -125,26 +126,55 @@ __device__ __forceinline__ void particle_weights(const Grid &g, int inElem, cons
     }
 }
 
-// per-warp shared staging: component-major so that a lane-as-node reads W[comp][srcLane]
-template <int NW, int NP>
+// ---- per-warp shared staging ----------------------------------------------------------------------
+// Each particle lane stores FACTORISED weights of its 27-node stencil: the three x factors and the
+// nine (y,z) products, so that a lane acting as node (i,j,k) forms S = X[i]*YZ[j+3k] with one
+// multiply.  Rows are 33 doubles long: particle lanes write consecutive words, node lanes read with
+// an odd stride -- both conflict-free.
+#define WS_STRIDE 33
+template <bool GRAD, int NQ>
 struct WarpStage {
-    double W[NW][32];    // weights: 0..8 S[axis*3+t], 9..17 dS[axis*3+t]
-    double Q[NP][32];    // payload
-    unsigned ok[32];
+    double X[3][WS_STRIDE];                     // Sx_i
+    double YZ[9][WS_STRIDE];                    // Sy_j * Sz_k
+    double DX[GRAD ? 3 : 1][WS_STRIDE];         // dSx_i           (scaled by 2/dx)
+    double DYZ[GRAD ? 9 : 1][WS_STRIDE];        // dSy_j * Sz_k
+    double YDZ[GRAD ? 9 : 1][WS_STRIDE];        // Sy_j * dSz_k
+    double Q[NQ][32];                           // payload, broadcast-read
 };
 
+template <bool GRAD, class Stage>
+__device__ __forceinline__ void stage_weights(Stage &st, int lane, const Weights3 &w)
+{
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        st.X[t][lane] = w.S[0][t];
+        if (GRAD) st.DX[t][lane] = w.dS[0][t];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            st.YZ[j + 3 * k][lane] = w.S[1][j] * w.S[2][k];
+            if (GRAD) {
+                st.DYZ[j + 3 * k][lane] = w.dS[1][j] * w.S[2][k];
+                st.YDZ[j + 3 * k][lane] = w.S[1][j] * w.dS[2][k];
+            }
+        }
+}
+
 // ---- the warp-cooperative scatter ----------------------------------------------------------------
-// NV values per node.  contrib(src, i, j, k, acc[]) adds particle `src`'s contribution for node
-// (i,j,k) of its stencil into acc.  Groups = lanes with equal key.
-template <int NV, bool COUNT, class Stage, class Contrib>
-__device__ __forceinline__ void warp_scatter(const Grid &g, const Stage &st, int key, bool active, double *const *dst, int *cnt, Contrib contrib)
+// Groups = lanes whose particles share a dual cell (equal key).  For each group, lanes 0..26 act as
+// the 27 nodes around the group's centre node: contrib(src, i, jk, acc[]) adds particle `src`'s
+// contribution for node (i, jk=j+3k) into registers; one RED per node and component leaves the warp.
+template <int NV, bool COUNT, class Contrib>
+__device__ __forceinline__ void warp_scatter(const Grid &g, int key, bool active, double *const *dst, int *cnt, Contrib contrib)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned mymask = __match_any_sync(full, active ? key : (-1 - lane));
     unsigned remaining = __ballot_sync(full, active);
-    const int li = lane % 3, lj = (lane / 3) % 3, lk = lane / 9;        // node of this lane (lane < 27)
-    const int okbit = (1 << li) | (1 << (3 + lj)) | (1 << (6 + lk));
+    const int li = lane % 3, ljk = lane / 3;                 // node of this lane (lane < 27): i, j+3k
+    const int nodeOff = (li - 1) + ((ljk % 3) - 1) * g.yplane + ((ljk / 3) - 1) * g.zplane;
     while (remaining) {
         const int leader = __ffs(remaining) - 1;
         const unsigned grp = __shfl_sync(full, mymask, leader);
@@ -157,13 +187,10 @@ __device__ __forceinline__ void warp_scatter(const Grid &g, const Stage &st, int
             int n = 0;
             for (unsigned mm = grp; mm; mm &= mm - 1) {
                 const int src = __ffs(mm) - 1;
-                if ((st.ok[src] & okbit) == okbit) {
-                    contrib(src, li, lj, lk, acc);
-                    n++;
-                }
+                n += contrib(src, li, ljk, acc);
             }
             if (n) {
-                const int nd = center + (li - 1) + (lj - 1) * g.yplane + (lk - 1) * g.zplane;
+                const int nd = center + nodeOff;
 #pragma unroll
                 for (int v = 0; v < NV; v++) atomAdd(&dst[v][nd], acc[v]);
                 if (COUNT) atomicAdd(&cnt[nd], n);
@@ -172,11 +199,47 @@ __device__ __forceinline__ void warp_scatter(const Grid &g, const Stage &st, int
     }
 }
 
+__device__ __forceinline__ void load_lp(const Grid &g, const Particles &P, int p, double lp[3])
+{
+    if (g.lpUniform) { lp[0] = g.lpU[0]; lp[1] = g.lpU[1]; lp[2] = g.lpU[2]; }
+    else { lp[0] = P.lp[0][p]; lp[1] = P.lp[1][p]; lp[2] = P.lp[2][p]; }
+}
+
+// ---- particle state <-> registers, specialised by what the materials in use touch ------------------
+// SK_ELASTIC: IsotropicMat only: F, sp, work, heat, entropy (+prevT read).  SK_FULL: everything.
+enum { SK_ELASTIC = 0, SK_FULL = 1 };
+
+template <int SK>
+__device__ __forceinline__ void load_state(const Particles &P, int p, PState &s)
+{
+    if (SK == SK_FULL) { load_pstate(P, p, s); return; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) s.F[i] = P.F[i][p];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { s.sp[i] = P.sp[i][p]; s.eplast[i] = 0.; }
+    s.pressure = 0.; s.res = 0.; s.plast = 0.;
+    s.work = P.work[p]; s.heat = P.heat[p]; s.entropy = P.entropy[p];
+    s.prevT = P.prevT[p];
+#pragma unroll
+    for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = 0.;
+}
+
+template <int SK>
+__device__ __forceinline__ void store_state(const Particles &P, int p, const PState &s)
+{
+    if (SK == SK_FULL) { store_pstate(P, p, s); return; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) P.F[i][p] = s.F[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) P.sp[i][p] = s.sp[i];
+    P.work[p] = s.work; P.heat[p] = s.heat; P.entropy[p] = s.entropy;
+}
+
 // ---- F1: ncpos + P2G mass and momentum ------------------------------------------------------------
 __global__ void __launch_bounds__(FUSED_THREADS) k_f1_mass_momentum(Grid g, Particles P, Nodes N)
 {
-    __shared__ WarpStage<9, 4> stage[FUSED_WARPS];
-    WarpStage<9, 4> &st = stage[threadIdx.x >> 5];
+    __shared__ WarpStage<false, 4> stage[FUSED_WARPS];
+    WarpStage<false, 4> &st = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
@@ -184,27 +247,25 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f1_mass_momentum(Grid g, Part
     if (active) {
         const int e = P.elem[p];
         double pos[3] = {P.pos[0][p], P.pos[1][p], P.pos[2][p]};
-        double xi[3], lp[3] = {P.lp[0][p], P.lp[1][p], P.lp[2][p]};
+        double xi[3], lp[3];
+        load_lp(g, P, p, lp);
         get_xipos<3>(g, e, pos, xi);
         P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
         Weights3 w;
         particle_weights<false>(g, e, xi, lp, w);
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-            for (int t = 0; t < 3; t++) st.W[a * 3 + t][lane] = w.S[a][t];
-        st.ok[lane] = w.ok;
+        stage_weights<false>(st, lane, w);
         st.Q[0][lane] = P.mp[p];
         st.Q[1][lane] = P.vel[0][p]; st.Q[2][lane] = P.vel[1][p]; st.Q[3][lane] = P.vel[2][p];
         key = w.center;
     }
     __syncwarp();
     double *dst[4] = {N.mass, N.pk[0], N.pk[1], N.pk[2]};
-    warp_scatter<4, true>(g, st, key, active, dst, N.cnt, [&](int src, int i, int j, int k, double *acc) {
-        const double S = st.W[i][src] * st.W[3 + j][src] * st.W[6 + k][src];
+    warp_scatter<4, true>(g, key, active, dst, N.cnt, [&](int src, int i, int jk, double *acc) {
+        const double S = st.X[i][src] * st.YZ[jk][src];
         const double fnmp = S * st.Q[0][src];
         acc[0] += fnmp;
         acc[1] += st.Q[1][src] * fnmp; acc[2] += st.Q[2][src] * fnmp; acc[3] += st.Q[3][src] * fnmp;
+        return S != 0. ? 1 : 0;
     });
 }
 
@@ -218,14 +279,15 @@ __device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, c
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const double syz = w.S[1][j] * w.S[2][k];
+            const double dyz = w.dS[1][j] * w.S[2][k];
+            const double ydz = w.S[1][j] * w.dS[2][k];
             const int row = w.center + (j - 1) * g.yplane + (k - 1) * g.zplane - 1;
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const double4 v = ldg4(&V[row + i]);
-                const double gx = w.dS[0][i] * w.S[1][j] * w.S[2][k];
-                const double gy = w.S[0][i] * w.dS[1][j] * w.S[2][k];
-                const double gz = w.S[0][i] * w.S[1][j] * w.dS[2][k];
-                (void)syz;
+                const double gx = w.dS[0][i] * syz;
+                const double gy = w.S[0][i] * dyz;
+                const double gz = w.S[0][i] * ydz;
                 dv[0] += v.x * gx; dv[1] += v.x * gy; dv[2] += v.x * gz;
                 dv[3] += v.y * gx; dv[4] += v.y * gy; dv[5] += v.y * gz;
                 dv[6] += v.z * gx; dv[7] += v.z * gy; dv[8] += v.z * gz;
@@ -235,12 +297,12 @@ __device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, c
 }
 
 // ---- F2: grad v + constitutive law + P2G forces ------------------------------------------------------
-template <bool FEXT>
+template <int SK, bool FEXT>
 __global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
                                                                     double strainTime, int doStrain)
 {
-    __shared__ WarpStage<18, FEXT ? 10 : 7> stage[FUSED_WARPS];
-    WarpStage<18, FEXT ? 10 : 7> &st = stage[threadIdx.x >> 5];
+    __shared__ WarpStage<true, FEXT ? 9 : 6> stage[FUSED_WARPS];
+    WarpStage<true, FEXT ? 9 : 6> &st = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
@@ -248,56 +310,54 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Part
     if (active) {
         const int e = P.elem[p];
         double xi[3], lp[3];
-        load_xi_lp(P, p, xi, lp);
-        Weights3 w;
-        particle_weights<true>(g, e, xi, lp, w);
-        key = w.center;
+        xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
+        load_lp(g, P, p, lp);
+        double sp[6], pr = 0.;
+        {
+            Weights3 w;
+            particle_weights<true>(g, e, xi, lp, w);
+            key = w.center;
+            stage_weights<true>(st, lane, w);
+            if (doStrain) {
+                double dv[9];
+                gather_gradv(g, w, FN.V, dv);
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+                for (int i = 0; i < 9; i++) dv[i] *= strainTime;
+                PState s;
+                load_state<SK>(P, p, s);
+                constitutive_law<3>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+                store_state<SK>(P, p, s);
 #pragma unroll
-            for (int t = 0; t < 3; t++) { st.W[a * 3 + t][lane] = w.S[a][t]; st.W[9 + a * 3 + t][lane] = w.dS[a][t]; }
-        st.ok[lane] = w.ok;
-        double sp[6], pr;
-        if (doStrain) {
-            double dv[9];
-            gather_gradv(g, w, FN.V, dv);
+                for (int i = 0; i < 6; i++) sp[i] = s.sp[i];
+                pr = s.pressure;
+            } else {
 #pragma unroll
-            for (int i = 0; i < 9; i++) dv[i] *= strainTime;
-            PState s;
-            load_pstate(P, p, s);
-            constitutive_law<3>(s, dv, strainTime, g.np, mats[P.mat[p]]);
-            store_pstate(P, p, s);
-#pragma unroll
-            for (int i = 0; i < 6; i++) sp[i] = s.sp[i];
-            pr = s.pressure;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 6; i++) sp[i] = P.sp[i][p];
-            pr = P.pressure[p];
+                for (int i = 0; i < 6; i++) sp[i] = P.sp[i][p];
+                if (SK == SK_FULL) pr = P.pressure[p];
+            }
         }
-        st.Q[0][lane] = P.mp[p];
-        st.Q[1][lane] = sp[XX] - pr; st.Q[2][lane] = sp[YY] - pr; st.Q[3][lane] = sp[ZZ] - pr;
-        st.Q[4][lane] = sp[YZ]; st.Q[5][lane] = sp[XZ]; st.Q[6][lane] = sp[XY];
-        if (FEXT) { st.Q[7][lane] = P.pfext[0][p]; st.Q[8][lane] = P.pfext[1][p]; st.Q[9][lane] = P.pfext[2][p]; }
+        const double nmp = -P.mp[p];            // f = -mp (sigma - p I) . grad S  (MatPoint3D.cpp:248-252)
+        st.Q[0][lane] = nmp * (sp[XX] - pr); st.Q[1][lane] = nmp * (sp[YY] - pr); st.Q[2][lane] = nmp * (sp[ZZ] - pr);
+        st.Q[3][lane] = nmp * sp[YZ]; st.Q[4][lane] = nmp * sp[XZ]; st.Q[5][lane] = nmp * sp[XY];
+        if (FEXT) { st.Q[6][lane] = P.pfext[0][p]; st.Q[7][lane] = P.pfext[1][p]; st.Q[8][lane] = P.pfext[2][p]; }
     }
     __syncwarp();
     double *dst[3] = {N.ftot[0], N.ftot[1], N.ftot[2]};
-    warp_scatter<3, false>(g, st, key, active, dst, (int *)0, [&](int src, int i, int j, int k, double *acc) {
-        const double Sx = st.W[i][src], Sy = st.W[3 + j][src], Sz = st.W[6 + k][src];
-        const double gx = st.W[9 + i][src] * Sy * Sz;
-        const double gy = Sx * st.W[12 + j][src] * Sz;
-        const double gz = Sx * Sy * st.W[15 + k][src];
-        const double mp = st.Q[0][src];
-        const double sxx = st.Q[1][src], syy = st.Q[2][src], szz = st.Q[3][src];
-        const double syz = st.Q[4][src], sxz = st.Q[5][src], sxy = st.Q[6][src];
-        double fx = -mp * (sxx * gx + sxy * gy + sxz * gz);
-        double fy = -mp * (sxy * gx + syy * gy + syz * gz);
-        double fz = -mp * (sxz * gx + syz * gy + szz * gz);
+    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
+        const double Sx = st.X[i][src];
+        const double gx = st.DX[i][src] * st.YZ[jk][src];
+        const double gy = Sx * st.DYZ[jk][src];
+        const double gz = Sx * st.YDZ[jk][src];
+        const double qxx = st.Q[0][src], qyy = st.Q[1][src], qzz = st.Q[2][src];
+        const double qyz = st.Q[3][src], qxz = st.Q[4][src], qxy = st.Q[5][src];
+        acc[0] += qxx * gx + qxy * gy + qxz * gz;
+        acc[1] += qxy * gx + qyy * gy + qyz * gz;
+        acc[2] += qxz * gx + qyz * gy + qzz * gz;
         if (FEXT) {
-            const double S = Sx * Sy * Sz;
-            fx += S * st.Q[7][src]; fy += S * st.Q[8][src]; fz += S * st.Q[9][src];
+            const double S = Sx * st.YZ[jk][src];
+            acc[0] += S * st.Q[6][src]; acc[1] += S * st.Q[7][src]; acc[2] += S * st.Q[8][src];
         }
-        acc[0] += fx; acc[1] += fy; acc[2] += fz;
+        return (gx != 0. || gy != 0. || gz != 0.) ? 1 : 0;
     });
 }
 
@@ -305,8 +365,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Part
 __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
                                                                       StepParams sp, int m, int doScatter)
 {
-    __shared__ WarpStage<9, 4> stage[FUSED_WARPS];
-    WarpStage<9, 4> &st = stage[threadIdx.x >> 5];
+    __shared__ WarpStage<false, 4> stage[FUSED_WARPS];
+    WarpStage<false, 4> &st = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
@@ -314,19 +374,22 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Pa
     if (active) {
         const int e = P.elem[p];
         double xi[3], lp[3];
-        load_xi_lp(P, p, xi, lp);
+        xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
+        load_lp(g, P, p, lp);
         Weights3 w;
         particle_weights<false>(g, e, xi, lp, w);
         key = w.center;
+        if (doScatter) stage_weights<false>(st, lane, w);
         double Svk[3] = {0., 0., 0.}, Sacc[3] = {0., 0., 0.};
 #pragma unroll
         for (int k = 0; k < 3; k++) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
+                const double syz = w.S[1][j] * w.S[2][k];
                 const int row = w.center + (j - 1) * g.yplane + (k - 1) * g.zplane - 1;
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
-                    const double S = w.S[0][i] * w.S[1][j] * w.S[2][k];
+                    const double S = w.S[0][i] * syz;
                     const double4 v = ldg4(&FN.V[row + i]);
                     Svk[0] += v.x * S; Svk[1] += v.y * S; Svk[2] += v.z * S;
                     if (m <= 0) {
@@ -372,11 +435,6 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Pa
             P.acc[c][p] = delV / dt;
         }
         if (doScatter) {
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-                for (int t = 0; t < 3; t++) st.W[a * 3 + t][lane] = w.S[a][t];
-            st.ok[lane] = w.ok;
             st.Q[0][lane] = P.mp[p];
             st.Q[1][lane] = vel[0]; st.Q[2][lane] = vel[1]; st.Q[3][lane] = vel[2];
         }
@@ -384,14 +442,16 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Pa
     if (!doScatter) return;
     __syncwarp();
     double *dst[3] = {N.pk[0], N.pk[1], N.pk[2]};
-    warp_scatter<3, false>(g, st, key, active, dst, (int *)0, [&](int src, int i, int j, int k, double *acc) {
-        const double S = st.W[i][src] * st.W[3 + j][src] * st.W[6 + k][src];
+    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
+        const double S = st.X[i][src] * st.YZ[jk][src];
         const double fnmp = S * st.Q[0][src];
         acc[0] += st.Q[1][src] * fnmp; acc[1] += st.Q[2][src] * fnmp; acc[2] += st.Q[3][src] * fnmp;
+        return S != 0. ? 1 : 0;
     });
 }
 
 // ---- F4: second strain update + element reset --------------------------------------------------------
+template <int SK>
 __global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Particles P, FusedNodes FN, const Material *mats,
                                                                    double strainTime, int doStrain, StatusFlags *flags, double dt)
 {
@@ -399,17 +459,20 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Parti
     if (p >= P.n) return;
     if (doStrain && p < P.nNR) {
         double xi[3], lp[3];
-        load_xi_lp(P, p, xi, lp);
-        Weights3 w;
-        particle_weights<true>(g, P.elem[p], xi, lp, w);
+        xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
+        load_lp(g, P, p, lp);
         double dv[9];
-        gather_gradv(g, w, FN.V, dv);
+        {
+            Weights3 w;
+            particle_weights<true>(g, P.elem[p], xi, lp, w);
+            gather_gradv(g, w, FN.V, dv);
+        }
 #pragma unroll
         for (int i = 0; i < 9; i++) dv[i] *= strainTime;
         PState s;
-        load_pstate(P, p, s);
+        load_state<SK>(P, p, s);
         constitutive_law<3>(s, dv, strainTime, g.np, mats[P.mat[p]]);
-        store_pstate(P, p, s);
+        store_state<SK>(P, p, s);
     }
     reset_element_one<3>(g, P, p, flags, dt);
 }

@@ -30,6 +30,8 @@ struct Grid {
     double gx, gy, gz;       // mpmgrid.grid
     double xmin, ymin, zmin; // mpmgrid.xmin... (= xpts[0]...)
     double rcrit;            // CPDI critical radius or <0
+    int lpUniform;           // every particle has the same dimensionless size lpU (skips the lp loads)
+    double lpU[3];
 };
 
 // one velocity field per node, component-major

@@ -1,0 +1,11 @@
+#!/bin/bash
+# ncu captures used for profiles/ (run under gpurun; 1 GPU).  $1 = tag
+TAG=${1:-r1}
+mkdir -p gpurun_out
+# launch list of one bench run (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1
+# full capture of the fused kernels (one launch each after warm-up)
+ncu --set full --clock-control none --import-source on -k regex:'k_f[1-4]|k_n[1-3]' -s 14 -c 7 -o gpurun_out/fused_$TAG -f \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ncell 64 > gpurun_out/ncu_full_$TAG.log 2>&1
+ls -la gpurun_out
