@@ -139,8 +139,16 @@ struct WarpStage {
     double DX[GRAD ? 3 : 1][WS_STRIDE];         // dSx_i           (scaled by 2/dx)
     double DYZ[GRAD ? 9 : 1][WS_STRIDE];        // dSy_j * Sz_k
     double YDZ[GRAD ? 9 : 1][WS_STRIDE];        // Sy_j * dSz_k
-    double Q[NQ][32];                           // payload, broadcast-read
+    alignas(16) double Q[32][NQ];               // payload per particle lane (NQ even: read as double2 broadcasts)
 };
+
+template <int NQ>
+__device__ __forceinline__ void load_payload(const double (*Q)[NQ], int src, double q[NQ])
+{
+    const double2 *r = reinterpret_cast<const double2 *>(Q[src]);
+#pragma unroll
+    for (int i = 0; i < NQ / 2; i++) { const double2 t = r[i]; q[2 * i] = t.x; q[2 * i + 1] = t.y; }
+}
 
 template <bool GRAD, class Stage>
 __device__ __forceinline__ void stage_weights(Stage &st, int lane, const Weights3 &w)
@@ -185,9 +193,14 @@ __device__ __forceinline__ void warp_scatter(const Grid &g, int key, bool active
 #pragma unroll
             for (int v = 0; v < NV; v++) acc[v] = 0.;
             int n = 0;
-            for (unsigned mm = grp; mm; mm &= mm - 1) {
-                const int src = __ffs(mm) - 1;
-                n += contrib(src, li, ljk, acc);
+            unsigned mm = grp;
+            while (mm) {                                   // two members per trip: independent loads in flight
+                const int s0 = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const bool two = mm != 0;
+                const int s1 = two ? __ffs(mm) - 1 : s0;
+                mm &= mm - 1;
+                n += contrib(s0, s1, two, li, ljk, acc);
             }
             if (n) {
                 const int nd = center + nodeOff;
@@ -235,6 +248,31 @@ __device__ __forceinline__ void store_state(const Particles &P, int p, const PSt
     P.work[p] = s.work; P.heat[p] = s.heat; P.entropy[p] = s.entropy;
 }
 
+// Pull the particle state this thread will need after its gather into L2 now (one lane per 128-byte
+// line), so the loads issued after the gather loop hit L2 instead of exposing a second DRAM latency.
+template <int SK>
+__device__ __forceinline__ void prefetch_state(const Particles &P, int p)
+{
+    if ((threadIdx.x & 15) != 0) return;
+#pragma unroll
+    for (int i = 0; i < 9; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.F[i] + p));
+#pragma unroll
+    for (int i = 0; i < 6; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.sp[i] + p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.work + p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.heat + p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.entropy + p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.prevT + p));
+    if (SK == SK_FULL) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.eplast[i] + p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pressure + p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.plast + p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res + p));
+#pragma unroll
+        for (int i = 0; i < MPM_MAX_HISTORY; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.hist[i] + p));
+    }
+}
+
 // ---- F1: ncpos + P2G mass and momentum ------------------------------------------------------------
 __global__ void __launch_bounds__(FUSED_THREADS) k_f1_mass_momentum(Grid g, Particles P, Nodes N)
 {
@@ -254,18 +292,29 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f1_mass_momentum(Grid g, Part
         Weights3 w;
         particle_weights<false>(g, e, xi, lp, w);
         stage_weights<false>(st, lane, w);
-        st.Q[0][lane] = P.mp[p];
-        st.Q[1][lane] = P.vel[0][p]; st.Q[2][lane] = P.vel[1][p]; st.Q[3][lane] = P.vel[2][p];
+        st.Q[lane][0] = P.mp[p];
+        st.Q[lane][1] = P.vel[0][p]; st.Q[lane][2] = P.vel[1][p]; st.Q[lane][3] = P.vel[2][p];
         key = w.center;
     }
     __syncwarp();
     double *dst[4] = {N.mass, N.pk[0], N.pk[1], N.pk[2]};
-    warp_scatter<4, true>(g, key, active, dst, N.cnt, [&](int src, int i, int jk, double *acc) {
-        const double S = st.X[i][src] * st.YZ[jk][src];
-        const double fnmp = S * st.Q[0][src];
-        acc[0] += fnmp;
-        acc[1] += st.Q[1][src] * fnmp; acc[2] += st.Q[2][src] * fnmp; acc[3] += st.Q[3][src] * fnmp;
-        return S != 0. ? 1 : 0;
+    warp_scatter<4, true>(g, key, active, dst, N.cnt, [&](int s0, int s1, bool two, int i, int jk, double *acc) {
+        const double Sa = st.X[i][s0] * st.YZ[jk][s0];
+        const double Sb = st.X[i][s1] * st.YZ[jk][s1];
+        double qa[4], qb[4];
+        load_payload<4>(st.Q, s0, qa);
+        load_payload<4>(st.Q, s1, qb);
+        const double fa = Sa * qa[0];
+        acc[0] += fa;
+        acc[1] += qa[1] * fa; acc[2] += qa[2] * fa; acc[3] += qa[3] * fa;
+        int n = Sa != 0. ? 1 : 0;
+        if (two) {
+            const double fb = Sb * qb[0];
+            acc[0] += fb;
+            acc[1] += qb[1] * fb; acc[2] += qb[2] * fb; acc[3] += qb[3] * fb;
+            n += Sb != 0. ? 1 : 0;
+        }
+        return n;
     });
 }
 
@@ -301,13 +350,14 @@ template <int SK, bool FEXT>
 __global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
                                                                     double strainTime, int doStrain)
 {
-    __shared__ WarpStage<true, FEXT ? 9 : 6> stage[FUSED_WARPS];
-    WarpStage<true, FEXT ? 9 : 6> &st = stage[threadIdx.x >> 5];
+    __shared__ WarpStage<true, FEXT ? 10 : 6> stage[FUSED_WARPS];
+    WarpStage<true, FEXT ? 10 : 6> &st = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
     int key = 0;
     if (active) {
+        if (doStrain) prefetch_state<SK>(P, p);
         const int e = P.elem[p];
         double xi[3], lp[3];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
@@ -337,27 +387,36 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Part
             }
         }
         const double nmp = -P.mp[p];            // f = -mp (sigma - p I) . grad S  (MatPoint3D.cpp:248-252)
-        st.Q[0][lane] = nmp * (sp[XX] - pr); st.Q[1][lane] = nmp * (sp[YY] - pr); st.Q[2][lane] = nmp * (sp[ZZ] - pr);
-        st.Q[3][lane] = nmp * sp[YZ]; st.Q[4][lane] = nmp * sp[XZ]; st.Q[5][lane] = nmp * sp[XY];
-        if (FEXT) { st.Q[6][lane] = P.pfext[0][p]; st.Q[7][lane] = P.pfext[1][p]; st.Q[8][lane] = P.pfext[2][p]; }
+        st.Q[lane][0] = nmp * (sp[XX] - pr); st.Q[lane][1] = nmp * (sp[YY] - pr); st.Q[lane][2] = nmp * (sp[ZZ] - pr);
+        st.Q[lane][3] = nmp * sp[YZ]; st.Q[lane][4] = nmp * sp[XZ]; st.Q[lane][5] = nmp * sp[XY];
+        if (FEXT) { st.Q[lane][6] = P.pfext[0][p]; st.Q[lane][7] = P.pfext[1][p]; st.Q[lane][8] = P.pfext[2][p]; st.Q[lane][9] = 0.; }
     }
     __syncwarp();
     double *dst[3] = {N.ftot[0], N.ftot[1], N.ftot[2]};
-    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
-        const double Sx = st.X[i][src];
-        const double gx = st.DX[i][src] * st.YZ[jk][src];
-        const double gy = Sx * st.DYZ[jk][src];
-        const double gz = Sx * st.YDZ[jk][src];
-        const double qxx = st.Q[0][src], qyy = st.Q[1][src], qzz = st.Q[2][src];
-        const double qyz = st.Q[3][src], qxz = st.Q[4][src], qxy = st.Q[5][src];
-        acc[0] += qxx * gx + qxy * gy + qxz * gz;
-        acc[1] += qxy * gx + qyy * gy + qyz * gz;
-        acc[2] += qxz * gx + qyz * gy + qzz * gz;
-        if (FEXT) {
-            const double S = Sx * st.YZ[jk][src];
-            acc[0] += S * st.Q[6][src]; acc[1] += S * st.Q[7][src]; acc[2] += S * st.Q[8][src];
+    constexpr int NQ = FEXT ? 10 : 6;
+    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int s0, int s1, bool two, int i, int jk, double *acc) {
+        int n = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int src = h ? s1 : s0;
+            const double Sx = st.X[i][src];
+            const double gx = st.DX[i][src] * st.YZ[jk][src];
+            const double gy = Sx * st.DYZ[jk][src];
+            const double gz = Sx * st.YDZ[jk][src];
+            double q[NQ];
+            load_payload<NQ>(st.Q, src, q);
+            if (h == 0 || two) {
+                acc[0] += q[0] * gx + q[5] * gy + q[4] * gz;
+                acc[1] += q[5] * gx + q[1] * gy + q[3] * gz;
+                acc[2] += q[4] * gx + q[3] * gy + q[2] * gz;
+                if (FEXT) {
+                    const double S = Sx * st.YZ[jk][src];
+                    acc[0] += S * q[6]; acc[1] += S * q[7]; acc[2] += S * q[8];
+                }
+                n += (gx != 0. || gy != 0. || gz != 0.) ? 1 : 0;
+            }
         }
-        return (gx != 0. || gy != 0. || gz != 0.) ? 1 : 0;
+        return n;
     });
 }
 
@@ -435,18 +494,28 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Pa
             P.acc[c][p] = delV / dt;
         }
         if (doScatter) {
-            st.Q[0][lane] = P.mp[p];
-            st.Q[1][lane] = vel[0]; st.Q[2][lane] = vel[1]; st.Q[3][lane] = vel[2];
+            st.Q[lane][0] = P.mp[p];
+            st.Q[lane][1] = vel[0]; st.Q[lane][2] = vel[1]; st.Q[lane][3] = vel[2];
         }
     }
     if (!doScatter) return;
     __syncwarp();
     double *dst[3] = {N.pk[0], N.pk[1], N.pk[2]};
-    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
-        const double S = st.X[i][src] * st.YZ[jk][src];
-        const double fnmp = S * st.Q[0][src];
-        acc[0] += st.Q[1][src] * fnmp; acc[1] += st.Q[2][src] * fnmp; acc[2] += st.Q[3][src] * fnmp;
-        return S != 0. ? 1 : 0;
+    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int s0, int s1, bool two, int i, int jk, double *acc) {
+        const double Sa = st.X[i][s0] * st.YZ[jk][s0];
+        const double Sb = st.X[i][s1] * st.YZ[jk][s1];
+        double qa[4], qb[4];
+        load_payload<4>(st.Q, s0, qa);
+        load_payload<4>(st.Q, s1, qb);
+        const double fa = Sa * qa[0];
+        acc[0] += qa[1] * fa; acc[1] += qa[2] * fa; acc[2] += qa[3] * fa;
+        int n = Sa != 0. ? 1 : 0;
+        if (two) {
+            const double fb = Sb * qb[0];
+            acc[0] += qb[1] * fb; acc[1] += qb[2] * fb; acc[2] += qb[3] * fb;
+            n += Sb != 0. ? 1 : 0;
+        }
+        return n;
     });
 }
 
@@ -458,6 +527,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Parti
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     if (doStrain && p < P.nNR) {
+        prefetch_state<SK>(P, p);
         double xi[3], lp[3];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
