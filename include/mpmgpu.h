@@ -141,6 +141,11 @@ typedef struct mpmgpu_particles {
     double *pfext;      /* [3][n]  MPMBase::pFext (external particle force, MatPtLoadBC) */
     int    *crossings;  /* [n]     MPMBase::elementCrossings */
     double *acc;        /* [3][n]  MPMBase::acc (download only) */
+    int    *ids;        /* [n]     optional caller-global particle ids.  Upload: when given (always in slab
+                                   mode, where particles migrate between processes) the ids travel with the
+                                   particles and downloads come back in DEVICE order with ids filled in;
+                                   when NULL particles are identified by their upload index and downloads come
+                                   back in upload order. */
 } mpmgpu_particles;
 
 /* download masks */
@@ -222,6 +227,35 @@ void *mpmgpu_stream(mpmgpu_ctx *ctx);
  * whole steps).  mpmgpu_task_times fills ms[10] (accumulated) and calls[10] in task order above. */
 int mpmgpu_set_profiling(mpmgpu_ctx *ctx, int on);
 int mpmgpu_task_times(mpmgpu_ctx *ctx, double *ms, long long *calls);
+
+/* ---- slab decomposition across the GPUs of one box (one process per GPU) ------------------------
+ * Replaces the reference's GridPatch/GhostNode OpenMP decomposition (Patches/GridPatch.cpp:32-138,
+ * Patches/GhostNode.cpp:58-185).  Every process creates a context over the WHOLE grid (node and element
+ * numbers stay global, so indexing is bit-identical to the single-GPU run) but holds only the particles
+ * whose element lies in its cell planes [cell_lo, cell_hi) along z, and touches only the node planes
+ * [cell_lo-1, cell_hi+2).  After each of the three particle->grid passes the partial node sums of the
+ * three node planes around an interior slab face are swapped with the neighbour and added (both sides
+ * then hold identical complete sums and run the node sweeps redundantly on those planes -- no
+ * broadcast step).  The library packs/adds; the HOST moves the buffers (NCCL send/recv via
+ * torch.distributed, see nairn_mpm_fea_b200/slab.py).  Particles whose new element leaves the slab are
+ * listed by the last phase and moved as rows. */
+int mpmgpu_slab_configure(mpmgpu_ctx *ctx, int cell_lo, int cell_hi, int has_lower, int has_upper, int migration_capacity);
+/* device pointers of the halo exchange buffers ([lower, upper] neighbour); a pass moves
+ * nvalues*3*plane_nodes doubles per neighbour, nvalues = 5, 3, 3 for the exchanges after phases 0, 1, 2 */
+int mpmgpu_slab_halo_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, long long *plane_nodes);
+/* phase 0: zero + P2G mass/momentum | exchange | 1: node sweep + G2P strain + P2G forces | exchange |
+ * 2: node sweep + G2P update + P2G momentum | exchange | 3: node sweep + G2P strain + element reset.
+ * Phases 0-2 return with the send buffers packed and the stream idle; the next phase adds the recv buffers. */
+int mpmgpu_slab_step_phase(mpmgpu_ctx *ctx, int phase);
+/* after phase 3: how many particles must move to the lower / upper neighbour */
+int mpmgpu_slab_migration_counts(mpmgpu_ctx *ctx, int *n_lo, int *n_hi);
+int mpmgpu_slab_migration_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, int *row_doubles, int *capacity_rows);
+int mpmgpu_slab_pack_migrants(mpmgpu_ctx *ctx);            /* rows -> send buffers */
+int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int n_from_hi);  /* drop leavers, append arrivals */
+int mpmgpu_num_particles(const mpmgpu_ctx *ctx);
+/* launch on the caller's CUDA stream (cudaStream_t as void*; NULL = back to the context's own), so the
+ * host's NCCL calls and the kernels are ordered on one stream without host synchronisation */
+int mpmgpu_set_stream(mpmgpu_ctx *ctx, void *cuda_stream);
 
 #ifdef __cplusplus
 }

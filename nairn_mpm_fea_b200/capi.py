@@ -28,7 +28,10 @@ EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last
            "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
-    "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times"]
+    "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times",
+    "mpmgpu_slab_configure", "mpmgpu_slab_halo_buffers", "mpmgpu_slab_step_phase", "mpmgpu_slab_migration_counts",
+    "mpmgpu_slab_migration_buffers", "mpmgpu_slab_pack_migrants", "mpmgpu_slab_finish_migration",
+    "mpmgpu_num_particles", "mpmgpu_set_stream"]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -54,7 +57,7 @@ class ParticlesView(C.Structure):
     _fields_ = [("n", C.c_int), ("n_nonrigid", C.c_int),
                 ("pos", _dp), ("vel", _dp), ("mp", _dp), ("lp", _dp), ("in_elem", _ip), ("matnum", _ip),
                 ("sp", _dp), ("pressure", _dp), ("ep", _dp), ("wrot", _dp), ("eplast", _dp),
-                ("energies", _dp), ("history", _dp), ("pfext", _dp), ("crossings", _ip), ("acc", _dp)]
+                ("energies", _dp), ("history", _dp), ("pfext", _dp), ("crossings", _ip), ("acc", _dp), ("ids", _ip)]
 
 
 class NodesView(C.Structure):
@@ -106,6 +109,16 @@ def load_library(path=None):
     lib.mpmgpu_stream.restype = vp
     lib.mpmgpu_set_profiling.argtypes = [vp, C.c_int]
     lib.mpmgpu_task_times.argtypes = [vp, _dp, C.POINTER(C.c_longlong)]
+    pvp = C.POINTER(vp)
+    lib.mpmgpu_slab_configure.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.mpmgpu_slab_halo_buffers.argtypes = [vp, pvp, pvp, pvp, pvp, C.POINTER(C.c_longlong)]
+    lib.mpmgpu_slab_step_phase.argtypes = [vp, C.c_int]
+    lib.mpmgpu_slab_migration_counts.argtypes = [vp, _ip, _ip]
+    lib.mpmgpu_slab_migration_buffers.argtypes = [vp, pvp, pvp, pvp, pvp, _ip, _ip]
+    lib.mpmgpu_slab_pack_migrants.argtypes = [vp]
+    lib.mpmgpu_slab_finish_migration.argtypes = [vp, C.c_int, C.c_int]
+    lib.mpmgpu_num_particles.argtypes = [vp]
+    lib.mpmgpu_set_stream.argtypes = [vp, vp]
     if lib.mpmgpu_abi_version() != ABI_VERSION:
         raise MpmGpuError(-1, "libmpmgpu ABI %d, binding expects %d" % (lib.mpmgpu_abi_version(), ABI_VERSION))
     if path == LIB_PATH:
@@ -206,7 +219,7 @@ class MpmGpu:
         for k in ("pos", "vel", "mp", "lp", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "pfext"):
             keep[k] = _c64(pt.get(k))
             setattr(v, k, _d(keep[k]))
-        for k in ("in_elem", "matnum", "crossings"):
+        for k in ("in_elem", "matnum", "crossings", "ids"):
             keep[k] = _c32(pt.get(k))
             setattr(v, k, _i(keep[k]))
         self.n = n
@@ -241,12 +254,13 @@ class MpmGpu:
 
     # -- device -> host -----------------------------------------------------------------------
     def download(self, mask=F_ALL):
-        n = self.n
+        n = self.num_particles()
         out = dict(pos=np.zeros((3, n)), vel=np.zeros((3, n)), sp=np.zeros((6, n)), pressure=np.zeros(n),
                    ep=np.zeros((6, n)), wrot=np.zeros((3, n)), eplast=np.zeros((6, n)), energies=np.zeros((6, n)),
                    history=np.zeros((MAX_HISTORY, n)), acc=np.zeros((3, n)),
-                   in_elem=np.zeros(n, np.int32), crossings=np.zeros(n, np.int32))
+                   in_elem=np.zeros(n, np.int32), crossings=np.zeros(n, np.int32), ids=np.zeros(n, np.int32))
         v = ParticlesView()
+        v.ids = _i(out["ids"])
         for k in ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "acc"):
             setattr(v, k, _d(out[k]))
         v.in_elem, v.crossings = _i(out["in_elem"]), _i(out["crossings"])
@@ -263,6 +277,42 @@ class MpmGpu:
             setattr(v, k, _d(out[k]))
         self._check(self.lib.mpmgpu_download_nodes(self.ctx, C.byref(v)))
         return out
+
+    def num_particles(self):
+        return int(self.lib.mpmgpu_num_particles(self.ctx))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.mpmgpu_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)))
+
+    # -- slab mode (see slab.py) ----------------------------------------------------------------
+    def slab_configure(self, cell_lo, cell_hi, has_lower, has_upper, migration_capacity=0):
+        self._check(self.lib.mpmgpu_slab_configure(self.ctx, cell_lo, cell_hi, int(has_lower), int(has_upper), migration_capacity))
+
+    def slab_halo_buffers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        pn = C.c_longlong()
+        self._check(self.lib.mpmgpu_slab_halo_buffers(self.ctx, *[C.byref(x) for x in p], C.byref(pn)))
+        return [x.value for x in p], int(pn.value)
+
+    def slab_migration_buffers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        row, cap = C.c_int(), C.c_int()
+        self._check(self.lib.mpmgpu_slab_migration_buffers(self.ctx, *[C.byref(x) for x in p], C.byref(row), C.byref(cap)))
+        return [x.value for x in p], int(row.value), int(cap.value)
+
+    def slab_phase(self, phase):
+        self._check(self.lib.mpmgpu_slab_step_phase(self.ctx, phase))
+
+    def slab_migration_counts(self):
+        a, b = C.c_int(), C.c_int()
+        self._check(self.lib.mpmgpu_slab_migration_counts(self.ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def slab_pack_migrants(self):
+        self._check(self.lib.mpmgpu_slab_pack_migrants(self.ctx))
+
+    def slab_finish_migration(self, n_from_lo, n_from_hi):
+        self._check(self.lib.mpmgpu_slab_finish_migration(self.ctx, n_from_lo, n_from_hi))
 
     def status(self):
         ms, cr, lg = C.c_longlong(), C.c_longlong(), C.c_longlong()

@@ -46,6 +46,9 @@ struct mpmgpu_ctx {
     double mtime;
     long long launches;
     bool uploaded, hasFext, hasBCs;
+    cudaStream_t ownStream; bool ownStreamSaved;
+    const int *dlSlot;                  // download slot map: P.orig, or identity when ids are global
+    bool globalIds;                     // particle ids are caller-global (slab mode): downloads come in device order + ids
     std::string err;
     // profiling
     bool profiling;
@@ -117,7 +120,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->dim = is3D ? 3 : 2;
     ctx->dMats = NULL; ctx->nmat = 0; ctx->dFlags = NULL;
     ctx->cap = 0; ctx->mstep = 0; ctx->mtime = 0.; ctx->launches = 0;
-    ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->profiling = false;
+    ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->profiling = false; ctx->globalIds = false; ctx->ownStreamSaved = false;
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
     ctx->hStage = NULL; ctx->hStageBytes = 0; ctx->nBCEntries = 0;
     memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B);
@@ -197,7 +200,7 @@ extern "C" int mpmgpu_destroy(mpmgpu_ctx *ctx)
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->hStage) cudaFreeHost(ctx->hStage);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->ownStreamSaved ? ctx->ownStream : ctx->stream);
     delete ctx;
     return MPMGPU_OK;
 }
@@ -380,7 +383,8 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     } else CK(cudaMemsetAsync(P.mat, 0, (size_t)n * sizeof(int), ctx->stream));
     if (h->crossings) CK(cudaMemcpyAsync(P.cross, h->crossings, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     else CK(cudaMemsetAsync(P.cross, 0, (size_t)n * sizeof(int), ctx->stream));
-    LAUNCH(k_iota, nblocks(n, T), T, n, P.orig);
+    if (h->ids) { CK(cudaMemcpyAsync(P.orig, h->ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); ctx->globalIds = true; }
+    else LAUNCH(k_iota, nblocks(n, T), T, n, P.orig);
     // strain + rotation -> deformation gradient (staged through a temporary device buffer)
     {
         double *tmp = NULL;
@@ -710,17 +714,67 @@ static int sort_particles(mpmgpu_ctx *ctx)
     return MPMGPU_OK;
 }
 
-static int fused_step(mpmgpu_ctx *ctx)
+__global__ void k_zero_node_range(int n0, int count, Nodes N)
+{
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + count) return;
+    N.mass[i] = 0.; N.cnt[i] = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { N.pk[c][i] = 0.; N.ftot[c][i] = 0.; N.vk[c][i] = 0.; N.pkc[c][i] = 0.; }
+}
+
+#define MIG_ROW (NPD + (NPI + 1) / 2)
+
+// halo planes shared with the lower (side 0) / upper (side 1) neighbour: three node planes around the slab face
+static inline void halo_range(const mpmgpu_ctx *ctx, int side, int &node0, int &count)
+{
+    const TiledState &t = ctx->tiled;
+    const int face = side == 0 ? t.slab.cellLo : t.slab.cellHi;
+    node0 = (face - 1) * ctx->g.zplane;
+    count = 3 * ctx->g.zplane;
+}
+
+static int halo_pack(mpmgpu_ctx *ctx, int which, bool real)
+{
+    TiledState &t = ctx->tiled;
+    const int nv = which == 0 ? 5 : 3;
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? t.hasLower : t.hasUpper)) continue;
+        int node0, count;
+        halo_range(ctx, side, node0, count);
+        if (real) LAUNCH(k_halo_pack, nblocks(count, 256), 256, which, node0, count, ctx->N, t.haloSend[side]);
+        else { CK(cudaMemsetAsync(t.haloSend[side], 0, (size_t)nv * count * sizeof(double), ctx->stream)); ctx->launches++; }
+    }
+    return MPMGPU_OK;
+}
+
+static int halo_add(mpmgpu_ctx *ctx, int which)
+{
+    TiledState &t = ctx->tiled;
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? t.hasLower : t.hasUpper)) continue;
+        int node0, count;
+        halo_range(ctx, side, node0, count);
+        LAUNCH(k_halo_add, nblocks(count, 256), 256, which, node0, count, ctx->N, t.haloRecv[side]);
+    }
+    return MPMGPU_OK;
+}
+
+// One step = four phases; in slab mode the host exchanges halo buffers between them.
+//  0: (sort) zero nodes, F1                      -> partial mass/momentum sums
+//  1: N1, F2                                     -> partial forces
+//  2: N2, F3                                     -> partial re-extrapolated momenta
+//  3: N3, F4                                     -> particles updated, leavers listed
+static int fused_phase(mpmgpu_ctx *ctx, int phase)
 {
     TiledState &t = ctx->tiled;
     const Grid &g = ctx->g;
     const StepParams &sp = ctx->sp;
     int rc;
-    if (t.stepsSinceSort >= t.sortInterval) { if ((rc = sort_particles(ctx))) return rc; }
-    t.stepsSinceSort++;
-    const size_t nnPad = ((size_t)g.nnodes + 31) & ~(size_t)31;
     const int n = ctx->P.n, nNR = ctx->P.nNR;
-    const int pgrid = nblocks(nNR, FUSED_THREADS), ngrid = nblocks(g.nnodes, 256);
+    const int pgrid = nblocks(nNR, FUSED_THREADS);
+    const int n0 = t.slab.on ? t.nodeLo : 0, ncount = t.slab.on ? t.nodeCount : g.nnodes;
+    const int ngrid = nblocks(ncount, 256);
     const bool hasUSF = sp.method == METHOD_USF || sp.method == METHOD_USAVG;
     const bool hasUSL = sp.method == METHOD_USL || sp.method == METHOD_USAVG;
     const bool reextrap = hasUSL && !sp.skipPost;
@@ -729,37 +783,65 @@ static int fused_step(mpmgpu_ctx *ctx)
     int m = sp.xpicOrder;
     if (!sp.usingFMPM) m = -m;
 
-    prof_begin(ctx);
-    CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 13 * sizeof(double), ctx->stream));      // mass, pk, ftot, vk, pkc
-    CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
-    ctx->launches += 2;
-    prof_end(ctx, T_INIT);
-    prof_begin(ctx);
-    LAUNCH(k_f1_mass_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N);
-    prof_end(ctx, T_MASSMOM);
-    prof_begin(ctx);
-    LAUNCH(k_n1_post_extrapolation, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp, hasUSF ? 1 : 0);
-    prof_end(ctx, T_POSTEXTRAP);
-    prof_begin(ctx);
-    if (t.stateKind == SK_ELASTIC) {
-        if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_ELASTIC, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
-        else LAUNCH((k_f2_strain_forces<SK_ELASTIC, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+    if (phase == 0) {
+        if (t.stepsSinceSort >= t.sortInterval) { if ((rc = sort_particles(ctx))) return rc; }
+        t.stepsSinceSort++;
+        prof_begin(ctx);
+        if (t.slab.on) LAUNCH(k_zero_node_range, ngrid, 256, n0, ncount, ctx->N);
+        else {
+            const size_t nnPad = ((size_t)g.nnodes + 31) & ~(size_t)31;
+            CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 13 * sizeof(double), ctx->stream));      // mass, pk, ftot, vk, pkc
+            CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
+            ctx->launches += 2;
+        }
+        prof_end(ctx, T_INIT);
+        prof_begin(ctx);
+        if (pgrid) LAUNCH(k_f1_mass_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N);
+        if (t.slab.on && (rc = halo_pack(ctx, 0, true))) return rc;
+        prof_end(ctx, T_MASSMOM);
+    } else if (phase == 1) {
+        prof_begin(ctx);
+        if (t.slab.on && (rc = halo_add(ctx, 0))) return rc;
+        LAUNCH(k_n1_post_extrapolation, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp, hasUSF ? 1 : 0);
+        prof_end(ctx, T_POSTEXTRAP);
+        prof_begin(ctx);
+        if (pgrid) {
+            if (t.stateKind == SK_ELASTIC) {
+                if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_ELASTIC, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+                else LAUNCH((k_f2_strain_forces<SK_ELASTIC, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+            } else {
+                if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_FULL, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+                else LAUNCH((k_f2_strain_forces<SK_FULL, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+            }
+        }
+        if (t.slab.on && (rc = halo_pack(ctx, 1, true))) return rc;
+        prof_end(ctx, T_USF);
+    } else if (phase == 2) {
+        prof_begin(ctx);
+        if (t.slab.on && (rc = halo_add(ctx, 1))) return rc;
+        LAUNCH(k_n2_forces_momenta, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp, reextrap ? 1 : 0);
+        prof_end(ctx, T_POSTFORCES);
+        prof_begin(ctx);
+        if (pgrid) LAUNCH(k_f3_update_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, sp, m, reextrap ? 1 : 0);
+        if (t.slab.on && (rc = halo_pack(ctx, 2, reextrap))) return rc;
+        prof_end(ctx, T_PARTICLES);
     } else {
-        if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_FULL, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
-        else LAUNCH((k_f2_strain_forces<SK_FULL, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+        prof_begin(ctx);
+        if (t.slab.on && (rc = halo_add(ctx, 2))) return rc;
+        if (reextrap) LAUNCH(k_n3_strains_last, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp);
+        if (n) {
+            if (t.stateKind == SK_ELASTIC) LAUNCH(k_f4_strain_reset<SK_ELASTIC>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
+            else LAUNCH(k_f4_strain_reset<SK_FULL>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
+        }
+        prof_end(ctx, T_USL);
     }
-    prof_end(ctx, T_USF);
-    prof_begin(ctx);
-    LAUNCH(k_n2_forces_momenta, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp, reextrap ? 1 : 0);
-    prof_end(ctx, T_POSTFORCES);
-    prof_begin(ctx);
-    LAUNCH(k_f3_update_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, sp, m, reextrap ? 1 : 0);
-    prof_end(ctx, T_PARTICLES);
-    prof_begin(ctx);
-    if (reextrap) LAUNCH(k_n3_strains_last, ngrid, 256, g.nnodes, ctx->N, t.FN, ctx->B, sp);
-    if (t.stateKind == SK_ELASTIC) LAUNCH(k_f4_strain_reset<SK_ELASTIC>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt);
-    else LAUNCH(k_f4_strain_reset<SK_FULL>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt);
-    prof_end(ctx, T_USL);
+    return MPMGPU_OK;
+}
+
+static int fused_step(mpmgpu_ctx *ctx)
+{
+    int rc;
+    for (int ph = 0; ph < 4; ph++) if ((rc = fused_phase(ctx, ph))) return rc;
     return MPMGPU_OK;
 }
 
@@ -780,7 +862,7 @@ static int down_field(mpmgpu_ctx *ctx, double *const *dev, double *host, int nco
     if (!host) return MPMGPU_OK;
     const int T = 256;
     for (int c = 0; c < ncomp; c++) {
-        LAUNCH(k_unpermute, nblocks(n, T), T, n, dev[c], ctx->P.orig, dtmp);
+        LAUNCH(k_unpermute, nblocks(n, T), T, n, dev[c], ctx->dlSlot, dtmp);
         CK(cudaMemcpyAsync(host + (size_t)c * n, dtmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     return MPMGPU_OK;
@@ -798,6 +880,14 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
     CK(cudaMalloc((void **)&dtmp, (size_t)n * 9 * sizeof(double)));
     int rc = MPMGPU_OK;
     const int T = 256;
+    int *ident = NULL;
+    ctx->dlSlot = ctx->P.orig;
+    if (ctx->globalIds) {       // device order; the caller re-assembles by id
+        CK(cudaMalloc((void **)&ident, (size_t)n * sizeof(int)));
+        LAUNCH(k_iota, nblocks(n, T), T, n, ident);
+        ctx->dlSlot = ident;
+        if (h->ids) CK(cudaMemcpyAsync(h->ids, ctx->P.orig, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     do {
         if ((mask & MPMGPU_F_POS) && (rc = down_field(ctx, P.pos, h->pos, 3, n, dtmp))) break;
         if ((mask & MPMGPU_F_VEL) && (rc = down_field(ctx, P.vel, h->vel, 3, n, dtmp))) break;
@@ -806,7 +896,7 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
             if ((rc = down_field(ctx, &P.pressure, h->pressure, 1, n, dtmp))) break;
         }
         if ((mask & MPMGPU_F_STRAIN) && h->ep && h->wrot) {
-            LAUNCH(k_F_to_epwrot, nblocks(n, T), T, n, ctx->dim, P, P.orig, dtmp, dtmp + (size_t)6 * n);
+            LAUNCH(k_F_to_epwrot, nblocks(n, T), T, n, ctx->dim, P, ctx->dlSlot, dtmp, dtmp + (size_t)6 * n);
             CK(cudaMemcpyAsync(h->ep, dtmp, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(h->wrot, dtmp + (size_t)6 * n, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
@@ -820,17 +910,18 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
         if (mask & MPMGPU_F_ELEM) {
             int *itmp = (int *)dtmp;
             if (h->in_elem) {
-                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.elem, P.orig, itmp, 0);
+                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.elem, ctx->dlSlot, itmp, 0);
                 CK(cudaMemcpyAsync(h->in_elem, itmp, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             }
             if (h->crossings) {
-                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.cross, P.orig, itmp + n, 0);
+                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.cross, ctx->dlSlot, itmp + n, 0);
                 CK(cudaMemcpyAsync(h->crossings, itmp + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             }
         }
     } while (0);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(dtmp);
+    if (ident) cudaFree(ident);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(ctx, MPMGPU_ECUDA, "mpmgpu_download_particles: %s", cudaGetErrorString(e));
     return MPMGPU_OK;
@@ -892,3 +983,160 @@ extern "C" int mpmgpu_task_times(mpmgpu_ctx *ctx, double *ms, long long *calls)
     for (int t = 0; t < T_NTASKS; t++) { ms[t] = ctx->taskMs[t]; if (calls) calls[t] = ctx->taskCalls[t]; }
     return MPMGPU_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// slab decomposition across GPUs (one process per GPU; the host moves the buffers with NCCL)
+extern "C" int mpmgpu_slab_configure(mpmgpu_ctx *ctx, int cell_lo, int cell_hi, int has_lower, int has_upper, int migration_capacity)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (ctx->dim != 3) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: slabs are along z of a 3D grid");
+    if (ctx->cfg.shape != MPMGPU_UNIFORM_GIMP || ctx->cfg.kernel_path == 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: slab mode runs on the fused 3D uGIMP path");
+    if (cell_lo < 0 || cell_hi > ctx->g.depth || cell_hi - cell_lo < 3) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: slab [%d,%d) of %d cell planes (need >= 3)", cell_lo, cell_hi, ctx->g.depth);
+    if ((has_lower && cell_lo < 2) || (has_upper && cell_hi > ctx->g.depth - 2)) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: interior faces must be >= 2 planes from the grid edge");
+    cudaSetDevice(ctx->cfg.device);
+    TiledState &t = ctx->tiled;
+    t.slab.on = 1; t.slab.cellLo = cell_lo; t.slab.cellHi = cell_hi;
+    t.hasLower = has_lower ? 1 : 0; t.hasUpper = has_upper ? 1 : 0;
+    const int planeLo = std::max(0, cell_lo - 1), planeHi = std::min(ctx->g.depth + 1, cell_hi + 2);
+    t.nodeLo = planeLo * ctx->g.zplane; t.nodeCount = (planeHi - planeLo) * ctx->g.zplane;
+    t.planeNodes = ctx->g.zplane;
+    const size_t haloDoubles = (size_t)5 * 3 * ctx->g.zplane;
+    t.migCap = migration_capacity > 0 ? migration_capacity : 65536;
+    t.slab.leaveCap = t.migCap;
+    for (int side = 0; side < 2; side++) {
+        CK(dalloc(ctx, &t.haloSend[side], haloDoubles)); CK(dalloc(ctx, &t.haloRecv[side], haloDoubles));
+        CK(dalloc(ctx, &t.migSend[side], (size_t)t.migCap * MIG_ROW)); CK(dalloc(ctx, &t.migRecv[side], (size_t)t.migCap * MIG_ROW));
+        CK(cudaMemset(t.haloSend[side], 0, haloDoubles * sizeof(double))); CK(cudaMemset(t.haloRecv[side], 0, haloDoubles * sizeof(double)));
+    }
+    CK(dalloc(ctx, &t.slab.leaveCount, 2)); CK(dalloc(ctx, &t.slab.leaveIdx, (size_t)2 * t.migCap));
+    CK(cudaMemset(t.slab.leaveCount, 0, 2 * sizeof(int)));
+    t.hLeave[0] = t.hLeave[1] = 0;
+    ctx->globalIds = true;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_slab_halo_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, long long *plane_nodes)
+{
+    if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_halo_buffers: slab mode not configured");
+    TiledState &t = ctx->tiled;
+    if (send_lo) *send_lo = t.haloSend[0];
+    if (send_hi) *send_hi = t.haloSend[1];
+    if (recv_lo) *recv_lo = t.haloRecv[0];
+    if (recv_hi) *recv_hi = t.haloRecv[1];
+    if (plane_nodes) *plane_nodes = (long long)t.planeNodes;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_slab_step_phase(mpmgpu_ctx *ctx, int phase)
+{
+    int rc = check_ready(ctx, "mpmgpu_slab_step_phase"); if (rc) return rc;
+    if (!ctx->tiled.enabled) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_step_phase: fused path not enabled for this problem");
+    if (phase < 0 || phase > 3) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_step_phase: phase %d", phase);
+    rc = fused_phase(ctx, phase);
+    if (rc) return rc;
+    if (phase == 3) {
+        ctx->mstep++; ctx->mtime += ctx->sp.dt;
+        if (ctx->tiled.slab.on) {
+            CK(cudaMemcpyAsync(ctx->tiled.hLeave, ctx->tiled.slab.leaveCount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        rc = poll_flags(ctx);
+        if (rc) return rc;
+        if (ctx->tiled.slab.on && (ctx->tiled.hLeave[0] > ctx->tiled.migCap || ctx->tiled.hLeave[1] > ctx->tiled.migCap))
+            return fail(ctx, MPMGPU_EINVAL, "slab migration capacity %d exceeded (%d, %d leavers)", ctx->tiled.migCap, ctx->tiled.hLeave[0], ctx->tiled.hLeave[1]);
+    }
+    return MPMGPU_OK;       // phases 0-2 are asynchronous: the host enqueues the halo exchange on the same stream
+}
+
+extern "C" int mpmgpu_slab_migration_counts(mpmgpu_ctx *ctx, int *n_lo, int *n_hi)
+{
+    if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_migration_counts: slab mode not configured");
+    if (n_lo) *n_lo = ctx->tiled.hLeave[0];
+    if (n_hi) *n_hi = ctx->tiled.hLeave[1];
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_slab_migration_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, int *row_doubles, int *capacity_rows)
+{
+    if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_migration_buffers: slab mode not configured");
+    TiledState &t = ctx->tiled;
+    if (send_lo) *send_lo = t.migSend[0];
+    if (send_hi) *send_hi = t.migSend[1];
+    if (recv_lo) *recv_lo = t.migRecv[0];
+    if (recv_hi) *recv_hi = t.migRecv[1];
+    if (row_doubles) *row_doubles = MIG_ROW;
+    if (capacity_rows) *capacity_rows = t.migCap;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_slab_pack_migrants(mpmgpu_ctx *ctx)
+{
+    if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_pack_migrants: slab mode not configured");
+    cudaSetDevice(ctx->cfg.device);
+    TiledState &t = ctx->tiled;
+    for (int side = 0; side < 2; side++) {
+        const int nl = t.hLeave[side];
+        if (nl <= 0) continue;
+        LAUNCH(k_mig_pack, nl, 64, nl, t.slab.leaveIdx + (size_t)side * t.migCap, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool, MIG_ROW, t.migSend[side]);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+// remove the particles that left (fill their slots from the end), then append the arrivals
+extern "C" int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int n_from_hi)
+{
+    if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_finish_migration: slab mode not configured");
+    cudaSetDevice(ctx->cfg.device);
+    TiledState &t = ctx->tiled;
+    const int L = t.hLeave[0] + t.hLeave[1];
+    int n = ctx->P.n;
+    if (L > 0) {
+        std::vector<int> idx(L);
+        if (t.hLeave[0]) CK(cudaMemcpyAsync(idx.data(), t.slab.leaveIdx, t.hLeave[0] * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (t.hLeave[1]) CK(cudaMemcpyAsync(idx.data() + t.hLeave[0], t.slab.leaveIdx + t.migCap, t.hLeave[1] * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const int nNew = n - L;
+        std::vector<char> leaving(L > 0 ? (size_t)(n - nNew) : 0, 0);      // flags for slots [nNew, n)
+        std::vector<int> holes;
+        for (int q : idx) { if (q >= nNew) leaving[q - nNew] = 1; else holes.push_back(q); }
+        std::vector<int> fillers;
+        for (int q = nNew; q < n; q++) if (!leaving[q - nNew]) fillers.push_back(q);
+        if (holes.size() != fillers.size()) return fail(ctx, MPMGPU_EINVAL, "migration bookkeeping: %zu holes, %zu fillers", holes.size(), fillers.size());
+        std::sort(holes.begin(), holes.end());
+        const int np = (int)holes.size();
+        if (np > 0) {
+            int *dpairs = NULL;
+            CK(cudaMalloc((void **)&dpairs, (size_t)2 * np * sizeof(int)));
+            CK(cudaMemcpyAsync(dpairs, holes.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(dpairs + np, fillers.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCH(k_mig_fill, np, 64, np, dpairs, dpairs + np, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool);
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(dpairs);
+        }
+        n = nNew;
+    }
+    const int R = n_from_lo + n_from_hi;
+    if ((size_t)(n + R) > ctx->cap) return fail(ctx, MPMGPU_EINVAL, "particle capacity %zu exceeded by migration (%d + %d); raise max_particles", ctx->cap, n, R);
+    if (n_from_lo > 0) LAUNCH(k_mig_unpack, n_from_lo, 64, n_from_lo, n, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool, MIG_ROW, t.migRecv[0]);
+    if (n_from_hi > 0) LAUNCH(k_mig_unpack, n_from_hi, 64, n_from_hi, n + n_from_lo, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool, MIG_ROW, t.migRecv[1]);
+    n += R;
+    ctx->P.n = n; ctx->P.nNR = n;
+    CK(cudaMemsetAsync(t.slab.leaveCount, 0, 2 * sizeof(int), ctx->stream));
+    t.hLeave[0] = t.hLeave[1] = 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+// Run on the caller's stream (e.g. torch's current stream, so NCCL calls and kernels are ordered
+// without host synchronisation).  The context's own stream is kept for destroy.
+extern "C" int mpmgpu_set_stream(mpmgpu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    cudaSetDevice(ctx->cfg.device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->ownStreamSaved) { ctx->ownStream = ctx->stream; ctx->ownStreamSaved = true; }
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->ownStream;
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_num_particles(const mpmgpu_ctx *ctx) { return ctx ? ctx->P.n : 0; }

@@ -39,6 +39,15 @@ struct FusedNodes {
     const int *bcOfNode; // [nnodes] index into VelBCs unique list or -1
 };
 
+// slab decomposition along z (one process per GPU): this rank owns cell planes [cellLo, cellHi)
+struct SlabInfo {
+    int on;
+    int cellLo, cellHi;
+    int *leaveCount;         // [2]: particles whose new element lies below / above the slab
+    int *leaveIdx;           // [2][leaveCap] their indices
+    int leaveCap;
+};
+
 struct TiledState {
     int enabled;         // fast path usable for this context
     int stateKind;       // SK_ELASTIC / SK_FULL: which particle fields the materials in use touch
@@ -50,6 +59,15 @@ struct TiledState {
     void *cubTemp; size_t cubTempBytes;
     double *altPool; int *altIntPool;       // second particle pool for the physical reorder
     size_t cap;
+    // slab mode
+    SlabInfo slab;
+    int hasLower, hasUpper;
+    int nodeLo, nodeCount;                  // node range the sweeps and the zeroing cover
+    double *haloSend[2], *haloRecv[2];      // [lower, upper]; 3 planes x up to 5 values
+    size_t planeNodes;
+    double *migSend[2], *migRecv[2];        // rows of MIG_ROW doubles
+    int migCap;
+    int hLeave[2];                          // host copy of leaveCount after the step
 };
 
 static inline void tiled_state_init(TiledState &t) { memset(&t, 0, sizeof t); }
@@ -522,7 +540,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Pa
 // ---- F4: second strain update + element reset --------------------------------------------------------
 template <int SK>
 __global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Particles P, FusedNodes FN, const Material *mats,
-                                                                   double strainTime, int doStrain, StatusFlags *flags, double dt)
+                                                                   double strainTime, int doStrain, StatusFlags *flags, double dt, SlabInfo slab)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
@@ -545,6 +563,79 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Parti
         store_state<SK>(P, p, s);
     }
     reset_element_one<3>(g, P, p, flags, dt);
+    if (slab.on) {          // particle migration between slabs (replaces GridPatch::AddMovingParticle, GridPatch.cpp:214)
+        const int k = (P.elem[p] - 1) / (g.horiz * g.vert);
+        const int side = k < slab.cellLo ? 0 : (k >= slab.cellHi ? 1 : -1);
+        if (side >= 0) {
+            const int slot = atomicAdd(&slab.leaveCount[side], 1);
+            if (slot < slab.leaveCap) slab.leaveIdx[side * slab.leaveCap + slot] = p;
+        }
+    }
+}
+
+// ---- slab halo: pack partial sums of the three node planes shared with a neighbour / add the neighbour's ----
+// which: 0 mass,pk,cnt (5 values)  1 ftot (3)  2 pk (3).  Buffer layout [value][3 planes * planeNodes].
+__global__ void k_halo_pack(int which, int node0, int count, Nodes N, double *buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int nd = node0 + i;
+    if (which == 0) {
+        buf[i] = N.mass[nd];
+        buf[count + i] = N.pk[0][nd]; buf[2 * count + i] = N.pk[1][nd]; buf[3 * count + i] = N.pk[2][nd];
+        buf[4 * count + i] = (double)N.cnt[nd];
+    } else if (which == 1) {
+        buf[i] = N.ftot[0][nd]; buf[count + i] = N.ftot[1][nd]; buf[2 * count + i] = N.ftot[2][nd];
+    } else {
+        buf[i] = N.pk[0][nd]; buf[count + i] = N.pk[1][nd]; buf[2 * count + i] = N.pk[2][nd];
+    }
+}
+
+__global__ void k_halo_add(int which, int node0, int count, Nodes N, const double *buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int nd = node0 + i;
+    if (which == 0) {
+        N.mass[nd] += buf[i];
+        N.pk[0][nd] += buf[count + i]; N.pk[1][nd] += buf[2 * count + i]; N.pk[2][nd] += buf[3 * count + i];
+        N.cnt[nd] += (int)buf[4 * count + i];
+    } else if (which == 1) {
+        N.ftot[0][nd] += buf[i]; N.ftot[1][nd] += buf[count + i]; N.ftot[2][nd] += buf[2 * count + i];
+    } else {
+        N.pk[0][nd] += buf[i]; N.pk[1][nd] += buf[count + i]; N.pk[2][nd] += buf[2 * count + i];
+    }
+}
+
+// ---- particle migration: rows of (nd doubles + ni ints bit-cast into ceil(ni/2) doubles) ----------------
+__global__ void k_mig_pack(int nrows, const int *idx, size_t stride, int nd, const double *pool, int ni, const int *ipool, int rowLen, double *rows)
+{
+    const int r = blockIdx.x;
+    if (r >= nrows) return;
+    const int p = idx[r];
+    for (int f = threadIdx.x; f < nd; f += blockDim.x) rows[(size_t)r * rowLen + f] = pool[(size_t)f * stride + p];
+    int *irow = reinterpret_cast<int *>(rows + (size_t)r * rowLen + nd);
+    for (int f = threadIdx.x; f < ni; f += blockDim.x) irow[f] = ipool[(size_t)f * stride + p];
+}
+
+__global__ void k_mig_unpack(int nrows, int first, size_t stride, int nd, double *pool, int ni, int *ipool, int rowLen, const double *rows)
+{
+    const int r = blockIdx.x;
+    if (r >= nrows) return;
+    const int p = first + r;
+    for (int f = threadIdx.x; f < nd; f += blockDim.x) pool[(size_t)f * stride + p] = rows[(size_t)r * rowLen + f];
+    const int *irow = reinterpret_cast<const int *>(rows + (size_t)r * rowLen + nd);
+    for (int f = threadIdx.x; f < ni; f += blockDim.x) ipool[(size_t)f * stride + p] = irow[f];
+}
+
+// fill the holes left by departed particles with particles taken from the end of the arrays
+__global__ void k_mig_fill(int npairs, const int *hole, const int *filler, size_t stride, int nd, double *pool, int ni, int *ipool)
+{
+    const int r = blockIdx.x;
+    if (r >= npairs) return;
+    const int h = hole[r], q = filler[r];
+    for (int f = threadIdx.x; f < nd; f += blockDim.x) pool[(size_t)f * stride + h] = pool[(size_t)f * stride + q];
+    for (int f = threadIdx.x; f < ni; f += blockDim.x) ipool[(size_t)f * stride + h] = ipool[(size_t)f * stride + q];
 }
 
 // ---- node sweeps -------------------------------------------------------------------------------------
@@ -588,10 +679,10 @@ __device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, doubl
 }
 
 // N1: tasks 3 + 4a.  pkc = pk; symmetry adjust; BCs(MASS_MOMENTUM) if a USF task exists; V = pk/mass
-__global__ void k_n1_post_extrapolation(int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp, int hasUSF)
+__global__ void k_n1_post_extrapolation(int n0, int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp, int hasUSF)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnodes) return;
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + nnodes) return;
     double4 v = make_double4(0., 0., 0., 0.);
     if (N.cnt[i] > 0) {
         double pk[3] = {N.pk[0][i], N.pk[1][i], N.pk[2][i]};
@@ -621,10 +712,10 @@ __global__ void k_n1_post_extrapolation(int nnodes, Nodes N, FusedNodes FN, VelB
 
 // N2: tasks 6 + 7 + 8a.  pk = pkc; ftot += m g; BCs(GRID_FORCES); pk += ftot dt; BCs(UPDATE_MOMENTUM);
 // V = pk/mass; A = ftot/mass; then (when a re-extrapolation follows) pk = 0 for task 9a.
-__global__ void k_n2_forces_momenta(int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp, int rezero)
+__global__ void k_n2_forces_momenta(int n0, int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp, int rezero)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnodes) return;
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + nnodes) return;
     double4 v = make_double4(0., 0., 0., 0.), a = make_double4(0., 0., 0., 0.);
     if (N.cnt[i] > 0) {
         double pk[3] = {N.pkc[0][i], N.pkc[1][i], N.pkc[2][i]};
@@ -650,10 +741,10 @@ __global__ void k_n2_forces_momenta(int nnodes, Nodes N, FusedNodes FN, VelBCs B
 }
 
 // N3: task 9b.  BCs(UPDATE_STRAINS_LAST); V = pk/mass
-__global__ void k_n3_strains_last(int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp)
+__global__ void k_n3_strains_last(int n0, int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnodes) return;
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + nnodes) return;
     double4 v = make_double4(0., 0., 0., 0.);
     if (N.cnt[i] > 0) {
         double pk[3] = {N.pk[0][i], N.pk[1][i], N.pk[2][i]};

@@ -71,12 +71,12 @@ class Problem:
             self.dt_strain_first = self.dt_strain_last = dt
 
 
-def jitter(arr, amplitude, seed=12345):
+def jitter(arr, amplitude, seed=12345, id_offset=0):
     """Deterministic integer-hash jitter (same on every platform):
     arr[c][p] += amplitude * (hash(p, c) / 2^32 - 0.5)."""
     arr = np.array(arr, dtype=np.float64, copy=True)
     n = arr.shape[1]
-    idx = np.arange(n, dtype=np.uint64)
+    idx = np.arange(n, dtype=np.uint64) + np.uint64(id_offset)
     for c in range(arr.shape[0]):
         h = (idx * np.uint64(2654435761) + np.uint64(seed + 7919 * c)) & np.uint64(0xFFFFFFFF)
         h ^= h >> np.uint64(16)
@@ -141,11 +141,14 @@ def lattice_points(xpts, ypts, zpts, elems_ijk, pts_per_side=2):
 
 def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0.0, 0.0, -1000.0), cfl=0.4,
             step_ms=1e-3, method=USAVG, shape=UNIFORM_GIMP, bottom_bc=True, gravity=None, velocity_fn=None,
-            pts_per_side=2, ncell_xyz=None, jitter_amp=0.0):
+            pts_per_side=2, ncell_xyz=None, jitter_amp=0.0, cells_z=None):
     """BASELINE.json config 2 family: block of ncell^3 cells (pts_per_side^3 particles per cell) of
     IsotropicMat inside a (ncell+2*margin)^3-cell grid (+1 border cell per side), initial velocity,
     bottom plane z<=margin held in z.  Numbers are XML (Legacy) units: mm, MPa, g/cm^3, mm/s, ms.
-    Same problem as tests/inputs.py::block3d(ncell, margin) fed to the reference."""
+    Same problem as tests/inputs.py::block3d(ncell, margin) fed to the reference.
+    cells_z=(lo, hi): generate only the particles of block cell planes [lo, hi) (one slab of a
+    multi-GPU run); the grid, BCs and time step are still those of the whole problem and the dict gets
+    'ids' = the particles' indices in the whole problem."""
     pr = Problem()
     pr.np = M.THREED_MPM
     pr.method = method
@@ -162,7 +165,9 @@ def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0
     # filled elements: cells [margin, margin+nc) of the user grid = element index +1 (border) per axis
     ii = np.arange(margin + 1, margin + 1 + ncx)
     jj = np.arange(margin + 1, margin + 1 + ncy)
-    kk = np.arange(margin + 1, margin + 1 + ncz)
+    kz0, kz1 = cells_z if cells_z is not None else (0, ncz)
+    kk = np.arange(margin + 1 + kz0, margin + 1 + kz1)
+    id_offset = kz0 * ncx * ncy * pts_per_side ** 3
     K, J, I = np.meshgrid(kk, jj, ii, indexing="ij")
     ei, ej, ek = I.ravel(), J.ravel(), K.ravel()
     pos, gap = lattice_points(pr.xpts, pr.ypts, pr.zpts, (ei, ej, ek), pts_per_side)
@@ -174,7 +179,7 @@ def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0
     if jitter_amp > 0.0:
         # off-lattice start (so the uGIMP stencils are the generic 27-node ones); elements re-found as
         # MeshInfo::FindElementFromPoint does (MeshInfo.cpp:593-633)
-        pos = jitter(pos, jitter_amp * cell, 12345)
+        pos = jitter(pos, jitter_amp * cell, 12345, id_offset)
         col = ((pos[0] - pr.xpts[0]) / gx).astype(np.int64)
         row = ((pos[1] - pr.ypts[0]) / gy).astype(np.int64)
         zrow = ((pos[2] - pr.zpts[0]) / gz).astype(np.int64)
@@ -195,6 +200,8 @@ def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0
     energies[5] = 1.0            # pPreviousTemperature: thermal.reference default... set by caller if needed
     pr.particles = dict(pos=pos, vel=vel, mp=mp, lp=lp, in_elem=in_elem, matnum=np.ones(n, np.int32),
                         n_nonrigid=n, energies=energies)
+    if cells_z is not None:
+        pr.particles["ids"] = (np.arange(n, dtype=np.int64) + id_offset).astype(np.int32)
     # time step (NairnMPM.cpp:695-699, :1207-1227): dcell = grid.x (cubic grid, MeshInfo.cpp:1555-1563)
     dt_cfl = cfl * (gx / mat["wave_speed"])
     pr.set_time_step(min(step_ms * 1.0e-3, dt_cfl))

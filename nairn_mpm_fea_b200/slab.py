@@ -1,0 +1,271 @@
+"""Slab domain decomposition across the GPUs of one box: one process per GPU, NCCL over NVLink.
+
+Replaces the reference's shared-memory GridPatch/GhostNode decomposition (Patches/GridPatch.cpp:32-138,
+Patches/GhostNode.cpp:58-185; MeshInfo::CreatePatches MeshInfo.cpp:869-1088):
+
+  * 1-D slabs of CELL PLANES along z; rank r holds the particles whose element lies in [cell_lo, cell_hi)
+    (the reference's GetPatchForElement, MeshInfo.cpp:1371-1413);
+  * after each particle->grid pass the partial sums on the three node planes around an interior slab
+    face are swapped with the neighbour and added (the reference's serial ghost->real reductions,
+    GhostNode.cpp:127-136,170-185); both sides then own identical complete sums, so the node sweeps run
+    redundantly there and no broadcast is needed;
+  * after the element reset, particles whose new element left the slab move to the neighbour as packed
+    rows (GridPatch::AddMovingParticle / MoveParticlesToNewPatches, GridPatch.cpp:214-251).
+
+libmpmgpu packs/adds the buffers on the device (mpmgpu_slab_* in include/mpmgpu.h); this module moves
+them with torch.distributed point-to-point ops.  The exchange logic is written against plain torch
+tensors, so the same code runs under gloo with CPU tensors in the CPU tests.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HALO_VALUES = (5, 3, 3)        # values per node exchanged after phases 0, 1, 2
+
+
+def slab_bounds(depth, cell_first, cell_last, world):
+    """Split the occupied cell planes [cell_first, cell_last) evenly over `world` ranks; the first and
+    last slabs extend to the grid edge.  Returns list of (cell_lo, cell_hi)."""
+    n = cell_last - cell_first
+    cuts = [cell_first + (n * r) // world for r in range(world + 1)]
+    cuts[0] = 0
+    cuts[-1] = depth
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def partition_particles(pt, horiz, vert, cell_lo, cell_hi, ids=None):
+    """Select the particles whose element z-index lies in [cell_lo, cell_hi); keeps global ids."""
+    in_elem = np.asarray(pt["in_elem"])
+    k = (in_elem - 1) // (horiz * vert)
+    sel = np.nonzero((k >= cell_lo) & (k < cell_hi))[0]
+    n = in_elem.shape[0]
+    out = {}
+    for key, v in pt.items():
+        if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[-1] == n:
+            out[key] = np.ascontiguousarray(v[..., sel])
+        else:
+            out[key] = v
+    out["ids"] = (np.arange(n, dtype=np.int32) if ids is None else np.asarray(ids, np.int32))[sel]
+    out["n_nonrigid"] = len(sel)
+    return out
+
+
+class DeviceBuffer:
+    """Zero-copy torch view of a raw device pointer owned by libmpmgpu."""
+
+    def __init__(self, ptr, ndoubles):
+        self.__cuda_array_interface__ = {"shape": (int(ndoubles),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, ndoubles, device):
+    return torch.as_tensor(DeviceBuffer(ptr, ndoubles), device=device)
+
+
+class NeighbourExchange:
+    """Point-to-point exchange with the lower / upper slab neighbour over a torch.distributed group.
+    Works on any tensors (CUDA+NCCL in production, CPU+gloo in the tests)."""
+
+    def __init__(self, rank, world, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.lower = rank - 1 if rank > 0 else None
+        self.upper = rank + 1 if rank < world - 1 else None
+
+    def swap(self, send_lo, send_hi, recv_lo, recv_hi):
+        """Send send_lo to the lower neighbour and send_hi to the upper one; receive theirs."""
+        ops = []
+        if self.lower is not None:
+            ops.append(dist.P2POp(dist.isend, send_lo, self.lower, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_lo, self.lower, self.group))
+        if self.upper is not None:
+            ops.append(dist.P2POp(dist.isend, send_hi, self.upper, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_hi, self.upper, self.group))
+        if not ops:
+            return
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def swap_counts(self, n_to_lo, n_to_hi, device):
+        """Tell each neighbour how many rows are coming; returns (n_from_lo, n_from_hi)."""
+        s_lo = torch.tensor([n_to_lo], dtype=torch.int64, device=device)
+        s_hi = torch.tensor([n_to_hi], dtype=torch.int64, device=device)
+        r_lo = torch.zeros(1, dtype=torch.int64, device=device)
+        r_hi = torch.zeros(1, dtype=torch.int64, device=device)
+        self.swap(s_lo, s_hi, r_lo, r_hi)
+        return int(r_lo.item()), int(r_hi.item())
+
+    def swap_rows(self, send_lo, send_hi, recv_lo, recv_hi, n_to_lo, n_to_hi, n_from_lo, n_from_hi, row):
+        """Variable-length row exchange (only the non-empty directions are posted; both sides know the counts)."""
+        ops = []
+        if self.lower is not None:
+            if n_to_lo:
+                ops.append(dist.P2POp(dist.isend, send_lo[: n_to_lo * row], self.lower, self.group))
+            if n_from_lo:
+                ops.append(dist.P2POp(dist.irecv, recv_lo[: n_from_lo * row], self.lower, self.group))
+        if self.upper is not None:
+            if n_to_hi:
+                ops.append(dist.P2POp(dist.isend, send_hi[: n_to_hi * row], self.upper, self.group))
+            if n_from_hi:
+                ops.append(dist.P2POp(dist.irecv, recv_hi[: n_from_hi * row], self.upper, self.group))
+        if not ops:
+            return
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class SlabSim:
+    """One rank of a slab-decomposed run.  `prob` describes the WHOLE grid; `particles` are this rank's
+    (see partition_particles) with global ids."""
+
+    def __init__(self, prob, particles, cell_lo, cell_hi, rank, world, device=0, capacity_factor=1.3,
+                 migration_capacity=1 << 16, sort_interval=0, group=None):
+        from .capi import MpmGpu
+        self.rank, self.world = rank, world
+        self.device = torch.device("cuda", device)
+        n = int(particles["n_nonrigid"])
+        self.sim = MpmGpu(prob, device=device, kernel_path=2, max_particles=int(n * capacity_factor) + 1024,
+                          sort_interval=sort_interval, upload=False)
+        self.sim.slab_configure(cell_lo, cell_hi, rank > 0, rank < world - 1, migration_capacity)
+        self.sim.upload(particles)
+        # kernels and NCCL calls share torch's current stream: ordered without host synchronisation
+        self.stream = torch.cuda.current_stream(self.device)
+        self.sim.set_stream(self.stream.cuda_stream)
+        ptrs, plane_nodes = self.sim.slab_halo_buffers()
+        hd = 5 * 3 * plane_nodes
+        self.halo = [device_tensor(p, hd, self.device) for p in ptrs]          # send_lo, send_hi, recv_lo, recv_hi
+        self.plane_nodes = plane_nodes
+        mptrs, self.row, self.mig_cap = self.sim.slab_migration_buffers()
+        self.mig = [device_tensor(p, self.row * self.mig_cap, self.device) for p in mptrs]
+        self.ex = NeighbourExchange(rank, world, group)
+        self.migrated_out = 0
+        self.migrated_in = 0
+
+    def _halo(self, which):
+        nd = HALO_VALUES[which] * 3 * self.plane_nodes
+        s_lo, s_hi, r_lo, r_hi = self.halo
+        self.ex.swap(s_lo[:nd], s_hi[:nd], r_lo[:nd], r_hi[:nd])
+
+    def step(self, nsteps=1):
+        for _ in range(nsteps):
+            for phase in range(3):
+                self.sim.slab_phase(phase)
+                if self.world > 1:
+                    self._halo(phase)
+            self.sim.slab_phase(3)
+            if self.world > 1:
+                self._migrate()
+
+    def _migrate(self):
+        n_lo, n_hi = self.sim.slab_migration_counts()
+        f_lo, f_hi = self.ex.swap_counts(n_lo, n_hi, self.device)
+        if n_lo or n_hi:
+            self.sim.slab_pack_migrants()
+        if n_lo or n_hi or f_lo or f_hi:
+            s_lo, s_hi, r_lo, r_hi = self.mig
+            self.ex.swap_rows(s_lo, s_hi, r_lo, r_hi, n_lo, n_hi, f_lo, f_hi, self.row)
+            self.stream.synchronize()
+            self.sim.slab_finish_migration(f_lo, f_hi)
+            self.migrated_out += n_lo + n_hi
+            self.migrated_in += f_lo + f_hi
+
+    def num_particles(self):
+        return self.sim.num_particles()
+
+    def download(self):
+        return self.sim.download()
+
+    def close(self):
+        self.sim.close()
+
+
+def gather_by_id(local, n_global, group=None):
+    """Assemble per-rank downloads (dicts with 'ids') into global arrays on every rank (test helper)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    parts = [None] * world
+    if world > 1:
+        dist.all_gather_object(parts, local, group=group)
+    else:
+        parts = [local]
+    out = {}
+    for key, v in parts[0].items():
+        if key == "ids":
+            continue
+        shape = v.shape[:-1] + (n_global,)
+        out[key] = np.zeros(shape, dtype=v.dtype)
+    seen = np.zeros(n_global, dtype=np.int32)
+    for part in parts:
+        ids = part["ids"]
+        seen[ids] += 1
+        for key in out:
+            out[key][..., ids] = part[key]
+    assert np.all(seen == 1), "particle ids lost or duplicated across slabs"
+    return out
+
+
+class LockstepCluster:
+    """All slabs of a run inside ONE process on ONE GPU, stepped in lockstep with device-to-device
+    copies standing in for the NCCL exchange.  Same library calls, same buffers, same order as the
+    multi-process run: used to debug and to test the slab logic where only one GPU is available."""
+
+    def __init__(self, prob, bounds, device=0, **kw):
+        self.sims = []
+        world = len(bounds)
+        n = prob.nparticles
+        for r, (lo, hi) in enumerate(bounds):
+            part = partition_particles(prob.particles, prob.horiz, prob.vert, lo, hi)
+            self.sims.append(SlabSim(prob, part, lo, hi, r, world, device=device, **kw))
+        self.n_global = n
+        self.world = world
+
+    def _swap_halo(self, which):
+        for r in range(self.world - 1):
+            a, b = self.sims[r], self.sims[r + 1]
+            nd = HALO_VALUES[which] * 3 * a.plane_nodes
+            b.halo[2][:nd].copy_(a.halo[1][:nd])      # a.send_hi -> b.recv_lo
+            a.halo[3][:nd].copy_(b.halo[0][:nd])      # b.send_lo -> a.recv_hi
+
+    def step(self, nsteps=1):
+        for _ in range(nsteps):
+            for phase in range(3):
+                for s in self.sims:
+                    s.sim.slab_phase(phase)
+                self._swap_halo(phase)
+            for s in self.sims:
+                s.sim.slab_phase(3)
+            counts = [s.sim.slab_migration_counts() for s in self.sims]
+            for s, (n_lo, n_hi) in zip(self.sims, counts):
+                if n_lo or n_hi:
+                    s.sim.slab_pack_migrants()
+            for r, s in enumerate(self.sims):
+                f_lo = counts[r - 1][1] if r > 0 else 0
+                f_hi = counts[r + 1][0] if r < self.world - 1 else 0
+                if f_lo:
+                    s.mig[2][: f_lo * s.row].copy_(self.sims[r - 1].mig[1][: f_lo * s.row])
+                if f_hi:
+                    s.mig[3][: f_hi * s.row].copy_(self.sims[r + 1].mig[0][: f_hi * s.row])
+            torch.cuda.synchronize()
+            for r, s in enumerate(self.sims):
+                f_lo = counts[r - 1][1] if r > 0 else 0
+                f_hi = counts[r + 1][0] if r < self.world - 1 else 0
+                if counts[r][0] or counts[r][1] or f_lo or f_hi:
+                    s.sim.slab_finish_migration(f_lo, f_hi)
+                    s.migrated_out += counts[r][0] + counts[r][1]
+                    s.migrated_in += f_lo + f_hi
+
+    def download(self):
+        parts = [s.download() for s in self.sims]
+        out = {}
+        for key, v in parts[0].items():
+            if key != "ids":
+                out[key] = np.zeros(v.shape[:-1] + (self.n_global,), dtype=v.dtype)
+        seen = np.zeros(self.n_global, np.int32)
+        for part in parts:
+            ids = part["ids"]
+            seen[ids] += 1
+            for key in out:
+                out[key][..., ids] = part[key]
+        assert np.all(seen == 1), "particle ids lost or duplicated across slabs"
+        return out
+
+    def close(self):
+        for s in self.sims:
+            s.close()

@@ -1,0 +1,62 @@
+"""Slab decomposition on the GPU: the multi-slab run must reproduce the reference (golden dumps) to the
+same tolerances as the single-GPU run, with particles migrating between slabs.
+
+ * LockstepCluster: every slab in one process on one GPU (same library calls and buffers as the
+   multi-process run, device copies instead of NCCL) -- runs wherever one GPU is available;
+ * torchrun with 2 ranks over NCCL when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.parity import TOL_100STEP, compare_particles, load_golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def occupied_planes(prob):
+    k = (np.asarray(prob.particles["in_elem"]) - 1) // (prob.horiz * prob.vert)
+    return int(k.min()), int(k.max()) + 1
+
+
+@pytest.mark.parametrize("case,world,sort_interval", [("block3d_fast_crossings", 2, 0), ("block3d_jitter", 2, 5),
+                                                       ("block3d_ugimp_usavg", 1, 0)])
+def test_lockstep_slabs_match_reference(case, world, sort_interval):
+    from nairn_mpm_fea_b200.problem import from_reference_dump
+    from nairn_mpm_fea_b200.slab import LockstepCluster, slab_bounds
+    z = load_golden(case)
+    prob = from_reference_dump(z)
+    first, last = occupied_planes(prob)
+    # cut one plane off-centre so the slab face is not a symmetry plane of the block
+    bounds = slab_bounds(prob.depth, first, last, world)
+    cl = LockstepCluster(prob, bounds, device=0, sort_interval=sort_interval)
+    snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
+    done = 0
+    for s in snaps:
+        cl.step(s - done)
+        done = s
+        got = cl.download()
+        errs, bad = compare_particles(got, z, "p%d" % s, TOL_100STEP)
+        assert not bad, "%s, %d slabs, after %d steps: %s" % (case, world, s, bad)
+        assert np.array_equal(got["in_elem"], z["p%d/inElem" % s])
+    if world > 1 and case == "block3d_fast_crossings":
+        moved = sum(s.migrated_out for s in cl.sims)
+        assert moved > 0, "test problem should push particles across the slab face"
+        assert sum(s.migrated_in for s in cl.sims) == moved
+    assert sum(s.num_particles() for s in cl.sims) == prob.nparticles
+    cl.close()
+
+
+def test_two_ranks_over_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "slab_worker.py"),
+           "block3d_fast_crossings"]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "SLAB_OK" in p.stdout
