@@ -165,7 +165,7 @@ def run_ours(args):
         lo, hi = bounds[rank]
         stepper = SlabSim(prob, prob.particles, lo, hi, rank, world, device=local, capacity_factor=1.2)
         sim = stepper.sim
-        stream = torch.cuda.current_stream()
+        stream = stepper.stream
 
     def barrier():
         sim.synchronize()
@@ -230,6 +230,7 @@ def run_ours(args):
             pinned[k] = v
     nb = len(prob.bc_value)
     bcv = np.zeros(nb)
+    dl = MpmGpu.pinned_download_buffers(int(n * 1.2) + 1024 if world > 1 else n)
     barrier()
     t0 = time.perf_counter()
     if world > 1:
@@ -241,7 +242,8 @@ def run_ours(args):
         sim.update_velocity_bc_values(bcv, prob.bc_active)
         stepper.step(1)
         st = sim.status()
-    out = sim.download()
+    n_end = sim.num_particles()
+    out = sim.download(out={k: (v[..., :n_end] if v.shape[-1] != n_end else v) for k, v in dl.items()} if n_end == n else None)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -265,7 +267,7 @@ def run_ours(args):
                        "kernel_path": sim_kernel_path_name(args.kernel_path),
                        "parallelism": "1 GPU" if world == 1 else
                        "%d z-slabs, one process per GPU: 3 halo-plane exchanges per step + particle migration over NCCL "
-                       "(migrated %d rows on rank 0)" % (world, stepper.migrated_out)},
+                       "(rank 0 sent %d and received %d particle rows)" % (world, stepper.migrated_out, stepper.migrated_in)},
             "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_ncell, args.cpu_steps)
@@ -355,8 +357,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m"])
     ap.add_argument("--ncell", type=int, default=0, help="override block edge in cells (testing)")

@@ -253,8 +253,11 @@ class MpmGpu:
         self._check(self.lib.mpmgpu_synchronize(self.ctx))
 
     # -- device -> host -----------------------------------------------------------------------
-    def download(self, mask=F_ALL):
+    def download(self, mask=F_ALL, out=None):
+        """Returns dict of host arrays.  `out`: reuse caller-provided (e.g. pinned) arrays of the right shape."""
         n = self.num_particles()
+        if out is not None:
+            return self._download_into(out, mask)
         out = dict(pos=np.zeros((3, n)), vel=np.zeros((3, n)), sp=np.zeros((6, n)), pressure=np.zeros(n),
                    ep=np.zeros((6, n)), wrot=np.zeros((3, n)), eplast=np.zeros((6, n)), energies=np.zeros((6, n)),
                    history=np.zeros((MAX_HISTORY, n)), acc=np.zeros((3, n)),
@@ -265,6 +268,28 @@ class MpmGpu:
             setattr(v, k, _d(out[k]))
         v.in_elem, v.crossings = _i(out["in_elem"]), _i(out["crossings"])
         self._check(self.lib.mpmgpu_download_particles(self.ctx, C.byref(v), mask))
+        return out
+
+    def _download_into(self, out, mask):
+        v = ParticlesView()
+        for k in ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "acc"):
+            if k in out:
+                setattr(v, k, _d(out[k]))
+        for k in ("in_elem", "crossings", "ids"):
+            if k in out:
+                setattr(v, k, _i(out[k]))
+        self._check(self.lib.mpmgpu_download_particles(self.ctx, C.byref(v), mask))
+        return out
+
+    @staticmethod
+    def pinned_download_buffers(n):
+        """Page-locked host arrays for download(out=...) (D2H at full PCIe rate)."""
+        import torch
+        shapes = dict(pos=(3, n), vel=(3, n), sp=(6, n), pressure=(n,), ep=(6, n), wrot=(3, n), eplast=(6, n),
+                      energies=(6, n), history=(MAX_HISTORY, n), acc=(3, n))
+        out = {k: torch.zeros(sh, dtype=torch.float64).pin_memory().numpy() for k, sh in shapes.items()}
+        for k in ("in_elem", "crossings", "ids"):
+            out[k] = torch.zeros(n, dtype=torch.int32).pin_memory().numpy()
         return out
 
     def download_nodes(self):

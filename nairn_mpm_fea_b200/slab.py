@@ -126,8 +126,9 @@ class SlabSim:
                           sort_interval=sort_interval, upload=False)
         self.sim.slab_configure(cell_lo, cell_hi, rank > 0, rank < world - 1, migration_capacity)
         self.sim.upload(particles)
-        # kernels and NCCL calls share torch's current stream: ordered without host synchronisation
-        self.stream = torch.cuda.current_stream(self.device)
+        # kernels and NCCL calls are issued on ONE dedicated stream: ordered without host synchronisation
+        # (a non-default stream: handle 0 means "the context's own stream" to mpmgpu_set_stream)
+        self.stream = torch.cuda.Stream(device=self.device)
         self.sim.set_stream(self.stream.cuda_stream)
         ptrs, plane_nodes = self.sim.slab_halo_buffers()
         hd = 5 * 3 * plane_nodes
@@ -145,14 +146,15 @@ class SlabSim:
         self.ex.swap(s_lo[:nd], s_hi[:nd], r_lo[:nd], r_hi[:nd])
 
     def step(self, nsteps=1):
-        for _ in range(nsteps):
-            for phase in range(3):
-                self.sim.slab_phase(phase)
+        with torch.cuda.stream(self.stream):
+            for _ in range(nsteps):
+                for phase in range(3):
+                    self.sim.slab_phase(phase)
+                    if self.world > 1:
+                        self._halo(phase)
+                self.sim.slab_phase(3)
                 if self.world > 1:
-                    self._halo(phase)
-            self.sim.slab_phase(3)
-            if self.world > 1:
-                self._migrate()
+                    self._migrate()
 
     def _migrate(self):
         n_lo, n_hi = self.sim.slab_migration_counts()
