@@ -1,0 +1,607 @@
+/*
+ * mpm_oracle.c -- TEST INFRASTRUCTURE.  Plain-C, single-thread restatement of the reference NairnMPM
+ * time step for the hot path (tasks 1-9, 11 + IsotropicMat), written to follow the REFERENCE's own
+ * loop structure (per-particle candidate tables, serial node accumulation, serial BC list), not the
+ * CUDA design.  It is the CPU checker ("port") for tests/ and the fallback cpu_baseline of bench.py.
+ * It is never linked into libmpmgpu and never called by the product path.
+ *
+ * Parity of THIS file is pinned by tests/test_oracle_cpu.py against the golden dumps of the unmodified
+ * reference (tests/golden/*.npz, produced by oracle/_ref = the reference's own sources compiled here).
+ *
+ * Data layout reuses the plain structs of include/mpmgpu.h (SoA host arrays); everything else is
+ * independent of the product.
+ *
+ * Reference lines each function restates are cited at the function.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/mpmgpu.h"
+
+typedef struct { double x, y, z; } Vec;
+
+typedef struct {        /* MatVelocityField (Nodes/MatVelocityField.hpp:44-48) */
+    int numberPoints;
+    double mass;
+    Vec pk, ftot, vk, pkCopy;
+} NodeField;
+
+typedef struct {
+    mpmgpu_config cfg;
+    int dim, horiz, vert, depth, nnodes, nelems, xplane, yplane, zplane;
+    double *xpts, *ypts, *zpts;
+    int nmat;
+    mpmgpu_material *mats;
+    int n, nNR;
+    /* particle state (AoS-of-arrays, caller order) */
+    double *pos, *vel, *mp, *lp, *ncpos, *sp, *pressure, *ep, *wrot, *eplast, *energies, *hist, *pfext, *acc;
+    int *inElem, *matnum, *cross;
+    NodeField *nd;      /* 0-based node index = reference node number - 1 */
+    int nbc;
+    int *bcNode; double *bcNorm, *bcValue; int *bcActive, *bcSym;
+    double dt, dtFirst, dtLast;
+    long long mstep;
+} Oracle;
+
+static Oracle *O = NULL;
+
+#define P3(a, c, p) (O->a[(size_t)(c) * O->n + (p)])
+
+/* ---- candidate tables: Elements/EightNodeIsoparamBrick.cpp:24-54, Common/Elements/FourNodeIsoparam.cpp:27-31 ---- */
+static const double g3xii[64] = {-1, 1, 1, -1, -1, 1, 1, -1, -3, -1, 1, 3, 3, 3, 3, 1, -1, -3, -3, -3, -3, -1, 1, 3, 3, 3, 3, 1, -1, -3, -3, -3,
+                                 -1, 1, 1, -1, -3, -1, 1, 3, 3, 3, 3, 1, -1, -3, -3, -3, -1, 1, 1, -1, -3, -1, 1, 3, 3, 3, 3, 1, -1, -3, -3, -3};
+static const double g3eti[64] = {-1, -1, 1, 1, -1, -1, 1, 1, -3, -3, -3, -3, -1, 1, 3, 3, 3, 3, 1, -1, -3, -3, -3, -3, -1, 1, 3, 3, 3, 3, 1, -1,
+                                 -1, -1, 1, 1, -3, -3, -3, -3, -1, 1, 3, 3, 3, 3, 1, -1, -1, -1, 1, 1, -3, -3, -3, -3, -1, 1, 3, 3, 3, 3, 1, -1};
+static const double g3zti[64] = {-1, -1, -1, -1, 1, 1, 1, 1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                 -3, -3, -3, -3, -3, -3, -3, -3, -3, -3, -3, -3, -3, -3, -3, -3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3};
+static const double gxii[16] = {-1, 1, 1, -1, -3, -1, 1, 3, 3, 3, 3, 1, -1, -3, -3, -3};
+static const double geti[16] = {-1, -1, 1, 1, -3, -3, -3, -3, -1, 1, 3, 3, 3, 3, 1, -1};
+
+static int off_of(double xi) { return (int)(0.5 * (xi + 1.)); }   /* -3->-1, -1->0, 1->1, 3->2 (tables :40-54) */
+
+/* element (1-based) -> col,row,rank and first node (0-based): Read_MPM/Generators.cpp:1917-1929 */
+static void elem_ijk(int inElem, int *i, int *j, int *k)
+{
+    int e0 = inElem - 1;
+    *i = e0 % O->horiz; e0 /= O->horiz;
+    *j = e0 % O->vert;
+    *k = e0 / O->vert;
+}
+
+/* ---- shape functions: returns count, fills nds (0-based), fn, derivatives ------------------------------
+ * uGIMP 3D: EightNodeIsoparamBrick.cpp:289-397;  2D: FourNodeIsoparam.cpp:431-519
+ * Linear 3D: EightNodeIsoparamBrick.cpp:87-105;  2D: FourNodeIsoparam.cpp:189-210 */
+static int shape(int p, int getDeriv, int *nds, double *fn, double *xd, double *yd, double *zd)
+{
+    int ei, ej, ek;
+    elem_ijk(O->inElem[p], &ei, &ej, &ek);
+    const int node0 = ek * O->zplane + ej * O->yplane + ei;
+    const double xi = P3(ncpos, 0, p), eta = P3(ncpos, 1, p), zeta = P3(ncpos, 2, p);
+    const double dx = O->xpts[ei + 1] - O->xpts[ei], dy = O->ypts[ej + 1] - O->ypts[ej];
+    const double dz = O->dim == 3 ? O->zpts[ek + 1] - O->zpts[ek] : 1.;
+    int i = 0;
+    if (O->cfg.shape == MPMGPU_POINT_GIMP) {
+        static const double xii[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, eti[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, zti[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+        const int nn = O->dim == 3 ? 8 : 4;
+        for (i = 0; i < nn; i++) {
+            double t1 = 1. + xii[i] * xi, t2 = 1. + eti[i] * eta, t3 = 1. + zti[i] * zeta;
+            int xo = xii[i] > 0, yo = eti[i] > 0, zo = zti[i] > 0;
+            if (O->dim == 3) {
+                fn[i] = 0.125 * t1 * t2 * t3;
+                if (getDeriv) { xd[i] = 0.25 * xii[i] * t2 * t3 / dx; yd[i] = 0.25 * eti[i] * t1 * t3 / dy; zd[i] = 0.25 * zti[i] * t1 * t2 / dz; }
+                nds[i] = node0 + xo + yo * O->yplane + zo * O->zplane;
+            } else {
+                fn[i] = 0.25 * t1 * t2;
+                if (getDeriv) { xd[i] = 0.5 * xii[i] * t2 / dx; yd[i] = 0.5 * eti[i] * t1 / dy; zd[i] = 0.; }
+                nds[i] = node0 + xo + yo * O->yplane;
+            }
+        }
+        return nn;
+    }
+    const double lpx = P3(lp, 0, p), lpy = P3(lp, 1, p), lpz = P3(lp, 2, p);
+    const double q1x = 2. - lpx, q2x = 2. + lpx, q1y = 2. - lpy, q2y = 2. + lpy, q1z = 2. - lpz, q2z = 2. + lpz;
+    const double isx = 1. / (4. * lpx), isy = 1. / (4. * lpy), isz = 1. / (4. * lpy);     /* :303 uses lp.y for z */
+    const double inv_dx = 2.0 / dx, inv_dy = 2.0 / dy, inv_dz = 2.0 / dz;
+    if (O->dim == 3) {
+        for (int id = 0; id < 64; id++) {
+            double xp = fabs(xi - g3xii[id]); if (xp >= q2x) continue;
+            double yp = fabs(eta - g3eti[id]); if (yp >= q2y) continue;
+            double zp = fabs(zeta - g3zti[id]); if (zp >= q2z) continue;
+            double Sx, Sy, Sz, argx = 0., argy = 0., argz = 0.;
+            if (xp < lpx) Sx = ((4. - lpx) * lpx - xp * xp) * isx; else if (xp <= q1x) Sx = 0.5 * (2. - xp); else { argx = (q2x - xp) * isx; Sx = 2. * lpx * argx * argx; }
+            if (yp < lpy) Sy = ((4. - lpy) * lpy - yp * yp) * isy; else if (yp <= q1y) Sy = 0.5 * (2. - yp); else { argy = (q2y - yp) * isy; Sy = 2. * lpy * argy * argy; }
+            if (zp < lpz) Sz = ((4. - lpz) * lpz - zp * zp) * isz; else if (zp <= q1z) Sz = 0.5 * (2. - zp); else { argz = (q2z - zp) * isz; Sz = 2. * lpz * argz * argz; }
+            fn[i] = Sx * Sy * Sz;
+            if (getDeriv) {
+                double xs = xi > g3xii[id] ? 1. : -1., ys = eta > g3eti[id] ? 1. : -1., zs = zeta > g3zti[id] ? 1. : -1.;
+                double dSx = xp < lpx ? -xp / (2. * lpx) : (xp <= q1x ? -0.5 : -argx);
+                double dSy = yp < lpy ? -yp / (2. * lpy) : (yp <= q1y ? -0.5 : -argy);
+                double dSz = zp < lpz ? -zp / (2. * lpz) : (zp <= q1z ? -0.5 : -argz);
+                xd[i] = xs * dSx * Sy * Sz * inv_dx; yd[i] = ys * Sx * dSy * Sz * inv_dy; zd[i] = zs * Sx * Sy * dSz * inv_dz;
+            }
+            nds[i] = node0 + off_of(g3xii[id]) + off_of(g3eti[id]) * O->yplane + off_of(g3zti[id]) * O->zplane;
+            i++;
+        }
+    } else {
+        for (int id = 0; id < 16; id++) {
+            double xp = fabs(xi - gxii[id]); if (xp >= q2x) continue;
+            double yp = fabs(eta - geti[id]); if (yp >= q2y) continue;
+            double Sx, Sy, argx = 0., argy = 0.;
+            if (xp < lpx) Sx = ((4. - lpx) * lpx - xp * xp) * isx; else if (xp <= q1x) Sx = (2. - xp) / 2.; else { argx = (q2x - xp) * isx; Sx = 2. * lpx * argx * argx; }
+            if (yp < lpy) Sy = ((4. - lpy) * lpy - yp * yp) * isy; else if (yp <= q1y) Sy = (2. - yp) / 2.; else { argy = (q2y - yp) * isy; Sy = 2. * lpy * argy * argy; }
+            fn[i] = Sx * Sy;
+            if (getDeriv) {
+                double xs = xi > gxii[id] ? 1. : -1., ys = eta > geti[id] ? 1. : -1.;
+                double dSx = xp < lpx ? -xp * isx * 2.0 : (xp <= q1x ? -0.5 : -argx);
+                double dSy = yp < lpy ? -yp * isy * 2.0 : (yp <= q1y ? -0.5 : -argy);
+                xd[i] = xs * dSx * Sy * inv_dx; yd[i] = ys * Sx * dSy * inv_dy; zd[i] = 0.;
+            }
+            nds[i] = node0 + off_of(gxii[id]) + off_of(geti[id]) * O->yplane;
+            i++;
+        }
+    }
+    return i;
+}
+
+/* ---- task 1: InitializationTask.cpp:49-85; GetXiPos EightNodeIsoparamBrick.cpp:276-281 ------------------- */
+static void task_initialization(void)
+{
+    for (int i = 0; i < O->nnodes; i++) memset(&O->nd[i], 0, sizeof(NodeField));       /* MatVelocityField::Zero :92-104 */
+    for (int p = 0; p < O->n; p++) {
+        int ei, ej, ek;
+        elem_ijk(O->inElem[p], &ei, &ej, &ek);
+        P3(ncpos, 0, p) = (2. * P3(pos, 0, p) - O->xpts[ei] - O->xpts[ei + 1]) / (O->xpts[ei + 1] - O->xpts[ei]);
+        P3(ncpos, 1, p) = (2. * P3(pos, 1, p) - O->ypts[ej] - O->ypts[ej + 1]) / (O->ypts[ej + 1] - O->ypts[ej]);
+        P3(ncpos, 2, p) = O->dim == 3 ? (2. * P3(pos, 2, p) - O->zpts[ek] - O->zpts[ek + 1]) / (O->zpts[ek + 1] - O->zpts[ek]) : 0.;
+    }
+}
+
+/* ---- task 2: MassAndMomentumTask.cpp:62-98, NodalPointMPM.cpp:419-453 ------------------------------------ */
+static void task_mass_and_momentum(void)
+{
+    int nds[64]; double fn[64];
+    for (int p = 0; p < O->nNR; p++) {
+        int nn = shape(p, 0, nds, fn, NULL, NULL, NULL);
+        for (int i = 0; i < nn; i++) {
+            NodeField *f = &O->nd[nds[i]];
+            double fnmp = fn[i] * O->mp[p];
+            f->pk.x += P3(vel, 0, p) * fnmp; f->pk.y += P3(vel, 1, p) * fnmp; f->pk.z += P3(vel, 2, p) * fnmp;
+            f->numberPoints += 1;
+            f->mass += fnmp;
+        }
+    }
+}
+
+/* ---- velocity BCs: NodalVelBC.cpp:321-400, MatVelocityField.cpp:490-575 ----------------------------------- */
+enum { MASS_MOMENTUM_CALL, GRID_FORCES_CALL, UPDATE_MOMENTUM_CALL, UPDATE_STRAINS_LAST_CALL };
+
+static void velocity_bc_loop(int pass)
+{
+    const double dt = O->dt;
+    for (int b = 0; b < O->nbc; b++) {         /* zero pass over the whole list */
+        if (!O->bcActive[b]) continue;
+        NodeField *f = &O->nd[O->bcNode[b] - 1];
+        if (f->numberPoints <= 0) continue;
+        const double *n = &O->bcNorm[3 * b];
+        if (pass == GRID_FORCES_CALL) {
+            double dotf = f->ftot.x * n[0] + f->ftot.y * n[1] + f->ftot.z * n[2];
+            double dotp = f->pk.x * n[0] + f->pk.y * n[1] + f->pk.z * n[2];
+            double s = -dotf - dotp / dt;
+            f->ftot.x += n[0] * s; f->ftot.y += n[1] * s; f->ftot.z += n[2] * s;
+        } else {
+            double dotn = f->pk.x * n[0] + f->pk.y * n[1] + f->pk.z * n[2];
+            f->pk.x += n[0] * (-dotn); f->pk.y += n[1] * (-dotn); f->pk.z += n[2] * (-dotn);
+            if (pass == UPDATE_MOMENTUM_CALL) { double s = -dotn / dt; f->ftot.x += n[0] * s; f->ftot.y += n[1] * s; f->ftot.z += n[2] * s; }
+        }
+    }
+    for (int b = 0; b < O->nbc; b++) {         /* then the add pass */
+        if (!O->bcActive[b]) continue;
+        NodeField *f = &O->nd[O->bcNode[b] - 1];
+        if (f->numberPoints <= 0) continue;
+        const double *n = &O->bcNorm[3 * b];
+        const double vel = O->bcValue[b];
+        if (pass == GRID_FORCES_CALL) {
+            double s = f->mass * vel / dt;
+            f->ftot.x += n[0] * s; f->ftot.y += n[1] * s; f->ftot.z += n[2] * s;
+        } else {
+            double pvel = f->mass * vel;
+            f->pk.x += n[0] * pvel; f->pk.y += n[1] * pvel; f->pk.z += n[2] * pvel;
+            if (pass == UPDATE_MOMENTUM_CALL) { double s = pvel / dt; f->ftot.x += n[0] * s; f->ftot.y += n[1] * s; f->ftot.z += n[2] * s; }
+        }
+    }
+}
+
+static void grid_velocity_conditions(int pass)
+{
+    if (O->nbc == 0) return;
+    if (pass == MASS_MOMENTUM_CALL) {
+        for (int b = 0; b < O->nbc; b++) {     /* ADJUST_COPIED_PK == 1: NodalVelBC.cpp:339-353 */
+            NodeField *f = &O->nd[O->bcNode[b] - 1];
+            if (f->numberPoints <= 0) continue;
+            int sd = O->bcSym ? O->bcSym[b] : 0;
+            if (sd & 32) f->pkCopy.x = 0.;
+            if (sd & 64) f->pkCopy.y = 0.;
+            if (sd & 128) f->pkCopy.z = 0.;
+        }
+        if (O->cfg.method == MPMGPU_USL) return;       /* no USF task: NodalVelBC.cpp:356 */
+    }
+    if (pass == UPDATE_MOMENTUM_CALL && O->cfg.xpic_order > 1) return;
+    velocity_bc_loop(pass);
+}
+
+/* ---- task 3: PostExtrapolationTask.cpp:62-165 -------------------------------------------------------------- */
+static void task_post_extrapolation(void)
+{
+    for (int i = 0; i < O->nnodes; i++) O->nd[i].pkCopy = O->nd[i].pk;         /* MatVelocityField.cpp:158-164 */
+    grid_velocity_conditions(MASS_MOMENTUM_CALL);
+}
+
+/* ---- IsotropicMat small-rotation law: MoreIsotropicMat.cpp:33-45,185-348; ElasticMPM.cpp:392-403;
+ *      Hypo3D/2D MaterialBaseMPM.cpp:1012-1047; IncrementHeatEnergy :982-1006 --------------------------------- */
+enum { XX, YY, ZZ, YZ, XZ, XY };
+
+static void isotropic_law(int p, const double du[3][3], const mpmgpu_material *m)
+{
+    const double *q = m->p;
+    double F[3][3], Fn[3][3], dF[3][3];
+    /* deformation gradient from ep + wrot (MatPoint3D.cpp:363-376) */
+    F[0][0] = 1. + P3(ep, XX, p); F[1][1] = 1. + P3(ep, YY, p); F[2][2] = 1. + P3(ep, ZZ, p);
+    F[0][1] = 0.5 * (P3(ep, XY, p) - P3(wrot, 0, p)); F[1][0] = 0.5 * (P3(ep, XY, p) + P3(wrot, 0, p));
+    F[0][2] = 0.5 * (P3(ep, XZ, p) - P3(wrot, 1, p)); F[2][0] = 0.5 * (P3(ep, XZ, p) + P3(wrot, 1, p));
+    F[1][2] = 0.5 * (P3(ep, YZ, p) - P3(wrot, 2, p)); F[2][1] = 0.5 * (P3(ep, YZ, p) + P3(wrot, 2, p));
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dF[i][j] = du[i][j] + (i == j ? 1. : 0.);
+    if (O->dim == 3) {
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Fn[i][j] = dF[i][0] * F[0][j] + dF[i][1] * F[1][j] + dF[i][2] * F[2][j];
+    } else {
+        memset(Fn, 0, sizeof Fn);
+        Fn[0][0] = dF[0][0] * F[0][0] + dF[0][1] * F[1][0]; Fn[0][1] = dF[0][0] * F[0][1] + dF[0][1] * F[1][1];
+        Fn[1][0] = dF[1][0] * F[0][0] + dF[1][1] * F[1][0]; Fn[1][1] = dF[1][0] * F[0][1] + dF[1][1] * F[1][1];
+        Fn[2][2] = dF[2][2] * F[2][2];
+    }
+    /* SetDeformationGradientMatrix (MatPoint3D.cpp:320-336) */
+    P3(ep, XX, p) = Fn[0][0] - 1.; P3(ep, YY, p) = Fn[1][1] - 1.; P3(ep, ZZ, p) = Fn[2][2] - 1.;
+    P3(ep, XY, p) = Fn[1][0] + Fn[0][1]; P3(wrot, 0, p) = Fn[1][0] - Fn[0][1];
+    if (O->dim == 3) {
+        P3(ep, XZ, p) = Fn[2][0] + Fn[0][2]; P3(ep, YZ, p) = Fn[2][1] + Fn[1][2];
+        P3(wrot, 1, p) = Fn[2][0] - Fn[0][2]; P3(wrot, 2, p) = Fn[2][1] - Fn[1][2];
+    }
+    const double gamma0 = q[20], Cv = q[1], prevT = P3(energies, 5, p);
+    double st0[6];
+    for (int c = 0; c < 6; c++) st0[c] = P3(sp, c, p);
+    double dVoverV, work;
+    if (O->dim == 3) {
+        double dvxx = du[0][0], dvyy = du[1][1], dvzz = du[2][2];
+        double dgamxy = du[0][1] + du[1][0], dgamxz = du[0][2] + du[2][0], dgamyz = du[1][2] + du[2][1];
+        double dwxy = du[1][0] - du[0][1], dwxz = du[2][0] - du[0][2], dwyz = du[2][1] - du[1][2];
+        dVoverV = dvxx + dvyy + dvzz;
+        double ds[6];
+        ds[XX] = q[8] * dvxx + q[9] * dvyy + q[10] * dvzz;
+        ds[YY] = q[9] * dvxx + q[11] * dvyy + q[12] * dvzz;
+        ds[ZZ] = q[10] * dvxx + q[12] * dvyy + q[13] * dvzz;
+        ds[YZ] = q[14] * dgamyz; ds[XZ] = q[15] * dgamxz; ds[XY] = q[16] * dgamxy;
+        double st[6];
+        st[XX] = -dwxy * st0[XY] - dwxz * st0[XZ];
+        st[YY] = dwxy * st0[XY] - dwyz * st0[YZ];
+        st[ZZ] = dwxz * st0[XZ] + dwyz * st0[YZ];
+        st[YZ] = 0.5 * (dwxy * st0[XZ] + dwxz * st0[XY] + dwyz * (st0[YY] - st0[ZZ]));
+        st[XZ] = 0.5 * (-dwxy * st0[YZ] + dwxz * (st0[XX] - st0[ZZ]) + dwyz * st0[XY]);
+        st[XY] = 0.5 * (dwxy * (st0[XX] - st0[YY]) - dwxz * st0[YZ] - dwyz * st0[XZ]);
+        for (int c = 0; c < 6; c++) P3(sp, c, p) += ds[c] + st[c];
+        work = 0.5 * ((st0[XX] + P3(sp, XX, p)) * dvxx + (st0[YY] + P3(sp, YY, p)) * dvyy + (st0[ZZ] + P3(sp, ZZ, p)) * dvzz +
+                      (st0[YZ] + P3(sp, YZ, p)) * dgamyz + (st0[XZ] + P3(sp, XZ, p)) * dgamxz + (st0[XY] + P3(sp, XY, p)) * dgamxy);
+    } else {
+        double dvxx = du[0][0], dvyy = du[1][1], dgam = du[0][1] + du[1][0], dwxy = du[1][0] - du[0][1];
+        dVoverV = dvxx + dvyy;
+        double c1 = q[8] * dvxx + q[9] * dvyy, c2 = q[9] * dvxx + q[11] * dvyy, c3 = q[16] * dgam;
+        double dnorm = dwxy * st0[XY], dshear = 0.5 * dwxy * (st0[XX] - st0[YY]);
+        P3(sp, XX, p) += c1 - dnorm; P3(sp, YY, p) += c2 + dnorm; P3(sp, XY, p) += c3 + dshear;
+        work = 0.5 * ((st0[XX] + P3(sp, XX, p)) * dvxx + (st0[YY] + P3(sp, YY, p)) * dvyy + (st0[XY] + P3(sp, XY, p)) * dgam);
+        if (O->cfg.np == MPMGPU_PLANE_STRAIN_MPM) {
+            P3(sp, ZZ, p) += q[21] * dvxx + q[22] * dvyy;
+        } else {
+            double dezz = q[21] * dvxx + q[22] * dvyy;
+            P3(ep, ZZ, p) += dezz;
+            work += 0.5 * (st0[ZZ] + P3(sp, ZZ, p)) * dezz;
+            dVoverV += dezz;
+        }
+    }
+    P3(energies, 0, p) += work;
+    double dTq0 = -gamma0 * prevT * dVoverV;
+    double baseHeat = -Cv * dTq0;
+    P3(energies, 2, p) += baseHeat;
+    P3(energies, 3, p) += baseHeat / prevT;
+}
+
+/* ---- tasks 4 / 9: FullStrainUpdate UpdateStrainsFirstTask.cpp:101-168, MatPoint3D.cpp:45-93 ------------------ */
+static void full_strain_update(double strainTime)
+{
+    for (int i = 0; i < O->nnodes; i++) {      /* GridValueCalculation MatVelocityField.cpp:239-251 */
+        NodeField *f = &O->nd[i];
+        if (f->numberPoints == 0 || f->mass == 0.) continue;
+        double rm = 1. / f->mass;
+        f->vk.x = f->pk.x * rm; f->vk.y = f->pk.y * rm; f->vk.z = f->pk.z * rm;
+    }
+    int nds[64]; double fn[64], xd[64], yd[64], zd[64];
+    for (int p = 0; p < O->nNR; p++) {
+        int nn = shape(p, 1, nds, fn, xd, yd, zd);
+        double dv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int i = 0; i < nn; i++) {
+            Vec v = O->nd[nds[i]].vk;
+            dv[0][0] += v.x * xd[i]; dv[0][1] += v.x * yd[i]; dv[1][0] += v.y * xd[i]; dv[1][1] += v.y * yd[i];
+            if (O->dim == 3) {
+                dv[0][2] += v.x * zd[i]; dv[1][2] += v.y * zd[i];
+                dv[2][0] += v.z * xd[i]; dv[2][1] += v.z * yd[i]; dv[2][2] += v.z * zd[i];
+            }
+        }
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) dv[a][b] *= strainTime;
+        const mpmgpu_material *m = &O->mats[O->matnum[p] - 1];
+        if (m->kind == MPMGPU_MAT_ISOTROPIC) isotropic_law(p, dv, m);
+    }
+}
+
+static void task_update_strains_first(void)
+{
+    if (O->cfg.method == MPMGPU_USL) return;
+    full_strain_update(O->cfg.method == MPMGPU_USAVG ? O->dtFirst : O->dt);
+}
+
+/* ---- task 5: GridForcesTask.cpp:55-117, MatPoint3D.cpp:248-252 ------------------------------------------------ */
+static void task_grid_forces(void)
+{
+    int nds[64]; double fn[64], xd[64], yd[64], zd[64];
+    for (int p = 0; p < O->nNR; p++) {
+        int nn = shape(p, 1, nds, fn, xd, yd, zd);
+        double mp = O->mp[p], pr = O->pressure[p];
+        double sxx = P3(sp, XX, p), syy = P3(sp, YY, p), szz = P3(sp, ZZ, p), syz = P3(sp, YZ, p), sxz = P3(sp, XZ, p), sxy = P3(sp, XY, p);
+        double fx = O->pfext ? P3(pfext, 0, p) : 0., fy = O->pfext ? P3(pfext, 1, p) : 0., fz = O->pfext ? P3(pfext, 2, p) : 0.;
+        for (int i = 0; i < nn; i++) {
+            NodeField *f = &O->nd[nds[i]];
+            if (O->dim == 3) {
+                f->ftot.x += -mp * ((sxx - pr) * xd[i] + sxy * yd[i] + sxz * zd[i]) + fn[i] * fx;
+                f->ftot.y += -mp * (sxy * xd[i] + (syy - pr) * yd[i] + syz * zd[i]) + fn[i] * fy;
+                f->ftot.z += -mp * (sxz * xd[i] + syz * yd[i] + (szz - pr) * zd[i]) + fn[i] * fz;
+            } else {
+                f->ftot.x += -mp * ((sxx - pr) * xd[i] + sxy * yd[i]) + fn[i] * fx;
+                f->ftot.y += -mp * (sxy * xd[i] + (syy - pr) * yd[i]) + fn[i] * fy;
+            }
+        }
+    }
+}
+
+/* ---- task 6: PostForcesTask.cpp:46-94 ---------------------------------------------------------------------- */
+static void task_post_forces(void)
+{
+    const double *g = O->cfg.gravity;
+    int hasG = g[0] != 0. || g[1] != 0. || g[2] != 0.;
+    for (int i = 0; i < O->nnodes; i++) {
+        NodeField *f = &O->nd[i];
+        if (f->numberPoints == 0) continue;
+        f->pk = f->pkCopy;                                                                  /* RestoreMomenta */
+        if (hasG) { f->ftot.x += f->mass * g[0]; f->ftot.y += f->mass * g[1]; f->ftot.z += f->mass * g[2]; }
+    }
+    grid_velocity_conditions(GRID_FORCES_CALL);
+}
+
+/* ---- task 7: UpdateMomentaTask.cpp:44-64 -------------------------------------------------------------------- */
+static void task_update_momenta(void)
+{
+    for (int i = 0; i < O->nnodes; i++) {
+        NodeField *f = &O->nd[i];
+        if (f->numberPoints == 0) continue;
+        f->pk.x += f->ftot.x * O->dt; f->pk.y += f->ftot.y * O->dt; f->pk.z += f->ftot.z * O->dt;
+    }
+    grid_velocity_conditions(UPDATE_MOMENTUM_CALL);
+}
+
+/* ---- task 8: UpdateParticlesTask.cpp:75-286, MatPoint3D::MoveParticle MatPoint3D.cpp:104-194 ------------------ */
+static void task_update_particles(void)
+{
+    for (int i = 0; i < O->nnodes; i++) {
+        NodeField *f = &O->nd[i];
+        if (f->numberPoints == 0 || f->mass == 0.) continue;
+        double rm = 1. / f->mass;
+        f->vk.x = f->pk.x * rm; f->vk.y = f->pk.y * rm; f->vk.z = f->pk.z * rm;
+    }
+    int m = O->cfg.xpic_order;
+    if (!O->cfg.using_fmpm) m = -m;
+    const double dt = O->dt;
+    int nds[64]; double fn[64];
+    for (int p = 0; p < O->nNR; p++) {
+        int nn = shape(p, 0, nds, fn, NULL, NULL, NULL);
+        double Svk[3] = {0, 0, 0}, Sacc[3] = {0, 0, 0};
+        for (int i = 0; i < nn; i++) {
+            NodeField *f = &O->nd[nds[i]];
+            Svk[0] += f->vk.x * fn[i]; Svk[1] += f->vk.y * fn[i]; Svk[2] += f->vk.z * fn[i];
+            if (m <= 0) { double mn = fn[i] / f->mass; Sacc[0] += f->ftot.x * mn; Sacc[1] += f->ftot.y * mn; Sacc[2] += f->ftot.z * mn; }
+        }
+        const mpmgpu_material *mat = &O->mats[O->matnum[p] - 1];
+        double pAlpha = mat->p[2] >= 0. ? mat->p[2] : O->cfg.particle_damping, gAlpha = O->cfg.grid_damping;
+        for (int c = 0; c < O->dim; c++) {
+            double v = P3(vel, c, p), x = P3(pos, c, p), vm = Svk[c], delV;
+            if (m == 0) vm += Sacc[c] * (-dt);
+            double Adamp0 = v * pAlpha;
+            Adamp0 += vm * gAlpha;
+            if (m > 0) { double r = v; v = vm; v += Adamp0 * (-dt); delV = v - r; r += v; x += r * (0.5 * dt); }
+            else if (m == 0) { delV = (Sacc[c] - Adamp0) * dt; v += delV; x += (vm + 0.5 * delV) * dt; }
+            else { double r = v; v = Svk[c] - Adamp0 * dt; delV = v - r; x += (vm + 0.5 * delV) * dt; }
+            P3(vel, c, p) = v; P3(pos, c, p) = x; P3(acc, c, p) = delV / dt;
+        }
+    }
+}
+
+/* ---- task 9: UpdateStrainsLastContactTask.cpp:60-152 / UpdateStrainsLastTask.cpp:43-48 ------------------------- */
+static void task_update_strains_last(void)
+{
+    if (O->cfg.method == MPMGPU_USF) return;
+    if (!O->cfg.skip_post_extrapolation) {
+        for (int i = 0; i < O->nnodes; i++) { O->nd[i].pk.x = O->nd[i].pk.y = O->nd[i].pk.z = 0.; }     /* RezeroNodeTask6 */
+        int nds[64]; double fn[64];
+        for (int p = 0; p < O->nNR; p++) {
+            int nn = shape(p, 0, nds, fn, NULL, NULL, NULL);
+            for (int i = 0; i < nn; i++) {
+                NodeField *f = &O->nd[nds[i]];
+                double fnmp = fn[i] * O->mp[p];
+                f->pk.x += P3(vel, 0, p) * fnmp; f->pk.y += P3(vel, 1, p) * fnmp; f->pk.z += P3(vel, 2, p) * fnmp;
+            }
+        }
+        grid_velocity_conditions(UPDATE_STRAINS_LAST_CALL);
+    }
+    full_strain_update(O->cfg.method == MPMGPU_USAVG ? O->dtLast : O->dt);
+}
+
+/* ---- task 11: ResetElementsTask.cpp:196-265, MeshInfo.cpp:171-199,593-633 ---------------------------------------- */
+static int pt_in_element(int inElem, const double *x)
+{
+    int i, j, k;
+    elem_ijk(inElem, &i, &j, &k);
+    if (x[0] < O->xpts[i] || x[0] >= O->xpts[i + 1]) return 0;
+    if (x[1] < O->ypts[j] || x[1] >= O->ypts[j + 1]) return 0;
+    if (O->dim == 3 && (x[2] < O->zpts[k] || x[2] >= O->zpts[k + 1])) return 0;
+    return 1;
+}
+
+static int edge_element(int num)
+{
+    if (O->dim == 3) {
+        int hv = O->horiz * O->vert;
+        if (num <= hv || num > O->nelems - hv) return 1;
+        if (num % O->horiz <= 1) return 1;
+        int xz = num % hv;
+        return xz <= O->horiz || xz > O->horiz * (O->vert - 1);
+    }
+    if (num <= O->horiz || num > O->nelems - O->horiz) return 1;
+    return num % O->horiz <= 1;
+}
+
+static void task_reset_elements(void)
+{
+    const double gx = O->cfg.gridx, gy = O->cfg.gridy, gz = O->cfg.gridz;
+    for (int p = 0; p < O->n; p++) {
+        double x[3] = {P3(pos, 0, p), P3(pos, 1, p), O->dim == 3 ? P3(pos, 2, p) : 0.};
+        if (pt_in_element(O->inElem[p], x)) continue;
+        int col = (int)((x[0] - O->xpts[0]) / gx), row = (int)((x[1] - O->ypts[0]) / gy), zrow = 0, ok = 1;
+        if (col < 0 || col >= O->horiz) { if (x[0] == O->xpts[0] + O->horiz * gx) col = O->horiz - 1; else ok = 0; }
+        if (row < 0 || row >= O->vert) { if (x[1] == O->ypts[0] + O->vert * gy) row = O->vert - 1; else ok = 0; }
+        if (O->dim == 3) {
+            zrow = (int)((x[2] - O->zpts[0]) / gz);
+            if (zrow < 0 || zrow >= O->depth) { if (x[2] == O->zpts[0] + O->depth * gz) zrow = O->depth - 1; else ok = 0; }
+        }
+        int ne = ok ? (O->dim == 3 ? O->horiz * (zrow * O->vert + row) + col + 1 : row * O->horiz + col + 1) : 0;
+        if (ne > 0 && !edge_element(ne)) {
+            O->inElem[p] = ne;
+            O->cross[p] = O->cross[p] >= 0 ? O->cross[p] + 1 : O->cross[p] - 1;
+            continue;
+        }
+        /* LEFT_GRID: count, mark, ReturnToElement by bisection (:232-265) */
+        { int c = O->cross[p]; c = c >= 0 ? c + 1 : c - 1; O->cross[p] = c > 0 ? -c : c; }
+        double outside[3] = {x[0], x[1], x[2]}, inside[3];
+        for (int c = 0; c < 3; c++) inside[c] = c < O->dim ? outside[c] - O->dt * P3(vel, c, p) : 0.;
+        if (!pt_in_element(O->inElem[p], inside)) {
+            int i, j, k;
+            elem_ijk(O->inElem[p], &i, &j, &k);
+            inside[0] = (O->xpts[i] + O->xpts[i + 1]) / 2.; inside[1] = (O->ypts[j] + O->ypts[j + 1]) / 2.;
+            inside[2] = O->dim == 3 ? (O->zpts[k] + O->zpts[k + 1]) / 2. : 0.;
+        }
+        for (int pass = 1; pass <= 10; pass++) {
+            double mid[3] = {(outside[0] + inside[0]) / 2., (outside[1] + inside[1]) / 2., (outside[2] + inside[2]) / 2.};
+            if (pt_in_element(O->inElem[p], mid)) memcpy(inside, mid, sizeof mid); else memcpy(outside, mid, sizeof mid);
+        }
+        for (int c = 0; c < O->dim; c++) P3(pos, c, p) = inside[c];
+    }
+}
+
+/* ---- driver ------------------------------------------------------------------------------------------------------- */
+typedef void (*taskfn)(void);
+static const taskfn TASKS[10] = {task_initialization, task_mass_and_momentum, task_post_extrapolation, task_update_strains_first,
+                                 task_grid_forces, task_post_forces, task_update_momenta, task_update_particles,
+                                 task_update_strains_last, task_reset_elements};
+
+static double *dupd(const double *src, size_t n) { double *d = (double *)calloc(n ? n : 1, sizeof(double)); if (src) memcpy(d, src, n * sizeof(double)); return d; }
+static int *dupi(const int *src, size_t n, int fill) { int *d = (int *)malloc((n ? n : 1) * sizeof(int)); for (size_t i = 0; i < n; i++) d[i] = src ? src[i] : fill; return d; }
+
+int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mats, const mpmgpu_particles *h,
+                  int nbc, const int *bcNode, const double *bcNorm, const double *bcValue, const int *bcActive, const int *bcSym,
+                  double dt, double dtFirst, double dtLast)
+{
+    O = (Oracle *)calloc(1, sizeof(Oracle));
+    O->cfg = *cfg;
+    O->dim = cfg->np == MPMGPU_THREED_MPM ? 3 : 2;
+    O->horiz = cfg->horiz; O->vert = cfg->vert; O->depth = O->dim == 3 ? cfg->depth : 1;
+    O->xplane = 1; O->yplane = O->horiz + 1; O->zplane = (O->horiz + 1) * (O->vert + 1);
+    O->nnodes = O->zplane * (O->dim == 3 ? O->depth + 1 : 1);
+    O->nelems = O->horiz * O->vert * O->depth;
+    O->xpts = dupd(cfg->xpts, O->horiz + 1); O->ypts = dupd(cfg->ypts, O->vert + 1);
+    O->zpts = O->dim == 3 ? dupd(cfg->zpts, O->depth + 1) : NULL;
+    O->nmat = nmat;
+    O->mats = (mpmgpu_material *)malloc(nmat * sizeof(mpmgpu_material));
+    memcpy(O->mats, mats, nmat * sizeof(mpmgpu_material));
+    size_t n = h->n;
+    O->n = h->n; O->nNR = h->n_nonrigid;
+    O->pos = dupd(h->pos, 3 * n); O->vel = dupd(h->vel, 3 * n); O->mp = dupd(h->mp, n); O->lp = dupd(h->lp, 3 * n);
+    O->ncpos = dupd(NULL, 3 * n); O->sp = dupd(h->sp, 6 * n); O->pressure = dupd(h->pressure, n);
+    O->ep = dupd(h->ep, 6 * n); O->wrot = dupd(h->wrot, 3 * n); O->eplast = dupd(h->eplast, 6 * n);
+    O->energies = dupd(h->energies, 6 * n); O->hist = dupd(h->history, MPMGPU_MAX_HISTORY * n);
+    O->pfext = h->pfext ? dupd(h->pfext, 3 * n) : NULL; O->acc = dupd(NULL, 3 * n);
+    O->inElem = dupi(h->in_elem, n, 1); O->matnum = dupi(h->matnum, n, 1); O->cross = dupi(h->crossings, n, 0);
+    O->nd = (NodeField *)calloc(O->nnodes, sizeof(NodeField));
+    O->nbc = nbc;
+    O->bcNode = dupi(bcNode, nbc, 0); O->bcNorm = dupd(bcNorm, 3 * (size_t)nbc); O->bcValue = dupd(bcValue, nbc);
+    O->bcActive = dupi(bcActive, nbc, 1); O->bcSym = dupi(bcSym, nbc, 0);
+    O->dt = dt; O->dtFirst = dtFirst; O->dtLast = dtLast;
+    return 0;
+}
+
+int oracle_task(int t) { if (!O || t < 0 || t > 9) return -1; TASKS[t](); if (t == 9) O->mstep++; return 0; }
+
+int oracle_step(int nsteps)
+{
+    if (!O) return -1;
+    for (int s = 0; s < nsteps; s++) for (int t = 0; t < 10; t++) oracle_task(t);
+    return 0;
+}
+
+int oracle_get_particles(mpmgpu_particles *h)
+{
+    size_t n = O->n;
+    if (h->pos) memcpy(h->pos, O->pos, 3 * n * sizeof(double));
+    if (h->vel) memcpy(h->vel, O->vel, 3 * n * sizeof(double));
+    if (h->sp) memcpy(h->sp, O->sp, 6 * n * sizeof(double));
+    if (h->pressure) memcpy(h->pressure, O->pressure, n * sizeof(double));
+    if (h->ep) memcpy(h->ep, O->ep, 6 * n * sizeof(double));
+    if (h->wrot) memcpy(h->wrot, O->wrot, 3 * n * sizeof(double));
+    if (h->eplast) memcpy(h->eplast, O->eplast, 6 * n * sizeof(double));
+    if (h->energies) memcpy(h->energies, O->energies, 6 * n * sizeof(double));
+    if (h->history) memcpy(h->history, O->hist, MPMGPU_MAX_HISTORY * n * sizeof(double));
+    if (h->acc) memcpy(h->acc, O->acc, 3 * n * sizeof(double));
+    if (h->in_elem) memcpy(h->in_elem, O->inElem, n * sizeof(int));
+    if (h->crossings) memcpy(h->crossings, O->cross, n * sizeof(int));
+    return 0;
+}
+
+int oracle_get_nodes(mpmgpu_nodes *h)
+{
+    size_t nn = O->nnodes;
+    for (size_t i = 0; i < nn; i++) {
+        const NodeField *f = &O->nd[i];
+        if (h->number_points) h->number_points[i] = f->numberPoints;
+        if (h->mass) h->mass[i] = f->mass;
+        if (h->pk) { h->pk[i] = f->pk.x; h->pk[nn + i] = f->pk.y; h->pk[2 * nn + i] = f->pk.z; }
+        if (h->ftot) { h->ftot[i] = f->ftot.x; h->ftot[nn + i] = f->ftot.y; h->ftot[2 * nn + i] = f->ftot.z; }
+        if (h->vk) { h->vk[i] = f->vk.x; h->vk[nn + i] = f->vk.y; h->vk[2 * nn + i] = f->vk.z; }
+        if (h->pk_copy) { h->pk_copy[i] = f->pkCopy.x; h->pk_copy[nn + i] = f->pkCopy.y; h->pk_copy[2 * nn + i] = f->pkCopy.z; }
+    }
+    return 0;
+}
+
+void oracle_destroy(void)
+{
+    if (!O) return;
+    free(O->xpts); free(O->ypts); free(O->zpts); free(O->mats);
+    free(O->pos); free(O->vel); free(O->mp); free(O->lp); free(O->ncpos); free(O->sp); free(O->pressure); free(O->ep);
+    free(O->wrot); free(O->eplast); free(O->energies); free(O->hist); free(O->pfext); free(O->acc);
+    free(O->inElem); free(O->matnum); free(O->cross); free(O->nd);
+    free(O->bcNode); free(O->bcNorm); free(O->bcValue); free(O->bcActive); free(O->bcSym);
+    free(O);
+    O = NULL;
+}
