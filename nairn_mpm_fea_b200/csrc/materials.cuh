@@ -140,7 +140,7 @@ __device__ __forceinline__ void isotropic_law(PState &s, const double du[9], int
         } else {
             // plane stress: out-of-plane strain increment (MoreIsotropicMat.cpp:249-258)
             double dezz = q[21] * dvxx + q[22] * dvyy;
-            s.F[8] += dezz;                               // MPMBase::IncrementDeformationGradientZZ (ep.zz += dezz)
+            s.F[8] += dezz * s.F[8];                      // MPMBase::IncrementDeformationGradientZZ: ep.zz += dezz*(1+ep.zz) (MPMBase.cpp:637-639)
             workEnergy += 0.5 * (st0[ZZ] + s.sp[ZZ]) * dezz;
             dVoverV += dezz;
         }

@@ -1,0 +1,307 @@
+// GpuTasks.cpp -- the reference-side binding of libmpmgpu: MPMTask subclasses that replace the
+// reference's CPU tasks 1-9 and 11 inside its own driver (NairnMPM::CreateTasks builds the list,
+// NairnMPM_Class/NairnMPM.cpp:870-1110; NairnMPM::MPMStep walks it, :284-335).
+//
+// This file is compiled AGAINST the reference's headers and linked WITH the reference's objects
+// (nairn_mpm_fea_b200/host/build_host.sh); it contains no reference code.  Flow:
+//   main()  (same steps as Common/System/main.cpp:25-140)
+//     ReadFile -> StartResultsOutput -> CMPreparations            reference code, unchanged
+//     GpuTasks::Install()     harvest grid, particles, materials, BC list -> mpmgpu_create/upload,
+//                             then swap each eligible CPU task object for a GpuTask with the same name
+//     CMAnalysis()                                                 reference code, unchanged
+// Host objects (mpm[]) are refreshed from the device before every archive the reference is about to
+// write (ArchiveData::ArchiveResults, System/ArchiveData.cpp:722-760) and at the end of the run.
+// Errors from the C ABI are re-thrown as the reference's CommonException.
+#include <omp.h>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#define private public
+#define protected public
+#include "NairnMPM_Class/NairnMPM.hpp"
+#include "NairnMPM_Class/MPMTask.hpp"
+#include "NairnMPM_Class/MeshInfo.hpp"
+#include "MPM_Classes/MPMBase.hpp"
+#include "Nodes/NodalPoint.hpp"
+#include "Elements/ElementBase.hpp"
+#include "Materials/MaterialBase.hpp"
+#include "Materials/IsotropicMat.hpp"
+#include "Boundary_Conditions/NodalVelBC.hpp"
+#include "Global_Quantities/BodyForce.hpp"
+#include "Custom_Tasks/CustomTask.hpp"
+#include "Custom_Tasks/TransportTask.hpp"
+#include "Cracks/CrackHeader.hpp"
+#include "System/ArchiveData.hpp"
+#include "Global_Quantities/GlobalQuantity.hpp"
+#include "Exceptions/CommonException.hpp"
+#undef private
+#undef protected
+
+#include "../../include/mpmgpu.h"
+
+extern MPMTask *firstMPMTask;
+extern double timestep, strainTimestepFirst, strainTimestepLast, fractionUSF, mtime;
+
+namespace {
+
+mpmgpu_ctx *gCtx = NULL;
+bool gHostStale = false;            // device is ahead of mpm[]
+std::vector<NodalVelBC *> gBCs;     // host BC list in list order
+bool gBCsVary = false;
+
+void check(int rc, const char *where)
+{
+    if (rc == MPMGPU_OK) return;
+    throw CommonException(mpmgpu_last_error(gCtx), where);
+}
+
+// device -> mpm[] (MPMBase fields; SetDeformationGradient is implicit: ep + wrot are downloaded)
+void DownloadToHost(void)
+{
+    if (!gHostStale) return;
+    const int n = nmpms;
+    std::vector<double> pos(3 * n), vel(3 * n), sp(6 * n), pr(n), ep(6 * n), wrot(3 * n), epl(6 * n), en(6 * n), hist(MPMGPU_MAX_HISTORY * n), acc(3 * n);
+    std::vector<int> elem(n), cross(n);
+    mpmgpu_particles h;
+    memset(&h, 0, sizeof h);
+    h.pos = pos.data(); h.vel = vel.data(); h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data();
+    h.eplast = epl.data(); h.energies = en.data(); h.history = hist.data(); h.acc = acc.data(); h.in_elem = elem.data(); h.crossings = cross.data();
+    check(mpmgpu_download_particles(gCtx, &h, MPMGPU_F_ALL), "GpuTasks::DownloadToHost");
+    for (int p = 0; p < n; p++) {
+        MPMBase *m = mpm[p];
+        m->pos = MakeVector(pos[p], pos[n + p], pos[2 * n + p]);
+        m->vel = MakeVector(vel[p], vel[n + p], vel[2 * n + p]);
+        m->acc = MakeVector(acc[p], acc[n + p], acc[2 * n + p]);
+        m->sp.xx = sp[p]; m->sp.yy = sp[n + p]; m->sp.zz = sp[2 * n + p]; m->sp.yz = sp[3 * n + p]; m->sp.xz = sp[4 * n + p]; m->sp.xy = sp[5 * n + p];
+        m->pressure = pr[p];
+        m->ep.xx = ep[p]; m->ep.yy = ep[n + p]; m->ep.zz = ep[2 * n + p]; m->ep.yz = ep[3 * n + p]; m->ep.xz = ep[4 * n + p]; m->ep.xy = ep[5 * n + p];
+        m->wrot.xy = wrot[p]; m->wrot.xz = wrot[n + p]; m->wrot.yz = wrot[2 * n + p];
+        m->eplast.xx = epl[p]; m->eplast.yy = epl[n + p]; m->eplast.zz = epl[2 * n + p]; m->eplast.yz = epl[3 * n + p]; m->eplast.xz = epl[4 * n + p]; m->eplast.xy = epl[5 * n + p];
+        m->workEnergy = en[p]; m->resEnergy = en[n + p]; m->heatEnergy = en[2 * n + p]; m->entropy = en[3 * n + p]; m->plastEnergy = en[4 * n + p];
+        if (elem[p] != m->inElem) { m->prevInElem = m->inElem; m->inElem = elem[p]; }
+        m->elementCrossings = cross[p];
+        const int nh = theMaterials[m->MatID()]->NumberOfHistoryDoubles();
+        for (int k = 0; k < nh && k < MPMGPU_MAX_HISTORY && m->matData != NULL; k++) ((double *)m->matData)[k] = hist[k * n + p];
+    }
+    gHostStale = false;
+}
+
+enum { G_INIT, G_MASSMOM, G_POSTEXTRAP, G_USF, G_FORCES, G_POSTFORCES, G_MOMENTA, G_PARTICLES, G_USL, G_RESET };
+
+// One class for all ten tasks: Execute() forwards to the matching C entry point.
+class GpuTask : public MPMTask
+{
+  public:
+    int which;
+    GpuTask(const char *name, int w) : MPMTask(name), which(w) {}
+    virtual bool Execute(int)
+    {
+        switch (which) {
+        case G_INIT: check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)"); break;
+        case G_MASSMOM: check(mpmgpu_task_mass_and_momentum(gCtx), "GpuTask(MassAndMomentum)"); break;
+        case G_POSTEXTRAP:
+            if (gBCsVary) {     // NodalVelBC::GridVelocityBCValues (NodalVelBC.cpp:293-302): values at this step's mtime
+                std::vector<double> v(gBCs.size()); std::vector<int> a(gBCs.size());
+                for (size_t i = 0; i < gBCs.size(); i++) { a[i] = gBCs[i]->GetNodeNum(mtime) > 0; v[i] = a[i] ? gBCs[i]->BCValue(mtime) : 0.; }
+                check(mpmgpu_update_velocity_bc_values(gCtx, (int)v.size(), v.data(), a.data()), "GpuTask(PostExtrapolation)");
+            }
+            check(mpmgpu_task_post_extrapolation(gCtx), "GpuTask(PostExtrapolation)");
+            break;
+        case G_USF: check(mpmgpu_task_update_strains_first(gCtx), "GpuTask(UpdateStrainsFirst)"); break;
+        case G_FORCES: check(mpmgpu_task_grid_forces(gCtx), "GpuTask(GridForces)"); break;
+        case G_POSTFORCES: check(mpmgpu_task_post_forces(gCtx), "GpuTask(PostForces)"); break;
+        case G_MOMENTA: check(mpmgpu_task_update_momenta(gCtx), "GpuTask(UpdateMomenta)"); break;
+        case G_PARTICLES: check(mpmgpu_task_update_particles(gCtx), "GpuTask(UpdateParticles)"); break;
+        case G_USL: check(mpmgpu_task_update_strains_last(gCtx), "GpuTask(UpdateStrainsLast)"); break;
+        case G_RESET: {
+            check(mpmgpu_task_reset_elements(gCtx), "GpuTask(ResetElements)");
+            gHostStale = true;
+            // will the reference archive after this step?  (ArchiveResults(mtime+timestep,...), ArchiveData.cpp:731-746)
+            const double atime = mtime + timestep;
+            bool due = atime >= archiver->nextArchTime || atime + timestep > fmobj->maxtime;
+            if (firstGlobal != NULL && archiver->globalTime >= 0. && atime > archiver->nextGlobalTime) due = true;
+            if (due || theTasks != NULL) DownloadToHost();
+            break;
+        }
+        }
+        return true;
+    }
+};
+
+int TaskCode(const char *name)
+{
+    static const struct { const char *nm; int code; } map[] = {
+        {"Initialize", G_INIT}, {"Extrapolate Mass and Momentum", G_MASSMOM}, {"Post Extrapolation Tasks", G_POSTEXTRAP},
+        {"Update Strains First", G_USF}, {"Extrapolate Grid Forces", G_FORCES}, {"Post Force Extrapolation Tasks", G_POSTFORCES},
+        {"Update Momenta", G_MOMENTA}, {"Update Particles", G_PARTICLES}, {"Update Strains Last with Extrapolation", G_USL},
+        {"Update Strains Last", G_USL}, {"Reset Elements", G_RESET}};
+    for (size_t i = 0; i < sizeof map / sizeof map[0]; i++) if (strcmp(name, map[i].nm) == 0) return map[i].code;
+    return -1;
+}
+
+} // namespace
+
+// Returns NULL when installed, else the reason the run stays on the CPU tasks.
+const char *GpuTasks_Install(int device)
+{
+    if (firstCrack != NULL) return "cracks present";
+    if (fmobj->multiMaterialMode) return "multimaterial mode";
+    if (transportTasks != NULL) return "transport tasks present";
+    if (nmpms != nmpmsNR) return "rigid particles present";
+    if (fmobj->np != PLANE_STRAIN_MPM && fmobj->np != PLANE_STRESS_MPM && fmobj->np != THREED_MPM) return "analysis type";
+    if (ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP) return "shape functions";
+    if (!mpmgrid.IsStructuredEqualElementsGrid()) return "grid is not structured with equal elements";
+    if (bodyFrc.GetXPICOrder() > 1) return "XPIC/FMPM order > 1";
+    for (int i = 0; i < nmat; i++) if (theMaterials[i]->MaterialID() != 1 || ((IsotropicMat *)theMaterials[i])->useLargeRotation) return "material type";
+    const bool is3D = fmobj->IsThreeD();
+
+    // grid: node coordinates per axis exactly as generated (Read_MPM/Generators.cpp:1823-1833)
+    const int nx = mpmgrid.horiz + 1, ny = mpmgrid.vert + 1, nz = is3D ? mpmgrid.depth + 1 : 1;
+    std::vector<double> xp(nx), yp(ny), zp(nz);
+    for (int i = 0; i < nx; i++) xp[i] = nd[1 + i]->x;
+    for (int j = 0; j < ny; j++) yp[j] = nd[1 + j * nx]->y;
+    for (int k = 0; k < nz && is3D; k++) zp[k] = nd[1 + k * nx * ny]->z;
+    mpmgpu_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.abi_version = MPMGPU_ABI_VERSION; cfg.device = device; cfg.np = fmobj->np;
+    cfg.horiz = mpmgrid.horiz; cfg.vert = mpmgrid.vert; cfg.depth = is3D ? mpmgrid.depth : 0;
+    cfg.xpts = xp.data(); cfg.ypts = yp.data(); cfg.zpts = is3D ? zp.data() : NULL;
+    cfg.gridx = mpmgrid.grid.x; cfg.gridy = mpmgrid.grid.y; cfg.gridz = mpmgrid.grid.z;
+    cfg.shape = ElementBase::useGimp; cfg.cpdi_rcrit = ElementBase::rcrit;
+    cfg.method = fmobj->mpmApproach; cfg.skip_post_extrapolation = fmobj->skipPostExtrapolation ? 1 : 0;
+    cfg.fraction_usf = fractionUSF;
+    cfg.xpic_order = bodyFrc.GetXPICOrder(); cfg.using_fmpm = bodyFrc.UsingFMPM() ? 1 : 0;
+    cfg.grid_damping = bodyFrc.GetGridDamping(mtime); cfg.particle_damping = bodyFrc.GetParticleDamping(mtime);
+    if (bodyFrc.gravity) { cfg.gravity[0] = bodyFrc.gforce.x; cfg.gravity[1] = bodyFrc.gforce.y; cfg.gravity[2] = bodyFrc.gforce.z; }
+    cfg.kernel_path = 1;        // per-task entry points keep the reference's task timing report meaningful
+    if (mpmgpu_create(&cfg, &gCtx) != MPMGPU_OK) return mpmgpu_last_error(NULL);
+
+    // materials: the block GetCopyOfMechanicalProps would hand out (Elastic::FillUnrotatedElasticProperties)
+    std::vector<mpmgpu_material> mats(nmat);
+    for (int i = 0; i < nmat; i++) {
+        IsotropicMat *im = (IsotropicMat *)theMaterials[i];
+        mpmgpu_material &m = mats[i];
+        memset(&m, 0, sizeof m);
+        m.kind = MPMGPU_MAT_ISOTROPIC; m.n_history = 0;
+        m.p[0] = im->rho; m.p[1] = im->heatCapacity; m.p[2] = im->matUsePDamping ? im->matPdamping : -1.;
+        const ElasticProperties &e = im->pr;
+        if (is3D) {
+            m.p[8] = e.C[0][0]; m.p[9] = e.C[0][1]; m.p[10] = e.C[0][2]; m.p[11] = e.C[1][1]; m.p[12] = e.C[1][2]; m.p[13] = e.C[2][2];
+            m.p[14] = e.C[3][3]; m.p[15] = e.C[4][4]; m.p[16] = e.C[5][5];
+            m.p[17] = e.alpha[0]; m.p[18] = e.alpha[1]; m.p[19] = e.alpha[2];
+        } else {
+            m.p[8] = e.C[1][1]; m.p[9] = e.C[1][2]; m.p[11] = e.C[2][2]; m.p[16] = e.C[3][3];
+            m.p[21] = e.C[4][1]; m.p[22] = e.C[4][2]; m.p[23] = e.C[4][4]; m.p[24] = e.C[5][1];
+            m.p[17] = e.alpha[1]; m.p[18] = e.alpha[2]; m.p[19] = e.alpha[4];
+        }
+        m.p[20] = im->gamma0;
+    }
+    if (mpmgpu_set_materials(gCtx, nmat, mats.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+
+    // particles: AoS heap objects -> SoA
+    const int n = nmpms;
+    std::vector<double> pos(3 * n), vel(3 * n), mp(n), lp(3 * n), sp(6 * n), pr(n), ep(6 * n), wrot(3 * n), epl(6 * n), en(6 * n), pf(3 * n);
+    std::vector<int> elem(n), matn(n), cross(n);
+    bool anyFext = false;
+    for (int p = 0; p < n; p++) {
+        MPMBase *m = mpm[p];
+        pos[p] = m->pos.x; pos[n + p] = m->pos.y; pos[2 * n + p] = m->pos.z;
+        vel[p] = m->vel.x; vel[n + p] = m->vel.y; vel[2 * n + p] = m->vel.z;
+        mp[p] = m->mp; lp[p] = m->mpm_lp.x; lp[n + p] = m->mpm_lp.y; lp[2 * n + p] = m->mpm_lp.z;
+        sp[p] = m->sp.xx; sp[n + p] = m->sp.yy; sp[2 * n + p] = m->sp.zz; sp[3 * n + p] = m->sp.yz; sp[4 * n + p] = m->sp.xz; sp[5 * n + p] = m->sp.xy;
+        pr[p] = m->pressure;
+        ep[p] = m->ep.xx; ep[n + p] = m->ep.yy; ep[2 * n + p] = m->ep.zz; ep[3 * n + p] = m->ep.yz; ep[4 * n + p] = m->ep.xz; ep[5 * n + p] = m->ep.xy;
+        wrot[p] = m->wrot.xy; wrot[n + p] = m->wrot.xz; wrot[2 * n + p] = m->wrot.yz;
+        epl[p] = m->eplast.xx; epl[n + p] = m->eplast.yy; epl[2 * n + p] = m->eplast.zz; epl[3 * n + p] = m->eplast.yz; epl[4 * n + p] = m->eplast.xz; epl[5 * n + p] = m->eplast.xy;
+        en[p] = m->workEnergy; en[n + p] = m->resEnergy; en[2 * n + p] = m->heatEnergy; en[3 * n + p] = m->entropy; en[4 * n + p] = m->plastEnergy;
+        en[5 * n + p] = m->pPreviousTemperature;
+        pf[p] = m->pFext.x; pf[n + p] = m->pFext.y; pf[2 * n + p] = m->pFext.z;
+        if (m->pFext.x != 0. || m->pFext.y != 0. || m->pFext.z != 0.) anyFext = true;
+        elem[p] = m->inElem; matn[p] = m->matnum; cross[p] = m->elementCrossings;
+    }
+    mpmgpu_particles h;
+    memset(&h, 0, sizeof h);
+    h.n = n; h.n_nonrigid = nmpmsNR;
+    h.pos = pos.data(); h.vel = vel.data(); h.mp = mp.data(); h.lp = lp.data(); h.in_elem = elem.data(); h.matnum = matn.data();
+    h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data(); h.eplast = epl.data(); h.energies = en.data();
+    h.pfext = anyFext ? pf.data() : NULL; h.crossings = cross.data();
+    if (mpmgpu_upload_particles(gCtx, &h) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    if (mpmgpu_set_time_step(gCtx, timestep, strainTimestepFirst, strainTimestepLast) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+
+    // grid velocity BCs in list order
+    std::vector<int> bnode, bact, bsym; std::vector<double> bnorm, bval;
+    for (NodalVelBC *bc = firstVelocityBC; bc != NULL; bc = (NodalVelBC *)bc->GetNextObject()) {
+        gBCs.push_back(bc);
+        bnode.push_back(bc->nodeNum);
+        bnorm.push_back(bc->norm.x); bnorm.push_back(bc->norm.y); bnorm.push_back(bc->norm.z);
+        bact.push_back(bc->GetNodeNum(mtime) > 0 ? 1 : 0);
+        bval.push_back(bact.back() ? bc->BCValue(mtime) : 0.);
+        bsym.push_back(nd[bc->nodeNum]->fixedDirection & ANYSYMMETRYPLANE_DIRECTION);
+        if (bc->style != CONSTANT_VALUE || bc->GetBCFirstTime() > 0.) gBCsVary = true;
+        if (bc->reflectedNode >= 0) return "reflected (mirrored) velocity BCs";
+    }
+    if (mpmgpu_set_velocity_bcs(gCtx, (int)bnode.size(), bnode.data(), bnorm.data(), bval.data(), bact.data(), bsym.data()) != MPMGPU_OK)
+        return mpmgpu_last_error(gCtx);
+
+    // swap the CPU task objects for GPU ones, keeping order and names (custom-task runner stays)
+    MPMTask *prev = NULL;
+    for (MPMTask *t = firstMPMTask; t != NULL;) {
+        MPMTask *next = (MPMTask *)t->GetNextTask();
+        const int code = TaskCode(t->GetTaskName());
+        if (code >= 0) {
+            GpuTask *g = new GpuTask(t->GetTaskName(), code);
+            g->SetNextTask(next);
+            if (prev) prev->SetNextTask(g); else firstMPMTask = g;
+            prev = g;
+        } else prev = t;
+        t = next;
+    }
+    std::cout << "GPU TASKS: tasks 1-9,11 run on libmpmgpu (device " << device << ", " << n << " particles)" << std::endl;
+    return NULL;
+}
+
+void GpuTasks_Finish(void)
+{
+    if (!gCtx) return;
+    gHostStale = true;
+    try { DownloadToHost(); } catch (...) {}
+    mpmgpu_destroy(gCtx);
+    gCtx = NULL;
+}
+
+// ---- the driver: Common/System/main.cpp steps with the install hook between preparations and analysis ----
+int main(int argc, const char *argv[])
+{
+    int numProcs = 1, device = 0, arg = 1;
+    bool useGpu = true;
+    for (; arg < argc && argv[arg][0] == '-'; arg++) {
+        if (strcmp(argv[arg], "-np") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &numProcs);
+        else if (strcmp(argv[arg], "-gpu") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &device);
+        else if (strcmp(argv[arg], "-cpu") == 0) useGpu = false;
+        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-cpu] input.fmcmd" << std::endl; return 1; }
+    }
+    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-cpu] input.fmcmd" << std::endl; return 1; }
+    fmobj = new NairnMPM();
+    omp_set_num_threads(numProcs);
+    fmobj->SetNumberOfProcessors(numProcs);
+    int rv = fmobj->ReadFile(argv[arg], false);
+    if (rv != 0) return rv;
+    InitRandom(fmobj->randseed > 0 ? (unsigned int)fmobj->randseed : 0);
+    try {
+        fmobj->StartResultsOutput();
+        fmobj->CMStartResultsOutput();
+        fmobj->CMPreparations();
+        if (useGpu) {
+            const char *why = GpuTasks_Install(device);
+            if (why != NULL) { std::cerr << "NairnMPM_gpu: cannot run this input on libmpmgpu: " << why << std::endl; return 2; }
+        }
+        fmobj->CMAnalysis(false);
+        GpuTasks_Finish();
+    }
+    catch (CommonException &e) { e.Display(); return 3; }
+    catch (const char *msg) { std::cerr << msg << std::endl; return 3; }
+    return 0;
+}

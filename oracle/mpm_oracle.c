@@ -301,7 +301,7 @@ static void isotropic_law(int p, const double du[3][3], const mpmgpu_material *m
             P3(sp, ZZ, p) += q[21] * dvxx + q[22] * dvyy;
         } else {
             double dezz = q[21] * dvxx + q[22] * dvyy;
-            P3(ep, ZZ, p) += dezz;
+            P3(ep, ZZ, p) += dezz * (1. + P3(ep, ZZ, p));      /* MPMBase::IncrementDeformationGradientZZ, MPMBase.cpp:637-639 */
             work += 0.5 * (st0[ZZ] + P3(sp, ZZ, p)) * dezz;
             dVoverV += dezz;
         }

@@ -22,6 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = {
     # name: (xml text, snapshots, per-task steps[, position jitter, velocity jitter])
     "block3d_jitter": (inputs.block3d(ncell=5, margin=3, E=100.0, vx=3.0e3, vy=-2.0e3, vz=-6.0e3), (1, 20, 60), 1, 0.35, 4000.0),
+    "disks2d_ugimp_planestrain": (inputs.disks2d(analysis=10, gimp="uGIMP"), (1, 100), 1),
+    "disks2d_linear_planestress": (inputs.disks2d(analysis=11, gimp=None, method=2), (1, 100), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

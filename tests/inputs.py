@@ -60,3 +60,42 @@ def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy
 </JANFEAInput>
 """ % (method, maxtime, cfl, gimp_tag, ppc_tag, damp, extra_header, n, n, n, vx, vy, vz,
        lo, hi, lo, hi, lo, hi, mat, bcs, grav, custom_tasks)
+
+
+def disks2d(analysis=10, gimp="uGIMP", method=2, cell=1.0, radius=6.0, gap=1.0, hmax=16.0, vmax=9.0, E=1.0, nu=0.33,
+            rho=1.5, vel=2500.0, alpha=60.0, maxtime=1.0, archive_ms=1000.0, root="res/disks.", extra_header=""):
+    """2D two-disk head-on impact (BASELINE config 1 family; modelled on the reference's TwoDisks example but
+    without symmetry planes): analysis 10 = plane strain, 11 = plane stress; gimp 'uGIMP' or None (Classic)."""
+    gimp_tag = '<GIMP type="%s"/>' % gimp if gimp else ""
+    x1 = -(gap / 2.0 + 2.0 * radius)
+    return """<?xml version='1.0'?>
+<!DOCTYPE JANFEAInput SYSTEM "NairnMPM.dtd">
+<JANFEAInput version='3'>
+  <Header><Description>2D disks</Description><Analysis>%d</Analysis></Header>
+  <MPMHeader>
+    <MPMMethod>%d</MPMMethod>
+    <MaxTime units="ms">%r</MaxTime>
+    <ArchiveTime units="ms">%r</ArchiveTime>
+    <ArchiveRoot>%s</ArchiveRoot>
+    <MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>
+    %s %s
+  </MPMHeader>
+  <Mesh output="file">
+    <Grid xmin="-%r" xmax="%r" ymin="-%r" ymax="%r">
+      <Horiz cellsize="%r"/><Vert cellsize="%r"/>
+    </Grid>
+  </Mesh>
+  <MaterialPoints>
+    <Body matname="Disk 1" angle="0" thick="1" vx="%r" vy="0">
+      <Oval xmin="%r" xmax="%r" ymin="-%r" ymax="%r"/>
+    </Body>
+    <Body matname="Disk 2" angle="0" thick="1" vx="-%r" vy="0">
+      <Oval xmin="%r" xmax="%r" ymin="-%r" ymax="%r"/>
+    </Body>
+  </MaterialPoints>
+  <Material Type="1" Name="Disk 1"><rho>%r</rho><E>%r</E><nu>%r</nu><alpha>%r</alpha></Material>
+  <Material Type="1" Name="Disk 2"><rho>%r</rho><E>%r</E><nu>%r</nu><alpha>%r</alpha></Material>
+</JANFEAInput>
+""" % (analysis, method, maxtime, archive_ms, root, gimp_tag, extra_header, hmax, hmax, vmax, vmax, cell, cell,
+       vel, x1, x1 + 2 * radius, radius, radius, vel, -x1 - 2 * radius, -x1, radius, radius,
+       rho, E, nu, alpha, rho, E, nu, alpha)

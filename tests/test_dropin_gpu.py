@@ -1,0 +1,59 @@
+"""The drop-in itself: the reference's own C++ driver (XML reader, set-up, archiver) with tasks 1-9,11
+replaced by GpuTask objects that call libmpmgpu (nairn_mpm_fea_b200/host/GpuTasks.cpp), run on the same XML
+input as the unmodified reference CLI; every binary archive both write must agree (element ids exactly,
+doubles to 1e-7 of the column max).  Needs the prebuilt oracle/_ref/NairnMPM and host/_build/NairnMPM_gpu."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import inputs
+from tests.archive import list_archives, read_archive
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "NairnMPM")
+GPU = os.path.join(ROOT, "nairn_mpm_fea_b200", "host", "_build", "NairnMPM_gpu")
+
+CASES = {
+    "block3d": (inputs.block3d(ncell=6, margin=3, maxtime=0.03).replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>",
+                                                                          "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), 6 ** 3 * 8, "res/blk."),
+    "disks2d": (inputs.disks2d(analysis=10, maxtime=2.0, archive_ms=0.5), None, "res/disks."),
+}
+
+
+def run(binary, xml, extra=()):
+    d = tempfile.mkdtemp(prefix="dropin_")
+    path = os.path.join(d, "in.fmcmd")
+    open(path, "w").write(xml)
+    p = subprocess.run([binary, *extra, path], cwd=d, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-2000:])
+    return d, p.stdout
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_reference_driver_with_gpu_tasks_matches_reference(case):
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("oracle/_ref/NairnMPM or host/_build/NairnMPM_gpu not built")
+    xml, npart, root = CASES[case]
+    dref, out_ref = run(REF, xml, ("-np", "4"))
+    dgpu, out_gpu = run(GPU, xml)
+    assert "GPU TASKS" in out_gpu
+    if npart is None:
+        for ln in out_ref.splitlines():
+            if "Number of Material Points:" in ln:
+                npart = int(ln.split(":")[1].split()[0])
+                break
+        assert npart, "could not find particle count in the reference report"
+    a_ref = list_archives(os.path.join(dref, root))
+    a_gpu = list_archives(os.path.join(dgpu, root))
+    assert [s for s, _ in a_ref] == [s for s, _ in a_gpu] and len(a_ref) >= 3, (a_ref, a_gpu)
+    for (step, fr), (_, fg) in zip(a_ref, a_gpu):
+        r, g = read_archive(fr, npart), read_archive(fg, npart)
+        assert np.array_equal(r["elem"], g["elem"]), "element ids differ at step %d" % step
+        assert np.array_equal(r["tail"], g["tail"]) and np.array_equal(r["mat"], g["mat"])
+        scale = np.maximum(np.max(np.abs(r["doubles"]), axis=0), 1e-300)
+        err = np.max(np.abs(r["doubles"] - g["doubles"]) / scale)
+        assert err < 1e-7, "archive at step %d differs: %.3e" % (step, err)

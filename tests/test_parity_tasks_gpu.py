@@ -12,11 +12,11 @@ from tests.parity import TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compar
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
+CASES = ["disks2d_ugimp_planestrain", "disks2d_linear_planestress", "block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
          "block3d_ugimp_usf"]
 
 
-FUSED_CASES = [c for c in CASES if "linear" not in c]
+FUSED_CASES = [c for c in CASES if "linear" not in c and "2d" not in c]
 
 
 def make_sim(z, kernel_path=1, sort_interval=0):
