@@ -32,7 +32,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "capi.cu"), "-o", LIB]
+    extra = os.environ.get("MPMGPU_NVCC_DEFS", "").split()        # e.g. "-DF2_MINB=5" for tuning runs
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "capi.cu"), "-o", LIB]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (p.stdout, p.stderr))

@@ -16,6 +16,7 @@
 #include "materials.cuh"
 #include "kernels_task.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_pipe.cuh"
 
 static std::string g_create_error;
 
@@ -143,6 +144,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     g.xmin = cfg->xpts[0]; g.ymin = cfg->ypts[0]; g.zmin = is3D ? cfg->zpts[0] : 0.;
     g.rcrit = cfg->cpdi_rcrit;
     g.lpUniform = 0; g.lpU[0] = g.lpU[1] = g.lpU[2] = 0.;
+    g.inv2d[0] = 2.0 / g.gx; g.inv2d[1] = 2.0 / g.gy; g.inv2d[2] = is3D ? 2.0 / g.gz : 0.;
     double *dx = NULL, *dy = NULL, *dz = NULL;
     int rc = MPMGPU_OK;
     do {
@@ -406,7 +408,11 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         bool uni = true;
         for (int c = 0; c < 3 && uni; c++) for (int q = 1; q < n; q++) if (h->lp[(size_t)c * n + q] != h->lp[(size_t)c * n]) { uni = false; break; }
         ctx->g.lpUniform = uni ? 1 : 0;
-        for (int c = 0; c < 3; c++) ctx->g.lpU[c] = h->lp[(size_t)c * n];
+        for (int c = 0; c < 3; c++) {
+            ctx->g.lpU[c] = h->lp[(size_t)c * n];
+            ctx->g.lpInvSize[c] = 1. / (4. * ctx->g.lpU[c]);
+            ctx->g.lpInv2[c] = 1. / (2. * ctx->g.lpU[c]);
+        }
         ctx->tiled.stateKind = SK_ELASTIC;
         for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC) ctx->tiled.stateKind = SK_FULL;
         if (ctx->cfg.kernel_path == 1) ok = false;
@@ -414,6 +420,15 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
             return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, XPIC order<=1 and no rigid particles");
         ctx->tiled.enabled = ok ? 1 : 0;
         ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 25;
+        {
+            // TMA-pipelined F4 (kernels_pipe.cuh): measured on B200 within 2 % of the plain kernel
+            // (profiles/tune_bounds_r1.txt), so it is opt-in: MPMGPU_PIPE=1
+            const char *e = getenv("MPMGPU_PIPE");
+            ctx->tiled.usePipe = e ? atoi(e) : 0;
+            cudaDeviceProp prop;
+            cudaGetDeviceProperties(&prop, ctx->cfg.device);
+            ctx->tiled.numSMs = prop.multiProcessorCount;
+        }
     }
     return MPMGPU_OK;
 }
@@ -829,7 +844,34 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_begin(ctx);
         if (t.slab.on && (rc = halo_add(ctx, 2))) return rc;
         if (reextrap) LAUNCH(k_n3_strains_last, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp);
-        if (n) {
+        if (n && t.usePipe) {
+            PipeFields pf;
+            memset(&pf, 0, sizeof pf);
+            int k = 0;
+            for (int c = 0; c < 3; c++) pf.d[k++] = ctx->P.ncpos[c];
+            for (int c = 0; c < 9; c++) pf.d[k++] = ctx->P.F[c];
+            for (int c = 0; c < 6; c++) pf.d[k++] = ctx->P.sp[c];
+            pf.d[k++] = ctx->P.work; pf.d[k++] = ctx->P.heat; pf.d[k++] = ctx->P.entropy; pf.d[k++] = ctx->P.prevT;
+            for (int c = 0; c < 3; c++) pf.d[k++] = ctx->P.pos[c];
+            if (t.stateKind == SK_FULL) {
+                for (int c = 0; c < 6; c++) pf.d[k++] = ctx->P.eplast[c];
+                pf.d[k++] = ctx->P.pressure; pf.d[k++] = ctx->P.plast; pf.d[k++] = ctx->P.res;
+                for (int c = 0; c < MPM_MAX_HISTORY; c++) pf.d[k++] = ctx->P.hist[c];
+            }
+            pf.nd = k; pf.i[0] = ctx->P.elem; pf.i[1] = ctx->P.mat; pf.ni = 2;
+            const size_t smemBytes = (size_t)FUSED_WARPS * PIPE_STAGES * pipe_stage_bytes(pf.nd, pf.ni) + FUSED_WARPS * PIPE_STAGES * sizeof(unsigned long long);
+            const int nchunks = (n + 31) / 32;
+            int blocksPerSM = (int)(220 * 1024 / smemBytes); if (blocksPerSM > 4) blocksPerSM = 4; if (blocksPerSM < 1) blocksPerSM = 1;
+            int grid = std::min((nchunks + FUSED_WARPS - 1) / FUSED_WARPS, t.numSMs * blocksPerSM);
+            if (t.stateKind == SK_ELASTIC) {
+                CK(cudaFuncSetAttribute(k_f4_pipe<SK_ELASTIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+                k_f4_pipe<SK_ELASTIC><<<grid, FUSED_THREADS, smemBytes, ctx->stream>>>(g, ctx->P, t.FN, ctx->dMats, pf, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
+            } else {
+                CK(cudaFuncSetAttribute(k_f4_pipe<SK_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+                k_f4_pipe<SK_FULL><<<grid, FUSED_THREADS, smemBytes, ctx->stream>>>(g, ctx->P, t.FN, ctx->dMats, pf, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
+            }
+            ctx->launches++;
+        } else if (n) {
             if (t.stateKind == SK_ELASTIC) LAUNCH(k_f4_strain_reset<SK_ELASTIC>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
             else LAUNCH(k_f4_strain_reset<SK_FULL>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
         }

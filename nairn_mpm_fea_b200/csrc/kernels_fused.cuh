@@ -32,6 +32,19 @@
 
 #define FUSED_THREADS 128
 #define FUSED_WARPS (FUSED_THREADS / 32)
+// minimum resident blocks per SM asked of the register allocator (tuned on B200, profiles/tune_bounds_r1.txt)
+#ifndef F1_MINB
+#define F1_MINB 8
+#endif
+#ifndef F2_MINB
+#define F2_MINB 5
+#endif
+#ifndef F3_MINB
+#define F3_MINB 8
+#endif
+#ifndef F4_MINB
+#define F4_MINB 6
+#endif
 
 struct FusedNodes {
     double4 *V;          // [nnodes] {vx,vy,vz,0}: vk[0]
@@ -51,6 +64,7 @@ struct SlabInfo {
 struct TiledState {
     int enabled;         // fast path usable for this context
     int stateKind;       // SK_ELASTIC / SK_FULL: which particle fields the materials in use touch
+    int usePipe, numSMs; // TMA-pipelined persistent kernels (kernels_pipe.cuh)
     int sortInterval;
     long long stepsSinceSort;
     FusedNodes FN;
@@ -82,11 +96,33 @@ __device__ __forceinline__ double4 ldg4(const double4 *p)
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// Ask for the 9 rows (3 consecutive 32-byte records each) of a particle's 27-node stencil to be brought
+// into L1 now; issued as soon as the centre node is known, long before the gather loop needs them, and
+// costs no registers (the gather's own loads otherwise serialise into several L2 round trips).
+__device__ __forceinline__ void prefetch_stencil(const Grid &g, int center, const double4 *R)
+{
+#pragma unroll
+    for (int k = -1; k <= 1; k++)
+#pragma unroll
+        for (int j = -1; j <= 1; j++) {
+            const double4 *row = R + (center + j * g.yplane + k * g.zplane - 1);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 2));
+        }
+}
+
+// centre node of the dual cell from the element and the sign of the natural coordinates
+__device__ __forceinline__ int dual_cell_center(const Grid &g, int inElem, const double xi[3])
+{
+    const ElemIJK c = elem_ijk(g, inElem);
+    return elem_node0(g, c) + (xi[0] < 0. ? 0 : 1) + (xi[1] < 0. ? 0 : 1) * g.yplane + (xi[2] < 0. ? 0 : 1) * g.zplane;
+}
+
 // ---- 3-node uGIMP weights around the dual-cell centre -------------------------------------------
 // base = -1 (xi<0: nodes at -3,-1,1) or 0 (xi>=0: nodes at -1,1,3); returns S[3], dS[3] (signed, not
 // yet scaled by 2/dx) and a 3-bit validity mask (xp < 2+lp).
 template <bool GRAD>
-__device__ __forceinline__ int gimp3(double xi, double lp, double inv_size, double lpd, double S[3], double dS[3], unsigned &ok)
+__device__ __forceinline__ int gimp3(double xi, double lp, double inv_size, double inv2lp, double S[3], double dS[3], unsigned &ok)
 {
     const int base = xi < 0. ? -1 : 0;
     const double q1 = 2. - lp, q2 = 2. + lp;
@@ -100,7 +136,7 @@ __device__ __forceinline__ int gimp3(double xi, double lp, double inv_size, doub
             ok |= 1u << t;
             if (xp < lp) {
                 s = ((4. - lp) * lp - xp * xp) * inv_size;
-                if (GRAD) d = -xp / (2. * lpd);
+                if (GRAD) d = -xp * inv2lp;
             } else if (xp <= q1) {
                 s = 0.5 * (2. - xp);
                 if (GRAD) d = -0.5;
@@ -130,15 +166,19 @@ __device__ __forceinline__ void particle_weights(const Grid &g, int inElem, cons
     const ElemIJK c = elem_ijk(g, inElem);
     unsigned okx, oky, okz;
     // inv_size and the branch-1 derivative divisor follow EightNodeIsoparamBrick.cpp:296-303,:365-387
-    const int bx = gimp3<GRAD>(xi[0], lp[0], 1. / (4. * lp[0]), lp[0], w.S[0], w.dS[0], okx);
-    const int by = gimp3<GRAD>(xi[1], lp[1], 1. / (4. * lp[1]), lp[1], w.S[1], w.dS[1], oky);
-    const int bz = gimp3<GRAD>(xi[2], lp[2], 1. / (4. * lp[1]), lp[2], w.S[2], w.dS[2], okz);
+    // (z uses 1/(4 lp.y)); with a uniform particle size the reciprocals are per-run constants
+    double isx, isy, i2x, i2y, i2z;
+    if (g.lpUniform) { isx = g.lpInvSize[0]; isy = g.lpInvSize[1]; i2x = g.lpInv2[0]; i2y = g.lpInv2[1]; i2z = g.lpInv2[2]; }
+    else { isx = 1. / (4. * lp[0]); isy = 1. / (4. * lp[1]); i2x = 1. / (2. * lp[0]); i2y = 1. / (2. * lp[1]); i2z = 1. / (2. * lp[2]); }
+    const int bx = gimp3<GRAD>(xi[0], lp[0], isx, i2x, w.S[0], w.dS[0], okx);
+    const int by = gimp3<GRAD>(xi[1], lp[1], isy, i2y, w.S[1], w.dS[1], oky);
+    const int bz = gimp3<GRAD>(xi[2], lp[2], isy, i2z, w.S[2], w.dS[2], okz);
     w.ok = okx | (oky << 3) | (okz << 6);
     w.center = elem_node0(g, c) + (bx + 1) + (by + 1) * g.yplane + (bz + 1) * g.zplane;
     if (GRAD) {
-        const double ix = 2.0 / (g.xpts[c.i + 1] - g.xpts[c.i]);
-        const double iy = 2.0 / (g.ypts[c.j + 1] - g.ypts[c.j]);
-        const double iz = 2.0 / (g.zpts[c.k + 1] - g.zpts[c.k]);
+        // 2/delta of the element: equal element sizes on this path (the reference divides by the element's own
+        // extent, which differs from the grid constant by at most an ulp)
+        const double ix = g.inv2d[0], iy = g.inv2d[1], iz = g.inv2d[2];
 #pragma unroll
         for (int t = 0; t < 3; t++) { w.dS[0][t] *= ix; w.dS[1][t] *= iy; w.dS[2][t] *= iz; }
     }
@@ -292,7 +332,7 @@ __device__ __forceinline__ void prefetch_state(const Particles &P, int p)
 }
 
 // ---- F1: ncpos + P2G mass and momentum ------------------------------------------------------------
-__global__ void __launch_bounds__(FUSED_THREADS) k_f1_mass_momentum(Grid g, Particles P, Nodes N)
+__global__ void __launch_bounds__(FUSED_THREADS, F1_MINB) k_f1_mass_momentum(Grid g, Particles P, Nodes N)
 {
     __shared__ WarpStage<false, 4> stage[FUSED_WARPS];
     WarpStage<false, 4> &st = stage[threadIdx.x >> 5];
@@ -365,7 +405,7 @@ __device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, c
 
 // ---- F2: grad v + constitutive law + P2G forces ------------------------------------------------------
 template <int SK, bool FEXT>
-__global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
+__global__ void __launch_bounds__(FUSED_THREADS, F2_MINB) k_f2_strain_forces(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
                                                                     double strainTime, int doStrain)
 {
     __shared__ WarpStage<true, FEXT ? 10 : 6> stage[FUSED_WARPS];
@@ -380,6 +420,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Part
         double xi[3], lp[3];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
+        if (doStrain) prefetch_stencil(g, dual_cell_center(g, e, xi), FN.V);
         double sp[6], pr = 0.;
         {
             Weights3 w;
@@ -439,7 +480,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f2_strain_forces(Grid g, Part
 }
 
 // ---- F3: particle update + P2G momentum with the new velocity ------------------------------------------
-__global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
+__global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
                                                                       StepParams sp, int m, int doScatter)
 {
     __shared__ WarpStage<false, 4> stage[FUSED_WARPS];
@@ -453,6 +494,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Pa
         double xi[3], lp[3];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
+        {
+            const int ctr = dual_cell_center(g, e, xi);
+            prefetch_stencil(g, ctr, FN.V);
+            if (m <= 0) prefetch_stencil(g, ctr, FN.A);
+        }
         Weights3 w;
         particle_weights<false>(g, e, xi, lp, w);
         key = w.center;
@@ -539,7 +585,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f3_update_momentum(Grid g, Pa
 
 // ---- F4: second strain update + element reset --------------------------------------------------------
 template <int SK>
-__global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Particles P, FusedNodes FN, const Material *mats,
+__global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid g, Particles P, FusedNodes FN, const Material *mats,
                                                                    double strainTime, int doStrain, StatusFlags *flags, double dt, SlabInfo slab)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -549,6 +595,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f4_strain_reset(Grid g, Parti
         double xi[3], lp[3];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
+        prefetch_stencil(g, dual_cell_center(g, P.elem[p], xi), FN.V);
         double dv[9];
         {
             Weights3 w;

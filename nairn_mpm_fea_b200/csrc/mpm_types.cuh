@@ -32,6 +32,9 @@ struct Grid {
     double rcrit;            // CPDI critical radius or <0
     int lpUniform;           // every particle has the same dimensionless size lpU (skips the lp loads)
     double lpU[3];
+    double lpInvSize[3];     // 1/(4 lpU)
+    double lpInv2[3];        // 1/(2 lpU)
+    double inv2d[3];         // 2/grid cell size per axis
 };
 
 // one velocity field per node, component-major

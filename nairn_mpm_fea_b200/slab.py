@@ -219,11 +219,13 @@ class LockstepCluster:
         self.world = world
 
     def _swap_halo(self, which):
+        torch.cuda.synchronize()                      # each slab packs on its own stream; the copies below run on torch's
         for r in range(self.world - 1):
             a, b = self.sims[r], self.sims[r + 1]
             nd = HALO_VALUES[which] * 3 * a.plane_nodes
             b.halo[2][:nd].copy_(a.halo[1][:nd])      # a.send_hi -> b.recv_lo
             a.halo[3][:nd].copy_(b.halo[0][:nd])      # b.send_lo -> a.recv_hi
+        torch.cuda.synchronize()
 
     def step(self, nsteps=1):
         for _ in range(nsteps):
@@ -237,6 +239,7 @@ class LockstepCluster:
             for s, (n_lo, n_hi) in zip(self.sims, counts):
                 if n_lo or n_hi:
                     s.sim.slab_pack_migrants()
+            torch.cuda.synchronize()
             for r, s in enumerate(self.sims):
                 f_lo = counts[r - 1][1] if r > 0 else 0
                 f_hi = counts[r + 1][0] if r < self.world - 1 else 0
