@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F2_MINB) k_f2_strain_forces(Gri
                 for (int i = 0; i < 9; i++) dv[i] *= strainTime;
                 PState s;
                 load_state<SK>(P, p, s);
-                constitutive_law<3>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+                constitutive_law<3, SK == SK_ELASTIC>(s, dv, strainTime, g.np, mats[P.mat[p]]);
                 store_state<SK>(P, p, s);
 #pragma unroll
                 for (int i = 0; i < 6; i++) sp[i] = s.sp[i];
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid
         for (int i = 0; i < 9; i++) dv[i] *= strainTime;
         PState s;
         load_state<SK>(P, p, s);
-        constitutive_law<3>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+        constitutive_law<3, SK == SK_ELASTIC>(s, dv, strainTime, g.np, mats[P.mat[p]]);
         store_state<SK>(P, p, s);
     }
     reset_element_one<3>(g, P, p, flags, dt);

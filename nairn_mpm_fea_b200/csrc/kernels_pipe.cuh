@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f4_pipe(Grid g, Particles P, 
                 for (int i = 0; i < 9; i++) dv[i] *= strainTime;
                 PState ps;
                 stage_to_state<SK>(st, lane, fullBase, ps);
-                constitutive_law<3>(ps, dv, strainTime, g.np, mats[sti[32 + lane]]);
+                constitutive_law<3, SK == SK_ELASTIC>(ps, dv, strainTime, g.np, mats[sti[32 + lane]]);
                 store_state<SK>(P, p, ps);
             }
         }

@@ -150,13 +150,254 @@ __device__ __forceinline__ void isotropic_law(PState &s, const double du[9], int
     }
 }
 
-// Dispatch on the particle's material kind (MaterialBase::MPMConstitutiveLaw virtual call)
+// ---- Neohookean (MaterialID 28) ---------------------------------------------------------------
+// Neohookean::MPMConstitutiveLaw (Materials/Neohookean.cpp:177-331) over HyperElastic::IncrementDeformation
+// (Materials/HyperElastic.cpp:104-139) and GetVolumetricTerms (:171-204).  Elastic left Cauchy-Green tensor B
+// lives in eplast, pressure separately, deviatoric Kirchhoff stress/rho0 in sp, history = {J, Jres}.
+// dF = exp(du) to incrementalDefGradTerms terms: 1 in 3D, 2 in 2D (System/StartOutput.cpp:116-120;
+// Matrix3::Exponential, Common/System/Matrix3.cpp:312-353).  Residual stretch increment is 1 (no thermal load);
+// artificial viscosity is off (rejected at set-up when on).
 template <int DIM>
+__device__ __forceinline__ void neohookean_law(PState &s, const double du[9], int np, const Material &m)
+{
+    const double Gsp = m.p[8], Ksp = m.p[9], Lamesp = m.p[10];
+    const int UofJ = (int)m.p[11];
+    const double gamma0 = m.p[13], Cv = m.p[1];
+    double dF[9], detDf;
+    double *B = s.eplast;       // xx,yy,zz,yz,xz,xy
+    if (DIM == 3) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) dF[i] = du[i];
+        dF[0] += 1.; dF[4] += 1.; dF[8] += 1.;
+        double Fn[9];
+        mat3_mul(dF, s.F, Fn);
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.F[i] = Fn[i];
+        const double Bm[9] = {B[XX], B[XY], B[XZ], B[XY], B[YY], B[YZ], B[XZ], B[YZ], B[ZZ]};
+        double dB[9];
+        mat3_mul(dF, Bm, dB);
+        const double bxx = dB[0] * dF[0] + dB[1] * dF[1] + dB[2] * dF[2];
+        const double bxy = dB[0] * dF[3] + dB[1] * dF[4] + dB[2] * dF[5];
+        const double byy = dB[3] * dF[3] + dB[4] * dF[4] + dB[5] * dF[5];
+        const double bzz = dB[6] * dF[6] + dB[7] * dF[7] + dB[8] * dF[8];
+        const double bxz = dB[0] * dF[6] + dB[1] * dF[7] + dB[2] * dF[8];
+        const double byz = dB[3] * dF[6] + dB[4] * dF[7] + dB[5] * dF[8];
+        B[XX] = bxx; B[XY] = bxy; B[YY] = byy; B[ZZ] = bzz; B[XZ] = bxz; B[YZ] = byz;
+        detDf = dF[0] * (dF[4] * dF[8] - dF[7] * dF[5]) - dF[3] * (dF[1] * dF[8] - dF[7] * dF[2]) + dF[6] * (dF[1] * dF[5] - dF[4] * dF[2]);
+    } else {
+        // two-term 2D exponential: alpha0 I + alpha1 m, zz separately
+        const double c0 = du[1] * du[3] - du[0] * du[4], c1 = du[0] + du[4];
+        const double beta1 = 0.5 * (c1 * 1. + 0.), beta0 = 0.5 * c0 * 1.;
+        const double betaz = du[8] * (0.5 * du[8]);
+        const double alpha0 = 1. + beta0, alpha1 = 1. + beta1, ezz = 1. + du[8] + betaz;
+        const double d00 = alpha0 + alpha1 * du[0], d01 = alpha1 * du[1], d10 = alpha1 * du[3], d11 = alpha0 + alpha1 * du[4];
+        const double f00 = d00 * s.F[0] + d01 * s.F[3], f01 = d00 * s.F[1] + d01 * s.F[4];
+        const double f10 = d10 * s.F[0] + d11 * s.F[3], f11 = d10 * s.F[1] + d11 * s.F[4];
+        s.F[0] = f00; s.F[1] = f01; s.F[3] = f10; s.F[4] = f11; s.F[8] = ezz * s.F[8];
+        const double e00 = d00 * B[XX] + d01 * B[XY], e01 = d00 * B[XY] + d01 * B[YY];
+        const double e10 = d10 * B[XX] + d11 * B[XY], e11 = d10 * B[XY] + d11 * B[YY];
+        const double e22 = ezz * B[ZZ];
+        B[XX] = e00 * d00 + e01 * d01;
+        B[XY] = e00 * d10 + e01 * d11;
+        B[YY] = e10 * d10 + e11 * d11;
+        B[ZZ] = e22 * ezz;
+        detDf = ezz * (d00 * d11 - d10 * d01);
+    }
+    double Jres = s.hist[1];
+    const double dJres = 1.;
+    Jres *= dJres;
+    s.hist[1] = Jres;
+    const double resStretch = pow(Jres, 1. / 3.);
+    const double Jres23 = resStretch * resStretch;
+    if (DIM == 2 && np == NP_PLANE_STRESS) {
+        const double arg = B[XX] * B[YY] - B[XY] * B[XY];
+        double xn;
+        if (UofJ == 1) {
+            const double a = Lamesp * arg + Gsp * pow(Jres, 4. / 3.);
+            const double b = Lamesp * sqrt(arg);
+            xn = Jres * (b + sqrt(b * b + 4. * Gsp * a)) / (2. * a);
+            xn *= xn;
+        } else if (UofJ == 2) {
+            xn = B[ZZ];
+            const double J23 = pow(Jres, 2. / 3.);
+            for (int iter = 1; iter < 20; iter++) {
+                const double fx = Gsp * (xn - J23) + 0.5 * Lamesp * J23 * log(xn * arg / (Jres * Jres));
+                const double fxp = Gsp + Lamesp * J23 / (2 * xn);
+                const double xnp1 = xn - fx / fxp;
+                if (fabs(xn - xnp1) < 1e-10) break;
+                xn = xnp1;
+            }
+        } else {
+            xn = Jres * Jres * (Lamesp + 2. * Gsp) / (Lamesp * arg + 2. * Gsp * pow(Jres, 4. / 3.));
+        }
+        const double dFzz = sqrt(xn / B[ZZ]);
+        B[ZZ] = xn;
+        s.F[8] = dFzz * s.F[8];          // ep.zz = dFzz*(1+ep.zz) - 1
+        detDf *= dFzz;
+    }
+    const double J = detDf * s.hist[0];
+    s.hist[0] = J;
+    double st0[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) st0[i] = s.sp[i];
+    const double Jeff = J / Jres;
+    const double p0 = s.pressure;
+    double Kterm;
+    if (UofJ == 1) Kterm = Lamesp * (Jeff - 1.);
+    else if (UofJ == 2) Kterm = Lamesp * log(Jeff) / Jeff;
+    else Kterm = 0.5 * Lamesp * (Jeff - 1. / Jeff);
+    const double Pterm = J * Kterm + Jres * Gsp * ((B[XX] + B[YY] + B[ZZ]) / (3. * Jres23) - 1.);
+    const double delV = 1. - 1. / detDf;
+    const double Pfinal = -Pterm;
+    s.pressure = Pfinal;
+    const double avgP = 0.5 * (p0 + Pfinal);
+    const double dilEnergy = -avgP * delV;
+    const double delVres = 1. - 1. / dJres;
+    const double resEnergy = -avgP * delVres;
+    const double GJeff = resStretch * Gsp;
+    const double I1third = (B[XX] + B[YY] + B[ZZ]) / 3.;
+    s.sp[XX] = GJeff * (B[XX] - I1third);
+    s.sp[YY] = GJeff * (B[YY] - I1third);
+    s.sp[ZZ] = GJeff * (B[ZZ] - I1third);
+    s.sp[XY] = GJeff * B[XY];
+    if (DIM == 3) { s.sp[XZ] = GJeff * B[XZ]; s.sp[YZ] = GJeff * B[YZ]; }
+    double shearEnergy = 0.5 * ((s.sp[XX] + st0[XX]) * du[0] + (s.sp[YY] + st0[YY]) * du[4] + (s.sp[ZZ] + st0[ZZ]) * du[8] +
+                                (s.sp[XY] + st0[XY]) * (du[1] + du[3]));
+    if (DIM == 3) shearEnergy += 0.5 * ((s.sp[XZ] + st0[XZ]) * (du[2] + du[6]) + (s.sp[YZ] + st0[YZ]) * (du[5] + du[7]));
+    s.work += dilEnergy + shearEnergy;
+    s.res += resEnergy;
+    const double Jres2third = pow(Jres, 2. / 3.);
+    const double Gterm = Gsp * (3. - I1third / Jres2third) / (3. * Jeff);
+    double Kratio;
+    if (UofJ == 1) Kratio = Lamesp * Jeff + Gterm;
+    else if (UofJ == 2) Kratio = Lamesp * (1 - log(Jeff)) / Jeff + Gterm;
+    else Kratio = 0.5 * Lamesp * (Jeff + 1. / Jeff) + Gterm;
+    Kratio /= Ksp;
+    const double dTq0 = -J * Kratio * gamma0 * s.prevT * delV;
+    increment_heat_energy(s, Cv, dTq0, 0.);
+}
+
+// ---- IsoPlasticity + LinearHardening (MaterialID 9) ------------------------------------------------
+// IsoPlasticity::MPMConstitutiveLaw / PlasticityConstLaw / UpdatePressure (Materials/IsoPlasticity.cpp:128-492),
+// small-rotation branch, J2 potential (:513-517), closed-form radial return of LinearHardening
+// (Materials/LinearHardening.cpp:93-145), history = cumulative plastic strain alpha.  3D and plane strain
+// (plane-stress plasticity needs the numerical return map and is rejected at set-up).
+// Reference quirks kept: 3D plastic-step work energy adds sp.zz*de.zz twice (:428-431); the 2D rotation of the
+// prior shear stress uses the plastic strain (:252).
+#define MPM_SQRT_TWOTHIRDS 0.8164965809277260
+template <int DIM>
+__device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9], int np, const Material &m)
+{
+    const double Gred = m.p[8], Kred = m.p[9], yldred = m.p[10], Epred = m.p[11];
+    const double gamma0 = m.p[13], Cv = m.p[1], alphaMax = m.p[14], yldredMin = m.p[15];
+    hypo_increment_deformation<DIM>(s, de);
+    const double delV = de[0] + de[4] + de[8];          // du.trace() - 3 eres, eres = 0
+    const double dgxy = de[1] + de[3];
+    double dgxz = 0., dgyz = 0.;
+    if (DIM == 3) { dgxz = de[2] + de[6]; dgyz = de[5] + de[7]; }
+    const double dexxr = de[0], deyyr = de[4], dezzr = de[8];
+    // UpdatePressure (:462-492)
+    const double dP = -Kred * delV;
+    const double dVoverV = delV;
+    s.pressure += dP;
+    const double Pfinal = s.pressure;
+    s.work += -Pfinal * dVoverV;
+    double dTq0 = -gamma0 * s.prevT * dVoverV;
+    double dispEnergy = 0.;
+    // rotate plastic strain and prior stress (:218-268)
+    double *ep = s.eplast, *sp = s.sp;
+    double e0[6], st0[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { e0[i] = ep[i]; st0[i] = sp[i]; }
+    const double dwrotxy = de[3] - de[1];
+    if (DIM == 2) {
+        const double dnorm = 0.5 * dwrotxy * e0[XY];
+        ep[XX] -= dnorm; ep[YY] += dnorm; ep[XY] += dwrotxy * (e0[XX] - e0[YY]);
+        const double dn = dwrotxy * sp[XY];
+        st0[XX] -= dn; st0[YY] += dn; st0[XY] += 0.5 * dwrotxy * (e0[XX] - e0[YY]);
+    } else {
+        const double dwrotxz = de[6] - de[2], dwrotyz = de[7] - de[5];
+        const double dxy = 0.5 * dwrotxy * e0[XY], dxz = 0.5 * dwrotxz * e0[XZ], dyz = 0.5 * dwrotyz * e0[YZ];
+        ep[XX] += -dxy - dxz; ep[YY] += dxy - dyz; ep[ZZ] += dxz + dyz;
+        ep[YZ] += dwrotyz * (e0[YY] - e0[ZZ]) + 0.5 * (dwrotxz * e0[XY] + dwrotxy * e0[XZ]);
+        ep[XZ] += dwrotxz * (e0[XX] - e0[ZZ]) + 0.5 * (dwrotyz * e0[XY] - dwrotxy * e0[YZ]);
+        ep[XY] += dwrotxy * (e0[XX] - e0[YY]) - 0.5 * (dwrotyz * e0[XZ] + dwrotxz * e0[YZ]);
+        const double sxy = dwrotxy * sp[XY], sxz = dwrotxz * sp[XZ], syz = dwrotyz * sp[YZ];
+        st0[XX] += -sxy - sxz; st0[YY] += sxy - syz; st0[ZZ] += sxz + syz;
+        st0[YZ] += 0.5 * (dwrotyz * (sp[YY] - sp[ZZ]) + dwrotxz * sp[XY] + dwrotxy * sp[XZ]);
+        st0[XZ] += 0.5 * (dwrotxz * (sp[XX] - sp[ZZ]) + dwrotyz * sp[XY] - dwrotxy * sp[YZ]);
+        st0[XY] += 0.5 * (dwrotxy * (sp[XX] - sp[YY]) - dwrotyz * sp[XZ] - dwrotxz * sp[YZ]);
+    }
+    // trial deviatoric stress (:271-295)
+    const double thirdDelV = delV / 3.;
+    double strial[6];
+    strial[XX] = st0[XX] + 2. * Gred * (dexxr - thirdDelV);
+    strial[YY] = st0[YY] + 2. * Gred * (deyyr - thirdDelV);
+    strial[ZZ] = st0[ZZ] + 2. * Gred * (dezzr - thirdDelV);
+    strial[XY] = st0[XY] + Gred * dgxy;
+    strial[YZ] = DIM == 3 ? st0[YZ] + Gred * dgyz : st0[YZ];
+    strial[XZ] = DIM == 3 ? st0[XZ] + Gred * dgxz : st0[XZ];
+    // plastic potential (:513-517, MoreIsotropicMat.cpp:354-372)
+    const double alpha0 = s.hist[0];
+    double ss = strial[XX] * strial[XX] + strial[YY] * strial[YY] + strial[ZZ] * strial[ZZ];
+    double tt = strial[XY] * strial[XY];
+    if (DIM == 3) tt += strial[XZ] * strial[XZ] + strial[YZ] * strial[YZ];
+    const double smag = sqrt(ss + tt + tt);
+    const double yield0 = alpha0 < alphaMax ? yldred + Epred * alpha0 : yldredMin;
+    const double ftrial = smag - MPM_SQRT_TWOTHIRDS * yield0;
+    if (ftrial < 0.) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) sp[i] = strial[i];
+        if (DIM == 3) s.work += sp[XX] * de[0] + sp[YY] * de[4] + sp[ZZ] * de[8] + sp[YZ] * dgyz + sp[XZ] * dgxz + sp[XY] * dgxy;
+        else s.work += sp[XX] * de[0] + sp[YY] * de[4] + sp[XY] * dgxy;
+        increment_heat_energy(s, Cv, dTq0, dispEnergy);
+        return;
+    }
+    // radial return, closed form (LinearHardening.cpp:124-145)
+    double lambdak = (smag - MPM_SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
+    if (alpha0 + MPM_SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - MPM_SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
+    const double alpint = alpha0 + MPM_SQRT_TWOTHIRDS * lambdak;
+    // df/dsigma = s/|s| (:496-509), plastic strain increment (:395-405)
+    double dep[6];
+    dep[XX] = lambdak * (strial[XX] / smag); dep[YY] = lambdak * (strial[YY] / smag); dep[ZZ] = lambdak * (strial[ZZ] / smag);
+    dep[XY] = 2. * lambdak * (strial[XY] / smag);
+    dep[XZ] = DIM == 3 ? 2. * lambdak * (strial[XZ] / smag) : 0.;
+    dep[YZ] = DIM == 3 ? 2. * lambdak * (strial[YZ] / smag) : 0.;
+    ep[XX] += dep[XX]; ep[YY] += dep[YY]; ep[ZZ] += dep[ZZ]; ep[XY] += dep[XY];
+    if (DIM == 3) { ep[XZ] += dep[XZ]; ep[YZ] += dep[YZ]; }
+    sp[XX] = strial[XX] - 2. * Gred * dep[XX];
+    sp[YY] = strial[YY] - 2. * Gred * dep[YY];
+    sp[ZZ] = strial[ZZ] - 2. * Gred * dep[ZZ];
+    sp[XY] = strial[XY] - Gred * dep[XY];
+    if (DIM == 3) { sp[YZ] = strial[YZ] - Gred * dep[YZ]; sp[XZ] = strial[XZ] - Gred * dep[XZ]; }
+    double workEnergy = sp[XX] * de[0] + sp[YY] * de[4] + sp[XY] * dgxy;
+    if (DIM == 3) workEnergy += sp[ZZ] * de[8] + sp[YZ] * dgyz + sp[XZ] * dgxz;
+    if (np != NP_PLANE_STRAIN) workEnergy += sp[ZZ] * de[8];
+    s.work += workEnergy;
+    double plastEnergy = sp[XX] * dep[XX] + sp[YY] * dep[YY] + sp[ZZ] * dep[ZZ] + sp[XY] * dep[XY];
+    if (DIM == 3) plastEnergy += sp[XZ] * dep[XZ] + sp[YZ] * dep[YZ];
+    const double yieldInc = fmax(Epred * alpint, yldredMin - yldred);      // LinearHardening::GetYieldIncrement
+    dispEnergy += plastEnergy - lambdak * MPM_SQRT_TWOTHIRDS * yieldInc;
+    s.plast += dispEnergy;
+    increment_heat_energy(s, Cv, dTq0, dispEnergy);
+    s.hist[0] = alpint;
+}
+
+// Dispatch on the particle's material kind (MaterialBase::MPMConstitutiveLaw virtual call)
+// ELASTIC_ONLY: the caller knows every material in use is IsotropicMat (keeps the other laws out of the kernel)
+template <int DIM, bool ELASTIC_ONLY = false>
 __device__ __forceinline__ void constitutive_law(PState &s, const double du[9], double delTime, int np, const Material &m)
 {
+    if (ELASTIC_ONLY) { isotropic_law<DIM>(s, du, np, m); return; }
     switch (m.kind) {
     case MAT_ISOTROPIC:
         isotropic_law<DIM>(s, du, np, m);
+        break;
+    case MAT_NEOHOOKEAN:
+        neohookean_law<DIM>(s, du, np, m);
+        break;
+    case MAT_ISOPLASTICITY:
+        isoplasticity_law<DIM>(s, du, np, m);
         break;
     default:
         break;

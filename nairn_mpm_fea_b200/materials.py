@@ -115,3 +115,43 @@ def rigid_bc(direction_bits):
     p = _base(1.0, DEFAULT_CV, None)
     p[8] = float(direction_bits)
     return dict(kind=RIGIDBC, n_history=0, p=p, rho=1.0, wave_speed=0.0)
+
+
+def neohookean(G, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None):
+    """Neohookean (MaterialID 28): Neohookean::VerifyAndLoadProperties (Materials/Neohookean.cpp:88-141).
+    History: J, Jres (both 1).  Particles start with elastic B = I in eplast (HyperElastic.cpp:51-60)."""
+    Lame = K - 2.0 * G / 3.0
+    p = _base(rho, Cv, pdamping)
+    Gsp = G / rho
+    Lamesp = Lame / rho
+    Ksp = Lamesp + 2.0 * Gsp / 3.0
+    gamma0 = K * (3.0e-6 * aI) / (rho * Cv)
+    p[8], p[9], p[10], p[11], p[12], p[13] = Gsp, Ksp, Lamesp, float(UofJOption), 1.0e-6 * aI, gamma0
+    return dict(kind=NEOHOOKEAN, n_history=2, p=p, rho=rho, wave_speed=float(np.sqrt((K + 4.0 * G / 3.0) / rho)),
+                init_history=[1.0, 1.0], init_eplast=[1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
+
+
+def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, yld_min=0.0):
+    """IsoPlasticity + LinearHardening (MaterialID 9): IsoPlasticity::VerifyAndLoadProperties
+    (Materials/IsoPlasticity.cpp:50-70), LinearHardening::VerifyAndLoadProperties (LinearHardening.cpp:55-80)."""
+    iso = isotropic(E, nu, rho, aI, Cv, np_, pdamping)
+    p = _base(rho, Cv, pdamping)
+    if np_ == THREED_MPM:
+        C66, C33 = iso["p"][16] * rho, iso["p"][13] * rho
+    else:
+        C66, C33 = iso["p"][16] * rho, iso["p"][23] * rho
+    G0red = C66 / rho
+    Kred = C33 / rho - 4.0 * G0red / 3.0
+    yldred = yld / rho
+    if Ep is not None and Ep >= 0.0:
+        beta = Ep / yld
+    else:
+        beta = Khard
+    Epred = yldred * beta
+    yldredMin = yld_min / rho
+    alphaMax = 1.0e50 if beta >= 0.0 else ((yldredMin / yldred) - 1.0) / beta
+    p[8], p[9], p[10], p[11] = G0red, Kred, yldred, Epred
+    p[12] = iso["p"][19]
+    p[13] = iso["p"][20]
+    p[14], p[15] = alphaMax, yldredMin
+    return dict(kind=ISOPLASTICITY, n_history=1, p=p, rho=rho, wave_speed=iso["wave_speed"])

@@ -313,6 +313,225 @@ static void isotropic_law(int p, const double du[3][3], const mpmgpu_material *m
     P3(energies, 3, p) += baseHeat / prevT;
 }
 
+/* ---- Neohookean: Materials/Neohookean.cpp:177-331, HyperElastic.cpp:104-139,171-204 ------------------------------ */
+static void get_F(int p, double F[3][3])
+{
+    memset(F, 0, 9 * sizeof(double));
+    F[0][0] = 1. + P3(ep, XX, p); F[1][1] = 1. + P3(ep, YY, p); F[2][2] = 1. + P3(ep, ZZ, p);
+    F[0][1] = 0.5 * (P3(ep, XY, p) - P3(wrot, 0, p)); F[1][0] = 0.5 * (P3(ep, XY, p) + P3(wrot, 0, p));
+    if (O->dim == 3) {
+        F[0][2] = 0.5 * (P3(ep, XZ, p) - P3(wrot, 1, p)); F[2][0] = 0.5 * (P3(ep, XZ, p) + P3(wrot, 1, p));
+        F[1][2] = 0.5 * (P3(ep, YZ, p) - P3(wrot, 2, p)); F[2][1] = 0.5 * (P3(ep, YZ, p) + P3(wrot, 2, p));
+    }
+}
+
+static void set_F(int p, double F[3][3])
+{
+    P3(ep, XX, p) = F[0][0] - 1.; P3(ep, YY, p) = F[1][1] - 1.; P3(ep, ZZ, p) = F[2][2] - 1.;
+    P3(ep, XY, p) = F[1][0] + F[0][1]; P3(wrot, 0, p) = F[1][0] - F[0][1];
+    if (O->dim == 3) {
+        P3(ep, XZ, p) = F[2][0] + F[0][2]; P3(ep, YZ, p) = F[2][1] + F[1][2];
+        P3(wrot, 1, p) = F[2][0] - F[0][2]; P3(wrot, 2, p) = F[2][1] - F[1][2];
+    }
+}
+
+static void mat_mul(double a[3][3], double b[3][3], double c[3][3])
+{
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j];
+}
+
+static void neohookean_law(int p, const double du[3][3], const mpmgpu_material *m)
+{
+    const double Gsp = m->p[8], Ksp = m->p[9], Lamesp = m->p[10], gamma0 = m->p[13], Cv = m->p[1];
+    const int UofJ = (int)m->p[11];
+    double dF[3][3], F[3][3], Fn[3][3], detDf;
+    memset(dF, 0, sizeof dF);
+    if (O->dim == 3) {          /* Exponential(1) */
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dF[i][j] = du[i][j] + (i == j ? 1. : 0.);
+    } else {                    /* 2D Exponential(2), Matrix3.cpp:312-345 */
+        double c0 = du[0][1] * du[1][0] - du[0][0] * du[1][1], c1 = du[0][0] + du[1][1];
+        double beta0 = 0., beta1 = 1., alpha0 = 1., alpha1 = 1., betaz = du[2][2], ezz = 1. + betaz;
+        for (int k = 2; k <= 2; k++) {
+            double factor = 1 / (double)k, temp = beta1;
+            beta1 = factor * (c1 * temp + beta0);
+            beta0 = factor * c0 * temp;
+            betaz *= factor * du[2][2];
+            alpha0 += beta0; alpha1 += beta1; ezz += betaz;
+        }
+        dF[0][0] = alpha0 + alpha1 * du[0][0]; dF[0][1] = alpha1 * du[0][1];
+        dF[1][0] = alpha1 * du[1][0]; dF[1][1] = alpha0 + alpha1 * du[1][1]; dF[2][2] = ezz;
+    }
+    get_F(p, F);
+    mat_mul(dF, F, Fn);
+    set_F(p, Fn);
+    double Bo[3][3] = {{P3(eplast, XX, p), P3(eplast, XY, p), P3(eplast, XZ, p)}, {P3(eplast, XY, p), P3(eplast, YY, p), P3(eplast, YZ, p)},
+                       {P3(eplast, XZ, p), P3(eplast, YZ, p), P3(eplast, ZZ, p)}};
+    if (O->dim == 2) { Bo[0][2] = Bo[2][0] = Bo[1][2] = Bo[2][1] = 0.; }
+    double dB[3][3];
+    mat_mul(dF, Bo, dB);
+    double bxx = dB[0][0] * dF[0][0] + dB[0][1] * dF[0][1] + dB[0][2] * dF[0][2];
+    double bxy = dB[0][0] * dF[1][0] + dB[0][1] * dF[1][1] + dB[0][2] * dF[1][2];
+    double byy = dB[1][0] * dF[1][0] + dB[1][1] * dF[1][1] + dB[1][2] * dF[1][2];
+    double bzz = dB[2][0] * dF[2][0] + dB[2][1] * dF[2][1] + dB[2][2] * dF[2][2];
+    P3(eplast, XX, p) = bxx; P3(eplast, XY, p) = bxy; P3(eplast, YY, p) = byy; P3(eplast, ZZ, p) = bzz;
+    if (O->dim == 3) {
+        P3(eplast, XZ, p) = dB[0][0] * dF[2][0] + dB[0][1] * dF[2][1] + dB[0][2] * dF[2][2];
+        P3(eplast, YZ, p) = dB[1][0] * dF[2][0] + dB[1][1] * dF[2][1] + dB[1][2] * dF[2][2];
+        detDf = dF[0][0] * (dF[1][1] * dF[2][2] - dF[2][1] * dF[1][2]) - dF[1][0] * (dF[0][1] * dF[2][2] - dF[2][1] * dF[0][2]) +
+                dF[2][0] * (dF[0][1] * dF[1][2] - dF[1][1] * dF[0][2]);
+    } else detDf = dF[2][2] * (dF[0][0] * dF[1][1] - dF[1][0] * dF[0][1]);
+    double Jres = P3(hist, 1, p), dJres = 1.;
+    Jres *= dJres;
+    P3(hist, 1, p) = Jres;
+    double resStretch = pow(Jres, 1. / 3.), Jres23 = resStretch * resStretch;
+    if (O->cfg.np == MPMGPU_PLANE_STRESS_MPM) {
+        double arg = P3(eplast, XX, p) * P3(eplast, YY, p) - P3(eplast, XY, p) * P3(eplast, XY, p), xn;
+        if (UofJ == 1) {
+            double a = Lamesp * arg + Gsp * pow(Jres, 4. / 3.), b = Lamesp * sqrt(arg);
+            xn = Jres * (b + sqrt(b * b + 4. * Gsp * a)) / (2. * a);
+            xn *= xn;
+        } else if (UofJ == 2) {
+            xn = P3(eplast, ZZ, p);
+            double J23 = pow(Jres, 2. / 3.);
+            for (int iter = 1; iter < 20; iter++) {
+                double fx = Gsp * (xn - J23) + 0.5 * Lamesp * J23 * log(xn * arg / (Jres * Jres));
+                double fxp = Gsp + Lamesp * J23 / (2 * xn);
+                double xnp1 = xn - fx / fxp;
+                if (fabs(xn - xnp1) < 1e-10) break;
+                xn = xnp1;
+            }
+        } else xn = Jres * Jres * (Lamesp + 2. * Gsp) / (Lamesp * arg + 2. * Gsp * pow(Jres, 4. / 3.));
+        double dFzz = sqrt(xn / P3(eplast, ZZ, p));
+        P3(eplast, ZZ, p) = xn;
+        P3(ep, ZZ, p) = dFzz * (1. + P3(ep, ZZ, p)) - 1.;
+        detDf *= dFzz;
+    }
+    double J = detDf * P3(hist, 0, p);
+    P3(hist, 0, p) = J;
+    double st0[6];
+    for (int c = 0; c < 6; c++) st0[c] = P3(sp, c, p);
+    double Jeff = J / Jres, p0 = O->pressure[p], Kterm;
+    if (UofJ == 1) Kterm = Lamesp * (Jeff - 1.);
+    else if (UofJ == 2) Kterm = Lamesp * log(Jeff) / Jeff;
+    else Kterm = 0.5 * Lamesp * (Jeff - 1. / Jeff);
+    double Bxx = P3(eplast, XX, p), Byy = P3(eplast, YY, p), Bzz = P3(eplast, ZZ, p);
+    double Pterm = J * Kterm + Jres * Gsp * ((Bxx + Byy + Bzz) / (3. * Jres23) - 1.);
+    double delV = 1. - 1. / detDf, Pfinal = -Pterm;
+    O->pressure[p] = Pfinal;
+    double avgP = 0.5 * (p0 + Pfinal), dilEnergy = -avgP * delV, resEnergy = -avgP * (1. - 1. / dJres);
+    double GJeff = resStretch * Gsp, I1third = (Bxx + Byy + Bzz) / 3.;
+    P3(sp, XX, p) = GJeff * (Bxx - I1third); P3(sp, YY, p) = GJeff * (Byy - I1third); P3(sp, ZZ, p) = GJeff * (Bzz - I1third);
+    P3(sp, XY, p) = GJeff * P3(eplast, XY, p);
+    if (O->dim == 3) { P3(sp, XZ, p) = GJeff * P3(eplast, XZ, p); P3(sp, YZ, p) = GJeff * P3(eplast, YZ, p); }
+    double shear = 0.5 * ((P3(sp, XX, p) + st0[XX]) * du[0][0] + (P3(sp, YY, p) + st0[YY]) * du[1][1] + (P3(sp, ZZ, p) + st0[ZZ]) * du[2][2] +
+                          (P3(sp, XY, p) + st0[XY]) * (du[0][1] + du[1][0]));
+    if (O->dim == 3) shear += 0.5 * ((P3(sp, XZ, p) + st0[XZ]) * (du[0][2] + du[2][0]) + (P3(sp, YZ, p) + st0[YZ]) * (du[1][2] + du[2][1]));
+    P3(energies, 0, p) += dilEnergy + shear;
+    P3(energies, 1, p) += resEnergy;
+    double Gterm = Gsp * (3. - I1third / pow(Jres, 2. / 3.)) / (3. * Jeff), Kratio;
+    if (UofJ == 1) Kratio = Lamesp * Jeff + Gterm;
+    else if (UofJ == 2) Kratio = Lamesp * (1 - log(Jeff)) / Jeff + Gterm;
+    else Kratio = 0.5 * Lamesp * (Jeff + 1. / Jeff) + Gterm;
+    Kratio /= Ksp;
+    double prevT = P3(energies, 5, p);
+    double dTq0 = -J * Kratio * gamma0 * prevT * delV, baseHeat = -Cv * dTq0;
+    P3(energies, 2, p) += baseHeat;
+    P3(energies, 3, p) += baseHeat / prevT;
+}
+
+/* ---- IsoPlasticity + LinearHardening: Materials/IsoPlasticity.cpp:128-517, LinearHardening.cpp:93-145 -------------- */
+#define SQRT_TWOTHIRDS 0.8164965809277260
+static void isoplasticity_law(int p, const double de[3][3], const mpmgpu_material *m)
+{
+    const double Gred = m->p[8], Kred = m->p[9], yldred = m->p[10], Epred = m->p[11], gamma0 = m->p[13], Cv = m->p[1];
+    const double alphaMax = m->p[14], yldredMin = m->p[15];
+    const int is2D = O->dim == 2;
+    double dF[3][3], F[3][3], Fn[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dF[i][j] = de[i][j] + (i == j ? 1. : 0.);
+    get_F(p, F);
+    if (is2D) { dF[0][2] = dF[2][0] = dF[1][2] = dF[2][1] = 0.; }
+    mat_mul(dF, F, Fn);
+    set_F(p, Fn);
+    double delV = de[0][0] + de[1][1] + de[2][2];
+    double dgxy = de[0][1] + de[1][0], dgxz = 0., dgyz = 0.;
+    if (!is2D) { dgxz = de[0][2] + de[2][0]; dgyz = de[1][2] + de[2][1]; }
+    /* UpdatePressure */
+    O->pressure[p] += -Kred * delV;
+    double Pfinal = O->pressure[p], prevT = P3(energies, 5, p);
+    P3(energies, 0, p) += -Pfinal * delV;
+    double dTq0 = -gamma0 * prevT * delV, dispEnergy = 0.;
+    double e0[6], s0[6], st0[6];
+    for (int c = 0; c < 6; c++) { e0[c] = P3(eplast, c, p); s0[c] = P3(sp, c, p); st0[c] = s0[c]; }
+    double dwxy = de[1][0] - de[0][1];
+    if (is2D) {
+        double dnorm = 0.5 * dwxy * e0[XY];
+        P3(eplast, XX, p) -= dnorm; P3(eplast, YY, p) += dnorm; P3(eplast, XY, p) += dwxy * (e0[XX] - e0[YY]);
+        double dn = dwxy * s0[XY];
+        st0[XX] -= dn; st0[YY] += dn; st0[XY] += 0.5 * dwxy * (e0[XX] - e0[YY]);        /* :252 uses plastic strain */
+    } else {
+        double dwxz = de[2][0] - de[0][2], dwyz = de[2][1] - de[1][2];
+        double dxy = 0.5 * dwxy * e0[XY], dxz = 0.5 * dwxz * e0[XZ], dyz = 0.5 * dwyz * e0[YZ];
+        P3(eplast, XX, p) += -dxy - dxz; P3(eplast, YY, p) += dxy - dyz; P3(eplast, ZZ, p) += dxz + dyz;
+        P3(eplast, YZ, p) += dwyz * (e0[YY] - e0[ZZ]) + 0.5 * (dwxz * e0[XY] + dwxy * e0[XZ]);
+        P3(eplast, XZ, p) += dwxz * (e0[XX] - e0[ZZ]) + 0.5 * (dwyz * e0[XY] - dwxy * e0[YZ]);
+        P3(eplast, XY, p) += dwxy * (e0[XX] - e0[YY]) - 0.5 * (dwyz * e0[XZ] + dwxz * e0[YZ]);
+        double sxy = dwxy * s0[XY], sxz = dwxz * s0[XZ], syz = dwyz * s0[YZ];
+        st0[XX] += -sxy - sxz; st0[YY] += sxy - syz; st0[ZZ] += sxz + syz;
+        st0[YZ] += 0.5 * (dwyz * (s0[YY] - s0[ZZ]) + dwxz * s0[XY] + dwxy * s0[XZ]);
+        st0[XZ] += 0.5 * (dwxz * (s0[XX] - s0[ZZ]) + dwyz * s0[XY] - dwxy * s0[YZ]);
+        st0[XY] += 0.5 * (dwxy * (s0[XX] - s0[YY]) - dwyz * s0[XZ] - dwxz * s0[YZ]);
+    }
+    double third = delV / 3., strial[6];
+    strial[XX] = st0[XX] + 2. * Gred * (de[0][0] - third);
+    strial[YY] = st0[YY] + 2. * Gred * (de[1][1] - third);
+    strial[ZZ] = st0[ZZ] + 2. * Gred * (de[2][2] - third);
+    strial[XY] = st0[XY] + Gred * dgxy;
+    strial[YZ] = is2D ? st0[YZ] : st0[YZ] + Gred * dgyz;
+    strial[XZ] = is2D ? st0[XZ] : st0[XZ] + Gred * dgxz;
+    double alpha0 = P3(hist, 0, p);
+    double ss = strial[XX] * strial[XX] + strial[YY] * strial[YY] + strial[ZZ] * strial[ZZ], tt = strial[XY] * strial[XY];
+    if (!is2D) tt += strial[XZ] * strial[XZ] + strial[YZ] * strial[YZ];
+    double smag = sqrt(ss + tt + tt);
+    double yield0 = alpha0 < alphaMax ? yldred + Epred * alpha0 : yldredMin;
+    if (smag - SQRT_TWOTHIRDS * yield0 < 0.) {
+        for (int c = 0; c < 6; c++) P3(sp, c, p) = strial[c];
+        if (!is2D) P3(energies, 0, p) += strial[XX] * de[0][0] + strial[YY] * de[1][1] + strial[ZZ] * de[2][2] + strial[YZ] * dgyz + strial[XZ] * dgxz + strial[XY] * dgxy;
+        else P3(energies, 0, p) += strial[XX] * de[0][0] + strial[YY] * de[1][1] + strial[XY] * dgxy;
+        double baseHeat = -Cv * dTq0;
+        P3(energies, 2, p) += baseHeat - dispEnergy;
+        P3(energies, 3, p) += baseHeat / prevT;
+        return;
+    }
+    double lambdak = (smag - SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
+    if (alpha0 + SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
+    double alpint = alpha0 + SQRT_TWOTHIRDS * lambdak;
+    double dep[6];
+    dep[XX] = lambdak * (strial[XX] / smag); dep[YY] = lambdak * (strial[YY] / smag); dep[ZZ] = lambdak * (strial[ZZ] / smag);
+    dep[XY] = 2. * lambdak * (strial[XY] / smag);
+    dep[XZ] = is2D ? 0. : 2. * lambdak * (strial[XZ] / smag);
+    dep[YZ] = is2D ? 0. : 2. * lambdak * (strial[YZ] / smag);
+    P3(eplast, XX, p) += dep[XX]; P3(eplast, YY, p) += dep[YY]; P3(eplast, ZZ, p) += dep[ZZ]; P3(eplast, XY, p) += dep[XY];
+    if (!is2D) { P3(eplast, XZ, p) += dep[XZ]; P3(eplast, YZ, p) += dep[YZ]; }
+    double sn[6];
+    sn[XX] = strial[XX] - 2. * Gred * dep[XX]; sn[YY] = strial[YY] - 2. * Gred * dep[YY]; sn[ZZ] = strial[ZZ] - 2. * Gred * dep[ZZ];
+    sn[XY] = strial[XY] - Gred * dep[XY];
+    sn[YZ] = is2D ? s0[YZ] : strial[YZ] - Gred * dep[YZ];
+    sn[XZ] = is2D ? s0[XZ] : strial[XZ] - Gred * dep[XZ];
+    for (int c = 0; c < 6; c++) P3(sp, c, p) = sn[c];
+    double work = sn[XX] * de[0][0] + sn[YY] * de[1][1] + sn[XY] * dgxy;
+    if (!is2D) work += sn[ZZ] * de[2][2] + sn[YZ] * dgyz + sn[XZ] * dgxz;
+    if (O->cfg.np != MPMGPU_PLANE_STRAIN_MPM) work += sn[ZZ] * de[2][2];          /* :428-431: zz term twice in 3D */
+    P3(energies, 0, p) += work;
+    double plast = sn[XX] * dep[XX] + sn[YY] * dep[YY] + sn[ZZ] * dep[ZZ] + sn[XY] * dep[XY];
+    if (!is2D) plast += sn[XZ] * dep[XZ] + sn[YZ] * dep[YZ];
+    dispEnergy += plast - lambdak * SQRT_TWOTHIRDS * fmax(Epred * alpint, yldredMin - yldred);
+    P3(energies, 4, p) += dispEnergy;
+    double baseHeat = -Cv * dTq0;
+    P3(energies, 2, p) += baseHeat - dispEnergy;
+    P3(energies, 3, p) += baseHeat / prevT;
+    P3(hist, 0, p) = alpint;
+}
+
 /* ---- tasks 4 / 9: FullStrainUpdate UpdateStrainsFirstTask.cpp:101-168, MatPoint3D.cpp:45-93 ------------------ */
 static void full_strain_update(double strainTime)
 {
@@ -337,6 +556,8 @@ static void full_strain_update(double strainTime)
         for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) dv[a][b] *= strainTime;
         const mpmgpu_material *m = &O->mats[O->matnum[p] - 1];
         if (m->kind == MPMGPU_MAT_ISOTROPIC) isotropic_law(p, dv, m);
+        else if (m->kind == MPMGPU_MAT_NEOHOOKEAN) neohookean_law(p, dv, m);
+        else if (m->kind == MPMGPU_MAT_ISOPLASTICITY) isoplasticity_law(p, dv, m);
     }
 }
 

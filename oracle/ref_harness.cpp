@@ -310,6 +310,7 @@ int ref_get_materials(int *ids, double *params)
         q[0] = m->rho; q[1] = m->heatCapacity; q[2] = m->GetField();
         q[3] = m->matUsePDamping ? m->matPdamping : -1.;
         q[4] = m->IsRigid() ? 1. : 0.;
+        q[5] = m->artificialViscosity ? 1. : 0.;
         if (ids[i] == 1) {
             IsotropicMat *im = (IsotropicMat *)m;
             q[8] = im->E; q[9] = im->nu; q[10] = im->G; q[11] = im->CTE3; q[12] = im->gamma0;
@@ -328,7 +329,8 @@ int ref_get_materials(int *ids, double *params)
             HardeningLawBase *h = pm->plasticLaw;
             if (h != NULL) { q[15] = h->yield; q[17] = h->yldred;
                              LinearHardening *lh = dynamic_cast<LinearHardening *>(h);
-                             if (lh != NULL) { q[16] = lh->Ep; q[18] = lh->Epred; } }
+                             q[20] = h->yldredMin;
+                             if (lh != NULL) { q[16] = lh->Ep; q[18] = lh->Epred; q[19] = lh->alphaMax; q[21] = lh->beta; } }
         }
     }
     return nmat;

@@ -24,6 +24,11 @@ CASES = {
     "block3d_jitter": (inputs.block3d(ncell=5, margin=3, E=100.0, vx=3.0e3, vy=-2.0e3, vz=-6.0e3), (1, 20, 60), 1, 0.35, 4000.0),
     "disks2d_ugimp_planestrain": (inputs.disks2d(analysis=10, gimp="uGIMP"), (1, 100), 1),
     "disks2d_linear_planestress": (inputs.disks2d(analysis=11, gimp=None, method=2), (1, 100), 1),
+    "block3d_neohookean": (inputs.block3d(ncell=4, margin=3, material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3), (1, 60), 1, 0.3, 2000.0),
+    "block3d_neohookean_uj1": (inputs.block3d(ncell=3, margin=3, material=inputs.neohookean_material(ujoption=1), vz=-8.0e3), (1, 40), 1),
+    "block3d_isoplastic": (inputs.block3d(ncell=4, margin=3, material=inputs.isoplastic_material(), vz=-4.0e4, vx=5.0e3), (1, 80), 1, 0.3, 3000.0),
+    "disks2d_neohookean": (inputs.disks2d(analysis=10).replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>', '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha></Material>'), (1, 100), 1),
+    "disks2d_isoplastic": (inputs.disks2d(analysis=10, vel=6000.0).replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>', '<Material Type="9" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep></Material>'), (1, 100), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

@@ -99,3 +99,16 @@ def disks2d(analysis=10, gimp="uGIMP", method=2, cell=1.0, radius=6.0, gap=1.0, 
 """ % (analysis, method, maxtime, archive_ms, root, gimp_tag, extra_header, hmax, hmax, vmax, vmax, cell, cell,
        vel, x1, x1 + 2 * radius, radius, radius, vel, -x1 - 2 * radius, -x1, radius, radius,
        rho, E, nu, alpha, rho, E, nu, alpha)
+
+
+NEOHOOKEAN_MAT = ('<Material Type="28" Name="Blk"><rho>1.0</rho><G>%r</G><K>%r</K><alpha>40</alpha>%s</Material>')
+ISOPLASTIC_MAT = ('<Material Type="9" Name="Blk"><rho>%r</rho><E>%r</E><nu>%r</nu><alpha>20</alpha>'
+                  '<Hardening>Linear</Hardening><yield>%r</yield><Ep>%r</Ep></Material>')
+
+
+def neohookean_material(G=40.0, K=200.0, ujoption=None):
+    return NEOHOOKEAN_MAT % (G, K, "" if ujoption is None else "<UJOption>%d</UJOption>" % ujoption)
+
+
+def isoplastic_material(rho=2.0, E=2000.0, nu=0.33, yld=20.0, Ep=100.0):
+    return ISOPLASTIC_MAT % (rho, E, nu, yld, Ep)

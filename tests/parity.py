@@ -55,10 +55,16 @@ def compare_particles(got, ref, prefix, tol, fields=None):
     pairs = [("pos", "pos"), ("vel", "vel"), ("sp", "sp"), ("pressure", "pressure"), ("ep", "ep"), ("wrot", "wrot"),
              ("eplast", "eplast")]
     errs = {}
+    # 2D runs: the out-of-plane shear components (yz, xz) are not part of the state -- the reference's
+    # IsoPlasticity even adds an uninitialised Tensor into eplast.yz/xz there (IsoPlasticity.cpp:395-405)
+    two_d = "info/np" in ref and int(ref["info/np"]) != 12
     for g, r in pairs:
         if fields and g not in fields:
             continue
-        errs[g] = rel_err(got[g], ref[prefix + "/" + r], ref[prefix + "/ep"] if g == "wrot" else None)
+        a, b = np.asarray(got[g]), np.asarray(ref[prefix + "/" + r])
+        if two_d and g in ("sp", "ep", "eplast"):
+            a, b = a[[0, 1, 2, 5]], b[[0, 1, 2, 5]]
+        errs[g] = rel_err(a, b, ref[prefix + "/ep"] if g == "wrot" else None)
     e = ref[prefix + "/energies"]
     names = ["work", "res", "heat", "entropy", "plast"]
     for i, nm in enumerate(names):

@@ -12,7 +12,8 @@ from tests.parity import TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compar
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["disks2d_ugimp_planestrain", "disks2d_linear_planestress", "block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
+CASES = ["block3d_neohookean", "block3d_neohookean_uj1", "block3d_isoplastic", "disks2d_neohookean", "disks2d_isoplastic",
+         "disks2d_ugimp_planestrain", "disks2d_linear_planestress", "block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
          "block3d_ugimp_usf"]
 
 
