@@ -114,7 +114,6 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
         return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: MPM method %d not supported", cfg->method);
     if (cfg->shape == MPMGPU_LINEAR_CPDI || cfg->shape == MPMGPU_QUADRATIC_CPDI)
         return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: CPDI shape functions are not built yet in this round");
-    if (cfg->xpic_order > 1) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: XPIC/FMPM order>1 is not built yet in this round");
 
     ctx = new mpmgpu_ctx();
     ctx->cfg = *cfg;
@@ -405,7 +404,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     ctx->uploaded = true;
     tiled_on_upload(ctx->tiled);
     {   // the fused path needs 3D uGIMP, particles no larger than a cell, FLIP/PIC, no rigid particles
-        bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && ctx->sp.xpicOrder <= 1 && h->n_nonrigid == n;
+        bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && h->n_nonrigid == n;   // (XPIC order is checked per step)
         if (ok) for (size_t i = 0; i < (size_t)3 * n; i++) if (!(h->lp[i] <= 1.0)) { ok = false; break; }
         bool uni = true;
         for (int c = 0; c < 3 && uni; c++) for (int q = 1; q < n; q++) if (h->lp[(size_t)c * n + q] != h->lp[(size_t)c * n]) { uni = false; break; }
@@ -445,7 +444,7 @@ extern "C" int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dtFirst, 
 extern "C" int mpmgpu_set_xpic(mpmgpu_ctx *ctx, int order, int usingFMPM)
 {
     if (!ctx) return MPMGPU_EINVAL;
-    if (order > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: order>1 is not built yet in this round");
+    if (order < 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: order %d", order);
     ctx->sp.xpicOrder = order; ctx->sp.usingFMPM = usingFMPM;
     return MPMGPU_OK;
 }
@@ -579,8 +578,25 @@ static int t_post_extrapolation(mpmgpu_ctx *ctx)
     return apply_bcs(ctx, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
 }
 
-static int strain_update(mpmgpu_ctx *ctx, double strainTime)
+// XPICExtrapolationTask::Execute (XPICExtrapolationTask.cpp:49-161): grid velocity v(k) for order k > 1
+static int xpic_extrapolation(mpmgpu_ctx *ctx, int particleUpdate)
 {
+    const int nn = ctx->g.nnodes, fmpm = ctx->sp.usingFMPM ? 1 : 0;
+    LAUNCH(k_xpic_init, nblocks(nn, 256), 256, nn, ctx->N, ctx->sp.dt, fmpm);
+    for (int k = 2; k <= ctx->sp.xpicOrder; k++) {
+        DISPATCH_DIM_SHAPE(k_xpic_iterate, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
+        LAUNCH(k_xpic_finish, nblocks(nn, 256), 256, nn, ctx->N, ctx->B, ctx->hasBCs ? ctx->tiled.FN.bcOfNode : (const int *)NULL,
+               ctx->sp.dt, particleUpdate, fmpm);
+    }
+    return MPMGPU_OK;
+}
+
+static int strain_update(mpmgpu_ctx *ctx, double strainTime, bool postUpdate = false)
+{
+    // FMPM(k>1) strain updates use v(k) (UpdateStrainsFirstTask.cpp:105-116); XPIC(k) and FLIP use the lumped velocity
+    if (ctx->sp.usingFMPM && ctx->sp.xpicOrder > 1) {
+        if (!postUpdate || !ctx->sp.skipPost) { int rc = xpic_extrapolation(ctx, 0); if (rc) return rc; }
+    } else
     LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
     DISPATCH_DIM_SHAPE(k_update_strains, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
     return MPMGPU_OK;
@@ -614,7 +630,8 @@ static int t_update_momenta(mpmgpu_ctx *ctx)
 
 static int t_update_particles(mpmgpu_ctx *ctx)
 {
-    LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+    if (ctx->sp.xpicOrder > 1) { int rc = xpic_extrapolation(ctx, 1); if (rc) return rc; }      // UpdateParticlesTask.cpp:66-71
+    else LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
     int m = ctx->sp.xpicOrder;
     if (!ctx->sp.usingFMPM) m = -m;
     DISPATCH_DIM_SHAPE(k_update_particles, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, ctx->sp, m);
@@ -631,7 +648,7 @@ static int t_update_strains_last(mpmgpu_ctx *ctx)
         if (rc) return rc;
     }
     double st = ctx->sp.method == METHOD_USAVG ? ctx->sp.dtStrainLast : ctx->sp.dt;
-    return strain_update(ctx, st);
+    return strain_update(ctx, st, true);
 }
 
 static int t_reset_elements(mpmgpu_ctx *ctx)
@@ -893,7 +910,7 @@ extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
 {
     int rc = check_ready(ctx, "mpmgpu_step"); if (rc) return rc;
     for (int s = 0; s < nsteps; s++) {
-        rc = ctx->tiled.enabled ? fused_step(ctx) : step_by_tasks(ctx);
+        rc = (ctx->tiled.enabled && ctx->sp.xpicOrder <= 1) ? fused_step(ctx) : step_by_tasks(ctx);
         if (rc) return rc;
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
     }

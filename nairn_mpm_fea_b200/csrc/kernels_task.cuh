@@ -291,6 +291,84 @@ __global__ void __launch_bounds__(TASK_THREADS) k_update_particles(Grid g, Parti
     }
 }
 
+// ---- XPIC(k) / FMPM(k), k > 1: XPICExtrapolationTask.cpp:49-161, MatVelocityField::XPICSupport :318-397 ----
+// vk = v* (VSTAR_VEC), vsp = v*prev, vsn = v*next.  The reference's per-particle double loop
+//   v*next_i += (mp S_ip S_jp / m_i) v*prev_j          (XPICDoubleLoop :183-214, S^2 pair operations)
+// is evaluated as a gather followed by a scatter, u_p = sum_j S_jp v*prev_j ; v*next_i += (mp S_ip / m_i) u_p.
+__global__ void k_xpic_init(int nnodes, Nodes N, double dt, int usingFMPM)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    N.vsn[0][i] = 0.; N.vsn[1][i] = 0.; N.vsn[2][i] = 0.;
+    if (N.cnt[i] == 0) return;
+    const double mass = N.mass[i], rm = 1. / mass;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (usingFMPM) {
+            const double v = N.pk[c][i] * rm;
+            N.vsp[c][i] = v; N.vk[c][i] = v;
+        } else {
+            double v = N.pk[c][i];
+            v += N.ftot[c][i] * (-dt);
+            v *= rm;
+            N.vsp[c][i] = v;
+            N.vk[c][i] = v + N.ftot[c][i] * (dt / mass);
+        }
+    }
+}
+
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_xpic_iterate(Grid g, Particles P, Nodes N)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double xi[3], lp[3];
+    load_xi_lp(P, p, xi, lp);
+    const int e = P.elem[p];
+    double u[3] = {0., 0., 0.};
+    for_each_node<DIM, SHAPE, false>(g, e, xi, lp, [&](int nd, double S, double, double, double) {
+        u[0] += S * N.vsp[0][nd]; u[1] += S * N.vsp[1][nd]; u[2] += S * N.vsp[2][nd];
+    });
+    const double mp = P.mp[p];
+    for_each_node<DIM, SHAPE, false>(g, e, xi, lp, [&](int nd, double S, double, double, double) {
+        const double w = mp * S / N.mass[nd];
+        atomAdd(&N.vsn[0][nd], w * u[0]);
+        atomAdd(&N.vsn[1][nd], w * u[1]);
+        if (DIM == 3) atomAdd(&N.vsn[2][nd], w * u[2]);
+    });
+}
+
+// GET_DELTAV, velocity BCs on the increment (XPIC_* pass of ZeroVelocityBC, MatVelocityField.cpp:529-541), UPDATE_VSTAR
+__global__ void k_xpic_finish(int nnodes, Nodes N, VelBCs B, const int *bcOfNode, double dt, int particleUpdate, int usingFMPM)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    if (N.cnt[i] == 0) return;
+    double d[3] = {N.vsp[0][i] - N.vsn[0][i], N.vsp[1][i] - N.vsn[1][i], N.vsp[2][i] - N.vsn[2][i]};
+    const int u = bcOfNode ? bcOfNode[i] : -1;
+    if (u >= 0) {
+        const double mass = N.mass[i];
+        double ft[3] = {N.ftot[0][i], N.ftot[1][i], N.ftot[2][i]};
+        for (int e = B.start[u]; e < B.start[u + 1]; e++) {
+            if (!B.active[e]) continue;
+            const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
+            const double dotn = d[0] * nx + d[1] * ny + d[2] * nz;
+            d[0] += nx * (-dotn); d[1] += ny * (-dotn); d[2] += nz * (-dotn);
+            if (particleUpdate && !usingFMPM) {
+                const double s = -mass * dotn / dt;
+                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+            }
+        }
+        if (particleUpdate && !usingFMPM) { N.ftot[0][i] = ft[0]; N.ftot[1][i] = ft[1]; N.ftot[2][i] = ft[2]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        N.vsp[c][i] = d[c];
+        N.vk[c][i] += d[c];
+        N.vsn[c][i] = 0.;
+    }
+}
+
 // ---- task 9a: UpdateStrainsLastContactTask re-extrapolation (UpdateStrainsLastContactTask.cpp:71-149) ----
 __global__ void k_rezero_momenta(int nnodes, Nodes N)
 {

@@ -25,6 +25,7 @@ typedef struct {        /* MatVelocityField (Nodes/MatVelocityField.hpp:44-48) *
     int numberPoints;
     double mass;
     Vec pk, ftot, vk, pkCopy;
+    Vec vprev, vnext;       /* vk[VSTARPREV_VEC], vk[VSTARNEXT_VEC] (vk = vk[VSTAR_VEC]) */
 } NodeField;
 
 typedef struct {
@@ -532,9 +533,75 @@ static void isoplasticity_law(int p, const double de[3][3], const mpmgpu_materia
     P3(hist, 0, p) = alpint;
 }
 
-/* ---- tasks 4 / 9: FullStrainUpdate UpdateStrainsFirstTask.cpp:101-168, MatPoint3D.cpp:45-93 ------------------ */
-static void full_strain_update(double strainTime)
+/* ---- XPIC(k)/FMPM(k): XPICExtrapolationTask.cpp:49-214, MatVelocityField::XPICSupport :318-397 ------------------- */
+static void xpic_extrapolation(int particleUpdate)
 {
+    const int m = O->cfg.xpic_order, fmpm = O->cfg.using_fmpm;
+    const double dt = O->dt;
+    if (m <= 1) return;
+    for (int i = 0; i < O->nnodes; i++) {          /* INITIALIZE_XPIC */
+        NodeField *f = &O->nd[i];
+        f->vnext.x = f->vnext.y = f->vnext.z = 0.;
+        if (f->numberPoints == 0) continue;
+        if (fmpm) {
+            double rm = 1. / f->mass;
+            f->vprev.x = f->pk.x * rm; f->vprev.y = f->pk.y * rm; f->vprev.z = f->pk.z * rm;
+            f->vk = f->vprev;
+        } else {
+            f->vprev = f->pk;
+            f->vprev.x += f->ftot.x * (-dt); f->vprev.y += f->ftot.y * (-dt); f->vprev.z += f->ftot.z * (-dt);
+            double rm = 1. / f->mass;
+            f->vprev.x *= rm; f->vprev.y *= rm; f->vprev.z *= rm;
+            f->vk = f->vprev;
+            double s = dt / f->mass;
+            f->vk.x += f->ftot.x * s; f->vk.y += f->ftot.y * s; f->vk.z += f->ftot.z * s;
+        }
+    }
+    int nds[64]; double fn[64];
+    for (int k = 2; k <= m; k++) {
+        for (int p = 0; p < O->nNR; p++) {         /* XPICDoubleLoop: all node pairs of the particle */
+            int nn = shape(p, 0, nds, fn, NULL, NULL, NULL);
+            for (int i = 0; i < nn; i++) {
+                NodeField *fi = &O->nd[nds[i]];
+                for (int j = 0; j < nn; j++) {
+                    const NodeField *fj = &O->nd[nds[j]];
+                    double w = O->mp[p] * (fn[i] * fn[j]) / fi->mass;
+                    fi->vnext.x += w * fj->vprev.x; fi->vnext.y += w * fj->vprev.y; fi->vnext.z += w * fj->vprev.z;
+                }
+            }
+        }
+        for (int i = 0; i < O->nnodes; i++) {      /* GET_DELTAV */
+            NodeField *f = &O->nd[i];
+            if (f->numberPoints == 0) continue;
+            f->vprev.x -= f->vnext.x; f->vprev.y -= f->vnext.y; f->vprev.z -= f->vnext.z;
+        }
+        for (int b = 0; b < O->nbc; b++) {         /* GridVelocityConditions(XPIC_*): zero pass only */
+            if (!O->bcActive[b]) continue;
+            NodeField *f = &O->nd[O->bcNode[b] - 1];
+            if (f->numberPoints <= 0) continue;
+            const double *n = &O->bcNorm[3 * b];
+            double dotn = f->vprev.x * n[0] + f->vprev.y * n[1] + f->vprev.z * n[2];
+            f->vprev.x += n[0] * (-dotn); f->vprev.y += n[1] * (-dotn); f->vprev.z += n[2] * (-dotn);
+            if (particleUpdate && !fmpm) {
+                double s = -f->mass * dotn / dt;
+                f->ftot.x += n[0] * s; f->ftot.y += n[1] * s; f->ftot.z += n[2] * s;
+            }
+        }
+        for (int i = 0; i < O->nnodes; i++) {      /* UPDATE_VSTAR */
+            NodeField *f = &O->nd[i];
+            if (f->numberPoints == 0) continue;
+            f->vk.x += f->vprev.x; f->vk.y += f->vprev.y; f->vk.z += f->vprev.z;
+            f->vnext.x = f->vnext.y = f->vnext.z = 0.;
+        }
+    }
+}
+
+/* ---- tasks 4 / 9: FullStrainUpdate UpdateStrainsFirstTask.cpp:101-168, MatPoint3D.cpp:45-93 ------------------ */
+static void full_strain_update(double strainTime, int postUpdate)
+{
+    if (O->cfg.using_fmpm && O->cfg.xpic_order > 1) {          /* UpdateStrainsFirstTask.cpp:105-116 */
+        if (!postUpdate || !O->cfg.skip_post_extrapolation) xpic_extrapolation(0);
+    } else
     for (int i = 0; i < O->nnodes; i++) {      /* GridValueCalculation MatVelocityField.cpp:239-251 */
         NodeField *f = &O->nd[i];
         if (f->numberPoints == 0 || f->mass == 0.) continue;
@@ -564,7 +631,7 @@ static void full_strain_update(double strainTime)
 static void task_update_strains_first(void)
 {
     if (O->cfg.method == MPMGPU_USL) return;
-    full_strain_update(O->cfg.method == MPMGPU_USAVG ? O->dtFirst : O->dt);
+    full_strain_update(O->cfg.method == MPMGPU_USAVG ? O->dtFirst : O->dt, 0);
 }
 
 /* ---- task 5: GridForcesTask.cpp:55-117, MatPoint3D.cpp:248-252 ------------------------------------------------ */
@@ -618,6 +685,8 @@ static void task_update_momenta(void)
 /* ---- task 8: UpdateParticlesTask.cpp:75-286, MatPoint3D::MoveParticle MatPoint3D.cpp:104-194 ------------------ */
 static void task_update_particles(void)
 {
+    if (O->cfg.xpic_order > 1) xpic_extrapolation(1);          /* UpdateParticlesTask.cpp:66-71 */
+    else
     for (int i = 0; i < O->nnodes; i++) {
         NodeField *f = &O->nd[i];
         if (f->numberPoints == 0 || f->mass == 0.) continue;
@@ -668,7 +737,7 @@ static void task_update_strains_last(void)
         }
         grid_velocity_conditions(UPDATE_STRAINS_LAST_CALL);
     }
-    full_strain_update(O->cfg.method == MPMGPU_USAVG ? O->dtLast : O->dt);
+    full_strain_update(O->cfg.method == MPMGPU_USAVG ? O->dtLast : O->dt, 1);
 }
 
 /* ---- task 11: ResetElementsTask.cpp:196-265, MeshInfo.cpp:171-199,593-633 ---------------------------------------- */
@@ -772,6 +841,8 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
     O->dt = dt; O->dtFirst = dtFirst; O->dtLast = dtLast;
     return 0;
 }
+
+int oracle_set_xpic(int order, int using_fmpm) { if (!O) return -1; O->cfg.xpic_order = order; O->cfg.using_fmpm = using_fmpm; return 0; }
 
 int oracle_task(int t) { if (!O || t < 0 || t > 9) return -1; TASKS[t](); if (t == 9) O->mstep++; return 0; }
 

@@ -66,6 +66,9 @@ class PortOracle:
                                     _i(bact), _i(bsym), prob.dt, prob.dt_strain_first, prob.dt_strain_last)
         assert rc == 0
 
+    def set_xpic(self, order, using_fmpm):
+        assert self.lib.oracle_set_xpic(int(order), int(using_fmpm)) == 0
+
     def step(self, n=1):
         assert self.lib.oracle_step(int(n)) == 0
 

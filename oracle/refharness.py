@@ -166,7 +166,14 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
     out["task_names"] = np.array(names)
     _flatten("p0", r.particles(), out)
     done = 0
+    xpic = []          # (order, usingFMPM) in force DURING each step (PeriodicXPIC changes it between steps)
+
+    def note_xpic():
+        inf = r.get_info()
+        xpic.append((inf["XPICOrder"], inf["usingFMPM"]))
+
     for s in range(per_task_steps):
+        note_xpic()
         for i, nm in enumerate(names):
             r.run_task(i)
             _flatten("s%d/t%d/nodes" % (s + 1, i), r.nodes(), out)
@@ -177,10 +184,13 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
             _flatten("n%d" % done, r.nodes(), out)
     for s in snaps:
         if s > done:
-            r.step(s - done)
-            done = s
+            while done < s:
+                note_xpic()
+                r.step(1)
+                done += 1
             _flatten("p%d" % done, r.particles(), out)
             _flatten("n%d" % done, r.nodes(), out)
+    out["xpic_by_step"] = np.array(xpic, dtype=np.int32).reshape(-1, 2)
     _flatten("info_end", r.get_info(), out)
     r.close()
     np.savez_compressed(out_npz, **out)

@@ -112,3 +112,10 @@ def neohookean_material(G=40.0, K=200.0, ujoption=None):
 
 def isoplastic_material(rho=2.0, E=2000.0, nu=0.33, yld=20.0, Ep=100.0):
     return ISOPLASTIC_MAT % (rho, E, nu, yld, Ep)
+
+
+def periodic_xpic(order, fmpm=False, periodic_steps=1):
+    """<CustomTasks> block scheduling the reference's PeriodicXPIC task (Custom_Tasks/PeriodicXPIC.cpp:62-157)."""
+    return ('<CustomTasks><Schedule name="PeriodicXPIC"><Parameter name="%s">%d</Parameter>'
+            '<Parameter name="periodicSteps">%d</Parameter></Schedule></CustomTasks>'
+            % ("FMPMOrder" if fmpm else "XPICOrder", order, periodic_steps))

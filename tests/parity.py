@@ -18,7 +18,25 @@ TASK_MAP = {
     "Update Strains Last with Extrapolation": "update_strains_last",
     "Update Strains Last": "update_strains_last",
     "Reset Elements": "reset_elements",
+    "Run Custom Tasks": None,        # host-side: PeriodicXPIC only changes the XPIC order for the next step
 }
+
+
+def xpic_for_step(z, step):
+    """(order, usingFMPM) the reference used during 1-based `step` (recorded by the harness), or None."""
+    if "xpic_by_step" not in z:
+        return None
+    x = z["xpic_by_step"]
+    if step - 1 < len(x):
+        return int(x[step - 1][0]), int(x[step - 1][1])
+    return int(x[-1][0]), int(x[-1][1])
+
+
+def per_task_steps(z):
+    n = 0
+    while ("s%d/t0/nodes/mass" % (n + 1)) in z:
+        n += 1
+    return n
 
 TOL_1STEP = 1.0e-10      # BASELINE.json north_star: relative 1e-10 after 1 step
 TOL_100STEP = 1.0e-7     # and 1e-7 after 100 steps (FP64), relative to the field's max magnitude

@@ -4,9 +4,10 @@ Runs on CPU."""
 import numpy as np
 import pytest
 
-from tests.parity import TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compare_particles, load_golden
+from tests.parity import (TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compare_particles, load_golden, per_task_steps,
+                          xpic_for_step)
 
-CASES = ["block3d_neohookean", "block3d_neohookean_uj1", "block3d_isoplastic", "disks2d_neohookean", "disks2d_isoplastic",
+CASES = ["block3d_xpic3", "block3d_fmpm2", "disks2d_fmpm3_neo", "block3d_neohookean", "block3d_neohookean_uj1", "block3d_isoplastic", "disks2d_neohookean", "disks2d_isoplastic",
          "disks2d_ugimp_planestrain", "disks2d_linear_planestress", "block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
          "block3d_ugimp_usf"]
 TASK_INDEX = {"initialization": 0, "mass_and_momentum": 1, "post_extrapolation": 2, "update_strains_first": 3, "grid_forces": 4,
@@ -23,15 +24,24 @@ def make(z):
 def test_port_tasks_match_reference(case):
     z = load_golden(case)
     o = make(z)
-    for i, nm in enumerate(str(s) for s in z["task_names"]):
-        o.run_task(TASK_INDEX[TASK_MAP[nm]])
-        pre = "s1/t%d" % i
-        errs, bad = compare_nodes(o.download_nodes(), z, pre + "/nodes", TOL_1STEP)
-        assert not bad, "%s task %d (%s): nodes %s" % (case, i, nm, bad)
-        got = o.download()
-        errs, bad = compare_particles(got, z, pre + "/p", TOL_1STEP)
-        assert not bad, "%s task %d (%s): particles %s" % (case, i, nm, bad)
-        assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"])
+    for step in range(1, per_task_steps(z) + 1):
+        x = xpic_for_step(z, step)
+        if x:
+            o.set_xpic(*x)
+        # 1e-10 holds for the first step; in later steps FMPM/XPIC iterations amplify round-off at nearly
+        # massless edge nodes, so the per-task check of step 2 uses 1e-8 (the 100-step bound is 1e-7)
+        TOL = TOL_1STEP if step == 1 else 1.0e-8
+        for i, nm in enumerate(str(s) for s in z["task_names"]):
+            if TASK_MAP[nm] is None:
+                continue
+            o.run_task(TASK_INDEX[TASK_MAP[nm]])
+            pre = "s%d/t%d" % (step, i)
+            errs, bad = compare_nodes(o.download_nodes(), z, pre + "/nodes", TOL)
+            assert not bad, "%s step %d task %d (%s): nodes %s" % (case, step, i, nm, bad)
+            got = o.download()
+            errs, bad = compare_particles(got, z, pre + "/p", TOL)
+            assert not bad, "%s step %d task %d (%s): particles %s" % (case, step, i, nm, bad)
+            assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"])
     o.close()
 
 
@@ -42,8 +52,12 @@ def test_port_whole_steps_match_reference(case):
     snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
     done = 0
     for s in snaps:
-        o.step(s - done)
-        done = s
+        while done < s:
+            x = xpic_for_step(z, done + 1)
+            if x:
+                o.set_xpic(*x)
+            o.step(1)
+            done += 1
         got = o.download()
         errs, bad = compare_particles(got, z, "p%d" % s, TOL_1STEP if s == 1 else TOL_100STEP)
         assert not bad, "%s after %d steps: %s" % (case, s, bad)

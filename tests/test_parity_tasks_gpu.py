@@ -8,16 +8,17 @@
 import numpy as np
 import pytest
 
-from tests.parity import TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compare_particles, load_golden
+from tests.parity import (TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compare_particles, load_golden, per_task_steps,
+                          xpic_for_step)
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["block3d_neohookean", "block3d_neohookean_uj1", "block3d_isoplastic", "disks2d_neohookean", "disks2d_isoplastic",
+CASES = ["block3d_xpic3", "block3d_fmpm2", "disks2d_fmpm3_neo", "block3d_neohookean", "block3d_neohookean_uj1", "block3d_isoplastic", "disks2d_neohookean", "disks2d_isoplastic",
          "disks2d_ugimp_planestrain", "disks2d_linear_planestress", "block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
          "block3d_ugimp_usf"]
 
 
-FUSED_CASES = [c for c in CASES if "linear" not in c and "2d" not in c]
+FUSED_CASES = [c for c in CASES if "linear" not in c and "2d" not in c and "fmpm" not in c]
 
 
 def make_sim(z, kernel_path=1, sort_interval=0):
@@ -32,18 +33,25 @@ def test_each_task_of_step_one(case):
     z = load_golden(case)
     sim, prob = make_sim(z)
     names = [str(s) for s in z["task_names"]]
-    for i, nm in enumerate(names):
-        sim.run_task(TASK_MAP[nm])
-        pre = "s1/t%d" % i
-        nodes = sim.download_nodes()
-        errs, bad = compare_nodes(nodes, z, pre + "/nodes", TOL_1STEP)
-        assert not bad, "%s after task %d (%s): node fields %s" % (case, i, nm, bad)
-        assert np.array_equal(nodes["number_points"] > 0, z[pre + "/nodes/numberPoints"] > 0), "active node set differs"
-        got = sim.download()
-        errs, bad = compare_particles(got, z, pre + "/p", TOL_1STEP)
-        assert not bad, "%s after task %d (%s): particle fields %s" % (case, i, nm, bad)
-        assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"]), "element ids differ after %s" % nm
-        assert np.array_equal(got["crossings"], z[pre + "/p/crossings"])
+    for step in range(1, per_task_steps(z) + 1):
+        x = xpic_for_step(z, step)
+        if x:
+            sim.set_xpic(*x)
+        TOL = TOL_1STEP if step == 1 else 1.0e-8       # see tests/test_oracle_cpu.py
+        for i, nm in enumerate(names):
+            if TASK_MAP[nm] is None:
+                continue
+            sim.run_task(TASK_MAP[nm])
+            pre = "s%d/t%d" % (step, i)
+            nodes = sim.download_nodes()
+            errs, bad = compare_nodes(nodes, z, pre + "/nodes", TOL)
+            assert not bad, "%s step %d after task %d (%s): node fields %s" % (case, step, i, nm, bad)
+            assert np.array_equal(nodes["number_points"] > 0, z[pre + "/nodes/numberPoints"] > 0), "active node set differs"
+            got = sim.download()
+            errs, bad = compare_particles(got, z, pre + "/p", TOL)
+            assert not bad, "%s step %d after task %d (%s): particle fields %s" % (case, step, i, nm, bad)
+            assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"]), "element ids differ after %s" % nm
+            assert np.array_equal(got["crossings"], z[pre + "/p/crossings"])
     sim.close()
 
 
@@ -57,8 +65,12 @@ def test_whole_steps(case, kernel_path, sort_interval):
     snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
     done = 0
     for s in snaps:
-        sim.step(s - done)
-        done = s
+        while done < s:
+            x = xpic_for_step(z, done + 1)
+            if x:
+                sim.set_xpic(*x)
+            sim.step(1)
+            done += 1
         tol = TOL_1STEP if s == 1 else TOL_100STEP
         got = sim.download()
         errs, bad = compare_particles(got, z, "p%d" % s, tol)
