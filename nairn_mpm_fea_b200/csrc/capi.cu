@@ -42,6 +42,7 @@ struct mpmgpu_ctx {
     double *particlePool;               // one slab for all particle doubles
     int *particleIntPool;
     double *nodePool;
+    int *cpElemPool; double *cpXiPool, *cpWgPool;   // CPDI domain data (only for CPDI shape functions)
     size_t cap;                         // particle capacity
     long long mstep;
     double mtime;
@@ -112,8 +113,6 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     if (cfg->shape == MPMGPU_QUADRATIC_CPDI && is3D) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: qCPDI is 2D only (as in the reference)");
     if (cfg->method != MPMGPU_USF && cfg->method != MPMGPU_USAVG && cfg->method != MPMGPU_USL)
         return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: MPM method %d not supported", cfg->method);
-    if (cfg->shape == MPMGPU_LINEAR_CPDI || cfg->shape == MPMGPU_QUADRATIC_CPDI)
-        return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: CPDI shape functions are not built yet in this round");
 
     ctx = new mpmgpu_ctx();
     ctx->cfg = *cfg;
@@ -122,6 +121,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->cap = 0; ctx->mstep = 0; ctx->mtime = 0.; ctx->launches = 0;
     ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->profiling = false; ctx->globalIds = false; ctx->ownStreamSaved = false;
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
+    ctx->cpElemPool = NULL; ctx->cpXiPool = NULL; ctx->cpWgPool = NULL;
     ctx->hStage = NULL; ctx->hStageBytes = 0; ctx->nBCEntries = 0;
     memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B);
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
@@ -243,6 +243,16 @@ static int alloc_particles(mpmgpu_ctx *ctx, size_t cap)
     CK(cudaMemsetAsync(ctx->particleIntPool, 0, capPad * NPI * sizeof(int), ctx->stream));
     bind_particles(ctx->P, ctx->particlePool, ctx->particleIntPool, capPad);
     ctx->cap = capPad;
+    if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI) {
+        const int nc = ctx->dim == 3 ? 8 : (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 9 : 4);
+        CK(dalloc(ctx, &ctx->cpElemPool, capPad * nc));
+        CK(dalloc(ctx, &ctx->cpXiPool, capPad * nc * 3));
+        CK(dalloc(ctx, &ctx->cpWgPool, capPad * nc * 3));
+        CK(cudaMemsetAsync(ctx->cpElemPool, 0, capPad * nc * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->cpXiPool, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->cpWgPool, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
+    }
+    ctx->P.cpElem = ctx->cpElemPool; ctx->P.cpXi = ctx->cpXiPool; ctx->P.cpWg = ctx->cpWgPool; ctx->P.cpStride = capPad;
     return MPMGPU_OK;
 }
 
@@ -517,9 +527,12 @@ extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const do
     if (grid_ > 0) { \
         if (ctx->dim == 3) { \
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<3, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<3, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else LAUNCH((KERNEL<3, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
         } else { \
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<2, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<2, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI) LAUNCH((KERNEL<2, SHAPE_QCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else LAUNCH((KERNEL<2, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
         } } } while (0)
 
@@ -558,9 +571,7 @@ static int t_initialization(mpmgpu_ctx *ctx)
     CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 22 * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
     ctx->launches += 2;
-    const int n = ctx->P.n;
-    if (ctx->dim == 3) LAUNCH(k_init_particles<3>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P);
-    else LAUNCH(k_init_particles<2>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P);
+    DISPATCH_DIM_SHAPE(k_init_particles, ctx->P.n, ctx->g, ctx->P, ctx->dFlags);
     return MPMGPU_OK;
 }
 
@@ -744,6 +755,7 @@ static int sort_particles(mpmgpu_ctx *ctx)
     int nn = ctx->P.n, nnr = ctx->P.nNR;
     bind_particles(ctx->P, ctx->particlePool, ctx->particleIntPool, ctx->cap);
     ctx->P.n = nn; ctx->P.nNR = nnr;
+    ctx->P.cpElem = ctx->cpElemPool; ctx->P.cpXi = ctx->cpXiPool; ctx->P.cpWg = ctx->cpWgPool; ctx->P.cpStride = ctx->cap;
     t.stepsSinceSort = 0;
     return MPMGPU_OK;
 }

@@ -15,19 +15,34 @@ __device__ __forceinline__ void load_xi_lp(const Particles &P, int p, double xi[
     lp[0] = P.lp[0][p]; lp[1] = P.lp[1][p]; lp[2] = P.lp[2][p];
 }
 
+// nodes of particle p for the configured shape function
+template <int DIM, int SHAPE, bool GRAD, class F>
+__device__ __forceinline__ void particle_nodes(const Grid &g, const Particles &P, int p, F &&f)
+{
+    if (SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI) {
+        for_each_node_cpdi<DIM, SHAPE, GRAD>(g, P, p, f);
+    } else {
+        double xi[3], lp[3];
+        load_xi_lp(P, p, xi, lp);
+        for_each_node<DIM, SHAPE, GRAD>(g, P.elem[p], xi, lp, f);
+    }
+}
+
 // ---- task 1: InitializationTask (InitializationTask.cpp:49-85) ------------------------------
 // node zeroing is a memset; this is the particle half: ncpos = GetXiPos(pos) in the current element
-template <int DIM>
-__global__ void __launch_bounds__(TASK_THREADS) k_init_particles(Grid g, Particles P)
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_init_particles(Grid g, Particles P, StatusFlags *flags)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     int e = P.elem[p];
-    if (e <= 1 && false) return;
     double pos[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
     double xi[3];
     get_xipos<DIM>(g, e, pos, xi);
     P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
+    if ((SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI) && p < P.nNR) {     // ElementBase::GetShapeFunctionData (MoreMPMElementBase.cpp:50-58)
+        if (!cpdi_setup<DIM, SHAPE>(g, P, p)) atomicCAS(&flags->cpdiLeft, 0, P.orig[p] + 1);
+    }
 }
 
 // ---- task 2: MassAndMomentumTask (MassAndMomentumTask.cpp:62-98, NodalPointMPM.cpp:419-453) ---
@@ -36,11 +51,9 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_mass_momentum(Grid g, Part
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
-    double xi[3], lp[3];
-    load_xi_lp(P, p, xi, lp);
     const double mp = P.mp[p];
     const double vx = P.vel[0][p], vy = P.vel[1][p], vz = DIM == 3 ? P.vel[2][p] : 0.;
-    for_each_node<DIM, SHAPE, false>(g, P.elem[p], xi, lp, [&](int nd, double S, double, double, double) {
+    particle_nodes<DIM, SHAPE, false>(g, P, p, [&](int nd, double S, double, double, double) {
         const double fnmp = S * mp;
         atomAdd(&N.pk[0][nd], vx * fnmp);
         atomAdd(&N.pk[1][nd], vy * fnmp);
@@ -160,10 +173,8 @@ __global__ void __launch_bounds__(TASK_THREADS) k_update_strains(Grid g, Particl
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
-    double xi[3], lp[3];
-    load_xi_lp(P, p, xi, lp);
     double dv[9] = {0., 0., 0., 0., 0., 0., 0., 0., 0.};
-    for_each_node<DIM, SHAPE, true>(g, P.elem[p], xi, lp, [&](int nd, double S, double gx, double gy, double gz) {
+    particle_nodes<DIM, SHAPE, true>(g, P, p, [&](int nd, double S, double gx, double gy, double gz) {
         const double vx = N.vk[0][nd], vy = N.vk[1][nd];
         dv[0] += vx * gx; dv[1] += vx * gy;
         dv[3] += vy * gx; dv[4] += vy * gy;
@@ -187,15 +198,13 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_forces(Grid g, Particles P
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
-    double xi[3], lp[3];
-    load_xi_lp(P, p, xi, lp);
     const double mp = P.mp[p], pr = P.pressure[p];
     const double sxx = P.sp[XX][p] - pr, syy = P.sp[YY][p] - pr, sxy = P.sp[XY][p];
     double szz = 0., syz = 0., sxz = 0.;
     if (DIM == 3) { szz = P.sp[ZZ][p] - pr; syz = P.sp[YZ][p]; sxz = P.sp[XZ][p]; }
     double fx = 0., fy = 0., fz = 0.;
     if (hasFext) { fx = P.pfext[0][p]; fy = P.pfext[1][p]; fz = P.pfext[2][p]; }
-    for_each_node<DIM, SHAPE, true>(g, P.elem[p], xi, lp, [&](int nd, double S, double gx, double gy, double gz) {
+    particle_nodes<DIM, SHAPE, true>(g, P, p, [&](int nd, double S, double gx, double gy, double gz) {
         if (DIM == 3) {
             atomAdd(&N.ftot[0][nd], -mp * (sxx * gx + sxy * gy + sxz * gz) + S * fx);
             atomAdd(&N.ftot[1][nd], -mp * (sxy * gx + syy * gy + syz * gz) + S * fy);
@@ -237,10 +246,8 @@ __global__ void __launch_bounds__(TASK_THREADS) k_update_particles(Grid g, Parti
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
-    double xi[3], lp[3];
-    load_xi_lp(P, p, xi, lp);
     double Svk[3] = {0., 0., 0.}, Sacc[3] = {0., 0., 0.};
-    for_each_node<DIM, SHAPE, false>(g, P.elem[p], xi, lp, [&](int nd, double S, double, double, double) {
+    particle_nodes<DIM, SHAPE, false>(g, P, p, [&](int nd, double S, double, double, double) {
         Svk[0] += N.vk[0][nd] * S; Svk[1] += N.vk[1][nd] * S; Svk[2] += N.vk[2][nd] * S;
         if (m <= 0) {
             const double mnode = S / N.mass[nd];
@@ -322,15 +329,12 @@ __global__ void __launch_bounds__(TASK_THREADS) k_xpic_iterate(Grid g, Particles
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
-    double xi[3], lp[3];
-    load_xi_lp(P, p, xi, lp);
-    const int e = P.elem[p];
     double u[3] = {0., 0., 0.};
-    for_each_node<DIM, SHAPE, false>(g, e, xi, lp, [&](int nd, double S, double, double, double) {
+    particle_nodes<DIM, SHAPE, false>(g, P, p, [&](int nd, double S, double, double, double) {
         u[0] += S * N.vsp[0][nd]; u[1] += S * N.vsp[1][nd]; u[2] += S * N.vsp[2][nd];
     });
     const double mp = P.mp[p];
-    for_each_node<DIM, SHAPE, false>(g, e, xi, lp, [&](int nd, double S, double, double, double) {
+    particle_nodes<DIM, SHAPE, false>(g, P, p, [&](int nd, double S, double, double, double) {
         const double w = mp * S / N.mass[nd];
         atomAdd(&N.vsn[0][nd], w * u[0]);
         atomAdd(&N.vsn[1][nd], w * u[1]);
@@ -382,11 +386,9 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_momentum_last(Grid g, Part
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
-    double xi[3], lp[3];
-    load_xi_lp(P, p, xi, lp);
     const double mp = P.mp[p];
     const double vx = P.vel[0][p], vy = P.vel[1][p], vz = DIM == 3 ? P.vel[2][p] : 0.;
-    for_each_node<DIM, SHAPE, false>(g, P.elem[p], xi, lp, [&](int nd, double S, double, double, double) {
+    particle_nodes<DIM, SHAPE, false>(g, P, p, [&](int nd, double S, double, double, double) {
         const double fnmp = S * mp;
         atomAdd(&N.pk[0][nd], vx * fnmp);
         atomAdd(&N.pk[1][nd], vy * fnmp);

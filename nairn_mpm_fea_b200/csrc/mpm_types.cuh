@@ -66,6 +66,12 @@ struct Particles {
     int *mat;                // 0-based material index
     int *cross;              // elementCrossings
     int *orig;               // caller's index of this particle
+    // CPDI domain data fixed for the step (CPDIDomain, Common/System/DataTypes.hpp:110-115), only allocated for
+    // CPDI shape functions: corner c of particle p at [c][p]
+    int *cpElem;             // [ncorner][cap]  1-based element holding the corner
+    double *cpXi;            // [ncorner*3][cap] natural coordinates of the corner in that element
+    double *cpWg;            // [ncorner*3][cap] gradient weights
+    size_t cpStride;         // cap
 };
 
 struct Material {

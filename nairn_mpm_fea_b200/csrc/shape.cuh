@@ -237,3 +237,198 @@ __device__ __forceinline__ void for_each_node(const Grid &g, int inElem, const d
         }
     }
 }
+
+
+// ---- CPDI (lCPDI 2D/3D, qCPDI 2D) ------------------------------------------------------------------------
+// Domain set-up once per step: MatPoint3D::GetCPDINodesAndWeights (MPM_Classes/MatPoint3D.cpp:538-621) with
+// GetSemiSideVectors (:413-433) and ScaleSemiSideVectorsForCPDI (:436-492); 2D: MatPoint2D.cpp:423-477,519-640.
+// Returns false when a corner has left the grid (the reference throws, MatPoint3D.cpp:596-601).
+template <int DIM, int SHAPE>
+struct CpdiTraits { static const int NC = (DIM == 3 ? 8 : (SHAPE == SHAPE_QCPDI ? 9 : 4)); };
+
+template <int DIM, int SHAPE>
+__device__ __forceinline__ bool cpdi_setup(const Grid &g, const Particles &P, int p)
+{
+    const int NC = CpdiTraits<DIM, SHAPE>::NC;
+    const int e = P.elem[p];
+    const ElemIJK c0 = elem_ijk(g, e);
+    const double cx = g.xpts[c0.i + 1] - g.xpts[c0.i], cy = g.ypts[c0.j + 1] - g.ypts[c0.j];
+    const double cz = DIM == 3 ? g.zpts[c0.k + 1] - g.zpts[c0.k] : 1.;
+    const double psx = cx * (0.5 * P.lp[0][p]), psy = cy * (0.5 * P.lp[1][p]), psz = DIM == 3 ? cz * (0.5 * P.lp[2][p]) : 0.;
+    const double pos[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = P.F[i][p];
+    double r1[3] = {F[0] * psx, F[3] * psx, DIM == 3 ? F[6] * psx : 0.};
+    double r2[3] = {F[1] * psy, F[4] * psy, DIM == 3 ? F[7] * psy : 0.};
+    double r3[3] = {F[2] * psz, F[5] * psz, F[8] * psz};
+    if (g.rcrit >= 0.) {
+        if (DIM == 3) {
+            const double rc = g.rcrit * fmin(cx, fmin(cy, cz));
+            double l[4][3];
+            const double sg[4][2] = {{1., 1.}, {1., -1.}, {-1., 1.}, {-1., -1.}};     // la, lb, lc, ld: signs of r1, r2
+            bool rescale = false;
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) l[a][d] = sg[a][0] * r1[d] + sg[a][1] * r2[d] + r3[d];
+                const double mag = sqrt(l[a][0] * l[a][0] + l[a][1] * l[a][1] + l[a][2] * l[a][2]);
+                if (mag > rc) {
+                    const double sc = rc / mag;
+                    l[a][0] *= sc; l[a][1] *= sc; l[a][2] *= sc;
+                    rescale = true;
+                }
+            }
+            if (rescale) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    r1[d] = 0.25 * (l[0][d] + l[1][d] - l[2][d] - l[3][d]);
+                    r2[d] = 0.25 * (l[0][d] - l[1][d] + l[2][d] - l[3][d]);
+                    r3[d] = 0.25 * (l[0][d] + l[1][d] + l[2][d] + l[3][d]);
+                }
+            }
+        } else {
+            const double rc = g.rcrit * fmin(cx, cy);
+            double la[2] = {r1[0] + r2[0], r1[1] + r2[1]}, lb[2] = {r1[0] - r2[0], r1[1] - r2[1]};
+            bool rescale = false;
+            const double lam = sqrt(la[0] * la[0] + la[1] * la[1]), lbm = sqrt(lb[0] * lb[0] + lb[1] * lb[1]);
+            if (lam > rc) { la[0] *= rc / lam; la[1] *= rc / lam; rescale = true; }
+            if (lbm > rc) { lb[0] *= rc / lbm; lb[1] *= rc / lbm; rescale = true; }
+            if (rescale) {
+                r1[0] = 0.5 * (la[0] + lb[0]); r1[1] = 0.5 * (la[1] + lb[1]);
+                r2[0] = 0.5 * (la[0] - lb[0]); r2[1] = 0.5 * (la[1] - lb[1]);
+            }
+        }
+    }
+    // corner positions
+    double cs[NC][3];
+    if (DIM == 3) {
+        const double s1[8] = {-1., 1., 1., -1., -1., 1., 1., -1.}, s2[8] = {-1., -1., 1., 1., -1., -1., 1., 1.}, s3[8] = {-1., -1., -1., -1., 1., 1., 1., 1.};
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int d = 0; d < 3; d++) cs[i][d] = pos[d] + s1[i] * r1[d] + s2[i] * r2[d] + s3[i] * r3[d];
+    } else {
+        const double s1[9] = {-1., 1., 1., -1., 0., 1., 0., -1., 0.}, s2[9] = {-1., -1., 1., 1., -1., 0., 1., 0., 0.};
+#pragma unroll
+        for (int i = 0; i < NC; i++) {
+            // the reference writes pos -r1 -r2 etc. as chained subtractions/additions of r1 then r2
+            double x = pos[0], y = pos[1];
+            if (s1[i] != 0.) { x += s1[i] * r1[0]; y += s1[i] * r1[1]; }
+            if (s2[i] != 0.) { x += s2[i] * r2[0]; y += s2[i] * r2[1]; }
+            cs[i][0] = x; cs[i][1] = y; cs[i][2] = 0.;
+        }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        int ce;
+        if (DIM == 2 && SHAPE == SHAPE_QCPDI && i == 8) ce = e;
+        else ce = find_element_from_point<DIM>(g, cs[i]);
+        if (ce <= 0) { ok = false; ce = e; }
+        double xi[3];
+        get_xipos<DIM>(g, ce, cs[i], xi);
+        P.cpElem[(size_t)i * P.cpStride + p] = ce;
+        P.cpXi[(size_t)(3 * i) * P.cpStride + p] = xi[0];
+        P.cpXi[(size_t)(3 * i + 1) * P.cpStride + p] = xi[1];
+        P.cpXi[(size_t)(3 * i + 2) * P.cpStride + p] = xi[2];
+    }
+    // gradient weights
+    double wg[NC][3];
+    if (DIM == 3) {
+        double Vp = 8. * (r1[0] * (r2[1] * r3[2] - r2[2] * r3[1]) + r1[1] * (r2[2] * r3[0] - r2[0] * r3[2]) + r1[2] * (r2[0] * r3[1] - r2[1] * r3[0]));
+        Vp = 1. / Vp;
+        const double r1x = r1[0], r1y = r1[1], r1z = r1[2], r2x = r2[0], r2y = r2[1], r2z = r2[2], r3x = r3[0], r3y = r3[1], r3z = r3[2];
+        wg[0][0] = (r1z * r2y - r1y * r2z - r1z * r3y + r2z * r3y + r1y * r3z - r2y * r3z) * Vp;
+        wg[0][1] = (-(r1z * r2x) + r1x * r2z + r1z * r3x - r2z * r3x - r1x * r3z + r2x * r3z) * Vp;
+        wg[0][2] = (r1y * r2x - r1x * r2y - r1y * r3x + r2y * r3x + r1x * r3y - r2x * r3y) * Vp;
+        wg[1][0] = (r1z * r2y - r1y * r2z - r1z * r3y - r2z * r3y + r1y * r3z + r2y * r3z) * Vp;
+        wg[1][1] = (-(r1z * r2x) + r1x * r2z + r1z * r3x + r2z * r3x - r1x * r3z - r2x * r3z) * Vp;
+        wg[1][2] = (r1y * r2x - r1x * r2y - r1y * r3x - r2y * r3x + r1x * r3y + r2x * r3y) * Vp;
+        wg[2][0] = (r1z * r2y - r1y * r2z + r1z * r3y - r2z * r3y - r1y * r3z + r2y * r3z) * Vp;
+        wg[2][1] = (-(r1z * r2x) + r1x * r2z - r1z * r3x + r2z * r3x + r1x * r3z - r2x * r3z) * Vp;
+        wg[2][2] = (r1y * r2x - r1x * r2y + r1y * r3x - r2y * r3x - r1x * r3y + r2x * r3y) * Vp;
+        wg[3][0] = (r1z * r2y - r1y * r2z + r1z * r3y + r2z * r3y - r1y * r3z - r2y * r3z) * Vp;
+        wg[3][1] = (-(r1z * r2x) + r1x * r2z - r1z * r3x - r2z * r3x + r1x * r3z + r2x * r3z) * Vp;
+        wg[3][2] = (r1y * r2x - r1x * r2y + r1y * r3x + r2y * r3x - r1x * r3y - r2x * r3y) * Vp;
+        wg[4][0] = (-(r1z * r2y) + r1y * r2z - r1z * r3y + r2z * r3y + r1y * r3z - r2y * r3z) * Vp;
+        wg[4][1] = (r1z * r2x - r1x * r2z + r1z * r3x - r2z * r3x - r1x * r3z + r2x * r3z) * Vp;
+        wg[4][2] = (-(r1y * r2x) + r1x * r2y - r1y * r3x + r2y * r3x + r1x * r3y - r2x * r3y) * Vp;
+        wg[5][0] = (-(r1z * r2y) + r1y * r2z - r1z * r3y - r2z * r3y + r1y * r3z + r2y * r3z) * Vp;
+        wg[5][1] = (r1z * r2x - r1x * r2z + r1z * r3x + r2z * r3x - r1x * r3z - r2x * r3z) * Vp;
+        wg[5][2] = (-(r1y * r2x) + r1x * r2y - r1y * r3x - r2y * r3x + r1x * r3y + r2x * r3y) * Vp;
+        wg[6][0] = (-(r1z * r2y) + r1y * r2z + r1z * r3y - r2z * r3y - r1y * r3z + r2y * r3z) * Vp;
+        wg[6][1] = (r1z * r2x - r1x * r2z - r1z * r3x + r2z * r3x + r1x * r3z - r2x * r3z) * Vp;
+        wg[6][2] = (-(r1y * r2x) + r1x * r2y + r1y * r3x - r2y * r3x - r1x * r3y + r2x * r3y) * Vp;
+        wg[7][0] = (-(r1z * r2y) + r1y * r2z + r1z * r3y + r2z * r3y - r1y * r3z - r2y * r3z) * Vp;
+        wg[7][1] = (r1z * r2x - r1x * r2z - r1z * r3x - r2z * r3x + r1x * r3z + r2x * r3z) * Vp;
+        wg[7][2] = (-(r1y * r2x) + r1x * r2y + r1y * r3x + r2y * r3x - r1x * r3y - r2x * r3y) * Vp;
+    } else {
+        double Ap = 4. * (r1[0] * r2[1] - r1[1] * r2[0]);
+        Ap = SHAPE == SHAPE_QCPDI ? 1. / (3. * Ap) : 1. / Ap;
+        wg[0][0] = (r1[1] - r2[1]) * Ap; wg[0][1] = (-r1[0] + r2[0]) * Ap;
+        wg[1][0] = (r1[1] + r2[1]) * Ap; wg[1][1] = (-r1[0] - r2[0]) * Ap;
+        wg[2][0] = (-r1[1] + r2[1]) * Ap; wg[2][1] = (r1[0] - r2[0]) * Ap;
+        wg[3][0] = (-r1[1] - r2[1]) * Ap; wg[3][1] = (r1[0] + r2[0]) * Ap;
+        if (SHAPE == SHAPE_QCPDI) {
+            wg[4 % NC][0] = 4. * r1[1] * Ap; wg[4 % NC][1] = -4. * r1[0] * Ap;
+            wg[5 % NC][0] = 4. * r2[1] * Ap; wg[5 % NC][1] = -4. * r2[0] * Ap;
+            wg[6 % NC][0] = -4. * r1[1] * Ap; wg[6 % NC][1] = 4. * r1[0] * Ap;
+            wg[7 % NC][0] = -4. * r2[1] * Ap; wg[7 % NC][1] = 4. * r2[0] * Ap;
+            wg[8 % NC][0] = 0.; wg[8 % NC][1] = 0.;
+        }
+#pragma unroll
+        for (int i = 0; i < NC; i++) wg[i][2] = 0.;
+    }
+#pragma unroll
+    for (int i = 0; i < NC; i++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) P.cpWg[(size_t)(3 * i + d) * P.cpStride + p] = wg[i][d];
+    return ok;
+}
+
+// ElementBase::GetCPDIFunctions (Elements/MoreMPMElementBase.cpp:581-657): node functions are the corner-weighted
+// linear element functions, S_i = sum_c ws_c N_i(x_c), grad S_i = sum_c wg_c N_i(x_c); N < 1e-15 dropped (:612).
+// The reference merges equal nodes before use; every consumer here is linear in (S, grad S), so the
+// (corner, node) pairs are handed out unmerged.
+template <int DIM, int SHAPE, bool GRAD, class F>
+__device__ __forceinline__ void for_each_node_cpdi(const Grid &g, const Particles &P, int p, F &&f)
+{
+    const int NC = CpdiTraits<DIM, SHAPE>::NC;
+#pragma unroll 1
+    for (int c = 0; c < NC; c++) {
+        const int ce = P.cpElem[(size_t)c * P.cpStride + p];
+        const double xi = P.cpXi[(size_t)(3 * c) * P.cpStride + p], eta = P.cpXi[(size_t)(3 * c + 1) * P.cpStride + p];
+        const double zeta = DIM == 3 ? P.cpXi[(size_t)(3 * c + 2) * P.cpStride + p] : 0.;
+        double ws;
+        if (DIM == 3) ws = 0.125;
+        else if (SHAPE == SHAPE_QCPDI) ws = c < 4 ? 1. / 36. : (c < 8 ? 1. / 9. : 4. / 9.);
+        else ws = 0.25;
+        double wx = 0., wy = 0., wz = 0.;
+        if (GRAD) {
+            wx = P.cpWg[(size_t)(3 * c) * P.cpStride + p]; wy = P.cpWg[(size_t)(3 * c + 1) * P.cpStride + p];
+            wz = DIM == 3 ? P.cpWg[(size_t)(3 * c + 2) * P.cpStride + p] : 0.;
+        }
+        const ElemIJK ec = elem_ijk(g, ce);
+        const int n0 = elem_node0(g, ec);
+        if (DIM == 3) {
+            const int xo[8] = {0, 1, 1, 0, 0, 1, 1, 0}, yo[8] = {0, 0, 1, 1, 0, 0, 1, 1}, zo[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const double t1 = 1. + (xo[a] ? 1. : -1.) * xi, t2 = 1. + (yo[a] ? 1. : -1.) * eta, t3 = 1. + (zo[a] ? 1. : -1.) * zeta;
+                const double N = 0.125 * t1 * t2 * t3;
+                if (N < 1e-15) continue;
+                f(n0 + xo[a] + yo[a] * g.yplane + zo[a] * g.zplane, ws * N, wx * N, wy * N, wz * N);
+            }
+        } else {
+            const int xo[4] = {0, 1, 1, 0}, yo[4] = {0, 0, 1, 1};
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const double t1 = 1. + (xo[a] ? 1. : -1.) * xi, t2 = 1. + (yo[a] ? 1. : -1.) * eta;
+                const double N = 0.25 * t1 * t2;
+                if (N < 1e-15) continue;
+                f(n0 + xo[a] + yo[a] * g.yplane, ws * N, wx * N, wy * N, 0.);
+            }
+        }
+    }
+}

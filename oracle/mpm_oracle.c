@@ -43,6 +43,10 @@ typedef struct {
     int *bcNode; double *bcNorm, *bcValue; int *bcActive, *bcSym;
     double dt, dtFirst, dtLast;
     long long mstep;
+    /* CPDI domains (CPDIDomain, Common/System/DataTypes.hpp:110-115): up to 9 per particle */
+    int ncorner;
+    int *cpElem; double *cpXi, *cpWg, *cpWs;
+    int cpdiLeftGrid;
 } Oracle;
 
 static Oracle *O = NULL;
@@ -82,6 +86,37 @@ static int shape(int p, int getDeriv, int *nds, double *fn, double *xd, double *
     const double dx = O->xpts[ei + 1] - O->xpts[ei], dy = O->ypts[ej + 1] - O->ypts[ej];
     const double dz = O->dim == 3 ? O->zpts[ek + 1] - O->zpts[ek] : 1.;
     int i = 0;
+    if (O->cfg.shape == MPMGPU_LINEAR_CPDI || O->cfg.shape == MPMGPU_QUADRATIC_CPDI) {
+        /* ElementBase::GetCPDIFunctions, Elements/MoreMPMElementBase.cpp:581-657: merge by node in first-seen order */
+        static const double xii[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, eti[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, zti[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+        const int nn = O->dim == 3 ? 8 : 4;
+        int ind = 0;
+        for (int c = 0; c < O->ncorner; c++) {
+            const size_t q = (size_t)p * O->ncorner + c;
+            int ci, cj, ck;
+            elem_ijk(O->cpElem[q], &ci, &cj, &ck);
+            const int cnode0 = ck * O->zplane + cj * O->yplane + ci;
+            const double *cx = &O->cpXi[3 * q], *wg = &O->cpWg[3 * q];
+            const double ws = O->cpWs[c];
+            for (int j = 0; j < nn; j++) {
+                double t1 = 1. + xii[j] * cx[0], t2 = 1. + eti[j] * cx[1], t3 = 1. + zti[j] * cx[2];
+                double cfn = O->dim == 3 ? 0.125 * t1 * t2 * t3 : 0.25 * t1 * t2;
+                if (cfn < 1e-15) continue;
+                int node = cnode0 + (xii[j] > 0) + (eti[j] > 0) * O->yplane + (O->dim == 3 ? (zti[j] > 0) * O->zplane : 0);
+                int look;
+                for (look = ind - 1; look >= 0; look--) if (nds[look] == node) break;
+                if (look >= 0) {
+                    fn[look] += ws * cfn;
+                    if (getDeriv) { xd[look] += wg[0] * cfn; yd[look] += wg[1] * cfn; zd[look] += wg[2] * cfn; }
+                } else {
+                    nds[ind] = node; fn[ind] = ws * cfn;
+                    if (getDeriv) { xd[ind] = wg[0] * cfn; yd[ind] = wg[1] * cfn; zd[ind] = wg[2] * cfn; }
+                    ind++;
+                }
+            }
+        }
+        return ind;
+    }
     if (O->cfg.shape == MPMGPU_POINT_GIMP) {
         static const double xii[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, eti[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, zti[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
         const int nn = O->dim == 3 ? 8 : 4;
@@ -145,6 +180,115 @@ static int shape(int p, int getDeriv, int *nds, double *fn, double *xd, double *
     return i;
 }
 
+static void get_F(int p, double F[3][3]);
+
+/* ---- CPDI domains: MatPoint3D.cpp:413-492,538-621; MatPoint2D.cpp:423-477,519-640 --------------------------------- */
+static int find_element(const double *x)        /* MeshInfo::FindElementFromPoint, MeshInfo.cpp:593-633; 0 = off grid */
+{
+    int col = (int)((x[0] - O->xpts[0]) / O->cfg.gridx), row = (int)((x[1] - O->ypts[0]) / O->cfg.gridy), zrow = 0;
+    if (col < 0 || col >= O->horiz) { if (x[0] == O->xpts[0] + O->horiz * O->cfg.gridx) col = O->horiz - 1; else return 0; }
+    if (row < 0 || row >= O->vert) { if (x[1] == O->ypts[0] + O->vert * O->cfg.gridy) row = O->vert - 1; else return 0; }
+    if (O->dim == 3) {
+        zrow = (int)((x[2] - O->zpts[0]) / O->cfg.gridz);
+        if (zrow < 0 || zrow >= O->depth) { if (x[2] == O->zpts[0] + O->depth * O->cfg.gridz) zrow = O->depth - 1; else return 0; }
+        return O->horiz * (zrow * O->vert + row) + col + 1;
+    }
+    return row * O->horiz + col + 1;
+}
+
+static void corner_into(int p, int c, const double *x, int forceElem)
+{
+    const size_t q = (size_t)p * O->ncorner + c;
+    int e = forceElem > 0 ? forceElem : find_element(x);
+    if (e <= 0) { O->cpdiLeftGrid = p + 1; e = O->inElem[p]; }
+    int i, j, k;
+    elem_ijk(e, &i, &j, &k);
+    O->cpElem[q] = e;
+    O->cpXi[3 * q] = (2. * x[0] - O->xpts[i] - O->xpts[i + 1]) / (O->xpts[i + 1] - O->xpts[i]);
+    O->cpXi[3 * q + 1] = (2. * x[1] - O->ypts[j] - O->ypts[j + 1]) / (O->ypts[j + 1] - O->ypts[j]);
+    O->cpXi[3 * q + 2] = O->dim == 3 ? (2. * x[2] - O->zpts[k] - O->zpts[k + 1]) / (O->zpts[k + 1] - O->zpts[k]) : 0.;
+}
+
+static void cpdi_nodes_and_weights(int p)
+{
+    int ei, ej, ek;
+    elem_ijk(O->inElem[p], &ei, &ej, &ek);
+    const double cx = O->xpts[ei + 1] - O->xpts[ei], cy = O->ypts[ej + 1] - O->ypts[ej], cz = O->dim == 3 ? O->zpts[ek + 1] - O->zpts[ek] : 1.;
+    const double psx = cx * (0.5 * P3(lp, 0, p)), psy = cy * (0.5 * P3(lp, 1, p)), psz = cz * (0.5 * P3(lp, 2, p));
+    double F[3][3];
+    get_F(p, F);
+    const double pos[3] = {P3(pos, 0, p), P3(pos, 1, p), O->dim == 3 ? P3(pos, 2, p) : 0.};
+    const size_t q0 = (size_t)p * O->ncorner;
+    if (O->dim == 3) {
+        double r1[3] = {F[0][0] * psx, F[1][0] * psx, F[2][0] * psx}, r2[3] = {F[0][1] * psy, F[1][1] * psy, F[2][1] * psy};
+        double r3[3] = {F[0][2] * psz, F[1][2] * psz, F[2][2] * psz};
+        if (O->cfg.cpdi_rcrit >= 0.) {
+            double rc = O->cfg.cpdi_rcrit * fmin(cx, fmin(cy, cz)), l[4][3];
+            static const double sg[4][2] = {{1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+            int rescale = 0;
+            for (int a = 0; a < 4; a++) {
+                for (int d = 0; d < 3; d++) l[a][d] = sg[a][0] * r1[d] + sg[a][1] * r2[d] + r3[d];
+                double mag = sqrt(l[a][0] * l[a][0] + l[a][1] * l[a][1] + l[a][2] * l[a][2]);
+                if (mag > rc) { for (int d = 0; d < 3; d++) l[a][d] *= rc / mag; rescale = 1; }
+            }
+            if (rescale) for (int d = 0; d < 3; d++) {
+                r1[d] = 0.25 * (l[0][d] + l[1][d] - l[2][d] - l[3][d]);
+                r2[d] = 0.25 * (l[0][d] - l[1][d] + l[2][d] - l[3][d]);
+                r3[d] = 0.25 * (l[0][d] + l[1][d] + l[2][d] + l[3][d]);
+            }
+        }
+        static const double r1s[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, r2s[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, r3s[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+        for (int i = 0; i < 8; i++) {
+            double c[3];
+            for (int d = 0; d < 3; d++) c[d] = pos[d] + r1s[i] * r1[d] + r2s[i] * r2[d] + r3s[i] * r3[d];
+            corner_into(p, i, c, 0);
+        }
+        double Vp = 8. * (r1[0] * (r2[1] * r3[2] - r2[2] * r3[1]) + r1[1] * (r2[2] * r3[0] - r2[0] * r3[2]) + r1[2] * (r2[0] * r3[1] - r2[1] * r3[0]));
+        Vp = 1. / Vp;
+        /* wg_c = (1/Vp) * [ s1 (r2 x r3) + s2 (r3 x r1) + s3 (r1 x r2) ] written out in the reference (:551-594);
+           evaluated here from the same closed forms */
+        for (int i = 0; i < 8; i++) {
+            double s1 = r1s[i], s2 = r2s[i], s3 = r3s[i];
+            double *w = &O->cpWg[3 * (q0 + i)];
+            /* expand exactly the reference polynomials: terms are +-(ra_b * rc_d) */
+            w[0] = (-s3 * r1[2] * r2[1] + s3 * r1[1] * r2[2] + s2 * r1[2] * r3[1] - s1 * r2[2] * r3[1] - s2 * r1[1] * r3[2] + s1 * r2[1] * r3[2]) * Vp;
+            w[1] = (s3 * r1[2] * r2[0] - s3 * r1[0] * r2[2] - s2 * r1[2] * r3[0] + s1 * r2[2] * r3[0] + s2 * r1[0] * r3[2] - s1 * r2[0] * r3[2]) * Vp;
+            w[2] = (-s3 * r1[1] * r2[0] + s3 * r1[0] * r2[1] + s2 * r1[1] * r3[0] - s1 * r2[1] * r3[0] - s2 * r1[0] * r3[1] + s1 * r2[0] * r3[1]) * Vp;
+        }
+    } else {
+        double r1[2] = {F[0][0] * psx, F[1][0] * psx}, r2[2] = {F[0][1] * psy, F[1][1] * psy};
+        if (O->cfg.cpdi_rcrit >= 0.) {
+            double rc = O->cfg.cpdi_rcrit * fmin(cx, cy);
+            double la[2] = {r1[0] + r2[0], r1[1] + r2[1]}, lb[2] = {r1[0] - r2[0], r1[1] - r2[1]};
+            double lam = sqrt(la[0] * la[0] + la[1] * la[1]), lbm = sqrt(lb[0] * lb[0] + lb[1] * lb[1]);
+            int rescale = 0;
+            if (lam > rc) { la[0] *= rc / lam; la[1] *= rc / lam; rescale = 1; }
+            if (lbm > rc) { lb[0] *= rc / lbm; lb[1] *= rc / lbm; rescale = 1; }
+            if (rescale) { r1[0] = 0.5 * (la[0] + lb[0]); r1[1] = 0.5 * (la[1] + lb[1]); r2[0] = 0.5 * (la[0] - lb[0]); r2[1] = 0.5 * (la[1] - lb[1]); }
+        }
+        static const double s1[9] = {-1, 1, 1, -1, 0, 1, 0, -1, 0}, s2[9] = {-1, -1, 1, 1, -1, 0, 1, 0, 0};
+        for (int i = 0; i < O->ncorner; i++) {
+            double c[3] = {pos[0], pos[1], 0.};
+            if (s1[i] != 0.) { c[0] += s1[i] * r1[0]; c[1] += s1[i] * r1[1]; }
+            if (s2[i] != 0.) { c[0] += s2[i] * r2[0]; c[1] += s2[i] * r2[1]; }
+            corner_into(p, i, c, i == 8 ? O->inElem[p] : 0);
+        }
+        double Ap = 4. * (r1[0] * r2[1] - r1[1] * r2[0]);
+        Ap = O->ncorner == 9 ? 1. / (3. * Ap) : 1. / Ap;
+        double (*w)[3] = (double (*)[3]) & O->cpWg[3 * q0];
+        w[0][0] = (r1[1] - r2[1]) * Ap; w[0][1] = (-r1[0] + r2[0]) * Ap;
+        w[1][0] = (r1[1] + r2[1]) * Ap; w[1][1] = (-r1[0] - r2[0]) * Ap;
+        w[2][0] = (-r1[1] + r2[1]) * Ap; w[2][1] = (r1[0] - r2[0]) * Ap;
+        w[3][0] = (-r1[1] - r2[1]) * Ap; w[3][1] = (r1[0] + r2[0]) * Ap;
+        if (O->ncorner == 9) {
+            w[4][0] = 4. * r1[1] * Ap; w[4][1] = -4. * r1[0] * Ap; w[5][0] = 4. * r2[1] * Ap; w[5][1] = -4. * r2[0] * Ap;
+            w[6][0] = -4. * r1[1] * Ap; w[6][1] = 4. * r1[0] * Ap; w[7][0] = -4. * r2[1] * Ap; w[7][1] = 4. * r2[0] * Ap;
+            w[8][0] = 0.; w[8][1] = 0.;
+        }
+        for (int i = 0; i < O->ncorner; i++) w[i][2] = 0.;
+    }
+}
+
 /* ---- task 1: InitializationTask.cpp:49-85; GetXiPos EightNodeIsoparamBrick.cpp:276-281 ------------------- */
 static void task_initialization(void)
 {
@@ -155,6 +299,7 @@ static void task_initialization(void)
         P3(ncpos, 0, p) = (2. * P3(pos, 0, p) - O->xpts[ei] - O->xpts[ei + 1]) / (O->xpts[ei + 1] - O->xpts[ei]);
         P3(ncpos, 1, p) = (2. * P3(pos, 1, p) - O->ypts[ej] - O->ypts[ej + 1]) / (O->ypts[ej + 1] - O->ypts[ej]);
         P3(ncpos, 2, p) = O->dim == 3 ? (2. * P3(pos, 2, p) - O->zpts[ek] - O->zpts[ek + 1]) / (O->zpts[ek + 1] - O->zpts[ek]) : 0.;
+        if (O->ncorner > 0 && p < O->nNR) cpdi_nodes_and_weights(p);
     }
 }
 
@@ -839,8 +984,19 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
     O->bcNode = dupi(bcNode, nbc, 0); O->bcNorm = dupd(bcNorm, 3 * (size_t)nbc); O->bcValue = dupd(bcValue, nbc);
     O->bcActive = dupi(bcActive, nbc, 1); O->bcSym = dupi(bcSym, nbc, 0);
     O->dt = dt; O->dtFirst = dtFirst; O->dtLast = dtLast;
+    O->ncorner = 0;
+    if (cfg->shape == MPMGPU_LINEAR_CPDI) O->ncorner = O->dim == 3 ? 8 : 4;
+    if (cfg->shape == MPMGPU_QUADRATIC_CPDI) O->ncorner = 9;
+    if (O->ncorner) {
+        O->cpElem = dupi(NULL, n * O->ncorner, 1); O->cpXi = dupd(NULL, 3 * n * O->ncorner); O->cpWg = dupd(NULL, 3 * n * O->ncorner);
+        O->cpWs = dupd(NULL, 9);
+        for (int c = 0; c < O->ncorner; c++)        /* MPMBase::AllocateCPDIorGIMPStructures, MPMBase.cpp:160-175 */
+            O->cpWs[c] = O->ncorner == 9 ? (c < 4 ? 1. / 36. : (c < 8 ? 1. / 9. : 4. / 9.)) : (O->dim == 3 ? 0.125 : 0.25);
+    }
     return 0;
 }
+
+int oracle_cpdi_left_grid(void) { return O ? O->cpdiLeftGrid : 0; }
 
 int oracle_set_xpic(int order, int using_fmpm) { if (!O) return -1; O->cfg.xpic_order = order; O->cfg.using_fmpm = using_fmpm; return 0; }
 

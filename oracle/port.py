@@ -36,6 +36,7 @@ class PortOracle:
         cfg.xpts, cfg.ypts, cfg.zpts = [_d(a) for a in self._keep]
         cfg.gridx, cfg.gridy, cfg.gridz = prob.grid
         cfg.shape, cfg.method = prob.shape, prob.method
+        cfg.cpdi_rcrit = prob.rcrit
         cfg.skip_post_extrapolation = int(prob.skip_post_extrapolation)
         cfg.fraction_usf = prob.fraction_usf
         cfg.xpic_order, cfg.using_fmpm = prob.xpic_order, int(prob.using_fmpm)

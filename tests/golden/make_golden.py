@@ -32,6 +32,11 @@ CASES = {
     "block3d_xpic3": (inputs.block3d(ncell=4, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(3, False, 2)), (1, 2, 3, 30), 2, 0.3, 3000.0),
     "block3d_fmpm2": (inputs.block3d(ncell=4, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(2, True, 1)), (1, 2, 30), 2, 0.3, 3000.0),
     "disks2d_fmpm3_neo": (inputs.disks2d(analysis=10, extra_header="").replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>', '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha></Material>').replace("</JANFEAInput>", inputs.periodic_xpic(3, True, 1) + "</JANFEAInput>"), (1, 2, 60), 2),
+    "block3d_lcpdi_neo_xpic2": (inputs.block3d(ncell=3, margin=3, gimp="lCPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3,
+                                               custom_tasks=inputs.periodic_xpic(2, False, 1)), (1, 2, 40), 2, 0.3, 2000.0),
+    "block3d_lcpdi_rcrit": (inputs.block3d(ncell=3, margin=3, gimp="lCPDI", E=50.0, vz=-2.0e4, vx=1.0e4, extra_header="<CPDIrcrit>0.6</CPDIrcrit>"), (1, 40), 1, 0.3, 5000.0),
+    "disks2d_lcpdi": (inputs.disks2d(analysis=10, gimp="lCPDI"), (1, 100), 1),
+    "disks2d_qcpdi": (inputs.disks2d(analysis=10, gimp="qCPDI"), (1, 100), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),
