@@ -202,7 +202,8 @@ int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps);
  * reference's per-task timing report (MPMTask.cpp:106-121) stays meaningful and each task can be
  * checked in isolation.  Call in pipeline order. */
 int mpmgpu_task_initialization(mpmgpu_ctx *ctx);        /* InitializationTask.cpp:43-103 */
-int mpmgpu_task_mass_and_momentum(mpmgpu_ctx *ctx);     /* MassAndMomentumTask.cpp:48-127 (+ProjectRigidBCsTask) */
+int mpmgpu_task_mass_and_momentum(mpmgpu_ctx *ctx);     /* MassAndMomentumTask.cpp:48-127 */
+int mpmgpu_task_project_rigid_bcs(mpmgpu_ctx *ctx);     /* ProjectRigidBCsTask.cpp:39-158 (no-op without rigid-BC particles) */
 int mpmgpu_task_post_extrapolation(mpmgpu_ctx *ctx);    /* PostExtrapolationTask.cpp:46-165 */
 int mpmgpu_task_update_strains_first(mpmgpu_ctx *ctx);  /* UpdateStrainsFirstTask.cpp:52-168 */
 int mpmgpu_task_grid_forces(mpmgpu_ctx *ctx);           /* GridForcesTask.cpp:40-153 */

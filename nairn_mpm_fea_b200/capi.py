@@ -27,6 +27,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
            "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
+    "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
     "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times",
     "mpmgpu_slab_configure", "mpmgpu_slab_halo_buffers", "mpmgpu_slab_step_phase", "mpmgpu_slab_migration_counts",
@@ -97,7 +98,7 @@ def load_library(path=None):
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
     lib.mpmgpu_update_velocity_bc_values.argtypes = [vp, C.c_int, _dp, _ip]
     lib.mpmgpu_step.argtypes = [vp, C.c_int]
-    for t in TASKS:
+    for t in TASKS + ["project_rigid_bcs"]:
         getattr(lib, "mpmgpu_task_" + t).argtypes = [vp]
     lib.mpmgpu_download_particles.argtypes = [vp, C.POINTER(ParticlesView), C.c_uint]
     lib.mpmgpu_download_nodes.argtypes = [vp, C.POINTER(NodesView)]

@@ -26,7 +26,11 @@ struct mpmgpu_ctx {
     mpmgpu_config cfg;
     int dim;
     Grid g;
-    Particles P;
+    Particles P;                        // nonrigid particles (P.n == P.nNR)
+    Particles PR;                       // rigid-BC particles, host order, in their own small pool
+    double *rigidPool; int *rigidIntPool; size_t rigidCap;
+    RigidBCs R;                         // node dofs claimed by rigid particles
+    std::vector<unsigned char> hFixedBits;
     Nodes N;
     StepParams sp;
     VelBCs B;
@@ -49,7 +53,7 @@ struct mpmgpu_ctx {
     long long launches;
     bool uploaded, hasFext, hasBCs;
     cudaStream_t ownStream; bool ownStreamSaved;
-    const int *dlSlot;                  // download slot map: P.orig, or identity when ids are global
+    const int *dlSlot, *dlSlotR;        // download slot maps: P.orig / PR.orig, or identity when ids are global
     bool globalIds;                     // particle ids are caller-global (slab mode): downloads come in device order + ids
     std::string err;
     // profiling
@@ -123,7 +127,9 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
     ctx->cpElemPool = NULL; ctx->cpXiPool = NULL; ctx->cpWgPool = NULL;
     ctx->hStage = NULL; ctx->hStageBytes = 0; ctx->nBCEntries = 0;
-    memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B);
+    memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R);
+    ctx->rigidPool = NULL; ctx->rigidIntPool = NULL; ctx->rigidCap = 0;
+    memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B);
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
     memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
     tiled_state_init(ctx->tiled);
@@ -287,20 +293,20 @@ static int ensure_stage(mpmgpu_ctx *ctx, size_t bytes)
     return MPMGPU_OK;
 }
 
-// copy a host [ncomp][n] array to device component arrays (zero-fill when host is NULL)
-static int up_field(mpmgpu_ctx *ctx, double *const *dev, const double *host, int ncomp, int n)
+// copy rows [off, off+cnt) of a host [ncomp][n] array to device component arrays (zero-fill when host is NULL)
+static int up_field(mpmgpu_ctx *ctx, double *const *dev, const double *host, int ncomp, int n, int off, int cnt)
 {
     for (int c = 0; c < ncomp; c++) {
-        if (host) CK(cudaMemcpyAsync(dev[c], host + (size_t)c * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        else CK(cudaMemsetAsync(dev[c], 0, (size_t)n * sizeof(double), ctx->stream));
+        if (host) CK(cudaMemcpyAsync(dev[c], host + (size_t)c * n + off, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(dev[c], 0, (size_t)cnt * sizeof(double), ctx->stream));
     }
     return MPMGPU_OK;
 }
 
-__global__ void k_epwrot_to_F(int n, int dim, const double *ep, const double *wrot, Particles P)
+__global__ void k_epwrot_to_F(int cnt, int n, int dim, const double *ep, const double *wrot, Particles P)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    if (p >= cnt) return;
     // MatPoint3D::GetDeformationGradient (MatPoint3D.cpp:363-376), 2D: MatPoint2D.cpp:369-377
     double exx = ep ? ep[p] : 0., eyy = ep ? ep[n + p] : 0., ezz = ep ? ep[2 * n + p] : 0.;
     double eyz = ep ? ep[3 * n + p] : 0., exz = ep ? ep[4 * n + p] : 0., exy = ep ? ep[5 * n + p] : 0.;
@@ -315,10 +321,10 @@ __global__ void k_epwrot_to_F(int n, int dim, const double *ep, const double *wr
     }
 }
 
-__global__ void k_F_to_epwrot(int n, int dim, Particles P, const int *slot, double *ep, double *wrot)
+__global__ void k_F_to_epwrot(int cnt, int n, int dim, Particles P, const int *slot, double *ep, double *wrot)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    if (p >= cnt) return;
     int o = slot[p];        // caller's index
     // MatPoint3D::SetDeformationGradientMatrix (MatPoint3D.cpp:320-336)
     double F0 = P.F[0][p], F1 = P.F[1][p], F2 = P.F[2][p], F3 = P.F[3][p], F4 = P.F[4][p], F5 = P.F[5][p], F6 = P.F[6][p], F7 = P.F[7][p], F8 = P.F[8][p];
@@ -332,7 +338,7 @@ __global__ void k_F_to_epwrot(int n, int dim, Particles P, const int *slot, doub
     }
 }
 
-__global__ void k_iota(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+__global__ void k_iota(int n, int *a, int first = 0) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = first + i; }
 __global__ void k_fill(int n, double *a, double v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = v; }
 __global__ void k_dec(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] -= 1; }
 
@@ -346,6 +352,82 @@ __global__ void k_unpermute_int(int n, const int *src, const int *slot, int *dst
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) dst[slot[p]] = src[p] + add;
+}
+
+// rows [off, off+cnt) of the caller's arrays -> one particle set
+static int upload_range(mpmgpu_ctx *ctx, Particles &P, const mpmgpu_particles *h, int off, int cnt)
+{
+    const int n = h->n;
+    int rc;
+    const int T = 256;
+    if ((rc = up_field(ctx, P.pos, h->pos, 3, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, P.vel, h->vel, 3, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, &P.mp, h->mp, 1, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, P.lp, h->lp, 3, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, P.sp, h->sp, 6, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, &P.pressure, h->pressure, 1, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, P.eplast, h->eplast, 6, n, off, cnt))) return rc;
+    if (h->energies) {
+        double *const e5[6] = {P.work, P.res, P.heat, P.entropy, P.plast, P.prevT};
+        if ((rc = up_field(ctx, e5, h->energies, 6, n, off, cnt))) return rc;
+    } else {
+        double *const e5[5] = {P.work, P.res, P.heat, P.entropy, P.plast};
+        if ((rc = up_field(ctx, e5, NULL, 5, n, off, cnt))) return rc;
+        LAUNCH(k_fill, nblocks(cnt, T), T, cnt, P.prevT, 1.);
+    }
+    if ((rc = up_field(ctx, P.hist, h->history, MPM_MAX_HISTORY, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, P.pfext, h->pfext, 3, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, P.acc, NULL, 3, n, off, cnt))) return rc;
+    if ((rc = up_field(ctx, P.ncpos, NULL, 3, n, off, cnt))) return rc;
+    CK(cudaMemcpyAsync(P.elem, h->in_elem + off, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (h->matnum) {
+        CK(cudaMemcpyAsync(P.mat, h->matnum + off, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_dec, nblocks(cnt, T), T, cnt, P.mat);
+    } else CK(cudaMemsetAsync(P.mat, 0, (size_t)cnt * sizeof(int), ctx->stream));
+    if (h->crossings) CK(cudaMemcpyAsync(P.cross, h->crossings + off, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(P.cross, 0, (size_t)cnt * sizeof(int), ctx->stream));
+    if (h->ids) CK(cudaMemcpyAsync(P.orig, h->ids + off, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    else LAUNCH(k_iota, nblocks(cnt, T), T, cnt, P.orig, off);
+    // strain + rotation -> deformation gradient (staged through a temporary device buffer)
+    {
+        double *tmp = NULL;
+        CK(cudaMalloc((void **)&tmp, (size_t)cnt * 9 * sizeof(double)));
+        const double *dep = NULL, *dw = NULL;
+        if (h->ep) {
+            for (int c = 0; c < 6; c++) CK(cudaMemcpyAsync(tmp + (size_t)c * cnt, h->ep + (size_t)c * n + off, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            dep = tmp;
+        }
+        if (h->wrot) {
+            for (int c = 0; c < 3; c++) CK(cudaMemcpyAsync(tmp + (size_t)(6 + c) * cnt, h->wrot + (size_t)c * n + off, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            dw = tmp + (size_t)6 * cnt;
+        }
+        LAUNCH(k_epwrot_to_F, nblocks(cnt, T), T, cnt, cnt, ctx->dim, dep, dw, P);
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    return MPMGPU_OK;
+}
+
+static int alloc_rigid(mpmgpu_ctx *ctx, size_t cap)
+{
+    if (ctx->rigidCap < cap) {
+        if (ctx->rigidCap != 0) return fail(ctx, MPMGPU_EINVAL, "rigid particle count grew from %zu to %zu", ctx->rigidCap, cap);
+        size_t capPad = (cap + 31) & ~(size_t)31;
+        CK(dalloc(ctx, &ctx->rigidPool, capPad * NPD));
+        CK(dalloc(ctx, &ctx->rigidIntPool, capPad * NPI));
+        CK(cudaMemsetAsync(ctx->rigidPool, 0, capPad * NPD * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->rigidIntPool, 0, capPad * NPI * sizeof(int), ctx->stream));
+        bind_particles(ctx->PR, ctx->rigidPool, ctx->rigidIntPool, capPad);
+        ctx->rigidCap = capPad;
+        const size_t nn = (size_t)ctx->g.nnodes;
+        for (int d = 0; d < 3; d++) { CK(dalloc(ctx, &ctx->R.owner[d], nn)); ctx->R.vel[d] = ctx->PR.vel[d]; }
+        unsigned char *fb = NULL;
+        CK(dalloc(ctx, &fb, nn));
+        if (ctx->hFixedBits.size() == nn) CK(cudaMemcpyAsync(fb, ctx->hFixedBits.data(), nn, cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(fb, 0, nn, ctx->stream));
+        ctx->R.fixedBits = fb;
+    }
+    return MPMGPU_OK;
 }
 
 extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *h)
@@ -366,58 +448,36 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         int e = h->in_elem[p];
         if (e < 1 || e > ctx->g.nelems) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d in element %d of %d", p, e, ctx->g.nelems);
     }
-    Particles &P = ctx->P;
-    P.n = n; P.nNR = h->n_nonrigid;
-    const int T = 256;
-    if ((rc = up_field(ctx, P.pos, h->pos, 3, n))) return rc;
-    if ((rc = up_field(ctx, P.vel, h->vel, 3, n))) return rc;
-    if ((rc = up_field(ctx, &P.mp, h->mp, 1, n))) return rc;
-    if ((rc = up_field(ctx, P.lp, h->lp, 3, n))) return rc;
-    if ((rc = up_field(ctx, P.sp, h->sp, 6, n))) return rc;
-    if ((rc = up_field(ctx, &P.pressure, h->pressure, 1, n))) return rc;
-    if ((rc = up_field(ctx, P.eplast, h->eplast, 6, n))) return rc;
-    if (h->energies) {
-        double *const e5[6] = {P.work, P.res, P.heat, P.entropy, P.plast, P.prevT};
-        if ((rc = up_field(ctx, e5, h->energies, 6, n))) return rc;
-    } else {
-        double *const e5[5] = {P.work, P.res, P.heat, P.entropy, P.plast};
-        if ((rc = up_field(ctx, e5, NULL, 5, n))) return rc;
-        LAUNCH(k_fill, nblocks(n, T), T, n, P.prevT, 1.);
+    const int nNR = h->n_nonrigid, nR = n - nNR;
+    if (nR > 0) {
+        if (ctx->cfg.shape != MPMGPU_POINT_GIMP && ctx->cfg.shape != MPMGPU_UNIFORM_GIMP)
+            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: rigid-BC particles need Linear or uGIMP shape functions");
+        for (int p = nNR; p < n; p++) {
+            const Material &m = ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1];
+            if (m.kind != MAT_RIGIDBC) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d (after n_nonrigid) is not a rigid-BC material", p);
+        }
+        if ((rc = alloc_rigid(ctx, (size_t)nR))) return rc;
     }
-    if ((rc = up_field(ctx, P.hist, h->history, MPM_MAX_HISTORY, n))) return rc;
-    if ((rc = up_field(ctx, P.pfext, h->pfext, 3, n))) return rc;
+    for (int p = 0; p < nNR; p++)
+        if (ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1].kind == MAT_RIGIDBC)
+            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: rigid particle %d before n_nonrigid=%d (the reference reorders them to the end, NairnMPM.cpp:1121-1150)", p, nNR);
+    ctx->P.n = nNR; ctx->P.nNR = nNR;
+    ctx->PR.n = nR; ctx->PR.nNR = 0;
     ctx->hasFext = h->pfext != NULL;
-    if ((rc = up_field(ctx, P.acc, NULL, 3, n))) return rc;
-    if ((rc = up_field(ctx, P.ncpos, NULL, 3, n))) return rc;
-    CK(cudaMemcpyAsync(P.elem, h->in_elem, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if (h->matnum) {
-        CK(cudaMemcpyAsync(P.mat, h->matnum, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(k_dec, nblocks(n, T), T, n, P.mat);
-    } else CK(cudaMemsetAsync(P.mat, 0, (size_t)n * sizeof(int), ctx->stream));
-    if (h->crossings) CK(cudaMemcpyAsync(P.cross, h->crossings, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    else CK(cudaMemsetAsync(P.cross, 0, (size_t)n * sizeof(int), ctx->stream));
-    if (h->ids) { CK(cudaMemcpyAsync(P.orig, h->ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); ctx->globalIds = true; }
-    else LAUNCH(k_iota, nblocks(n, T), T, n, P.orig);
-    // strain + rotation -> deformation gradient (staged through a temporary device buffer)
-    {
-        double *tmp = NULL;
-        CK(cudaMalloc((void **)&tmp, (size_t)n * 9 * sizeof(double)));
-        const double *dep = NULL, *dw = NULL;
-        if (h->ep) { CK(cudaMemcpyAsync(tmp, h->ep, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); dep = tmp; }
-        if (h->wrot) { CK(cudaMemcpyAsync(tmp + (size_t)6 * n, h->wrot, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); dw = tmp + (size_t)6 * n; }
-        LAUNCH(k_epwrot_to_F, nblocks(n, T), T, n, ctx->dim, dep, dw, P);
-        CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp);
-    }
+    if (h->ids) ctx->globalIds = true;
+    if (nNR > 0 && (rc = upload_range(ctx, ctx->P, h, 0, nNR))) return rc;
+    if (nR > 0 && (rc = upload_range(ctx, ctx->PR, h, nNR, nR))) return rc;
+    ctx->R.on = nR > 0 ? 1 : 0;
+    ctx->tiled.FN.R = ctx->R;
     CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(StatusFlags), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
     tiled_on_upload(ctx->tiled);
     {   // the fused path needs 3D uGIMP, particles no larger than a cell, FLIP/PIC, no rigid particles
-        bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && h->n_nonrigid == n;   // (XPIC order is checked per step)
-        if (ok) for (size_t i = 0; i < (size_t)3 * n; i++) if (!(h->lp[i] <= 1.0)) { ok = false; break; }
+        bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && nNR > 0;   // (XPIC order is checked per step)
+        if (ok) for (int c = 0; c < 3 && ok; c++) for (int q = 0; q < nNR; q++) if (!(h->lp[(size_t)c * n + q] <= 1.0)) { ok = false; break; }
         bool uni = true;
-        for (int c = 0; c < 3 && uni; c++) for (int q = 1; q < n; q++) if (h->lp[(size_t)c * n + q] != h->lp[(size_t)c * n]) { uni = false; break; }
+        for (int c = 0; c < 3 && uni; c++) for (int q = 1; q < nNR; q++) if (h->lp[(size_t)c * n + q] != h->lp[(size_t)c * n]) { uni = false; break; }
         ctx->g.lpUniform = uni ? 1 : 0;
         for (int c = 0; c < 3; c++) {
             ctx->g.lpU[c] = h->lp[(size_t)c * n];
@@ -425,10 +485,10 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
             ctx->g.lpInv2[c] = 1. / (2. * ctx->g.lpU[c]);
         }
         ctx->tiled.stateKind = SK_ELASTIC;
-        for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC) ctx->tiled.stateKind = SK_FULL;
+        for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC && ctx->hMats[i].kind != MAT_RIGIDBC) ctx->tiled.stateKind = SK_FULL;
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
-            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, XPIC order<=1 and no rigid particles");
+            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1 and XPIC order<=1");
         ctx->tiled.enabled = ok ? 1 : 0;
         ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 25;
         {
@@ -466,6 +526,16 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
     cudaSetDevice(ctx->cfg.device);
     ctx->hasBCs = n > 0;
     ctx->nBCEntries = n;
+    {   // dofs fixed by grid BCs, for rigid-particle projection (nd[]->fixedDirection bits 1,2,4: NodalVelBC.cpp:40-45)
+        ctx->hFixedBits.assign((size_t)ctx->g.nnodes, 0);
+        for (int i = 0; i < n && node && norm; i++) {
+            if (node[i] < 1 || node[i] > ctx->g.nnodes) continue;
+            unsigned char b = symdir ? (unsigned char)(symdir[i] & 7) : 0;
+            for (int d = 0; d < 3; d++) if (norm[3 * i + d] != 0.) b |= (unsigned char)(1 << d);
+            ctx->hFixedBits[node[i] - 1] |= b;
+        }
+        if (ctx->R.fixedBits) cudaMemcpy((void *)ctx->R.fixedBits, ctx->hFixedBits.data(), ctx->hFixedBits.size(), cudaMemcpyHostToDevice);
+    }
     if (n == 0) { ctx->B.nUnique = 0; ctx->tiled.FN.bcOfNode = NULL; return MPMGPU_OK; }
     if (!node || !norm || !value) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: null arrays");
     for (int i = 0; i < n; i++)
@@ -558,8 +628,43 @@ static void prof_end(mpmgpu_ctx *ctx, int task)
 
 static int apply_bcs(mpmgpu_ctx *ctx, int pass, int adjustSym)
 {
-    if (!ctx->hasBCs || ctx->B.nUnique == 0) return MPMGPU_OK;
-    LAUNCH(k_velocity_bcs, nblocks(ctx->B.nUnique, 128), 128, ctx->B, ctx->N, pass, ctx->sp.dt, adjustSym);
+    if (ctx->hasBCs && ctx->B.nUnique > 0)
+        LAUNCH(k_velocity_bcs, nblocks(ctx->B.nUnique, 128), 128, ctx->B, ctx->N, pass, ctx->sp.dt, adjustSym);
+    if (ctx->R.on && adjustSym != 2)
+        LAUNCH(k_rigid_velocity_bcs, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->R, ctx->N, pass, ctx->sp.dt);
+    return MPMGPU_OK;
+}
+
+// ProjectRigidBCsTask: runs between mass/momentum and post-extrapolation (NairnMPM.cpp:982-987)
+static int t_project_rigid_bcs(mpmgpu_ctx *ctx)
+{
+    if (!ctx->R.on) return MPMGPU_OK;
+    for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->R.owner[d], 0x7f, (size_t)ctx->g.nnodes * sizeof(int), ctx->stream));
+    ctx->launches += 3;
+    const int grid = nblocks(ctx->PR.n, TASK_THREADS);
+    if (ctx->dim == 3) {
+        if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((k_project_rigid_bcs<3, SHAPE_UGIMP>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
+        else LAUNCH((k_project_rigid_bcs<3, SHAPE_LINEAR>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
+    } else {
+        if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((k_project_rigid_bcs<2, SHAPE_UGIMP>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
+        else LAUNCH((k_project_rigid_bcs<2, SHAPE_LINEAR>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
+    }
+    return MPMGPU_OK;
+}
+
+static int move_rigid(mpmgpu_ctx *ctx)
+{
+    if (ctx->PR.n <= 0) return MPMGPU_OK;
+    if (ctx->dim == 3) LAUNCH(k_move_rigid<3>, nblocks(ctx->PR.n, 128), 128, ctx->PR, ctx->sp.dt);
+    else LAUNCH(k_move_rigid<2>, nblocks(ctx->PR.n, 128), 128, ctx->PR, ctx->sp.dt);
+    return MPMGPU_OK;
+}
+
+static int reset_rigid(mpmgpu_ctx *ctx)
+{
+    if (ctx->PR.n <= 0) return MPMGPU_OK;
+    if (ctx->dim == 3) LAUNCH(k_reset_elements<3>, nblocks(ctx->PR.n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->PR, ctx->dFlags, ctx->sp.dt);
+    else LAUNCH(k_reset_elements<2>, nblocks(ctx->PR.n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->PR, ctx->dFlags, ctx->sp.dt);
     return MPMGPU_OK;
 }
 
@@ -596,7 +701,7 @@ static int xpic_extrapolation(mpmgpu_ctx *ctx, int particleUpdate)
     LAUNCH(k_xpic_init, nblocks(nn, 256), 256, nn, ctx->N, ctx->sp.dt, fmpm);
     for (int k = 2; k <= ctx->sp.xpicOrder; k++) {
         DISPATCH_DIM_SHAPE(k_xpic_iterate, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
-        LAUNCH(k_xpic_finish, nblocks(nn, 256), 256, nn, ctx->N, ctx->B, ctx->hasBCs ? ctx->tiled.FN.bcOfNode : (const int *)NULL,
+        LAUNCH(k_xpic_finish, nblocks(nn, 256), 256, nn, ctx->N, ctx->B, ctx->hasBCs ? ctx->tiled.FN.bcOfNode : (const int *)NULL, ctx->R,
                ctx->sp.dt, particleUpdate, fmpm);
     }
     return MPMGPU_OK;
@@ -646,7 +751,7 @@ static int t_update_particles(mpmgpu_ctx *ctx)
     int m = ctx->sp.xpicOrder;
     if (!ctx->sp.usingFMPM) m = -m;
     DISPATCH_DIM_SHAPE(k_update_particles, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, ctx->sp, m);
-    return MPMGPU_OK;
+    return move_rigid(ctx);
 }
 
 static int t_update_strains_last(mpmgpu_ctx *ctx)
@@ -665,9 +770,10 @@ static int t_update_strains_last(mpmgpu_ctx *ctx)
 static int t_reset_elements(mpmgpu_ctx *ctx)
 {
     const int n = ctx->P.n;
+    if (n == 0) return reset_rigid(ctx);
     if (ctx->dim == 3) LAUNCH(k_reset_elements<3>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->dFlags, ctx->sp.dt);
     else LAUNCH(k_reset_elements<2>, nblocks(n, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->dFlags, ctx->sp.dt);
-    return MPMGPU_OK;
+    return reset_rigid(ctx);
 }
 
 static int poll_flags(mpmgpu_ctx *ctx)
@@ -692,6 +798,7 @@ extern "C" int NAME(mpmgpu_ctx *ctx) \
 
 TASK_ENTRY(mpmgpu_task_initialization, t_initialization, T_INIT)
 TASK_ENTRY(mpmgpu_task_mass_and_momentum, t_mass_and_momentum, T_MASSMOM)
+TASK_ENTRY(mpmgpu_task_project_rigid_bcs, t_project_rigid_bcs, T_POSTEXTRAP)
 TASK_ENTRY(mpmgpu_task_post_extrapolation, t_post_extrapolation, T_POSTEXTRAP)
 TASK_ENTRY(mpmgpu_task_update_strains_first, t_update_strains_first, T_USF)
 TASK_ENTRY(mpmgpu_task_grid_forces, t_grid_forces, T_FORCES)
@@ -719,6 +826,7 @@ static int step_by_tasks(mpmgpu_ctx *ctx)
     for (int t = 0; t < T_NTASKS; t++) {
         prof_begin(ctx);
         rc = seq[t](ctx);
+        if (!rc && t == T_MASSMOM) rc = t_project_rigid_bcs(ctx);
         prof_end(ctx, t);
         if (rc) return rc;
     }
@@ -843,6 +951,7 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_end(ctx, T_INIT);
         prof_begin(ctx);
         if (pgrid) LAUNCH(k_f1_mass_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N);
+        if ((rc = t_project_rigid_bcs(ctx))) return rc;
         if (t.slab.on && (rc = halo_pack(ctx, 0, true))) return rc;
         prof_end(ctx, T_MASSMOM);
     } else if (phase == 1) {
@@ -869,6 +978,7 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_end(ctx, T_POSTFORCES);
         prof_begin(ctx);
         if (pgrid) LAUNCH(k_f3_update_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, sp, m, reextrap ? 1 : 0);
+        if ((rc = move_rigid(ctx))) return rc;
         if (t.slab.on && (rc = halo_pack(ctx, 2, reextrap))) return rc;
         prof_end(ctx, T_PARTICLES);
     } else {
@@ -906,6 +1016,7 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
             if (t.stateKind == SK_ELASTIC) LAUNCH(k_f4_strain_reset<SK_ELASTIC>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
             else LAUNCH(k_f4_strain_reset<SK_FULL>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
         }
+        if ((rc = reset_rigid(ctx))) return rc;
         prof_end(ctx, T_USL);
     }
     return MPMGPU_OK;
@@ -930,12 +1041,14 @@ extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
 }
 
 // ------------------------------------------------------------------------------------------------
-static int down_field(mpmgpu_ctx *ctx, double *const *dev, double *host, int ncomp, int n, double *dtmp)
+static int down_field(mpmgpu_ctx *ctx, double *const *dev, double *const *devR, double *host, int ncomp, int n, double *dtmp)
 {
     if (!host) return MPMGPU_OK;
     const int T = 256;
+    const int nNR = ctx->P.n, nR = ctx->PR.n;
     for (int c = 0; c < ncomp; c++) {
-        LAUNCH(k_unpermute, nblocks(n, T), T, n, dev[c], ctx->dlSlot, dtmp);
+        if (nNR) LAUNCH(k_unpermute, nblocks(nNR, T), T, nNR, dev[c], ctx->dlSlot, dtmp);
+        if (nR) LAUNCH(k_unpermute, nblocks(nR, T), T, nR, devR[c], ctx->dlSlotR, dtmp);
         CK(cudaMemcpyAsync(host + (size_t)c * n, dtmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     return MPMGPU_OK;
@@ -946,48 +1059,55 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
     if (!ctx || !h) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_download_particles: null argument");
     if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_download_particles: nothing uploaded");
     cudaSetDevice(ctx->cfg.device);
-    Particles &P = ctx->P;
-    const int n = P.n;
-    h->n = n; h->n_nonrigid = P.nNR;
+    Particles &P = ctx->P, &PR = ctx->PR;
+    const int nNR = P.n, nR = PR.n, n = nNR + nR;
+    h->n = n; h->n_nonrigid = nNR;
     double *dtmp = NULL;
     CK(cudaMalloc((void **)&dtmp, (size_t)n * 9 * sizeof(double)));
     int rc = MPMGPU_OK;
     const int T = 256;
     int *ident = NULL;
-    ctx->dlSlot = ctx->P.orig;
-    if (ctx->globalIds) {       // device order; the caller re-assembles by id
+    ctx->dlSlot = P.orig; ctx->dlSlotR = PR.orig;
+    if (ctx->globalIds) {       // device order (rigid particles last); the caller re-assembles by id
         CK(cudaMalloc((void **)&ident, (size_t)n * sizeof(int)));
-        LAUNCH(k_iota, nblocks(n, T), T, n, ident);
-        ctx->dlSlot = ident;
-        if (h->ids) CK(cudaMemcpyAsync(h->ids, ctx->P.orig, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LAUNCH(k_iota, nblocks(n, T), T, n, ident, 0);
+        ctx->dlSlot = ident; ctx->dlSlotR = ident + nNR;
+        if (h->ids) {
+            if (nNR) CK(cudaMemcpyAsync(h->ids, P.orig, (size_t)nNR * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            if (nR) CK(cudaMemcpyAsync(h->ids + nNR, PR.orig, (size_t)nR * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        }
     }
     do {
-        if ((mask & MPMGPU_F_POS) && (rc = down_field(ctx, P.pos, h->pos, 3, n, dtmp))) break;
-        if ((mask & MPMGPU_F_VEL) && (rc = down_field(ctx, P.vel, h->vel, 3, n, dtmp))) break;
+        if ((mask & MPMGPU_F_POS) && (rc = down_field(ctx, P.pos, PR.pos, h->pos, 3, n, dtmp))) break;
+        if ((mask & MPMGPU_F_VEL) && (rc = down_field(ctx, P.vel, PR.vel, h->vel, 3, n, dtmp))) break;
         if (mask & MPMGPU_F_STRESS) {
-            if ((rc = down_field(ctx, P.sp, h->sp, 6, n, dtmp))) break;
-            if ((rc = down_field(ctx, &P.pressure, h->pressure, 1, n, dtmp))) break;
+            if ((rc = down_field(ctx, P.sp, PR.sp, h->sp, 6, n, dtmp))) break;
+            if ((rc = down_field(ctx, &P.pressure, &PR.pressure, h->pressure, 1, n, dtmp))) break;
         }
         if ((mask & MPMGPU_F_STRAIN) && h->ep && h->wrot) {
-            LAUNCH(k_F_to_epwrot, nblocks(n, T), T, n, ctx->dim, P, ctx->dlSlot, dtmp, dtmp + (size_t)6 * n);
+            if (nNR) LAUNCH(k_F_to_epwrot, nblocks(nNR, T), T, nNR, n, ctx->dim, P, ctx->dlSlot, dtmp, dtmp + (size_t)6 * n);
+            if (nR) LAUNCH(k_F_to_epwrot, nblocks(nR, T), T, nR, n, ctx->dim, PR, ctx->dlSlotR, dtmp, dtmp + (size_t)6 * n);
             CK(cudaMemcpyAsync(h->ep, dtmp, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(h->wrot, dtmp + (size_t)6 * n, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
-        if ((mask & MPMGPU_F_EPLAST) && (rc = down_field(ctx, P.eplast, h->eplast, 6, n, dtmp))) break;
+        if ((mask & MPMGPU_F_EPLAST) && (rc = down_field(ctx, P.eplast, PR.eplast, h->eplast, 6, n, dtmp))) break;
         if ((mask & MPMGPU_F_ENERGY) && h->energies) {
             double *const e6[6] = {P.work, P.res, P.heat, P.entropy, P.plast, P.prevT};
-            if ((rc = down_field(ctx, e6, h->energies, 6, n, dtmp))) break;
+            double *const e6R[6] = {PR.work, PR.res, PR.heat, PR.entropy, PR.plast, PR.prevT};
+            if ((rc = down_field(ctx, e6, e6R, h->energies, 6, n, dtmp))) break;
         }
-        if ((mask & MPMGPU_F_HISTORY) && (rc = down_field(ctx, P.hist, h->history, MPM_MAX_HISTORY, n, dtmp))) break;
-        if ((mask & MPMGPU_F_ACC) && (rc = down_field(ctx, P.acc, h->acc, 3, n, dtmp))) break;
+        if ((mask & MPMGPU_F_HISTORY) && (rc = down_field(ctx, P.hist, PR.hist, h->history, MPM_MAX_HISTORY, n, dtmp))) break;
+        if ((mask & MPMGPU_F_ACC) && (rc = down_field(ctx, P.acc, PR.acc, h->acc, 3, n, dtmp))) break;
         if (mask & MPMGPU_F_ELEM) {
             int *itmp = (int *)dtmp;
             if (h->in_elem) {
-                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.elem, ctx->dlSlot, itmp, 0);
+                if (nNR) LAUNCH(k_unpermute_int, nblocks(nNR, T), T, nNR, P.elem, ctx->dlSlot, itmp, 0);
+                if (nR) LAUNCH(k_unpermute_int, nblocks(nR, T), T, nR, PR.elem, ctx->dlSlotR, itmp, 0);
                 CK(cudaMemcpyAsync(h->in_elem, itmp, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             }
             if (h->crossings) {
-                LAUNCH(k_unpermute_int, nblocks(n, T), T, n, P.cross, ctx->dlSlot, itmp + n, 0);
+                if (nNR) LAUNCH(k_unpermute_int, nblocks(nNR, T), T, nNR, P.cross, ctx->dlSlot, itmp + n, 0);
+                if (nR) LAUNCH(k_unpermute_int, nblocks(nR, T), T, nR, PR.cross, ctx->dlSlotR, itmp + n, 0);
                 CK(cudaMemcpyAsync(h->crossings, itmp + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             }
         }
@@ -1212,4 +1332,4 @@ extern "C" int mpmgpu_set_stream(mpmgpu_ctx *ctx, void *cuda_stream)
     return MPMGPU_OK;
 }
 
-extern "C" int mpmgpu_num_particles(const mpmgpu_ctx *ctx) { return ctx ? ctx->P.n : 0; }
+extern "C" int mpmgpu_num_particles(const mpmgpu_ctx *ctx) { return ctx ? ctx->P.n + ctx->PR.n : 0; }

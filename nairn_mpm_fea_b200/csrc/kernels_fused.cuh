@@ -50,6 +50,7 @@ struct FusedNodes {
     double4 *V;          // [nnodes] {vx,vy,vz,0}: vk[0]
     double4 *A;          // [nnodes] {ax,ay,az,0}: ftot/mass
     const int *bcOfNode; // [nnodes] index into VelBCs unique list or -1
+    RigidBCs R;          // BCs projected from rigid particles (k_project_rigid_bcs)
 };
 
 // slab decomposition along z (one process per GPU): this rank owns cell planes [cellLo, cellHi)
@@ -686,44 +687,7 @@ __global__ void k_mig_fill(int npairs, const int *hole, const int *filler, size_
 }
 
 // ---- node sweeps -------------------------------------------------------------------------------------
-// BC application for one node inside a sweep: same arithmetic as k_velocity_bcs
-__device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3])
-{
-    const int e0 = B.start[u], e1 = B.start[u + 1];
-    for (int e = e0; e < e1; e++) {
-        if (!B.active[e]) continue;
-        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
-        if (pass == PASS_GRID_FORCES) {
-            double dotf = ft[0] * nx + ft[1] * ny + ft[2] * nz;
-            double dotp = pk[0] * nx + pk[1] * ny + pk[2] * nz;
-            double s = -dotf - dotp / dt;
-            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-        } else {
-            double dotn = pk[0] * nx + pk[1] * ny + pk[2] * nz;
-            pk[0] += nx * (-dotn); pk[1] += ny * (-dotn); pk[2] += nz * (-dotn);
-            if (pass == PASS_UPDATE_MOMENTUM) {
-                double s = -dotn / dt;
-                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-            }
-        }
-    }
-    for (int e = e0; e < e1; e++) {
-        if (!B.active[e]) continue;
-        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
-        const double vel = B.value[e];
-        if (pass == PASS_GRID_FORCES) {
-            double s = mass * vel / dt;
-            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-        } else {
-            double pvel = mass * vel;
-            pk[0] += nx * pvel; pk[1] += ny * pvel; pk[2] += nz * pvel;
-            if (pass == PASS_UPDATE_MOMENTUM) {
-                double s = pvel / dt;
-                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-            }
-        }
-    }
-}
+// (node_bcs / node_rigid_bcs: kernels_task.cuh)
 
 // N1: tasks 3 + 4a.  pkc = pk; symmetry adjust; BCs(MASS_MOMENTUM) if a USF task exists; V = pk/mass
 __global__ void k_n1_post_extrapolation(int n0, int nnodes, Nodes N, FusedNodes FN, VelBCs B, StepParams sp, int hasUSF)
@@ -741,11 +705,13 @@ __global__ void k_n1_post_extrapolation(int n0, int nnodes, Nodes N, FusedNodes 
             if (sd & 32) pkc[0] = 0.;
             if (sd & 64) pkc[1] = 0.;
             if (sd & 128) pkc[2] = 0.;
-            if (hasUSF) {
-                double ft[3] = {0., 0., 0.};
-                node_bcs(B, u, PASS_MASS_MOMENTUM, sp.dt, mass, pk, ft);
-                N.pk[0][i] = pk[0]; N.pk[1][i] = pk[1]; N.pk[2][i] = pk[2];
-            }
+        }
+        if (hasUSF) {
+            double ft[3] = {0., 0., 0.};
+            bool changed = u >= 0;
+            if (u >= 0) node_bcs(B, u, PASS_MASS_MOMENTUM, sp.dt, mass, pk, ft);
+            if (FN.R.on) changed |= node_rigid_bcs(FN.R, i, PASS_MASS_MOMENTUM, sp.dt, mass, pk, ft);
+            if (changed) { N.pk[0][i] = pk[0]; N.pk[1][i] = pk[1]; N.pk[2][i] = pk[2]; }
         }
         N.pkc[0][i] = pkc[0]; N.pkc[1][i] = pkc[1]; N.pkc[2][i] = pkc[2];
         if (mass != 0.) {
@@ -771,8 +737,12 @@ __global__ void k_n2_forces_momenta(int n0, int nnodes, Nodes N, FusedNodes FN, 
         if (sp.hasGravity) { ft[0] += mass * sp.grav[0]; ft[1] += mass * sp.grav[1]; ft[2] += mass * sp.grav[2]; }
         const int u = FN.bcOfNode ? FN.bcOfNode[i] : -1;
         if (u >= 0) node_bcs(B, u, PASS_GRID_FORCES, sp.dt, mass, pk, ft);
+        if (FN.R.on) node_rigid_bcs(FN.R, i, PASS_GRID_FORCES, sp.dt, mass, pk, ft);
         pk[0] += ft[0] * sp.dt; pk[1] += ft[1] * sp.dt; pk[2] += ft[2] * sp.dt;
-        if (u >= 0 && sp.xpicOrder <= 1) node_bcs(B, u, PASS_UPDATE_MOMENTUM, sp.dt, mass, pk, ft);
+        if (sp.xpicOrder <= 1) {
+            if (u >= 0) node_bcs(B, u, PASS_UPDATE_MOMENTUM, sp.dt, mass, pk, ft);
+            if (FN.R.on) node_rigid_bcs(FN.R, i, PASS_UPDATE_MOMENTUM, sp.dt, mass, pk, ft);
+        }
         N.ftot[0][i] = ft[0]; N.ftot[1][i] = ft[1]; N.ftot[2][i] = ft[2];
         if (mass != 0.) {
             const double rm = 1. / mass;
@@ -797,10 +767,12 @@ __global__ void k_n3_strains_last(int n0, int nnodes, Nodes N, FusedNodes FN, Ve
         double pk[3] = {N.pk[0][i], N.pk[1][i], N.pk[2][i]};
         const double mass = N.mass[i];
         const int u = FN.bcOfNode ? FN.bcOfNode[i] : -1;
-        if (u >= 0) {
+        {
             double ft[3] = {0., 0., 0.};
-            node_bcs(B, u, PASS_UPDATE_STRAINS_LAST, sp.dt, mass, pk, ft);
-            N.pk[0][i] = pk[0]; N.pk[1][i] = pk[1]; N.pk[2][i] = pk[2];
+            bool changed = u >= 0;
+            if (u >= 0) node_bcs(B, u, PASS_UPDATE_STRAINS_LAST, sp.dt, mass, pk, ft);
+            if (FN.R.on) changed |= node_rigid_bcs(FN.R, i, PASS_UPDATE_STRAINS_LAST, sp.dt, mass, pk, ft);
+            if (changed) { N.pk[0][i] = pk[0]; N.pk[1][i] = pk[1]; N.pk[2][i] = pk[2]; }
         }
         if (mass != 0.) {
             const double rm = 1. / mass;

@@ -72,9 +72,75 @@ __global__ void k_copy_momenta(int nnodes, Nodes N)
 }
 
 // ---- grid velocity BCs (NodalVelBC.cpp:321-400, MatVelocityField.cpp:490-575) ----------------
-// One thread per node that has BCs; its entries are walked in list order, first the zero pass
-// over all of them, then the add pass (VelocityBCLoop).  BCs act only on active fields
-// (numberPoints>0, NodalPointMPM.cpp:1849-1862).
+// zero pass of one BC with unit direction n (ZeroVelocityBC / SetFtotDirection / ZeroMomentumBC)
+__device__ __forceinline__ void bc_zero(int pass, double dt, double nx, double ny, double nz, double pk[3], double ft[3])
+{
+    if (pass == PASS_GRID_FORCES) {
+        double dotf = ft[0] * nx + ft[1] * ny + ft[2] * nz;
+        double dotp = pk[0] * nx + pk[1] * ny + pk[2] * nz;
+        double s = -dotf - dotp / dt;
+        ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+    } else {
+        double dotn = pk[0] * nx + pk[1] * ny + pk[2] * nz;
+        pk[0] += nx * (-dotn); pk[1] += ny * (-dotn); pk[2] += nz * (-dotn);
+        if (pass == PASS_UPDATE_MOMENTUM) {
+            double s = -dotn / dt;
+            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        }
+    }
+}
+
+// add pass (AddVelocityBC / AddFtotDirection / AddMomentumBC)
+__device__ __forceinline__ void bc_add(int pass, double dt, double mass, double vel, double nx, double ny, double nz, double pk[3], double ft[3])
+{
+    if (pass == PASS_GRID_FORCES) {
+        double s = mass * vel / dt;
+        ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+    } else {
+        double pvel = mass * vel;
+        pk[0] += nx * pvel; pk[1] += ny * pvel; pk[2] += nz * pvel;
+        if (pass == PASS_UPDATE_MOMENTUM) {
+            double s = pvel / dt;
+            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        }
+    }
+}
+
+// BC application for one node: its entries are walked in list order, first the zero pass over all of
+// them, then the add pass (VelocityBCLoop)
+__device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3])
+{
+    const int e0 = B.start[u], e1 = B.start[u + 1];
+    for (int e = e0; e < e1; e++) {
+        if (!B.active[e]) continue;
+        bc_zero(pass, dt, B.norm[3 * e], B.norm[3 * e + 1], B.norm[3 * e + 2], pk, ft);
+    }
+    for (int e = e0; e < e1; e++) {
+        if (!B.active[e]) continue;
+        bc_add(pass, dt, mass, B.value[e], B.norm[3 * e], B.norm[3 * e + 1], B.norm[3 * e + 2], pk, ft);
+    }
+}
+
+// The BCs rigid particles made on this node.  They sit after the grid BCs in the reference's list and
+// only on dofs no grid BC fixes (ProjectRigidBCsTask.cpp:202), each along one axis, so applying them
+// after the node's grid BCs gives the same sums as the reference's zero-all-then-add-all walk.
+__device__ __forceinline__ bool node_rigid_bcs(const RigidBCs &R, int nd, int pass, double dt, double mass, double pk[3], double ft[3])
+{
+    int o[3];
+    bool any = false;
+#pragma unroll
+    for (int d = 0; d < 3; d++) { o[d] = R.owner[d][nd]; any |= o[d] != RIGID_NONE; }
+    if (!any) return false;
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        if (o[d] != RIGID_NONE) bc_zero(pass, dt, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft);
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        if (o[d] != RIGID_NONE) bc_add(pass, dt, mass, R.vel[d][o[d]], d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft);
+    return true;
+}
+
+// One thread per node that has BCs.  BCs act only on active fields (numberPoints>0, NodalPointMPM.cpp:1849-1862).
 __global__ void k_velocity_bcs(VelBCs B, Nodes N, int pass, double dt, int adjustSym)
 {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,43 +156,54 @@ __global__ void k_velocity_bcs(VelBCs B, Nodes N, int pass, double dt, int adjus
     }
     double pk[3] = {N.pk[0][nd], N.pk[1][nd], N.pk[2][nd]};
     double ft[3] = {N.ftot[0][nd], N.ftot[1][nd], N.ftot[2][nd]};
-    const double mass = N.mass[nd];
-    const int e0 = B.start[u], e1 = B.start[u + 1];
-    for (int e = e0; e < e1; e++) {
-        if (!B.active[e]) continue;
-        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
-        if (pass == PASS_GRID_FORCES) {
-            double dotf = ft[0] * nx + ft[1] * ny + ft[2] * nz;
-            double dotp = pk[0] * nx + pk[1] * ny + pk[2] * nz;
-            double s = -dotf - dotp / dt;
-            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-        } else {
-            double dotn = pk[0] * nx + pk[1] * ny + pk[2] * nz;
-            pk[0] += nx * (-dotn); pk[1] += ny * (-dotn); pk[2] += nz * (-dotn);
-            if (pass == PASS_UPDATE_MOMENTUM) {
-                double s = -dotn / dt;
-                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-            }
-        }
-    }
-    for (int e = e0; e < e1; e++) {
-        if (!B.active[e]) continue;
-        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
-        const double vel = B.value[e];
-        if (pass == PASS_GRID_FORCES) {
-            double s = mass * vel / dt;
-            ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-        } else {
-            double pvel = mass * vel;
-            pk[0] += nx * pvel; pk[1] += ny * pvel; pk[2] += nz * pvel;
-            if (pass == PASS_UPDATE_MOMENTUM) {
-                double s = pvel / dt;
-                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
-            }
-        }
-    }
+    node_bcs(B, u, pass, dt, N.mass[nd], pk, ft);
     N.pk[0][nd] = pk[0]; N.pk[1][nd] = pk[1]; N.pk[2][nd] = pk[2];
     N.ftot[0][nd] = ft[0]; N.ftot[1][nd] = ft[1]; N.ftot[2][nd] = ft[2];
+}
+
+// rigid-particle BCs on every node, launched after k_velocity_bcs
+__global__ void k_rigid_velocity_bcs(int nnodes, RigidBCs R, Nodes N, int pass, double dt)
+{
+    int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= nnodes) return;
+    if (N.cnt[nd] <= 0) return;
+    double pk[3] = {N.pk[0][nd], N.pk[1][nd], N.pk[2][nd]};
+    double ft[3] = {N.ftot[0][nd], N.ftot[1][nd], N.ftot[2][nd]};
+    if (!node_rigid_bcs(R, nd, pass, dt, N.mass[nd], pk, ft)) return;
+    N.pk[0][nd] = pk[0]; N.pk[1][nd] = pk[1]; N.pk[2][nd] = pk[2];
+    N.ftot[0][nd] = ft[0]; N.ftot[1][nd] = ft[1]; N.ftot[2][nd] = ft[2];
+}
+
+// ---- ProjectRigidBCsTask (ProjectRigidBCsTask.cpp:39-158) ---------------------------------------
+// PR holds the rigid-BC particles in host order; the reference walks them serially and the first one
+// to reach a free dof of a node keeps it, which is the minimum index here.
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_project_rigid_bcs(Grid g, Particles PR, const Material *mats, RigidBCs R)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= PR.n) return;
+    const int dirs = (int)mats[PR.mat[p]].p[8];      // RigidMaterial::setDirection: x=1, y=2, z=4
+    const int e = PR.elem[p];
+    double pos[3] = {PR.pos[0][p], PR.pos[1][p], DIM == 3 ? PR.pos[2][p] : 0.};
+    double xi[3], lp[3] = {PR.lp[0][p], PR.lp[1][p], PR.lp[2][p]};
+    get_xipos<DIM>(g, e, pos, xi);
+    for_each_node<DIM, SHAPE, false>(g, e, xi, lp, [&](int nd, double, double, double, double) {
+        const int fixed = R.fixedBits ? R.fixedBits[nd] : 0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++)
+            if ((dirs >> d & 1) && !(fixed >> d & 1)) atomicMin(&R.owner[d][nd], p);
+    });
+}
+
+// rigid particles move at their own velocity (UpdateParticlesTask.cpp:292-295, MatPoint3D.cpp:197-201)
+template <int DIM>
+__global__ void k_move_rigid(Particles PR, double dt)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= PR.n) return;
+    PR.pos[0][p] += PR.vel[0][p] * dt;
+    PR.pos[1][p] += PR.vel[1][p] * dt;
+    if (DIM == 3) PR.pos[2][p] += PR.vel[2][p] * dt;
 }
 
 // ---- grid velocity for strain / particle update (MatVelocityField.cpp:239-251) ---------------
@@ -343,7 +420,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_xpic_iterate(Grid g, Particles
 }
 
 // GET_DELTAV, velocity BCs on the increment (XPIC_* pass of ZeroVelocityBC, MatVelocityField.cpp:529-541), UPDATE_VSTAR
-__global__ void k_xpic_finish(int nnodes, Nodes N, VelBCs B, const int *bcOfNode, double dt, int particleUpdate, int usingFMPM)
+__global__ void k_xpic_finish(int nnodes, Nodes N, VelBCs B, const int *bcOfNode, RigidBCs R, double dt, int particleUpdate, int usingFMPM)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnodes) return;
@@ -364,6 +441,16 @@ __global__ void k_xpic_finish(int nnodes, Nodes N, VelBCs B, const int *bcOfNode
             }
         }
         if (particleUpdate && !usingFMPM) { N.ftot[0][i] = ft[0]; N.ftot[1][i] = ft[1]; N.ftot[2][i] = ft[2]; }
+    }
+    if (R.on) {         // the rigid-particle BCs follow in the list, one axis each
+        const double mass = N.mass[i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (R.owner[c][i] == RIGID_NONE) continue;
+            const double dotn = d[c];
+            d[c] += -dotn;
+            if (particleUpdate && !usingFMPM) N.ftot[c][i] += -mass * dotn / dt;
+        }
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) {

@@ -101,6 +101,16 @@ struct VelBCs {
     const int *active;       // [nEntries]
 };
 
+// Velocity BCs made by rigid-BC particles (ProjectRigidBCsTask.cpp:39-158): per node and direction the
+// first rigid particle (lowest index) that claims a dof not fixed by a grid BC sets it to its velocity.
+#define RIGID_NONE 0x7f7f7f7f
+struct RigidBCs {
+    int on;
+    int *owner[3];           // [nnodes] claiming rigid particle per direction, RIGID_NONE when free
+    const double *vel[3];    // rigid particle velocities
+    const unsigned char *fixedBits;   // [nnodes] x=1,y=2,z=4 dofs fixed by grid BCs (NodalPoint::fixedDirection), or NULL
+};
+
 struct StatusFlags {         // device -> host error reporting (ResetElementsTask.cpp:71-151)
     unsigned long long crossings;
     unsigned long long leftGrid;

@@ -264,6 +264,10 @@ def from_reference_dump(z, snapshot="p0"):
         elif mid == M.ISOPLASTICITY:
             m = M.isoplasticity(q[8], q[9], q[0], q[15], q[16] if q[16] >= 0 else None, q[21], q[11] * 1.0e6, q[1], pr.np, pd,
                                 q[20] * q[0])
+        elif mid == M.RIGIDBC:
+            if q[9] != 0 or q[10] != 0 or q[11] != 0:
+                raise NotImplementedError("rigid material with mirrored / setting functions / temperature or concentration")
+            m = M.rigid_bc(int(q[8]))
         else:
             raise NotImplementedError("material id %d" % mid)
         pr.materials.append(m)

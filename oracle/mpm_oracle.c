@@ -39,7 +39,9 @@ typedef struct {
     double *pos, *vel, *mp, *lp, *ncpos, *sp, *pressure, *ep, *wrot, *eplast, *energies, *hist, *pfext, *acc;
     int *inElem, *matnum, *cross;
     NodeField *nd;      /* 0-based node index = reference node number - 1 */
-    int nbc;
+    int nbc, nbcGrid, bcCap;        /* BCs [nbcGrid, nbc) are the ones rigid particles made this step */
+    int *fixedDirection;            /* NodalPoint::fixedDirection bits x=1, y=2, z=4 */
+    int *bcDir;
     int *bcNode; double *bcNorm, *bcValue; int *bcActive, *bcSym;
     double dt, dtFirst, dtLast;
     long long mstep;
@@ -374,6 +376,44 @@ static void grid_velocity_conditions(int pass)
     }
     if (pass == UPDATE_MOMENTUM_CALL && O->cfg.xpic_order > 1) return;
     velocity_bc_loop(pass);
+}
+
+/* ---- ProjectRigidBCsTask.cpp:39-158 (SetRigidBCs :194-266, UnsetRigidBCs :166-191) ---------------------------
+ * Rigid-BC particles (mpm[nmpmsRC..nmpms)) append a constant velocity BC to the list on every node of their
+ * shape-function stencil, in each direction their material sets, unless that dof is already fixed. */
+static void task_project_rigid_bcs(void)
+{
+    if (O->n == O->nNR) return;
+    for (int b = O->nbcGrid; b < O->nbc; b++) {             /* BoundaryCondition::UnsetDirection */
+        int *fd = &O->fixedDirection[O->bcNode[b] - 1];
+        if (*fd & O->bcDir[b]) *fd ^= O->bcDir[b];
+    }
+    O->nbc = O->nbcGrid;
+    int nds[64]; double fn[64];
+    for (int p = O->nNR; p < O->n; p++) {
+        const mpmgpu_material *mat = &O->mats[O->matnum[p] - 1];
+        const int setDirection = (int)mat->p[8];
+        int nn = shape(p, 0, nds, fn, NULL, NULL, NULL);
+        for (int i = 0; i < nn; i++) {
+            for (int d = 0; d < 3; d++) {
+                const int type = 1 << d;
+                if ((setDirection & type) != type) continue;            /* RigidMaterial::RigidDirection */
+                if (O->fixedDirection[nds[i]] & type) continue;         /* :202 */
+                if (O->nbc == O->bcCap) {
+                    O->bcCap = O->bcCap ? 2 * O->bcCap : 1024;
+                    O->bcNode = (int *)realloc(O->bcNode, O->bcCap * sizeof(int)); O->bcDir = (int *)realloc(O->bcDir, O->bcCap * sizeof(int));
+                    O->bcActive = (int *)realloc(O->bcActive, O->bcCap * sizeof(int)); O->bcSym = (int *)realloc(O->bcSym, O->bcCap * sizeof(int));
+                    O->bcNorm = (double *)realloc(O->bcNorm, 3 * (size_t)O->bcCap * sizeof(double));
+                    O->bcValue = (double *)realloc(O->bcValue, O->bcCap * sizeof(double));
+                }
+                const int b = O->nbc++;
+                O->bcNode[b] = nds[i] + 1; O->bcDir[b] = type; O->bcActive[b] = 1; O->bcSym[b] = 0;
+                O->bcNorm[3 * b] = d == 0; O->bcNorm[3 * b + 1] = d == 1; O->bcNorm[3 * b + 2] = d == 2;
+                O->bcValue[b] = P3(vel, d, p);                           /* CONSTANT_VALUE, ftime 0 */
+                O->fixedDirection[nds[i]] |= type;
+            }
+        }
+    }
 }
 
 /* ---- task 3: PostExtrapolationTask.cpp:62-165 -------------------------------------------------------------- */
@@ -863,6 +903,8 @@ static void task_update_particles(void)
             P3(vel, c, p) = v; P3(pos, c, p) = x; P3(acc, c, p) = delV / dt;
         }
     }
+    for (int p = O->nNR; p < O->n; p++)            /* rigid particles: MovePosition, UpdateParticlesTask.cpp:292-295 */
+        for (int c = 0; c < O->dim; c++) P3(pos, c, p) += dt * P3(vel, c, p);
 }
 
 /* ---- task 9: UpdateStrainsLastContactTask.cpp:60-152 / UpdateStrainsLastTask.cpp:43-48 ------------------------- */
@@ -948,9 +990,10 @@ static void task_reset_elements(void)
 
 /* ---- driver ------------------------------------------------------------------------------------------------------- */
 typedef void (*taskfn)(void);
-static const taskfn TASKS[10] = {task_initialization, task_mass_and_momentum, task_post_extrapolation, task_update_strains_first,
+static const taskfn TASKS[11] = {task_initialization, task_mass_and_momentum, task_post_extrapolation, task_update_strains_first,
                                  task_grid_forces, task_post_forces, task_update_momenta, task_update_particles,
-                                 task_update_strains_last, task_reset_elements};
+                                 task_update_strains_last, task_reset_elements,
+                                 task_project_rigid_bcs};      /* 10: runs between tasks 1 and 2 */
 
 static double *dupd(const double *src, size_t n) { double *d = (double *)calloc(n ? n : 1, sizeof(double)); if (src) memcpy(d, src, n * sizeof(double)); return d; }
 static int *dupi(const int *src, size_t n, int fill) { int *d = (int *)malloc((n ? n : 1) * sizeof(int)); for (size_t i = 0; i < n; i++) d[i] = src ? src[i] : fill; return d; }
@@ -983,6 +1026,15 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
     O->nbc = nbc;
     O->bcNode = dupi(bcNode, nbc, 0); O->bcNorm = dupd(bcNorm, 3 * (size_t)nbc); O->bcValue = dupd(bcValue, nbc);
     O->bcActive = dupi(bcActive, nbc, 1); O->bcSym = dupi(bcSym, nbc, 0);
+    O->nbcGrid = nbc; O->bcCap = nbc;
+    O->bcDir = dupi(NULL, nbc, 0);
+    O->fixedDirection = (int *)calloc(O->nnodes, sizeof(int));
+    for (int b = 0; b < nbc; b++) {            /* NodalVelBC.cpp:40-45: direction bits of the grid BCs */
+        int bits = bcSym ? bcSym[b] & 7 : 0;
+        for (int d = 0; d < 3; d++) if (bcNorm[3 * b + d] != 0.) bits |= 1 << d;
+        O->bcDir[b] = bits;
+        O->fixedDirection[bcNode[b] - 1] |= bits;
+    }
     O->dt = dt; O->dtFirst = dtFirst; O->dtLast = dtLast;
     O->ncorner = 0;
     if (cfg->shape == MPMGPU_LINEAR_CPDI) O->ncorner = O->dim == 3 ? 8 : 4;
@@ -1000,12 +1052,12 @@ int oracle_cpdi_left_grid(void) { return O ? O->cpdiLeftGrid : 0; }
 
 int oracle_set_xpic(int order, int using_fmpm) { if (!O) return -1; O->cfg.xpic_order = order; O->cfg.using_fmpm = using_fmpm; return 0; }
 
-int oracle_task(int t) { if (!O || t < 0 || t > 9) return -1; TASKS[t](); if (t == 9) O->mstep++; return 0; }
+int oracle_task(int t) { if (!O || t < 0 || t > 10) return -1; TASKS[t](); if (t == 9) O->mstep++; return 0; }
 
 int oracle_step(int nsteps)
 {
     if (!O) return -1;
-    for (int s = 0; s < nsteps; s++) for (int t = 0; t < 10; t++) oracle_task(t);
+    for (int s = 0; s < nsteps; s++) for (int t = 0; t < 10; t++) { oracle_task(t); if (t == 1) oracle_task(10); }
     return 0;
 }
 
@@ -1049,7 +1101,7 @@ void oracle_destroy(void)
     free(O->pos); free(O->vel); free(O->mp); free(O->lp); free(O->ncpos); free(O->sp); free(O->pressure); free(O->ep);
     free(O->wrot); free(O->eplast); free(O->energies); free(O->hist); free(O->pfext); free(O->acc);
     free(O->inElem); free(O->matnum); free(O->cross); free(O->nd);
-    free(O->bcNode); free(O->bcNorm); free(O->bcValue); free(O->bcActive); free(O->bcSym);
+    free(O->bcNode); free(O->bcNorm); free(O->bcValue); free(O->bcActive); free(O->bcSym); free(O->bcDir); free(O->fixedDirection);
     free(O);
     O = NULL;
 }

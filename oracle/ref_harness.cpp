@@ -322,6 +322,12 @@ int ref_get_materials(int *ids, double *params)
             q[8] = nm->G; q[9] = nm->Kbulk; q[10] = nm->Lame; q[11] = nm->pr.Gsp; q[12] = nm->pr.Ksp;
             q[13] = nm->pr.Lamesp; q[14] = nm->UofJOption; q[15] = nm->CTE1; q[16] = nm->gamma0;
         }
+        else if (ids[i] == 11) {
+            RigidMaterial *rm = (RigidMaterial *)m;
+            q[8] = rm->setDirection; q[9] = rm->mirrored;
+            q[10] = (rm->function != NULL || rm->function2 != NULL || rm->function3 != NULL) ? 1. : 0.;
+            q[11] = (rm->setTemperature || rm->setConcentration) ? 1. : 0.;
+        }
         else if (ids[i] == 9) {
             IsoPlasticity *pm = (IsoPlasticity *)m;
             q[8] = pm->E; q[9] = pm->nu; q[10] = pm->G; q[11] = pm->CTE3; q[12] = pm->gamma0;

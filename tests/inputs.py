@@ -7,11 +7,15 @@ format so the same text drives the reference (oracle/_ref) and the GPU path (via
 
 def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy=0.0, cfl=0.4,
             method=2, gimp="uGIMP", maxtime=1.0, material=None, extra_header="", bc=True,
-            gravity=None, damping=None, pdamping=None, ppc=None, custom_tasks=""):
+            gravity=None, damping=None, pdamping=None, ppc=None, custom_tasks="", rigid=None):
     """3D block of ncell^3 cells (8 particles per cell) inside a (ncell+2*margin)^3 grid, 1 mm cells.
 
     Config 2 of BASELINE.json is block3d(ncell=50, margin=7).  The bottom plane z<=margin is held
     with a zero z-velocity grid BC.
+
+    rigid = (where, set_direction, (vx, vy, vz)) adds a one-cell-thick plate of rigid-BC particles
+    (RigidMaterial, Type 11) under ("wall") or on top of ("piston") the block, one cell wider than it
+    (BASELINE config 4 family: Taylor bar against a rigid wall).
     """
     n = ncell + 2 * margin
     lo, hi = margin, margin + ncell
@@ -31,6 +35,13 @@ def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy
         damp += "<Damping>%r</Damping>" % damping
     if pdamping is not None:
         damp += "<PDamping>%r</PDamping>" % pdamping
+    rigid_body = ""
+    if rigid:
+        where, setdir, rv = rigid
+        z0, z1 = (lo - 1, lo) if where == "wall" else (hi, hi + 1)
+        rigid_body = ('<Body matname="Plate" vx="%r" vy="%r" vz="%r"><Box xmin="%d" xmax="%d" ymin="%d" ymax="%d" zmin="%d" zmax="%d"/></Body>'
+                      % (rv[0], rv[1], rv[2], lo - 1, hi + 1, lo - 1, hi + 1, z0, z1))
+        mat += '<Material Type="11" Name="Plate"><SetDirection>%d</SetDirection></Material>' % setdir
     return """<?xml version='1.0'?>
 <!DOCTYPE JANFEAInput SYSTEM "NairnMPM.dtd">
 <JANFEAInput version='3'>
@@ -52,6 +63,7 @@ def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy
     <Body matname="Blk" vx="%r" vy="%r" vz="%r">
       <Box xmin="%d" xmax="%d" ymin="%d" ymax="%d" zmin="%d" zmax="%d"/>
     </Body>
+    %s
   </MaterialPoints>
   %s
   %s
@@ -59,7 +71,7 @@ def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy
   %s
 </JANFEAInput>
 """ % (method, maxtime, cfl, gimp_tag, ppc_tag, damp, extra_header, n, n, n, vx, vy, vz,
-       lo, hi, lo, hi, lo, hi, mat, bcs, grav, custom_tasks)
+       lo, hi, lo, hi, lo, hi, rigid_body, mat, bcs, grav, custom_tasks)
 
 
 def disks2d(analysis=10, gimp="uGIMP", method=2, cell=1.0, radius=6.0, gap=1.0, hmax=16.0, vmax=9.0, E=1.0, nu=0.33,

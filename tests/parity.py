@@ -9,6 +9,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TASK_MAP = {
     "Initialize": "initialization",
     "Extrapolate Mass and Momentum": "mass_and_momentum",
+    "Rigid BCs by Projection": "project_rigid_bcs",
     "Post Extrapolation Tasks": "post_extrapolation",
     "Update Strains First": "update_strains_first",
     "Extrapolate Grid Forces": "grid_forces",
