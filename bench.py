@@ -9,6 +9,8 @@ One "step" = one full MPMStep (tasks 1-9, 11) over the resident particle block. 
   block8m  (default)  100^3 cells x 8 particles = 8,000,000 particles per GPU: config 5 at N GPUs
                       (and the size the north_star target is quoted on at N=1)
   block1m             50^3 cells = 1,000,000 particles: config 2
+  taylor16m           100x100x200-cell IsoPlasticity bar hitting a plate of rigid-BC particles at 200 m/s,
+                      16,000,000 particles TOTAL split over the GPUs (config 4, strong scaling); taylor2m = 50x50x100
 Prints ONE JSON line (see README / DESIGN.md for the keys).
 """
 import argparse
@@ -108,10 +110,19 @@ class ClockSampler:
 
 
 def make_problem(workload, ncell_override=None, rank=0, world=1):
-    from nairn_mpm_fea_b200 import problem
-    ncell = {"block8m": 100, "block1m": 50}[workload]
+    from nairn_mpm_fea_b200 import materials as M, problem
+    ncell = {"block8m": 100, "block1m": 50, "taylor16m": 100, "taylor2m": 50}[workload]
     if ncell_override:
         ncell = ncell_override
+    if workload.startswith("taylor"):
+        # config 4: copper-like von Mises bar (E 117 GPa, yield 400 MPa, linear hardening), 200 m/s onto a rigid plate
+        u = M.xml_units(E=117.0e3, rho=8.94, yld=400.0, Ep=100.0)
+        mat = M.isoplasticity(u["E"], 0.35, u["rho"], u["yld"], u["Ep"])
+        ncz = 2 * ncell
+        cz = None if world == 1 else ((ncz * rank) // world, (ncz * (rank + 1)) // world)
+        pr = problem.block3d(ncell=ncell, margin=7, velocity=(0.0, 0.0, -2.0e5), jitter_amp=0.4, bottom_bc=False, material=mat,
+                             ncell_xyz=(ncell, ncell, ncz), cells_z=cz, rigid_wall=dict(set_direction=4, overhang=2))
+        return pr, ncell
     # small uniform compression velocity + sinusoidal perturbation along z so particles cross cells
     L = float(ncell)
 
@@ -154,14 +165,15 @@ def run_ours(args):
     hbm_peak, peak_src = read_peaks()
 
     prob, ncell = make_problem(args.workload, args.ncell, rank, world)
-    n = prob.nparticles
+    taylor = args.workload.startswith("taylor")
+    n = int(prob.particles["n_nonrigid"])          # rigid-BC particles (replicated on every rank) are not counted
     if world == 1:
         sim = MpmGpu(prob, device=local, kernel_path=args.kernel_path)
         stepper = sim
         stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local))
     else:
         from nairn_mpm_fea_b200.slab import SlabSim, slab_bounds
-        bounds = slab_bounds(prob.depth, 8, 8 + ncell * world, world)
+        bounds = slab_bounds(prob.depth, 8, 8 + (2 * ncell if taylor else ncell * world), world)
         lo, hi = bounds[rank]
         stepper = SlabSim(prob, prob.particles, lo, hi, rank, world, device=local, capacity_factor=1.2)
         sim = stepper.sim
@@ -195,7 +207,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    total_particles = n * world
+    t = torch.tensor([n], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    total_particles = int(t.item())
     value = total_particles * args.steps / (ms_total * 1e-3)
 
     # ---- per-task device times (events around every task; serialises, so done OUTSIDE the timed region)
@@ -207,13 +222,16 @@ def run_ours(args):
     sim.set_profiling(False)
     task_ms = {k: v[0] / max(1, v[1]) for k, v in tt.items()}
     dom = max(task_ms, key=lambda k: task_ms[k])
-    dom_bytes = TASK_ALGO_BYTES[dom] * n
+    # IsoPlasticity carries eplast(6), pressure, plastic energy and one history double through both strain updates
+    full_state = 2 * (6 + 1 + 1 + 1) * 8 if taylor else 0
+    algo_step = ALGO_BYTES_PER_PARTICLE_STEP + 2 * full_state
+    dom_bytes = (TASK_ALGO_BYTES[dom] + (full_state if dom in ("update_strains_first", "update_strains_last") else 0)) * n
     dom_gbs = dom_bytes / (task_ms[dom] * 1e-3) / 1e9
-    step_gbs = ALGO_BYTES_PER_PARTICLE_STEP * n / (ms_per_step * 1e-3) / 1e9
+    step_gbs = algo_step * n / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": task_ms[dom], "kernel_share_of_step": task_ms[dom] / sum(task_ms.values()),
-                "whole_step": {"algorithmic_bytes_per_particle_step": ALGO_BYTES_PER_PARTICLE_STEP,
+                "whole_step": {"algorithmic_bytes_per_particle_step": algo_step,
                                "achieved": step_gbs, "frac": step_gbs / hbm_peak},
                 "task_ms": task_ms}
 
@@ -230,7 +248,7 @@ def run_ours(args):
             pinned[k] = v
     nb = len(prob.bc_value)
     bcv = np.zeros(nb)
-    dl = MpmGpu.pinned_download_buffers(n) if world == 1 else None     # slabs: particle count changes by migration
+    dl = MpmGpu.pinned_download_buffers(prob.nparticles) if world == 1 else None     # slabs: particle count changes by migration
     barrier()
     t0 = time.perf_counter()
     if world > 1:
@@ -258,9 +276,12 @@ def run_ours(args):
                    "+ download full particle state, wall clock" % args.steps}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if taylor else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: 3D uGIMP isotropic-elastic block, %d^3 cells x 8 = %d particles per GPU, FLIP, USAVG+, "
+            "config": {"workload": ("%s: 3D uGIMP IsoPlasticity (von Mises, linear hardening) bar of %dx%dx%d cells x 8 = %d particles in total, "
+                                    "200 m/s onto a plate of %d rigid-BC particles, FLIP, USAVG+, positions hash-jittered"
+                                    % (args.workload, ncell, ncell, 2 * ncell, total_particles, prob.nparticles - n)) if taylor else
+                                   "%s: 3D uGIMP isotropic-elastic block, %d^3 cells x 8 = %d particles per GPU, FLIP, USAVG+, "
                                    "grid %d^3 cells, particle positions hash-jittered +-0.2 cell off the lattice" % (args.workload, ncell, n, prob.horiz),
                        "particles_per_gpu": n, "nodes": prob.nnodes, "l2_policy": "inputs larger than L2 (%.0f MB state)" % (n * 460 / 1e6),
                        "kernel_path": sim_kernel_path_name(args.kernel_path),
@@ -359,7 +380,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m"])
+    ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m", "taylor16m", "taylor2m"])
     ap.add_argument("--ncell", type=int, default=0, help="override block edge in cells (testing)")
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--cpu-ncell", type=int, default=50, help="block edge of the CPU sample (50 -> 1M particles)")

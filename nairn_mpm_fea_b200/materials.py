@@ -8,6 +8,7 @@ Cv J/(kg-K)*1e6).  `from_xml_units` converts from the numbers written in an XML 
 import numpy as np
 
 NPARAMS = 32
+MAX_HISTORY = 4            # MPMGPU_MAX_HISTORY
 ISOTROPIC, ISOPLASTICITY, RIGIDBC, NEOHOOKEAN = 1, 9, 11, 28
 PLANE_STRAIN_MPM, PLANE_STRESS_MPM, THREED_MPM = 10, 11, 12
 

@@ -141,14 +141,19 @@ def lattice_points(xpts, ypts, zpts, elems_ijk, pts_per_side=2):
 
 def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0.0, 0.0, -1000.0), cfl=0.4,
             step_ms=1e-3, method=USAVG, shape=UNIFORM_GIMP, bottom_bc=True, gravity=None, velocity_fn=None,
-            pts_per_side=2, ncell_xyz=None, jitter_amp=0.0, cells_z=None):
+            pts_per_side=2, ncell_xyz=None, jitter_amp=0.0, cells_z=None, material=None, rigid_wall=None):
     """BASELINE.json config 2 family: block of ncell^3 cells (pts_per_side^3 particles per cell) of
     IsotropicMat inside a (ncell+2*margin)^3-cell grid (+1 border cell per side), initial velocity,
     bottom plane z<=margin held in z.  Numbers are XML (Legacy) units: mm, MPa, g/cm^3, mm/s, ms.
     Same problem as tests/inputs.py::block3d(ncell, margin) fed to the reference.
     cells_z=(lo, hi): generate only the particles of block cell planes [lo, hi) (one slab of a
     multi-GPU run); the grid, BCs and time step are still those of the whole problem and the dict gets
-    'ids' = the particles' indices in the whole problem."""
+    'ids' = the particles' indices in the whole problem.
+    material: a materials.py block (internal units) replacing the IsotropicMat.
+    rigid_wall = dict(set_direction=4, velocity=(0, 0, 0), overhang=1): BASELINE config 4 family (Taylor bar
+    on a rigid wall) -- a one-cell-thick plate of rigid-BC particles (RigidMaterial, rho 1 so mp = volume)
+    under the block, `overhang` cells wider on each side; they follow the nonrigid particles as in the
+    reference's ordering (NairnMPM.cpp:1121-1190) and every slab of a multi-GPU run gets all of them."""
     pr = Problem()
     pr.np = M.THREED_MPM
     pr.method = method
@@ -160,7 +165,7 @@ def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0
     pr.depth, pr.zpts, gz = structured_axis(0.0, ext[2] * cell, cell)
     pr.grid = (gx, gy, gz)
     u = M.xml_units(E=E, rho=rho)
-    mat = M.isotropic(u["E"], nu, u["rho"], 0.0, M.DEFAULT_CV, M.THREED_MPM)
+    mat = material or M.isotropic(u["E"], nu, u["rho"], 0.0, M.DEFAULT_CV, M.THREED_MPM)
     pr.materials = [mat]
     # filled elements: cells [margin, margin+nc) of the user grid = element index +1 (border) per axis
     ii = np.arange(margin + 1, margin + 1 + ncx)
@@ -189,7 +194,7 @@ def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0
     dye = (pr.ypts[ej + 1] - pr.ypts[ej])
     dze = (pr.zpts[ek + 1] - pr.zpts[ek])
     psx, psy, psz = dxe * (0.5 * gap), dye * (0.5 * gap), dze * (0.5 * gap)
-    mp = np.repeat(u["rho"] * (8.0 * psx * psy * psz), npp)
+    mp = np.repeat(mat["rho"] * (8.0 * psx * psy * psz), npp)
     vel = np.zeros((3, n))
     if velocity_fn is not None:
         vel[:] = velocity_fn(pos)
@@ -202,6 +207,38 @@ def block3d(ncell=50, margin=7, cell=1.0, E=1000.0, nu=0.3, rho=1.0, velocity=(0
                         n_nonrigid=n, energies=energies)
     if cells_z is not None:
         pr.particles["ids"] = (np.arange(n, dtype=np.int64) + id_offset).astype(np.int32)
+    if mat.get("init_history") is not None:
+        hist = np.zeros((M.MAX_HISTORY, n))
+        for i, v in enumerate(mat["init_history"]):
+            hist[i] = v
+        pr.particles["history"] = hist
+    if mat.get("init_eplast") is not None:
+        pr.particles["eplast"] = np.tile(np.asarray(mat["init_eplast"], float)[:, None], (1, n))
+    if rigid_wall is not None:
+        oh = int(rigid_wall.get("overhang", 1))
+        pr.materials.append(M.rigid_bc(int(rigid_wall.get("set_direction", 4))))
+        ri = np.arange(margin + 1 - oh, margin + 1 + ncx + oh)
+        rj = np.arange(margin + 1 - oh, margin + 1 + ncy + oh)
+        RK, RJ, RI = np.meshgrid(np.array([margin]), rj, ri, indexing="ij")
+        ri, rj, rk = RI.ravel(), RJ.ravel(), RK.ravel()
+        rpos, _ = lattice_points(pr.xpts, pr.ypts, pr.zpts, (ri, rj, rk), pts_per_side)
+        nr = rpos.shape[1]
+        relem = np.repeat((pr.horiz * (rk * pr.vert + rj) + ri + 1).astype(np.int32), npp)
+        rmp = np.repeat(8.0 * ((pr.xpts[ri + 1] - pr.xpts[ri]) * (0.5 * gap)) * ((pr.ypts[rj + 1] - pr.ypts[rj]) * (0.5 * gap))
+                        * ((pr.zpts[rk + 1] - pr.zpts[rk]) * (0.5 * gap)), npp)
+        rvel = np.tile(np.asarray(rigid_wall.get("velocity", (0.0, 0.0, 0.0)), float)[:, None], (1, nr))
+        n_total_nr = ncx * ncy * ncz * npp
+        add = dict(pos=rpos, vel=rvel, mp=rmp, lp=np.full((3, nr), gap), in_elem=relem, matnum=np.full(nr, 2, np.int32),
+                   energies=np.concatenate([np.zeros((5, nr)), np.ones((1, nr))]))
+        if "ids" in pr.particles:
+            add["ids"] = (n_total_nr + np.arange(nr)).astype(np.int32)
+        if "history" in pr.particles:
+            add["history"] = np.zeros((M.MAX_HISTORY, nr))
+        if "eplast" in pr.particles:
+            add["eplast"] = np.zeros((6, nr))
+        for key, v in add.items():
+            pr.particles[key] = np.concatenate([pr.particles[key], v], axis=-1)
+        pr.n_rigid = nr
     # time step (NairnMPM.cpp:695-699, :1207-1227): dcell = grid.x (cubic grid, MeshInfo.cpp:1555-1563)
     dt_cfl = cfl * (gx / mat["wave_speed"])
     pr.set_time_step(min(step_ms * 1.0e-3, dt_cfl))

@@ -34,11 +34,15 @@ def slab_bounds(depth, cell_first, cell_last, world):
 
 
 def partition_particles(pt, horiz, vert, cell_lo, cell_hi, ids=None):
-    """Select the particles whose element z-index lies in [cell_lo, cell_hi); keeps global ids."""
+    """Select the particles whose element z-index lies in [cell_lo, cell_hi); keeps global ids.
+    Rigid-BC particles (after n_nonrigid) are few and make node BCs on both sides of a slab face, so every
+    rank keeps all of them (they move identically everywhere and never migrate)."""
     in_elem = np.asarray(pt["in_elem"])
-    k = (in_elem - 1) // (horiz * vert)
-    sel = np.nonzero((k >= cell_lo) & (k < cell_hi))[0]
     n = in_elem.shape[0]
+    n_nr = int(pt.get("n_nonrigid", n))
+    k = (in_elem - 1) // (horiz * vert)
+    nonrigid = np.arange(n) < n_nr
+    sel = np.nonzero(((k >= cell_lo) & (k < cell_hi) & nonrigid) | ~nonrigid)[0]
     out = {}
     for key, v in pt.items():
         if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[-1] == n:
@@ -46,7 +50,7 @@ def partition_particles(pt, horiz, vert, cell_lo, cell_hi, ids=None):
         else:
             out[key] = v
     out["ids"] = (np.arange(n, dtype=np.int32) if ids is None else np.asarray(ids, np.int32))[sel]
-    out["n_nonrigid"] = len(sel)
+    out["n_nonrigid"] = int(np.count_nonzero(sel < n_nr))
     return out
 
 
@@ -179,28 +183,33 @@ class SlabSim:
         self.sim.close()
 
 
-def gather_by_id(local, n_global, group=None):
-    """Assemble per-rank downloads (dicts with 'ids') into global arrays on every rank (test helper)."""
+def assemble_by_id(parts, n_global, n_rigid=0):
+    """Per-slab downloads (dicts with 'ids') -> global arrays.  The last n_rigid ids are the replicated
+    rigid particles: taken from the first slab."""
+    out = {}
+    for key, v in parts[0].items():
+        if key != "ids":
+            out[key] = np.zeros(v.shape[:-1] + (n_global,), dtype=v.dtype)
+    seen = np.zeros(n_global, dtype=np.int32)
+    for r, part in enumerate(parts):
+        ids = np.asarray(part["ids"])
+        keep = np.ones(ids.shape[0], bool) if r == 0 else ids < n_global - n_rigid
+        seen[ids[keep]] += 1
+        for key in out:
+            out[key][..., ids[keep]] = part[key][..., keep]
+    assert np.all(seen == 1), "particle ids lost or duplicated across slabs"
+    return out
+
+
+def gather_by_id(local, n_global, group=None, n_rigid=0):
+    """Assemble per-rank downloads into global arrays on every rank (test helper)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     parts = [None] * world
     if world > 1:
         dist.all_gather_object(parts, local, group=group)
     else:
         parts = [local]
-    out = {}
-    for key, v in parts[0].items():
-        if key == "ids":
-            continue
-        shape = v.shape[:-1] + (n_global,)
-        out[key] = np.zeros(shape, dtype=v.dtype)
-    seen = np.zeros(n_global, dtype=np.int32)
-    for part in parts:
-        ids = part["ids"]
-        seen[ids] += 1
-        for key in out:
-            out[key][..., ids] = part[key]
-    assert np.all(seen == 1), "particle ids lost or duplicated across slabs"
-    return out
+    return assemble_by_id(parts, n_global, n_rigid)
 
 
 class LockstepCluster:
@@ -216,6 +225,7 @@ class LockstepCluster:
             part = partition_particles(prob.particles, prob.horiz, prob.vert, lo, hi)
             self.sims.append(SlabSim(prob, part, lo, hi, r, world, device=device, **kw))
         self.n_global = n
+        self.n_rigid = n - int(prob.particles.get("n_nonrigid", n))
         self.world = world
 
     def _swap_halo(self, which):
@@ -257,19 +267,7 @@ class LockstepCluster:
                     s.migrated_in += f_lo + f_hi
 
     def download(self):
-        parts = [s.download() for s in self.sims]
-        out = {}
-        for key, v in parts[0].items():
-            if key != "ids":
-                out[key] = np.zeros(v.shape[:-1] + (self.n_global,), dtype=v.dtype)
-        seen = np.zeros(self.n_global, np.int32)
-        for part in parts:
-            ids = part["ids"]
-            seen[ids] += 1
-            for key in out:
-                out[key][..., ids] = part[key]
-        assert np.all(seen == 1), "particle ids lost or duplicated across slabs"
-        return out
+        return assemble_by_id([s.download() for s in self.sims], self.n_global, self.n_rigid)
 
     def close(self):
         for s in self.sims:

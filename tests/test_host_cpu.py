@@ -52,6 +52,26 @@ def test_block3d_generator_matches_reference_setup():
     assert np.array_equal(a.materials[0]["p"], b.materials[0]["p"])
 
 
+def test_taylor_bar_generator_matches_reference_setup():
+    """IsoPlasticity block on a plate of rigid-BC particles (BASELINE config 4 family): the host generator gives
+    the particles, their order (rigid ones last) and both material blocks exactly as the reference sets them up."""
+    from nairn_mpm_fea_b200 import materials as M, problem
+    z = load_golden("block3d_rigid_wall_lattice")
+    a = problem.from_reference_dump(z)
+    u = M.xml_units(E=2000.0, rho=2.0, yld=20.0, Ep=100.0)
+    mat = M.isoplasticity(u["E"], 0.33, u["rho"], u["yld"], u["Ep"], aI=20.0)
+    b = problem.block3d(ncell=2, margin=3, velocity=(0.0, 0.0, -4.0e4), bottom_bc=False, material=mat,
+                        rigid_wall=dict(set_direction=4))
+    for k in ("np", "horiz", "vert", "depth", "grid", "shape", "method", "dt", "dt_strain_first", "dt_strain_last"):
+        assert getattr(a, k) == getattr(b, k), k
+    for k in ("pos", "vel", "mp", "lp", "in_elem", "matnum"):
+        assert np.array_equal(np.asarray(a.particles[k]), np.asarray(b.particles[k])), k
+    assert a.particles["n_nonrigid"] == b.particles["n_nonrigid"] == 64 and b.nparticles == 192
+    for i in range(2):
+        assert a.materials[i]["kind"] == b.materials[i]["kind"] and np.array_equal(a.materials[i]["p"], b.materials[i]["p"])
+    assert len(b.bc_node) == 0
+
+
 def test_material_block_matches_reference_properties():
     from nairn_mpm_fea_b200 import problem
     for case in ("block3d_ugimp_usavg", "block3d_fast_crossings"):

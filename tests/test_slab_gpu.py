@@ -18,12 +18,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def occupied_planes(prob):
-    k = (np.asarray(prob.particles["in_elem"]) - 1) // (prob.horiz * prob.vert)
+    nnr = int(prob.particles.get("n_nonrigid", prob.nparticles))
+    k = (np.asarray(prob.particles["in_elem"])[:nnr] - 1) // (prob.horiz * prob.vert)
     return int(k.min()), int(k.max()) + 1
 
 
 @pytest.mark.parametrize("case,world,sort_interval", [("block3d_fast_crossings", 2, 0), ("block3d_jitter", 2, 5),
-                                                       ("block3d_ugimp_usavg", 1, 0)])
+                                                       ("block3d_ugimp_usavg", 1, 0), ("block3d_rigid_wall", 2, 4),
+                                                       ("block3d_rigid_piston", 2, 0)])
 def test_lockstep_slabs_match_reference(case, world, sort_interval):
     from nairn_mpm_fea_b200.problem import from_reference_dump
     from nairn_mpm_fea_b200.slab import LockstepCluster, slab_bounds
@@ -46,7 +48,7 @@ def test_lockstep_slabs_match_reference(case, world, sort_interval):
         moved = sum(s.migrated_out for s in cl.sims)
         assert moved > 0, "test problem should push particles across the slab face"
         assert sum(s.migrated_in for s in cl.sims) == moved
-    assert sum(s.num_particles() for s in cl.sims) == prob.nparticles
+    assert sum(s.num_particles() for s in cl.sims) == prob.nparticles + (world - 1) * cl.n_rigid
     cl.close()
 
 

@@ -35,6 +35,24 @@ def test_partition_is_a_partition():
         assert np.array_equal(p["pos"], pr.particles["pos"][:, p["ids"]])
 
 
+def test_partition_replicates_rigid_particles():
+    """Rigid-BC particles go to every slab; assemble_by_id takes them once."""
+    from nairn_mpm_fea_b200.slab import assemble_by_id
+    from tests.parity import load_golden
+    pr = problem.from_reference_dump(load_golden("block3d_rigid_wall"))
+    n, nnr = pr.nparticles, int(pr.particles["n_nonrigid"])
+    assert 0 < nnr < n
+    k = (pr.particles["in_elem"][:nnr] - 1) // (pr.horiz * pr.vert)
+    bounds = slab_bounds(pr.depth, int(k.min()), int(k.max()) + 1, 3)
+    parts = [partition_particles(pr.particles, pr.horiz, pr.vert, lo, hi) for lo, hi in bounds]
+    assert sum(p["n_nonrigid"] for p in parts) == nnr
+    for p in parts:
+        assert np.array_equal(p["ids"][p["n_nonrigid"]:], np.arange(nnr, n))
+    down = [dict(ids=p["ids"], pos=p["pos"], in_elem=p["in_elem"]) for p in parts]
+    whole = assemble_by_id(down, n, n - nnr)
+    assert np.array_equal(whole["pos"], pr.particles["pos"]) and np.array_equal(whole["in_elem"], pr.particles["in_elem"])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
