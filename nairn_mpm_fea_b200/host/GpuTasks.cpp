@@ -29,6 +29,11 @@
 #include "Elements/ElementBase.hpp"
 #include "Materials/MaterialBase.hpp"
 #include "Materials/IsotropicMat.hpp"
+#include "Materials/Neohookean.hpp"
+#include "Materials/IsoPlasticity.hpp"
+#include "Materials/HardeningLawBase.hpp"
+#include "Materials/LinearHardening.hpp"
+#include "Materials/RigidMaterial.hpp"
 #include "Boundary_Conditions/NodalVelBC.hpp"
 #include "Global_Quantities/BodyForce.hpp"
 #include "Custom_Tasks/CustomTask.hpp"
@@ -89,7 +94,7 @@ void DownloadToHost(void)
     gHostStale = false;
 }
 
-enum { G_INIT, G_MASSMOM, G_POSTEXTRAP, G_USF, G_FORCES, G_POSTFORCES, G_MOMENTA, G_PARTICLES, G_USL, G_RESET };
+enum { G_INIT, G_MASSMOM, G_POSTEXTRAP, G_USF, G_FORCES, G_POSTFORCES, G_MOMENTA, G_PARTICLES, G_USL, G_RESET, G_RIGIDBC };
 
 // One class for all ten tasks: Execute() forwards to the matching C entry point.
 class GpuTask : public MPMTask
@@ -100,7 +105,12 @@ class GpuTask : public MPMTask
     virtual bool Execute(int)
     {
         switch (which) {
-        case G_INIT: check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)"); break;
+        case G_INIT:
+            // the PeriodicXPIC custom task changes the order between steps (Custom_Tasks/PeriodicXPIC.cpp:161-240)
+            check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(Initialize)");
+            check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)");
+            break;
+        case G_RIGIDBC: check(mpmgpu_task_project_rigid_bcs(gCtx), "GpuTask(ProjectRigidBCs)"); break;
         case G_MASSMOM: check(mpmgpu_task_mass_and_momentum(gCtx), "GpuTask(MassAndMomentum)"); break;
         case G_POSTEXTRAP:
             if (gBCsVary) {     // NodalVelBC::GridVelocityBCValues (NodalVelBC.cpp:293-302): values at this step's mtime
@@ -135,6 +145,7 @@ int TaskCode(const char *name)
 {
     static const struct { const char *nm; int code; } map[] = {
         {"Initialize", G_INIT}, {"Extrapolate Mass and Momentum", G_MASSMOM}, {"Post Extrapolation Tasks", G_POSTEXTRAP},
+        {"Rigid BCs by Projection", G_RIGIDBC},
         {"Update Strains First", G_USF}, {"Extrapolate Grid Forces", G_FORCES}, {"Post Force Extrapolation Tasks", G_POSTFORCES},
         {"Update Momenta", G_MOMENTA}, {"Update Particles", G_PARTICLES}, {"Update Strains Last with Extrapolation", G_USL},
         {"Update Strains Last", G_USL}, {"Reset Elements", G_RESET}};
@@ -150,12 +161,33 @@ const char *GpuTasks_Install(int device)
     if (firstCrack != NULL) return "cracks present";
     if (fmobj->multiMaterialMode) return "multimaterial mode";
     if (transportTasks != NULL) return "transport tasks present";
-    if (nmpms != nmpmsNR) return "rigid particles present";
+    if (nmpmsRC != nmpmsNR) return "rigid contact or rigid block particles present";
+    if (nmpms != nmpmsNR && MaterialBase::extrapolateRigidBCs) return "rigid BCs by extrapolation";
     if (fmobj->np != PLANE_STRAIN_MPM && fmobj->np != PLANE_STRESS_MPM && fmobj->np != THREED_MPM) return "analysis type";
-    if (ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP) return "shape functions";
+    if (ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP && ElementBase::useGimp != LINEAR_CPDI &&
+        ElementBase::useGimp != QUADRATIC_CPDI) return "shape functions";
+    if (nmpms != nmpmsNR && ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP) return "rigid-BC particles with CPDI";
     if (!mpmgrid.IsStructuredEqualElementsGrid()) return "grid is not structured with equal elements";
-    if (bodyFrc.GetXPICOrder() > 1) return "XPIC/FMPM order > 1";
-    for (int i = 0; i < nmat; i++) if (theMaterials[i]->MaterialID() != 1 || ((IsotropicMat *)theMaterials[i])->useLargeRotation) return "material type";
+    for (int i = 0; i < nmat; i++) {
+        MaterialBase *mb = theMaterials[i];
+        if (mb->artificialViscosity) return "artificial viscosity";
+        switch (mb->MaterialID()) {
+        case 1: if (((IsotropicMat *)mb)->useLargeRotation) return "IsotropicMat with large rotation"; break;
+        case 28: break;
+        case 9:
+            if (dynamic_cast<LinearHardening *>(((IsoPlasticity *)mb)->plasticLaw) == NULL) return "IsoPlasticity hardening law other than Linear";
+            if (fmobj->np == PLANE_STRESS_MPM) return "IsoPlasticity in plane stress";
+            break;
+        case 11: {
+            RigidMaterial *rm = (RigidMaterial *)mb;
+            if (!rm->IsRigidBC()) return "rigid contact material";
+            if (rm->function != NULL || rm->function2 != NULL || rm->function3 != NULL || rm->Vfunction != NULL) return "rigid material with setting functions";
+            if (rm->mirrored != 0 || rm->setTemperature || rm->setConcentration) return "rigid material with mirrored / temperature / concentration";
+            break;
+        }
+        default: return "material type";
+        }
+    }
     const bool is3D = fmobj->IsThreeD();
 
     // grid: node coordinates per axis exactly as generated (Read_MPM/Generators.cpp:1823-1833)
@@ -182,28 +214,46 @@ const char *GpuTasks_Install(int device)
     // materials: the block GetCopyOfMechanicalProps would hand out (Elastic::FillUnrotatedElasticProperties)
     std::vector<mpmgpu_material> mats(nmat);
     for (int i = 0; i < nmat; i++) {
-        IsotropicMat *im = (IsotropicMat *)theMaterials[i];
+        MaterialBase *mb = theMaterials[i];
         mpmgpu_material &m = mats[i];
         memset(&m, 0, sizeof m);
-        m.kind = MPMGPU_MAT_ISOTROPIC; m.n_history = 0;
-        m.p[0] = im->rho; m.p[1] = im->heatCapacity; m.p[2] = im->matUsePDamping ? im->matPdamping : -1.;
-        const ElasticProperties &e = im->pr;
-        if (is3D) {
-            m.p[8] = e.C[0][0]; m.p[9] = e.C[0][1]; m.p[10] = e.C[0][2]; m.p[11] = e.C[1][1]; m.p[12] = e.C[1][2]; m.p[13] = e.C[2][2];
-            m.p[14] = e.C[3][3]; m.p[15] = e.C[4][4]; m.p[16] = e.C[5][5];
-            m.p[17] = e.alpha[0]; m.p[18] = e.alpha[1]; m.p[19] = e.alpha[2];
-        } else {
-            m.p[8] = e.C[1][1]; m.p[9] = e.C[1][2]; m.p[11] = e.C[2][2]; m.p[16] = e.C[3][3];
-            m.p[21] = e.C[4][1]; m.p[22] = e.C[4][2]; m.p[23] = e.C[4][4]; m.p[24] = e.C[5][1];
-            m.p[17] = e.alpha[1]; m.p[18] = e.alpha[2]; m.p[19] = e.alpha[4];
+        m.p[0] = mb->rho; m.p[1] = mb->heatCapacity; m.p[2] = mb->matUsePDamping ? mb->matPdamping : -1.;
+        m.n_history = mb->NumberOfHistoryDoubles();
+        if (mb->MaterialID() == 1) {
+            IsotropicMat *im = (IsotropicMat *)mb;
+            m.kind = MPMGPU_MAT_ISOTROPIC;
+            const ElasticProperties &e = im->pr;
+            if (is3D) {
+                m.p[8] = e.C[0][0]; m.p[9] = e.C[0][1]; m.p[10] = e.C[0][2]; m.p[11] = e.C[1][1]; m.p[12] = e.C[1][2]; m.p[13] = e.C[2][2];
+                m.p[14] = e.C[3][3]; m.p[15] = e.C[4][4]; m.p[16] = e.C[5][5];
+                m.p[17] = e.alpha[0]; m.p[18] = e.alpha[1]; m.p[19] = e.alpha[2];
+            } else {
+                m.p[8] = e.C[1][1]; m.p[9] = e.C[1][2]; m.p[11] = e.C[2][2]; m.p[16] = e.C[3][3];
+                m.p[21] = e.C[4][1]; m.p[22] = e.C[4][2]; m.p[23] = e.C[4][4]; m.p[24] = e.C[5][1];
+                m.p[17] = e.alpha[1]; m.p[18] = e.alpha[2]; m.p[19] = e.alpha[4];
+            }
+            m.p[20] = im->gamma0;
+        } else if (mb->MaterialID() == 28) {        // Neohookean::GetCopyOfMechanicalProps hands out pr (Neohookean.cpp:143-150)
+            Neohookean *nm = (Neohookean *)mb;
+            m.kind = MPMGPU_MAT_NEOHOOKEAN;
+            m.p[8] = nm->pr.Gsp; m.p[9] = nm->pr.Ksp; m.p[10] = nm->pr.Lamesp; m.p[11] = nm->UofJOption; m.p[12] = nm->CTE1; m.p[13] = nm->gamma0;
+        } else if (mb->MaterialID() == 9) {         // IsoPlasticity::pr + LinearHardening reduced properties
+            IsoPlasticity *pm = (IsoPlasticity *)mb;
+            LinearHardening *lh = (LinearHardening *)pm->plasticLaw;
+            m.kind = MPMGPU_MAT_ISOPLASTICITY;
+            m.p[8] = pm->pr.Gred; m.p[9] = pm->pr.Kred; m.p[10] = lh->yldred; m.p[11] = lh->Epred; m.p[12] = pm->CTE3; m.p[13] = pm->gamma0;
+            m.p[14] = lh->alphaMax; m.p[15] = lh->yldredMin;
+        } else {                                     // rigid BC particles: directions they control
+            m.kind = MPMGPU_MAT_RIGIDBC; m.n_history = 0;
+            m.p[8] = ((RigidMaterial *)mb)->setDirection;
         }
-        m.p[20] = im->gamma0;
     }
     if (mpmgpu_set_materials(gCtx, nmat, mats.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
 
     // particles: AoS heap objects -> SoA
     const int n = nmpms;
-    std::vector<double> pos(3 * n), vel(3 * n), mp(n), lp(3 * n), sp(6 * n), pr(n), ep(6 * n), wrot(3 * n), epl(6 * n), en(6 * n), pf(3 * n);
+    std::vector<double> pos(3 * n), vel(3 * n), mp(n), lp(3 * n), sp(6 * n), pr(n), ep(6 * n), wrot(3 * n), epl(6 * n), en(6 * n), pf(3 * n),
+        hist((size_t)MPMGPU_MAX_HISTORY * n, 0.);
     std::vector<int> elem(n), matn(n), cross(n);
     bool anyFext = false;
     for (int p = 0; p < n; p++) {
@@ -221,13 +271,15 @@ const char *GpuTasks_Install(int device)
         pf[p] = m->pFext.x; pf[n + p] = m->pFext.y; pf[2 * n + p] = m->pFext.z;
         if (m->pFext.x != 0. || m->pFext.y != 0. || m->pFext.z != 0.) anyFext = true;
         elem[p] = m->inElem; matn[p] = m->matnum; cross[p] = m->elementCrossings;
+        const int nh = theMaterials[m->MatID()]->NumberOfHistoryDoubles();
+        for (int k = 0; k < nh && k < MPMGPU_MAX_HISTORY && m->matData != NULL; k++) hist[(size_t)k * n + p] = ((double *)m->matData)[k];
     }
     mpmgpu_particles h;
     memset(&h, 0, sizeof h);
     h.n = n; h.n_nonrigid = nmpmsNR;
     h.pos = pos.data(); h.vel = vel.data(); h.mp = mp.data(); h.lp = lp.data(); h.in_elem = elem.data(); h.matnum = matn.data();
     h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data(); h.eplast = epl.data(); h.energies = en.data();
-    h.pfext = anyFext ? pf.data() : NULL; h.crossings = cross.data();
+    h.pfext = anyFext ? pf.data() : NULL; h.crossings = cross.data(); h.history = hist.data();
     if (mpmgpu_upload_particles(gCtx, &h) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     if (mpmgpu_set_time_step(gCtx, timestep, strainTimestepFirst, strainTimestepLast) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
 

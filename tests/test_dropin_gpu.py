@@ -21,6 +21,14 @@ CASES = {
     "block3d": (inputs.block3d(ncell=6, margin=3, maxtime=0.03).replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>",
                                                                           "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), 6 ** 3 * 8, "res/blk."),
     "disks2d": (inputs.disks2d(analysis=10, maxtime=2.0, archive_ms=0.5), None, "res/disks."),
+    # config 3 family: Neo-Hookean, lCPDI, XPIC(2) scheduled by the reference's own PeriodicXPIC custom task
+    "block3d_neo_lcpdi_xpic2": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, gimp="lCPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3,
+                                               custom_tasks=inputs.periodic_xpic(2, False, 1))
+                                .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
+    # config 4 family: IsoPlasticity bar on a plate of rigid-BC particles
+    "block3d_isoplastic_rigid_wall": (inputs.block3d(ncell=4, margin=3, maxtime=0.02, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
+                                                     rigid=("wall", 4, (0.0, 0.0, 0.0)))
+                                      .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.005</ArchiveTime>"), None, "res/blk."),
 }
 
 
