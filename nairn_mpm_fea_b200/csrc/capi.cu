@@ -64,6 +64,7 @@ struct mpmgpu_ctx {
     // staging
     double *hStage; size_t hStageBytes;
     TiledState tiled;
+    bool f2Attr[2][2];                  // dynamic shared memory opt-in done for k_f2_strain_forces<SK, FEXT> on this device
 };
 
 static int fail(mpmgpu_ctx *c, int code, const char *fmt, ...)
@@ -133,6 +134,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
     memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
     tiled_state_init(ctx->tiled);
+    memset(ctx->f2Attr, 0, sizeof ctx->f2Attr);
 
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { int rc = fail(NULL, MPMGPU_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); delete ctx; return rc; }
@@ -961,12 +963,14 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_end(ctx, T_POSTEXTRAP);
         prof_begin(ctx);
         if (pgrid) {
+#define LAUNCH_F2(SKV, FX) do { \
+                if (!ctx->f2Attr[SKV][FX ? 1 : 0]) { CK(cudaFuncSetAttribute(k_f2_strain_forces<SKV, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_smem_bytes<FX>())); ctx->f2Attr[SKV][FX ? 1 : 0] = true; } \
+                k_f2_strain_forces<SKV, FX><<<pgrid, FUSED_THREADS, f2_smem_bytes<FX>(), ctx->stream>>>(g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0); \
+                ctx->launches++; } while (0)
             if (t.stateKind == SK_ELASTIC) {
-                if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_ELASTIC, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
-                else LAUNCH((k_f2_strain_forces<SK_ELASTIC, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+                if (ctx->hasFext) LAUNCH_F2(SK_ELASTIC, true); else LAUNCH_F2(SK_ELASTIC, false);
             } else {
-                if (ctx->hasFext) LAUNCH((k_f2_strain_forces<SK_FULL, true>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
-                else LAUNCH((k_f2_strain_forces<SK_FULL, false>), pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, stFirst, hasUSF ? 1 : 0);
+                if (ctx->hasFext) LAUNCH_F2(SK_FULL, true); else LAUNCH_F2(SK_FULL, false);
             }
         }
         if (t.slab.on && (rc = halo_pack(ctx, 1, true))) return rc;

@@ -112,6 +112,52 @@ __device__ __forceinline__ void prefetch_stencil(const Grid &g, int center, cons
         }
 }
 
+// ---- per-warp node tile in shared memory -----------------------------------------------------------
+// The particles of a warp are (nearly) sorted by dual cell, so their 27-node stencils overlap in a window
+// of TILE_W consecutive node columns: nine linear runs of TILE_W 32-byte records (the node index is linear,
+// so a run that crosses the end of a grid row simply continues into the next row).  The warp copies the
+// window once with cp.async (one L2 round trip for the whole warp) and every lane gathers its 27 records
+// from shared memory; a lane whose stencil is not inside the window (a particle that drifted since the
+// last sort, or a warp spanning more than TILE_W-2 dual cells) reads global memory as before.
+#ifndef TILE_W
+#define TILE_W 8
+#endif
+struct WarpTile { double4 r[9][TILE_W]; };
+
+// window start (centre-row node index of column 0 is anchor-1): covers centres anchor .. anchor+TILE_W-3
+__device__ __forceinline__ int tile_anchor(int key, bool active)
+{
+    const unsigned full = 0xffffffffu;
+    const unsigned act = __ballot_sync(full, active);
+    const int kmin = __reduce_min_sync(full, active ? key : 0x7fffffff);
+    const int ref = __shfl_sync(full, key, __popc(act) >> 1);       // active lanes are the low ones
+    return max(kmin, ref - (TILE_W - 3));
+}
+
+__device__ __forceinline__ void tile_load_async(const Grid &g, WarpTile &t, int anchor, const double4 *__restrict__ R)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c0 = 0; c0 < 9 * TILE_W * 2; c0 += 32) {
+        const int c = c0 + lane;
+        if (c < 9 * TILE_W * 2) {
+            const int rec = c >> 1, half = c & 1;
+            const int row = rec / TILE_W, xo = rec - row * TILE_W;
+            int node = anchor - 1 + xo + ((row % 3) - 1) * g.yplane + ((row / 3) - 1) * g.zplane;
+            node = min(max(node, 0), g.nnodes - 1);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<char *>(&t.r[row][xo]) + 16 * half);
+            const char *src = reinterpret_cast<const char *>(R + node) + 16 * half;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+        }
+    }
+}
+
+__device__ __forceinline__ void tile_wait()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+}
+
 // centre node of the dual cell from the element and the sign of the natural coordinates
 __device__ __forceinline__ int dual_cell_center(const Grid &g, int inElem, const double xi[3])
 {
@@ -195,10 +241,16 @@ template <bool GRAD, int NQ>
 struct WarpStage {
     double X[3][WS_STRIDE];                     // Sx_i
     double YZ[9][WS_STRIDE];                    // Sy_j * Sz_k
-    double DX[GRAD ? 3 : 1][WS_STRIDE];         // dSx_i           (scaled by 2/dx)
-    double DYZ[GRAD ? 9 : 1][WS_STRIDE];        // dSy_j * Sz_k
-    double YDZ[GRAD ? 9 : 1][WS_STRIDE];        // Sy_j * dSz_k
     alignas(16) double Q[32][NQ];               // payload per particle lane (NQ even: read as double2 broadcasts)
+};
+// With gradients the stage keeps the six per-axis factor triplets (18 rows instead of 33: shared memory is what
+// limits the resident warps of the force kernel); the node lane forms the (y,z) products itself, in the same
+// order as the particle lane would, so the sums are unchanged.
+template <int NQ>
+struct WarpStage<true, NQ> {
+    double X[3][WS_STRIDE], Y[3][WS_STRIDE], Z[3][WS_STRIDE];       // S
+    double DX[3][WS_STRIDE], DY[3][WS_STRIDE], DZ[3][WS_STRIDE];    // dS (scaled by 2/delta)
+    alignas(16) double Q[32][NQ];
 };
 
 template <int NQ>
@@ -209,24 +261,25 @@ __device__ __forceinline__ void load_payload(const double (*Q)[NQ], int src, dou
     for (int i = 0; i < NQ / 2; i++) { const double2 t = r[i]; q[2 * i] = t.x; q[2 * i + 1] = t.y; }
 }
 
-template <bool GRAD, class Stage>
-__device__ __forceinline__ void stage_weights(Stage &st, int lane, const Weights3 &w)
+template <int NQ>
+__device__ __forceinline__ void stage_weights(WarpStage<false, NQ> &st, int lane, const Weights3 &w)
 {
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
-        st.X[t][lane] = w.S[0][t];
-        if (GRAD) st.DX[t][lane] = w.dS[0][t];
-    }
+    for (int t = 0; t < 3; t++) st.X[t][lane] = w.S[0][t];
 #pragma unroll
     for (int k = 0; k < 3; k++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            st.YZ[j + 3 * k][lane] = w.S[1][j] * w.S[2][k];
-            if (GRAD) {
-                st.DYZ[j + 3 * k][lane] = w.dS[1][j] * w.S[2][k];
-                st.YDZ[j + 3 * k][lane] = w.S[1][j] * w.dS[2][k];
-            }
-        }
+        for (int j = 0; j < 3; j++) st.YZ[j + 3 * k][lane] = w.S[1][j] * w.S[2][k];
+}
+
+template <int NQ>
+__device__ __forceinline__ void stage_weights(WarpStage<true, NQ> &st, int lane, const Weights3 &w)
+{
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        st.X[t][lane] = w.S[0][t]; st.Y[t][lane] = w.S[1][t]; st.Z[t][lane] = w.S[2][t];
+        st.DX[t][lane] = w.dS[0][t]; st.DY[t][lane] = w.dS[1][t]; st.DZ[t][lane] = w.dS[2][t];
+    }
 }
 
 // ---- the warp-cooperative scatter ----------------------------------------------------------------
@@ -252,14 +305,19 @@ __device__ __forceinline__ void warp_scatter(const Grid &g, int key, bool active
 #pragma unroll
             for (int v = 0; v < NV; v++) acc[v] = 0.;
             int n = 0;
-            unsigned mm = grp;
-            while (mm) {                                   // two members per trip: independent loads in flight
-                const int s0 = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const bool two = mm != 0;
-                const int s1 = two ? __ffs(mm) - 1 : s0;
-                mm &= mm - 1;
-                n += contrib(s0, s1, two, li, ljk, acc);
+            // sorted particles: the members of a group are consecutive lanes starting at the leader, so the
+            // loop is a plain counted one (constant address strides); any other mask takes the bit scan
+            const int members = __popc(grp);
+            if ((grp >> leader) == (0xffffffffu >> (32 - members))) {
+#pragma unroll 2
+                for (int s = leader; s < leader + members; s++) n += contrib(s, li, ljk, acc);
+            } else {
+                unsigned mm = grp;
+                while (mm) {
+                    const int s = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    n += contrib(s, li, ljk, acc);
+                }
             }
             if (n) {
                 const int nd = center + nodeOff;
@@ -350,35 +408,27 @@ __global__ void __launch_bounds__(FUSED_THREADS, F1_MINB) k_f1_mass_momentum(Gri
         P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
         Weights3 w;
         particle_weights<false>(g, e, xi, lp, w);
-        stage_weights<false>(st, lane, w);
+        stage_weights(st, lane, w);
         st.Q[lane][0] = P.mp[p];
         st.Q[lane][1] = P.vel[0][p]; st.Q[lane][2] = P.vel[1][p]; st.Q[lane][3] = P.vel[2][p];
         key = w.center;
     }
     __syncwarp();
     double *dst[4] = {N.mass, N.pk[0], N.pk[1], N.pk[2]};
-    warp_scatter<4, true>(g, key, active, dst, N.cnt, [&](int s0, int s1, bool two, int i, int jk, double *acc) {
-        const double Sa = st.X[i][s0] * st.YZ[jk][s0];
-        const double Sb = st.X[i][s1] * st.YZ[jk][s1];
-        double qa[4], qb[4];
-        load_payload<4>(st.Q, s0, qa);
-        load_payload<4>(st.Q, s1, qb);
-        const double fa = Sa * qa[0];
-        acc[0] += fa;
-        acc[1] += qa[1] * fa; acc[2] += qa[2] * fa; acc[3] += qa[3] * fa;
-        int n = Sa != 0. ? 1 : 0;
-        if (two) {
-            const double fb = Sb * qb[0];
-            acc[0] += fb;
-            acc[1] += qb[1] * fb; acc[2] += qb[2] * fb; acc[3] += qb[3] * fb;
-            n += Sb != 0. ? 1 : 0;
-        }
-        return n;
+    warp_scatter<4, true>(g, key, active, dst, N.cnt, [&](int src, int i, int jk, double *acc) {
+        const double S = st.X[i][src] * st.YZ[jk][src];
+        double q[4];
+        load_payload<4>(st.Q, src, q);
+        const double f = S * q[0];
+        acc[0] += f;
+        acc[1] += q[1] * f; acc[2] += q[2] * f; acc[3] += q[3] * f;
+        return S != 0. ? 1 : 0;
     });
 }
 
 // ---- gather of grad v from the V records -----------------------------------------------------------
-__device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, const double4 *__restrict__ V, double dv[9])
+template <bool TILED>
+__device__ __forceinline__ void gather_gradv_impl(const Grid &g, const Weights3 &w, const double4 *__restrict__ V, const WarpTile *t, int d, double dv[9])
 {
 #pragma unroll
     for (int i = 0; i < 9; i++) dv[i] = 0.;
@@ -392,7 +442,7 @@ __device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, c
             const int row = w.center + (j - 1) * g.yplane + (k - 1) * g.zplane - 1;
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                const double4 v = ldg4(&V[row + i]);
+                const double4 v = TILED ? t->r[j + 3 * k][d + i] : ldg4(&V[row + i]);
                 const double gx = w.dS[0][i] * syz;
                 const double gy = w.S[0][i] * dyz;
                 const double gz = w.S[0][i] * ydz;
@@ -404,33 +454,55 @@ __device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, c
     }
 }
 
+// d = centre - anchor; the stencil is inside the warp's tile iff 0 <= d <= TILE_W-3
+__device__ __forceinline__ void gather_gradv(const Grid &g, const Weights3 &w, const double4 *__restrict__ V, const WarpTile &t, int anchor, double dv[9])
+{
+    const int d = w.center - anchor;
+    if ((unsigned)d <= (unsigned)(TILE_W - 3)) gather_gradv_impl<true>(g, w, V, &t, d, dv);
+    else gather_gradv_impl<false>(g, w, V, &t, 0, dv);
+}
+
 // ---- F2: grad v + constitutive law + P2G forces ------------------------------------------------------
+template <bool FEXT>
+constexpr size_t f2_smem_bytes() { return FUSED_WARPS * (sizeof(WarpStage<true, FEXT ? 10 : 6>) + sizeof(WarpTile)); }
+
 template <int SK, bool FEXT>
 __global__ void __launch_bounds__(FUSED_THREADS, F2_MINB) k_f2_strain_forces(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
                                                                     double strainTime, int doStrain)
 {
-    __shared__ WarpStage<true, FEXT ? 10 : 6> stage[FUSED_WARPS];
-    WarpStage<true, FEXT ? 10 : 6> &st = stage[threadIdx.x >> 5];
+    // dynamic shared memory (above the 48 KB static limit): per warp one weight stage + one node tile
+    extern __shared__ __align__(16) unsigned char f2_smem[];
+    typedef WarpStage<true, FEXT ? 10 : 6> Stage;
+    Stage &st = reinterpret_cast<Stage *>(f2_smem)[threadIdx.x >> 5];
+    WarpTile &tile = reinterpret_cast<WarpTile *>(f2_smem + FUSED_WARPS * sizeof(Stage))[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
-    int key = 0;
+    int key = 0, e = 0, anchor = 0;
+    double xi[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
     if (active) {
         if (doStrain) prefetch_state<SK>(P, p);
-        const int e = P.elem[p];
-        double xi[3], lp[3];
+        e = P.elem[p];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
-        if (doStrain) prefetch_stencil(g, dual_cell_center(g, e, xi), FN.V);
+        key = dual_cell_center(g, e, xi);
+    }
+    if (doStrain) {         // start the warp's node window on its way while the weights are computed
+        anchor = tile_anchor(key, active);
+        tile_load_async(g, tile, anchor, FN.V);
+    }
+    Weights3 w;
+    if (active) {
+        particle_weights<true>(g, e, xi, lp, w);
+        stage_weights(st, lane, w);
+    }
+    if (doStrain) tile_wait();
+    if (active) {
         double sp[6], pr = 0.;
         {
-            Weights3 w;
-            particle_weights<true>(g, e, xi, lp, w);
-            key = w.center;
-            stage_weights<true>(st, lane, w);
             if (doStrain) {
                 double dv[9];
-                gather_gradv(g, w, FN.V, dv);
+                gather_gradv(g, w, FN.V, tile, anchor, dv);
 #pragma unroll
                 for (int i = 0; i < 9; i++) dv[i] *= strainTime;
                 PState s;
@@ -454,29 +526,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, F2_MINB) k_f2_strain_forces(Gri
     __syncwarp();
     double *dst[3] = {N.ftot[0], N.ftot[1], N.ftot[2]};
     constexpr int NQ = FEXT ? 10 : 6;
-    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int s0, int s1, bool two, int i, int jk, double *acc) {
-        int n = 0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int src = h ? s1 : s0;
-            const double Sx = st.X[i][src];
-            const double gx = st.DX[i][src] * st.YZ[jk][src];
-            const double gy = Sx * st.DYZ[jk][src];
-            const double gz = Sx * st.YDZ[jk][src];
-            double q[NQ];
-            load_payload<NQ>(st.Q, src, q);
-            if (h == 0 || two) {
-                acc[0] += q[0] * gx + q[5] * gy + q[4] * gz;
-                acc[1] += q[5] * gx + q[1] * gy + q[3] * gz;
-                acc[2] += q[4] * gx + q[3] * gy + q[2] * gz;
-                if (FEXT) {
-                    const double S = Sx * st.YZ[jk][src];
-                    acc[0] += S * q[6]; acc[1] += S * q[7]; acc[2] += S * q[8];
-                }
-                n += (gx != 0. || gy != 0. || gz != 0.) ? 1 : 0;
-            }
+    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
+        const int j = jk % 3, k = jk / 3;
+        const double Sx = st.X[i][src], Sy = st.Y[j][src], Sz = st.Z[k][src];
+        const double gx = st.DX[i][src] * (Sy * Sz);
+        const double gy = Sx * (st.DY[j][src] * Sz);
+        const double gz = Sx * (Sy * st.DZ[k][src]);
+        double q[NQ];
+        load_payload<NQ>(st.Q, src, q);
+        acc[0] += q[0] * gx + q[5] * gy + q[4] * gz;
+        acc[1] += q[5] * gx + q[1] * gy + q[3] * gz;
+        acc[2] += q[4] * gx + q[3] * gy + q[2] * gz;
+        if (FEXT) {
+            const double S = Sx * (Sy * Sz);
+            acc[0] += S * q[6]; acc[1] += S * q[7]; acc[2] += S * q[8];
         }
-        return n;
+        return (gx != 0. || gy != 0. || gz != 0.) ? 1 : 0;
     });
 }
 
@@ -484,27 +549,32 @@ __global__ void __launch_bounds__(FUSED_THREADS, F2_MINB) k_f2_strain_forces(Gri
 __global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(Grid g, Particles P, Nodes N, FusedNodes FN, const Material *mats,
                                                                       StepParams sp, int m, int doScatter)
 {
-    __shared__ WarpStage<false, 4> stage[FUSED_WARPS];
-    WarpStage<false, 4> &st = stage[threadIdx.x >> 5];
+    // the node tiles (gather) and the weight stage (scatter) are live one after the other: same shared memory
+    union F3Shared { WarpTile t[2]; WarpStage<false, 4> st; };
+    __shared__ F3Shared shared[FUSED_WARPS];
+    WarpStage<false, 4> &st = shared[threadIdx.x >> 5].st;
+    WarpTile &tv = shared[threadIdx.x >> 5].t[0], &ta = shared[threadIdx.x >> 5].t[1];
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
-    int key = 0;
+    int key = 0, e = 0;
+    double xi[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
     if (active) {
-        const int e = P.elem[p];
-        double xi[3], lp[3];
+        e = P.elem[p];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
-        {
-            const int ctr = dual_cell_center(g, e, xi);
-            prefetch_stencil(g, ctr, FN.V);
-            if (m <= 0) prefetch_stencil(g, ctr, FN.A);
-        }
-        Weights3 w;
-        particle_weights<false>(g, e, xi, lp, w);
-        key = w.center;
-        if (doScatter) stage_weights<false>(st, lane, w);
-        double Svk[3] = {0., 0., 0.}, Sacc[3] = {0., 0., 0.};
+        key = dual_cell_center(g, e, xi);
+    }
+    const int anchor = tile_anchor(key, active);
+    tile_load_async(g, tv, anchor, FN.V);
+    if (m <= 0) tile_load_async(g, ta, anchor, FN.A);
+    Weights3 w;
+    if (active) particle_weights<false>(g, e, xi, lp, w);
+    tile_wait();
+    double Svk[3] = {0., 0., 0.}, Sacc[3] = {0., 0., 0.};
+    if (active) {
+        const int d = key - anchor;
+        const bool tiled = (unsigned)d <= (unsigned)(TILE_W - 3);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
 #pragma unroll
@@ -514,15 +584,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(G
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     const double S = w.S[0][i] * syz;
-                    const double4 v = ldg4(&FN.V[row + i]);
+                    const double4 v = tiled ? tv.r[j + 3 * k][d + i] : ldg4(&FN.V[row + i]);
                     Svk[0] += v.x * S; Svk[1] += v.y * S; Svk[2] += v.z * S;
                     if (m <= 0) {
-                        const double4 a = ldg4(&FN.A[row + i]);
+                        const double4 a = tiled ? ta.r[j + 3 * k][d + i] : ldg4(&FN.A[row + i]);
                         Sacc[0] += a.x * S; Sacc[1] += a.y * S; Sacc[2] += a.z * S;
                     }
                 }
             }
         }
+    }
+    __syncwarp();           // every lane is done with the tiles: reuse the memory for the scatter stage
+    if (active) {
+        if (doScatter) stage_weights(st, lane, w);
         const double dt = sp.dt;
         const double matDamp = mats[P.mat[p]].p[2];
         const double pAlpha = matDamp >= 0. ? matDamp : sp.particleAlpha;
@@ -566,21 +640,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(G
     if (!doScatter) return;
     __syncwarp();
     double *dst[3] = {N.pk[0], N.pk[1], N.pk[2]};
-    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int s0, int s1, bool two, int i, int jk, double *acc) {
-        const double Sa = st.X[i][s0] * st.YZ[jk][s0];
-        const double Sb = st.X[i][s1] * st.YZ[jk][s1];
-        double qa[4], qb[4];
-        load_payload<4>(st.Q, s0, qa);
-        load_payload<4>(st.Q, s1, qb);
-        const double fa = Sa * qa[0];
-        acc[0] += qa[1] * fa; acc[1] += qa[2] * fa; acc[2] += qa[3] * fa;
-        int n = Sa != 0. ? 1 : 0;
-        if (two) {
-            const double fb = Sb * qb[0];
-            acc[0] += qb[1] * fb; acc[1] += qb[2] * fb; acc[2] += qb[3] * fb;
-            n += Sb != 0. ? 1 : 0;
-        }
-        return n;
+    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
+        const double S = st.X[i][src] * st.YZ[jk][src];
+        double q[4];
+        load_payload<4>(st.Q, src, q);
+        const double f = S * q[0];
+        acc[0] += q[1] * f; acc[1] += q[2] * f; acc[2] += q[3] * f;
+        return S != 0. ? 1 : 0;
     });
 }
 
@@ -589,27 +655,37 @@ template <int SK>
 __global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid g, Particles P, FusedNodes FN, const Material *mats,
                                                                    double strainTime, int doStrain, StatusFlags *flags, double dt, SlabInfo slab)
 {
+    __shared__ WarpTile tiles[FUSED_WARPS];
+    WarpTile &tile = tiles[threadIdx.x >> 5];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
-    if (doStrain && p < P.nNR) {
-        prefetch_state<SK>(P, p);
-        double xi[3], lp[3];
-        xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
-        load_lp(g, P, p, lp);
-        prefetch_stencil(g, dual_cell_center(g, P.elem[p], xi), FN.V);
-        double dv[9];
-        {
-            Weights3 w;
-            particle_weights<true>(g, P.elem[p], xi, lp, w);
-            gather_gradv(g, w, FN.V, dv);
+    if (doStrain) {
+        const bool active = p < P.nNR;
+        int key = 0, e = 0;
+        double xi[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
+        if (active) {
+            prefetch_state<SK>(P, p);
+            e = P.elem[p];
+            xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
+            load_lp(g, P, p, lp);
+            key = dual_cell_center(g, e, xi);
         }
+        const int anchor = tile_anchor(key, active);
+        tile_load_async(g, tile, anchor, FN.V);
+        Weights3 w;
+        if (active) particle_weights<true>(g, e, xi, lp, w);
+        tile_wait();
+        if (active) {
+            double dv[9];
+            gather_gradv(g, w, FN.V, tile, anchor, dv);
 #pragma unroll
-        for (int i = 0; i < 9; i++) dv[i] *= strainTime;
-        PState s;
-        load_state<SK>(P, p, s);
-        constitutive_law<3, SK == SK_ELASTIC>(s, dv, strainTime, g.np, mats[P.mat[p]]);
-        store_state<SK>(P, p, s);
+            for (int i = 0; i < 9; i++) dv[i] *= strainTime;
+            PState s;
+            load_state<SK>(P, p, s);
+            constitutive_law<3, SK == SK_ELASTIC>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+            store_state<SK>(P, p, s);
+        }
     }
+    if (p >= P.n) return;
     reset_element_one<3>(g, P, p, flags, dt);
     if (slab.on) {          // particle migration between slabs (replaces GridPatch::AddMovingParticle, GridPatch.cpp:214)
         const int k = (P.elem[p] - 1) / (g.horiz * g.vert);

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f4_pipe(Grid g, Particles P, 
                 {
                     Weights3 w;
                     particle_weights<true>(g, elem, xi, lp, w);
-                    gather_gradv(g, w, FN.V, dv);
+                    gather_gradv_impl<false>(g, w, FN.V, (const WarpTile *)0, 0, dv);
                 }
 #pragma unroll
                 for (int i = 0; i < 9; i++) dv[i] *= strainTime;
