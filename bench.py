@@ -109,6 +109,28 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# fused path: the four particle kernels, elastic state, uniform lp
+FUSED_ALGO_BYTES = {"mass_and_momentum": 84, "update_strains_first": 336, "update_particles": 160, "update_strains_last": 356}
+
+TASK_KERNEL = {"mass_and_momentum": "k_f1_mass_momentum", "update_strains_first": "k_f2_strain_forces",
+               "update_particles": "k_f3_update_momentum", "update_strains_last": "k_f4_strain_reset"}
+
+
+def ncu_traffic(task, workload, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the task's kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/run_ncu_final.sh); None when there is no capture of it."""
+    path = os.path.join(ROOT, "profiles", "r1f_dram_traffic.json")
+    if not os.path.exists(path) or task not in TASK_KERNEL:
+        return None, None
+    d = json.load(open(path))
+    if d.get("workload") != workload or d.get("particles") != n:
+        return None, None
+    for k, v in d["dram_bytes_per_launch"].items():
+        if k.startswith(TASK_KERNEL[task]):
+            return v, "profiles/r1f_dram_traffic.json (%s)" % k
+    return None, None
+
+
 def make_problem(workload, ncell_override=None, rank=0, world=1):
     from nairn_mpm_fea_b200 import materials as M, problem
     ncell = {"block8m": 100, "block1m": 50, "taylor16m": 100, "taylor2m": 50}[workload]
@@ -225,11 +247,14 @@ def run_ours(args):
     # IsoPlasticity carries eplast(6), pressure, plastic energy and one history double through both strain updates
     full_state = 2 * (6 + 1 + 1 + 1) * 8 if taylor else 0
     algo_step = ALGO_BYTES_PER_PARTICLE_STEP + 2 * full_state
-    dom_bytes = (TASK_ALGO_BYTES[dom] + (full_state if dom in ("update_strains_first", "update_strains_last") else 0)) * n
+    per_particle = FUSED_ALGO_BYTES.get(dom, TASK_ALGO_BYTES[dom]) if args.kernel_path != 1 else TASK_ALGO_BYTES[dom]
+    dom_bytes = (per_particle + (full_state if dom in ("update_strains_first", "update_strains_last") else 0)) * n
     dom_gbs = dom_bytes / (task_ms[dom] * 1e-3) / 1e9
     step_gbs = algo_step * n / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom, args.workload, n)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": dom_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src,
                 "kernel_ms": task_ms[dom], "kernel_share_of_step": task_ms[dom] / sum(task_ms.values()),
                 "whole_step": {"algorithmic_bytes_per_particle_step": algo_step,
                                "achieved": step_gbs, "frac": step_gbs / hbm_peak},

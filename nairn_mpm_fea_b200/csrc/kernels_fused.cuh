@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid
             gather_gradv(g, w, FN.V, tile, anchor, dv);
 #pragma unroll
             for (int i = 0; i < 9; i++) dv[i] *= strainTime;
-            PState s;
+            PState s;               // (loading the state before the gather was measured slower: registers, not latency, limit this kernel)
             load_state<SK>(P, p, s);
             constitutive_law<3, SK == SK_ELASTIC>(s, dv, strainTime, g.np, mats[P.mat[p]]);
             store_state<SK>(P, p, s);
