@@ -164,7 +164,7 @@ typedef struct mpmgpu_particles {
  * Arrays are nnodes long (vectors [3][nnodes]), reference node order; NULL = skip. */
 typedef struct mpmgpu_nodes {
     int nnodes;
-    int    *number_points;  /* MatVelocityField::numberPoints */
+    int    *number_points;  /* MatVelocityField::numberPoints (per-task path); the fused path keeps only the 0/1 activity flag numberPoints>0 */
     double *mass;           /* MatVelocityField::mass */
     double *pk;             /* [3][nnodes] momentum */
     double *ftot;           /* [3][nnodes] force */

@@ -893,7 +893,7 @@ static inline void halo_range(const mpmgpu_ctx *ctx, int side, int &node0, int &
 static int halo_pack(mpmgpu_ctx *ctx, int which, bool real)
 {
     TiledState &t = ctx->tiled;
-    const int nv = which == 0 ? 5 : 3;
+    const int nv = which == 0 ? 4 : 3;
     for (int side = 0; side < 2; side++) {
         if (!(side == 0 ? t.hasLower : t.hasUpper)) continue;
         int node0, count;
@@ -947,8 +947,7 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         else {
             const size_t nnPad = ((size_t)g.nnodes + 31) & ~(size_t)31;
             CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 13 * sizeof(double), ctx->stream));      // mass, pk, ftot, vk, pkc
-            CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
-            ctx->launches += 2;
+            ctx->launches += 1;
         }
         prof_end(ctx, T_INIT);
         prof_begin(ctx);

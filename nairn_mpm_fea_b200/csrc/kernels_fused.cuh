@@ -261,11 +261,13 @@ __device__ __forceinline__ void load_payload(const double (*Q)[NQ], int src, dou
     for (int i = 0; i < NQ / 2; i++) { const double2 t = r[i]; q[2 * i] = t.x; q[2 * i + 1] = t.y; }
 }
 
+// `scale` (the particle mass in the two momentum scatters) rides on the x factors, so the node lanes need one
+// payload double less per member: S*mp = (Sx*mp)*(Sy*Sz)
 template <int NQ>
-__device__ __forceinline__ void stage_weights(WarpStage<false, NQ> &st, int lane, const Weights3 &w)
+__device__ __forceinline__ void stage_weights(WarpStage<false, NQ> &st, int lane, const Weights3 &w, double scale)
 {
 #pragma unroll
-    for (int t = 0; t < 3; t++) st.X[t][lane] = w.S[0][t];
+    for (int t = 0; t < 3; t++) st.X[t][lane] = w.S[0][t] * scale;
 #pragma unroll
     for (int k = 0; k < 3; k++)
 #pragma unroll
@@ -408,21 +410,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, F1_MINB) k_f1_mass_momentum(Gri
         P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
         Weights3 w;
         particle_weights<false>(g, e, xi, lp, w);
-        stage_weights(st, lane, w);
-        st.Q[lane][0] = P.mp[p];
-        st.Q[lane][1] = P.vel[0][p]; st.Q[lane][2] = P.vel[1][p]; st.Q[lane][3] = P.vel[2][p];
+        stage_weights(st, lane, w, P.mp[p]);
+        st.Q[lane][0] = P.vel[0][p]; st.Q[lane][1] = P.vel[1][p]; st.Q[lane][2] = P.vel[2][p];
         key = w.center;
     }
     __syncwarp();
     double *dst[4] = {N.mass, N.pk[0], N.pk[1], N.pk[2]};
-    warp_scatter<4, true>(g, key, active, dst, N.cnt, [&](int src, int i, int jk, double *acc) {
-        const double S = st.X[i][src] * st.YZ[jk][src];
-        double q[4];
-        load_payload<4>(st.Q, src, q);
-        const double f = S * q[0];
+    // (the node's particle count is only ever used as an activity flag: N1 derives it from mass != 0)
+    warp_scatter<4, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
+        const double f = st.X[i][src] * st.YZ[jk][src];          // fn * mp
+        const double2 vxy = *reinterpret_cast<const double2 *>(st.Q[src]);
+        const double vz = st.Q[src][2];
         acc[0] += f;
-        acc[1] += q[1] * f; acc[2] += q[2] * f; acc[3] += q[3] * f;
-        return S != 0. ? 1 : 0;
+        acc[1] += vxy.x * f; acc[2] += vxy.y * f; acc[3] += vz * f;
+        return f != 0. ? 1 : 0;
     });
 }
 
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(G
     }
     __syncwarp();           // every lane is done with the tiles: reuse the memory for the scatter stage
     if (active) {
-        if (doScatter) stage_weights(st, lane, w);
+        if (doScatter) stage_weights(st, lane, w, P.mp[p]);
         const double dt = sp.dt;
         const double matDamp = mats[P.mat[p]].p[2];
         const double pAlpha = matDamp >= 0. ? matDamp : sp.particleAlpha;
@@ -632,21 +633,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(G
             P.pos[c][p] = pos[c];
             P.acc[c][p] = delV / dt;
         }
-        if (doScatter) {
-            st.Q[lane][0] = P.mp[p];
-            st.Q[lane][1] = vel[0]; st.Q[lane][2] = vel[1]; st.Q[lane][3] = vel[2];
-        }
+        if (doScatter) { st.Q[lane][0] = vel[0]; st.Q[lane][1] = vel[1]; st.Q[lane][2] = vel[2]; }
     }
     if (!doScatter) return;
     __syncwarp();
     double *dst[3] = {N.pk[0], N.pk[1], N.pk[2]};
     warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
-        const double S = st.X[i][src] * st.YZ[jk][src];
-        double q[4];
-        load_payload<4>(st.Q, src, q);
-        const double f = S * q[0];
-        acc[0] += q[1] * f; acc[1] += q[2] * f; acc[2] += q[3] * f;
-        return S != 0. ? 1 : 0;
+        const double f = st.X[i][src] * st.YZ[jk][src];          // fn * mp
+        const double2 vxy = *reinterpret_cast<const double2 *>(st.Q[src]);
+        const double vz = st.Q[src][2];
+        acc[0] += vxy.x * f; acc[1] += vxy.y * f; acc[2] += vz * f;
+        return f != 0. ? 1 : 0;
     });
 }
 
@@ -698,7 +695,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid
 }
 
 // ---- slab halo: pack partial sums of the three node planes shared with a neighbour / add the neighbour's ----
-// which: 0 mass,pk,cnt (5 values)  1 ftot (3)  2 pk (3).  Buffer layout [value][3 planes * planeNodes].
+// which: 0 mass,pk (4 values)  1 ftot (3)  2 pk (3).  Buffer layout [value][3 planes * planeNodes].
 __global__ void k_halo_pack(int which, int node0, int count, Nodes N, double *buf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -707,7 +704,6 @@ __global__ void k_halo_pack(int which, int node0, int count, Nodes N, double *bu
     if (which == 0) {
         buf[i] = N.mass[nd];
         buf[count + i] = N.pk[0][nd]; buf[2 * count + i] = N.pk[1][nd]; buf[3 * count + i] = N.pk[2][nd];
-        buf[4 * count + i] = (double)N.cnt[nd];
     } else if (which == 1) {
         buf[i] = N.ftot[0][nd]; buf[count + i] = N.ftot[1][nd]; buf[2 * count + i] = N.ftot[2][nd];
     } else {
@@ -723,7 +719,6 @@ __global__ void k_halo_add(int which, int node0, int count, Nodes N, const doubl
     if (which == 0) {
         N.mass[nd] += buf[i];
         N.pk[0][nd] += buf[count + i]; N.pk[1][nd] += buf[2 * count + i]; N.pk[2][nd] += buf[3 * count + i];
-        N.cnt[nd] += (int)buf[4 * count + i];
     } else if (which == 1) {
         N.ftot[0][nd] += buf[i]; N.ftot[1][nd] += buf[count + i]; N.ftot[2][nd] += buf[2 * count + i];
     } else {
@@ -771,10 +766,13 @@ __global__ void k_n1_post_extrapolation(int n0, int nnodes, Nodes N, FusedNodes 
     const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n0 + nnodes) return;
     double4 v = make_double4(0., 0., 0., 0.);
-    if (N.cnt[i] > 0) {
+    // active node = some particle has a nonzero weight on it (numberPoints > 0 in the reference) = mass != 0, since
+    // the weights and particle masses are positive; the flag is kept in N.cnt for the later sweeps
+    const double mass = N.mass[i];
+    N.cnt[i] = mass != 0. ? 1 : 0;
+    if (mass != 0.) {
         double pk[3] = {N.pk[0][i], N.pk[1][i], N.pk[2][i]};
         double pkc[3] = {pk[0], pk[1], pk[2]};
-        const double mass = N.mass[i];
         const int u = FN.bcOfNode ? FN.bcOfNode[i] : -1;
         if (u >= 0) {
             const int sd = B.symdir[u];

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-HALO_VALUES = (5, 3, 3)        # values per node exchanged after phases 0, 1, 2
+HALO_VALUES = (4, 3, 3)        # values per node exchanged after phases 0, 1, 2 (mass + momentum, force, momentum)
 
 
 def slab_bounds(depth, cell_first, cell_last, world):

@@ -1,7 +1,9 @@
 """XML inputs (NairnMPM.dtd format) for the parity tests and the bench.
 
 These are the synthetic cases SURVEY.md section 8(d) names, written in the reference's own input
-format so the same text drives the reference (oracle/_ref) and the GPU path (via xml_input.read_xml).
+format so the same text drives the reference (oracle/_ref: goldens, CPU baseline) and the drop-in driver
+(host/_build/NairnMPM_gpu); the Python host gets the same problems from the reference's own set-up dump
+(problem.from_reference_dump) or from its generators (problem.block3d).
 """
 
 
