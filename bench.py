@@ -131,6 +131,23 @@ def ncu_traffic(task, workload, n):
     return None, None
 
 
+BLOCK_JITTER = 0.4          # hash-jitter amplitude of the block workloads, in cells (positions move by up to +-0.2 cell)
+
+
+def block_velocity(ncell):
+    """Initial velocity field of the block workloads, the same for this repo's arm and the reference arm: 10 m/s
+    compression along z with a sinusoidal perturbation (period = one block, so particles cross cell and slab faces:
+    ~0.3 % of a cell per step) plus a shear wave in x."""
+    L = float(ncell)
+
+    def vel(pos):
+        v = np.zeros_like(pos)
+        v[2] = -1.0e4 + 2.0e3 * np.sin(2.0 * np.pi * (pos[2] - 7.0) / L)
+        v[0] = 1.0e3 * np.sin(2.0 * np.pi * (pos[1] - 7.0) / L)
+        return v
+    return vel
+
+
 def make_problem(workload, ncell_override=None, rank=0, world=1):
     from nairn_mpm_fea_b200 import materials as M, problem
     ncell = {"block8m": 100, "block1m": 50, "taylor16m": 100, "taylor2m": 50}[workload]
@@ -145,20 +162,13 @@ def make_problem(workload, ncell_override=None, rank=0, world=1):
         pr = problem.block3d(ncell=ncell, margin=7, velocity=(0.0, 0.0, -2.0e5), jitter_amp=0.4, bottom_bc=False, material=mat,
                              ncell_xyz=(ncell, ncell, ncz), cells_z=cz, rigid_wall=dict(set_direction=4, overhang=2))
         return pr, ncell
-    # small uniform compression velocity + sinusoidal perturbation along z so particles cross cells
-    L = float(ncell)
-
-    def vel(pos):
-        v = np.zeros_like(pos)
-        v[2] = -1000.0 + 200.0 * np.sin(2.0 * np.pi * (pos[2] - 7.0) / L)     # period = one slab: particles cross slab faces
-        v[0] = 100.0 * np.sin(2.0 * np.pi * (pos[1] - 7.0) / L)
-        return v
+    vel = block_velocity(ncell)
 
     if world == 1:
-        pr = problem.block3d(ncell=ncell, margin=7, velocity_fn=vel, jitter_amp=0.4)
+        pr = problem.block3d(ncell=ncell, margin=7, velocity_fn=vel, jitter_amp=BLOCK_JITTER)
     else:
         # config 5: one ncell^3 block per GPU stacked along z; this rank generates only its own slab
-        pr = problem.block3d(ncell=ncell, margin=7, velocity_fn=vel, jitter_amp=0.4,
+        pr = problem.block3d(ncell=ncell, margin=7, velocity_fn=vel, jitter_amp=BLOCK_JITTER,
                              ncell_xyz=(ncell, ncell, ncell * world), cells_z=(ncell * rank, ncell * (rank + 1)))
     return pr, ncell
 
@@ -190,14 +200,14 @@ def run_ours(args):
     taylor = args.workload.startswith("taylor")
     n = int(prob.particles["n_nonrigid"])          # rigid-BC particles (replicated on every rank) are not counted
     if world == 1:
-        sim = MpmGpu(prob, device=local, kernel_path=args.kernel_path)
+        sim = MpmGpu(prob, device=local, kernel_path=args.kernel_path, sort_interval=args.sort_interval)
         stepper = sim
         stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local))
     else:
         from nairn_mpm_fea_b200.slab import SlabSim, slab_bounds
         bounds = slab_bounds(prob.depth, 8, 8 + (2 * ncell if taylor else ncell * world), world)
         lo, hi = bounds[rank]
-        stepper = SlabSim(prob, prob.particles, lo, hi, rank, world, device=local, capacity_factor=1.2)
+        stepper = SlabSim(prob, prob.particles, lo, hi, rank, world, device=local, capacity_factor=1.2, sort_interval=args.sort_interval)
         sim = stepper.sim
         stream = stepper.stream
 
@@ -307,7 +317,8 @@ def run_ours(args):
                                     "200 m/s onto a plate of %d rigid-BC particles, FLIP, USAVG+, positions hash-jittered"
                                     % (args.workload, ncell, ncell, 2 * ncell, total_particles, prob.nparticles - n)) if taylor else
                                    "%s: 3D uGIMP isotropic-elastic block, %d^3 cells x 8 = %d particles per GPU, FLIP, USAVG+, "
-                                   "grid %d^3 cells, particle positions hash-jittered +-0.2 cell off the lattice" % (args.workload, ncell, n, prob.horiz),
+                                   "grid %d^3 cells, particle positions hash-jittered +-0.2 cell off the lattice, 10 m/s compression + sinusoidal perturbation "
+                                   "(particles cross cell and slab faces)" % (args.workload, ncell, n, prob.horiz),
                        "particles_per_gpu": n, "nodes": prob.nnodes, "l2_policy": "inputs larger than L2 (%.0f MB state)" % (n * 460 / 1e6),
                        "kernel_path": sim_kernel_path_name(args.kernel_path),
                        "parallelism": "1 GPU" if world == 1 else
@@ -333,6 +344,8 @@ import sys, time, json
 sys.path.insert(0, %(root)r)
 from oracle.refharness import RefRun
 from tests.inputs import block3d
+from nairn_mpm_fea_b200.problem import jitter
+import bench
 import tempfile, os
 d = tempfile.mkdtemp(prefix="mpmbench_")
 xml = os.path.join(d, "in.fmcmd")
@@ -340,6 +353,10 @@ open(xml, "w").write(block3d(ncell=%(ncell)d, margin=7, maxtime=1.0))
 os.chdir(d)
 t0 = time.perf_counter()
 r = RefRun(xml, nprocs=%(nprocs)d)
+# the same off-lattice start and velocity field the GPU arm gets (problem.block3d(jitter_amp, velocity_fn))
+pos = jitter(r.particles()["pos"], bench.BLOCK_JITTER, 12345)
+bad = r.set_particles(pos, bench.block_velocity(%(ncell)d)(pos))
+assert bad == 0, bad
 t1 = time.perf_counter()
 r.step(%(warm)d)
 t2 = time.perf_counter()
@@ -374,7 +391,7 @@ def cpu_baseline(ncell, steps):
     if "error" in d:
         return {"value": None, "unit": UNIT, "cores": d.get("cores", 0), "kind": "reference", "sample": d["error"]}
     return {"value": d["n"] * d["steps"] / d["run_s"], "unit": UNIT, "cores": d["cores"], "kind": "reference",
-            "sample": "reference NairnMPM (oracle/_ref, -O3 -fopenmp) on the same block input at %d^3 cells = %d particles, "
+            "sample": "reference NairnMPM (oracle/_ref, -O3 -fopenmp) on the same block input (same jittered start and velocity field) at %d^3 cells = %d particles, "
                       "%d steps after 1 warm-up, %d OpenMP threads, %.1f s" % (ncell, d["n"], d["steps"], d["cores"], d["run_s"])}
 
 
@@ -388,7 +405,7 @@ def run_reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built or failed: %s" % (d or {}).get("error", "")}))
         return
     v = d["n"] * d["steps"] / d["run_s"]
-    sample = ("reference NairnMPM (oracle/_ref) on the bench block input at %d^3 cells = %d particles (bounded sample of the "
+    sample = ("reference NairnMPM (oracle/_ref) on the bench block input (same jittered start and velocity field) at %d^3 cells = %d particles (bounded sample of the "
               "%s workload), %d steps, %d OpenMP threads" % (args.cpu_ncell, d["n"], args.workload, d["steps"], d["cores"]))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * d["run_s"] / d["steps"], "higher_is_better": True, "scaling": "weak",
@@ -408,6 +425,7 @@ def main():
     ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m", "taylor16m", "taylor2m"])
     ap.add_argument("--ncell", type=int, default=0, help="override block edge in cells (testing)")
     ap.add_argument("--kernel-path", type=int, default=0)
+    ap.add_argument("--sort-interval", type=int, default=0, help="steps between physical particle sorts (0 = library default)")
     ap.add_argument("--cpu-ncell", type=int, default=50, help="block edge of the CPU sample (50 -> 1M particles)")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

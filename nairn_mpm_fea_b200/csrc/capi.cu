@@ -64,7 +64,11 @@ struct mpmgpu_ctx {
     // staging
     double *hStage; size_t hStageBytes;
     TiledState tiled;
-    bool f2Attr[2][2];                  // dynamic shared memory opt-in done for k_f2_strain_forces<SK, FEXT> on this device
+    bool f2Attr[2][2];
+    // slab mode: leave counts + status flags land here (pinned) right after the early element reset; the host
+    // waits on slabEvent while the strain kernel of the same step is still running
+    struct SlabHost { int leave[2]; StatusFlags flags; } *slabHost;
+    cudaEvent_t slabEvent; bool slabPending;                  // dynamic shared memory opt-in done for k_f2_strain_forces<SK, FEXT> on this device
 };
 
 static int fail(mpmgpu_ctx *c, int code, const char *fmt, ...)
@@ -135,6 +139,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
     tiled_state_init(ctx->tiled);
     memset(ctx->f2Attr, 0, sizeof ctx->f2Attr);
+    ctx->slabHost = NULL; ctx->slabPending = false;
 
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { int rc = fail(NULL, MPMGPU_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); delete ctx; return rc; }
@@ -208,6 +213,7 @@ extern "C" int mpmgpu_destroy(mpmgpu_ctx *ctx)
     tiled_state_free(ctx->tiled);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->hStage) cudaFreeHost(ctx->hStage);
+    if (ctx->slabHost) { cudaFreeHost(ctx->slabHost); cudaEventDestroy(ctx->slabEvent); }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->ownStreamSaved ? ctx->ownStream : ctx->stream);
     delete ctx;
@@ -236,7 +242,7 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
 
 // number of double arrays per particle in the pool
 #define NPD (3 + 3 + 1 + 3 + 3 + 9 + 6 + 1 + 6 + 6 + MPM_MAX_HISTORY + 3 + 3)
-#define NPI 4
+#define NPI 5
 
 static void bind_particles(Particles &P, double *pool, int *ipool, size_t capPad);
 
@@ -282,7 +288,7 @@ static void bind_particles(Particles &P, double *pool, int *ipool, size_t capPad
     for (int c = 0; c < 3; c++) P.pfext[c] = take();
     for (int c = 0; c < 3; c++) P.acc[c] = take();
     int *qi = ipool;
-    P.elem = qi; qi += capPad; P.mat = qi; qi += capPad; P.cross = qi; qi += capPad; P.orig = qi;
+    P.elem = qi; qi += capPad; P.mat = qi; qi += capPad; P.cross = qi; qi += capPad; P.orig = qi; qi += capPad; P.key = qi;
 }
 
 static int ensure_stage(mpmgpu_ctx *ctx, size_t bytes)
@@ -492,7 +498,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         if (ctx->cfg.kernel_path == 2 && !ok)
             return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1 and XPIC order<=1");
         ctx->tiled.enabled = ok ? 1 : 0;
-        ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 25;
+        ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 12;
         {
             // TMA-pipelined F4 (kernels_pipe.cuh): measured on B200 within 2 % of the plain kernel
             // (profiles/tune_bounds_r1.txt), so it is opt-in: MPMGPU_PIPE=1
@@ -988,6 +994,14 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_begin(ctx);
         if (t.slab.on && (rc = halo_add(ctx, 2))) return rc;
         if (reextrap) LAUNCH(k_n3_strains_last, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp);
+        const bool earlyReset = t.slab.on && !t.usePipe && n > 0;
+        if (earlyReset) {
+            LAUNCH(k_reset_slab, nblocks(n, 256), 256, g, ctx->P, ctx->dFlags, sp.dt, t.slab);
+            CK(cudaMemcpyAsync(ctx->slabHost->leave, t.slab.leaveCount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&ctx->slabHost->flags, ctx->dFlags, sizeof(StatusFlags), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaEventRecord(ctx->slabEvent, ctx->stream));
+            ctx->slabPending = true;
+        }
         if (n && t.usePipe) {
             PipeFields pf;
             memset(&pf, 0, sizeof pf);
@@ -1016,8 +1030,11 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
             }
             ctx->launches++;
         } else if (n) {
-            if (t.stateKind == SK_ELASTIC) LAUNCH(k_f4_strain_reset<SK_ELASTIC>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
-            else LAUNCH(k_f4_strain_reset<SK_FULL>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, ctx->dFlags, sp.dt, t.slab);
+            // slab mode: the reset ran as its own kernel before this one (see k_reset_slab) unless there is no strain update to hide behind
+            const int doReset = earlyReset ? 0 : 1;
+            if (!doReset && !hasUSL) { /* nothing left to do */ }
+            else if (t.stateKind == SK_ELASTIC) LAUNCH(k_f4_strain_reset<SK_ELASTIC>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, doReset, ctx->dFlags, sp.dt, t.slab);
+            else LAUNCH(k_f4_strain_reset<SK_FULL>, nblocks(n, FUSED_THREADS), FUSED_THREADS, g, ctx->P, t.FN, ctx->dMats, stLast, hasUSL ? 1 : 0, doReset, ctx->dFlags, sp.dt, t.slab);
         }
         if ((rc = reset_rigid(ctx))) return rc;
         prof_end(ctx, T_USL);
@@ -1205,6 +1222,17 @@ extern "C" int mpmgpu_slab_configure(mpmgpu_ctx *ctx, int cell_lo, int cell_hi, 
         CK(cudaMemset(t.haloSend[side], 0, haloDoubles * sizeof(double))); CK(cudaMemset(t.haloRecv[side], 0, haloDoubles * sizeof(double)));
     }
     CK(dalloc(ctx, &t.slab.leaveCount, 2)); CK(dalloc(ctx, &t.slab.leaveIdx, (size_t)2 * t.migCap));
+    CK(dalloc(ctx, &t.migSorted, (size_t)2 * t.migCap)); CK(dalloc(ctx, &t.migKeys, (size_t)2 * t.migCap));
+    CK(dalloc(ctx, &t.migFillers, (size_t)2 * t.migCap)); CK(dalloc(ctx, &t.migFlags, (size_t)2 * t.migCap));
+    CK(dalloc(ctx, &t.migPairs, 1));
+    if (!ctx->slabHost) {
+        CK(cudaMallocHost((void **)&ctx->slabHost, sizeof(*ctx->slabHost)));
+        memset(ctx->slabHost, 0, sizeof(*ctx->slabHost));
+        CK(cudaEventCreateWithFlags(&ctx->slabEvent, cudaEventDisableTiming));
+    }
+    t.migCubBytes = 0;
+    cub::DeviceRadixSort::SortKeys(NULL, t.migCubBytes, t.migKeys, t.migSorted, 2 * t.migCap, 0, 32, ctx->stream);
+    CK(dalloc(ctx, (char **)&t.migCubTemp, t.migCubBytes));
     CK(cudaMemset(t.slab.leaveCount, 0, 2 * sizeof(int)));
     t.hLeave[0] = t.hLeave[1] = 0;
     ctx->globalIds = true;
@@ -1232,6 +1260,7 @@ extern "C" int mpmgpu_slab_step_phase(mpmgpu_ctx *ctx, int phase)
     if (rc) return rc;
     if (phase == 3) {
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
+        if (ctx->slabPending) return MPMGPU_OK;     // counts + flags are on their way: mpmgpu_slab_migration_counts waits for them
         if (ctx->tiled.slab.on) {
             CK(cudaMemcpyAsync(ctx->tiled.hLeave, ctx->tiled.slab.leaveCount, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         }
@@ -1246,6 +1275,17 @@ extern "C" int mpmgpu_slab_step_phase(mpmgpu_ctx *ctx, int phase)
 extern "C" int mpmgpu_slab_migration_counts(mpmgpu_ctx *ctx, int *n_lo, int *n_hi)
 {
     if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_migration_counts: slab mode not configured");
+    if (ctx->slabPending) {         // waits for the element reset only; the strain kernel behind it keeps the GPU busy
+        cudaSetDevice(ctx->cfg.device);
+        CK(cudaEventSynchronize(ctx->slabEvent));
+        ctx->slabPending = false;
+        TiledState &t = ctx->tiled;
+        t.hLeave[0] = ctx->slabHost->leave[0]; t.hLeave[1] = ctx->slabHost->leave[1];
+        ctx->hFlags = ctx->slabHost->flags;
+        if (ctx->hFlags.nanParticle) return fail(ctx, MPMGPU_ENAN, "particle %d left grid with position nan (ResetElementsTask)", ctx->hFlags.nanParticle - 1);
+        if (t.hLeave[0] > t.migCap || t.hLeave[1] > t.migCap)
+            return fail(ctx, MPMGPU_EINVAL, "slab migration capacity %d exceeded (%d, %d leavers)", t.migCap, t.hLeave[0], t.hLeave[1]);
+    }
     if (n_lo) *n_lo = ctx->tiled.hLeave[0];
     if (n_hi) *n_hi = ctx->tiled.hLeave[1];
     return MPMGPU_OK;
@@ -1264,21 +1304,29 @@ extern "C" int mpmgpu_slab_migration_buffers(mpmgpu_ctx *ctx, void **send_lo, vo
     return MPMGPU_OK;
 }
 
+// Leavers are packed in ascending slot order (the order F4 appended them in is not reproducible), so the
+// particle order on the receiving rank -- and with it every later sum -- is the same from run to run.
 extern "C" int mpmgpu_slab_pack_migrants(mpmgpu_ctx *ctx)
 {
     if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_pack_migrants: slab mode not configured");
     cudaSetDevice(ctx->cfg.device);
     TiledState &t = ctx->tiled;
+    int bits = 1;
+    while ((1ll << bits) < (long long)ctx->cap + 1) bits++;
     for (int side = 0; side < 2; side++) {
         const int nl = t.hLeave[side];
         if (nl <= 0) continue;
-        LAUNCH(k_mig_pack, nl, 64, nl, t.slab.leaveIdx + (size_t)side * t.migCap, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool, MIG_ROW, t.migSend[side]);
+        int *list = t.slab.leaveIdx + (size_t)side * t.migCap;
+        size_t tb = t.migCubBytes;
+        CK(cub::DeviceRadixSort::SortKeys(t.migCubTemp, tb, list, t.migKeys, nl, 0, bits, ctx->stream));
+        CK(cudaMemcpyAsync(list, t.migKeys, (size_t)nl * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->launches += 3;
+        LAUNCH(k_mig_pack, nl, 64, nl, list, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool, MIG_ROW, t.migSend[side]);
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    return MPMGPU_OK;
+    return MPMGPU_OK;       // stream-ordered: the exchange is enqueued on the same stream
 }
 
-// remove the particles that left (fill their slots from the end), then append the arrivals
+// remove the particles that left (fill their slots from the end), then append the arrivals; all on the device, no host sync
 extern "C" int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int n_from_hi)
 {
     if (!ctx || !ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_finish_migration: slab mode not configured");
@@ -1287,29 +1335,16 @@ extern "C" int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int 
     const int L = t.hLeave[0] + t.hLeave[1];
     int n = ctx->P.n;
     if (L > 0) {
-        std::vector<int> idx(L);
-        if (t.hLeave[0]) CK(cudaMemcpyAsync(idx.data(), t.slab.leaveIdx, t.hLeave[0] * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        if (t.hLeave[1]) CK(cudaMemcpyAsync(idx.data() + t.hLeave[0], t.slab.leaveIdx + t.migCap, t.hLeave[1] * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        const int nNew = n - L;
-        std::vector<char> leaving(L > 0 ? (size_t)(n - nNew) : 0, 0);      // flags for slots [nNew, n)
-        std::vector<int> holes;
-        for (int q : idx) { if (q >= nNew) leaving[q - nNew] = 1; else holes.push_back(q); }
-        std::vector<int> fillers;
-        for (int q = nNew; q < n; q++) if (!leaving[q - nNew]) fillers.push_back(q);
-        if (holes.size() != fillers.size()) return fail(ctx, MPMGPU_EINVAL, "migration bookkeeping: %zu holes, %zu fillers", holes.size(), fillers.size());
-        std::sort(holes.begin(), holes.end());
-        const int np = (int)holes.size();
-        if (np > 0) {
-            int *dpairs = NULL;
-            CK(cudaMalloc((void **)&dpairs, (size_t)2 * np * sizeof(int)));
-            CK(cudaMemcpyAsync(dpairs, holes.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(dpairs + np, fillers.data(), np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            LAUNCH(k_mig_fill, np, 64, np, dpairs, dpairs + np, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool);
-            CK(cudaStreamSynchronize(ctx->stream));
-            cudaFree(dpairs);
-        }
-        n = nNew;
+        if (t.hLeave[0]) CK(cudaMemcpyAsync(t.migKeys, t.slab.leaveIdx, (size_t)t.hLeave[0] * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (t.hLeave[1]) CK(cudaMemcpyAsync(t.migKeys + t.hLeave[0], t.slab.leaveIdx + t.migCap, (size_t)t.hLeave[1] * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        int bits = 1;
+        while ((1ll << bits) < (long long)ctx->cap + 1) bits++;
+        size_t tb = t.migCubBytes;
+        CK(cub::DeviceRadixSort::SortKeys(t.migCubTemp, tb, t.migKeys, t.migSorted, L, 0, bits, ctx->stream));
+        ctx->launches += 4;
+        LAUNCH(k_mig_plan, 1, MIG_PLAN_THREADS, n, L, t.migSorted, t.migFillers, t.migPairs, t.migFlags);
+        LAUNCH(k_mig_fill, L, 64, t.migPairs, t.migSorted, t.migFillers, ctx->cap, NPD, ctx->particlePool, NPI, ctx->particleIntPool);
+        n -= L;
     }
     const int R = n_from_lo + n_from_hi;
     if ((size_t)(n + R) > ctx->cap) return fail(ctx, MPMGPU_EINVAL, "particle capacity %zu exceeded by migration (%d + %d); raise max_particles", ctx->cap, n, R);
@@ -1319,7 +1354,6 @@ extern "C" int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int 
     ctx->P.n = n; ctx->P.nNR = n;
     CK(cudaMemsetAsync(t.slab.leaveCount, 0, 2 * sizeof(int), ctx->stream));
     t.hLeave[0] = t.hLeave[1] = 0;
-    CK(cudaStreamSynchronize(ctx->stream));
     return MPMGPU_OK;
 }
 

@@ -81,6 +81,8 @@ struct TiledState {
     double *haloSend[2], *haloRecv[2];      // [lower, upper]; 3 planes x up to 5 values
     size_t planeNodes;
     double *migSend[2], *migRecv[2];        // rows of MIG_ROW doubles
+    int *migSorted, *migKeys, *migFillers, *migFlags, *migPairs;     // device-side bookkeeping (k_mig_plan)
+    void *migCubTemp; size_t migCubBytes;
     int migCap;
     int hLeave[2];                          // host copy of leaveCount after the step
 };
@@ -207,21 +209,21 @@ struct Weights3 {
     int center;          // 0-based node index of the dual-cell centre
 };
 
+// center = dual_cell_center(element, xi): F1 computes it once per step and keeps it in P.key for the later kernels
 template <bool GRAD>
-__device__ __forceinline__ void particle_weights(const Grid &g, int inElem, const double xi[3], const double lp[3], Weights3 &w)
+__device__ __forceinline__ void particle_weights(const Grid &g, int center, const double xi[3], const double lp[3], Weights3 &w)
 {
-    const ElemIJK c = elem_ijk(g, inElem);
     unsigned okx, oky, okz;
     // inv_size and the branch-1 derivative divisor follow EightNodeIsoparamBrick.cpp:296-303,:365-387
     // (z uses 1/(4 lp.y)); with a uniform particle size the reciprocals are per-run constants
     double isx, isy, i2x, i2y, i2z;
     if (g.lpUniform) { isx = g.lpInvSize[0]; isy = g.lpInvSize[1]; i2x = g.lpInv2[0]; i2y = g.lpInv2[1]; i2z = g.lpInv2[2]; }
     else { isx = 1. / (4. * lp[0]); isy = 1. / (4. * lp[1]); i2x = 1. / (2. * lp[0]); i2y = 1. / (2. * lp[1]); i2z = 1. / (2. * lp[2]); }
-    const int bx = gimp3<GRAD>(xi[0], lp[0], isx, i2x, w.S[0], w.dS[0], okx);
-    const int by = gimp3<GRAD>(xi[1], lp[1], isy, i2y, w.S[1], w.dS[1], oky);
-    const int bz = gimp3<GRAD>(xi[2], lp[2], isy, i2z, w.S[2], w.dS[2], okz);
+    gimp3<GRAD>(xi[0], lp[0], isx, i2x, w.S[0], w.dS[0], okx);
+    gimp3<GRAD>(xi[1], lp[1], isy, i2y, w.S[1], w.dS[1], oky);
+    gimp3<GRAD>(xi[2], lp[2], isy, i2z, w.S[2], w.dS[2], okz);
     w.ok = okx | (oky << 3) | (okz << 6);
-    w.center = elem_node0(g, c) + (bx + 1) + (by + 1) * g.yplane + (bz + 1) * g.zplane;
+    w.center = center;
     if (GRAD) {
         // 2/delta of the element: equal element sizes on this path (the reference divides by the element's own
         // extent, which differs from the grid constant by at most an ulp)
@@ -409,10 +411,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, F1_MINB) k_f1_mass_momentum(Gri
         get_xipos<3>(g, e, pos, xi);
         P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
         Weights3 w;
-        particle_weights<false>(g, e, xi, lp, w);
+        key = dual_cell_center(g, e, xi);
+        P.key[p] = key;
+        particle_weights<false>(g, key, xi, lp, w);
         stage_weights(st, lane, w, P.mp[p]);
         st.Q[lane][0] = P.vel[0][p]; st.Q[lane][1] = P.vel[1][p]; st.Q[lane][2] = P.vel[2][p];
-        key = w.center;
     }
     __syncwarp();
     double *dst[4] = {N.mass, N.pk[0], N.pk[1], N.pk[2]};
@@ -479,14 +482,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, F2_MINB) k_f2_strain_forces(Gri
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
-    int key = 0, e = 0, anchor = 0;
+    int key = 0, anchor = 0;
     double xi[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
     if (active) {
         if (doStrain) prefetch_state<SK>(P, p);
-        e = P.elem[p];
+        key = P.key[p];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
-        key = dual_cell_center(g, e, xi);
     }
     if (doStrain) {         // start the warp's node window on its way while the weights are computed
         anchor = tile_anchor(key, active);
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F2_MINB) k_f2_strain_forces(Gri
     }
     Weights3 w;
     if (active) {
-        particle_weights<true>(g, e, xi, lp, w);
+        particle_weights<true>(g, key, xi, lp, w);
         stage_weights(st, lane, w);
     }
     if (doStrain) tile_wait();
@@ -558,19 +560,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(G
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < P.nNR;
-    int key = 0, e = 0;
+    int key = 0;
     double xi[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
     if (active) {
-        e = P.elem[p];
+        key = P.key[p];
         xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
         load_lp(g, P, p, lp);
-        key = dual_cell_center(g, e, xi);
     }
     const int anchor = tile_anchor(key, active);
     tile_load_async(g, tv, anchor, FN.V);
     if (m <= 0) tile_load_async(g, ta, anchor, FN.A);
     Weights3 w;
-    if (active) particle_weights<false>(g, e, xi, lp, w);
+    if (active) particle_weights<false>(g, key, xi, lp, w);
     tile_wait();
     double Svk[3] = {0., 0., 0.}, Sacc[3] = {0., 0., 0.};
     if (active) {
@@ -647,29 +648,52 @@ __global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_f3_update_momentum(G
     });
 }
 
+// ---- element reset as its own pass (slab mode) --------------------------------------------------------
+// The reset needs only the updated positions, and the second strain update needs only the dual-cell key and
+// ncpos of the start of the step, so in slab mode the reset runs BEFORE the strain kernel: the list of particles
+// that left the slab is known one kernel earlier and the host does the migration handshake with its neighbours
+// while the GPU is busy with the strain update.
+__device__ __forceinline__ void reset_and_list(const Grid &g, const Particles &P, int p, StatusFlags *flags, double dt, const SlabInfo &slab)
+{
+    reset_element_one<3>(g, P, p, flags, dt);
+    if (slab.on) {          // particle migration between slabs (replaces GridPatch::AddMovingParticle, GridPatch.cpp:214)
+        const int k = (P.elem[p] - 1) / (g.horiz * g.vert);
+        const int side = k < slab.cellLo ? 0 : (k >= slab.cellHi ? 1 : -1);
+        if (side >= 0) {
+            const int slot = atomicAdd(&slab.leaveCount[side], 1);
+            if (slot < slab.leaveCap) slab.leaveIdx[side * slab.leaveCap + slot] = p;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_reset_slab(Grid g, Particles P, StatusFlags *flags, double dt, SlabInfo slab)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P.n) reset_and_list(g, P, p, flags, dt, slab);
+}
+
 // ---- F4: second strain update + element reset --------------------------------------------------------
 template <int SK>
 __global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid g, Particles P, FusedNodes FN, const Material *mats,
-                                                                   double strainTime, int doStrain, StatusFlags *flags, double dt, SlabInfo slab)
+                                                                   double strainTime, int doStrain, int doReset, StatusFlags *flags, double dt, SlabInfo slab)
 {
     __shared__ WarpTile tiles[FUSED_WARPS];
     WarpTile &tile = tiles[threadIdx.x >> 5];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (doStrain) {
         const bool active = p < P.nNR;
-        int key = 0, e = 0;
+        int key = 0;
         double xi[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
         if (active) {
             prefetch_state<SK>(P, p);
-            e = P.elem[p];
+            key = P.key[p];
             xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
             load_lp(g, P, p, lp);
-            key = dual_cell_center(g, e, xi);
         }
         const int anchor = tile_anchor(key, active);
         tile_load_async(g, tile, anchor, FN.V);
         Weights3 w;
-        if (active) particle_weights<true>(g, e, xi, lp, w);
+        if (active) particle_weights<true>(g, key, xi, lp, w);
         tile_wait();
         if (active) {
             double dv[9];
@@ -682,16 +706,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid
             store_state<SK>(P, p, s);
         }
     }
-    if (p >= P.n) return;
-    reset_element_one<3>(g, P, p, flags, dt);
-    if (slab.on) {          // particle migration between slabs (replaces GridPatch::AddMovingParticle, GridPatch.cpp:214)
-        const int k = (P.elem[p] - 1) / (g.horiz * g.vert);
-        const int side = k < slab.cellLo ? 0 : (k >= slab.cellHi ? 1 : -1);
-        if (side >= 0) {
-            const int slot = atomicAdd(&slab.leaveCount[side], 1);
-            if (slot < slab.leaveCap) slab.leaveIdx[side * slab.leaveCap + slot] = p;
-        }
-    }
+    if (doReset && p < P.n) reset_and_list(g, P, p, flags, dt, slab);
 }
 
 // ---- slab halo: pack partial sums of the three node planes shared with a neighbour / add the neighbour's ----
@@ -747,11 +762,39 @@ __global__ void k_mig_unpack(int nrows, int first, size_t stride, int nd, double
     for (int f = threadIdx.x; f < ni; f += blockDim.x) ipool[(size_t)f * stride + p] = irow[f];
 }
 
+// Bookkeeping of one migration on the device (one block): the n - L particles that stay must end up in slots
+// [0, n-L).  sorted = all L leavers in ascending slot order.  Leavers below n-L are holes (the first *npairs entries of
+// `sorted`); the slots [n-L, n) that are not leaving are the fillers, listed in ascending order.
+#define MIG_PLAN_THREADS 1024
+__global__ void __launch_bounds__(MIG_PLAN_THREADS) k_mig_plan(int n, int L, const int *sorted, int *fillers, int *npairs, int *flags)
+{
+    typedef cub::BlockScan<int, MIG_PLAN_THREADS> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int base;
+    const int nNew = n - L, tid = threadIdx.x;
+    for (int s = tid; s < L; s += MIG_PLAN_THREADS) flags[s] = 0;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int t = tid; t < L; t += MIG_PLAN_THREADS) { const int q = sorted[t]; if (q >= nNew) flags[q - nNew] = 1; }
+    __syncthreads();
+    for (int c0 = 0; c0 < L; c0 += MIG_PLAN_THREADS) {
+        const int s = c0 + tid;
+        const int keep = (s < L && !flags[s]) ? 1 : 0;
+        int pos, total;
+        Scan(tmp).ExclusiveSum(keep, pos, total);
+        if (keep) fillers[base + pos] = nNew + s;
+        __syncthreads();
+        if (tid == 0) base += total;
+        __syncthreads();
+    }
+    if (tid == 0) *npairs = base;
+}
+
 // fill the holes left by departed particles with particles taken from the end of the arrays
-__global__ void k_mig_fill(int npairs, const int *hole, const int *filler, size_t stride, int nd, double *pool, int ni, int *ipool)
+__global__ void k_mig_fill(const int *npairs, const int *hole, const int *filler, size_t stride, int nd, double *pool, int ni, int *ipool)
 {
     const int r = blockIdx.x;
-    if (r >= npairs) return;
+    if (r >= *npairs) return;
     const int h = hole[r], q = filler[r];
     for (int f = threadIdx.x; f < nd; f += blockDim.x) pool[(size_t)f * stride + h] = pool[(size_t)f * stride + q];
     for (int f = threadIdx.x; f < ni; f += blockDim.x) ipool[(size_t)f * stride + h] = ipool[(size_t)f * stride + q];

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_f4_pipe(Grid g, Particles P, 
                 double dv[9];
                 {
                     Weights3 w;
-                    particle_weights<true>(g, elem, xi, lp, w);
+                    particle_weights<true>(g, dual_cell_center(g, elem, xi), xi, lp, w);
                     gather_gradv_impl<false>(g, w, FN.V, (const WarpTile *)0, 0, dv);
                 }
 #pragma unroll

@@ -63,6 +63,7 @@ struct Particles {
     double *pfext[3];
     double *acc[3];
     int *elem;               // 1-based inElem
+    int *key;                // fused path: centre node of the particle's dual cell at the start of the step (set by F1)
     int *mat;                // 0-based material index
     int *cross;              // elementCrossings
     int *orig;               // caller's index of this particle

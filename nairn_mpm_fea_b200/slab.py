@@ -69,33 +69,49 @@ class NeighbourExchange:
     """Point-to-point exchange with the lower / upper slab neighbour over a torch.distributed group.
     Works on any tensors (CUDA+NCCL in production, CPU+gloo in the tests)."""
 
-    def __init__(self, rank, world, group=None):
+    def __init__(self, rank, world, group=None, cpu_group=None):
         self.rank, self.world, self.group = rank, world, group
+        self.cpu_group = cpu_group      # optional gloo group for the two-integer handshake (keeps it off the GPU stream)
         self.lower = rank - 1 if rank > 0 else None
         self.upper = rank + 1 if rank < world - 1 else None
 
-    def swap(self, send_lo, send_hi, recv_lo, recv_hi):
+    def swap(self, send_lo, send_hi, recv_lo, recv_hi, group=None):
         """Send send_lo to the lower neighbour and send_hi to the upper one; receive theirs."""
+        group = group if group is not None else self.group
         ops = []
         if self.lower is not None:
-            ops.append(dist.P2POp(dist.isend, send_lo, self.lower, self.group))
-            ops.append(dist.P2POp(dist.irecv, recv_lo, self.lower, self.group))
+            ops.append(dist.P2POp(dist.isend, send_lo, self.lower, group))
+            ops.append(dist.P2POp(dist.irecv, recv_lo, self.lower, group))
         if self.upper is not None:
-            ops.append(dist.P2POp(dist.isend, send_hi, self.upper, self.group))
-            ops.append(dist.P2POp(dist.irecv, recv_hi, self.upper, self.group))
+            ops.append(dist.P2POp(dist.isend, send_hi, self.upper, group))
+            ops.append(dist.P2POp(dist.irecv, recv_hi, self.upper, group))
         if not ops:
             return
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
     def swap_counts(self, n_to_lo, n_to_hi, device):
-        """Tell each neighbour how many rows are coming; returns (n_from_lo, n_from_hi)."""
-        s_lo = torch.tensor([n_to_lo], dtype=torch.int64, device=device)
-        s_hi = torch.tensor([n_to_hi], dtype=torch.int64, device=device)
-        r_lo = torch.zeros(1, dtype=torch.int64, device=device)
-        r_hi = torch.zeros(1, dtype=torch.int64, device=device)
-        self.swap(s_lo, s_hi, r_lo, r_hi)
-        return int(r_lo.item()), int(r_hi.item())
+        """Tell each neighbour how many rows are coming; returns (n_from_lo, n_from_hi).  One small host->device
+        copy, one exchange and one device->host read per step (the buffers are allocated once).  With a CPU (gloo)
+        group the handshake never touches the GPU stream, so it overlaps whatever kernel is running."""
+        if self.cpu_group is not None:
+            s_lo = torch.tensor([n_to_lo], dtype=torch.int64)
+            s_hi = torch.tensor([n_to_hi], dtype=torch.int64)
+            r_lo = torch.zeros(1, dtype=torch.int64)
+            r_hi = torch.zeros(1, dtype=torch.int64)
+            self.swap(s_lo, s_hi, r_lo, r_hi, group=self.cpu_group)
+            return int(r_lo[0]), int(r_hi[0])
+        if getattr(self, "_cnt", None) is None or self._cnt[0].device != torch.device(device):
+            pin = torch.device(device).type == "cuda"
+            self._cnt = (torch.zeros(4, dtype=torch.int64, device=device),
+                         torch.zeros(2, dtype=torch.int64).pin_memory() if pin else torch.zeros(2, dtype=torch.int64))
+        dev, host = self._cnt
+        host[0], host[1] = n_to_lo, n_to_hi
+        dev[:2].copy_(host, non_blocking=True)
+        dev[2:].zero_()
+        self.swap(dev[0:1], dev[1:2], dev[2:3], dev[3:4])
+        back = dev[2:].tolist()
+        return int(back[0]), int(back[1])
 
     def swap_rows(self, send_lo, send_hi, recv_lo, recv_hi, n_to_lo, n_to_hi, n_from_lo, n_from_hi, row):
         """Variable-length row exchange (only the non-empty directions are posted; both sides know the counts)."""
@@ -140,7 +156,10 @@ class SlabSim:
         self.plane_nodes = plane_nodes
         mptrs, self.row, self.mig_cap = self.sim.slab_migration_buffers()
         self.mig = [device_tensor(p, self.row * self.mig_cap, self.device) for p in mptrs]
-        self.ex = NeighbourExchange(rank, world, group)
+        cpu_group = None
+        if world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            cpu_group = dist.new_group(backend="gloo")      # collective: every rank builds its SlabSim
+        self.ex = NeighbourExchange(rank, world, group, cpu_group)
         self.migrated_out = 0
         self.migrated_in = 0
 
@@ -156,20 +175,22 @@ class SlabSim:
                     self.sim.slab_phase(phase)
                     if self.world > 1:
                         self._halo(phase)
+                # phase 3 = node sweep, element reset (leavers listed), counts on their way to the host, second
+                # strain update: the handshake below runs while that last kernel is still busy
                 self.sim.slab_phase(3)
-                if self.world > 1:
-                    self._migrate()
+                self._migrate()
 
     def _migrate(self):
-        n_lo, n_hi = self.sim.slab_migration_counts()
+        n_lo, n_hi = self.sim.slab_migration_counts()           # waits for the reset kernel only; raises on NaN / overflow
+        if self.world == 1:
+            return
         f_lo, f_hi = self.ex.swap_counts(n_lo, n_hi, self.device)
         if n_lo or n_hi:
             self.sim.slab_pack_migrants()
         if n_lo or n_hi or f_lo or f_hi:
             s_lo, s_hi, r_lo, r_hi = self.mig
             self.ex.swap_rows(s_lo, s_hi, r_lo, r_hi, n_lo, n_hi, f_lo, f_hi, self.row)
-            self.stream.synchronize()
-            self.sim.slab_finish_migration(f_lo, f_hi)
+            self.sim.slab_finish_migration(f_lo, f_hi)       # stream-ordered after the exchange: no host sync
             self.migrated_out += n_lo + n_hi
             self.migrated_in += f_lo + f_hi
 
