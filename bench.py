@@ -9,6 +9,8 @@ One "step" = one full MPMStep (tasks 1-9, 11) over the resident particle block. 
   block8m  (default)  100^3 cells x 8 particles = 8,000,000 particles per GPU: config 5 at N GPUs
                       (and the size the north_star target is quoted on at N=1)
   block1m             50^3 cells = 1,000,000 particles: config 2
+  neo8m               100^3-cell Neo-Hookean block, lCPDI shape functions, XPIC(2) every step, gravity, clamped bottom plane
+                      (config 3 family; general per-task kernels, one GPU); neo1m = 50^3
   taylor16m           100x100x200-cell IsoPlasticity bar hitting a plate of rigid-BC particles at 200 m/s,
                       16,000,000 particles TOTAL split over the GPUs (config 4, strong scaling); taylor2m = 50x50x100
 Prints ONE JSON line (see README / DESIGN.md for the keys).
@@ -150,7 +152,7 @@ def block_velocity(ncell):
 
 def make_problem(workload, ncell_override=None, rank=0, world=1):
     from nairn_mpm_fea_b200 import materials as M, problem
-    ncell = {"block8m": 100, "block1m": 50, "taylor16m": 100, "taylor2m": 50}[workload]
+    ncell = {"block8m": 100, "block1m": 50, "taylor16m": 100, "taylor2m": 50, "neo8m": 100, "neo1m": 50}[workload]
     if ncell_override:
         ncell = ncell_override
     if workload.startswith("taylor"):
@@ -163,6 +165,16 @@ def make_problem(workload, ncell_override=None, rank=0, world=1):
                              ncell_xyz=(ncell, ncell, ncz), cells_z=cz, rigid_wall=dict(set_direction=4, overhang=2))
         return pr, ncell
     vel = block_velocity(ncell)
+    if workload.startswith("neo"):
+        # config 3: soft Neo-Hookean solid (G 40 MPa, K 200 MPa), lCPDI, XPIC(2), gravity + the block velocity field
+        if world != 1:
+            raise SystemExit("bench.py: the neo workloads run on the per-task kernels, one GPU")
+        u = M.xml_units(G=40.0, K=200.0, rho=1.0)
+        mat = M.neohookean(u["G"], u["K"], u["rho"])
+        pr = problem.block3d(ncell=ncell, margin=7, velocity_fn=vel, jitter_amp=BLOCK_JITTER, material=mat,
+                             shape=problem.LINEAR_CPDI, gravity=(0.0, 0.0, -9.8e6))
+        pr.xpic_order = 2
+        return pr, ncell
 
     if world == 1:
         pr = problem.block3d(ncell=ncell, margin=7, velocity_fn=vel, jitter_amp=BLOCK_JITTER)
@@ -198,6 +210,7 @@ def run_ours(args):
 
     prob, ncell = make_problem(args.workload, args.ncell, rank, world)
     taylor = args.workload.startswith("taylor")
+    neo = args.workload.startswith("neo")
     n = int(prob.particles["n_nonrigid"])          # rigid-BC particles (replicated on every rank) are not counted
     if world == 1:
         sim = MpmGpu(prob, device=local, kernel_path=args.kernel_path, sort_interval=args.sort_interval)
@@ -255,7 +268,7 @@ def run_ours(args):
     task_ms = {k: v[0] / max(1, v[1]) for k, v in tt.items()}
     dom = max(task_ms, key=lambda k: task_ms[k])
     # IsoPlasticity carries eplast(6), pressure, plastic energy and one history double through both strain updates
-    full_state = 2 * (6 + 1 + 1 + 1) * 8 if taylor else 0
+    full_state = 2 * (6 + 1 + 1 + 1) * 8 if (taylor or neo) else 0
     algo_step = ALGO_BYTES_PER_PARTICLE_STEP + 2 * full_state
     per_particle = FUSED_ALGO_BYTES.get(dom, TASK_ALGO_BYTES[dom]) if args.kernel_path != 1 else TASK_ALGO_BYTES[dom]
     dom_bytes = (per_particle + (full_state if dom in ("update_strains_first", "update_strains_last") else 0)) * n
@@ -313,7 +326,9 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if taylor else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": ("%s: 3D uGIMP IsoPlasticity (von Mises, linear hardening) bar of %dx%dx%d cells x 8 = %d particles in total, "
+            "config": {"workload": ("%s: 3D lCPDI Neo-Hookean block, %d^3 cells x 8 = %d particles, XPIC(2), gravity, USAVG+, positions hash-jittered "
+                                    "(general per-task kernels)" % (args.workload, ncell, n)) if neo else
+                                   ("%s: 3D uGIMP IsoPlasticity (von Mises, linear hardening) bar of %dx%dx%d cells x 8 = %d particles in total, "
                                     "200 m/s onto a plate of %d rigid-BC particles, FLIP, USAVG+, positions hash-jittered"
                                     % (args.workload, ncell, ncell, 2 * ncell, total_particles, prob.nparticles - n)) if taylor else
                                    "%s: 3D uGIMP isotropic-elastic block, %d^3 cells x 8 = %d particles per GPU, FLIP, USAVG+, "
@@ -422,7 +437,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m", "taylor16m", "taylor2m"])
+    ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m", "taylor16m", "taylor2m", "neo8m", "neo1m"])
     ap.add_argument("--ncell", type=int, default=0, help="override block edge in cells (testing)")
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--sort-interval", type=int, default=0, help="steps between physical particle sorts (0 = library default)")

@@ -110,6 +110,60 @@ def test_free_block_keeps_momentum_over_many_steps():
     sim.close()
 
 
+# ---- known answers that need no oracle ------------------------------------------------------
+@pytest.mark.parametrize("kernel_path", [1, 2])
+def test_rigid_translation_keeps_velocity_and_zero_stress(kernel_path):
+    """Uniform velocity, no BCs: the weights sum to one, so every node and particle keeps that velocity, the velocity
+    gradient vanishes and the stress stays zero while the block crosses cells."""
+    from nairn_mpm_fea_b200 import MpmGpu, problem
+    v0 = (3.0e4, -2.0e4, 1.0e4)
+    prob = problem.block3d(ncell=8, margin=4, velocity=v0, bottom_bc=False, jitter_amp=0.4)
+    p0 = prob.particles["pos"].copy()
+    sim = MpmGpu(prob, device=0, kernel_path=kernel_path, sort_interval=7)
+    nsteps = 60
+    sim.step(nsteps)
+    got = sim.download()
+    for c in range(3):
+        assert np.max(np.abs(got["vel"][c] - v0[c])) <= 1e-12 * abs(v0[c])
+        assert np.max(np.abs(got["pos"][c] - (p0[c] + v0[c] * nsteps * prob.dt))) <= 1e-11
+    # E = 1e9 internal units / rho 1e-3: specific stress scale ~1e12; zero gradient leaves round-off only
+    assert np.max(np.abs(got["sp"])) <= 1e-14 * 1.0e12
+    assert np.count_nonzero(got["crossings"]) > 100
+    sim.close()
+
+
+def test_uniform_stretch_gives_hookes_law():
+    """Velocity field v = (a x, 0, 0) on an interior block: after one USF step every interior particle has
+    exx = a dt and the specific stress C:eps/rho (IsotropicMat small-strain law, MoreIsotropicMat.cpp:185-348)."""
+    from nairn_mpm_fea_b200 import MpmGpu, problem, materials as M
+    a = 50.0
+
+    def vel(pos):
+        v = np.zeros_like(pos)
+        v[0] = a * (pos[0] - 10.0)
+        return v
+
+    prob = problem.block3d(ncell=12, margin=4, velocity_fn=vel, bottom_bc=False, method=problem.USF)
+    sim = MpmGpu(prob, device=0, kernel_path=1)
+    sim.step(1)
+    got = sim.download()
+    pos = prob.particles["pos"]
+    inner = np.all((pos > 4.0 + 3.0) & (pos < 16.0 - 3.0), axis=0)        # three cells away from the free faces
+    assert np.count_nonzero(inner) > 500
+    exx = a * prob.dt
+    assert np.max(np.abs(got["ep"][0][inner] - exx)) <= 1e-9 * exx
+    assert np.max(np.abs(got["ep"][1:][:, inner])) <= 1e-9 * exx
+    u = M.xml_units(E=1000.0, rho=1.0)
+    E, nu, rho = u["E"], 0.3, u["rho"]
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    mu = E / (2 * (1 + nu))
+    sxx, syy = (lam + 2 * mu) * exx / rho, lam * exx / rho
+    assert np.max(np.abs(got["sp"][0][inner] - sxx)) <= 1e-8 * sxx
+    assert np.max(np.abs(got["sp"][1][inner] - syy)) <= 1e-8 * sxx and np.max(np.abs(got["sp"][2][inner] - syy)) <= 1e-8 * sxx
+    assert np.max(np.abs(got["sp"][3:][:, inner])) <= 1e-8 * sxx
+    sim.close()
+
+
 # ---- error behaviour through the C ABI (INTEGRATION.md table) -------------------------------------------------
 def _small():
     from nairn_mpm_fea_b200 import problem
