@@ -209,6 +209,8 @@ def run_ours(args):
     hbm_peak, peak_src = read_peaks()
 
     prob, ncell = make_problem(args.workload, args.ncell, rank, world)
+    if args.xpic_order > 0:
+        prob.xpic_order, prob.using_fmpm = args.xpic_order, bool(args.fmpm)
     taylor = args.workload.startswith("taylor")
     neo = args.workload.startswith("neo")
     n = int(prob.particles["n_nonrigid"])          # rigid-BC particles (replicated on every rank) are not counted
@@ -336,6 +338,7 @@ def run_ours(args):
                                    "(particles cross cell and slab faces)" % (args.workload, ncell, n, prob.horiz),
                        "particles_per_gpu": n, "nodes": prob.nnodes, "l2_policy": "inputs larger than L2 (%.0f MB state)" % (n * 460 / 1e6),
                        "kernel_path": sim_kernel_path_name(args.kernel_path),
+                       "particle_update": ("FMPM(%d)" if prob.using_fmpm else "XPIC(%d)") % prob.xpic_order if prob.xpic_order > 0 else "FLIP",
                        "parallelism": "1 GPU" if world == 1 else
                        "%d z-slabs, one process per GPU: 3 halo-plane exchanges per step + particle migration over NCCL "
                        "(rank 0 sent %d and received %d particle rows)" % (world, stepper.migrated_out, stepper.migrated_in)},
@@ -440,6 +443,8 @@ def main():
     ap.add_argument("--workload", default="block8m", choices=["block8m", "block1m", "taylor16m", "taylor2m", "neo8m", "neo1m"])
     ap.add_argument("--ncell", type=int, default=0, help="override block edge in cells (testing)")
     ap.add_argument("--kernel-path", type=int, default=0)
+    ap.add_argument("--xpic-order", type=int, default=0, help="block workloads: XPIC(k) particle update (with --fmpm: FMPM(k)); 0 = FLIP")
+    ap.add_argument("--fmpm", action="store_true")
     ap.add_argument("--sort-interval", type=int, default=0, help="steps between physical particle sorts (0 = library default)")
     ap.add_argument("--cpu-ncell", type=int, default=50, help="block edge of the CPU sample (50 -> 1M particles)")
     ap.add_argument("--cpu-steps", type=int, default=8)

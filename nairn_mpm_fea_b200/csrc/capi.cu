@@ -187,8 +187,10 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
         cudaMemset(ctx->dFlags, 0, sizeof(StatusFlags));
         if (dalloc(ctx, &ctx->dMats, MPM_MAX_MATERIALS) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
         if (is3D) {
-            if (dalloc(ctx, &ctx->tiled.FN.V, nnPad) != cudaSuccess || dalloc(ctx, &ctx->tiled.FN.A, nnPad) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
+            if (dalloc(ctx, &ctx->tiled.FN.V, nnPad) != cudaSuccess || dalloc(ctx, &ctx->tiled.FN.A, nnPad) != cudaSuccess ||
+                dalloc(ctx, &ctx->tiled.FN.VS, nnPad) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
             cudaMemset(ctx->tiled.FN.V, 0, nnPad * sizeof(double4)); cudaMemset(ctx->tiled.FN.A, 0, nnPad * sizeof(double4));
+            cudaMemset(ctx->tiled.FN.VS, 0, nnPad * sizeof(double4));
         }
     } while (0);
     if (rc != MPMGPU_OK) { fail(NULL, rc, "mpmgpu_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); mpmgpu_destroy(ctx); return rc; }
@@ -885,6 +887,13 @@ __global__ void k_zero_node_range(int n0, int count, Nodes N)
     for (int c = 0; c < 3; c++) { N.pk[c][i] = 0.; N.ftot[c][i] = 0.; N.vk[c][i] = 0.; N.pkc[c][i] = 0.; }
 }
 
+__global__ void k_rezero_range(int n0, int count, Nodes N)      // NodalPoint::RezeroNodeTask6 (NodalPointMPM.cpp:725-730)
+{
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + count) return;
+    N.pk[0][i] = 0.; N.pk[1][i] = 0.; N.pk[2][i] = 0.;
+}
+
 #define MIG_ROW (NPD + (NPI + 1) / 2)
 
 // halo planes shared with the lower (side 0) / upper (side 1) neighbour: three node planes around the slab face
@@ -922,6 +931,21 @@ static int halo_add(mpmgpu_ctx *ctx, int which)
     return MPMGPU_OK;
 }
 
+// XPICExtrapolationTask in fused form (kernels_fused.cuh): grid velocity v*(m) for order m > 1 into the V records
+static int xpic_fused(mpmgpu_ctx *ctx, int particleUpdate)
+{
+    TiledState &t = ctx->tiled;
+    const int n0 = 0, ncount = ctx->g.nnodes, ngrid = nblocks(ncount, 256);
+    const int pgrid = nblocks(ctx->P.nNR, FUSED_THREADS);
+    const int fmpm = ctx->sp.usingFMPM ? 1 : 0;
+    LAUNCH(k_nx_init, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->sp.dt, fmpm);
+    for (int k = 2; k <= ctx->sp.xpicOrder; k++) {
+        if (pgrid) LAUNCH(k_fx_iterate, pgrid, FUSED_THREADS, ctx->g, ctx->P, ctx->N, t.FN);
+        LAUNCH(k_nx_finish, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, ctx->sp.dt, particleUpdate, fmpm, k == ctx->sp.xpicOrder ? 1 : 0);
+    }
+    return MPMGPU_OK;
+}
+
 // One step = four phases; in slab mode the host exchanges halo buffers between them.
 //  0: (sort) zero nodes, F1                      -> partial mass/momentum sums
 //  1: N1, F2                                     -> partial forces
@@ -944,6 +968,7 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
     const double stLast = sp.method == METHOD_USAVG ? sp.dtStrainLast : sp.dt;
     int m = sp.xpicOrder;
     if (!sp.usingFMPM) m = -m;
+    const bool highOrder = sp.xpicOrder > 1;
 
     if (phase == 0) {
         if (t.stepsSinceSort >= t.sortInterval) { if ((rc = sort_particles(ctx))) return rc; }
@@ -965,6 +990,8 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_begin(ctx);
         if (t.slab.on && (rc = halo_add(ctx, 0))) return rc;
         LAUNCH(k_n1_post_extrapolation, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp, hasUSF ? 1 : 0);
+        // FMPM(k>1) strain updates use v*(k) (UpdateStrainsFirstTask.cpp:105-116)
+        if (highOrder && sp.usingFMPM && hasUSF && (rc = xpic_fused(ctx, 0))) return rc;
         prof_end(ctx, T_POSTEXTRAP);
         prof_begin(ctx);
         if (pgrid) {
@@ -983,7 +1010,12 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
     } else if (phase == 2) {
         prof_begin(ctx);
         if (t.slab.on && (rc = halo_add(ctx, 1))) return rc;
-        LAUNCH(k_n2_forces_momenta, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp, reextrap ? 1 : 0);
+        // (with order > 1 the re-zeroing of pk for task 9a waits until v* has been formed from it)
+        LAUNCH(k_n2_forces_momenta, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp, (reextrap && !highOrder) ? 1 : 0);
+        if (highOrder) {                                       // UpdateParticlesTask.cpp:66-71
+            if ((rc = xpic_fused(ctx, 1))) return rc;
+            if (reextrap) LAUNCH(k_rezero_range, ngrid, 256, n0, ncount, ctx->N);
+        }
         prof_end(ctx, T_POSTFORCES);
         prof_begin(ctx);
         if (pgrid) LAUNCH(k_f3_update_momentum, pgrid, FUSED_THREADS, g, ctx->P, ctx->N, t.FN, ctx->dMats, sp, m, reextrap ? 1 : 0);
@@ -994,6 +1026,10 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_begin(ctx);
         if (t.slab.on && (rc = halo_add(ctx, 2))) return rc;
         if (reextrap) LAUNCH(k_n3_strains_last, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp);
+        if (highOrder && hasUSL) {
+            if (sp.usingFMPM) { if (reextrap && (rc = xpic_fused(ctx, 0))) return rc; }        // second strain update on v*(k) of the new momenta
+            else if (!reextrap) LAUNCH(k_n_grid_velocity, ngrid, 256, n0, ncount, ctx->N, t.FN);   // XPIC: lumped velocity again
+        }
         const bool earlyReset = t.slab.on && !t.usePipe && n > 0;
         if (earlyReset) {
             LAUNCH(k_reset_slab, nblocks(n, 256), 256, g, ctx->P, ctx->dFlags, sp.dt, t.slab);
@@ -1053,7 +1089,8 @@ extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
 {
     int rc = check_ready(ctx, "mpmgpu_step"); if (rc) return rc;
     for (int s = 0; s < nsteps; s++) {
-        rc = (ctx->tiled.enabled && ctx->sp.xpicOrder <= 1) ? fused_step(ctx) : step_by_tasks(ctx);
+        // XPIC/FMPM of order > 1 needs one more halo exchange per iteration: fused on one GPU, per-task kernels otherwise
+        rc = (ctx->tiled.enabled && (ctx->sp.xpicOrder <= 1 || !ctx->tiled.slab.on)) ? fused_step(ctx) : step_by_tasks(ctx);
         if (rc) return rc;
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
     }
@@ -1256,6 +1293,8 @@ extern "C" int mpmgpu_slab_step_phase(mpmgpu_ctx *ctx, int phase)
     int rc = check_ready(ctx, "mpmgpu_slab_step_phase"); if (rc) return rc;
     if (!ctx->tiled.enabled) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_step_phase: fused path not enabled for this problem");
     if (phase < 0 || phase > 3) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_step_phase: phase %d", phase);
+    if (ctx->sp.xpicOrder > 1 && ctx->tiled.slab.on && (ctx->tiled.hasLower || ctx->tiled.hasUpper))
+        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_step_phase: XPIC/FMPM order %d > 1 is not built for slabs (one halo exchange per iteration)", ctx->sp.xpicOrder);
     rc = fused_phase(ctx, phase);
     if (rc) return rc;
     if (phase == 3) {

@@ -49,6 +49,7 @@
 struct FusedNodes {
     double4 *V;          // [nnodes] {vx,vy,vz,0}: vk[0]
     double4 *A;          // [nnodes] {ax,ay,az,0}: ftot/mass
+    double4 *VS;         // [nnodes] {v*prev}: the vector the XPIC/FMPM iterations gather (order > 1)
     const int *bcOfNode; // [nnodes] index into VelBCs unique list or -1
     RigidBCs R;          // BCs projected from rigid particles (k_project_rigid_bcs)
 };
@@ -896,6 +897,160 @@ __global__ void k_n3_strains_last(int n0, int nnodes, Nodes N, FusedNodes FN, Ve
             v = make_double4(pk[0] * rm, pk[1] * rm, pk[2] * rm, 0.);
             N.vk[0][i] = v.x; N.vk[1][i] = v.y; N.vk[2][i] = v.z;
         }
+    }
+    FN.V[i] = v;
+}
+
+// ---- XPIC(k) / FMPM(k), k > 1: XPICExtrapolationTask.cpp:49-161 in fused form ------------------------------------
+// v*(1) = lumped velocity; for k = 2..m:  v*next_i = sum_p (mp S_ip / m_i) sum_j S_jp v*prev_j,  dv = v*prev - v*next,
+// BCs zero the increment, v* += dv, v*prev = dv.  One node sweep to start, then per iteration one particle kernel
+// (gather u_p from the VS records through the warp tile, warp-cooperative scatter of mp S_ip u_p) and one node sweep.
+__global__ void k_nx_init(int n0, int nnodes, Nodes N, FusedNodes FN, double dt, int usingFMPM)
+{
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + nnodes) return;
+    N.vsn[0][i] = 0.; N.vsn[1][i] = 0.; N.vsn[2][i] = 0.;
+    double4 vs = make_double4(0., 0., 0., 0.);
+    if (N.cnt[i] > 0) {
+        const double mass = N.mass[i], rm = 1. / mass;
+        double v[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (usingFMPM) {
+                v[c] = N.pk[c][i] * rm;
+                N.vsp[c][i] = v[c]; N.vk[c][i] = v[c];
+            } else {            // XPIC: v*(1) is the velocity before the force increment (MatVelocityField.cpp:318-345)
+                double t = N.pk[c][i];
+                t += N.ftot[c][i] * (-dt);
+                t *= rm;
+                v[c] = t;
+                N.vsp[c][i] = t;
+                N.vk[c][i] = t + N.ftot[c][i] * (dt / mass);
+            }
+        }
+        vs = make_double4(v[0], v[1], v[2], 0.);
+    }
+    FN.VS[i] = vs;
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, F3_MINB) k_fx_iterate(Grid g, Particles P, Nodes N, FusedNodes FN)
+{
+    union FxShared { WarpTile t; WarpStage<false, 4> st; };
+    __shared__ FxShared shared[FUSED_WARPS];
+    WarpStage<false, 4> &st = shared[threadIdx.x >> 5].st;
+    WarpTile &tile = shared[threadIdx.x >> 5].t;
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = p < P.nNR;
+    int key = 0;
+    double xi[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
+    if (active) {
+        key = P.key[p];
+        xi[0] = P.ncpos[0][p]; xi[1] = P.ncpos[1][p]; xi[2] = P.ncpos[2][p];
+        load_lp(g, P, p, lp);
+    }
+    const int anchor = tile_anchor(key, active);
+    tile_load_async(g, tile, anchor, FN.VS);
+    Weights3 w;
+    if (active) particle_weights<false>(g, key, xi, lp, w);
+    tile_wait();
+    double u[3] = {0., 0., 0.};
+    if (active) {
+        const int d = key - anchor;
+        const bool tiled = (unsigned)d <= (unsigned)(TILE_W - 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double syz = w.S[1][j] * w.S[2][k];
+                const int row = w.center + (j - 1) * g.yplane + (k - 1) * g.zplane - 1;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double S = w.S[0][i] * syz;
+                    const double4 v = tiled ? tile.r[j + 3 * k][d + i] : ldg4(&FN.VS[row + i]);
+                    u[0] += S * v.x; u[1] += S * v.y; u[2] += S * v.z;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (active) {
+        stage_weights(st, lane, w, P.mp[p]);
+        st.Q[lane][0] = u[0]; st.Q[lane][1] = u[1]; st.Q[lane][2] = u[2];
+    }
+    __syncwarp();
+    double *dst[3] = {N.vsn[0], N.vsn[1], N.vsn[2]};
+    warp_scatter<3, false>(g, key, active, dst, (int *)0, [&](int src, int i, int jk, double *acc) {
+        const double f = st.X[i][src] * st.YZ[jk][src];          // fn * mp
+        const double2 uxy = *reinterpret_cast<const double2 *>(st.Q[src]);
+        const double uz = st.Q[src][2];
+        acc[0] += uxy.x * f; acc[1] += uxy.y * f; acc[2] += uz * f;
+        return f != 0. ? 1 : 0;
+    });
+}
+
+// GET_DELTAV, BCs on the increment (XPIC_* pass of ZeroVelocityBC, MatVelocityField.cpp:529-541), UPDATE_VSTAR; after the
+// last iteration the gather record V is v*(m)
+__global__ void k_nx_finish(int n0, int nnodes, Nodes N, FusedNodes FN, VelBCs B, double dt, int particleUpdate, int usingFMPM, int last)
+{
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + nnodes) return;
+    if (N.cnt[i] == 0) {
+        FN.VS[i] = make_double4(0., 0., 0., 0.);
+        if (last) FN.V[i] = make_double4(0., 0., 0., 0.);
+        return;
+    }
+    const double mass = N.mass[i];
+    double d[3] = {N.vsp[0][i] - N.vsn[0][i] / mass, N.vsp[1][i] - N.vsn[1][i] / mass, N.vsp[2][i] - N.vsn[2][i] / mass};
+    const bool addReaction = particleUpdate && !usingFMPM;
+    double ft[3] = {N.ftot[0][i], N.ftot[1][i], N.ftot[2][i]};
+    const int u = FN.bcOfNode ? FN.bcOfNode[i] : -1;
+    if (u >= 0) {
+        for (int e = B.start[u]; e < B.start[u + 1]; e++) {
+            if (!B.active[e]) continue;
+            const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
+            const double dotn = d[0] * nx + d[1] * ny + d[2] * nz;
+            d[0] += nx * (-dotn); d[1] += ny * (-dotn); d[2] += nz * (-dotn);
+            if (addReaction) {
+                const double s = -mass * dotn / dt;
+                ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+            }
+        }
+    }
+    if (FN.R.on) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (FN.R.owner[c][i] == RIGID_NONE) continue;
+            const double dotn = d[c];
+            d[c] += -dotn;
+            if (addReaction) ft[c] += -mass * dotn / dt;
+        }
+    }
+    if (addReaction) { N.ftot[0][i] = ft[0]; N.ftot[1][i] = ft[1]; N.ftot[2][i] = ft[2]; }
+    double vk[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        N.vsp[c][i] = d[c];
+        vk[c] = N.vk[c][i] + d[c];
+        N.vk[c][i] = vk[c];
+        N.vsn[c][i] = 0.;
+    }
+    FN.VS[i] = make_double4(d[0], d[1], d[2], 0.);
+    if (last) FN.V[i] = make_double4(vk[0], vk[1], vk[2], 0.);
+}
+
+// lumped grid velocity V = pk/mass (strain update after the particle update when no re-extrapolation follows and the
+// V records still hold v*(m) of an XPIC particle update: MatVelocityField::GridValueCalculation :239-251)
+__global__ void k_n_grid_velocity(int n0, int nnodes, Nodes N, FusedNodes FN)
+{
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + nnodes) return;
+    double4 v = make_double4(0., 0., 0., 0.);
+    const double mass = N.mass[i];
+    if (N.cnt[i] > 0 && mass != 0.) {
+        const double rm = 1. / mass;
+        v = make_double4(N.pk[0][i] * rm, N.pk[1][i] * rm, N.pk[2][i] * rm, 0.);
+        N.vk[0][i] = v.x; N.vk[1][i] = v.y; N.vk[2][i] = v.z;
     }
     FN.V[i] = v;
 }

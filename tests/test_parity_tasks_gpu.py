@@ -18,7 +18,8 @@ CASES = ["block3d_rigid_wall", "block3d_rigid_piston", "block3d_rigid_linear_xpi
          "block3d_ugimp_usf"]
 
 
-FUSED_CASES = [c for c in CASES if "linear" not in c and "2d" not in c and "fmpm" not in c and "cpdi" not in c]
+# the fused path: 3D uGIMP, any of the materials, FLIP/PIC and XPIC(k)/FMPM(k), rigid-BC particles
+FUSED_CASES = [c for c in CASES if "linear" not in c and "2d" not in c and "cpdi" not in c]
 
 
 def make_sim(z, kernel_path=1, sort_interval=0):
