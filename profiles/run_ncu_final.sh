@@ -2,7 +2,7 @@
 # Round-1 captures of the shipped kernels (run under gpurun on one B200).  $1 = tag
 #  1. launch list of the default bench command (serialised, cold-cache: compare SHARES of the step, not absolutes)
 #  2. one --set full capture of each fused kernel at the bench size (8M particles) -> dram bytes per launch
-TAG=${1:-r1f}
+TAG=${1:-r1g}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_$TAG.log 2>&1
