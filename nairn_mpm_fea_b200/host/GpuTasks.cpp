@@ -56,6 +56,7 @@ mpmgpu_ctx *gCtx = NULL;
 bool gHostStale = false;            // device is ahead of mpm[]
 std::vector<NodalVelBC *> gBCs;     // host BC list in list order
 bool gBCsVary = false;
+bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
 void check(int rc, const char *where)
 {
@@ -102,8 +103,32 @@ class GpuTask : public MPMTask
   public:
     int which;
     GpuTask(const char *name, int w) : MPMTask(name), which(w) {}
+    void UpdateBCValues(void)
+    {   // NodalVelBC::GridVelocityBCValues (NodalVelBC.cpp:293-302): values at this step's mtime
+        if (!gBCsVary) return;
+        std::vector<double> v(gBCs.size()); std::vector<int> a(gBCs.size());
+        for (size_t i = 0; i < gBCs.size(); i++) { a[i] = gBCs[i]->GetNodeNum(mtime) > 0; v[i] = a[i] ? gBCs[i]->BCValue(mtime) : 0.; }
+        check(mpmgpu_update_velocity_bc_values(gCtx, (int)v.size(), v.data(), a.data()), "GpuTask(BC values)");
+    }
+    void AfterStep(void)
+    {
+        gHostStale = true;
+        // will the reference archive after this step?  (ArchiveResults(mtime+timestep,...), ArchiveData.cpp:731-746)
+        const double atime = mtime + timestep;
+        bool due = atime >= archiver->nextArchTime || atime + timestep > fmobj->maxtime;
+        if (firstGlobal != NULL && archiver->globalTime >= 0. && atime > archiver->nextGlobalTime) due = true;
+        if (due || theTasks != NULL) DownloadToHost();
+    }
     virtual bool Execute(int)
     {
+        if (gFusedStep) {       // one call per step; the per-task rows of the timing report then show the whole step under "Initialize"
+            if (which == G_INIT) {
+                check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(step)");
+                UpdateBCValues();
+                check(mpmgpu_step(gCtx, 1), "GpuTask(step)");
+            } else if (which == G_RESET) AfterStep();
+            return true;
+        }
         switch (which) {
         case G_INIT:
             // the PeriodicXPIC custom task changes the order between steps (Custom_Tasks/PeriodicXPIC.cpp:161-240)
@@ -113,11 +138,7 @@ class GpuTask : public MPMTask
         case G_RIGIDBC: check(mpmgpu_task_project_rigid_bcs(gCtx), "GpuTask(ProjectRigidBCs)"); break;
         case G_MASSMOM: check(mpmgpu_task_mass_and_momentum(gCtx), "GpuTask(MassAndMomentum)"); break;
         case G_POSTEXTRAP:
-            if (gBCsVary) {     // NodalVelBC::GridVelocityBCValues (NodalVelBC.cpp:293-302): values at this step's mtime
-                std::vector<double> v(gBCs.size()); std::vector<int> a(gBCs.size());
-                for (size_t i = 0; i < gBCs.size(); i++) { a[i] = gBCs[i]->GetNodeNum(mtime) > 0; v[i] = a[i] ? gBCs[i]->BCValue(mtime) : 0.; }
-                check(mpmgpu_update_velocity_bc_values(gCtx, (int)v.size(), v.data(), a.data()), "GpuTask(PostExtrapolation)");
-            }
+            UpdateBCValues();
             check(mpmgpu_task_post_extrapolation(gCtx), "GpuTask(PostExtrapolation)");
             break;
         case G_USF: check(mpmgpu_task_update_strains_first(gCtx), "GpuTask(UpdateStrainsFirst)"); break;
@@ -126,16 +147,10 @@ class GpuTask : public MPMTask
         case G_MOMENTA: check(mpmgpu_task_update_momenta(gCtx), "GpuTask(UpdateMomenta)"); break;
         case G_PARTICLES: check(mpmgpu_task_update_particles(gCtx), "GpuTask(UpdateParticles)"); break;
         case G_USL: check(mpmgpu_task_update_strains_last(gCtx), "GpuTask(UpdateStrainsLast)"); break;
-        case G_RESET: {
+        case G_RESET:
             check(mpmgpu_task_reset_elements(gCtx), "GpuTask(ResetElements)");
-            gHostStale = true;
-            // will the reference archive after this step?  (ArchiveResults(mtime+timestep,...), ArchiveData.cpp:731-746)
-            const double atime = mtime + timestep;
-            bool due = atime >= archiver->nextArchTime || atime + timestep > fmobj->maxtime;
-            if (firstGlobal != NULL && archiver->globalTime >= 0. && atime > archiver->nextGlobalTime) due = true;
-            if (due || theTasks != NULL) DownloadToHost();
+            AfterStep();
             break;
-        }
         }
         return true;
     }
@@ -156,8 +171,9 @@ int TaskCode(const char *name)
 } // namespace
 
 // Returns NULL when installed, else the reason the run stays on the CPU tasks.
-const char *GpuTasks_Install(int device)
+const char *GpuTasks_Install(int device, bool fusedStep)
 {
+    gFusedStep = fusedStep;
     if (firstCrack != NULL) return "cracks present";
     if (fmobj->multiMaterialMode) return "multimaterial mode";
     if (transportTasks != NULL) return "transport tasks present";
@@ -208,7 +224,8 @@ const char *GpuTasks_Install(int device)
     cfg.xpic_order = bodyFrc.GetXPICOrder(); cfg.using_fmpm = bodyFrc.UsingFMPM() ? 1 : 0;
     cfg.grid_damping = bodyFrc.GetGridDamping(mtime); cfg.particle_damping = bodyFrc.GetParticleDamping(mtime);
     if (bodyFrc.gravity) { cfg.gravity[0] = bodyFrc.gforce.x; cfg.gravity[1] = bodyFrc.gforce.y; cfg.gravity[2] = bodyFrc.gforce.z; }
-    cfg.kernel_path = 1;        // per-task entry points keep the reference's task timing report meaningful
+    cfg.kernel_path = fusedStep ? 0 : 1;    // per-task entry points keep the reference's task timing report meaningful; -fused runs
+                                            // mpmgpu_step (fused kernels when the problem is eligible, per-task kernels otherwise)
     if (mpmgpu_create(&cfg, &gCtx) != MPMGPU_OK) return mpmgpu_last_error(NULL);
 
     // materials: the block GetCopyOfMechanicalProps would hand out (Elastic::FillUnrotatedElasticProperties)
@@ -311,7 +328,8 @@ const char *GpuTasks_Install(int device)
         } else prev = t;
         t = next;
     }
-    std::cout << "GPU TASKS: tasks 1-9,11 run on libmpmgpu (device " << device << ", " << n << " particles)" << std::endl;
+    std::cout << "GPU TASKS: tasks 1-9,11 run on libmpmgpu (device " << device << ", " << n << " particles"
+              << (fusedStep ? ", whole-step entry point" : ", per-task entry points") << ")" << std::endl;
     return NULL;
 }
 
@@ -328,14 +346,15 @@ void GpuTasks_Finish(void)
 int main(int argc, const char *argv[])
 {
     int numProcs = 1, device = 0, arg = 1;
-    bool useGpu = true;
+    bool useGpu = true, fused = false;
     for (; arg < argc && argv[arg][0] == '-'; arg++) {
         if (strcmp(argv[arg], "-np") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &numProcs);
         else if (strcmp(argv[arg], "-gpu") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &device);
         else if (strcmp(argv[arg], "-cpu") == 0) useGpu = false;
-        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-cpu] input.fmcmd" << std::endl; return 1; }
+        else if (strcmp(argv[arg], "-fused") == 0) fused = true;
+        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-cpu] input.fmcmd" << std::endl; return 1; }
     }
-    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-cpu] input.fmcmd" << std::endl; return 1; }
+    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-cpu] input.fmcmd" << std::endl; return 1; }
     fmobj = new NairnMPM();
     omp_set_num_threads(numProcs);
     fmobj->SetNumberOfProcessors(numProcs);
@@ -347,7 +366,7 @@ int main(int argc, const char *argv[])
         fmobj->CMStartResultsOutput();
         fmobj->CMPreparations();
         if (useGpu) {
-            const char *why = GpuTasks_Install(device);
+            const char *why = GpuTasks_Install(device, fused);
             if (why != NULL) { std::cerr << "NairnMPM_gpu: cannot run this input on libmpmgpu: " << why << std::endl; return 2; }
         }
         fmobj->CMAnalysis(false);

@@ -41,14 +41,17 @@ def run(binary, xml, extra=()):
     return d, p.stdout
 
 
+@pytest.mark.parametrize("mode", ["tasks", "fused"])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_reference_driver_with_gpu_tasks_matches_reference(case):
+def test_reference_driver_with_gpu_tasks_matches_reference(case, mode):
+    """mode tasks: every reference task replaced by the entry point of the same name (per-task kernels);
+    mode fused: `NairnMPM_gpu -fused`, the whole step in one call (fused kernels for 3D uGIMP, else per-task)."""
     if not (os.path.exists(REF) and os.path.exists(GPU)):
         pytest.skip("oracle/_ref/NairnMPM or host/_build/NairnMPM_gpu not built")
     xml, npart, root = CASES[case]
     dref, out_ref = run(REF, xml, ("-np", "4"))
-    dgpu, out_gpu = run(GPU, xml)
-    assert "GPU TASKS" in out_gpu
+    dgpu, out_gpu = run(GPU, xml, ("-fused",) if mode == "fused" else ())
+    assert "GPU TASKS" in out_gpu and ("whole-step" in out_gpu) == (mode == "fused")
     if npart is None:
         for ln in out_ref.splitlines():
             if "Number of Material Points:" in ln:
