@@ -242,12 +242,18 @@ int mpmgpu_task_times(mpmgpu_ctx *ctx, double *ms, long long *calls);
  * listed by the last phase and moved as rows. */
 int mpmgpu_slab_configure(mpmgpu_ctx *ctx, int cell_lo, int cell_hi, int has_lower, int has_upper, int migration_capacity);
 /* device pointers of the halo exchange buffers ([lower, upper] neighbour); a pass moves
- * nvalues*3*plane_nodes doubles per neighbour, nvalues = 5, 3, 3 for the exchanges after phases 0, 1, 2 */
+ * nvalues*3*plane_nodes doubles per neighbour, nvalues = 4, 3, 3 for the exchanges after phases 0, 1, 2
+ * (and 3 for the exchange inside an XPIC/FMPM iteration, halo kind 3) */
 int mpmgpu_slab_halo_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, long long *plane_nodes);
 /* phase 0: zero + P2G mass/momentum | exchange | 1: node sweep + G2P strain + P2G forces | exchange |
  * 2: node sweep + G2P update + P2G momentum | exchange | 3: node sweep + G2P strain + element reset.
  * Phases 0-2 return with the send buffers packed and the stream idle; the next phase adds the recv buffers. */
 int mpmgpu_slab_step_phase(mpmgpu_ctx *ctx, int phase);
+/* XPIC(k)/FMPM(k), k > 1 (XPICExtrapolationTask.cpp:49-161) needs one more exchange per iteration, in the middle of a
+ * phase: the library packs the send buffers, calls fn(user, 3) -- the host enqueues the swap of halo kind 3 on the
+ * context's stream, exactly as it does between phases -- and then adds the recv buffers.  fn must not throw. */
+typedef void (*mpmgpu_halo_fn)(void *user, int which);
+int mpmgpu_slab_set_halo_callback(mpmgpu_ctx *ctx, mpmgpu_halo_fn fn, void *user);
 /* after phase 3: how many particles must move to the lower / upper neighbour */
 int mpmgpu_slab_migration_counts(mpmgpu_ctx *ctx, int *n_lo, int *n_hi);
 int mpmgpu_slab_migration_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, int *row_doubles, int *capacity_rows);

@@ -30,10 +30,11 @@ EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
     "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times",
-    "mpmgpu_slab_configure", "mpmgpu_slab_halo_buffers", "mpmgpu_slab_step_phase", "mpmgpu_slab_migration_counts",
+    "mpmgpu_slab_configure", "mpmgpu_slab_halo_buffers", "mpmgpu_slab_step_phase", "mpmgpu_slab_set_halo_callback", "mpmgpu_slab_migration_counts",
     "mpmgpu_slab_migration_buffers", "mpmgpu_slab_pack_migrants", "mpmgpu_slab_finish_migration",
     "mpmgpu_num_particles", "mpmgpu_set_stream"]
 
+HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)     # mpmgpu_halo_fn
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
@@ -114,6 +115,7 @@ def load_library(path=None):
     lib.mpmgpu_slab_configure.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.mpmgpu_slab_halo_buffers.argtypes = [vp, pvp, pvp, pvp, pvp, C.POINTER(C.c_longlong)]
     lib.mpmgpu_slab_step_phase.argtypes = [vp, C.c_int]
+    lib.mpmgpu_slab_set_halo_callback.argtypes = [vp, HALO_FN, vp]
     lib.mpmgpu_slab_migration_counts.argtypes = [vp, _ip, _ip]
     lib.mpmgpu_slab_migration_buffers.argtypes = [vp, pvp, pvp, pvp, pvp, _ip, _ip]
     lib.mpmgpu_slab_pack_migrants.argtypes = [vp]
@@ -326,8 +328,26 @@ class MpmGpu:
         self._check(self.lib.mpmgpu_slab_migration_buffers(self.ctx, *[C.byref(x) for x in p], C.byref(row), C.byref(cap)))
         return [x.value for x in p], int(row.value), int(cap.value)
 
+    def slab_set_halo_callback(self, fn):
+        """fn(which): enqueue the swap of halo kind `which` with the neighbours (called from inside a phase when the
+        XPIC/FMPM order is > 1).  An exception raised by fn is kept and re-raised when the phase returns."""
+        self._halo_error = None
+
+        def tramp(_user, which):
+            try:
+                fn(int(which))
+            except BaseException as e:      # must not unwind through the C frames
+                self._halo_error = e
+        self._halo_cb = HALO_FN(tramp)      # keep the thunk alive
+        self._check(self.lib.mpmgpu_slab_set_halo_callback(self.ctx, self._halo_cb, None))
+
     def slab_phase(self, phase):
-        self._check(self.lib.mpmgpu_slab_step_phase(self.ctx, phase))
+        rc = self.lib.mpmgpu_slab_step_phase(self.ctx, phase)
+        err = getattr(self, "_halo_error", None)
+        if err is not None:
+            self._halo_error = None
+            raise err
+        self._check(rc)
 
     def slab_migration_counts(self):
         a, b = C.c_int(), C.c_int()

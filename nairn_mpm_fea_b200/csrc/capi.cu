@@ -67,6 +67,7 @@ struct mpmgpu_ctx {
     bool f2Attr[2][2];
     // slab mode: leave counts + status flags land here (pinned) right after the early element reset; the host
     // waits on slabEvent while the strain kernel of the same step is still running
+    mpmgpu_halo_fn haloFn; void *haloUser;     // host hook that exchanges halo `which` with the neighbours (XPIC iterations)
     struct SlabHost { int leave[2]; StatusFlags flags; } *slabHost;
     cudaEvent_t slabEvent; bool slabPending;                  // dynamic shared memory opt-in done for k_f2_strain_forces<SK, FEXT> on this device
 };
@@ -139,7 +140,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
     tiled_state_init(ctx->tiled);
     memset(ctx->f2Attr, 0, sizeof ctx->f2Attr);
-    ctx->slabHost = NULL; ctx->slabPending = false;
+    ctx->slabHost = NULL; ctx->slabPending = false; ctx->haloFn = NULL; ctx->haloUser = NULL;
 
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { int rc = fail(NULL, MPMGPU_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); delete ctx; return rc; }
@@ -935,12 +936,19 @@ static int halo_add(mpmgpu_ctx *ctx, int which)
 static int xpic_fused(mpmgpu_ctx *ctx, int particleUpdate)
 {
     TiledState &t = ctx->tiled;
-    const int n0 = 0, ncount = ctx->g.nnodes, ngrid = nblocks(ncount, 256);
+    const int n0 = t.slab.on ? t.nodeLo : 0, ncount = t.slab.on ? t.nodeCount : ctx->g.nnodes, ngrid = nblocks(ncount, 256);
     const int pgrid = nblocks(ctx->P.nNR, FUSED_THREADS);
     const int fmpm = ctx->sp.usingFMPM ? 1 : 0;
+    const bool exchange = t.slab.on && (t.hasLower || t.hasUpper);
+    int rc;
     LAUNCH(k_nx_init, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->sp.dt, fmpm);
     for (int k = 2; k <= ctx->sp.xpicOrder; k++) {
         if (pgrid) LAUNCH(k_fx_iterate, pgrid, FUSED_THREADS, ctx->g, ctx->P, ctx->N, t.FN);
+        if (exchange) {         // partial v*next sums on the planes around the slab faces: swap with the neighbours and add
+            if ((rc = halo_pack(ctx, 3, true))) return rc;
+            ctx->haloFn(ctx->haloUser, 3);
+            if ((rc = halo_add(ctx, 3))) return rc;
+        }
         LAUNCH(k_nx_finish, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, ctx->sp.dt, particleUpdate, fmpm, k == ctx->sp.xpicOrder ? 1 : 0);
     }
     return MPMGPU_OK;
@@ -1090,7 +1098,7 @@ extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
     int rc = check_ready(ctx, "mpmgpu_step"); if (rc) return rc;
     for (int s = 0; s < nsteps; s++) {
         // XPIC/FMPM of order > 1 needs one more halo exchange per iteration: fused on one GPU, per-task kernels otherwise
-        rc = (ctx->tiled.enabled && (ctx->sp.xpicOrder <= 1 || !ctx->tiled.slab.on)) ? fused_step(ctx) : step_by_tasks(ctx);
+        rc = (ctx->tiled.enabled && (ctx->sp.xpicOrder <= 1 || !ctx->tiled.slab.on || !(ctx->tiled.hasLower || ctx->tiled.hasUpper))) ? fused_step(ctx) : step_by_tasks(ctx);
         if (rc) return rc;
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
     }
@@ -1288,13 +1296,20 @@ extern "C" int mpmgpu_slab_halo_buffers(mpmgpu_ctx *ctx, void **send_lo, void **
     return MPMGPU_OK;
 }
 
+extern "C" int mpmgpu_slab_set_halo_callback(mpmgpu_ctx *ctx, mpmgpu_halo_fn fn, void *user)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    ctx->haloFn = fn; ctx->haloUser = user;
+    return MPMGPU_OK;
+}
+
 extern "C" int mpmgpu_slab_step_phase(mpmgpu_ctx *ctx, int phase)
 {
     int rc = check_ready(ctx, "mpmgpu_slab_step_phase"); if (rc) return rc;
     if (!ctx->tiled.enabled) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_step_phase: fused path not enabled for this problem");
     if (phase < 0 || phase > 3) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_step_phase: phase %d", phase);
-    if (ctx->sp.xpicOrder > 1 && ctx->tiled.slab.on && (ctx->tiled.hasLower || ctx->tiled.hasUpper))
-        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_step_phase: XPIC/FMPM order %d > 1 is not built for slabs (one halo exchange per iteration)", ctx->sp.xpicOrder);
+    if (ctx->sp.xpicOrder > 1 && ctx->tiled.slab.on && (ctx->tiled.hasLower || ctx->tiled.hasUpper) && !ctx->haloFn)
+        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_step_phase: XPIC/FMPM order %d > 1 needs one halo exchange per iteration: register mpmgpu_slab_set_halo_callback", ctx->sp.xpicOrder);
     rc = fused_phase(ctx, phase);
     if (rc) return rc;
     if (phase == 3) {

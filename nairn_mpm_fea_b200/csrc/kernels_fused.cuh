@@ -134,6 +134,7 @@ __device__ __forceinline__ int tile_anchor(int key, bool active)
     const unsigned act = __ballot_sync(full, active);
     const int kmin = __reduce_min_sync(full, active ? key : 0x7fffffff);
     const int ref = __shfl_sync(full, key, __popc(act) >> 1);       // active lanes are the low ones
+    if (!act) return 1;                                             // a warp past the last particle: any valid window
     return max(kmin, ref - (TILE_W - 3));
 }
 
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, F4_MINB) k_f4_strain_reset(Grid
 }
 
 // ---- slab halo: pack partial sums of the three node planes shared with a neighbour / add the neighbour's ----
-// which: 0 mass,pk (4 values)  1 ftot (3)  2 pk (3).  Buffer layout [value][3 planes * planeNodes].
+// which: 0 mass,pk (4 values)  1 ftot (3)  2 pk (3)  3 XPIC v*next sums (3).  Buffer layout [value][3 planes * planeNodes].
 __global__ void k_halo_pack(int which, int node0, int count, Nodes N, double *buf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -722,8 +723,10 @@ __global__ void k_halo_pack(int which, int node0, int count, Nodes N, double *bu
         buf[count + i] = N.pk[0][nd]; buf[2 * count + i] = N.pk[1][nd]; buf[3 * count + i] = N.pk[2][nd];
     } else if (which == 1) {
         buf[i] = N.ftot[0][nd]; buf[count + i] = N.ftot[1][nd]; buf[2 * count + i] = N.ftot[2][nd];
-    } else {
+    } else if (which == 2) {
         buf[i] = N.pk[0][nd]; buf[count + i] = N.pk[1][nd]; buf[2 * count + i] = N.pk[2][nd];
+    } else {
+        buf[i] = N.vsn[0][nd]; buf[count + i] = N.vsn[1][nd]; buf[2 * count + i] = N.vsn[2][nd];
     }
 }
 
@@ -737,8 +740,10 @@ __global__ void k_halo_add(int which, int node0, int count, Nodes N, const doubl
         N.pk[0][nd] += buf[count + i]; N.pk[1][nd] += buf[2 * count + i]; N.pk[2][nd] += buf[3 * count + i];
     } else if (which == 1) {
         N.ftot[0][nd] += buf[i]; N.ftot[1][nd] += buf[count + i]; N.ftot[2][nd] += buf[2 * count + i];
-    } else {
+    } else if (which == 2) {
         N.pk[0][nd] += buf[i]; N.pk[1][nd] += buf[count + i]; N.pk[2][nd] += buf[2 * count + i];
+    } else {
+        N.vsn[0][nd] += buf[i]; N.vsn[1][nd] += buf[count + i]; N.vsn[2][nd] += buf[2 * count + i];
     }
 }
 

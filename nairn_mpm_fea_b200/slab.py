@@ -20,7 +20,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-HALO_VALUES = (4, 3, 3)        # values per node exchanged after phases 0, 1, 2 (mass + momentum, force, momentum)
+# values per node in a halo exchange: after phases 0, 1, 2 (mass + momentum, force, momentum) and, kind 3, inside
+# each XPIC/FMPM iteration (v*next sums)
+HALO_VALUES = (4, 3, 3, 3)
 
 
 def slab_bounds(depth, cell_first, cell_last, world):
@@ -160,6 +162,8 @@ class SlabSim:
         if world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
             cpu_group = dist.new_group(backend="gloo")      # collective: every rank builds its SlabSim
         self.ex = NeighbourExchange(rank, world, group, cpu_group)
+        if world > 1:
+            self.sim.slab_set_halo_callback(self._halo)      # XPIC/FMPM iterations exchange in the middle of a phase
         self.migrated_out = 0
         self.migrated_in = 0
 

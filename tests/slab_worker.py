@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nairn_mpm_fea_b200.problem import from_reference_dump  # noqa: E402
 from nairn_mpm_fea_b200.slab import SlabSim, gather_by_id, partition_particles, slab_bounds  # noqa: E402
-from tests.parity import TOL_100STEP, compare_particles, load_golden  # noqa: E402
+from tests.parity import TOL_100STEP, compare_particles, load_golden, xpic_for_step  # noqa: E402
 
 
 def main(case):
@@ -19,7 +19,8 @@ def main(case):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     z = load_golden(case)
     prob = from_reference_dump(z)
-    k = (np.asarray(prob.particles["in_elem"]) - 1) // (prob.horiz * prob.vert)
+    nnr = int(prob.particles.get("n_nonrigid", prob.nparticles))
+    k = (np.asarray(prob.particles["in_elem"])[:nnr] - 1) // (prob.horiz * prob.vert)
     bounds = slab_bounds(prob.depth, int(k.min()), int(k.max()) + 1, world)
     lo, hi = bounds[rank]
     part = partition_particles(prob.particles, prob.horiz, prob.vert, lo, hi)
@@ -28,9 +29,13 @@ def main(case):
     done = 0
     ok = True
     for s in snaps:
-        sim.step(s - done)
-        done = s
-        got = gather_by_id(sim.download(), prob.nparticles)
+        while done < s:                 # the PeriodicXPIC schedule of the golden run, if it has one
+            x = xpic_for_step(z, done + 1)
+            if x:
+                sim.sim.set_xpic(*x)
+            sim.step(1)
+            done += 1
+        got = gather_by_id(sim.download(), prob.nparticles, n_rigid=prob.nparticles - nnr)
         errs, bad = compare_particles(got, z, "p%d" % s, TOL_100STEP)
         if bad or not np.array_equal(got["in_elem"], z["p%d/inElem" % s]):
             ok = False
@@ -39,7 +44,7 @@ def main(case):
     dist.all_reduce(moved)
     if rank == 0:
         print("migrated rows:", int(moved.item()))
-        if ok and int(moved.item()) > 0:
+        if ok and (int(moved.item()) > 0 or "--no-migration-needed" in sys.argv):
             print("SLAB_OK")
     sim.close()
     dist.destroy_process_group()

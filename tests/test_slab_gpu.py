@@ -52,13 +52,17 @@ def test_lockstep_slabs_match_reference(case, world, sort_interval):
     cl.close()
 
 
-def test_two_ranks_over_nccl():
+@pytest.mark.parametrize("case,extra", [("block3d_fast_crossings", ()), ("block3d_xpic3", ("--no-migration-needed",)),
+                                        ("block3d_fmpm2", ("--no-migration-needed",)), ("block3d_rigid_wall", ("--no-migration-needed",))])
+def test_two_ranks_over_nccl(case, extra):
+    """2 processes, 2 GPUs, NCCL: halo exchanges (incl. the ones inside XPIC/FMPM iterations), migration, replicated
+    rigid particles; compared with the reference dump."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "slab_worker.py"),
-           "block3d_fast_crossings"]
+           case, *extra]
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "SLAB_OK" in p.stdout
