@@ -102,14 +102,16 @@ typedef struct mpmgpu_config {
  * (what GetCopyOfMechanicalProps would hand to MPMConstitutiveLaw, MaterialBase.hpp:143-165).
  * Parameter slots by kind (all stiffness-like values are SPECIFIC, i.e. divided by rho):
  *  all kinds:  [0] rho   [1] heat capacity Cv   [2] particle damping override or -1
+ *              [3] artificial viscosity on (1) / off (0)  [4] avA1  [5] avA2   (MaterialBaseMPM.cpp:202-216,1824-1829;
+ *              Neohookean and IsoPlasticity only)   [6] reserved: the library stores the average cell size here
  *  ISOTROPIC (3D):  [8] C11 [9] C12 [10] C13 [11] C22 [12] C23 [13] C33 [14] C44 [15] C55 [16] C66
  *                   [17] CTE1 [18] CTE2 [19] CTE3 [20] gamma0
  *  ISOTROPIC (2D, ElasticProperties 2D slots, Common/Materials/Elastic.cpp:90-140):
  *                   [8] C[1][1] [9] C[1][2] [11] C[2][2] [16] C[3][3] [21] C[4][1] [22] C[4][2]
  *                   [23] C[4][4] [24] C[5][1]  (+CTE/gamma0 as above)
- *  NEOHOOKEAN:      [8] Gsp [9] Ksp [10] Lamesp [11] UofJOption [12] CTE1 [13] gamma0-related Ka2sp
- *  ISOPLASTICITY:   [8] Gred [9] Kred [10] yldred [11] Epred [12] CTE(1 or 3) [13] gamma0
- *                   [14] psRed [15] psLr2G [16] psKred  (plane stress only)
+ *  NEOHOOKEAN:      [8] Gsp [9] Ksp [10] Lamesp [11] UofJOption [12] CTE1 [13] gamma0
+ *  ISOPLASTICITY:   [8] Gred [9] Kred [10] yldred [11] Epred [12] CTE3 [13] gamma0
+ *                   [14] alphaMax [15] yldredMin  (LinearHardening.cpp:55-80)
  *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)
  */
 typedef struct mpmgpu_material {

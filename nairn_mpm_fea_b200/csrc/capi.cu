@@ -61,8 +61,6 @@ struct mpmgpu_ctx {
     cudaEvent_t ev0, ev1;
     double taskMs[T_NTASKS];
     long long taskCalls[T_NTASKS];
-    // staging
-    double *hStage; size_t hStageBytes;
     TiledState tiled;
     bool f2Attr[2][2];
     // slab mode: leave counts + status flags land here (pinned) right after the early element reset; the host
@@ -132,7 +130,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->profiling = false; ctx->globalIds = false; ctx->ownStreamSaved = false;
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
     ctx->cpElemPool = NULL; ctx->cpXiPool = NULL; ctx->cpWgPool = NULL;
-    ctx->hStage = NULL; ctx->hStageBytes = 0; ctx->nBCEntries = 0;
+    ctx->nBCEntries = 0;
     memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R);
     ctx->rigidPool = NULL; ctx->rigidIntPool = NULL; ctx->rigidCap = 0;
     memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B);
@@ -215,7 +213,6 @@ extern "C" int mpmgpu_destroy(mpmgpu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     tiled_state_free(ctx->tiled);
     for (void *p : ctx->allocs) cudaFree(p);
-    if (ctx->hStage) cudaFreeHost(ctx->hStage);
     if (ctx->slabHost) { cudaFreeHost(ctx->slabHost); cudaEventDestroy(ctx->slabEvent); }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->ownStreamSaved ? ctx->ownStream : ctx->stream);
@@ -236,6 +233,10 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
         if (mats[i].n_history < 0 || mats[i].n_history > MPM_MAX_HISTORY) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: %d history doubles (max %d)", mats[i].n_history, MPM_MAX_HISTORY);
         ctx->hMats[i].kind = k; ctx->hMats[i].nhist = mats[i].n_history;
         memcpy(ctx->hMats[i].p, mats[i].p, sizeof(double) * MPM_MAT_NPARAMS);
+        if (mats[i].p[3] != 0. && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY)
+            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d does not support artificial viscosity (MaterialBase::SupportsArtificialViscosity)", k);
+        // MeshInfo::GetAverageCellSize for equal elements (MeshInfo.cpp:1517-1523): a grid constant the law needs
+        ctx->hMats[i].p[6] = ctx->dim == 3 ? (ctx->cfg.gridx + ctx->cfg.gridy + ctx->cfg.gridz) / 3. : (ctx->cfg.gridx + ctx->cfg.gridy) / 2.;
     }
     ctx->nmat = nmat;
     CK(cudaMemcpyAsync(ctx->dMats, ctx->hMats.data(), nmat * sizeof(Material), cudaMemcpyHostToDevice, ctx->stream));
@@ -292,16 +293,6 @@ static void bind_particles(Particles &P, double *pool, int *ipool, size_t capPad
     for (int c = 0; c < 3; c++) P.acc[c] = take();
     int *qi = ipool;
     P.elem = qi; qi += capPad; P.mat = qi; qi += capPad; P.cross = qi; qi += capPad; P.orig = qi; qi += capPad; P.key = qi;
-}
-
-static int ensure_stage(mpmgpu_ctx *ctx, size_t bytes)
-{
-    if (ctx->hStageBytes >= bytes) return MPMGPU_OK;
-    if (ctx->hStage) cudaFreeHost(ctx->hStage);
-    ctx->hStage = NULL; ctx->hStageBytes = 0;
-    CK(cudaMallocHost((void **)&ctx->hStage, bytes));
-    ctx->hStageBytes = bytes;
-    return MPMGPU_OK;
 }
 
 // copy rows [off, off+cnt) of a host [ncomp][n] array to device component arrays (zero-fill when host is NULL)

@@ -348,27 +348,31 @@ enum { SK_ELASTIC = 0, SK_FULL = 1 };
 template <int SK>
 __device__ __forceinline__ void load_state(const Particles &P, int p, PState &s)
 {
-    if (SK == SK_FULL) { load_pstate(P, p, s); return; }
+    if constexpr (SK == SK_FULL) load_pstate(P, p, s);
+    else {
 #pragma unroll
-    for (int i = 0; i < 9; i++) s.F[i] = P.F[i][p];
+        for (int i = 0; i < 9; i++) s.F[i] = P.F[i][p];
 #pragma unroll
-    for (int i = 0; i < 6; i++) { s.sp[i] = P.sp[i][p]; s.eplast[i] = 0.; }
-    s.pressure = 0.; s.res = 0.; s.plast = 0.;
-    s.work = P.work[p]; s.heat = P.heat[p]; s.entropy = P.entropy[p];
-    s.prevT = P.prevT[p];
+        for (int i = 0; i < 6; i++) { s.sp[i] = P.sp[i][p]; s.eplast[i] = 0.; }
+        s.pressure = 0.; s.res = 0.; s.plast = 0.;
+        s.work = P.work[p]; s.heat = P.heat[p]; s.entropy = P.entropy[p];
+        s.prevT = P.prevT[p];
 #pragma unroll
-    for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = 0.;
+        for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = 0.;
+    }
 }
 
 template <int SK>
 __device__ __forceinline__ void store_state(const Particles &P, int p, const PState &s)
 {
-    if (SK == SK_FULL) { store_pstate(P, p, s); return; }
+    if constexpr (SK == SK_FULL) store_pstate(P, p, s);
+    else {
 #pragma unroll
-    for (int i = 0; i < 9; i++) P.F[i][p] = s.F[i];
+        for (int i = 0; i < 9; i++) P.F[i][p] = s.F[i];
 #pragma unroll
-    for (int i = 0; i < 6; i++) P.sp[i][p] = s.sp[i];
-    P.work[p] = s.work; P.heat[p] = s.heat; P.entropy[p] = s.entropy;
+        for (int i = 0; i < 6; i++) P.sp[i][p] = s.sp[i];
+        P.work[p] = s.work; P.heat[p] = s.heat; P.entropy[p] = s.entropy;
+    }
 }
 
 // Pull the particle state this thread will need after its gather into L2 now (one lane per 128-byte

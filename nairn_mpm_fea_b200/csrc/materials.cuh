@@ -44,6 +44,15 @@ __device__ __forceinline__ void increment_heat_energy(PState &s, double Cv, doub
 }
 
 // Elastic::HypoIncrementDeformation (Materials/ElasticMPM.cpp:392-403): F <- (I + du) F
+// MaterialBase::GetArtificialViscosity (MaterialBaseMPM.cpp:1824-1829): Dkk = relative volume change rate (< 0), c = current
+// wave speed; material slots p[3] on/off, p[4] avA1, p[5] avA2, p[6] average cell size (MeshInfo::GetAverageCellSize)
+__device__ __forceinline__ double artificial_viscosity(double Dkk, double c, const Material &m)
+{
+    const double divuij = fabs(Dkk);
+    const double dcell = m.p[6];
+    return dcell * divuij * (m.p[4] * c + m.p[5] * dcell * divuij);
+}
+
 template <int DIM>
 __device__ __forceinline__ void hypo_increment_deformation(PState &s, const double du[9])
 {
@@ -158,7 +167,7 @@ __device__ __forceinline__ void isotropic_law(PState &s, const double du[9], int
 // Matrix3::Exponential, Common/System/Matrix3.cpp:312-353).  Residual stretch increment is 1 (no thermal load);
 // artificial viscosity is off (rejected at set-up when on).
 template <int DIM>
-__device__ __forceinline__ void neohookean_law(PState &s, const double du[9], int np, const Material &m)
+__device__ __forceinline__ void neohookean_law(PState &s, const double du[9], double delTime, int np, const Material &m)
 {
     const double Gsp = m.p[8], Ksp = m.p[9], Lamesp = m.p[10];
     const int UofJ = (int)m.p[11];
@@ -248,7 +257,12 @@ __device__ __forceinline__ void neohookean_law(PState &s, const double du[9], in
     else Kterm = 0.5 * Lamesp * (Jeff - 1. / Jeff);
     const double Pterm = J * Kterm + Jres * Gsp * ((B[XX] + B[YY] + B[ZZ]) / (3. * Jres23) - 1.);
     const double delV = 1. - 1. / detDf;
-    const double Pfinal = -Pterm;
+    double QAVred = 0., AVEnergy = 0.;          // Neohookean.cpp:261-266
+    if (delV < 0. && m.p[3] != 0.) {
+        QAVred = artificial_viscosity(delV / delTime, sqrt(Ksp * J), m);
+        AVEnergy = fabs(QAVred * delV);
+    }
+    const double Pfinal = -Pterm + QAVred;
     s.pressure = Pfinal;
     const double avgP = 0.5 * (p0 + Pfinal);
     const double dilEnergy = -avgP * delV;
@@ -274,7 +288,7 @@ __device__ __forceinline__ void neohookean_law(PState &s, const double du[9], in
     else Kratio = 0.5 * Lamesp * (Jeff + 1. / Jeff) + Gterm;
     Kratio /= Ksp;
     const double dTq0 = -J * Kratio * gamma0 * s.prevT * delV;
-    increment_heat_energy(s, Cv, dTq0, 0.);
+    increment_heat_energy(s, Cv, dTq0, AVEnergy);
 }
 
 // ---- IsoPlasticity + LinearHardening (MaterialID 9) ------------------------------------------------
@@ -286,7 +300,7 @@ __device__ __forceinline__ void neohookean_law(PState &s, const double du[9], in
 // prior shear stress uses the plastic strain (:252).
 #define MPM_SQRT_TWOTHIRDS 0.8164965809277260
 template <int DIM>
-__device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9], int np, const Material &m)
+__device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9], double delTime, int np, const Material &m)
 {
     const double Gred = m.p[8], Kred = m.p[9], yldred = m.p[10], Epred = m.p[11];
     const double gamma0 = m.p[13], Cv = m.p[1], alphaMax = m.p[14], yldredMin = m.p[15];
@@ -297,13 +311,18 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9],
     if (DIM == 3) { dgxz = de[2] + de[6]; dgyz = de[5] + de[7]; }
     const double dexxr = de[0], deyyr = de[4], dezzr = de[8];
     // UpdatePressure (:462-492)
-    const double dP = -Kred * delV;
+    double dP = -Kred * delV;
     const double dVoverV = delV;
+    double dispEnergy = 0.;
+    if (dVoverV < 0. && m.p[3] != 0.) {         // artificial viscosity (:474-479)
+        const double QAVred = artificial_viscosity(dVoverV / delTime, sqrt(Kred), m);
+        dispEnergy += fabs(QAVred * dVoverV);
+        dP += QAVred;
+    }
     s.pressure += dP;
     const double Pfinal = s.pressure;
     s.work += -Pfinal * dVoverV;
     double dTq0 = -gamma0 * s.prevT * dVoverV;
-    double dispEnergy = 0.;
     // rotate plastic strain and prior stress (:218-268)
     double *ep = s.eplast, *sp = s.sp;
     double e0[6], st0[6];
@@ -394,10 +413,10 @@ __device__ __forceinline__ void constitutive_law(PState &s, const double du[9], 
         isotropic_law<DIM>(s, du, np, m);
         break;
     case MAT_NEOHOOKEAN:
-        neohookean_law<DIM>(s, du, np, m);
+        neohookean_law<DIM>(s, du, delTime, np, m);
         break;
     case MAT_ISOPLASTICITY:
-        isoplasticity_law<DIM>(s, du, np, m);
+        isoplasticity_law<DIM>(s, du, delTime, np, m);
         break;
     default:
         break;

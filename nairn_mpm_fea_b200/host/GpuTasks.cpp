@@ -186,7 +186,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (!mpmgrid.IsStructuredEqualElementsGrid()) return "grid is not structured with equal elements";
     for (int i = 0; i < nmat; i++) {
         MaterialBase *mb = theMaterials[i];
-        if (mb->artificialViscosity) return "artificial viscosity";
+        if (mb->artificialViscosity && mb->MaterialID() != 28 && mb->MaterialID() != 9) return "artificial viscosity on this material";
         switch (mb->MaterialID()) {
         case 1: if (((IsotropicMat *)mb)->useLargeRotation) return "IsotropicMat with large rotation"; break;
         case 28: break;
@@ -236,6 +236,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         memset(&m, 0, sizeof m);
         m.p[0] = mb->rho; m.p[1] = mb->heatCapacity; m.p[2] = mb->matUsePDamping ? mb->matPdamping : -1.;
         m.n_history = mb->NumberOfHistoryDoubles();
+        if (mb->artificialViscosity) { m.p[3] = 1.; m.p[4] = mb->avA1; m.p[5] = mb->avA2; }
         if (mb->MaterialID() == 1) {
             IsotropicMat *im = (IsotropicMat *)mb;
             m.kind = MPMGPU_MAT_ISOTROPIC;

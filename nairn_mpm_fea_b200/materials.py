@@ -37,11 +37,14 @@ def xml_units(E=None, rho=None, alpha=None, Cv=None, G=None, K=None, yld=None, E
     return out
 
 
-def _base(rho, Cv, pdamping):
+def _base(rho, Cv, pdamping, av=None):
+    """av = (avA1, avA2) switches the artificial viscosity on (MaterialBaseMPM.cpp:202-216; defaults 0.2, 2.0)."""
     p = np.zeros(NPARAMS)
     p[0] = rho
     p[1] = Cv
     p[2] = -1.0 if pdamping is None else pdamping
+    if av is not None:
+        p[3], p[4], p[5] = 1.0, av[0], av[1]
     return p
 
 
@@ -118,11 +121,11 @@ def rigid_bc(direction_bits):
     return dict(kind=RIGIDBC, n_history=0, p=p, rho=1.0, wave_speed=0.0)
 
 
-def neohookean(G, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None):
+def neohookean(G, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None, av=None):
     """Neohookean (MaterialID 28): Neohookean::VerifyAndLoadProperties (Materials/Neohookean.cpp:88-141).
     History: J, Jres (both 1).  Particles start with elastic B = I in eplast (HyperElastic.cpp:51-60)."""
     Lame = K - 2.0 * G / 3.0
-    p = _base(rho, Cv, pdamping)
+    p = _base(rho, Cv, pdamping, av)
     Gsp = G / rho
     Lamesp = Lame / rho
     Ksp = Lamesp + 2.0 * Gsp / 3.0
@@ -132,11 +135,11 @@ def neohookean(G, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None):
                 init_history=[1.0, 1.0], init_eplast=[1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
 
 
-def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, yld_min=0.0):
+def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, yld_min=0.0, av=None):
     """IsoPlasticity + LinearHardening (MaterialID 9): IsoPlasticity::VerifyAndLoadProperties
     (Materials/IsoPlasticity.cpp:50-70), LinearHardening::VerifyAndLoadProperties (LinearHardening.cpp:55-80)."""
     iso = isotropic(E, nu, rho, aI, Cv, np_, pdamping)
-    p = _base(rho, Cv, pdamping)
+    p = _base(rho, Cv, pdamping, av)
     if np_ == THREED_MPM:
         C66, C33 = iso["p"][16] * rho, iso["p"][13] * rho
     else:

@@ -526,7 +526,15 @@ static void mat_mul(double a[3][3], double b[3][3], double c[3][3])
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j];
 }
 
-static void neohookean_law(int p, const double du[3][3], const mpmgpu_material *m)
+/* MaterialBase::GetArtificialViscosity, MaterialBaseMPM.cpp:1824-1829; dcell = MeshInfo::GetAverageCellSize (equal elements) */
+static double artificial_viscosity(double Dkk, double c, const mpmgpu_material *m)
+{
+    double divuij = fabs(Dkk);
+    double dcell = O->dim == 3 ? (O->cfg.gridx + O->cfg.gridy + O->cfg.gridz) / 3. : (O->cfg.gridx + O->cfg.gridy) / 2.;
+    return dcell * divuij * (m->p[4] * c + m->p[5] * dcell * divuij);
+}
+
+static void neohookean_law(int p, const double du[3][3], double delTime, const mpmgpu_material *m)
 {
     const double Gsp = m->p[8], Ksp = m->p[9], Lamesp = m->p[10], gamma0 = m->p[13], Cv = m->p[1];
     const int UofJ = (int)m->p[11];
@@ -602,7 +610,12 @@ static void neohookean_law(int p, const double du[3][3], const mpmgpu_material *
     else Kterm = 0.5 * Lamesp * (Jeff - 1. / Jeff);
     double Bxx = P3(eplast, XX, p), Byy = P3(eplast, YY, p), Bzz = P3(eplast, ZZ, p);
     double Pterm = J * Kterm + Jres * Gsp * ((Bxx + Byy + Bzz) / (3. * Jres23) - 1.);
-    double delV = 1. - 1. / detDf, Pfinal = -Pterm;
+    double delV = 1. - 1. / detDf, QAVred = 0., AVEnergy = 0.;
+    if (delV < 0. && m->p[3] != 0.) {           /* Neohookean.cpp:261-266 */
+        QAVred = artificial_viscosity(delV / delTime, sqrt(Ksp * J), m);
+        AVEnergy = fabs(QAVred * delV);
+    }
+    double Pfinal = -Pterm + QAVred;
     O->pressure[p] = Pfinal;
     double avgP = 0.5 * (p0 + Pfinal), dilEnergy = -avgP * delV, resEnergy = -avgP * (1. - 1. / dJres);
     double GJeff = resStretch * Gsp, I1third = (Bxx + Byy + Bzz) / 3.;
@@ -621,13 +634,13 @@ static void neohookean_law(int p, const double du[3][3], const mpmgpu_material *
     Kratio /= Ksp;
     double prevT = P3(energies, 5, p);
     double dTq0 = -J * Kratio * gamma0 * prevT * delV, baseHeat = -Cv * dTq0;
-    P3(energies, 2, p) += baseHeat;
+    P3(energies, 2, p) += baseHeat - AVEnergy;
     P3(energies, 3, p) += baseHeat / prevT;
 }
 
 /* ---- IsoPlasticity + LinearHardening: Materials/IsoPlasticity.cpp:128-517, LinearHardening.cpp:93-145 -------------- */
 #define SQRT_TWOTHIRDS 0.8164965809277260
-static void isoplasticity_law(int p, const double de[3][3], const mpmgpu_material *m)
+static void isoplasticity_law(int p, const double de[3][3], double delTime, const mpmgpu_material *m)
 {
     const double Gred = m->p[8], Kred = m->p[9], yldred = m->p[10], Epred = m->p[11], gamma0 = m->p[13], Cv = m->p[1];
     const double alphaMax = m->p[14], yldredMin = m->p[15];
@@ -642,10 +655,16 @@ static void isoplasticity_law(int p, const double de[3][3], const mpmgpu_materia
     double dgxy = de[0][1] + de[1][0], dgxz = 0., dgyz = 0.;
     if (!is2D) { dgxz = de[0][2] + de[2][0]; dgyz = de[1][2] + de[2][1]; }
     /* UpdatePressure */
-    O->pressure[p] += -Kred * delV;
+    double dP = -Kred * delV, dispEnergy = 0.;
+    if (delV < 0. && m->p[3] != 0.) {           /* IsoPlasticity::UpdatePressure :474-479 */
+        double QAVred = artificial_viscosity(delV / delTime, sqrt(Kred), m);
+        dispEnergy += fabs(QAVred * delV);
+        dP += QAVred;
+    }
+    O->pressure[p] += dP;
     double Pfinal = O->pressure[p], prevT = P3(energies, 5, p);
     P3(energies, 0, p) += -Pfinal * delV;
-    double dTq0 = -gamma0 * prevT * delV, dispEnergy = 0.;
+    double dTq0 = -gamma0 * prevT * delV;
     double e0[6], s0[6], st0[6];
     for (int c = 0; c < 6; c++) { e0[c] = P3(eplast, c, p); s0[c] = P3(sp, c, p); st0[c] = s0[c]; }
     double dwxy = de[1][0] - de[0][1];
@@ -808,8 +827,8 @@ static void full_strain_update(double strainTime, int postUpdate)
         for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) dv[a][b] *= strainTime;
         const mpmgpu_material *m = &O->mats[O->matnum[p] - 1];
         if (m->kind == MPMGPU_MAT_ISOTROPIC) isotropic_law(p, dv, m);
-        else if (m->kind == MPMGPU_MAT_NEOHOOKEAN) neohookean_law(p, dv, m);
-        else if (m->kind == MPMGPU_MAT_ISOPLASTICITY) isoplasticity_law(p, dv, m);
+        else if (m->kind == MPMGPU_MAT_NEOHOOKEAN) neohookean_law(p, dv, strainTime, m);
+        else if (m->kind == MPMGPU_MAT_ISOPLASTICITY) isoplasticity_law(p, dv, strainTime, m);
     }
 }
 

@@ -310,7 +310,7 @@ int ref_get_materials(int *ids, double *params)
         q[0] = m->rho; q[1] = m->heatCapacity; q[2] = m->GetField();
         q[3] = m->matUsePDamping ? m->matPdamping : -1.;
         q[4] = m->IsRigid() ? 1. : 0.;
-        q[5] = m->artificialViscosity ? 1. : 0.;
+        q[5] = m->artificialViscosity ? 1. : 0.; q[6] = m->avA1; q[7] = m->avA2;
         if (ids[i] == 1) {
             IsotropicMat *im = (IsotropicMat *)m;
             q[8] = im->E; q[9] = im->nu; q[10] = im->G; q[11] = im->CTE3; q[12] = im->gamma0;

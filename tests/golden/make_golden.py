@@ -37,6 +37,8 @@ CASES = {
     "block3d_lcpdi_rcrit": (inputs.block3d(ncell=3, margin=3, gimp="lCPDI", E=50.0, vz=-2.0e4, vx=1.0e4, extra_header="<CPDIrcrit>0.6</CPDIrcrit>"), (1, 40), 1, 0.3, 5000.0),
     "disks2d_lcpdi": (inputs.disks2d(analysis=10, gimp="lCPDI"), (1, 100), 1),
     "disks2d_qcpdi": (inputs.disks2d(analysis=10, gimp="qCPDI"), (1, 100), 1),
+    "block3d_neohookean_av": (inputs.block3d(ncell=3, margin=3, material=inputs.neohookean_material(av=(0.3, 1.5)), vz=-3.0e4, vx=4.0e3), (1, 40), 1, 0.3, 3000.0),
+    "block3d_isoplastic_av": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_material(av=(0.2, 2.0)), vz=-5.0e4), (1, 40), 1, 0.3, 3000.0),
     "block3d_rigid_wall": (inputs.block3d(ncell=4, margin=3, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
                                           rigid=("wall", 4, (0.0, 0.0, 0.0))), (1, 2, 80), 2, 0.3, 2000.0),
     "block3d_rigid_wall_lattice": (inputs.block3d(ncell=2, margin=3, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,

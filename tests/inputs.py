@@ -120,12 +120,21 @@ ISOPLASTIC_MAT = ('<Material Type="9" Name="Blk"><rho>%r</rho><E>%r</E><nu>%r</n
                   '<Hardening>Linear</Hardening><yield>%r</yield><Ep>%r</Ep></Material>')
 
 
-def neohookean_material(G=40.0, K=200.0, ujoption=None):
-    return NEOHOOKEAN_MAT % (G, K, "" if ujoption is None else "<UJOption>%d</UJOption>" % ujoption)
+AV_TAGS = "<ArtificialVisc/><avA1>%r</avA1><avA2>%r</avA2>"
 
 
-def isoplastic_material(rho=2.0, E=2000.0, nu=0.33, yld=20.0, Ep=100.0):
-    return ISOPLASTIC_MAT % (rho, E, nu, yld, Ep)
+def neohookean_material(G=40.0, K=200.0, ujoption=None, av=None):
+    extra = "" if ujoption is None else "<UJOption>%d</UJOption>" % ujoption
+    if av is not None:
+        extra += AV_TAGS % av
+    return NEOHOOKEAN_MAT % (G, K, extra)
+
+
+def isoplastic_material(rho=2.0, E=2000.0, nu=0.33, yld=20.0, Ep=100.0, av=None):
+    m = ISOPLASTIC_MAT % (rho, E, nu, yld, Ep)
+    if av is not None:
+        m = m.replace("</Material>", AV_TAGS % av + "</Material>")
+    return m
 
 
 def periodic_xpic(order, fmpm=False, periodic_steps=1):
