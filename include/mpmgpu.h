@@ -195,6 +195,9 @@ int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, const doubl
                             const double *value, const int *active, const int *symdir);
 /* update only the values/active flags of the BC list set above (same n, same order) */
 int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const double *value, const int *active);
+/* velocities [3][n_rigid] of the rigid-BC particles (host order) for this step: the host evaluates the material's
+ * setting functions (RigidMaterial::GetVectorSetting, Materials/RigidMaterial.cpp:376-531) before the projection task */
+int mpmgpu_update_rigid_velocities(mpmgpu_ctx *ctx, int n_rigid, const double *vel);
 
 /* ---- the step ---------------------------------------------------------------------------- */
 /* nsteps full MPMSteps (tasks 1-9, 11) with the configured method; mtime advances by dt each step */

@@ -26,7 +26,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
            "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
-           "mpmgpu_update_velocity_bc_values", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
+           "mpmgpu_update_velocity_bc_values", "mpmgpu_update_rigid_velocities", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
     "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times",
@@ -98,6 +98,7 @@ def load_library(path=None):
     lib.mpmgpu_set_xpic.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
     lib.mpmgpu_update_velocity_bc_values.argtypes = [vp, C.c_int, _dp, _ip]
+    lib.mpmgpu_update_rigid_velocities.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_step.argtypes = [vp, C.c_int]
     for t in TASKS + ["project_rigid_bcs"]:
         getattr(lib, "mpmgpu_task_" + t).argtypes = [vp]
@@ -237,6 +238,11 @@ class MpmGpu:
     def update_velocity_bc_values(self, value, active=None):
         value, active = _c64(value), _c32(active)
         self._check(self.lib.mpmgpu_update_velocity_bc_values(self.ctx, len(value), _d(value), _i(active)))
+
+    def update_rigid_velocities(self, vel):
+        """vel [3][n_rigid]: this step's velocities of the rigid-BC particles (setting functions evaluated by the host)."""
+        vel = _c64(vel)
+        self._check(self.lib.mpmgpu_update_rigid_velocities(self.ctx, int(vel.shape[-1]), _d(vel)))
 
     def set_time_step(self, dt, dt_first, dt_last):
         self._check(self.lib.mpmgpu_set_time_step(self.ctx, dt, dt_first, dt_last))

@@ -579,6 +579,20 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
     return MPMGPU_OK;
 }
 
+// Rigid-BC particles whose material has setting functions: the host evaluates them each step
+// (RigidMaterial::GetVectorSetting, Materials/RigidMaterial.cpp:376-531) and hands over the velocities
+extern "C" int mpmgpu_update_rigid_velocities(mpmgpu_ctx *ctx, int n_rigid, const double *vel)
+{
+    if (!ctx || !vel) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_rigid_velocities: null argument");
+    if (!ctx->uploaded || n_rigid != ctx->PR.n) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_rigid_velocities: %d velocities for %d rigid particles", n_rigid, ctx ? ctx->PR.n : 0);
+    if (n_rigid == 0) return MPMGPU_OK;
+    cudaSetDevice(ctx->cfg.device);
+    for (int c = 0; c < 3; c++)
+        CK(cudaMemcpyAsync(ctx->PR.vel[c], vel + (size_t)c * n_rigid, (size_t)n_rigid * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
 extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const double *value, const int *active)
 {
     if (!ctx || n != ctx->nBCEntries) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_velocity_bc_values: n=%d but %d BCs are set", n, ctx ? ctx->nBCEntries : 0);

@@ -56,6 +56,7 @@ mpmgpu_ctx *gCtx = NULL;
 bool gHostStale = false;            // device is ahead of mpm[]
 std::vector<NodalVelBC *> gBCs;     // host BC list in list order
 bool gBCsVary = false;
+bool gRigidFunctions = false;       // some rigid-BC material sets its velocity by functions of time and position
 bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
 void check(int rc, const char *where)
@@ -110,8 +111,25 @@ class GpuTask : public MPMTask
         for (size_t i = 0; i < gBCs.size(); i++) { a[i] = gBCs[i]->GetNodeNum(mtime) > 0; v[i] = a[i] ? gBCs[i]->BCValue(mtime) : 0.; }
         check(mpmgpu_update_velocity_bc_values(gCtx, (int)v.size(), v.data(), a.data()), "GpuTask(BC values)");
     }
+    // RigidMaterial::GetVectorSetting evaluated by the reference's own Expression objects (ProjectRigidBCsTask.cpp:75-93)
+    void UpdateRigidVelocities(void)
+    {
+        if (!gRigidFunctions) return;
+        const int nr = nmpms - nmpmsRC;
+        std::vector<double> v(3 * (size_t)nr);
+        for (int p = nmpmsRC; p < nmpms; p++) {
+            MPMBase *m = mpm[p];
+            bool hasDir[3];
+            ((RigidMaterial *)theMaterials[m->MatID()])->GetVectorSetting(&m->vel, hasDir, mtime, &m->pos);
+            const int j = p - nmpmsRC;
+            v[j] = m->vel.x; v[nr + j] = m->vel.y; v[2 * (size_t)nr + j] = m->vel.z;
+        }
+        check(mpmgpu_update_rigid_velocities(gCtx, nr, v.data()), "GpuTask(rigid velocities)");
+    }
     void AfterStep(void)
     {
+        if (gRigidFunctions)        // keep the host copy of the rigid positions current for the next evaluation
+            for (int p = nmpmsRC; p < nmpms; p++) mpm[p]->MovePosition(timestep);
         gHostStale = true;
         // will the reference archive after this step?  (ArchiveResults(mtime+timestep,...), ArchiveData.cpp:731-746)
         const double atime = mtime + timestep;
@@ -125,6 +143,7 @@ class GpuTask : public MPMTask
             if (which == G_INIT) {
                 check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(step)");
                 UpdateBCValues();
+                UpdateRigidVelocities();
                 check(mpmgpu_step(gCtx, 1), "GpuTask(step)");
             } else if (which == G_RESET) AfterStep();
             return true;
@@ -135,7 +154,10 @@ class GpuTask : public MPMTask
             check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(Initialize)");
             check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)");
             break;
-        case G_RIGIDBC: check(mpmgpu_task_project_rigid_bcs(gCtx), "GpuTask(ProjectRigidBCs)"); break;
+        case G_RIGIDBC:
+            UpdateRigidVelocities();
+            check(mpmgpu_task_project_rigid_bcs(gCtx), "GpuTask(ProjectRigidBCs)");
+            break;
         case G_MASSMOM: check(mpmgpu_task_mass_and_momentum(gCtx), "GpuTask(MassAndMomentum)"); break;
         case G_POSTEXTRAP:
             UpdateBCValues();
@@ -197,8 +219,9 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         case 11: {
             RigidMaterial *rm = (RigidMaterial *)mb;
             if (!rm->IsRigidBC()) return "rigid contact material";
-            if (rm->function != NULL || rm->function2 != NULL || rm->function3 != NULL || rm->Vfunction != NULL) return "rigid material with setting functions";
+            if (rm->Vfunction != NULL || rm->useControlVelocity) return "rigid material with value function or control velocity";
             if (rm->mirrored != 0 || rm->setTemperature || rm->setConcentration) return "rigid material with mirrored / temperature / concentration";
+            if (rm->function != NULL) gRigidFunctions = true;
             break;
         }
         default: return "material type";

@@ -17,7 +17,8 @@ def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy
 
     rigid = (where, set_direction, (vx, vy, vz)) adds a one-cell-thick plate of rigid-BC particles
     (RigidMaterial, Type 11) under ("wall") or on top of ("piston") the block, one cell wider than it
-    (BASELINE config 4 family: Taylor bar against a rigid wall).
+    (BASELINE config 4 family: Taylor bar against a rigid wall).  A fourth entry lists setting functions of time (ms) and
+    position for the controlled directions (RigidMaterial SettingFunction, SettingFunction2, ...).
     """
     n = ncell + 2 * margin
     lo, hi = margin, margin + ncell
@@ -39,11 +40,13 @@ def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy
         damp += "<PDamping>%r</PDamping>" % pdamping
     rigid_body = ""
     if rigid:
-        where, setdir, rv = rigid
+        where, setdir, rv = rigid[:3]
         z0, z1 = (lo - 1, lo) if where == "wall" else (hi, hi + 1)
         rigid_body = ('<Body matname="Plate" vx="%r" vy="%r" vz="%r"><Box xmin="%d" xmax="%d" ymin="%d" ymax="%d" zmin="%d" zmax="%d"/></Body>'
                       % (rv[0], rv[1], rv[2], lo - 1, hi + 1, lo - 1, hi + 1, z0, z1))
-        mat += '<Material Type="11" Name="Plate"><SetDirection>%d</SetDirection></Material>' % setdir
+        fxn = "".join("<SettingFunction%s>%s</SettingFunction%s>" % ("" if i == 0 else str(i + 1), f, "" if i == 0 else str(i + 1))
+                      for i, f in enumerate(rigid[3])) if len(rigid) > 3 else ""
+        mat += '<Material Type="11" Name="Plate"><SetDirection>%d</SetDirection>%s</Material>' % (setdir, fxn)
     return """<?xml version='1.0'?>
 <!DOCTYPE JANFEAInput SYSTEM "NairnMPM.dtd">
 <JANFEAInput version='3'>

@@ -25,6 +25,10 @@ CASES = {
     "block3d_neo_lcpdi_xpic2": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, gimp="lCPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3,
                                                custom_tasks=inputs.periodic_xpic(2, False, 1))
                                 .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
+    # a rigid piston whose velocity follows setting functions of time and position (evaluated by the host every step)
+    "block3d_rigid_piston_functions": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=0.0,
+                                                      rigid=("piston", 5, (0.0, 0.0, 0.0), ("300*sin(40*t)*(1+0.05*y)", "-9000*(1-exp(-t/0.004))")))
+                                       .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
     # config 4 family: IsoPlasticity bar on a plate of rigid-BC particles
     "block3d_isoplastic_rigid_wall": (inputs.block3d(ncell=4, margin=3, maxtime=0.02, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
                                                      rigid=("wall", 4, (0.0, 0.0, 0.0)))
