@@ -37,6 +37,16 @@ CASES = {
     "block3d_lcpdi_rcrit": (inputs.block3d(ncell=3, margin=3, gimp="lCPDI", E=50.0, vz=-2.0e4, vx=1.0e4, extra_header="<CPDIrcrit>0.6</CPDIrcrit>"), (1, 40), 1, 0.3, 5000.0),
     "disks2d_lcpdi": (inputs.disks2d(analysis=10, gimp="lCPDI"), (1, 100), 1),
     "disks2d_qcpdi": (inputs.disks2d(analysis=10, gimp="qCPDI"), (1, 100), 1),
+    # small cases for the particle-update / post-extrapolation variants (PIC = XPIC(1), FMPM(1), USAVG- and USL- with and
+    # without higher-order velocity extrapolation)
+    "block3d_pic": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(1, False, 1)), (1, 30), 1, 0.3, 3000.0),
+    "block3d_fmpm1": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(1, True, 1)), (1, 30), 1, 0.3, 3000.0),
+    "block3d_usavg_minus": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, extra_header="<SkipPostExtrapolation/>"), (1, 30), 1, 0.3, 3000.0),
+    "block3d_usavg_minus_xpic2": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, extra_header="<SkipPostExtrapolation/>",
+                                                 custom_tasks=inputs.periodic_xpic(2, False, 1)), (1, 2, 30), 2, 0.3, 3000.0),
+    "block3d_usl_minus_fmpm2": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, method=3, extra_header="<SkipPostExtrapolation/>",
+                                               custom_tasks=inputs.periodic_xpic(2, True, 1)), (1, 2, 30), 2, 0.3, 3000.0),
+    "block3d_usf_fmpm2": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, method=0, custom_tasks=inputs.periodic_xpic(2, True, 1)), (1, 2, 30), 2, 0.3, 3000.0),
     "block3d_neohookean_av": (inputs.block3d(ncell=3, margin=3, material=inputs.neohookean_material(av=(0.3, 1.5)), vz=-3.0e4, vx=4.0e3), (1, 40), 1, 0.3, 3000.0),
     "block3d_isoplastic_av": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_material(av=(0.2, 2.0)), vz=-5.0e4), (1, 40), 1, 0.3, 3000.0),
     "block3d_rigid_wall": (inputs.block3d(ncell=4, margin=3, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
