@@ -868,7 +868,9 @@ static int sort_particles(mpmgpu_ctx *ctx)
         CK(dalloc(ctx, (char **)&t.cubTemp, t.cubTempBytes));
         t.cap = ctx->cap;
     }
-    LAUNCH(k_sort_keys, nblocks(n, 256), 256, ctx->g, ctx->P, t.keysIn, t.idxIn);
+    const char *leadEnv = getenv("MPMGPU_SORT_LEAD");        // fraction of the sort interval to look ahead (default 0.5)
+    const double lead = (leadEnv ? atof(leadEnv) : 0.5) * t.sortInterval * ctx->sp.dt;
+    LAUNCH(k_sort_keys, nblocks(n, 256), 256, ctx->g, ctx->P, t.keysIn, t.idxIn, lead);
     int bits = 1;
     while ((1ll << bits) < (long long)ctx->g.nnodes + (n - ctx->P.nNR) + 1) bits++;
     CK(cub::DeviceRadixSort::SortPairs(t.cubTemp, t.cubTempBytes, t.keysIn, t.keysOut, t.idxIn, t.idxOut, n, 0, bits, ctx->stream));

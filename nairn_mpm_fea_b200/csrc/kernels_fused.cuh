@@ -1065,14 +1065,22 @@ __global__ void k_n_grid_velocity(int n0, int nnodes, Nodes N, FusedNodes FN)
 }
 
 // ---- physical sort by dual cell -----------------------------------------------------------------------
-__global__ void k_sort_keys(Grid g, Particles P, int *keys, int *idx)
+// lead = half a sort interval: the particles are ordered by the dual cell they will be in halfway to the next sort, so
+// the order is most accurate in the middle of the interval instead of decaying from the sort onwards (the kernels
+// group by the ACTUAL dual cell, so the order only affects speed)
+__global__ void k_sort_keys(Grid g, Particles P, int *keys, int *idx, double lead)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     int key;
     if (p < P.nNR) {
-        const int e = P.elem[p];
+        int e = P.elem[p];
         double pos[3] = {P.pos[0][p], P.pos[1][p], P.pos[2][p]};
+        if (lead > 0.) {
+            double ahead[3] = {pos[0] + lead * P.vel[0][p], pos[1] + lead * P.vel[1][p], pos[2] + lead * P.vel[2][p]};
+            const int e2 = find_element_from_point<3>(g, ahead);
+            if (e2 > 0 && !edge_element<3>(g, e2)) { e = e2; pos[0] = ahead[0]; pos[1] = ahead[1]; pos[2] = ahead[2]; }
+        }
         double xi[3];
         get_xipos<3>(g, e, pos, xi);
         const ElemIJK c = elem_ijk(g, e);
