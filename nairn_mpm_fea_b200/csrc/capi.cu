@@ -875,7 +875,16 @@ static int sort_particles(mpmgpu_ctx *ctx)
     while ((1ll << bits) < (long long)ctx->g.nnodes + (n - ctx->P.nNR) + 1) bits++;
     CK(cub::DeviceRadixSort::SortPairs(t.cubTemp, t.cubTempBytes, t.keysIn, t.keysOut, t.idxIn, t.idxOut, n, 0, bits, ctx->stream));
     ctx->launches += 4;
-    LAUNCH(k_permute_pool, nblocks(n, 256), 256, n, ctx->cap, NPD, ctx->particlePool, t.altPool, NPI, ctx->particleIntPool, t.altIntPool, t.idxOut);
+    // field order = bind_particles: pos 0-2 vel 3-5 mp 6 lp 7-9 ncpos 10-12 F 13-21 sp 22-27 pressure 28 eplast 29-34 work 35 res 36
+    // heat 37 entropy 38 plast 39 prevT 40 hist 41-44 pfext 45-47 acc 48-50 | ints: elem mat cross orig key.
+    // ncpos, key (F1 rewrites them right after the sort) and acc (F3 writes it before anyone reads it) never move; with
+    // IsotropicMat only, eplast, the plastic energy and the history are zero in both pools; likewise pfext without particle loads.
+    unsigned long long live = (1ull << NPD) - 1ull;
+    live &= ~(7ull << 10); live &= ~(7ull << 48);
+    if (t.stateKind == SK_ELASTIC) { live &= ~(63ull << 29); live &= ~(1ull << 39); live &= ~(15ull << 41); }
+    if (!ctx->hasFext) live &= ~(7ull << 45);
+    const unsigned ilive = 0xfu;
+    LAUNCH(k_permute_pool, nblocks(n, 256), 256, n, ctx->cap, NPD, live, ctx->particlePool, t.altPool, NPI, ilive, ctx->particleIntPool, t.altIntPool, t.idxOut);
     std::swap(ctx->particlePool, t.altPool);
     std::swap(ctx->particleIntPool, t.altIntPool);
     int nn = ctx->P.n, nnr = ctx->P.nNR;

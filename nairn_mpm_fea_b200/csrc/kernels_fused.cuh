@@ -1092,12 +1092,14 @@ __global__ void k_sort_keys(Grid g, Particles P, int *keys, int *idx, double lea
     idx[p] = p;
 }
 
-__global__ void k_permute_pool(int n, size_t stride, int nd, const double *__restrict__ src, double *__restrict__ dst,
-                               int ni, const int *__restrict__ isrc, int *__restrict__ idst, const int *__restrict__ perm)
+// live: bit f set = double field f carries information at sort time (fields that are recomputed before their next
+// read, or that the materials in use never touch, stay behind: both pools hold the same zeros there)
+__global__ void k_permute_pool(int n, size_t stride, int nd, unsigned long long live, const double *__restrict__ src, double *__restrict__ dst,
+                               int ni, unsigned ilive, const int *__restrict__ isrc, int *__restrict__ idst, const int *__restrict__ perm)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int q = perm[p];
-    for (int f = 0; f < nd; f++) dst[(size_t)f * stride + p] = src[(size_t)f * stride + q];
-    for (int f = 0; f < ni; f++) idst[(size_t)f * stride + p] = isrc[(size_t)f * stride + q];
+    for (int f = 0; f < nd; f++) if (live >> f & 1ull) dst[(size_t)f * stride + p] = src[(size_t)f * stride + q];
+    for (int f = 0; f < ni; f++) if (ilive >> f & 1u) idst[(size_t)f * stride + p] = isrc[(size_t)f * stride + q];
 }
