@@ -228,8 +228,6 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
         int k = mats[i].kind;
         if (k != MAT_ISOTROPIC && k != MAT_RIGIDBC && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY)
             return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d is not supported (IsotropicMat 1, IsoPlasticity 9, rigid BC 11, Neohookean 28)", k);
-        if (k == MAT_ISOPLASTICITY && ctx->cfg.np == MPMGPU_PLANE_STRESS_MPM)
-            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: IsoPlasticity in plane stress (numerical return map) is not built");
         if (mats[i].n_history < 0 || mats[i].n_history > MPM_MAX_HISTORY) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: %d history doubles (max %d)", mats[i].n_history, MPM_MAX_HISTORY);
         ctx->hMats[i].kind = k; ctx->hMats[i].nhist = mats[i].n_history;
         memcpy(ctx->hMats[i].p, mats[i].p, sizeof(double) * MPM_MAT_NPARAMS);

@@ -294,8 +294,8 @@ __device__ __forceinline__ void neohookean_law(PState &s, const double du[9], do
 // ---- IsoPlasticity + LinearHardening (MaterialID 9) ------------------------------------------------
 // IsoPlasticity::MPMConstitutiveLaw / PlasticityConstLaw / UpdatePressure (Materials/IsoPlasticity.cpp:128-492),
 // small-rotation branch, J2 potential (:513-517), closed-form radial return of LinearHardening
-// (Materials/LinearHardening.cpp:93-145), history = cumulative plastic strain alpha.  3D and plane strain
-// (plane-stress plasticity needs the numerical return map and is rejected at set-up).
+// (Materials/LinearHardening.cpp:93-145), history = cumulative plastic strain alpha.  3D, plane strain and plane stress
+// (the latter with the numerical solve for lambda of HardeningLawBase::SolveForLambda).
 // Reference quirks kept: 3D plastic-step work energy adds sp.zz*de.zz twice (:428-431); the 2D rotation of the
 // prior shear stress uses the plastic strain (:252).
 #define MPM_SQRT_TWOTHIRDS 0.8164965809277260
@@ -305,7 +305,11 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9],
     const double Gred = m.p[8], Kred = m.p[9], yldred = m.p[10], Epred = m.p[11];
     const double gamma0 = m.p[13], Cv = m.p[1], alphaMax = m.p[14], yldredMin = m.p[15];
     hypo_increment_deformation<DIM>(s, de);
-    const double delV = de[0] + de[4] + de[8];          // du.trace() - 3 eres, eres = 0
+    // plane stress terms (IsoPlasticity::GetCopyOfMechanicalProps :551-556)
+    const bool planeStress = DIM == 2 && np == NP_PLANE_STRESS;
+    const double psRed = 1. / (Kred / (2. * Gred) + 2. / 3.), psLr2G = (Kred / (2. * Gred) - 1. / 3.) * psRed, psKred = Kred * psRed;
+    const double delV = planeStress ? psRed * (de[0] + de[4]) : de[0] + de[4] + de[8];          // :171-174 (eres = 0)
+    const double P0 = s.pressure;
     const double dgxy = de[1] + de[3];
     double dgxz = 0., dgyz = 0.;
     if (DIM == 3) { dgxz = de[2] + de[6]; dgyz = de[5] + de[7]; }
@@ -320,7 +324,7 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9],
         dP += QAVred;
     }
     s.pressure += dP;
-    const double Pfinal = s.pressure;
+    double Pfinal = s.pressure;
     s.work += -Pfinal * dVoverV;
     double dTq0 = -gamma0 * s.prevT * dVoverV;
     // rotate plastic strain and prior stress (:218-268)
@@ -352,7 +356,7 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9],
     double strial[6];
     strial[XX] = st0[XX] + 2. * Gred * (dexxr - thirdDelV);
     strial[YY] = st0[YY] + 2. * Gred * (deyyr - thirdDelV);
-    strial[ZZ] = st0[ZZ] + 2. * Gred * (dezzr - thirdDelV);
+    strial[ZZ] = st0[ZZ] + (planeStress ? Pfinal - P0 : 2. * Gred * (dezzr - thirdDelV));       // :275-278
     strial[XY] = st0[XY] + Gred * dgxy;
     strial[YZ] = DIM == 3 ? st0[YZ] + Gred * dgyz : st0[YZ];
     strial[XZ] = DIM == 3 ? st0[XZ] + Gred * dgxz : st0[XZ];
@@ -368,20 +372,71 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9],
 #pragma unroll
         for (int i = 0; i < 6; i++) sp[i] = strial[i];
         if (DIM == 3) s.work += sp[XX] * de[0] + sp[YY] * de[4] + sp[ZZ] * de[8] + sp[YZ] * dgyz + sp[XZ] * dgxz + sp[XY] * dgxy;
-        else s.work += sp[XX] * de[0] + sp[YY] * de[4] + sp[XY] * dgxy;
+        else {
+            if (planeStress) {          // zz deformation (:315-320), MPMBase::IncrementDeformationGradientZZ
+                const double dezz = -psLr2G * (dexxr + deyyr);
+                s.F[8] += dezz * s.F[8];
+            }
+            s.work += sp[XX] * de[0] + sp[YY] * de[4] + sp[XY] * dgxy;
+        }
         increment_heat_energy(s, Cv, dTq0, dispEnergy);
         return;
     }
-    // radial return, closed form (LinearHardening.cpp:124-145)
-    double lambdak = (smag - MPM_SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
-    if (alpha0 + MPM_SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - MPM_SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
-    const double alpint = alpha0 + MPM_SQRT_TWOTHIRDS * lambdak;
-    // df/dsigma = s/|s| (:496-509), plastic strain increment (:395-405)
+    double lambdak, alpint, dfds[6], dezzTotal = de[8];
+    double spPS[4] = {0., 0., 0., 0.};
+    if (planeStress) {
+        // plane stress: the return direction changes with lambda; unbracketed Newton of HardeningLawBase::SolveForLambda
+        // (HardeningLawBase.cpp:157-202, chosen by LinearHardening.cpp:128-131)
+        lambdak = 0.;
+        alpint = alpha0;
+        double n2trial = -strial[XX] + strial[YY];
+        n2trial *= n2trial / 2;
+        n2trial += 2. * strial[XY] * strial[XY];
+        double n1trial = strial[XX] + strial[YY] - 2. * Pfinal;
+        n1trial *= n1trial / 6.;
+        for (int step = 1;;) {
+            const double d1 = (1 + psKred * lambdak), d2 = (1. + 2. * Gred * lambdak);
+            const double fnp12 = n1trial / (d1 * d1) + n2trial / (d2 * d2);
+            const double kyld = alpint < alphaMax ? yldred + Epred * alpint : yldredMin;
+            const double glam = 0.5 * fnp12 - kyld * kyld / 3.;
+            const double fnp1 = sqrt(fnp12);
+            const double k2prime = alpint < alphaMax ? 0.5443310539518174 * (yldred + Epred * alpint) * Epred * fnp1 : 0.;    // GetK2Prime
+            const double slope = -(psKred * n1trial / (d1 * d1 * d1) + 2 * Gred * n2trial / (d2 * d2 * d2)) - k2prime;
+            const double delLam = -glam / slope;
+            lambdak += delLam;
+            alpint = alpha0 + MPM_SQRT_TWOTHIRDS * lambdak * fnp1;          // UpdateTrialAlpha, plane stress
+            if (step++ > 20 || fabs(delLam / lambdak) < 0.0001) break;      // LambdaConverged
+        }
+        // final stress and direction (:345-389)
+        const double d1 = (1. + psKred * lambdak), d2 = (1. + 2. * Gred * lambdak);
+        const double n1 = (strial[XX] + strial[YY] - 2. * Pfinal) / d1, n2 = (-strial[XX] + strial[YY]) / d2;
+        const double sxx = (n1 - n2) / 2., syy = (n1 + n2) / 2., txy = strial[XY] / d2;
+        dfds[XX] = (2. * sxx - syy) / 3.; dfds[YY] = (2. * syy - sxx) / 3.; dfds[ZZ] = -(dfds[XX] + dfds[YY]); dfds[XY] = txy;
+        dfds[XZ] = 0.; dfds[YZ] = 0.;
+        const double dPps = -n1 / 3. - Pfinal;
+        s.pressure += dPps;
+        const double dezzp = lambdak * dfds[ZZ];
+        const double dVtot = delV + psRed * dezzp;
+        s.work += -Pfinal * psRed * dezzp - dPps * dVtot;
+        Pfinal = s.pressure;
+        dezzTotal = -psLr2G * (dexxr + deyyr - lambdak * (dfds[XX] + dfds[YY])) + dezzp;
+        s.F[8] += dezzTotal * s.F[8];
+        dTq0 -= gamma0 * s.prevT * dezzp;
+        spPS[0] = sxx + Pfinal; spPS[1] = syy + Pfinal; spPS[2] = Pfinal; spPS[3] = txy;
+    } else {
+        // radial return, closed form (LinearHardening.cpp:124-145)
+        lambdak = (smag - MPM_SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
+        if (alpha0 + MPM_SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - MPM_SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
+        alpint = alpha0 + MPM_SQRT_TWOTHIRDS * lambdak;
+#pragma unroll
+        for (int i = 0; i < 6; i++) dfds[i] = strial[i] / smag;           // df/dsigma = s/|s| (:496-509)
+    }
+    // plastic strain increment (:395-405)
     double dep[6];
-    dep[XX] = lambdak * (strial[XX] / smag); dep[YY] = lambdak * (strial[YY] / smag); dep[ZZ] = lambdak * (strial[ZZ] / smag);
-    dep[XY] = 2. * lambdak * (strial[XY] / smag);
-    dep[XZ] = DIM == 3 ? 2. * lambdak * (strial[XZ] / smag) : 0.;
-    dep[YZ] = DIM == 3 ? 2. * lambdak * (strial[YZ] / smag) : 0.;
+    dep[XX] = lambdak * dfds[XX]; dep[YY] = lambdak * dfds[YY]; dep[ZZ] = lambdak * dfds[ZZ];
+    dep[XY] = 2. * lambdak * dfds[XY];
+    dep[XZ] = DIM == 3 ? 2. * lambdak * dfds[XZ] : 0.;
+    dep[YZ] = DIM == 3 ? 2. * lambdak * dfds[YZ] : 0.;
     ep[XX] += dep[XX]; ep[YY] += dep[YY]; ep[ZZ] += dep[ZZ]; ep[XY] += dep[XY];
     if (DIM == 3) { ep[XZ] += dep[XZ]; ep[YZ] += dep[YZ]; }
     sp[XX] = strial[XX] - 2. * Gred * dep[XX];
@@ -389,9 +444,10 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9],
     sp[ZZ] = strial[ZZ] - 2. * Gred * dep[ZZ];
     sp[XY] = strial[XY] - Gred * dep[XY];
     if (DIM == 3) { sp[YZ] = strial[YZ] - Gred * dep[YZ]; sp[XZ] = strial[XZ] - Gred * dep[XZ]; }
+    if (planeStress) { sp[XX] = spPS[0]; sp[YY] = spPS[1]; sp[ZZ] = spPS[2]; sp[XY] = spPS[3]; }      // set by the plane-stress return (:386-389)
     double workEnergy = sp[XX] * de[0] + sp[YY] * de[4] + sp[XY] * dgxy;
     if (DIM == 3) workEnergy += sp[ZZ] * de[8] + sp[YZ] * dgyz + sp[XZ] * dgxz;
-    if (np != NP_PLANE_STRAIN) workEnergy += sp[ZZ] * de[8];
+    if (np != NP_PLANE_STRAIN) workEnergy += sp[ZZ] * dezzTotal;
     s.work += workEnergy;
     double plastEnergy = sp[XX] * dep[XX] + sp[YY] * dep[YY] + sp[ZZ] * dep[ZZ] + sp[XY] * dep[XY];
     if (DIM == 3) plastEnergy += sp[XZ] * dep[XZ] + sp[YZ] * dep[YZ];

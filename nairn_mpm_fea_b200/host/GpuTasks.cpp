@@ -214,7 +214,6 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         case 28: break;
         case 9:
             if (dynamic_cast<LinearHardening *>(((IsoPlasticity *)mb)->plasticLaw) == NULL) return "IsoPlasticity hardening law other than Linear";
-            if (fmobj->np == PLANE_STRESS_MPM) return "IsoPlasticity in plane stress";
             break;
         case 11: {
             RigidMaterial *rm = (RigidMaterial *)mb;

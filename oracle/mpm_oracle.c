@@ -651,9 +651,13 @@ static void isoplasticity_law(int p, const double de[3][3], double delTime, cons
     if (is2D) { dF[0][2] = dF[2][0] = dF[1][2] = dF[2][1] = 0.; }
     mat_mul(dF, F, Fn);
     set_F(p, Fn);
-    double delV = de[0][0] + de[1][1] + de[2][2];
+    /* plane stress terms (IsoPlasticity::GetCopyOfMechanicalProps :551-556) */
+    const int planeStress = O->cfg.np == MPMGPU_PLANE_STRESS_MPM;
+    const double psRed = 1. / (Kred / (2. * Gred) + 2. / 3.), psLr2G = (Kred / (2. * Gred) - 1. / 3.) * psRed, psKred = Kred * psRed;
+    double delV = planeStress ? psRed * (de[0][0] + de[1][1]) : de[0][0] + de[1][1] + de[2][2];       /* :171-174, eres = 0 */
     double dgxy = de[0][1] + de[1][0], dgxz = 0., dgyz = 0.;
     if (!is2D) { dgxz = de[0][2] + de[2][0]; dgyz = de[1][2] + de[2][1]; }
+    const double P0 = O->pressure[p];
     /* UpdatePressure */
     double dP = -Kred * delV, dispEnergy = 0.;
     if (delV < 0. && m->p[3] != 0.) {           /* IsoPlasticity::UpdatePressure :474-479 */
@@ -689,7 +693,7 @@ static void isoplasticity_law(int p, const double de[3][3], double delTime, cons
     double third = delV / 3., strial[6];
     strial[XX] = st0[XX] + 2. * Gred * (de[0][0] - third);
     strial[YY] = st0[YY] + 2. * Gred * (de[1][1] - third);
-    strial[ZZ] = st0[ZZ] + 2. * Gred * (de[2][2] - third);
+    strial[ZZ] = st0[ZZ] + (planeStress ? Pfinal - P0 : 2. * Gred * (de[2][2] - third));        /* :275-278 */
     strial[XY] = st0[XY] + Gred * dgxy;
     strial[YZ] = is2D ? st0[YZ] : st0[YZ] + Gred * dgyz;
     strial[XZ] = is2D ? st0[XZ] : st0[XZ] + Gred * dgxz;
@@ -701,20 +705,68 @@ static void isoplasticity_law(int p, const double de[3][3], double delTime, cons
     if (smag - SQRT_TWOTHIRDS * yield0 < 0.) {
         for (int c = 0; c < 6; c++) P3(sp, c, p) = strial[c];
         if (!is2D) P3(energies, 0, p) += strial[XX] * de[0][0] + strial[YY] * de[1][1] + strial[ZZ] * de[2][2] + strial[YZ] * dgyz + strial[XZ] * dgxz + strial[XY] * dgxy;
-        else P3(energies, 0, p) += strial[XX] * de[0][0] + strial[YY] * de[1][1] + strial[XY] * dgxy;
+        else {
+            if (planeStress) {          /* zz deformation :315-320 */
+                double dezz = -psLr2G * (de[0][0] + de[1][1]);
+                P3(ep, ZZ, p) += dezz * (1. + P3(ep, ZZ, p));
+            }
+            P3(energies, 0, p) += strial[XX] * de[0][0] + strial[YY] * de[1][1] + strial[XY] * dgxy;
+        }
         double baseHeat = -Cv * dTq0;
         P3(energies, 2, p) += baseHeat - dispEnergy;
         P3(energies, 3, p) += baseHeat / prevT;
         return;
     }
-    double lambdak = (smag - SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
-    if (alpha0 + SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
-    double alpint = alpha0 + SQRT_TWOTHIRDS * lambdak;
+    double lambdak, alpint, dfds[6], dezzTotal = de[2][2], spPS[6] = {0, 0, 0, 0, 0, 0};
+    if (planeStress) {
+        /* HardeningLawBase::SolveForLambda (unbracketed Newton, HardeningLawBase.cpp:157-202; LinearHardening.cpp:128-131) */
+        lambdak = 0.;
+        alpint = alpha0;
+        double n2trial = -strial[XX] + strial[YY];
+        n2trial *= n2trial / 2;
+        n2trial += 2. * strial[XY] * strial[XY];
+        double n1trial = strial[XX] + strial[YY] - 2. * Pfinal;
+        n1trial *= n1trial / 6.;
+        for (int step = 1;; ) {
+            double d1 = (1 + psKred * lambdak), d2 = (1. + 2. * Gred * lambdak);
+            double fnp12 = n1trial / (d1 * d1) + n2trial / (d2 * d2);
+            double kyld = alpint < alphaMax ? yldred + Epred * alpint : yldredMin;
+            double glam = 0.5 * fnp12 - kyld * kyld / 3.;
+            double fnp1 = sqrt(fnp12);
+            double k2prime = alpint < alphaMax ? 0.5443310539518174 * (yldred + Epred * alpint) * Epred * fnp1 : 0.;
+            double slope = -(psKred * n1trial / (d1 * d1 * d1) + 2 * Gred * n2trial / (d2 * d2 * d2)) - k2prime;
+            double delLam = -glam / slope;
+            lambdak += delLam;
+            alpint = alpha0 + SQRT_TWOTHIRDS * lambdak * fnp1;          /* UpdateTrialAlpha, plane stress */
+            if (step++ > 20 || fabs(delLam / lambdak) < 0.0001) break;      /* LambdaConverged */
+        }
+        /* :345-389 */
+        double d1 = (1. + psKred * lambdak), d2 = (1. + 2. * Gred * lambdak);
+        double n1 = (strial[XX] + strial[YY] - 2. * Pfinal) / d1, n2 = (-strial[XX] + strial[YY]) / d2;
+        double sxx = (n1 - n2) / 2., syy = (n1 + n2) / 2., txy = strial[XY] / d2;
+        dfds[XX] = (2. * sxx - syy) / 3.; dfds[YY] = (2. * syy - sxx) / 3.; dfds[ZZ] = -(dfds[XX] + dfds[YY]); dfds[XY] = txy;
+        dfds[XZ] = dfds[YZ] = 0.;
+        double dPps = -n1 / 3. - Pfinal;
+        O->pressure[p] += dPps;
+        double dezzp = lambdak * dfds[ZZ];
+        double dVoverV = delV + psRed * dezzp;
+        P3(energies, 0, p) += -Pfinal * psRed * dezzp - dPps * dVoverV;
+        Pfinal = O->pressure[p];
+        dezzTotal = -psLr2G * (de[0][0] + de[1][1] - lambdak * (dfds[XX] + dfds[YY])) + dezzp;
+        P3(ep, ZZ, p) += dezzTotal * (1. + P3(ep, ZZ, p));
+        dTq0 -= gamma0 * prevT * dezzp;
+        spPS[XX] = sxx + Pfinal; spPS[YY] = syy + Pfinal; spPS[XY] = txy; spPS[ZZ] = Pfinal;
+    } else {
+        lambdak = (smag - SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
+        if (alpha0 + SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
+        alpint = alpha0 + SQRT_TWOTHIRDS * lambdak;
+        for (int c = 0; c < 6; c++) dfds[c] = strial[c] / smag;
+    }
     double dep[6];
-    dep[XX] = lambdak * (strial[XX] / smag); dep[YY] = lambdak * (strial[YY] / smag); dep[ZZ] = lambdak * (strial[ZZ] / smag);
-    dep[XY] = 2. * lambdak * (strial[XY] / smag);
-    dep[XZ] = is2D ? 0. : 2. * lambdak * (strial[XZ] / smag);
-    dep[YZ] = is2D ? 0. : 2. * lambdak * (strial[YZ] / smag);
+    dep[XX] = lambdak * dfds[XX]; dep[YY] = lambdak * dfds[YY]; dep[ZZ] = lambdak * dfds[ZZ];
+    dep[XY] = 2. * lambdak * dfds[XY];
+    dep[XZ] = is2D ? 0. : 2. * lambdak * dfds[XZ];
+    dep[YZ] = is2D ? 0. : 2. * lambdak * dfds[YZ];
     P3(eplast, XX, p) += dep[XX]; P3(eplast, YY, p) += dep[YY]; P3(eplast, ZZ, p) += dep[ZZ]; P3(eplast, XY, p) += dep[XY];
     if (!is2D) { P3(eplast, XZ, p) += dep[XZ]; P3(eplast, YZ, p) += dep[YZ]; }
     double sn[6];
@@ -722,10 +774,11 @@ static void isoplasticity_law(int p, const double de[3][3], double delTime, cons
     sn[XY] = strial[XY] - Gred * dep[XY];
     sn[YZ] = is2D ? s0[YZ] : strial[YZ] - Gred * dep[YZ];
     sn[XZ] = is2D ? s0[XZ] : strial[XZ] - Gred * dep[XZ];
+    if (planeStress) { sn[XX] = spPS[XX]; sn[YY] = spPS[YY]; sn[ZZ] = spPS[ZZ]; sn[XY] = spPS[XY]; }      /* set above (:386-389) */
     for (int c = 0; c < 6; c++) P3(sp, c, p) = sn[c];
     double work = sn[XX] * de[0][0] + sn[YY] * de[1][1] + sn[XY] * dgxy;
     if (!is2D) work += sn[ZZ] * de[2][2] + sn[YZ] * dgyz + sn[XZ] * dgxz;
-    if (O->cfg.np != MPMGPU_PLANE_STRAIN_MPM) work += sn[ZZ] * de[2][2];          /* :428-431: zz term twice in 3D */
+    if (O->cfg.np != MPMGPU_PLANE_STRAIN_MPM) work += sn[ZZ] * dezzTotal;          /* :428-431: zz term twice in 3D */
     P3(energies, 0, p) += work;
     double plast = sn[XX] * dep[XX] + sn[YY] * dep[YY] + sn[ZZ] * dep[ZZ] + sn[XY] * dep[XY];
     if (!is2D) plast += sn[XZ] * dep[XZ] + sn[YZ] * dep[YZ];
