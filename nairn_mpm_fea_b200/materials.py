@@ -111,7 +111,8 @@ def isotropic(E, nu, rho, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None):
     else:
         raise ValueError("analysis type %r not supported" % np_)
     p[20] = gamma0
-    return dict(kind=ISOTROPIC, n_history=0, p=p, rho=rho, wave_speed=float(np.sqrt(2.0 * G * (1.0 - nu) / (rho * (1.0 - 2.0 * nu)))))
+    return dict(kind=ISOTROPIC, n_history=0, p=p, rho=rho, wave_speed=float(np.sqrt(2.0 * G * (1.0 - nu) / (rho * (1.0 - 2.0 * nu)))),
+                C33=C33, C66=C66)          # unreduced, as IsoPlasticity::VerifyAndLoadProperties reads them
 
 
 def rigid_bc(direction_bits):
@@ -140,10 +141,7 @@ def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np
     (Materials/IsoPlasticity.cpp:50-70), LinearHardening::VerifyAndLoadProperties (LinearHardening.cpp:55-80)."""
     iso = isotropic(E, nu, rho, aI, Cv, np_, pdamping)
     p = _base(rho, Cv, pdamping, av)
-    if np_ == THREED_MPM:
-        C66, C33 = iso["p"][16] * rho, iso["p"][13] * rho
-    else:
-        C66, C33 = iso["p"][16] * rho, iso["p"][23] * rho
+    C66, C33 = iso["C66"], iso["C33"]
     G0red = C66 / rho
     Kred = C33 / rho - 4.0 * G0red / 3.0
     yldred = yld / rho

@@ -81,3 +81,34 @@ def test_material_block_matches_reference_properties():
         p = a.materials[0]["p"]
         assert p[8] == q[14] and p[9] == q[15] and p[16] == q[16], (p[8:17], q[14:17])
         assert p[20] == q[12]
+
+
+def test_neohookean_and_isoplasticity_blocks_match_reference_properties():
+    """materials.py reproduces what the reference's VerifyAndLoadProperties computed (values read from the live
+    reference objects by oracle/ref_harness.cpp): Neohookean Gsp, Ksp, Lamesp, gamma0; IsoPlasticity Gred, Kred,
+    yldred, Epred, alphaMax, yldredMin, gamma0; rigid direction bits; artificial viscosity coefficients."""
+    from nairn_mpm_fea_b200 import materials as M, problem
+    seen = set()
+    for case in ("block3d_neohookean", "block3d_neohookean_uj1", "disks2d_neohookean", "block3d_isoplastic", "disks2d_isoplastic",
+                 "disks2d_isoplastic_planestress", "block3d_rigid_piston", "block3d_neohookean_av", "block3d_isoplastic_av"):
+        z = load_golden(case)
+        a = problem.from_reference_dump(z)
+        for mid, q, m in zip(z["mat_ids"], z["mat_params"], a.materials):
+            p = m["p"]
+            assert p[0] == q[0] and p[1] == q[1]
+            assert (p[3] != 0.0) == bool(q[5])
+            if q[5]:
+                assert p[4] == q[6] and p[5] == q[7]
+            if mid == M.NEOHOOKEAN:
+                assert p[8] == q[11] and p[9] == q[12] and p[10] == q[13] and p[11] == q[14], (case, p[8:14], q[8:17])
+                assert abs(p[13] - q[16]) <= 1e-15 * max(abs(q[16]), 1e-300)
+                seen.add("neo")
+            elif mid == M.ISOPLASTICITY:
+                assert p[8] == q[13] and p[9] == q[14] and p[10] == q[17] and p[11] == q[18], (case, p[8:16], q[8:22])
+                assert p[14] == q[19] and p[15] == q[20]
+                assert abs(p[13] - q[12]) <= 1e-15 * max(abs(q[12]), 1e-300)
+                seen.add("isoplastic")
+            elif mid == M.RIGIDBC:
+                assert p[8] == q[8]
+                seen.add("rigid")
+    assert seen == {"neo", "isoplastic", "rigid"}
