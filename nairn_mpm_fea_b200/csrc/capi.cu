@@ -426,6 +426,15 @@ static int alloc_rigid(mpmgpu_ctx *ctx, size_t cap)
         if (ctx->hFixedBits.size() == nn) CK(cudaMemcpyAsync(fb, ctx->hFixedBits.data(), nn, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(fb, 0, nn, ctx->stream));
         ctx->R.fixedBits = fb;
+        if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI) {     // CPDI domains of the rigid particles
+            const int nc = ctx->dim == 3 ? 8 : (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 9 : 4);
+            int *ce; double *cx, *cw;
+            CK(dalloc(ctx, &ce, capPad * nc)); CK(dalloc(ctx, &cx, capPad * nc * 3)); CK(dalloc(ctx, &cw, capPad * nc * 3));
+            CK(cudaMemsetAsync(ce, 0, capPad * nc * sizeof(int), ctx->stream));
+            CK(cudaMemsetAsync(cx, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
+            CK(cudaMemsetAsync(cw, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
+            ctx->PR.cpElem = ce; ctx->PR.cpXi = cx; ctx->PR.cpWg = cw; ctx->PR.cpStride = capPad;
+        }
     }
     return MPMGPU_OK;
 }
@@ -450,8 +459,6 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     }
     const int nNR = h->n_nonrigid, nR = n - nNR;
     if (nR > 0) {
-        if (ctx->cfg.shape != MPMGPU_POINT_GIMP && ctx->cfg.shape != MPMGPU_UNIFORM_GIMP)
-            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: rigid-BC particles need Linear or uGIMP shape functions");
         for (int p = nNR; p < n; p++) {
             const Material &m = ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1];
             if (m.kind != MAT_RIGIDBC) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d (after n_nonrigid) is not a rigid-BC material", p);
@@ -655,14 +662,7 @@ static int t_project_rigid_bcs(mpmgpu_ctx *ctx)
     if (!ctx->R.on) return MPMGPU_OK;
     for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->R.owner[d], 0x7f, (size_t)ctx->g.nnodes * sizeof(int), ctx->stream));
     ctx->launches += 3;
-    const int grid = nblocks(ctx->PR.n, TASK_THREADS);
-    if (ctx->dim == 3) {
-        if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((k_project_rigid_bcs<3, SHAPE_UGIMP>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
-        else LAUNCH((k_project_rigid_bcs<3, SHAPE_LINEAR>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
-    } else {
-        if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((k_project_rigid_bcs<2, SHAPE_UGIMP>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
-        else LAUNCH((k_project_rigid_bcs<2, SHAPE_LINEAR>), grid, TASK_THREADS, ctx->g, ctx->PR, ctx->dMats, ctx->R);
-    }
+    DISPATCH_DIM_SHAPE(k_project_rigid_bcs, ctx->PR.n, ctx->g, ctx->PR, ctx->dMats, ctx->R, ctx->dFlags);
     return MPMGPU_OK;
 }
 

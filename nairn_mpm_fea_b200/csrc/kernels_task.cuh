@@ -178,21 +178,28 @@ __global__ void k_rigid_velocity_bcs(int nnodes, RigidBCs R, Nodes N, int pass, 
 // PR holds the rigid-BC particles in host order; the reference walks them serially and the first one
 // to reach a free dof of a node keeps it, which is the minimum index here.
 template <int DIM, int SHAPE>
-__global__ void __launch_bounds__(TASK_THREADS) k_project_rigid_bcs(Grid g, Particles PR, const Material *mats, RigidBCs R)
+__global__ void __launch_bounds__(TASK_THREADS) k_project_rigid_bcs(Grid g, Particles PR, const Material *mats, RigidBCs R, StatusFlags *flags)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= PR.n) return;
     const int dirs = (int)mats[PR.mat[p]].p[8];      // RigidMaterial::setDirection: x=1, y=2, z=4
-    const int e = PR.elem[p];
-    double pos[3] = {PR.pos[0][p], PR.pos[1][p], DIM == 3 ? PR.pos[2][p] : 0.};
-    double xi[3], lp[3] = {PR.lp[0][p], PR.lp[1][p], PR.lp[2][p]};
-    get_xipos<DIM>(g, e, pos, xi);
-    for_each_node<DIM, SHAPE, false>(g, e, xi, lp, [&](int nd, double, double, double, double) {
+    auto claim = [&](int nd, double, double, double, double) {
         const int fixed = R.fixedBits ? R.fixedBits[nd] : 0;
 #pragma unroll
         for (int d = 0; d < DIM; d++)
             if ((dirs >> d & 1) && !(fixed >> d & 1)) atomicMin(&R.owner[d][nd], p);
-    });
+    };
+    if (SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI) {
+        // the nodes of the particle domain's corners (the reference's InitializationTask finds them for rigid particles too)
+        if (!cpdi_setup<DIM, SHAPE>(g, PR, p)) { atomicCAS(&flags->cpdiLeft, 0, PR.orig[p] + 1); return; }
+        for_each_node_cpdi<DIM, SHAPE, false>(g, PR, p, claim);
+    } else {
+        const int e = PR.elem[p];
+        double pos[3] = {PR.pos[0][p], PR.pos[1][p], DIM == 3 ? PR.pos[2][p] : 0.};
+        double xi[3], lp[3] = {PR.lp[0][p], PR.lp[1][p], PR.lp[2][p]};
+        get_xipos<DIM>(g, e, pos, xi);
+        for_each_node<DIM, SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI ? SHAPE_LINEAR : SHAPE, false>(g, e, xi, lp, claim);
+    }
 }
 
 // rigid particles move at their own velocity (UpdateParticlesTask.cpp:292-295, MatPoint3D.cpp:197-201)

@@ -204,7 +204,6 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (fmobj->np != PLANE_STRAIN_MPM && fmobj->np != PLANE_STRESS_MPM && fmobj->np != THREED_MPM) return "analysis type";
     if (ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP && ElementBase::useGimp != LINEAR_CPDI &&
         ElementBase::useGimp != QUADRATIC_CPDI) return "shape functions";
-    if (nmpms != nmpmsNR && ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP) return "rigid-BC particles with CPDI";
     if (!mpmgrid.IsStructuredEqualElementsGrid()) return "grid is not structured with equal elements";
     for (int i = 0; i < nmat; i++) {
         MaterialBase *mb = theMaterials[i];

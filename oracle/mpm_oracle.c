@@ -301,7 +301,7 @@ static void task_initialization(void)
         P3(ncpos, 0, p) = (2. * P3(pos, 0, p) - O->xpts[ei] - O->xpts[ei + 1]) / (O->xpts[ei + 1] - O->xpts[ei]);
         P3(ncpos, 1, p) = (2. * P3(pos, 1, p) - O->ypts[ej] - O->ypts[ej + 1]) / (O->ypts[ej + 1] - O->ypts[ej]);
         P3(ncpos, 2, p) = O->dim == 3 ? (2. * P3(pos, 2, p) - O->zpts[ek] - O->zpts[ek + 1]) / (O->zpts[ek + 1] - O->zpts[ek]) : 0.;
-        if (O->ncorner > 0 && p < O->nNR) cpdi_nodes_and_weights(p);
+        if (O->ncorner > 0) cpdi_nodes_and_weights(p);      /* all particles, rigid ones too (InitializationTask.cpp:62-67) */
     }
 }
 
