@@ -25,6 +25,13 @@ CASES = {
     "block3d_neo_lcpdi_xpic2": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, gimp="lCPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3,
                                                custom_tasks=inputs.periodic_xpic(2, False, 1))
                                 .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
+    # grid velocity BCs that vary in time: a function of time and position on the bottom plane, a linear ramp that starts
+    # late, and a skewed (xy) condition on one side -- the adapter re-evaluates the list every step
+    "block3d_bc_functions": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=-3.0e3)
+                             .replace('<DisBC dir="3" vel="0"/>', '<DisBC dir="3" style="6" function="400*sin(200*t)*(1+0.1*x)"/>')
+                             .replace("</GridBCs>", '<BCBox xmin="-1" xmax="3.01" ymin="-1" ymax="20" zmin="-1" zmax="20">'
+                                                    '<DisBC dir="12" angle="30" style="2" vel="50000" time="0.01"/></BCBox></GridBCs>')
+                             .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
     # a rigid piston whose velocity follows setting functions of time and position (evaluated by the host every step)
     "block3d_rigid_piston_functions": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=0.0,
                                                       rigid=("piston", 5, (0.0, 0.0, 0.0), ("300*sin(40*t)*(1+0.05*y)", "-9000*(1-exp(-t/0.004))")))
