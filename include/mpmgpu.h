@@ -112,7 +112,7 @@ typedef struct mpmgpu_config {
  *  NEOHOOKEAN:      [8] Gsp [9] Ksp [10] Lamesp [11] UofJOption [12] CTE1 [13] gamma0
  *  ISOPLASTICITY:   [8] Gred [9] Kred [10] yldred [11] Epred [12] CTE3 [13] gamma0
  *                   [14] alphaMax [15] yldredMin  (LinearHardening.cpp:55-80)
- *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)
+ *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)  [9] mirrored (-1, 0, +1)
  */
 typedef struct mpmgpu_material {
     int kind;

@@ -475,6 +475,10 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     if (nNR > 0 && (rc = upload_range(ctx, ctx->P, h, 0, nNR))) return rc;
     if (nR > 0 && (rc = upload_range(ctx, ctx->PR, h, nNR, nR))) return rc;
     ctx->R.on = nR > 0 ? 1 : 0;
+    ctx->R.mirrored = 0;
+    for (int p = nNR; p < n; p++) if (ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1].p[9] != 0.) ctx->R.mirrored = 1;
+    ctx->R.mat = ctx->PR.mat; ctx->R.mats = ctx->dMats;
+    ctx->R.stride[0] = 1; ctx->R.stride[1] = ctx->g.yplane; ctx->R.stride[2] = ctx->g.zplane; ctx->R.nnodes = ctx->g.nnodes;
     ctx->tiled.FN.R = ctx->R;
     CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(StatusFlags), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -493,9 +497,10 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         }
         ctx->tiled.stateKind = SK_ELASTIC;
         for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC && ctx->hMats[i].kind != MAT_RIGIDBC) ctx->tiled.stateKind = SK_FULL;
+        if (ctx->R.mirrored) ok = false;        // a mirrored rigid BC reads a neighbour node's momentum between the node updates: per-task kernels
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
-            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1 and XPIC order<=1");
+            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1 and no mirrored rigid BCs");
         ctx->tiled.enabled = ok ? 1 : 0;
         ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 12;
         {

@@ -124,7 +124,10 @@ __device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, doubl
 // The BCs rigid particles made on this node.  They sit after the grid BCs in the reference's list and
 // only on dofs no grid BC fixes (ProjectRigidBCsTask.cpp:202), each along one axis, so applying them
 // after the node's grid BCs gives the same sums as the reference's zero-all-then-add-all walk.
-__device__ __forceinline__ bool node_rigid_bcs(const RigidBCs &R, int nd, int pass, double dt, double mass, double pk[3], double ft[3])
+__device__ __forceinline__ double rigid_bc_velocity(const RigidBCs &R, const Nodes &N, int nd, int d, int owner, bool &skip);
+
+template <bool MIRROR = false>
+__device__ __forceinline__ bool node_rigid_bcs(const RigidBCs &R, int nd, int pass, double dt, double mass, double pk[3], double ft[3], const Nodes *N = nullptr)
 {
     int o[3];
     bool any = false;
@@ -136,8 +139,35 @@ __device__ __forceinline__ bool node_rigid_bcs(const RigidBCs &R, int nd, int pa
         if (o[d] != RIGID_NONE) bc_zero(pass, dt, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft);
 #pragma unroll
     for (int d = 0; d < 3; d++)
-        if (o[d] != RIGID_NONE) bc_add(pass, dt, mass, R.vel[d][o[d]], d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft);
+        if (o[d] != RIGID_NONE) {
+            double v = R.vel[d][o[d]];
+            if (MIRROR) { bool skip; v = rigid_bc_velocity(R, *N, nd, d, o[d], skip); if (skip) continue; }
+            bc_add(pass, dt, mass, v, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft);
+        }
     return true;
+}
+
+// dof d of node nd is fixed by a grid BC or by a rigid particle this step (NodalPoint::fixedDirection)
+__device__ __forceinline__ bool rigid_dof_fixed(const RigidBCs &R, int nd, int d)
+{
+    return (R.fixedBits && (R.fixedBits[nd] >> d & 1)) || R.owner[d][nd] != RIGID_NONE;
+}
+
+// Mirrored rigid BCs (RigidMaterial::mirrored, NodalVelBC::SetMirroredVelBC :214-244, ReflectVelocityBC): when the next node
+// towards the body is fixed too and the one after it is a free node of the body, the BC velocity becomes
+// v0 + (v0 - v_mirror).  Returns the velocity to impose, or sets skip when the reference adds nothing.
+__device__ __forceinline__ double rigid_bc_velocity(const RigidBCs &R, const Nodes &N, int nd, int d, int owner, bool &skip)
+{
+    skip = false;
+    const double v0 = R.vel[d][owner];
+    if (!R.mirrored) return v0;
+    const int mirrored = (int)R.mats[R.mat[owner]].p[9];
+    if (mirrored == 0) return v0;
+    const int s = mirrored < 0 ? R.stride[d] : -R.stride[d];
+    const int neighbor = nd + s, mirror = nd + 2 * s;
+    if (neighbor < 0 || neighbor >= R.nnodes || !rigid_dof_fixed(R, neighbor, d)) return v0;
+    if (mirror < 0 || mirror >= R.nnodes || rigid_dof_fixed(R, mirror, d) || N.cnt[mirror] <= 0) return v0;
+    return v0 + (v0 - N.pk[d][mirror] / N.mass[mirror]);
 }
 
 // One thread per node that has BCs.  BCs act only on active fields (numberPoints>0, NodalPointMPM.cpp:1849-1862).
@@ -169,7 +199,7 @@ __global__ void k_rigid_velocity_bcs(int nnodes, RigidBCs R, Nodes N, int pass, 
     if (N.cnt[nd] <= 0) return;
     double pk[3] = {N.pk[0][nd], N.pk[1][nd], N.pk[2][nd]};
     double ft[3] = {N.ftot[0][nd], N.ftot[1][nd], N.ftot[2][nd]};
-    if (!node_rigid_bcs(R, nd, pass, dt, N.mass[nd], pk, ft)) return;
+    if (!(R.mirrored ? node_rigid_bcs<true>(R, nd, pass, dt, N.mass[nd], pk, ft, &N) : node_rigid_bcs<false>(R, nd, pass, dt, N.mass[nd], pk, ft))) return;
     N.pk[0][nd] = pk[0]; N.pk[1][nd] = pk[1]; N.pk[2][nd] = pk[2];
     N.ftot[0][nd] = ft[0]; N.ftot[1][nd] = ft[1]; N.ftot[2][nd] = ft[2];
 }

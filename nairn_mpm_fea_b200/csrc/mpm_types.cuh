@@ -110,6 +110,11 @@ struct RigidBCs {
     int *owner[3];           // [nnodes] claiming rigid particle per direction, RIGID_NONE when free
     const double *vel[3];    // rigid particle velocities
     const unsigned char *fixedBits;   // [nnodes] x=1,y=2,z=4 dofs fixed by grid BCs (NodalPoint::fixedDirection), or NULL
+    int mirrored;            // some rigid material reflects (RigidMaterial::mirrored): per-task path only
+    const int *mat;          // rigid particles' material index
+    const Material *mats;
+    int stride[3];           // node spacing along x, y, z
+    int nnodes;
 };
 
 struct StatusFlags {         // device -> host error reporting (ResetElementsTask.cpp:71-151)

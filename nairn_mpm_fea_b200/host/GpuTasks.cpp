@@ -218,7 +218,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
             RigidMaterial *rm = (RigidMaterial *)mb;
             if (!rm->IsRigidBC()) return "rigid contact material";
             if (rm->Vfunction != NULL || rm->useControlVelocity) return "rigid material with value function or control velocity";
-            if (rm->mirrored != 0 || rm->setTemperature || rm->setConcentration) return "rigid material with mirrored / temperature / concentration";
+            if (rm->setTemperature || rm->setConcentration) return "rigid material that sets temperature or concentration";
             if (rm->function != NULL) gRigidFunctions = true;
             break;
         }
@@ -285,6 +285,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         } else {                                     // rigid BC particles: directions they control
             m.kind = MPMGPU_MAT_RIGIDBC; m.n_history = 0;
             m.p[8] = ((RigidMaterial *)mb)->setDirection;
+            m.p[9] = ((RigidMaterial *)mb)->mirrored;
         }
     }
     if (mpmgpu_set_materials(gCtx, nmat, mats.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);

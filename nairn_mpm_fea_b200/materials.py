@@ -115,10 +115,12 @@ def isotropic(E, nu, rho, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None):
                 C33=C33, C66=C66)          # unreduced, as IsoPlasticity::VerifyAndLoadProperties reads them
 
 
-def rigid_bc(direction_bits):
-    """RigidMaterial as moving velocity BC (MaterialID 11, Materials/RigidMaterial.hpp)."""
+def rigid_bc(direction_bits, mirrored=0):
+    """RigidMaterial as moving velocity BC (MaterialID 11, Materials/RigidMaterial.hpp).  mirrored = -1 / +1: the BC nodes
+    reflect the velocity of the body at the minimum / maximum edge (NodalVelBC::SetMirroredVelBC)."""
     p = _base(1.0, DEFAULT_CV, None)
     p[8] = float(direction_bits)
+    p[9] = float(mirrored)
     return dict(kind=RIGIDBC, n_history=0, p=p, rho=1.0, wave_speed=0.0)
 
 

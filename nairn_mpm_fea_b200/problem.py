@@ -303,9 +303,9 @@ def from_reference_dump(z, snapshot="p0"):
             m = M.isoplasticity(q[8], q[9], q[0], q[15], q[16] if q[16] >= 0 else None, q[21], q[11] * 1.0e6, q[1], pr.np, pd,
                                 q[20] * q[0], av)
         elif mid == M.RIGIDBC:
-            if q[9] != 0 or q[10] != 0 or q[11] != 0:
-                raise NotImplementedError("rigid material with mirrored / setting functions / temperature or concentration")
-            m = M.rigid_bc(int(q[8]))
+            if q[10] != 0 or q[11] != 0:
+                raise NotImplementedError("rigid material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")
+            m = M.rigid_bc(int(q[8]), int(q[9]))
         else:
             raise NotImplementedError("material id %d" % mid)
         pr.materials.append(m)

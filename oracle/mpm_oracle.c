@@ -42,6 +42,7 @@ typedef struct {
     int nbc, nbcGrid, bcCap;        /* BCs [nbcGrid, nbc) are the ones rigid particles made this step */
     int *fixedDirection;            /* NodalPoint::fixedDirection bits x=1, y=2, z=4 */
     int *bcDir;
+    int *bcMirror, *bcReflect;      /* rigid BCs: node spacing towards the mirrored side (0 = none), reflected node this step or -1 */
     int *bcNode; double *bcNorm, *bcValue; int *bcActive, *bcSym;
     double dt, dtFirst, dtLast;
     long long mstep;
@@ -348,7 +349,12 @@ static void velocity_bc_loop(int pass)
         NodeField *f = &O->nd[O->bcNode[b] - 1];
         if (f->numberPoints <= 0) continue;
         const double *n = &O->bcNorm[3 * b];
-        const double vel = O->bcValue[b];
+        double vel = O->bcValue[b];
+        if (b >= O->nbcGrid && O->bcReflect[b] >= 0) {      /* CrackVelocityFieldSingle::ReflectVelocityBC :133-143 */
+            const NodeField *r = &O->nd[O->bcReflect[b] - 1];
+            if (r->numberPoints <= 0) continue;
+            vel = vel + 1. * (vel - (n[0] * r->pk.x + n[1] * r->pk.y + n[2] * r->pk.z) / r->mass);
+        }
         if (pass == GRID_FORCES_CALL) {
             double s = f->mass * vel / dt;
             f->ftot.x += n[0] * s; f->ftot.y += n[1] * s; f->ftot.z += n[2] * s;
@@ -403,6 +409,7 @@ static void task_project_rigid_bcs(void)
                     O->bcCap = O->bcCap ? 2 * O->bcCap : 1024;
                     O->bcNode = (int *)realloc(O->bcNode, O->bcCap * sizeof(int)); O->bcDir = (int *)realloc(O->bcDir, O->bcCap * sizeof(int));
                     O->bcActive = (int *)realloc(O->bcActive, O->bcCap * sizeof(int)); O->bcSym = (int *)realloc(O->bcSym, O->bcCap * sizeof(int));
+                    O->bcMirror = (int *)realloc(O->bcMirror, O->bcCap * sizeof(int)); O->bcReflect = (int *)realloc(O->bcReflect, O->bcCap * sizeof(int));
                     O->bcNorm = (double *)realloc(O->bcNorm, 3 * (size_t)O->bcCap * sizeof(double));
                     O->bcValue = (double *)realloc(O->bcValue, O->bcCap * sizeof(double));
                 }
@@ -410,6 +417,11 @@ static void task_project_rigid_bcs(void)
                 O->bcNode[b] = nds[i] + 1; O->bcDir[b] = type; O->bcActive[b] = 1; O->bcSym[b] = 0;
                 O->bcNorm[3 * b] = d == 0; O->bcNorm[3 * b + 1] = d == 1; O->bcNorm[3 * b + 2] = d == 2;
                 O->bcValue[b] = P3(vel, d, p);                           /* CONSTANT_VALUE, ftime 0 */
+                {   /* NodalVelBC::SetMirrorSpacing :264-283 */
+                    const int mirrored = (int)mat->p[9], plane = d == 0 ? O->xplane : (d == 1 ? O->yplane : O->zplane);
+                    O->bcMirror[b] = mirrored == 0 ? 0 : (mirrored < 0 ? plane : -plane);
+                    O->bcReflect[b] = -1;
+                }
                 O->fixedDirection[nds[i]] |= type;
             }
         }
@@ -420,6 +432,17 @@ static void task_project_rigid_bcs(void)
 static void task_post_extrapolation(void)
 {
     for (int i = 0; i < O->nnodes; i++) O->nd[i].pkCopy = O->nd[i].pk;         /* MatVelocityField.cpp:158-164 */
+    for (int b = O->nbcGrid; b < O->nbc; b++) {        /* NodalVelBC::SetMirroredVelBC :214-244 (PostExtrapolationTask.cpp:146-151) */
+        const int s = O->bcMirror[b], i = O->bcNode[b], dir = O->bcDir[b];
+        O->bcReflect[b] = -1;
+        if (s == 0) continue;
+        const int neighbor = i + s;
+        if (O->nd[i - 1].numberPoints > 0 && neighbor > 0 && neighbor <= O->nnodes && (O->fixedDirection[neighbor - 1] & dir)) {
+            const int mirror = neighbor + s;
+            if (mirror > 0 && mirror <= O->nnodes && (O->fixedDirection[mirror - 1] & dir) == 0 && O->nd[mirror - 1].numberPoints > 0)
+                O->bcReflect[b] = mirror;
+        }
+    }
     grid_velocity_conditions(MASS_MOMENTUM_CALL);
 }
 
@@ -1100,6 +1123,7 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
     O->bcActive = dupi(bcActive, nbc, 1); O->bcSym = dupi(bcSym, nbc, 0);
     O->nbcGrid = nbc; O->bcCap = nbc;
     O->bcDir = dupi(NULL, nbc, 0);
+    O->bcMirror = dupi(NULL, nbc, 0); O->bcReflect = dupi(NULL, nbc, -1);
     O->fixedDirection = (int *)calloc(O->nnodes, sizeof(int));
     for (int b = 0; b < nbc; b++) {            /* NodalVelBC.cpp:40-45: direction bits of the grid BCs */
         int bits = bcSym ? bcSym[b] & 7 : 0;
@@ -1173,7 +1197,7 @@ void oracle_destroy(void)
     free(O->pos); free(O->vel); free(O->mp); free(O->lp); free(O->ncpos); free(O->sp); free(O->pressure); free(O->ep);
     free(O->wrot); free(O->eplast); free(O->energies); free(O->hist); free(O->pfext); free(O->acc);
     free(O->inElem); free(O->matnum); free(O->cross); free(O->nd);
-    free(O->bcNode); free(O->bcNorm); free(O->bcValue); free(O->bcActive); free(O->bcSym); free(O->bcDir); free(O->fixedDirection);
+    free(O->bcNode); free(O->bcNorm); free(O->bcValue); free(O->bcActive); free(O->bcSym); free(O->bcDir); free(O->fixedDirection); free(O->bcMirror); free(O->bcReflect);
     free(O);
     O = NULL;
 }

@@ -54,6 +54,7 @@ CASES = {
                                           rigid=("wall", 4, (0.0, 0.0, 0.0))), (1, 2, 80), 2, 0.3, 2000.0),
     "block3d_rigid_wall_lattice": (inputs.block3d(ncell=2, margin=3, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
                                                   rigid=("wall", 4, (0.0, 0.0, 0.0))), (1, 5), 0),
+    "block3d_rigid_mirrored": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-8.0e3, vx=1.0e3, bc=False, rigid=("mirror_wall", 4, (0.0, 0.0, 0.0))), (1, 2, 40), 2, 0.3, 2000.0),
     "block3d_lcpdi_rigid_wall": (inputs.block3d(ncell=3, margin=3, gimp="lCPDI", E=100.0, vz=-8.0e3, vx=2.0e3, bc=False, rigid=("wall", 5, (0.0, 0.0, 0.0))), (1, 40), 1, 0.3, 2000.0),
     "block3d_rigid_piston": (inputs.block3d(ncell=4, margin=3, E=100.0, vz=0.0, rigid=("piston", 7, (1.5e3, -1.0e3, -8.0e3))), (1, 2, 60), 2, 0.3, 1500.0),
     "block3d_rigid_linear_xpic2": (inputs.block3d(ncell=3, margin=3, E=100.0, gimp=None, vz=-5.0e3, bc=False, rigid=("wall", 5, (0.0, 0.0, 0.0)),

@@ -41,11 +41,17 @@ def block3d(ncell=4, margin=2, E=1000.0, nu=0.3, rho=1.0, vz=-1000.0, vx=0.0, vy
     rigid_body = ""
     if rigid:
         where, setdir, rv = rigid[:3]
-        z0, z1 = (lo - 1, lo) if where == "wall" else (hi, hi + 1)
+        mirrored = 0
+        if where == "mirror_wall":      # two cells thick, overlapping the first cell layer of the block, reflecting at its lower edge
+            z0, z1, mirrored = lo - 1, lo + 1, -1
+        else:
+            z0, z1 = (lo - 1, lo) if where == "wall" else (hi, hi + 1)
         rigid_body = ('<Body matname="Plate" vx="%r" vy="%r" vz="%r"><Box xmin="%d" xmax="%d" ymin="%d" ymax="%d" zmin="%d" zmax="%d"/></Body>'
                       % (rv[0], rv[1], rv[2], lo - 1, hi + 1, lo - 1, hi + 1, z0, z1))
         fxn = "".join("<SettingFunction%s>%s</SettingFunction%s>" % ("" if i == 0 else str(i + 1), f, "" if i == 0 else str(i + 1))
                       for i, f in enumerate(rigid[3])) if len(rigid) > 3 else ""
+        if mirrored:
+            fxn += "<mirrored>%d</mirrored>" % mirrored
         mat += '<Material Type="11" Name="Plate"><SetDirection>%d</SetDirection>%s</Material>' % (setdir, fxn)
     return """<?xml version='1.0'?>
 <!DOCTYPE JANFEAInput SYSTEM "NairnMPM.dtd">
