@@ -1115,9 +1115,10 @@ static int fused_step(mpmgpu_ctx *ctx)
 extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
 {
     int rc = check_ready(ctx, "mpmgpu_step"); if (rc) return rc;
+    if (ctx->tiled.slab.on && (ctx->tiled.hasLower || ctx->tiled.hasUpper))
+        return fail(ctx, MPMGPU_ESTATE, "mpmgpu_step: this context is one slab of a multi-GPU run; drive it with mpmgpu_slab_step_phase and the halo exchanges");
     for (int s = 0; s < nsteps; s++) {
-        // XPIC/FMPM of order > 1 needs one more halo exchange per iteration: fused on one GPU, per-task kernels otherwise
-        rc = (ctx->tiled.enabled && (ctx->sp.xpicOrder <= 1 || !ctx->tiled.slab.on || !(ctx->tiled.hasLower || ctx->tiled.hasUpper))) ? fused_step(ctx) : step_by_tasks(ctx);
+        rc = ctx->tiled.enabled ? fused_step(ctx) : step_by_tasks(ctx);
         if (rc) return rc;
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
     }

@@ -29,6 +29,12 @@ CASES = {
     "block3d_isoplastic": (inputs.block3d(ncell=4, margin=3, material=inputs.isoplastic_material(), vz=-4.0e4, vx=5.0e3), (1, 80), 1, 0.3, 3000.0),
     "disks2d_neohookean": (inputs.disks2d(analysis=10).replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>', '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha></Material>'), (1, 100), 1),
     "disks2d_isoplastic": (inputs.disks2d(analysis=10, vel=6000.0).replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>', '<Material Type="9" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep></Material>'), (1, 100), 1),
+    # 2D: a disk hits a plate of rigid-BC particles that fixes x and moves in y
+    "disks2d_rigid_plate": (inputs.disks2d(analysis=10, vel=4000.0)
+                            .replace('<Body matname="Disk 2" angle="0" thick="1" vx="-4000.0" vy="0">\n      <Oval xmin="0.5" xmax="12.5" ymin="-6.0" ymax="6.0"/>',
+                                     '<Body matname="Disk 2" angle="0" thick="1" vx="0" vy="300">\n      <Rect xmin="0" xmax="1" ymin="-7" ymax="7"/>')
+                            .replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>',
+                                     '<Material Type="11" Name="Disk 2"><SetDirection>3</SetDirection></Material>'), (1, 2, 100), 2),
     "disks2d_isoplastic_planestress": (inputs.disks2d(analysis=11, vel=6000.0).replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>', '<Material Type="9" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep></Material>'), (1, 100), 1),
     "block3d_xpic3": (inputs.block3d(ncell=4, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(3, False, 2)), (1, 2, 3, 30), 2, 0.3, 3000.0),
     "block3d_fmpm2": (inputs.block3d(ncell=4, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(2, True, 1)), (1, 2, 30), 2, 0.3, 3000.0),
