@@ -10,7 +10,7 @@
 # NairnMPM/build/makefile (objects = ... at :550-581, "name = $(src|com)/path" lines at :167-362) and
 # each TU is compiled directly with the reference's flags (-O3 -fopenmp -std=c++11, makefile:129) plus
 # -fPIC -w, force-including MPMPrefix.hpp (makefile:365).  Xerces-C (not installed) is replaced by the
-# expat-backed stand-in in oracle/xerces_shim.  Nothing is copied out of the reference tree.
+# expat-backed stand-in in nairn_mpm_fea_b200/host/xerces_shim (shared with the drop-in driver's build).  Nothing is copied out of the reference tree.
 set -e
 R=${MPM_REFERENCE:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -29,7 +29,7 @@ compile_one() {
     [ -z "$p" ] && { echo "build_ref: no path for $b"; return 1; }
     [ "$OUT/obj/$o" -nt "$p.cpp" ] && return 0
     g++ -c $OPT -fopenmp -std=c++11 -fPIC -w \
-        -I"$R/NairnMPM/src" -I"$R/Common/Headers" -I"$R/Common" -I"$HERE/xerces_shim" \
+        -I"$R/NairnMPM/src" -I"$R/Common/Headers" -I"$R/Common" -I"$HERE/../nairn_mpm_fea_b200/host/xerces_shim" \
         -include "$R/NairnMPM/src/System/MPMPrefix.hpp" "$p.cpp" -o "$OUT/obj/$o" \
         || { echo "build_ref: FAILED $b"; return 1; }
 }
@@ -41,7 +41,7 @@ g++ -fopenmp -o "$OUT/NairnMPM" $(for o in $OBJS; do echo "$OUT/obj/$o"; done) -
 
 # harness library = reference objects (minus main.o) + our C accessors
 g++ -c $OPT -fopenmp -std=c++11 -fPIC -w \
-    -I"$R/NairnMPM/src" -I"$R/Common/Headers" -I"$R/Common" -I"$HERE/xerces_shim" \
+    -I"$R/NairnMPM/src" -I"$R/Common/Headers" -I"$R/Common" -I"$HERE/../nairn_mpm_fea_b200/host/xerces_shim" \
     -include "$R/NairnMPM/src/System/MPMPrefix.hpp" "$HERE/ref_harness.cpp" -o "$OUT/obj/ref_harness.o"
 g++ -shared -fopenmp -o "$OUT/libnairnmpm_ref.so" "$OUT/obj/ref_harness.o" \
     $(for o in $OBJS; do [ "$o" = main.o ] || echo "$OUT/obj/$o"; done) -lexpat
