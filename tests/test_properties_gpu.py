@@ -164,6 +164,18 @@ def test_uniform_stretch_gives_hookes_law():
     sim.close()
 
 
+@pytest.mark.parametrize("kernel_path", [1, 2])
+@pytest.mark.parametrize("check", ["hooke", "neohookean", "radial_return"])
+def test_closed_form_constitutive_answers(check, kernel_path):
+    """The same closed-form checks that pin the C oracle (tests/test_known_answers_cpu.py), on both CUDA paths."""
+    from nairn_mpm_fea_b200 import MpmGpu
+    from tests import test_known_answers_cpu as ka
+
+    def engine(prob):
+        return MpmGpu(prob, device=0, kernel_path=kernel_path)
+    {"hooke": ka.check_hookes_law, "neohookean": ka.check_neohookean_closed_form, "radial_return": ka.check_radial_return}[check](engine)
+
+
 # ---- error behaviour through the C ABI (INTEGRATION.md table) -------------------------------------------------
 def _small():
     from nairn_mpm_fea_b200 import problem
