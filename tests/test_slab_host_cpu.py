@@ -99,6 +99,12 @@ def _worker(rank, world, port, q):
     if f_hi:
         ok &= bool(torch.equal(r_hi[: f_hi * row], torch.arange(f_hi * row, dtype=torch.float64) + 1000 * (rank + 1)))
     ok &= bool(torch.all(r_lo[f_lo * row:] == 0)) and bool(torch.all(r_hi[f_hi * row:] == 0))
+    # the two-integer handshake over a separate CPU group (what SlabSim uses next to NCCL so that it stays off the GPU stream)
+    ex2 = NeighbourExchange(rank, world, cpu_group=dist.new_group(backend="gloo"))
+    for step in range(3):
+        g_lo, g_hi = ex2.swap_counts(100 * step + rank, 200 * step + rank, torch.device("cpu"))
+        ok &= g_lo == (200 * step + rank - 1 if rank > 0 else 0)
+        ok &= g_hi == (100 * step + rank + 1 if rank < world - 1 else 0)
     q.put((rank, ok))
     dist.destroy_process_group()
 
