@@ -35,6 +35,8 @@
 #include "Materials/LinearHardening.hpp"
 #include "Materials/RigidMaterial.hpp"
 #include "Boundary_Conditions/NodalVelBC.hpp"
+#include "Boundary_Conditions/MatPtLoadBC.hpp"
+#include "Boundary_Conditions/MatPtTractionBC.hpp"
 #include "Global_Quantities/BodyForce.hpp"
 #include "Custom_Tasks/CustomTask.hpp"
 #include "Custom_Tasks/TransportTask.hpp"
@@ -199,6 +201,16 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (firstCrack != NULL) return "cracks present";
     if (fmobj->multiMaterialMode) return "multimaterial mode";
     if (transportTasks != NULL) return "transport tasks present";
+    // everything the replaced CPU tasks would do on the side must be absent, or the run would silently differ:
+    // particle loads / tractions are re-evaluated every step by InitializationTask and GridForcesTask
+    if (firstLoadedPt != NULL) return "particle load BCs (MatPtLoadBC)";
+    if (firstTractionPt != NULL) return "particle traction BCs (MatPtTractionBC)";
+    // damping that changes during the run (functions of time, feedback on the kinetic energy: BodyForce.cpp:167-230)
+    if (bodyFrc.useFeedback || bodyFrc.usePFeedback || bodyFrc.gridfunction != NULL || bodyFrc.pgridfunction != NULL)
+        return "time-dependent or feedback damping";
+    // custom tasks run on the host particles between the step tasks; only the one that just switches the XPIC/FMPM order is safe
+    for (CustomTask *ct = theTasks; ct != NULL; ct = ct->nextTask)
+        if (strcmp(ct->TaskName(), "Periodic XPIC Implementation") != 0) return "custom tasks other than PeriodicXPIC";
     if (nmpmsRC != nmpmsNR) return "rigid contact or rigid block particles present";
     if (nmpms != nmpmsNR && MaterialBase::extrapolateRigidBCs) return "rigid BCs by extrapolation";
     if (fmobj->np != PLANE_STRAIN_MPM && fmobj->np != PLANE_STRESS_MPM && fmobj->np != THREED_MPM) return "analysis type";
