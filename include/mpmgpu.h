@@ -59,7 +59,7 @@ extern "C" {
 #define MPMGPU_QUADRATIC_CPDI 11  /* qCPDI (2D only, as in the reference) */
 
 /* material kinds: reference MaterialID() values, Common/Read_XML/MaterialController.cpp:105-232 */
-#define MPMGPU_MAT_ISOTROPIC      1   /* IsotropicMat, small-rotation hypoelastic */
+#define MPMGPU_MAT_ISOTROPIC      1   /* IsotropicMat, small- or large-rotation hypoelastic */
 #define MPMGPU_MAT_ISOPLASTICITY  9   /* IsoPlasticity + LinearHardening */
 #define MPMGPU_MAT_RIGIDBC       11   /* RigidMaterial used as moving velocity BC */
 #define MPMGPU_MAT_NEOHOOKEAN    28   /* Neohookean */
@@ -104,6 +104,9 @@ typedef struct mpmgpu_config {
  *  all kinds:  [0] rho   [1] heat capacity Cv   [2] particle damping override or -1
  *              [3] artificial viscosity on (1) / off (0)  [4] avA1  [5] avA2   (MaterialBaseMPM.cpp:202-216,1824-1829;
  *              Neohookean and IsoPlasticity only)   [6] reserved: the library stores the average cell size here
+ *              [7] Elastic::useLargeRotation (<largeRotation>1</largeRotation>, Common/Materials/Elastic.cpp:27-33): ISOTROPIC
+ *              and ISOPLASTICITY take the small-strain / large-rotation update (IsotropicMat::LRConstitutiveLaw,
+ *              Materials/MoreIsotropicMat.cpp:54-174; IsoPlasticity.cpp:140-158,214-222) on the per-task kernels
  *  ISOTROPIC (3D):  [8] C11 [9] C12 [10] C13 [11] C22 [12] C23 [13] C33 [14] C44 [15] C55 [16] C66
  *                   [17] CTE1 [18] CTE2 [19] CTE3 [20] gamma0
  *  ISOTROPIC (2D, ElasticProperties 2D slots, Common/Materials/Elastic.cpp:90-140):

@@ -55,6 +55,7 @@ struct mpmgpu_ctx {
     cudaStream_t ownStream; bool ownStreamSaved;
     const int *dlSlot, *dlSlotR;        // download slot maps: P.orig / PR.orig, or identity when ids are global
     bool globalIds;                     // particle ids are caller-global (slab mode): downloads come in device order + ids
+    bool largeRotation = false;         // some material has Elastic::useLargeRotation: per-task kernels, k_update_strains_lr
     std::string err;
     // profiling
     bool profiling;
@@ -224,6 +225,7 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
 {
     if (!ctx || !mats || nmat < 1 || nmat > MPM_MAX_MATERIALS) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: need 1..%d materials", MPM_MAX_MATERIALS);
     ctx->hMats.resize(nmat);
+    ctx->largeRotation = false;
     for (int i = 0; i < nmat; i++) {
         int k = mats[i].kind;
         if (k != MAT_ISOTROPIC && k != MAT_RIGIDBC && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY)
@@ -234,6 +236,11 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
         if (mats[i].p[3] != 0. && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY)
             return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d does not support artificial viscosity (MaterialBase::SupportsArtificialViscosity)", k);
         // MeshInfo::GetAverageCellSize for equal elements (MeshInfo.cpp:1517-1523): a grid constant the law needs
+        if (mats[i].p[7] != 0.) {
+            if (k != MAT_ISOTROPIC && k != MAT_ISOPLASTICITY)
+                return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d has no large-rotation mode (Elastic::useLargeRotation: IsotropicMat, IsoPlasticity)", k);
+            ctx->largeRotation = true;
+        }
         ctx->hMats[i].p[6] = ctx->dim == 3 ? (ctx->cfg.gridx + ctx->cfg.gridy + ctx->cfg.gridz) / 3. : (ctx->cfg.gridx + ctx->cfg.gridy) / 2.;
     }
     ctx->nmat = nmat;
@@ -497,10 +504,11 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         }
         ctx->tiled.stateKind = SK_ELASTIC;
         for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC && ctx->hMats[i].kind != MAT_RIGIDBC) ctx->tiled.stateKind = SK_FULL;
+        if (ctx->largeRotation) ok = false;     // large-rotation hypoelastic laws (polar decompositions) live in the per-task strain kernel
         if (ctx->R.mirrored) ok = false;        // a mirrored rigid BC reads a neighbour node's momentum between the node updates: per-task kernels
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
-            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1 and no mirrored rigid BCs");
+            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, no mirrored rigid BCs and no large-rotation materials");
         ctx->tiled.enabled = ok ? 1 : 0;
         ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 12;
         {
@@ -733,7 +741,8 @@ static int strain_update(mpmgpu_ctx *ctx, double strainTime, bool postUpdate = f
         if (!postUpdate || !ctx->sp.skipPost) { int rc = xpic_extrapolation(ctx, 0); if (rc) return rc; }
     } else
     LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
-    DISPATCH_DIM_SHAPE(k_update_strains, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
+    if (ctx->largeRotation) DISPATCH_DIM_SHAPE(k_update_strains_lr, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
+    else DISPATCH_DIM_SHAPE(k_update_strains, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
     return MPMGPU_OK;
 }
 

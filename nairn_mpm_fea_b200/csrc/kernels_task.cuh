@@ -281,9 +281,9 @@ __device__ __forceinline__ void store_pstate(const Particles &P, int p, const PS
 }
 
 // ---- tasks 4 and 9b: FullStrainUpdate (UpdateStrainsFirstTask.cpp:101-168, MatPoint3D.cpp:45-93) ----
-template <int DIM, int SHAPE>
-__global__ void __launch_bounds__(TASK_THREADS) k_update_strains(Grid g, Particles P, Nodes N, const Material *mats,
-                                                                 double strainTime)
+template <int DIM, int SHAPE, bool LRLAW>
+__device__ __forceinline__ void update_strains_body(const Grid &g, const Particles &P, const Nodes &N, const Material *mats,
+                                                    double strainTime)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
@@ -302,8 +302,24 @@ __global__ void __launch_bounds__(TASK_THREADS) k_update_strains(Grid g, Particl
     for (int i = 0; i < 9; i++) dv[i] *= strainTime;
     PState s;
     load_pstate(P, p, s);
-    constitutive_law<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+    if (LRLAW) constitutive_law_lr<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
+    else constitutive_law<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
     store_pstate(P, p, s);
+}
+
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_update_strains(Grid g, Particles P, Nodes N, const Material *mats,
+                                                                 double strainTime)
+{
+    update_strains_body<DIM, SHAPE, false>(g, P, N, mats, strainTime);
+}
+
+// the same task when some material asks for the large-rotation hypoelastic update (Elastic::useLargeRotation)
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_update_strains_lr(Grid g, Particles P, Nodes N, const Material *mats,
+                                                                    double strainTime)
+{
+    update_strains_body<DIM, SHAPE, true>(g, P, N, mats, strainTime);
 }
 
 // ---- task 5: GridForcesTask (GridForcesTask.cpp:55-117, MatPoint3D.cpp:248-252) ---------------

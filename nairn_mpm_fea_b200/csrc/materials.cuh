@@ -159,6 +159,184 @@ __device__ __forceinline__ void isotropic_law(PState &s, const double du[9], int
     }
 }
 
+// ---- small-strain / large-rotation option (Elastic::useLargeRotation, <largeRotation>1</largeRotation>) ---------------
+// MaterialBase::LRGetStrainIncrement (Materials/MaterialBaseMPM.cpp:882-927) over Matrix3::Exponential, Eigenvalues,
+// RightDecompose / LeftDecompose and RVoightRT (Common/System/Matrix3.cpp:312-384, 464-520, 564-740, 190-232).
+// The 3D decomposition goes through the trigonometric eigenvalues of C = F^T F; for the strain increments of an explicit
+// step (|du| << 1) those are dominated by cancellation, which makes the reference's own result reproducible to ~1e-6 of the
+// increment only (tests/parity.py TOL_LR3D); the same formulas are used here so the behaviour is the reference's.
+template <int DIM>
+__device__ __forceinline__ void exp_du(const double du[9], double dF[9])
+{
+    if (DIM == 3) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) dF[i] = du[i];
+        dF[0] += 1.; dF[4] += 1.; dF[8] += 1.;
+    } else {
+        // two terms in 2D (System/StartOutput.cpp:116-120): alpha0 I + alpha1 du, zz separately
+        const double c0 = du[1] * du[3] - du[0] * du[4], c1 = du[0] + du[4];
+        const double beta1 = 0.5 * (c1 * 1. + 0.), beta0 = 0.5 * c0 * 1.;
+        const double betaz = du[8] * (0.5 * du[8]);
+        const double alpha0 = 1. + beta0, alpha1 = 1. + beta1;
+#pragma unroll
+        for (int i = 0; i < 9; i++) dF[i] = 0.;
+        dF[0] = alpha0 + alpha1 * du[0]; dF[1] = alpha1 * du[1]; dF[3] = alpha1 * du[3]; dF[4] = alpha0 + alpha1 * du[4];
+        dF[8] = 1. + du[8] + betaz;
+    }
+}
+
+__device__ __forceinline__ void sym_eigenvalues3(const double m[9], double lam[3])
+{
+    const double de = m[1] * m[5], dd = m[1] * m[1], ee = m[5] * m[5], ff = m[2] * m[2];
+    const double mm = m[0] + m[4] + m[8];
+    const double c1 = (m[0] * m[4] + m[0] * m[8] + m[4] * m[8]) - (dd + ee + ff);
+    const double c0 = m[8] * dd + m[0] * ee + m[4] * ff - m[0] * m[4] * m[8] - 2.0 * m[2] * de;
+    const double pp = mm * mm - 3.0 * c1;
+    const double q = mm * (pp - 1.5 * c1) - 13.5 * c0;
+    const double sqrt_p = sqrt(fabs(pp));
+    double phi = 27.0 * (0.25 * c1 * c1 * (pp - c1) + c0 * (q + 6.75 * c0));
+    phi = (1.0 / 3.0) * atan2(sqrt(fabs(phi)), q);
+    double sn, cs;
+    sincos(phi, &sn, &cs);
+    const double c = sqrt_p * cs, s = (1.0 / 1.73205080756887729352744634151) * sqrt_p * sn;
+    lam[1] = (1.0 / 3.0) * (mm - c);
+    lam[2] = lam[1] + s;
+    lam[0] = lam[1] + c;
+    lam[1] -= s;
+}
+
+// rotation of the polar decomposition: F = R U (LEFT false, through C = F^T F) or F = V R (LEFT true, through B = F F^T)
+template <int DIM, bool LEFT>
+__device__ __forceinline__ void polar_rotation(const double F[9], double R[9])
+{
+    if (DIM == 2) {
+        double Fsum = F[0] + F[4], Fdif = F[1] - F[3];
+        const double denom = sqrt(Fsum * Fsum + Fdif * Fdif);
+        Fsum /= denom; Fdif /= denom;
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = 0.;
+        R[0] = Fsum; R[1] = Fdif; R[3] = -Fdif; R[4] = Fsum; R[8] = 1.;
+        return;
+    }
+    double Ft[9], C[9], C2[9], lam[3], U[9], Ui[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Ft[3 * i + j] = F[3 * j + i];
+    if (LEFT) mat3_mul(F, Ft, C); else mat3_mul(Ft, F, C);
+    mat3_mul(C, C, C2);
+    sym_eigenvalues3(C, lam);
+    const double l1 = sqrt(lam[0]), l2 = sqrt(lam[1]), l3 = sqrt(lam[2]);
+    const double i1 = l1 + l2 + l3, i2 = l1 * l2 + l1 * l3 + l2 * l3, i3 = l1 * l2 * l3;
+    const double d1 = 1. / (i1 * i2 - i3), c2 = -d1, c1 = (i1 * i1 - i2) * d1, cI = i1 * i3 * d1;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int a = (!LEFT && i > j) ? 3 * j + i : 3 * i + j;         // RightDecompose fills U from the upper triangle
+            U[3 * i + j] = c2 * C2[a] + c1 * C[a] + (i == j ? cI : 0.);
+        }
+    const double b1 = 1. / i3, bU = -i1 * b1, bI = i2 * b1;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int a = (!LEFT && i > j) ? 3 * j + i : 3 * i + j;
+            Ui[3 * i + j] = b1 * C[a] + bU * U[a] + (i == j ? bI : 0.);
+        }
+    if (LEFT) mat3_mul(Ui, F, R); else mat3_mul(F, Ui, R);
+}
+
+// Matrix3::RVoightRT: o = R t R^T for a Voight tensor (stress: shear not doubled; strain: engineering shear)
+template <int DIM>
+__device__ __forceinline__ void rotate_voight(const double m[9], const double t[6], bool stress, double o[6])
+{
+    const double ur = stress ? 2. : 1., ll = stress ? 1. : 2.;
+    const double txx = t[XX], tyy = t[YY], tzz = t[ZZ], tyz = t[YZ], txz = t[XZ], txy = t[XY];     // o may alias t
+    if (DIM == 2) {
+        o[XX] = m[0] * m[0] * txx + m[1] * m[1] * tyy + ur * m[0] * m[1] * txy;
+        o[YY] = m[3] * m[3] * txx + m[4] * m[4] * tyy + ur * m[4] * m[3] * txy;
+        o[XY] = ll * (m[0] * m[3] * txx + m[4] * m[1] * tyy) + (m[1] * m[3] + m[0] * m[4]) * txy;
+        o[ZZ] = tzz; o[YZ] = 0.; o[XZ] = 0.;
+        return;
+    }
+    o[XX] = m[0] * m[0] * txx + m[1] * m[1] * tyy + m[2] * m[2] * tzz + ur * (m[1] * m[2] * tyz + m[0] * m[2] * txz + m[0] * m[1] * txy);
+    o[YY] = m[3] * m[3] * txx + m[4] * m[4] * tyy + m[5] * m[5] * tzz + ur * (m[4] * m[5] * tyz + m[3] * m[5] * txz + m[4] * m[3] * txy);
+    o[ZZ] = m[6] * m[6] * txx + m[7] * m[7] * tyy + m[8] * m[8] * tzz + ur * (m[8] * m[7] * tyz + m[8] * m[6] * txz + m[6] * m[7] * txy);
+    o[YZ] = ll * (m[3] * m[6] * txx + m[4] * m[7] * tyy + m[8] * m[5] * tzz)
+            + (m[5] * m[7] + m[4] * m[8]) * tyz + (m[5] * m[6] + m[3] * m[8]) * txz + (m[4] * m[6] + m[3] * m[7]) * txy;
+    o[XZ] = ll * (m[0] * m[6] * txx + m[1] * m[7] * tyy + m[8] * m[2] * tzz)
+            + (m[2] * m[7] + m[8] * m[1]) * tyz + (m[2] * m[6] + m[0] * m[8]) * txz + (m[1] * m[6] + m[0] * m[7]) * txy;
+    o[XY] = ll * (m[0] * m[3] * txx + m[1] * m[4] * tyy + m[2] * m[5] * tzz)
+            + (m[4] * m[2] + m[5] * m[1]) * tyz + (m[2] * m[3] + m[0] * m[5]) * txz + (m[1] * m[3] + m[0] * m[4]) * txy;
+}
+
+// LRGetStrainIncrement(CURRENT_CONFIGURATION): F <- exp(du) F; de = (dF - dR) F(n-1) Rn^T, dR = Rn Rn-1^T
+template <int DIM>
+__device__ __forceinline__ void lr_strain_increment(PState &s, const double du[9], double de[9], double dR[9])
+{
+    double F0[9], dF[9], F1[9], Rm[9], Rn[9], T[9], FR[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) F0[i] = s.F[i];
+    if (DIM == 2) { F0[2] = 0.; F0[5] = 0.; F0[6] = 0.; F0[7] = 0.; }
+    exp_du<DIM>(du, dF);
+    mat3_mul(dF, F0, F1);
+#pragma unroll
+    for (int i = 0; i < 9; i++) s.F[i] = F1[i];
+    polar_rotation<DIM, false>(F0, Rm);
+    polar_rotation<DIM, true>(F1, Rn);
+    // dR = Rn Rm^T
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) dR[3 * i + j] = Rn[3 * i] * Rm[3 * j] + Rn[3 * i + 1] * Rm[3 * j + 1] + Rn[3 * i + 2] * Rm[3 * j + 2];
+#pragma unroll
+    for (int i = 0; i < 9; i++) T[i] = dF[i] - dR[i];
+    // FR = F0 Rn^T
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) FR[3 * i + j] = F0[3 * i] * Rn[3 * j] + F0[3 * i + 1] * Rn[3 * j + 1] + F0[3 * i + 2] * Rn[3 * j + 2];
+    mat3_mul(T, FR, de);
+}
+
+// IsotropicMat::LRConstitutiveLaw (Materials/MoreIsotropicMat.cpp:54-174); residual strains are zero on this path
+template <int DIM>
+__device__ __forceinline__ void isotropic_lr_law(PState &s, const double du[9], int np, const Material &m)
+{
+    const double *q = m.p;
+    const double gamma0 = q[20], Cv = q[1];
+    double de[9], dR[9];
+    lr_strain_increment<DIM>(s, du, de, dR);
+    rotate_voight<DIM>(dR, s.sp, true, s.sp);
+    const double dgamxy = de[1] + de[3];
+    double dVoverV = de[0] + de[4], work;
+    if (DIM == 3) {
+        const double dgamyz = de[5] + de[7], dgamxz = de[2] + de[6];
+        dVoverV += de[8];
+        s.sp[XX] += q[8] * de[0] + q[9] * de[4] + q[10] * de[8];
+        s.sp[YY] += q[9] * de[0] + q[11] * de[4] + q[12] * de[8];
+        s.sp[ZZ] += q[10] * de[0] + q[12] * de[4] + q[13] * de[8];
+        s.sp[YZ] += q[14] * dgamyz; s.sp[XZ] += q[15] * dgamxz; s.sp[XY] += q[16] * dgamxy;
+        work = s.sp[XX] * de[0] + s.sp[YY] * de[4] + s.sp[ZZ] * de[8] + s.sp[YZ] * dgamyz + s.sp[XZ] * dgamxz + s.sp[XY] * dgamxy;
+    } else {
+        s.sp[XX] += q[8] * de[0] + q[9] * de[4];
+        s.sp[YY] += q[9] * de[0] + q[11] * de[4];
+        s.sp[XY] += q[16] * dgamxy;
+        work = s.sp[XX] * de[0] + s.sp[YY] * de[4] + s.sp[XY] * dgamxy;
+        if (np == NP_PLANE_STRAIN) {
+            s.sp[ZZ] += q[21] * de[0] + q[22] * de[4];
+        } else {
+            const double dezz = q[21] * de[0] + q[22] * de[4];
+            s.F[8] += dezz * s.F[8];
+            work += s.sp[ZZ] * dezz;
+            dVoverV += dezz;
+        }
+    }
+    s.work += work;
+    increment_heat_energy(s, Cv, -gamma0 * s.prevT * dVoverV, 0.);
+}
+
 // ---- Neohookean (MaterialID 28) ---------------------------------------------------------------
 // Neohookean::MPMConstitutiveLaw (Materials/Neohookean.cpp:177-331) over HyperElastic::IncrementDeformation
 // (Materials/HyperElastic.cpp:104-139) and GetVolumetricTerms (:171-204).  Elastic left Cauchy-Green tensor B
@@ -299,12 +477,16 @@ __device__ __forceinline__ void neohookean_law(PState &s, const double du[9], do
 // Reference quirks kept: 3D plastic-step work energy adds sp.zz*de.zz twice (:428-431); the 2D rotation of the
 // prior shear stress uses the plastic strain (:252).
 #define MPM_SQRT_TWOTHIRDS 0.8164965809277260
-template <int DIM>
-__device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9], double delTime, int np, const Material &m)
+template <int DIM, bool LR = false>
+__device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9], double delTime, int np, const Material &m)
 {
     const double Gred = m.p[8], Kred = m.p[9], yldred = m.p[10], Epred = m.p[11];
     const double gamma0 = m.p[13], Cv = m.p[1], alphaMax = m.p[14], yldredMin = m.p[15];
-    hypo_increment_deformation<DIM>(s, de);
+    // large rotation (:140-158): the strain increment in the current configuration replaces du, state n-1 is rotated by dR
+    double deLR[9], dR[9];
+    if (LR) lr_strain_increment<DIM>(s, du, deLR, dR);
+    else hypo_increment_deformation<DIM>(s, du);
+    const double *de = LR ? deLR : du;
     // plane stress terms (IsoPlasticity::GetCopyOfMechanicalProps :551-556)
     const bool planeStress = DIM == 2 && np == NP_PLANE_STRESS;
     const double psRed = 1. / (Kred / (2. * Gred) + 2. / 3.), psLr2G = (Kred / (2. * Gred) - 1. / 3.) * psRed, psKred = Kred * psRed;
@@ -333,7 +515,10 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double de[9],
 #pragma unroll
     for (int i = 0; i < 6; i++) { e0[i] = ep[i]; st0[i] = sp[i]; }
     const double dwrotxy = de[3] - de[1];
-    if (DIM == 2) {
+    if (LR) {                   // :214-222
+        rotate_voight<DIM>(dR, e0, false, ep);
+        rotate_voight<DIM>(dR, sp, true, st0);
+    } else if (DIM == 2) {
         const double dnorm = 0.5 * dwrotxy * e0[XY];
         ep[XX] -= dnorm; ep[YY] += dnorm; ep[XY] += dwrotxy * (e0[XX] - e0[YY]);
         const double dn = dwrotxy * sp[XY];
@@ -473,6 +658,27 @@ __device__ __forceinline__ void constitutive_law(PState &s, const double du[9], 
         break;
     case MAT_ISOPLASTICITY:
         isoplasticity_law<DIM>(s, du, delTime, np, m);
+        break;
+    default:
+        break;
+    }
+}
+
+// The same dispatch with the large-rotation variants of IsotropicMat and IsoPlasticity (material slot p[7], Elastic::useLargeRotation);
+// kept apart so that the kernels of the other configurations do not carry the polar decompositions
+template <int DIM>
+__device__ __forceinline__ void constitutive_law_lr(PState &s, const double du[9], double delTime, int np, const Material &m)
+{
+    const bool lr = m.p[7] != 0.;
+    switch (m.kind) {
+    case MAT_ISOTROPIC:
+        if (lr) isotropic_lr_law<DIM>(s, du, np, m); else isotropic_law<DIM>(s, du, np, m);
+        break;
+    case MAT_NEOHOOKEAN:
+        neohookean_law<DIM>(s, du, delTime, np, m);
+        break;
+    case MAT_ISOPLASTICITY:
+        if (lr) isoplasticity_law<DIM, true>(s, du, delTime, np, m); else isoplasticity_law<DIM, false>(s, du, delTime, np, m);
         break;
     default:
         break;

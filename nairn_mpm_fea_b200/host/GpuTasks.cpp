@@ -221,7 +221,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         MaterialBase *mb = theMaterials[i];
         if (mb->artificialViscosity && mb->MaterialID() != 28 && mb->MaterialID() != 9) return "artificial viscosity on this material";
         switch (mb->MaterialID()) {
-        case 1: if (((IsotropicMat *)mb)->useLargeRotation) return "IsotropicMat with large rotation"; break;
+        case 1: break;          // small- and large-rotation hypoelasticity (Elastic::useLargeRotation -> material slot 7)
         case 28: break;
         case 9:
             if (dynamic_cast<LinearHardening *>(((IsoPlasticity *)mb)->plasticLaw) == NULL) return "IsoPlasticity hardening law other than Linear";
@@ -284,6 +284,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
                 m.p[17] = e.alpha[1]; m.p[18] = e.alpha[2]; m.p[19] = e.alpha[4];
             }
             m.p[20] = im->gamma0;
+            m.p[7] = im->useLargeRotation ? 1. : 0.;
         } else if (mb->MaterialID() == 28) {        // Neohookean::GetCopyOfMechanicalProps hands out pr (Neohookean.cpp:143-150)
             Neohookean *nm = (Neohookean *)mb;
             m.kind = MPMGPU_MAT_NEOHOOKEAN;
@@ -294,6 +295,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
             m.kind = MPMGPU_MAT_ISOPLASTICITY;
             m.p[8] = pm->pr.Gred; m.p[9] = pm->pr.Kred; m.p[10] = lh->yldred; m.p[11] = lh->Epred; m.p[12] = pm->CTE3; m.p[13] = pm->gamma0;
             m.p[14] = lh->alphaMax; m.p[15] = lh->yldredMin;
+            m.p[7] = pm->useLargeRotation ? 1. : 0.;
         } else {                                     // rigid BC particles: directions they control
             m.kind = MPMGPU_MAT_RIGIDBC; m.n_history = 0;
             m.p[8] = ((RigidMaterial *)mb)->setDirection;

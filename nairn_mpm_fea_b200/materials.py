@@ -37,9 +37,11 @@ def xml_units(E=None, rho=None, alpha=None, Cv=None, G=None, K=None, yld=None, E
     return out
 
 
-def _base(rho, Cv, pdamping, av=None):
-    """av = (avA1, avA2) switches the artificial viscosity on (MaterialBaseMPM.cpp:202-216; defaults 0.2, 2.0)."""
+def _base(rho, Cv, pdamping, av=None, large_rotation=False):
+    """av = (avA1, avA2) switches the artificial viscosity on (MaterialBaseMPM.cpp:202-216; defaults 0.2, 2.0).
+    large_rotation = Elastic::useLargeRotation (<largeRotation>1</largeRotation>, Common/Materials/Elastic.cpp:27-33)."""
     p = np.zeros(NPARAMS)
+    p[7] = 1.0 if large_rotation else 0.0
     p[0] = rho
     p[1] = Cv
     p[2] = -1.0 if pdamping is None else pdamping
@@ -48,7 +50,7 @@ def _base(rho, Cv, pdamping, av=None):
     return p
 
 
-def isotropic(E, nu, rho, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None):
+def isotropic(E, nu, rho, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, large_rotation=False):
     """IsotropicMat (MaterialID 1).  aI in ppm/K as in the XML <alpha>.
 
     Follows IsotropicMat::VerifyAndLoadProperties (Common/Materials/IsotropicMat.cpp:93-168) ->
@@ -65,7 +67,7 @@ def isotropic(E, nu, rho, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None):
     v32 = v23 * e3 / e2
     v31 = v13 * e3 / e1
     v21 = v12 * e2 / e1
-    p = _base(rho, Cv, pdamping)
+    p = _base(rho, Cv, pdamping, None, large_rotation)
     rrho = 1.0 / rho
     if np_ == THREED_MPM:
         xx = 1.0 - v13 * v31 - v23 * v32 - v12 * v21 - 2.0 * v13 * v32 * v21
@@ -138,11 +140,12 @@ def neohookean(G, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None, av
                 init_history=[1.0, 1.0], init_eplast=[1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
 
 
-def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, yld_min=0.0, av=None):
+def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, yld_min=0.0, av=None,
+                  large_rotation=False):
     """IsoPlasticity + LinearHardening (MaterialID 9): IsoPlasticity::VerifyAndLoadProperties
     (Materials/IsoPlasticity.cpp:50-70), LinearHardening::VerifyAndLoadProperties (LinearHardening.cpp:55-80)."""
     iso = isotropic(E, nu, rho, aI, Cv, np_, pdamping)
-    p = _base(rho, Cv, pdamping, av)
+    p = _base(rho, Cv, pdamping, av, large_rotation)
     C66, C33 = iso["C66"], iso["C33"]
     G0red = C66 / rho
     Kred = C33 / rho - 4.0 * G0red / 3.0

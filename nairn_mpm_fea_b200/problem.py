@@ -296,12 +296,12 @@ def from_reference_dump(z, snapshot="p0"):
         if av is not None and mid not in (M.NEOHOOKEAN, M.ISOPLASTICITY):
             raise NotImplementedError("artificial viscosity on material id %d" % mid)
         if mid == M.ISOTROPIC:
-            m = M.isotropic(q[8], q[9], q[0], q[11] * 1.0e6, q[1], pr.np, pd)
+            m = M.isotropic(q[8], q[9], q[0], q[11] * 1.0e6, q[1], pr.np, pd, large_rotation=bool(q[13]))
         elif mid == M.NEOHOOKEAN:
             m = M.neohookean(q[8], q[9], q[0], q[15] * 1.0e6, q[1], int(q[14]), pd, av)
         elif mid == M.ISOPLASTICITY:
             m = M.isoplasticity(q[8], q[9], q[0], q[15], q[16] if q[16] >= 0 else None, q[21], q[11] * 1.0e6, q[1], pr.np, pd,
-                                q[20] * q[0], av)
+                                q[20] * q[0], av, large_rotation=bool(q[22]) if len(q) > 22 else False)
         elif mid == M.RIGIDBC:
             if q[10] != 0 or q[11] != 0:
                 raise NotImplementedError("rigid material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")

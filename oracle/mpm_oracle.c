@@ -549,6 +549,168 @@ static void mat_mul(double a[3][3], double b[3][3], double c[3][3])
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j];
 }
 
+/* ---- small-strain / large-rotation helpers (Elastic::useLargeRotation): MaterialBase::LRGetStrainIncrement
+ *      (Materials/MaterialBaseMPM.cpp:882-927), Matrix3::Exponential (Common/System/Matrix3.cpp:312-384),
+ *      Eigenvalues (:464-520), RightDecompose / LeftDecompose (:564-740), RVoightRT (:190-232) -------------------------- */
+/* dF = exp(du) to incrementalDefGradTerms terms: 1 in 3D, 2 in 2D (StartOutput.cpp:116-120) */
+static void exp_du(const double du[3][3], double dF[3][3])
+{
+    memset(dF, 0, 9 * sizeof(double));
+    if (O->dim == 3) {
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dF[i][j] = du[i][j] + (i == j ? 1. : 0.);
+        return;
+    }
+    double c0 = du[0][1] * du[1][0] - du[0][0] * du[1][1], c1 = du[0][0] + du[1][1];
+    double beta0 = 0., beta1 = 1., alpha0 = 1., alpha1 = 1., betaz = du[2][2], ezz = 1. + betaz;
+    for (int k = 2; k <= 2; k++) {
+        double factor = 1 / (double)k, temp = beta1;
+        beta1 = factor * (c1 * temp + beta0);
+        beta0 = factor * c0 * temp;
+        betaz *= factor * du[2][2];
+        alpha0 += beta0; alpha1 += beta1; ezz += betaz;
+    }
+    dF[0][0] = alpha0 + alpha1 * du[0][0]; dF[0][1] = alpha1 * du[0][1];
+    dF[1][0] = alpha1 * du[1][0]; dF[1][1] = alpha0 + alpha1 * du[1][1]; dF[2][2] = ezz;
+}
+
+/* eigenvalues of a symmetric positive definite 3x3 matrix, trigonometric solution of the characteristic cubic */
+static void sym_eigenvalues3(double m[3][3], double lam[3])
+{
+    double de = m[0][1] * m[1][2], dd = m[0][1] * m[0][1], ee = m[1][2] * m[1][2], ff = m[0][2] * m[0][2];
+    double mm = m[0][0] + m[1][1] + m[2][2];
+    double c1 = (m[0][0] * m[1][1] + m[0][0] * m[2][2] + m[1][1] * m[2][2]) - (dd + ee + ff);
+    double c0 = m[2][2] * dd + m[0][0] * ee + m[1][1] * ff - m[0][0] * m[1][1] * m[2][2] - 2.0 * m[0][2] * de;
+    double pp = mm * mm - 3.0 * c1;
+    double q = mm * (pp - (3.0 / 2.0) * c1) - (27.0 / 2.0) * c0;
+    double sqrt_p = sqrt(fabs(pp));
+    double phi = 27.0 * (0.25 * c1 * c1 * (pp - c1) + c0 * (q + 27.0 / 4.0 * c0));
+    phi = (1.0 / 3.0) * atan2(sqrt(fabs(phi)), q);
+    double c = sqrt_p * cos(phi), s = (1.0 / 1.73205080756887729352744634151) * sqrt_p * sin(phi);
+    lam[1] = (1.0 / 3.0) * (mm - c);
+    lam[2] = lam[1] + s;
+    lam[0] = lam[1] + c;
+    lam[1] -= s;
+}
+
+/* rotation R of the polar decomposition F = RU (left = 0, through C = F^T F) or F = VR (left = 1, through B = F F^T) */
+static void polar_rotation(double F[3][3], int left, double R[3][3])
+{
+    if (O->dim == 2) {
+        double Fsum = F[0][0] + F[1][1], Fdif = F[0][1] - F[1][0], denom = sqrt(Fsum * Fsum + Fdif * Fdif);
+        Fsum /= denom; Fdif /= denom;
+        memset(R, 0, 9 * sizeof(double));
+        R[0][0] = Fsum; R[0][1] = Fdif; R[1][0] = -Fdif; R[1][1] = Fsum; R[2][2] = 1.;
+        return;
+    }
+    double Ft[3][3], C[3][3], C2[3][3], lam[3], U[3][3], Ui[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Ft[i][j] = F[j][i];
+    if (left) mat_mul(F, Ft, C); else mat_mul(Ft, F, C);
+    mat_mul(C, C, C2);
+    sym_eigenvalues3(C, lam);
+    double l1 = sqrt(lam[0]), l2 = sqrt(lam[1]), l3 = sqrt(lam[2]);
+    double i1 = l1 + l2 + l3, i2 = l1 * l2 + l1 * l3 + l2 * l3, i3 = l1 * l2 * l3;
+    double d1 = 1. / (i1 * i2 - i3), c2 = -d1, c1 = (i1 * i1 - i2) * d1, cI = i1 * i3 * d1;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        int a = i, b = j;
+        if (!left && i > j) { a = j; b = i; }          /* RightDecompose builds U from the upper triangle */
+        U[i][j] = c2 * C2[a][b] + c1 * C[a][b] + (i == j ? cI : 0.);
+    }
+    c1 = 1 / i3;
+    double cU = -i1 * c1;
+    cI = i2 * c1;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        int a = i, b = j;
+        if (!left && i > j) { a = j; b = i; }
+        Ui[i][j] = c1 * C[a][b] + cU * U[a][b] + (i == j ? cI : 0.);
+    }
+    if (left) mat_mul(Ui, F, R); else mat_mul(F, Ui, R);
+}
+
+/* Matrix3::RVoightRT: R t R^T of a Voight tensor, stress (engineering shear not doubled) or strain */
+static void rotate_voight(double m[3][3], const double t[6], int stress, double o[6])
+{
+    const double ur = stress ? 2. : 1., ll = stress ? 1. : 2.;
+    if (O->dim == 2) {
+        o[XX] = m[0][0] * m[0][0] * t[XX] + m[0][1] * m[0][1] * t[YY] + ur * m[0][0] * m[0][1] * t[XY];
+        o[YY] = m[1][0] * m[1][0] * t[XX] + m[1][1] * m[1][1] * t[YY] + ur * m[1][1] * m[1][0] * t[XY];
+        o[XY] = ll * (m[0][0] * m[1][0] * t[XX] + m[1][1] * m[0][1] * t[YY]) + (m[0][1] * m[1][0] + m[0][0] * m[1][1]) * t[XY];
+        o[ZZ] = t[ZZ]; o[YZ] = 0.; o[XZ] = 0.;
+        return;
+    }
+    o[XX] = m[0][0] * m[0][0] * t[XX] + m[0][1] * m[0][1] * t[YY] + m[0][2] * m[0][2] * t[ZZ]
+            + ur * (m[0][1] * m[0][2] * t[YZ] + m[0][0] * m[0][2] * t[XZ] + m[0][0] * m[0][1] * t[XY]);
+    o[YY] = m[1][0] * m[1][0] * t[XX] + m[1][1] * m[1][1] * t[YY] + m[1][2] * m[1][2] * t[ZZ]
+            + ur * (m[1][1] * m[1][2] * t[YZ] + m[1][0] * m[1][2] * t[XZ] + m[1][1] * m[1][0] * t[XY]);
+    o[ZZ] = m[2][0] * m[2][0] * t[XX] + m[2][1] * m[2][1] * t[YY] + m[2][2] * m[2][2] * t[ZZ]
+            + ur * (m[2][2] * m[2][1] * t[YZ] + m[2][2] * m[2][0] * t[XZ] + m[2][0] * m[2][1] * t[XY]);
+    o[YZ] = ll * (m[1][0] * m[2][0] * t[XX] + m[1][1] * m[2][1] * t[YY] + m[2][2] * m[1][2] * t[ZZ])
+            + (m[1][2] * m[2][1] + m[1][1] * m[2][2]) * t[YZ] + (m[1][2] * m[2][0] + m[1][0] * m[2][2]) * t[XZ]
+            + (m[1][1] * m[2][0] + m[1][0] * m[2][1]) * t[XY];
+    o[XZ] = ll * (m[0][0] * m[2][0] * t[XX] + m[0][1] * m[2][1] * t[YY] + m[2][2] * m[0][2] * t[ZZ])
+            + (m[0][2] * m[2][1] + m[2][2] * m[0][1]) * t[YZ] + (m[0][2] * m[2][0] + m[0][0] * m[2][2]) * t[XZ]
+            + (m[0][1] * m[2][0] + m[0][0] * m[2][1]) * t[XY];
+    o[XY] = ll * (m[0][0] * m[1][0] * t[XX] + m[0][1] * m[1][1] * t[YY] + m[0][2] * m[1][2] * t[ZZ])
+            + (m[1][1] * m[0][2] + m[1][2] * m[0][1]) * t[YZ] + (m[0][2] * m[1][0] + m[0][0] * m[1][2]) * t[XZ]
+            + (m[0][1] * m[1][0] + m[0][0] * m[1][1]) * t[XY];
+}
+
+/* LRGetStrainIncrement(CURRENT_CONFIGURATION): F <- exp(du) F on the particle; returns the strain increment in the current
+ * configuration de = (dF - dR) F(n-1) Rn^T and the incremental rotation dR = Rn Rn-1^T */
+static void lr_strain_increment(int p, const double du[3][3], double de[3][3], double dR[3][3])
+{
+    double F0[3][3], dF[3][3], F1[3][3], Rnm1[3][3], Rn[3][3], RnT[3][3], Rnm1T[3][3], D[3][3], FR[3][3];
+    get_F(p, F0);
+    exp_du(du, dF);
+    mat_mul(dF, F0, F1);
+    set_F(p, F1);
+    polar_rotation(F0, 0, Rnm1);
+    polar_rotation(F1, 1, Rn);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { RnT[i][j] = Rn[j][i]; Rnm1T[i][j] = Rnm1[j][i]; }
+    mat_mul(Rn, Rnm1T, dR);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D[i][j] = dF[i][j] - dR[i][j];
+    mat_mul(F0, RnT, FR);
+    mat_mul(D, FR, de);
+}
+
+/* IsotropicMat::LRConstitutiveLaw (Materials/MoreIsotropicMat.cpp:54-174); residual strains are zero on this path */
+static void isotropic_lr_law(int p, const double du[3][3], const mpmgpu_material *m)
+{
+    const double *q = m->p;
+    double de[3][3], dR[3][3], s0[6], sr[6];
+    lr_strain_increment(p, du, de, dR);
+    for (int c = 0; c < 6; c++) s0[c] = P3(sp, c, p);
+    rotate_voight(dR, s0, 1, sr);
+    const double gamma0 = q[20], Cv = q[1], prevT = P3(energies, 5, p);
+    double dgamxy = de[0][1] + de[1][0], dVoverV = de[0][0] + de[1][1], work;
+    if (O->dim == 3) {
+        double dgamyz = de[1][2] + de[2][1], dgamxz = de[0][2] + de[2][0];
+        dVoverV += de[2][2];
+        sr[XX] += q[8] * de[0][0] + q[9] * de[1][1] + q[10] * de[2][2];
+        sr[YY] += q[9] * de[0][0] + q[11] * de[1][1] + q[12] * de[2][2];
+        sr[ZZ] += q[10] * de[0][0] + q[12] * de[1][1] + q[13] * de[2][2];
+        sr[YZ] += q[14] * dgamyz; sr[XZ] += q[15] * dgamxz; sr[XY] += q[16] * dgamxy;
+        work = sr[XX] * de[0][0] + sr[YY] * de[1][1] + sr[ZZ] * de[2][2] + sr[YZ] * dgamyz + sr[XZ] * dgamxz + sr[XY] * dgamxy;
+    } else {
+        sr[XX] += q[8] * de[0][0] + q[9] * de[1][1];
+        sr[YY] += q[9] * de[0][0] + q[11] * de[1][1];
+        sr[XY] += q[16] * dgamxy;
+        work = sr[XX] * de[0][0] + sr[YY] * de[1][1] + sr[XY] * dgamxy;
+        if (O->cfg.np == MPMGPU_PLANE_STRAIN_MPM) {
+            sr[ZZ] += q[21] * de[0][0] + q[22] * de[1][1];
+        } else {
+            double dezz = q[21] * de[0][0] + q[22] * de[1][1];
+            P3(ep, ZZ, p) += dezz * (1. + P3(ep, ZZ, p));
+            work += sr[ZZ] * dezz;
+            dVoverV += dezz;
+        }
+    }
+    for (int c = 0; c < 6; c++) P3(sp, c, p) = sr[c];
+    P3(energies, 0, p) += work;
+    double dTq0 = -gamma0 * prevT * dVoverV, baseHeat = -Cv * dTq0;
+    P3(energies, 2, p) += baseHeat;
+    P3(energies, 3, p) += baseHeat / prevT;
+}
+
 /* MaterialBase::GetArtificialViscosity, MaterialBaseMPM.cpp:1824-1829; dcell = MeshInfo::GetAverageCellSize (equal elements) */
 static double artificial_viscosity(double Dkk, double c, const mpmgpu_material *m)
 {
@@ -663,17 +825,23 @@ static void neohookean_law(int p, const double du[3][3], double delTime, const m
 
 /* ---- IsoPlasticity + LinearHardening: Materials/IsoPlasticity.cpp:128-517, LinearHardening.cpp:93-145 -------------- */
 #define SQRT_TWOTHIRDS 0.8164965809277260
-static void isoplasticity_law(int p, const double de[3][3], double delTime, const mpmgpu_material *m)
+static void isoplasticity_law(int p, const double (*de)[3], double delTime, const mpmgpu_material *m)
 {
     const double Gred = m->p[8], Kred = m->p[9], yldred = m->p[10], Epred = m->p[11], gamma0 = m->p[13], Cv = m->p[1];
     const double alphaMax = m->p[14], yldredMin = m->p[15];
     const int is2D = O->dim == 2;
-    double dF[3][3], F[3][3], Fn[3][3];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dF[i][j] = de[i][j] + (i == j ? 1. : 0.);
-    get_F(p, F);
-    if (is2D) { dF[0][2] = dF[2][0] = dF[1][2] = dF[2][1] = 0.; }
-    mat_mul(dF, F, Fn);
-    set_F(p, Fn);
+    const int largeRotation = m->p[7] != 0.;
+    double dF[3][3], F[3][3], Fn[3][3], deLR[3][3], dR[3][3];
+    if (largeRotation) {        /* :140-158: strain increment in the current configuration replaces du */
+        lr_strain_increment(p, de, deLR, dR);
+        de = deLR;
+    } else {
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dF[i][j] = de[i][j] + (i == j ? 1. : 0.);
+        get_F(p, F);
+        if (is2D) { dF[0][2] = dF[2][0] = dF[1][2] = dF[2][1] = 0.; }
+        mat_mul(dF, F, Fn);
+        set_F(p, Fn);
+    }
     /* plane stress terms (IsoPlasticity::GetCopyOfMechanicalProps :551-556) */
     const int planeStress = O->cfg.np == MPMGPU_PLANE_STRESS_MPM;
     const double psRed = 1. / (Kred / (2. * Gred) + 2. / 3.), psLr2G = (Kred / (2. * Gred) - 1. / 3.) * psRed, psKred = Kred * psRed;
@@ -695,7 +863,12 @@ static void isoplasticity_law(int p, const double de[3][3], double delTime, cons
     double e0[6], s0[6], st0[6];
     for (int c = 0; c < 6; c++) { e0[c] = P3(eplast, c, p); s0[c] = P3(sp, c, p); st0[c] = s0[c]; }
     double dwxy = de[1][0] - de[0][1];
-    if (is2D) {
+    if (largeRotation) {        /* :214-222: rotate the plastic strain (stored) and the prior stress by dR */
+        double er[6];
+        rotate_voight(dR, e0, 0, er);
+        rotate_voight(dR, s0, 1, st0);
+        for (int c = 0; c < 6; c++) P3(eplast, c, p) = er[c];
+    } else if (is2D) {
         double dnorm = 0.5 * dwxy * e0[XY];
         P3(eplast, XX, p) -= dnorm; P3(eplast, YY, p) += dnorm; P3(eplast, XY, p) += dwxy * (e0[XX] - e0[YY]);
         double dn = dwxy * s0[XY];
@@ -902,7 +1075,7 @@ static void full_strain_update(double strainTime, int postUpdate)
         }
         for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) dv[a][b] *= strainTime;
         const mpmgpu_material *m = &O->mats[O->matnum[p] - 1];
-        if (m->kind == MPMGPU_MAT_ISOTROPIC) isotropic_law(p, dv, m);
+        if (m->kind == MPMGPU_MAT_ISOTROPIC) { if (m->p[7] != 0.) isotropic_lr_law(p, dv, m); else isotropic_law(p, dv, m); }
         else if (m->kind == MPMGPU_MAT_NEOHOOKEAN) neohookean_law(p, dv, strainTime, m);
         else if (m->kind == MPMGPU_MAT_ISOPLASTICITY) isoplasticity_law(p, dv, strainTime, m);
     }
@@ -1187,6 +1360,31 @@ int oracle_get_nodes(mpmgpu_nodes *h)
         if (h->vk) { h->vk[i] = f->vk.x; h->vk[nn + i] = f->vk.y; h->vk[2 * nn + i] = f->vk.z; }
         if (h->pk_copy) { h->pk_copy[i] = f->pkCopy.x; h->pk_copy[nn + i] = f->pkCopy.y; h->pk_copy[2 * nn + i] = f->pkCopy.z; }
     }
+    return 0;
+}
+
+/* The constitutive laws alone, on caller-owned state arrays ([component][n], as in mpmgpu_particles): lets tests check a
+ * law against closed forms or against another implementation without building a grid.  du is [n][9], row-major. */
+int oracle_law_batch(int np, double gridx, double gridy, double gridz, const mpmgpu_material *m, int n,
+                     double *sp, double *pressure, double *ep, double *wrot, double *eplast, double *energies, double *hist,
+                     const double *du, double delTime)
+{
+    Oracle *saved = O, tmp;
+    memset(&tmp, 0, sizeof tmp);
+    tmp.cfg.np = np; tmp.cfg.gridx = gridx; tmp.cfg.gridy = gridy; tmp.cfg.gridz = gridz;
+    tmp.dim = np == MPMGPU_THREED_MPM ? 3 : 2;
+    tmp.n = n; tmp.nNR = n;
+    tmp.sp = sp; tmp.pressure = pressure; tmp.ep = ep; tmp.wrot = wrot; tmp.eplast = eplast; tmp.energies = energies; tmp.hist = hist;
+    O = &tmp;
+    for (int p = 0; p < n; p++) {
+        double d[3][3];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) d[i][j] = du[(size_t)9 * p + 3 * i + j];
+        if (m->kind == MPMGPU_MAT_ISOTROPIC) { if (m->p[7] != 0.) isotropic_lr_law(p, d, m); else isotropic_law(p, d, m); }
+        else if (m->kind == MPMGPU_MAT_NEOHOOKEAN) neohookean_law(p, d, delTime, m);
+        else if (m->kind == MPMGPU_MAT_ISOPLASTICITY) isoplasticity_law(p, d, delTime, m);
+        else { O = saved; return -1; }
+    }
+    O = saved;
     return 0;
 }
 

@@ -299,7 +299,8 @@ void ref_get_velbcs(int *node, int *dir, int *style, double *norm, double *value
 //  all:   0 rho  1 heatCapacity(Cv)  2 field  3 damping-or-(-1)  4 rigid flag
 //  iso(1):      8 E 9 nu 10 G 11 CTE3 12 gamma0 13 useLargeRotation  14.. C11 C12 C44 (specific, /rho) from pr
 //  neo(28):     8 G 9 K 10 Lame 11 Gsp 12 Ksp 13 Lamesp 14 UofJOption 15 CTE1 16 gamma0(as used)
-//  isoplas(9):  8 E 9 nu 10 G 11 CTE3 12 gamma0 13 Gred 14 Kred 15 yield 16 Ep 17 yldred 18 Epred
+//  isoplas(9):  8 E 9 nu 10 G 11 CTE3 12 gamma0 13 Gred 14 Kred 15 yield 16 Ep 17 yldred 18 Epred 19 alphaMax 20 yldredMin 21 beta
+//               22 useLargeRotation
 int ref_get_materials(int *ids, double *params)
 {
     for (int i = 0; i < nmat; i++) {
@@ -331,7 +332,7 @@ int ref_get_materials(int *ids, double *params)
         else if (ids[i] == 9) {
             IsoPlasticity *pm = (IsoPlasticity *)m;
             q[8] = pm->E; q[9] = pm->nu; q[10] = pm->G; q[11] = pm->CTE3; q[12] = pm->gamma0;
-            q[13] = pm->pr.Gred; q[14] = pm->pr.Kred;
+            q[13] = pm->pr.Gred; q[14] = pm->pr.Kred; q[22] = pm->useLargeRotation;
             HardeningLawBase *h = pm->plasticLaw;
             if (h != NULL) { q[15] = h->yield; q[17] = h->yldred;
                              LinearHardening *lh = dynamic_cast<LinearHardening *>(h);

@@ -1,0 +1,55 @@
+// TEST INFRASTRUCTURE: the device constitutive laws of libmpmgpu (csrc/materials.cuh), compiled for the host through
+// the stub in tests/devlaws/stub, behind one C entry point.  The test compares them with oracle/mpm_oracle.c on random
+// states -- it checks the CUDA SOURCE without a GPU; the GPU parity tests check the compiled kernels.
+#include "materials.cuh"
+#include <string.h>
+
+// state arrays are [component][n] as in mpmgpu_particles; F is [9][n] row-major components; du is [n][9]
+extern "C" int devlaws_batch(int dim, int np, int kind, int nhist, const double *params, int n,
+                             double *F, double *sp, double *pressure, double *eplast, double *energies /* work res heat entropy plast prevT */,
+                             double *hist, const double *du, double delTime)
+{
+    Material m;
+    m.kind = kind; m.nhist = nhist;
+    memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
+    for (int p = 0; p < n; p++) {
+        PState s;
+        for (int i = 0; i < 9; i++) s.F[i] = F[(size_t)i * n + p];
+        for (int i = 0; i < 6; i++) { s.sp[i] = sp[(size_t)i * n + p]; s.eplast[i] = eplast[(size_t)i * n + p]; }
+        s.pressure = pressure[p];
+        s.work = energies[p]; s.res = energies[(size_t)n + p]; s.heat = energies[(size_t)2 * n + p];
+        s.entropy = energies[(size_t)3 * n + p]; s.plast = energies[(size_t)4 * n + p]; s.prevT = energies[(size_t)5 * n + p];
+        for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = hist[(size_t)i * n + p];
+        const double *d = du + (size_t)9 * p;
+        if (dim == 3) constitutive_law_lr<3>(s, d, delTime, np, m); else constitutive_law_lr<2>(s, d, delTime, np, m);
+        for (int i = 0; i < 9; i++) F[(size_t)i * n + p] = s.F[i];
+        for (int i = 0; i < 6; i++) { sp[(size_t)i * n + p] = s.sp[i]; eplast[(size_t)i * n + p] = s.eplast[i]; }
+        pressure[p] = s.pressure;
+        energies[p] = s.work; energies[(size_t)n + p] = s.res; energies[(size_t)2 * n + p] = s.heat;
+        energies[(size_t)3 * n + p] = s.entropy; energies[(size_t)4 * n + p] = s.plast;
+        for (int i = 0; i < MPM_MAX_HISTORY; i++) hist[(size_t)i * n + p] = s.hist[i];
+    }
+    return 0;
+}
+
+// the plain dispatch (what every kernel except k_update_strains_lr calls): must agree with the _lr dispatch when p[7] = 0
+extern "C" int devlaws_plain_one(int dim, int np, int kind, const double *params, double *F, double *sp, double *pressure, double *eplast,
+                                 double *energies, double *hist, const double *du, double delTime)
+{
+    Material m;
+    m.kind = kind; m.nhist = 0;
+    memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
+    PState s;
+    for (int i = 0; i < 9; i++) s.F[i] = F[i];
+    for (int i = 0; i < 6; i++) { s.sp[i] = sp[i]; s.eplast[i] = eplast[i]; }
+    s.pressure = *pressure;
+    s.work = energies[0]; s.res = energies[1]; s.heat = energies[2]; s.entropy = energies[3]; s.plast = energies[4]; s.prevT = energies[5];
+    for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = hist[i];
+    if (dim == 3) constitutive_law<3>(s, du, delTime, np, m); else constitutive_law<2>(s, du, delTime, np, m);
+    for (int i = 0; i < 9; i++) F[i] = s.F[i];
+    for (int i = 0; i < 6; i++) { sp[i] = s.sp[i]; eplast[i] = s.eplast[i]; }
+    *pressure = s.pressure;
+    energies[0] = s.work; energies[1] = s.res; energies[2] = s.heat; energies[3] = s.entropy; energies[4] = s.plast;
+    for (int i = 0; i < MPM_MAX_HISTORY; i++) hist[i] = s.hist[i];
+    return 0;
+}

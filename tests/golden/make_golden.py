@@ -65,6 +65,24 @@ CASES = {
     "block3d_rigid_piston": (inputs.block3d(ncell=4, margin=3, E=100.0, vz=0.0, rigid=("piston", 7, (1.5e3, -1.0e3, -8.0e3))), (1, 2, 60), 2, 0.3, 1500.0),
     "block3d_rigid_linear_xpic2": (inputs.block3d(ncell=3, margin=3, E=100.0, gimp=None, vz=-5.0e3, bc=False, rigid=("wall", 5, (0.0, 0.0, 0.0)),
                                                   custom_tasks=inputs.periodic_xpic(2, False, 1)), (1, 2, 40), 2, 0.3, 1500.0),
+    # small-strain / large-rotation hypoelasticity (<largeRotation>1</largeRotation>): polar-decomposed strain increment,
+    # stress and plastic strain rotated by dR (IsotropicMat::LRConstitutiveLaw, IsoPlasticity with useLargeRotation)
+    "block3d_isotropic_lr": (inputs.block3d(ncell=4, margin=3, E=20.0, vz=-6.0e3, vx=5.0e3, vy=-2.0e3).replace("<alpha>0</alpha>", "<alpha>30</alpha><largeRotation>1</largeRotation>"),
+                             (1, 80), 1, 0.3, 6000.0),
+    "block3d_isoplastic_lr": (inputs.block3d(ncell=4, margin=3, material=inputs.isoplastic_material().replace("</Material>", "<largeRotation>1</largeRotation></Material>"),
+                                             vz=-4.0e4, vx=1.5e4), (1, 80), 1, 0.3, 8000.0),
+    "disks2d_lr_planestrain": (inputs.disks2d(analysis=10, vel=5000.0)
+                               .replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>',
+                                        '<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha><largeRotation>1</largeRotation></Material>')
+                               .replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>',
+                                        '<Material Type="9" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep><largeRotation>1</largeRotation></Material>')
+                               .replace('vx="-5000.0" vy="0"', 'vx="-5000.0" vy="1500"'), (1, 100), 1),
+    "disks2d_lr_planestress": (inputs.disks2d(analysis=11, gimp=None, vel=5000.0)
+                               .replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>',
+                                        '<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha><largeRotation>1</largeRotation></Material>')
+                               .replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>',
+                                        '<Material Type="9" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep><largeRotation>1</largeRotation></Material>')
+                               .replace('vx="-5000.0" vy="0"', 'vx="-5000.0" vy="1500"'), (1, 100), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

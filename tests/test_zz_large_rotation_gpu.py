@@ -1,0 +1,67 @@
+"""GPU parity of the large-rotation hypoelastic laws (Elastic::useLargeRotation: IsotropicMat::LRConstitutiveLaw and
+IsoPlasticity with LRGetStrainIncrement), through the C ABI, against golden dumps of the unmodified reference.
+
+2D cases: the standard tolerances (1e-10 after one step, 1e-7 after 100).  3D cases: TOL_LR3D -- the reference's own
+polar decomposition is ill-conditioned for small strain increments, see tests/parity.py and
+tests/test_oracle_cpu.py::test_large_rotation_3d_is_ill_conditioned_in_the_reference_algorithm."""
+import numpy as np
+import pytest
+
+from tests.parity import TASK_MAP, compare_nodes, compare_particles, load_golden, tolerances
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["block3d_isotropic_lr", "block3d_isoplastic_lr", "disks2d_lr_planestrain", "disks2d_lr_planestress"]
+
+
+def make_sim(z, kernel_path=0):
+    from nairn_mpm_fea_b200 import MpmGpu
+    from nairn_mpm_fea_b200.problem import from_reference_dump
+    return MpmGpu(from_reference_dump(z), device=0, kernel_path=kernel_path)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_each_task_of_step_one(case):
+    z = load_golden(case)
+    sim = make_sim(z, 1)
+    tol = tolerances(case)[0]
+    for i, nm in enumerate(str(s) for s in z["task_names"]):
+        if TASK_MAP[nm] is None:
+            continue
+        sim.run_task(TASK_MAP[nm])
+        pre = "s1/t%d" % i
+        errs, bad = compare_nodes(sim.download_nodes(), z, pre + "/nodes", tol)
+        assert not bad, "%s after task %d (%s): node fields %s" % (case, i, nm, bad)
+        got = sim.download()
+        errs, bad = compare_particles(got, z, pre + "/p", tol)
+        assert not bad, "%s after task %d (%s): particle fields %s" % (case, i, nm, bad)
+        assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"])
+    sim.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_whole_steps(case):
+    """kernel_path 0 (auto): a large-rotation material sends the run to the per-task kernels."""
+    z = load_golden(case)
+    sim = make_sim(z, 0)
+    snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
+    done = 0
+    for s in snaps:
+        sim.step(s - done)
+        done = s
+        tol = tolerances(case)[0] if s == 1 else tolerances(case)[2]
+        got = sim.download()
+        errs, bad = compare_particles(got, z, "p%d" % s, tol)
+        assert not bad, "%s after %d steps: %s (all: %s)" % (case, s, bad, errs)
+        assert np.array_equal(got["in_elem"], z["p%d/inElem" % s])
+        assert np.array_equal(got["crossings"], z["p%d/crossings" % s])
+        errs, bad = compare_nodes(sim.download_nodes(), z, "n%d" % s, tol)
+        assert not bad, "%s after %d steps: nodes %s" % (case, s, bad)
+    sim.close()
+
+
+def test_fused_path_refuses_large_rotation():
+    from nairn_mpm_fea_b200.capi import MpmGpuError
+    z = load_golden("block3d_isotropic_lr")
+    with pytest.raises(MpmGpuError):
+        make_sim(z, 2)
