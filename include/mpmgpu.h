@@ -26,6 +26,7 @@
 #ifndef MPMGPU_H
 #define MPMGPU_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -271,6 +272,37 @@ int mpmgpu_num_particles(const mpmgpu_ctx *ctx);
 /* launch on the caller's CUDA stream (cudaStream_t as void*; NULL = back to the context's own), so the
  * host's NCCL calls and the kernels are ordered on one stream without host synchronisation */
 int mpmgpu_set_stream(mpmgpu_ctx *ctx, void *cuda_stream);
+
+/* ---- output side on the device --------------------------------------------------------
+ * Particle-archive records in the reference's binary format (ArchiveData::ArchiveResults, System/ArchiveData.cpp:806-1100;
+ * record size CalcArchiveSize :328-396), packed on the device in the caller's particle order: an archive step moves one
+ * record block instead of the whole state.  `order` is the <MPMArchiveOrder> string (ArchiveData.hpp:22-32).  Items this
+ * path does not produce (shear components, damage normal, spin, history 5-19, particle size) give MPMGPU_EINVAL.
+ * The 64-byte file header (ArchiveData.cpp:464-489) is the host's to write (nairn_mpm_fea_b200/archive.py::header). */
+int mpmgpu_archive_record_size(const mpmgpu_ctx *ctx, const char *order);      /* bytes per particle, or -1 */
+/* constants the records carry and the step does not: original positions [3][n] and initial material angles [3][n]
+ * (z, y, x; radians) in the caller's order, either may be NULL (records then repeat the current position / use 0);
+ * thickness: 2D particle thickness.  Call once after mpmgpu_upload_particles. */
+int mpmgpu_set_archive_origin(mpmgpu_ctx *ctx, const double *origpos, const double *angles0, double thickness);
+int mpmgpu_pack_archive(mpmgpu_ctx *ctx, const char *order, void *records, size_t capacity_bytes);
+
+/* Raw sums behind the reference's GlobalQuantity rows (Global_Quantities/GlobalQuantity.cpp:394-1075) over the non-rigid
+ * particles, per material: sums[m * MPMGPU_GS_NSUMS + k], internal units; the host divides the volume-weighted ones by
+ * MPMGPU_GS_VOLUME and applies the reference's unit scalings.  Fixed summation order (no atomics): repeatable. */
+#define MPMGPU_GS_MASS           0   /* sum mp */
+#define MPMGPU_GS_VOLUME         1   /* sum Vp, Vp = J mp / rho0 */
+#define MPMGPU_GS_LINMOM         2   /* 2..4   sum mp v                 (LINMOMX/Y/Z) */
+#define MPMGPU_GS_KINETIC        5   /* sum mp |v|^2 / 2                (KINE_ENERGY) */
+#define MPMGPU_GS_WORK           6   /* sum mp workEnergy               (WORK_ENERGY) */
+#define MPMGPU_GS_STRAIN_ENERGY  7   /* sum mp (work - residual energy) (STRAIN_ENERGY) */
+#define MPMGPU_GS_HEAT           8   /* sum mp heatEnergy               (HEAT_ENERGY) */
+#define MPMGPU_GS_ENTROPY        9   /* sum mp entropy                  (ENTROPY_ENERGY) */
+#define MPMGPU_GS_PLASTIC       10   /* sum mp plastEnergy              (PLAS_ENERGY) */
+#define MPMGPU_GS_STRESS        11   /* 11..16 sum mp (total specific stress) xx yy zz yz xz xy   (AVG_Sij = this / volume) */
+#define MPMGPU_GS_VOL_VEL       17   /* 17..19 sum Vp v                 (AVG_VELX/Y/Z = this / volume) */
+#define MPMGPU_GS_VOL_F         20   /* 20..28 sum Vp F (row-major)     (AVG_Fij = this / volume) */
+#define MPMGPU_GS_NSUMS         29
+int mpmgpu_global_sums(mpmgpu_ctx *ctx, double *sums /* [nmat][MPMGPU_GS_NSUMS] */);
 
 #ifdef __cplusplus
 }

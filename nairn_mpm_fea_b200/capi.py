@@ -32,7 +32,8 @@ EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last
     "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times",
     "mpmgpu_slab_configure", "mpmgpu_slab_halo_buffers", "mpmgpu_slab_step_phase", "mpmgpu_slab_set_halo_callback", "mpmgpu_slab_migration_counts",
     "mpmgpu_slab_migration_buffers", "mpmgpu_slab_pack_migrants", "mpmgpu_slab_finish_migration",
-    "mpmgpu_num_particles", "mpmgpu_set_stream"]
+    "mpmgpu_num_particles", "mpmgpu_set_stream",
+    "mpmgpu_archive_record_size", "mpmgpu_set_archive_origin", "mpmgpu_pack_archive", "mpmgpu_global_sums"]
 
 HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)     # mpmgpu_halo_fn
 _dp = C.POINTER(C.c_double)
@@ -65,6 +66,11 @@ class ParticlesView(C.Structure):
 class NodesView(C.Structure):
     _fields_ = [("nnodes", C.c_int), ("number_points", _ip), ("mass", _dp), ("pk", _dp), ("ftot", _dp),
                 ("vk", _dp), ("pk_copy", _dp)]
+
+
+GS_NSUMS = 29
+(GS_MASS, GS_VOLUME, GS_LINMOM, GS_KINETIC, GS_WORK, GS_STRAIN_ENERGY, GS_HEAT, GS_ENTROPY, GS_PLASTIC, GS_STRESS, GS_VOL_VEL,
+ GS_VOL_F) = (0, 1, 2, 5, 6, 7, 8, 9, 10, 11, 17, 20)
 
 
 class MpmGpuError(RuntimeError):
@@ -123,6 +129,10 @@ def load_library(path=None):
     lib.mpmgpu_slab_finish_migration.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_num_particles.argtypes = [vp]
     lib.mpmgpu_set_stream.argtypes = [vp, vp]
+    lib.mpmgpu_archive_record_size.argtypes = [vp, C.c_char_p]
+    lib.mpmgpu_set_archive_origin.argtypes = [vp, _dp, _dp, C.c_double]
+    lib.mpmgpu_pack_archive.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.mpmgpu_global_sums.argtypes = [vp, _dp]
     if lib.mpmgpu_abi_version() != ABI_VERSION:
         raise MpmGpuError(-1, "libmpmgpu ABI %d, binding expects %d" % (lib.mpmgpu_abi_version(), ABI_VERSION))
     if path == LIB_PATH:
@@ -310,6 +320,35 @@ class MpmGpu:
         for k in ("mass", "pk", "ftot", "vk", "pk_copy"):
             setattr(v, k, _d(out[k]))
         self._check(self.lib.mpmgpu_download_nodes(self.ctx, C.byref(v)))
+        return out
+
+    # ---- output side on the device ----
+    def set_archive_origin(self, origpos=None, angles0=None, thickness=1.0):
+        """Constants of the archive records: original positions [3][n], initial material angles [3][n] (z, y, x; radians),
+        2D thickness.  Defaults: the positions in the problem this context was made from, zero angles."""
+        if origpos is None:
+            origpos = self.prob.particles["pos"]
+        self._keep_arch = [_c64(origpos), _c64(angles0)]
+        self._check(self.lib.mpmgpu_set_archive_origin(self.ctx, _d(self._keep_arch[0]), _d(self._keep_arch[1]), float(thickness)))
+
+    def archive_record_size(self, order):
+        return int(self.lib.mpmgpu_archive_record_size(self.ctx, order.encode("latin-1")))
+
+    def pack_archive(self, order, out=None):
+        """The record block of one particle archive (reference binary format, caller's particle order), packed on the
+        device: bytes (or the filled `out`, a uint8 array that may be pinned).  archive.header() makes the file header."""
+        rec = self.archive_record_size(order)
+        if rec < 0:
+            raise MpmGpuError(-1, "archive order %r asks for an item this path does not produce" % order)
+        nbytes = rec * self.num_particles()
+        buf = np.empty(nbytes, np.uint8) if out is None else out
+        self._check(self.lib.mpmgpu_pack_archive(self.ctx, order.encode("latin-1"), buf.ctypes.data_as(C.c_void_p), buf.nbytes))
+        return buf[:nbytes].tobytes() if out is None else buf
+
+    def global_sums(self):
+        """[nmat][GS_NSUMS] raw sums behind the reference's GlobalQuantity rows (see include/mpmgpu.h MPMGPU_GS_*)."""
+        out = np.zeros((len(self.prob.materials), GS_NSUMS))
+        self._check(self.lib.mpmgpu_global_sums(self.ctx, _d(out)))
         return out
 
     def num_particles(self):

@@ -17,6 +17,7 @@
 #include "kernels_task.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_pipe.cuh"
+#include "archive.cuh"
 
 static std::string g_create_error;
 
@@ -56,6 +57,10 @@ struct mpmgpu_ctx {
     const int *dlSlot, *dlSlotR;        // download slot maps: P.orig / PR.orig, or identity when ids are global
     bool globalIds;                     // particle ids are caller-global (slab mode): downloads come in device order + ids
     bool largeRotation = false;         // some material has Elastic::useLargeRotation: per-task kernels, k_update_strains_lr
+    double *archOrigin = NULL, *archAngles = NULL;   // [3][n] caller order, for the archive records (mpmgpu_set_archive_origin)
+    double archThickness = 1.;
+    uint32_t *archBuf = NULL; size_t archBufWords = 0;
+    double *gsumBuf = NULL; size_t gsumBufLen = 0;
     std::string err;
     // profiling
     bool profiling;
@@ -1211,6 +1216,84 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
     if (ident) cudaFree(ident);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(ctx, MPMGPU_ECUDA, "mpmgpu_download_particles: %s", cudaGetErrorString(e));
+    return MPMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// output side: archive records and global sums on the device (archive.cuh)
+extern "C" int mpmgpu_archive_record_size(const mpmgpu_ctx *ctx, const char *order)
+{
+    if (!ctx || !order) return -1;
+    ArchiveLayout L;
+    return archive_layout_from_order(order, ctx->dim, L);
+}
+
+extern "C" int mpmgpu_set_archive_origin(mpmgpu_ctx *ctx, const double *origpos, const double *angles0, double thickness)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_archive_origin: upload the particles first");
+    if (ctx->globalIds) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_archive_origin: not available in slab mode (each rank downloads its particles)");
+    cudaSetDevice(ctx->cfg.device);
+    const size_t n = (size_t)ctx->P.n + (size_t)ctx->PR.n;
+    if (origpos) {
+        if (!ctx->archOrigin) CK(dalloc(ctx, &ctx->archOrigin, 3 * n));
+        CK(cudaMemcpyAsync(ctx->archOrigin, origpos, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (angles0) {
+        if (!ctx->archAngles) CK(dalloc(ctx, &ctx->archAngles, 3 * n));
+        CK(cudaMemcpyAsync(ctx->archAngles, angles0, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->archThickness = thickness;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_pack_archive(mpmgpu_ctx *ctx, const char *order, void *records, size_t capacity_bytes)
+{
+    if (!ctx || !order || !records) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_pack_archive: null argument");
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_pack_archive: nothing uploaded");
+    if (ctx->globalIds) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_pack_archive: not available in slab mode (each rank downloads its particles)");
+    cudaSetDevice(ctx->cfg.device);
+    ArchiveLayout L;
+    const int recBytes = archive_layout_from_order(order, ctx->dim, L);
+    if (recBytes < 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_pack_archive: <MPMArchiveOrder> \"%s\" asks for an item this path does not produce (shear components, damage normal, spin, history 5-19, size)", order);
+    const int nNR = ctx->P.n, nR = ctx->PR.n;
+    const size_t n = (size_t)nNR + (size_t)nR, words = n * (size_t)L.recWords;
+    if (capacity_bytes < words * 4) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_pack_archive: %zu bytes needed (%zu particles x %d), %zu given", words * 4, n, recBytes, capacity_bytes);
+    if (ctx->archBufWords < words) {
+        CK(dalloc(ctx, &ctx->archBuf, words));       // earlier (smaller) buffers stay on the context's free list until destroy
+        ctx->archBufWords = words;
+    }
+    L.thickness = ctx->archThickness; L.origpos = ctx->archOrigin; L.angles0 = ctx->archAngles; L.stride = n;
+    if (nNR) LAUNCH(k_pack_archive, nblocks(nNR, ARCHIVE_THREADS), ARCHIVE_THREADS, nNR, ctx->P, ctx->P.orig, ctx->dMats, L, ctx->archBuf);
+    if (nR) LAUNCH(k_pack_archive, nblocks(nR, ARCHIVE_THREADS), ARCHIVE_THREADS, nR, ctx->PR, ctx->PR.orig, ctx->dMats, L, ctx->archBuf);
+    CK(cudaMemcpyAsync(records, ctx->archBuf, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_global_sums(mpmgpu_ctx *ctx, double *sums)
+{
+    if (!ctx || !sums) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_global_sums: null argument");
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_global_sums: nothing uploaded");
+    cudaSetDevice(ctx->cfg.device);
+    const int nNR = ctx->P.n, nmat = ctx->nmat;
+    int nblk = nblocks(nNR, ARCHIVE_THREADS);
+    if (nblk > 592) nblk = 592;                       // 4 blocks per SM of a B200; grid-stride beyond that
+    if (nblk < 1) nblk = 1;
+    const size_t need = ((size_t)nblk + 1) * nmat * GS_NSUMS;
+    if (ctx->gsumBufLen < need) { CK(dalloc(ctx, &ctx->gsumBuf, need)); ctx->gsumBufLen = need; }
+    double *partial = ctx->gsumBuf, *out = ctx->gsumBuf + (size_t)nblk * nmat * GS_NSUMS;
+    Particles P = ctx->P;
+    P.nNR = nNR;
+    {
+        dim3 grid(nblk, nmat);
+        k_global_partial<<<grid, ARCHIVE_THREADS, 0, ctx->stream>>>(P, ctx->dMats, ctx->dim, partial);
+        ctx->launches++;
+    }
+    LAUNCH(k_global_final, nblocks(nmat * GS_NSUMS, 128), 128, nmat, nblk, partial, out);
+    CK(cudaMemcpyAsync(sums, out, (size_t)nmat * GS_NSUMS * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return MPMGPU_OK;
 }
 

@@ -53,3 +53,62 @@ extern "C" int devlaws_plain_one(int dim, int np, int kind, const double *params
     for (int i = 0; i < MPM_MAX_HISTORY; i++) hist[i] = s.hist[i];
     return 0;
 }
+
+// ---- archive records and global summands (csrc/archive.cuh) on the host -----------------------------------------------
+#include "archive.cuh"
+
+static void bind_host_particles(Particles &P, int n, double *pos, double *vel, double *mp, double *F, double *sp, double *pressure,
+                                double *eplast, double *energies, double *hist, int *elem, int *mat0, int *cross)
+{
+    memset(&P, 0, sizeof P);
+    P.n = n; P.nNR = n;
+    for (int c = 0; c < 3; c++) { P.pos[c] = pos + (size_t)c * n; P.vel[c] = vel + (size_t)c * n; }
+    P.mp = mp;
+    for (int i = 0; i < 9; i++) P.F[i] = F + (size_t)i * n;
+    for (int i = 0; i < 6; i++) { P.sp[i] = sp + (size_t)i * n; P.eplast[i] = eplast + (size_t)i * n; }
+    P.pressure = pressure;
+    P.work = energies; P.res = energies + n; P.heat = energies + (size_t)2 * n; P.entropy = energies + (size_t)3 * n;
+    P.plast = energies + (size_t)4 * n; P.prevT = energies + (size_t)5 * n;
+    for (int i = 0; i < MPM_MAX_HISTORY; i++) P.hist[i] = hist + (size_t)i * n;
+    P.elem = elem; P.mat = mat0; P.cross = cross;
+}
+
+static void make_materials(Material *m, int nmat, const int *kinds, const double *params)
+{
+    for (int i = 0; i < nmat; i++) { m[i].kind = kinds[i]; m[i].nhist = 0; memcpy(m[i].p, params + (size_t)i * MPM_MAT_NPARAMS, sizeof(double) * MPM_MAT_NPARAMS); }
+}
+
+// returns the record size in bytes (or -1); out must hold n records
+extern "C" int devarch_records(int dim, int n, const char *order, double *pos, double *vel, double *mp, double *F, double *sp, double *pressure,
+                               double *eplast, double *energies, double *hist, int *elem, int *mat0, int *cross, int nmat, const int *kinds,
+                               const double *params, const double *origpos, const double *angles0, double thickness, unsigned char *out)
+{
+    Particles P;
+    bind_host_particles(P, n, pos, vel, mp, F, sp, pressure, eplast, energies, hist, elem, mat0, cross);
+    Material mats[MPM_MAX_MATERIALS];
+    make_materials(mats, nmat, kinds, params);
+    ArchiveLayout L;
+    const int rec = archive_layout_from_order(order, dim, L);
+    if (rec < 0 || out == NULL) return rec;
+    L.thickness = thickness; L.origpos = origpos; L.angles0 = angles0; L.stride = n;
+    for (int p = 0; p < n; p++) archive_record(P, p, p, mats, L, (uint32_t *)out + (size_t)p * L.recWords);
+    return rec;
+}
+
+// sums[m][GS_NSUMS], particle order
+extern "C" int devarch_global_sums(int dim, int n, double *pos, double *vel, double *mp, double *F, double *sp, double *pressure, double *eplast,
+                                   double *energies, double *hist, int *elem, int *mat0, int *cross, int nmat, const int *kinds,
+                                   const double *params, double *sums)
+{
+    Particles P;
+    bind_host_particles(P, n, pos, vel, mp, F, sp, pressure, eplast, energies, hist, elem, mat0, cross);
+    Material mats[MPM_MAX_MATERIALS];
+    make_materials(mats, nmat, kinds, params);
+    for (int i = 0; i < nmat * GS_NSUMS; i++) sums[i] = 0.;
+    for (int p = 0; p < n; p++) {
+        double q[GS_NSUMS];
+        global_summands(P, p, mats[mat0[p]], dim, q);
+        for (int k = 0; k < GS_NSUMS; k++) sums[mat0[p] * GS_NSUMS + k] += q[k];
+    }
+    return GS_NSUMS;
+}
