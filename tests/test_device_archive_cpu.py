@@ -162,3 +162,77 @@ def test_device_global_summands_match_numpy(libs, case):  # noqa: F811
     want = reference_sums(prob, state, dim)
     assert sums_close(sums, want), np.abs(sums - want[0]).max(axis=0)
     assert want[0][0][0] > 0 and np.isfinite(want[0][0][5])
+
+
+# ---- the sums' DEFINITIONS against the reference itself: its CLI writes the global quantities to <root>.global ----------
+GLOBAL_TYPES = ["Kinetic Energy", "Work Energy", "Strain Energy", "Heat Energy", "Plastic Energy", "sxx", "syy", "szz", "sxy", "sxz", "syz",
+                "velx", "vely", "velz", "Fxx", "Fxy", "Fxz", "Fyx", "Fyy", "Fyz", "Fzx", "Fzy", "Fzz"]
+
+
+def quantities_from_sums(sums):
+    """What GlobalQuantity::AppendQuantity prints (Legacy units), from the per-material raw sums (all non-rigid materials)."""
+    from nairn_mpm_fea_b200 import capi as K
+    t = np.nansum(sums, axis=0)
+    vol = t[K.GS_VOLUME]
+    out = {"Kinetic Energy": 1e-9 * t[K.GS_KINETIC], "Work Energy": 1e-9 * t[K.GS_WORK], "Strain Energy": 1e-9 * t[K.GS_STRAIN_ENERGY],
+           "Heat Energy": 1e-9 * t[K.GS_HEAT], "Plastic Energy": 1e-9 * t[K.GS_PLASTIC]}
+    for name, c in (("sxx", 0), ("syy", 1), ("szz", 2), ("syz", 3), ("sxz", 4), ("sxy", 5)):
+        out[name] = 1e-6 * t[K.GS_STRESS + c] / vol
+    for c, name in enumerate(("velx", "vely", "velz")):
+        out[name] = t[K.GS_VOL_VEL + c] / vol
+    for i, name in enumerate(("Fxx", "Fxy", "Fxz", "Fyx", "Fyy", "Fyz", "Fzx", "Fzy", "Fzz")):
+        out[name] = 100.0 * t[K.GS_VOL_F + i] / vol
+    return out
+
+
+# cases whose golden state comes from the XML alone (no harness-side jitter), so the CLI run reproduces it
+@pytest.mark.parametrize("case", ["block3d_neohookean_uj1", "disks2d_isoplastic", "block3d_rigid_wall_lattice", "disks2d_neohookean"])
+def test_global_sums_reproduce_the_reference_cli_global_file(libs, case):  # noqa: F811
+    import os
+    import re
+    import subprocess
+    import tempfile
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "NairnMPM")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/NairnMPM not built")
+    dev_lib, _ = libs
+    z = load_golden(case)
+    prob = problem.from_reference_dump(z)
+    xml = str(z["xml"])
+    dt_ms = prob.dt * 1.0e3
+    snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
+    glob = '<GlobalArchiveTime units="ms">%r</GlobalArchiveTime>' % (0.999 * dt_ms) + "".join('<GlobalArchive type="%s"/>' % t for t in GLOBAL_TYPES)
+    xml = xml.replace("</MPMHeader>", glob + "</MPMHeader>")
+    tmax = (snaps[-1] + 0.5) * dt_ms
+    xml = re.sub(r'<MaxTime units="ms">[^<]*</MaxTime>', '<MaxTime units="ms">%r</MaxTime>' % tmax, xml)
+    d = tempfile.mkdtemp(prefix="glob_")
+    open(os.path.join(d, "in.fmcmd"), "w").write(xml)
+    p = subprocess.run([ref, "-np", "1", "in.fmcmd"], cwd=d, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-1000:] + p.stderr[-1000:]
+    root = re.search(r"<ArchiveRoot>([^<]*)</ArchiveRoot>", xml).group(1).rstrip(".")
+    rows = [ln.split("\t") for ln in open(os.path.join(d, root + ".global")) if ln and not ln.startswith("#")]
+    names = None
+    for ln in open(os.path.join(d, root + ".global")):
+        if ln.startswith("#setName"):
+            names = [s.strip().strip('"') for s in ln.rstrip("\n").split("\t")[1:]]
+    table = np.array([[float(x) for x in r] for r in rows if len(r) > 1])
+    dim = 3 if prob.is3d else 2
+    checked = 0
+    for step in snaps:
+        row = table[np.argmin(np.abs(table[:, 0] - step * dt_ms))]
+        assert abs(row[0] - step * dt_ms) < 0.01 * dt_ms
+        _, n, dev, state, kinds, params = device_view(z, prob, step)
+        nn = int(prob.particles.get("n_nonrigid", n))
+        dev_nr = {k: np.ascontiguousarray(v[..., :nn]) for k, v in dev.items()}
+        head, tail = _args(dim, nn, dev_nr, kinds, params)
+        sums = np.zeros((len(kinds), GS_NSUMS))
+        assert dev_lib.devarch_global_sums(*head, *tail, _dp(sums)) == GS_NSUMS
+        got = quantities_from_sums(sums)
+        big = max(abs(v) for k, v in got.items() if k[0] == "s")
+        for k, nm in enumerate(names):
+            want = row[1 + k]
+            scale = {"s": big, "v": float(np.abs(state["vel"]).max()), "F": 100.0}.get(nm[0], abs(want))
+            # the file carries 7 significant digits
+            assert abs(got[nm] - want) <= 2.0e-6 * max(scale, abs(want)) + 1e-300, (case, step, nm, got[nm], want)
+            checked += 1
+    assert checked >= len(GLOBAL_TYPES)
