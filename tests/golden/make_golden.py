@@ -19,6 +19,9 @@ from tests import inputs  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
+DISK1 = '<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>'
+DISK2 = '<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>'
+
 CASES = {
     # name: (xml text, snapshots, per-task steps[, position jitter, velocity jitter])
     "block3d_jitter": (inputs.block3d(ncell=5, margin=3, E=100.0, vx=3.0e3, vy=-2.0e3, vz=-6.0e3), (1, 20, 60), 1, 0.35, 4000.0),
@@ -83,6 +86,20 @@ CASES = {
                                .replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>',
                                         '<Material Type="9" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep><largeRotation>1</largeRotation></Material>')
                                .replace('vx="-5000.0" vy="0"', 'vx="-5000.0" vy="1500"'), (1, 100), 1),
+    # branches of the laws no other case reaches: Neo-Hookean in plane stress (the three U(J) options solve for the zz stretch
+    # differently, Neohookean.cpp:204-245), 2D artificial viscosity, softening with a minimum yield stress (LinearHardening
+    # alphaMax), a material's own particle damping (<PDamping> inside <Material>, MaterialBase::GetMaterialDamping)
+    "disks2d_neo_planestress": (inputs.disks2d(analysis=11, vel=4000.0)
+                                .replace(DISK1, '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha><UJOption>1</UJOption></Material>')
+                                .replace(DISK2, '<Material Type="28" Name="Disk 2"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha><UJOption>2</UJOption><PDamping>300</PDamping></Material>'),
+                                (1, 100), 1),
+    "disks2d_neo_planestress_av": (inputs.disks2d(analysis=11, vel=6000.0)
+                                   .replace(DISK1, '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha><ArtificialVisc/><avA1>0.3</avA1><avA2>1.5</avA2></Material>'),
+                                   (1, 100), 1),
+    "block3d_isoplastic_softening": (inputs.block3d(ncell=4, margin=3, material=inputs.isoplastic_material(Ep=-1.0).replace("<Ep>-1.0</Ep>", "<Khard>-4.0</Khard><yieldMin>12.0</yieldMin>"),
+                                                    vz=-6.0e4, vx=5.0e3), (1, 80), 1, 0.3, 3000.0),
+    "block3d_material_pdamping": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3).replace("<alpha>0</alpha>", "<alpha>0</alpha><PDamping>2000</PDamping>"),
+                                  (1, 30), 1, 0.3, 3000.0),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

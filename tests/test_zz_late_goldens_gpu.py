@@ -1,5 +1,8 @@
-"""GPU parity of the large-rotation hypoelastic laws (Elastic::useLargeRotation: IsotropicMat::LRConstitutiveLaw and
-IsoPlasticity with LRGetStrainIncrement), through the C ABI, against golden dumps of the unmodified reference.
+"""GPU parity, through the C ABI, against golden dumps of the unmodified reference for the cases added late in round 1:
+the large-rotation hypoelastic laws (Elastic::useLargeRotation: IsotropicMat::LRConstitutiveLaw and IsoPlasticity with
+LRGetStrainIncrement; verified on a B200 before the round's GPU budget ran out) and four cases that reach branches of the
+laws no earlier golden did (Neo-Hookean in plane stress with the three U(J) options, 2D artificial viscosity, softening down
+to a minimum yield stress, a material's own particle damping).  Same checks as tests/test_parity_tasks_gpu.py.
 
 2D cases: the standard tolerances (1e-10 after one step, 1e-7 after 100).  3D cases: TOL_LR3D -- the reference's own
 polar decomposition is ill-conditioned for small strain increments, see tests/parity.py and
@@ -11,7 +14,10 @@ from tests.parity import TASK_MAP, compare_nodes, compare_particles, load_golden
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["block3d_isotropic_lr", "block3d_isoplastic_lr", "disks2d_lr_planestrain", "disks2d_lr_planestress"]
+LR_CASES = ["block3d_isotropic_lr", "block3d_isoplastic_lr", "disks2d_lr_planestrain", "disks2d_lr_planestress"]
+BRANCH_CASES = ["disks2d_neo_planestress", "disks2d_neo_planestress_av", "block3d_isoplastic_softening", "block3d_material_pdamping"]
+CASES = LR_CASES + BRANCH_CASES
+FUSED_CASES = ["block3d_isoplastic_softening", "block3d_material_pdamping"]          # 3D uGIMP without large rotation
 
 
 def make_sim(z, kernel_path=0):
@@ -39,11 +45,11 @@ def test_each_task_of_step_one(case):
     sim.close()
 
 
-@pytest.mark.parametrize("case", CASES)
-def test_whole_steps(case):
-    """kernel_path 0 (auto): a large-rotation material sends the run to the per-task kernels."""
+@pytest.mark.parametrize("case,kernel_path", [(c, 0) for c in LR_CASES] + [(c, 1) for c in BRANCH_CASES] + [(c, 2) for c in FUSED_CASES])
+def test_whole_steps(case, kernel_path):
+    """kernel_path 0 (auto): a large-rotation material sends the run to the per-task kernels; 1 = per-task, 2 = fused."""
     z = load_golden(case)
-    sim = make_sim(z, 0)
+    sim = make_sim(z, kernel_path)
     snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
     done = 0
     for s in snaps:
