@@ -1,7 +1,7 @@
 """The DEVICE source of the output side (nairn_mpm_fea_b200/csrc/archive.cuh: archive records, global-quantity summands),
 compiled for the host (tests/devlaws), against nairn_mpm_fea_b200/archive.py -- itself byte-identical to the files of the
 reference's CLI (tests/test_archive_cpu.py) -- and against plain numpy sums, on golden states.  No GPU needed; the compiled
-kernels are checked by tests/test_zz_archive_gpu.py."""
+kernels are checked by tests/test_zzz_archive_gpu.py."""
 import ctypes as C
 
 import numpy as np
