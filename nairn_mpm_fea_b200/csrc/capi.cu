@@ -56,6 +56,7 @@ struct mpmgpu_ctx {
     cudaStream_t ownStream; bool ownStreamSaved;
     const int *dlSlot, *dlSlotR;        // download slot maps: P.orig / PR.orig, or identity when ids are global
     bool globalIds;                     // particle ids are caller-global (slab mode): downloads come in device order + ids
+    bool cpdiMerge = false;             // CPDI kernels merge the corners' contributions per node (MPMGPU_CPDI_MERGE=1; shape.cuh)
     bool largeRotation = false;         // some material has Elastic::useLargeRotation: per-task kernels, k_update_strains_lr
     double *archOrigin = NULL, *archAngles = NULL;   // [3][n] caller order, for the archive records (mpmgpu_set_archive_origin)
     double archThickness = 1.;
@@ -130,6 +131,10 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
 
     ctx = new mpmgpu_ctx();
     ctx->cfg = *cfg;
+    {   // opt-in until it has been measured on a B200 (written after the round-1 GPU budget was spent)
+        const char *e = getenv("MPMGPU_CPDI_MERGE");
+        ctx->cpdiMerge = e && atoi(e) != 0;
+    }
     ctx->dim = is3D ? 3 : 2;
     ctx->dMats = NULL; ctx->nmat = 0; ctx->dFlags = NULL;
     ctx->cap = 0; ctx->mstep = 0; ctx->mtime = 0.; ctx->launches = 0;
@@ -636,11 +641,14 @@ extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const do
     if (grid_ > 0) { \
         if (ctx->dim == 3) { \
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<3, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<3, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<3, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else LAUNCH((KERNEL<3, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
         } else { \
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<2, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<2, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<2, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<2, SHAPE_QCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI) LAUNCH((KERNEL<2, SHAPE_QCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else LAUNCH((KERNEL<2, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
         } } } while (0)

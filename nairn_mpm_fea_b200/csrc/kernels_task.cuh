@@ -19,7 +19,9 @@ __device__ __forceinline__ void load_xi_lp(const Particles &P, int p, double xi[
 template <int DIM, int SHAPE, bool GRAD, class F>
 __device__ __forceinline__ void particle_nodes(const Grid &g, const Particles &P, int p, F &&f)
 {
-    if (SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI) {
+    if (SHAPE_IS_MERGED(SHAPE)) {
+        for_each_node_cpdi_merged<DIM, SHAPE, GRAD>(g, P, p, f);
+    } else if (SHAPE_IS_CPDI(SHAPE)) {
         for_each_node_cpdi<DIM, SHAPE, GRAD>(g, P, p, f);
     } else {
         double xi[3], lp[3];
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_init_particles(Grid g, Particl
     double xi[3];
     get_xipos<DIM>(g, e, pos, xi);
     P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
-    if ((SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI) && p < P.nNR) {     // ElementBase::GetShapeFunctionData (MoreMPMElementBase.cpp:50-58)
+    if (SHAPE_IS_CPDI(SHAPE) && p < P.nNR) {     // ElementBase::GetShapeFunctionData (MoreMPMElementBase.cpp:50-58)
         if (!cpdi_setup<DIM, SHAPE>(g, P, p)) atomicCAS(&flags->cpdiLeft, 0, P.orig[p] + 1);
     }
 }
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_project_rigid_bcs(Grid g, Part
         for (int d = 0; d < DIM; d++)
             if ((dirs >> d & 1) && !(fixed >> d & 1)) atomicMin(&R.owner[d][nd], p);
     };
-    if (SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI) {
+    if (SHAPE_IS_CPDI(SHAPE)) {
         // the nodes of the particle domain's corners (the reference's InitializationTask finds them for rigid particles too)
         if (!cpdi_setup<DIM, SHAPE>(g, PR, p)) { atomicCAS(&flags->cpdiLeft, 0, PR.orig[p] + 1); return; }
         for_each_node_cpdi<DIM, SHAPE, false>(g, PR, p, claim);
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_project_rigid_bcs(Grid g, Part
         double pos[3] = {PR.pos[0][p], PR.pos[1][p], DIM == 3 ? PR.pos[2][p] : 0.};
         double xi[3], lp[3] = {PR.lp[0][p], PR.lp[1][p], PR.lp[2][p]};
         get_xipos<DIM>(g, e, pos, xi);
-        for_each_node<DIM, SHAPE == SHAPE_LCPDI || SHAPE == SHAPE_QCPDI ? SHAPE_LINEAR : SHAPE, false>(g, e, xi, lp, claim);
+        for_each_node<DIM, SHAPE_IS_CPDI(SHAPE) ? SHAPE_LINEAR : SHAPE, false>(g, e, xi, lp, claim);
     }
 }
 

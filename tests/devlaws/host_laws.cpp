@@ -112,3 +112,40 @@ extern "C" int devarch_global_sums(int dim, int n, double *pos, double *vel, dou
     }
     return GS_NSUMS;
 }
+
+// ---- CPDI node iteration (csrc/shape.cuh): plain (one call per corner node) against merged (one call per node) ----------
+#include "shape.cuh"
+
+// Calls the device iteration for particle p and accumulates what f receives per node into out[4][nnodes] (S, gx, gy, gz) and the
+// number of calls into calls[nnodes].  shape: SHAPE_LCPDI / SHAPE_QCPDI; merged selects the _MERGED variant.
+template <int DIM, int SHAPE>
+static void run_cpdi(const Grid &g, const Particles &P, int n, double *out, int *calls)
+{
+    const size_t nn = (size_t)g.nnodes;
+    for (int p = 0; p < n; p++) {
+        auto f = [&](int nd, double S, double gx, double gy, double gz) {
+            out[nd] += S; out[nn + nd] += gx; out[2 * nn + nd] += gy; out[3 * nn + nd] += gz; calls[nd]++;
+        };
+        if (SHAPE_IS_MERGED(SHAPE)) for_each_node_cpdi_merged<DIM, SHAPE, true>(g, P, p, f);
+        else for_each_node_cpdi<DIM, SHAPE, true>(g, P, p, f);
+    }
+}
+
+extern "C" int devshape_cpdi_nodes(int dim, int shape, int merged, int horiz, int vert, int depth, int n, int *cpElem, double *cpXi, double *cpWg,
+                                   double *out, int *calls)
+{
+    Grid g;
+    memset(&g, 0, sizeof g);
+    g.dim = dim; g.horiz = horiz; g.vert = vert; g.depth = dim == 3 ? depth : 1;
+    g.yplane = horiz + 1; g.zplane = (horiz + 1) * (vert + 1);
+    g.nnodes = g.zplane * (dim == 3 ? depth + 1 : 1);
+    g.nelems = g.horiz * g.vert * g.depth;
+    Particles P;
+    memset(&P, 0, sizeof P);
+    P.n = n; P.nNR = n; P.cpElem = cpElem; P.cpXi = cpXi; P.cpWg = cpWg; P.cpStride = (size_t)n;
+    if (dim == 3 && shape == SHAPE_LCPDI) { if (merged) run_cpdi<3, SHAPE_LCPDI_MERGED>(g, P, n, out, calls); else run_cpdi<3, SHAPE_LCPDI>(g, P, n, out, calls); }
+    else if (dim == 2 && shape == SHAPE_LCPDI) { if (merged) run_cpdi<2, SHAPE_LCPDI_MERGED>(g, P, n, out, calls); else run_cpdi<2, SHAPE_LCPDI>(g, P, n, out, calls); }
+    else if (dim == 2 && shape == SHAPE_QCPDI) { if (merged) run_cpdi<2, SHAPE_QCPDI_MERGED>(g, P, n, out, calls); else run_cpdi<2, SHAPE_QCPDI>(g, P, n, out, calls); }
+    else return -1;
+    return 0;
+}

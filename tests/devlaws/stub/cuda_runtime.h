@@ -9,3 +9,8 @@
 #define __global__
 #define __forceinline__ inline
 static inline double atomicAdd(double *a, double v) { double o = *a; *a += v; return o; }
+// round-to-nearest intrinsics = plain IEEE operations (the host build uses -ffp-contract=off)
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }

@@ -27,7 +27,7 @@ def _dp(a):
 def libs():
     src = os.path.join(DEV, "host_laws.cpp")
     csrc = os.path.join(ROOT, "nairn_mpm_fea_b200", "csrc")
-    deps = [src, os.path.join(csrc, "materials.cuh"), os.path.join(csrc, "mpm_types.cuh"), os.path.join(csrc, "archive.cuh")]
+    deps = [src, os.path.join(csrc, "materials.cuh"), os.path.join(csrc, "mpm_types.cuh"), os.path.join(csrc, "archive.cuh"), os.path.join(csrc, "shape.cuh"), os.path.join(DEV, "stub", "cuda_runtime.h")]
     if not os.path.exists(LIBDEV) or any(os.path.getmtime(d) > os.path.getmtime(LIBDEV) for d in deps):
         os.makedirs(os.path.dirname(LIBDEV), exist_ok=True)
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-std=c++17", "-I" + os.path.join(DEV, "stub"),

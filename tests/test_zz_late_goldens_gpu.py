@@ -71,3 +71,34 @@ def test_fused_path_refuses_large_rotation():
     z = load_golden("block3d_isotropic_lr")
     with pytest.raises(MpmGpuError):
         make_sim(z, 2)
+
+
+# ---- CPDI kernels with the corners' contributions merged per node (opt-in MPMGPU_CPDI_MERGE=1, shape.cuh) ----------------
+CPDI_CASES = ["block3d_lcpdi_neo_xpic2", "block3d_lcpdi_rcrit", "block3d_lcpdi_rigid_wall", "disks2d_lcpdi", "disks2d_qcpdi"]
+
+
+@pytest.mark.parametrize("case", CPDI_CASES)
+def test_cpdi_merged_whole_steps(case, monkeypatch):
+    """Same goldens and tolerances as the plain CPDI kernels (tests/test_parity_tasks_gpu.py): merging only changes the order in
+    which a node's corner contributions are summed."""
+    from tests.parity import xpic_for_step
+    monkeypatch.setenv("MPMGPU_CPDI_MERGE", "1")
+    z = load_golden(case)
+    sim = make_sim(z, 1)
+    snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
+    done = 0
+    for s in snaps:
+        while done < s:
+            x = xpic_for_step(z, done + 1)
+            if x:
+                sim.set_xpic(*x)
+            sim.step(1)
+            done += 1
+        tol = tolerances(case)[0] if s == 1 else tolerances(case)[2]
+        got = sim.download()
+        errs, bad = compare_particles(got, z, "p%d" % s, tol)
+        assert not bad, "%s (merged CPDI) after %d steps: %s" % (case, s, bad)
+        assert np.array_equal(got["in_elem"], z["p%d/inElem" % s])
+        errs, bad = compare_nodes(sim.download_nodes(), z, "n%d" % s, tol)
+        assert not bad, "%s (merged CPDI) after %d steps: nodes %s" % (case, s, bad)
+    sim.close()
