@@ -1388,6 +1388,46 @@ int oracle_law_batch(int np, double gridx, double gridy, double gridz, const mpm
     return 0;
 }
 
+/* Shape functions and element search alone, on caller-owned arrays: for tests that compare another implementation of the same
+ * formulas (the device source compiled for the host, tests/test_device_shape_cpu.py) without building a run.
+ * Linear and uGIMP only (cfg->shape); nds/fn/xd/yd/zd are [n][64], count[n]. */
+static void batch_grid(Oracle *t, const mpmgpu_config *cfg)
+{
+    memset(t, 0, sizeof *t);
+    t->cfg = *cfg;
+    t->dim = cfg->np == MPMGPU_THREED_MPM ? 3 : 2;
+    t->horiz = cfg->horiz; t->vert = cfg->vert; t->depth = t->dim == 3 ? cfg->depth : 1;
+    t->xplane = 1; t->yplane = t->horiz + 1; t->zplane = (t->horiz + 1) * (t->vert + 1);
+    t->nnodes = t->zplane * (t->dim == 3 ? t->depth + 1 : 1);
+    t->nelems = t->horiz * t->vert * t->depth;
+    t->xpts = (double *)cfg->xpts; t->ypts = (double *)cfg->ypts; t->zpts = (double *)cfg->zpts;
+}
+
+int oracle_shape_batch(const mpmgpu_config *cfg, int n, int *inElem, double *ncpos, double *lp, int getDeriv,
+                       int *count, int *nds, double *fn, double *xd, double *yd, double *zd)
+{
+    if (cfg->shape != MPMGPU_POINT_GIMP && cfg->shape != MPMGPU_UNIFORM_GIMP) return -1;
+    Oracle *saved = O, tmp;
+    batch_grid(&tmp, cfg);
+    tmp.n = n; tmp.nNR = n; tmp.inElem = inElem; tmp.ncpos = ncpos; tmp.lp = lp;
+    O = &tmp;
+    for (int p = 0; p < n; p++)
+        count[p] = shape(p, getDeriv, nds + (size_t)64 * p, fn + (size_t)64 * p, xd + (size_t)64 * p, yd + (size_t)64 * p, zd + (size_t)64 * p);
+    O = saved;
+    return 0;
+}
+
+/* x is [n][3]; elem[n] = MeshInfo::FindElementFromPoint (0 = off the grid) */
+int oracle_find_element_batch(const mpmgpu_config *cfg, int n, const double *x, int *elem)
+{
+    Oracle *saved = O, tmp;
+    batch_grid(&tmp, cfg);
+    O = &tmp;
+    for (int p = 0; p < n; p++) elem[p] = find_element(x + (size_t)3 * p);
+    O = saved;
+    return 0;
+}
+
 void oracle_destroy(void)
 {
     if (!O) return;

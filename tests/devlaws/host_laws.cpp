@@ -149,3 +149,67 @@ extern "C" int devshape_cpdi_nodes(int dim, int shape, int merged, int horiz, in
     else return -1;
     return 0;
 }
+
+// ---- Linear / uGIMP shape functions and the element search of the device source ---------------------------------------
+static void host_grid(Grid &g, int dim, int np, int horiz, int vert, int depth, const double *xpts, const double *ypts, const double *zpts,
+                      double gx, double gy, double gz)
+{
+    memset(&g, 0, sizeof g);
+    g.dim = dim; g.np = np; g.horiz = horiz; g.vert = vert; g.depth = dim == 3 ? depth : 1;
+    g.yplane = horiz + 1; g.zplane = (horiz + 1) * (vert + 1);
+    g.nnodes = g.zplane * (dim == 3 ? depth + 1 : 1);
+    g.nelems = g.horiz * g.vert * g.depth;
+    g.xpts = xpts; g.ypts = ypts; g.zpts = zpts;
+    g.gx = gx; g.gy = gy; g.gz = gz;
+    g.xmin = xpts[0]; g.ymin = ypts[0]; g.zmin = dim == 3 ? zpts[0] : 0.;
+    g.rcrit = -1.;
+}
+
+template <int DIM, int SHAPE>
+static void run_shape(const Grid &g, int n, const int *inElem, const double *ncpos, const double *lp, int *count, int *nds, double *fn,
+                      double *xd, double *yd, double *zd)
+{
+    for (int p = 0; p < n; p++) {
+        const double xi[3] = {ncpos[p], ncpos[(size_t)n + p], ncpos[(size_t)2 * n + p]};
+        const double l[3] = {lp[p], lp[(size_t)n + p], lp[(size_t)2 * n + p]};
+        int k = 0;
+        const size_t o = (size_t)64 * p;
+        for_each_node<DIM, SHAPE, true>(g, inElem[p], xi, l, [&](int nd, double S, double gxv, double gyv, double gzv) {
+            nds[o + k] = nd; fn[o + k] = S; xd[o + k] = gxv; yd[o + k] = gyv; zd[o + k] = gzv; k++;
+        });
+        count[p] = k;
+    }
+}
+
+extern "C" int devshape_nodes(int dim, int np, int shape, int horiz, int vert, int depth, const double *xpts, const double *ypts, const double *zpts,
+                              double gx, double gy, double gz, int n, const int *inElem, const double *ncpos, const double *lp,
+                              int *count, int *nds, double *fn, double *xd, double *yd, double *zd)
+{
+    Grid g;
+    host_grid(g, dim, np, horiz, vert, depth, xpts, ypts, zpts, gx, gy, gz);
+    if (dim == 3 && shape == SHAPE_LINEAR) run_shape<3, SHAPE_LINEAR>(g, n, inElem, ncpos, lp, count, nds, fn, xd, yd, zd);
+    else if (dim == 3 && shape == SHAPE_UGIMP) run_shape<3, SHAPE_UGIMP>(g, n, inElem, ncpos, lp, count, nds, fn, xd, yd, zd);
+    else if (dim == 2 && shape == SHAPE_LINEAR) run_shape<2, SHAPE_LINEAR>(g, n, inElem, ncpos, lp, count, nds, fn, xd, yd, zd);
+    else if (dim == 2 && shape == SHAPE_UGIMP) run_shape<2, SHAPE_UGIMP>(g, n, inElem, ncpos, lp, count, nds, fn, xd, yd, zd);
+    else return -1;
+    return 0;
+}
+
+// x [n][3] -> elem[n] (0 = off grid), xi[n][3] natural coordinates in that element, inside[n] = PtInElement(elem, x)
+extern "C" int devshape_find_element(int dim, int np, int horiz, int vert, int depth, const double *xpts, const double *ypts, const double *zpts,
+                                     double gx, double gy, double gz, int n, const double *x, int *elem, double *xi, int *inside)
+{
+    Grid g;
+    host_grid(g, dim, np, horiz, vert, depth, xpts, ypts, zpts, gx, gy, gz);
+    for (int p = 0; p < n; p++) {
+        const double *pos = x + (size_t)3 * p;
+        const int e = dim == 3 ? find_element_from_point<3>(g, pos) : find_element_from_point<2>(g, pos);
+        elem[p] = e;
+        inside[p] = 0;
+        if (e > 0) {
+            if (dim == 3) { get_xipos<3>(g, e, pos, xi + (size_t)3 * p); inside[p] = pt_in_element<3>(g, e, pos) ? 1 : 0; }
+            else { get_xipos<2>(g, e, pos, xi + (size_t)3 * p); inside[p] = pt_in_element<2>(g, e, pos) ? 1 : 0; }
+        }
+    }
+    return 0;
+}

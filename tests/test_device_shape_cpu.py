@@ -85,3 +85,101 @@ def test_merged_iteration_calls_once_per_node_inside_one_element(libs):  # noqa:
         assert dev.devshape_cpdi_nodes(3, LCPDI, merged, horiz, vert, depth, n, _ip(elem), _dp(xi), _dp(wg), _dp(out), _ip(calls)) == 0
         tot.append(int(calls.sum()))
     assert tot == [64 * n, 8 * n]
+
+
+# ---- Linear / uGIMP shape functions and the element search: device source against the C restatement ---------------------
+def _grid(dim, horiz=9, vert=8, depth=7, cell=(1.0, 0.5, 0.25), origin=(-2.0, 1.0, 0.125)):
+    from nairn_mpm_fea_b200.capi import ABI_VERSION, Config
+    xp = origin[0] + cell[0] * np.arange(horiz + 1)
+    yp = origin[1] + cell[1] * np.arange(vert + 1)
+    zp = origin[2] + cell[2] * np.arange(depth + 1)
+    cfg = Config()
+    cfg.abi_version = ABI_VERSION
+    cfg.np = 12 if dim == 3 else 10
+    cfg.horiz, cfg.vert, cfg.depth = horiz, vert, depth if dim == 3 else 0
+    cfg.xpts, cfg.ypts, cfg.zpts = _dp(xp), _dp(yp), (_dp(zp) if dim == 3 else None)
+    cfg.gridx, cfg.gridy, cfg.gridz = cell[0], cell[1], (cell[2] if dim == 3 else 0.0)
+    return cfg, (xp, yp, zp), (horiz, vert, depth)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("shape", [0, 1])          # Linear ("Classic"), uGIMP
+def test_shape_functions_of_the_device_source_are_bitwise_those_of_the_oracle(libs, dim, shape):  # noqa: F811
+    dev, orc = libs
+    cfg, (xp, yp, zp), (horiz, vert, depth) = _grid(dim)
+    cfg.shape = shape
+    n = 3000
+    rng = np.random.default_rng(17 + 2 * dim + shape)
+    ei, ej = rng.integers(1, horiz - 1, n), rng.integers(1, vert - 1, n)
+    ek = rng.integers(1, depth - 1, n) if dim == 3 else np.zeros(n, np.int64)
+    in_elem = np.ascontiguousarray(1 + ei + horiz * (ej + vert * ek), dtype=np.int32)
+    ncpos = rng.uniform(-1.0, 1.0, (3, n))
+    # the branch points of the GIMP weight: on the element faces, at |xi - xi_node| = lp and 2 - lp
+    special = np.array([-1.0, 1.0, 0.0, -0.5, 0.5, -0.25, 0.75])
+    pick = rng.random((3, n)) < 0.3
+    ncpos = np.where(pick, special[rng.integers(0, special.size, (3, n))], ncpos)
+    lp = np.where(rng.random((3, n)) < 0.5, 0.5, rng.uniform(0.2, 1.0, (3, n)))
+    if dim == 2:
+        ncpos[2] = 0.0
+    ncpos, lp = np.ascontiguousarray(ncpos), np.ascontiguousarray(lp)
+    out = []
+    for which in ("oracle", "device"):
+        count = np.zeros(n, np.int32)
+        nds = np.full((n, 64), -1, np.int32)
+        fn, xd, yd, zd = (np.zeros((n, 64)) for _ in range(4))
+        if which == "oracle":
+            rc = orc.oracle_shape_batch(C.byref(cfg), n, _ip(in_elem), _dp(ncpos), _dp(lp), 1, _ip(count), _ip(nds), _dp(fn), _dp(xd), _dp(yd), _dp(zd))
+        else:
+            rc = dev.devshape_nodes(dim, cfg.np, shape, horiz, vert, depth, _dp(xp), _dp(yp), _dp(zp), C.c_double(cfg.gridx), C.c_double(cfg.gridy),
+                                    C.c_double(cfg.gridz), n, _ip(in_elem), _dp(ncpos), _dp(lp), _ip(count), _ip(nds), _dp(fn), _dp(xd), _dp(yd), _dp(zd))
+        assert rc == 0
+        out.append((count, nds, fn, xd, yd, zd))
+    (co, no, fo, xo, yo, zo), (cd, nd_, fd, xdd, ydd, zdd) = out
+    assert np.array_equal(co, cd), "same number of nodes per particle"
+    assert co.min() >= (4 if dim == 2 else 8) and co.max() <= (16 if dim == 2 else 64)
+    for p in range(n):
+        k = co[p]
+        # the device walks its own node order; the values per node must be the same bits
+        io, idv = np.argsort(no[p, :k], kind="stable"), np.argsort(nd_[p, :k], kind="stable")
+        assert np.array_equal(no[p, :k][io], nd_[p, :k][idv]), p
+        for a, b, nm in ((fo, fd, "S"), (xo, xdd, "dS/dx"), (yo, ydd, "dS/dy"), (zo, zdd, "dS/dz")):
+            assert np.array_equal(a[p, :k][io], b[p, :k][idv]), (p, nm, a[p, :k][io] - b[p, :k][idv])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_element_search_of_the_device_source_is_the_oracles(libs, dim):  # noqa: F811
+    """MeshInfo::FindElementFromPoint on points inside, on cell faces (the integer must be the reference's), on the far grid
+    faces (the reference assigns them to the last element) and off the grid."""
+    dev, orc = libs
+    cfg, (xp, yp, zp), (horiz, vert, depth) = _grid(dim)
+    rng = np.random.default_rng(23 + dim)
+    n = 6000
+    lo = np.array([xp[0], yp[0], zp[0]])
+    hi = np.array([xp[-1], yp[-1], zp[-1]])
+    x = lo + (hi - lo) * rng.uniform(-0.05, 1.05, (n, 3))
+    faces = [xp, yp, zp]
+    for c in range(3):
+        on_face = rng.random(n) < 0.3
+        x[:, c] = np.where(on_face, faces[c][rng.integers(0, faces[c].size, n)], x[:, c])
+        nudge = rng.random(n) < 0.15
+        x[:, c] = np.where(nudge, np.nextafter(x[:, c], np.where(rng.random(n) < 0.5, -np.inf, np.inf)), x[:, c])
+    if dim == 2:
+        x[:, 2] = 0.0
+    x = np.ascontiguousarray(x)
+    eo, ed = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    xi, inside = np.zeros((n, 3)), np.zeros(n, np.int32)
+    assert orc.oracle_find_element_batch(C.byref(cfg), n, _dp(x), _ip(eo)) == 0
+    assert dev.devshape_find_element(dim, cfg.np, horiz, vert, depth, _dp(xp), _dp(yp), _dp(zp), C.c_double(cfg.gridx), C.c_double(cfg.gridy),
+                                     C.c_double(cfg.gridz), n, _dp(x), _ip(ed), _dp(xi), _ip(inside)) == 0
+    assert np.array_equal(eo, ed)
+    assert 0.05 < np.mean(eo == 0) < 0.6 and np.count_nonzero(eo) > n // 3
+    # natural coordinates of a point of the grid box lie in [-1, 1] in the element found for it, and PtInElement agrees except
+    # on the far faces (the (int) truncation also "finds" points up to one cell below the low faces -- the reference's behaviour,
+    # reproduced by both)
+    d = 3 if dim == 3 else 2
+    # (a point one ulp inside a far face rounds to column = horiz in (x - xmin)/dx and is declared off the grid by the reference's
+    # arithmetic -- also reproduced by both -- so the sanity check stays 1e-9 away from the far faces)
+    box = np.all((x[:, :d] >= lo[:d]) & (x[:, :d] <= hi[:d] - 1e-9), axis=1)
+    assert np.all(ed[box] > 0)
+    assert np.all(np.abs(xi[box][:, :d]) <= 1.0 + 1e-12)          # a point one ulp under a face can land in the cell above it
+    assert np.mean(inside[box] == 1) > 0.95
