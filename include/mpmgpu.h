@@ -268,6 +268,11 @@ int mpmgpu_slab_migration_counts(mpmgpu_ctx *ctx, int *n_lo, int *n_hi);
 int mpmgpu_slab_migration_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, int *row_doubles, int *capacity_rows);
 int mpmgpu_slab_pack_migrants(mpmgpu_ctx *ctx);            /* rows -> send buffers */
 int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int n_from_hi);  /* drop leavers, append arrivals */
+/* particles that left the grid and were pushed back (ResetElementsTask.cpp:71-151,232-265) since the upload: `exits` counts
+ * every push-back, `particles` the particles leaving for the first time -- the events the reference issues its
+ * "Particle has left the grid" warning for (abort threshold <LeaveLimit>, NairnMPM.cpp:814-832); the host feeds its own
+ * MPMWarnings with the increase of `particles`.  Synchronises the stream. */
+int mpmgpu_left_grid_counts(mpmgpu_ctx *ctx, long long *exits, long long *particles);
 int mpmgpu_num_particles(const mpmgpu_ctx *ctx);
 /* launch on the caller's CUDA stream (cudaStream_t as void*; NULL = back to the context's own), so the
  * host's NCCL calls and the kernels are ordered on one stream without host synchronisation */

@@ -33,6 +33,7 @@ EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last
     "mpmgpu_slab_configure", "mpmgpu_slab_halo_buffers", "mpmgpu_slab_step_phase", "mpmgpu_slab_set_halo_callback", "mpmgpu_slab_migration_counts",
     "mpmgpu_slab_migration_buffers", "mpmgpu_slab_pack_migrants", "mpmgpu_slab_finish_migration",
     "mpmgpu_num_particles", "mpmgpu_set_stream",
+    "mpmgpu_left_grid_counts",
     "mpmgpu_archive_record_size", "mpmgpu_set_archive_origin", "mpmgpu_pack_archive", "mpmgpu_global_sums"]
 
 HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)     # mpmgpu_halo_fn
@@ -129,6 +130,7 @@ def load_library(path=None):
     lib.mpmgpu_slab_finish_migration.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_num_particles.argtypes = [vp]
     lib.mpmgpu_set_stream.argtypes = [vp, vp]
+    lib.mpmgpu_left_grid_counts.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.mpmgpu_archive_record_size.argtypes = [vp, C.c_char_p]
     lib.mpmgpu_set_archive_origin.argtypes = [vp, _dp, _dp, C.c_double]
     lib.mpmgpu_pack_archive.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
@@ -410,6 +412,12 @@ class MpmGpu:
         mt = C.c_double()
         self._check(self.lib.mpmgpu_get_status(self.ctx, C.byref(ms), C.byref(mt), C.byref(cr), C.byref(lg)))
         return dict(mstep=ms.value, mtime=mt.value, crossings=cr.value, left_grid=lg.value)
+
+    def left_grid_counts(self):
+        """(push-backs, particles that left the grid for the first time) since the upload."""
+        ex, pt = C.c_longlong(0), C.c_longlong(0)
+        self._check(self.lib.mpmgpu_left_grid_counts(self.ctx, C.byref(ex), C.byref(pt)))
+        return ex.value, pt.value
 
     def launch_count(self):
         return int(self.lib.mpmgpu_launch_count(self.ctx))

@@ -1340,7 +1340,18 @@ extern "C" int mpmgpu_get_status(mpmgpu_ctx *ctx, long long *mstep, double *mtim
     if (mstep) *mstep = ctx->mstep;
     if (mtime) *mtime = ctx->mtime;
     if (crossings) *crossings = (long long)ctx->hFlags.crossings;
-    if (leftGrid) *leftGrid = (long long)ctx->hFlags.leftGrid;
+    if (leftGrid) *leftGrid = (long long)(ctx->hFlags.leftGrid & 0xffffffffull);       // exits (the high word counts first-time leavers)
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_left_grid_counts(mpmgpu_ctx *ctx, long long *exits, long long *particles)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    cudaSetDevice(ctx->cfg.device);
+    CK(cudaMemcpyAsync(&ctx->hFlags, ctx->dFlags, sizeof(StatusFlags), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (exits) *exits = (long long)(ctx->hFlags.leftGrid & 0xffffffffull);
+    if (particles) *particles = (long long)(ctx->hFlags.leftGrid >> 32);
     return MPMGPU_OK;
 }
 

@@ -562,7 +562,9 @@ __device__ __forceinline__ void reset_element_one(const Grid &g, const Particles
     {
         int c = P.cross[p];
         P.cross[p] = c > 0 ? -(c + 1) : c - 1;
-        atomicAdd(&flags->leftGrid, 1ull);
+        // low word: exits; high word: particles leaving for the first time (MPMBase::HasLeftTheGridBefore = negative crossings) --
+        // the ones the reference issues its "left the grid" warning for (ResetElementsTask.cpp:71-95)
+        atomicAdd(&flags->leftGrid, c >= 0 ? ((1ull << 32) | 1ull) : 1ull);
     }
     double outside[3] = {pos[0], pos[1], pos[2]};
     double inside[3];

@@ -44,6 +44,8 @@
 #include "System/ArchiveData.hpp"
 #include "Global_Quantities/GlobalQuantity.hpp"
 #include "Exceptions/CommonException.hpp"
+#include "Exceptions/MPMWarnings.hpp"
+#include "Materials/Elastic.hpp"
 #undef private
 #undef protected
 
@@ -59,6 +61,7 @@ bool gHostStale = false;            // device is ahead of mpm[]
 std::vector<NodalVelBC *> gBCs;     // host BC list in list order
 bool gBCsVary = false;
 bool gRigidFunctions = false;       // some rigid-BC material sets its velocity by functions of time and position
+long long gLeftGridWarned = 0;     // first-time grid leavers already handed to the reference's MPMWarnings
 bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
 void check(int rc, const char *where)
@@ -133,6 +136,16 @@ class GpuTask : public MPMTask
         if (gRigidFunctions)        // keep the host copy of the rigid positions current for the next evaluation
             for (int p = nmpmsRC; p < nmpms; p++) mpm[p]->MovePosition(timestep);
         gHostStale = true;
+        {   // particles pushed back into the grid: the reference warns once per particle and aborts at the <LeaveLimit>
+            // threshold (ResetElementsTask.cpp:71-95); same warning object, same exception
+            long long exits = 0, first = 0;
+            check(mpmgpu_left_grid_counts(gCtx, &exits, &first), "GpuTask(ResetElements)");
+            for (; gLeftGridWarned < first; gLeftGridWarned++)
+                if (warnings.Issue(fmobj->warnParticleLeftGrid, -1) == REACHED_MAX_WARNINGS) {
+                    DownloadToHost();
+                    throw CommonException("Too many particles have left the grid\n  (plot x displacement to see last one).", "ResetElementsTask::Execute");
+                }
+        }
         // will the reference archive after this step?  (ArchiveResults(mtime+timestep,...), ArchiveData.cpp:731-746)
         const double atime = mtime + timestep;
         bool due = atime >= archiver->nextArchTime || atime + timestep > fmobj->maxtime;
@@ -211,6 +224,10 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     // custom tasks run on the host particles between the step tasks; only the one that just switches the XPIC/FMPM order is safe
     for (CustomTask *ct = theTasks; ct != NULL; ct = ct->nextTask)
         if (strcmp(ct->TaskName(), "Periodic XPIC Implementation") != 0) return "custom tasks other than PeriodicXPIC";
+    // failure handling the replaced ResetElements / PostForces tasks would do on the host objects
+    if (fabs(fmobj->restartScaling) > 1.e-6) return "time-step restarts (<RestartScaling>)";
+    if (fmobj->deleteLeavingParticles) return "deleting particles that leave the grid (<LeaveLimit> < 0)";
+    if (warnings.GetMaxIssues(fmobj->warnParticleDeleted) >= 2) return "deleting nan particles (<DeleteLimit> > 1)";
     if (nmpmsRC != nmpmsNR) return "rigid contact or rigid block particles present";
     if (nmpms != nmpmsNR && MaterialBase::extrapolateRigidBCs) return "rigid BCs by extrapolation";
     if (fmobj->np != PLANE_STRAIN_MPM && fmobj->np != PLANE_STRESS_MPM && fmobj->np != THREED_MPM) return "analysis type";
@@ -220,6 +237,9 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     for (int i = 0; i < nmat; i++) {
         MaterialBase *mb = theMaterials[i];
         if (mb->artificialViscosity && mb->MaterialID() != 28 && mb->MaterialID() != 9) return "artificial viscosity on this material";
+        // dF = exp(du) to <DefGradTerms> terms (Neohookean, large-rotation laws): the device uses the defaults, 1 in 3D and 2 in 2D
+        if ((mb->MaterialID() == 28 || ((mb->MaterialID() == 1 || mb->MaterialID() == 9) && ((Elastic *)mb)->useLargeRotation)) &&
+            MaterialBase::incrementalDefGradTerms != (fmobj->IsThreeD() ? 1 : 2)) return "<DefGradTerms> other than the default";
         switch (mb->MaterialID()) {
         case 1: break;          // small- and large-rotation hypoelasticity (Elastic::useLargeRotation -> material slot 7)
         case 28: break;

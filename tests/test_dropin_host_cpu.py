@@ -17,14 +17,23 @@ LOAD_BC = ('<ParticleBCs><BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="3"
            '</BCBox></ParticleBCs>')
 
 CASES = {
-    "archiving custom task": (inputs.block3d(ncell=2, margin=2, maxtime=0.003, custom_tasks='<CustomTasks><Schedule name="VTKArchive">'
+    "archiving custom task": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, custom_tasks='<CustomTasks><Schedule name="VTKArchive">'
                                              '<Parameter name="mass"/></Schedule></CustomTasks>'), "custom tasks other than PeriodicXPIC"),
-    "feedback damping": (inputs.block3d(ncell=2, margin=2, maxtime=0.003, extra_header="<FeedbackDamping>10</FeedbackDamping>"),
+    "feedback damping": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<FeedbackDamping>10</FeedbackDamping>"),
                          "time-dependent or feedback damping"),
-    "particle loads": (inputs.block3d(ncell=2, margin=2, maxtime=0.003).replace("</GridBCs>", "</GridBCs>" + LOAD_BC), "particle load BCs"),
-    "unsupported material": (inputs.block3d(ncell=2, margin=2, maxtime=0.003, material='<Material Type="8" Name="Blk"><rho>1</rho><G1>30</G1>'
+    "particle loads": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</GridBCs>", "</GridBCs>" + LOAD_BC), "particle load BCs"),
+    "unsupported material": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="8" Name="Blk"><rho>1</rho><G1>30</G1>'
                                             '<G2>0</G2><K>100</K><alpha>0</alpha></Material>'), "material type"),
-    "unsupported shape functions": (inputs.block3d(ncell=2, margin=2, maxtime=0.003, gimp="B2GIMP"), "shape functions"),
+    "unsupported shape functions": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, gimp="B2GIMP"), "shape functions"),
+    # failure handling of the replaced tasks that libmpmgpu does not do
+    "time-step restarts": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, method=3, extra_header="<RestartScaling>0.5</RestartScaling>"),
+                           "time-step restarts"),
+    # (with fewer than 100 particles the reference's DEFAULT LeaveLimit, 1 % of the particles, rounds to 0 and lands in the delete
+    # branch too -- NairnMPM.cpp:814-832 -- which is why every input of this file has at least 200 particles)
+    "deleting leavers": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<LeaveLimit>-5</LeaveLimit>"), "deleting particles that leave the grid"),
+    "deleting nan particles": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<DeleteLimit>5</DeleteLimit>"), "deleting nan particles"),
+    "more exponential terms": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material=inputs.neohookean_material(),
+                                              extra_header="<DefGradTerms>3</DefGradTerms>"), "<DefGradTerms> other than the default"),
 }
 
 
@@ -51,7 +60,19 @@ def test_eligible_input_reaches_the_device_and_has_no_cpu_fallback():
         pytest.skip("host/_build/NairnMPM_gpu not built")
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by tests/test_dropin_gpu.py")
-    p = run(inputs.block3d(ncell=2, margin=2, maxtime=0.003))
+    p = run(inputs.block3d(ncell=3, margin=2, maxtime=0.003))
+    assert p.returncode == 2 and "no CUDA device" in p.stderr, (p.returncode, p.stderr[-500:])
+
+
+def test_options_that_do_not_matter_to_the_built_laws_are_accepted():
+    """<DefGradTerms> only enters laws that exponentiate du (Neohookean, large rotation): a small-rotation IsotropicMat run stays
+    eligible; so does <LeaveLimit> > 0 (push back, the default behaviour with another threshold)."""
+    import torch
+    if not os.path.exists(GPU):
+        pytest.skip("host/_build/NairnMPM_gpu not built")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_dropin_gpu.py")
+    p = run(inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<DefGradTerms>3</DefGradTerms><LeaveLimit>20</LeaveLimit>"))
     assert p.returncode == 2 and "no CUDA device" in p.stderr, (p.returncode, p.stderr[-500:])
 
 
@@ -59,5 +80,5 @@ def test_cpu_switch_runs_the_reference_tasks_unchanged():
     """`-cpu` leaves the reference's own tasks in place: the same binary is then the reference."""
     if not os.path.exists(GPU):
         pytest.skip("host/_build/NairnMPM_gpu not built")
-    p = run(inputs.block3d(ncell=2, margin=2, maxtime=0.003), ("-cpu",))
+    p = run(inputs.block3d(ncell=3, margin=2, maxtime=0.003), ("-cpu",))
     assert p.returncode == 0 and "GPU TASKS" not in p.stdout and "Calculation Steps" in p.stdout
