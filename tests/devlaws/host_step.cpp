@@ -1,0 +1,268 @@
+// TEST INFRASTRUCTURE: the per-task kernels of libmpmgpu (csrc/kernels_task.cuh, with shape.cuh and materials.cuh) compiled
+// for the host through tests/devlaws/stub and run one CUDA thread after the other, in the task order of capi.cu::step_by_tasks
+// (= the reference's MPMTask list), for inputs without velocity BCs and without rigid particles.  tests/test_device_step_cpu.py
+// compares the result with the golden dumps of the unmodified reference: the CUDA SOURCE of the general path is checked on
+// every CPU run; the compiled kernels and the host orchestration of capi.cu are checked by the GPU parity tests.
+// This is not a product path: nothing outside tests/ builds or loads it.
+#include "kernels_task.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+struct EmuSim {
+    Grid g;
+    Particles P;
+    Nodes N;
+    StepParams sp;
+    StatusFlags flags;
+    std::vector<Material> mats;
+    std::vector<double> xpts, ypts, zpts, ppool, npool, cpXi, cpWg;
+    std::vector<int> ipool, ncnt, cpElem;
+    int dim, shape, n;
+    bool largeRotation;
+    long long mstep;
+};
+
+inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+#define DISPATCH(KERNEL, n, ...) do { \
+    const int grid_ = nblk((n), TASK_THREADS); \
+    if (S->dim == 3) { \
+        if (S->shape == SHAPE_UGIMP) EMU_LAUNCH((KERNEL<3, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_LCPDI) EMU_LAUNCH((KERNEL<3, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_LCPDI_MERGED) EMU_LAUNCH((KERNEL<3, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else EMU_LAUNCH((KERNEL<3, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
+    } else { \
+        if (S->shape == SHAPE_UGIMP) EMU_LAUNCH((KERNEL<2, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_LCPDI) EMU_LAUNCH((KERNEL<2, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_LCPDI_MERGED) EMU_LAUNCH((KERNEL<2, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_QCPDI) EMU_LAUNCH((KERNEL<2, SHAPE_QCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_QCPDI_MERGED) EMU_LAUNCH((KERNEL<2, SHAPE_QCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else EMU_LAUNCH((KERNEL<2, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
+    } } while (0)
+
+const VelBCs NO_BCS = {0, NULL, NULL, NULL, NULL, NULL, NULL};
+
+RigidBCs no_rigid()
+{
+    RigidBCs R;
+    memset(&R, 0, sizeof R);
+    return R;
+}
+
+void xpic_extrapolation(EmuSim *S, int particleUpdate)
+{
+    const int nn = S->g.nnodes, fmpm = S->sp.usingFMPM ? 1 : 0;
+    EMU_LAUNCH(k_xpic_init, nblk(nn, 256), 256, nn, S->N, S->sp.dt, fmpm);
+    for (int k = 2; k <= S->sp.xpicOrder; k++) {
+        DISPATCH(k_xpic_iterate, S->P.nNR, S->g, S->P, S->N);
+        EMU_LAUNCH(k_xpic_finish, nblk(nn, 256), 256, nn, S->N, NO_BCS, (const int *)NULL, no_rigid(), S->sp.dt, particleUpdate, fmpm);
+    }
+}
+
+void strain_update(EmuSim *S, double strainTime, bool postUpdate)
+{
+    if (S->sp.usingFMPM && S->sp.xpicOrder > 1) {
+        if (!postUpdate || !S->sp.skipPost) xpic_extrapolation(S, 0);
+    } else
+        EMU_LAUNCH(k_grid_velocity, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->N);
+    if (S->largeRotation) DISPATCH(k_update_strains_lr, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime);
+    else DISPATCH(k_update_strains, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime);
+}
+
+// task numbers as in capi.cu: 0 initialization ... 9 reset elements
+void run_task(EmuSim *S, int t)
+{
+    const int nn = S->g.nnodes;
+    switch (t) {
+    case 0:
+        std::fill(S->npool.begin(), S->npool.end(), 0.);
+        std::fill(S->ncnt.begin(), S->ncnt.end(), 0);
+        DISPATCH(k_init_particles, S->P.n, S->g, S->P, &S->flags);
+        break;
+    case 1: DISPATCH(k_p2g_mass_momentum, S->P.nNR, S->g, S->P, S->N); break;
+    case 2: EMU_LAUNCH(k_copy_momenta, nblk(nn, 256), 256, nn, S->N); break;                       // no BCs on this path
+    case 3:
+        if (S->sp.method != METHOD_USL) strain_update(S, S->sp.method == METHOD_USAVG ? S->sp.dtStrainFirst : S->sp.dt, false);
+        break;
+    case 4: DISPATCH(k_p2g_forces, S->P.nNR, S->g, S->P, S->N, 0); break;
+    case 5: EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp); break;
+    case 6: EMU_LAUNCH(k_update_momenta, nblk(nn, 256), 256, nn, S->N, S->sp.dt); break;
+    case 7: {
+        if (S->sp.xpicOrder > 1) xpic_extrapolation(S, 1);
+        else EMU_LAUNCH(k_grid_velocity, nblk(nn, 256), 256, nn, S->N);
+        int m = S->sp.xpicOrder;
+        if (!S->sp.usingFMPM) m = -m;
+        DISPATCH(k_update_particles, S->P.nNR, S->g, S->P, S->N, S->mats.data(), S->sp, m);
+        break;
+    }
+    case 8:
+        if (S->sp.method == METHOD_USF) break;
+        if (!S->sp.skipPost) {
+            EMU_LAUNCH(k_rezero_momenta, nblk(nn, 256), 256, nn, S->N);
+            DISPATCH(k_p2g_momentum_last, S->P.nNR, S->g, S->P, S->N);
+        }
+        strain_update(S, S->sp.method == METHOD_USAVG ? S->sp.dtStrainLast : S->sp.dt, true);
+        break;
+    case 9:
+        if (S->dim == 3) EMU_LAUNCH(k_reset_elements<3>, nblk(S->P.n, TASK_THREADS), TASK_THREADS, S->g, S->P, &S->flags, S->sp.dt);
+        else EMU_LAUNCH(k_reset_elements<2>, nblk(S->P.n, TASK_THREADS), TASK_THREADS, S->g, S->P, &S->flags, S->sp.dt);
+        S->mstep++;
+        break;
+    }
+}
+
+} // namespace
+
+// Inputs follow include/mpmgpu.h: cfg fields by value, particle arrays [component][n].  Returns an opaque handle.
+extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double *xpts, const double *ypts, const double *zpts,
+                            double gridx, double gridy, double gridz, int shape, double rcrit, int method, int skipPost, double fractionUSF,
+                            int xpicOrder, int usingFMPM, double gridAlpha, double particleAlpha, const double *gravity,
+                            double dt, double dtFirst, double dtLast,
+                            int nmat, const int *kinds, const int *nhist, const double *params,
+                            int n, const double *pos, const double *vel, const double *mp, const double *lp, const int *inElem, const int *matnum,
+                            const double *sp, const double *pressure, const double *ep, const double *wrot, const double *eplast,
+                            const double *energies, const double *history, const int *crossings)
+{
+    EmuSim *S = new EmuSim;
+    S->dim = np == NP_THREED ? 3 : 2;
+    S->shape = shape; S->n = n; S->mstep = 0;
+    Grid &g = S->g;
+    memset(&g, 0, sizeof g);
+    g.dim = S->dim; g.np = np; g.horiz = horiz; g.vert = vert; g.depth = S->dim == 3 ? depth : 1;
+    g.yplane = horiz + 1; g.zplane = (horiz + 1) * (vert + 1);
+    g.nnodes = g.zplane * (S->dim == 3 ? depth + 1 : 1);
+    g.nelems = g.horiz * g.vert * g.depth;
+    S->xpts.assign(xpts, xpts + horiz + 1); S->ypts.assign(ypts, ypts + vert + 1);
+    if (S->dim == 3) S->zpts.assign(zpts, zpts + depth + 1); else S->zpts.assign(2, 0.);
+    g.xpts = S->xpts.data(); g.ypts = S->ypts.data(); g.zpts = S->zpts.data();
+    g.gx = gridx; g.gy = gridy; g.gz = gridz;
+    g.xmin = xpts[0]; g.ymin = ypts[0]; g.zmin = S->dim == 3 ? zpts[0] : 0.;
+    g.rcrit = rcrit;
+    g.lpUniform = 0;
+    S->mats.resize(nmat);
+    S->largeRotation = false;
+    for (int i = 0; i < nmat; i++) {
+        S->mats[i].kind = kinds[i]; S->mats[i].nhist = nhist[i];
+        memcpy(S->mats[i].p, params + (size_t)i * MPM_MAT_NPARAMS, sizeof(double) * MPM_MAT_NPARAMS);
+        S->mats[i].p[6] = S->dim == 3 ? (gridx + gridy + gridz) / 3. : (gridx + gridy) / 2.;       // as mpmgpu_set_materials
+        if (S->mats[i].p[7] != 0.) S->largeRotation = true;
+    }
+    StepParams &q = S->sp;
+    memset(&q, 0, sizeof q);
+    q.dt = dt; q.dtStrainFirst = dtFirst; q.dtStrainLast = dtLast; q.fractionUSF = fractionUSF;
+    q.gridAlpha = gridAlpha; q.particleAlpha = particleAlpha;
+    q.grav[0] = gravity[0]; q.grav[1] = gravity[1]; q.grav[2] = gravity[2];
+    q.hasGravity = gravity[0] != 0. || gravity[1] != 0. || gravity[2] != 0.;
+    q.method = method; q.skipPost = skipPost; q.xpicOrder = xpicOrder; q.usingFMPM = usingFMPM;
+    memset(&S->flags, 0, sizeof S->flags);
+    // particle pool: same fields as capi.cu::bind_particles
+    const size_t N = (size_t)n;
+    const int ND = 3 + 3 + 1 + 3 + 3 + 9 + 6 + 1 + 6 + 6 + MPM_MAX_HISTORY + 3 + 3;
+    S->ppool.assign(N * ND, 0.);
+    S->ipool.assign(N * 5, 0);
+    Particles &P = S->P;
+    memset(&P, 0, sizeof P);
+    double *d = S->ppool.data();
+    auto take = [&]() { double *r = d; d += N; return r; };
+    for (int c = 0; c < 3; c++) P.pos[c] = take();
+    for (int c = 0; c < 3; c++) P.vel[c] = take();
+    P.mp = take();
+    for (int c = 0; c < 3; c++) P.lp[c] = take();
+    for (int c = 0; c < 3; c++) P.ncpos[c] = take();
+    for (int c = 0; c < 9; c++) P.F[c] = take();
+    for (int c = 0; c < 6; c++) P.sp[c] = take();
+    P.pressure = take();
+    for (int c = 0; c < 6; c++) P.eplast[c] = take();
+    P.work = take(); P.res = take(); P.heat = take(); P.entropy = take(); P.plast = take(); P.prevT = take();
+    for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c] = take();
+    for (int c = 0; c < 3; c++) P.pfext[c] = take();
+    for (int c = 0; c < 3; c++) P.acc[c] = take();
+    int *ii = S->ipool.data();
+    P.elem = ii; P.mat = ii + N; P.cross = ii + 2 * N; P.orig = ii + 3 * N; P.key = ii + 4 * N;
+    P.n = n; P.nNR = n;
+    for (size_t p = 0; p < N; p++) {
+        for (int c = 0; c < 3; c++) { P.pos[c][p] = pos[c * N + p]; P.vel[c][p] = vel[c * N + p]; P.lp[c][p] = lp[c * N + p]; }
+        P.mp[p] = mp[p];
+        // MatPoint3D::GetDeformationGradient from ep + wrot (MatPoint3D.cpp:363-376), as capi.cu::k_epwrot_to_F
+        P.F[0][p] = 1. + ep[p]; P.F[4][p] = 1. + ep[N + p]; P.F[8][p] = 1. + ep[2 * N + p];
+        P.F[1][p] = 0.5 * (ep[5 * N + p] - wrot[p]); P.F[3][p] = 0.5 * (ep[5 * N + p] + wrot[p]);
+        if (S->dim == 3) {
+            P.F[2][p] = 0.5 * (ep[4 * N + p] - wrot[N + p]); P.F[6][p] = 0.5 * (ep[4 * N + p] + wrot[N + p]);
+            P.F[5][p] = 0.5 * (ep[3 * N + p] - wrot[2 * N + p]); P.F[7][p] = 0.5 * (ep[3 * N + p] + wrot[2 * N + p]);
+        }
+        for (int c = 0; c < 6; c++) { P.sp[c][p] = sp[c * N + p]; P.eplast[c][p] = eplast[c * N + p]; }
+        P.pressure[p] = pressure[p];
+        P.work[p] = energies[p]; P.res[p] = energies[N + p]; P.heat[p] = energies[2 * N + p]; P.entropy[p] = energies[3 * N + p];
+        P.plast[p] = energies[4 * N + p]; P.prevT[p] = energies[5 * N + p];
+        for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c][p] = history[c * N + p];
+        P.elem[p] = inElem[p]; P.mat[p] = matnum[p] - 1; P.cross[p] = crossings[p]; P.orig[p] = (int)p;
+    }
+    if (SHAPE_IS_CPDI(shape)) {
+        const int nc = S->dim == 3 ? 8 : (SHAPE_IS_QCPDI(shape) ? 9 : 4);
+        S->cpElem.assign(N * nc, 0); S->cpXi.assign(N * nc * 3, 0.); S->cpWg.assign(N * nc * 3, 0.);
+        P.cpElem = S->cpElem.data(); P.cpXi = S->cpXi.data(); P.cpWg = S->cpWg.data(); P.cpStride = N;
+    }
+    // node pool: mass, pk, ftot, vk, pkCopy, v*prev, v*next (capi.cu::mpmgpu_create)
+    const size_t nn = (size_t)g.nnodes;
+    S->npool.assign(nn * 22, 0.);
+    S->ncnt.assign(nn, 0);
+    Nodes &Nd = S->N;
+    memset(&Nd, 0, sizeof Nd);
+    double *qn = S->npool.data();
+    Nd.mass = qn; qn += nn;
+    for (int c = 0; c < 3; c++) { Nd.pk[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.ftot[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.vk[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.pkc[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.vsp[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.vsn[c] = qn; qn += nn; }
+    Nd.cnt = S->ncnt.data();
+    return S;
+}
+
+extern "C" void emu_set_xpic(void *h, int order, int usingFMPM) { EmuSim *S = (EmuSim *)h; S->sp.xpicOrder = order; S->sp.usingFMPM = usingFMPM; }
+extern "C" void emu_task(void *h, int t) { run_task((EmuSim *)h, t); }
+extern "C" void emu_step(void *h, int nsteps) { for (int s = 0; s < nsteps; s++) for (int t = 0; t < 10; t++) run_task((EmuSim *)h, t); }
+extern "C" int emu_flags(void *h, long long *crossings, long long *leftGrid, int *nanParticle, int *cpdiLeft)
+{
+    EmuSim *S = (EmuSim *)h;
+    *crossings = (long long)S->flags.crossings; *leftGrid = (long long)S->flags.leftGrid; *nanParticle = S->flags.nanParticle; *cpdiLeft = S->flags.cpdiLeft;
+    return 0;
+}
+
+extern "C" void emu_get_particles(void *h, double *pos, double *vel, double *sp, double *pressure, double *ep, double *wrot, double *eplast,
+                                  double *energies, double *history, double *acc, int *inElem, int *crossings)
+{
+    EmuSim *S = (EmuSim *)h;
+    const Particles &P = S->P;
+    const size_t N = (size_t)S->n;
+    for (size_t p = 0; p < N; p++) {
+        for (int c = 0; c < 3; c++) { pos[c * N + p] = P.pos[c][p]; vel[c * N + p] = P.vel[c][p]; acc[c * N + p] = P.acc[c][p]; }
+        for (int c = 0; c < 6; c++) { sp[c * N + p] = P.sp[c][p]; eplast[c * N + p] = P.eplast[c][p]; }
+        pressure[p] = P.pressure[p];
+        // capi.cu::k_F_to_epwrot
+        const double F0 = P.F[0][p], F1 = P.F[1][p], F2 = P.F[2][p], F3 = P.F[3][p], F4 = P.F[4][p], F5 = P.F[5][p], F6 = P.F[6][p], F7 = P.F[7][p], F8 = P.F[8][p];
+        ep[p] = F0 - 1.; ep[N + p] = F4 - 1.; ep[2 * N + p] = F8 - 1.; ep[5 * N + p] = F3 + F1; wrot[p] = F3 - F1;
+        if (S->dim == 3) { ep[4 * N + p] = F6 + F2; ep[3 * N + p] = F7 + F5; wrot[N + p] = F6 - F2; wrot[2 * N + p] = F7 - F5; }
+        else { ep[4 * N + p] = 0.; ep[3 * N + p] = 0.; wrot[N + p] = 0.; wrot[2 * N + p] = 0.; }
+        energies[p] = P.work[p]; energies[N + p] = P.res[p]; energies[2 * N + p] = P.heat[p]; energies[3 * N + p] = P.entropy[p];
+        energies[4 * N + p] = P.plast[p]; energies[5 * N + p] = P.prevT[p];
+        for (int c = 0; c < MPM_MAX_HISTORY; c++) history[c * N + p] = P.hist[c][p];
+        inElem[p] = P.elem[p]; crossings[p] = P.cross[p];
+    }
+}
+
+extern "C" void emu_get_nodes(void *h, int *cnt, double *mass, double *pk, double *ftot, double *vk, double *pkc)
+{
+    EmuSim *S = (EmuSim *)h;
+    const size_t nn = (size_t)S->g.nnodes;
+    for (size_t i = 0; i < nn; i++) {
+        cnt[i] = S->N.cnt[i]; mass[i] = S->N.mass[i];
+        for (int c = 0; c < 3; c++) { pk[c * nn + i] = S->N.pk[c][i]; ftot[c * nn + i] = S->N.ftot[c][i]; vk[c * nn + i] = S->N.vk[c][i]; pkc[c * nn + i] = S->N.pkc[c][i]; }
+    }
+}
+
+extern "C" void emu_destroy(void *h) { delete (EmuSim *)h; }

@@ -100,6 +100,10 @@ CASES = {
                                                     vz=-6.0e4, vx=5.0e3), (1, 80), 1, 0.3, 3000.0),
     "block3d_material_pdamping": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3).replace("<alpha>0</alpha>", "<alpha>0</alpha><PDamping>2000</PDamping>"),
                                   (1, 30), 1, 0.3, 3000.0),
+    # free-flying 3D blocks (no grid BCs): also run by the host-compiled device source, tests/test_device_step_cpu.py
+    "block3d_free_ugimp": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, bc=False), (1, 30), 1, 0.3, 4000.0),
+    "block3d_free_lcpdi_xpic2": (inputs.block3d(ncell=3, margin=3, gimp="lCPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3, bc=False,
+                                                custom_tasks=inputs.periodic_xpic(2, False, 1)), (1, 2, 30), 2, 0.3, 3000.0),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

@@ -15,9 +15,10 @@ from tests.parity import TASK_MAP, compare_nodes, compare_particles, load_golden
 pytestmark = pytest.mark.gpu
 
 LR_CASES = ["block3d_isotropic_lr", "block3d_isoplastic_lr", "disks2d_lr_planestrain", "disks2d_lr_planestress"]
-BRANCH_CASES = ["disks2d_neo_planestress", "disks2d_neo_planestress_av", "block3d_isoplastic_softening", "block3d_material_pdamping"]
+BRANCH_CASES = ["disks2d_neo_planestress", "disks2d_neo_planestress_av", "block3d_isoplastic_softening", "block3d_material_pdamping",
+                "block3d_free_ugimp", "block3d_free_lcpdi_xpic2"]          # the last two: free flight, no grid BCs
 CASES = LR_CASES + BRANCH_CASES
-FUSED_CASES = ["block3d_isoplastic_softening", "block3d_material_pdamping"]          # 3D uGIMP without large rotation
+FUSED_CASES = ["block3d_isoplastic_softening", "block3d_material_pdamping", "block3d_free_ugimp"]          # 3D uGIMP without large rotation
 
 
 def make_sim(z, kernel_path=0):
@@ -29,8 +30,12 @@ def make_sim(z, kernel_path=0):
 @pytest.mark.parametrize("case", CASES)
 def test_each_task_of_step_one(case):
     z = load_golden(case)
+    from tests.parity import xpic_for_step
     sim = make_sim(z, 1)
     tol = tolerances(case)[0]
+    x = xpic_for_step(z, 1)
+    if x:
+        sim.set_xpic(*x)
     for i, nm in enumerate(str(s) for s in z["task_names"]):
         if TASK_MAP[nm] is None:
             continue
@@ -51,10 +56,15 @@ def test_whole_steps(case, kernel_path):
     z = load_golden(case)
     sim = make_sim(z, kernel_path)
     snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
+    from tests.parity import xpic_for_step
     done = 0
     for s in snaps:
-        sim.step(s - done)
-        done = s
+        while done < s:
+            x = xpic_for_step(z, done + 1)
+            if x:
+                sim.set_xpic(*x)
+            sim.step(1)
+            done += 1
         tol = tolerances(case)[0] if s == 1 else tolerances(case)[2]
         got = sim.download()
         errs, bad = compare_particles(got, z, "p%d" % s, tol)
@@ -74,7 +84,7 @@ def test_fused_path_refuses_large_rotation():
 
 
 # ---- CPDI kernels with the corners' contributions merged per node (opt-in MPMGPU_CPDI_MERGE=1, shape.cuh) ----------------
-CPDI_CASES = ["block3d_lcpdi_neo_xpic2", "block3d_lcpdi_rcrit", "block3d_lcpdi_rigid_wall", "disks2d_lcpdi", "disks2d_qcpdi"]
+CPDI_CASES = ["block3d_free_lcpdi_xpic2", "block3d_lcpdi_neo_xpic2", "block3d_lcpdi_rcrit", "block3d_lcpdi_rigid_wall", "disks2d_lcpdi", "disks2d_qcpdi"]
 
 
 @pytest.mark.parametrize("case", CPDI_CASES)
