@@ -1,12 +1,13 @@
 // TEST INFRASTRUCTURE: the per-task kernels of libmpmgpu (csrc/kernels_task.cuh, with shape.cuh and materials.cuh) compiled
 // for the host through tests/devlaws/stub and run one CUDA thread after the other, in the task order of capi.cu::step_by_tasks
-// (= the reference's MPMTask list), for inputs without velocity BCs and without rigid particles.  tests/test_device_step_cpu.py
+// (= the reference's MPMTask list), for inputs without rigid particles (grid velocity BCs with constant values included).  tests/test_device_step_cpu.py
 // compares the result with the golden dumps of the unmodified reference: the CUDA SOURCE of the general path is checked on
 // every CPU run; the compiled kernels and the host orchestration of capi.cu are checked by the GPU parity tests.
 // This is not a product path: nothing outside tests/ builds or loads it.
 #include "kernels_task.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 namespace {
@@ -20,6 +21,11 @@ struct EmuSim {
     std::vector<Material> mats;
     std::vector<double> xpts, ypts, zpts, ppool, npool, cpXi, cpWg;
     std::vector<int> ipool, ncnt, cpElem;
+    // grid velocity BCs grouped by node, as capi.cu::mpmgpu_set_velocity_bcs builds them
+    VelBCs B;
+    bool hasBCs;
+    std::vector<int> bcNode, bcStart, bcSym, bcActive, bcOfNode;
+    std::vector<double> bcNorm, bcValue;
     int dim, shape, n;
     bool largeRotation;
     long long mstep;
@@ -43,7 +49,10 @@ inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
         else EMU_LAUNCH((KERNEL<2, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
     } } while (0)
 
-const VelBCs NO_BCS = {0, NULL, NULL, NULL, NULL, NULL, NULL};
+void apply_bcs(EmuSim *S, int pass, int adjustSym)
+{
+    if (S->hasBCs && S->B.nUnique > 0) EMU_LAUNCH(k_velocity_bcs, nblk(S->B.nUnique, 128), 128, S->B, S->N, pass, S->sp.dt, adjustSym);
+}
 
 RigidBCs no_rigid()
 {
@@ -58,7 +67,7 @@ void xpic_extrapolation(EmuSim *S, int particleUpdate)
     EMU_LAUNCH(k_xpic_init, nblk(nn, 256), 256, nn, S->N, S->sp.dt, fmpm);
     for (int k = 2; k <= S->sp.xpicOrder; k++) {
         DISPATCH(k_xpic_iterate, S->P.nNR, S->g, S->P, S->N);
-        EMU_LAUNCH(k_xpic_finish, nblk(nn, 256), 256, nn, S->N, NO_BCS, (const int *)NULL, no_rigid(), S->sp.dt, particleUpdate, fmpm);
+        EMU_LAUNCH(k_xpic_finish, nblk(nn, 256), 256, nn, S->N, S->B, S->hasBCs ? S->bcOfNode.data() : (const int *)NULL, no_rigid(), S->sp.dt, particleUpdate, fmpm);
     }
 }
 
@@ -83,13 +92,21 @@ void run_task(EmuSim *S, int t)
         DISPATCH(k_init_particles, S->P.n, S->g, S->P, &S->flags);
         break;
     case 1: DISPATCH(k_p2g_mass_momentum, S->P.nNR, S->g, S->P, S->N); break;
-    case 2: EMU_LAUNCH(k_copy_momenta, nblk(nn, 256), 256, nn, S->N); break;                       // no BCs on this path
+    case 2: {
+        EMU_LAUNCH(k_copy_momenta, nblk(nn, 256), 256, nn, S->N);
+        const bool hasUSF = S->sp.method == METHOD_USF || S->sp.method == METHOD_USAVG;
+        apply_bcs(S, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
+        break;
+    }
     case 3:
         if (S->sp.method != METHOD_USL) strain_update(S, S->sp.method == METHOD_USAVG ? S->sp.dtStrainFirst : S->sp.dt, false);
         break;
     case 4: DISPATCH(k_p2g_forces, S->P.nNR, S->g, S->P, S->N, 0); break;
-    case 5: EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp); break;
-    case 6: EMU_LAUNCH(k_update_momenta, nblk(nn, 256), 256, nn, S->N, S->sp.dt); break;
+    case 5: EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp); apply_bcs(S, PASS_GRID_FORCES, 0); break;
+    case 6:
+        EMU_LAUNCH(k_update_momenta, nblk(nn, 256), 256, nn, S->N, S->sp.dt);
+        if (S->sp.xpicOrder <= 1) apply_bcs(S, PASS_UPDATE_MOMENTUM, 0);
+        break;
     case 7: {
         if (S->sp.xpicOrder > 1) xpic_extrapolation(S, 1);
         else EMU_LAUNCH(k_grid_velocity, nblk(nn, 256), 256, nn, S->N);
@@ -103,6 +120,7 @@ void run_task(EmuSim *S, int t)
         if (!S->sp.skipPost) {
             EMU_LAUNCH(k_rezero_momenta, nblk(nn, 256), 256, nn, S->N);
             DISPATCH(k_p2g_momentum_last, S->P.nNR, S->g, S->P, S->N);
+            apply_bcs(S, PASS_UPDATE_STRAINS_LAST, 0);
         }
         strain_update(S, S->sp.method == METHOD_USAVG ? S->sp.dtStrainLast : S->sp.dt, true);
         break;
@@ -129,6 +147,8 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     EmuSim *S = new EmuSim;
     S->dim = np == NP_THREED ? 3 : 2;
     S->shape = shape; S->n = n; S->mstep = 0;
+    S->hasBCs = false;
+    memset(&S->B, 0, sizeof S->B);
     Grid &g = S->g;
     memset(&g, 0, sizeof g);
     g.dim = S->dim; g.np = np; g.horiz = horiz; g.vert = vert; g.depth = S->dim == 3 ? depth : 1;
@@ -221,6 +241,31 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     for (int c = 0; c < 3; c++) { Nd.vsn[c] = qn; qn += nn; }
     Nd.cnt = S->ncnt.data();
     return S;
+}
+
+// the grouping of capi.cu::mpmgpu_set_velocity_bcs: by node, list order kept inside a node
+extern "C" void emu_set_bcs(void *h, int n, const int *node, const double *norm, const double *value, const int *active, const int *symdir)
+{
+    EmuSim *S = (EmuSim *)h;
+    S->hasBCs = n > 0;
+    if (n == 0) return;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return node[a] < node[b]; });
+    S->bcNode.clear(); S->bcStart.clear(); S->bcSym.clear();
+    S->bcActive.assign(n, 1); S->bcNorm.assign(3 * (size_t)n, 0.); S->bcValue.assign(n, 0.);
+    for (int e = 0; e < n; e++) {
+        const int i = order[e];
+        if (e == 0 || node[i] != node[order[e - 1]]) { S->bcNode.push_back(node[i] - 1); S->bcStart.push_back(e); S->bcSym.push_back(0); }
+        if (symdir) S->bcSym.back() |= symdir[i];
+        for (int c = 0; c < 3; c++) S->bcNorm[3 * e + c] = norm[3 * i + c];
+        S->bcValue[e] = value[i]; S->bcActive[e] = active ? active[i] : 1;
+    }
+    S->bcStart.push_back(n);
+    S->B.nUnique = (int)S->bcNode.size(); S->B.node = S->bcNode.data(); S->B.start = S->bcStart.data(); S->B.symdir = S->bcSym.data();
+    S->B.active = S->bcActive.data(); S->B.norm = S->bcNorm.data(); S->B.value = S->bcValue.data();
+    S->bcOfNode.assign((size_t)S->g.nnodes, -1);
+    for (int u = 0; u < S->B.nUnique; u++) S->bcOfNode[S->bcNode[u]] = u;
 }
 
 extern "C" void emu_set_xpic(void *h, int order, int usingFMPM) { EmuSim *S = (EmuSim *)h; S->sp.xpicOrder = order; S->sp.usingFMPM = usingFMPM; }
