@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE: the per-task kernels of libmpmgpu (csrc/kernels_task.cuh, with shape.cuh and materials.cuh) compiled
 // for the host through tests/devlaws/stub and run one CUDA thread after the other, in the task order of capi.cu::step_by_tasks
-// (= the reference's MPMTask list), for inputs without rigid particles (grid velocity BCs with constant values included).  tests/test_device_step_cpu.py
+// (= the reference's MPMTask list), with grid velocity BCs (constant values) and rigid-BC particles (constant velocities).  tests/test_device_step_cpu.py
 // compares the result with the golden dumps of the unmodified reference: the CUDA SOURCE of the general path is checked on
 // every CPU run; the compiled kernels and the host orchestration of capi.cu are checked by the GPU parity tests.
 // This is not a product path: nothing outside tests/ builds or loads it.
@@ -21,6 +21,12 @@ struct EmuSim {
     std::vector<Material> mats;
     std::vector<double> xpts, ypts, zpts, ppool, npool, cpXi, cpWg;
     std::vector<int> ipool, ncnt, cpElem;
+    // rigid-BC particles (host order, after the non-rigid ones) and the BCs they make (capi.cu: ctx->PR, ctx->R)
+    Particles PR;
+    RigidBCs R;
+    std::vector<double> rpool, rcpXi, rcpWg;
+    std::vector<int> ripool, rcpElem, owner;
+    std::vector<unsigned char> fixedBits;
     // grid velocity BCs grouped by node, as capi.cu::mpmgpu_set_velocity_bcs builds them
     VelBCs B;
     bool hasBCs;
@@ -30,6 +36,63 @@ struct EmuSim {
     bool largeRotation;
     long long mstep;
 };
+
+struct HostArrays {
+    const double *pos, *vel, *mp, *lp; const int *inElem, *matnum;
+    const double *sp, *pressure, *ep, *wrot, *eplast, *energies, *history; const int *crossings;
+};
+
+// one particle set over its own pools: the fields of capi.cu::bind_particles, filled from host arrays [component][N] at [off, off+cnt)
+void fill_set(Particles &P, std::vector<double> &pool, std::vector<int> &ipool, std::vector<int> &cpElem, std::vector<double> &cpXi,
+              std::vector<double> &cpWg, int dim, int shape, size_t N, size_t off, size_t cnt, const HostArrays &H)
+{
+    const int ND = 3 + 3 + 1 + 3 + 3 + 9 + 6 + 1 + 6 + 6 + MPM_MAX_HISTORY + 3 + 3;
+    const size_t C = cnt ? cnt : 1;
+    pool.assign(C * ND, 0.);
+    ipool.assign(C * 5, 0);
+    memset(&P, 0, sizeof P);
+    double *d = pool.data();
+    auto take = [&]() { double *r = d; d += C; return r; };
+    for (int c = 0; c < 3; c++) P.pos[c] = take();
+    for (int c = 0; c < 3; c++) P.vel[c] = take();
+    P.mp = take();
+    for (int c = 0; c < 3; c++) P.lp[c] = take();
+    for (int c = 0; c < 3; c++) P.ncpos[c] = take();
+    for (int c = 0; c < 9; c++) P.F[c] = take();
+    for (int c = 0; c < 6; c++) P.sp[c] = take();
+    P.pressure = take();
+    for (int c = 0; c < 6; c++) P.eplast[c] = take();
+    P.work = take(); P.res = take(); P.heat = take(); P.entropy = take(); P.plast = take(); P.prevT = take();
+    for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c] = take();
+    for (int c = 0; c < 3; c++) P.pfext[c] = take();
+    for (int c = 0; c < 3; c++) P.acc[c] = take();
+    int *ii = ipool.data();
+    P.elem = ii; P.mat = ii + C; P.cross = ii + 2 * C; P.orig = ii + 3 * C; P.key = ii + 4 * C;
+    P.n = (int)cnt; P.nNR = (int)cnt;
+    for (size_t p = 0; p < cnt; p++) {
+        const size_t q = off + p;
+        for (int c = 0; c < 3; c++) { P.pos[c][p] = H.pos[c * N + q]; P.vel[c][p] = H.vel[c * N + q]; P.lp[c][p] = H.lp[c * N + q]; }
+        P.mp[p] = H.mp[q];
+        // MatPoint3D::GetDeformationGradient from ep + wrot (MatPoint3D.cpp:363-376), as capi.cu::k_epwrot_to_F
+        P.F[0][p] = 1. + H.ep[q]; P.F[4][p] = 1. + H.ep[N + q]; P.F[8][p] = 1. + H.ep[2 * N + q];
+        P.F[1][p] = 0.5 * (H.ep[5 * N + q] - H.wrot[q]); P.F[3][p] = 0.5 * (H.ep[5 * N + q] + H.wrot[q]);
+        if (dim == 3) {
+            P.F[2][p] = 0.5 * (H.ep[4 * N + q] - H.wrot[N + q]); P.F[6][p] = 0.5 * (H.ep[4 * N + q] + H.wrot[N + q]);
+            P.F[5][p] = 0.5 * (H.ep[3 * N + q] - H.wrot[2 * N + q]); P.F[7][p] = 0.5 * (H.ep[3 * N + q] + H.wrot[2 * N + q]);
+        }
+        for (int c = 0; c < 6; c++) { P.sp[c][p] = H.sp[c * N + q]; P.eplast[c][p] = H.eplast[c * N + q]; }
+        P.pressure[p] = H.pressure[q];
+        P.work[p] = H.energies[q]; P.res[p] = H.energies[N + q]; P.heat[p] = H.energies[2 * N + q]; P.entropy[p] = H.energies[3 * N + q];
+        P.plast[p] = H.energies[4 * N + q]; P.prevT[p] = H.energies[5 * N + q];
+        for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c][p] = H.history[c * N + q];
+        P.elem[p] = H.inElem[q]; P.mat[p] = H.matnum[q] - 1; P.cross[p] = H.crossings[q]; P.orig[p] = (int)q;
+    }
+    if (SHAPE_IS_CPDI(shape)) {
+        const int nc = dim == 3 ? 8 : (SHAPE_IS_QCPDI(shape) ? 9 : 4);
+        cpElem.assign(C * nc, 0); cpXi.assign(C * nc * 3, 0.); cpWg.assign(C * nc * 3, 0.);
+        P.cpElem = cpElem.data(); P.cpXi = cpXi.data(); P.cpWg = cpWg.data(); P.cpStride = C;
+    }
+}
 
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
@@ -52,14 +115,9 @@ inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 void apply_bcs(EmuSim *S, int pass, int adjustSym)
 {
     if (S->hasBCs && S->B.nUnique > 0) EMU_LAUNCH(k_velocity_bcs, nblk(S->B.nUnique, 128), 128, S->B, S->N, pass, S->sp.dt, adjustSym);
+    if (S->R.on && adjustSym != 2) EMU_LAUNCH(k_rigid_velocity_bcs, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->R, S->N, pass, S->sp.dt);
 }
 
-RigidBCs no_rigid()
-{
-    RigidBCs R;
-    memset(&R, 0, sizeof R);
-    return R;
-}
 
 void xpic_extrapolation(EmuSim *S, int particleUpdate)
 {
@@ -67,7 +125,7 @@ void xpic_extrapolation(EmuSim *S, int particleUpdate)
     EMU_LAUNCH(k_xpic_init, nblk(nn, 256), 256, nn, S->N, S->sp.dt, fmpm);
     for (int k = 2; k <= S->sp.xpicOrder; k++) {
         DISPATCH(k_xpic_iterate, S->P.nNR, S->g, S->P, S->N);
-        EMU_LAUNCH(k_xpic_finish, nblk(nn, 256), 256, nn, S->N, S->B, S->hasBCs ? S->bcOfNode.data() : (const int *)NULL, no_rigid(), S->sp.dt, particleUpdate, fmpm);
+        EMU_LAUNCH(k_xpic_finish, nblk(nn, 256), 256, nn, S->N, S->B, S->hasBCs ? S->bcOfNode.data() : (const int *)NULL, S->R, S->sp.dt, particleUpdate, fmpm);
     }
 }
 
@@ -113,6 +171,10 @@ void run_task(EmuSim *S, int t)
         int m = S->sp.xpicOrder;
         if (!S->sp.usingFMPM) m = -m;
         DISPATCH(k_update_particles, S->P.nNR, S->g, S->P, S->N, S->mats.data(), S->sp, m);
+        if (S->PR.n > 0) {
+            if (S->dim == 3) EMU_LAUNCH(k_move_rigid<3>, nblk(S->PR.n, 128), 128, S->PR, S->sp.dt);
+            else EMU_LAUNCH(k_move_rigid<2>, nblk(S->PR.n, 128), 128, S->PR, S->sp.dt);
+        }
         break;
     }
     case 8:
@@ -127,7 +189,16 @@ void run_task(EmuSim *S, int t)
     case 9:
         if (S->dim == 3) EMU_LAUNCH(k_reset_elements<3>, nblk(S->P.n, TASK_THREADS), TASK_THREADS, S->g, S->P, &S->flags, S->sp.dt);
         else EMU_LAUNCH(k_reset_elements<2>, nblk(S->P.n, TASK_THREADS), TASK_THREADS, S->g, S->P, &S->flags, S->sp.dt);
+        if (S->PR.n > 0) {
+            if (S->dim == 3) EMU_LAUNCH(k_reset_elements<3>, nblk(S->PR.n, TASK_THREADS), TASK_THREADS, S->g, S->PR, &S->flags, S->sp.dt);
+            else EMU_LAUNCH(k_reset_elements<2>, nblk(S->PR.n, TASK_THREADS), TASK_THREADS, S->g, S->PR, &S->flags, S->sp.dt);
+        }
         S->mstep++;
+        break;
+    case 10:            // ProjectRigidBCsTask: between mass/momentum and post-extrapolation (capi.cu::t_project_rigid_bcs)
+        if (!S->R.on) break;
+        std::fill(S->owner.begin(), S->owner.end(), RIGID_NONE);
+        DISPATCH(k_project_rigid_bcs, S->PR.n, S->g, S->PR, S->mats.data(), S->R, &S->flags);
         break;
     }
 }
@@ -140,7 +211,7 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
                             int xpicOrder, int usingFMPM, double gridAlpha, double particleAlpha, const double *gravity,
                             double dt, double dtFirst, double dtLast,
                             int nmat, const int *kinds, const int *nhist, const double *params,
-                            int n, const double *pos, const double *vel, const double *mp, const double *lp, const int *inElem, const int *matnum,
+                            int n, int nNR, const double *pos, const double *vel, const double *mp, const double *lp, const int *inElem, const int *matnum,
                             const double *sp, const double *pressure, const double *ep, const double *wrot, const double *eplast,
                             const double *energies, const double *history, const int *crossings)
 {
@@ -178,53 +249,23 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     q.hasGravity = gravity[0] != 0. || gravity[1] != 0. || gravity[2] != 0.;
     q.method = method; q.skipPost = skipPost; q.xpicOrder = xpicOrder; q.usingFMPM = usingFMPM;
     memset(&S->flags, 0, sizeof S->flags);
-    // particle pool: same fields as capi.cu::bind_particles
-    const size_t N = (size_t)n;
-    const int ND = 3 + 3 + 1 + 3 + 3 + 9 + 6 + 1 + 6 + 6 + MPM_MAX_HISTORY + 3 + 3;
-    S->ppool.assign(N * ND, 0.);
-    S->ipool.assign(N * 5, 0);
-    Particles &P = S->P;
-    memset(&P, 0, sizeof P);
-    double *d = S->ppool.data();
-    auto take = [&]() { double *r = d; d += N; return r; };
-    for (int c = 0; c < 3; c++) P.pos[c] = take();
-    for (int c = 0; c < 3; c++) P.vel[c] = take();
-    P.mp = take();
-    for (int c = 0; c < 3; c++) P.lp[c] = take();
-    for (int c = 0; c < 3; c++) P.ncpos[c] = take();
-    for (int c = 0; c < 9; c++) P.F[c] = take();
-    for (int c = 0; c < 6; c++) P.sp[c] = take();
-    P.pressure = take();
-    for (int c = 0; c < 6; c++) P.eplast[c] = take();
-    P.work = take(); P.res = take(); P.heat = take(); P.entropy = take(); P.plast = take(); P.prevT = take();
-    for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c] = take();
-    for (int c = 0; c < 3; c++) P.pfext[c] = take();
-    for (int c = 0; c < 3; c++) P.acc[c] = take();
-    int *ii = S->ipool.data();
-    P.elem = ii; P.mat = ii + N; P.cross = ii + 2 * N; P.orig = ii + 3 * N; P.key = ii + 4 * N;
-    P.n = n; P.nNR = n;
-    for (size_t p = 0; p < N; p++) {
-        for (int c = 0; c < 3; c++) { P.pos[c][p] = pos[c * N + p]; P.vel[c][p] = vel[c * N + p]; P.lp[c][p] = lp[c * N + p]; }
-        P.mp[p] = mp[p];
-        // MatPoint3D::GetDeformationGradient from ep + wrot (MatPoint3D.cpp:363-376), as capi.cu::k_epwrot_to_F
-        P.F[0][p] = 1. + ep[p]; P.F[4][p] = 1. + ep[N + p]; P.F[8][p] = 1. + ep[2 * N + p];
-        P.F[1][p] = 0.5 * (ep[5 * N + p] - wrot[p]); P.F[3][p] = 0.5 * (ep[5 * N + p] + wrot[p]);
-        if (S->dim == 3) {
-            P.F[2][p] = 0.5 * (ep[4 * N + p] - wrot[N + p]); P.F[6][p] = 0.5 * (ep[4 * N + p] + wrot[N + p]);
-            P.F[5][p] = 0.5 * (ep[3 * N + p] - wrot[2 * N + p]); P.F[7][p] = 0.5 * (ep[3 * N + p] + wrot[2 * N + p]);
-        }
-        for (int c = 0; c < 6; c++) { P.sp[c][p] = sp[c * N + p]; P.eplast[c][p] = eplast[c * N + p]; }
-        P.pressure[p] = pressure[p];
-        P.work[p] = energies[p]; P.res[p] = energies[N + p]; P.heat[p] = energies[2 * N + p]; P.entropy[p] = energies[3 * N + p];
-        P.plast[p] = energies[4 * N + p]; P.prevT[p] = energies[5 * N + p];
-        for (int c = 0; c < MPM_MAX_HISTORY; c++) P.hist[c][p] = history[c * N + p];
-        P.elem[p] = inElem[p]; P.mat[p] = matnum[p] - 1; P.cross[p] = crossings[p]; P.orig[p] = (int)p;
-    }
-    if (SHAPE_IS_CPDI(shape)) {
-        const int nc = S->dim == 3 ? 8 : (SHAPE_IS_QCPDI(shape) ? 9 : 4);
-        S->cpElem.assign(N * nc, 0); S->cpXi.assign(N * nc * 3, 0.); S->cpWg.assign(N * nc * 3, 0.);
-        P.cpElem = S->cpElem.data(); P.cpXi = S->cpXi.data(); P.cpWg = S->cpWg.data(); P.cpStride = N;
-    }
+    // particle pools: the non-rigid particles [0, nNR) and the rigid-BC particles [nNR, n), as capi.cu::mpmgpu_upload_particles
+    const HostArrays H = {pos, vel, mp, lp, inElem, matnum, sp, pressure, ep, wrot, eplast, energies, history, crossings};
+    fill_set(S->P, S->ppool, S->ipool, S->cpElem, S->cpXi, S->cpWg, S->dim, shape, (size_t)n, 0, (size_t)nNR, H);
+    S->P.nNR = nNR;
+    fill_set(S->PR, S->rpool, S->ripool, S->rcpElem, S->rcpXi, S->rcpWg, S->dim, shape, (size_t)n, (size_t)nNR, (size_t)(n - nNR), H);
+    S->PR.nNR = 0;
+    // BCs made by the rigid particles (capi.cu: ctx->R)
+    RigidBCs &R = S->R;
+    memset(&R, 0, sizeof R);
+    R.on = n - nNR > 0 ? 1 : 0;
+    S->owner.assign(3 * (size_t)g.nnodes, RIGID_NONE);
+    S->fixedBits.assign((size_t)g.nnodes, 0);
+    for (int dd = 0; dd < 3; dd++) { R.owner[dd] = S->owner.data() + (size_t)dd * g.nnodes; R.vel[dd] = S->PR.vel[dd]; }
+    R.fixedBits = S->fixedBits.data();
+    for (int p = nNR; p < n; p++) if (S->mats[matnum[p] - 1].p[9] != 0.) R.mirrored = 1;
+    R.mat = S->PR.mat; R.mats = S->mats.data();
+    R.stride[0] = 1; R.stride[1] = g.yplane; R.stride[2] = g.zplane; R.nnodes = g.nnodes;
     // node pool: mass, pk, ftot, vk, pkCopy, v*prev, v*next (capi.cu::mpmgpu_create)
     const size_t nn = (size_t)g.nnodes;
     S->npool.assign(nn * 22, 0.);
@@ -248,6 +289,13 @@ extern "C" void emu_set_bcs(void *h, int n, const int *node, const double *norm,
 {
     EmuSim *S = (EmuSim *)h;
     S->hasBCs = n > 0;
+    // dofs fixed by grid BCs, for the rigid-particle projection (capi.cu: hFixedBits)
+    std::fill(S->fixedBits.begin(), S->fixedBits.end(), (unsigned char)0);
+    for (int i = 0; i < n; i++) {
+        unsigned char b = symdir ? (unsigned char)(symdir[i] & 7) : 0;
+        for (int dd = 0; dd < 3; dd++) if (norm[3 * i + dd] != 0.) b |= (unsigned char)(1 << dd);
+        S->fixedBits[node[i] - 1] |= b;
+    }
     if (n == 0) return;
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
@@ -270,7 +318,11 @@ extern "C" void emu_set_bcs(void *h, int n, const int *node, const double *norm,
 
 extern "C" void emu_set_xpic(void *h, int order, int usingFMPM) { EmuSim *S = (EmuSim *)h; S->sp.xpicOrder = order; S->sp.usingFMPM = usingFMPM; }
 extern "C" void emu_task(void *h, int t) { run_task((EmuSim *)h, t); }
-extern "C" void emu_step(void *h, int nsteps) { for (int s = 0; s < nsteps; s++) for (int t = 0; t < 10; t++) run_task((EmuSim *)h, t); }
+extern "C" void emu_step(void *h, int nsteps)
+{
+    static const int seq[11] = {0, 1, 10, 2, 3, 4, 5, 6, 7, 8, 9};
+    for (int s = 0; s < nsteps; s++) for (int t = 0; t < 11; t++) run_task((EmuSim *)h, seq[t]);
+}
 extern "C" int emu_flags(void *h, long long *crossings, long long *leftGrid, int *nanParticle, int *cpdiLeft)
 {
     EmuSim *S = (EmuSim *)h;
@@ -278,26 +330,33 @@ extern "C" int emu_flags(void *h, long long *crossings, long long *leftGrid, int
     return 0;
 }
 
+static void get_set(const Particles &P, int dim, size_t N, size_t off, double *pos, double *vel, double *sp, double *pressure, double *ep, double *wrot,
+                    double *eplast, double *energies, double *history, double *acc, int *inElem, int *crossings)
+{
+    for (size_t p = 0; p < (size_t)P.n; p++) {
+        const size_t q = off + p;
+        for (int c = 0; c < 3; c++) { pos[c * N + q] = P.pos[c][p]; vel[c * N + q] = P.vel[c][p]; acc[c * N + q] = P.acc[c][p]; }
+        for (int c = 0; c < 6; c++) { sp[c * N + q] = P.sp[c][p]; eplast[c * N + q] = P.eplast[c][p]; }
+        pressure[q] = P.pressure[p];
+        // capi.cu::k_F_to_epwrot
+        const double F0 = P.F[0][p], F1 = P.F[1][p], F2 = P.F[2][p], F3 = P.F[3][p], F4 = P.F[4][p], F5 = P.F[5][p], F6 = P.F[6][p], F7 = P.F[7][p], F8 = P.F[8][p];
+        ep[q] = F0 - 1.; ep[N + q] = F4 - 1.; ep[2 * N + q] = F8 - 1.; ep[5 * N + q] = F3 + F1; wrot[q] = F3 - F1;
+        if (dim == 3) { ep[4 * N + q] = F6 + F2; ep[3 * N + q] = F7 + F5; wrot[N + q] = F6 - F2; wrot[2 * N + q] = F7 - F5; }
+        else { ep[4 * N + q] = 0.; ep[3 * N + q] = 0.; wrot[N + q] = 0.; wrot[2 * N + q] = 0.; }
+        energies[q] = P.work[p]; energies[N + q] = P.res[p]; energies[2 * N + q] = P.heat[p]; energies[3 * N + q] = P.entropy[p];
+        energies[4 * N + q] = P.plast[p]; energies[5 * N + q] = P.prevT[p];
+        for (int c = 0; c < MPM_MAX_HISTORY; c++) history[c * N + q] = P.hist[c][p];
+        inElem[q] = P.elem[p]; crossings[q] = P.cross[p];
+    }
+}
+
 extern "C" void emu_get_particles(void *h, double *pos, double *vel, double *sp, double *pressure, double *ep, double *wrot, double *eplast,
                                   double *energies, double *history, double *acc, int *inElem, int *crossings)
 {
     EmuSim *S = (EmuSim *)h;
-    const Particles &P = S->P;
     const size_t N = (size_t)S->n;
-    for (size_t p = 0; p < N; p++) {
-        for (int c = 0; c < 3; c++) { pos[c * N + p] = P.pos[c][p]; vel[c * N + p] = P.vel[c][p]; acc[c * N + p] = P.acc[c][p]; }
-        for (int c = 0; c < 6; c++) { sp[c * N + p] = P.sp[c][p]; eplast[c * N + p] = P.eplast[c][p]; }
-        pressure[p] = P.pressure[p];
-        // capi.cu::k_F_to_epwrot
-        const double F0 = P.F[0][p], F1 = P.F[1][p], F2 = P.F[2][p], F3 = P.F[3][p], F4 = P.F[4][p], F5 = P.F[5][p], F6 = P.F[6][p], F7 = P.F[7][p], F8 = P.F[8][p];
-        ep[p] = F0 - 1.; ep[N + p] = F4 - 1.; ep[2 * N + p] = F8 - 1.; ep[5 * N + p] = F3 + F1; wrot[p] = F3 - F1;
-        if (S->dim == 3) { ep[4 * N + p] = F6 + F2; ep[3 * N + p] = F7 + F5; wrot[N + p] = F6 - F2; wrot[2 * N + p] = F7 - F5; }
-        else { ep[4 * N + p] = 0.; ep[3 * N + p] = 0.; wrot[N + p] = 0.; wrot[2 * N + p] = 0.; }
-        energies[p] = P.work[p]; energies[N + p] = P.res[p]; energies[2 * N + p] = P.heat[p]; energies[3 * N + p] = P.entropy[p];
-        energies[4 * N + p] = P.plast[p]; energies[5 * N + p] = P.prevT[p];
-        for (int c = 0; c < MPM_MAX_HISTORY; c++) history[c * N + p] = P.hist[c][p];
-        inElem[p] = P.elem[p]; crossings[p] = P.cross[p];
-    }
+    get_set(S->P, S->dim, N, 0, pos, vel, sp, pressure, ep, wrot, eplast, energies, history, acc, inElem, crossings);
+    get_set(S->PR, S->dim, N, (size_t)S->P.n, pos, vel, sp, pressure, ep, wrot, eplast, energies, history, acc, inElem, crossings);
 }
 
 extern "C" void emu_get_nodes(void *h, int *cnt, double *mass, double *pk, double *ftot, double *vk, double *pkc)

@@ -1,7 +1,7 @@
 """The per-task kernels of libmpmgpu (csrc/kernels_task.cuh + shape.cuh + materials.cuh) compiled for the host and run one CUDA
 thread after the other (tests/devlaws/host_step.cpp), in the reference's task order, against the golden dumps of the unmodified
-reference: every task of step 1 and whole runs, same tolerances as the GPU parity tests.  Every golden without rigid
-particles (the rigid-BC projection needs more of capi.cu's host side and stays with the GPU tests).
+reference: every task of step 1 and whole runs, same tolerances as the GPU parity tests, for EVERY golden case (grid velocity
+BCs, rigid-BC particles, XPIC/FMPM, CPDI, every material and analysis type).
 
 This checks the CUDA SOURCE of the general path on a machine without a GPU.  It is test infrastructure -- the product has no
 CPU path (tests/test_host_cpu.py::test_no_device_fails_loudly)."""
@@ -21,10 +21,10 @@ ROOT = os.path.dirname(HERE)
 DEV = os.path.join(HERE, "devlaws")
 LIB = os.path.join(DEV, "_build", "libdevstep.so")
 
-# every golden without rigid particles
-CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and "rigid" not in f)
+CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz"))
 TASK_INDEX = {"initialization": 0, "mass_and_momentum": 1, "post_extrapolation": 2, "update_strains_first": 3, "grid_forces": 4,
-              "post_forces": 5, "update_momenta": 6, "update_particles": 7, "update_strains_last": 8, "reset_elements": 9}
+              "post_forces": 5, "update_momenta": 6, "update_particles": 7, "update_strains_last": 8, "reset_elements": 9,
+              "project_rigid_bcs": 10}
 MERGED = {10: 20, 11: 21}          # SHAPE_LCPDI -> SHAPE_LCPDI_MERGED, SHAPE_QCPDI -> SHAPE_QCPDI_MERGED
 
 
@@ -54,7 +54,6 @@ def lib():
 
 class EmuSim:
     def __init__(self, lib, prob, merged_cpdi=False):
-        assert int(prob.particles.get("n_nonrigid", prob.nparticles)) == prob.nparticles, "no rigid particles on this path"
         self.lib, self.prob = lib, prob
         c = np.ascontiguousarray
         pt = prob.particles
@@ -81,7 +80,7 @@ class EmuSim:
             shape, d(prob.rcrit), prob.method, int(prob.skip_post_extrapolation), d(prob.fraction_usf), prob.xpic_order, int(prob.using_fmpm),
             d(prob.grid_damping), d(prob.particle_damping), _dp(grav), d(prob.dt), d(prob.dt_strain_first), d(prob.dt_strain_last),
             len(prob.materials), _ip(kinds), _ip(nhist), _dp(params),
-            n, _dp(keep["pos"]), _dp(keep["vel"]), _dp(keep["mp"]), _dp(keep["lp"]), _ip(elem), _ip(matnum), _dp(keep["sp"]), _dp(keep["pressure"]),
+            n, int(pt.get("n_nonrigid", n)), _dp(keep["pos"]), _dp(keep["vel"]), _dp(keep["mp"]), _dp(keep["lp"]), _ip(elem), _ip(matnum), _dp(keep["sp"]), _dp(keep["pressure"]),
             _dp(keep["ep"]), _dp(keep["wrot"]), _dp(keep["eplast"]), _dp(keep["energies"]), _dp(hist), _ip(cross)))
         nb = int(np.asarray(prob.bc_node).size)
         if nb:
