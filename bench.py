@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--fmpm", action="store_true")
     ap.add_argument("--sort-interval", type=int, default=0, help="steps between physical particle sorts (0 = library default)")
     ap.add_argument("--cpu-ncell", type=int, default=50, help="block edge of the CPU sample (50 -> 1M particles)")
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the CPU sample (about 10 s of CPU work on 16 threads at 1M particles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
