@@ -1,0 +1,121 @@
+"""Combinatorial parity sweep: seeded random combinations of analysis type, shape function, MPM method, particle update
+(FLIP / PIC / XPIC(k) / FMPM(k)), material (with large rotation, artificial viscosity, softening, material damping), damping,
+gravity, grid BCs and rigid-BC particles -- run by the UNMODIFIED reference (oracle/_ref, live) and by the device source of
+libmpmgpu compiled for the host (tests/devlaws/host_step.cpp); the particle and node fields must agree after 1 and after N
+steps to the tolerances of the golden tests.  The goldens pin chosen cases; this pins the combinations nobody chose.
+
+Needs oracle/_ref (built where /root/reference exists; the prebuilt library travels with the repo)."""
+import zlib
+
+import numpy as np
+import pytest
+
+from nairn_mpm_fea_b200.problem import from_reference_dump
+from oracle import refharness
+from tests import inputs
+from tests.parity import TOL_1STEP, TOL_100STEP, TOL_LR3D, compare_nodes, compare_particles, xpic_for_step
+from tests.test_device_step_cpu import EmuSim, lib  # noqa: F401
+
+NCONFIG = 64
+NSTEPS = 12
+
+DISK = '<Material Type="1" Name="Disk %d"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>'
+
+
+def material(rng, name, two_d):
+    """(xml, is_large_rotation) of a random in-scope material; 2D materials use the disks' scale (E = 1 MPa)."""
+    kind = rng.choice(["iso", "iso_lr", "neo", "plastic", "plastic_lr"])
+    E, G, K, yld, Ep = (1.0, 0.4, 1.0, 0.02, 0.1) if two_d else (100.0, 40.0, 200.0, 4.0, 20.0)
+    extra = ""
+    if rng.random() < 0.25:
+        extra += "<PDamping>%r</PDamping>" % float(rng.choice([200.0, 2000.0]))
+    if kind.startswith("iso"):
+        lr = kind.endswith("lr")
+        return ('<Material Type="1" Name="%s"><rho>1.5</rho><E>%r</E><nu>0.33</nu><alpha>40</alpha>%s%s</Material>'
+                % (name, E, "<largeRotation>1</largeRotation>" if lr else "", extra)), lr
+    if kind == "neo":
+        if rng.random() < 0.4:
+            extra += "<ArtificialVisc/><avA1>0.3</avA1><avA2>1.5</avA2>"
+        return ('<Material Type="28" Name="%s"><rho>1.5</rho><G>%r</G><K>%r</K><alpha>40</alpha><UJOption>%d</UJOption>%s</Material>'
+                % (name, G, K, int(rng.integers(0, 3)), extra)), False
+    lr = kind.endswith("lr")
+    if rng.random() < 0.3:
+        extra += "<ArtificialVisc/><avA1>0.2</avA1><avA2>2.0</avA2>"
+    hard = "<Ep>%r</Ep>" % Ep if rng.random() < 0.7 else "<Khard>-3.0</Khard><yieldMin>%r</yieldMin>" % (0.5 * yld)
+    return ('<Material Type="9" Name="%s"><rho>1.5</rho><E>%r</E><nu>0.33</nu><alpha>20</alpha><Hardening>Linear</Hardening><yield>%r</yield>%s%s%s</Material>'
+            % (name, E, yld, hard, "<largeRotation>1</largeRotation>" if lr else "", extra)), lr
+
+
+def make_config(seed):
+    rng = np.random.default_rng(seed)
+    two_d = rng.random() < 0.4
+    method = int(rng.choice([0, 2, 2, 3]))
+    shapes = ["uGIMP", "uGIMP", None, "lCPDI"] + (["qCPDI"] if two_d else [])
+    gimp = shapes[int(rng.integers(0, len(shapes)))]
+    skip = method != 0 and gimp is not None and rng.random() < 0.25          # Classic with USL-/USAVG- is refused by the reference
+    header = "<SkipPostExtrapolation/>" if skip else ""
+    if gimp == "lCPDI" and not two_d and rng.random() < 0.3:
+        header += "<CPDIrcrit>0.6</CPDIrcrit>"
+    upd = rng.choice(["flip", "flip", "xpic", "fmpm"])
+    order = int(rng.integers(1, 4))
+    custom = "" if upd == "flip" else inputs.periodic_xpic(order, upd == "fmpm", int(rng.integers(1, 3)))
+    lr3d = False
+    if two_d:
+        analysis = int(rng.choice([10, 11]))
+        xml = inputs.disks2d(analysis=analysis, gimp=gimp, method=method, vel=float(rng.choice([2500.0, 5000.0])), extra_header=header)
+        for k in (1, 2):
+            m, _ = material(rng, "Disk %d" % k, True)
+            xml = xml.replace(DISK % k, m)
+        if custom:
+            xml = xml.replace("</JANFEAInput>", custom + "</JANFEAInput>")
+        desc = "2D np=%d" % analysis
+    else:
+        m, lr3d = material(rng, "Blk", False)
+        rigid = None
+        r = rng.random()
+        if r < 0.2:
+            rigid = ("wall", int(rng.choice([4, 5, 7])), (0.0, 0.0, 0.0))
+        elif r < 0.3:
+            rigid = ("piston", 7, (1.0e3, -5.0e2, -6.0e3))
+        grav = (0.0, 0.0, -9.8e6) if rng.random() < 0.3 else None
+        damp = float(rng.choice([50.0, 500.0])) if rng.random() < 0.3 else None
+        pdamp = float(rng.choice([20.0, 300.0])) if rng.random() < 0.3 else None
+        xml = inputs.block3d(ncell=3, margin=3, material=m, gimp=gimp, method=method, vz=float(rng.choice([-6.0e3, -2.0e4])), vx=float(rng.choice([0.0, 4.0e3])),
+                             vy=float(rng.choice([0.0, -2.0e3])), bc=bool(rng.random() < 0.7) and rigid is None or (rigid is not None and rigid[0] == "piston"),
+                             rigid=rigid, gravity=grav, damping=damp, pdamping=pdamp, extra_header=header, custom_tasks=custom)
+        desc = "3D rigid=%s" % (rigid[0] if rigid else None)
+    # 3D blocks always get hash-jittered positions and velocities: a lattice block in uniform free flight has no strain at all, and
+    # comparing two implementations' round-off noise relative to its own maximum says nothing
+    jitter = (0.3, 3000.0) if not two_d else (0.0, 0.0)
+    return xml, jitter, lr3d, "%s shape=%s method=%d skip=%s update=%s(%d)" % (desc, gimp, method, skip, upd, order)
+
+
+@pytest.mark.parametrize("seed", range(NCONFIG))
+def test_random_combination_matches_the_live_reference(lib, seed):  # noqa: F811
+    if not refharness.available():
+        pytest.skip("oracle/_ref not built")
+    xml, (ja, va), lr3d, desc = make_config(1000 + seed)
+    try:
+        z = refharness.run_reference(xml, snaps=(1, NSTEPS), per_task_steps=0, nprocs=1, jitter_amp=ja, vel_amp=va)
+    except RuntimeError as e:
+        pytest.fail("the reference rejected a generated input (%s): %s" % (desc, str(e)[-400:]))
+    sim = EmuSim(lib, from_reference_dump(z))
+    done = 0
+    for s in (1, NSTEPS):
+        while done < s:
+            x = xpic_for_step(z, done + 1)
+            if x:
+                sim.set_xpic(*x)
+            sim.step(1)
+            done += 1
+        tol = TOL_LR3D if lr3d else (TOL_1STEP if s == 1 else TOL_100STEP)
+        got = sim.download()
+        errs, bad = compare_particles(got, z, "p%d" % s, tol)
+        assert not bad, "[%s] after %d steps: particles %s" % (desc, s, bad)
+        assert np.array_equal(got["in_elem"], z["p%d/inElem" % s]), desc
+        assert np.array_equal(got["crossings"], z["p%d/crossings" % s]), desc
+        errs, bad = compare_nodes(sim.download_nodes(), z, "n%d" % s, tol)
+        assert not bad, "[%s] after %d steps: nodes %s" % (desc, s, bad)
+    f = sim.flags()
+    assert f["nan"] == 0 and f["cpdi_left"] == 0, desc
+    sim.close()
