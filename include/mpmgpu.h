@@ -61,6 +61,7 @@ extern "C" {
 
 /* material kinds: reference MaterialID() values, Common/Read_XML/MaterialController.cpp:105-232 */
 #define MPMGPU_MAT_ISOTROPIC      1   /* IsotropicMat, small- or large-rotation hypoelastic */
+#define MPMGPU_MAT_MOONEY         8   /* Mooney (Mooney-Rivlin hyperelastic; per-task kernels) */
 #define MPMGPU_MAT_ISOPLASTICITY  9   /* IsoPlasticity + LinearHardening */
 #define MPMGPU_MAT_RIGIDBC       11   /* RigidMaterial used as moving velocity BC */
 #define MPMGPU_MAT_NEOHOOKEAN    28   /* Neohookean */
@@ -114,6 +115,7 @@ typedef struct mpmgpu_config {
  *                   [8] C[1][1] [9] C[1][2] [11] C[2][2] [16] C[3][3] [21] C[4][1] [22] C[4][2]
  *                   [23] C[4][4] [24] C[5][1]  (+CTE/gamma0 as above)
  *  NEOHOOKEAN:      [8] Gsp [9] Ksp [10] Lamesp [11] UofJOption [12] CTE1 [13] gamma0
+ *  MOONEY:          [8] G1sp [9] G2sp [10] Ksp [11] UofJOption [12] CTE1 [13] gamma0   (Materials/Mooney.cpp:104-147; history J, Jres)
  *  ISOPLASTICITY:   [8] Gred [9] Kred [10] yldred [11] Epred [12] CTE3 [13] gamma0
  *                   [14] alphaMax [15] yldredMin  (LinearHardening.cpp:55-80)
  *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)  [9] mirrored (-1, 0, +1)

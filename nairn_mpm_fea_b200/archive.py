@@ -72,11 +72,11 @@ def records(prob, state, order, origpos=None, thickness=None, angles0=None, temp
     rho0 = np.array([prob.materials[m - 1]["rho"] for m in matnum])
     hist = np.asarray(state["history"], np.float64)
     # current density: rho0 / GetCurrentRelativeVolume (1 unless the material tracks J: Neohookean.cpp:374-376)
-    relvol = np.where(kinds == M.NEOHOOKEAN, hist[0], 1.0)
+    relvol = np.where((kinds == M.NEOHOOKEAN) | (kinds == M.MOONEY), hist[0], 1.0)
     rho = rho0 / relvol
     # total stress: materials that keep the pressure apart add it back (MaterialBase::GetStressPandDev, MaterialBaseMPM.cpp:1635-1641)
     sp = np.array(state["sp"], np.float64, copy=True)
-    pand = (kinds == M.NEOHOOKEAN) | (kinds == M.ISOPLASTICITY)
+    pand = (kinds == M.NEOHOOKEAN) | (kinds == M.ISOPLASTICITY) | (kinds == M.MOONEY)
     for c in range(3):
         sp[c] = np.where(pand, sp[c] - np.asarray(state["pressure"]), sp[c])
     en = np.asarray(state["energies"], np.float64)

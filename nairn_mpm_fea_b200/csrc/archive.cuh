@@ -108,9 +108,9 @@ __host__ __device__ inline void archive_record(const Particles &P, int p, int sl
     if (L.items & (1u << ARCH_Stress)) {
         // Cauchy stress = rho * specific stress, rho = rho0 / relative volume (1 unless the material tracks J: Neohookean.cpp:374-376);
         // materials that keep the pressure apart add it back (MaterialBase::GetStressPandDev, MaterialBaseMPM.cpp:1635-1641)
-        const double relvol = m.kind == MAT_NEOHOOKEAN ? P.hist[0][p] : 1.0;
+        const double relvol = (m.kind == MAT_NEOHOOKEAN || m.kind == MAT_MOONEY) ? P.hist[0][p] : 1.0;
         const double rho = m.p[0] / relvol;
-        const bool pand = m.kind == MAT_NEOHOOKEAN || m.kind == MAT_ISOPLASTICITY;
+        const bool pand = m.kind == MAT_NEOHOOKEAN || m.kind == MAT_ISOPLASTICITY || m.kind == MAT_MOONEY;
         const double pr = P.pressure[p];
         for (int i = 0; i < nt; i++) {
             double s = P.sp[tens[i]][p];
@@ -154,7 +154,7 @@ enum { GS_MASS = 0,          // sum mp
 __host__ __device__ inline void global_summands(const Particles &P, int p, const Material &m, int dim, double q[GS_NSUMS])
 {
     const double mp = P.mp[p];
-    const double relvol = m.kind == MAT_NEOHOOKEAN ? P.hist[0][p] : 1.0;
+    const double relvol = (m.kind == MAT_NEOHOOKEAN || m.kind == MAT_MOONEY) ? P.hist[0][p] : 1.0;
     const double Vp = relvol * mp / m.p[0];
     const double vx = P.vel[0][p], vy = P.vel[1][p], vz = dim == 3 ? P.vel[2][p] : 0.;
     q[GS_MASS] = mp;
@@ -166,7 +166,7 @@ __host__ __device__ inline void global_summands(const Particles &P, int p, const
     q[GS_HEAT] = mp * P.heat[p];
     q[GS_ENTROPY] = mp * P.entropy[p];
     q[GS_PLASTIC] = mp * P.plast[p];
-    const bool pand = m.kind == MAT_NEOHOOKEAN || m.kind == MAT_ISOPLASTICITY;
+    const bool pand = m.kind == MAT_NEOHOOKEAN || m.kind == MAT_ISOPLASTICITY || m.kind == MAT_MOONEY;
     const double pr = pand ? P.pressure[p] : 0.;
     for (int c = 0; c < 6; c++) q[GS_STRESS + c] = mp * (c < 3 ? P.sp[c][p] - pr : P.sp[c][p]);
     q[GS_VOL_VEL] = Vp * vx; q[GS_VOL_VEL + 1] = Vp * vy; q[GS_VOL_VEL + 2] = Vp * vz;

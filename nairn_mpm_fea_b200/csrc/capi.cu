@@ -57,7 +57,7 @@ struct mpmgpu_ctx {
     const int *dlSlot, *dlSlotR;        // download slot maps: P.orig / PR.orig, or identity when ids are global
     bool globalIds;                     // particle ids are caller-global (slab mode): downloads come in device order + ids
     bool cpdiMerge = false;             // CPDI kernels merge the corners' contributions per node (MPMGPU_CPDI_MERGE=1; shape.cuh)
-    bool largeRotation = false;         // some material has Elastic::useLargeRotation: per-task kernels, k_update_strains_lr
+    bool largeRotation = false;         // some material needs the extended law dispatch (Elastic::useLargeRotation, Mooney): per-task kernels, k_update_strains_lr
     double *archOrigin = NULL, *archAngles = NULL;   // [3][n] caller order, for the archive records (mpmgpu_set_archive_origin)
     double archThickness = 1.;
     uint32_t *archBuf = NULL; size_t archBufWords = 0;
@@ -238,14 +238,15 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
     ctx->largeRotation = false;
     for (int i = 0; i < nmat; i++) {
         int k = mats[i].kind;
-        if (k != MAT_ISOTROPIC && k != MAT_RIGIDBC && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY)
-            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d is not supported (IsotropicMat 1, IsoPlasticity 9, rigid BC 11, Neohookean 28)", k);
+        if (k != MAT_ISOTROPIC && k != MAT_RIGIDBC && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY && k != MAT_MOONEY)
+            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d is not supported (IsotropicMat 1, Mooney 8, IsoPlasticity 9, rigid BC 11, Neohookean 28)", k);
         if (mats[i].n_history < 0 || mats[i].n_history > MPM_MAX_HISTORY) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: %d history doubles (max %d)", mats[i].n_history, MPM_MAX_HISTORY);
         ctx->hMats[i].kind = k; ctx->hMats[i].nhist = mats[i].n_history;
         memcpy(ctx->hMats[i].p, mats[i].p, sizeof(double) * MPM_MAT_NPARAMS);
-        if (mats[i].p[3] != 0. && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY)
+        if (mats[i].p[3] != 0. && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY && k != MAT_MOONEY)
             return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d does not support artificial viscosity (MaterialBase::SupportsArtificialViscosity)", k);
         // MeshInfo::GetAverageCellSize for equal elements (MeshInfo.cpp:1517-1523): a grid constant the law needs
+        if (k == MAT_MOONEY) ctx->largeRotation = true;       // laws of the extended dispatch: per-task kernels, k_update_strains_lr
         if (mats[i].p[7] != 0.) {
             if (k != MAT_ISOTROPIC && k != MAT_ISOPLASTICITY)
                 return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d has no large-rotation mode (Elastic::useLargeRotation: IsotropicMat, IsoPlasticity)", k);
@@ -514,11 +515,11 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         }
         ctx->tiled.stateKind = SK_ELASTIC;
         for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC && ctx->hMats[i].kind != MAT_RIGIDBC) ctx->tiled.stateKind = SK_FULL;
-        if (ctx->largeRotation) ok = false;     // large-rotation hypoelastic laws (polar decompositions) live in the per-task strain kernel
+        if (ctx->largeRotation) ok = false;     // large-rotation hypoelastic laws and Mooney live in the per-task strain kernel
         if (ctx->R.mirrored) ok = false;        // a mirrored rigid BC reads a neighbour node's momentum between the node updates: per-task kernels
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
-            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, no mirrored rigid BCs and no large-rotation materials");
+            return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, no mirrored rigid BCs and no large-rotation or Mooney materials");
         ctx->tiled.enabled = ok ? 1 : 0;
         ctx->tiled.sortInterval = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 12;
         {

@@ -469,6 +469,128 @@ __device__ __forceinline__ void neohookean_law(PState &s, const double du[9], do
     increment_heat_energy(s, Cv, dTq0, AVEnergy);
 }
 
+// ---- Mooney (MaterialID 8) ----------------------------------------------------------------------------------------
+// Mooney::MPMConstitutiveLaw (Materials/Mooney.cpp:184-365) over HyperElastic::IncrementDeformation (HyperElastic.cpp:104-139),
+// GetVolumetricTerms (:171-204) and GetNewtonPressureTerms (:208-238).  Same state as Neohookean: elastic B in eplast,
+// pressure apart, deviatoric Kirchhoff stress / rho0 in sp, history = {J, Jres}.  The IdealRubber option is refused at set-up.
+template <int DIM>
+__device__ __forceinline__ void mooney_law(PState &s, const double du[9], double delTime, int np, const Material &m)
+{
+    const double G1sp = m.p[8], G2sp = m.p[9], Ksp = m.p[10];
+    const int UofJ = (int)m.p[11];
+    const double gamma0 = m.p[13], Cv = m.p[1];
+    double dF[9], detDf;
+    double *B = s.eplast;       // xx,yy,zz,yz,xz,xy
+    exp_du<DIM>(du, dF);
+    if (DIM == 3) {
+        double Fn[9];
+        mat3_mul(dF, s.F, Fn);
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.F[i] = Fn[i];
+        const double Bm[9] = {B[XX], B[XY], B[XZ], B[XY], B[YY], B[YZ], B[XZ], B[YZ], B[ZZ]};
+        double dB[9];
+        mat3_mul(dF, Bm, dB);
+        const double bxx = dB[0] * dF[0] + dB[1] * dF[1] + dB[2] * dF[2];
+        const double bxy = dB[0] * dF[3] + dB[1] * dF[4] + dB[2] * dF[5];
+        const double byy = dB[3] * dF[3] + dB[4] * dF[4] + dB[5] * dF[5];
+        const double bzz = dB[6] * dF[6] + dB[7] * dF[7] + dB[8] * dF[8];
+        const double bxz = dB[0] * dF[6] + dB[1] * dF[7] + dB[2] * dF[8];
+        const double byz = dB[3] * dF[6] + dB[4] * dF[7] + dB[5] * dF[8];
+        B[XX] = bxx; B[XY] = bxy; B[YY] = byy; B[ZZ] = bzz; B[XZ] = bxz; B[YZ] = byz;
+        detDf = dF[0] * (dF[4] * dF[8] - dF[7] * dF[5]) - dF[3] * (dF[1] * dF[8] - dF[7] * dF[2]) + dF[6] * (dF[1] * dF[5] - dF[4] * dF[2]);
+    } else {
+        const double d00 = dF[0], d01 = dF[1], d10 = dF[3], d11 = dF[4], ezz = dF[8];
+        const double f00 = d00 * s.F[0] + d01 * s.F[3], f01 = d00 * s.F[1] + d01 * s.F[4];
+        const double f10 = d10 * s.F[0] + d11 * s.F[3], f11 = d10 * s.F[1] + d11 * s.F[4];
+        s.F[0] = f00; s.F[1] = f01; s.F[3] = f10; s.F[4] = f11; s.F[8] = ezz * s.F[8];
+        const double e00 = d00 * B[XX] + d01 * B[XY], e01 = d00 * B[XY] + d01 * B[YY];
+        const double e10 = d10 * B[XX] + d11 * B[XY], e11 = d10 * B[XY] + d11 * B[YY];
+        const double e22 = ezz * B[ZZ];
+        B[XX] = e00 * d00 + e01 * d01;
+        B[XY] = e00 * d10 + e01 * d11;
+        B[YY] = e10 * d10 + e11 * d11;
+        B[ZZ] = e22 * ezz;
+        detDf = ezz * (d00 * d11 - d10 * d01);
+    }
+    double Jres = s.hist[1];
+    const double dJres = 1.;
+    Jres *= dJres;
+    s.hist[1] = Jres;
+    if (DIM == 2 && np == NP_PLANE_STRESS) {
+        // B.zz that zeroes the zz stress: Newton from the current (1 + ezz)^2 (:204-258)
+        const double arg = B[XX] * B[YY] - B[XY] * B[XY];
+        const double arg12 = sqrt(arg), arg16 = pow(arg, 1. / 6.), arg2 = B[XX] + B[YY];
+        double xn = s.F[8] * s.F[8];
+        for (int iter = 1; iter < 20; iter++) {
+            const double xn16 = pow(xn, 1. / 6.), xn12 = sqrt(xn);
+            const double J13 = xn16 * arg16, J0 = xn12 * arg12, Je = J0 / Jres;
+            double mJ2P, mdJ2PdJ;
+            if (UofJ == 1) { mJ2P = Ksp * Je * Je * (Je - 1.); mdJ2PdJ = Ksp * Je * (3. * Je - 2.); }
+            else if (UofJ == 2) { mJ2P = Ksp * Je * log(Je); mdJ2PdJ = Ksp * (log(Je) + 1.); }
+            else { mJ2P = 0.5 * Ksp * Je * (Je * Je - 1.); mdJ2PdJ = 0.5 * Ksp * (3. * Je * Je - 1.); }
+            const double fx = 3. * Jres * mJ2P + G1sp * (2. * xn - arg2) * J13 + G2sp * (xn * arg2 - 2. * arg) / J13;
+            const double fxp = (1.5 * J0 / xn) * mdJ2PdJ + G1sp * J13 * (14. * xn - arg2) / (6. * xn) + G2sp * (2. * arg + 5. * xn * arg2) / (6. * J13 * xn);
+            const double xnp1 = xn - fx / fxp;
+            if (fabs(xn - xnp1) < 1e-10) break;
+            xn = xnp1;
+        }
+        const double dFzz = sqrt(xn / B[ZZ]);
+        B[ZZ] = xn;
+        s.F[8] = dFzz * s.F[8];
+        detDf *= dFzz;
+    }
+    const double J = detDf * s.hist[0];
+    s.hist[0] = J;
+    double st0[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) st0[i] = s.sp[i];
+    const double Jeff = J / Jres;
+    const double p0 = s.pressure;
+    double Kvol;
+    if (UofJ == 1) Kvol = Ksp * (Jeff - 1.);
+    else if (UofJ == 2) Kvol = Ksp * log(Jeff) / Jeff;
+    else Kvol = 0.5 * Ksp * (Jeff - 1. / Jeff);
+    const double Kterm = J * Kvol;
+    const double delV = 1. - 1. / detDf;
+    double QAVred = 0., AVEnergy = 0.;
+    if (delV < 0. && m.p[3] != 0.) {
+        QAVred = artificial_viscosity(delV / delTime, sqrt(Ksp * J), m);
+        AVEnergy = fabs(QAVred * delV);
+    }
+    const double Pfinal = -Kterm + QAVred;
+    s.pressure = Pfinal;
+    const double avgP = 0.5 * (p0 + Pfinal);
+    const double dilEnergy = -avgP * delV;
+    const double delVres = 1. - 1. / dJres;
+    const double resEnergy = -avgP * delVres;
+    const double J23 = pow(J, 2. / 3.);
+    const double J43 = J23 * J23;
+    const double JforG1 = J23 / Jres, JforG2 = J43 / Jres;
+    double *sp = s.sp;
+    sp[XX] = (2 * B[XX] - B[YY] - B[ZZ]) * G1sp / (3. * JforG1) + (B[XX] * (B[YY] + B[ZZ]) - 2 * B[YY] * B[ZZ] - B[XY] * B[XY]) * G2sp / (3. * JforG2);
+    sp[YY] = (2 * B[YY] - B[XX] - B[ZZ]) * G1sp / (3. * JforG1) + (B[YY] * (B[XX] + B[ZZ]) - 2 * B[XX] * B[ZZ] - B[XY] * B[XY]) * G2sp / (3. * JforG2);
+    sp[ZZ] = (2 * B[ZZ] - B[XX] - B[YY]) * G1sp / (3. * JforG1) + (B[ZZ] * (B[XX] + B[YY]) - 2 * B[XX] * B[YY] + 2. * B[XY] * B[XY]) * G2sp / (3. * JforG2);
+    sp[XY] = B[XY] * G1sp / JforG1 + (B[ZZ] * B[XY]) * G2sp / JforG2;
+    if (DIM == 3) {
+        sp[XX] += (2. * B[YZ] * B[YZ] - B[XZ] * B[XZ]) * G2sp / (3. * JforG2);
+        sp[YY] += (2. * B[XZ] * B[XZ] - B[YZ] * B[YZ]) * G2sp / (3. * JforG2);
+        sp[ZZ] -= (B[XZ] * B[XZ] + B[YZ] * B[YZ]) * G2sp / (3. * JforG2);
+        sp[XY] -= B[XZ] * B[YZ] * G2sp / JforG2;
+        sp[XZ] = B[XZ] * G1sp / JforG1 + (B[YY] * B[XZ] - B[XY] * B[YZ]) * G2sp / JforG2;
+        sp[YZ] = B[YZ] * G1sp / JforG1 + (B[XX] * B[YZ] - B[XY] * B[XZ]) * G2sp / JforG2;
+    }
+    double shearEnergy = 0.5 * ((sp[XX] + st0[XX]) * du[0] + (sp[YY] + st0[YY]) * du[4] + (sp[ZZ] + st0[ZZ]) * du[8] + (sp[XY] + st0[XY]) * (du[1] + du[3]));
+    if (DIM == 3) shearEnergy += 0.5 * ((sp[XZ] + st0[XZ]) * (du[2] + du[6]) + (sp[YZ] + st0[YZ]) * (du[5] + du[7]));
+    s.work += dilEnergy + shearEnergy;
+    s.res += resEnergy;
+    double Kratio;
+    if (UofJ == 1) Kratio = Jeff;
+    else if (UofJ == 2) Kratio = (1 - log(Jeff)) / (Jeff * Jeff);
+    else Kratio = 0.5 * (Jeff + 1. / Jeff);
+    const double dTq0 = -J * Kratio * gamma0 * s.prevT * delV;
+    increment_heat_energy(s, Cv, dTq0, AVEnergy);
+}
+
 // ---- IsoPlasticity + LinearHardening (MaterialID 9) ------------------------------------------------
 // IsoPlasticity::MPMConstitutiveLaw / PlasticityConstLaw / UpdatePressure (Materials/IsoPlasticity.cpp:128-492),
 // small-rotation branch, J2 potential (:513-517), closed-form radial return of LinearHardening
@@ -664,8 +786,8 @@ __device__ __forceinline__ void constitutive_law(PState &s, const double du[9], 
     }
 }
 
-// The same dispatch with the large-rotation variants of IsotropicMat and IsoPlasticity (material slot p[7], Elastic::useLargeRotation);
-// kept apart so that the kernels of the other configurations do not carry the polar decompositions
+// The same dispatch extended by the large-rotation variants of IsotropicMat and IsoPlasticity (material slot p[7],
+// Elastic::useLargeRotation) and by Mooney; kept apart so that the kernels of the other configurations do not carry them
 template <int DIM>
 __device__ __forceinline__ void constitutive_law_lr(PState &s, const double du[9], double delTime, int np, const Material &m)
 {
@@ -679,6 +801,9 @@ __device__ __forceinline__ void constitutive_law_lr(PState &s, const double du[9
         break;
     case MAT_ISOPLASTICITY:
         if (lr) isoplasticity_law<DIM, true>(s, du, delTime, np, m); else isoplasticity_law<DIM, false>(s, du, delTime, np, m);
+        break;
+    case MAT_MOONEY:
+        mooney_law<DIM>(s, du, delTime, np, m);
         break;
     default:
         break;

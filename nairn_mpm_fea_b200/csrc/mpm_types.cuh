@@ -20,7 +20,7 @@ enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_LCPDI = 10, SHAPE_QCPDI = 11,
 #define SHAPE_IS_QCPDI(S) ((S) == SHAPE_QCPDI || (S) == SHAPE_QCPDI_MERGED)
 #define SHAPE_IS_CPDI(S) ((S) == SHAPE_LCPDI || (S) == SHAPE_LCPDI_MERGED || SHAPE_IS_QCPDI(S))
 #define SHAPE_IS_MERGED(S) ((S) == SHAPE_LCPDI_MERGED || (S) == SHAPE_QCPDI_MERGED)
-enum { MAT_ISOTROPIC = 1, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28 };
+enum { MAT_ISOTROPIC = 1, MAT_MOONEY = 8, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28 };
 
 // BC pass types (reference NodalVelBC.cpp:321-380)
 enum { PASS_MASS_MOMENTUM = 0, PASS_GRID_FORCES = 1, PASS_UPDATE_MOMENTUM = 2, PASS_UPDATE_STRAINS_LAST = 3,

@@ -30,6 +30,7 @@
 #include "Materials/MaterialBase.hpp"
 #include "Materials/IsotropicMat.hpp"
 #include "Materials/Neohookean.hpp"
+#include "Materials/Mooney.hpp"
 #include "Materials/IsoPlasticity.hpp"
 #include "Materials/HardeningLawBase.hpp"
 #include "Materials/LinearHardening.hpp"
@@ -236,13 +237,14 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (!mpmgrid.IsStructuredEqualElementsGrid()) return "grid is not structured with equal elements";
     for (int i = 0; i < nmat; i++) {
         MaterialBase *mb = theMaterials[i];
-        if (mb->artificialViscosity && mb->MaterialID() != 28 && mb->MaterialID() != 9) return "artificial viscosity on this material";
+        if (mb->artificialViscosity && mb->MaterialID() != 28 && mb->MaterialID() != 9 && mb->MaterialID() != 8) return "artificial viscosity on this material";
         // dF = exp(du) to <DefGradTerms> terms (Neohookean, large-rotation laws): the device uses the defaults, 1 in 3D and 2 in 2D
-        if ((mb->MaterialID() == 28 || ((mb->MaterialID() == 1 || mb->MaterialID() == 9) && ((Elastic *)mb)->useLargeRotation)) &&
+        if ((mb->MaterialID() == 28 || mb->MaterialID() == 8 || ((mb->MaterialID() == 1 || mb->MaterialID() == 9) && ((Elastic *)mb)->useLargeRotation)) &&
             MaterialBase::incrementalDefGradTerms != (fmobj->IsThreeD() ? 1 : 2)) return "<DefGradTerms> other than the default";
         switch (mb->MaterialID()) {
         case 1: break;          // small- and large-rotation hypoelasticity (Elastic::useLargeRotation -> material slot 7)
         case 28: break;
+        case 8: if (((Mooney *)mb)->rubber) return "Mooney with the IdealRubber option"; break;
         case 9:
             if (dynamic_cast<LinearHardening *>(((IsoPlasticity *)mb)->plasticLaw) == NULL) return "IsoPlasticity hardening law other than Linear";
             break;
@@ -309,6 +311,10 @@ const char *GpuTasks_Install(int device, bool fusedStep)
             Neohookean *nm = (Neohookean *)mb;
             m.kind = MPMGPU_MAT_NEOHOOKEAN;
             m.p[8] = nm->pr.Gsp; m.p[9] = nm->pr.Ksp; m.p[10] = nm->pr.Lamesp; m.p[11] = nm->UofJOption; m.p[12] = nm->CTE1; m.p[13] = nm->gamma0;
+        } else if (mb->MaterialID() == 8) {         // Mooney: specific moduli (Mooney.cpp:139-147, HyperElastic.cpp:63-81)
+            Mooney *mm = (Mooney *)mb;
+            m.kind = MPMGPU_MAT_MOONEY;
+            m.p[8] = mm->G1sp; m.p[9] = mm->G2sp; m.p[10] = mm->Ksp; m.p[11] = mm->UofJOption; m.p[12] = mm->CTE1; m.p[13] = mm->gamma0;
         } else if (mb->MaterialID() == 9) {         // IsoPlasticity::pr + LinearHardening reduced properties
             IsoPlasticity *pm = (IsoPlasticity *)mb;
             LinearHardening *lh = (LinearHardening *)pm->plasticLaw;

@@ -9,7 +9,7 @@ import numpy as np
 
 NPARAMS = 32
 MAX_HISTORY = 4            # MPMGPU_MAX_HISTORY
-ISOTROPIC, ISOPLASTICITY, RIGIDBC, NEOHOOKEAN = 1, 9, 11, 28
+ISOTROPIC, MOONEY, ISOPLASTICITY, RIGIDBC, NEOHOOKEAN = 1, 8, 9, 11, 28
 PLANE_STRAIN_MPM, PLANE_STRESS_MPM, THREED_MPM = 10, 11, 12
 
 DEFAULT_CV = 1.0e6          # MaterialBase.cpp:74 heatCapacity = Scaling(1.e6)
@@ -137,6 +137,16 @@ def neohookean(G, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None, av
     gamma0 = K * (3.0e-6 * aI) / (rho * Cv)
     p[8], p[9], p[10], p[11], p[12], p[13] = Gsp, Ksp, Lamesp, float(UofJOption), 1.0e-6 * aI, gamma0
     return dict(kind=NEOHOOKEAN, n_history=2, p=p, rho=rho, wave_speed=float(np.sqrt((K + 4.0 * G / 3.0) / rho)),
+                init_history=[1.0, 1.0], init_eplast=[1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
+
+
+def mooney(G1, G2, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None, av=None):
+    """Mooney (MaterialID 8): Mooney::VerifyAndLoadProperties (Materials/Mooney.cpp:104-147) with G1, G2 and K given.
+    History: J, Jres (both 1).  Particles start with elastic B = I in eplast (HyperElastic.cpp:51-60)."""
+    p = _base(rho, Cv, pdamping, av)
+    gamma0 = K * (3.0e-6 * aI) / (rho * Cv)
+    p[8], p[9], p[10], p[11], p[12], p[13] = G1 / rho, G2 / rho, K / rho, float(UofJOption), 1.0e-6 * aI, gamma0
+    return dict(kind=MOONEY, n_history=2, p=p, rho=rho, wave_speed=float(np.sqrt((K + 4.0 * (G1 + G2) / 3.0) / rho)),
                 init_history=[1.0, 1.0], init_eplast=[1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
 
 

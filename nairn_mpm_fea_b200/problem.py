@@ -293,12 +293,16 @@ def from_reference_dump(z, snapshot="p0"):
     for mid, q in zip(z["mat_ids"], z["mat_params"]):
         pd = None if q[3] < 0 else q[3]
         av = (q[6], q[7]) if q[5] else None
-        if av is not None and mid not in (M.NEOHOOKEAN, M.ISOPLASTICITY):
+        if av is not None and mid not in (M.NEOHOOKEAN, M.ISOPLASTICITY, M.MOONEY):
             raise NotImplementedError("artificial viscosity on material id %d" % mid)
         if mid == M.ISOTROPIC:
             m = M.isotropic(q[8], q[9], q[0], q[11] * 1.0e6, q[1], pr.np, pd, large_rotation=bool(q[13]))
         elif mid == M.NEOHOOKEAN:
             m = M.neohookean(q[8], q[9], q[0], q[15] * 1.0e6, q[1], int(q[14]), pd, av)
+        elif mid == M.MOONEY:
+            if q[17] != 0:
+                raise NotImplementedError("Mooney with the IdealRubber option")
+            m = M.mooney(q[8], q[9], q[10], q[0], q[15] * 1.0e6, q[1], int(q[14]), pd, av)
         elif mid == M.ISOPLASTICITY:
             m = M.isoplasticity(q[8], q[9], q[0], q[15], q[16] if q[16] >= 0 else None, q[21], q[11] * 1.0e6, q[1], pr.np, pd,
                                 q[20] * q[0], av, large_rotation=bool(q[22]) if len(q) > 22 else False)

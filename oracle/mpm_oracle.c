@@ -823,6 +823,102 @@ static void neohookean_law(int p, const double du[3][3], double delTime, const m
     P3(energies, 3, p) += baseHeat / prevT;
 }
 
+/* ---- Mooney: Materials/Mooney.cpp:184-365, HyperElastic.cpp:104-139,171-238 ------------------------------------------ */
+static void mooney_law(int p, const double du[3][3], double delTime, const mpmgpu_material *m)
+{
+    const double G1sp = m->p[8], G2sp = m->p[9], Ksp = m->p[10], gamma0 = m->p[13], Cv = m->p[1];
+    const int UofJ = (int)m->p[11];
+    double dF[3][3], F[3][3], Fn[3][3], detDf;
+    exp_du(du, dF);
+    get_F(p, F);
+    mat_mul(dF, F, Fn);
+    set_F(p, Fn);
+    double Bo[3][3] = {{P3(eplast, XX, p), P3(eplast, XY, p), P3(eplast, XZ, p)}, {P3(eplast, XY, p), P3(eplast, YY, p), P3(eplast, YZ, p)},
+                       {P3(eplast, XZ, p), P3(eplast, YZ, p), P3(eplast, ZZ, p)}};
+    if (O->dim == 2) { Bo[0][2] = Bo[2][0] = Bo[1][2] = Bo[2][1] = 0.; }
+    double dB[3][3], Bn[3][3], dFt[3][3];
+    mat_mul(dF, Bo, dB);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dFt[i][j] = dF[j][i];
+    mat_mul(dB, dFt, Bn);
+    P3(eplast, XX, p) = Bn[0][0]; P3(eplast, YY, p) = Bn[1][1]; P3(eplast, ZZ, p) = Bn[2][2]; P3(eplast, XY, p) = Bn[0][1];
+    if (O->dim == 3) {
+        P3(eplast, XZ, p) = Bn[0][2]; P3(eplast, YZ, p) = Bn[1][2];
+        detDf = dF[0][0] * (dF[1][1] * dF[2][2] - dF[2][1] * dF[1][2]) - dF[1][0] * (dF[0][1] * dF[2][2] - dF[2][1] * dF[0][2]) +
+                dF[2][0] * (dF[0][1] * dF[1][2] - dF[1][1] * dF[0][2]);
+    } else detDf = dF[2][2] * (dF[0][0] * dF[1][1] - dF[1][0] * dF[0][1]);
+    double Jres = P3(hist, 1, p), dJres = 1.;
+    Jres *= dJres;
+    P3(hist, 1, p) = Jres;
+    double Bxx = P3(eplast, XX, p), Byy = P3(eplast, YY, p), Bzz = P3(eplast, ZZ, p), Bxy = P3(eplast, XY, p);
+    if (O->cfg.np == MPMGPU_PLANE_STRESS_MPM) {         /* :204-258 */
+        double arg = Bxx * Byy - Bxy * Bxy, arg12 = sqrt(arg), arg16 = pow(arg, 1. / 6.), arg2 = Bxx + Byy;
+        double xn = (1. + P3(ep, ZZ, p)) * (1. + P3(ep, ZZ, p));
+        for (int iter = 1; iter < 20; iter++) {
+            double xn16 = pow(xn, 1. / 6.), xn12 = sqrt(xn), J13 = xn16 * arg16, J0 = xn12 * arg12, Je = J0 / Jres, mJ2P, mdJ2PdJ;
+            if (UofJ == 1) { mJ2P = Ksp * Je * Je * (Je - 1.); mdJ2PdJ = Ksp * Je * (3. * Je - 2.); }
+            else if (UofJ == 2) { mJ2P = Ksp * Je * log(Je); mdJ2PdJ = Ksp * (log(Je) + 1.); }
+            else { mJ2P = 0.5 * Ksp * Je * (Je * Je - 1.); mdJ2PdJ = 0.5 * Ksp * (3. * Je * Je - 1.); }
+            double fx = 3. * Jres * mJ2P + G1sp * (2. * xn - arg2) * J13 + G2sp * (xn * arg2 - 2. * arg) / J13;
+            double fxp = (1.5 * J0 / xn) * mdJ2PdJ + G1sp * J13 * (14. * xn - arg2) / (6. * xn) + G2sp * (2. * arg + 5. * xn * arg2) / (6. * J13 * xn);
+            double xnp1 = xn - fx / fxp;
+            if (fabs(xn - xnp1) < 1e-10) break;
+            xn = xnp1;
+        }
+        double dFzz = sqrt(xn / Bzz);
+        Bzz = xn;
+        P3(eplast, ZZ, p) = xn;
+        P3(ep, ZZ, p) = dFzz * (1. + P3(ep, ZZ, p)) - 1.;
+        detDf *= dFzz;
+    }
+    double J = detDf * P3(hist, 0, p);
+    P3(hist, 0, p) = J;
+    double st0[6];
+    for (int c = 0; c < 6; c++) st0[c] = P3(sp, c, p);
+    double Jeff = J / Jres, p0 = O->pressure[p], Kvol;
+    if (UofJ == 1) Kvol = Ksp * (Jeff - 1.);
+    else if (UofJ == 2) Kvol = Ksp * log(Jeff) / Jeff;
+    else Kvol = 0.5 * Ksp * (Jeff - 1. / Jeff);
+    double Kterm = J * Kvol;
+    double delV = 1. - 1. / detDf, QAVred = 0., AVEnergy = 0.;
+    if (delV < 0. && m->p[3] != 0.) {
+        QAVred = artificial_viscosity(delV / delTime, sqrt(Ksp * J), m);
+        AVEnergy = fabs(QAVred * delV);
+    }
+    double Pfinal = -Kterm + QAVred;
+    O->pressure[p] = Pfinal;
+    double avgP = 0.5 * (p0 + Pfinal), dilEnergy = -avgP * delV, resEnergy = -avgP * (1. - 1. / dJres);
+    double J23 = pow(J, 2. / 3.), J43 = J23 * J23, JforG1 = J23 / Jres, JforG2 = J43 / Jres;
+    double Bxz = O->dim == 3 ? P3(eplast, XZ, p) : 0., Byz = O->dim == 3 ? P3(eplast, YZ, p) : 0.;
+    double sn[6];
+    sn[XX] = (2 * Bxx - Byy - Bzz) * G1sp / (3. * JforG1) + (Bxx * (Byy + Bzz) - 2 * Byy * Bzz - Bxy * Bxy) * G2sp / (3. * JforG2);
+    sn[YY] = (2 * Byy - Bxx - Bzz) * G1sp / (3. * JforG1) + (Byy * (Bxx + Bzz) - 2 * Bxx * Bzz - Bxy * Bxy) * G2sp / (3. * JforG2);
+    sn[ZZ] = (2 * Bzz - Bxx - Byy) * G1sp / (3. * JforG1) + (Bzz * (Bxx + Byy) - 2 * Bxx * Byy + 2. * Bxy * Bxy) * G2sp / (3. * JforG2);
+    sn[XY] = Bxy * G1sp / JforG1 + (Bzz * Bxy) * G2sp / JforG2;
+    sn[XZ] = st0[XZ]; sn[YZ] = st0[YZ];
+    if (O->dim == 3) {
+        sn[XX] += (2. * Byz * Byz - Bxz * Bxz) * G2sp / (3. * JforG2);
+        sn[YY] += (2. * Bxz * Bxz - Byz * Byz) * G2sp / (3. * JforG2);
+        sn[ZZ] -= (Bxz * Bxz + Byz * Byz) * G2sp / (3. * JforG2);
+        sn[XY] -= Bxz * Byz * G2sp / JforG2;
+        sn[XZ] = Bxz * G1sp / JforG1 + (Byy * Bxz - Bxy * Byz) * G2sp / JforG2;
+        sn[YZ] = Byz * G1sp / JforG1 + (Bxx * Byz - Bxy * Bxz) * G2sp / JforG2;
+    }
+    for (int c = 0; c < 6; c++) P3(sp, c, p) = sn[c];
+    double shear = 0.5 * ((sn[XX] + st0[XX]) * du[0][0] + (sn[YY] + st0[YY]) * du[1][1] + (sn[ZZ] + st0[ZZ]) * du[2][2] +
+                          (sn[XY] + st0[XY]) * (du[0][1] + du[1][0]));
+    if (O->dim == 3) shear += 0.5 * ((sn[XZ] + st0[XZ]) * (du[0][2] + du[2][0]) + (sn[YZ] + st0[YZ]) * (du[1][2] + du[2][1]));
+    P3(energies, 0, p) += dilEnergy + shear;
+    P3(energies, 1, p) += resEnergy;
+    double Kratio;
+    if (UofJ == 1) Kratio = Jeff;
+    else if (UofJ == 2) Kratio = (1 - log(Jeff)) / (Jeff * Jeff);
+    else Kratio = 0.5 * (Jeff + 1. / Jeff);
+    double prevT = P3(energies, 5, p);
+    double dTq0 = -J * Kratio * gamma0 * prevT * delV, baseHeat = -Cv * dTq0;
+    P3(energies, 2, p) += baseHeat - AVEnergy;
+    P3(energies, 3, p) += baseHeat / prevT;
+}
+
 /* ---- IsoPlasticity + LinearHardening: Materials/IsoPlasticity.cpp:128-517, LinearHardening.cpp:93-145 -------------- */
 #define SQRT_TWOTHIRDS 0.8164965809277260
 static void isoplasticity_law(int p, const double (*de)[3], double delTime, const mpmgpu_material *m)
@@ -1077,6 +1173,7 @@ static void full_strain_update(double strainTime, int postUpdate)
         const mpmgpu_material *m = &O->mats[O->matnum[p] - 1];
         if (m->kind == MPMGPU_MAT_ISOTROPIC) { if (m->p[7] != 0.) isotropic_lr_law(p, dv, m); else isotropic_law(p, dv, m); }
         else if (m->kind == MPMGPU_MAT_NEOHOOKEAN) neohookean_law(p, dv, strainTime, m);
+        else if (m->kind == MPMGPU_MAT_MOONEY) mooney_law(p, dv, strainTime, m);
         else if (m->kind == MPMGPU_MAT_ISOPLASTICITY) isoplasticity_law(p, dv, strainTime, m);
     }
 }
@@ -1381,6 +1478,7 @@ int oracle_law_batch(int np, double gridx, double gridy, double gridz, const mpm
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) d[i][j] = du[(size_t)9 * p + 3 * i + j];
         if (m->kind == MPMGPU_MAT_ISOTROPIC) { if (m->p[7] != 0.) isotropic_lr_law(p, d, m); else isotropic_law(p, d, m); }
         else if (m->kind == MPMGPU_MAT_NEOHOOKEAN) neohookean_law(p, d, delTime, m);
+        else if (m->kind == MPMGPU_MAT_MOONEY) mooney_law(p, d, delTime, m);
         else if (m->kind == MPMGPU_MAT_ISOPLASTICITY) isoplasticity_law(p, d, delTime, m);
         else { O = saved; return -1; }
     }

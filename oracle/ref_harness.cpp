@@ -32,6 +32,7 @@
 #include "Materials/MaterialBase.hpp"
 #include "Materials/IsotropicMat.hpp"
 #include "Materials/Neohookean.hpp"
+#include "Materials/Mooney.hpp"
 #include "Materials/IsoPlasticity.hpp"
 #include "Materials/HardeningLawBase.hpp"
 #include "Materials/LinearHardening.hpp"
@@ -299,6 +300,7 @@ void ref_get_velbcs(int *node, int *dir, int *style, double *norm, double *value
 //  all:   0 rho  1 heatCapacity(Cv)  2 field  3 damping-or-(-1)  4 rigid flag
 //  iso(1):      8 E 9 nu 10 G 11 CTE3 12 gamma0 13 useLargeRotation  14.. C11 C12 C44 (specific, /rho) from pr
 //  neo(28):     8 G 9 K 10 Lame 11 Gsp 12 Ksp 13 Lamesp 14 UofJOption 15 CTE1 16 gamma0(as used)
+//  mooney(8):   8 G1 9 G2 10 K 11 G1sp 12 G2sp 13 Ksp 14 UofJOption 15 CTE1 16 gamma0 17 IdealRubber
 //  isoplas(9):  8 E 9 nu 10 G 11 CTE3 12 gamma0 13 Gred 14 Kred 15 yield 16 Ep 17 yldred 18 Epred 19 alphaMax 20 yldredMin 21 beta
 //               22 useLargeRotation
 int ref_get_materials(int *ids, double *params)
@@ -322,6 +324,11 @@ int ref_get_materials(int *ids, double *params)
             Neohookean *nm = (Neohookean *)m;
             q[8] = nm->G; q[9] = nm->Kbulk; q[10] = nm->Lame; q[11] = nm->pr.Gsp; q[12] = nm->pr.Ksp;
             q[13] = nm->pr.Lamesp; q[14] = nm->UofJOption; q[15] = nm->CTE1; q[16] = nm->gamma0;
+        }
+        else if (ids[i] == 8) {
+            Mooney *mm = (Mooney *)m;
+            q[8] = mm->G1; q[9] = mm->G2; q[10] = mm->Kbulk; q[11] = mm->G1sp; q[12] = mm->G2sp; q[13] = mm->Ksp;
+            q[14] = mm->UofJOption; q[15] = mm->CTE1; q[16] = mm->gamma0; q[17] = mm->rubber ? 1. : 0.;
         }
         else if (ids[i] == 11) {
             RigidMaterial *rm = (RigidMaterial *)m;

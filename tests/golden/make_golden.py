@@ -104,6 +104,17 @@ CASES = {
     "block3d_free_ugimp": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-6.0e3, vx=3.0e3, bc=False), (1, 30), 1, 0.3, 4000.0),
     "block3d_free_lcpdi_xpic2": (inputs.block3d(ncell=3, margin=3, gimp="lCPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3, bc=False,
                                                 custom_tasks=inputs.periodic_xpic(2, False, 1)), (1, 2, 30), 2, 0.3, 3000.0),
+    # Mooney-Rivlin (MaterialID 8): 3D with artificial viscosity, plane strain / plane stress with the three U(J) options
+    "block3d_mooney": (inputs.block3d(ncell=3, margin=3, material=inputs.mooney_material(av=(0.3, 1.5)), vz=-1.0e4, vx=3.0e3), (1, 40), 1, 0.3, 3000.0),
+    "block3d_mooney_uj2": (inputs.block3d(ncell=3, margin=3, material=inputs.mooney_material(ujoption=2), vz=-1.0e4, bc=False), (1, 30), 1, 0.3, 3000.0),
+    "disks2d_mooney_planestrain": (inputs.disks2d(analysis=10, vel=4000.0)
+                                   .replace(DISK1, inputs.mooney_material(0.3, 0.1, 1.0, 1, name="Disk 1", rho=1.5))
+                                   .replace(DISK2, inputs.mooney_material(0.25, 0.15, 1.0, None, name="Disk 2", rho=1.5)), (1, 100), 1),
+    "disks2d_mooney_planestress": (inputs.disks2d(analysis=11, vel=4000.0)
+                                   .replace(DISK1, inputs.mooney_material(0.3, 0.1, 1.0, 1, name="Disk 1", rho=1.5))
+                                   .replace(DISK2, inputs.mooney_material(0.25, 0.15, 1.0, 2, name="Disk 2", rho=1.5)), (1, 100), 1),
+    "disks2d_mooney_planestress_uj0": (inputs.disks2d(analysis=11, gimp=None, vel=5000.0)
+                                       .replace(DISK1, inputs.mooney_material(0.3, 0.1, 1.0, 0, av=(0.2, 2.0), name="Disk 1", rho=1.5)), (1, 100), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

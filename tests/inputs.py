@@ -139,6 +139,13 @@ def neohookean_material(G=40.0, K=200.0, ujoption=None, av=None):
     return NEOHOOKEAN_MAT % (G, K, extra)
 
 
+def mooney_material(G1=30.0, G2=10.0, K=200.0, ujoption=None, av=None, name="Blk", rho=1.0):
+    extra = "" if ujoption is None else "<UJOption>%d</UJOption>" % ujoption
+    if av is not None:
+        extra += AV_TAGS % av
+    return '<Material Type="8" Name="%s"><rho>%r</rho><G1>%r</G1><G2>%r</G2><K>%r</K><alpha>40</alpha>%s</Material>' % (name, rho, G1, G2, K, extra)
+
+
 def isoplastic_material(rho=2.0, E=2000.0, nu=0.33, yld=20.0, Ep=100.0, av=None):
     m = ISOPLASTIC_MAT % (rho, E, nu, yld, Ep)
     if av is not None:

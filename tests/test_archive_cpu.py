@@ -22,7 +22,8 @@ FULL_ORDER = "iYYYYYNYYYNNYYYYYY"        # every item this path produces (bytes 
 
 
 @pytest.mark.parametrize("case,order_in", [(c, None) for c in CASES] +
-                         [("block3d_neohookean_uj1", FULL_ORDER), ("disks2d_isoplastic", FULL_ORDER), ("disks2d_neohookean", "iYYYYYNYYYNNYCYYYY")])
+                         [("block3d_neohookean_uj1", FULL_ORDER), ("disks2d_isoplastic", FULL_ORDER), ("disks2d_neohookean", "iYYYYYNYYYNNYCYYYY"),
+                          ("disks2d_mooney_planestress", "iYYYYYNYYYNNYCYYYY")])
 def test_archives_match_the_reference_cli_byte_for_byte(case, order_in):
     if not os.path.exists(REF):
         pytest.skip("oracle/_ref/NairnMPM not built")

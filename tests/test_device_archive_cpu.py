@@ -14,7 +14,8 @@ from tests.parity import load_golden
 from tests.test_device_laws_cpu import libs  # noqa: F401  (fixture: builds tests/devlaws)
 
 CASES = [("block3d_ugimp_usavg", "iYYYYNNNNNNNNNNNNN"), ("block3d_neohookean_uj1", "iYYYYYNYYYNNYYYYYY"), ("disks2d_isoplastic", "iYYYYYNYYYNNYYYYYY"),
-         ("disks2d_neohookean", "iYYYYYNYYYNNYCYYYY"), ("block3d_rigid_wall", "iYYYYNNYNNNNNYNNYN"), ("block3d_isoplastic", "iNYNYNNYNYNNYANNNY")]
+         ("disks2d_neohookean", "iYYYYYNYYYNNYCYYYY"), ("block3d_rigid_wall", "iYYYYNNYNNNNNYNNYN"), ("block3d_isoplastic", "iNYNYNNYNYNNYANNNY"),
+         ("block3d_mooney", "iYYYYYNYYYNNYCYYYY")]
 
 
 def _dp(a):
@@ -119,11 +120,11 @@ def reference_sums(prob, state, dim):
         sel = np.nonzero(mat0[:nn] == m)[0]
         if mat["kind"] == M.RIGIDBC or sel.size == 0:
             continue
-        J = state["history"][0][sel] if mat["kind"] == M.NEOHOOKEAN else 1.0
+        J = state["history"][0][sel] if mat["kind"] in (M.NEOHOOKEAN, M.MOONEY) else 1.0
         Vp = J * mp[sel] / mat["rho"]
         v = state["vel"][:, sel]
         en = state["energies"][:, sel]
-        pr = state["pressure"][sel] if mat["kind"] in (M.NEOHOOKEAN, M.ISOPLASTICITY) else 0.0
+        pr = state["pressure"][sel] if mat["kind"] in (M.NEOHOOKEAN, M.ISOPLASTICITY, M.MOONEY) else 0.0
         put(m, 0, mp[sel])
         put(m, 1, Vp * np.ones(sel.size))
         for c in range(dim):
@@ -186,7 +187,7 @@ def quantities_from_sums(sums):
 
 
 # cases whose golden state comes from the XML alone (no harness-side jitter), so the CLI run reproduces it
-@pytest.mark.parametrize("case", ["block3d_neohookean_uj1", "disks2d_isoplastic", "block3d_rigid_wall_lattice", "disks2d_neohookean"])
+@pytest.mark.parametrize("case", ["block3d_neohookean_uj1", "disks2d_isoplastic", "block3d_rigid_wall_lattice", "disks2d_neohookean", "disks2d_mooney_planestrain"])
 def test_global_sums_reproduce_the_reference_cli_global_file(libs, case):  # noqa: F811
     import os
     import re

@@ -60,7 +60,7 @@ def _random_state(kind, dim, n, rng, modulus):
         eplast[[3, 4]] = 0.0
     pressure = 1.0e-3 * modulus * rng.standard_normal(n)
     hist = np.zeros((M.MAX_HISTORY, n))
-    if kind == M.NEOHOOKEAN:
+    if kind in (M.NEOHOOKEAN, M.MOONEY):
         # elastic left Cauchy-Green tensor B = F F^T (xx,yy,zz,yz,xz,xy), J = det F, Jres = 1
         Fm = F.T.reshape(n, 3, 3)
         B = Fm @ np.transpose(Fm, (0, 2, 1))
@@ -101,6 +101,8 @@ def _mat(name, np_):
         return M.isotropic(U["E"], 0.3, U["rho"], aI=40.0, np_=np_, large_rotation=True)
     if name.startswith("neohookean"):
         return M.neohookean(U["G"], U["K"], U["rho"], aI=40.0, UofJOption=int(name[-1]), av=(0.3, 1.5) if name[-1] == "0" else None)
+    if name.startswith("mooney"):
+        return M.mooney(0.75 * U["G"], 0.25 * U["G"], U["K"], U["rho"], aI=40.0, UofJOption=int(name[-1]), av=(0.3, 1.5) if name[-1] == "1" else None)
     if name == "isoplasticity":
         return M.isoplasticity(U["E"], 0.3, U["rho"], U["yld"], U["Ep"], aI=20.0, np_=np_, av=(0.2, 2.0))
     if name == "isoplasticity_lr":
@@ -108,7 +110,7 @@ def _mat(name, np_):
     raise KeyError(name)
 
 
-LAWS = ["isotropic", "isotropic_lr", "neohookean0", "neohookean1", "neohookean2", "isoplasticity", "isoplasticity_lr"]
+LAWS = ["isotropic", "isotropic_lr", "neohookean0", "neohookean1", "neohookean2", "mooney0", "mooney1", "mooney2", "isoplasticity", "isoplasticity_lr"]
 
 
 @pytest.mark.parametrize("analysis", list(NPS))

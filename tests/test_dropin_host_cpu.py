@@ -22,8 +22,10 @@ CASES = {
     "feedback damping": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<FeedbackDamping>10</FeedbackDamping>"),
                          "time-dependent or feedback damping"),
     "particle loads": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</GridBCs>", "</GridBCs>" + LOAD_BC), "particle load BCs"),
-    "unsupported material": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="8" Name="Blk"><rho>1</rho><G1>30</G1>'
-                                            '<G2>0</G2><K>100</K><alpha>0</alpha></Material>'), "material type"),
+    "unsupported material": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="2" Name="Blk"><rho>1</rho><EA>1000</EA>'
+                                            '<ET>500</ET><GA>300</GA><nuT>0.3</nuT><nuA>0.25</nuA><alphaA>0</alphaA><alphaT>0</alphaT></Material>'), "material type"),
+    "ideal rubber": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="8" Name="Blk"><rho>1</rho><G1>30</G1><G2>0</G2><K>100</K>'
+                                    '<alpha>0</alpha><IdealRubber/></Material>'), "IdealRubber"),
     "unsupported shape functions": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, gimp="B2GIMP"), "shape functions"),
     # failure handling of the replaced tasks that libmpmgpu does not do
     "time-step restarts": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, method=3, extra_header="<RestartScaling>0.5</RestartScaling>"),

@@ -24,7 +24,7 @@ DISK = '<Material Type="1" Name="Disk %d"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><
 
 def material(rng, name, two_d):
     """(xml, is_large_rotation) of a random in-scope material; 2D materials use the disks' scale (E = 1 MPa)."""
-    kind = rng.choice(["iso", "iso_lr", "neo", "plastic", "plastic_lr"])
+    kind = rng.choice(["iso", "iso_lr", "neo", "mooney", "plastic", "plastic_lr"])
     E, G, K, yld, Ep = (1.0, 0.4, 1.0, 0.02, 0.1) if two_d else (100.0, 40.0, 200.0, 4.0, 20.0)
     extra = ""
     if rng.random() < 0.25:
@@ -38,6 +38,11 @@ def material(rng, name, two_d):
             extra += "<ArtificialVisc/><avA1>0.3</avA1><avA2>1.5</avA2>"
         return ('<Material Type="28" Name="%s"><rho>1.5</rho><G>%r</G><K>%r</K><alpha>40</alpha><UJOption>%d</UJOption>%s</Material>'
                 % (name, G, K, int(rng.integers(0, 3)), extra)), False
+    if kind == "mooney":
+        if rng.random() < 0.4:
+            extra += "<ArtificialVisc/><avA1>0.3</avA1><avA2>1.5</avA2>"
+        return ('<Material Type="8" Name="%s"><rho>1.5</rho><G1>%r</G1><G2>%r</G2><K>%r</K><alpha>40</alpha><UJOption>%d</UJOption>%s</Material>'
+                % (name, 0.7 * G, 0.3 * G, K, int(rng.integers(0, 3)), extra)), False
     lr = kind.endswith("lr")
     if rng.random() < 0.3:
         extra += "<ArtificialVisc/><avA1>0.2</avA1><avA2>2.0</avA2>"

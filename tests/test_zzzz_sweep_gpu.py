@@ -23,7 +23,7 @@ def test_random_combination_on_the_gpu_matches_the_live_reference(seed):
     xml, (ja, va), lr3d, desc = make_config(1000 + seed)
     z = refharness.run_reference(xml, snaps=(1, NSTEPS), per_task_steps=0, nprocs=1, jitter_amp=ja, vel_amp=va)
     prob = from_reference_dump(z)
-    lr = any(m["p"][7] != 0.0 for m in prob.materials)
+    lr = any(m["p"][7] != 0.0 or m["kind"] == 8 for m in prob.materials)          # extended law dispatch: per-task kernels only
     mirrored = any(m["kind"] == 11 and m["p"][9] != 0.0 for m in prob.materials)
     fused_ok = prob.is3d and prob.shape == 1 and not lr and not mirrored
     for kernel_path in (1, 2) if fused_ok else (1,):
