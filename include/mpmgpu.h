@@ -118,6 +118,12 @@ typedef struct mpmgpu_config {
  *  MOONEY:          [8] G1sp [9] G2sp [10] Ksp [11] UofJOption [12] CTE1 [13] gamma0   (Materials/Mooney.cpp:104-147; history J, Jres)
  *  ISOPLASTICITY:   [8] Gred [9] Kred [10] yldred [11] Epred [12] CTE3 [13] gamma0
  *                   [14] alphaMax [15] yldredMin  (LinearHardening.cpp:55-80)
+ *                   [16] hardening law, ids of MaterialBase::SetHardeningLaw (MaterialBaseMPM.cpp:548-595): 0 or 1 Linear (closed-form
+ *                   return; fused path), else returned by the bracketed Newton's method of HardeningLawBase (per-task kernels):
+ *                   2 Nonlinear  yldred (1 + beta alpha)^n   [17] beta [18] n
+ *                   6 Nonlinear2 yldred (1 + beta alpha^n)   [17] beta [18] n
+ *                   3 JohnsonCook  [17] Bred [18] n [19] C [20] ep0 [21] D [22] n2 [23] Tm [24] m [25] reference temperature
+ *                                  [26] edotMin [27] eminTerm  (JohnsonCook.cpp:106-127)
  *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)  [9] mirrored (-1, 0, +1)
  */
 typedef struct mpmgpu_material {

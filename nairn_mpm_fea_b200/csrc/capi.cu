@@ -246,7 +246,7 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
         if (mats[i].p[3] != 0. && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY && k != MAT_MOONEY)
             return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d does not support artificial viscosity (MaterialBase::SupportsArtificialViscosity)", k);
         // MeshInfo::GetAverageCellSize for equal elements (MeshInfo.cpp:1517-1523): a grid constant the law needs
-        if (k == MAT_MOONEY) ctx->largeRotation = true;       // laws of the extended dispatch: per-task kernels, k_update_strains_lr
+        if (k == MAT_MOONEY || (k == MAT_ISOPLASTICITY && mats[i].p[16] > 1.)) ctx->largeRotation = true;     // laws of the extended dispatch (Mooney, hardening laws other than Linear): per-task kernels, k_update_strains_lr
         if (mats[i].p[7] != 0.) {
             if (k != MAT_ISOTROPIC && k != MAT_ISOPLASTICITY)
                 return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d has no large-rotation mode (Elastic::useLargeRotation: IsotropicMat, IsoPlasticity)", k);

@@ -599,9 +599,207 @@ __device__ __forceinline__ void mooney_law(PState &s, const double du[9], double
 // Reference quirks kept: 3D plastic-step work energy adds sp.zz*de.zz twice (:428-431); the 2D rotation of the
 // prior shear stress uses the plastic strain (:252).
 #define MPM_SQRT_TWOTHIRDS 0.8164965809277260
-template <int DIM, bool LR = false>
+
+// ---- hardening laws other than Linear (HardeningLawBase and subclasses) ---------------------------------------------------
+// Law ids as in MaterialBase::SetHardeningLaw (MaterialBaseMPM.cpp:548-595).  Parameter slots of an ISOPLASTICITY material:
+// [16] law id (0 or 1 = Linear, closed-form return), then
+//   Nonlinear  (2, Materials/NonlinearHardening.cpp):  yield = yldred (1 + beta alpha)^n        [17] beta [18] n
+//   Nonlinear2 (6, Materials/Nonlinear2Hardening.cpp): yield = yldred (1 + beta alpha^n)        [17] beta [18] n
+//   JohnsonCook (3, Materials/JohnsonCook.cpp): (yldred + Bred alpha^n)(1 + C ln(epdot/ep0) [+ D ln^n2])(1 - T*^m)
+//        [17] Bred [18] n [19] C [20] ep0 [21] D [22] n2 [23] Tm [24] m [25] reference temperature [26] edotMin [27] eminTerm
+// alphaMax [14] and yldredMin [15] keep their meaning for the two power laws.
+enum { HARD_LINEAR = 1, HARD_NONLINEAR = 2, HARD_JOHNSONCOOK = 3, HARD_NONLINEAR2 = 6 };
+#define MPM_TWOTHIRDS 0.6666666666666667
+#define MPM_SQRT_EIGHT27THS 0.5443310539518174
+
+struct HardAlpha { double alpint, dalpha; };      // HardeningAlpha (Materials/HardeningLawBase.hpp)
+struct HardProps { int law; double TjcTerm, hmlgTemp; };       // JCProperties (JohnsonCook::GetCopyOfHardeningProps :130-152)
+
+__device__ __forceinline__ HardProps hard_props(const Material &m, double prevT)
+{
+    HardProps h;
+    h.law = (int)m.p[16]; h.TjcTerm = 1.; h.hmlgTemp = 0.;
+    if (h.law == HARD_JOHNSONCOOK) {
+        h.hmlgTemp = (prevT - m.p[25]) / (m.p[23] - m.p[25]);
+        if (h.hmlgTemp > 1.) h.TjcTerm = 0.;
+        else if (h.hmlgTemp > 0.) h.TjcTerm = 1. - pow(h.hmlgTemp, m.p[24]);
+        else h.TjcTerm = 1.;
+    }
+    return h;
+}
+
+__device__ __forceinline__ bool dble_equal(double A, double B)      // Common/System/CommonUtilities.cpp:46-62
+{
+    const double diff = fabs(A - B);
+    if (diff <= 1.0e-16) return true;
+    A = fabs(A); B = fabs(B);
+    const double largest = (B > A) ? B : A;
+    return diff <= largest * 1.0e-7;
+}
+
+// the rate term of Johnson-Cook and its derivative factor (JohnsonCook.cpp:158-228)
+__device__ __forceinline__ void jc_rate_terms(const Material &m, double delTime, const HardAlpha &a, double &term2, double &dterm2, bool &above)
+{
+    const double Cjc = m.p[19], ep0 = m.p[20], Djc = m.p[21], n2 = m.p[22], edotMin = m.p[26], eminTerm = m.p[27];
+    const double ep = a.dalpha / (delTime * ep0);
+    above = ep > edotMin;
+    dterm2 = 0.;
+    if (above) {
+        term2 = 1. + Cjc * log(ep);
+        dterm2 = Cjc * ep0 / a.dalpha;
+        if (Djc != 0. && ep > 1.) {
+            term2 += Djc * pow(log(ep), n2);
+            dterm2 += Djc * ep0 * n2 * pow(log(ep), n2 - 1.) / a.dalpha;
+        }
+    } else term2 = eminTerm;
+}
+
+__device__ __forceinline__ double hard_yield(const Material &m, const HardProps &h, double delTime, const HardAlpha &a)
+{
+    const double yldred = m.p[10];
+    if (h.law == HARD_NONLINEAR) return a.alpint < m.p[14] ? yldred * pow(1. + m.p[17] * a.alpint, m.p[18]) : m.p[15];
+    if (h.law == HARD_NONLINEAR2) return a.alpint < m.p[14] ? yldred * (1. + m.p[17] * pow(a.alpint, m.p[18])) : m.p[15];
+    if (h.hmlgTemp >= 1.) return 0.;
+    const double term1 = yldred + m.p[17] * pow(a.alpint, m.p[18]);
+    const double ep = a.dalpha / (delTime * m.p[20]);
+    double term2 = ep > m.p[26] ? 1. + m.p[19] * log(ep) : m.p[27];
+    if (m.p[21] != 0. && ep > 1.) term2 += m.p[21] * pow(log(ep), m.p[22]);
+    return term1 * term2 * h.TjcTerm;
+}
+
+// d(sqrt(2/3) yield)/d lambda, 3D and plane strain
+__device__ __forceinline__ double hard_kprime(const Material &m, const HardProps &h, double delTime, const HardAlpha &a)
+{
+    const double yldred = m.p[10];
+    if (h.law == HARD_NONLINEAR) return a.alpint < m.p[14] ? MPM_TWOTHIRDS * yldred * m.p[17] * m.p[18] * pow(1. + m.p[17] * a.alpint, m.p[18] - 1) : 0.;
+    if (h.law == HARD_NONLINEAR2) return a.alpint < m.p[14] ? MPM_TWOTHIRDS * yldred * m.p[17] * m.p[18] * pow(a.alpint, m.p[18] - 1.) : 0.;
+    if (h.hmlgTemp >= 1.) return 0.;
+    const double dterm1 = m.p[17] * m.p[18] * pow(a.alpint, m.p[18] - 1.);
+    double term2, dterm2; bool above;
+    jc_rate_terms(m, delTime, a, term2, dterm2, above);
+    if (above) {
+        const double term1 = yldred + m.p[17] * pow(a.alpint, m.p[18]);
+        return MPM_TWOTHIRDS * h.TjcTerm * (dterm1 * term2 + term1 * dterm2);
+    }
+    return MPM_TWOTHIRDS * h.TjcTerm * dterm1 * term2;
+}
+
+// d(yield^2 / 3)/d lambda, plane stress
+__device__ __forceinline__ double hard_k2prime(const Material &m, const HardProps &h, double fnp1, double delTime, const HardAlpha &a)
+{
+    const double yldred = m.p[10];
+    if (h.law == HARD_NONLINEAR)
+        return a.alpint < m.p[14] ? MPM_SQRT_EIGHT27THS * yldred * yldred * m.p[17] * m.p[18] * pow(1. + m.p[17] * a.alpint, 2. * m.p[18] - 1) * fnp1 : 0.;
+    if (h.law == HARD_NONLINEAR2) {
+        if (dble_equal(a.alpint, 0.)) return 0.;
+        if (a.alpint < m.p[14]) {
+            const double alphan = pow(a.alpint, m.p[18]);
+            return MPM_SQRT_EIGHT27THS * yldred * yldred * m.p[17] * m.p[18] * (1. + m.p[17] * alphan) * alphan * fnp1 / a.alpint;
+        }
+        return 0.;
+    }
+    if (dble_equal(a.alpint, 0.)) return 0.;
+    if (h.hmlgTemp >= 1.) return 0.;
+    const double term1 = yldred + m.p[17] * pow(a.alpint, m.p[18]);
+    const double dterm1 = m.p[17] * m.p[18] * pow(a.alpint, m.p[18] - 1.);
+    double term2, dterm2; bool above;
+    jc_rate_terms(m, delTime, a, term2, dterm2, above);
+    if (above) return MPM_SQRT_EIGHT27THS * term1 * term2 * fnp1 * h.TjcTerm * h.TjcTerm * (dterm1 * term2 + dterm2 * term1);
+    return MPM_SQRT_EIGHT27THS * term1 * term2 * fnp1 * h.TjcTerm * h.TjcTerm * dterm1 * term2;
+}
+
+// K(alpha) - K(0) for the dissipated energy (HardeningLawBase.cpp:110-113; JohnsonCook.cpp:230-238)
+__device__ __forceinline__ double hard_yield_increment(const Material &m, const HardProps &h, double delTime, const HardAlpha &a)
+{
+    if (h.law != HARD_JOHNSONCOOK) return hard_yield(m, h, delTime, a) - m.p[10];
+    if (h.hmlgTemp >= 1.) return 0.;
+    const double ep = a.dalpha / (delTime * m.p[20]);
+    double term2 = ep > m.p[26] ? 1. + m.p[19] * log(ep) : m.p[27];
+    if (m.p[21] != 0. && ep > 1.) term2 += m.p[21] * pow(log(ep), m.p[22]);
+    return m.p[17] * pow(a.alpint, m.p[18]) * term2 * h.TjcTerm;
+}
+
+// HardeningLawBase::SolveForLambdaBracketed with BracketSolution (HardeningLawBase.cpp:211-381): Newton's method kept inside a
+// bracket, bisecting when a step would leave it.  a holds alpha at the start of the step (dalpha = 0) and the solution at the end.
+// ok = false: the plane-stress bracket was not found in 20 decades of strain rate (the reference throws).
+template <bool PLANE_STRESS>
+__device__ __forceinline__ double solve_lambda_bracketed(const Material &m, const HardProps &h, double alpha0, double strial, const double stk[6],
+                                                         double Gred, double psKred, double Pfinal, double delTime, HardAlpha &a, bool &ok)
+{
+    ok = true;
+    if (h.law == HARD_JOHNSONCOOK && h.hmlgTemp >= 1.) return strial / (2. * Gred);          // melted (JohnsonCook.cpp:244-249)
+    double xl = 0., xh = 0.;        // xl: g < 0 (higher lambda), xh: g > 0 (lower lambda)
+    double n1trial = 0., n2trial = 0.;
+    if (PLANE_STRESS) {
+        n2trial = -stk[XX] + stk[YY];
+        n2trial *= 0.5 * n2trial;
+        n2trial += 2. * stk[XY] * stk[XY];
+        n1trial = stk[XX] + stk[YY] - 2. * Pfinal;
+        n1trial *= n1trial / 6.;
+        double epdot = 1.;
+        bool found = false;
+        for (int step = 0; step < 20; step++) {
+            a.dalpha = epdot * delTime;
+            a.alpint = alpha0 + a.dalpha;
+            const double lambdak = a.dalpha / MPM_SQRT_TWOTHIRDS;
+            const double d1 = (1 + psKred * lambdak), d2 = (1. + 2. * Gred * lambdak);
+            const double fnp12 = n1trial / (d1 * d1) + n2trial / (d2 * d2);
+            const double kyld = hard_yield(m, h, delTime, a);
+            const double gmax = 0.5 * fnp12 - kyld * kyld / 3.;
+            if (gmax < 0.) { xl = a.dalpha / MPM_SQRT_TWOTHIRDS; found = true; break; }
+            xh = lambdak;
+            epdot *= 10.;
+        }
+        if (!found) { ok = false; return 0.; }
+    } else {
+        const double dalpha = strial / (2. * Gred);
+        a.alpint = alpha0 + dalpha;
+        if (hard_yield(m, h, delTime, a) <= 0.) xh = dalpha / MPM_SQRT_TWOTHIRDS;
+        xl = dalpha / MPM_SQRT_TWOTHIRDS;
+    }
+    if (xh > xl) return xh;
+    double lambdak = 0.5 * (xl + xh);
+    a.dalpha = PLANE_STRESS ? 0. : MPM_SQRT_TWOTHIRDS * lambdak;        // UpdateTrialAlpha(lambdak, fnp1 = 0): zero in plane stress
+    a.alpint = alpha0 + a.dalpha;
+    double dxold = fabs(xh - xl), dx = dxold;
+    for (int step = 1;;) {
+        double glam, slope, fnp1 = 0.;
+        if (PLANE_STRESS) {
+            const double d1 = (1 + psKred * lambdak), d2 = (1. + 2. * Gred * lambdak);
+            const double fnp12 = n1trial / (d1 * d1) + n2trial / (d2 * d2);
+            const double kyld = hard_yield(m, h, delTime, a);
+            glam = 0.5 * fnp12 - kyld * kyld / 3.;
+            fnp1 = sqrt(fnp12);
+            slope = -(psKred * n1trial / (d1 * d1 * d1) + 2 * Gred * n2trial / (d2 * d2 * d2)) - hard_k2prime(m, h, fnp1, delTime, a);
+        } else {
+            glam = strial - 2 * Gred * lambdak - MPM_SQRT_TWOTHIRDS * hard_yield(m, h, delTime, a);
+            slope = -2. * Gred - hard_kprime(m, h, delTime, a);
+        }
+        if (((lambdak - xh) * slope - glam) * ((lambdak - xl) * slope - glam) >= 0. || fabs(2. * glam) > fabs(dxold * slope)) {
+            dxold = dx;
+            dx = 0.5 * (xh - xl);
+            lambdak = xl + dx;
+            if (xl == lambdak) break;
+        } else {
+            dxold = dx;
+            dx = glam / slope;
+            const double temp = lambdak;
+            lambdak -= dx;
+            if (temp == lambdak) break;
+        }
+        a.dalpha = PLANE_STRESS ? MPM_SQRT_TWOTHIRDS * lambdak * fnp1 : MPM_SQRT_TWOTHIRDS * lambdak;
+        a.alpint = alpha0 + a.dalpha;
+        if (step++ > 20 || fabs(dx / lambdak) < 0.0001) break;
+        if (glam < 0.) xl = lambdak; else xh = lambdak;
+    }
+    return lambdak;
+}
+template <int DIM, bool LR = false, bool GENERAL = false>
 __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9], double delTime, int np, const Material &m)
 {
+    // GENERAL: a hardening law other than Linear (slot 16): numerical return by the bracketed Newton's method of HardeningLawBase
+    HardProps hp;
+    if (GENERAL) hp = hard_props(m, s.prevT);
     const double Gred = m.p[8], Kred = m.p[9], yldred = m.p[10], Epred = m.p[11];
     const double gamma0 = m.p[13], Cv = m.p[1], alphaMax = m.p[14], yldredMin = m.p[15];
     // large rotation (:140-158): the strain increment in the current configuration replaces du, state n-1 is rotated by dR
@@ -673,7 +871,9 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
     double tt = strial[XY] * strial[XY];
     if (DIM == 3) tt += strial[XZ] * strial[XZ] + strial[YZ] * strial[YZ];
     const double smag = sqrt(ss + tt + tt);
-    const double yield0 = alpha0 < alphaMax ? yldred + Epred * alpha0 : yldredMin;
+    HardAlpha ha;
+    ha.alpint = alpha0; ha.dalpha = 0.;                 // UpdateTrialAlpha(mptr, np, &alpha, 0)
+    const double yield0 = GENERAL ? hard_yield(m, hp, delTime, ha) : (alpha0 < alphaMax ? yldred + Epred * alpha0 : yldredMin);
     const double ftrial = smag - MPM_SQRT_TWOTHIRDS * yield0;
     if (ftrial < 0.) {
 #pragma unroll
@@ -696,6 +896,11 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
         // (HardeningLawBase.cpp:157-202, chosen by LinearHardening.cpp:128-131)
         lambdak = 0.;
         alpint = alpha0;
+        if (GENERAL) {
+            bool ok;
+            lambdak = solve_lambda_bracketed<true>(m, hp, alpha0, smag, strial, Gred, psKred, Pfinal, delTime, ha, ok);
+            alpint = ha.alpint;
+        } else {
         double n2trial = -strial[XX] + strial[YY];
         n2trial *= n2trial / 2;
         n2trial += 2. * strial[XY] * strial[XY];
@@ -714,6 +919,7 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
             alpint = alpha0 + MPM_SQRT_TWOTHIRDS * lambdak * fnp1;          // UpdateTrialAlpha, plane stress
             if (step++ > 20 || fabs(delLam / lambdak) < 0.0001) break;      // LambdaConverged
         }
+        }
         // final stress and direction (:345-389)
         const double d1 = (1. + psKred * lambdak), d2 = (1. + 2. * Gred * lambdak);
         const double n1 = (strial[XX] + strial[YY] - 2. * Pfinal) / d1, n2 = (-strial[XX] + strial[YY]) / d2;
@@ -731,10 +937,16 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
         dTq0 -= gamma0 * s.prevT * dezzp;
         spPS[0] = sxx + Pfinal; spPS[1] = syy + Pfinal; spPS[2] = Pfinal; spPS[3] = txy;
     } else {
-        // radial return, closed form (LinearHardening.cpp:124-145)
-        lambdak = (smag - MPM_SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
-        if (alpha0 + MPM_SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - MPM_SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
-        alpint = alpha0 + MPM_SQRT_TWOTHIRDS * lambdak;
+        if (GENERAL) {
+            bool ok;
+            lambdak = solve_lambda_bracketed<false>(m, hp, alpha0, smag, strial, Gred, 0., Pfinal, delTime, ha, ok);
+            alpint = ha.alpint;
+        } else {
+            // radial return, closed form (LinearHardening.cpp:124-145)
+            lambdak = (smag - MPM_SQRT_TWOTHIRDS * (yldred + Epred * alpha0)) / (2. * (Gred + Epred / 3.));
+            if (alpha0 + MPM_SQRT_TWOTHIRDS * lambdak > alphaMax) lambdak = (smag - MPM_SQRT_TWOTHIRDS * yldredMin) / (2. * Gred);
+            alpint = alpha0 + MPM_SQRT_TWOTHIRDS * lambdak;
+        }
 #pragma unroll
         for (int i = 0; i < 6; i++) dfds[i] = strial[i] / smag;           // df/dsigma = s/|s| (:496-509)
     }
@@ -758,7 +970,8 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
     s.work += workEnergy;
     double plastEnergy = sp[XX] * dep[XX] + sp[YY] * dep[YY] + sp[ZZ] * dep[ZZ] + sp[XY] * dep[XY];
     if (DIM == 3) plastEnergy += sp[XZ] * dep[XZ] + sp[YZ] * dep[YZ];
-    const double yieldInc = fmax(Epred * alpint, yldredMin - yldred);      // LinearHardening::GetYieldIncrement
+    const double yieldInc = GENERAL ? hard_yield_increment(m, hp, delTime, ha)
+                                    : fmax(Epred * alpint, yldredMin - yldred);      // LinearHardening::GetYieldIncrement
     dispEnergy += plastEnergy - lambdak * MPM_SQRT_TWOTHIRDS * yieldInc;
     s.plast += dispEnergy;
     increment_heat_energy(s, Cv, dTq0, dispEnergy);
@@ -800,7 +1013,8 @@ __device__ __forceinline__ void constitutive_law_lr(PState &s, const double du[9
         neohookean_law<DIM>(s, du, delTime, np, m);
         break;
     case MAT_ISOPLASTICITY:
-        if (lr) isoplasticity_law<DIM, true>(s, du, delTime, np, m); else isoplasticity_law<DIM, false>(s, du, delTime, np, m);
+        if (m.p[16] > 1.) { if (lr) isoplasticity_law<DIM, true, true>(s, du, delTime, np, m); else isoplasticity_law<DIM, false, true>(s, du, delTime, np, m); }
+        else if (lr) isoplasticity_law<DIM, true>(s, du, delTime, np, m); else isoplasticity_law<DIM, false>(s, du, delTime, np, m);
         break;
     case MAT_MOONEY:
         mooney_law<DIM>(s, du, delTime, np, m);

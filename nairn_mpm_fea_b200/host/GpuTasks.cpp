@@ -34,6 +34,10 @@
 #include "Materials/IsoPlasticity.hpp"
 #include "Materials/HardeningLawBase.hpp"
 #include "Materials/LinearHardening.hpp"
+#include "Materials/NonlinearHardening.hpp"
+#include "Materials/Nonlinear2Hardening.hpp"
+#include "Materials/JohnsonCook.hpp"
+#include "Global_Quantities/ThermalRamp.hpp"
 #include "Materials/RigidMaterial.hpp"
 #include "Boundary_Conditions/NodalVelBC.hpp"
 #include "Boundary_Conditions/MatPtLoadBC.hpp"
@@ -246,7 +250,10 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         case 28: break;
         case 8: if (((Mooney *)mb)->rubber) return "Mooney with the IdealRubber option"; break;
         case 9:
-            if (dynamic_cast<LinearHardening *>(((IsoPlasticity *)mb)->plasticLaw) == NULL) return "IsoPlasticity hardening law other than Linear";
+            {   HardeningLawBase *hl = ((IsoPlasticity *)mb)->plasticLaw;
+                if (dynamic_cast<LinearHardening *>(hl) == NULL && dynamic_cast<NonlinearHardening *>(hl) == NULL && dynamic_cast<JohnsonCook *>(hl) == NULL)
+                    return "IsoPlasticity hardening law other than Linear, Nonlinear, Nonlinear2 and JohnsonCook";
+            }
             break;
         case 11: {
             RigidMaterial *rm = (RigidMaterial *)mb;
@@ -317,10 +324,22 @@ const char *GpuTasks_Install(int device, bool fusedStep)
             m.p[8] = mm->G1sp; m.p[9] = mm->G2sp; m.p[10] = mm->Ksp; m.p[11] = mm->UofJOption; m.p[12] = mm->CTE1; m.p[13] = mm->gamma0;
         } else if (mb->MaterialID() == 9) {         // IsoPlasticity::pr + LinearHardening reduced properties
             IsoPlasticity *pm = (IsoPlasticity *)mb;
-            LinearHardening *lh = (LinearHardening *)pm->plasticLaw;
+            HardeningLawBase *hl = pm->plasticLaw;
+            LinearHardening *lh = dynamic_cast<LinearHardening *>(hl);
+            NonlinearHardening *nh = dynamic_cast<NonlinearHardening *>(hl);
+            JohnsonCook *jc = dynamic_cast<JohnsonCook *>(hl);
             m.kind = MPMGPU_MAT_ISOPLASTICITY;
-            m.p[8] = pm->pr.Gred; m.p[9] = pm->pr.Kred; m.p[10] = lh->yldred; m.p[11] = lh->Epred; m.p[12] = pm->CTE3; m.p[13] = pm->gamma0;
-            m.p[14] = lh->alphaMax; m.p[15] = lh->yldredMin;
+            m.p[8] = pm->pr.Gred; m.p[9] = pm->pr.Kred; m.p[10] = hl->yldred; m.p[12] = pm->CTE3; m.p[13] = pm->gamma0;
+            m.p[14] = 1.e50; m.p[15] = hl->yldredMin;
+            if (lh != NULL) { m.p[11] = lh->Epred; m.p[14] = lh->alphaMax; }
+            else if (nh != NULL) {      // Nonlinear (2) and its subclass Nonlinear2 (6): NonlinearHardening.cpp:49-60, Nonlinear2Hardening.cpp:28-39
+                m.p[16] = dynamic_cast<Nonlinear2Hardening *>(hl) != NULL ? 6. : 2.;
+                m.p[17] = nh->beta; m.p[18] = nh->npow; m.p[14] = nh->alphaMax;
+            } else {                    // Johnson-Cook (3): JohnsonCook.cpp:106-127
+                m.p[16] = 3.;
+                m.p[17] = jc->Bred; m.p[18] = jc->njc; m.p[19] = jc->Cjc; m.p[20] = jc->ep0jc; m.p[21] = jc->Djc; m.p[22] = jc->n2jc;
+                m.p[23] = jc->Tmjc; m.p[24] = jc->mjc; m.p[25] = thermal.reference; m.p[26] = jc->edotMin; m.p[27] = jc->eminTerm;
+            }
             m.p[7] = pm->useLargeRotation ? 1. : 0.;
         } else {                                     // rigid BC particles: directions they control
             m.kind = MPMGPU_MAT_RIGIDBC; m.n_history = 0;

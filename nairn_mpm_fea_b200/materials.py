@@ -150,10 +150,16 @@ def mooney(G1, G2, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None, a
                 init_history=[1.0, 1.0], init_eplast=[1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
 
 
+HARD_LINEAR, HARD_NONLINEAR, HARD_JOHNSONCOOK, HARD_NONLINEAR2 = 1, 2, 3, 6        # MaterialBase::SetHardeningLaw ids
+
+
 def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, yld_min=0.0, av=None,
-                  large_rotation=False):
-    """IsoPlasticity + LinearHardening (MaterialID 9): IsoPlasticity::VerifyAndLoadProperties
-    (Materials/IsoPlasticity.cpp:50-70), LinearHardening::VerifyAndLoadProperties (LinearHardening.cpp:55-80)."""
+                  large_rotation=False, hardening=None):
+    """IsoPlasticity (MaterialID 9): IsoPlasticity::VerifyAndLoadProperties (Materials/IsoPlasticity.cpp:50-70) with
+    LinearHardening (LinearHardening.cpp:55-80; the default) or, through `hardening`,
+      ("nonlinear", beta, n)   yield (1 + beta alpha)^n        NonlinearHardening.cpp:49-60
+      ("nonlinear2", beta, n)  yield (1 + beta alpha^n)        Nonlinear2Hardening.cpp:28-39
+      ("johnsoncook", dict(B=, n=, C=, ep0=, D=0, n2=1, Tm=, m=, Tref=))  JohnsonCook.cpp:106-127 (yld is A; B in the units of yld)."""
     iso = isotropic(E, nu, rho, aI, Cv, np_, pdamping)
     p = _base(rho, Cv, pdamping, av, large_rotation)
     C66, C33 = iso["C66"], iso["C33"]
@@ -171,4 +177,26 @@ def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np
     p[12] = iso["p"][19]
     p[13] = iso["p"][20]
     p[14], p[15] = alphaMax, yldredMin
+    if hardening is not None:
+        law = hardening[0]
+        if law in ("nonlinear", "nonlinear2"):
+            hb, hn = float(hardening[1]), float(hardening[2])
+            p[16] = HARD_NONLINEAR if law == "nonlinear" else HARD_NONLINEAR2
+            p[17], p[18] = hb, hn
+            p[11] = 0.0
+            p[14] = 1.0e50
+            if hb < 0.0:
+                p[14] = ((yldredMin / yldred) ** (1.0 / hn) - 1.0) / hb if law == "nonlinear" else ((yldredMin / yldred - 1.0) / hb) ** (1.0 / hn)
+        elif law == "johnsoncook":
+            j = hardening[1]
+            C = float(j["C"])
+            edot_min = float(np.exp(-0.5 / C)) if C != 0.0 else 1.0e-20
+            edot_min = min(float(j["ep0"]), edot_min)
+            p[16] = HARD_JOHNSONCOOK
+            p[17], p[18], p[19], p[20], p[21], p[22] = j["B"] / rho, j["n"], C, j["ep0"], j.get("D", 0.0), j.get("n2", 1.0)
+            p[23], p[24], p[25], p[26], p[27] = j["Tm"], j["m"], j.get("Tref", 0.0), edot_min, 1.0 + C * float(np.log(edot_min))
+            p[11] = 0.0
+            p[14] = 1.0e50
+        else:
+            raise ValueError("hardening law %r" % (law,))
     return dict(kind=ISOPLASTICITY, n_history=1, p=p, rho=rho, wave_speed=iso["wave_speed"])

@@ -304,8 +304,20 @@ def from_reference_dump(z, snapshot="p0"):
                 raise NotImplementedError("Mooney with the IdealRubber option")
             m = M.mooney(q[8], q[9], q[10], q[0], q[15] * 1.0e6, q[1], int(q[14]), pd, av)
         elif mid == M.ISOPLASTICITY:
-            m = M.isoplasticity(q[8], q[9], q[0], q[15], q[16] if q[16] >= 0 else None, q[21], q[11] * 1.0e6, q[1], pr.np, pd,
-                                q[20] * q[0], av, large_rotation=bool(q[22]) if len(q) > 22 else False)
+            law = int(q[23]) if len(q) > 23 else 1
+            lr = bool(q[22]) if len(q) > 22 else False
+            if law in (0, M.HARD_LINEAR):
+                m = M.isoplasticity(q[8], q[9], q[0], q[15], q[16] if q[16] >= 0 else None, q[21], q[11] * 1.0e6, q[1], pr.np, pd,
+                                    q[20] * q[0], av, large_rotation=lr)
+            elif law in (M.HARD_NONLINEAR, M.HARD_NONLINEAR2):
+                m = M.isoplasticity(q[8], q[9], q[0], q[15], None, 0.0, q[11] * 1.0e6, q[1], pr.np, pd, q[20] * q[0], av, large_rotation=lr,
+                                    hardening=("nonlinear" if law == M.HARD_NONLINEAR else "nonlinear2", q[24], q[25]))
+            elif law == M.HARD_JOHNSONCOOK:
+                m = M.isoplasticity(q[8], q[9], q[0], q[15], None, 0.0, q[11] * 1.0e6, q[1], pr.np, pd, q[20] * q[0], av, large_rotation=lr,
+                                    hardening=("johnsoncook", dict(B=q[24] * q[0], n=q[25], C=q[26], ep0=q[27], D=q[28], n2=q[29], Tm=q[30],
+                                                                   m=q[31], Tref=q[16])))
+            else:
+                raise NotImplementedError("hardening law %d" % law)
         elif mid == M.RIGIDBC:
             if q[10] != 0 or q[11] != 0:
                 raise NotImplementedError("rigid material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")

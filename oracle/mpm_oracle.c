@@ -1367,6 +1367,10 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
                   int nbc, const int *bcNode, const double *bcNorm, const double *bcValue, const int *bcActive, const int *bcSym,
                   double dt, double dtFirst, double dtLast)
 {
+    /* Not restated here: IsoPlasticity with the numerically returned hardening laws (material slot 16 > 1: Nonlinear, Nonlinear2,
+     * JohnsonCook).  Those are pinned against the reference directly, at the law level (tests/test_device_laws_vs_reference_cpu.py) and
+     * through goldens run by the host-compiled device source (tests/test_device_step_cpu.py). */
+    for (int i = 0; i < nmat; i++) if (mats[i].kind == MPMGPU_MAT_ISOPLASTICITY && mats[i].p[16] > 1.) return -2;
     O = (Oracle *)calloc(1, sizeof(Oracle));
     O->cfg = *cfg;
     O->dim = cfg->np == MPMGPU_THREED_MPM ? 3 : 2;

@@ -32,6 +32,10 @@
 #include "Materials/MaterialBase.hpp"
 #include "Materials/IsotropicMat.hpp"
 #include "Materials/Neohookean.hpp"
+#include "Materials/NonlinearHardening.hpp"
+#include "Materials/Nonlinear2Hardening.hpp"
+#include "Materials/JohnsonCook.hpp"
+#include "Global_Quantities/ThermalRamp.hpp"
 #include "Materials/Mooney.hpp"
 #include "Materials/IsoPlasticity.hpp"
 #include "Materials/HardeningLawBase.hpp"
@@ -302,7 +306,9 @@ void ref_get_velbcs(int *node, int *dir, int *style, double *norm, double *value
 //  neo(28):     8 G 9 K 10 Lame 11 Gsp 12 Ksp 13 Lamesp 14 UofJOption 15 CTE1 16 gamma0(as used)
 //  mooney(8):   8 G1 9 G2 10 K 11 G1sp 12 G2sp 13 Ksp 14 UofJOption 15 CTE1 16 gamma0 17 IdealRubber
 //  isoplas(9):  8 E 9 nu 10 G 11 CTE3 12 gamma0 13 Gred 14 Kred 15 yield 16 Ep 17 yldred 18 Epred 19 alphaMax 20 yldredMin 21 beta
-//               22 useLargeRotation
+//               22 useLargeRotation 23 hardening law id (1 Linear, 2 Nonlinear, 6 Nonlinear2, 3 JohnsonCook)
+//               Nonlinear/Nonlinear2: 24 beta 25 npow (19 alphaMax);  JohnsonCook: 24 Bred 25 njc 26 Cjc 27 ep0jc 28 Djc 29 n2jc 30 Tmjc 31 mjc
+//               16 thermal.reference
 int ref_get_materials(int *ids, double *params)
 {
     for (int i = 0; i < nmat; i++) {
@@ -344,7 +350,13 @@ int ref_get_materials(int *ids, double *params)
             if (h != NULL) { q[15] = h->yield; q[17] = h->yldred;
                              LinearHardening *lh = dynamic_cast<LinearHardening *>(h);
                              q[20] = h->yldredMin;
-                             if (lh != NULL) { q[16] = lh->Ep; q[18] = lh->Epred; q[19] = lh->alphaMax; q[21] = lh->beta; } }
+                             if (lh != NULL) { q[16] = lh->Ep; q[18] = lh->Epred; q[19] = lh->alphaMax; q[21] = lh->beta; q[23] = 1.; }
+                             Nonlinear2Hardening *n2h = dynamic_cast<Nonlinear2Hardening *>(h);
+                             NonlinearHardening *nh = dynamic_cast<NonlinearHardening *>(h);
+                             JohnsonCook *jc = dynamic_cast<JohnsonCook *>(h);
+                             if (nh != NULL) { q[23] = n2h != NULL ? 6. : 2.; q[24] = nh->beta; q[25] = nh->npow; q[19] = nh->alphaMax; }
+                             if (jc != NULL) { q[23] = 3.; q[24] = jc->Bred; q[25] = jc->njc; q[26] = jc->Cjc; q[27] = jc->ep0jc; q[28] = jc->Djc;
+                                               q[29] = jc->n2jc; q[30] = jc->Tmjc; q[31] = jc->mjc; q[16] = thermal.reference; } }
         }
     }
     return nmat;
@@ -372,6 +384,50 @@ int ref_set_particles(const double *pos, const double *vel)
         }
     }
     return bad;
+}
+
+// The hardening law of IsoPlasticity material `mat` (0-based) evaluated alone (for tests of other implementations of the same law):
+// out = {GetYield, GetKPrime, GetK2Prime(fnp1), GetYieldIncrement}.  particle 0 supplies the temperature for Johnson-Cook.
+int ref_hardening_terms(int mat, double alpint, double dalpha, double delTime, double fnp1, double *out)
+{
+    if (mat < 0 || mat >= nmat || theMaterials[mat]->MaterialID() != 9) return -1;
+    IsoPlasticity *pm = (IsoPlasticity *)theMaterials[mat];
+    HardeningLawBase *h = pm->plasticLaw;
+    HardeningAlpha a;
+    a.alpint = alpint; a.dalpha = dalpha;
+    char buffer[256];
+    void *props = h->GetCopyOfHardeningProps(mpm[0], fmobj->np, (void *)buffer, 0);
+    out[0] = h->GetYield(mpm[0], fmobj->np, delTime, &a, props);
+    out[1] = h->GetKPrime(mpm[0], fmobj->np, delTime, &a, props);
+    out[2] = h->GetK2Prime(mpm[0], fnp1, delTime, &a, props);
+    out[3] = h->GetYieldIncrement(mpm[0], fmobj->np, delTime, &a, props);
+    return 0;
+}
+
+// The reference's own MPMConstitutiveLaw applied to every non-rigid particle with a caller-given du[p][9] (row-major): the law alone,
+// on the state the particles are in.  Lets tests compare another implementation of a law with the reference at the law level.
+int ref_constitutive_law_all(const double *du, double delTime)
+{
+    static char *matBuf = NULL, *altBuf = NULL;
+    if (matBuf == NULL) { matBuf = new char[MaterialBase::maxPropertyBufferSize + 64]; altBuf = new char[MaterialBase::maxAltBufferSize + 64]; }
+    try {
+        for (int p = 0; p < nmpmsNR; p++) {
+            MPMBase *mptr = mpm[p];
+            const MaterialBase *matRef = theMaterials[mptr->MatID()];
+            void *props = matRef->GetCopyOfMechanicalProps(mptr, fmobj->np, (void *)matBuf, (void *)altBuf, 0);
+            const double *d = du + (size_t)9 * p;
+            ResidualStrains res;
+            res.dT = 0.; res.dC = 0.; res.doopse = 0.;
+            if (fmobj->IsThreeD()) {
+                Matrix3 dm(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8]);
+                matRef->MPMConstitutiveLaw(mptr, dm, delTime, fmobj->np, props, &res, 0);
+            } else {
+                Matrix3 dm(d[0], d[1], d[3], d[4], d[8]);
+                matRef->MPMConstitutiveLaw(mptr, dm, delTime, fmobj->np, props, &res, 0);
+            }
+        }
+    } catch (CommonException &err) { set_err(err.Message()); return -1; }
+    return 0;
 }
 
 void ref_close(void)

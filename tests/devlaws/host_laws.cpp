@@ -213,3 +213,19 @@ extern "C" int devshape_find_element(int dim, int np, int horiz, int vert, int d
     }
     return 0;
 }
+
+// the hardening-law terms of the device source alone: out = {yield, K', K2'(fnp1), yield increment}
+extern "C" int devlaws_hardening_terms(const double *params, double prevT, double alpint, double dalpha, double delTime, double fnp1, double *out)
+{
+    Material m;
+    m.kind = MAT_ISOPLASTICITY; m.nhist = 1;
+    memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
+    const HardProps h = hard_props(m, prevT);
+    HardAlpha a;
+    a.alpint = alpint; a.dalpha = dalpha;
+    out[0] = hard_yield(m, h, delTime, a);
+    out[1] = hard_kprime(m, h, delTime, a);
+    out[2] = hard_k2prime(m, h, fnp1, delTime, a);
+    out[3] = hard_yield_increment(m, h, delTime, a);
+    return 0;
+}

@@ -239,7 +239,7 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
         S->mats[i].kind = kinds[i]; S->mats[i].nhist = nhist[i];
         memcpy(S->mats[i].p, params + (size_t)i * MPM_MAT_NPARAMS, sizeof(double) * MPM_MAT_NPARAMS);
         S->mats[i].p[6] = S->dim == 3 ? (gridx + gridy + gridz) / 3. : (gridx + gridy) / 2.;       // as mpmgpu_set_materials
-        if (S->mats[i].p[7] != 0. || kinds[i] == MAT_MOONEY) S->largeRotation = true;       // extended law dispatch, as mpmgpu_set_materials
+        if (S->mats[i].p[7] != 0. || kinds[i] == MAT_MOONEY || (kinds[i] == MAT_ISOPLASTICITY && S->mats[i].p[16] > 1.)) S->largeRotation = true;       // extended law dispatch, as mpmgpu_set_materials
     }
     StepParams &q = S->sp;
     memset(&q, 0, sizeof q);

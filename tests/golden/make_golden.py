@@ -115,6 +115,22 @@ CASES = {
                                    .replace(DISK2, inputs.mooney_material(0.25, 0.15, 1.0, 2, name="Disk 2", rho=1.5)), (1, 100), 1),
     "disks2d_mooney_planestress_uj0": (inputs.disks2d(analysis=11, gimp=None, vel=5000.0)
                                        .replace(DISK1, inputs.mooney_material(0.3, 0.1, 1.0, 0, av=(0.2, 2.0), name="Disk 1", rho=1.5)), (1, 100), 1),
+    # IsoPlasticity with the numerically returned hardening laws (bracketed Newton of HardeningLawBase): power laws, Johnson-Cook.
+    # Short runs in 2D: the reference's solver stops at |d lambda/lambda| < 1e-4, so long runs of these soft, heavily yielding disks
+    # amplify last-bit differences (tests/parity.py TOL_ITERATIVE); the law itself is pinned bit for bit by
+    # tests/test_device_laws_vs_reference_cpu.py
+    "block3d_isoplastic_nonlinear": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_hardening_material("Nonlinear"), vz=-4.0e4, vx=5.0e3), (1, 60), 1, 0.3, 3000.0),
+    "block3d_isoplastic_nonlinear2_soft": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_hardening_material("Nonlinear2", Khard=-2.0, nhard=0.8, yieldMin=8.0),
+                                                          vz=-5.0e4, vx=5.0e3), (1, 60), 1, 0.3, 3000.0),
+    "block3d_johnsoncook": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_hardening_material("JohnsonCook", Djc=0.01), vz=-4.0e4, vx=5.0e3,
+                                           extra_header="<StressFreeTemp>300</StressFreeTemp>"), (1, 60), 1, 0.3, 3000.0),
+    "disks2d_johnsoncook_planestress": (inputs.disks2d(analysis=11, vel=3000.0, extra_header="<StressFreeTemp>300</StressFreeTemp>")
+                                        .replace(DISK2, inputs.isoplastic_hardening_material("JohnsonCook", rho=1.5, E=1.0, yld=0.02, Bjc=0.03, name="Disk 2")), (1, 20), 1),
+    "disks2d_nonlinear_planestrain_lr": (inputs.disks2d(analysis=10, vel=3000.0)
+                                         .replace(DISK2, inputs.isoplastic_hardening_material("Nonlinear", rho=1.5, E=1.0, yld=0.02, name="Disk 2",
+                                                                                              extra="<largeRotation>1</largeRotation>")), (1, 20), 1),
+    "disks2d_nonlinear2_planestress": (inputs.disks2d(analysis=11, gimp=None, vel=3000.0)
+                                       .replace(DISK1, inputs.isoplastic_hardening_material("Nonlinear2", rho=1.5, E=1.0, yld=0.02, name="Disk 1")), (1, 20), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

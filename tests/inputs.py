@@ -153,6 +153,22 @@ def isoplastic_material(rho=2.0, E=2000.0, nu=0.33, yld=20.0, Ep=100.0, av=None)
     return m
 
 
+def isoplastic_hardening_material(law, rho=2.0, E=2000.0, nu=0.33, yld=20.0, name="Blk", **k):
+    """IsoPlasticity with <Hardening>Nonlinear|Nonlinear2|JohnsonCook</Hardening> and that law's own properties."""
+    if law in ("Nonlinear", "Nonlinear2"):
+        props = "<yield>%r</yield><Khard>%r</Khard><nhard>%r</nhard>" % (yld, k.get("Khard", 8.0), k.get("nhard", 0.4))
+        if k.get("yieldMin") is not None:
+            props += "<yieldMin>%r</yieldMin>" % k["yieldMin"]
+    else:
+        props = ("<Ajc>%r</Ajc><Bjc>%r</Bjc><njc>%r</njc><Cjc>%r</Cjc><ep0jc>%r</ep0jc><Tmjc>%r</Tmjc><mjc>%r</mjc>"
+                 % (yld, k.get("Bjc", 30.0), k.get("njc", 0.5), k.get("Cjc", 0.02), k.get("ep0jc", 1.0), k.get("Tmjc", 1600.0), k.get("mjc", 1.1)))
+        if k.get("Djc"):
+            props += "<Djc>%r</Djc><n2jc>%r</n2jc>" % (k["Djc"], k.get("n2jc", 2.0))
+    extra = k.get("extra", "")
+    return ('<Material Type="9" Name="%s"><rho>%r</rho><E>%r</E><nu>%r</nu><alpha>20</alpha><Hardening>%s</Hardening>%s%s</Material>'
+            % (name, rho, E, nu, law, props, extra))
+
+
 def periodic_xpic(order, fmpm=False, periodic_steps=1):
     """<CustomTasks> block scheduling the reference's PeriodicXPIC task (Custom_Tasks/PeriodicXPIC.cpp:62-157)."""
     return ('<CustomTasks><Schedule name="PeriodicXPIC"><Parameter name="%s">%d</Parameter>'

@@ -52,10 +52,19 @@ LR3D_CASES = ("block3d_isotropic_lr", "block3d_isoplastic_lr")
 TOL_LR3D = 1.0e-4          # observed: <= 3e-6 on the two goldens (80 steps), <= 3e-5 over the random combinations of tests/test_sweep_cpu.py
 
 
+# Hardening laws returned numerically (Nonlinear, Nonlinear2, JohnsonCook): the reference stops the bracketed Newton iteration for
+# lambda at |d lambda / lambda| < 1e-4 (HardeningLawBase::LambdaConverged, HardeningLawBase.cpp:386-390), so the plastic increment
+# is DEFINED to 1e-4 only: a last-bit difference upstream can end the iteration one step earlier or later, or turn a Newton step
+# into a bisection.  One step still agrees to 1e-10 in practice; long runs are held to the solver's own tolerance.
+TOL_ITERATIVE = 1.0e-4          # observed <= 2e-5 after 100 steps
+
+
 def tolerances(case):
     """(after 1 step / per task of step 1, per task of later steps, after N <= 100 steps)"""
     if case in LR3D_CASES:
         return TOL_LR3D, TOL_LR3D, TOL_LR3D
+    if "johnsoncook" in case or "nonlinear" in case:
+        return TOL_1STEP, 1.0e-8, TOL_ITERATIVE
     return TOL_1STEP, 1.0e-8, TOL_100STEP
 
 

@@ -1,0 +1,151 @@
+"""Law-level parity with the reference ITSELF: the reference is stepped to a deformed state, then its own
+MaterialBase::MPMConstitutiveLaw is applied to every particle with a random velocity-gradient increment (oracle/ref_harness.cpp
+::ref_constitutive_law_all); the device source of the same law (csrc/materials.cuh compiled for the host, tests/devlaws) gets the same
+states and increments.  Same inputs, so the results must agree to round-off (1e-13 of each field; the 3D large-rotation laws to 1e-4: ill-conditioned polar
+decomposition, tests/parity.py) -- including the iteration path of the bracketed Newton return of the Nonlinear / Nonlinear2 /
+Johnson-Cook hardening laws and of the plane-stress solves, whose own convergence tolerance is only 1e-4."""
+import ctypes as C
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import inputs
+from tests.golden.make_golden import DISK2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MATERIALS = {
+    "isotropic": lambda d: '<Material Type="1" Name="%s"><rho>1.5</rho><E>%r</E><nu>0.33</nu><alpha>40</alpha></Material>' % ("%s", 1.0 if d == 2 else 100.0),
+    "isotropic_lr": lambda d: '<Material Type="1" Name="%s"><rho>1.5</rho><E>%r</E><nu>0.33</nu><alpha>40</alpha><largeRotation>1</largeRotation></Material>' % ("%s", 1.0 if d == 2 else 100.0),
+    "neohookean_uj1_av": lambda d: '<Material Type="28" Name="%s"><rho>1.5</rho><G>%r</G><K>%r</K><alpha>40</alpha><UJOption>1</UJOption><ArtificialVisc/><avA1>0.3</avA1><avA2>1.5</avA2></Material>' % (("%s",) + ((0.4, 1.0) if d == 2 else (40.0, 200.0))),
+    "mooney_uj2": lambda d: '<Material Type="8" Name="%s"><rho>1.5</rho><G1>%r</G1><G2>%r</G2><K>%r</K><alpha>40</alpha><UJOption>2</UJOption></Material>' % (("%s",) + ((0.3, 0.1, 1.0) if d == 2 else (30.0, 10.0, 200.0))),
+    "isoplastic_linear_soft": lambda d: inputs.isoplastic_material(rho=1.5, E=1.0 if d == 2 else 100.0, yld=0.02 if d == 2 else 2.0, Ep=-1.0).replace("Blk", "%s").replace("<Ep>-1.0</Ep>", "<Khard>-2.0</Khard><yieldMin>%r</yieldMin>" % (0.01 if d == 2 else 1.0)),
+    "isoplastic_lr": lambda d: inputs.isoplastic_material(rho=1.5, E=1.0 if d == 2 else 100.0, yld=0.02 if d == 2 else 2.0, Ep=0.1 if d == 2 else 10.0).replace("Blk", "%s").replace("</Material>", "<largeRotation>1</largeRotation></Material>"),
+    "nonlinear": lambda d: inputs.isoplastic_hardening_material("Nonlinear", rho=1.5, E=1.0 if d == 2 else 100.0, yld=0.02 if d == 2 else 2.0, name="%s"),
+    "nonlinear2": lambda d: inputs.isoplastic_hardening_material("Nonlinear2", rho=1.5, E=1.0 if d == 2 else 100.0, yld=0.02 if d == 2 else 2.0, name="%s"),
+    "johnsoncook": lambda d: inputs.isoplastic_hardening_material("JohnsonCook", rho=1.5, E=1.0 if d == 2 else 100.0, yld=0.02 if d == 2 else 2.0,
+                                                                  Bjc=0.03 if d == 2 else 3.0, Djc=0.01, name="%s"),
+}
+
+_WORKER = r'''
+import sys, json, ctypes as C
+sys.path.insert(0, %(root)r)
+import numpy as np
+from oracle import refharness
+from nairn_mpm_fea_b200.problem import from_reference_dump
+xml_path, nsteps, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+r = refharness.RefRun(xml_path, 1)
+r.step(nsteps)
+ids = np.zeros(16, np.int32); params = np.zeros((16, 32))
+nm = r.lib.ref_get_materials(ids.ctypes.data_as(C.POINTER(C.c_int)), params.ctypes.data_as(C.POINTER(C.c_double)))
+before = r.particles()
+n = before["mp"].shape[0]
+rng = np.random.default_rng(5)
+du = 3.0e-2 * rng.standard_normal((n, 9))          # large enough to yield from most states
+if not r.info["is3D"]:
+    du[:, [2, 5, 6, 7, 8]] = 0.0
+du = np.ascontiguousarray(du)
+assert r.lib.ref_constitutive_law_all(du.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(r.info["timestep"])) == 0, r.lib.ref_last_error()
+after = r.particles()
+np.savez(out, du=du, mat_ids=ids[:nm], mat_params=params[:nm], dt=r.info["timestep"], np_=r.info["np"], nNR=r.info["nmpmsNR"],
+         **{"b_" + k: v for k, v in before.items()}, **{"a_" + k: v for k, v in after.items()})
+'''
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("analysis", ["3d", "planestrain", "planestress"])
+@pytest.mark.parametrize("law", sorted(MATERIALS))
+def test_device_law_equals_the_references_own_law_on_the_same_input(law, analysis):
+    from oracle import refharness
+    if not refharness.available():
+        pytest.skip("oracle/_ref not built")
+    from nairn_mpm_fea_b200.problem import from_reference_dump
+    from tests.test_device_laws_cpu import LIBDEV
+    dim = 3 if analysis == "3d" else 2
+    mat = MATERIALS[law](dim)
+    if dim == 3:
+        xml = inputs.block3d(ncell=3, margin=3, material=mat % "Blk", vz=-2.0e4, vx=5.0e3, extra_header="<StressFreeTemp>300</StressFreeTemp>")
+        nsteps = 25
+    else:
+        xml = inputs.disks2d(analysis=10 if analysis == "planestrain" else 11, vel=3000.0, extra_header="<StressFreeTemp>300</StressFreeTemp>").replace(DISK2, mat % "Disk 2")
+        nsteps = 30
+    d = tempfile.mkdtemp(prefix="lawref_")
+    open(os.path.join(d, "in.fmcmd"), "w").write(xml)
+    out = os.path.join(d, "law.npz")
+    p = subprocess.run([sys.executable, "-c", _WORKER % dict(root=ROOT), os.path.join(d, "in.fmcmd"), str(nsteps), out], cwd=d, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-1500:]
+    z = dict(np.load(out))
+    if not os.path.exists(LIBDEV):
+        pytest.skip("tests/devlaws not built (run tests/test_device_laws_cpu.py first)")
+    dev = C.CDLL(LIBDEV)
+    prob = from_reference_dump({"mat_ids": z["mat_ids"], "mat_params": z["mat_params"], **_fake_dump(z)})
+    np_, dt, nNR = int(z["np_"]), float(z["dt"]), int(z["nNR"])
+    checked = 0
+    for mi, m in enumerate(prob.materials):
+        if m["kind"] == 11:
+            continue
+        sel = np.nonzero(z["b_matnum"][:nNR] == mi + 1)[0]
+        if sel.size == 0:
+            continue
+        ns = sel.size
+        ep, w = z["b_ep"][:, sel], z["b_wrot"][:, sel]
+        F = np.zeros((9, ns))
+        F[0], F[4], F[8] = 1 + ep[0], 1 + ep[1], 1 + ep[2]
+        F[1], F[3] = 0.5 * (ep[5] - w[0]), 0.5 * (ep[5] + w[0])
+        if dim == 3:
+            F[2], F[6] = 0.5 * (ep[4] - w[1]), 0.5 * (ep[4] + w[1])
+            F[5], F[7] = 0.5 * (ep[3] - w[2]), 0.5 * (ep[3] + w[2])
+        c = np.ascontiguousarray
+        st = dict(F=F, sp=c(z["b_sp"][:, sel]), pressure=c(z["b_pressure"][sel]), eplast=c(z["b_eplast"][:, sel]), energies=c(z["b_energies"][:, sel]),
+                  hist=c(z["b_hist"][:, sel]), du=c(z["du"][sel]))
+        if dim == 2:
+            st["eplast"][[3, 4]] = 0.0          # the reference's 2D IsoPlasticity leaves garbage in the out-of-plane shear slots
+        pm = c(m["p"], dtype=np.float64)
+        pm[6] = 1.0
+        assert dev.devlaws_batch(dim, np_, m["kind"], m.get("n_history", 0), _dp(pm), ns, _dp(st["F"]), _dp(st["sp"]), _dp(st["pressure"]), _dp(st["eplast"]),
+                                 _dp(st["energies"]), _dp(st["hist"]), _dp(st["du"]), C.c_double(dt)) == 0
+        comp = [0, 1, 2, 5] if dim == 2 else slice(None)
+        tol = 1.0e-4 if (dim == 3 and law.endswith("_lr")) else 1.0e-13
+        got_ep = np.stack([st["F"][0] - 1, st["F"][4] - 1, st["F"][8] - 1, st["F"][7] + st["F"][5], st["F"][6] + st["F"][2], st["F"][3] + st["F"][1]])
+        pairs = [("sp", st["sp"][comp], z["a_sp"][:, sel][comp]), ("pressure", st["pressure"], z["a_pressure"][sel]),
+                 ("eplast", st["eplast"][comp], z["a_eplast"][:, sel][comp]), ("history", st["hist"][:m.get("n_history", 0)], z["a_hist"][:m.get("n_history", 0), sel]),
+                 ("ep", got_ep[comp], z["a_ep"][:, sel][comp])] + [(nm, st["energies"][i], z["a_energies"][i, sel]) for i, nm in enumerate(["work", "res", "heat", "entropy", "plast"])]
+        for name, a, b in pairs:
+            if a.size == 0:
+                continue
+            scale = max(float(np.max(np.abs(b))), 1e-300)
+            err = float(np.max(np.abs(a - b))) / scale
+            assert err <= tol, "%s %s material %d: %s differs from the reference's own law by %.2e" % (law, analysis, mi + 1, name, err)
+        if m["kind"] == 9:
+            yielded = z["a_hist"][0, sel] != z["b_hist"][0, sel]
+            assert yielded.sum() > 5, "the sample should yield"
+            if tol < 1e-10:
+                # same iteration path of the return solver: the plastic strain INCREMENTS agree to round-off, not to the solver's 1e-4
+                inc_ref = z["a_hist"][0, sel] - z["b_hist"][0, sel]
+                inc_dev = st["hist"][0] - z["b_hist"][0, sel]
+                assert float(np.max(np.abs(inc_dev - inc_ref))) <= 1.0e-11 * float(np.max(np.abs(inc_ref)))
+        checked += 1
+    assert checked >= 1
+
+
+def _fake_dump(z):
+    """from_reference_dump only needs the material tables here; give it a minimal particle/grid block."""
+    n = z["b_mp"].shape[0]
+    info = {"np": int(z["np_"]), "horiz": 1, "vert": 1, "depth": 1, "gridx": 1.0, "gridy": 1.0, "gridz": 1.0, "thickness": 1.0, "useGimp": 0, "rcrit": -1.0,
+            "mpmApproach": 2, "skipPostExtrapolation": 0, "fractionUSF": 0.5, "XPICOrder": 0, "usingFMPM": 0, "damping": 0.0, "pdamping": 0.0,
+            "hasGravity": 0, "gx": 0.0, "gy": 0.0, "gz": 0.0, "timestep": float(z["dt"]), "strainTimestepFirst": 0.0, "strainTimestepLast": 0.0, "maxtime": 1.0,
+            "nmpmsNR": int(z["nNR"])}
+    d = {"info/" + k: np.array(v) for k, v in info.items()}
+    d["node_coords"] = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 1.0], [0.0, 1.0, 1.0], [1.0, 1.0, 1.0]])
+    for k in ("pos", "vel", "mp", "lp", "inElem", "matnum", "sp", "pressure", "ep", "wrot", "eplast", "energies", "hist", "crossings", "pFext"):
+        d["p0/" + k] = z["b_" + k]
+    for k in ("node", "norm", "value", "style", "ftime"):
+        d["velbcs/" + k] = np.zeros((0, 3)) if k == "norm" else np.zeros(0)
+    return d

@@ -13,7 +13,7 @@ import pytest
 from nairn_mpm_fea_b200.problem import from_reference_dump
 from oracle import refharness
 from tests import inputs
-from tests.parity import TOL_1STEP, TOL_100STEP, TOL_LR3D, compare_nodes, compare_particles, xpic_for_step
+from tests.parity import TOL_1STEP, TOL_100STEP, TOL_ITERATIVE, TOL_LR3D, compare_nodes, compare_particles, xpic_for_step
 from tests.test_device_step_cpu import EmuSim, lib  # noqa: F401
 
 NCONFIG = 64
@@ -24,7 +24,7 @@ DISK = '<Material Type="1" Name="Disk %d"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><
 
 def material(rng, name, two_d):
     """(xml, is_large_rotation) of a random in-scope material; 2D materials use the disks' scale (E = 1 MPa)."""
-    kind = rng.choice(["iso", "iso_lr", "neo", "mooney", "plastic", "plastic_lr"])
+    kind = rng.choice(["iso", "iso_lr", "neo", "mooney", "plastic", "plastic_lr", "plastic_nl"])
     E, G, K, yld, Ep = (1.0, 0.4, 1.0, 0.02, 0.1) if two_d else (100.0, 40.0, 200.0, 4.0, 20.0)
     extra = ""
     if rng.random() < 0.25:
@@ -43,6 +43,9 @@ def material(rng, name, two_d):
             extra += "<ArtificialVisc/><avA1>0.3</avA1><avA2>1.5</avA2>"
         return ('<Material Type="8" Name="%s"><rho>1.5</rho><G1>%r</G1><G2>%r</G2><K>%r</K><alpha>40</alpha><UJOption>%d</UJOption>%s</Material>'
                 % (name, 0.7 * G, 0.3 * G, K, int(rng.integers(0, 3)), extra)), False
+    if kind == "plastic_nl":            # hardening laws returned numerically (bracketed Newton)
+        law = str(rng.choice(["Nonlinear", "Nonlinear2", "JohnsonCook"]))
+        return inputs.isoplastic_hardening_material(law, rho=1.5, E=E, yld=yld, Bjc=1.5 * yld, name=name, extra=extra), False
     lr = kind.endswith("lr")
     if rng.random() < 0.3:
         extra += "<ArtificialVisc/><avA1>0.2</avA1><avA2>2.0</avA2>"
@@ -103,6 +106,8 @@ def test_random_combination_matches_the_live_reference(lib, seed):  # noqa: F811
     try:
         z = refharness.run_reference(xml, snaps=(1, NSTEPS), per_task_steps=0, nprocs=1, jitter_amp=ja, vel_amp=va)
     except RuntimeError as e:
+        if "could not be bracketed" in str(e):
+            pytest.skip("the reference itself aborts on this combination (plane-stress return not bracketed): %s" % desc)
         pytest.fail("the reference rejected a generated input (%s): %s" % (desc, str(e)[-400:]))
     sim = EmuSim(lib, from_reference_dump(z))
     done = 0
@@ -113,7 +118,7 @@ def test_random_combination_matches_the_live_reference(lib, seed):  # noqa: F811
                 sim.set_xpic(*x)
             sim.step(1)
             done += 1
-        tol = TOL_LR3D if lr3d else (TOL_1STEP if s == 1 else TOL_100STEP)
+        tol = TOL_LR3D if lr3d else (TOL_1STEP if s == 1 else (TOL_ITERATIVE if "<Hardening>Nonlinear" in xml or "<Hardening>JohnsonCook" in xml else TOL_100STEP))
         got = sim.download()
         errs, bad = compare_particles(got, z, "p%d" % s, tol)
         assert not bad, "[%s] after %d steps: particles %s" % (desc, s, bad)

@@ -17,7 +17,10 @@ pytestmark = pytest.mark.gpu
 LR_CASES = ["block3d_isotropic_lr", "block3d_isoplastic_lr", "disks2d_lr_planestrain", "disks2d_lr_planestress"]
 BRANCH_CASES = ["disks2d_neo_planestress", "disks2d_neo_planestress_av", "block3d_isoplastic_softening", "block3d_material_pdamping",
                 "block3d_free_ugimp", "block3d_free_lcpdi_xpic2",          # free flight, no grid BCs
-                "block3d_mooney", "block3d_mooney_uj2", "disks2d_mooney_planestrain", "disks2d_mooney_planestress", "disks2d_mooney_planestress_uj0"]
+                "block3d_mooney", "block3d_mooney_uj2", "disks2d_mooney_planestrain", "disks2d_mooney_planestress", "disks2d_mooney_planestress_uj0",
+                # hardening laws returned numerically
+                "block3d_isoplastic_nonlinear", "block3d_isoplastic_nonlinear2_soft", "block3d_johnsoncook", "disks2d_johnsoncook_planestress",
+                "disks2d_nonlinear_planestrain_lr", "disks2d_nonlinear2_planestress"]
 CASES = LR_CASES + BRANCH_CASES
 FUSED_CASES = ["block3d_isoplastic_softening", "block3d_material_pdamping", "block3d_free_ugimp"]          # 3D uGIMP without large rotation
 
