@@ -721,7 +721,8 @@ __device__ __forceinline__ double hard_yield_increment(const Material &m, const 
 
 // HardeningLawBase::SolveForLambdaBracketed with BracketSolution (HardeningLawBase.cpp:211-381): Newton's method kept inside a
 // bracket, bisecting when a step would leave it.  a holds alpha at the start of the step (dalpha = 0) and the solution at the end.
-// ok = false: the plane-stress bracket was not found in 20 decades of strain rate (the reference throws).
+// ok = false: the plane-stress bracket was not found in 20 decades of strain rate (the reference throws); lambda = NaN then
+// poisons the particle so that the run stops loudly (MPMGPU_ENAN) instead of continuing on a wrong state.
 template <bool PLANE_STRESS>
 __device__ __forceinline__ double solve_lambda_bracketed(const Material &m, const HardProps &h, double alpha0, double strial, const double stk[6],
                                                          double Gred, double psKred, double Pfinal, double delTime, HardAlpha &a, bool &ok)
@@ -750,7 +751,7 @@ __device__ __forceinline__ double solve_lambda_bracketed(const Material &m, cons
             xh = lambdak;
             epdot *= 10.;
         }
-        if (!found) { ok = false; return 0.; }
+        if (!found) { ok = false; return (double)NAN; }        // the reference throws here; NaN stops the run with MPMGPU_ENAN at the next element reset
     } else {
         const double dalpha = strial / (2. * Gred);
         a.alpint = alpha0 + dalpha;
