@@ -56,6 +56,8 @@ extern "C" {
 /* shape functions: reference ElementBase::useGimp codes, System/MPMPrefix.hpp:127-140 */
 #define MPMGPU_POINT_GIMP     0   /* "Classic": linear element shape functions */
 #define MPMGPU_UNIFORM_GIMP   1   /* uGIMP */
+#define MPMGPU_BSPLINE_GIMP    5   /* B2GIMP: quadratic B-spline GIMP (per-task kernels) */
+#define MPMGPU_BSPLINE         6   /* B2SPLINE: quadratic B-splines (per-task kernels) */
 #define MPMGPU_LINEAR_CPDI   10   /* lCPDI (2D and 3D) */
 #define MPMGPU_QUADRATIC_CPDI 11  /* qCPDI (2D only, as in the reference) */
 
@@ -84,7 +86,7 @@ typedef struct mpmgpu_config {
     const double *zpts;     /*   zpts NULL in 2D.  Element extents are taken from these.      */
     double gridx, gridy, gridz; /* mpmgrid.grid (MeshInfo::SetCartesian); gridz = 0 in 2D */
     double thickness;       /* 2D grid thickness (unused by the step, kept for archives) */
-    int shape;              /* MPMGPU_POINT_GIMP | _UNIFORM_GIMP | _LINEAR_CPDI | _QUADRATIC_CPDI */
+    int shape;              /* MPMGPU_POINT_GIMP | _UNIFORM_GIMP | _BSPLINE_GIMP | _BSPLINE | _LINEAR_CPDI | _QUADRATIC_CPDI */
     double cpdi_rcrit;      /* ElementBase::rcrit, <0 for none (MatPoint3D.cpp:436-442) */
     int method;             /* MPMGPU_USF | _USAVG | _USL */
     int skip_post_extrapolation; /* <SkipPostExtrapolation/>: USL-/USAVG- (NairnMPM.cpp:1076-1087) */

@@ -123,7 +123,8 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     const bool is3D = cfg->np == MPMGPU_THREED_MPM;
     if (cfg->horiz < 3 || cfg->vert < 3 || (is3D && cfg->depth < 3)) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: grid needs >=3 cells per axis incl. border");
     if (!cfg->xpts || !cfg->ypts || (is3D && !cfg->zpts)) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: node coordinate arrays missing");
-    if (cfg->shape != MPMGPU_POINT_GIMP && cfg->shape != MPMGPU_UNIFORM_GIMP && cfg->shape != MPMGPU_LINEAR_CPDI && cfg->shape != MPMGPU_QUADRATIC_CPDI)
+    if (cfg->shape != MPMGPU_POINT_GIMP && cfg->shape != MPMGPU_UNIFORM_GIMP && cfg->shape != MPMGPU_LINEAR_CPDI && cfg->shape != MPMGPU_QUADRATIC_CPDI &&
+        cfg->shape != MPMGPU_BSPLINE_GIMP && cfg->shape != MPMGPU_BSPLINE)
         return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: shape function code %d not supported", cfg->shape);
     if (cfg->shape == MPMGPU_QUADRATIC_CPDI && is3D) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: qCPDI is 2D only (as in the reference)");
     if (cfg->method != MPMGPU_USF && cfg->method != MPMGPU_USAVG && cfg->method != MPMGPU_USL)
@@ -642,11 +643,15 @@ extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const do
     if (grid_ > 0) { \
         if (ctx->dim == 3) { \
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<3, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_BSPLINE) LAUNCH((KERNEL<3, SHAPE_B2SPLINE>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_BSPLINE_GIMP) LAUNCH((KERNEL<3, SHAPE_B2GIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<3, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<3, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else LAUNCH((KERNEL<3, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
         } else { \
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<2, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_BSPLINE) LAUNCH((KERNEL<2, SHAPE_B2SPLINE>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_BSPLINE_GIMP) LAUNCH((KERNEL<2, SHAPE_B2GIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<2, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<2, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<2, SHAPE_QCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \

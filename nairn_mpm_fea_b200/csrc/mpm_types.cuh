@@ -13,7 +13,7 @@
 // reference codes (System/MPMPrefix.hpp:110-140)
 enum { NP_PLANE_STRAIN = 10, NP_PLANE_STRESS = 11, NP_THREED = 12 };
 enum { METHOD_USF = 0, METHOD_USAVG = 2, METHOD_USL = 3 };
-enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_LCPDI = 10, SHAPE_QCPDI = 11,
+enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_B2GIMP = 5, SHAPE_B2SPLINE = 6, SHAPE_LCPDI = 10, SHAPE_QCPDI = 11,
        // internal variants of the two CPDI codes: same functions, corner contributions to one node merged before the node is
        // touched (shape.cuh::for_each_node_cpdi_merged); chosen at launch, never seen through the ABI
        SHAPE_LCPDI_MERGED = 20, SHAPE_QCPDI_MERGED = 21 };

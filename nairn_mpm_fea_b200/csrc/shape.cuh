@@ -145,6 +145,77 @@ __device__ __forceinline__ void gimp_1d(double xi, double lp, double inv_size, G
     }
 }
 
+// ---- 1-D quadratic B-spline weights (B2SPLINE) and their GIMP form (B2GIMP) ------------------------------------------------
+// Same four node columns as uGIMP.  B2SPLINE: EightNodeIsoparamBrick::SplineShapeFunction (Elements/EightNodeIsoparamBrick.cpp:110-204),
+// FourNodeIsoparam::SplineShapeFunction (Common/Elements/FourNodeIsoparam.cpp:217-294): support |eta| < 3, dS carries the sign, the caller
+// multiplies by 1/dx.  B2GIMP: BGimpShapeFunction (EightNodeIsoparamBrick.cpp:477-634, FourNodeIsoparam.cpp:770-884): support
+// |eta| < 3 + lp, the caller multiplies by 2/dx.
+template <bool GRAD>
+__device__ __forceinline__ void bspline_1d(double xi, Gimp1D &w)
+{
+    w.ok = 0;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        const double xn = (double)(2 * o - 3);
+        const double etai = xi - xn;
+        const double t = fabs(etai);
+        double S = 0., dS = 0.;
+        if (!(t >= 3.)) {
+            w.ok |= 1u << o;
+            if (t <= 1.0) {
+                S = 0.25 * (3. - etai * etai);
+                if (GRAD) dS = -etai;
+            } else {
+                const double arg = 3. - t;
+                S = 0.125 * arg * arg;
+                if (GRAD) dS = etai >= 0. ? 0.5 * (etai - 3) : 0.5 * (etai + 3);
+            }
+        }
+        w.S[o] = S;
+        w.dS[o] = dS;
+    }
+}
+
+// xiSign: the coordinate the reference compares with the node to pick the sign of the gradient (its own axis, except the 3D
+// z gradient, which uses the y coordinate: EightNodeIsoparamBrick.cpp:586)
+template <bool GRAD, bool TWO_D_FORM>
+__device__ __forceinline__ void bgimp_1d(double xi, double xiSign, double lp, Gimp1D &w)
+{
+    const double b1 = 1. - lp, b2 = 1. + lp, b3 = 3. - lp, b4 = 3. + lp;
+    const double inv_size = 1. / (48. * lp), oneTwelth = 1. / 12.;
+    w.ok = 0;
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        const double xn = (double)(2 * o - 3);
+        const double xp = fabs(xi - xn);
+        double S = 0., dS = 0.;
+        if (!(xp >= b4)) {
+            w.ok |= 1u << o;
+            if (xp < b1) {
+                S = TWO_D_FORM ? (9. - lp * lp - 3. * xp * xp) * oneTwelth : (9. - lp * lp - 3 * xp * xp) * oneTwelth;
+                if (GRAD) dS = -0.5 * xp;
+            } else if (xp < b2) {
+                const double arg = xp - 1.;
+                const double lp2 = lp * lp;
+                if (TWO_D_FORM) S = (lp2 * (9. * arg - lp) + 3. * arg * arg * arg + 3. * lp * (15. - xp * (6. + xp))) * inv_size;
+                else { const double lp3 = lp2 * lp; S = (9. * lp2 * arg + 3. * arg * arg * arg + 3. * lp * (15. - xp * (6. + xp)) - lp3) * inv_size; }
+                if (GRAD) dS = (3 * lp2 + 3. * arg * arg - 2. * lp * (3. + xp)) * 3. * inv_size;
+            } else if (xp <= b3) {
+                const double arg = xp - 3.;
+                S = (lp * lp + 3. * arg * arg) * 0.5 * oneTwelth;
+                if (GRAD) dS = 0.25 * (xp - 3.);
+            } else {
+                const double arg = 3. + lp - xp;
+                S = arg * arg * arg * inv_size;
+                if (GRAD) dS = -arg * arg * 3. * inv_size;
+            }
+            if (GRAD && !(xiSign > xn)) dS = -dS;
+        }
+        w.S[o] = S;
+        w.dS[o] = dS;
+    }
+}
+
 // ---- per-particle node loop ----------------------------------------------------------------
 // f(node0based, S, dSdx, dSdy, dSdz) is called for every node of the particle's stencil.
 template <int DIM, int SHAPE, bool GRAD, class F>
@@ -186,18 +257,29 @@ __device__ __forceinline__ void for_each_node(const Grid &g, int inElem, const d
                 f(n0 + xo[a] + yo[a] * g.yplane, S, gxv, gyv, 0.);
             }
         }
-    } else if (SHAPE == SHAPE_UGIMP) {
+    } else if (SHAPE == SHAPE_UGIMP || SHAPE == SHAPE_B2SPLINE || SHAPE == SHAPE_B2GIMP) {
         Gimp1D wx, wy, wz;
-        gimp_1d<GRAD, DIM == 2>(xi[0], lp[0], 1. / (4. * lp[0]), wx);
-        gimp_1d<GRAD, DIM == 2>(xi[1], lp[1], 1. / (4. * lp[1]), wy);
+        const double gnum = SHAPE == SHAPE_B2SPLINE ? 1.0 : 2.0;       // the spline gradients are per half cell
+        if (SHAPE == SHAPE_UGIMP) {
+            gimp_1d<GRAD, DIM == 2>(xi[0], lp[0], 1. / (4. * lp[0]), wx);
+            gimp_1d<GRAD, DIM == 2>(xi[1], lp[1], 1. / (4. * lp[1]), wy);
+        } else if (SHAPE == SHAPE_B2SPLINE) {
+            bspline_1d<GRAD>(xi[0], wx);
+            bspline_1d<GRAD>(xi[1], wy);
+        } else {
+            bgimp_1d<GRAD, DIM == 2>(xi[0], xi[0], lp[0], wx);
+            bgimp_1d<GRAD, DIM == 2>(xi[1], xi[1], lp[1], wy);
+        }
         double inv_dx = 0., inv_dy = 0., inv_dz = 0.;
         if (GRAD) {
-            inv_dx = 2.0 / (g.xpts[c.i + 1] - g.xpts[c.i]);
-            inv_dy = 2.0 / (g.ypts[c.j + 1] - g.ypts[c.j]);
+            inv_dx = gnum / (g.xpts[c.i + 1] - g.xpts[c.i]);
+            inv_dy = gnum / (g.ypts[c.j + 1] - g.ypts[c.j]);
         }
         if (DIM == 3) {
-            gimp_1d<GRAD, false>(xi[2], lp[2], 1. / (4. * lp[1]), wz);      // reference quirk: lp.y
-            if (GRAD) inv_dz = 2.0 / (g.zpts[c.k + 1] - g.zpts[c.k]);
+            if (SHAPE == SHAPE_UGIMP) gimp_1d<GRAD, false>(xi[2], lp[2], 1. / (4. * lp[1]), wz);      // reference quirk: lp.y
+            else if (SHAPE == SHAPE_B2SPLINE) bspline_1d<GRAD>(xi[2], wz);
+            else bgimp_1d<GRAD, false>(xi[2], xi[1], lp[2], wz);              // reference quirk: the sign of the z gradient looks at xi.y
+            if (GRAD) inv_dz = gnum / (g.zpts[c.k + 1] - g.zpts[c.k]);
 #pragma unroll
             for (int kz = 0; kz < 4; kz++) {
                 if (!(wz.ok >> kz & 1u)) continue;

@@ -131,6 +131,14 @@ CASES = {
                                                                                               extra="<largeRotation>1</largeRotation>")), (1, 20), 1),
     "disks2d_nonlinear2_planestress": (inputs.disks2d(analysis=11, gimp=None, vel=3000.0)
                                        .replace(DISK1, inputs.isoplastic_hardening_material("Nonlinear2", rho=1.5, E=1.0, yld=0.02, name="Disk 1")), (1, 20), 1),
+    # quadratic B-spline shape functions: B2SPLINE and its GIMP form B2GIMP (3D incl. rigid-BC particles, 2D)
+    "block3d_b2spline": (inputs.block3d(ncell=3, margin=3, E=100.0, gimp="B2SPLINE", vz=-6.0e3, vx=3.0e3), (1, 30), 1, 0.3, 3000.0),
+    "block3d_b2gimp": (inputs.block3d(ncell=3, margin=3, E=100.0, gimp="B2GIMP", vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(2, True, 1)), (1, 2, 30), 2, 0.3, 3000.0),
+    "block3d_b2gimp_rigid_wall": (inputs.block3d(ncell=3, margin=3, gimp="B2GIMP", material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
+                                                 rigid=("wall", 4, (0.0, 0.0, 0.0))), (1, 40), 1, 0.3, 2000.0),
+    "disks2d_b2spline": (inputs.disks2d(analysis=10, gimp="B2SPLINE"), (1, 60), 1),
+    "disks2d_b2gimp_planestress": (inputs.disks2d(analysis=11, gimp="B2GIMP").replace(DISK1, '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha></Material>'),
+                                   (1, 60), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),
