@@ -60,6 +60,7 @@ extern "C" {
 #define MPMGPU_BSPLINE         6   /* B2SPLINE: quadratic B-splines (per-task kernels) */
 #define MPMGPU_LINEAR_CPDI   10   /* lCPDI (2D and 3D) */
 #define MPMGPU_QUADRATIC_CPDI 11  /* qCPDI (2D only, as in the reference) */
+#define MPMGPU_BSPLINE_CPDI   13  /* B2CPDI: linear CPDI domains over quadratic B-splines (per-task kernels) */
 
 /* material kinds: reference MaterialID() values, Common/Read_XML/MaterialController.cpp:105-232 */
 #define MPMGPU_MAT_ISOTROPIC      1   /* IsotropicMat, small- or large-rotation hypoelastic */

@@ -124,7 +124,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     if (cfg->horiz < 3 || cfg->vert < 3 || (is3D && cfg->depth < 3)) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: grid needs >=3 cells per axis incl. border");
     if (!cfg->xpts || !cfg->ypts || (is3D && !cfg->zpts)) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: node coordinate arrays missing");
     if (cfg->shape != MPMGPU_POINT_GIMP && cfg->shape != MPMGPU_UNIFORM_GIMP && cfg->shape != MPMGPU_LINEAR_CPDI && cfg->shape != MPMGPU_QUADRATIC_CPDI &&
-        cfg->shape != MPMGPU_BSPLINE_GIMP && cfg->shape != MPMGPU_BSPLINE)
+        cfg->shape != MPMGPU_BSPLINE_GIMP && cfg->shape != MPMGPU_BSPLINE && cfg->shape != MPMGPU_BSPLINE_CPDI)
         return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: shape function code %d not supported", cfg->shape);
     if (cfg->shape == MPMGPU_QUADRATIC_CPDI && is3D) return fail(NULL, MPMGPU_EINVAL, "mpmgpu_create: qCPDI is 2D only (as in the reference)");
     if (cfg->method != MPMGPU_USF && cfg->method != MPMGPU_USAVG && cfg->method != MPMGPU_USL)
@@ -278,7 +278,7 @@ static int alloc_particles(mpmgpu_ctx *ctx, size_t cap)
     CK(cudaMemsetAsync(ctx->particleIntPool, 0, capPad * NPI * sizeof(int), ctx->stream));
     bind_particles(ctx->P, ctx->particlePool, ctx->particleIntPool, capPad);
     ctx->cap = capPad;
-    if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI) {
+    if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI) {
         const int nc = ctx->dim == 3 ? 8 : (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 9 : 4);
         CK(dalloc(ctx, &ctx->cpElemPool, capPad * nc));
         CK(dalloc(ctx, &ctx->cpXiPool, capPad * nc * 3));
@@ -445,7 +445,7 @@ static int alloc_rigid(mpmgpu_ctx *ctx, size_t cap)
         if (ctx->hFixedBits.size() == nn) CK(cudaMemcpyAsync(fb, ctx->hFixedBits.data(), nn, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(fb, 0, nn, ctx->stream));
         ctx->R.fixedBits = fb;
-        if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI) {     // CPDI domains of the rigid particles
+        if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI) {     // CPDI domains of the rigid particles
             const int nc = ctx->dim == 3 ? 8 : (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 9 : 4);
             int *ce; double *cx, *cw;
             CK(dalloc(ctx, &ce, capPad * nc)); CK(dalloc(ctx, &cx, capPad * nc * 3)); CK(dalloc(ctx, &cw, capPad * nc * 3));
@@ -645,6 +645,7 @@ extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const do
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<3, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_BSPLINE) LAUNCH((KERNEL<3, SHAPE_B2SPLINE>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_BSPLINE_GIMP) LAUNCH((KERNEL<3, SHAPE_B2GIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_BSPLINE_CPDI) LAUNCH((KERNEL<3, SHAPE_B2CPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<3, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<3, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else LAUNCH((KERNEL<3, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
@@ -652,6 +653,7 @@ extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const do
             if (ctx->cfg.shape == MPMGPU_UNIFORM_GIMP) LAUNCH((KERNEL<2, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_BSPLINE) LAUNCH((KERNEL<2, SHAPE_B2SPLINE>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_BSPLINE_GIMP) LAUNCH((KERNEL<2, SHAPE_B2GIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+            else if (ctx->cfg.shape == MPMGPU_BSPLINE_CPDI) LAUNCH((KERNEL<2, SHAPE_B2CPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<2, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI) LAUNCH((KERNEL<2, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
             else if (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI && ctx->cpdiMerge) LAUNCH((KERNEL<2, SHAPE_QCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \

@@ -13,12 +13,12 @@
 // reference codes (System/MPMPrefix.hpp:110-140)
 enum { NP_PLANE_STRAIN = 10, NP_PLANE_STRESS = 11, NP_THREED = 12 };
 enum { METHOD_USF = 0, METHOD_USAVG = 2, METHOD_USL = 3 };
-enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_B2GIMP = 5, SHAPE_B2SPLINE = 6, SHAPE_LCPDI = 10, SHAPE_QCPDI = 11,
+enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_B2GIMP = 5, SHAPE_B2SPLINE = 6, SHAPE_LCPDI = 10, SHAPE_QCPDI = 11, SHAPE_B2CPDI = 13,
        // internal variants of the two CPDI codes: same functions, corner contributions to one node merged before the node is
        // touched (shape.cuh::for_each_node_cpdi_merged); chosen at launch, never seen through the ABI
        SHAPE_LCPDI_MERGED = 20, SHAPE_QCPDI_MERGED = 21 };
 #define SHAPE_IS_QCPDI(S) ((S) == SHAPE_QCPDI || (S) == SHAPE_QCPDI_MERGED)
-#define SHAPE_IS_CPDI(S) ((S) == SHAPE_LCPDI || (S) == SHAPE_LCPDI_MERGED || SHAPE_IS_QCPDI(S))
+#define SHAPE_IS_CPDI(S) ((S) == SHAPE_LCPDI || (S) == SHAPE_LCPDI_MERGED || (S) == SHAPE_B2CPDI || SHAPE_IS_QCPDI(S))
 #define SHAPE_IS_MERGED(S) ((S) == SHAPE_LCPDI_MERGED || (S) == SHAPE_QCPDI_MERGED)
 enum { MAT_ISOTROPIC = 1, MAT_MOONEY = 8, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28 };
 

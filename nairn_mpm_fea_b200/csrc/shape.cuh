@@ -493,7 +493,29 @@ __device__ __forceinline__ void for_each_node_cpdi(const Grid &g, const Particle
         }
         const ElemIJK ec = elem_ijk(g, ce);
         const int n0 = elem_node0(g, ec);
-        if (DIM == 3) {
+        if (SHAPE == SHAPE_B2CPDI) {
+            // B2CPDI: the corners are evaluated with the quadratic B-splines of the grid (ElementBase::GetShapeFunctionsForTractions
+            // -> SplineShapeFunction, MoreMPMElementBase.cpp:90-105), 27 (9) nodes per corner
+            Gimp1D sx, sy, sz;
+            bspline_1d<false>(xi, sx);
+            bspline_1d<false>(eta, sy);
+            if (DIM == 3) bspline_1d<false>(zeta, sz); else { sz.ok = 2u; sz.S[1] = 1.; }
+#pragma unroll 1
+            for (int kz = 0; kz < 4; kz++) {
+                if (!(sz.ok >> kz & 1u)) continue;
+#pragma unroll 1
+                for (int jy = 0; jy < 4; jy++) {
+                    if (!(sy.ok >> jy & 1u)) continue;
+#pragma unroll
+                    for (int ix = 0; ix < 4; ix++) {
+                        if (!(sx.ok >> ix & 1u)) continue;
+                        const double N = DIM == 3 ? sx.S[ix] * sy.S[jy] * sz.S[kz] : sx.S[ix] * sy.S[jy];
+                        if (N < 1e-15) continue;
+                        f(n0 + (ix - 1) + (jy - 1) * g.yplane + (DIM == 3 ? (kz - 1) * g.zplane : 0), ws * N, wx * N, wy * N, DIM == 3 ? wz * N : 0.);
+                    }
+                }
+            }
+        } else if (DIM == 3) {
             const int xo[8] = {0, 1, 1, 0, 0, 1, 1, 0}, yo[8] = {0, 0, 1, 1, 0, 0, 1, 1}, zo[8] = {0, 0, 0, 0, 1, 1, 1, 1};
 #pragma unroll
             for (int a = 0; a < 8; a++) {

@@ -237,7 +237,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (nmpms != nmpmsNR && MaterialBase::extrapolateRigidBCs) return "rigid BCs by extrapolation";
     if (fmobj->np != PLANE_STRAIN_MPM && fmobj->np != PLANE_STRESS_MPM && fmobj->np != THREED_MPM) return "analysis type";
     if (ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP && ElementBase::useGimp != LINEAR_CPDI &&
-        ElementBase::useGimp != QUADRATIC_CPDI && ElementBase::useGimp != BSPLINE_GIMP && ElementBase::useGimp != BSPLINE) return "shape functions";
+        ElementBase::useGimp != QUADRATIC_CPDI && ElementBase::useGimp != BSPLINE_GIMP && ElementBase::useGimp != BSPLINE && ElementBase::useGimp != BSPLINE_CPDI) return "shape functions";
     if (!mpmgrid.IsStructuredEqualElementsGrid()) return "grid is not structured with equal elements";
     for (int i = 0; i < nmat; i++) {
         MaterialBase *mb = theMaterials[i];

@@ -1371,7 +1371,7 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
      * JohnsonCook).  Those are pinned against the reference directly, at the law level (tests/test_device_laws_vs_reference_cpu.py) and
      * through goldens run by the host-compiled device source (tests/test_device_step_cpu.py). */
     for (int i = 0; i < nmat; i++) if (mats[i].kind == MPMGPU_MAT_ISOPLASTICITY && mats[i].p[16] > 1.) return -2;
-    if (cfg->shape == MPMGPU_BSPLINE_GIMP || cfg->shape == MPMGPU_BSPLINE) return -2;      /* B2GIMP / B2SPLINE: pinned the same way */
+    if (cfg->shape == MPMGPU_BSPLINE_GIMP || cfg->shape == MPMGPU_BSPLINE || cfg->shape == MPMGPU_BSPLINE_CPDI) return -2;      /* B2GIMP / B2SPLINE: pinned the same way */
     O = (Oracle *)calloc(1, sizeof(Oracle));
     O->cfg = *cfg;
     O->dim = cfg->np == MPMGPU_THREED_MPM ? 3 : 2;

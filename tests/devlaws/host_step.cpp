@@ -102,6 +102,7 @@ inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
         if (S->shape == SHAPE_UGIMP) EMU_LAUNCH((KERNEL<3, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_B2SPLINE) EMU_LAUNCH((KERNEL<3, SHAPE_B2SPLINE>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_B2GIMP) EMU_LAUNCH((KERNEL<3, SHAPE_B2GIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_B2CPDI) EMU_LAUNCH((KERNEL<3, SHAPE_B2CPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_LCPDI) EMU_LAUNCH((KERNEL<3, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_LCPDI_MERGED) EMU_LAUNCH((KERNEL<3, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
         else EMU_LAUNCH((KERNEL<3, SHAPE_LINEAR>), grid_, TASK_THREADS, __VA_ARGS__); \
@@ -109,6 +110,7 @@ inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
         if (S->shape == SHAPE_UGIMP) EMU_LAUNCH((KERNEL<2, SHAPE_UGIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_B2SPLINE) EMU_LAUNCH((KERNEL<2, SHAPE_B2SPLINE>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_B2GIMP) EMU_LAUNCH((KERNEL<2, SHAPE_B2GIMP>), grid_, TASK_THREADS, __VA_ARGS__); \
+        else if (S->shape == SHAPE_B2CPDI) EMU_LAUNCH((KERNEL<2, SHAPE_B2CPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_LCPDI) EMU_LAUNCH((KERNEL<2, SHAPE_LCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_LCPDI_MERGED) EMU_LAUNCH((KERNEL<2, SHAPE_LCPDI_MERGED>), grid_, TASK_THREADS, __VA_ARGS__); \
         else if (S->shape == SHAPE_QCPDI) EMU_LAUNCH((KERNEL<2, SHAPE_QCPDI>), grid_, TASK_THREADS, __VA_ARGS__); \

@@ -139,6 +139,8 @@ CASES = {
     "disks2d_b2spline": (inputs.disks2d(analysis=10, gimp="B2SPLINE"), (1, 60), 1),
     "disks2d_b2gimp_planestress": (inputs.disks2d(analysis=11, gimp="B2GIMP").replace(DISK1, '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha></Material>'),
                                    (1, 60), 1),
+    "block3d_b2cpdi": (inputs.block3d(ncell=3, margin=3, gimp="B2CPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3), (1, 30), 1, 0.3, 2000.0),
+    "disks2d_b2cpdi": (inputs.disks2d(analysis=10, gimp="B2CPDI"), (1, 60), 1),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

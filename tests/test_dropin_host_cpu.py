@@ -29,7 +29,7 @@ CASES = {
                                            '<yieldMax>640</yieldMax></Material>'), "hardening law other than"),
     "ideal rubber": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="8" Name="Blk"><rho>1</rho><G1>30</G1><G2>0</G2><K>100</K>'
                                     '<alpha>0</alpha><IdealRubber/></Material>'), "IdealRubber"),
-    "unsupported shape functions": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, gimp="B2CPDI"), "shape functions"),
+    "unsupported shape functions": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, gimp="Finite"), "shape functions"),
     # failure handling of the replaced tasks that libmpmgpu does not do
     "time-step restarts": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, method=3, extra_header="<RestartScaling>0.5</RestartScaling>"),
                            "time-step restarts"),

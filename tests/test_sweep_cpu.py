@@ -58,7 +58,7 @@ def make_config(seed):
     rng = np.random.default_rng(seed)
     two_d = rng.random() < 0.4
     method = int(rng.choice([0, 2, 2, 3]))
-    shapes = ["uGIMP", "uGIMP", None, "lCPDI", "B2GIMP", "B2SPLINE"] + (["qCPDI"] if two_d else [])
+    shapes = ["uGIMP", "uGIMP", None, "lCPDI", "B2GIMP", "B2SPLINE", "B2CPDI"] + (["qCPDI"] if two_d else [])
     gimp = shapes[int(rng.integers(0, len(shapes)))]
     skip = method != 0 and gimp is not None and rng.random() < 0.25          # Classic with USL-/USAVG- is refused by the reference
     header = "<SkipPostExtrapolation/>" if skip else ""

@@ -22,7 +22,8 @@ BRANCH_CASES = ["disks2d_neo_planestress", "disks2d_neo_planestress_av", "block3
                 "block3d_isoplastic_nonlinear", "block3d_isoplastic_nonlinear2_soft", "block3d_johnsoncook", "disks2d_johnsoncook_planestress",
                 "disks2d_nonlinear_planestrain_lr", "disks2d_nonlinear2_planestress",
                 # quadratic B-spline shape functions
-                "block3d_b2spline", "block3d_b2gimp", "block3d_b2gimp_rigid_wall", "disks2d_b2spline", "disks2d_b2gimp_planestress"]
+                "block3d_b2spline", "block3d_b2gimp", "block3d_b2gimp_rigid_wall", "disks2d_b2spline", "disks2d_b2gimp_planestress",
+                "block3d_b2cpdi", "disks2d_b2cpdi"]
 CASES = LR_CASES + BRANCH_CASES
 FUSED_CASES = ["block3d_isoplastic_softening", "block3d_material_pdamping", "block3d_free_ugimp"]          # 3D uGIMP without large rotation
 
