@@ -24,7 +24,7 @@ def test_random_combination_on_the_gpu_matches_the_live_reference(seed):
     try:
         z = refharness.run_reference(xml, snaps=(1, NSTEPS), per_task_steps=0, nprocs=1, jitter_amp=ja, vel_amp=va)
     except RuntimeError as e:
-        if "could not be bracketed" in str(e):
+        if "could not be bracketed" in str(e) or "position nan" in str(e):
             pytest.skip("the reference itself aborts on this combination: %s" % desc)
         raise
     prob = from_reference_dump(z)
