@@ -89,6 +89,91 @@ static int shape(int p, int getDeriv, int *nds, double *fn, double *xd, double *
     const double dx = O->xpts[ei + 1] - O->xpts[ei], dy = O->ypts[ej + 1] - O->ypts[ej];
     const double dz = O->dim == 3 ? O->zpts[ek + 1] - O->zpts[ek] : 1.;
     int i = 0;
+    if (O->cfg.shape == MPMGPU_BSPLINE_CPDI) {
+        /* B2CPDI: GetCPDIFunctions with the corners evaluated by SplineShapeFunction (MoreMPMElementBase.cpp:90-105,581-657) */
+        int ind = 0;
+        for (int c = 0; c < O->ncorner; c++) {
+            const size_t q = (size_t)p * O->ncorner + c;
+            int ci, cj, ck;
+            elem_ijk(O->cpElem[q], &ci, &cj, &ck);
+            const int cnode0 = ck * O->zplane + cj * O->yplane + ci;
+            const double *cx = &O->cpXi[3 * q], *wg = &O->cpWg[3 * q];
+            const double ws = O->cpWs[c];
+            const int ncand = O->dim == 3 ? 64 : 16;
+            for (int id = 0; id < ncand; id++) {
+                const double xn = O->dim == 3 ? g3xii[id] : gxii[id], yn = O->dim == 3 ? g3eti[id] : geti[id], zn = O->dim == 3 ? g3zti[id] : 0.;
+                double e1 = cx[0] - xn, t1 = fabs(e1); if (t1 >= 3.) continue;
+                double e2 = cx[1] - yn, t2 = fabs(e2); if (t2 >= 3.) continue;
+                double e3 = O->dim == 3 ? cx[2] - zn : 0., t3 = fabs(e3); if (O->dim == 3 && t3 >= 3.) continue;
+                double sx = t1 <= 1.0 ? 0.25 * (3. - e1 * e1) : 0.125 * (3. - t1) * (3. - t1);
+                double sy = t2 <= 1.0 ? 0.25 * (3. - e2 * e2) : 0.125 * (3. - t2) * (3. - t2);
+                double sz = O->dim == 3 ? (t3 <= 1.0 ? 0.25 * (3. - e3 * e3) : 0.125 * (3. - t3) * (3. - t3)) : 1.;
+                double cfn = O->dim == 3 ? sx * sy * sz : sx * sy;
+                if (cfn < 1e-15) continue;
+                int node = cnode0 + off_of(xn) + off_of(yn) * O->yplane + (O->dim == 3 ? off_of(zn) * O->zplane : 0);
+                int look;
+                for (look = ind - 1; look >= 0; look--) if (nds[look] == node) break;
+                if (look >= 0) {
+                    fn[look] += ws * cfn;
+                    if (getDeriv) { xd[look] += wg[0] * cfn; yd[look] += wg[1] * cfn; zd[look] += wg[2] * cfn; }
+                } else {
+                    nds[ind] = node; fn[ind] = ws * cfn;
+                    if (getDeriv) { xd[ind] = wg[0] * cfn; yd[ind] = wg[1] * cfn; zd[ind] = wg[2] * cfn; }
+                    ind++;
+                }
+            }
+        }
+        return ind;
+    }
+    if (O->cfg.shape == MPMGPU_BSPLINE || O->cfg.shape == MPMGPU_BSPLINE_GIMP) {
+        /* B2SPLINE: EightNodeIsoparamBrick::SplineShapeFunction :110-204, FourNodeIsoparam.cpp:217-294
+         * B2GIMP:   EightNodeIsoparamBrick::BGimpShapeFunction :477-634 (z-gradient sign from xi.y, :586), FourNodeIsoparam.cpp:770-884 */
+        const int spline = O->cfg.shape == MPMGPU_BSPLINE, ncand = O->dim == 3 ? 64 : 16;
+        const double lpv[3] = {P3(lp, 0, p), P3(lp, 1, p), P3(lp, 2, p)};
+        const double xv[3] = {xi, eta, zeta};
+        const double inv_d[3] = {(spline ? 1. : 2.0) / dx, (spline ? 1. : 2.0) / dy, (spline ? 1. : 2.0) / dz};
+        for (int id = 0; id < ncand; id++) {
+            const double nn3[3] = {O->dim == 3 ? g3xii[id] : gxii[id], O->dim == 3 ? g3eti[id] : geti[id], O->dim == 3 ? g3zti[id] : 0.};
+            double S[3] = {1., 1., 1.}, dS[3] = {0., 0., 0.};
+            int skip = 0;
+            for (int a = 0; a < O->dim && !skip; a++) {
+                if (spline) {
+                    double e = xv[a] - nn3[a], t = fabs(e);
+                    if (t >= 3.) { skip = 1; break; }
+                    if (t <= 1.0) { S[a] = 0.25 * (3. - e * e); dS[a] = -e; }
+                    else { double arg = 3. - t; S[a] = 0.125 * arg * arg; dS[a] = e >= 0. ? 0.5 * (e - 3) : 0.5 * (e + 3); }
+                } else {
+                    const double l = lpv[a], b1 = 1. - l, b2 = 1. + l, b3 = 3. - l, b4 = 3. + l, inv_size = 1. / (48. * l), oneTwelth = 1. / 12.;
+                    double xp = fabs(xv[a] - nn3[a]);
+                    if (xp >= b4) { skip = 1; break; }
+                    if (xp < b1) { S[a] = O->dim == 3 ? (9. - l * l - 3 * xp * xp) * oneTwelth : (9. - l * l - 3. * xp * xp) * oneTwelth; dS[a] = -0.5 * xp; }
+                    else if (xp < b2) {
+                        double arg = xp - 1., lp2 = l * l;
+                        if (O->dim == 3) { double lp3 = lp2 * l; S[a] = (9. * lp2 * arg + 3. * arg * arg * arg + 3. * l * (15. - xp * (6. + xp)) - lp3) * inv_size; }
+                        else S[a] = (lp2 * (9. * arg - l) + 3. * arg * arg * arg + 3. * l * (15. - xp * (6. + xp))) * inv_size;
+                        dS[a] = (3 * lp2 + 3. * arg * arg - 2. * l * (3. + xp)) * 3. * inv_size;
+                    }
+                    else if (xp <= b3) { double arg = xp - 3.; S[a] = (l * l + 3. * arg * arg) * 0.5 * oneTwelth; dS[a] = 0.25 * (xp - 3.); }
+                    else { double arg = 3. + l - xp; S[a] = arg * arg * arg * inv_size; dS[a] = -arg * arg * 3. * inv_size; }
+                    /* xsign, ysign and (3D) zsign = xi.y > node z */
+                    const double ref = (a == 2) ? xv[1] : xv[a];
+                    if (!(ref > nn3[a])) dS[a] = -dS[a];
+                }
+            }
+            if (skip) continue;
+            if (O->dim == 3) {
+                fn[i] = S[0] * S[1] * S[2];
+                if (getDeriv) { xd[i] = dS[0] * S[1] * S[2] * inv_d[0]; yd[i] = S[0] * dS[1] * S[2] * inv_d[1]; zd[i] = S[0] * S[1] * dS[2] * inv_d[2]; }
+                nds[i] = node0 + off_of(nn3[0]) + off_of(nn3[1]) * O->yplane + off_of(nn3[2]) * O->zplane;
+            } else {
+                fn[i] = S[0] * S[1];
+                if (getDeriv) { xd[i] = dS[0] * S[1] * inv_d[0]; yd[i] = S[0] * dS[1] * inv_d[1]; zd[i] = 0.; }
+                nds[i] = node0 + off_of(nn3[0]) + off_of(nn3[1]) * O->yplane;
+            }
+            i++;
+        }
+        return i;
+    }
     if (O->cfg.shape == MPMGPU_LINEAR_CPDI || O->cfg.shape == MPMGPU_QUADRATIC_CPDI) {
         /* ElementBase::GetCPDIFunctions, Elements/MoreMPMElementBase.cpp:581-657: merge by node in first-seen order */
         static const double xii[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, eti[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, zti[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
@@ -1371,7 +1456,6 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
      * JohnsonCook).  Those are pinned against the reference directly, at the law level (tests/test_device_laws_vs_reference_cpu.py) and
      * through goldens run by the host-compiled device source (tests/test_device_step_cpu.py). */
     for (int i = 0; i < nmat; i++) if (mats[i].kind == MPMGPU_MAT_ISOPLASTICITY && mats[i].p[16] > 1.) return -2;
-    if (cfg->shape == MPMGPU_BSPLINE_GIMP || cfg->shape == MPMGPU_BSPLINE || cfg->shape == MPMGPU_BSPLINE_CPDI) return -2;      /* B2GIMP / B2SPLINE: pinned the same way */
     O = (Oracle *)calloc(1, sizeof(Oracle));
     O->cfg = *cfg;
     O->dim = cfg->np == MPMGPU_THREED_MPM ? 3 : 2;
@@ -1408,7 +1492,7 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
     }
     O->dt = dt; O->dtFirst = dtFirst; O->dtLast = dtLast;
     O->ncorner = 0;
-    if (cfg->shape == MPMGPU_LINEAR_CPDI) O->ncorner = O->dim == 3 ? 8 : 4;
+    if (cfg->shape == MPMGPU_LINEAR_CPDI || cfg->shape == MPMGPU_BSPLINE_CPDI) O->ncorner = O->dim == 3 ? 8 : 4;
     if (cfg->shape == MPMGPU_QUADRATIC_CPDI) O->ncorner = 9;
     if (O->ncorner) {
         O->cpElem = dupi(NULL, n * O->ncorner, 1); O->cpXi = dupd(NULL, 3 * n * O->ncorner); O->cpWg = dupd(NULL, 3 * n * O->ncorner);
