@@ -65,8 +65,6 @@ class PortOracle:
                                            C.POINTER(C.c_int), C.c_double, C.c_double, C.c_double]
         rc = self.lib.oracle_create(C.byref(cfg), len(prob.materials), mats, C.byref(v), len(bn), _i(bn), _d(bnorm), _d(bval),
                                     _i(bact), _i(bsym), prob.dt, prob.dt_strain_first, prob.dt_strain_last)
-        if rc == -2:
-            raise NotImplementedError("oracle/mpm_oracle.c does not restate the numerically returned hardening laws (pinned against the reference directly)")
         assert rc == 0
 
     def set_xpic(self, order, using_fmpm):

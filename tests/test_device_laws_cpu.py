@@ -103,6 +103,11 @@ def _mat(name, np_):
         return M.neohookean(U["G"], U["K"], U["rho"], aI=40.0, UofJOption=int(name[-1]), av=(0.3, 1.5) if name[-1] == "0" else None)
     if name.startswith("mooney"):
         return M.mooney(0.75 * U["G"], 0.25 * U["G"], U["K"], U["rho"], aI=40.0, UofJOption=int(name[-1]), av=(0.3, 1.5) if name[-1] == "1" else None)
+    if name in ("nonlinear", "nonlinear2"):
+        return M.isoplasticity(U["E"], 0.3, U["rho"], U["yld"], None, 0.0, aI=20.0, np_=np_, hardening=(name, 8.0, 0.4))
+    if name == "johnsoncook":
+        return M.isoplasticity(U["E"], 0.3, U["rho"], U["yld"], None, 0.0, aI=20.0, np_=np_,
+                               hardening=("johnsoncook", dict(B=1.5 * U["yld"], n=0.5, C=0.02, ep0=1.0, D=0.01, n2=2.0, Tm=1600.0, m=1.1, Tref=250.0)))
     if name == "isoplasticity":
         return M.isoplasticity(U["E"], 0.3, U["rho"], U["yld"], U["Ep"], aI=20.0, np_=np_, av=(0.2, 2.0))
     if name == "isoplasticity_lr":
@@ -110,7 +115,8 @@ def _mat(name, np_):
     raise KeyError(name)
 
 
-LAWS = ["isotropic", "isotropic_lr", "neohookean0", "neohookean1", "neohookean2", "mooney0", "mooney1", "mooney2", "isoplasticity", "isoplasticity_lr"]
+LAWS = ["isotropic", "isotropic_lr", "neohookean0", "neohookean1", "neohookean2", "mooney0", "mooney1", "mooney2", "isoplasticity", "isoplasticity_lr",
+        "nonlinear", "nonlinear2", "johnsoncook"]
 
 
 @pytest.mark.parametrize("analysis", list(NPS))
@@ -158,9 +164,10 @@ def test_device_law_source_matches_oracle(libs, law, analysis):
     for i, nm in enumerate(["work", "res", "heat", "entropy", "plast"]):
         check(nm, d["energies"][i], o["energies"][i])
     check("history", d["hist"], o["hist"])
-    if law.startswith("isoplasticity"):
+    if law.startswith("isoplasticity") or law in ("nonlinear", "nonlinear2", "johnsoncook"):
         assert np.count_nonzero(d["hist"][0] != st["hist"][0]) > n // 10, "the sample should yield on a good part of the particles"
-        assert np.count_nonzero(d["hist"][0] == st["hist"][0]) > 0, "and stay elastic on some"
+        if law.startswith("isoplasticity"):
+            assert np.count_nonzero(d["hist"][0] == st["hist"][0]) > 0, "and stay elastic on some"
 
 
 @pytest.mark.parametrize("law", ["isotropic", "neohookean0", "isoplasticity"])
