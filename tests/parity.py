@@ -55,7 +55,8 @@ TOL_LR3D = 1.0e-4          # observed: <= 3e-6 on the two goldens (80 steps), <=
 # Hardening laws returned numerically (Nonlinear, Nonlinear2, JohnsonCook): the reference stops the bracketed Newton iteration for
 # lambda at |d lambda / lambda| < 1e-4 (HardeningLawBase::LambdaConverged, HardeningLawBase.cpp:386-390), so the plastic increment
 # is DEFINED to 1e-4 only: a last-bit difference upstream can end the iteration one step earlier or later, or turn a Newton step
-# into a bisection.  One step still agrees to 1e-10 in practice; long runs are held to the solver's own tolerance.
+# into a bisection.  With the same libm one step agrees to round-off (tests/test_device_laws_vs_reference_cpu.py holds the law to 1e-13 on
+# identical inputs); whole-step and long-run comparisons are held to the solver's own tolerance.
 TOL_ITERATIVE = 1.0e-4          # observed <= 2e-5 after 100 steps
 
 
@@ -64,7 +65,8 @@ def tolerances(case):
     if case in LR3D_CASES:
         return TOL_LR3D, TOL_LR3D, TOL_LR3D
     if "johnsoncook" in case or "nonlinear" in case:
-        return TOL_1STEP, 1.0e-8, TOL_ITERATIVE
+        # also for a single step: a device libm that rounds pow/log differently can flip one particle's iteration path
+        return TOL_ITERATIVE, TOL_ITERATIVE, TOL_ITERATIVE
     return TOL_1STEP, 1.0e-8, TOL_100STEP
 
 
