@@ -1,6 +1,6 @@
 // Per-task kernels: one kernel (or a node sweep) per reference MPMTask, particles in any order,
 // node accumulation by global FP64 atomics.  This is the general path (every shape function,
-// 2D and 3D, every material); the cell-sorted tiled kernels in kernels_tiled.cuh replace the
+// 2D and 3D, every material); the cell-sorted fused kernels in kernels_fused.cuh replace the
 // particle<->grid transfers of the 3D uGIMP step when the configuration is eligible.
 #pragma once
 #include "mpm_types.cuh"
