@@ -375,4 +375,31 @@ extern "C" void emu_get_nodes(void *h, int *cnt, double *mass, double *pk, doubl
     }
 }
 
+// device-layout view of the current state for the archive / global-sum functions of csrc/archive.cuh (tests only): arrays [component][n],
+// non-rigid particles first, in the caller's order (the emulation never permutes)
+extern "C" void emu_get_device_state(void *h, double *pos, double *vel, double *mp, double *F, double *sp, double *pressure, double *eplast,
+                                     double *energies, double *hist, int *elem, int *mat0, int *cross)
+{
+    EmuSim *S = (EmuSim *)h;
+    const size_t N = (size_t)S->n;
+    const Particles *sets[2] = {&S->P, &S->PR};
+    size_t off = 0;
+    for (int k = 0; k < 2; k++) {
+        const Particles &P = *sets[k];
+        for (size_t p = 0; p < (size_t)P.n; p++) {
+            const size_t q = off + p;
+            for (int c = 0; c < 3; c++) { pos[c * N + q] = P.pos[c][p]; vel[c * N + q] = P.vel[c][p]; }
+            mp[q] = P.mp[p];
+            for (int c = 0; c < 9; c++) F[c * N + q] = P.F[c][p];
+            for (int c = 0; c < 6; c++) { sp[c * N + q] = P.sp[c][p]; eplast[c * N + q] = P.eplast[c][p]; }
+            pressure[q] = P.pressure[p];
+            energies[q] = P.work[p]; energies[N + q] = P.res[p]; energies[2 * N + q] = P.heat[p]; energies[3 * N + q] = P.entropy[p];
+            energies[4 * N + q] = P.plast[p]; energies[5 * N + q] = P.prevT[p];
+            for (int c = 0; c < MPM_MAX_HISTORY; c++) hist[c * N + q] = P.hist[c][p];
+            elem[q] = P.elem[p]; mat0[q] = P.mat[p]; cross[q] = P.cross[p];
+        }
+        off += (size_t)P.n;
+    }
+}
+
 extern "C" void emu_destroy(void *h) { delete (EmuSim *)h; }

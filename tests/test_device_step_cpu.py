@@ -47,7 +47,7 @@ def lib():
                         src, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.emu_create.restype = C.c_void_p
-    for f in ("emu_set_bcs", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_destroy"):
+    for f in ("emu_set_bcs", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
         getattr(lib, f).argtypes = None
     return lib
 
