@@ -172,35 +172,48 @@ __device__ __forceinline__ int dual_cell_center(const Grid &g, int inElem, const
 // ---- 3-node uGIMP weights around the dual-cell centre -------------------------------------------
 // base = -1 (xi<0: nodes at -3,-1,1) or 0 (xi>=0: nodes at -1,1,3); returns S[3], dS[3] (signed, not
 // yet scaled by 2/dx) and a 3-bit validity mask (xp < 2+lp).
+// Written with selects instead of the reference's branch ladder (EightNodeIsoparamBrick.cpp:316-387): the lanes of a warp
+// sit in different pieces of the piecewise weight, so branches would run every piece one after the other anyway.
+// Each piece is the reference's expression, so the selected value is bit-identical to the ladder's result.  With the
+// particle inside its element (|xi| <= 1) and lp <= 1 a side node is at least one cell away (xp >= 1 >= lp), so its
+// first piece is never taken; the centre node is closer than 2+lp, so it is never outside the support.
+template <bool GRAD, bool CENTRE>
+__device__ __forceinline__ void gimp_piece(double xi, double xn, double lp, double q1, double q2, double inv_size, double inv2lp, double &S, double &dS, bool &ok)
+{
+    const double xp = fabs(xi - xn);
+    const double arg = (q2 - xp) * inv_size;
+    const double s3 = 2. * lp * arg * arg;
+    const double s2 = 0.5 * (2. - xp);
+    double s, d;
+    if (CENTRE) {
+        const double s1 = ((4. - lp) * lp - xp * xp) * inv_size;
+        const bool in1 = xp < lp, in2 = xp <= q1;
+        s = in1 ? s1 : (in2 ? s2 : s3);
+        d = in1 ? -xp * inv2lp : (in2 ? -0.5 : -arg);
+        ok = true;
+    } else {
+        const bool in2 = xp <= q1;
+        ok = xp < q2;
+        s = in2 ? s2 : (ok ? s3 : 0.);
+        d = in2 ? -0.5 : (ok ? -arg : 0.);
+    }
+    S = s;
+    if (GRAD) dS = (xi > xn) ? d : -d;
+}
+
 template <bool GRAD>
 __device__ __forceinline__ int gimp3(double xi, double lp, double inv_size, double inv2lp, double S[3], double dS[3], unsigned &ok)
 {
     const int base = xi < 0. ? -1 : 0;
     const double q1 = 2. - lp, q2 = 2. + lp;
-    ok = 0;
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-        const double xn = (double)(2 * (base + t) - 1);
-        const double xp = fabs(xi - xn);
-        double s = 0., d = 0.;
-        if (xp < q2) {
-            ok |= 1u << t;
-            if (xp < lp) {
-                s = ((4. - lp) * lp - xp * xp) * inv_size;
-                if (GRAD) d = -xp * inv2lp;
-            } else if (xp <= q1) {
-                s = 0.5 * (2. - xp);
-                if (GRAD) d = -0.5;
-            } else {
-                double arg = (q2 - xp) * inv_size;
-                s = 2. * lp * arg * arg;
-                if (GRAD) d = -arg;
-            }
-            if (GRAD && !(xi > xn)) d = -d;
-        }
-        S[t] = s;
-        if (GRAD) dS[t] = d;
-    }
+    const double xc = xi < 0. ? -1. : 1.;          // centre node of the dual cell
+    bool ok0, ok1, ok2;
+    double d0 = 0., d1 = 0., d2 = 0.;
+    gimp_piece<GRAD, false>(xi, xc - 2., lp, q1, q2, inv_size, inv2lp, S[0], d0, ok0);
+    gimp_piece<GRAD, true>(xi, xc, lp, q1, q2, inv_size, inv2lp, S[1], d1, ok1);
+    gimp_piece<GRAD, false>(xi, xc + 2., lp, q1, q2, inv_size, inv2lp, S[2], d2, ok2);
+    if (GRAD) { dS[0] = d0; dS[1] = d1; dS[2] = d2; }
+    ok = (ok0 ? 1u : 0u) | 2u | (ok2 ? 4u : 0u);
     return base;
 }
 

@@ -45,6 +45,7 @@
 #include "Global_Quantities/BodyForce.hpp"
 #include "Custom_Tasks/CustomTask.hpp"
 #include "Custom_Tasks/TransportTask.hpp"
+#include "Custom_Tasks/ConductionTask.hpp"
 #include "Cracks/CrackHeader.hpp"
 #include "System/ArchiveData.hpp"
 #include "Global_Quantities/GlobalQuantity.hpp"
@@ -226,6 +227,17 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     // damping that changes during the run (functions of time, feedback on the kinetic energy: BodyForce.cpp:167-230)
     if (bodyFrc.useFeedback || bodyFrc.usePFeedback || bodyFrc.gridfunction != NULL || bodyFrc.pgridfunction != NULL)
         return "time-dependent or feedback damping";
+    // grid body forces that are functions of position and time are added to the grid force by PostForcesTask
+    // (BodyForce::GetGridBodyForce, BodyForce.cpp:97-117); the device applies constant gravity only
+    if (bodyFrc.hasGridBodyForce) return "grid body force functions (<BodyXForce> ...)";
+    // <EnergyCoupling>: IncrementHeatEnergy takes the adiabatic branch (temperature rise from dissipated energy,
+    // MaterialBaseMPM.cpp:982-1006, UpdateParticlesTask.cpp:228-235); the device laws are isothermal
+    if (ConductionTask::adiabatic) return "adiabatic energy coupling (<EnergyCoupling>)";
+    // a particle temperature other than the one its previous strain update saw gives a thermal strain increment
+    // res.dT = pTemperature - pPreviousTemperature in the first particle update (UpdateParticlesTask.cpp:252-256);
+    // the device has no residual strains (eres = 0)
+    for (int p = 0; p < nmpmsNR; p++)
+        if (mpm[p]->pTemperature != mpm[p]->pPreviousTemperature) return "particle temperatures that differ from the stress-free temperature (thermal strains)";
     // custom tasks run on the host particles between the step tasks; only the one that just switches the XPIC/FMPM order is safe
     for (CustomTask *ct = theTasks; ct != NULL; ct = ct->nextTask)
         if (strcmp(ct->TaskName(), "Periodic XPIC Implementation") != 0) return "custom tasks other than PeriodicXPIC";

@@ -37,6 +37,14 @@ CASES = {
     # branch too -- NairnMPM.cpp:814-832 -- which is why every input of this file has at least 200 particles)
     "deleting leavers": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<LeaveLimit>-5</LeaveLimit>"), "deleting particles that leave the grid"),
     "deleting nan particles": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<DeleteLimit>5</DeleteLimit>"), "deleting nan particles"),
+    # silent-divergence holes closed in round 2: the replaced tasks would add position/time dependent grid forces, an adiabatic
+    # temperature rise, or a thermal strain from particles that start away from the stress-free temperature
+    "grid body force function": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
+        "</JANFEAInput>", "<Gravity><GridBodyXForce>10*x</GridBodyXForce></Gravity></JANFEAInput>"), "grid body force functions"),
+    "adiabatic coupling": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
+        "</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>"), "adiabatic energy coupling"),
+    "particle temperature": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace('<Body ', '<Body temp="350" ', 1),
+                             "particle temperatures that differ"),
     "more exponential terms": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material=inputs.neohookean_material(),
                                               extra_header="<DefGradTerms>3</DefGradTerms>"), "<DefGradTerms> other than the default"),
 }
