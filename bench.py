@@ -343,9 +343,20 @@ def run_ours(args):
                        "%d z-slabs, one process per GPU: 3 halo-plane exchanges per step + particle migration over NCCL "
                        "(rank 0 sent %d and received %d particle rows)" % (world, stepper.migrated_out, stepper.migrated_in)},
             "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
-    if rank == 0 and not args.no_cpu_baseline and world >= 1:
-        line["cpu_baseline"] = cpu_baseline(args.cpu_ncell, args.cpu_steps)
     sim.close()
+    if not args.no_cpu_baseline:
+        # the reference's CPU path on a bounded sample of the workload (rank 0, host cores), and the parity of this arm
+        # against the state that sample ends in (every rank takes part: at N > 1 the sample is run as N slabs)
+        import tempfile
+        ref_npz = os.path.join(tempfile.mkdtemp(prefix="mpmbench_ref_"), "ref_state.npz") if rank == 0 else None
+        if rank == 0:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_ncell, args.cpu_steps, dump=ref_npz)
+        if world > 1:
+            dist.barrier()
+        par = parity_leg(args, rank, world, local, ref_npz)
+        if rank == 0:
+            line["parity"] = par
+            line["parity_max_rel"] = par["max_rel"] if par else None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -360,7 +371,8 @@ def sim_kernel_path_name(k):
 _REF_WORKER = r"""
 import sys, time, json
 sys.path.insert(0, %(root)r)
-from oracle.refharness import RefRun
+import numpy as np
+from oracle.refharness import RefRun, _flatten
 from tests.inputs import block3d
 from nairn_mpm_fea_b200.problem import jitter
 import bench
@@ -375,22 +387,36 @@ r = RefRun(xml, nprocs=%(nprocs)d)
 pos = jitter(r.particles()["pos"], bench.BLOCK_JITTER, 12345)
 bad = r.set_particles(pos, bench.block_velocity(%(ncell)d)(pos))
 assert bad == 0, bad
+dump = %(dump)r
+out = {}
+def snap(tag, nodes):
+    if dump:
+        _flatten(tag, r.particles(), out)
+        if nodes:
+            _flatten(tag + "n", r.nodes(), out)
 t1 = time.perf_counter()
 r.step(%(warm)d)
 t2 = time.perf_counter()
+snap("a", %(nodes)d)
+t2b = time.perf_counter()
 r.step(%(steps)d)
 t3 = time.perf_counter()
-print(json.dumps({"n": r.info["nmpms"], "setup_s": t1 - t0, "warm_s": t2 - t1, "run_s": t3 - t2, "patches": r.info["numPatches"]}))
+snap("b", 0)
+if dump:
+    np.savez(dump, **out)
+print(json.dumps({"n": r.info["nmpms"], "setup_s": t1 - t0, "warm_s": t2 - t1, "run_s": t3 - t2b, "patches": r.info["numPatches"]}))
 """
 
 
-def time_reference(ncell, steps, warm=1, nprocs=None):
-    """Time the UNMODIFIED reference (oracle/_ref/libnairnmpm_ref.so) on the host cores."""
+def time_reference(ncell, steps, warm=1, nprocs=None, dump=None, nodes=False):
+    """Time the UNMODIFIED reference (oracle/_ref/libnairnmpm_ref.so) on the host cores.  dump: path of an .npz that
+    receives the reference's particle state after the warm-up steps (keys a/...) and at the end (b/...); nodes: also the
+    node state after the warm-up steps (an/...)."""
     from oracle import refharness
     if not refharness.available():
         return None
     nprocs = nprocs or os.cpu_count() or 1
-    code = _REF_WORKER % dict(root=ROOT, ncell=ncell, nprocs=nprocs, warm=warm, steps=steps)
+    code = _REF_WORKER % dict(root=ROOT, ncell=ncell, nprocs=nprocs, warm=warm, steps=steps, dump=dump, nodes=1 if nodes else 0)
     env = dict(os.environ)
     env["OMP_NUM_THREADS"] = str(nprocs)
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
@@ -399,11 +425,54 @@ def time_reference(ncell, steps, warm=1, nprocs=None):
     d = json.loads(p.stdout.strip().splitlines()[-1])
     d["cores"] = nprocs
     d["steps"] = steps
+    d["warm"] = warm
     return d
 
 
-def cpu_baseline(ncell, steps):
-    d = time_reference(ncell, steps)
+PARITY_FIELDS = ("pos", "vel", "sp", "ep", "wrot")
+
+
+def parity_leg(args, rank, world, local, ref_npz):
+    """Parity of the bench workload itself: the CPU sample of the reference arm (the same block at cpu_ncell^3 cells, same
+    jittered start and velocity field) is run by THIS arm too -- on one GPU, or cut into `world` z-slabs with halo
+    exchange and particle migration over NCCL -- for the same number of steps; rank 0 compares the final particle state
+    with the reference's.  Returns max over fields of max|ours - ref| / max|ref| (None on the other ranks)."""
+    import torch.distributed as dist
+    from nairn_mpm_fea_b200 import MpmGpu, problem
+    ncell = args.cpu_ncell
+    nsteps = 1 + args.cpu_steps
+    prob = problem.block3d(ncell=ncell, margin=7, velocity_fn=block_velocity(ncell), jitter_amp=BLOCK_JITTER)
+    n = prob.nparticles
+    if world == 1:
+        sim = MpmGpu(prob, device=local, kernel_path=args.kernel_path)
+        sim.step(nsteps)
+        got = sim.download()
+        sim.close()
+    else:
+        from nairn_mpm_fea_b200.slab import SlabSim, gather_by_id, partition_particles, slab_bounds
+        lo, hi = slab_bounds(prob.depth, 8, 8 + ncell, world)[rank]
+        part = partition_particles(prob.particles, prob.horiz, prob.vert, lo, hi)
+        ss = SlabSim(prob, part, lo, hi, rank, world, device=local, capacity_factor=1.5)
+        ss.step(nsteps)
+        got = gather_by_id(ss.download(), n)
+        moved = ss.migrated_out
+        ss.close()
+    if rank != 0 or ref_npz is None or not os.path.exists(ref_npz):
+        return None
+    z = np.load(ref_npz)
+    errs = {}
+    for k in PARITY_FIELDS:
+        a, b = np.asarray(got[k]), z["b/" + k]
+        scale = max(float(np.max(np.abs(z["b/ep"] if k == "wrot" else b))), 1e-300)
+        errs[k] = float(np.max(np.abs(a - b))) / scale
+    same_elem = bool(np.array_equal(got["in_elem"], z["b/inElem"]))
+    return {"max_rel": max(errs.values()), "per_field": errs, "element_ids_identical": same_elem, "steps": nsteps, "particles": int(n),
+            "what": "this arm (%s) against the reference arm's CPU sample: %d^3-cell block, same start, %d steps; max |diff| / max |ref| per field"
+                    % ("1 GPU" if world == 1 else "%d z-slabs over NCCL" % world, ncell, nsteps)}
+
+
+def cpu_baseline(ncell, steps, dump=None):
+    d = time_reference(ncell, steps, dump=dump)
     if d is None:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     if "error" in d:

@@ -208,6 +208,12 @@ int mpmgpu_set_xpic(mpmgpu_ctx *ctx, int order, int using_fmpm);
  * fixedDirection symmetry-plane bits (32|64|128, ADJUST_COPIED_PK) or 0.  Call again whenever values change. */
 int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *norm,
                             const double *value, const int *active, const int *symdir);
+/* BCs next to a symmetry plane (<Horiz symmin=...>: Read_MPM/Generators.cpp:2178-2190) reflect the velocity of the node
+ * across the plane instead of imposing value[i]: v = value + ratio (value - n.pk_r/m_r) when node r has particles
+ * (NodalVelBC::AddVelocityBC -> NodalPoint::ReflectVelocityBC, NodalVelBC.cpp:196-210, CrackVelocityFieldSingle.cpp:133-144).
+ * reflected_node[i] = NodalVelBC::reflectedNode (1-based, <= 0 for a plain BC), ratio[i] = reflectRatio; same n and order
+ * as the list above; call after mpmgpu_set_velocity_bcs.  Runs on the per-task kernels (kernel_path 2 is refused). */
+int mpmgpu_set_velocity_bc_reflections(mpmgpu_ctx *ctx, int n, const int *reflected_node, const double *ratio);
 /* update only the values/active flags of the BC list set above (same n, same order) */
 int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const double *value, const int *active);
 /* velocities [3][n_rigid] of the rigid-BC particles (host order) for this step: the host evaluates the material's

@@ -26,7 +26,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
            "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
-           "mpmgpu_update_velocity_bc_values", "mpmgpu_update_rigid_velocities", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
+           "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_rigid_velocities", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
     "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times",
@@ -105,6 +105,7 @@ def load_library(path=None):
     lib.mpmgpu_set_xpic.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
     lib.mpmgpu_update_velocity_bc_values.argtypes = [vp, C.c_int, _dp, _ip]
+    lib.mpmgpu_set_velocity_bc_reflections.argtypes = [vp, C.c_int, _ip, _dp]
     lib.mpmgpu_update_rigid_velocities.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_step.argtypes = [vp, C.c_int]
     for t in TASKS + ["project_rigid_bcs"]:
@@ -205,6 +206,8 @@ class MpmGpu:
         self._check(self.lib.mpmgpu_set_materials(self.ctx, len(prob.materials), mats))
         self._check(self.lib.mpmgpu_set_time_step(self.ctx, prob.dt, prob.dt_strain_first, prob.dt_strain_last))
         self.set_velocity_bcs(prob.bc_node, prob.bc_norm, prob.bc_value, prob.bc_active, prob.bc_symdir)
+        if getattr(prob, "bc_reflected", None) is not None:
+            self.set_velocity_bc_reflections(prob.bc_reflected, prob.bc_ratio)
         if upload:
             self.upload(prob.particles)
 
@@ -246,6 +249,11 @@ class MpmGpu:
         node, norm, value = _c32(node), _c64(norm), _c64(value)
         active, symdir = _c32(active), _c32(symdir)
         self._check(self.lib.mpmgpu_set_velocity_bcs(self.ctx, n, _i(node), _d(norm), _d(value), _i(active), _i(symdir)))
+
+    def set_velocity_bc_reflections(self, reflected_node, ratio):
+        """Symmetry-plane BCs: per BC of the list the 1-based node it reflects (<= 0: plain BC) and the cell-size ratio."""
+        reflected_node, ratio = _c32(reflected_node), _c64(ratio)
+        self._check(self.lib.mpmgpu_set_velocity_bc_reflections(self.ctx, len(reflected_node), _i(reflected_node), _d(ratio)))
 
     def update_velocity_bc_values(self, value, active=None):
         value, active = _c64(value), _c32(active)

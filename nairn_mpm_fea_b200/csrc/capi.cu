@@ -52,7 +52,7 @@ struct mpmgpu_ctx {
     long long mstep;
     double mtime;
     long long launches;
-    bool uploaded, hasFext, hasBCs;
+    bool uploaded, hasFext, hasBCs, hasReflectedBCs;
     cudaStream_t ownStream; bool ownStreamSaved;
     const int *dlSlot, *dlSlotR;        // download slot maps: P.orig / PR.orig, or identity when ids are global
     bool globalIds;                     // particle ids are caller-global (slab mode): downloads come in device order + ids
@@ -139,7 +139,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->dim = is3D ? 3 : 2;
     ctx->dMats = NULL; ctx->nmat = 0; ctx->dFlags = NULL;
     ctx->cap = 0; ctx->mstep = 0; ctx->mtime = 0.; ctx->launches = 0;
-    ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->profiling = false; ctx->globalIds = false; ctx->ownStreamSaved = false;
+    ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->hasReflectedBCs = false; ctx->profiling = false; ctx->globalIds = false; ctx->ownStreamSaved = false;
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
     ctx->cpElemPool = NULL; ctx->cpXiPool = NULL; ctx->cpWgPool = NULL;
     ctx->nBCEntries = 0;
@@ -517,6 +517,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         ctx->tiled.stateKind = SK_ELASTIC;
         for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind != MAT_ISOTROPIC && ctx->hMats[i].kind != MAT_RIGIDBC) ctx->tiled.stateKind = SK_FULL;
         if (ctx->largeRotation) ok = false;     // large-rotation hypoelastic laws and Mooney live in the per-task strain kernel
+        if (ctx->hasReflectedBCs) ok = false;   // symmetry-plane BCs read the momentum of the node across the plane: per-task kernels
         if (ctx->R.mirrored) ok = false;        // a mirrored rigid BC reads a neighbour node's momentum between the node updates: per-task kernels
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
@@ -597,6 +598,7 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
     CK(cudaMemcpy(da, ac.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dnm, nm.data(), 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dva, va.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->B.refl = NULL; ctx->B.reflRatio = NULL;
     ctx->B.nUnique = nu; ctx->B.node = dn; ctx->B.start = ds; ctx->B.symdir = dsd; ctx->B.active = da; ctx->B.norm = dnm; ctx->B.value = dva;
     {   // node -> BC group lookup for the fused node sweeps
         std::vector<int> of(ctx->g.nnodes, -1);
@@ -606,6 +608,34 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
         CK(cudaMemcpy(dof, of.data(), (size_t)ctx->g.nnodes * sizeof(int), cudaMemcpyHostToDevice));
         ctx->tiled.FN.bcOfNode = dof;
     }
+    return MPMGPU_OK;
+}
+
+// Symmetry-plane BCs (<Horiz symmin=...>, Generators.cpp:2178-2190): entry i of the list set by mpmgpu_set_velocity_bcs
+// reflects node reflected_node[i] (1-based; <= 0: a plain BC) with the cell-size ratio ratio[i].
+extern "C" int mpmgpu_set_velocity_bc_reflections(mpmgpu_ctx *ctx, int n, const int *reflected_node, const double *ratio)
+{
+    if (!ctx || n != ctx->nBCEntries) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bc_reflections: n=%d but %d BCs are set", n, ctx ? ctx->nBCEntries : 0);
+    if (n == 0) return MPMGPU_OK;
+    if (!reflected_node || !ratio) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bc_reflections: null arrays");
+    cudaSetDevice(ctx->cfg.device);
+    std::vector<int> re(n); std::vector<double> ra(n);
+    bool any = false;
+    for (int e = 0; e < n; e++) {
+        const int i = ctx->bcOrder[e];
+        if (reflected_node[i] > ctx->g.nnodes) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bc_reflections: BC %d reflects node %d of %d", i, reflected_node[i], ctx->g.nnodes);
+        re[e] = reflected_node[i] > 0 ? reflected_node[i] - 1 : -1; ra[e] = ratio[i];
+        any |= re[e] >= 0;
+    }
+    if (!any) { ctx->B.refl = NULL; ctx->B.reflRatio = NULL; return MPMGPU_OK; }
+    if (ctx->cfg.kernel_path == 2) return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) cannot apply reflected (symmetry-plane) velocity BCs");
+    int *dre; double *dra;
+    CK(dalloc(ctx, &dre, n)); CK(dalloc(ctx, &dra, n));
+    CK(cudaMemcpy(dre, re.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dra, ra.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->B.refl = dre; ctx->B.reflRatio = dra;
+    ctx->hasReflectedBCs = true;
+    ctx->tiled.enabled = 0;         // the reflected node's momentum must be complete before the BC reads it: per-task kernels
     return MPMGPU_OK;
 }
 

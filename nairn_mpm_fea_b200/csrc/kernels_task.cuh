@@ -109,8 +109,12 @@ __device__ __forceinline__ void bc_add(int pass, double dt, double mass, double 
 }
 
 // BC application for one node: its entries are walked in list order, first the zero pass over all of
-// them, then the add pass (VelocityBCLoop)
-__device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3])
+// them, then the add pass (VelocityBCLoop).  A BC next to a symmetry plane REFLECTS the velocity of the node on the other
+// side of the plane (NodalVelBC::AddVelocityBC -> NodalPoint::ReflectVelocityBC, NodalVelBC.cpp:196-210,
+// CrackVelocityFieldSingle.cpp:133-144): v = v0 + ratio (v0 - n.pk_r / m_r) when that node has particles, else v0.
+// Only the per-task kernels pass N (the reflected node's momentum has to be complete: its own BCs act on other
+// components); contexts with reflected BCs do not use the fused node sweeps.
+__device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3], const Nodes *N = nullptr)
 {
     const int e0 = B.start[u], e1 = B.start[u + 1];
     for (int e = e0; e < e1; e++) {
@@ -119,7 +123,16 @@ __device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, doubl
     }
     for (int e = e0; e < e1; e++) {
         if (!B.active[e]) continue;
-        bc_add(pass, dt, mass, B.value[e], B.norm[3 * e], B.norm[3 * e + 1], B.norm[3 * e + 2], pk, ft);
+        const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
+        double v = B.value[e];
+        if (N && B.refl && B.refl[e] >= 0) {
+            const int r = B.refl[e];
+            if (N->cnt[r] > 0) {
+                const double dotn = nx * N->pk[0][r] + ny * N->pk[1][r] + nz * N->pk[2][r];
+                v = v + B.reflRatio[e] * (v - dotn / N->mass[r]);
+            }
+        }
+        bc_add(pass, dt, mass, v, nx, ny, nz, pk, ft);
     }
 }
 
@@ -188,7 +201,7 @@ __global__ void k_velocity_bcs(VelBCs B, Nodes N, int pass, double dt, int adjus
     }
     double pk[3] = {N.pk[0][nd], N.pk[1][nd], N.pk[2][nd]};
     double ft[3] = {N.ftot[0][nd], N.ftot[1][nd], N.ftot[2][nd]};
-    node_bcs(B, u, pass, dt, N.mass[nd], pk, ft);
+    node_bcs(B, u, pass, dt, N.mass[nd], pk, ft, &N);
     N.pk[0][nd] = pk[0]; N.pk[1][nd] = pk[1]; N.pk[2][nd] = pk[2];
     N.ftot[0][nd] = ft[0]; N.ftot[1][nd] = ft[1]; N.ftot[2][nd] = ft[2];
 }

@@ -106,6 +106,8 @@ struct VelBCs {
     const double *norm;      // [3*nEntries]
     const double *value;     // [nEntries]
     const int *active;       // [nEntries]
+    const int *refl;         // [nEntries] 0-based node whose velocity a symmetry-plane BC reflects, -1 = plain BC; NULL = none at all
+    const double *reflRatio; // [nEntries] cell-size ratio across the plane (NodalVelBC::reflectRatio)
 };
 
 // Velocity BCs made by rigid-BC particles (ProjectRigidBCsTask.cpp:39-158): per node and direction the

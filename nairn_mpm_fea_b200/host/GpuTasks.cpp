@@ -395,7 +395,8 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (mpmgpu_set_time_step(gCtx, timestep, strainTimestepFirst, strainTimestepLast) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
 
     // grid velocity BCs in list order
-    std::vector<int> bnode, bact, bsym; std::vector<double> bnorm, bval;
+    std::vector<int> bnode, bact, bsym, brefl; std::vector<double> bnorm, bval, bratio;
+    bool anyReflected = false;
     for (NodalVelBC *bc = firstVelocityBC; bc != NULL; bc = (NodalVelBC *)bc->GetNextObject()) {
         gBCs.push_back(bc);
         bnode.push_back(bc->nodeNum);
@@ -404,9 +405,14 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         bval.push_back(bact.back() ? bc->BCValue(mtime) : 0.);
         bsym.push_back(nd[bc->nodeNum]->fixedDirection & ANYSYMMETRYPLANE_DIRECTION);
         if (bc->style != CONSTANT_VALUE || bc->GetBCFirstTime() > 0.) gBCsVary = true;
-        if (bc->reflectedNode >= 0) return "reflected (mirrored) velocity BCs";
+        // symmetry-plane neighbours reflect the node across the plane (Generators.cpp:2178-2190); BCs that rigid particles
+        // would mirror at run time (SetMirroredVelBC) are handled by the device's rigid-BC projection instead
+        brefl.push_back(bc->reflectedNode); bratio.push_back(bc->reflectRatio);
+        if (bc->reflectedNode >= 0) anyReflected = true;
     }
     if (mpmgpu_set_velocity_bcs(gCtx, (int)bnode.size(), bnode.data(), bnorm.data(), bval.data(), bact.data(), bsym.data()) != MPMGPU_OK)
+        return mpmgpu_last_error(gCtx);
+    if (anyReflected && mpmgpu_set_velocity_bc_reflections(gCtx, (int)bnode.size(), brefl.data(), bratio.data()) != MPMGPU_OK)
         return mpmgpu_last_error(gCtx);
 
     // swap the CPU task objects for GPU ones, keeping order and names (custom-task runner stays)

@@ -42,6 +42,8 @@ class Problem:
         self.bc_value = np.zeros(0)
         self.bc_active = np.zeros(0, np.int32)
         self.bc_symdir = np.zeros(0, np.int32)
+        self.bc_reflected = None        # per BC: 1-based node across a symmetry plane (NodalVelBC::reflectedNode) or -1; None = no such BCs
+        self.bc_ratio = None            # per BC: NodalVelBC::reflectRatio
         self.particles = {}
 
     @property
@@ -342,4 +344,11 @@ def from_reference_dump(z, snapshot="p0"):
     pr.bc_symdir = np.zeros(nb, np.int32)
     pr.bc_style = z["velbcs/style"]
     pr.bc_ftime = z["velbcs/ftime"]
+    if "velbcs/reflected" in z and np.any(z["velbcs/reflected"] > 0):
+        # symmetry planes (<Horiz symmin=...>): the plane's nodes carry the symmetry bits of NodalPoint::fixedDirection
+        # (32|64|128, ADJUST_COPIED_PK), their outer neighbours reflect the inner ones (Generators.cpp:2150-2260)
+        pr.bc_reflected = z["velbcs/reflected"].astype(np.int32)
+        pr.bc_ratio = z["velbcs/ratio"].astype(np.float64)
+        fixed = z["n1/fixedDirection"] if "n1/fixedDirection" in z else z["s1/t0/nodes/fixedDirection"]
+        pr.bc_symdir = (fixed[pr.bc_node - 1] & (32 | 64 | 128)).astype(np.int32)
     return pr

@@ -43,6 +43,7 @@ typedef struct {
     int *fixedDirection;            /* NodalPoint::fixedDirection bits x=1, y=2, z=4 */
     int *bcDir;
     int *bcMirror, *bcReflect;      /* rigid BCs: node spacing towards the mirrored side (0 = none), reflected node this step or -1 */
+    double *gridRatio;              /* grid BCs next to a symmetry plane: bcReflect = the node across the plane (set once), reflectRatio */
     int *bcNode; double *bcNorm, *bcValue; int *bcActive, *bcSym;
     double dt, dtFirst, dtLast;
     long long mstep;
@@ -439,6 +440,12 @@ static void velocity_bc_loop(int pass)
             const NodeField *r = &O->nd[O->bcReflect[b] - 1];
             if (r->numberPoints <= 0) continue;
             vel = vel + 1. * (vel - (n[0] * r->pk.x + n[1] * r->pk.y + n[2] * r->pk.z) / r->mass);
+        } else if (b < O->nbcGrid && O->bcReflect[b] >= 0) {
+            /* symmetry-plane neighbour (Generators.cpp:2178-2190): NodalPoint::ReflectVelocityBC, NodalPointMPM.cpp:1865-1881 --
+               a reflected node without particles gives the plain BC */
+            const NodeField *r = &O->nd[O->bcReflect[b] - 1];
+            if (r->numberPoints > 0)
+                vel = vel + O->gridRatio[b] * (vel - (n[0] * r->pk.x + n[1] * r->pk.y + n[2] * r->pk.z) / r->mass);
         }
         if (pass == GRID_FORCES_CALL) {
             double s = f->mass * vel / dt;
@@ -1637,6 +1644,9 @@ static const taskfn TASKS[11] = {task_initialization, task_mass_and_momentum, ta
 static double *dupd(const double *src, size_t n) { double *d = (double *)calloc(n ? n : 1, sizeof(double)); if (src) memcpy(d, src, n * sizeof(double)); return d; }
 static int *dupi(const int *src, size_t n, int fill) { int *d = (int *)malloc((n ? n : 1) * sizeof(int)); for (size_t i = 0; i < n; i++) d[i] = src ? src[i] : fill; return d; }
 
+/* NodalVelBC::reflectedNode (1-based, <= 0 none) and reflectRatio of the grid BCs, in list order */
+int oracle_set_bc_reflections(int n, const int *reflected, const double *ratio);
+
 int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mats, const mpmgpu_particles *h,
                   int nbc, const int *bcNode, const double *bcNorm, const double *bcValue, const int *bcActive, const int *bcSym,
                   double dt, double dtFirst, double dtLast)
@@ -1668,6 +1678,7 @@ int oracle_create(const mpmgpu_config *cfg, int nmat, const mpmgpu_material *mat
     O->nbcGrid = nbc; O->bcCap = nbc;
     O->bcDir = dupi(NULL, nbc, 0);
     O->bcMirror = dupi(NULL, nbc, 0); O->bcReflect = dupi(NULL, nbc, -1);
+    O->gridRatio = dupd(NULL, nbc);
     O->fixedDirection = (int *)calloc(O->nnodes, sizeof(int));
     for (int b = 0; b < nbc; b++) {            /* NodalVelBC.cpp:40-45: direction bits of the grid BCs */
         int bits = bcSym ? bcSym[b] & 7 : 0;
@@ -1807,7 +1818,14 @@ void oracle_destroy(void)
     free(O->pos); free(O->vel); free(O->mp); free(O->lp); free(O->ncpos); free(O->sp); free(O->pressure); free(O->ep);
     free(O->wrot); free(O->eplast); free(O->energies); free(O->hist); free(O->pfext); free(O->acc);
     free(O->inElem); free(O->matnum); free(O->cross); free(O->nd);
-    free(O->bcNode); free(O->bcNorm); free(O->bcValue); free(O->bcActive); free(O->bcSym); free(O->bcDir); free(O->fixedDirection); free(O->bcMirror); free(O->bcReflect);
+    free(O->bcNode); free(O->bcNorm); free(O->bcValue); free(O->bcActive); free(O->bcSym); free(O->bcDir); free(O->fixedDirection); free(O->bcMirror); free(O->bcReflect); free(O->gridRatio);
     free(O);
     O = NULL;
+}
+
+int oracle_set_bc_reflections(int n, const int *reflected, const double *ratio)
+{
+    if (!O || n != O->nbcGrid) return 1;
+    for (int b = 0; b < n; b++) { O->bcReflect[b] = reflected[b] > 0 ? reflected[b] : -1; O->gridRatio[b] = ratio[b]; }
+    return 0;
 }

@@ -66,6 +66,10 @@ class PortOracle:
         rc = self.lib.oracle_create(C.byref(cfg), len(prob.materials), mats, C.byref(v), len(bn), _i(bn), _d(bnorm), _d(bval),
                                     _i(bact), _i(bsym), prob.dt, prob.dt_strain_first, prob.dt_strain_last)
         assert rc == 0
+        if getattr(prob, "bc_reflected", None) is not None:
+            refl, ratio = _c32(prob.bc_reflected), _c64(prob.bc_ratio)
+            self.lib.oracle_set_bc_reflections.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+            assert self.lib.oracle_set_bc_reflections(len(refl), _i(refl), _d(ratio)) == 0
 
     def set_xpic(self, order, using_fmpm):
         assert self.lib.oracle_set_xpic(int(order), int(using_fmpm)) == 0

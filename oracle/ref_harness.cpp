@@ -300,6 +300,15 @@ void ref_get_velbcs(int *node, int *dir, int *style, double *norm, double *value
     }
 }
 
+// per BC: NodalVelBC::reflectedNode (1-based node across a symmetry plane, -1 none) and reflectRatio
+void ref_get_velbc_reflections(int *reflected, double *ratio)
+{
+    int k = 0;
+    for (NodalVelBC *bc = firstVelocityBC; bc != NULL; bc = (NodalVelBC *)bc->GetNextObject(), k++) {
+        reflected[k] = bc->reflectedNode; ratio[k] = bc->reflectRatio;
+    }
+}
+
 // material facts. ids[i] = MaterialID(); params: 32 doubles per material, meaning by type
 //  all:   0 rho  1 heatCapacity(Cv)  2 field  3 damping-or-(-1)  4 rigid flag
 //  iso(1):      8 E 9 nu 10 G 11 CTE3 12 gamma0 13 useLargeRotation  14.. C11 C12 C44 (specific, /rho) from pr

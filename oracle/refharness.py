@@ -119,10 +119,11 @@ class RefRun:
         n = self.lib.ref_num_velbcs()
         o = dict(node=np.zeros(n, np.int32), dir=np.zeros(n, np.int32), style=np.zeros(n, np.int32),
                  norm=np.zeros((n, 3)), value=np.zeros(n), ftime=np.zeros(n), offset=np.zeros(n),
-                 currentValue=np.zeros(n))
+                 currentValue=np.zeros(n), reflected=np.full(n, -1, np.int32), ratio=np.ones(n))
         if n:
             self.lib.ref_get_velbcs(_ip(o["node"]), _ip(o["dir"]), _ip(o["style"]), _dp(o["norm"]),
                                     _dp(o["value"]), _dp(o["ftime"]), _dp(o["offset"]), _dp(o["currentValue"]))
+            self.lib.ref_get_velbc_reflections(_ip(o["reflected"]), _dp(o["ratio"]))
         return o
 
     def materials(self):
@@ -212,7 +213,7 @@ def run_reference(xml_text_or_path, snaps=(1,), per_task_steps=0, nprocs=1, work
            ",".join(str(s) for s in sorted(snaps)), str(per_task_steps), repr(jitter_amp), repr(vel_amp)]
     p = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
     if p.returncode != 0:
-        raise RuntimeError("reference worker failed:\n%s\n%s" % (p.stdout[-2000:], p.stderr[-2000:]))
+        raise RuntimeError("reference worker failed (rc %d):\n%s\n%s" % (p.returncode, p.stdout[-2000:], p.stderr[-2000:]))
     with np.load(out) as z:
         return {k: z[k] for k in z.files}
 

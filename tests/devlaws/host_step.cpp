@@ -31,7 +31,8 @@ struct EmuSim {
     VelBCs B;
     bool hasBCs;
     std::vector<int> bcNode, bcStart, bcSym, bcActive, bcOfNode;
-    std::vector<double> bcNorm, bcValue;
+    std::vector<double> bcNorm, bcValue, bcRatio;
+    std::vector<int> bcRefl, bcOrder;
     int dim, shape, n;
     bool largeRotation;
     long long mstep;
@@ -318,8 +319,19 @@ extern "C" void emu_set_bcs(void *h, int n, const int *node, const double *norm,
     S->bcStart.push_back(n);
     S->B.nUnique = (int)S->bcNode.size(); S->B.node = S->bcNode.data(); S->B.start = S->bcStart.data(); S->B.symdir = S->bcSym.data();
     S->B.active = S->bcActive.data(); S->B.norm = S->bcNorm.data(); S->B.value = S->bcValue.data();
+    S->B.refl = NULL; S->B.reflRatio = NULL;
+    S->bcOrder = order;
     S->bcOfNode.assign((size_t)S->g.nnodes, -1);
     for (int u = 0; u < S->B.nUnique; u++) S->bcOfNode[S->bcNode[u]] = u;
+}
+
+// capi.cu::mpmgpu_set_velocity_bc_reflections
+extern "C" void emu_set_bc_reflections(void *h, int n, const int *reflected, const double *ratio)
+{
+    EmuSim *S = (EmuSim *)h;
+    S->bcRefl.assign(n, -1); S->bcRatio.assign(n, 1.);
+    for (int e = 0; e < n; e++) { const int i = S->bcOrder[e]; S->bcRefl[e] = reflected[i] > 0 ? reflected[i] - 1 : -1; S->bcRatio[e] = ratio[i]; }
+    S->B.refl = S->bcRefl.data(); S->B.reflRatio = S->bcRatio.data();
 }
 
 extern "C" void emu_set_xpic(void *h, int order, int usingFMPM) { EmuSim *S = (EmuSim *)h; S->sp.xpicOrder = order; S->sp.usingFMPM = usingFMPM; }

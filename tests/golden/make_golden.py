@@ -27,6 +27,13 @@ CASES = {
     # name: (xml text, snapshots, per-task steps[, position jitter, velocity jitter])
     "block3d_jitter": (inputs.block3d(ncell=5, margin=3, E=100.0, vx=3.0e3, vy=-2.0e3, vz=-6.0e3), (1, 20, 60), 1, 0.35, 4000.0),
     "disks2d_ugimp_planestrain": (inputs.disks2d(analysis=10, gimp="uGIMP"), (1, 100), 1),
+    # symmetry planes (config 1: the reference's TwoDisks input has them on all four grid edges): the left disk hits the plane
+    # x = 0 (its mirror image), a second plane along y = -6 touches it from below; the BCs beside the planes reflect
+    "disks2d_symmetry_planes": (inputs.disks2d(analysis=10, gimp="uGIMP", vel=3000.0, hmax=16.0, vmax=9.0)
+                                .replace('<Horiz cellsize="1.0"/><Vert cellsize="1.0"/>', '<Horiz cellsize="1.0" symmax="0"/><Vert cellsize="1.0" symmin="-6"/>')
+                                .replace('<Grid xmin="-16.0" xmax="16.0" ymin="-9.0"', '<Grid xmin="-16.0" xmax="2.0" ymin="-7.0"')
+                                .split('<Body matname="Disk 2"')[0] + '</MaterialPoints>' +
+                                inputs.disks2d(analysis=10, gimp="uGIMP", vel=3000.0).split('</MaterialPoints>')[1], (1, 2, 100), 2),
     "disks2d_linear_planestress": (inputs.disks2d(analysis=11, gimp=None, method=2), (1, 100), 1),
     "block3d_neohookean": (inputs.block3d(ncell=4, margin=3, material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3), (1, 60), 1, 0.3, 2000.0),
     "block3d_neohookean_uj1": (inputs.block3d(ncell=3, margin=3, material=inputs.neohookean_material(ujoption=1), vz=-8.0e3), (1, 40), 1),

@@ -47,7 +47,7 @@ def lib():
                         src, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.emu_create.restype = C.c_void_p
-    for f in ("emu_set_bcs", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
+    for f in ("emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
         getattr(lib, f).argtypes = None
     return lib
 
@@ -87,6 +87,9 @@ class EmuSim:
             self._bc = [c(prob.bc_node, dtype=np.int32), c(prob.bc_norm, dtype=np.float64), c(prob.bc_value, dtype=np.float64),
                         c(prob.bc_active, dtype=np.int32), c(prob.bc_symdir, dtype=np.int32)]
             lib.emu_set_bcs(self.h, nb, _ip(self._bc[0]), _dp(self._bc[1]), _dp(self._bc[2]), _ip(self._bc[3]), _ip(self._bc[4]))
+            if getattr(prob, "bc_reflected", None) is not None:
+                self._bc += [c(prob.bc_reflected, dtype=np.int32), c(prob.bc_ratio, dtype=np.float64)]
+                lib.emu_set_bc_reflections(self.h, nb, _ip(self._bc[5]), _dp(self._bc[6]))
         self.nnodes = (prob.horiz + 1) * (prob.vert + 1) * ((prob.depth + 1) if prob.is3d else 1)
 
     def set_xpic(self, order, fmpm):

@@ -7,7 +7,7 @@ import pytest
 from tests.parity import (LR3D_CASES, TASK_MAP, TOL_1STEP, compare_nodes, compare_particles, load_golden, per_task_steps,
                           tolerances, xpic_for_step)
 
-CASES = ["block3d_isoplastic_nonlinear", "block3d_isoplastic_nonlinear2_soft", "block3d_johnsoncook", "disks2d_johnsoncook_planestress", "disks2d_nonlinear_planestrain_lr", "disks2d_nonlinear2_planestress", "block3d_b2spline", "block3d_b2gimp", "block3d_b2gimp_rigid_wall", "disks2d_b2spline", "disks2d_b2gimp_planestress", "block3d_b2cpdi", "disks2d_b2cpdi", "block3d_mooney", "block3d_mooney_uj2", "disks2d_mooney_planestrain", "disks2d_mooney_planestress", "disks2d_mooney_planestress_uj0", "block3d_free_ugimp", "block3d_free_lcpdi_xpic2", "disks2d_neo_planestress", "disks2d_neo_planestress_av", "block3d_isoplastic_softening", "block3d_material_pdamping", "block3d_isotropic_lr", "block3d_isoplastic_lr", "disks2d_lr_planestrain", "disks2d_lr_planestress", "disks2d_rigid_plate", "block3d_rigid_mirrored", "block3d_lcpdi_rigid_wall", "disks2d_isoplastic_planestress", "block3d_pic", "block3d_fmpm1", "block3d_usavg_minus", "block3d_usavg_minus_xpic2", "block3d_usl_minus_fmpm2", "block3d_usf_fmpm2",
+CASES = ["disks2d_symmetry_planes", "block3d_isoplastic_nonlinear", "block3d_isoplastic_nonlinear2_soft", "block3d_johnsoncook", "disks2d_johnsoncook_planestress", "disks2d_nonlinear_planestrain_lr", "disks2d_nonlinear2_planestress", "block3d_b2spline", "block3d_b2gimp", "block3d_b2gimp_rigid_wall", "disks2d_b2spline", "disks2d_b2gimp_planestress", "block3d_b2cpdi", "disks2d_b2cpdi", "block3d_mooney", "block3d_mooney_uj2", "disks2d_mooney_planestrain", "disks2d_mooney_planestress", "disks2d_mooney_planestress_uj0", "block3d_free_ugimp", "block3d_free_lcpdi_xpic2", "disks2d_neo_planestress", "disks2d_neo_planestress_av", "block3d_isoplastic_softening", "block3d_material_pdamping", "block3d_isotropic_lr", "block3d_isoplastic_lr", "disks2d_lr_planestrain", "disks2d_lr_planestress", "disks2d_rigid_plate", "block3d_rigid_mirrored", "block3d_lcpdi_rigid_wall", "disks2d_isoplastic_planestress", "block3d_pic", "block3d_fmpm1", "block3d_usavg_minus", "block3d_usavg_minus_xpic2", "block3d_usl_minus_fmpm2", "block3d_usf_fmpm2",
          "block3d_neohookean_av", "block3d_isoplastic_av", "block3d_rigid_wall", "block3d_rigid_piston", "block3d_rigid_linear_xpic2", "block3d_lcpdi_neo_xpic2", "block3d_lcpdi_rcrit", "disks2d_lcpdi", "disks2d_qcpdi", "block3d_xpic3", "block3d_fmpm2", "disks2d_fmpm3_neo", "block3d_neohookean", "block3d_neohookean_uj1", "block3d_isoplastic", "disks2d_neohookean", "disks2d_isoplastic",
          "disks2d_ugimp_planestrain", "disks2d_linear_planestress", "block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
          "block3d_ugimp_usf"]
