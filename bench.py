@@ -286,31 +286,36 @@ def run_ours(args):
                 "task_ms": task_ms}
 
     # ---- end to end through the public API with HOST buffers ------------------------------------
-    # One archive interval: upload the full particle state from pinned host memory, run K steps with
-    # the per-step BC values going H2D and the status word coming D2H, download the full state.
+    # One archive interval of a run, every byte through host memory: upload the particle state an input file defines (positions,
+    # velocities, masses, sizes, elements, materials: a fresh body has no stress or strain yet, so those arrays are not sent --
+    # mpmgpu_upload_particles zero-fills them on the device) from pinned host memory, run K steps with the per-step BC values
+    # going H2D and the status word coming D2H, then write one particle archive: the records (the reference's binary format,
+    # <MPMArchiveOrder> of the reference's examples: position, velocity, stress, strain, work and strain energy, element
+    # crossings) are packed on the device and only they come back.
     pt = prob.particles
+    lean_keys = ("pos", "vel", "mp", "lp", "in_elem", "matnum", "ids")
     pinned = {}
     for k, v in pt.items():
         if isinstance(v, np.ndarray):
-            tt_ = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
-            pinned[k] = tt_.numpy()
+            if k in lean_keys:
+                pinned[k] = torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
         else:
             pinned[k] = v
     nb = len(prob.bc_value)
     bcv = np.zeros(nb)
-    dl = MpmGpu.pinned_download_buffers(prob.nparticles) if world == 1 else None     # slabs: particle count changes by migration
+    ARCHIVE_ORDER = "iYYYYNNNNNNNYNNNNY"
+    rec = sim.archive_record_size(ARCHIVE_ORDER)
+    arch = torch.empty(int(rec * n * (1.3 if world > 1 else 1.0)) + 4096, dtype=torch.uint8).pin_memory().numpy()    # slabs: particle count changes by migration
     barrier()
     t0 = time.perf_counter()
-    if world > 1:
-        n_now = sim.num_particles()
-        if n_now != n:          # particles migrated during the device-resident run: re-upload this rank's original block
-            pass
     sim.upload(pinned)
     for _ in range(args.steps):
         sim.update_velocity_bc_values(bcv, prob.bc_active)
         stepper.step(1)
         st = sim.status()
-    out = sim.download(out=dl)
+    n_now = sim.num_particles()
+    sim.pack_archive(ARCHIVE_ORDER, out=arch)
+    ids = sim.download_ids() if world > 1 else None        # slabs: the records come in device order, the ids say whose they are
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -318,12 +323,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     up_bytes = host_state_bytes(pinned)
-    down_bytes = sum(v.nbytes for v in out.values())
+    down_bytes = rec * n_now + (4 * n_now if world > 1 else 0)
     e2e = {"value": total_particles * args.steps / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": (up_bytes / args.steps + nb * 12) * world,
            "d2h_bytes_per_step": (down_bytes / args.steps + 32) * world,
-           "what": "upload full particle state (pinned host) + %d steps with per-step BC values H2D and status D2H "
-                   "+ download full particle state, wall clock" % args.steps}
+           "what": "one archive interval through host memory: upload of the input state (pos, vel, mp, lp, element, material; pinned host) "
+                   "+ %d steps with per-step BC values H2D and status D2H + one particle archive (%d-byte records '%s' packed on the device) "
+                   "D2H, wall clock" % (args.steps, rec, ARCHIVE_ORDER)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if taylor else "weak", "vs_baseline": None,

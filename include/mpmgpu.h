@@ -303,10 +303,17 @@ int mpmgpu_set_stream(mpmgpu_ctx *ctx, void *cuda_stream);
  * The 64-byte file header (ArchiveData.cpp:464-489) is the host's to write (nairn_mpm_fea_b200/archive.py::header). */
 int mpmgpu_archive_record_size(const mpmgpu_ctx *ctx, const char *order);      /* bytes per particle, or -1 */
 /* constants the records carry and the step does not: original positions [3][n] and initial material angles [3][n]
- * (z, y, x; radians) in the caller's order, either may be NULL (records then repeat the current position / use 0);
- * thickness: 2D particle thickness.  Call once after mpmgpu_upload_particles. */
+ * (z, y, x; radians) in the caller's order; thickness: 2D particle thickness.  Defaults without this call: the positions
+ * at mpmgpu_upload_particles, zero angles, mpmgpu_config.thickness.  Either array may be NULL (keeps the default).
+ * Call after mpmgpu_upload_particles. */
 int mpmgpu_set_archive_origin(mpmgpu_ctx *ctx, const double *origpos, const double *angles0, double thickness);
+/* The "temperature" item writes the temperature of the particle's last strain update; this path is isothermal (particle
+ * temperatures other than the stress-free one are refused by the adapter), so it equals ArchiveData.cpp:976's pTemperature.
+ * One slab of a multi-GPU run packs ITS particles in device order (mpmgpu_download_ids gives the ids in the same order);
+ * the original-position column then repeats the current position (the caller's constants are indexed by its own order). */
 int mpmgpu_pack_archive(mpmgpu_ctx *ctx, const char *order, void *records, size_t capacity_bytes);
+/* particle ids in device order: the ids handed over at upload (slab mode) or the caller's particle index */
+int mpmgpu_download_ids(mpmgpu_ctx *ctx, int *ids, int capacity);
 
 /* Raw sums behind the reference's GlobalQuantity rows (Global_Quantities/GlobalQuantity.cpp:394-1075) over the non-rigid
  * particles, per material: sums[m * MPMGPU_GS_NSUMS + k], internal units; the host divides the volume-weighted ones by

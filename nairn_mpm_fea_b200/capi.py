@@ -34,7 +34,7 @@ EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last
     "mpmgpu_slab_migration_buffers", "mpmgpu_slab_pack_migrants", "mpmgpu_slab_finish_migration",
     "mpmgpu_num_particles", "mpmgpu_set_stream",
     "mpmgpu_left_grid_counts",
-    "mpmgpu_archive_record_size", "mpmgpu_set_archive_origin", "mpmgpu_pack_archive", "mpmgpu_global_sums"]
+    "mpmgpu_archive_record_size", "mpmgpu_set_archive_origin", "mpmgpu_pack_archive", "mpmgpu_global_sums", "mpmgpu_download_ids"]
 
 HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)     # mpmgpu_halo_fn
 _dp = C.POINTER(C.c_double)
@@ -136,6 +136,7 @@ def load_library(path=None):
     lib.mpmgpu_set_archive_origin.argtypes = [vp, _dp, _dp, C.c_double]
     lib.mpmgpu_pack_archive.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.mpmgpu_global_sums.argtypes = [vp, _dp]
+    lib.mpmgpu_download_ids.argtypes = [vp, _ip, C.c_int]
     if lib.mpmgpu_abi_version() != ABI_VERSION:
         raise MpmGpuError(-1, "libmpmgpu ABI %d, binding expects %d" % (lib.mpmgpu_abi_version(), ABI_VERSION))
     if path == LIB_PATH:
@@ -333,13 +334,12 @@ class MpmGpu:
         return out
 
     # ---- output side on the device ----
-    def set_archive_origin(self, origpos=None, angles0=None, thickness=1.0):
+    def set_archive_origin(self, origpos=None, angles0=None, thickness=None):
         """Constants of the archive records: original positions [3][n], initial material angles [3][n] (z, y, x; radians),
-        2D thickness.  Defaults: the positions in the problem this context was made from, zero angles."""
-        if origpos is None:
-            origpos = self.prob.particles["pos"]
+        2D thickness.  Without this call (or for None): the positions at upload, zero angles, the problem's thickness."""
         self._keep_arch = [_c64(origpos), _c64(angles0)]
-        self._check(self.lib.mpmgpu_set_archive_origin(self.ctx, _d(self._keep_arch[0]), _d(self._keep_arch[1]), float(thickness)))
+        self._check(self.lib.mpmgpu_set_archive_origin(self.ctx, _d(self._keep_arch[0]), _d(self._keep_arch[1]),
+                                                       float(self.prob.thickness if thickness is None else thickness)))
 
     def archive_record_size(self, order):
         return int(self.lib.mpmgpu_archive_record_size(self.ctx, order.encode("latin-1")))
@@ -354,6 +354,12 @@ class MpmGpu:
         buf = np.empty(nbytes, np.uint8) if out is None else out
         self._check(self.lib.mpmgpu_pack_archive(self.ctx, order.encode("latin-1"), buf.ctypes.data_as(C.c_void_p), buf.nbytes))
         return buf[:nbytes].tobytes() if out is None else buf
+
+    def download_ids(self):
+        """Particle ids in device order (slab mode: global ids, the order of pack_archive's records there)."""
+        ids = np.zeros(self.num_particles(), np.int32)
+        self._check(self.lib.mpmgpu_download_ids(self.ctx, _i(ids), len(ids)))
+        return ids
 
     def global_sums(self):
         """[nmat][GS_NSUMS] raw sums behind the reference's GlobalQuantity rows (see include/mpmgpu.h MPMGPU_GS_*)."""

@@ -177,12 +177,13 @@ __host__ __device__ inline void global_summands(const Particles &P, int p, const
 #define ARCHIVE_THREADS 256
 
 // records of one particle set (non-rigid or rigid-BC) into the caller-ordered record block
-__global__ void __launch_bounds__(ARCHIVE_THREADS) k_pack_archive(int cnt, Particles P, const int *slot, const Material *mats, ArchiveLayout L,
+// (slot == NULL: device order, record base + p)
+__global__ void __launch_bounds__(ARCHIVE_THREADS) k_pack_archive(int cnt, Particles P, const int *slot, int base, const Material *mats, ArchiveLayout L,
                                                                    uint32_t *records)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= cnt) return;
-    const int o = slot[p];
+    const int o = slot ? slot[p] : base + p;
     archive_record(P, p, o, mats, L, records + (size_t)o * L.recWords);
 }
 

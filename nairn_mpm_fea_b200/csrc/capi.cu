@@ -21,6 +21,9 @@
 
 static std::string g_create_error;
 
+// result of the device-side check of an upload (k_validate_upload): lowest offending particle per rule, or 0x7fffffff
+struct UploadCheck { int badMat, badElem, notRigid, rigidEarly, lpLarge, lpVaries; };
+
 enum { T_INIT = 0, T_MASSMOM, T_POSTEXTRAP, T_USF, T_FORCES, T_POSTFORCES, T_MOMENTA, T_PARTICLES, T_USL, T_RESET, T_NTASKS };
 
 struct mpmgpu_ctx {
@@ -60,6 +63,10 @@ struct mpmgpu_ctx {
     bool largeRotation = false;         // some material needs the extended law dispatch (Elastic::useLargeRotation, Mooney): per-task kernels, k_update_strains_lr
     double *archOrigin = NULL, *archAngles = NULL;   // [3][n] caller order, for the archive records (mpmgpu_set_archive_origin)
     double archThickness = 1.;
+    bool archOriginFromCaller = false;
+    size_t archOriginLen = 0;
+    UploadCheck *dUploadCheck = NULL;
+    double *stage = NULL; size_t stageLen = 0;       // staging buffer of uploads/downloads (grown on demand, freed with the context)
     uint32_t *archBuf = NULL; size_t archBufWords = 0;
     double *gsumBuf = NULL; size_t gsumBufLen = 0;
     std::string err;
@@ -101,7 +108,8 @@ static cudaError_t dalloc(mpmgpu_ctx *ctx, T **p, size_t n)
 
 static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
 
-#define LAUNCH(kernel, grid, block, ...) do { kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } while (0)
+// (a grid computed from a particle count can be empty: a slab that holds no particles at the moment)
+#define LAUNCH(kernel, grid, block, ...) do { if ((grid) > 0) { kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } } while (0)
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int mpmgpu_abi_version(void) { return MPMGPU_ABI_VERSION; }
@@ -139,6 +147,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->dim = is3D ? 3 : 2;
     ctx->dMats = NULL; ctx->nmat = 0; ctx->dFlags = NULL;
     ctx->cap = 0; ctx->mstep = 0; ctx->mtime = 0.; ctx->launches = 0;
+    ctx->archThickness = cfg->thickness > 0. ? cfg->thickness : 1.;      // the archive records of a 2D run carry the particle thickness
     ctx->uploaded = false; ctx->hasFext = false; ctx->hasBCs = false; ctx->hasReflectedBCs = false; ctx->profiling = false; ctx->globalIds = false; ctx->ownStreamSaved = false;
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
     ctx->cpElemPool = NULL; ctx->cpXiPool = NULL; ctx->cpWgPool = NULL;
@@ -374,6 +383,19 @@ __global__ void k_unpermute_int(int n, const int *src, const int *slot, int *dst
 }
 
 // rows [off, off+cnt) of the caller's arrays -> one particle set
+// one staging buffer per context, grown on demand: no cudaMalloc/cudaFree (and their device-wide syncs) per transfer
+static int stage_buffer(mpmgpu_ctx *ctx, size_t ndoubles, double **out)
+{
+    if (ctx->stageLen < ndoubles) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->stage) { cudaFree(ctx->stage); for (auto &a : ctx->allocs) if (a == (void *)ctx->stage) a = NULL; ctx->stage = NULL; ctx->stageLen = 0; }
+        CK(dalloc(ctx, &ctx->stage, ndoubles));
+        ctx->stageLen = ndoubles;
+    }
+    *out = ctx->stage;
+    return MPMGPU_OK;
+}
+
 static int upload_range(mpmgpu_ctx *ctx, Particles &P, const mpmgpu_particles *h, int off, int cnt)
 {
     const int n = h->n;
@@ -410,7 +432,8 @@ static int upload_range(mpmgpu_ctx *ctx, Particles &P, const mpmgpu_particles *h
     // strain + rotation -> deformation gradient (staged through a temporary device buffer)
     {
         double *tmp = NULL;
-        CK(cudaMalloc((void **)&tmp, (size_t)cnt * 9 * sizeof(double)));
+        int rcs = stage_buffer(ctx, (size_t)cnt * 9, &tmp);
+        if (rcs) return rcs;
         const double *dep = NULL, *dw = NULL;
         if (h->ep) {
             for (int c = 0; c < 6; c++) CK(cudaMemcpyAsync(tmp + (size_t)c * cnt, h->ep + (size_t)c * n + off, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -422,7 +445,6 @@ static int upload_range(mpmgpu_ctx *ctx, Particles &P, const mpmgpu_particles *h
         }
         LAUNCH(k_epwrot_to_F, nblocks(cnt, T), T, cnt, cnt, ctx->dim, dep, dw, P);
         CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp);
     }
     return MPMGPU_OK;
 }
@@ -458,59 +480,90 @@ static int alloc_rigid(mpmgpu_ctx *ctx, size_t cap)
     return MPMGPU_OK;
 }
 
+__global__ void k_validate_upload(int cnt, int off, int rigidPart, Particles P, const Material *mats, int nmat, int nelems, UploadCheck *out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= cnt) return;
+    const int m = P.mat[p], e = P.elem[p];          // P.mat is 0-based on the device
+    if (m < 0 || m >= nmat) { atomicMin(&out->badMat, off + p); return; }
+    if (e < 1 || e > nelems) atomicMin(&out->badElem, off + p);
+    const bool rigid = mats[m].kind == MAT_RIGIDBC;
+    if (rigidPart && !rigid) atomicMin(&out->notRigid, off + p);
+    if (!rigidPart && rigid) atomicMin(&out->rigidEarly, off + p);
+    if (!rigidPart) {
+        bool large = false, varies = false;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const double l = P.lp[c][p]; large |= !(l <= 1.0); varies |= l != P.lp[c][0]; }
+        if (large) out->lpLarge = 1;
+        if (varies) out->lpVaries = 1;
+    }
+}
+
 extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *h)
 {
     if (!ctx || !h) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: null argument");
     if (ctx->nmat == 0) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_upload_particles: call mpmgpu_set_materials first");
     const int n = h->n;
-    if (n < 1 || h->n_nonrigid < 0 || h->n_nonrigid > n) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: bad counts n=%d nonrigid=%d", n, h->n_nonrigid);
-    if (!h->pos || !h->mp || !h->in_elem || !h->lp) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: pos, mp, lp and in_elem are required");
+    // (a slab of a multi-GPU run may start without particles: a body can enter it later)
+    const bool emptySlab = n == 0 && ctx->tiled.slab.on;
+    if ((n < 1 && !emptySlab) || h->n_nonrigid < 0 || h->n_nonrigid > n) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: bad counts n=%d nonrigid=%d", n, h->n_nonrigid);
+    if (!emptySlab && (!h->pos || !h->mp || !h->in_elem || !h->lp)) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: pos, mp, lp and in_elem are required");
     cudaSetDevice(ctx->cfg.device);
     size_t want = ctx->cfg.max_particles > n ? (size_t)ctx->cfg.max_particles : (size_t)n;
     int rc = alloc_particles(ctx, want);
     if (rc) return rc;
-    // validate on the host: materials and elements in range
-    for (int p = 0; p < n; p++) {
-        int m = h->matnum ? h->matnum[p] : 1;
-        if (m < 1 || m > ctx->nmat) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d has material %d of %d", p, m, ctx->nmat);
-        int e = h->in_elem[p];
-        if (e < 1 || e > ctx->g.nelems) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d in element %d of %d", p, e, ctx->g.nelems);
-    }
     const int nNR = h->n_nonrigid, nR = n - nNR;
-    if (nR > 0) {
-        for (int p = nNR; p < n; p++) {
-            const Material &m = ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1];
-            if (m.kind != MAT_RIGIDBC) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d (after n_nonrigid) is not a rigid-BC material", p);
-        }
-        if ((rc = alloc_rigid(ctx, (size_t)nR))) return rc;
-    }
-    for (int p = 0; p < nNR; p++)
-        if (ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1].kind == MAT_RIGIDBC)
-            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: rigid particle %d before n_nonrigid=%d (the reference reorders them to the end, NairnMPM.cpp:1121-1150)", p, nNR);
+    if (nR > 0 && (rc = alloc_rigid(ctx, (size_t)nR))) return rc;
     ctx->P.n = nNR; ctx->P.nNR = nNR;
     ctx->PR.n = nR; ctx->PR.nNR = 0;
     ctx->hasFext = h->pfext != NULL;
-    if (h->ids) ctx->globalIds = true;
+    if (h->ids || emptySlab) ctx->globalIds = true;
     if (nNR > 0 && (rc = upload_range(ctx, ctx->P, h, 0, nNR))) return rc;
     if (nR > 0 && (rc = upload_range(ctx, ctx->PR, h, nNR, nR))) return rc;
+    // validate what arrived, on the device (a host pass over 8M particles costs more than the copy): materials and elements in
+    // range, rigid-BC particles after the non-rigid ones (the reference reorders them to the end, NairnMPM.cpp:1121-1150), and
+    // the two facts the fused path depends on (particles no larger than a cell, one particle size)
+    UploadCheck chk;
+    {
+        UploadCheck init = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff, 0, 0};
+        if (!ctx->dUploadCheck) CK(dalloc(ctx, &ctx->dUploadCheck, 1));
+        CK(cudaMemcpyAsync(ctx->dUploadCheck, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+        if (nNR) LAUNCH(k_validate_upload, nblocks(nNR, 256), 256, nNR, 0, 0, ctx->P, ctx->dMats, ctx->nmat, ctx->g.nelems, ctx->dUploadCheck);
+        if (nR) LAUNCH(k_validate_upload, nblocks(nR, 256), 256, nR, nNR, 1, ctx->PR, ctx->dMats, ctx->nmat, ctx->g.nelems, ctx->dUploadCheck);
+        CK(cudaMemcpyAsync(&chk, ctx->dUploadCheck, sizeof chk, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (chk.badMat != 0x7fffffff) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d has material %d of %d", chk.badMat, h->matnum ? h->matnum[chk.badMat] : 1, ctx->nmat);
+    if (chk.badElem != 0x7fffffff) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d in element %d of %d", chk.badElem, h->in_elem[chk.badElem], ctx->g.nelems);
+    if (chk.notRigid != 0x7fffffff) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d (after n_nonrigid) is not a rigid-BC material", chk.notRigid);
+    if (chk.rigidEarly != 0x7fffffff)
+        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: rigid particle %d before n_nonrigid=%d (the reference reorders them to the end, NairnMPM.cpp:1121-1150)", chk.rigidEarly, nNR);
     ctx->R.on = nR > 0 ? 1 : 0;
     ctx->R.mirrored = 0;
     for (int p = nNR; p < n; p++) if (ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1].p[9] != 0.) ctx->R.mirrored = 1;
     ctx->R.mat = ctx->PR.mat; ctx->R.mats = ctx->dMats;
     ctx->R.stride[0] = 1; ctx->R.stride[1] = ctx->g.yplane; ctx->R.stride[2] = ctx->g.zplane; ctx->R.nnodes = ctx->g.nnodes;
     ctx->tiled.FN.R = ctx->R;
+    if (!ctx->globalIds && !ctx->archOriginFromCaller) {
+        // "original position" column of the archive records (ArchiveData.cpp:868-872): the positions at upload unless the caller
+        // hands over others with mpmgpu_set_archive_origin
+        if (ctx->archOrigin && ctx->archOriginLen < (size_t)3 * n) ctx->archOrigin = NULL;
+        if (!ctx->archOrigin) { CK(dalloc(ctx, &ctx->archOrigin, (size_t)3 * n)); ctx->archOriginLen = (size_t)3 * n; }
+        for (int c = 0; c < 3; c++) {
+            if (nNR) CK(cudaMemcpyAsync(ctx->archOrigin + (size_t)c * n, ctx->P.pos[c], (size_t)nNR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (nR) CK(cudaMemcpyAsync(ctx->archOrigin + (size_t)c * n + nNR, ctx->PR.pos[c], (size_t)nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
     CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(StatusFlags), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
     tiled_on_upload(ctx->tiled);
     {   // the fused path needs 3D uGIMP, particles no larger than a cell, FLIP/PIC, no rigid particles
-        bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && nNR > 0;   // (XPIC order is checked per step)
-        if (ok) for (int c = 0; c < 3 && ok; c++) for (int q = 0; q < nNR; q++) if (!(h->lp[(size_t)c * n + q] <= 1.0)) { ok = false; break; }
-        bool uni = true;
-        for (int c = 0; c < 3 && uni; c++) for (int q = 1; q < nNR; q++) if (h->lp[(size_t)c * n + q] != h->lp[(size_t)c * n]) { uni = false; break; }
-        ctx->g.lpUniform = uni ? 1 : 0;
+        bool ok = ctx->dim == 3 && ctx->cfg.shape == MPMGPU_UNIFORM_GIMP && (nNR > 0 || emptySlab);   // (XPIC order is checked per step)
+        if (chk.lpLarge) ok = false;
+        ctx->g.lpUniform = (chk.lpVaries || emptySlab) ? 0 : 1;        // an empty slab learns the sizes from the particles that migrate in
         for (int c = 0; c < 3; c++) {
-            ctx->g.lpU[c] = h->lp[(size_t)c * n];
+            ctx->g.lpU[c] = emptySlab ? 0.5 : h->lp[(size_t)c * n];
             ctx->g.lpInvSize[c] = 1. / (4. * ctx->g.lpU[c]);
             ctx->g.lpInv2[c] = 1. / (2. * ctx->g.lpU[c]);
         }
@@ -919,6 +972,7 @@ static int sort_particles(mpmgpu_ctx *ctx)
 {
     TiledState &t = ctx->tiled;
     const int n = ctx->P.n;
+    if (n == 0) { t.stepsSinceSort = 0; return MPMGPU_OK; }        // an empty slab
     if (t.cap < ctx->cap) {
         if (t.cap != 0) return fail(ctx, MPMGPU_EINVAL, "sort workspace capacity changed");
         CK(dalloc(ctx, &t.keysIn, ctx->cap)); CK(dalloc(ctx, &t.keysOut, ctx->cap));
@@ -1208,13 +1262,13 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
     const int nNR = P.n, nR = PR.n, n = nNR + nR;
     h->n = n; h->n_nonrigid = nNR;
     double *dtmp = NULL;
-    CK(cudaMalloc((void **)&dtmp, (size_t)n * 9 * sizeof(double)));
-    int rc = MPMGPU_OK;
+    int rc = stage_buffer(ctx, (size_t)n * 10, &dtmp);        // 9 doubles per particle of field staging + the identity map of slab mode
+    if (rc) return rc;
     const int T = 256;
     int *ident = NULL;
     ctx->dlSlot = P.orig; ctx->dlSlotR = PR.orig;
     if (ctx->globalIds) {       // device order (rigid particles last); the caller re-assembles by id
-        CK(cudaMalloc((void **)&ident, (size_t)n * sizeof(int)));
+        ident = reinterpret_cast<int *>(dtmp + (size_t)n * 9);
         LAUNCH(k_iota, nblocks(n, T), T, n, ident, 0);
         ctx->dlSlot = ident; ctx->dlSlotR = ident + nNR;
         if (h->ids) {
@@ -1258,8 +1312,6 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
         }
     } while (0);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dtmp);
-    if (ident) cudaFree(ident);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(ctx, MPMGPU_ECUDA, "mpmgpu_download_particles: %s", cudaGetErrorString(e));
     return MPMGPU_OK;
@@ -1282,8 +1334,10 @@ extern "C" int mpmgpu_set_archive_origin(mpmgpu_ctx *ctx, const double *origpos,
     cudaSetDevice(ctx->cfg.device);
     const size_t n = (size_t)ctx->P.n + (size_t)ctx->PR.n;
     if (origpos) {
-        if (!ctx->archOrigin) CK(dalloc(ctx, &ctx->archOrigin, 3 * n));
+        if (ctx->archOrigin && ctx->archOriginLen < 3 * n) ctx->archOrigin = NULL;
+        if (!ctx->archOrigin) { CK(dalloc(ctx, &ctx->archOrigin, 3 * n)); ctx->archOriginLen = 3 * n; }
         CK(cudaMemcpyAsync(ctx->archOrigin, origpos, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->archOriginFromCaller = true;
     }
     if (angles0) {
         if (!ctx->archAngles) CK(dalloc(ctx, &ctx->archAngles, 3 * n));
@@ -1298,7 +1352,6 @@ extern "C" int mpmgpu_pack_archive(mpmgpu_ctx *ctx, const char *order, void *rec
 {
     if (!ctx || !order || !records) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_pack_archive: null argument");
     if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_pack_archive: nothing uploaded");
-    if (ctx->globalIds) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_pack_archive: not available in slab mode (each rank downloads its particles)");
     cudaSetDevice(ctx->cfg.device);
     ArchiveLayout L;
     const int recBytes = archive_layout_from_order(order, ctx->dim, L);
@@ -1311,9 +1364,31 @@ extern "C" int mpmgpu_pack_archive(mpmgpu_ctx *ctx, const char *order, void *rec
         ctx->archBufWords = words;
     }
     L.thickness = ctx->archThickness; L.origpos = ctx->archOrigin; L.angles0 = ctx->archAngles; L.stride = n;
-    if (nNR) LAUNCH(k_pack_archive, nblocks(nNR, ARCHIVE_THREADS), ARCHIVE_THREADS, nNR, ctx->P, ctx->P.orig, ctx->dMats, L, ctx->archBuf);
-    if (nR) LAUNCH(k_pack_archive, nblocks(nR, ARCHIVE_THREADS), ARCHIVE_THREADS, nR, ctx->PR, ctx->PR.orig, ctx->dMats, L, ctx->archBuf);
+    if (ctx->globalIds) {
+        // one slab of a multi-GPU run: records in this rank's device order (mpmgpu_download_ids gives the particle ids in the same
+        // order); the constants indexed by the caller's particle order are not on this rank: "original position" = the current one
+        L.origpos = NULL; L.angles0 = NULL;
+        if (nNR) LAUNCH(k_pack_archive, nblocks(nNR, ARCHIVE_THREADS), ARCHIVE_THREADS, nNR, ctx->P, (const int *)NULL, 0, ctx->dMats, L, ctx->archBuf);
+        if (nR) LAUNCH(k_pack_archive, nblocks(nR, ARCHIVE_THREADS), ARCHIVE_THREADS, nR, ctx->PR, (const int *)NULL, nNR, ctx->dMats, L, ctx->archBuf);
+    } else {
+        if (nNR) LAUNCH(k_pack_archive, nblocks(nNR, ARCHIVE_THREADS), ARCHIVE_THREADS, nNR, ctx->P, ctx->P.orig, 0, ctx->dMats, L, ctx->archBuf);
+        if (nR) LAUNCH(k_pack_archive, nblocks(nR, ARCHIVE_THREADS), ARCHIVE_THREADS, nR, ctx->PR, ctx->PR.orig, 0, ctx->dMats, L, ctx->archBuf);
+    }
     CK(cudaMemcpyAsync(records, ctx->archBuf, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+// particle ids in device order (slab mode: the global ids handed over at upload; otherwise the caller's particle index)
+extern "C" int mpmgpu_download_ids(mpmgpu_ctx *ctx, int *ids, int capacity)
+{
+    if (!ctx || !ids) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_download_ids: null argument");
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_download_ids: nothing uploaded");
+    const int nNR = ctx->P.n, nR = ctx->PR.n;
+    if (capacity < nNR + nR) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_download_ids: %d ids, room for %d", nNR + nR, capacity);
+    cudaSetDevice(ctx->cfg.device);
+    if (nNR) CK(cudaMemcpyAsync(ids, ctx->P.orig, (size_t)nNR * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nR) CK(cudaMemcpyAsync(ids + nNR, ctx->PR.orig, (size_t)nR * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return MPMGPU_OK;
 }

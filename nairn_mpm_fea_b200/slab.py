@@ -139,12 +139,13 @@ class SlabSim:
     (see partition_particles) with global ids."""
 
     def __init__(self, prob, particles, cell_lo, cell_hi, rank, world, device=0, capacity_factor=1.3,
-                 migration_capacity=1 << 16, sort_interval=0, group=None):
+                 migration_capacity=1 << 16, sort_interval=0, group=None, min_capacity=1 << 16):
         from .capi import MpmGpu
         self.rank, self.world = rank, world
         self.device = torch.device("cuda", device)
         n = int(particles["n_nonrigid"])
-        self.sim = MpmGpu(prob, device=device, kernel_path=2, max_particles=int(n * capacity_factor) + 1024,
+        # (a slab may start empty and fill by migration: room for at least min_capacity particles)
+        self.sim = MpmGpu(prob, device=device, kernel_path=2, max_particles=max(int(n * capacity_factor) + 1024, min_capacity),
                           sort_interval=sort_interval, upload=False)
         self.sim.slab_configure(cell_lo, cell_hi, rank > 0, rank < world - 1, migration_capacity)
         self.sim.upload(particles)

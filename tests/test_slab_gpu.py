@@ -52,6 +52,26 @@ def test_lockstep_slabs_match_reference(case, world, sort_interval):
     cl.close()
 
 
+def test_lockstep_slab_that_starts_empty():
+    """A body moving along z enters a slab that held no particles at upload: the free-flying block of
+    block3d_free_ugimp starts in cell planes 4-6 and has 10 particles in plane 3 after 30 steps; slab 0 = planes [0, 4)."""
+    from nairn_mpm_fea_b200.problem import from_reference_dump
+    from nairn_mpm_fea_b200.slab import LockstepCluster
+    z = load_golden("block3d_free_ugimp")
+    prob = from_reference_dump(z)
+    first, last = occupied_planes(prob)
+    assert first == 4
+    cl = LockstepCluster(prob, [(0, first), (first, prob.depth)], device=0, sort_interval=3)
+    assert cl.sims[0].num_particles() == 0
+    cl.step(30)
+    got = cl.download()
+    errs, bad = compare_particles(got, z, "p30", TOL_100STEP)
+    assert not bad, bad
+    assert np.array_equal(got["in_elem"], z["p30/inElem"])
+    assert cl.sims[0].num_particles() == int(np.count_nonzero((z["p30/inElem"] - 1) // (prob.horiz * prob.vert) < first)) > 0
+    cl.close()
+
+
 @pytest.mark.parametrize("case,extra", [("block3d_fast_crossings", ()), ("block3d_xpic3", ("--no-migration-needed",)),
                                         ("block3d_fmpm2", ("--no-migration-needed",)), ("block3d_rigid_wall", ("--no-migration-needed",))])
 def test_two_ranks_over_nccl(case, extra):
