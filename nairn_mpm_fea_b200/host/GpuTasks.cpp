@@ -15,6 +15,7 @@
 #include <omp.h>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -46,6 +47,8 @@
 #include "Custom_Tasks/CustomTask.hpp"
 #include "Custom_Tasks/TransportTask.hpp"
 #include "Custom_Tasks/ConductionTask.hpp"
+#include "NairnMPM_Class/Reservoir.hpp"
+#include "System/UnitsController.hpp"
 #include "Cracks/CrackHeader.hpp"
 #include "System/ArchiveData.hpp"
 #include "Global_Quantities/GlobalQuantity.hpp"
@@ -68,6 +71,7 @@ std::vector<NodalVelBC *> gBCs;     // host BC list in list order
 bool gBCsVary = false;
 bool gRigidFunctions = false;       // some rigid-BC material sets its velocity by functions of time and position
 long long gLeftGridWarned = 0;     // first-time grid leavers already handed to the reference's MPMWarnings
+bool gCustomTasksReadParticles = false;     // (the only custom task the adapter admits, PeriodicXPIC, touches bodyFrc alone)
 bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
 void check(int rc, const char *where)
@@ -105,6 +109,156 @@ void DownloadToHost(void)
         for (int k = 0; k < nh && k < MPMGPU_MAX_HISTORY && m->matData != NULL; k++) ((double *)m->matData)[k] = hist[k * n + p];
     }
     gHostStale = false;
+}
+
+// ---- output from the device --------------------------------------------------------------
+// The reference writes a particle archive from mpm[] (ArchiveData::ArchiveResults, System/ArchiveData.cpp:720-1290) and the
+// global quantities by looping over mpm[] once per quantity (GlobalQuantity::AppendQuantity, GlobalQuantity.cpp:394-1075).
+// Neither is virtual, so this adapter runs them FIRST -- at the end of the step's last task, before NairnMPM::CMAnalysis calls
+// ArchiveResults(mtime+timestep) -- from device data: the record block comes packed from mpmgpu_pack_archive, the sums from
+// mpmgpu_global_sums; file names, header, the line printed to the output file and the advance of nextArchTime /
+// nextGlobalTime repeat the reference's statements, so its own call then finds nothing due.  The last step of a run (which the
+// reference archives unconditionally) and anything the device does not produce (an archive item or a global quantity outside
+// the lists in include/mpmgpu.h, a tracer particle) take the old route: full download, reference code.
+bool gDeviceOutput = true;          // -hostoutput switches it off
+std::vector<char> gArchiveBlock;
+long long gArchiveBytes = 0, gArchiveCount = 0;
+double gArchiveSeconds = 0.;
+
+// value of a global quantity from the per-material device sums; false = not covered
+bool QuantityFromSums(GlobalQuantity *g, const std::vector<double> &sums, double &value)
+{
+    const int NS = MPMGPU_GS_NSUMS;
+    if (g->ptNum >= 0 || g->ptPos != NULL) return false;
+    double t[MPMGPU_GS_NSUMS];
+    for (int k = 0; k < NS; k++) t[k] = 0.;
+    for (int m = 0; m < nmat; m++) {
+        if (!g->IncludeThisMaterial(m, false)) continue;
+        if (theMaterials[m]->IsRigid()) return false;           // the sums run over the non-rigid particles
+        for (int k = 0; k < NS; k++) { const double v = sums[(size_t)m * NS + k]; if (v == v) t[k] += v; }
+    }
+    const double vol = t[MPMGPU_GS_VOLUME];
+    int c = -1;
+    switch (g->quantity) {
+    case AVG_SXX: c = 0; break; case AVG_SYY: c = 1; break; case AVG_SZZ: c = 2; break;
+    case AVG_SYZ: c = 3; break; case AVG_SXZ: c = 4; break; case AVG_SXY: c = 5; break;
+    default: break;
+    }
+    if (c >= 0) { value = t[MPMGPU_GS_STRESS + c]; if (vol > 0.) value /= vol; value *= UnitsController::Scaling(1.e-6); return true; }
+    switch (g->quantity) {
+    case KINE_ENERGY: value = t[MPMGPU_GS_KINETIC] * UnitsController::Scaling(1.e-9); return true;
+    case WORK_ENERGY: value = t[MPMGPU_GS_WORK] * UnitsController::Scaling(1.e-9); return true;
+    case STRAIN_ENERGY: value = t[MPMGPU_GS_STRAIN_ENERGY] * UnitsController::Scaling(1.e-9); return true;
+    case HEAT_ENERGY: value = t[MPMGPU_GS_HEAT] * UnitsController::Scaling(1.e-9); return true;
+    case ENTROPY_ENERGY: value = t[MPMGPU_GS_ENTROPY] * UnitsController::Scaling(1.e-9); return true;
+    case INTERNAL_ENERGY: value = (t[MPMGPU_GS_WORK] + t[MPMGPU_GS_HEAT]) * UnitsController::Scaling(1.e-9); return true;
+    case PLAS_ENERGY: value = t[MPMGPU_GS_PLASTIC] * UnitsController::Scaling(1.e-9); return true;
+    case AVG_VELX: value = t[MPMGPU_GS_VOL_VEL]; if (vol > 0.) value /= vol; return true;
+    case AVG_VELY: value = t[MPMGPU_GS_VOL_VEL + 1]; if (vol > 0.) value /= vol; return true;
+    case AVG_VELZ: value = t[MPMGPU_GS_VOL_VEL + 2]; if (vol > 0.) value /= vol; return true;
+    case LINMOMX: value = t[MPMGPU_GS_LINMOM] * UnitsController::Scaling(1.e-6); return true;
+    case LINMOMY: value = t[MPMGPU_GS_LINMOM + 1] * UnitsController::Scaling(1.e-6); return true;
+    case LINMOMZ: value = t[MPMGPU_GS_LINMOM + 2] * UnitsController::Scaling(1.e-6); return true;
+    default: break;
+    }
+    static const int fq[9] = {AVG_FXX, AVG_FXY, AVG_FXZ, AVG_FYX, AVG_FYY, AVG_FYZ, AVG_FZX, AVG_FZY, AVG_FZZ};
+    for (int i = 0; i < 9; i++)
+        if (g->quantity == fq[i]) { value = t[MPMGPU_GS_VOL_F + i]; if (vol > 0.) value /= vol; value *= UnitsController::Scaling(100.); return true; }
+    return false;
+}
+
+// quantities that do not read the particles (step number, times, grid damping values ...): the reference's own code serves
+bool QuantityIsParticleFree(int q)
+{
+    return q == STEP_NUMBER || q == CPU_TIME || q == ELAPSED_TIME || q == GRID_ALPHA || q == PARTICLE_ALPHA;
+}
+
+bool GlobalsCoveredByDevice(void)
+{
+    std::vector<double> zero((size_t)nmat * MPMGPU_GS_NSUMS, 0.);
+    for (GlobalQuantity *g = firstGlobal; g != NULL; g = g->GetNextGlobal()) {
+        double v;
+        if (!QuantityIsParticleFree(g->quantity) && !QuantityFromSums(g, zero, v)) return false;
+    }
+    return true;
+}
+
+// ArchiveData::GlobalArchive (ArchiveData.cpp:1508-1553) with the particle loops replaced by the device sums
+void GlobalArchiveFromDevice(double atime)
+{
+    if (archiver->globalFile == NULL) return;
+    std::vector<double> sums((size_t)nmat * MPMGPU_GS_NSUMS, 0.);
+    check(mpmgpu_global_sums(gCtx, sums.data()), "GpuTasks::GlobalArchive");
+    archiver->lastArchived.clear();
+    archiver->lastArchivedStep = fmobj->mstep;
+    for (GlobalQuantity *g = firstGlobal; g != NULL;) {
+        double v;
+        if (QuantityIsParticleFree(g->quantity)) g = g->AppendQuantity(archiver->lastArchived);
+        else { QuantityFromSums(g, sums, v); archiver->lastArchived.push_back(v); g = g->GetNextGlobal(); }
+    }
+    char fline[1000], numStr[100];
+    snprintf(fline, sizeof fline, "%g", UnitsController::Scaling(1000.) * atime);
+    for (size_t i = 0; i < archiver->lastArchived.size(); i++) { snprintf(numStr, sizeof numStr, "\t%e", archiver->lastArchived[i]); strcat(fline, numStr); }
+    std::ofstream global;
+    global.open(archiver->globalFile, std::ios::out | std::ios::app);
+    if (!global.is_open()) throw CommonException("File error opening global results", "GpuTasks::GlobalArchive");
+    global << fline << std::endl;
+    global.close();
+}
+
+// the part of ArchiveData::ArchiveResults (ArchiveData.cpp:720-1290) that is due after this step, from device data.
+// Returns false when the reference has to do it itself from a downloaded mpm[].
+bool OutputFromDevice(double atime)
+{
+    if (!gDeviceOutput || atime > fmobj->maxtime) return false;         // last step: archived unconditionally by the reference
+    const bool globalByTime = firstGlobal != NULL && archiver->globalTime >= 0.;
+    const bool globalDue = globalByTime && atime > archiver->nextGlobalTime;
+    const bool archiveDue = atime >= archiver->nextArchTime;
+    if (!globalDue && !archiveDue) return true;
+    if (firstGlobal != NULL && !GlobalsCoveredByDevice()) return false;
+    char order[60];
+    strncpy(order, archiver->mpmOrder, sizeof order - 1); order[sizeof order - 1] = 0;
+    if (archiveDue) {
+        const int rec = mpmgpu_archive_record_size(gCtx, order);
+        if (rec < 0 || rec != archiver->mpmRecSize || archiver->recSize < rec || fmobj->GetReverseBytes()) return false;
+    }
+    if (globalDue) { GlobalArchiveFromDevice(atime); archiver->nextGlobalTime += archiver->globalTime; }
+    if (!archiveDue) return true;
+    // next archive time (ArchiveData.cpp:748-756)
+    archiver->nextArchTime += archiver->archTimes[archiver->archBlock];
+    if (archiver->archBlock + 1 < (int)archiver->firstArchTimes.size()) {
+        if (archiver->nextArchTime > archiver->firstArchTimes[archiver->archBlock + 1]) {
+            archiver->archBlock++;
+            archiver->nextArchTime = atime + archiver->archTimes[archiver->archBlock];
+        }
+    }
+    if (firstGlobal != NULL && archiver->globalTime < 0.) GlobalArchiveFromDevice(atime);
+    if (mpmReservoir != NULL) archiver->ArchiveResizings(atime * UnitsController::Scaling(1.e3), fmobj->mstep);     // (reads no particles)
+    const double t0 = fmobj->ElapsedTime();
+    char fname[500], fline[600];
+    archiver->GetFilePathNum(fname, sizeof fname, "%s%s.%d", fmobj->mstep);
+    int i;
+    for (i = (int)strlen(fname); i >= 0; i--) if (fname[i] == '/' || fname[i] == '\\') break;
+    snprintf(fline, sizeof fline, "%7d %15.7e  %s", fmobj->mstep, atime * UnitsController::Scaling(1.e3), &fname[i + 1]);
+    std::cout << fline << std::endl;
+    const size_t rec = (size_t)archiver->mpmRecSize, bytes = rec * (size_t)nmpms;
+    if (gArchiveBlock.size() < bytes) gArchiveBlock.resize(bytes);
+    check(mpmgpu_pack_archive(gCtx, order, gArchiveBlock.data(), gArchiveBlock.size()), "GpuTasks::ArchiveResults");
+    std::ofstream afile;
+    afile.open(fname, std::ios::out | std::ios::binary);
+    if (!afile.is_open()) throw CommonException("Cannot open an archive file", "GpuTasks::ArchiveResults");
+    *archiver->timeStamp = (float)(atime * UnitsController::Scaling(1.e3));
+    afile.write(archiver->archHeader, HEADER_LENGTH);
+    if ((size_t)archiver->recSize == rec) afile.write(gArchiveBlock.data(), (std::streamsize)bytes);
+    else {      // records padded to the size of the longer crack-segment record (ArchiveData.cpp:1274-1276)
+        std::vector<char> padded((size_t)archiver->recSize * (size_t)nmpms, 0);
+        for (int p = 0; p < nmpms; p++) memcpy(&padded[(size_t)p * archiver->recSize], &gArchiveBlock[(size_t)p * rec], rec);
+        afile.write(padded.data(), (std::streamsize)padded.size());
+    }
+    if (afile.bad()) throw CommonException("File error writing archive file", "GpuTasks::ArchiveResults");
+    afile.close();
+    gArchiveBytes += (long long)bytes; gArchiveCount++; gArchiveSeconds += fmobj->ElapsedTime() - t0;
+    return true;
 }
 
 enum { G_INIT, G_MASSMOM, G_POSTEXTRAP, G_USF, G_FORCES, G_POSTFORCES, G_MOMENTA, G_PARTICLES, G_USL, G_RESET, G_RIGIDBC };
@@ -156,7 +310,8 @@ class GpuTask : public MPMTask
         const double atime = mtime + timestep;
         bool due = atime >= archiver->nextArchTime || atime + timestep > fmobj->maxtime;
         if (firstGlobal != NULL && archiver->globalTime >= 0. && atime > archiver->nextGlobalTime) due = true;
-        if (due || theTasks != NULL) DownloadToHost();
+        if (due && OutputFromDevice(atime)) due = atime + timestep > fmobj->maxtime;       // written from device data: nothing left for the host
+        if (due || (theTasks != NULL && gCustomTasksReadParticles)) DownloadToHost();
     }
     virtual bool Execute(int)
     {
@@ -393,6 +548,17 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     h.pfext = anyFext ? pf.data() : NULL; h.crossings = cross.data(); h.history = hist.data();
     if (mpmgpu_upload_particles(gCtx, &h) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     if (mpmgpu_set_time_step(gCtx, timestep, strainTimestepFirst, strainTimestepLast) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    {   // constants of the archive records (ArchiveData.cpp:820-875): original position, initial material angles, 2D thickness
+        std::vector<double> op(3 * (size_t)n), ang(3 * (size_t)n);
+        double thick = is3D ? 1. : mpm[0]->thickness();
+        for (int p = 0; p < n; p++) {
+            MPMBase *m = mpm[p];
+            op[p] = m->origpos.x; op[n + p] = m->origpos.y; op[2 * (size_t)n + p] = m->origpos.z;
+            ang[p] = m->GetAnglez0InRadians(); ang[n + p] = m->GetAngley0InRadians(); ang[2 * (size_t)n + p] = m->GetAnglex0InRadians();
+            if (!is3D && m->thickness() != thick) gDeviceOutput = false;    // one thickness per run on the device: the host writes otherwise
+        }
+        if (mpmgpu_set_archive_origin(gCtx, op.data(), ang.data(), thick) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    }
 
     // grid velocity BCs in list order
     std::vector<int> bnode, bact, bsym, brefl; std::vector<double> bnorm, bval, bratio;
@@ -433,9 +599,14 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     return NULL;
 }
 
+void GpuTasks_SetDeviceOutput(bool on) { gDeviceOutput = on; }
+
 void GpuTasks_Finish(void)
 {
     if (!gCtx) return;
+    if (gArchiveCount > 0)
+        std::cout << "GPU ARCHIVES: " << gArchiveCount << " particle archives packed on the device, " << gArchiveBytes / gArchiveCount
+                  << " bytes each (D2H), " << 1.e3 * gArchiveSeconds / (double)gArchiveCount << " ms each including the file write" << std::endl;
     gHostStale = true;
     try { DownloadToHost(); } catch (...) {}
     mpmgpu_destroy(gCtx);
@@ -443,6 +614,9 @@ void GpuTasks_Finish(void)
 }
 
 // ---- the driver: Common/System/main.cpp steps with the install hook between preparations and analysis ----
+static bool gDeviceOutputSwitch = true;
+void GpuTasks_SetDeviceOutput(bool on);
+
 int main(int argc, const char *argv[])
 {
     int numProcs = 1, device = 0, arg = 1;
@@ -452,9 +626,10 @@ int main(int argc, const char *argv[])
         else if (strcmp(argv[arg], "-gpu") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &device);
         else if (strcmp(argv[arg], "-cpu") == 0) useGpu = false;
         else if (strcmp(argv[arg], "-fused") == 0) fused = true;
-        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-cpu] input.fmcmd" << std::endl; return 1; }
+        else if (strcmp(argv[arg], "-hostoutput") == 0) gDeviceOutputSwitch = false;
+        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
     }
-    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-cpu] input.fmcmd" << std::endl; return 1; }
+    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
     fmobj = new NairnMPM();
     omp_set_num_threads(numProcs);
     fmobj->SetNumberOfProcessors(numProcs);
@@ -466,6 +641,7 @@ int main(int argc, const char *argv[])
         fmobj->CMStartResultsOutput();
         fmobj->CMPreparations();
         if (useGpu) {
+            GpuTasks_SetDeviceOutput(gDeviceOutputSwitch);
             const char *why = GpuTasks_Install(device, fused);
             if (why != NULL) { std::cerr << "NairnMPM_gpu: cannot run this input on libmpmgpu: " << why << std::endl; return 2; }
         }

@@ -63,6 +63,7 @@ def test_reference_driver_with_gpu_tasks_matches_reference(case, mode):
     dref, out_ref = run(REF, xml, ("-np", "4"))
     dgpu, out_gpu = run(GPU, xml, ("-fused",) if mode == "fused" else ())
     assert "GPU TASKS" in out_gpu and ("whole-step" in out_gpu) == (mode == "fused")
+    assert "GPU ARCHIVES" in out_gpu, "the archives of this run should have been packed on the device (SURVEY.md 8(f) row 1)"
     if npart is None:
         for ln in out_ref.splitlines():
             if "Number of Material Points:" in ln:
@@ -79,3 +80,38 @@ def test_reference_driver_with_gpu_tasks_matches_reference(case, mode):
         scale = np.maximum(np.max(np.abs(r["doubles"]), axis=0), 1e-300)
         err = np.max(np.abs(r["doubles"] - g["doubles"]) / scale)
         assert err < 1e-7, "archive at step %d differs: %.3e" % (step, err)
+
+
+def test_device_packed_archives_equal_the_host_writers():
+    """Same input twice: records packed on the device (default) and `-hostoutput` (full download, the reference's own
+    ArchiveResults on mpm[]).  Two runs differ in the last bits (FP64 atomics add in another order from run to run), so the
+    files are compared field by field to 1e-9; that the packer writes the same BYTES as the host writer from one state is
+    tests/test_zzz_archive_gpu.py.  The global-quantity files are compared to their printed precision."""
+    if not os.path.exists(GPU):
+        pytest.skip("host/_build/NairnMPM_gpu not built")
+    xml = (inputs.block3d(ncell=6, margin=3, maxtime=0.03, material=inputs.isoplastic_material(), vz=-4.0e4)
+           .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.004</ArchiveTime>"
+                    "<GlobalArchiveTime units=\"ms\">0.002</GlobalArchiveTime><GlobalArchive type=\"Kinetic Energy\"/>"
+                    "<GlobalArchive type=\"Strain Energy\"/><GlobalArchive type=\"Plastic Energy\"/><GlobalArchive type=\"szz\"/>"
+                    "<GlobalArchive type=\"velz\"/><GlobalArchive type=\"Fzz\"/><GlobalArchive type=\"Step number\"/>"))
+    npart = 6 ** 3 * 8
+    ddev, out_dev = run(GPU, xml, ("-fused",))
+    dhost, out_host = run(GPU, xml, ("-fused", "-hostoutput"))
+    assert "GPU ARCHIVES" in out_dev and "GPU ARCHIVES" not in out_host
+    a_dev, a_host = list_archives(os.path.join(ddev, "res/blk.")), list_archives(os.path.join(dhost, "res/blk."))
+    assert [s for s, _ in a_dev] == [s for s, _ in a_host] and len(a_dev) >= 5
+    for (step, fd), (_, fh) in zip(a_dev, a_host):
+        assert open(fd, "rb").read(64) == open(fh, "rb").read(64), "header of archive %d differs" % step
+        d, h = read_archive(fd, npart), read_archive(fh, npart)
+        assert np.array_equal(d["elem"], h["elem"]) and np.array_equal(d["tail"], h["tail"]) and np.array_equal(d["mat"], h["mat"])
+        scale = np.maximum(np.max(np.abs(h["doubles"]), axis=0), 1e-300)
+        assert np.max(np.abs(d["doubles"] - h["doubles"]) / scale) < 1e-9, "archive %d differs" % step
+    gd, gh = open(os.path.join(ddev, "res/blk.global")).read(), open(os.path.join(dhost, "res/blk.global")).read()
+    assert gd.count("\n") >= 8
+    rows_d = [ln.split("\t") for ln in gd.splitlines() if not ln.startswith("#")]
+    rows_h = [ln.split("\t") for ln in gh.splitlines() if not ln.startswith("#")]
+    assert len(rows_d) == len(rows_h)
+    for rd, rh in zip(rows_d, rows_h):
+        assert len(rd) == len(rh)
+        for x, y in zip(rd, rh):
+            assert abs(float(x) - float(y)) <= 2e-6 * max(abs(float(y)), 1e-300) + 1e-30, (rd, rh)
