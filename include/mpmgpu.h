@@ -216,6 +216,11 @@ int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, const doubl
 int mpmgpu_set_velocity_bc_reflections(mpmgpu_ctx *ctx, int n, const int *reflected_node, const double *ratio);
 /* update only the values/active flags of the BC list set above (same n, same order) */
 int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const double *value, const int *active);
+/* Particle load BCs (MatPtLoadBC): the reference re-evaluates them at the start of every step (MatPtLoadBC::SetParticleFext,
+ * InitializationTask.cpp:91, MatPtLoadBC.cpp:210-222).  The host evaluates the BCs at this step's time and hands over the
+ * external force fext[3][n_loaded] of the loaded particles only; particle[k] = 0-based index (upload order) of loaded particle k
+ * on the first call, NULL afterwards (same particles).  The particles must have been uploaded with a pfext array. */
+int mpmgpu_update_particle_loads(mpmgpu_ctx *ctx, int n_loaded, const int *particle, const double *fext);
 /* velocities [3][n_rigid] of the rigid-BC particles (host order) for this step: the host evaluates the material's
  * setting functions (RigidMaterial::GetVectorSetting, Materials/RigidMaterial.cpp:376-531) before the projection task */
 int mpmgpu_update_rigid_velocities(mpmgpu_ctx *ctx, int n_rigid, const double *vel);
@@ -223,6 +228,11 @@ int mpmgpu_update_rigid_velocities(mpmgpu_ctx *ctx, int n_rigid, const double *v
 /* ---- the step ---------------------------------------------------------------------------- */
 /* nsteps full MPMSteps (tasks 1-9, 11) with the configured method; mtime advances by dt each step */
 int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps);
+/* mpmgpu_step reads the device's status word (position NaN, CPDI corner off the grid: the reference's exceptions of
+ * ResetElementsTask.cpp:200-203 and MatPoint3D.cpp:596-601) at the end of every call, which costs one stream synchronisation.
+ * With k > 1 it does so every k-th call only: the host keeps enqueueing steps, an error is reported up to k-1 steps late and
+ * mpmgpu_left_grid_counts returns the counts of the last poll in between.  Default 1 (the reference's behaviour). */
+int mpmgpu_set_poll_interval(mpmgpu_ctx *ctx, int k);
 
 /* The same step as separate entry points named after the reference's tasks, so that the
  * reference's per-task timing report (MPMTask.cpp:106-121) stays meaningful and each task can be

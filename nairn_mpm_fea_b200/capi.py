@@ -26,7 +26,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
            "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
-           "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_rigid_velocities", "mpmgpu_step"] + ["mpmgpu_task_" + t for t in TASKS] + [
+           "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
     "mpmgpu_launch_count", "mpmgpu_stream", "mpmgpu_set_profiling", "mpmgpu_task_times",
@@ -106,6 +106,7 @@ def load_library(path=None):
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
     lib.mpmgpu_update_velocity_bc_values.argtypes = [vp, C.c_int, _dp, _ip]
     lib.mpmgpu_set_velocity_bc_reflections.argtypes = [vp, C.c_int, _ip, _dp]
+    lib.mpmgpu_update_particle_loads.argtypes = [vp, C.c_int, _ip, _dp]
     lib.mpmgpu_update_rigid_velocities.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_step.argtypes = [vp, C.c_int]
     for t in TASKS + ["project_rigid_bcs"]:
@@ -260,6 +261,12 @@ class MpmGpu:
         value, active = _c64(value), _c32(active)
         self._check(self.lib.mpmgpu_update_velocity_bc_values(self.ctx, len(value), _d(value), _i(active)))
 
+    def update_particle_loads(self, fext, particle=None):
+        """fext [3][n_loaded]: this step's external forces on the loaded particles (MatPtLoadBC evaluated by the host);
+        particle: their 0-based indices, on the first call."""
+        fext, particle = _c64(fext), _c32(particle)
+        self._check(self.lib.mpmgpu_update_particle_loads(self.ctx, int(fext.shape[-1]), _i(particle), _d(fext)))
+
     def update_rigid_velocities(self, vel):
         """vel [3][n_rigid]: this step's velocities of the rigid-BC particles (setting functions evaluated by the host)."""
         vel = _c64(vel)
@@ -272,6 +279,10 @@ class MpmGpu:
         self._check(self.lib.mpmgpu_set_xpic(self.ctx, order, int(using_fmpm)))
 
     # -- the step -----------------------------------------------------------------------------
+    def set_poll_interval(self, k):
+        """Read the status word (one stream synchronisation) every k-th step() call only; errors surface up to k-1 steps late."""
+        self._check(self.lib.mpmgpu_set_poll_interval(self.ctx, int(k)))
+
     def step(self, nsteps=1):
         self._check(self.lib.mpmgpu_step(self.ctx, int(nsteps)))
 

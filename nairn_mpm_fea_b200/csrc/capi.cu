@@ -45,6 +45,7 @@ struct mpmgpu_ctx {
     std::vector<Material> hMats;
     StatusFlags *dFlags;
     StatusFlags hFlags;
+    int pollInterval = 1, callsSincePoll = 0;       // mpmgpu_set_poll_interval: status word read (one stream sync) every k-th mpmgpu_step call
     cudaStream_t stream;
     std::vector<void *> allocs;         // everything cudaMalloc'd, for destroy
     double *particlePool;               // one slab for all particle doubles
@@ -66,6 +67,7 @@ struct mpmgpu_ctx {
     bool archOriginFromCaller = false;
     size_t archOriginLen = 0;
     UploadCheck *dUploadCheck = NULL;
+    int *dLoadOf = NULL; double *dLoadFext = NULL; int loadCap = 0, nLoaded = 0;     // particle loads (mpmgpu_update_particle_loads)
     double *stage = NULL; size_t stageLen = 0;       // staging buffer of uploads/downloads (grown on demand, freed with the context)
     uint32_t *archBuf = NULL; size_t archBufWords = 0;
     double *gsumBuf = NULL; size_t gsumBufLen = 0;
@@ -692,6 +694,46 @@ extern "C" int mpmgpu_set_velocity_bc_reflections(mpmgpu_ctx *ctx, int n, const 
     return MPMGPU_OK;
 }
 
+// Particle loads (MatPtLoadBC::SetParticleFext at the start of every step, InitializationTask.cpp:91, MatPtLoadBC.cpp:210-222): the
+// host evaluates the load BCs at this step's time and hands over the external force of the loaded particles only.
+// index_of_particle[i] stays on the device after the first call (NULL afterwards = same particles as before).
+__global__ void k_scatter_particle_loads(int n, Particles P, const int *loadOf, int nload, const double *fext)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int k = loadOf[P.orig[p]];
+    if (k < 0) return;
+    P.pfext[0][p] = fext[k]; P.pfext[1][p] = fext[nload + k]; P.pfext[2][p] = fext[2 * nload + k];
+}
+
+extern "C" int mpmgpu_update_particle_loads(mpmgpu_ctx *ctx, int n_loaded, const int *particle, const double *fext)
+{
+    if (!ctx || !fext || n_loaded < 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_particle_loads: bad argument");
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_update_particle_loads: upload the particles first");
+    if (!ctx->hasFext) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_update_particle_loads: the particles were uploaded without an external-force array (pfext)");
+    if (ctx->globalIds) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_update_particle_loads: not available in slab mode");
+    if (n_loaded == 0) return MPMGPU_OK;
+    cudaSetDevice(ctx->cfg.device);
+    const int nNR = ctx->P.n, nAll = nNR + ctx->PR.n;
+    if (particle) {
+        std::vector<int> of((size_t)nAll, -1);
+        for (int k = 0; k < n_loaded; k++) {
+            if (particle[k] < 0 || particle[k] >= nNR) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_particle_loads: entry %d is particle %d of %d non-rigid particles", k, particle[k], nNR);
+            if (of[particle[k]] >= 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_particle_loads: particle %d listed twice", particle[k]);
+            of[particle[k]] = k;
+        }
+        if (!ctx->dLoadOf) CK(dalloc(ctx, &ctx->dLoadOf, (size_t)nAll));
+        if (ctx->loadCap < n_loaded) { CK(dalloc(ctx, &ctx->dLoadFext, (size_t)3 * n_loaded)); ctx->loadCap = n_loaded; }
+        CK(cudaMemcpyAsync(ctx->dLoadOf, of.data(), (size_t)nAll * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));        // `of` goes out of scope
+        ctx->nLoaded = n_loaded;
+    } else if (n_loaded != ctx->nLoaded) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_particle_loads: %d forces for %d loaded particles", n_loaded, ctx->nLoaded);
+    CK(cudaMemcpyAsync(ctx->dLoadFext, fext, (size_t)3 * n_loaded * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(k_scatter_particle_loads, nblocks(nNR, 256), 256, nNR, ctx->P, ctx->dLoadOf, n_loaded, ctx->dLoadFext);
+    CK(cudaStreamSynchronize(ctx->stream));            // the caller's array may change after the return
+    return MPMGPU_OK;
+}
+
 // Rigid-BC particles whose material has setting functions: the host evaluates them each step
 // (RigidMaterial::GetVectorSetting, Materials/RigidMaterial.cpp:376-531) and hands over the velocities
 extern "C" int mpmgpu_update_rigid_velocities(mpmgpu_ctx *ctx, int n_rigid, const double *vel)
@@ -908,8 +950,12 @@ static int t_reset_elements(mpmgpu_ctx *ctx)
     return reset_rigid(ctx);
 }
 
-static int poll_flags(mpmgpu_ctx *ctx)
+static int poll_flags(mpmgpu_ctx *ctx, bool force = true)
 {
+    // the status word costs a stream synchronisation: with a poll interval k > 1 the host keeps enqueueing steps and looks at it
+    // every k-th call (an error -- NaN position, CPDI corner off the grid -- is then reported up to k-1 steps late)
+    if (!force && ++ctx->callsSincePoll < ctx->pollInterval) return MPMGPU_OK;
+    ctx->callsSincePoll = 0;
     CK(cudaMemcpyAsync(&ctx->hFlags, ctx->dFlags, sizeof(StatusFlags), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
@@ -1236,7 +1282,14 @@ extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
         if (rc) return rc;
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
     }
-    return poll_flags(ctx);
+    return poll_flags(ctx, false);
+}
+
+extern "C" int mpmgpu_set_poll_interval(mpmgpu_ctx *ctx, int k)
+{
+    if (!ctx || k < 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_poll_interval: interval must be >= 1");
+    ctx->pollInterval = k; ctx->callsSincePoll = 0;
+    return MPMGPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1461,8 +1514,10 @@ extern "C" int mpmgpu_left_grid_counts(mpmgpu_ctx *ctx, long long *exits, long l
 {
     if (!ctx) return MPMGPU_EINVAL;
     cudaSetDevice(ctx->cfg.device);
-    CK(cudaMemcpyAsync(&ctx->hFlags, ctx->dFlags, sizeof(StatusFlags), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pollInterval <= 1 || ctx->callsSincePoll == 0) {      // (between polls: the counts of the last poll, no synchronisation)
+        CK(cudaMemcpyAsync(&ctx->hFlags, ctx->dFlags, sizeof(StatusFlags), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     if (exits) *exits = (long long)(ctx->hFlags.leftGrid & 0xffffffffull);
     if (particles) *particles = (long long)(ctx->hFlags.leftGrid >> 32);
     return MPMGPU_OK;

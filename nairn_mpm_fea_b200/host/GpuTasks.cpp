@@ -72,6 +72,8 @@ bool gBCsVary = false;
 bool gRigidFunctions = false;       // some rigid-BC material sets its velocity by functions of time and position
 long long gLeftGridWarned = 0;     // first-time grid leavers already handed to the reference's MPMWarnings
 bool gCustomTasksReadParticles = false;     // (the only custom task the adapter admits, PeriodicXPIC, touches bodyFrc alone)
+std::vector<int> gLoadPts;          // particles with load BCs (MatPtLoadBC), 0-based, each once
+bool gLoadsSent = false;
 bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
 void check(int rc, const char *where)
@@ -276,6 +278,18 @@ class GpuTask : public MPMTask
         for (size_t i = 0; i < gBCs.size(); i++) { a[i] = gBCs[i]->GetNodeNum(mtime) > 0; v[i] = a[i] ? gBCs[i]->BCValue(mtime) : 0.; }
         check(mpmgpu_update_velocity_bc_values(gCtx, (int)v.size(), v.data(), a.data()), "GpuTask(BC values)");
     }
+    // MatPtLoadBC::SetParticleFext (InitializationTask.cpp:91) by the reference's own BC objects on mpm[]->pFext; the forces of the
+    // loaded particles go to the device
+    void UpdateParticleLoads(void)
+    {
+        if (gLoadPts.empty()) return;
+        MatPtLoadBC::SetParticleFext(mtime);
+        const size_t nl = gLoadPts.size();
+        std::vector<double> f(3 * nl);
+        for (size_t k = 0; k < nl; k++) { const Vector *pf = mpm[gLoadPts[k]]->GetPFext(); f[k] = pf->x; f[nl + k] = pf->y; f[2 * nl + k] = pf->z; }
+        check(mpmgpu_update_particle_loads(gCtx, (int)nl, gLoadsSent ? NULL : gLoadPts.data(), f.data()), "GpuTask(particle loads)");
+        gLoadsSent = true;
+    }
     // RigidMaterial::GetVectorSetting evaluated by the reference's own Expression objects (ProjectRigidBCsTask.cpp:75-93)
     void UpdateRigidVelocities(void)
     {
@@ -320,6 +334,7 @@ class GpuTask : public MPMTask
                 check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(step)");
                 UpdateBCValues();
                 UpdateRigidVelocities();
+                UpdateParticleLoads();
                 check(mpmgpu_step(gCtx, 1), "GpuTask(step)");
             } else if (which == G_RESET) AfterStep();
             return true;
@@ -328,6 +343,7 @@ class GpuTask : public MPMTask
         case G_INIT:
             // the PeriodicXPIC custom task changes the order between steps (Custom_Tasks/PeriodicXPIC.cpp:161-240)
             check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(Initialize)");
+            UpdateParticleLoads();
             check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)");
             break;
         case G_RIGIDBC:
@@ -377,7 +393,14 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (transportTasks != NULL) return "transport tasks present";
     // everything the replaced CPU tasks would do on the side must be absent, or the run would silently differ:
     // particle loads / tractions are re-evaluated every step by InitializationTask and GridForcesTask
-    if (firstLoadedPt != NULL) return "particle load BCs (MatPtLoadBC)";
+    // particle loads are re-evaluated every step (MatPtLoadBC::SetParticleFext): values that are functions of time only are
+    // evaluated by the host and sent down; silent BCs (need the particle velocity) and function styles (may use the particle
+    // position and rotation) would need the current particle state on the host
+    for (MatPtLoadBC *lb = firstLoadedPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
+        if (lb->style == SILENT) return "silent particle load BCs";
+        if (lb->style == FUNCTION_VALUE) return "particle load BCs set by a function";
+        if (lb->ptNum - 1 >= nmpmsNR) return "load BCs on rigid particles";
+    }
     if (firstTractionPt != NULL) return "particle traction BCs (MatPtTractionBC)";
     // damping that changes during the run (functions of time, feedback on the kinetic energy: BodyForce.cpp:167-230)
     if (bodyFrc.useFeedback || bodyFrc.usePFeedback || bodyFrc.gridfunction != NULL || bodyFrc.pgridfunction != NULL)
@@ -521,7 +544,12 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     std::vector<double> pos(3 * n), vel(3 * n), mp(n), lp(3 * n), sp(6 * n), pr(n), ep(6 * n), wrot(3 * n), epl(6 * n), en(6 * n), pf(3 * n),
         hist((size_t)MPMGPU_MAX_HISTORY * n, 0.);
     std::vector<int> elem(n), matn(n), cross(n);
-    bool anyFext = false;
+    bool anyFext = firstLoadedPt != NULL;
+    {
+        std::vector<char> seen((size_t)n, 0);
+        for (MatPtLoadBC *lb = firstLoadedPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject())
+            if (!seen[lb->ptNum - 1]) { seen[lb->ptNum - 1] = 1; gLoadPts.push_back(lb->ptNum - 1); }
+    }
     for (int p = 0; p < n; p++) {
         MPMBase *m = mpm[p];
         pos[p] = m->pos.x; pos[n + p] = m->pos.y; pos[2 * n + p] = m->pos.z;
@@ -594,6 +622,8 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         } else prev = t;
         t = next;
     }
+    extern int gPollInterval;
+    if (fusedStep && gPollInterval > 1 && mpmgpu_set_poll_interval(gCtx, gPollInterval) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     std::cout << "GPU TASKS: tasks 1-9,11 run on libmpmgpu (device " << device << ", " << n << " particles"
               << (fusedStep ? ", whole-step entry point" : ", per-task entry points") << ")" << std::endl;
     return NULL;
@@ -615,6 +645,7 @@ void GpuTasks_Finish(void)
 
 // ---- the driver: Common/System/main.cpp steps with the install hook between preparations and analysis ----
 static bool gDeviceOutputSwitch = true;
+int gPollInterval = 1;              // -poll K (with -fused): look at the device's status word every K-th step (mpmgpu_set_poll_interval)
 void GpuTasks_SetDeviceOutput(bool on);
 
 int main(int argc, const char *argv[])
@@ -627,9 +658,10 @@ int main(int argc, const char *argv[])
         else if (strcmp(argv[arg], "-cpu") == 0) useGpu = false;
         else if (strcmp(argv[arg], "-fused") == 0) fused = true;
         else if (strcmp(argv[arg], "-hostoutput") == 0) gDeviceOutputSwitch = false;
-        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
+        else if (strcmp(argv[arg], "-poll") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &gPollInterval);
+        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-poll K] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
     }
-    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
+    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-poll K] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
     fmobj = new NairnMPM();
     omp_set_num_threads(numProcs);
     fmobj->SetNumberOfProcessors(numProcs);

@@ -36,6 +36,15 @@ CASES = {
     "block3d_rigid_piston_functions": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=0.0,
                                                       rigid=("piston", 5, (0.0, 0.0, 0.0), ("300*sin(40*t)*(1+0.05*y)", "-9000*(1-exp(-t/0.004))")))
                                        .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
+    # particle load BCs (MatPtLoadBC) re-evaluated every step: a constant load on the top layer, a linear ramp that starts late on one
+    # side and a sine load on another face; two BCs overlap on the corner particles
+    "block3d_particle_loads": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=0.0)
+                               .replace("</GridBCs>", "</GridBCs><ParticleBCs>"
+                                        '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="6.5" zmax="20"><LoadBC dir="3" style="1" load="-0.5"/></BCBox>'
+                                        '<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20"><LoadBC dir="1" style="2" load="40" time="0.005"/></BCBox>'
+                                        '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="3.5" zmin="-1" zmax="20"><LoadBC dir="2" style="3" load="0.3" time="300"/></BCBox>'
+                                        "</ParticleBCs>")
+                               .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
     # config 4 family: IsoPlasticity bar on a plate of rigid-BC particles
     "block3d_isoplastic_rigid_wall": (inputs.block3d(ncell=4, margin=3, maxtime=0.02, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
                                                      rigid=("wall", 4, (0.0, 0.0, 0.0)))

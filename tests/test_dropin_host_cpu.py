@@ -21,7 +21,11 @@ CASES = {
                                              '<Parameter name="mass"/></Schedule></CustomTasks>'), "custom tasks other than PeriodicXPIC"),
     "feedback damping": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<FeedbackDamping>10</FeedbackDamping>"),
                          "time-dependent or feedback damping"),
-    "particle loads": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</GridBCs>", "</GridBCs>" + LOAD_BC), "particle load BCs"),
+    # (load BCs that are functions of time alone run on the device since round 2: tests/test_dropin_gpu.py)
+    "silent particle loads": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</GridBCs>", "</GridBCs>" + LOAD_BC.replace('style="1" load="10"', 'style="5"')),
+                              "silent particle load BCs"),
+    "particle loads by function": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</GridBCs>", "</GridBCs>" + LOAD_BC.replace('style="1" load="10"', 'style="6" function="10*x*t"')),
+                                   "particle load BCs set by a function"),
     "unsupported material": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="2" Name="Blk"><rho>1</rho><EA>1000</EA>'
                                             '<ET>500</ET><GA>300</GA><nuT>0.3</nuT><nuA>0.25</nuA><alphaA>0</alphaA><alphaT>0</alphaT></Material>'), "material type"),
     "other hardening law": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="9" Name="Blk"><rho>8.9</rho><E>100000</E><nu>0.33</nu>'
