@@ -121,7 +121,7 @@ TASK_KERNEL = {"mass_and_momentum": "k_f1_mass_momentum", "update_strains_first"
 def ncu_traffic(task, workload, n):
     """dram__bytes_read.sum + dram__bytes_write.sum of the task's kernel, per launch, from the committed
     `ncu --set full` capture of this workload (profiles/run_ncu_final.sh); None when there is no capture of it."""
-    path = os.path.join(ROOT, "profiles", "r1g_dram_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2b_dram_traffic.json")
     if not os.path.exists(path) or task not in TASK_KERNEL:
         return None, None
     d = json.load(open(path))
@@ -129,7 +129,7 @@ def ncu_traffic(task, workload, n):
         return None, None
     for k, v in d["dram_bytes_per_launch"].items():
         if k.startswith(TASK_KERNEL[task]):
-            return v, "profiles/r1g_dram_traffic.json (%s)" % k
+            return v, "profiles/r2b_dram_traffic.json (%s)" % k
     return None, None
 
 

@@ -52,6 +52,7 @@ struct mpmgpu_ctx {
     int *particleIntPool;
     double *nodePool;
     int *cpElemPool; double *cpXiPool, *cpWgPool;   // CPDI domain data (only for CPDI shape functions)
+    size_t cpDomOffset = 0;             // rows of cpXiPool before the 12 rows of Particles::cpDom
     size_t cap;                         // particle capacity
     long long mstep;
     double mtime;
@@ -143,9 +144,12 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
 
     ctx = new mpmgpu_ctx();
     ctx->cfg = *cfg;
-    {   // opt-in until it has been measured on a B200 (written after the round-1 GPU budget was spent)
+    {   // CPDI: one call per touched node instead of one per (corner, node) pair.  3D lCPDI walks the window in registers
+        // (shape.cuh::for_each_node_lcpdi3_hat) in every kernel; 2D keeps thread-local sums, which pay off in the value-only
+        // kernels and spill in the gradient kernels (measured on B200: profiles/r2_experiments/README.md).
+        // MPMGPU_CPDI_MERGE=0/1 forces all kernels, MPMGPU_CPDI_MERGE_VALUES=0 switches the value-only kernels back.
         const char *e = getenv("MPMGPU_CPDI_MERGE");
-        ctx->cpdiMerge = e && atoi(e) != 0;
+        ctx->cpdiMerge = e ? atoi(e) != 0 : is3D;
         const char *v = getenv("MPMGPU_CPDI_MERGE_VALUES");
         ctx->cpdiMergeValues = ctx->cpdiMerge || !(v && atoi(v) == 0);
     }
@@ -295,13 +299,15 @@ static int alloc_particles(mpmgpu_ctx *ctx, size_t cap)
     if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI) {
         const int nc = ctx->dim == 3 ? 8 : (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 9 : 4);
         CK(dalloc(ctx, &ctx->cpElemPool, capPad * nc));
-        CK(dalloc(ctx, &ctx->cpXiPool, capPad * nc * 3));
+        CK(dalloc(ctx, &ctx->cpXiPool, capPad * (nc * 3 + 12)));         // + the 12 rows of Particles::cpDom
         CK(dalloc(ctx, &ctx->cpWgPool, capPad * nc * 3));
         CK(cudaMemsetAsync(ctx->cpElemPool, 0, capPad * nc * sizeof(int), ctx->stream));
-        CK(cudaMemsetAsync(ctx->cpXiPool, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->cpXiPool, 0, capPad * (nc * 3 + 12) * sizeof(double), ctx->stream));
+        ctx->cpDomOffset = (size_t)nc * 3;
         CK(cudaMemsetAsync(ctx->cpWgPool, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
     }
     ctx->P.cpElem = ctx->cpElemPool; ctx->P.cpXi = ctx->cpXiPool; ctx->P.cpWg = ctx->cpWgPool; ctx->P.cpStride = capPad;
+    ctx->P.cpDom = ctx->cpXiPool ? ctx->cpXiPool + ctx->cpDomOffset * capPad : NULL;
     return MPMGPU_OK;
 }
 
@@ -475,11 +481,12 @@ static int alloc_rigid(mpmgpu_ctx *ctx, size_t cap)
         if (ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI) {     // CPDI domains of the rigid particles
             const int nc = ctx->dim == 3 ? 8 : (ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 9 : 4);
             int *ce; double *cx, *cw;
-            CK(dalloc(ctx, &ce, capPad * nc)); CK(dalloc(ctx, &cx, capPad * nc * 3)); CK(dalloc(ctx, &cw, capPad * nc * 3));
+            CK(dalloc(ctx, &ce, capPad * nc)); CK(dalloc(ctx, &cx, capPad * (nc * 3 + 12))); CK(dalloc(ctx, &cw, capPad * nc * 3));
             CK(cudaMemsetAsync(ce, 0, capPad * nc * sizeof(int), ctx->stream));
-            CK(cudaMemsetAsync(cx, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
+            CK(cudaMemsetAsync(cx, 0, capPad * (nc * 3 + 12) * sizeof(double), ctx->stream));
             CK(cudaMemsetAsync(cw, 0, capPad * nc * 3 * sizeof(double), ctx->stream));
             ctx->PR.cpElem = ce; ctx->PR.cpXi = cx; ctx->PR.cpWg = cw; ctx->PR.cpStride = capPad;
+            ctx->PR.cpDom = cx + (size_t)nc * 3 * capPad;
         }
     }
     return MPMGPU_OK;
@@ -1062,6 +1069,7 @@ static int sort_particles(mpmgpu_ctx *ctx)
     bind_particles(ctx->P, ctx->particlePool, ctx->particleIntPool, ctx->cap);
     ctx->P.n = nn; ctx->P.nNR = nnr;
     ctx->P.cpElem = ctx->cpElemPool; ctx->P.cpXi = ctx->cpXiPool; ctx->P.cpWg = ctx->cpWgPool; ctx->P.cpStride = ctx->cap;
+    ctx->P.cpDom = ctx->cpXiPool ? ctx->cpXiPool + ctx->cpDomOffset * ctx->cap : NULL;
     t.stepsSinceSort = 0;
     return MPMGPU_OK;
 }

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(TASK_THREADS) k_init_particles(Grid g, Particl
     get_xipos<DIM>(g, e, pos, xi);
     P.ncpos[0][p] = xi[0]; P.ncpos[1][p] = xi[1]; P.ncpos[2][p] = xi[2];
     if (SHAPE_IS_CPDI(SHAPE) && p < P.nNR) {     // ElementBase::GetShapeFunctionData (MoreMPMElementBase.cpp:50-58)
-        if (!cpdi_setup<DIM, SHAPE>(g, P, p)) atomicCAS(&flags->cpdiLeft, 0, P.orig[p] + 1);
+        // (merged instantiation = every kernel of the step walks the merged window: the lean set-up will do)
+        if (!cpdi_setup<DIM, SHAPE, DIM == 3 && SHAPE == SHAPE_LCPDI_MERGED>(g, P, p)) atomicCAS(&flags->cpdiLeft, 0, P.orig[p] + 1);
     }
 }
 

@@ -78,6 +78,8 @@ struct Particles {
     int *cpElem;             // [ncorner][cap]  1-based element holding the corner
     double *cpXi;            // [ncorner*3][cap] natural coordinates of the corner in that element
     double *cpWg;            // [ncorner*3][cap] gradient weights
+    double *cpDom;           // [12][cap] the domain itself in grid units, frozen for the step like the corner data: centre (3), semi-side
+                             // vectors (3 x 3); rows after the ncorner*3 rows of cpXi.  3D lCPDI: for_each_node_lcpdi3_hat (shape.cuh)
     size_t cpStride;         // cap
 };
 

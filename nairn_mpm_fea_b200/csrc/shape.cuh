@@ -328,7 +328,9 @@ __device__ __forceinline__ void for_each_node(const Grid &g, int inElem, const d
 template <int DIM, int SHAPE>
 struct CpdiTraits { static const int NC = (DIM == 3 ? 8 : (SHAPE_IS_QCPDI(SHAPE) ? 9 : 4)); };
 
-template <int DIM, int SHAPE>
+// LEAN (3D lCPDI with the merged walk in every kernel): a domain that fits the 3x3x3 window stores its 12 domain numbers only --
+// nothing reads the 52 bytes per corner -- and cannot have a corner off the grid when the window is inside it.
+template <int DIM, int SHAPE, bool LEAN = false>
 __device__ __forceinline__ bool cpdi_setup(const Grid &g, const Particles &P, int p)
 {
     const int NC = CpdiTraits<DIM, SHAPE>::NC;
@@ -380,6 +382,27 @@ __device__ __forceinline__ bool cpdi_setup(const Grid &g, const Particles &P, in
                 r1[0] = 0.5 * (la[0] + lb[0]); r1[1] = 0.5 * (la[1] + lb[1]);
                 r2[0] = 0.5 * (la[0] - lb[0]); r2[1] = 0.5 * (la[1] - lb[1]);
             }
+        }
+    }
+    if (DIM == 3 && P.cpDom) {          // the domain in grid units for the merged walk (for_each_node_lcpdi3_hat)
+        const double ic[3] = {1. / g.gx, 1. / g.gy, 1. / g.gz}, mn[3] = {g.xmin, g.ymin, g.zmin};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            P.cpDom[(size_t)d * P.cpStride + p] = (pos[d] - mn[d]) * ic[d];
+            P.cpDom[(size_t)(3 + d) * P.cpStride + p] = r1[d] * ic[d];
+            P.cpDom[(size_t)(6 + d) * P.cpStride + p] = r2[d] * ic[d];
+            P.cpDom[(size_t)(9 + d) * P.cpStride + p] = r3[d] * ic[d];
+        }
+        if (LEAN) {         // the test of for_each_node_lcpdi3_hat
+            bool fits = true;
+            const int nmax[3] = {g.horiz, g.vert, g.depth};
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double ud = (pos[d] - mn[d]) * ic[d], ext = fabs(r1[d] * ic[d]) + fabs(r2[d] * ic[d]) + fabs(r3[d] * ic[d]);
+                const int lo = (int)floor(ud - ext);
+                if ((int)floor(ud + ext) - lo > 1 || lo < 0 || lo + 2 > nmax[d]) fits = false;
+            }
+            if (fits) return true;
         }
     }
     // corner positions
@@ -537,6 +560,90 @@ __device__ __forceinline__ void for_each_node_cpdi(const Grid &g, const Particle
     }
 }
 
+// ---- 3D lCPDI with the corners merged per node, in registers ---------------------------------------------------------
+// The shape function of corner c at node n of its element is the trilinear hat  N_n(x_c) = prod_d max(0, 1 - |v_cd - m_nd|)
+// in grid units (v = (x - min)/cell, m = integer node coordinates: the same polynomial as (1 +- xi)(1 +- eta)(1 +- zeta)/8 of
+// EightNodeIsoparamBrick::ShapeFunction :87-105), and the corner gradient weights of MatPoint3D::GetCPDINodesAndWeights
+// (:551-594) are  wg_c = (s1 r2xr3 + s2 r3xr1 + s3 r1xr2)/Vp  with the corner's signs (s1, s2, s3).  So
+//     S_n = 1/8 sum_c N_n(x_c),     grad S_n = [ (r2xr3) sum_c s1 N_n + (r3xr1) sum_c s2 N_n + (r1xr2) sum_c s3 N_n ] / Vp:
+// four scalar sums per node.  A domain no longer than a cell per axis touches at most 3 nodes per axis; the 3x3x3 window is
+// walked row by row (three nodes at a time: 12 running sums, no thread-local array), each node is handed to f ONCE --
+// 8 to 27 calls instead of 64, which is what the P2G kernels pay for in atomics and the G2P kernels in node reads -- and
+// nothing of the per-corner data cpdi_setup stores (52 bytes per corner) is read.  Returns false for a domain that spans
+// more than two cells along some axis (stretched): the caller then walks the stored corners.
+template <bool GRAD, class F>
+__device__ __forceinline__ bool for_each_node_lcpdi3_hat(const Grid &g, const Particles &P, int p, F &&f)
+{
+    // the domain of this step (position and semi-side vectors in grid units), stored by cpdi_setup: like the reference's corner data
+    // it is made once per step from the state at the start of the step and does not follow the strain and position updates
+    double u[3], a1[3], a2[3], a3[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        u[d] = P.cpDom[(size_t)d * P.cpStride + p];
+        a1[d] = P.cpDom[(size_t)(3 + d) * P.cpStride + p]; a2[d] = P.cpDom[(size_t)(6 + d) * P.cpStride + p]; a3[d] = P.cpDom[(size_t)(9 + d) * P.cpStride + p];
+    }
+    const double r1[3] = {a1[0] * g.gx, a1[1] * g.gy, a1[2] * g.gz}, r2[3] = {a2[0] * g.gx, a2[1] * g.gy, a2[2] * g.gz},
+                 r3[3] = {a3[0] * g.gx, a3[1] * g.gy, a3[2] * g.gz};
+    int lo[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double ext = fabs(a1[d]) + fabs(a2[d]) + fabs(a3[d]);
+        lo[d] = (int)floor(u[d] - ext);
+        if ((int)floor(u[d] + ext) - lo[d] > 1) return false;
+    }
+    if (lo[0] < 0 || lo[1] < 0 || lo[2] < 0 || lo[0] + 2 > g.horiz || lo[1] + 2 > g.vert || lo[2] + 2 > g.depth) return false;
+    // corner coordinates relative to the window's first node, corner order and signs of MatPoint3D.cpp:23-25
+    double cx[8], cy[8], cz[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const double s1 = ((c + 1) & 2) ? 1. : -1., s2 = (c & 2) ? 1. : -1., s3 = (c & 4) ? 1. : -1.;       // s1: - + + - - + + -
+        cx[c] = (u[0] - lo[0]) + s1 * a1[0] + s2 * a2[0] + s3 * a3[0];
+        cy[c] = (u[1] - lo[1]) + s1 * a1[1] + s2 * a2[1] + s3 * a3[1];
+        cz[c] = (u[2] - lo[2]) + s1 * a1[2] + s2 * a2[2] + s3 * a3[2];
+    }
+    double A[3] = {0., 0., 0.}, B[3] = {0., 0., 0.}, C[3] = {0., 0., 0.};
+    if (GRAD) {
+        const double c23[3] = {r2[1] * r3[2] - r2[2] * r3[1], r2[2] * r3[0] - r2[0] * r3[2], r2[0] * r3[1] - r2[1] * r3[0]};
+        const double c31[3] = {r3[1] * r1[2] - r3[2] * r1[1], r3[2] * r1[0] - r3[0] * r1[2], r3[0] * r1[1] - r3[1] * r1[0]};
+        const double c12[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+        const double iVp = 1. / (8. * (r1[0] * c23[0] + r1[1] * c23[1] + r1[2] * c23[2]));
+#pragma unroll
+        for (int d = 0; d < 3; d++) { A[d] = c23[d] * iVp; B[d] = c31[d] * iVp; C[d] = c12[d] * iVp; }
+    }
+    const int n0 = lo[2] * g.zplane + lo[1] * g.yplane + lo[0];
+#pragma unroll 1
+    for (int kz = 0; kz < 3; kz++) {
+#pragma unroll 1
+        for (int jy = 0; jy < 3; jy++) {
+            double s0[3] = {0., 0., 0.}, t1[3] = {0., 0., 0.}, t2[3] = {0., 0., 0.}, t3[3] = {0., 0., 0.};
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const double hy = fmax(0., 1. - fabs(cy[c] - (double)jy)), hz = fmax(0., 1. - fabs(cz[c] - (double)kz));
+                const double yz = hy * hz;
+#pragma unroll
+                for (int ix = 0; ix < 3; ix++) {
+                    const double w = fmax(0., 1. - fabs(cx[c] - (double)ix)) * yz;
+                    s0[ix] += w;
+                    if (GRAD) {
+                        if ((c + 1) & 2) t1[ix] += w; else t1[ix] -= w;
+                        if (c & 2) t2[ix] += w; else t2[ix] -= w;
+                        if (c & 4) t3[ix] += w; else t3[ix] -= w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int ix = 0; ix < 3; ix++) {
+                if (s0[ix] < 1e-15) continue;           // (the reference drops corner weights below 1e-15, MoreMPMElementBase.cpp:618)
+                const int nd = n0 + ix + jy * g.yplane + kz * g.zplane;
+                if (GRAD) f(nd, 0.125 * s0[ix], A[0] * t1[ix] + B[0] * t2[ix] + C[0] * t3[ix], A[1] * t1[ix] + B[1] * t2[ix] + C[1] * t3[ix],
+                            A[2] * t1[ix] + B[2] * t2[ix] + C[2] * t3[ix]);
+                else f(nd, 0.125 * s0[ix], 0., 0., 0.);
+            }
+        }
+    }
+    return true;
+}
+
 // The same node set with the corners' contributions to one node merged before f sees them.  The corners of a domain lie in
 // at most two elements per axis unless the domain is stretched beyond a cell, i.e. on a window of three nodes per axis anchored
 // at the lowest corner element.  The weights are accumulated per window node in thread-local memory and f is called once per
@@ -547,6 +654,11 @@ __device__ __forceinline__ void for_each_node_cpdi(const Grid &g, const Particle
 template <int DIM, int SHAPE, bool GRAD, class F>
 __device__ __forceinline__ void for_each_node_cpdi_merged(const Grid &g, const Particles &P, int p, F &&f)
 {
+    if constexpr (DIM == 3 && SHAPE == SHAPE_LCPDI_MERGED) {
+        // 3D: the register-only walk of the window; a stretched domain (more than two cells along an axis) walks its corners
+        if (!for_each_node_lcpdi3_hat<GRAD>(g, P, p, f)) for_each_node_cpdi<DIM, SHAPE, GRAD>(g, P, p, f);
+        return;
+    }
     const int NC = CpdiTraits<DIM, SHAPE>::NC;
     const int WN = DIM == 3 ? 27 : 9;
     int i0 = 0x7fffffff, j0 = 0x7fffffff, k0 = DIM == 3 ? 0x7fffffff : 0;

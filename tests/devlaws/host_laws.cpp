@@ -114,6 +114,7 @@ extern "C" int devarch_global_sums(int dim, int n, double *pos, double *vel, dou
 }
 
 // ---- CPDI node iteration (csrc/shape.cuh): plain (one call per corner node) against merged (one call per node) ----------
+#include <vector>
 #include "shape.cuh"
 
 // Calls the device iteration for particle p and accumulates what f receives per node into out[4][nnodes] (S, gx, gy, gz) and the
@@ -147,6 +148,49 @@ extern "C" int devshape_cpdi_nodes(int dim, int shape, int merged, int horiz, in
     else if (dim == 2 && shape == SHAPE_LCPDI) { if (merged) run_cpdi<2, SHAPE_LCPDI_MERGED>(g, P, n, out, calls); else run_cpdi<2, SHAPE_LCPDI>(g, P, n, out, calls); }
     else if (dim == 2 && shape == SHAPE_QCPDI) { if (merged) run_cpdi<2, SHAPE_QCPDI_MERGED>(g, P, n, out, calls); else run_cpdi<2, SHAPE_QCPDI>(g, P, n, out, calls); }
     else return -1;
+    return 0;
+}
+
+// 3D lCPDI on REAL domains: the merged iteration derives the corners from pos, F and lp itself (for_each_node_lcpdi3_hat), so the two
+// iterations are compared on particles whose corner data cpdi_setup has just made.  pos[3][n], F[9][n], lp[3][n]; out*[4][nnodes].
+extern "C" int devshape_cpdi3_particles(int horiz, int vert, int depth, const double *xpts, const double *ypts, const double *zpts, double rcrit,
+                                        int n, double *pos, double *F, double *lp, int *elem, double *outPlain, int *callsPlain,
+                                        double *outMerged, int *callsMerged, int *fallbacks)
+{
+    Grid g;
+    memset(&g, 0, sizeof g);
+    g.dim = 3; g.np = 12; g.horiz = horiz; g.vert = vert; g.depth = depth;
+    g.yplane = horiz + 1; g.zplane = (horiz + 1) * (vert + 1);
+    g.nnodes = g.zplane * (depth + 1);
+    g.nelems = horiz * vert * depth;
+    g.xpts = xpts; g.ypts = ypts; g.zpts = zpts;
+    g.xmin = xpts[0]; g.ymin = ypts[0]; g.zmin = zpts[0];
+    g.gx = xpts[1] - xpts[0]; g.gy = ypts[1] - ypts[0]; g.gz = zpts[1] - zpts[0];
+    g.rcrit = rcrit;
+    Particles P;
+    memset(&P, 0, sizeof P);
+    P.n = n; P.nNR = n; P.elem = elem;
+    for (int c = 0; c < 3; c++) { P.pos[c] = pos + (size_t)c * n; P.lp[c] = lp + (size_t)c * n; }
+    for (int c = 0; c < 9; c++) P.F[c] = F + (size_t)c * n;
+    std::vector<int> ce((size_t)8 * n);
+    std::vector<double> cxi((size_t)36 * n), cwg((size_t)24 * n);
+    P.cpElem = ce.data(); P.cpXi = cxi.data(); P.cpWg = cwg.data(); P.cpStride = (size_t)n;
+    P.cpDom = cxi.data() + (size_t)24 * n;
+    const size_t nn = (size_t)g.nnodes;
+    *fallbacks = 0;
+    for (int p = 0; p < n; p++) {
+        if (!cpdi_setup<3, SHAPE_LCPDI>(g, P, p)) return -2;
+        auto fp = [&](int nd, double S, double gx, double gy, double gz) {
+            outPlain[nd] += S; outPlain[nn + nd] += gx; outPlain[2 * nn + nd] += gy; outPlain[3 * nn + nd] += gz; callsPlain[nd]++;
+        };
+        for_each_node_cpdi<3, SHAPE_LCPDI, true>(g, P, p, fp);
+        auto fm = [&](int nd, double S, double gx, double gy, double gz) {
+            outMerged[nd] += S; outMerged[nn + nd] += gx; outMerged[2 * nn + nd] += gy; outMerged[3 * nn + nd] += gz; callsMerged[nd]++;
+        };
+        auto none = [](int, double, double, double, double) {};
+        if (!for_each_node_lcpdi3_hat<true>(g, P, p, none)) (*fallbacks)++;
+        for_each_node_cpdi_merged<3, SHAPE_LCPDI_MERGED, true>(g, P, p, fm);
+    }
     return 0;
 }
 

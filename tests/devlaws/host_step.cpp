@@ -90,8 +90,9 @@ void fill_set(Particles &P, std::vector<double> &pool, std::vector<int> &ipool, 
     }
     if (SHAPE_IS_CPDI(shape)) {
         const int nc = dim == 3 ? 8 : (SHAPE_IS_QCPDI(shape) ? 9 : 4);
-        cpElem.assign(C * nc, 0); cpXi.assign(C * nc * 3, 0.); cpWg.assign(C * nc * 3, 0.);
+        cpElem.assign(C * nc, 0); cpXi.assign(C * (nc * 3 + 12), 0.); cpWg.assign(C * nc * 3, 0.);
         P.cpElem = cpElem.data(); P.cpXi = cpXi.data(); P.cpWg = cpWg.data(); P.cpStride = C;
+        P.cpDom = cpXi.data() + C * nc * 3;
     }
 }
 

@@ -45,7 +45,53 @@ def synthetic_domains(dim, nc, n, horiz, vert, depth, rng):
     return elem, np.ascontiguousarray(xi), np.ascontiguousarray(wg), kind
 
 
-@pytest.mark.parametrize("dim,shape,nc", [(3, LCPDI, 8), (2, LCPDI, 4), (2, QCPDI, 9)])
+def _real_domains(n, horiz, vert, depth, rng, stretch, cell=(1.0, 0.5, 0.25), origin=(-2.0, 1.0, 0.125)):
+    """Particles with deformation gradients around the identity (rotation + stretch up to `stretch`) well inside a grid with unequal
+    cell sizes per axis: the input of the 3D lCPDI iterations (corners are derived from pos, F, lp)."""
+    xp, yp, zp = (origin[d] + cell[d] * np.arange(m + 1) for d, m in enumerate((horiz, vert, depth)))
+    ijk = np.stack([rng.integers(2, m - 2, n) for m in (horiz, vert, depth)])
+    frac = rng.uniform(0.0, 1.0, (3, n))
+    pos = np.stack([origin[d] + cell[d] * (ijk[d] + frac[d]) for d in range(3)])
+    elem = (1 + ijk[0] + horiz * (ijk[1] + vert * ijk[2])).astype(np.int32)
+    F = np.zeros((9, n))
+    for p in range(n):
+        a = rng.standard_normal((3, 3)) * 0.25 * stretch
+        m = np.eye(3) + a
+        if np.linalg.det(m) < 0.2:
+            m = np.eye(3)
+        F[:, p] = m.reshape(9)
+    lp = np.full((3, n), 0.5)
+    return xp, yp, zp, np.ascontiguousarray(pos), np.ascontiguousarray(F), lp, elem
+
+
+@pytest.mark.parametrize("stretch,rcrit", [(0.3, -1.0), (1.0, -1.0), (2.5, 0.6)])
+def test_register_merged_lcpdi3_gives_every_node_the_same_weights(libs, stretch, rcrit):  # noqa: F811
+    """3D lCPDI: the merged iteration (hat functions in grid units, signed corner sums, one call per node) against the plain walk of
+    the stored corners, on real domains: mildly deformed, strongly deformed (some span three cells: corner-walk fallback), and with
+    the rcrit rescaling of ScaleSemiSideVectorsForCPDI."""
+    dev, _ = libs
+    horiz, vert, depth, n = 14, 13, 12, 1500
+    rng = np.random.default_rng(int(10 * stretch) + 3)
+    xp, yp, zp, pos, F, lp, elem = _real_domains(n, horiz, vert, depth, rng, stretch)
+    nnodes = (horiz + 1) * (vert + 1) * (depth + 1)
+    plain, mer = np.zeros((4, nnodes)), np.zeros((4, nnodes))
+    cp, cm = np.zeros(nnodes, np.int32), np.zeros(nnodes, np.int32)
+    fb = C.c_int(0)
+    rc = dev.devshape_cpdi3_particles(horiz, vert, depth, _dp(xp), _dp(yp), _dp(zp), C.c_double(rcrit), n, _dp(pos), _dp(F), _dp(lp), _ip(elem),
+                                      _dp(plain), _ip(cp), _dp(mer), _ip(cm), C.byref(fb))
+    assert rc == 0
+    scale = np.abs(plain).max(axis=1, keepdims=True)
+    assert np.all(np.abs(mer - plain) <= 1e-12 * scale), float((np.abs(mer - plain) / scale).max())
+    assert abs(plain[0].sum() - n) < 1e-9 * n and abs(mer[0].sum() - n) < 1e-9 * n          # partition of unity
+    assert np.all(np.abs(mer[1:].sum(axis=1)) < 1e-9 * n)                                       # gradients sum to zero
+    assert cm.sum() < 0.5 * cp.sum(), (cm.sum(), cp.sum())
+    if stretch < 0.5:
+        assert fb.value == 0
+    if stretch > 2.0 and rcrit < 0:
+        assert fb.value > 0, "some strongly stretched domains should take the corner-walk fallback"
+
+
+@pytest.mark.parametrize("dim,shape,nc", [(2, LCPDI, 4), (2, QCPDI, 9)])
 def test_merged_cpdi_iteration_gives_every_node_the_same_weights(libs, dim, shape, nc):  # noqa: F811
     dev, _ = libs
     horiz, vert, depth = 12, 11, 10
@@ -69,22 +115,23 @@ def test_merged_cpdi_iteration_gives_every_node_the_same_weights(libs, dim, shap
 
 
 def test_merged_iteration_calls_once_per_node_inside_one_element(libs):  # noqa: F811
-    """Undeformed lattice: all 8 corners in the particle's own element -> 8 calls instead of 64."""
+    """Undeformed domains that fit inside their own element: 8 calls instead of 64."""
     dev, _ = libs
-    horiz, vert, depth, n, nc = 8, 8, 8, 50, 8
+    horiz, vert, depth, n = 8, 8, 8, 50
     rng = np.random.default_rng(1)
-    elem = np.zeros((nc, n), np.int32)
-    base = 1 + rng.integers(1, 6, n) + horiz * (rng.integers(1, 6, n) + vert * rng.integers(1, 6, n))
-    elem[:] = base
-    xi = np.ascontiguousarray(rng.uniform(-0.9, 0.9, (3 * nc, n)))
-    wg = np.ascontiguousarray(rng.standard_normal((3 * nc, n)))
+    xp, yp, zp, pos, F, lp, elem = _real_domains(n, horiz, vert, depth, rng, 0.0)
+    cell = np.array([xp[1] - xp[0], yp[1] - yp[0], zp[1] - zp[0]])
+    org = np.array([xp[0], yp[0], zp[0]])
+    ijk = np.floor((pos - org[:, None]) / cell[:, None])
+    pos = org[:, None] + cell[:, None] * (ijk + rng.uniform(0.3, 0.7, (3, n)))        # corners at +-0.25 cell stay inside
+    pos = np.ascontiguousarray(pos)
     nnodes = 9 * 9 * 9
-    tot = []
-    for merged in (0, 1):
-        out, calls = np.zeros((4, nnodes)), np.zeros(nnodes, np.int32)
-        assert dev.devshape_cpdi_nodes(3, LCPDI, merged, horiz, vert, depth, n, _ip(elem), _dp(xi), _dp(wg), _dp(out), _ip(calls)) == 0
-        tot.append(int(calls.sum()))
-    assert tot == [64 * n, 8 * n]
+    plain, mer = np.zeros((4, nnodes)), np.zeros((4, nnodes))
+    cp, cm = np.zeros(nnodes, np.int32), np.zeros(nnodes, np.int32)
+    fb = C.c_int(0)
+    assert dev.devshape_cpdi3_particles(horiz, vert, depth, _dp(xp), _dp(yp), _dp(zp), C.c_double(-1.0), n, _dp(pos), _dp(F), _dp(lp), _ip(elem),
+                                        _dp(plain), _ip(cp), _dp(mer), _ip(cm), C.byref(fb)) == 0
+    assert [int(cp.sum()), int(cm.sum())] == [64 * n, 8 * n]
 
 
 # ---- Linear / uGIMP shape functions and the element search: device source against the C restatement ---------------------
