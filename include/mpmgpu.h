@@ -295,6 +295,22 @@ int mpmgpu_slab_migration_counts(mpmgpu_ctx *ctx, int *n_lo, int *n_hi);
 int mpmgpu_slab_migration_buffers(mpmgpu_ctx *ctx, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, int *row_doubles, int *capacity_rows);
 int mpmgpu_slab_pack_migrants(mpmgpu_ctx *ctx);            /* rows -> send buffers */
 int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int n_from_hi);  /* drop leavers, append arrivals */
+
+/* The same exchanges done by the library itself over NCCL (ncclSend/ncclRecv with the lower and upper z-neighbour on the
+ * context's stream; libnccl.so.2 is resolved at run time): the multi-GPU form of the reference's shared-memory patch
+ * reductions and particle moves (Patches/GhostNode.cpp:127-185, Patches/GridPatch.cpp:214-251).
+ *   mpmgpu_nccl_unique_ids   rank 0: 2 x 128 bytes (ncclUniqueId of the data and of the count communicator); the caller hands
+ *                            them to every rank (MPI, torch.distributed, a file ...)
+ *   mpmgpu_slab_connect      every rank, after mpmgpu_slab_configure: joins the two communicators (collective)
+ *   mpmgpu_slab_step         nsteps full steps: phases 0-3 with the three halo exchanges (and the one inside every XPIC/FMPM
+ *                            iteration) in stream order, then the migration -- the two-integer count handshake runs on the
+ *                            second communicator and stream while the last strain kernel is busy.  Every rank calls it with
+ *                            the same nsteps.
+ *   mpmgpu_slab_migrated     particle rows sent / received so far */
+int mpmgpu_nccl_unique_ids(void *ids256);
+int mpmgpu_slab_connect(mpmgpu_ctx *ctx, int rank, int world, const void *ids256);
+int mpmgpu_slab_step(mpmgpu_ctx *ctx, int nsteps);
+int mpmgpu_slab_migrated(const mpmgpu_ctx *ctx, long long *rows_out, long long *rows_in);
 /* particles that left the grid and were pushed back (ResetElementsTask.cpp:71-151,232-265) since the upload: `exits` counts
  * every push-back, `particles` the particles leaving for the first time -- the events the reference issues its
  * "Particle has left the grid" warning for (abort threshold <LeaveLimit>, NairnMPM.cpp:814-832); the host feeds its own

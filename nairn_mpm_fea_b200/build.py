@@ -11,6 +11,18 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
 
 
+def nccl_include():
+    """nccl.h for the TYPES of the run-time-resolved NCCL calls in capi.cu (the system's, else the wheel torch depends on)."""
+    for d in ("/usr/include", os.path.join(os.path.dirname(os.path.dirname(shutil.which("python") or "")), "lib")):
+        if os.path.exists(os.path.join(d, "nccl.h")):
+            return ["-I" + d]
+    try:
+        import nvidia.nccl
+        return ["-I" + os.path.join(list(nvidia.nccl.__path__)[0], "include")]
+    except Exception:
+        return []
+
+
 def sources():
     out = []
     for f in sorted(os.listdir(CSRC)):
@@ -33,7 +45,7 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     extra = os.environ.get("MPMGPU_NVCC_DEFS", "").split()        # e.g. "-DF2_MINB=5" for tuning runs
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "capi.cu"), "-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "capi.cu"), "-o", LIB, "-ldl"] + nccl_include()
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (p.stdout, p.stderr))

@@ -34,6 +34,7 @@ EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last
     "mpmgpu_slab_migration_buffers", "mpmgpu_slab_pack_migrants", "mpmgpu_slab_finish_migration",
     "mpmgpu_num_particles", "mpmgpu_set_stream",
     "mpmgpu_left_grid_counts",
+    "mpmgpu_nccl_unique_ids", "mpmgpu_slab_connect", "mpmgpu_slab_step", "mpmgpu_slab_migrated",
     "mpmgpu_archive_record_size", "mpmgpu_set_archive_origin", "mpmgpu_pack_archive", "mpmgpu_global_sums", "mpmgpu_download_ids"]
 
 HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)     # mpmgpu_halo_fn
@@ -138,6 +139,10 @@ def load_library(path=None):
     lib.mpmgpu_pack_archive.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.mpmgpu_global_sums.argtypes = [vp, _dp]
     lib.mpmgpu_download_ids.argtypes = [vp, _ip, C.c_int]
+    lib.mpmgpu_nccl_unique_ids.argtypes = [vp]
+    lib.mpmgpu_slab_connect.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.mpmgpu_slab_step.argtypes = [vp, C.c_int]
+    lib.mpmgpu_slab_migrated.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     if lib.mpmgpu_abi_version() != ABI_VERSION:
         raise MpmGpuError(-1, "libmpmgpu ABI %d, binding expects %d" % (lib.mpmgpu_abi_version(), ABI_VERSION))
     if path == LIB_PATH:
@@ -365,6 +370,26 @@ class MpmGpu:
         buf = np.empty(nbytes, np.uint8) if out is None else out
         self._check(self.lib.mpmgpu_pack_archive(self.ctx, order.encode("latin-1"), buf.ctypes.data_as(C.c_void_p), buf.nbytes))
         return buf[:nbytes].tobytes() if out is None else buf
+
+    # ---- NCCL inside the library ----
+    def nccl_unique_ids(self):
+        """256 bytes: the ids of the two NCCL communicators of a slab run (rank 0 makes them, every rank gets them)."""
+        buf = C.create_string_buffer(256)
+        if self.lib.mpmgpu_nccl_unique_ids(buf) != 0:
+            raise MpmGpuError(-1, "mpmgpu_nccl_unique_ids failed (libnccl.so.2 not found?)")
+        return buf.raw
+
+    def slab_connect(self, rank, world, ids):
+        buf = C.create_string_buffer(bytes(ids), 256)
+        self._check(self.lib.mpmgpu_slab_connect(self.ctx, int(rank), int(world), buf))
+
+    def slab_step(self, nsteps=1):
+        self._check(self.lib.mpmgpu_slab_step(self.ctx, int(nsteps)))
+
+    def slab_migrated(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._check(self.lib.mpmgpu_slab_migrated(self.ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def download_ids(self):
         """Particle ids in device order (slab mode: global ids, the order of pack_archive's records there)."""

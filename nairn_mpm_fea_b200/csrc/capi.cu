@@ -18,6 +18,8 @@
 #include "kernels_fused.cuh"
 #include "kernels_pipe.cuh"
 #include "archive.cuh"
+#include <dlfcn.h>
+#include <nccl.h>        // types only: the library is resolved at run time (slab_nccl below)
 
 static std::string g_create_error;
 
@@ -85,6 +87,12 @@ struct mpmgpu_ctx {
     // waits on slabEvent while the strain kernel of the same step is still running
     mpmgpu_halo_fn haloFn; void *haloUser;     // host hook that exchanges halo `which` with the neighbours (XPIC iterations)
     struct SlabHost { int leave[2]; StatusFlags flags; } *slabHost;
+    // NCCL inside the library (mpmgpu_slab_connect / mpmgpu_slab_step): halo and migrant exchange on `comm` in stream order, the
+    // two-integer count handshake on `commSide` + sideStream while the last kernel of the step is still running
+    ncclComm_t comm = NULL, commSide = NULL; int rank = 0, world = 1;
+    cudaStream_t sideStream = NULL; cudaEvent_t sideEvent = NULL;
+    int *dCounts = NULL; int *hCounts = NULL;       // [4] device / pinned host: to lower, to upper, from lower, from upper
+    long long migratedOut = 0, migratedIn = 0;
     cudaEvent_t slabEvent; bool slabPending;                  // dynamic shared memory opt-in done for k_f2_strain_forces<SK, FEXT> on this device
 };
 
@@ -116,6 +124,7 @@ static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
 #define LAUNCH(kernel, grid, block, ...) do { if ((grid) > 0) { kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } } while (0)
 
 // ------------------------------------------------------------------------------------------------
+static void slab_disconnect(mpmgpu_ctx *ctx);
 extern "C" int mpmgpu_abi_version(void) { return MPMGPU_ABI_VERSION; }
 
 extern "C" const char *mpmgpu_last_error(const mpmgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -244,6 +253,7 @@ extern "C" int mpmgpu_destroy(mpmgpu_ctx *ctx)
     tiled_state_free(ctx->tiled);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->slabHost) { cudaFreeHost(ctx->slabHost); cudaEventDestroy(ctx->slabEvent); }
+    slab_disconnect(ctx);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->ownStreamSaved ? ctx->ownStream : ctx->stream);
     delete ctx;
@@ -1723,6 +1733,173 @@ extern "C" int mpmgpu_slab_finish_migration(mpmgpu_ctx *ctx, int n_from_lo, int 
     ctx->P.n = n; ctx->P.nNR = n;
     CK(cudaMemsetAsync(t.slab.leaveCount, 0, 2 * sizeof(int), ctx->stream));
     t.hLeave[0] = t.hLeave[1] = 0;
+    return MPMGPU_OK;
+}
+
+
+// ---- NCCL inside the library ---------------------------------------------------------------------------------------------
+// The slab exchange of the reference's GridPatch/GhostNode decomposition (Patches/GridPatch.cpp:214-251, GhostNode.cpp:127-185) as
+// ncclSend/ncclRecv pairs with the lower and upper z-neighbour, issued by the library itself on the context's stream.
+// libnccl is resolved at run time (the copy the process already holds -- torch's -- or the system's), so libmpmgpu has no link-time
+// dependency on it and a single-GPU user never loads it.
+struct NcclApi {
+    void *lib;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+
+static NcclApi *slab_nccl(void)
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : NULL;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return NULL;
+    api.GetUniqueId = (ncclResult_t (*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (ncclResult_t (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    api.CommDestroy = (ncclResult_t (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    api.Send = (ncclResult_t (*)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+    api.Recv = (ncclResult_t (*)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+    api.GroupStart = (ncclResult_t (*)(void))dlsym(h, "ncclGroupStart");
+    api.GroupEnd = (ncclResult_t (*)(void))dlsym(h, "ncclGroupEnd");
+    api.GetErrorString = (const char *(*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.GetErrorString) return NULL;
+    api.lib = h;
+    return &api;
+}
+
+#define NCCLCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(ctx, MPMGPU_ECUDA, "NCCL: %s (%s)", nccl->GetErrorString(r_), #call); } while (0)
+
+static void slab_disconnect(mpmgpu_ctx *ctx)
+{
+    NcclApi *nccl = slab_nccl();
+    if (nccl && ctx->comm) { nccl->CommDestroy(ctx->comm); ctx->comm = NULL; }
+    if (nccl && ctx->commSide) { nccl->CommDestroy(ctx->commSide); ctx->commSide = NULL; }
+    if (ctx->sideStream) { cudaStreamDestroy(ctx->sideStream); ctx->sideStream = NULL; }
+    if (ctx->sideEvent) { cudaEventDestroy(ctx->sideEvent); ctx->sideEvent = NULL; }
+    if (ctx->hCounts) { cudaFreeHost(ctx->hCounts); ctx->hCounts = NULL; }
+}
+
+// 2 x 128 bytes: the ids of the two communicators of a run (rank 0 makes them, the caller hands them to every rank)
+extern "C" int mpmgpu_nccl_unique_ids(void *ids256)
+{
+    NcclApi *nccl = slab_nccl();
+    if (!nccl || !ids256) { g_create_error = "mpmgpu_nccl_unique_ids: libnccl.so.2 not found"; return MPMGPU_EINVAL; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+    for (int k = 0; k < 2; k++) {
+        ncclUniqueId id;
+        if (nccl->GetUniqueId(&id) != ncclSuccess) return MPMGPU_ECUDA;
+        memcpy((char *)ids256 + 128 * k, &id, 128);
+    }
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_slab_connect(mpmgpu_ctx *ctx, int rank, int world, const void *ids256)
+{
+    if (!ctx || !ids256 || world < 1 || rank < 0 || rank >= world) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_connect: bad argument");
+    if (!ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_connect: call mpmgpu_slab_configure first");
+    NcclApi *nccl = slab_nccl();
+    if (!nccl) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_connect: libnccl.so.2 not found");
+    if ((ctx->tiled.hasLower != 0) != (rank > 0) || (ctx->tiled.hasUpper != 0) != (rank < world - 1))
+        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_connect: rank %d of %d does not match the neighbours given to mpmgpu_slab_configure", rank, world);
+    cudaSetDevice(ctx->cfg.device);
+    ncclUniqueId id[2];
+    memcpy(id, ids256, 256);
+    NCCLCK(nccl->CommInitRank(&ctx->comm, world, id[0], rank));
+    NCCLCK(nccl->CommInitRank(&ctx->commSide, world, id[1], rank));
+    ctx->rank = rank; ctx->world = world;
+    CK(cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->sideEvent, cudaEventDisableTiming));
+    CK(dalloc(ctx, &ctx->dCounts, 4));
+    CK(cudaMallocHost((void **)&ctx->hCounts, 4 * sizeof(int)));
+    return MPMGPU_OK;
+}
+
+// swap halo kind `which` with the neighbours: both directions of both faces in one NCCL group, in stream order
+static int slab_exchange_halo(mpmgpu_ctx *ctx, int which)
+{
+    NcclApi *nccl = slab_nccl();
+    TiledState &t = ctx->tiled;
+    static const int values[4] = {4, 3, 3, 3};
+    const size_t nd = (size_t)values[which] * 3 * t.planeNodes;
+    if (!t.hasLower && !t.hasUpper) return MPMGPU_OK;
+    NCCLCK(nccl->GroupStart());
+    if (t.hasLower) { NCCLCK(nccl->Send(t.haloSend[0], nd, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream)); NCCLCK(nccl->Recv(t.haloRecv[0], nd, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream)); }
+    if (t.hasUpper) { NCCLCK(nccl->Send(t.haloSend[1], nd, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream)); NCCLCK(nccl->Recv(t.haloRecv[1], nd, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream)); }
+    NCCLCK(nccl->GroupEnd());
+    ctx->launches++;
+    return MPMGPU_OK;
+}
+
+static void slab_halo_hook(void *user, int which) { slab_exchange_halo((mpmgpu_ctx *)user, which); }
+
+// particle migration after the element reset: counts to the neighbours on the side communicator (while the second strain
+// update is still running on the main stream), rows on the main one
+static int slab_migrate(mpmgpu_ctx *ctx)
+{
+    NcclApi *nccl = slab_nccl();
+    TiledState &t = ctx->tiled;
+    int nLo = 0, nHi = 0, rc;
+    if ((rc = mpmgpu_slab_migration_counts(ctx, &nLo, &nHi))) return rc;
+    if (!t.hasLower && !t.hasUpper) return MPMGPU_OK;
+    int *h = ctx->hCounts;
+    h[0] = nLo; h[1] = nHi; h[2] = 0; h[3] = 0;
+    CK(cudaMemcpyAsync(ctx->dCounts, h, 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->sideStream));
+    NCCLCK(nccl->GroupStart());
+    if (t.hasLower) { NCCLCK(nccl->Send(ctx->dCounts + 0, 1, ncclInt32, ctx->rank - 1, ctx->commSide, ctx->sideStream)); NCCLCK(nccl->Recv(ctx->dCounts + 2, 1, ncclInt32, ctx->rank - 1, ctx->commSide, ctx->sideStream)); }
+    if (t.hasUpper) { NCCLCK(nccl->Send(ctx->dCounts + 1, 1, ncclInt32, ctx->rank + 1, ctx->commSide, ctx->sideStream)); NCCLCK(nccl->Recv(ctx->dCounts + 3, 1, ncclInt32, ctx->rank + 1, ctx->commSide, ctx->sideStream)); }
+    NCCLCK(nccl->GroupEnd());
+    CK(cudaMemcpyAsync(h + 2, ctx->dCounts + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->sideStream));
+    CK(cudaStreamSynchronize(ctx->sideStream));
+    const int fLo = t.hasLower ? h[2] : 0, fHi = t.hasUpper ? h[3] : 0;
+    if (fLo > t.migCap || fHi > t.migCap) return fail(ctx, MPMGPU_EINVAL, "slab migration capacity %d exceeded by arrivals (%d, %d)", t.migCap, fLo, fHi);
+    if (nLo || nHi) { if ((rc = mpmgpu_slab_pack_migrants(ctx))) return rc; }
+    if (nLo || nHi || fLo || fHi) {
+        NCCLCK(nccl->GroupStart());
+        if (t.hasLower && nLo) NCCLCK(nccl->Send(t.migSend[0], (size_t)nLo * MIG_ROW, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream));
+        if (t.hasLower && fLo) NCCLCK(nccl->Recv(t.migRecv[0], (size_t)fLo * MIG_ROW, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream));
+        if (t.hasUpper && nHi) NCCLCK(nccl->Send(t.migSend[1], (size_t)nHi * MIG_ROW, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream));
+        if (t.hasUpper && fHi) NCCLCK(nccl->Recv(t.migRecv[1], (size_t)fHi * MIG_ROW, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream));
+        NCCLCK(nccl->GroupEnd());
+        ctx->launches++;
+        if ((rc = mpmgpu_slab_finish_migration(ctx, fLo, fHi))) return rc;
+        ctx->migratedOut += nLo + nHi; ctx->migratedIn += fLo + fHi;
+    }
+    return MPMGPU_OK;
+}
+
+// nsteps full steps of one slab of a multi-GPU run, exchanges included (every rank calls it with the same nsteps)
+extern "C" int mpmgpu_slab_step(mpmgpu_ctx *ctx, int nsteps)
+{
+    int rc = check_ready(ctx, "mpmgpu_slab_step"); if (rc) return rc;
+    if (!ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_step: slab mode not configured");
+    const bool alone = !ctx->tiled.hasLower && !ctx->tiled.hasUpper;
+    if (!alone && !ctx->comm) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_slab_step: call mpmgpu_slab_connect first");
+    if (!alone && !ctx->haloFn) { ctx->haloFn = slab_halo_hook; ctx->haloUser = ctx; }     // the exchange inside each XPIC/FMPM iteration
+    for (int s = 0; s < nsteps; s++) {
+        for (int phase = 0; phase < 3; phase++) {
+            if ((rc = mpmgpu_slab_step_phase(ctx, phase))) return rc;
+            if (!alone && (rc = slab_exchange_halo(ctx, phase))) return rc;
+        }
+        if ((rc = mpmgpu_slab_step_phase(ctx, 3))) return rc;
+        if ((rc = slab_migrate(ctx))) return rc;
+    }
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_slab_migrated(const mpmgpu_ctx *ctx, long long *out, long long *in)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (out) *out = ctx->migratedOut;
+    if (in) *in = ctx->migratedIn;
     return MPMGPU_OK;
 }
 

@@ -160,13 +160,39 @@ class SlabSim:
         mptrs, self.row, self.mig_cap = self.sim.slab_migration_buffers()
         self.mig = [device_tensor(p, self.row * self.mig_cap, self.device) for p in mptrs]
         cpu_group = None
-        if world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
+        # production: the library does the exchanges itself over NCCL (mpmgpu_slab_connect / mpmgpu_slab_step); torch.distributed
+        # only carries the communicator ids.  MPMGPU_SLAB_TORCH_EXCHANGE=1 keeps the exchange in this module (torch P2P ops on
+        # the library's buffers), which is also what the lock-step cluster and the gloo tests on CPU exercise.
+        import os
+        self.c_exchange = (world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl"
+                           and os.environ.get("MPMGPU_SLAB_TORCH_EXCHANGE", "0") != "1")
+        if self.c_exchange:
+            obj = [self.sim.nccl_unique_ids() if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0, group=group)
+            self.sim.slab_connect(rank, world, obj[0])
+        elif world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
             cpu_group = dist.new_group(backend="gloo")      # collective: every rank builds its SlabSim
         self.ex = NeighbourExchange(rank, world, group, cpu_group)
-        if world > 1:
+        if world > 1 and not self.c_exchange:
             self.sim.slab_set_halo_callback(self._halo)      # XPIC/FMPM iterations exchange in the middle of a phase
-        self.migrated_out = 0
-        self.migrated_in = 0
+        self._migrated_out = 0
+        self._migrated_in = 0
+
+    @property
+    def migrated_out(self):
+        return self.sim.slab_migrated()[0] if self.c_exchange else self._migrated_out
+
+    @migrated_out.setter
+    def migrated_out(self, v):
+        self._migrated_out = v
+
+    @property
+    def migrated_in(self):
+        return self.sim.slab_migrated()[1] if self.c_exchange else self._migrated_in
+
+    @migrated_in.setter
+    def migrated_in(self, v):
+        self._migrated_in = v
 
     def _halo(self, which):
         nd = HALO_VALUES[which] * 3 * self.plane_nodes
@@ -174,6 +200,9 @@ class SlabSim:
         self.ex.swap(s_lo[:nd], s_hi[:nd], r_lo[:nd], r_hi[:nd])
 
     def step(self, nsteps=1):
+        if self.c_exchange:
+            self.sim.slab_step(nsteps)
+            return
         with torch.cuda.stream(self.stream):
             for _ in range(nsteps):
                 for phase in range(3):

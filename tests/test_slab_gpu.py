@@ -72,17 +72,20 @@ def test_lockstep_slab_that_starts_empty():
     cl.close()
 
 
+@pytest.mark.parametrize("exchange", ["library", "torch"])
 @pytest.mark.parametrize("case,extra", [("block3d_fast_crossings", ()), ("block3d_xpic3", ("--no-migration-needed",)),
                                         ("block3d_fmpm2", ("--no-migration-needed",)), ("block3d_rigid_wall", ("--no-migration-needed",))])
-def test_two_ranks_over_nccl(case, extra):
+def test_two_ranks_over_nccl(case, extra, exchange):
     """2 processes, 2 GPUs, NCCL: halo exchanges (incl. the ones inside XPIC/FMPM iterations), migration, replicated
-    rigid particles; compared with the reference dump."""
+    rigid particles; compared with the reference dump.  exchange = library: ncclSend/ncclRecv issued by libmpmgpu itself
+    (mpmgpu_slab_connect / mpmgpu_slab_step, the production path); torch: the same buffers moved by torch.distributed P2P ops."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "slab_worker.py"),
            case, *extra]
-    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, MPMGPU_SLAB_TORCH_EXCHANGE="1" if exchange == "torch" else "0")
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "SLAB_OK" in p.stdout
