@@ -312,7 +312,7 @@ def run_ours(args):
     bcv = np.zeros(nb)
     ARCHIVE_ORDER = "iYYYYNNNNNNNYNNNNY"
     rec = sim.archive_record_size(ARCHIVE_ORDER)
-    arch = torch.empty(int(rec * n * (1.3 if world > 1 else 1.0)) + 4096, dtype=torch.uint8).pin_memory().numpy()    # slabs: particle count changes by migration
+    arch = torch.empty(int(rec * sim.num_particles() * (1.3 if world > 1 else 1.0)) + 4096, dtype=torch.uint8).pin_memory().numpy()    # slabs: particle count changes by migration
     barrier()
     t0 = time.perf_counter()
     sim.upload(pinned)
