@@ -185,6 +185,37 @@ def make_problem(workload, ncell_override=None, rank=0, world=1):
     return pr, ncell
 
 
+def time_workload(workload, local, steps=20, warmup=3):
+    """Device-resident ms/step of another BASELINE config on this GPU (one line of the `configs` key of the default run)."""
+    import torch
+    from nairn_mpm_fea_b200 import MpmGpu
+    if workload == "disks2d":
+        # config 1: the 2D plane-strain uGIMP disk impact the parity tests use (reference dump, tests/golden)
+        from nairn_mpm_fea_b200.problem import from_reference_dump
+        z = np.load(os.path.join(ROOT, "tests", "golden", "disks2d_ugimp_planestrain.npz"), allow_pickle=False)
+        prob = from_reference_dump({k: z[k] for k in z.files if not k.startswith("s1/")})
+        n = prob.nparticles
+    else:
+        prob, _ = make_problem(workload)
+        n = int(prob.particles["n_nonrigid"])
+    sim = MpmGpu(prob, device=local)
+    sim.set_poll_interval(16)
+    stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local))
+    for _ in range(warmup):
+        sim.step(1)
+    sim.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        sim.step(1)
+    e1.record(stream)
+    sim.synchronize()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    sim.close()
+    return {"particles": n, "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": UNIT, "steps": steps}
+
+
 def host_state_bytes(pt):
     n = 0
     for k, v in pt.items():
@@ -370,6 +401,13 @@ def run_ours(args):
         if rank == 0:
             line["parity"] = par
             line["parity_max_rel"] = par["max_rel"] if par else None
+        if world == 1 and args.workload == "block8m" and not args.no_other_configs:
+            # the other BASELINE.json configs on this GPU, device-resident (their own lines: profiles/bench_r2/)
+            line["configs"] = {"1: 2D plane-strain uGIMP disk impact (tests/golden/disks2d_ugimp_planestrain)": time_workload("disks2d", local, 200, 20),
+                               "2: block1m (3D uGIMP elastic block, 1M particles, FLIP)": time_workload("block1m", local, 50, 5),
+                               "3: neo8m (3D Neo-Hookean block, 8M particles, lCPDI, XPIC(2))": time_workload("neo8m", local, 10, 3),
+                               "4: taylor16m on ONE GPU (IsoPlasticity bar on rigid-BC plate, 16M particles)": time_workload("taylor16m", local, 10, 3),
+                               "5: block8m": "this line"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -531,6 +569,7 @@ def main():
     ap.add_argument("--cpu-ncell", type=int, default=50, help="block edge of the CPU sample (50 -> 1M particles)")
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the CPU sample (about 10 s of CPU work on 16 threads at 1M particles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short device-resident runs of BASELINE configs 1-4 (default workload, 1 GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

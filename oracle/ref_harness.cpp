@@ -42,6 +42,8 @@
 #include "Materials/LinearHardening.hpp"
 #include "Materials/RigidMaterial.hpp"
 #include "Boundary_Conditions/NodalVelBC.hpp"
+#include "Materials/ContactLaw.hpp"
+#include "Materials/CoulombFriction.hpp"
 #include "Boundary_Conditions/MatPtLoadBC.hpp"
 #include "Global_Quantities/BodyForce.hpp"
 #include "Custom_Tasks/CustomTask.hpp"
@@ -277,6 +279,62 @@ void ref_get_nodes(int *numberPoints, double *mass, double *pk, double *ftot, do
         if (pkcopy) { Vector &c = mvf->vk[MatVelocityField::pkCopy];
                       pkcopy[k] = c.x; pkcopy[n + k] = c.y; pkcopy[2 * n + k] = c.z; }
     }
+}
+
+// ---- multimaterial mode: one set of node accumulators per material velocity field cvf[0]->mvf[f] -----------------------------
+int ref_num_fields(void) { return fmobj->multiMaterialMode ? maxMaterialFields : 1; }
+
+// field f of every node: the accumulators of ref_get_nodes plus the contact extrapolations (volume, volume gradient, displacement)
+void ref_get_nodes_field(int f, int *numberPoints, double *mass, double *pk, double *ftot, double *vk0, double *pkcopy,
+                         double *cvolume, double *cgrad, double *cdisp)
+{
+    int n = nnodes;
+    for (int i = 1; i <= n; i++) {
+        int k = i - 1;
+        MatVelocityField *mvf = NULL;
+        if (nd[i]->cvf != NULL && nd[i]->cvf[0] != NULL && nd[i]->cvf[0]->mvf != NULL && f < maxMaterialFields) mvf = nd[i]->cvf[0]->mvf[f];
+        numberPoints[k] = 0; mass[k] = 0.; cvolume[k] = 0.;
+        for (int c = 0; c < 3; c++) { pk[c * n + k] = 0.; ftot[c * n + k] = 0.; vk0[c * n + k] = 0.; pkcopy[c * n + k] = 0.; cgrad[c * n + k] = 0.; cdisp[c * n + k] = 0.; }
+        if (mvf == NULL) continue;
+        numberPoints[k] = mvf->numberPoints;
+        mass[k] = mvf->mass;
+        pk[k] = mvf->pk.x; pk[n + k] = mvf->pk.y; pk[2 * n + k] = mvf->pk.z;
+        Vector ft = mvf->GetFtot();
+        ftot[k] = ft.x; ftot[n + k] = ft.y; ftot[2 * n + k] = ft.z;
+        vk0[k] = mvf->vk[0].x; vk0[n + k] = mvf->vk[0].y; vk0[2 * n + k] = mvf->vk[0].z;
+        Vector &c = mvf->vk[MatVelocityField::pkCopy];
+        pkcopy[k] = c.x; pkcopy[n + k] = c.y; pkcopy[2 * n + k] = c.z;
+        if (mvf->contactInfo != NULL) {
+            cvolume[k] = mvf->contactInfo->cvolume;
+            if (mpmgrid.volumeGradientIndex >= 0) { Vector &v = mvf->contactInfo->terms[mpmgrid.volumeGradientIndex]; cgrad[k] = v.x; cgrad[n + k] = v.y; cgrad[2 * n + k] = v.z; }
+            if (mpmgrid.displacementIndex >= 0) { Vector &v = mvf->contactInfo->terms[mpmgrid.displacementIndex]; cdisp[k] = v.x; cdisp[n + k] = v.y; cdisp[2 * n + k] = v.z; }
+        }
+    }
+}
+
+// multimaterial settings: out[0] normal method, out[1] contactByDisplacements, out[2] number of materials; field[m] = velocity field of
+// material m (-1 unused); law[(i*nmat+j)*4 ..]: contact law of the pair (kind: 0 ignore, 1 stick, 2 frictionless, 3 frictional, -1 other;
+// friction coefficient; static coefficient; 0)
+void ref_get_multimaterial(int *out, int *field, double *law)
+{
+    out[0] = mpmgrid.materialNormalMethod; out[1] = mpmgrid.contactByDisplacements ? 1 : 0; out[2] = nmat;
+    for (int i = 0; i < nmat; i++) field[i] = theMaterials[i]->GetField();
+    for (int i = 0; i < nmat; i++)
+        for (int j = 0; j < nmat; j++) {
+            double *q = law + ((size_t)i * nmat + j) * 4;
+            q[0] = -1.; q[1] = 0.; q[2] = 0.; q[3] = 0.;
+            if (!fmobj->multiMaterialMode || field[i] < 0 || field[j] < 0 || i == j) continue;
+            ContactLaw *cl = mpmgrid.GetMaterialContactLaw(field[i], field[j]);
+            if (cl == NULL) continue;
+            if (cl->IgnoreContact()) q[0] = 0.;
+            else if (cl->IsImperfectInterface()) q[0] = -1.;
+            else {
+                CoulombFriction *cf = dynamic_cast<CoulombFriction *>(cl);
+                if (cf == NULL || strcmp(cl->MaterialType(), "Coulomb Friction") != 0) continue;
+                q[0] = cf->IsStick() ? 1. : (cf->IsFrictionless() ? 2. : 3.);
+                q[1] = cf->frictionCoeff; q[2] = cf->frictionCoeffStatic;
+            }
+        }
 }
 
 // grid velocity BC list, in the reference's list order
