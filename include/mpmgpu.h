@@ -63,6 +63,7 @@ extern "C" {
 #define MPMGPU_BSPLINE_CPDI   13  /* B2CPDI: linear CPDI domains over quadratic B-splines (per-task kernels) */
 
 /* material kinds: reference MaterialID() values, Common/Read_XML/MaterialController.cpp:105-232 */
+#define MPMGPU_MAT_NONE           0   /* place holder for a host materials-list entry that is not a particle material (a contact law) */
 #define MPMGPU_MAT_ISOTROPIC      1   /* IsotropicMat, small- or large-rotation hypoelastic */
 #define MPMGPU_MAT_MOONEY         8   /* Mooney (Mooney-Rivlin hyperelastic; per-task kernels) */
 #define MPMGPU_MAT_ISOPLASTICITY  9   /* IsoPlasticity + LinearHardening */
@@ -187,6 +188,11 @@ typedef struct mpmgpu_nodes {
     double *ftot;           /* [3][nnodes] force */
     double *vk;             /* [3][nnodes] vk[0] */
     double *pk_copy;        /* [3][nnodes] vk[pkCopy] */
+    /* multimaterial mode only (mpmgpu_set_multimaterial): every array above and below is n_fields * (grid nodes) long,
+     * field-major -- material velocity field f of node i at [f * nodes + i] -- and nnodes returns that length */
+    double *contact_volume;   /* MatVelocityField::contactInfo->cvolume */
+    double *contact_gradient; /* [3][nnodes] volume gradient (terms[volumeGradientIndex]) */
+    double *contact_disp;     /* [3][nnodes] mass-weighted displacement or position (contactByDisplacements) */
 } mpmgpu_nodes;
 
 /* ---- life cycle -------------------------------------------------------------------------- */
@@ -197,6 +203,29 @@ const char *mpmgpu_last_error(const mpmgpu_ctx *ctx);   /* ctx may be NULL for c
 
 /* ---- set-up (host -> device) ------------------------------------------------------------- */
 int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_material *mats);
+/* Multimaterial mode (<MultiMaterialMode>, fmobj->multiMaterialMode): every node carries one velocity field per material
+ * field (CrackVelocityFieldMulti::mvf[], Nodes/CrackVelocityFieldMulti.cpp:51-191 with a single crack field) and nodes seen by
+ * two or more materials get material contact after the mass/momentum extrapolation, the momentum update and the
+ * re-extrapolation of USAVG+/USL+ (MaterialContactNode::ContactOnKnownNodes -> MaterialContactOnCVFLumped,
+ * CrackVelocityFieldMulti.cpp:302-674; UpdateMomentaTask::ContactAndMomentaBCs).  Built: nonrigid materials, normals from the
+ * volume gradients (methods 0-3, GetNormalVector :960-1071) or specified (4), contact detected by displacements or positions
+ * (CrackSurfaceContact::MaterialSeparation), contact laws ignore / stick / frictionless / Coulomb friction with optional static
+ * coefficient (Materials/CoulombFriction.cpp:150-272), three or more materials lumped as the reference does.  Refused: the
+ * regression normals (5, 6), imperfect interfaces, adhesion, rigid contact materials, XPIC/FMPM order > 1 (FMPM contact
+ * increments), slab mode.  Runs on the per-task kernels.  Call after mpmgpu_set_materials and before mpmgpu_upload_particles;
+ * displacements are taken against the original positions of mpmgpu_set_archive_origin (default: the positions at upload). */
+typedef struct mpmgpu_multimaterial {
+    int n_fields;                   /* maxMaterialFields: material velocity fields per node (<= 8) */
+    const int *field_of_material;   /* [nmat] MaterialBase::GetField() of every material (ignored for rigid-BC materials) */
+    int normal_method;              /* mpmgrid.materialNormalMethod: 0 MAXG, 1 MAXV, 2 AVGG, 3 OWNG, 4 SN (MeshInfo.hpp:31) */
+    int contact_by_displacements;   /* mpmgrid.contactByDisplacements */
+    double position_cutoff;         /* mpmgrid.positionCutoff (<ContactPosition>; < 0: the power-law form) */
+    double contact_normal[3];       /* mpmgrid.contactNormal (method 4) */
+    const int *law_kind;            /* [n_fields][n_fields] mpmgrid.GetMaterialContactLaw(i, j): 0 ignore, 1 stick, 2 frictionless, 3 Coulomb friction */
+    const double *law_friction;     /* [n_fields][n_fields] CoulombFriction::frictionCoeff (NULL: 0) */
+    const double *law_static;       /* [n_fields][n_fields] frictionCoeffStatic, <= 0 for none (NULL: none) */
+} mpmgpu_multimaterial;
+int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm);
 int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
 /* timestep, strainTimestepFirst, strainTimestepLast (NairnMPM.cpp:1207-1240) */
 int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dt_strain_first, double dt_strain_last);

@@ -25,7 +25,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
-           "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
+           "mpmgpu_set_multimaterial", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
@@ -67,7 +67,13 @@ class ParticlesView(C.Structure):
 
 class NodesView(C.Structure):
     _fields_ = [("nnodes", C.c_int), ("number_points", _ip), ("mass", _dp), ("pk", _dp), ("ftot", _dp),
-                ("vk", _dp), ("pk_copy", _dp)]
+                ("vk", _dp), ("pk_copy", _dp), ("contact_volume", _dp), ("contact_gradient", _dp), ("contact_disp", _dp)]
+
+
+class MultiMaterial(C.Structure):
+    _fields_ = [("n_fields", C.c_int), ("field_of_material", _ip), ("normal_method", C.c_int), ("contact_by_displacements", C.c_int),
+                ("position_cutoff", C.c_double), ("contact_normal", C.c_double * 3), ("law_kind", _ip), ("law_friction", _dp),
+                ("law_static", _dp)]
 
 
 GS_NSUMS = 29
@@ -102,6 +108,7 @@ def load_library(path=None):
     lib.mpmgpu_last_error.restype = C.c_char_p
     lib.mpmgpu_set_materials.argtypes = [vp, C.c_int, C.POINTER(Material)]
     lib.mpmgpu_upload_particles.argtypes = [vp, C.POINTER(ParticlesView)]
+    lib.mpmgpu_set_multimaterial.argtypes = [vp, C.POINTER(MultiMaterial)]
     lib.mpmgpu_set_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.mpmgpu_set_xpic.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
@@ -212,11 +219,16 @@ class MpmGpu:
                 mats[k].p[j] = v
         self._check(self.lib.mpmgpu_set_materials(self.ctx, len(prob.materials), mats))
         self._check(self.lib.mpmgpu_set_time_step(self.ctx, prob.dt, prob.dt_strain_first, prob.dt_strain_last))
+        mm = getattr(prob, "multimaterial", None)
+        if mm is not None:
+            self.set_multimaterial(mm)
         self.set_velocity_bcs(prob.bc_node, prob.bc_norm, prob.bc_value, prob.bc_active, prob.bc_symdir)
         if getattr(prob, "bc_reflected", None) is not None:
             self.set_velocity_bc_reflections(prob.bc_reflected, prob.bc_ratio)
         if upload:
             self.upload(prob.particles)
+            if mm is not None and getattr(prob, "origpos", None) is not None:
+                self.set_archive_origin(origpos=prob.origpos)        # contact by displacements: MPMBase::origpos
 
     # -- plumbing -----------------------------------------------------------------------------
     def _check(self, rc):
@@ -250,6 +262,23 @@ class MpmGpu:
             setattr(v, k, _i(keep[k]))
         self.n = n
         self._check(self.lib.mpmgpu_upload_particles(self.ctx, C.byref(v)))
+
+    def set_multimaterial(self, mm):
+        """<MultiMaterialMode> settings (Problem.multimaterial): one velocity field per material field + material contact."""
+        v = MultiMaterial()
+        nf = int(mm["n_fields"])
+        keep = [_c32(mm["field_of_material"]), _c32(np.asarray(mm["law_kind"]).reshape(nf * nf)),
+                _c64(np.asarray(mm["law_friction"], float).reshape(nf * nf)), _c64(np.asarray(mm["law_static"], float).reshape(nf * nf))]
+        v.n_fields = nf
+        v.field_of_material = _i(keep[0])
+        v.normal_method = int(mm["normal_method"])
+        v.contact_by_displacements = int(mm["by_displacements"])
+        v.position_cutoff = float(mm["position_cutoff"])
+        v.contact_normal = (C.c_double * 3)(*[float(x) for x in mm["contact_normal"]])
+        v.law_kind, v.law_friction, v.law_static = _i(keep[1]), _d(keep[2]), _d(keep[3])
+        self._check(self.lib.mpmgpu_set_multimaterial(self.ctx, C.byref(v)))
+        self.nnodes = self.prob.nnodes * nf          # node arrays are field-major from now on
+        self.n_fields = nf
 
     def set_velocity_bcs(self, node, norm, value, active=None, symdir=None):
         n = 0 if node is None else len(node)
@@ -346,6 +375,10 @@ class MpmGpu:
         v.number_points = _i(out["number_points"])
         for k in ("mass", "pk", "ftot", "vk", "pk_copy"):
             setattr(v, k, _d(out[k]))
+        if getattr(self, "n_fields", 0):
+            out.update(contact_volume=np.zeros(n), contact_gradient=np.zeros((3, n)), contact_disp=np.zeros((3, n)))
+            for k in ("contact_volume", "contact_gradient", "contact_disp"):
+                setattr(v, k, _d(out[k]))
         self._check(self.lib.mpmgpu_download_nodes(self.ctx, C.byref(v)))
         return out
 

@@ -81,6 +81,16 @@ struct mpmgpu_ctx {
     cudaEvent_t ev0, ev1;
     double taskMs[T_NTASKS];
     long long taskCalls[T_NTASKS];
+    // multimaterial mode (mpmgpu_set_multimaterial): nf material velocity fields per node, node arrays field-major
+    bool multimaterial = false;
+    int nf = 1;                         // fields per node
+    int nvn = 0;                        // "virtual" nodes = nf * g.nnodes: the length the per-task node kernels run over
+    size_t nodePad = 0;                 // padded length of one node array
+    ContactNodes C;                     // contact extrapolations (volume, volume gradient, displacement/position)
+    double *contactPool = NULL;
+    ContactParams cp;
+    int *dFieldOfMat = NULL, *foffPool = NULL;
+    std::vector<int> hFieldOfMat;
     TiledState tiled;
     bool f2Attr[2][2];
     // slab mode: leave counts + status flags land here (pinned) right after the early element reset; the host
@@ -122,6 +132,27 @@ static inline int nblocks(long long n, int t) { return (int)((n + t - 1) / t); }
 
 // (a grid computed from a particle count can be empty: a slab that holds no particles at the moment)
 #define LAUNCH(kernel, grid, block, ...) do { if ((grid) > 0) { kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); ctx->launches++; } } while (0)
+
+// node arrays: mass + 7 vectors in one pool, `count` entries each (count = fields x nodes in multimaterial mode)
+static int alloc_node_arrays(mpmgpu_ctx *ctx, size_t count)
+{
+    const size_t pad = (count + 31) & ~(size_t)31;
+    if (dalloc(ctx, &ctx->nodePool, pad * 22) != cudaSuccess) return MPMGPU_ECUDA;
+    cudaMemset(ctx->nodePool, 0, pad * 22 * sizeof(double));
+    double *q = ctx->nodePool;
+    ctx->N.mass = q; q += pad;
+    for (int c = 0; c < 3; c++) { ctx->N.pk[c] = q; q += pad; }
+    for (int c = 0; c < 3; c++) { ctx->N.ftot[c] = q; q += pad; }
+    for (int c = 0; c < 3; c++) { ctx->N.vk[c] = q; q += pad; }
+    for (int c = 0; c < 3; c++) { ctx->N.pkc[c] = q; q += pad; }
+    for (int c = 0; c < 3; c++) { ctx->N.vsp[c] = q; q += pad; }
+    for (int c = 0; c < 3; c++) { ctx->N.vsn[c] = q; q += pad; }
+    if (dalloc(ctx, &ctx->N.cnt, pad) != cudaSuccess) return MPMGPU_ECUDA;
+    cudaMemset(ctx->N.cnt, 0, pad * sizeof(int));
+    ctx->nodePad = pad;
+    ctx->nvn = (int)count;
+    return MPMGPU_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 static void slab_disconnect(mpmgpu_ctx *ctx);
@@ -172,7 +203,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->nBCEntries = 0;
     memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R);
     ctx->rigidPool = NULL; ctx->rigidIntPool = NULL; ctx->rigidCap = 0;
-    memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B);
+    memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B); memset(&ctx->C, 0, sizeof ctx->C); memset(&ctx->cp, 0, sizeof ctx->cp);
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
     memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
     tiled_state_init(ctx->tiled);
@@ -206,21 +237,9 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
             cudaMemcpy(dz, cfg->zpts, (g.depth + 1) * sizeof(double), cudaMemcpyHostToDevice);
         }
         g.xpts = dx; g.ypts = dy; g.zpts = dz;
-        // node arrays: mass + 7 vectors, one pool
         size_t nn = (size_t)g.nnodes;
         size_t nnPad = (nn + 31) & ~(size_t)31;
-        if (dalloc(ctx, &ctx->nodePool, nnPad * 22) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
-        cudaMemset(ctx->nodePool, 0, nnPad * 22 * sizeof(double));
-        double *q = ctx->nodePool;
-        ctx->N.mass = q; q += nnPad;
-        for (int c = 0; c < 3; c++) { ctx->N.pk[c] = q; q += nnPad; }
-        for (int c = 0; c < 3; c++) { ctx->N.ftot[c] = q; q += nnPad; }
-        for (int c = 0; c < 3; c++) { ctx->N.vk[c] = q; q += nnPad; }
-        for (int c = 0; c < 3; c++) { ctx->N.pkc[c] = q; q += nnPad; }
-        for (int c = 0; c < 3; c++) { ctx->N.vsp[c] = q; q += nnPad; }
-        for (int c = 0; c < 3; c++) { ctx->N.vsn[c] = q; q += nnPad; }
-        if (dalloc(ctx, &ctx->N.cnt, nnPad) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
-        cudaMemset(ctx->N.cnt, 0, nnPad * sizeof(int));
+        if (alloc_node_arrays(ctx, nn) != MPMGPU_OK) { rc = MPMGPU_ECUDA; break; }
         if (dalloc(ctx, &ctx->dFlags, 1) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
         cudaMemset(ctx->dFlags, 0, sizeof(StatusFlags));
         if (dalloc(ctx, &ctx->dMats, MPM_MAX_MATERIALS) != cudaSuccess) { rc = MPMGPU_ECUDA; break; }
@@ -267,6 +286,11 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
     ctx->largeRotation = false;
     for (int i = 0; i < nmat; i++) {
         int k = mats[i].kind;
+        if (k == MAT_NONE) {        // a contact law's place in the host's materials list: no particle may use it
+            ctx->hMats[i].kind = k; ctx->hMats[i].nhist = 0;
+            memset(ctx->hMats[i].p, 0, sizeof ctx->hMats[i].p);
+            continue;
+        }
         if (k != MAT_ISOTROPIC && k != MAT_RIGIDBC && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY && k != MAT_MOONEY)
             return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d is not supported (IsotropicMat 1, Mooney 8, IsoPlasticity 9, rigid BC 11, Neohookean 28)", k);
         if (mats[i].n_history < 0 || mats[i].n_history > MPM_MAX_HISTORY) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: %d history doubles (max %d)", mats[i].n_history, MPM_MAX_HISTORY);
@@ -286,6 +310,63 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
     ctx->nmat = nmat;
     CK(cudaMemcpyAsync(ctx->dMats, ctx->hMats.data(), nmat * sizeof(Material), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+// <MultiMaterialMode>: mvf[field] per node + material contact.  After mpmgpu_set_materials, before mpmgpu_upload_particles.
+extern "C" int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm)
+{
+    if (!ctx || !mm) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: null argument");
+    if (ctx->nmat == 0) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_multimaterial: call mpmgpu_set_materials first");
+    if (ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_multimaterial: call before mpmgpu_upload_particles");
+    if (ctx->tiled.slab.on) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: not available in slab mode");
+    if (ctx->cfg.kernel_path == 2) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: multimaterial mode runs on the per-task kernels (kernel_path 2 asked for the fused path)");
+    if (mm->n_fields < 1 || mm->n_fields > MPM_MAX_FIELDS) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: %d material velocity fields (1..%d)", mm->n_fields, MPM_MAX_FIELDS);
+    if (mm->normal_method < NORMALS_MAXG || mm->normal_method > NORMALS_SPECIFIED)
+        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: normal method %d is not supported (0 MAXG, 1 MAXV, 2 AVGG, 3 OWNG, 4 SN; the regression methods 5 and 6 are not built)", mm->normal_method);
+    if (!mm->field_of_material || !mm->law_kind) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: field_of_material and law_kind are required");
+    if (ctx->sp.xpicOrder > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: XPIC/FMPM of order > 1 with material contact (MaterialXPICIncrementOnCVF) is not built");
+    cudaSetDevice(ctx->cfg.device);
+    const int nf = mm->n_fields;
+    ctx->hFieldOfMat.assign(ctx->nmat, 0);
+    for (int m = 0; m < ctx->nmat; m++) {
+        const int f = mm->field_of_material[m];
+        if (ctx->hMats[m].kind == MAT_RIGIDBC) { ctx->hFieldOfMat[m] = 0; continue; }       // rigid-BC particles have no field
+        if (f < 0 || f >= nf) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: material %d has velocity field %d of %d", m + 1, f, nf);
+        ctx->hFieldOfMat[m] = f;
+    }
+    ContactParams &cp = ctx->cp;
+    memset(&cp, 0, sizeof cp);
+    cp.nf = nf; cp.normalMethod = mm->normal_method; cp.byDisplacements = mm->contact_by_displacements ? 1 : 0;
+    cp.positionCutoff = mm->position_cutoff;
+    for (int c = 0; c < 3; c++) cp.normal[c] = mm->contact_normal[c];
+    {   // MeshInfo::SetCartesian (MeshInfo.cpp:1466-1480): square / cubic cells by DbleEqual
+        auto dbleEqual = [](double a, double b) { const double d = fabs(a - b); if (d <= 1.0e-16) return true; a = fabs(a); b = fabs(b); return d <= (b > a ? b : a) * 1.0e-7; };
+        cp.cubic = dbleEqual(ctx->g.gx, ctx->g.gy) && (ctx->dim == 2 || dbleEqual(ctx->g.gx, ctx->g.gz)) ? 1 : 0;
+    }
+    for (int i = 0; i < nf; i++)
+        for (int j = 0; j < nf; j++) {
+            const int k = mm->law_kind[i * nf + j];
+            if (i != j && (k < LAW_IGNORE || k > LAW_FRICTIONAL))
+                return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: contact law %d between fields %d and %d is not supported (0 ignore, 1 stick, 2 frictionless, 3 Coulomb friction)", k, i, j);
+            cp.lawKind[i * nf + j] = i == j ? LAW_IGNORE : k;
+            cp.lawFriction[i * nf + j] = mm->law_friction ? mm->law_friction[i * nf + j] : 0.;
+            cp.lawStatic[i * nf + j] = mm->law_static ? mm->law_static[i * nf + j] : -1.;
+        }
+    // node arrays for nf fields per node, field-major, plus the contact extrapolations
+    if (alloc_node_arrays(ctx, (size_t)nf * ctx->g.nnodes) != MPMGPU_OK) return fail(ctx, MPMGPU_ECUDA, "mpmgpu_set_multimaterial: node arrays: %s", cudaGetErrorString(cudaGetLastError()));
+    CK(dalloc(ctx, &ctx->contactPool, ctx->nodePad * 7));
+    CK(cudaMemset(ctx->contactPool, 0, ctx->nodePad * 7 * sizeof(double)));
+    {
+        double *q = ctx->contactPool;
+        ctx->C.cvol = q; q += ctx->nodePad;
+        for (int c = 0; c < 3; c++) { ctx->C.cgrad[c] = q; q += ctx->nodePad; }
+        for (int c = 0; c < 3; c++) { ctx->C.cdisp[c] = q; q += ctx->nodePad; }
+    }
+    CK(dalloc(ctx, &ctx->dFieldOfMat, (size_t)MPM_MAX_MATERIALS));
+    CK(cudaMemcpy(ctx->dFieldOfMat, ctx->hFieldOfMat.data(), ctx->nmat * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->nf = nf;
+    ctx->multimaterial = true;
     return MPMGPU_OK;
 }
 
@@ -507,7 +588,7 @@ __global__ void k_validate_upload(int cnt, int off, int rigidPart, Particles P, 
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= cnt) return;
     const int m = P.mat[p], e = P.elem[p];          // P.mat is 0-based on the device
-    if (m < 0 || m >= nmat) { atomicMin(&out->badMat, off + p); return; }
+    if (m < 0 || m >= nmat || mats[m].kind == MAT_NONE) { atomicMin(&out->badMat, off + p); return; }
     if (e < 1 || e > nelems) atomicMin(&out->badElem, off + p);
     const bool rigid = mats[m].kind == MAT_RIGIDBC;
     if (rigidPart && !rigid) atomicMin(&out->notRigid, off + p);
@@ -576,6 +657,13 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
             if (nR) CK(cudaMemcpyAsync(ctx->archOrigin + (size_t)c * n + nNR, ctx->PR.pos[c], (size_t)nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
+    if (ctx->multimaterial) {
+        if (ctx->globalIds) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: multimaterial mode with caller-global particle ids (slab mode) is not built");
+        if (ctx->R.mirrored) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: mirrored rigid BCs in multimaterial mode are not built");
+        if (!ctx->foffPool) CK(dalloc(ctx, &ctx->foffPool, ctx->cap));
+        if (nNR) LAUNCH(k_set_field_offsets, nblocks(nNR, 256), 256, nNR, ctx->P.mat, ctx->dFieldOfMat, ctx->g.nnodes, ctx->foffPool);
+        ctx->P.foff = ctx->foffPool;
+    }
     CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(StatusFlags), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->uploaded = true;
@@ -594,6 +682,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         if (ctx->largeRotation) ok = false;     // large-rotation hypoelastic laws and Mooney live in the per-task strain kernel
         if (ctx->hasReflectedBCs) ok = false;   // symmetry-plane BCs read the momentum of the node across the plane: per-task kernels
         if (ctx->R.mirrored) ok = false;        // a mirrored rigid BC reads a neighbour node's momentum between the node updates: per-task kernels
+        if (ctx->multimaterial) ok = false;     // material velocity fields + contact: per-task kernels
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
             return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, no mirrored rigid BCs and no large-rotation or Mooney materials");
@@ -621,6 +710,7 @@ extern "C" int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dtFirst, 
 
 extern "C" int mpmgpu_set_xpic(mpmgpu_ctx *ctx, int order, int usingFMPM)
 {
+    if (ctx && ctx->multimaterial && order > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: XPIC/FMPM of order > 1 with material contact is not built");
     if (!ctx) return MPMGPU_EINVAL;
     if (order < 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: order %d", order);
     ctx->sp.xpicOrder = order; ctx->sp.usingFMPM = usingFMPM;
@@ -834,9 +924,28 @@ static void prof_end(mpmgpu_ctx *ctx, int task)
 static int apply_bcs(mpmgpu_ctx *ctx, int pass, int adjustSym)
 {
     if (ctx->hasBCs && ctx->B.nUnique > 0)
-        LAUNCH(k_velocity_bcs, nblocks(ctx->B.nUnique, 128), 128, ctx->B, ctx->N, pass, ctx->sp.dt, adjustSym);
+        LAUNCH(k_velocity_bcs, nblocks((long long)ctx->B.nUnique * ctx->nf, 128), 128, ctx->B, ctx->N, pass, ctx->sp.dt, adjustSym, ctx->nf, ctx->g.nnodes);
     if (ctx->R.on && adjustSym != 2)
-        LAUNCH(k_rigid_velocity_bcs, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->R, ctx->N, pass, ctx->sp.dt);
+        LAUNCH(k_rigid_velocity_bcs, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->R, ctx->N, pass, ctx->sp.dt);
+    return MPMGPU_OK;
+}
+
+// multimaterial mode: the contact extrapolations of the particles (after a mass/momentum extrapolation) and the contact
+// pass over the nodes (UpdateMomentaTask::ContactAndMomentaBCs, UpdateMomentaTask.cpp:76-99: contact first, then the BCs)
+static int contact_extrapolation(mpmgpu_ctx *ctx)
+{
+    if (!ctx->multimaterial) return MPMGPU_OK;
+    const size_t norig = (size_t)ctx->P.n + (size_t)ctx->PR.n;
+    DISPATCH_DIM_SHAPE(k_p2g_contact_terms, ctx->P.nNR, ctx->g, ctx->P, ctx->dMats, ctx->C, ctx->archOrigin, norig, ctx->cp.byDisplacements,
+                       ctx->cp.normalMethod != NORMALS_SPECIFIED ? 1 : 0);
+    return MPMGPU_OK;
+}
+
+static int material_contact(mpmgpu_ctx *ctx, int callType)
+{
+    if (!ctx->multimaterial) return MPMGPU_OK;
+    LAUNCH(k_material_contact, nblocks(ctx->g.nnodes, 128), 128, ctx->g, ctx->N, ctx->C, ctx->cp, ctx->B,
+           ctx->hasBCs ? ctx->tiled.FN.bcOfNode : (const int *)NULL, callType, ctx->sp.dt);
     return MPMGPU_OK;
 }
 
@@ -869,11 +978,13 @@ static int reset_rigid(mpmgpu_ctx *ctx)
 static int t_initialization(mpmgpu_ctx *ctx)
 {
     const Grid &g = ctx->g;
-    size_t nnPad = ((size_t)g.nnodes + 31) & ~(size_t)31;
+    (void)g;
+    size_t nnPad = ctx->nodePad;
     // MatVelocityField::Zero: mass, pk, ftot, vk[0], vk[pkCopy] (+XPIC vectors), numberPoints
     CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 22 * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
     ctx->launches += 2;
+    if (ctx->multimaterial) { CK(cudaMemsetAsync(ctx->contactPool, 0, nnPad * 7 * sizeof(double), ctx->stream)); ctx->launches++; }
     DISPATCH_DIM_SHAPE(k_init_particles, ctx->P.n, ctx->g, ctx->P, ctx->dFlags);
     return MPMGPU_OK;
 }
@@ -881,12 +992,13 @@ static int t_initialization(mpmgpu_ctx *ctx)
 static int t_mass_and_momentum(mpmgpu_ctx *ctx)
 {
     DISPATCH_DIM_SHAPE_VALUES(k_p2g_mass_momentum, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
-    return MPMGPU_OK;
+    return contact_extrapolation(ctx);
 }
 
 static int t_post_extrapolation(mpmgpu_ctx *ctx)
 {
-    LAUNCH(k_copy_momenta, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+    LAUNCH(k_copy_momenta, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N);
+    { int rc = material_contact(ctx, CALL_MASS_MOMENTUM); if (rc) return rc; }
     // MASS_MOMENTUM_CALL: symmetry adjust always, BC loop only when a USF task exists (NodalVelBC.cpp:339-361)
     const bool hasUSF = ctx->sp.method == METHOD_USF || ctx->sp.method == METHOD_USAVG;
     return apply_bcs(ctx, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
@@ -895,7 +1007,7 @@ static int t_post_extrapolation(mpmgpu_ctx *ctx)
 // XPICExtrapolationTask::Execute (XPICExtrapolationTask.cpp:49-161): grid velocity v(k) for order k > 1
 static int xpic_extrapolation(mpmgpu_ctx *ctx, int particleUpdate)
 {
-    const int nn = ctx->g.nnodes, fmpm = ctx->sp.usingFMPM ? 1 : 0;
+    const int nn = ctx->nvn, fmpm = ctx->sp.usingFMPM ? 1 : 0;
     LAUNCH(k_xpic_init, nblocks(nn, 256), 256, nn, ctx->N, ctx->sp.dt, fmpm);
     for (int k = 2; k <= ctx->sp.xpicOrder; k++) {
         DISPATCH_DIM_SHAPE_VALUES(k_xpic_iterate, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
@@ -911,7 +1023,7 @@ static int strain_update(mpmgpu_ctx *ctx, double strainTime, bool postUpdate = f
     if (ctx->sp.usingFMPM && ctx->sp.xpicOrder > 1) {
         if (!postUpdate || !ctx->sp.skipPost) { int rc = xpic_extrapolation(ctx, 0); if (rc) return rc; }
     } else
-    LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+    LAUNCH(k_grid_velocity, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N);
     if (ctx->largeRotation) DISPATCH_DIM_SHAPE(k_update_strains_lr, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
     else DISPATCH_DIM_SHAPE(k_update_strains, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
     return MPMGPU_OK;
@@ -932,13 +1044,14 @@ static int t_grid_forces(mpmgpu_ctx *ctx)
 
 static int t_post_forces(mpmgpu_ctx *ctx)
 {
-    LAUNCH(k_post_forces, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N, ctx->sp);
+    LAUNCH(k_post_forces, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N, ctx->sp);
     return apply_bcs(ctx, PASS_GRID_FORCES, 0);
 }
 
 static int t_update_momenta(mpmgpu_ctx *ctx)
 {
-    LAUNCH(k_update_momenta, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N, ctx->sp.dt);
+    LAUNCH(k_update_momenta, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N, ctx->sp.dt);
+    { int rc = material_contact(ctx, CALL_UPDATE_MOMENTUM); if (rc) return rc; }
     if (ctx->sp.xpicOrder <= 1) return apply_bcs(ctx, PASS_UPDATE_MOMENTUM, 0);      // NodalVelBC.cpp:367-375
     return MPMGPU_OK;
 }
@@ -946,7 +1059,7 @@ static int t_update_momenta(mpmgpu_ctx *ctx)
 static int t_update_particles(mpmgpu_ctx *ctx)
 {
     if (ctx->sp.xpicOrder > 1) { int rc = xpic_extrapolation(ctx, 1); if (rc) return rc; }      // UpdateParticlesTask.cpp:66-71
-    else LAUNCH(k_grid_velocity, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+    else LAUNCH(k_grid_velocity, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N);
     int m = ctx->sp.xpicOrder;
     if (!ctx->sp.usingFMPM) m = -m;
     DISPATCH_DIM_SHAPE(k_update_particles, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, ctx->sp, m);
@@ -957,9 +1070,12 @@ static int t_update_strains_last(mpmgpu_ctx *ctx)
 {
     if (ctx->sp.method == METHOD_USF) return MPMGPU_OK;
     if (!ctx->sp.skipPost) {
-        LAUNCH(k_rezero_momenta, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->N);
+        LAUNCH(k_rezero_momenta, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N);
+        if (ctx->multimaterial) LAUNCH(k_zero_contact_terms, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->C);      // MatVelocityField::RezeroNodeTask6
         DISPATCH_DIM_SHAPE_VALUES(k_p2g_momentum_last, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
-        int rc = apply_bcs(ctx, PASS_UPDATE_STRAINS_LAST, 0);
+        int rc = contact_extrapolation(ctx);
+        if (!rc) rc = material_contact(ctx, CALL_UPDATE_STRAINS_LAST);
+        if (!rc) rc = apply_bcs(ctx, PASS_UPDATE_STRAINS_LAST, 0);
         if (rc) return rc;
     }
     double st = ctx->sp.method == METHOD_USAVG ? ctx->sp.dtStrainLast : ctx->sp.dt;
@@ -1501,8 +1617,15 @@ extern "C" int mpmgpu_download_nodes(mpmgpu_ctx *ctx, mpmgpu_nodes *h)
 {
     if (!ctx || !h) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_download_nodes: null argument");
     cudaSetDevice(ctx->cfg.device);
-    const size_t nn = ctx->g.nnodes;
+    const size_t nn = ctx->nvn;          // fields x nodes in multimaterial mode (field-major)
     h->nnodes = (int)nn;
+    if (ctx->multimaterial) {
+        if (h->contact_volume) CK(cudaMemcpyAsync(h->contact_volume, ctx->C.cvol, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        for (int c = 0; c < 3; c++) {
+            if (h->contact_gradient) CK(cudaMemcpyAsync(h->contact_gradient + c * nn, ctx->C.cgrad[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (h->contact_disp) CK(cudaMemcpyAsync(h->contact_disp + c * nn, ctx->C.cdisp[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
     if (h->number_points) CK(cudaMemcpyAsync(h->number_points, ctx->N.cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (h->mass) CK(cudaMemcpyAsync(h->mass, ctx->N.mass, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     for (int c = 0; c < 3; c++) {

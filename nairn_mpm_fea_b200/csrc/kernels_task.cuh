@@ -15,9 +15,20 @@ __device__ __forceinline__ void load_xi_lp(const Particles &P, int p, double xi[
     lp[0] = P.lp[0][p]; lp[1] = P.lp[1][p]; lp[2] = P.lp[2][p];
 }
 
-// nodes of particle p for the configured shape function
+// nodes of particle p for the configured shape function; in multimaterial mode the node index handed to f is the
+// particle's own material velocity field of that node (field-major node arrays, mpm_types.cuh)
+template <int DIM, int SHAPE, bool GRAD, class F>
+__device__ __forceinline__ void particle_nodes_one_field(const Grid &g, const Particles &P, int p, F &&f);
+
 template <int DIM, int SHAPE, bool GRAD, class F>
 __device__ __forceinline__ void particle_nodes(const Grid &g, const Particles &P, int p, F &&f)
+{
+    const int off = P.foff ? P.foff[p] : 0;
+    particle_nodes_one_field<DIM, SHAPE, GRAD>(g, P, p, [&](int nd, double S, double gx, double gy, double gz) { f(nd + off, S, gx, gy, gz); });
+}
+
+template <int DIM, int SHAPE, bool GRAD, class F>
+__device__ __forceinline__ void particle_nodes_one_field(const Grid &g, const Particles &P, int p, F &&f)
 {
     if (SHAPE_IS_MERGED(SHAPE)) {
         for_each_node_cpdi_merged<DIM, SHAPE, GRAD>(g, P, p, f);
@@ -115,7 +126,7 @@ __device__ __forceinline__ void bc_add(int pass, double dt, double mass, double 
 // CrackVelocityFieldSingle.cpp:133-144): v = v0 + ratio (v0 - n.pk_r / m_r) when that node has particles, else v0.
 // Only the per-task kernels pass N (the reflected node's momentum has to be complete: its own BCs act on other
 // components); contexts with reflected BCs do not use the fused node sweeps.
-__device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3], const Nodes *N = nullptr)
+__device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3], const Nodes *N = nullptr, int off = 0)
 {
     const int e0 = B.start[u], e1 = B.start[u + 1];
     for (int e = e0; e < e1; e++) {
@@ -127,7 +138,7 @@ __device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, doubl
         const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
         double v = B.value[e];
         if (N && B.refl && B.refl[e] >= 0) {
-            const int r = B.refl[e];
+            const int r = B.refl[e] + off;      // the same material field of the node across the plane (CrackVelocityFieldMulti::ReflectVelocityBC)
             if (N->cnt[r] > 0) {
                 const double dotn = nx * N->pk[0][r] + ny * N->pk[1][r] + nz * N->pk[2][r];
                 v = v + B.reflRatio[e] * (v - dotn / N->mass[r]);
@@ -186,12 +197,14 @@ __device__ __forceinline__ double rigid_bc_velocity(const RigidBCs &R, const Nod
     return v0 + (v0 - N.pk[d][mirror] / N.mass[mirror]);
 }
 
-// One thread per node that has BCs.  BCs act only on active fields (numberPoints>0, NodalPointMPM.cpp:1849-1862).
-__global__ void k_velocity_bcs(VelBCs B, Nodes N, int pass, double dt, int adjustSym)
+// One thread per node that has BCs and material velocity field.  BCs act only on active fields (numberPoints>0,
+// NodalPointMPM.cpp:1849-1862; every active nonrigid field in multimaterial mode, CrackVelocityFieldMulti.cpp:1243-1260).
+__global__ void k_velocity_bcs(VelBCs B, Nodes N, int pass, double dt, int adjustSym, int nf = 1, int nnodes = 0)
 {
-    int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= B.nUnique) return;
-    const int nd = B.node[u];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B.nUnique * nf) return;
+    const int u = t % B.nUnique, off = (t / B.nUnique) * nnodes;
+    const int nd = B.node[u] + off;
     if (N.cnt[nd] <= 0) return;
     if (adjustSym) {        // ADJUST_COPIED_PK==1 (NodalVelBC.cpp:339-353, MatVelocityField.cpp:579-586)
         int sd = B.symdir[u];
@@ -202,12 +215,13 @@ __global__ void k_velocity_bcs(VelBCs B, Nodes N, int pass, double dt, int adjus
     }
     double pk[3] = {N.pk[0][nd], N.pk[1][nd], N.pk[2][nd]};
     double ft[3] = {N.ftot[0][nd], N.ftot[1][nd], N.ftot[2][nd]};
-    node_bcs(B, u, pass, dt, N.mass[nd], pk, ft, &N);
+    node_bcs(B, u, pass, dt, N.mass[nd], pk, ft, &N, off);
     N.pk[0][nd] = pk[0]; N.pk[1][nd] = pk[1]; N.pk[2][nd] = pk[2];
     N.ftot[0][nd] = ft[0]; N.ftot[1][nd] = ft[1]; N.ftot[2][nd] = ft[2];
 }
 
 // rigid-particle BCs on every node, launched after k_velocity_bcs
+// (nnodes = fields x real nodes in multimaterial mode; the claims are per real node)
 __global__ void k_rigid_velocity_bcs(int nnodes, RigidBCs R, Nodes N, int pass, double dt)
 {
     int nd = blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,7 +229,8 @@ __global__ void k_rigid_velocity_bcs(int nnodes, RigidBCs R, Nodes N, int pass, 
     if (N.cnt[nd] <= 0) return;
     double pk[3] = {N.pk[0][nd], N.pk[1][nd], N.pk[2][nd]};
     double ft[3] = {N.ftot[0][nd], N.ftot[1][nd], N.ftot[2][nd]};
-    if (!(R.mirrored ? node_rigid_bcs<true>(R, nd, pass, dt, N.mass[nd], pk, ft, &N) : node_rigid_bcs<false>(R, nd, pass, dt, N.mass[nd], pk, ft))) return;
+    const int real = nd % R.nnodes;
+    if (!(R.mirrored ? node_rigid_bcs<true>(R, nd, pass, dt, N.mass[nd], pk, ft, &N) : node_rigid_bcs<false>(R, real, pass, dt, N.mass[nd], pk, ft))) return;
     N.pk[0][nd] = pk[0]; N.pk[1][nd] = pk[1]; N.pk[2][nd] = pk[2];
     N.ftot[0][nd] = ft[0]; N.ftot[1][nd] = ft[1]; N.ftot[2][nd] = ft[2];
 }
@@ -606,4 +621,308 @@ __global__ void __launch_bounds__(TASK_THREADS) k_reset_elements(Grid g, Particl
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     reset_element_one<DIM>(g, P, p, flags, dt);
+}
+
+// =================================================================================================================
+// Multimaterial mode: one velocity field per material field on every node + material contact
+// (CrackVelocityFieldMulti with a single crack field)
+// =================================================================================================================
+
+// node offset of every particle's material velocity field (MaterialBase::GetField), fixed for the run
+__global__ void k_set_field_offsets(int n, const int *mat, const int *fieldOfMat, int nnodes, int *foff)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) foff[p] = fieldOfMat[mat[p]] * nnodes;
+}
+
+// The extrapolations contact needs besides mass and momentum (NodalPoint::AddMassMomentum / AddMassMomentumLast,
+// NodalPointMPM.cpp:419-453, :479-496): contact volume, mass-weighted displacement or position
+// (CrackVelocityField::AddVolumeDisplacement, CrackVelocityField.cpp:395-401) and the volume gradient
+// (CrackVelocityFieldMulti::AddVolumeGradient, CrackVelocityFieldMulti.cpp:108-112).
+// origpos: [3][norig] in the caller's particle order (MPMBase::origpos).
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_p2g_contact_terms(Grid g, Particles P, const Material *mats, ContactNodes C,
+                                                                    const double *origpos, size_t norig, int byDisplacements, int needGradient)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    const double mp = P.mp[p], rho = mats[P.mat[p]].p[0];
+    // MPMBase::GetVolume(DEFORMED_AREA): 3D det(F) mp / rho (MatPoint3D.cpp:395-408); 2D the in-plane part of F (MatPoint2D.cpp:407-417)
+    double vol;
+    if (DIM == 3) {
+        const double F00 = P.F[0][p], F01 = P.F[1][p], F02 = P.F[2][p], F10 = P.F[3][p], F11 = P.F[4][p], F12 = P.F[5][p],
+                     F20 = P.F[6][p], F21 = P.F[7][p], F22 = P.F[8][p];
+        const double J = F00 * (F11 * F22 - F21 * F12) - F01 * (F10 * F22 - F20 * F12) + F02 * (F10 * F21 - F20 * F11);
+        vol = J * mp / rho;
+    } else {
+        vol = (P.F[0][p] * P.F[4][p] - P.F[3][p] * P.F[1][p]) * mp / rho;
+    }
+    double d[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
+    if (byDisplacements) {
+        const size_t q = (size_t)P.orig[p];
+        d[0] -= origpos[q]; d[1] -= origpos[norig + q];
+        if (DIM == 3) d[2] -= origpos[2 * norig + q];
+    }
+    particle_nodes<DIM, SHAPE, true>(g, P, p, [&](int nd, double S, double gx, double gy, double gz) {
+        const double fnmp = S * mp;
+        atomAdd(&C.cvol[nd], S * vol);
+        atomAdd(&C.cdisp[0][nd], d[0] * fnmp);
+        atomAdd(&C.cdisp[1][nd], d[1] * fnmp);
+        if (DIM == 3) atomAdd(&C.cdisp[2][nd], d[2] * fnmp);
+        if (needGradient) {
+            atomAdd(&C.cgrad[0][nd], gx * vol);
+            atomAdd(&C.cgrad[1][nd], gy * vol);
+            if (DIM == 3) atomAdd(&C.cgrad[2][nd], gz * vol);
+        }
+    });
+}
+
+__global__ void k_zero_contact_terms(int n, ContactNodes C)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    C.cvol[i] = 0.;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { C.cgrad[c][i] = 0.; C.cdisp[c][i] = 0.; }
+}
+
+// symmetry-plane bits of NodalPoint::fixedDirection (32 x, 64 y, 128 z) zero a vector's components (CrackVelocityField::AdjustForSymmetry)
+__device__ __forceinline__ bool adjust_for_symmetry(int sd, double v[3])
+{
+    bool any = false;
+    if (sd & 32) { v[0] = 0.; any = true; }
+    if (sd & 64) { v[1] = 0.; any = true; }
+    if (sd & 128) { v[2] = 0.; any = true; }
+    return any;
+}
+
+// MeshInfo::GetPerpendicularDistance (MeshInfo.cpp:1741-1869), structured grid of equal elements: hperp along norm
+__device__ __forceinline__ double perpendicular_distance(const Grid &g, int cubic, const double n[3])
+{
+    if (cubic) return g.gx;
+    if (g.dim == 3) {
+        double t1[3];
+        if (n[2] > n[0] && n[2] > n[1]) { t1[0] = 0.; t1[1] = -n[2]; t1[2] = n[1]; }
+        else { t1[0] = -n[1]; t1[1] = n[0]; t1[2] = 0.; }
+        const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+        const double a1 = t1[0] / g.gx, b1 = t1[1] / g.gy, c1 = t1[2] / g.gz;
+        const double a2 = t2[0] / g.gx, b2 = t2[1] / g.gy, c2 = t2[2] / g.gz;
+        return g.gx * g.gy * g.gz * sqrt((a1 * a1 + b1 * b1 + c1 * c1) * (a2 * a2 + b2 * b2 + c2 * c2));
+    }
+    const double a = g.gx * n[0], b = g.gy * n[1];
+    return sqrt(a * a + b * b);
+}
+
+// CrackSurfaceContact::MaterialSeparation (CrackSurfaceContact.cpp:278-303)
+__device__ __forceinline__ double material_separation(const Grid &g, const ContactParams &cp, double dbdotn, double dadotn, const double n[3],
+                                                      const double xn[3])
+{
+    if (cp.byDisplacements) return dbdotn - dadotn;
+    double r = cp.positionCutoff;
+    const double hperp = perpendicular_distance(g, cp.cubic, n);
+    if (r > 0.) return dbdotn - dadotn - r * hperp;
+    r = -r;
+    const double xdotn = xn[0] * n[0] + xn[1] * n[1] + xn[2] * n[2];
+    const double pa = dadotn - xn[0] * n[0] - xn[1] * n[1] - xn[2] * n[2];
+    const double da = pa > 0. ? 2. * pow(pa / (1.25 * hperp), r) - 1. : 1 - 2. * pow(-pa / (1.25 * hperp), r);
+    const double pb = dbdotn - xn[0] * n[0] - xn[1] * n[1] - xn[2] * n[2];
+    const double db = pb > 0. ? 2. * pow(pb / (1.25 * hperp), r) - 1. : 1 - 2. * pow(-pb / (1.25 * hperp), r);
+    (void)xdotn;
+    return (db - da) * hperp;
+}
+
+// CoulombFriction::GetFrictionalDeltaMomentum (CoulombFriction.cpp:150-272) without frictional heating (no conduction on this path).
+// delFi != NULL in the momentum update.  Returns false when the law decides the materials are not in contact.
+__device__ __forceinline__ bool frictional_delta_momentum(int kind, double mu, double muStatic, double delPi[3], const double n[3], double dotn,
+                                                          double deltaDotn, double mred, double dt, const double *delFi)
+{
+    if (kind == LAW_STICK) return true;
+    if (delFi) {
+        const double fn = delFi[0] * n[0] + delFi[1] * n[1] + delFi[2] * n[2];
+        deltaDotn += dt * (dotn - 0.5 * fn * dt) / mred;
+    }
+    const bool inContact = deltaDotn < 0. && dotn < 0.;
+    if (kind == LAW_FRICTIONLESS) {
+        if (!inContact) return false;
+        delPi[0] = n[0] * dotn; delPi[1] = n[1] * dotn; delPi[2] = n[2] * dotn;
+        return true;
+    }
+    if (!inContact) return false;                 // HasFreeSeparation
+    double dott = 0.;
+    double tang[3] = {delPi[0], delPi[1], delPi[2]};
+    tang[0] += n[0] * (-dotn); tang[1] += n[1] * (-dotn); tang[2] += n[2] * (-dotn);
+    const double tangMag = sqrt(tang[0] * tang[0] + tang[1] * tang[1] + tang[2] * tang[2]);
+    if (tangMag > 0.) {
+        const double s = 1. / tangMag;
+        tang[0] *= s; tang[1] *= s; tang[2] *= s;
+        dott = delPi[0] * tang[0] + delPi[1] * tang[1] + delPi[2] * tang[2];
+        if (dott < 0.) { tang[0] *= -1.; tang[1] *= -1.; tang[2] *= -1.; dott = -dott; }
+    }
+    // GetSslideAcDt(-dotn, dott, ...)
+    const double NAcDt = -dotn;
+    double SslideAcDt;
+    if (muStatic > 0. && dott <= muStatic * NAcDt) SslideAcDt = muStatic * NAcDt;
+    else SslideAcDt = mu * NAcDt;
+    if (SslideAcDt <= 0.) {
+        delPi[0] = n[0] * dotn; delPi[1] = n[1] * dotn; delPi[2] = n[2] * dotn;
+    } else if (dott > SslideAcDt) {
+        delPi[0] = n[0] * dotn; delPi[1] = n[1] * dotn; delPi[2] = n[2] * dotn;
+        delPi[0] += tang[0] * SslideAcDt; delPi[1] += tang[1] * SslideAcDt; delPi[2] += tang[2] * SslideAcDt;
+    }
+    return true;
+}
+
+// MaterialContactNode::ContactOnKnownNodes -> CrackVelocityFieldMulti::MaterialContactOnCVF / MaterialContactOnCVFLumped
+// (CrackVelocityFieldMulti.cpp:302-674) for nonrigid materials: one thread per node walks the node's active material fields in
+// field order, as the reference does (with three or more materials the lumped loop reads the forces the earlier
+// iterations changed).  bcOfNode/B give the node's symmetry-plane bits.
+__global__ void k_material_contact(Grid g, Nodes N, ContactNodes C, ContactParams cp, VelBCs B, const int *bcOfNode, int callType, double dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nn = g.nnodes;
+    if (i >= nn) return;
+    int act[MPM_MAX_FIELDS];
+    int numMats = 0;
+    double Pc[3] = {0., 0., 0.}, Mc = 0.;
+    for (int f = 0; f < cp.nf; f++) {
+        const int v = f * nn + i;
+        if (N.cnt[v] > 0) {
+            Pc[0] += N.pk[0][v]; Pc[1] += N.pk[1][v]; Pc[2] += N.pk[2][v];
+            Mc += N.mass[v];
+            act[numMats++] = f;
+        }
+    }
+    if (numMats <= 1) return;
+    int sd = 0;
+    if (bcOfNode) { const int u = bcOfNode[i]; if (u >= 0) sd = B.symdir[u]; }
+    const bool postUpdate = callType == CALL_UPDATE_MOMENTUM;
+    const bool useGrad = cp.normalMethod != NORMALS_SPECIFIED;
+    const bool doingPairs = numMats == 2 && cp.normalMethod != NORMALS_OWNG;
+    const int miMax = doingPairs ? numMats - 1 : numMats;
+    // centre-of-mass displacement (or position) and total contact volume of the nonrigid materials
+    double dispc[3] = {0., 0., 0.}, volAll = 0.;
+    for (int k = 0; k < numMats; k++) {
+        const int v = act[k] * nn + i;
+        dispc[0] += C.cdisp[0][v]; dispc[1] += C.cdisp[1][v]; dispc[2] += C.cdisp[2][v];
+        volAll += C.cvol[v];
+    }
+    adjust_for_symmetry(sd, dispc);
+    { const double s = 1. / Mc; dispc[0] *= s; dispc[1] *= s; dispc[2] *= s; }
+    double xn[3];
+    {   // node coordinates (power-law position cutoff only)
+        const int iz = g.dim == 3 ? i / g.zplane : 0, r = i - iz * g.zplane, iy = r / g.yplane, ix = r - iy * g.yplane;
+        xn[0] = g.xpts[ix]; xn[1] = g.ypts[iy]; xn[2] = g.dim == 3 ? g.zpts[iz] : 0.;
+    }
+    for (int mi = 0; mi < miMax; mi++) {
+        const int fi = act[mi], vi = fi * nn + i;
+        const double massi = N.mass[vi];
+        const double voli = C.cvol[vi];
+        const double volj = volAll - voli;
+        int fj = -1;
+        double gradj[3] = {0., 0., 0.};
+        double maxOther = 0.;
+        for (int kj = 0; kj < numMats; kj++) {
+            if (kj == mi) continue;
+            const int jj = act[kj], vj = jj * nn + i;
+            const double matVolume = C.cvol[vj];
+            if (matVolume > maxOther) { maxOther = matVolume; fj = jj; }
+            if (useGrad) {      // GetVolumeGradient(jj, ndptr, &normj, -1.)
+                double normj[3] = {C.cgrad[0][vj] * -1., C.cgrad[1][vj] * -1., C.cgrad[2][vj] * -1.};
+                adjust_for_symmetry(sd, normj);
+                gradj[0] += normj[0]; gradj[1] += normj[1]; gradj[2] += normj[2];
+            }
+        }
+        if (fj < 0) continue;
+        const int vj = fj * nn + i;
+        const int law = cp.lawKind[fi * cp.nf + fj];
+        const double massRatio = massi / Mc;
+        double mred = 1. - massRatio;
+        double norm[3] = {0., 0., 0.};
+        double dotn = 0., deln = 0.;
+        double delPi[3] = {N.pk[0][vi] * -1., N.pk[1][vi] * -1., N.pk[2][vi] * -1.};
+        delPi[0] += Pc[0] * massRatio; delPi[1] += Pc[1] * massRatio; delPi[2] += Pc[2] * massRatio;
+        adjust_for_symmetry(sd, delPi);
+        if (law != LAW_IGNORE) {
+            // CrackVelocityFieldMulti::GetNormalVector (:960-1071), volume-gradient methods and the specified normal
+            double normi[3] = {0., 0., 0.};
+            if (useGrad) { normi[0] = C.cgrad[0][vi]; normi[1] = C.cgrad[1][vi]; normi[2] = C.cgrad[2][vi]; adjust_for_symmetry(sd, normi); }
+            switch (cp.normalMethod) {
+            case NORMALS_MAXG: {
+                const double magi = sqrt(normi[0] * normi[0] + normi[1] * normi[1] + normi[2] * normi[2]);
+                const double magj = sqrt(gradj[0] * gradj[0] + gradj[1] * gradj[1] + gradj[2] * gradj[2]);
+                if (magi >= magj) { const double s = 1. / magi; norm[0] = normi[0] * s; norm[1] = normi[1] * s; norm[2] = normi[2] * s; }
+                else { const double s = 1. / magj; norm[0] = gradj[0] * s; norm[1] = gradj[1] * s; norm[2] = gradj[2] * s; }
+                break;
+            }
+            case NORMALS_MAXV: {
+                if (voli >= volj) { norm[0] = normi[0]; norm[1] = normi[1]; norm[2] = normi[2]; }
+                else { norm[0] = gradj[0]; norm[1] = gradj[1]; norm[2] = gradj[2]; }
+                const double s = 1. / sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
+                norm[0] *= s; norm[1] *= s; norm[2] *= s;
+                break;
+            }
+            case NORMALS_AVGG: {
+                norm[0] = normi[0] + gradj[0]; norm[1] = normi[1] + gradj[1]; norm[2] = normi[2] + gradj[2];
+                const double magi = norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2];
+                const double s = 1. / sqrt(magi);
+                norm[0] *= s; norm[1] *= s; norm[2] *= s;
+                break;
+            }
+            case NORMALS_OWNG: {
+                const double s = 1. / sqrt(normi[0] * normi[0] + normi[1] * normi[1] + normi[2] * normi[2]);
+                norm[0] = normi[0] * s; norm[1] = normi[1] * s; norm[2] = normi[2] * s;
+                break;
+            }
+            default: {          // NORMALS_SPECIFIED
+                norm[0] = cp.normal[0]; norm[1] = cp.normal[1]; norm[2] = cp.normal[2];
+                if (adjust_for_symmetry(sd, norm)) {
+                    const double s = 1. / sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
+                    norm[0] *= s; norm[1] *= s; norm[2] *= s;
+                }
+                break;
+            }
+            }
+            // a volume gradient normal to a symmetry plane leaves no direction
+            if (norm[0] != norm[0] || norm[1] != norm[1] || norm[2] != norm[2]) continue;
+            dotn = delPi[0] * norm[0] + delPi[1] * norm[1] + delPi[2] * norm[2];
+            double dispa[3];
+            { const double s = 1. / massi; dispa[0] = C.cdisp[0][vi] * s; dispa[1] = C.cdisp[1][vi] * s; dispa[2] = C.cdisp[2][vi] * s; }
+            adjust_for_symmetry(sd, dispa);
+            double delta[3] = {dispc[0] - dispa[0], dispc[1] - dispa[1], dispc[2] - dispa[2]};
+            { const double s = 1. / mred; delta[0] *= s; delta[1] *= s; delta[2] *= s; }
+            const double dispb[3] = {delta[0] + dispa[0], delta[1] + dispa[1], delta[2] + dispa[2]};
+            deln = material_separation(g, cp, dispb[0] * norm[0] + dispb[1] * norm[1] + dispb[2] * norm[2],
+                                       dispa[0] * norm[0] + dispa[1] * norm[1] + dispa[2] * norm[2], norm, xn);
+            mred *= massi;
+            double delFi[3];
+            if (postUpdate) {   // (ma Fc / Mc) - Fa, with the forces as they are now (GetCMatFtot)
+                double fk[3] = {0., 0., 0.};
+                for (int k = 0; k < numMats; k++) {
+                    const int v = act[k] * nn + i;
+                    fk[0] += N.ftot[0][v]; fk[1] += N.ftot[1][v]; fk[2] += N.ftot[2][v];
+                }
+                const double s = massi / Mc;
+                delFi[0] = fk[0] * s; delFi[1] = fk[1] * s; delFi[2] = fk[2] * s;
+                delFi[0] += N.ftot[0][vi] * -1.; delFi[1] += N.ftot[1][vi] * -1.; delFi[2] += N.ftot[2][vi] * -1.;
+            }
+#ifdef EMU_DEBUG_NODE
+            if (i == EMU_DEBUG_NODE) printf("node %d call %d fi %d fj %d law %d norm %.17g %.17g %.17g dotn %.17g deln %.17g mred %.17g delPi %.17g %.17g %.17g\n", i, callType, fi, fj, law, norm[0], norm[1], norm[2], dotn, deln, mred, delPi[0], delPi[1], delPi[2]);
+#endif
+            if (!frictional_delta_momentum(law, cp.lawFriction[fi * cp.nf + fj], cp.lawStatic[fi * cp.nf + fj], delPi, norm, dotn, deln, mred, dt,
+                                           postUpdate ? delFi : (const double *)0)) continue;
+        }
+        // MatVelocityField::ChangeMatMomentum (MatVelocityField.cpp:197-224)
+        for (int side = 0; side < (doingPairs ? 2 : 1); side++) {
+            const int v = side == 0 ? vi : vj;
+            const double sg = side == 0 ? 1. : -1.;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double dp = side == 0 ? delPi[c] : delPi[c] * sg;
+                const double pk = N.pk[c][v] + dp;
+                N.pk[c][v] = pk;
+                if (callType == CALL_UPDATE_MOMENTUM) N.ftot[c][v] += dp * (1. / dt);
+                else if (callType == CALL_MASS_MOMENTUM) N.pkc[c][v] = pk;
+            }
+        }
+    }
 }

@@ -20,7 +20,7 @@ enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_B2GIMP = 5, SHAPE_B2SPLINE = 6, 
 #define SHAPE_IS_QCPDI(S) ((S) == SHAPE_QCPDI || (S) == SHAPE_QCPDI_MERGED)
 #define SHAPE_IS_CPDI(S) ((S) == SHAPE_LCPDI || (S) == SHAPE_LCPDI_MERGED || (S) == SHAPE_B2CPDI || SHAPE_IS_QCPDI(S))
 #define SHAPE_IS_MERGED(S) ((S) == SHAPE_LCPDI_MERGED || (S) == SHAPE_QCPDI_MERGED)
-enum { MAT_ISOTROPIC = 1, MAT_MOONEY = 8, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28 };
+enum { MAT_NONE = 0, MAT_ISOTROPIC = 1, MAT_MOONEY = 8, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28 };
 
 // BC pass types (reference NodalVelBC.cpp:321-380)
 enum { PASS_MASS_MOMENTUM = 0, PASS_GRID_FORCES = 1, PASS_UPDATE_MOMENTUM = 2, PASS_UPDATE_STRAINS_LAST = 3,
@@ -81,6 +81,33 @@ struct Particles {
     double *cpDom;           // [12][cap] the domain itself in grid units, frozen for the step like the corner data: centre (3), semi-side
                              // vectors (3 x 3); rows after the ncorner*3 rows of cpXi.  3D lCPDI: for_each_node_lcpdi3_hat (shape.cuh)
     size_t cpStride;         // cap
+    // multimaterial mode: node-index offset of the particle's material velocity field (field * nnodes), NULL = one field
+    const int *foff;
+};
+
+// ---- multimaterial mode (<MultiMaterialMode>): CrackVelocityFieldMulti with one crack field -----------------------------
+// Every node array holds nf fields, field-major: field f of node i at [f * nnodes + i] (a "virtual node"), so the
+// particle<->grid kernels only add the particle's field offset to the node index.  Contact needs three more
+// extrapolations per field (NodalPoint::AddMassMomentum, NodalPointMPM.cpp:419-453; ContactTerms of MatVelocityField).
+#define MPM_MAX_FIELDS 8
+enum { NORMALS_MAXG = 0, NORMALS_MAXV = 1, NORMALS_AVGG = 2, NORMALS_OWNG = 3, NORMALS_SPECIFIED = 4 };   // MeshInfo.hpp:31
+enum { LAW_IGNORE = 0, LAW_STICK = 1, LAW_FRICTIONLESS = 2, LAW_FRICTIONAL = 3 };
+enum { CALL_MASS_MOMENTUM = 0, CALL_UPDATE_MOMENTUM = 1, CALL_UPDATE_STRAINS_LAST = 2 };
+struct ContactNodes {
+    double *cvol;            // [nf*nnodes] contactInfo->cvolume
+    double *cgrad[3];        // volume gradient (terms[volumeGradientIndex])
+    double *cdisp[3];        // mass-weighted displacement (contactByDisplacements) or position
+};
+struct ContactParams {
+    int nf;                  // material velocity fields per node (maxMaterialFields)
+    int normalMethod;        // mpmgrid.materialNormalMethod (0..4)
+    int byDisplacements;     // mpmgrid.contactByDisplacements
+    int cubic;               // 3D cubic / 2D square cells (MeshInfo::GetPerpendicularDistance short cut)
+    double positionCutoff;   // mpmgrid.positionCutoff
+    double normal[3];        // SPECIFIED_NORMAL
+    int lawKind[MPM_MAX_FIELDS * MPM_MAX_FIELDS];
+    double lawFriction[MPM_MAX_FIELDS * MPM_MAX_FIELDS];
+    double lawStatic[MPM_MAX_FIELDS * MPM_MAX_FIELDS];
 };
 
 struct Material {

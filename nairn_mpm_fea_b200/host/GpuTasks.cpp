@@ -55,6 +55,8 @@
 #include "Exceptions/CommonException.hpp"
 #include "Exceptions/MPMWarnings.hpp"
 #include "Materials/Elastic.hpp"
+#include "Materials/ContactLaw.hpp"
+#include "Materials/CoulombFriction.hpp"
 #undef private
 #undef protected
 
@@ -389,7 +391,15 @@ const char *GpuTasks_Install(int device, bool fusedStep)
 {
     gFusedStep = fusedStep;
     if (firstCrack != NULL) return "cracks present";
-    if (fmobj->multiMaterialMode) return "multimaterial mode";
+    if (fmobj->multiMaterialMode) {
+        // material velocity fields + contact (mpmgpu_set_multimaterial): what the device path covers, the rest stays refused
+        if (mpmgrid.materialNormalMethod > SPECIFIED_NORMAL) return "multimaterial contact normals by linear or logistic regression (<MultiMaterialMode Normals=\"5|6\">)";
+        if (mpmgrid.materialNormalMethod == EACH_MATERIALS_MASS_GRADIENT) return "multimaterial contact with each material's own normal (the reference itself fails there without FMPM order > 1)";
+        if (mpmgrid.hasImperfectInterface) return "imperfect interfaces between materials";
+        if (ConductionTask::matContactHeating) return "frictional heating in material contact";
+        if (bodyFrc.GetXPICOrder() > 1) return "XPIC/FMPM of order > 1 in multimaterial mode";
+        if (maxMaterialFields > 8) return "more than 8 material velocity fields";
+    }
     if (transportTasks != NULL) return "transport tasks present";
     // everything the replaced CPU tasks would do on the side must be absent, or the run would silently differ:
     // particle loads / tractions are re-evaluated every step by InitializationTask and GridForcesTask
@@ -453,8 +463,29 @@ const char *GpuTasks_Install(int device, bool fusedStep)
             if (rm->function != NULL) gRigidFunctions = true;
             break;
         }
+        case CONTACTLAW: case COULOMBFRICTIONLAW:        // a contact law's place in theMaterials[] (multimaterial mode): checked pair by pair below
+            if (!fmobj->multiMaterialMode) return "material type";
+            break;
         default: return "material type";
         }
+    }
+    // multimaterial mode: the contact law of every pair of material velocity fields must be one the device applies
+    std::vector<int> mmField, mmKind; std::vector<double> mmFriction, mmStatic;
+    if (fmobj->multiMaterialMode) {
+        const int nf = maxMaterialFields;
+        mmField.assign(nmat, 0); mmKind.assign((size_t)nf * nf, 0); mmFriction.assign((size_t)nf * nf, 0.); mmStatic.assign((size_t)nf * nf, -1.);
+        for (int i = 0; i < nmat; i++) mmField[i] = theMaterials[i]->GetField() >= 0 ? theMaterials[i]->GetField() : 0;
+        for (int i = 0; i < nf; i++)
+            for (int j = 0; j < nf; j++) {
+                if (i == j) continue;
+                ContactLaw *cl = mpmgrid.GetMaterialContactLaw(i, j);
+                if (cl == NULL) return "multimaterial mode without a contact law for a pair of materials";
+                if (cl->IgnoreContact()) continue;                                           // kind 0
+                CoulombFriction *cf = dynamic_cast<CoulombFriction *>(cl);
+                if (cf == NULL || strcmp(cl->MaterialType(), "Coulomb Friction") != 0) return "contact law other than ignore / stick / frictionless / Coulomb friction";
+                mmKind[(size_t)i * nf + j] = cf->IsStick() ? 1 : (cf->IsFrictionless() ? 2 : 3);
+                mmFriction[(size_t)i * nf + j] = cf->frictionCoeff; mmStatic[(size_t)i * nf + j] = cf->frictionCoeffStatic;
+            }
     }
     const bool is3D = fmobj->IsThreeD();
 
@@ -531,6 +562,9 @@ const char *GpuTasks_Install(int device, bool fusedStep)
                 m.p[23] = jc->Tmjc; m.p[24] = jc->mjc; m.p[25] = thermal.reference; m.p[26] = jc->edotMin; m.p[27] = jc->eminTerm;
             }
             m.p[7] = pm->useLargeRotation ? 1. : 0.;
+        } else if (mb->MaterialID() == CONTACTLAW || mb->MaterialID() == COULOMBFRICTIONLAW) {
+            m.kind = MPMGPU_MAT_NONE; m.n_history = 0;          // keeps the particles' material numbers in place
+            memset(m.p, 0, sizeof m.p);
         } else {                                     // rigid BC particles: directions they control
             m.kind = MPMGPU_MAT_RIGIDBC; m.n_history = 0;
             m.p[8] = ((RigidMaterial *)mb)->setDirection;
@@ -538,6 +572,16 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         }
     }
     if (mpmgpu_set_materials(gCtx, nmat, mats.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    if (fmobj->multiMaterialMode) {
+        mpmgpu_multimaterial mm;
+        memset(&mm, 0, sizeof mm);
+        mm.n_fields = maxMaterialFields; mm.field_of_material = mmField.data();
+        mm.normal_method = mpmgrid.materialNormalMethod; mm.contact_by_displacements = mpmgrid.contactByDisplacements ? 1 : 0;
+        mm.position_cutoff = mpmgrid.positionCutoff;
+        mm.contact_normal[0] = mpmgrid.contactNormal.x; mm.contact_normal[1] = mpmgrid.contactNormal.y; mm.contact_normal[2] = mpmgrid.contactNormal.z;
+        mm.law_kind = mmKind.data(); mm.law_friction = mmFriction.data(); mm.law_static = mmStatic.data();
+        if (mpmgpu_set_multimaterial(gCtx, &mm) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    }
 
     // particles: AoS heap objects -> SoA
     const int n = nmpms;
@@ -614,6 +658,13 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     for (MPMTask *t = firstMPMTask; t != NULL;) {
         MPMTask *next = (MPMTask *)t->GetNextTask();
         const int code = TaskCode(t->GetTaskName());
+        if (strcmp(t->GetTaskName(), "Decipher Crack and Material Fields") == 0) {
+            // InitVelocityFieldsTask (multimaterial mode without cracks): it assigns every particle's velocity field on the host
+            // objects; the device knows the field from the particle's material.  Dropped from the list.
+            if (prev) prev->SetNextTask(next); else firstMPMTask = next;
+            t = next;
+            continue;
+        }
         if (code >= 0) {
             GpuTask *g = new GpuTask(t->GetTaskName(), code);
             g->SetNextTask(next);

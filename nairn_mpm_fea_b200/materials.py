@@ -10,6 +10,8 @@ import numpy as np
 NPARAMS = 32
 MAX_HISTORY = 4            # MPMGPU_MAX_HISTORY
 ISOTROPIC, MOONEY, ISOPLASTICITY, RIGIDBC, NEOHOOKEAN = 1, 8, 9, 11, 28
+NOT_A_PARTICLE_MATERIAL = 0      # MPMGPU_MAT_NONE: keeps the place of a contact law in the materials list (ContactLaw, MaterialID 60-63)
+CONTACT_LAW, COULOMB_FRICTION_LAW = 60, 61        # Materials/ContactLaw.hpp:14 (ignore contact), Materials/CoulombFriction.hpp:14
 PLANE_STRAIN_MPM, PLANE_STRESS_MPM, THREED_MPM = 10, 11, 12
 
 DEFAULT_CV = 1.0e6          # MaterialBase.cpp:74 heatCapacity = Scaling(1.e6)
@@ -115,6 +117,12 @@ def isotropic(E, nu, rho, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, 
     p[20] = gamma0
     return dict(kind=ISOTROPIC, n_history=0, p=p, rho=rho, wave_speed=float(np.sqrt(2.0 * G * (1.0 - nu) / (rho * (1.0 - 2.0 * nu)))),
                 C33=C33, C66=C66)          # unreduced, as IsoPlasticity::VerifyAndLoadProperties reads them
+
+
+def contact_law_placeholder():
+    """The reference keeps contact laws in theMaterials[] beside the particle materials (Materials/ContactLaw.hpp); the entry
+    keeps the material numbering of the particles intact.  No particle may use it."""
+    return dict(kind=NOT_A_PARTICLE_MATERIAL, n_history=0, p=np.zeros(NPARAMS), rho=0.0, wave_speed=0.0)
 
 
 def rigid_bc(direction_bits, mirrored=0):

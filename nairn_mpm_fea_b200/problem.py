@@ -44,6 +44,10 @@ class Problem:
         self.bc_symdir = np.zeros(0, np.int32)
         self.bc_reflected = None        # per BC: 1-based node across a symmetry plane (NodalVelBC::reflectedNode) or -1; None = no such BCs
         self.bc_ratio = None            # per BC: NodalVelBC::reflectRatio
+        # <MultiMaterialMode>: None, or dict(n_fields, field_of_material [nmat], normal_method, by_displacements, position_cutoff,
+        # contact_normal [3], law_kind / law_friction / law_static [n_fields][n_fields]) -- mpmgpu_multimaterial in include/mpmgpu.h
+        self.multimaterial = None
+        self.origpos = None             # [3][n] MPMBase::origpos when it differs from the uploaded positions
         self.particles = {}
 
     @property
@@ -320,6 +324,8 @@ def from_reference_dump(z, snapshot="p0"):
                                                                    m=q[31], Tref=q[16])))
             else:
                 raise NotImplementedError("hardening law %d" % law)
+        elif mid in (M.CONTACT_LAW, M.COULOMB_FRICTION_LAW) and "mm/nfields" in z:
+            m = M.contact_law_placeholder()
         elif mid == M.RIGIDBC:
             if q[10] != 0 or q[11] != 0:
                 raise NotImplementedError("rigid material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")
@@ -336,6 +342,28 @@ def from_reference_dump(z, snapshot="p0"):
                         n_nonrigid=int(info["nmpmsNR"]))
     if np.any(z[s + "/pFext"] != 0.0):
         pr.particles["pfext"] = z[s + "/pFext"]
+    if "mm/nfields" in z:
+        # multimaterial mode: the reference's table is by material pair; the device wants it by velocity-field pair
+        nf = int(z["mm/nfields"])
+        field = np.asarray(z["mm/field"], np.int32)
+        law = np.asarray(z["mm/law"])
+        kind = np.zeros((nf, nf), np.int32)
+        fric = np.zeros((nf, nf))
+        stat = np.full((nf, nf), -1.0)
+        for i, fi in enumerate(field):
+            for j, fj in enumerate(field):
+                if fi < 0 or fj < 0 or fi == fj:
+                    continue
+                if law[i, j, 0] < 0:
+                    raise NotImplementedError("contact law between materials %d and %d (imperfect interface, adhesion, ...)" % (i + 1, j + 1))
+                kind[fi, fj], fric[fi, fj], stat[fi, fj] = int(law[i, j, 0]), law[i, j, 1], law[i, j, 2]
+        if int(z["mm/normal_method"]) > 4:
+            raise NotImplementedError("contact normals by linear / logistic regression")
+        pr.multimaterial = dict(n_fields=nf, field_of_material=np.where(field < 0, 0, field).astype(np.int32),
+                                normal_method=int(z["mm/normal_method"]), by_displacements=int(z["mm/by_displacements"]),
+                                position_cutoff=float(z["mm/position_cutoff"]), contact_normal=np.asarray(z["mm/contact_normal"], float),
+                                law_kind=kind, law_friction=fric, law_static=stat)
+        pr.origpos = np.asarray(z[s + "/origpos"], float) if (s + "/origpos") in z else None
     nb = z["velbcs/node"].shape[0]
     pr.bc_node = z["velbcs/node"].astype(np.int32)
     pr.bc_norm = z["velbcs/norm"]

@@ -307,7 +307,9 @@ void ref_get_nodes_field(int f, int *numberPoints, double *mass, double *pk, dou
         if (mvf->contactInfo != NULL) {
             cvolume[k] = mvf->contactInfo->cvolume;
             if (mpmgrid.volumeGradientIndex >= 0) { Vector &v = mvf->contactInfo->terms[mpmgrid.volumeGradientIndex]; cgrad[k] = v.x; cgrad[n + k] = v.y; cgrad[2 * n + k] = v.z; }
-            if (mpmgrid.displacementIndex >= 0) { Vector &v = mvf->contactInfo->terms[mpmgrid.displacementIndex]; cdisp[k] = v.x; cdisp[n + k] = v.y; cdisp[2 * n + k] = v.z; }
+            // the extrapolation contact detection uses: displacements (contactByDisplacements) or positions
+            int di = mpmgrid.contactByDisplacements ? mpmgrid.displacementIndex : mpmgrid.positionIndex;
+            if (di >= 0) { Vector &v = mvf->contactInfo->terms[di]; cdisp[k] = v.x; cdisp[n + k] = v.y; cdisp[2 * n + k] = v.z; }
         }
     }
 }
@@ -315,9 +317,14 @@ void ref_get_nodes_field(int f, int *numberPoints, double *mass, double *pk, dou
 // multimaterial settings: out[0] normal method, out[1] contactByDisplacements, out[2] number of materials; field[m] = velocity field of
 // material m (-1 unused); law[(i*nmat+j)*4 ..]: contact law of the pair (kind: 0 ignore, 1 stick, 2 frictionless, 3 frictional, -1 other;
 // friction coefficient; static coefficient; 0)
-void ref_get_multimaterial(int *out, int *field, double *law)
+int ref_multimaterial_on(void) { return fmobj->multiMaterialMode ? 1 : 0; }
+
+void ref_get_multimaterial(int *out, int *field, double *law, double *normal)
 {
     out[0] = mpmgrid.materialNormalMethod; out[1] = mpmgrid.contactByDisplacements ? 1 : 0; out[2] = nmat;
+    out[3] = fmobj->multiMaterialMode ? 1 : 0;
+    normal[0] = mpmgrid.contactNormal.x; normal[1] = mpmgrid.contactNormal.y; normal[2] = mpmgrid.contactNormal.z;
+    normal[3] = mpmgrid.positionCutoff;
     for (int i = 0; i < nmat; i++) field[i] = theMaterials[i]->GetField();
     for (int i = 0; i < nmat; i++)
         for (int j = 0; j < nmat; j++) {

@@ -96,7 +96,40 @@ class RefRun:
                                    _dp(o["ncpos"]), _dp(o["acc"]))
         return out
 
+    def multimaterial(self):
+        """<MultiMaterialMode> settings (None when off): fields, normal method, contact laws per field pair."""
+        nf = self.lib.ref_num_fields()
+        nm = self.info["nmat"]
+        out = np.zeros(8, np.int32)
+        field = np.zeros(nm, np.int32)
+        law = np.zeros((nm, nm, 4))
+        normal = np.zeros(4)
+        self.lib.ref_get_multimaterial(_ip(out), _ip(field), _dp(law), _dp(normal))
+        if not out[3]:
+            return None
+        return dict(nfields=nf, normal_method=int(out[0]), by_displacements=int(out[1]), field=field, law=law,
+                    position_cutoff=float(normal[3]), contact_normal=normal[:3].copy())
+
     def nodes(self):
+        nf = self.lib.ref_num_fields()
+        if nf > 1 or self.lib.ref_multimaterial_on():
+            # multimaterial mode: every array is field-major, [field][node] flattened (vectors [3][field*nnodes + node])
+            n = self.info["nnodes"]
+            N = nf * n
+            o = dict(numberPoints=np.zeros(N, np.int32), mass=np.zeros(N), pk=np.zeros((3, N)), ftot=np.zeros((3, N)),
+                     vk0=np.zeros((3, N)), pkcopy=np.zeros((3, N)), cvolume=np.zeros(N), cgrad=np.zeros((3, N)), cdisp=np.zeros((3, N)))
+            for f in range(nf):
+                t = dict(numberPoints=np.zeros(n, np.int32), mass=np.zeros(n), pk=np.zeros((3, n)), ftot=np.zeros((3, n)),
+                         vk0=np.zeros((3, n)), pkcopy=np.zeros((3, n)), cvolume=np.zeros(n), cgrad=np.zeros((3, n)), cdisp=np.zeros((3, n)))
+                self.lib.ref_get_nodes_field(f, _ip(t["numberPoints"]), _dp(t["mass"]), _dp(t["pk"]), _dp(t["ftot"]), _dp(t["vk0"]),
+                                             _dp(t["pkcopy"]), _dp(t["cvolume"]), _dp(t["cgrad"]), _dp(t["cdisp"]))
+                for k, v in t.items():
+                    o[k][..., f * n:(f + 1) * n] = v
+            fixed = np.zeros(n, np.int32)
+            dummy = [np.zeros(n, np.int32), np.zeros(n)] + [np.zeros((3, n)) for _ in range(4)]
+            self.lib.ref_get_nodes(_ip(dummy[0]), _dp(dummy[1]), _dp(dummy[2]), _dp(dummy[3]), _dp(dummy[4]), _dp(dummy[5]), _ip(fixed))
+            o["fixedDirection"] = fixed
+            return o
         n = self.info["nnodes"]
         o = dict(numberPoints=np.zeros(n, np.int32), mass=np.zeros(n), pk=np.zeros((3, n)),
                  ftot=np.zeros((3, n)), vk0=np.zeros((3, n)), pkcopy=np.zeros((3, n)),
@@ -163,6 +196,9 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
     _flatten("velbcs", r.velbcs(), out)
     ids, par = r.materials()
     out["mat_ids"], out["mat_params"] = ids, par
+    mm = r.multimaterial()
+    if mm is not None:
+        _flatten("mm", mm, out)
     names = r.task_names()
     out["task_names"] = np.array(names)
     _flatten("p0", r.particles(), out)

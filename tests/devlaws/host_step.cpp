@@ -36,6 +36,13 @@ struct EmuSim {
     int dim, shape, n;
     bool largeRotation;
     long long mstep;
+    // multimaterial mode (capi.cu: ctx->multimaterial, nf, nvn, C, cp)
+    bool multimaterial = false;
+    int nf = 1, nvn = 0;
+    ContactNodes C;
+    ContactParams cp;
+    std::vector<double> cpool, origpos;
+    std::vector<int> foff, fieldOfMat;
 };
 
 struct HostArrays {
@@ -98,6 +105,25 @@ void fill_set(Particles &P, std::vector<double> &pool, std::vector<int> &ipool, 
 
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
+// node pool: mass, pk, ftot, vk, pkCopy, v*prev, v*next (capi.cu::alloc_node_arrays); nn = fields x nodes
+void bind_nodes(EmuSim *S, size_t nn)
+{
+    S->npool.assign(nn * 22, 0.);
+    S->ncnt.assign(nn, 0);
+    S->nvn = (int)nn;
+    Nodes &Nd = S->N;
+    memset(&Nd, 0, sizeof Nd);
+    double *qn = S->npool.data();
+    Nd.mass = qn; qn += nn;
+    for (int c = 0; c < 3; c++) { Nd.pk[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.ftot[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.vk[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.pkc[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.vsp[c] = qn; qn += nn; }
+    for (int c = 0; c < 3; c++) { Nd.vsn[c] = qn; qn += nn; }
+    Nd.cnt = S->ncnt.data();
+}
+
 #define DISPATCH(KERNEL, n, ...) do { \
     const int grid_ = nblk((n), TASK_THREADS); \
     if (S->dim == 3) { \
@@ -122,14 +148,29 @@ inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 void apply_bcs(EmuSim *S, int pass, int adjustSym)
 {
-    if (S->hasBCs && S->B.nUnique > 0) EMU_LAUNCH(k_velocity_bcs, nblk(S->B.nUnique, 128), 128, S->B, S->N, pass, S->sp.dt, adjustSym);
-    if (S->R.on && adjustSym != 2) EMU_LAUNCH(k_rigid_velocity_bcs, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->R, S->N, pass, S->sp.dt);
+    if (S->hasBCs && S->B.nUnique > 0) EMU_LAUNCH(k_velocity_bcs, nblk((long long)S->B.nUnique * S->nf, 128), 128, S->B, S->N, pass, S->sp.dt, adjustSym, S->nf, S->g.nnodes);
+    if (S->R.on && adjustSym != 2) EMU_LAUNCH(k_rigid_velocity_bcs, nblk(S->nvn, 256), 256, S->nvn, S->R, S->N, pass, S->sp.dt);
+}
+
+// capi.cu::contact_extrapolation / material_contact
+void contact_extrapolation(EmuSim *S)
+{
+    if (!S->multimaterial) return;
+    DISPATCH(k_p2g_contact_terms, S->P.nNR, S->g, S->P, S->mats.data(), S->C, S->origpos.data(), (size_t)S->n, S->cp.byDisplacements,
+             S->cp.normalMethod != NORMALS_SPECIFIED ? 1 : 0);
+}
+
+void material_contact(EmuSim *S, int callType)
+{
+    if (!S->multimaterial) return;
+    if (getenv("EMU_SKIP_CONTACT") && atoi(getenv("EMU_SKIP_CONTACT")) == callType + 1 && S->mstep + 1 == atoi(getenv("EMU_SKIP_STEP"))) return;      // debugging aid
+    EMU_LAUNCH(k_material_contact, nblk(S->g.nnodes, 128), 128, S->g, S->N, S->C, S->cp, S->B, S->hasBCs ? S->bcOfNode.data() : (const int *)NULL, callType, S->sp.dt);
 }
 
 
 void xpic_extrapolation(EmuSim *S, int particleUpdate)
 {
-    const int nn = S->g.nnodes, fmpm = S->sp.usingFMPM ? 1 : 0;
+    const int nn = S->nvn, fmpm = S->sp.usingFMPM ? 1 : 0;
     EMU_LAUNCH(k_xpic_init, nblk(nn, 256), 256, nn, S->N, S->sp.dt, fmpm);
     for (int k = 2; k <= S->sp.xpicOrder; k++) {
         DISPATCH(k_xpic_iterate, S->P.nNR, S->g, S->P, S->N);
@@ -142,7 +183,7 @@ void strain_update(EmuSim *S, double strainTime, bool postUpdate)
     if (S->sp.usingFMPM && S->sp.xpicOrder > 1) {
         if (!postUpdate || !S->sp.skipPost) xpic_extrapolation(S, 0);
     } else
-        EMU_LAUNCH(k_grid_velocity, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->N);
+        EMU_LAUNCH(k_grid_velocity, nblk(S->nvn, 256), 256, S->nvn, S->N);
     if (S->largeRotation) DISPATCH(k_update_strains_lr, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime);
     else DISPATCH(k_update_strains, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime);
 }
@@ -150,16 +191,18 @@ void strain_update(EmuSim *S, double strainTime, bool postUpdate)
 // task numbers as in capi.cu: 0 initialization ... 9 reset elements
 void run_task(EmuSim *S, int t)
 {
-    const int nn = S->g.nnodes;
+    const int nn = S->nvn;
     switch (t) {
     case 0:
         std::fill(S->npool.begin(), S->npool.end(), 0.);
         std::fill(S->ncnt.begin(), S->ncnt.end(), 0);
+        std::fill(S->cpool.begin(), S->cpool.end(), 0.);
         DISPATCH(k_init_particles, S->P.n, S->g, S->P, &S->flags);
         break;
-    case 1: DISPATCH(k_p2g_mass_momentum, S->P.nNR, S->g, S->P, S->N); break;
+    case 1: DISPATCH(k_p2g_mass_momentum, S->P.nNR, S->g, S->P, S->N); contact_extrapolation(S); break;
     case 2: {
         EMU_LAUNCH(k_copy_momenta, nblk(nn, 256), 256, nn, S->N);
+        material_contact(S, CALL_MASS_MOMENTUM);
         const bool hasUSF = S->sp.method == METHOD_USF || S->sp.method == METHOD_USAVG;
         apply_bcs(S, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
         break;
@@ -171,6 +214,7 @@ void run_task(EmuSim *S, int t)
     case 5: EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp); apply_bcs(S, PASS_GRID_FORCES, 0); break;
     case 6:
         EMU_LAUNCH(k_update_momenta, nblk(nn, 256), 256, nn, S->N, S->sp.dt);
+        material_contact(S, CALL_UPDATE_MOMENTUM);
         if (S->sp.xpicOrder <= 1) apply_bcs(S, PASS_UPDATE_MOMENTUM, 0);
         break;
     case 7: {
@@ -189,7 +233,10 @@ void run_task(EmuSim *S, int t)
         if (S->sp.method == METHOD_USF) break;
         if (!S->sp.skipPost) {
             EMU_LAUNCH(k_rezero_momenta, nblk(nn, 256), 256, nn, S->N);
+            if (S->multimaterial) EMU_LAUNCH(k_zero_contact_terms, nblk(nn, 256), 256, nn, S->C);
             DISPATCH(k_p2g_momentum_last, S->P.nNR, S->g, S->P, S->N);
+            contact_extrapolation(S);
+            material_contact(S, CALL_UPDATE_STRAINS_LAST);
             apply_bcs(S, PASS_UPDATE_STRAINS_LAST, 0);
         }
         strain_update(S, S->sp.method == METHOD_USAVG ? S->sp.dtStrainLast : S->sp.dt, true);
@@ -274,22 +321,46 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     for (int p = nNR; p < n; p++) if (S->mats[matnum[p] - 1].p[9] != 0.) R.mirrored = 1;
     R.mat = S->PR.mat; R.mats = S->mats.data();
     R.stride[0] = 1; R.stride[1] = g.yplane; R.stride[2] = g.zplane; R.nnodes = g.nnodes;
-    // node pool: mass, pk, ftot, vk, pkCopy, v*prev, v*next (capi.cu::mpmgpu_create)
-    const size_t nn = (size_t)g.nnodes;
-    S->npool.assign(nn * 22, 0.);
-    S->ncnt.assign(nn, 0);
-    Nodes &Nd = S->N;
-    memset(&Nd, 0, sizeof Nd);
-    double *qn = S->npool.data();
-    Nd.mass = qn; qn += nn;
-    for (int c = 0; c < 3; c++) { Nd.pk[c] = qn; qn += nn; }
-    for (int c = 0; c < 3; c++) { Nd.ftot[c] = qn; qn += nn; }
-    for (int c = 0; c < 3; c++) { Nd.vk[c] = qn; qn += nn; }
-    for (int c = 0; c < 3; c++) { Nd.pkc[c] = qn; qn += nn; }
-    for (int c = 0; c < 3; c++) { Nd.vsp[c] = qn; qn += nn; }
-    for (int c = 0; c < 3; c++) { Nd.vsn[c] = qn; qn += nn; }
-    Nd.cnt = S->ncnt.data();
+    bind_nodes(S, (size_t)g.nnodes);
+    memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp);
     return S;
+}
+
+// capi.cu::mpmgpu_set_multimaterial: nf fields per node (field-major node arrays), contact extrapolations, particle field offsets
+extern "C" void emu_set_multimaterial(void *h, int nf, const int *fieldOfMat, int normalMethod, int byDisplacements, double positionCutoff,
+                                      const double *normal, const int *lawKind, const double *lawFriction, const double *lawStatic, const double *origpos)
+{
+    EmuSim *S = (EmuSim *)h;
+    S->multimaterial = true; S->nf = nf;
+    const size_t nv = (size_t)nf * S->g.nnodes;
+    bind_nodes(S, nv);
+    S->cpool.assign(nv * 7, 0.);
+    double *q = S->cpool.data();
+    S->C.cvol = q; q += nv;
+    for (int c = 0; c < 3; c++) { S->C.cgrad[c] = q; q += nv; }
+    for (int c = 0; c < 3; c++) { S->C.cdisp[c] = q; q += nv; }
+    ContactParams &cp = S->cp;
+    memset(&cp, 0, sizeof cp);
+    cp.nf = nf; cp.normalMethod = normalMethod; cp.byDisplacements = byDisplacements; cp.positionCutoff = positionCutoff;
+    for (int c = 0; c < 3; c++) cp.normal[c] = normal[c];
+    auto dbleEqual = [](double a, double b) { const double d = fabs(a - b); if (d <= 1.0e-16) return true; a = fabs(a); b = fabs(b); return d <= (b > a ? b : a) * 1.0e-7; };
+    cp.cubic = dbleEqual(S->g.gx, S->g.gy) && (S->dim == 2 || dbleEqual(S->g.gx, S->g.gz)) ? 1 : 0;
+    for (int i = 0; i < nf * nf; i++) { cp.lawKind[i] = (i / nf == i % nf) ? LAW_IGNORE : lawKind[i]; cp.lawFriction[i] = lawFriction[i]; cp.lawStatic[i] = lawStatic[i]; }
+    S->fieldOfMat.assign(fieldOfMat, fieldOfMat + S->mats.size());
+    S->foff.assign(S->P.n ? S->P.n : 1, 0);
+    for (int p = 0; p < S->P.n; p++) S->foff[p] = S->fieldOfMat[S->P.mat[p]] * S->g.nnodes;
+    S->P.foff = S->foff.data();
+    S->origpos.assign(origpos, origpos + 3 * (size_t)S->n);
+}
+
+extern "C" void emu_get_contact(void *h, double *cvol, double *cgrad, double *cdisp)
+{
+    EmuSim *S = (EmuSim *)h;
+    const size_t nn = (size_t)S->nvn;
+    for (size_t i = 0; i < nn; i++) {
+        cvol[i] = S->C.cvol[i];
+        for (int c = 0; c < 3; c++) { cgrad[c * nn + i] = S->C.cgrad[c][i]; cdisp[c * nn + i] = S->C.cdisp[c][i]; }
+    }
 }
 
 // the grouping of capi.cu::mpmgpu_set_velocity_bcs: by node, list order kept inside a node
@@ -381,7 +452,7 @@ extern "C" void emu_get_particles(void *h, double *pos, double *vel, double *sp,
 extern "C" void emu_get_nodes(void *h, int *cnt, double *mass, double *pk, double *ftot, double *vk, double *pkc)
 {
     EmuSim *S = (EmuSim *)h;
-    const size_t nn = (size_t)S->g.nnodes;
+    const size_t nn = (size_t)S->nvn;
     for (size_t i = 0; i < nn; i++) {
         cnt[i] = S->N.cnt[i]; mass[i] = S->N.mass[i];
         for (int c = 0; c < 3; c++) { pk[c * nn + i] = S->N.pk[c][i]; ftot[c * nn + i] = S->N.ftot[c][i]; vk[c * nn + i] = S->N.vk[c][i]; pkc[c * nn + i] = S->N.pkc[c][i]; }

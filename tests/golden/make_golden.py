@@ -149,6 +149,20 @@ CASES = {
                                    (1, 60), 1),
     "block3d_b2cpdi": (inputs.block3d(ncell=3, margin=3, gimp="B2CPDI", material=inputs.neohookean_material(), vz=-8.0e3, vx=2.0e3), (1, 30), 1, 0.3, 2000.0),
     "disks2d_b2cpdi": (inputs.disks2d(analysis=10, gimp="B2CPDI"), (1, 60), 1),
+    # multimaterial mode: one velocity field per material + material contact.  The bodies touch
+    # from the start (contact, and with it real strains, from the first step on) and the disks meet obliquely (inputs.oblique_disks: in the mirror-symmetric head-on case the friction law's tangent is rounding noise).
+    "mm2d_friction_avgg": (inputs.oblique_disks(inputs.disks2d(analysis=10, vel=4000.0, vmax=11.0, gap=0.0, extra_header=inputs.multimaterial(2, 0.3))), (1, 2, 60), 2),
+    "mm2d_frictionless_maxg_position": (inputs.oblique_disks(inputs.disks2d(analysis=11, vel=4000.0, vmax=11.0, gap=0.0, extra_header=inputs.multimaterial(0, None, 0.8))), (1, 2, 60), 2),
+    "mm2d_stick_maxv_linear_usl": (inputs.oblique_disks(inputs.disks2d(analysis=10, gimp=None, method=3, vel=4000.0, vmax=11.0, gap=0.0, extra_header=inputs.multimaterial(1, -1.0))), (1, 2, 60), 2),
+    "mm2d_ignore_lcpdi_usf": (inputs.oblique_disks(inputs.disks2d(analysis=10, gimp="lCPDI", method=0, vel=4000.0, vmax=11.0, gap=0.0, extra_header=inputs.multimaterial(2, -11.0))), (1, 2, 40), 2),
+    "mm2d_friction_sn_powerlaw": (inputs.oblique_disks(inputs.disks2d(analysis=10, vel=4000.0, vmax=11.0, gap=0.0,
+                                                       extra_header=inputs.multimaterial(4, 0.5, -0.7, ' Polar="0" Azimuth="8"'))), (1, 2, 60), 2),
+    # (the reference itself crashes when a contact node is not handled as ONE PAIR that includes material field 0 -- three
+    # materials on a node, or Normals="3" -- unless FMPM order > 1: MaterialContactNode::GetContactInfo indexes a NULL
+    # FMPMContact array, MaterialContactNode.cpp:137-139; so two-material cases only)
+    "mm3d_two_blocks_avgg_position": (inputs.blocks3d_contact(inputs.multimaterial(2, 0.4, 0.9), gimp=None, materials=2), (1, 2, 40), 2),
+    "mm3d_two_blocks_maxg_stick_b2gimp": (inputs.blocks3d_contact(inputs.multimaterial(0, -1.0), gimp="B2GIMP", materials=2), (1, 2, 40), 2),
+    "mm3d_two_blocks_maxv_friction_ugimp": (inputs.blocks3d_contact(inputs.multimaterial(1, 0.25), materials=2), (1, 2, 40), 2),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

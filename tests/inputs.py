@@ -174,3 +174,59 @@ def periodic_xpic(order, fmpm=False, periodic_steps=1):
     return ('<CustomTasks><Schedule name="PeriodicXPIC"><Parameter name="%s">%d</Parameter>'
             '<Parameter name="periodicSteps">%d</Parameter></Schedule></CustomTasks>'
             % ("FMPMOrder" if fmpm else "XPICOrder", order, periodic_steps))
+
+
+def oblique_disks(xml, vy=1300.0, shift=2.5):
+    """Break the mirror symmetry of disks2d: the second disk is shifted in y and moves in y too, so the contact between
+    the disks is oblique.  (In the head-on case the tangential stick momentum is rounding noise, which the reference's
+    friction law normalises into a direction: CoulombFriction.cpp:217-229.)"""
+    a, b = xml.split('<Body matname="Disk 2"')
+    b = b.replace('vy="0"', 'vy="%r"' % vy, 1).replace('ymin="-6.0" ymax="6.0"', 'ymin="%r" ymax="%r"' % (-6.0 + shift, 6.0 + shift), 1)
+    return a + '<Body matname="Disk 2"' + b
+
+
+def multimaterial(normals=2, friction=None, position=None, extra=""):
+    """<MultiMaterialMode> header element: Normals 0 MAXG, 1 MAXV, 2 AVGG, 3 OWNG, 4 SN (MPMReadHandler.cpp:607-652);
+    friction: None (default law: frictionless), < -10 ignore, < 0 stick, else the coefficient; position: <ContactPosition>."""
+    inner = ""
+    if friction is not None:
+        inner += "<Friction>%r</Friction>" % friction
+    if position is not None:
+        inner += "<ContactPosition>%r</ContactPosition>" % position
+    return '<MultiMaterialMode Normals="%d"%s>%s</MultiMaterialMode>' % (normals, extra, inner)
+
+
+def blocks3d_contact(header, gimp="uGIMP", method=2, materials=3):
+    """Three (or two) 3D blocks of different materials flying into each other inside a 12 x 10 x 10 grid (A and B touch from the start, so the first steps already carry contact): nodes seen by two
+    and by three materials (the lumped branch of MaterialContactOnCVFLumped)."""
+    gimp_tag = '<GIMP type="%s"/>' % gimp if gimp else ""
+    third = ('<Body matname="C" vx="-500" vy="-4000" vz="-1500"><Box xmin="4" xmax="7" ymin="6.5" ymax="8.5" zmin="3.5" zmax="6.5"/></Body>'
+             if materials > 2 else "")
+    third_mat = ('<Material Type="28" Name="C"><rho>1.2</rho><G>30</G><K>90</K><alpha>40</alpha></Material>' if materials > 2 else "")
+    return """<?xml version='1.0'?>
+<!DOCTYPE JANFEAInput SYSTEM "NairnMPM.dtd">
+<JANFEAInput version='3'>
+  <Header><Description>3D blocks in contact</Description><Analysis>12</Analysis></Header>
+  <MPMHeader>
+    <MPMMethod>%d</MPMMethod>
+    <Timing step="1e-3" max="1.0" CFL="0.4" units="ms"/>
+    <ArchiveTime units="ms">1000</ArchiveTime>
+    <ArchiveRoot>res/blk.</ArchiveRoot>
+    <MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>
+    %s %s
+  </MPMHeader>
+  <Mesh output="file">
+    <Grid xmin="0" xmax="12" ymin="0" ymax="10" zmin="0" zmax="10">
+      <Horiz cellsize="1"/><Vert cellsize="1"/><Depth cellsize="1"/>
+    </Grid>
+  </Mesh>
+  <MaterialPoints>
+    <Body matname="A" vx="5000" vy="600" vz="-300"><Box xmin="2" xmax="5" ymin="3" ymax="6" zmin="3" zmax="6"/></Body>
+    <Body matname="B" vx="-4000" vy="-200" vz="900"><Box xmin="5" xmax="8" ymin="3.5" ymax="6.5" zmin="4" zmax="7"/></Body>
+    %s
+  </MaterialPoints>
+  <Material Type="1" Name="A"><rho>1.0</rho><E>100</E><nu>0.3</nu><alpha>0</alpha></Material>
+  <Material Type="9" Name="B"><rho>2.0</rho><E>400</E><nu>0.33</nu><alpha>20</alpha><Hardening>Linear</Hardening><yield>8</yield><Ep>40</Ep></Material>
+  %s
+</JANFEAInput>
+""" % (method, gimp_tag, header, third, third_mat)

@@ -19,6 +19,7 @@ TASK_MAP = {
     "Update Strains Last with Extrapolation": "update_strains_last",
     "Update Strains Last": "update_strains_last",
     "Reset Elements": "reset_elements",
+    "Decipher Crack and Material Fields": None,      # InitVelocityFieldsTask: the device knows every particle's field from its material
     "Run Custom Tasks": None,        # host-side: PeriodicXPIC only changes the XPIC order for the next step
 }
 
@@ -134,15 +135,25 @@ def rel_err(a, b, scale_with=None):
         return 0.0
     d = np.where(nb, 0.0, np.abs(a - b))
     scale = np.max(np.where(nb, 0.0, np.abs(b)))
-    if scale_with is not None:
+    if scale_with is not None and not np.all(np.isnan(scale_with)):
         scale = max(scale, float(np.nanmax(np.abs(scale_with))))
     if scale == 0.0:
         return float(np.max(d))          # reference field identically zero: absolute error
     return float(np.max(d) / scale)
 
 
-def compare_particles(got, ref, prefix, tol, fields=None):
-    """got: MpmGpu.download() dict; ref: golden dict with keys prefix/<field>.  Returns {field: err}."""
+def _scales(ref, key, scale_prefix, prefix, extra=None):
+    """other reference arrays of the same physical quantity to scale an error with (rel_err's scale_with)"""
+    out = [] if extra is None else [np.ravel(extra)]
+    if scale_prefix is not None:
+        out.append(np.ravel(ref[key.replace(prefix, scale_prefix, 1)]))
+    return np.concatenate(out) if out else None
+
+
+def compare_particles(got, ref, prefix, tol, fields=None, scale_prefix=None):
+    """got: MpmGpu.download() dict; ref: golden dict with keys prefix/<field>.  Returns {field: err}.
+    scale_prefix: a second dump (same task of a later step) whose magnitudes also scale the errors -- for fields that are
+    rounding noise in `prefix` (the strains of two bodies in uniform motion before their first contact)."""
     pairs = [("pos", "pos"), ("vel", "vel"), ("sp", "sp"), ("pressure", "pressure"), ("ep", "ep"), ("wrot", "wrot"),
              ("eplast", "eplast")]
     errs = {}
@@ -155,23 +166,90 @@ def compare_particles(got, ref, prefix, tol, fields=None):
         a, b = np.asarray(got[g]), np.asarray(ref[prefix + "/" + r])
         if two_d and g in ("sp", "ep", "eplast"):
             a, b = a[[0, 1, 2, 5]], b[[0, 1, 2, 5]]
-        errs[g] = rel_err(a, b, ref[prefix + "/ep"] if g == "wrot" else None)
+        errs[g] = rel_err(a, b, _scales(ref, prefix + "/" + r, scale_prefix, prefix, ref[prefix + "/ep"] if g == "wrot" else None))
     e = ref[prefix + "/energies"]
     names = ["work", "res", "heat", "entropy", "plast"]
     for i, nm in enumerate(names):
-        errs[nm] = rel_err(got["energies"][i], e[i])
+        errs[nm] = rel_err(got["energies"][i], e[i], None if scale_prefix is None else ref[scale_prefix + "/energies"][i])
     nh = min(got["history"].shape[0], ref[prefix + "/hist"].shape[0])
     errs["history"] = rel_err(got["history"][:nh], ref[prefix + "/hist"][:nh])
     bad = {k: v for k, v in errs.items() if not v <= tol}
     return errs, bad
 
 
-def compare_nodes(got, ref, prefix, tol):
+def compare_nodes(got, ref, prefix, tol, scale_prefix=None):
     errs = {}
+    sc = lambda k: None if scale_prefix is None else ref[scale_prefix + "/" + k]          # noqa: E731
     errs["mass"] = rel_err(got["mass"], ref[prefix + "/mass"])
     errs["pk"] = rel_err(got["pk"], ref[prefix + "/pk"])
-    errs["ftot"] = rel_err(got["ftot"], ref[prefix + "/ftot"])
-    errs["vk"] = rel_err(got["vk"], ref[prefix + "/vk0"])
+    errs["ftot"] = rel_err(got["ftot"], ref[prefix + "/ftot"], sc("ftot"))
+    if "contact_volume" in got and (prefix + "/cvolume") in ref:
+        # Pair contact hands the SECOND field of a node minus the momentum change computed for the first one
+        # (CrackVelocityFieldMulti.cpp:640-645), so a field with a vanishing share of the node's mass (the tails of the
+        # spline shape functions: 1e-13 of its neighbour) keeps its momentum only to an ulp of the OTHER field's momentum and
+        # its velocity p/m is rounding noise -- in the reference too.  Velocities are compared where the field carries mass.
+        heavy = ref[prefix + "/mass"] >= 1.0e-6 * np.max(ref[prefix + "/mass"])
+        errs["vk"] = rel_err(got["vk"][:, heavy], ref[prefix + "/vk0"][:, heavy])
+    else:
+        errs["vk"] = rel_err(got["vk"], ref[prefix + "/vk0"])
     errs["pk_copy"] = rel_err(got["pk_copy"], ref[prefix + "/pkcopy"])
+    if "contact_volume" in got and (prefix + "/cvolume") in ref:
+        # multimaterial mode: the contact extrapolations (field-major arrays on both sides)
+        errs["contact_volume"] = rel_err(got["contact_volume"], ref[prefix + "/cvolume"])
+        errs["contact_gradient"] = rel_err(got["contact_gradient"], ref[prefix + "/cgrad"])
+        errs["contact_disp"] = rel_err(got["contact_disp"], ref[prefix + "/cdisp"])
     bad = {k: v for k, v in errs.items() if not v <= tol}
     return errs, bad
+
+
+# ---- multimaterial mode (goldens mm*): shared by the CPU run of the device source and the GPU run through the C ABI ----------
+MM_CASES = ["mm2d_friction_avgg", "mm2d_frictionless_maxg_position", "mm2d_stick_maxv_linear_usl", "mm2d_ignore_lcpdi_usf",
+            "mm2d_friction_sn_powerlaw", "mm3d_two_blocks_avgg_position", "mm3d_two_blocks_maxg_stick_b2gimp",
+            "mm3d_two_blocks_maxv_friction_ugimp"]
+
+
+def check_multimaterial_tasks(sim, z, case):
+    """Every task of the first two steps: node fields of every material velocity field (field-major arrays), the contact
+    extrapolations, particle fields.  Until the first contact changes a field's velocities the bodies move uniformly and their
+    strains and forces are rounding noise, so the errors of step 1 are also scaled with the same task's dump of step 2."""
+    names = [str(s) for s in z["task_names"]]
+    for step in range(1, per_task_steps(z) + 1):
+        tol = TOL_1STEP if step == 1 else 1.0e-8
+        for i, nm in enumerate(names):
+            if TASK_MAP[nm] is None:
+                continue
+            sim.run_task(TASK_MAP[nm])
+            pre = "s%d/t%d" % (step, i)
+            later = "s2/t%d" % i if step == 1 else None
+            nodes = sim.download_nodes()
+            errs, bad = compare_nodes(nodes, z, pre + "/nodes", tol, later and later + "/nodes")
+            assert not bad, "%s step %d after task %d (%s): node fields %s" % (case, step, i, nm, bad)
+            assert "contact_volume" in errs
+            assert np.array_equal(nodes["number_points"] > 0, z[pre + "/nodes/numberPoints"] > 0), "active (field, node) set differs"
+            got = sim.download()
+            errs, bad = compare_particles(got, z, pre + "/p", tol, scale_prefix=later and later + "/p")
+            assert not bad, "%s step %d after task %d (%s): particle fields %s" % (case, step, i, nm, bad)
+            assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"])
+
+
+def check_multimaterial_run(sim, z, case):
+    """Whole steps: 1 step to 1e-10 (noise fields scaled as above), N steps to 1e-7; element ids and crossings exact.
+    Returns the number of nodes that carry more than one material at the end (the test wants contact to have happened)."""
+    snaps = sorted(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/pos") and k[1] != "0")
+    done = 0
+    for s in snaps:
+        sim.step(s - done)
+        done = s
+        tol = TOL_1STEP if s <= 2 else TOL_100STEP
+        later = "p2" if s == 1 else None
+        got = sim.download()
+        errs, bad = compare_particles(got, z, "p%d" % s, tol, scale_prefix=later)
+        assert not bad, "%s after %d steps: %s" % (case, s, bad)
+        assert np.array_equal(got["in_elem"], z["p%d/inElem" % s])
+        assert np.array_equal(got["crossings"], z["p%d/crossings" % s])
+        nodes = sim.download_nodes()
+        errs, bad = compare_nodes(nodes, z, "n%d" % s, tol, "n2" if s == 1 else None)
+        assert not bad, "%s after %d steps: nodes %s" % (case, s, bad)
+    nf = int(z["mm/nfields"])
+    cnt = nodes["number_points"].reshape(nf, -1) > 0
+    return int(np.sum(cnt.sum(axis=0) > 1))

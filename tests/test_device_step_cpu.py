@@ -21,7 +21,8 @@ ROOT = os.path.dirname(HERE)
 DEV = os.path.join(HERE, "devlaws")
 LIB = os.path.join(DEV, "_build", "libdevstep.so")
 
-CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz"))
+# (the multimaterial goldens mm* have their own checks: tests/test_multimaterial_cpu.py)
+CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and not f.startswith("mm"))
 TASK_INDEX = {"initialization": 0, "mass_and_momentum": 1, "post_extrapolation": 2, "update_strains_first": 3, "grid_forces": 4,
               "post_forces": 5, "update_momenta": 6, "update_particles": 7, "update_strains_last": 8, "reset_elements": 9,
               "project_rigid_bcs": 10}
@@ -47,7 +48,7 @@ def lib():
                         src, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.emu_create.restype = C.c_void_p
-    for f in ("emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
+    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
         getattr(lib, f).argtypes = None
     return lib
 
@@ -91,6 +92,17 @@ class EmuSim:
                 self._bc += [c(prob.bc_reflected, dtype=np.int32), c(prob.bc_ratio, dtype=np.float64)]
                 lib.emu_set_bc_reflections(self.h, nb, _ip(self._bc[5]), _dp(self._bc[6]))
         self.nnodes = (prob.horiz + 1) * (prob.vert + 1) * ((prob.depth + 1) if prob.is3d else 1)
+        self.n_fields = 0
+        mm = getattr(prob, "multimaterial", None)
+        if mm is not None:
+            nf = int(mm["n_fields"])
+            orig = c(prob.origpos if prob.origpos is not None else keep["pos"], dtype=np.float64)
+            self._mm = [c(mm["field_of_material"], dtype=np.int32), c(mm["contact_normal"], dtype=np.float64), c(np.asarray(mm["law_kind"]).reshape(-1), dtype=np.int32),
+                        c(np.asarray(mm["law_friction"]).reshape(-1), dtype=np.float64), c(np.asarray(mm["law_static"]).reshape(-1), dtype=np.float64), orig]
+            lib.emu_set_multimaterial(self.h, nf, _ip(self._mm[0]), int(mm["normal_method"]), int(mm["by_displacements"]), d(mm["position_cutoff"]),
+                                      _dp(self._mm[1]), _ip(self._mm[2]), _dp(self._mm[3]), _dp(self._mm[4]), _dp(self._mm[5]))
+            self.nnodes *= nf
+            self.n_fields = nf
 
     def set_xpic(self, order, fmpm):
         self.lib.emu_set_xpic(self.h, int(order), int(fmpm))
@@ -115,6 +127,9 @@ class EmuSim:
         o = dict(number_points=np.zeros(nn, np.int32), mass=np.zeros(nn), pk=np.zeros((3, nn)), ftot=np.zeros((3, nn)), vk=np.zeros((3, nn)),
                  pk_copy=np.zeros((3, nn)))
         self.lib.emu_get_nodes(self.h, _ip(o["number_points"]), _dp(o["mass"]), _dp(o["pk"]), _dp(o["ftot"]), _dp(o["vk"]), _dp(o["pk_copy"]))
+        if self.n_fields:
+            o.update(contact_volume=np.zeros(nn), contact_gradient=np.zeros((3, nn)), contact_disp=np.zeros((3, nn)))
+            self.lib.emu_get_contact(self.h, _dp(o["contact_volume"]), _dp(o["contact_gradient"]), _dp(o["contact_disp"]))
         return o
 
     def flags(self):
