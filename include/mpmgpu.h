@@ -164,6 +164,7 @@ typedef struct mpmgpu_particles {
                                    particles and downloads come back in DEVICE order with ids filled in;
                                    when NULL particles are identified by their upload index and downloads come
                                    back in upload order. */
+    double *temperature;/* [n]     MPMBase::pTemperature; used with conduction only (mpmgpu_set_conduction); NULL on upload = energies[5] */
 } mpmgpu_particles;
 
 /* download masks */
@@ -177,6 +178,7 @@ typedef struct mpmgpu_particles {
 #define MPMGPU_F_ELEM     0x080   /* in_elem + crossings */
 #define MPMGPU_F_ACC      0x100
 #define MPMGPU_F_ALL      0x1ff
+#define MPMGPU_F_TEMPERATURE 0x200 /* pTemperature (conduction only; not part of MPMGPU_F_ALL) */
 
 /* Host view of the node accumulators (debug / global quantities / parity tests).
  * Arrays are nnodes long (vectors [3][nnodes]), reference node order; NULL = skip. */
@@ -193,6 +195,10 @@ typedef struct mpmgpu_nodes {
     double *contact_volume;   /* MatVelocityField::contactInfo->cvolume */
     double *contact_gradient; /* [3][nnodes] volume gradient (terms[volumeGradientIndex]) */
     double *contact_disp;     /* [3][nnodes] mass-weighted displacement or position (contactByDisplacements) */
+    /* conduction only (mpmgpu_set_conduction): NodalPoint::gCond, one value per GRID node (also in multimaterial mode) */
+    double *transport_value;    /* gTValue: nodal temperature (sum mp Cv T S before the division of task 3) */
+    double *transport_capacity; /* gVCT: sum mp Cv S */
+    double *transport_rate;     /* gQ: heat flow into the node, the temperature rate after the momentum update */
 } mpmgpu_nodes;
 
 /* ---- life cycle -------------------------------------------------------------------------- */
@@ -226,6 +232,18 @@ typedef struct mpmgpu_multimaterial {
     const double *law_static;       /* [n_fields][n_fields] frictionCoeffStatic, <= 0 for none (NULL: none) */
 } mpmgpu_multimaterial;
 int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm);
+/* Heat conduction, the first transport task (<Thermal><Conduction/></Thermal>; Custom_Tasks/ConductionTask.cpp + TransportTask.cpp,
+ * hooked into the step at NodalPointMPM.cpp:444-447, PostExtrapolationTask.cpp:88,160, GridForcesTask.cpp:108-112,
+ * UpdateMomentaTask.cpp:55, UpdateParticlesTask.cpp:134-245): nodal temperature sum(mp Cv T S)/sum(mp Cv S), temperature gradient
+ * on the particles, conduction flow -mp (Vp/V0) (k/rho) grad T . grad S, grid rate and value update, FLIP update of the particle
+ * temperature, heat energy and entropy of the conducted heat; the laws see the grid-extrapolated temperature as their
+ * previous temperature.  kcond[m] = conductivity / rho of material m in the host's units (TransportProperties::kCondTensor,
+ * isotropic: MaterialBaseMPM.cpp:320-326; ignored for rigid-BC materials).  Built: isothermal energy mode, insulated boundaries,
+ * any number of materials (also in multimaterial mode: transport values live on the node, not on a velocity field).  Refused:
+ * materials with thermal expansion (the device laws carry no residual strains), XPIC/FMPM order > 1, slab mode; temperature and
+ * heat-flux BCs, adiabatic coupling and contact heating are the adapter's to refuse.  Per-task kernels.  Call after
+ * mpmgpu_set_materials and before mpmgpu_upload_particles. */
+int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kcond);
 int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
 /* timestep, strainTimestepFirst, strainTimestepLast (NairnMPM.cpp:1207-1240) */
 int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dt_strain_first, double dt_strain_last);

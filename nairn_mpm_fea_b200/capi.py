@@ -18,6 +18,7 @@ MAX_HISTORY = 4
 
 F_POS, F_VEL, F_STRESS, F_STRAIN, F_EPLAST, F_ENERGY, F_HISTORY, F_ELEM, F_ACC = (
     0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040, 0x080, 0x100)
+F_TEMPERATURE = 0x200
 F_ALL = 0x1FF
 
 TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_strains_first", "grid_forces",
@@ -25,7 +26,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
-           "mpmgpu_set_multimaterial", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
+           "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
@@ -62,12 +63,13 @@ class ParticlesView(C.Structure):
     _fields_ = [("n", C.c_int), ("n_nonrigid", C.c_int),
                 ("pos", _dp), ("vel", _dp), ("mp", _dp), ("lp", _dp), ("in_elem", _ip), ("matnum", _ip),
                 ("sp", _dp), ("pressure", _dp), ("ep", _dp), ("wrot", _dp), ("eplast", _dp),
-                ("energies", _dp), ("history", _dp), ("pfext", _dp), ("crossings", _ip), ("acc", _dp), ("ids", _ip)]
+                ("energies", _dp), ("history", _dp), ("pfext", _dp), ("crossings", _ip), ("acc", _dp), ("ids", _ip), ("temperature", _dp)]
 
 
 class NodesView(C.Structure):
     _fields_ = [("nnodes", C.c_int), ("number_points", _ip), ("mass", _dp), ("pk", _dp), ("ftot", _dp),
-                ("vk", _dp), ("pk_copy", _dp), ("contact_volume", _dp), ("contact_gradient", _dp), ("contact_disp", _dp)]
+                ("vk", _dp), ("pk_copy", _dp), ("contact_volume", _dp), ("contact_gradient", _dp), ("contact_disp", _dp),
+                ("transport_value", _dp), ("transport_capacity", _dp), ("transport_rate", _dp)]
 
 
 class MultiMaterial(C.Structure):
@@ -109,6 +111,7 @@ def load_library(path=None):
     lib.mpmgpu_set_materials.argtypes = [vp, C.c_int, C.POINTER(Material)]
     lib.mpmgpu_upload_particles.argtypes = [vp, C.POINTER(ParticlesView)]
     lib.mpmgpu_set_multimaterial.argtypes = [vp, C.POINTER(MultiMaterial)]
+    lib.mpmgpu_set_conduction.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_set_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.mpmgpu_set_xpic.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
@@ -222,6 +225,10 @@ class MpmGpu:
         mm = getattr(prob, "multimaterial", None)
         if mm is not None:
             self.set_multimaterial(mm)
+        self.conduction = getattr(prob, "conduction", None) is not None
+        if self.conduction:
+            k = _c64(prob.conduction["kcond"])
+            self._check(self.lib.mpmgpu_set_conduction(self.ctx, len(prob.materials), _d(k)))
         self.set_velocity_bcs(prob.bc_node, prob.bc_norm, prob.bc_value, prob.bc_active, prob.bc_symdir)
         if getattr(prob, "bc_reflected", None) is not None:
             self.set_velocity_bc_reflections(prob.bc_reflected, prob.bc_ratio)
@@ -254,7 +261,7 @@ class MpmGpu:
         v.n = n
         v.n_nonrigid = int(pt.get("n_nonrigid", n))
         keep = {}
-        for k in ("pos", "vel", "mp", "lp", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "pfext"):
+        for k in ("pos", "vel", "mp", "lp", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "pfext", "temperature"):
             keep[k] = _c64(pt.get(k))
             setattr(v, k, _d(keep[k]))
         for k in ("in_elem", "matnum", "crossings", "ids"):
@@ -342,6 +349,10 @@ class MpmGpu:
         for k in ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "acc"):
             setattr(v, k, _d(out[k]))
         v.in_elem, v.crossings = _i(out["in_elem"]), _i(out["crossings"])
+        if getattr(self, "conduction", False):
+            out["temperature"] = np.zeros(n)
+            v.temperature = _d(out["temperature"])
+            mask |= F_TEMPERATURE
         self._check(self.lib.mpmgpu_download_particles(self.ctx, C.byref(v), mask))
         return out
 
@@ -375,6 +386,11 @@ class MpmGpu:
         v.number_points = _i(out["number_points"])
         for k in ("mass", "pk", "ftot", "vk", "pk_copy"):
             setattr(v, k, _d(out[k]))
+        if getattr(self, "conduction", False):
+            nr = self.prob.nnodes
+            out.update(transport_value=np.zeros(nr), transport_capacity=np.zeros(nr), transport_rate=np.zeros(nr))
+            for k in ("transport_value", "transport_capacity", "transport_rate"):
+                setattr(v, k, _d(out[k]))
         if getattr(self, "n_fields", 0):
             out.update(contact_volume=np.zeros(n), contact_gradient=np.zeros((3, n)), contact_disp=np.zeros((3, n)))
             for k in ("contact_volume", "contact_gradient", "contact_disp"):

@@ -91,6 +91,10 @@ struct mpmgpu_ctx {
     ContactParams cp;
     int *dFieldOfMat = NULL, *foffPool = NULL;
     std::vector<int> hFieldOfMat;
+    // conduction (mpmgpu_set_conduction): nodal transport field, particle temperature + gradient
+    bool conduction = false;
+    TransportNodes T;
+    double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
     TiledState tiled;
     bool f2Attr[2][2];
     // slab mode: leave counts + status flags land here (pinned) right after the early element reset; the host
@@ -203,7 +207,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->nBCEntries = 0;
     memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R);
     ctx->rigidPool = NULL; ctx->rigidIntPool = NULL; ctx->rigidCap = 0;
-    memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B); memset(&ctx->C, 0, sizeof ctx->C); memset(&ctx->cp, 0, sizeof ctx->cp);
+    memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B); memset(&ctx->C, 0, sizeof ctx->C); memset(&ctx->cp, 0, sizeof ctx->cp); memset(&ctx->T, 0, sizeof ctx->T);
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
     memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
     tiled_state_init(ctx->tiled);
@@ -367,6 +371,36 @@ extern "C" int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimater
     CK(cudaMemcpy(ctx->dFieldOfMat, ctx->hFieldOfMat.data(), ctx->nmat * sizeof(int), cudaMemcpyHostToDevice));
     ctx->nf = nf;
     ctx->multimaterial = true;
+    return MPMGPU_OK;
+}
+
+// <Thermal><Conduction/></Thermal>: heat conduction on the grid.  After mpmgpu_set_materials, before mpmgpu_upload_particles.
+extern "C" int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kcond)
+{
+    if (!ctx || !kcond) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: null argument");
+    if (ctx->nmat == 0) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_conduction: call mpmgpu_set_materials first");
+    if (nmat != ctx->nmat) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: %d conductivities for %d materials", nmat, ctx->nmat);
+    if (ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_conduction: call before mpmgpu_upload_particles");
+    if (ctx->tiled.slab.on) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: not available in slab mode");
+    if (ctx->cfg.kernel_path == 2) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: transport tasks run on the per-task kernels (kernel_path 2 asked for the fused path)");
+    if (ctx->sp.xpicOrder > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: XPIC/FMPM of order > 1 with transport (XPICExtrapolationTaskTO) is not built");
+    for (int i = 0; i < nmat; i++) {
+        const Material &m = ctx->hMats[i];
+        // thermal expansion: the device laws carry no residual strains (materials.cuh), so a temperature change must not strain
+        const bool cte = (m.kind == MAT_ISOTROPIC && (m.p[17] != 0. || m.p[18] != 0. || m.p[19] != 0.)) ||
+                         ((m.kind == MAT_NEOHOOKEAN || m.kind == MAT_MOONEY || m.kind == MAT_ISOPLASTICITY) && m.p[12] != 0.);
+        if (cte) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: material %d has a thermal expansion coefficient; thermal strains are not built (conduction runs for materials with zero expansion)", i + 1);
+        if (m.kind != MAT_NONE && m.kind != MAT_RIGIDBC && !(m.p[1] > 0.)) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: material %d has no heat capacity", i + 1);
+    }
+    cudaSetDevice(ctx->cfg.device);
+    const size_t nnPad = ((size_t)ctx->g.nnodes + 31) & ~(size_t)31;
+    if (!ctx->transportPool) CK(dalloc(ctx, &ctx->transportPool, nnPad * 3));
+    CK(cudaMemset(ctx->transportPool, 0, nnPad * 3 * sizeof(double)));
+    ctx->T.gT = ctx->transportPool; ctx->T.gVCT = ctx->transportPool + nnPad; ctx->T.gQ = ctx->transportPool + 2 * nnPad;
+    if (!ctx->dKcond) CK(dalloc(ctx, &ctx->dKcond, (size_t)MPM_MAX_MATERIALS));
+    CK(cudaMemcpy(ctx->dKcond, kcond, nmat * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->T.kcond = ctx->dKcond;
+    ctx->conduction = true;
     return MPMGPU_OK;
 }
 
@@ -657,6 +691,17 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
             if (nR) CK(cudaMemcpyAsync(ctx->archOrigin + (size_t)c * n + nNR, ctx->PR.pos[c], (size_t)nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
+    if (ctx->conduction) {
+        if (ctx->globalIds) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: conduction with caller-global particle ids (slab mode) is not built");
+        if (!ctx->tempPool) { CK(dalloc(ctx, &ctx->tempPool, ctx->cap * 4)); CK(cudaMemsetAsync(ctx->tempPool, 0, ctx->cap * 4 * sizeof(double), ctx->stream)); }
+        ctx->P.temp = ctx->tempPool;
+        for (int c = 0; c < 3; c++) ctx->P.tgrad[c] = ctx->tempPool + (size_t)(c + 1) * ctx->cap;
+        if (nNR) {
+            // pTemperature; without the array every particle starts at the temperature of its last strain update (energies[5])
+            if (h->temperature) { if ((rc = up_field(ctx, &ctx->P.temp, h->temperature, 1, n, 0, nNR))) return rc; }
+            else CK(cudaMemcpyAsync(ctx->P.temp, ctx->P.prevT, (size_t)nNR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
     if (ctx->multimaterial) {
         if (ctx->globalIds) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: multimaterial mode with caller-global particle ids (slab mode) is not built");
         if (ctx->R.mirrored) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: mirrored rigid BCs in multimaterial mode are not built");
@@ -683,6 +728,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         if (ctx->hasReflectedBCs) ok = false;   // symmetry-plane BCs read the momentum of the node across the plane: per-task kernels
         if (ctx->R.mirrored) ok = false;        // a mirrored rigid BC reads a neighbour node's momentum between the node updates: per-task kernels
         if (ctx->multimaterial) ok = false;     // material velocity fields + contact: per-task kernels
+        if (ctx->conduction) ok = false;        // transport tasks: per-task kernels
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
             return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, no mirrored rigid BCs and no large-rotation or Mooney materials");
@@ -711,6 +757,7 @@ extern "C" int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dtFirst, 
 extern "C" int mpmgpu_set_xpic(mpmgpu_ctx *ctx, int order, int usingFMPM)
 {
     if (ctx && ctx->multimaterial && order > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: XPIC/FMPM of order > 1 with material contact is not built");
+    if (ctx && ctx->conduction && order > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: XPIC/FMPM of order > 1 with transport is not built");
     if (!ctx) return MPMGPU_EINVAL;
     if (order < 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: order %d", order);
     ctx->sp.xpicOrder = order; ctx->sp.usingFMPM = usingFMPM;
@@ -985,6 +1032,9 @@ static int t_initialization(mpmgpu_ctx *ctx)
     CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
     ctx->launches += 2;
     if (ctx->multimaterial) { CK(cudaMemsetAsync(ctx->contactPool, 0, nnPad * 7 * sizeof(double), ctx->stream)); ctx->launches++; }
+    if (ctx->conduction) {      // TransportField zeroed with the node (NodalPoint::InitializeForTimeStep)
+        CK(cudaMemsetAsync(ctx->transportPool, 0, (((size_t)ctx->g.nnodes + 31) & ~(size_t)31) * 3 * sizeof(double), ctx->stream)); ctx->launches++;
+    }
     DISPATCH_DIM_SHAPE(k_init_particles, ctx->P.n, ctx->g, ctx->P, ctx->dFlags);
     return MPMGPU_OK;
 }
@@ -992,6 +1042,7 @@ static int t_initialization(mpmgpu_ctx *ctx)
 static int t_mass_and_momentum(mpmgpu_ctx *ctx)
 {
     DISPATCH_DIM_SHAPE_VALUES(k_p2g_mass_momentum, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
+    if (ctx->conduction) DISPATCH_DIM_SHAPE_VALUES(k_p2g_temperature, ctx->P.nNR, ctx->g, ctx->P, ctx->dMats, ctx->T);
     return contact_extrapolation(ctx);
 }
 
@@ -1001,7 +1052,12 @@ static int t_post_extrapolation(mpmgpu_ctx *ctx)
     { int rc = material_contact(ctx, CALL_MASS_MOMENTUM); if (rc) return rc; }
     // MASS_MOMENTUM_CALL: symmetry adjust always, BC loop only when a USF task exists (NodalVelBC.cpp:339-361)
     const bool hasUSF = ctx->sp.method == METHOD_USF || ctx->sp.method == METHOD_USAVG;
-    return apply_bcs(ctx, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
+    { int rc = apply_bcs(ctx, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2); if (rc) return rc; }
+    if (ctx->conduction) {      // TransportTask::GetTransportValues + TransportBCsAndGradients (PostExtrapolationTask.cpp:88,160)
+        LAUNCH(k_transport_nodal_value, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->nf, ctx->N, ctx->T);
+        DISPATCH_DIM_SHAPE(k_transport_gradients, ctx->P.nNR, ctx->g, ctx->P, ctx->T);
+    }
+    return MPMGPU_OK;
 }
 
 // XPICExtrapolationTask::Execute (XPICExtrapolationTask.cpp:49-161): grid velocity v(k) for order k > 1
@@ -1039,6 +1095,7 @@ static int t_update_strains_first(mpmgpu_ctx *ctx)
 static int t_grid_forces(mpmgpu_ctx *ctx)
 {
     DISPATCH_DIM_SHAPE(k_p2g_forces, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->hasFext ? 1 : 0);
+    if (ctx->conduction) DISPATCH_DIM_SHAPE(k_p2g_conduction, ctx->P.nNR, ctx->g, ctx->P, ctx->T);        // GridForcesTask.cpp:108-112
     return MPMGPU_OK;
 }
 
@@ -1051,6 +1108,7 @@ static int t_post_forces(mpmgpu_ctx *ctx)
 static int t_update_momenta(mpmgpu_ctx *ctx)
 {
     LAUNCH(k_update_momenta, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N, ctx->sp.dt);
+    if (ctx->conduction) LAUNCH(k_transport_update, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->nf, ctx->N, ctx->T, ctx->sp.dt);    // UpdateMomentaTask.cpp:55
     { int rc = material_contact(ctx, CALL_UPDATE_MOMENTUM); if (rc) return rc; }
     if (ctx->sp.xpicOrder <= 1) return apply_bcs(ctx, PASS_UPDATE_MOMENTUM, 0);      // NodalVelBC.cpp:367-375
     return MPMGPU_OK;
@@ -1063,6 +1121,7 @@ static int t_update_particles(mpmgpu_ctx *ctx)
     int m = ctx->sp.xpicOrder;
     if (!ctx->sp.usingFMPM) m = -m;
     DISPATCH_DIM_SHAPE(k_update_particles, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, ctx->sp, m);
+    if (ctx->conduction) DISPATCH_DIM_SHAPE_VALUES(k_update_temperature, ctx->P.nNR, ctx->g, ctx->P, ctx->dMats, ctx->T, ctx->sp.dt);
     return move_rigid(ctx);
 }
 
@@ -1492,6 +1551,11 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
         }
         if ((mask & MPMGPU_F_HISTORY) && (rc = down_field(ctx, P.hist, PR.hist, h->history, MPM_MAX_HISTORY, n, dtmp))) break;
         if ((mask & MPMGPU_F_ACC) && (rc = down_field(ctx, P.acc, PR.acc, h->acc, 3, n, dtmp))) break;
+        if ((mask & MPMGPU_F_TEMPERATURE) && h->temperature && ctx->conduction) {
+            // pTemperature of the nonrigid particles (rigid-BC particles: the temperature of energies[5])
+            double *const t1[1] = {P.temp}, *const t1R[1] = {PR.prevT};
+            if ((rc = down_field(ctx, t1, t1R, h->temperature, 1, n, dtmp))) break;
+        }
         if (mask & MPMGPU_F_ELEM) {
             int *itmp = (int *)dtmp;
             if (h->in_elem) {
@@ -1619,6 +1683,12 @@ extern "C" int mpmgpu_download_nodes(mpmgpu_ctx *ctx, mpmgpu_nodes *h)
     cudaSetDevice(ctx->cfg.device);
     const size_t nn = ctx->nvn;          // fields x nodes in multimaterial mode (field-major)
     h->nnodes = (int)nn;
+    if (ctx->conduction) {
+        const size_t nr = ctx->g.nnodes;
+        if (h->transport_value) CK(cudaMemcpyAsync(h->transport_value, ctx->T.gT, nr * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h->transport_capacity) CK(cudaMemcpyAsync(h->transport_capacity, ctx->T.gVCT, nr * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h->transport_rate) CK(cudaMemcpyAsync(h->transport_rate, ctx->T.gQ, nr * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (ctx->multimaterial) {
         if (h->contact_volume) CK(cudaMemcpyAsync(h->contact_volume, ctx->C.cvol, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         for (int c = 0; c < 3; c++) {

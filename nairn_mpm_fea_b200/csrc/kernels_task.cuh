@@ -926,3 +926,110 @@ __global__ void k_material_contact(Grid g, Nodes N, ContactNodes C, ContactParam
         }
     }
 }
+
+// =================================================================================================================
+// Conduction: the first transport task on the same scatter/gather skeleton (Custom_Tasks/ConductionTask.cpp,
+// TransportTask.cpp).  One scalar per node and particle; isothermal energy mode;
+// FLIP transport update; no temperature or heat-flux BCs (insulated boundaries); materials without thermal expansion.
+// Transport values live on the NODE (NodalPoint::gCond), not on a material velocity field, so these kernels use the
+// particle's real node numbers also in multimaterial mode.
+// =================================================================================================================
+
+// task 2: ConductionTask::Task1Extrapolation (ConductionTask.cpp:101-112), called from NodalPoint::AddMassMomentum
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_p2g_temperature(Grid g, Particles P, const Material *mats, TransportNodes T)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    const double mpCv = P.mp[p] * mats[P.mat[p]].p[1];
+    const double Tp = P.temp[p];
+    particle_nodes_one_field<DIM, SHAPE, false>(g, P, p, [&](int nd, double S, double, double, double) {
+        const double CTShape = mpCv * S;
+        atomAdd(&T.gT[nd], Tp * CTShape);
+        atomAdd(&T.gVCT[nd], CTShape);
+    });
+}
+
+// a node "has nonrigid particles" when any of its material velocity fields saw one (NodalPoint::NodeHasNonrigidParticles)
+__device__ __forceinline__ bool node_has_particles(const Nodes &N, int i, int nnodes, int nf)
+{
+    for (int f = 0; f < nf; f++) if (N.cnt[f * nnodes + i] > 0) return true;
+    return false;
+}
+
+// task 3: TransportTask::GetTransportNodalValue (TransportTask.cpp:152-161)
+__global__ void k_transport_nodal_value(int nnodes, int nf, Nodes N, TransportNodes T)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes || !node_has_particles(N, i, nnodes, nf)) return;
+    T.gT[i] /= T.gVCT[i];
+}
+
+// task 3: TransportTask::GetGradients (TransportTask.cpp:224-272): grad T on the particle from the nodal temperatures
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_transport_gradients(Grid g, Particles P, TransportNodes T)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double tg[3] = {0., 0., 0.};
+    particle_nodes_one_field<DIM, SHAPE, true>(g, P, p, [&](int nd, double, double gx, double gy, double gz) {
+        const double Ti = T.gT[nd];
+        tg[0] += gx * Ti; tg[1] += gy * Ti;
+        if (DIM == 3) tg[2] += gz * Ti;
+    });
+    P.tgrad[0][p] = tg[0]; P.tgrad[1][p] = tg[1]; P.tgrad[2][p] = tg[2];
+}
+
+// task 5: ConductionTask::AddForces -> MatPoint3D::FCond / MatPoint2D::FCond (MatPoint3D.cpp:280-287, MatPoint2D.cpp:272-278)
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_p2g_conduction(Grid g, Particles P, TransportNodes T)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    const double k = T.kcond[P.mat[p]];
+    double relVol;          // MatPoint3D/2D::GetRelativeVolume: det F
+    if (DIM == 3) {
+        const double F00 = P.F[0][p], F01 = P.F[1][p], F02 = P.F[2][p], F10 = P.F[3][p], F11 = P.F[4][p], F12 = P.F[5][p],
+                     F20 = P.F[6][p], F21 = P.F[7][p], F22 = P.F[8][p];
+        relVol = F00 * (F11 * F22 - F21 * F12) - F01 * (F10 * F22 - F20 * F12) + F02 * (F10 * F21 - F20 * F11);
+    } else {
+        relVol = P.F[8][p] * (P.F[0][p] * P.F[4][p] - P.F[3][p] * P.F[1][p]);
+    }
+    const double c = -P.mp[p] * relVol;
+    const double qx = k * P.tgrad[0][p], qy = k * P.tgrad[1][p], qz = DIM == 3 ? k * P.tgrad[2][p] : 0.;
+    particle_nodes_one_field<DIM, SHAPE, true>(g, P, p, [&](int nd, double, double gx, double gy, double gz) {
+        atomAdd(&T.gQ[nd], DIM == 3 ? c * (qx * gx + qy * gy + qz * gz) : c * (qx * gx + qy * gy));
+    });
+}
+
+// task 7: TransportTask::UpdateTransport (TransportTask.cpp:419-428)
+__global__ void k_transport_update(int nnodes, int nf, Nodes N, TransportNodes T, double dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes || !node_has_particles(N, i, nnodes, nf)) return;
+    const double rate = T.gQ[i] / T.gVCT[i];
+    T.gQ[i] = rate;
+    T.gT[i] += rate * dt;
+}
+
+// task 8: the transport part of UpdateParticlesTask (UpdateParticlesTask.cpp:134-245): value and rate from the grid, change of
+// the grid-extrapolated temperature since the last update (TransportTask::GetDeltaValue), FLIP update of the particle
+// temperature (MoveTransportValue), heat energy and entropy of the conducted heat.
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_update_temperature(Grid g, Particles P, const Material *mats, TransportNodes T, double dt)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    double value = 0., rate = 0.;
+    particle_nodes_one_field<DIM, SHAPE, false>(g, P, p, [&](int nd, double S, double, double, double) {
+        value += T.gT[nd] * S;
+        rate += T.gQ[nd] * S;
+    });
+    const double prev = P.prevT[p];
+    const double dTcond = value - prev;
+    P.prevT[p] = value;
+    P.temp[p] += dt * rate;
+    const double cv = mats[P.mat[p]].p[1];
+    P.heat[p] += cv * dTcond;
+    P.entropy[p] += cv * log(value / (value - dTcond));
+}

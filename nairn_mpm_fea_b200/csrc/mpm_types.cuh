@@ -81,6 +81,9 @@ struct Particles {
     double *cpDom;           // [12][cap] the domain itself in grid units, frozen for the step like the corner data: centre (3), semi-side
                              // vectors (3 x 3); rows after the ncorner*3 rows of cpXi.  3D lCPDI: for_each_node_lcpdi3_hat (shape.cuh)
     size_t cpStride;         // cap
+    // conduction (mpmgpu_set_conduction): pTemperature and the temperature gradient of the step (MPMBase::pTemp), NULL = off
+    double *temp;
+    double *tgrad[3];
     // multimaterial mode: node-index offset of the particle's material velocity field (field * nnodes), NULL = one field
     const int *foff;
 };
@@ -98,6 +101,15 @@ struct ContactNodes {
     double *cgrad[3];        // volume gradient (terms[volumeGradientIndex])
     double *cdisp[3];        // mass-weighted displacement (contactByDisplacements) or position
 };
+// ---- conduction (ConductionTask, the first transport task) ------------------------------------
+// NodalPoint::gCond (TransportField): one value per NODE (not per material velocity field)
+struct TransportNodes {
+    double *gT;              // gTValue: sum mp Cv T S, then the nodal temperature
+    double *gVCT;            // gVCT: sum mp Cv S
+    double *gQ;              // gQ: heat flow, then the temperature rate
+    const double *kcond;     // [nmat] conductivity / rho of every material (TransportProperties::kCondTensor, isotropic)
+};
+
 struct ContactParams {
     int nf;                  // material velocity fields per node (maxMaterialFields)
     int normalMethod;        // mpmgrid.materialNormalMethod (0..4)

@@ -48,6 +48,8 @@ class Problem:
         # contact_normal [3], law_kind / law_friction / law_static [n_fields][n_fields]) -- mpmgpu_multimaterial in include/mpmgpu.h
         self.multimaterial = None
         self.origpos = None             # [3][n] MPMBase::origpos when it differs from the uploaded positions
+        # <Thermal><Conduction/>: None, or dict(kcond [nmat] = conductivity / rho); particles["temperature"] = pTemperature
+        self.conduction = None
         self.particles = {}
 
     @property
@@ -342,6 +344,12 @@ def from_reference_dump(z, snapshot="p0"):
                         n_nonrigid=int(info["nmpmsNR"]))
     if np.any(z[s + "/pFext"] != 0.0):
         pr.particles["pfext"] = z[s + "/pFext"]
+    if "conduction/kcond" in z:
+        for k in ("adiabatic", "n_temp_bcs", "n_flux_bcs", "contact_heating"):
+            if int(z["conduction/" + k]):
+                raise NotImplementedError("conduction with " + k)
+        pr.conduction = dict(kcond=np.asarray(z["conduction/kcond"], float))
+        pr.particles["temperature"] = np.asarray(z[s + "/temperature"], float)
     if "mm/nfields" in z:
         # multimaterial mode: the reference's table is by material pair; the device wants it by velocity-field pair
         nf = int(z["mm/nfields"])

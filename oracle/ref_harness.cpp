@@ -45,6 +45,10 @@
 #include "Materials/ContactLaw.hpp"
 #include "Materials/CoulombFriction.hpp"
 #include "Boundary_Conditions/MatPtLoadBC.hpp"
+#include "Boundary_Conditions/NodalTempBC.hpp"
+#include "Boundary_Conditions/MatPtHeatFluxBC.hpp"
+#include "Custom_Tasks/ConductionTask.hpp"
+#include "Custom_Tasks/TransportTask.hpp"
 #include "Global_Quantities/BodyForce.hpp"
 #include "Custom_Tasks/CustomTask.hpp"
 #include "Custom_Tasks/ConductionTask.hpp"
@@ -342,6 +346,39 @@ void ref_get_multimaterial(int *out, int *field, double *law, double *normal)
                 q[1] = cf->frictionCoeff; q[2] = cf->frictionCoeffStatic;
             }
         }
+}
+
+// ---- conduction (the first transport task): settings, particle temperatures, nodal transport field ------------------------
+// out[0] ConductionTask::active, [1] adiabatic, [2] number of temperature BCs, [3] number of heat-flux BCs, [4] material contact heating;
+// kcond[m] = conductivity / rho (MaterialBase::kCond after VerifyAndLoadProperties)
+void ref_get_conduction(int *out, double *kcond)
+{
+    out[0] = ConductionTask::active ? 1 : 0; out[1] = ConductionTask::adiabatic ? 1 : 0;
+    int nb = 0; for (BoundaryCondition *b = (BoundaryCondition *)firstTempBC; b != NULL; b = (BoundaryCondition *)b->GetNextObject()) nb++;
+    out[2] = nb;
+    nb = 0; for (BoundaryCondition *b = (BoundaryCondition *)firstHeatFluxPt; b != NULL; b = (BoundaryCondition *)b->GetNextObject()) nb++;
+    out[3] = nb;
+    out[4] = ConductionTask::matContactHeating ? 1 : 0;
+    for (int i = 0; i < nmat; i++) kcond[i] = theMaterials[i]->kCond;
+}
+
+int ref_conduction_on(void) { return ConductionTask::active ? 1 : 0; }
+
+// pTemperature [n] and the particle's temperature gradient of the step [3][n]
+void ref_get_temperatures(double *T, double *grad)
+{
+    const int n = nmpms;
+    for (int p = 0; p < n; p++) {
+        T[p] = mpm[p]->pTemperature;
+        for (int c = 0; c < 3; c++) grad[c * n + p] = 0.;
+        if (mpm[p]->pTemp != NULL && p < nmpmsNR) { grad[p] = mpm[p]->pTemp[0]; grad[n + p] = mpm[p]->pTemp[1]; if (fmobj->IsThreeD()) grad[2 * n + p] = mpm[p]->pTemp[2]; }
+    }
+}
+
+// NodalPoint::gCond of every node
+void ref_get_node_transport(double *gT, double *gVCT, double *gQ)
+{
+    for (int i = 1; i <= nnodes; i++) { gT[i - 1] = nd[i]->gCond.gTValue; gVCT[i - 1] = nd[i]->gCond.gVCT; gQ[i - 1] = nd[i]->gCond.gQ; }
 }
 
 // grid velocity BC list, in the reference's list order

@@ -94,6 +94,9 @@ class RefRun:
                                    _dp(o["wrot"]), _dp(o["eplast"]), _dp(o["energies"]), _dp(o["hist"]),
                                    C.c_int(nhist), _dp(o["pFext"]), _dp(o["origpos"]), _ip(o["crossings"]),
                                    _dp(o["ncpos"]), _dp(o["acc"]))
+        if self.lib.ref_conduction_on():
+            out.update(temperature=np.zeros(n), tgrad=np.zeros((3, n)))
+            self.lib.ref_get_temperatures(_dp(out["temperature"]), _dp(out["tgrad"]))
         return out
 
     def multimaterial(self):
@@ -110,7 +113,26 @@ class RefRun:
         return dict(nfields=nf, normal_method=int(out[0]), by_displacements=int(out[1]), field=field, law=law,
                     position_cutoff=float(normal[3]), contact_normal=normal[:3].copy())
 
+    def conduction(self):
+        """Conduction settings (None when the task is off): kcond per material, counts of the BCs this repo does not build."""
+        out = np.zeros(8, np.int32)
+        k = np.zeros(self.info["nmat"])
+        self.lib.ref_get_conduction(_ip(out), _dp(k))
+        if not out[0]:
+            return None
+        return dict(kcond=k, adiabatic=int(out[1]), n_temp_bcs=int(out[2]), n_flux_bcs=int(out[3]), contact_heating=int(out[4]))
+
+    def _transport(self, o):
+        if self.lib.ref_conduction_on():
+            n = self.info["nnodes"]
+            o.update(gT=np.zeros(n), gVCT=np.zeros(n), gQ=np.zeros(n))
+            self.lib.ref_get_node_transport(_dp(o["gT"]), _dp(o["gVCT"]), _dp(o["gQ"]))
+        return o
+
     def nodes(self):
+        return self._transport(self._nodes())
+
+    def _nodes(self):
         nf = self.lib.ref_num_fields()
         if nf > 1 or self.lib.ref_multimaterial_on():
             # multimaterial mode: every array is field-major, [field][node] flattened (vectors [3][field*nnodes + node])
@@ -199,6 +221,9 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
     mm = r.multimaterial()
     if mm is not None:
         _flatten("mm", mm, out)
+    cond = r.conduction()
+    if cond is not None:
+        _flatten("conduction", cond, out)
     names = r.task_names()
     out["task_names"] = np.array(names)
     _flatten("p0", r.particles(), out)

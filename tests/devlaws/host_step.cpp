@@ -43,6 +43,10 @@ struct EmuSim {
     ContactParams cp;
     std::vector<double> cpool, origpos;
     std::vector<int> foff, fieldOfMat;
+    // conduction (capi.cu: ctx->conduction, T)
+    bool conduction = false;
+    TransportNodes T;
+    std::vector<double> tpool, kcond, temps;
 };
 
 struct HostArrays {
@@ -197,23 +201,36 @@ void run_task(EmuSim *S, int t)
         std::fill(S->npool.begin(), S->npool.end(), 0.);
         std::fill(S->ncnt.begin(), S->ncnt.end(), 0);
         std::fill(S->cpool.begin(), S->cpool.end(), 0.);
+        std::fill(S->tpool.begin(), S->tpool.end(), 0.);
         DISPATCH(k_init_particles, S->P.n, S->g, S->P, &S->flags);
         break;
-    case 1: DISPATCH(k_p2g_mass_momentum, S->P.nNR, S->g, S->P, S->N); contact_extrapolation(S); break;
+    case 1:
+        DISPATCH(k_p2g_mass_momentum, S->P.nNR, S->g, S->P, S->N);
+        if (S->conduction) DISPATCH(k_p2g_temperature, S->P.nNR, S->g, S->P, S->mats.data(), S->T);
+        contact_extrapolation(S);
+        break;
     case 2: {
         EMU_LAUNCH(k_copy_momenta, nblk(nn, 256), 256, nn, S->N);
         material_contact(S, CALL_MASS_MOMENTUM);
         const bool hasUSF = S->sp.method == METHOD_USF || S->sp.method == METHOD_USAVG;
         apply_bcs(S, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
+        if (S->conduction) {
+            EMU_LAUNCH(k_transport_nodal_value, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->nf, S->N, S->T);
+            DISPATCH(k_transport_gradients, S->P.nNR, S->g, S->P, S->T);
+        }
         break;
     }
     case 3:
         if (S->sp.method != METHOD_USL) strain_update(S, S->sp.method == METHOD_USAVG ? S->sp.dtStrainFirst : S->sp.dt, false);
         break;
-    case 4: DISPATCH(k_p2g_forces, S->P.nNR, S->g, S->P, S->N, 0); break;
+    case 4:
+        DISPATCH(k_p2g_forces, S->P.nNR, S->g, S->P, S->N, 0);
+        if (S->conduction) DISPATCH(k_p2g_conduction, S->P.nNR, S->g, S->P, S->T);
+        break;
     case 5: EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp); apply_bcs(S, PASS_GRID_FORCES, 0); break;
     case 6:
         EMU_LAUNCH(k_update_momenta, nblk(nn, 256), 256, nn, S->N, S->sp.dt);
+        if (S->conduction) EMU_LAUNCH(k_transport_update, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->nf, S->N, S->T, S->sp.dt);
         material_contact(S, CALL_UPDATE_MOMENTUM);
         if (S->sp.xpicOrder <= 1) apply_bcs(S, PASS_UPDATE_MOMENTUM, 0);
         break;
@@ -223,6 +240,7 @@ void run_task(EmuSim *S, int t)
         int m = S->sp.xpicOrder;
         if (!S->sp.usingFMPM) m = -m;
         DISPATCH(k_update_particles, S->P.nNR, S->g, S->P, S->N, S->mats.data(), S->sp, m);
+        if (S->conduction) DISPATCH(k_update_temperature, S->P.nNR, S->g, S->P, S->mats.data(), S->T, S->sp.dt);
         if (S->PR.n > 0) {
             if (S->dim == 3) EMU_LAUNCH(k_move_rigid<3>, nblk(S->PR.n, 128), 128, S->PR, S->sp.dt);
             else EMU_LAUNCH(k_move_rigid<2>, nblk(S->PR.n, 128), 128, S->PR, S->sp.dt);
@@ -351,6 +369,29 @@ extern "C" void emu_set_multimaterial(void *h, int nf, const int *fieldOfMat, in
     for (int p = 0; p < S->P.n; p++) S->foff[p] = S->fieldOfMat[S->P.mat[p]] * S->g.nnodes;
     S->P.foff = S->foff.data();
     S->origpos.assign(origpos, origpos + 3 * (size_t)S->n);
+}
+
+// capi.cu::mpmgpu_set_conduction + the temperature part of mpmgpu_upload_particles
+extern "C" void emu_set_conduction(void *h, const double *kcond, const double *temperature)
+{
+    EmuSim *S = (EmuSim *)h;
+    S->conduction = true;
+    const size_t nn = (size_t)S->g.nnodes;
+    S->tpool.assign(nn * 3, 0.);
+    S->kcond.assign(kcond, kcond + S->mats.size());
+    S->T.gT = S->tpool.data(); S->T.gVCT = S->tpool.data() + nn; S->T.gQ = S->tpool.data() + 2 * nn; S->T.kcond = S->kcond.data();
+    const size_t C = S->P.n ? (size_t)S->P.n : 1;
+    S->temps.assign(C * 4, 0.);
+    for (int p = 0; p < S->P.n; p++) S->temps[p] = temperature[p];
+    S->P.temp = S->temps.data();
+    for (int c = 0; c < 3; c++) S->P.tgrad[c] = S->temps.data() + (size_t)(c + 1) * C;
+}
+
+extern "C" void emu_get_transport(void *h, double *gT, double *gVCT, double *gQ, double *temperature)
+{
+    EmuSim *S = (EmuSim *)h;
+    for (int i = 0; i < S->g.nnodes; i++) { gT[i] = S->T.gT[i]; gVCT[i] = S->T.gVCT[i]; gQ[i] = S->T.gQ[i]; }
+    for (int p = 0; p < S->n; p++) temperature[p] = p < S->P.n ? S->P.temp[p] : S->PR.prevT[p - S->P.n];
 }
 
 extern "C" void emu_get_contact(void *h, double *cvol, double *cgrad, double *cdisp)

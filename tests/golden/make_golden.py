@@ -163,6 +163,16 @@ CASES = {
     "mm3d_two_blocks_avgg_position": (inputs.blocks3d_contact(inputs.multimaterial(2, 0.4, 0.9), gimp=None, materials=2), (1, 2, 40), 2),
     "mm3d_two_blocks_maxg_stick_b2gimp": (inputs.blocks3d_contact(inputs.multimaterial(0, -1.0), gimp="B2GIMP", materials=2), (1, 2, 40), 2),
     "mm3d_two_blocks_maxv_friction_ugimp": (inputs.blocks3d_contact(inputs.multimaterial(1, 0.25), materials=2), (1, 2, 40), 2),
+    # heat conduction: bodies of different temperature, conductivity and heat capacity in contact;
+    # one velocity field, then material velocity fields with frictional contact in 3D (transport stays on the node)
+    "cond2d_disks_usavg": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=0.0)),
+                                             (380.0, 290.0), (2000.0, 500.0), (800.0, 1500.0)), (1, 2, 60), 2),
+    "cond2d_disks_lcpdi_usl_neo": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=11, gimp="lCPDI", method=3, vel=2000.0, vmax=11.0, gap=0.0, alpha=0.0))
+                                                     .replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>0.0</alpha>',
+                                                              '<Material Type="28" Name="Disk 1"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>0</alpha>'),
+                                                     (250.0, 420.0), (900.0, 3000.0), (1200.0, 700.0)), (1, 2, 60), 2),
+    "cond3d_blocks_multimaterial": (inputs.conduction(inputs.blocks3d_contact(inputs.multimaterial(2, 0.3), materials=2).replace("<alpha>20</alpha>", "<alpha>0</alpha>"),
+                                                      (400.0, 280.0), (5000.0, 1500.0), (600.0, 900.0)), (1, 2, 40), 2),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),
@@ -171,7 +181,7 @@ CASES = {
     "block3d_ugimp_usf": (inputs.block3d(ncell=3, margin=2, method=0), (1, 50), 1),
 }
 
-KEEP_P = ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "hist", "inElem", "crossings", "ncpos", "acc")
+KEEP_P = ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "hist", "inElem", "crossings", "ncpos", "acc", "temperature")
 
 
 def slim(z):

@@ -196,6 +196,20 @@ def multimaterial(normals=2, friction=None, position=None, extra=""):
     return '<MultiMaterialMode Normals="%d"%s>%s</MultiMaterialMode>' % (normals, extra, inner)
 
 
+def conduction(xml, temps, kcond, cp, stress_free=300.0):
+    """Switch heat conduction on in an input: <Thermal><Conduction/></Thermal>, a start temperature per <Body> (temps), kCond and
+    Cp per <Material> (in input order; materials must have zero thermal expansion on the device path), <StressFreeTemp>."""
+    parts = xml.split("<Body ")
+    assert len(parts) - 1 == len(temps), (len(parts) - 1, temps)
+    xml = parts[0] + "".join('<Body temp="%r" %s' % (t, rest) for t, rest in zip(temps, parts[1:]))
+    parts = xml.split("</Material>")
+    assert len(parts) - 1 >= len(kcond)
+    xml = "".join(seg + ("<kCond>%r</kCond><Cp>%r</Cp></Material>" % (kcond[i], cp[i]) if i < len(kcond) else ("</Material>" if i < len(parts) - 1 else ""))
+                  for i, seg in enumerate(parts))
+    xml = xml.replace("</MPMHeader>", "<StressFreeTemp>%r</StressFreeTemp></MPMHeader>" % stress_free)
+    return xml.replace("</JANFEAInput>", "<Thermal><Conduction/></Thermal></JANFEAInput>")
+
+
 def blocks3d_contact(header, gimp="uGIMP", method=2, materials=3):
     """Three (or two) 3D blocks of different materials flying into each other inside a 12 x 10 x 10 grid (A and B touch from the start, so the first steps already carry contact): nodes seen by two
     and by three materials (the lumped branch of MaterialContactOnCVFLumped)."""

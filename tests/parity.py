@@ -173,6 +173,8 @@ def compare_particles(got, ref, prefix, tol, fields=None, scale_prefix=None):
         errs[nm] = rel_err(got["energies"][i], e[i], None if scale_prefix is None else ref[scale_prefix + "/energies"][i])
     nh = min(got["history"].shape[0], ref[prefix + "/hist"].shape[0])
     errs["history"] = rel_err(got["history"][:nh], ref[prefix + "/hist"][:nh])
+    if "temperature" in got and (prefix + "/temperature") in ref:      # conduction: pTemperature
+        errs["temperature"] = rel_err(got["temperature"], ref[prefix + "/temperature"])
     bad = {k: v for k, v in errs.items() if not v <= tol}
     return errs, bad
 
@@ -193,6 +195,12 @@ def compare_nodes(got, ref, prefix, tol, scale_prefix=None):
     else:
         errs["vk"] = rel_err(got["vk"], ref[prefix + "/vk0"])
     errs["pk_copy"] = rel_err(got["pk_copy"], ref[prefix + "/pkcopy"])
+    if "transport_value" in got and (prefix + "/gT") in ref:
+        # conduction: NodalPoint::gCond.  The heat flow gQ is a sum of conduction terms that cancel inside a body of uniform
+        # temperature: it is scaled with the capacity-weighted temperature rate the same node could carry.
+        errs["transport_value"] = rel_err(got["transport_value"], ref[prefix + "/gT"])
+        errs["transport_capacity"] = rel_err(got["transport_capacity"], ref[prefix + "/gVCT"])
+        errs["transport_rate"] = rel_err(got["transport_rate"], ref[prefix + "/gQ"], sc("gQ"))
     if "contact_volume" in got and (prefix + "/cvolume") in ref:
         # multimaterial mode: the contact extrapolations (field-major arrays on both sides)
         errs["contact_volume"] = rel_err(got["contact_volume"], ref[prefix + "/cvolume"])
@@ -208,7 +216,10 @@ MM_CASES = ["mm2d_friction_avgg", "mm2d_frictionless_maxg_position", "mm2d_stick
             "mm3d_two_blocks_maxv_friction_ugimp"]
 
 
-def check_multimaterial_tasks(sim, z, case):
+COND_CASES = ["cond2d_disks_usavg", "cond2d_disks_lcpdi_usl_neo", "cond3d_blocks_multimaterial"]
+
+
+def check_multimaterial_tasks(sim, z, case, require="contact_volume"):
     """Every task of the first two steps: node fields of every material velocity field (field-major arrays), the contact
     extrapolations, particle fields.  Until the first contact changes a field's velocities the bodies move uniformly and their
     strains and forces are rounding noise, so the errors of step 1 are also scaled with the same task's dump of step 2."""
@@ -224,11 +235,12 @@ def check_multimaterial_tasks(sim, z, case):
             nodes = sim.download_nodes()
             errs, bad = compare_nodes(nodes, z, pre + "/nodes", tol, later and later + "/nodes")
             assert not bad, "%s step %d after task %d (%s): node fields %s" % (case, step, i, nm, bad)
-            assert "contact_volume" in errs
+            assert require in errs
             assert np.array_equal(nodes["number_points"] > 0, z[pre + "/nodes/numberPoints"] > 0), "active (field, node) set differs"
             got = sim.download()
             errs, bad = compare_particles(got, z, pre + "/p", tol, scale_prefix=later and later + "/p")
             assert not bad, "%s step %d after task %d (%s): particle fields %s" % (case, step, i, nm, bad)
+            assert require != "transport_value" or "temperature" in errs
             assert np.array_equal(got["in_elem"], z[pre + "/p/inElem"])
 
 
@@ -250,6 +262,6 @@ def check_multimaterial_run(sim, z, case):
         nodes = sim.download_nodes()
         errs, bad = compare_nodes(nodes, z, "n%d" % s, tol, "n2" if s == 1 else None)
         assert not bad, "%s after %d steps: nodes %s" % (case, s, bad)
-    nf = int(z["mm/nfields"])
+    nf = int(z["mm/nfields"]) if "mm/nfields" in z else 1
     cnt = nodes["number_points"].reshape(nf, -1) > 0
     return int(np.sum(cnt.sum(axis=0) > 1))

@@ -21,8 +21,8 @@ ROOT = os.path.dirname(HERE)
 DEV = os.path.join(HERE, "devlaws")
 LIB = os.path.join(DEV, "_build", "libdevstep.so")
 
-# (the multimaterial goldens mm* have their own checks: tests/test_multimaterial_cpu.py)
-CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and not f.startswith("mm"))
+# (the multimaterial goldens mm* and the conduction goldens cond* have their own checks: tests/test_multimaterial_cpu.py, tests/test_conduction_cpu.py)
+CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and not f.startswith(("mm", "cond")))
 TASK_INDEX = {"initialization": 0, "mass_and_momentum": 1, "post_extrapolation": 2, "update_strains_first": 3, "grid_forces": 4,
               "post_forces": 5, "update_momenta": 6, "update_particles": 7, "update_strains_last": 8, "reset_elements": 9,
               "project_rigid_bcs": 10}
@@ -48,7 +48,7 @@ def lib():
                         src, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.emu_create.restype = C.c_void_p
-    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
+    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_conduction", "emu_get_transport", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
         getattr(lib, f).argtypes = None
     return lib
 
@@ -93,6 +93,11 @@ class EmuSim:
                 lib.emu_set_bc_reflections(self.h, nb, _ip(self._bc[5]), _dp(self._bc[6]))
         self.nnodes = (prob.horiz + 1) * (prob.vert + 1) * ((prob.depth + 1) if prob.is3d else 1)
         self.n_fields = 0
+        self.conduction = getattr(prob, "conduction", None) is not None
+        self.real_nodes = self.nnodes
+        if self.conduction:
+            self._cond = [c(prob.conduction["kcond"], dtype=np.float64), c(pt["temperature"], dtype=np.float64)]
+            lib.emu_set_conduction(self.h, _dp(self._cond[0]), _dp(self._cond[1]))
         mm = getattr(prob, "multimaterial", None)
         if mm is not None:
             nf = int(mm["n_fields"])
@@ -120,6 +125,10 @@ class EmuSim:
                  in_elem=np.zeros(n, np.int32), crossings=np.zeros(n, np.int32))
         self.lib.emu_get_particles(self.h, _dp(o["pos"]), _dp(o["vel"]), _dp(o["sp"]), _dp(o["pressure"]), _dp(o["ep"]), _dp(o["wrot"]),
                                    _dp(o["eplast"]), _dp(o["energies"]), _dp(o["history"]), _dp(o["acc"]), _ip(o["in_elem"]), _ip(o["crossings"]))
+        if self.conduction:
+            o["temperature"] = np.zeros(n)
+            t = [np.zeros(self.real_nodes) for _ in range(3)]
+            self.lib.emu_get_transport(self.h, _dp(t[0]), _dp(t[1]), _dp(t[2]), _dp(o["temperature"]))
         return o
 
     def download_nodes(self):
@@ -127,6 +136,9 @@ class EmuSim:
         o = dict(number_points=np.zeros(nn, np.int32), mass=np.zeros(nn), pk=np.zeros((3, nn)), ftot=np.zeros((3, nn)), vk=np.zeros((3, nn)),
                  pk_copy=np.zeros((3, nn)))
         self.lib.emu_get_nodes(self.h, _ip(o["number_points"]), _dp(o["mass"]), _dp(o["pk"]), _dp(o["ftot"]), _dp(o["vk"]), _dp(o["pk_copy"]))
+        if self.conduction:
+            o.update(transport_value=np.zeros(self.real_nodes), transport_capacity=np.zeros(self.real_nodes), transport_rate=np.zeros(self.real_nodes))
+            self.lib.emu_get_transport(self.h, _dp(o["transport_value"]), _dp(o["transport_capacity"]), _dp(o["transport_rate"]), _dp(np.zeros(self.n)))
         if self.n_fields:
             o.update(contact_volume=np.zeros(nn), contact_gradient=np.zeros((3, nn)), contact_disp=np.zeros((3, nn)))
             self.lib.emu_get_contact(self.h, _dp(o["contact_volume"]), _dp(o["contact_gradient"]), _dp(o["contact_disp"]))

@@ -45,6 +45,12 @@ CASES = {
                                         '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="3.5" zmin="-1" zmax="20"><LoadBC dir="2" style="3" load="0.3" time="300"/></BCBox>'
                                         "</ParticleBCs>")
                                .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
+    # multimaterial mode: the two disks keep their own velocity fields and meet with Coulomb friction
+    "disks2d_multimaterial_friction": (inputs.oblique_disks(inputs.disks2d(analysis=10, vel=4000.0, vmax=11.0, gap=0.0, maxtime=0.6, archive_ms=0.15,
+                                                            extra_header=inputs.multimaterial(2, 0.3))), None, "res/disks."),
+    "blocks3d_multimaterial_position": (inputs.blocks3d_contact(inputs.multimaterial(0, 0.25, 0.8), materials=2)
+                                        .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+                                        .replace('max="1.0"', 'max="0.03"'), None, "res/blk."),
     # config 4 family: IsoPlasticity bar on a plate of rigid-BC particles
     "block3d_isoplastic_rigid_wall": (inputs.block3d(ncell=4, margin=3, maxtime=0.02, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
                                                      rigid=("wall", 4, (0.0, 0.0, 0.0)))

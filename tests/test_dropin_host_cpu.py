@@ -49,6 +49,16 @@ CASES = {
         "</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>"), "adiabatic energy coupling"),
     "particle temperature": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace('<Body ', '<Body temp="350" ', 1),
                              "particle temperatures that differ"),
+    # multimaterial mode runs on the device (tests/test_dropin_gpu.py) except for what mpmgpu_set_multimaterial does not cover
+    "regression contact normals": (inputs.oblique_disks(inputs.disks2d(analysis=10, maxtime=0.5, extra_header="<MultiMaterialMode/>")),
+                                   "contact normals by linear or logistic regression"),
+    "own-gradient contact normals": (inputs.oblique_disks(inputs.disks2d(analysis=10, maxtime=0.5, extra_header=inputs.multimaterial(3, 0.3))),
+                                     "each material's own normal"),
+    "imperfect interface": (inputs.oblique_disks(inputs.disks2d(analysis=10, maxtime=0.5,
+                                                 extra_header='<MultiMaterialMode Normals="2"><Friction Dn="1000" Dt="500">11</Friction></MultiMaterialMode>')),
+                            "imperfect interfaces"),
+    "multimaterial fmpm2": (inputs.oblique_disks(inputs.disks2d(analysis=10, maxtime=0.5, extra_header=inputs.multimaterial(2, 0.3)))
+                            .replace("</JANFEAInput>", inputs.periodic_xpic(2, True, 1) + "</JANFEAInput>"), "order > 1 in multimaterial mode"),
     "more exponential terms": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material=inputs.neohookean_material(),
                                               extra_header="<DefGradTerms>3</DefGradTerms>"), "<DefGradTerms> other than the default"),
 }
