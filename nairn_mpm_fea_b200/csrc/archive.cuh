@@ -125,7 +125,7 @@ __host__ __device__ inline void archive_record(const Particles &P, int p, int sl
     if (L.items & (1u << ARCH_PlasticStrain)) for (int i = 0; i < nt; i++) r.f64(P.eplast[tens[i]][p]);
     const double sc = 1.0e-9 * mp;
     if (L.items & (1u << ARCH_WorkEnergy)) r.f64(sc * P.work[p]);
-    if (L.items & (1u << ARCH_DeltaTemp)) r.f64(P.prevT[p]);
+    if (L.items & (1u << ARCH_DeltaTemp)) r.f64(P.temp ? P.temp[p] : P.prevT[p]);        // pTemperature (ArchiveData.cpp:976); without conduction it equals prevT
     if (L.items & (1u << ARCH_PlasticEnergy)) r.f64(sc * P.plast[p]);
     if (L.items & (1u << ARCH_StrainEnergy)) { const double se = P.work[p] - P.res[p]; r.f64(sc * se); }
     for (int k = 0; k < 4; k++) if (L.histMask & (1u << k)) r.f64(P.hist[k][p]);

@@ -43,6 +43,8 @@
 #include "Boundary_Conditions/NodalVelBC.hpp"
 #include "Boundary_Conditions/MatPtLoadBC.hpp"
 #include "Boundary_Conditions/MatPtTractionBC.hpp"
+#include "Boundary_Conditions/MatPtHeatFluxBC.hpp"
+#include "Boundary_Conditions/NodalTempBC.hpp"
 #include "Global_Quantities/BodyForce.hpp"
 #include "Custom_Tasks/CustomTask.hpp"
 #include "Custom_Tasks/TransportTask.hpp"
@@ -95,7 +97,9 @@ void DownloadToHost(void)
     memset(&h, 0, sizeof h);
     h.pos = pos.data(); h.vel = vel.data(); h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data();
     h.eplast = epl.data(); h.energies = en.data(); h.history = hist.data(); h.acc = acc.data(); h.in_elem = elem.data(); h.crossings = cross.data();
-    check(mpmgpu_download_particles(gCtx, &h, MPMGPU_F_ALL), "GpuTasks::DownloadToHost");
+    std::vector<double> temp;
+    if (ConductionTask::active) { temp.resize(n); h.temperature = temp.data(); }
+    check(mpmgpu_download_particles(gCtx, &h, MPMGPU_F_ALL | (ConductionTask::active ? MPMGPU_F_TEMPERATURE : 0)), "GpuTasks::DownloadToHost");
     for (int p = 0; p < n; p++) {
         MPMBase *m = mpm[p];
         m->pos = MakeVector(pos[p], pos[n + p], pos[2 * n + p]);
@@ -107,6 +111,7 @@ void DownloadToHost(void)
         m->wrot.xy = wrot[p]; m->wrot.xz = wrot[n + p]; m->wrot.yz = wrot[2 * n + p];
         m->eplast.xx = epl[p]; m->eplast.yy = epl[n + p]; m->eplast.zz = epl[2 * n + p]; m->eplast.yz = epl[3 * n + p]; m->eplast.xz = epl[4 * n + p]; m->eplast.xy = epl[5 * n + p];
         m->workEnergy = en[p]; m->resEnergy = en[n + p]; m->heatEnergy = en[2 * n + p]; m->entropy = en[3 * n + p]; m->plastEnergy = en[4 * n + p];
+        if (ConductionTask::active) { m->pTemperature = temp[p]; m->pPreviousTemperature = en[5 * n + p]; }
         if (elem[p] != m->inElem) { m->prevInElem = m->inElem; m->inElem = elem[p]; }
         m->elementCrossings = cross[p];
         const int nh = theMaterials[m->MatID()]->NumberOfHistoryDoubles();
@@ -400,7 +405,16 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         if (bodyFrc.GetXPICOrder() > 1) return "XPIC/FMPM of order > 1 in multimaterial mode";
         if (maxMaterialFields > 8) return "more than 8 material velocity fields";
     }
-    if (transportTasks != NULL) return "transport tasks present";
+    if (transportTasks != NULL) {
+        // heat conduction runs on the device (mpmgpu_set_conduction); every other transport task and every option of the
+        // conduction task the device does not have stays refused
+        if (transportTasks != conduction || conduction->GetNextTransportTask() != NULL) return "transport tasks other than conduction (diffusion, poroelasticity, ...)";
+        if (firstTempBC != NULL || firstRigidTempBC != NULL) return "nodal temperature BCs";
+        if (firstHeatFluxPt != NULL) return "particle heat-flux BCs";
+        if (ConductionTask::crackTipHeating || ConductionTask::crackContactHeating || ConductionTask::matContactHeating) return "crack-tip or contact heating";
+        if (TransportTask::hasXPICOption) return "XPIC/FMPM options for transport tasks";
+        if (bodyFrc.GetXPICOrder() > 1) return "XPIC/FMPM of order > 1 with transport tasks";
+    }
     // everything the replaced CPU tasks would do on the side must be absent, or the run would silently differ:
     // particle loads / tractions are re-evaluated every step by InitializationTask and GridForcesTask
     // particle loads are re-evaluated every step (MatPtLoadBC::SetParticleFext): values that are functions of time only are
@@ -424,7 +438,9 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     // a particle temperature other than the one its previous strain update saw gives a thermal strain increment
     // res.dT = pTemperature - pPreviousTemperature in the first particle update (UpdateParticlesTask.cpp:252-256);
     // the device has no residual strains (eres = 0)
-    for (int p = 0; p < nmpmsNR; p++)
+    // (with conduction the particle temperatures are state of the transport task; materials with thermal expansion are then
+    // refused by mpmgpu_set_conduction)
+    for (int p = 0; p < nmpmsNR && !ConductionTask::active; p++)
         if (mpm[p]->pTemperature != mpm[p]->pPreviousTemperature) return "particle temperatures that differ from the stress-free temperature (thermal strains)";
     // custom tasks run on the host particles between the step tasks; only the one that just switches the XPIC/FMPM order is safe
     for (CustomTask *ct = theTasks; ct != NULL; ct = ct->nextTask)
@@ -572,6 +588,11 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         }
     }
     if (mpmgpu_set_materials(gCtx, nmat, mats.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    if (ConductionTask::active) {
+        std::vector<double> kc(nmat, 0.);
+        for (int i = 0; i < nmat; i++) kc[i] = theMaterials[i]->kCond;          // conductivity / rho (MaterialBaseMPM.cpp:233)
+        if (mpmgpu_set_conduction(gCtx, nmat, kc.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    }
     if (fmobj->multiMaterialMode) {
         mpmgpu_multimaterial mm;
         memset(&mm, 0, sizeof mm);
@@ -618,6 +639,12 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     h.pos = pos.data(); h.vel = vel.data(); h.mp = mp.data(); h.lp = lp.data(); h.in_elem = elem.data(); h.matnum = matn.data();
     h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data(); h.eplast = epl.data(); h.energies = en.data();
     h.pfext = anyFext ? pf.data() : NULL; h.crossings = cross.data(); h.history = hist.data();
+    std::vector<double> temp0;
+    if (ConductionTask::active) {
+        temp0.resize(n);
+        for (int p = 0; p < n; p++) temp0[p] = mpm[p]->pTemperature;
+        h.temperature = temp0.data();
+    }
     if (mpmgpu_upload_particles(gCtx, &h) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     if (mpmgpu_set_time_step(gCtx, timestep, strainTimestepFirst, strainTimestepLast) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     {   // constants of the archive records (ArchiveData.cpp:820-875): original position, initial material angles, 2D thickness

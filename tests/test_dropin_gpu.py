@@ -51,6 +51,11 @@ CASES = {
     "blocks3d_multimaterial_position": (inputs.blocks3d_contact(inputs.multimaterial(0, 0.25, 0.8), materials=2)
                                         .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
                                         .replace('max="1.0"', 'max="0.03"'), None, "res/blk."),
+    # heat conduction between two disks of different temperature, conductivity and heat capacity; the archives carry the
+    # particle temperature
+    "disks2d_conduction": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=0.0, maxtime=0.6, archive_ms=0.15)),
+                                             (380.0, 290.0), (2000.0, 500.0), (800.0, 1500.0))
+                           .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/disks."),
     # config 4 family: IsoPlasticity bar on a plate of rigid-BC particles
     "block3d_isoplastic_rigid_wall": (inputs.block3d(ncell=4, margin=3, maxtime=0.02, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
                                                      rigid=("wall", 4, (0.0, 0.0, 0.0)))

@@ -59,6 +59,12 @@ CASES = {
                             "imperfect interfaces"),
     "multimaterial fmpm2": (inputs.oblique_disks(inputs.disks2d(analysis=10, maxtime=0.5, extra_header=inputs.multimaterial(2, 0.3)))
                             .replace("</JANFEAInput>", inputs.periodic_xpic(2, True, 1) + "</JANFEAInput>"), "order > 1 in multimaterial mode"),
+    # conduction runs on the device (tests/test_dropin_gpu.py); its BCs, other transport tasks and thermal expansion do not
+    "temperature BCs": (inputs.conduction(inputs.block3d(ncell=3, margin=2, maxtime=0.003), (350.0,), (2000.0,), (800.0,))
+                        .replace("</JANFEAInput>", '<GridBCs><BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="2.01"><TempBC value="400"/></BCBox></GridBCs></JANFEAInput>'),
+                        "nodal temperature BCs"),
+    "diffusion": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</MPMHeader>", '<Diffusion reference="0"/></MPMHeader>'),
+                  "transport tasks other than conduction"),
     "more exponential terms": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material=inputs.neohookean_material(),
                                               extra_header="<DefGradTerms>3</DefGradTerms>"), "<DefGradTerms> other than the default"),
 }
