@@ -95,6 +95,12 @@ struct mpmgpu_ctx {
     bool conduction = false;
     TransportNodes T;
     double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
+    // CUDA graphs of one whole step (mpmgpu_step): keyed by a byte signature of everything the step's launches capture by value
+    // (particle / node / BC structs with their device pointers, step parameters, mode flags); a setter that changes any of it,
+    // or a physical sort that swaps the particle pools, simply selects or creates another graph.  MPMGPU_GRAPHS=0 switches it off.
+    struct StepGraph { std::string sig; cudaGraphExec_t exec; long long launches; };
+    std::vector<StepGraph> stepGraphs;
+    bool useGraphs = true, inGraphStep = false;
     TiledState tiled;
     bool f2Attr[2][2];
     // slab mode: leave counts + status flags land here (pinned) right after the early element reset; the host
@@ -160,6 +166,7 @@ static int alloc_node_arrays(mpmgpu_ctx *ctx, size_t count)
 
 // ------------------------------------------------------------------------------------------------
 static void slab_disconnect(mpmgpu_ctx *ctx);
+static void drop_step_graphs(mpmgpu_ctx *ctx);
 extern "C" int mpmgpu_abi_version(void) { return MPMGPU_ABI_VERSION; }
 
 extern "C" const char *mpmgpu_last_error(const mpmgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -192,6 +199,8 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
         // (shape.cuh::for_each_node_lcpdi3_hat) in every kernel; 2D keeps thread-local sums, which pay off in the value-only
         // kernels and spill in the gradient kernels (measured on B200: profiles/r2_experiments/README.md).
         // MPMGPU_CPDI_MERGE=0/1 forces all kernels, MPMGPU_CPDI_MERGE_VALUES=0 switches the value-only kernels back.
+        const char *ge = getenv("MPMGPU_GRAPHS");
+        ctx->useGraphs = ge ? atoi(ge) != 0 : true;
         const char *e = getenv("MPMGPU_CPDI_MERGE");
         ctx->cpdiMerge = e ? atoi(e) != 0 : is3D;
         const char *v = getenv("MPMGPU_CPDI_MERGE_VALUES");
@@ -274,6 +283,7 @@ extern "C" int mpmgpu_destroy(mpmgpu_ctx *ctx)
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     tiled_state_free(ctx->tiled);
+    drop_step_graphs(ctx);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->slabHost) { cudaFreeHost(ctx->slabHost); cudaEventDestroy(ctx->slabEvent); }
     slab_disconnect(ctx);
@@ -312,6 +322,7 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
         ctx->hMats[i].p[6] = ctx->dim == 3 ? (ctx->cfg.gridx + ctx->cfg.gridy + ctx->cfg.gridz) / 3. : (ctx->cfg.gridx + ctx->cfg.gridy) / 2.;
     }
     ctx->nmat = nmat;
+    drop_step_graphs(ctx);
     CK(cudaMemcpyAsync(ctx->dMats, ctx->hMats.data(), nmat * sizeof(Material), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return MPMGPU_OK;
@@ -1359,8 +1370,10 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
     const bool highOrder = sp.xpicOrder > 1;
 
     if (phase == 0) {
-        if (t.stepsSinceSort >= t.sortInterval) { if ((rc = sort_particles(ctx))) return rc; }
-        t.stepsSinceSort++;
+        if (!ctx->inGraphStep) {        // (a step that is captured or replayed as a graph sorts and counts in mpmgpu_step)
+            if (t.stepsSinceSort >= t.sortInterval) { if ((rc = sort_particles(ctx))) return rc; }
+            t.stepsSinceSort++;
+        }
         prof_begin(ctx);
         if (t.slab.on) LAUNCH(k_zero_node_range, ngrid, 256, n0, ncount, ctx->N);
         else {
@@ -1473,14 +1486,105 @@ static int fused_step(mpmgpu_ctx *ctx)
     return MPMGPU_OK;
 }
 
+// everything one step's launches take by value: when these bytes are the same, a captured step can be replayed
+static void step_signature(const mpmgpu_ctx *ctx, std::string &sig)
+{
+    sig.clear();
+    auto add = [&](const void *p, size_t n) { sig.append((const char *)p, n); };
+    add(&ctx->g, sizeof ctx->g); add(&ctx->P, sizeof ctx->P); add(&ctx->PR, sizeof ctx->PR); add(&ctx->N, sizeof ctx->N);
+    add(&ctx->B, sizeof ctx->B); add(&ctx->R, sizeof ctx->R); add(&ctx->sp, sizeof ctx->sp); add(&ctx->tiled.FN, sizeof ctx->tiled.FN);
+    add(&ctx->C, sizeof ctx->C); add(&ctx->cp, sizeof ctx->cp); add(&ctx->T, sizeof ctx->T);
+    const long long misc[16] = {ctx->tiled.enabled, ctx->tiled.stateKind, ctx->tiled.usePipe, ctx->hasFext, ctx->hasBCs, ctx->largeRotation, ctx->multimaterial,
+                                ctx->conduction, ctx->nf, ctx->nvn, ctx->cpdiMerge, ctx->cpdiMergeValues, (long long)(size_t)ctx->dMats, (long long)(size_t)ctx->archOrigin,
+                                (long long)(size_t)ctx->nodePool, (long long)(size_t)ctx->stream};
+    add(misc, sizeof misc);
+}
+
+static void drop_step_graphs(mpmgpu_ctx *ctx)
+{
+    for (auto &sg : ctx->stepGraphs) cudaGraphExecDestroy(sg.exec);
+    ctx->stepGraphs.clear();
+}
+
+// the sort and the step count of this step are already done: run the phases as a graph step would, without a graph
+static int graph_step_plain(mpmgpu_ctx *ctx, bool &done)
+{
+    ctx->inGraphStep = true;
+    const int rc = ctx->tiled.enabled ? fused_step(ctx) : step_by_tasks(ctx);
+    ctx->inGraphStep = false;
+    done = true;
+    return rc;
+}
+
+// one step as a CUDA graph: captured the first time a signature is seen (the capture only records, so the graph is launched
+// for that step too), replayed afterwards -- one launch instead of 10-30, which is what a small problem's step costs
+static int graph_step(mpmgpu_ctx *ctx, bool &done)
+{
+    done = false;
+    int rc;
+    TiledState &t = ctx->tiled;
+    if (t.enabled) {            // the host-side part of phase 0
+        if (t.stepsSinceSort >= t.sortInterval) { if ((rc = sort_particles(ctx))) return rc; }
+        t.stepsSinceSort++;
+        if (t.usePipe) return graph_step_plain(ctx, done);          // (sets a function attribute per launch: not captured)
+        // the dynamic shared-memory opt-in of F2 is not a stream operation: do it before capturing
+        const int fx = ctx->hasFext ? 1 : 0;
+        if (!ctx->f2Attr[t.stateKind][fx]) {
+            cudaError_t e;
+            if (t.stateKind == SK_ELASTIC) e = fx ? cudaFuncSetAttribute(k_f2_strain_forces<SK_ELASTIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_smem_bytes<true>())
+                                                  : cudaFuncSetAttribute(k_f2_strain_forces<SK_ELASTIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_smem_bytes<false>());
+            else e = fx ? cudaFuncSetAttribute(k_f2_strain_forces<SK_FULL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_smem_bytes<true>())
+                        : cudaFuncSetAttribute(k_f2_strain_forces<SK_FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_smem_bytes<false>());
+            CK(e);
+            ctx->f2Attr[t.stateKind][fx] = true;
+        }
+    }
+    std::string sig;
+    step_signature(ctx, sig);
+    mpmgpu_ctx::StepGraph *hit = NULL;
+    for (auto &sg : ctx->stepGraphs) if (sg.sig == sig) { hit = &sg; break; }
+    if (!hit) {
+        if (ctx->stepGraphs.size() >= 4) { cudaGraphExecDestroy(ctx->stepGraphs.front().exec); ctx->stepGraphs.erase(ctx->stepGraphs.begin()); }
+        const long long before = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); ctx->useGraphs = false; return graph_step_plain(ctx, done); }
+        ctx->inGraphStep = true;
+        rc = t.enabled ? fused_step(ctx) : step_by_tasks(ctx);
+        ctx->inGraphStep = false;
+        cudaGraph_t graph = NULL;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        const long long captured = ctx->launches - before;
+        ctx->launches = before;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        cudaGraphExec_t exec = NULL;
+        if (e != cudaSuccess || graph == NULL || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            // something in this configuration cannot be captured: run it the plain way from now on
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            ctx->useGraphs = false;
+            return graph_step_plain(ctx, done);
+        }
+        cudaGraphDestroy(graph);
+        ctx->stepGraphs.push_back({sig, exec, captured});
+        hit = &ctx->stepGraphs.back();
+    }
+    CK(cudaGraphLaunch(hit->exec, ctx->stream));
+    ctx->launches += hit->launches;
+    done = true;
+    return MPMGPU_OK;
+}
+
 extern "C" int mpmgpu_step(mpmgpu_ctx *ctx, int nsteps)
 {
     int rc = check_ready(ctx, "mpmgpu_step"); if (rc) return rc;
     if (ctx->tiled.slab.on && (ctx->tiled.hasLower || ctx->tiled.hasUpper))
         return fail(ctx, MPMGPU_ESTATE, "mpmgpu_step: this context is one slab of a multi-GPU run; drive it with mpmgpu_slab_step_phase and the halo exchanges");
     for (int s = 0; s < nsteps; s++) {
-        rc = ctx->tiled.enabled ? fused_step(ctx) : step_by_tasks(ctx);
-        if (rc) return rc;
+        bool done = false;
+        if (ctx->useGraphs && !ctx->profiling && !ctx->tiled.slab.on) { if ((rc = graph_step(ctx, done))) return rc; }
+        if (!done) {
+            rc = ctx->tiled.enabled ? fused_step(ctx) : step_by_tasks(ctx);
+            if (rc) return rc;
+        }
         ctx->mstep++; ctx->mtime += ctx->sp.dt;
     }
     return poll_flags(ctx, false);
