@@ -70,6 +70,10 @@ extern double timestep, strainTimestepFirst, strainTimestepLast, fractionUSF, mt
 namespace {
 
 mpmgpu_ctx *gCtx = NULL;
+// -gpus N: one context per GPU, each holding the particles of its z-slab of cell planes (mpmgpu_slab_*; the library does the halo
+// and migrant exchanges itself over NCCL).  gCtx is slab 0 then; one OpenMP thread per GPU drives mpmgpu_slab_step.
+std::vector<mpmgpu_ctx *> gSlabs;
+int gNumGpus = 1;
 bool gHostStale = false;            // device is ahead of mpm[]
 std::vector<NodalVelBC *> gBCs;     // host BC list in list order
 bool gBCsVary = false;
@@ -80,16 +84,55 @@ std::vector<int> gLoadPts;          // particles with load BCs (MatPtLoadBC), 0-
 bool gLoadsSent = false;
 bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
-void check(int rc, const char *where)
+void check(int rc, const char *where, mpmgpu_ctx *ctx = NULL)
 {
     if (rc == MPMGPU_OK) return;
-    throw CommonException(mpmgpu_last_error(gCtx), where);
+    throw CommonException(mpmgpu_last_error(ctx ? ctx : gCtx), where);
+}
+
+// the same call on every slab context (one context without -gpus)
+template <class F>
+void each_ctx(F f, const char *where)
+{
+    if (gSlabs.empty()) { check(f(gCtx), where); return; }
+    for (mpmgpu_ctx *c : gSlabs) check(f(c), where, c);
+}
+
+void AssignParticle(MPMBase *m, int n, int q, const double *pos, const double *vel, const double *acc, const double *sp, const double *pr, const double *ep,
+                    const double *wrot, const double *epl, const double *en, const double *hist, const int *elem, const int *cross);
+
+// -gpus N: every slab hands back ITS particles in device order with their ids (the host's particle numbers); rigid-BC particles
+// live on every slab and move identically, slab 0's copy is taken
+void DownloadSlabsToHost(void)
+{
+    for (size_t r = 0; r < gSlabs.size(); r++) {
+        mpmgpu_ctx *c = gSlabs[r];
+        const int n = mpmgpu_num_particles(c);
+        if (n == 0) continue;
+        std::vector<double> pos(3 * (size_t)n), vel(3 * (size_t)n), sp(6 * (size_t)n), pr(n), ep(6 * (size_t)n), wrot(3 * (size_t)n), epl(6 * (size_t)n), en(6 * (size_t)n),
+            hist((size_t)MPMGPU_MAX_HISTORY * n), acc(3 * (size_t)n);
+        std::vector<int> elem(n), cross(n), ids(n);
+        mpmgpu_particles h;
+        memset(&h, 0, sizeof h);
+        h.pos = pos.data(); h.vel = vel.data(); h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data();
+        h.eplast = epl.data(); h.energies = en.data(); h.history = hist.data(); h.acc = acc.data(); h.in_elem = elem.data(); h.crossings = cross.data();
+        h.ids = ids.data();
+        check(mpmgpu_download_particles(c, &h, MPMGPU_F_ALL), "GpuTasks::DownloadSlabsToHost", c);
+        for (int q = 0; q < n; q++) {
+            const int p = ids[q];
+            if (p < 0 || p >= nmpms) throw CommonException("a slab returned a particle id outside the host's list", "GpuTasks::DownloadSlabsToHost");
+            if (p >= nmpmsNR && r != 0) continue;
+            AssignParticle(mpm[p], n, q, pos.data(), vel.data(), acc.data(), sp.data(), pr.data(), ep.data(), wrot.data(), epl.data(), en.data(), hist.data(),
+                           elem.data(), cross.data());
+        }
+    }
 }
 
 // device -> mpm[] (MPMBase fields; SetDeformationGradient is implicit: ep + wrot are downloaded)
 void DownloadToHost(void)
 {
     if (!gHostStale) return;
+    if (!gSlabs.empty()) { DownloadSlabsToHost(); gHostStale = false; return; }
     const int n = nmpms;
     std::vector<double> pos(3 * n), vel(3 * n), sp(6 * n), pr(n), ep(6 * n), wrot(3 * n), epl(6 * n), en(6 * n), hist(MPMGPU_MAX_HISTORY * n), acc(3 * n);
     std::vector<int> elem(n), cross(n);
@@ -102,22 +145,30 @@ void DownloadToHost(void)
     check(mpmgpu_download_particles(gCtx, &h, MPMGPU_F_ALL | (ConductionTask::active ? MPMGPU_F_TEMPERATURE : 0)), "GpuTasks::DownloadToHost");
     for (int p = 0; p < n; p++) {
         MPMBase *m = mpm[p];
-        m->pos = MakeVector(pos[p], pos[n + p], pos[2 * n + p]);
-        m->vel = MakeVector(vel[p], vel[n + p], vel[2 * n + p]);
-        m->acc = MakeVector(acc[p], acc[n + p], acc[2 * n + p]);
-        m->sp.xx = sp[p]; m->sp.yy = sp[n + p]; m->sp.zz = sp[2 * n + p]; m->sp.yz = sp[3 * n + p]; m->sp.xz = sp[4 * n + p]; m->sp.xy = sp[5 * n + p];
-        m->pressure = pr[p];
-        m->ep.xx = ep[p]; m->ep.yy = ep[n + p]; m->ep.zz = ep[2 * n + p]; m->ep.yz = ep[3 * n + p]; m->ep.xz = ep[4 * n + p]; m->ep.xy = ep[5 * n + p];
-        m->wrot.xy = wrot[p]; m->wrot.xz = wrot[n + p]; m->wrot.yz = wrot[2 * n + p];
-        m->eplast.xx = epl[p]; m->eplast.yy = epl[n + p]; m->eplast.zz = epl[2 * n + p]; m->eplast.yz = epl[3 * n + p]; m->eplast.xz = epl[4 * n + p]; m->eplast.xy = epl[5 * n + p];
-        m->workEnergy = en[p]; m->resEnergy = en[n + p]; m->heatEnergy = en[2 * n + p]; m->entropy = en[3 * n + p]; m->plastEnergy = en[4 * n + p];
+        AssignParticle(m, n, p, pos.data(), vel.data(), acc.data(), sp.data(), pr.data(), ep.data(), wrot.data(), epl.data(), en.data(), hist.data(), elem.data(), cross.data());
         if (ConductionTask::active) { m->pTemperature = temp[p]; m->pPreviousTemperature = en[5 * n + p]; }
-        if (elem[p] != m->inElem) { m->prevInElem = m->inElem; m->inElem = elem[p]; }
-        m->elementCrossings = cross[p];
-        const int nh = theMaterials[m->MatID()]->NumberOfHistoryDoubles();
-        for (int k = 0; k < nh && k < MPMGPU_MAX_HISTORY && m->matData != NULL; k++) ((double *)m->matData)[k] = hist[k * n + p];
     }
     gHostStale = false;
+}
+
+// column q of component-major arrays of length n -> one host particle
+void AssignParticle(MPMBase *m, int n, int q, const double *pos, const double *vel, const double *acc, const double *sp, const double *pr, const double *ep,
+                    const double *wrot, const double *epl, const double *en, const double *hist, const int *elem, const int *cross)
+{
+    const size_t N = (size_t)n, p = (size_t)q;
+    m->pos = MakeVector(pos[p], pos[N + p], pos[2 * N + p]);
+    m->vel = MakeVector(vel[p], vel[N + p], vel[2 * N + p]);
+    m->acc = MakeVector(acc[p], acc[N + p], acc[2 * N + p]);
+    m->sp.xx = sp[p]; m->sp.yy = sp[N + p]; m->sp.zz = sp[2 * N + p]; m->sp.yz = sp[3 * N + p]; m->sp.xz = sp[4 * N + p]; m->sp.xy = sp[5 * N + p];
+    m->pressure = pr[p];
+    m->ep.xx = ep[p]; m->ep.yy = ep[N + p]; m->ep.zz = ep[2 * N + p]; m->ep.yz = ep[3 * N + p]; m->ep.xz = ep[4 * N + p]; m->ep.xy = ep[5 * N + p];
+    m->wrot.xy = wrot[p]; m->wrot.xz = wrot[N + p]; m->wrot.yz = wrot[2 * N + p];
+    m->eplast.xx = epl[p]; m->eplast.yy = epl[N + p]; m->eplast.zz = epl[2 * N + p]; m->eplast.yz = epl[3 * N + p]; m->eplast.xz = epl[4 * N + p]; m->eplast.xy = epl[5 * N + p];
+    m->workEnergy = en[p]; m->resEnergy = en[N + p]; m->heatEnergy = en[2 * N + p]; m->entropy = en[3 * N + p]; m->plastEnergy = en[4 * N + p];
+    if (elem[p] != m->inElem) { m->prevInElem = m->inElem; m->inElem = elem[p]; }
+    m->elementCrossings = cross[p];
+    const int nh = theMaterials[m->MatID()]->NumberOfHistoryDoubles();
+    for (int k = 0; k < nh && k < MPMGPU_MAX_HISTORY && m->matData != NULL; k++) ((double *)m->matData)[k] = hist[(size_t)k * N + p];
 }
 
 // ---- output from the device --------------------------------------------------------------
@@ -283,7 +334,7 @@ class GpuTask : public MPMTask
         if (!gBCsVary) return;
         std::vector<double> v(gBCs.size()); std::vector<int> a(gBCs.size());
         for (size_t i = 0; i < gBCs.size(); i++) { a[i] = gBCs[i]->GetNodeNum(mtime) > 0; v[i] = a[i] ? gBCs[i]->BCValue(mtime) : 0.; }
-        check(mpmgpu_update_velocity_bc_values(gCtx, (int)v.size(), v.data(), a.data()), "GpuTask(BC values)");
+        each_ctx([&](mpmgpu_ctx *c) { return mpmgpu_update_velocity_bc_values(c, (int)v.size(), v.data(), a.data()); }, "GpuTask(BC values)");
     }
     // MatPtLoadBC::SetParticleFext (InitializationTask.cpp:91) by the reference's own BC objects on mpm[]->pFext; the forces of the
     // loaded particles go to the device
@@ -310,7 +361,7 @@ class GpuTask : public MPMTask
             const int j = p - nmpmsRC;
             v[j] = m->vel.x; v[nr + j] = m->vel.y; v[2 * (size_t)nr + j] = m->vel.z;
         }
-        check(mpmgpu_update_rigid_velocities(gCtx, nr, v.data()), "GpuTask(rigid velocities)");
+        each_ctx([&](mpmgpu_ctx *c) { return mpmgpu_update_rigid_velocities(c, nr, v.data()); }, "GpuTask(rigid velocities)");
     }
     void AfterStep(void)
     {
@@ -320,7 +371,7 @@ class GpuTask : public MPMTask
         {   // particles pushed back into the grid: the reference warns once per particle and aborts at the <LeaveLimit>
             // threshold (ResetElementsTask.cpp:71-95); same warning object, same exception
             long long exits = 0, first = 0;
-            check(mpmgpu_left_grid_counts(gCtx, &exits, &first), "GpuTask(ResetElements)");
+            each_ctx([&](mpmgpu_ctx *c) { long long e = 0, f = 0; const int rc = mpmgpu_left_grid_counts(c, &e, &f); exits += e; first += f; return rc; }, "GpuTask(ResetElements)");
             for (; gLeftGridWarned < first; gLeftGridWarned++)
                 if (warnings.Issue(fmobj->warnParticleLeftGrid, -1) == REACHED_MAX_WARNINGS) {
                     DownloadToHost();
@@ -338,10 +389,21 @@ class GpuTask : public MPMTask
     {
         if (gFusedStep) {       // one call per step; the per-task rows of the timing report then show the whole step under "Initialize"
             if (which == G_INIT) {
-                check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(step)");
+                each_ctx([&](mpmgpu_ctx *c) { return mpmgpu_set_xpic(c, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0); }, "GpuTask(step)");
                 UpdateBCValues();
                 UpdateRigidVelocities();
                 UpdateParticleLoads();
+                if (!gSlabs.empty()) {
+                    // every slab steps at the same time: the halo and migrant exchanges inside mpmgpu_slab_step are NCCL calls that
+                    // wait for the neighbours
+                    std::vector<int> rcs(gSlabs.size(), MPMGPU_OK);
+#pragma omp parallel num_threads((int)gSlabs.size())
+                    {
+                        const int r = omp_get_thread_num();
+                        if (r < (int)gSlabs.size()) rcs[r] = mpmgpu_slab_step(gSlabs[r], 1);
+                    }
+                    for (size_t r = 0; r < gSlabs.size(); r++) check(rcs[r], "GpuTask(slab step)", gSlabs[r]);
+                } else
                 check(mpmgpu_step(gCtx, 1), "GpuTask(step)");
             } else if (which == G_RESET) AfterStep();
             return true;
@@ -392,8 +454,18 @@ int TaskCode(const char *name)
 } // namespace
 
 // Returns NULL when installed, else the reason the run stays on the CPU tasks.
-const char *GpuTasks_Install(int device, bool fusedStep)
+const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
 {
+    gNumGpus = ngpus < 1 ? 1 : ngpus;
+    if (gNumGpus > 1) {
+        // -gpus N: z-slabs of cell planes, one per GPU, on the fused kernels; the whole step runs in mpmgpu_slab_step and the
+        // output takes the host route (every slab downloads its particles, the reference's writers run on mpm[])
+        fusedStep = true;
+        gDeviceOutput = false;
+        omp_set_dynamic(0);             // the slabs step in lock-step: exactly one thread per GPU
+        if (!fmobj->IsThreeD()) return "-gpus N needs a 3D problem (slabs of cell planes along z)";
+        if (firstLoadedPt != NULL) return "particle load BCs with -gpus N (particles change slabs)";
+    }
     gFusedStep = fusedStep;
     if (firstCrack != NULL) return "cracks present";
     if (fmobj->multiMaterialMode) {
@@ -525,7 +597,42 @@ const char *GpuTasks_Install(int device, bool fusedStep)
     if (bodyFrc.gravity) { cfg.gravity[0] = bodyFrc.gforce.x; cfg.gravity[1] = bodyFrc.gforce.y; cfg.gravity[2] = bodyFrc.gforce.z; }
     cfg.kernel_path = fusedStep ? 0 : 1;    // per-task entry points keep the reference's task timing report meaningful; -fused runs
                                             // mpmgpu_step (fused kernels when the problem is eligible, per-task kernels otherwise)
-    if (mpmgpu_create(&cfg, &gCtx) != MPMGPU_OK) return mpmgpu_last_error(NULL);
+    // -gpus N: split the occupied cell planes evenly (the first and last slab reach the grid edges), as slab.py::slab_bounds
+    std::vector<std::vector<int> > slabSel(gNumGpus);
+    std::vector<int> slabLo(gNumGpus, 0), slabHi(gNumGpus, 0);
+    if (gNumGpus > 1) {
+        int ndev = 0;
+        const int perPlane = mpmgrid.horiz * mpmgrid.vert;
+        int kFirst = mpmgrid.depth, kLast = 0;
+        for (int p = 0; p < nmpmsNR; p++) { const int k = (mpm[p]->inElem - 1) / perPlane; if (k < kFirst) kFirst = k; if (k + 1 > kLast) kLast = k + 1; }
+        const int planes = kLast - kFirst;
+        if (planes < gNumGpus) return "-gpus N: fewer occupied cell planes than GPUs";
+        for (int r = 0; r < gNumGpus; r++) {
+            slabLo[r] = r == 0 ? 0 : kFirst + (int)(((long long)planes * r) / gNumGpus);
+            slabHi[r] = r == gNumGpus - 1 ? mpmgrid.depth : kFirst + (int)(((long long)planes * (r + 1)) / gNumGpus);
+        }
+        for (int p = 0; p < nmpms; p++) {
+            if (p >= nmpmsNR) { for (int r = 0; r < gNumGpus; r++) slabSel[r].push_back(p); continue; }     // rigid-BC particles: on every slab
+            const int k = (mpm[p]->inElem - 1) / perPlane;
+            for (int r = 0; r < gNumGpus; r++) if (k >= slabLo[r] && k < slabHi[r]) { slabSel[r].push_back(p); break; }
+        }
+        (void)ndev;
+        gSlabs.assign(gNumGpus, (mpmgpu_ctx *)NULL);
+        for (int r = 0; r < gNumGpus; r++) {
+            mpmgpu_config c = cfg;
+            c.device = device + r;
+            c.kernel_path = 2;
+            const long long want = (long long)(1.3 * (double)slabSel[r].size()) + 1024;
+            c.max_particles = (int)(want < 65536 ? 65536 : want);
+            if (mpmgpu_create(&c, &gSlabs[r]) != MPMGPU_OK) return mpmgpu_last_error(NULL);
+            if (mpmgpu_slab_configure(gSlabs[r], slabLo[r], slabHi[r], r > 0 ? 1 : 0, r < gNumGpus - 1 ? 1 : 0, 65536) != MPMGPU_OK) return mpmgpu_last_error(gSlabs[r]);
+        }
+        gCtx = gSlabs[0];
+    }
+    else if (mpmgpu_create(&cfg, &gCtx) != MPMGPU_OK) return mpmgpu_last_error(NULL);
+    // one call on every context, first failure reported
+#define ALL_CTX(CALL) do { if (gSlabs.empty()) { mpmgpu_ctx *ctx_ = gCtx; if ((CALL) != MPMGPU_OK) return mpmgpu_last_error(ctx_); } \
+                           else for (mpmgpu_ctx *ctx_ : gSlabs) if ((CALL) != MPMGPU_OK) return mpmgpu_last_error(ctx_); } while (0)
 
     // materials: the block GetCopyOfMechanicalProps would hand out (Elastic::FillUnrotatedElasticProperties)
     std::vector<mpmgpu_material> mats(nmat);
@@ -587,7 +694,7 @@ const char *GpuTasks_Install(int device, bool fusedStep)
             m.p[9] = ((RigidMaterial *)mb)->mirrored;
         }
     }
-    if (mpmgpu_set_materials(gCtx, nmat, mats.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    ALL_CTX(mpmgpu_set_materials(ctx_, nmat, mats.data()));
     if (ConductionTask::active) {
         std::vector<double> kc(nmat, 0.);
         for (int i = 0; i < nmat; i++) kc[i] = theMaterials[i]->kCond;          // conductivity / rho (MaterialBaseMPM.cpp:233)
@@ -645,8 +752,34 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         for (int p = 0; p < n; p++) temp0[p] = mpm[p]->pTemperature;
         h.temperature = temp0.data();
     }
-    if (mpmgpu_upload_particles(gCtx, &h) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
-    if (mpmgpu_set_time_step(gCtx, timestep, strainTimestepFirst, strainTimestepLast) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    if (!gSlabs.empty()) {
+        // every slab gets the columns of its particles, with the host's particle numbers as ids
+        for (int r = 0; r < gNumGpus; r++) {
+            const std::vector<int> &sel = slabSel[r];
+            const size_t m = sel.size();
+            auto cols = [&](const std::vector<double> &a, int ncomp) {
+                std::vector<double> o((size_t)ncomp * m);
+                for (int c = 0; c < ncomp; c++) for (size_t q = 0; q < m; q++) o[(size_t)c * m + q] = a[(size_t)c * n + sel[q]];
+                return o;
+            };
+            auto icols = [&](const std::vector<int> &a) { std::vector<int> o(m); for (size_t q = 0; q < m; q++) o[q] = a[sel[q]]; return o; };
+            std::vector<double> spos = cols(pos, 3), svel = cols(vel, 3), smp = cols(mp, 1), slp = cols(lp, 3), ssp = cols(sp, 6), spr = cols(pr, 1), sep = cols(ep, 6),
+                swrot = cols(wrot, 3), sepl = cols(epl, 6), sen = cols(en, 6), shist = cols(hist, MPMGPU_MAX_HISTORY);
+            std::vector<int> selem = icols(elem), smat = icols(matn), scross = icols(cross), ids(sel.begin(), sel.end());
+            mpmgpu_particles hs;
+            memset(&hs, 0, sizeof hs);
+            hs.n = (int)m;
+            hs.n_nonrigid = 0;
+            for (size_t q = 0; q < m; q++) if (sel[q] < nmpmsNR) hs.n_nonrigid++;
+            hs.pos = spos.data(); hs.vel = svel.data(); hs.mp = smp.data(); hs.lp = slp.data(); hs.in_elem = selem.data(); hs.matnum = smat.data();
+            hs.sp = ssp.data(); hs.pressure = spr.data(); hs.ep = sep.data(); hs.wrot = swrot.data(); hs.eplast = sepl.data(); hs.energies = sen.data();
+            hs.crossings = scross.data(); hs.history = shist.data(); hs.ids = ids.data();
+            if (mpmgpu_upload_particles(gSlabs[r], &hs) != MPMGPU_OK) return mpmgpu_last_error(gSlabs[r]);
+        }
+    }
+    else if (mpmgpu_upload_particles(gCtx, &h) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    ALL_CTX(mpmgpu_set_time_step(ctx_, timestep, strainTimestepFirst, strainTimestepLast));
+    if (gSlabs.empty())
     {   // constants of the archive records (ArchiveData.cpp:820-875): original position, initial material angles, 2D thickness
         std::vector<double> op(3 * (size_t)n), ang(3 * (size_t)n);
         double thick = is3D ? 1. : mpm[0]->thickness();
@@ -675,10 +808,20 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         brefl.push_back(bc->reflectedNode); bratio.push_back(bc->reflectRatio);
         if (bc->reflectedNode >= 0) anyReflected = true;
     }
-    if (mpmgpu_set_velocity_bcs(gCtx, (int)bnode.size(), bnode.data(), bnorm.data(), bval.data(), bact.data(), bsym.data()) != MPMGPU_OK)
-        return mpmgpu_last_error(gCtx);
-    if (anyReflected && mpmgpu_set_velocity_bc_reflections(gCtx, (int)bnode.size(), brefl.data(), bratio.data()) != MPMGPU_OK)
-        return mpmgpu_last_error(gCtx);
+    ALL_CTX(mpmgpu_set_velocity_bcs(ctx_, (int)bnode.size(), bnode.data(), bnorm.data(), bval.data(), bact.data(), bsym.data()));
+    if (anyReflected) ALL_CTX(mpmgpu_set_velocity_bc_reflections(ctx_, (int)bnode.size(), brefl.data(), bratio.data()));
+    if (!gSlabs.empty()) {
+        // the slabs join the two NCCL communicators of the run (collective: one thread per GPU)
+        char ids[256];
+        if (mpmgpu_nccl_unique_ids(ids) != MPMGPU_OK) return "mpmgpu_nccl_unique_ids failed (libnccl.so.2 not found?)";
+        std::vector<int> rcs(gSlabs.size(), MPMGPU_OK);
+#pragma omp parallel num_threads((int)gSlabs.size())
+        {
+            const int r = omp_get_thread_num();
+            if (r < (int)gSlabs.size()) rcs[r] = mpmgpu_slab_connect(gSlabs[r], r, (int)gSlabs.size(), ids);
+        }
+        for (size_t r = 0; r < gSlabs.size(); r++) if (rcs[r] != MPMGPU_OK) return mpmgpu_last_error(gSlabs[r]);
+    }
 
     // swap the CPU task objects for GPU ones, keeping order and names (custom-task runner stays)
     MPMTask *prev = NULL;
@@ -701,9 +844,14 @@ const char *GpuTasks_Install(int device, bool fusedStep)
         t = next;
     }
     extern int gPollInterval;
-    if (fusedStep && gPollInterval > 1 && mpmgpu_set_poll_interval(gCtx, gPollInterval) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    if (fusedStep && gPollInterval > 1 && gSlabs.empty() && mpmgpu_set_poll_interval(gCtx, gPollInterval) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     std::cout << "GPU TASKS: tasks 1-9,11 run on libmpmgpu (device " << device << ", " << n << " particles"
               << (fusedStep ? ", whole-step entry point" : ", per-task entry points") << ")" << std::endl;
+    if (!gSlabs.empty()) {
+        std::cout << "GPU SLABS: " << gSlabs.size() << " GPUs, cell planes";
+        for (int r = 0; r < gNumGpus; r++) std::cout << " [" << slabLo[r] << "," << slabHi[r] << "):" << slabSel[r].size();
+        std::cout << " particles (rigid-BC particles on every slab)" << std::endl;
+    }
     return NULL;
 }
 
@@ -717,6 +865,18 @@ void GpuTasks_Finish(void)
                   << " bytes each (D2H), " << 1.e3 * gArchiveSeconds / (double)gArchiveCount << " ms each including the file write" << std::endl;
     gHostStale = true;
     try { DownloadToHost(); } catch (...) {}
+    if (!gSlabs.empty()) {
+        long long out = 0, in = 0;
+        for (mpmgpu_ctx *c : gSlabs) { long long o = 0, i = 0; mpmgpu_slab_migrated(c, &o, &i); out += o; in += i; }
+        std::cout << "GPU SLABS: " << out << " particle rows changed slabs during the run" << std::endl;
+        // (communicators are torn down collectively)
+#pragma omp parallel num_threads((int)gSlabs.size())
+        {
+            const int r = omp_get_thread_num();
+            if (r < (int)gSlabs.size()) mpmgpu_destroy(gSlabs[r]);
+        }
+        gSlabs.clear();
+    } else
     mpmgpu_destroy(gCtx);
     gCtx = NULL;
 }
@@ -728,18 +888,19 @@ void GpuTasks_SetDeviceOutput(bool on);
 
 int main(int argc, const char *argv[])
 {
-    int numProcs = 1, device = 0, arg = 1;
+    int numProcs = 1, device = 0, arg = 1, ngpus = 1;
     bool useGpu = true, fused = false;
     for (; arg < argc && argv[arg][0] == '-'; arg++) {
         if (strcmp(argv[arg], "-np") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &numProcs);
         else if (strcmp(argv[arg], "-gpu") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &device);
+        else if (strcmp(argv[arg], "-gpus") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &ngpus);
         else if (strcmp(argv[arg], "-cpu") == 0) useGpu = false;
         else if (strcmp(argv[arg], "-fused") == 0) fused = true;
         else if (strcmp(argv[arg], "-hostoutput") == 0) gDeviceOutputSwitch = false;
         else if (strcmp(argv[arg], "-poll") == 0 && arg + 1 < argc) sscanf(argv[++arg], "%d", &gPollInterval);
-        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-poll K] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
+        else { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-gpus N] [-fused] [-poll K] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
     }
-    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-fused] [-poll K] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
+    if (arg + 1 != argc) { std::cerr << "usage: NairnMPM_gpu [-np N] [-gpu DEVICE] [-gpus N] [-fused] [-poll K] [-hostoutput] [-cpu] input.fmcmd" << std::endl; return 1; }
     fmobj = new NairnMPM();
     omp_set_num_threads(numProcs);
     fmobj->SetNumberOfProcessors(numProcs);
@@ -752,7 +913,7 @@ int main(int argc, const char *argv[])
         fmobj->CMPreparations();
         if (useGpu) {
             GpuTasks_SetDeviceOutput(gDeviceOutputSwitch);
-            const char *why = GpuTasks_Install(device, fused);
+            const char *why = GpuTasks_Install(device, fused, ngpus);
             if (why != NULL) { std::cerr << "NairnMPM_gpu: cannot run this input on libmpmgpu: " << why << std::endl; return 2; }
         }
         fmobj->CMAnalysis(false);

@@ -102,6 +102,43 @@ def test_reference_driver_with_gpu_tasks_matches_reference(case, mode):
         assert err < 1e-7, "archive at step %d differs: %.3e" % (step, err)
 
 
+@pytest.mark.parametrize("case,ngpus", [("block3d_two_slabs", 2), ("block3d_rigid_wall_two_slabs", 2)])
+def test_drop_in_on_several_gpus_matches_reference(case, ngpus):
+    """`NairnMPM_gpu -gpus N`: the reference driver with one slab context per GPU (cell planes along z, NCCL halo and migrant
+    exchanges inside libmpmgpu, one host thread per GPU); every archive against the unmodified reference CLI.  The block is
+    thrown downwards and sideways so that particles change slabs during the run."""
+    import torch
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip("needs %d GPUs" % ngpus)
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("oracle/_ref/NairnMPM or host/_build/NairnMPM_gpu not built")
+    if case == "block3d_two_slabs":
+        xml = inputs.block3d(ncell=8, margin=3, maxtime=0.06, E=100.0, vz=-2.5e4, vx=4.0e3)
+    else:
+        xml = inputs.block3d(ncell=6, margin=3, maxtime=0.04, material=inputs.isoplastic_material(), vz=-4.0e4, bc=False, rigid=("wall", 4, (0.0, 0.0, 0.0)))
+    xml = xml.replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+    dref, out_ref = run(REF, xml, ("-np", "4"))
+    dgpu, out_gpu = run(GPU, xml, ("-gpus", str(ngpus)))
+    assert "GPU SLABS: %d GPUs" % ngpus in out_gpu, out_gpu[-1500:]
+    moved = [int(ln.split()[2]) for ln in out_gpu.splitlines() if ln.startswith("GPU SLABS:") and "changed slabs" in ln]
+    assert moved and moved[0] > 0, "no particle changed slabs: the test does not exercise the migration"
+    npart = None
+    for ln in out_ref.splitlines():
+        if "Number of Material Points:" in ln:
+            npart = int(ln.split(":")[1].split()[0])
+            break
+    a_ref = list_archives(os.path.join(dref, "res/blk."))
+    a_gpu = list_archives(os.path.join(dgpu, "res/blk."))
+    assert [s for s, _ in a_ref] == [s for s, _ in a_gpu] and len(a_ref) >= 3, (a_ref, a_gpu)
+    for (step, fr), (_, fg) in zip(a_ref, a_gpu):
+        r, g = read_archive(fr, npart), read_archive(fg, npart)
+        assert np.array_equal(r["elem"], g["elem"]), "element ids differ at step %d" % step
+        assert np.array_equal(r["tail"], g["tail"]) and np.array_equal(r["mat"], g["mat"])
+        scale = np.maximum(np.max(np.abs(r["doubles"]), axis=0), 1e-300)
+        err = np.max(np.abs(r["doubles"] - g["doubles"]) / scale)
+        assert err < 1e-7, "archive at step %d differs: %.3e" % (step, err)
+
+
 def test_device_packed_archives_equal_the_host_writers():
     """Same input twice: records packed on the device (default) and `-hostoutput` (full download, the reference's own
     ArchiveResults on mpm[]).  Two runs differ in the last bits (FP64 atomics add in another order from run to run), so the
