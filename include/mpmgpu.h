@@ -69,6 +69,11 @@ extern "C" {
 #define MPMGPU_MAT_ISOPLASTICITY  9   /* IsoPlasticity + LinearHardening */
 #define MPMGPU_MAT_RIGIDBC       11   /* RigidMaterial used as moving velocity BC */
 #define MPMGPU_MAT_NEOHOOKEAN    28   /* Neohookean */
+#define MPMGPU_MAT_RIGIDCONTACT  35   /* RigidMaterial in contact mode (SetDirection 8): multimaterial mode only.  Its particles follow the
+                                         nonrigid ones and precede the rigid-BC particles in the host's order (NairnMPM.cpp:1121-1190), move at
+                                         their own velocity (mpmgpu_update_rigid_velocities covers them) and extrapolate to their material's
+                                         velocity field, against which every nonrigid material of a node makes contact
+                                         (CrackVelocityFieldMulti::RigidMaterialContactOnCVF :676-955).  Slot [0] rho (1). */
 
 #define MPMGPU_MAT_NPARAMS 32
 #define MPMGPU_MAX_HISTORY 4
@@ -216,9 +221,9 @@ int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_material *mats)
  * CrackVelocityFieldMulti.cpp:302-674; UpdateMomentaTask::ContactAndMomentaBCs).  Built: nonrigid materials, normals from the
  * volume gradients (methods 0-3, GetNormalVector :960-1071) or specified (4), contact detected by displacements or positions
  * (CrackSurfaceContact::MaterialSeparation), contact laws ignore / stick / frictionless / Coulomb friction with optional static
- * coefficient (Materials/CoulombFriction.cpp:150-272), three or more materials lumped as the reference does.  Refused: the
- * regression normals (5, 6), imperfect interfaces, adhesion, rigid contact materials, XPIC/FMPM order > 1 (FMPM contact
- * increments), slab mode.  Runs on the per-task kernels.  Call after mpmgpu_set_materials and before mpmgpu_upload_particles;
+ * coefficient (Materials/CoulombFriction.cpp:150-272), three or more materials lumped as the reference does, rigid contact
+ * materials (MPMGPU_MAT_RIGIDCONTACT).  Refused: the regression normals (5, 6), imperfect interfaces, adhesion, XPIC/FMPM
+ * order > 1 (FMPM contact increments), slab mode.  Runs on the per-task kernels.  Call after mpmgpu_set_materials and before mpmgpu_upload_particles;
  * displacements are taken against the original positions of mpmgpu_set_archive_origin (default: the positions at upload). */
 typedef struct mpmgpu_multimaterial {
     int n_fields;                   /* maxMaterialFields: material velocity fields per node (<= 8) */
@@ -230,6 +235,8 @@ typedef struct mpmgpu_multimaterial {
     const int *law_kind;            /* [n_fields][n_fields] mpmgrid.GetMaterialContactLaw(i, j): 0 ignore, 1 stick, 2 frictionless, 3 Coulomb friction */
     const double *law_friction;     /* [n_fields][n_fields] CoulombFriction::frictionCoeff (NULL: 0) */
     const double *law_static;       /* [n_fields][n_fields] frictionCoeffStatic, <= 0 for none (NULL: none) */
+    double rigid_gradient_bias;     /* mpmgrid.rigidGradientBias as the reference holds it after set-up (RigidBias squared,
+                                       MeshInfo.cpp:1196): preference for the rigid material's normal; 0 = 1 */
 } mpmgpu_multimaterial;
 int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm);
 /* Heat conduction, the first transport task (<Thermal><Conduction/></Thermal>; Custom_Tasks/ConductionTask.cpp + TransportTask.cpp,

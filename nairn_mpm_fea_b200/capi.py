@@ -75,7 +75,7 @@ class NodesView(C.Structure):
 class MultiMaterial(C.Structure):
     _fields_ = [("n_fields", C.c_int), ("field_of_material", _ip), ("normal_method", C.c_int), ("contact_by_displacements", C.c_int),
                 ("position_cutoff", C.c_double), ("contact_normal", C.c_double * 3), ("law_kind", _ip), ("law_friction", _dp),
-                ("law_static", _dp)]
+                ("law_static", _dp), ("rigid_gradient_bias", C.c_double)]
 
 
 GS_NSUMS = 29
@@ -283,6 +283,7 @@ class MpmGpu:
         v.position_cutoff = float(mm["position_cutoff"])
         v.contact_normal = (C.c_double * 3)(*[float(x) for x in mm["contact_normal"]])
         v.law_kind, v.law_friction, v.law_static = _i(keep[1]), _d(keep[2]), _d(keep[3])
+        v.rigid_gradient_bias = float(mm.get("rigid_gradient_bias", 1.0))
         self._check(self.lib.mpmgpu_set_multimaterial(self.ctx, C.byref(v)))
         self.nnodes = self.prob.nnodes * nf          # node arrays are field-major from now on
         self.n_fields = nf

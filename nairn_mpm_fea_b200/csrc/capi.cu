@@ -89,7 +89,7 @@ struct mpmgpu_ctx {
     ContactNodes C;                     // contact extrapolations (volume, volume gradient, displacement/position)
     double *contactPool = NULL;
     ContactParams cp;
-    int *dFieldOfMat = NULL, *foffPool = NULL;
+    int *dFieldOfMat = NULL, *foffPool = NULL, *foffRigidPool = NULL;
     std::vector<int> hFieldOfMat;
     // conduction (mpmgpu_set_conduction): nodal transport field, particle temperature + gradient
     bool conduction = false;
@@ -305,6 +305,13 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
             memset(ctx->hMats[i].p, 0, sizeof ctx->hMats[i].p);
             continue;
         }
+        if (k == MAT_RIGIDCONTACT) {    // RigidMaterial in contact mode: its particles ride in the rigid set and claim no BC (direction bits 0)
+            ctx->hMats[i].kind = k; ctx->hMats[i].nhist = 0;
+            memcpy(ctx->hMats[i].p, mats[i].p, sizeof(double) * MPM_MAT_NPARAMS);
+            ctx->hMats[i].p[8] = 0.; ctx->hMats[i].p[9] = 0.;
+            if (!(ctx->hMats[i].p[0] > 0.)) ctx->hMats[i].p[0] = 1.;
+            continue;
+        }
         if (k != MAT_ISOTROPIC && k != MAT_RIGIDBC && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY && k != MAT_MOONEY)
             return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d is not supported (IsotropicMat 1, Mooney 8, IsoPlasticity 9, rigid BC 11, Neohookean 28)", k);
         if (mats[i].n_history < 0 || mats[i].n_history > MPM_MAX_HISTORY) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: %d history doubles (max %d)", mats[i].n_history, MPM_MAX_HISTORY);
@@ -346,7 +353,7 @@ extern "C" int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimater
     ctx->hFieldOfMat.assign(ctx->nmat, 0);
     for (int m = 0; m < ctx->nmat; m++) {
         const int f = mm->field_of_material[m];
-        if (ctx->hMats[m].kind == MAT_RIGIDBC) { ctx->hFieldOfMat[m] = 0; continue; }       // rigid-BC particles have no field
+        if (ctx->hMats[m].kind == MAT_RIGIDBC || ctx->hMats[m].kind == MAT_NONE) { ctx->hFieldOfMat[m] = 0; continue; }       // rigid-BC particles have no field
         if (f < 0 || f >= nf) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: material %d has velocity field %d of %d", m + 1, f, nf);
         ctx->hFieldOfMat[m] = f;
     }
@@ -355,6 +362,11 @@ extern "C" int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimater
     cp.nf = nf; cp.normalMethod = mm->normal_method; cp.byDisplacements = mm->contact_by_displacements ? 1 : 0;
     cp.positionCutoff = mm->position_cutoff;
     for (int c = 0; c < 3; c++) cp.normal[c] = mm->contact_normal[c];
+    cp.rigidBias = mm->rigid_gradient_bias > 0. ? mm->rigid_gradient_bias : 1.;
+    for (int m = 0; m < ctx->nmat; m++) if (ctx->hMats[m].kind == MAT_RIGIDCONTACT) cp.rigidMask |= 1 << ctx->hFieldOfMat[m];
+    for (int m = 0; m < ctx->nmat; m++)
+        if (ctx->hMats[m].kind != MAT_RIGIDCONTACT && ctx->hMats[m].kind != MAT_RIGIDBC && ctx->hMats[m].kind != MAT_NONE && (cp.rigidMask >> ctx->hFieldOfMat[m] & 1))
+            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_multimaterial: material %d shares velocity field %d with a rigid contact material", m + 1, ctx->hFieldOfMat[m]);
     {   // MeshInfo::SetCartesian (MeshInfo.cpp:1466-1480): square / cubic cells by DbleEqual
         auto dbleEqual = [](double a, double b) { const double d = fabs(a - b); if (d <= 1.0e-16) return true; a = fabs(a); b = fabs(b); return d <= (b > a ? b : a) * 1.0e-7; };
         cp.cubic = dbleEqual(ctx->g.gx, ctx->g.gy) && (ctx->dim == 2 || dbleEqual(ctx->g.gx, ctx->g.gz)) ? 1 : 0;
@@ -372,6 +384,14 @@ extern "C" int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimater
     if (alloc_node_arrays(ctx, (size_t)nf * ctx->g.nnodes) != MPMGPU_OK) return fail(ctx, MPMGPU_ECUDA, "mpmgpu_set_multimaterial: node arrays: %s", cudaGetErrorString(cudaGetLastError()));
     CK(dalloc(ctx, &ctx->contactPool, ctx->nodePad * 7));
     CK(cudaMemset(ctx->contactPool, 0, ctx->nodePad * 7 * sizeof(double)));
+    CK(dalloc(ctx, &ctx->C.rcnt, ctx->nodePad));
+    CK(cudaMemset(ctx->C.rcnt, 0, ctx->nodePad * sizeof(int)));
+    {
+        double *rf = NULL;
+        CK(dalloc(ctx, &rf, ctx->nodePad * 3));
+        CK(cudaMemset(rf, 0, ctx->nodePad * 3 * sizeof(double)));
+        for (int c = 0; c < 3; c++) ctx->C.rforce[c] = rf + (size_t)c * ctx->nodePad;
+    }
     {
         double *q = ctx->contactPool;
         ctx->C.cvol = q; q += ctx->nodePad;
@@ -635,7 +655,7 @@ __global__ void k_validate_upload(int cnt, int off, int rigidPart, Particles P, 
     const int m = P.mat[p], e = P.elem[p];          // P.mat is 0-based on the device
     if (m < 0 || m >= nmat || mats[m].kind == MAT_NONE) { atomicMin(&out->badMat, off + p); return; }
     if (e < 1 || e > nelems) atomicMin(&out->badElem, off + p);
-    const bool rigid = mats[m].kind == MAT_RIGIDBC;
+    const bool rigid = mats[m].kind == MAT_RIGIDBC || mats[m].kind == MAT_RIGIDCONTACT;
     if (rigidPart && !rigid) atomicMin(&out->notRigid, off + p);
     if (!rigidPart && rigid) atomicMin(&out->rigidEarly, off + p);
     if (!rigidPart) {
@@ -713,12 +733,20 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
             else CK(cudaMemcpyAsync(ctx->P.temp, ctx->P.prevT, (size_t)nNR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
+    if (!ctx->multimaterial)
+        for (int i = 0; i < ctx->nmat; i++)
+            if (ctx->hMats[i].kind == MAT_RIGIDCONTACT) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: material %d is a rigid contact material: call mpmgpu_set_multimaterial first", i + 1);
     if (ctx->multimaterial) {
         if (ctx->globalIds) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: multimaterial mode with caller-global particle ids (slab mode) is not built");
         if (ctx->R.mirrored) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: mirrored rigid BCs in multimaterial mode are not built");
         if (!ctx->foffPool) CK(dalloc(ctx, &ctx->foffPool, ctx->cap));
         if (nNR) LAUNCH(k_set_field_offsets, nblocks(nNR, 256), 256, nNR, ctx->P.mat, ctx->dFieldOfMat, ctx->g.nnodes, ctx->foffPool);
         ctx->P.foff = ctx->foffPool;
+        if (nR) {       // rigid contact particles extrapolate to their material's field too
+            if (!ctx->foffRigidPool) CK(dalloc(ctx, &ctx->foffRigidPool, ctx->rigidCap));
+            LAUNCH(k_set_field_offsets, nblocks(nR, 256), 256, nR, ctx->PR.mat, ctx->dFieldOfMat, ctx->g.nnodes, ctx->foffRigidPool);
+            ctx->PR.foff = ctx->foffRigidPool;
+        }
     }
     CK(cudaMemsetAsync(ctx->dFlags, 0, sizeof(StatusFlags), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -990,10 +1018,13 @@ static int apply_bcs(mpmgpu_ctx *ctx, int pass, int adjustSym)
 
 // multimaterial mode: the contact extrapolations of the particles (after a mass/momentum extrapolation) and the contact
 // pass over the nodes (UpdateMomentaTask::ContactAndMomentaBCs, UpdateMomentaTask.cpp:76-99: contact first, then the BCs)
-static int contact_extrapolation(mpmgpu_ctx *ctx)
+static int contact_extrapolation(mpmgpu_ctx *ctx, bool rigidToo = false)
 {
     if (!ctx->multimaterial) return MPMGPU_OK;
     const size_t norig = (size_t)ctx->P.n + (size_t)ctx->PR.n;
+    if (rigidToo && ctx->cp.rigidMask && ctx->PR.n > 0)
+        DISPATCH_DIM_SHAPE(k_p2g_rigid_contact, ctx->PR.n, ctx->g, ctx->PR, ctx->dMats, ctx->N, ctx->C, ctx->archOrigin, norig, ctx->cp.byDisplacements,
+                           ctx->cp.normalMethod != NORMALS_SPECIFIED ? 1 : 0, ctx->dFlags);
     DISPATCH_DIM_SHAPE(k_p2g_contact_terms, ctx->P.nNR, ctx->g, ctx->P, ctx->dMats, ctx->C, ctx->archOrigin, norig, ctx->cp.byDisplacements,
                        ctx->cp.normalMethod != NORMALS_SPECIFIED ? 1 : 0);
     return MPMGPU_OK;
@@ -1042,7 +1073,11 @@ static int t_initialization(mpmgpu_ctx *ctx)
     CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 22 * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->N.cnt, 0, nnPad * sizeof(int), ctx->stream));
     ctx->launches += 2;
-    if (ctx->multimaterial) { CK(cudaMemsetAsync(ctx->contactPool, 0, nnPad * 7 * sizeof(double), ctx->stream)); ctx->launches++; }
+    if (ctx->multimaterial) {
+        CK(cudaMemsetAsync(ctx->contactPool, 0, nnPad * 7 * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->C.rcnt, 0, nnPad * sizeof(int), ctx->stream));
+        ctx->launches += 2;
+    }
     if (ctx->conduction) {      // TransportField zeroed with the node (NodalPoint::InitializeForTimeStep)
         CK(cudaMemsetAsync(ctx->transportPool, 0, (((size_t)ctx->g.nnodes + 31) & ~(size_t)31) * 3 * sizeof(double), ctx->stream)); ctx->launches++;
     }
@@ -1054,7 +1089,7 @@ static int t_mass_and_momentum(mpmgpu_ctx *ctx)
 {
     DISPATCH_DIM_SHAPE_VALUES(k_p2g_mass_momentum, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
     if (ctx->conduction) DISPATCH_DIM_SHAPE_VALUES(k_p2g_temperature, ctx->P.nNR, ctx->g, ctx->P, ctx->dMats, ctx->T);
-    return contact_extrapolation(ctx);
+    return contact_extrapolation(ctx, true);
 }
 
 static int t_post_extrapolation(mpmgpu_ctx *ctx)
@@ -1140,8 +1175,8 @@ static int t_update_strains_last(mpmgpu_ctx *ctx)
 {
     if (ctx->sp.method == METHOD_USF) return MPMGPU_OK;
     if (!ctx->sp.skipPost) {
-        LAUNCH(k_rezero_momenta, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N);
-        if (ctx->multimaterial) LAUNCH(k_zero_contact_terms, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->C);      // MatVelocityField::RezeroNodeTask6
+        if (ctx->multimaterial) LAUNCH(k_rezero_fields_task6, nblocks(ctx->nvn, 256), 256, ctx->g.nnodes, ctx->nf, ctx->cp.rigidMask, ctx->N, ctx->C, ctx->sp.dt);
+        else LAUNCH(k_rezero_momenta, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N);
         DISPATCH_DIM_SHAPE_VALUES(k_p2g_momentum_last, ctx->P.nNR, ctx->g, ctx->P, ctx->N);
         int rc = contact_extrapolation(ctx);
         if (!rc) rc = material_contact(ctx, CALL_UPDATE_STRAINS_LAST);
@@ -1801,6 +1836,11 @@ extern "C" int mpmgpu_download_nodes(mpmgpu_ctx *ctx, mpmgpu_nodes *h)
         }
     }
     if (h->number_points) CK(cudaMemcpyAsync(h->number_points, ctx->N.cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int> rcnt;
+    if (h->number_points && ctx->multimaterial && ctx->cp.rigidMask) {
+        rcnt.resize(nn);
+        CK(cudaMemcpyAsync(rcnt.data(), ctx->C.rcnt, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (h->mass) CK(cudaMemcpyAsync(h->mass, ctx->N.mass, nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     for (int c = 0; c < 3; c++) {
         if (h->pk) CK(cudaMemcpyAsync(h->pk + c * nn, ctx->N.pk[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1809,6 +1849,14 @@ extern "C" int mpmgpu_download_nodes(mpmgpu_ctx *ctx, mpmgpu_nodes *h)
         if (h->pk_copy) CK(cudaMemcpyAsync(h->pk_copy + c * nn, ctx->N.pkc[c], nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < rcnt.size(); i++) h->number_points[i] += rcnt[i];       // a rigid material's field counts its points apart
+    if (h->ftot && ctx->multimaterial && ctx->cp.rigidMask) {
+        // ... and its force row is the cumulative contact force (ContactNodes::rforce)
+        const size_t nr = ctx->g.nnodes;
+        for (int f = 0; f < ctx->nf; f++)
+            if (ctx->cp.rigidMask >> f & 1)
+                for (int c = 0; c < 3; c++) CK(cudaMemcpy(h->ftot + c * nn + f * nr, ctx->C.rforce[c] + f * nr, nr * sizeof(double), cudaMemcpyDeviceToHost));
+    }
     return MPMGPU_OK;
 }
 

@@ -78,10 +78,12 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_mass_momentum(Grid g, Part
 }
 
 // ---- task 3: PostExtrapolationTask node pass (MatVelocityField.cpp:158-164) ------------------
+// (fields without nonrigid points -- empty ones, and a rigid contact material's field in multimaterial mode -- keep the zeros of
+// MatVelocityField::Zero: CrackVelocityFieldMulti::GetTotalMassAndCount copies nonrigid fields only)
 __global__ void k_copy_momenta(int nnodes, Nodes N)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnodes) return;
+    if (i >= nnodes || N.cnt[i] <= 0) return;
     N.pkc[0][i] = N.pk[0][i]; N.pkc[1][i] = N.pk[1][i]; N.pkc[2][i] = N.pk[2][i];
 }
 
@@ -677,13 +679,65 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_contact_terms(Grid g, Part
     });
 }
 
-__global__ void k_zero_contact_terms(int n, ContactNodes C)
+// CrackVelocityFieldMulti::RezeroNodeTask6 (:157-176): nonrigid fields lose momentum and contact terms; a rigid field keeps its
+// momentum and moves its displacement / position extrapolation on by pk dt (its particle mass is its volume)
+__global__ void k_rezero_fields_task6(int nnodes, int nf, int rigidMask, Nodes N, ContactNodes C, double dt)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    C.cvol[i] = 0.;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nnodes * nf) return;
+    if (rigidMask >> (v / nnodes) & 1) {
+        if (C.rcnt[v] > 0) { C.cdisp[0][v] += N.pk[0][v] * dt; C.cdisp[1][v] += N.pk[1][v] * dt; C.cdisp[2][v] += N.pk[2][v] * dt; }
+        return;
+    }
+    N.pk[0][v] = 0.; N.pk[1][v] = 0.; N.pk[2][v] = 0.;
+    C.cvol[v] = 0.;
 #pragma unroll
-    for (int c = 0; c < 3; c++) { C.cgrad[c][i] = 0.; C.cdisp[c][i] = 0.; }
+    for (int c = 0; c < 3; c++) { C.cgrad[c][v] = 0.; C.cdisp[c][v] = 0.; }
+}
+
+// Rigid contact particles (RigidMaterial with SetDirection 8; the host's block FIRST_RIGID_CONTACT) extrapolate to the velocity
+// field of their material: momentum, "mass" (= their volume: rho is 1), point count, contact volume from the unscaled volume,
+// displacement / position and volume gradient (NodalPoint::AddMassMomentum with nonRigid == false, NodalPointMPM.cpp:419-453).
+// They live in the rigid particle set PR beside the rigid-BC particles (which claim no field).
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(TASK_THREADS) k_p2g_rigid_contact(Grid g, Particles PR, const Material *mats, Nodes N, ContactNodes C,
+                                                                    const double *origpos, size_t norig, int byDisplacements, int needGradient, StatusFlags *flags)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= PR.n) return;
+    const Material &m = mats[PR.mat[p]];
+    if (m.kind != MAT_RIGIDCONTACT) return;
+    double pos[3] = {PR.pos[0][p], PR.pos[1][p], DIM == 3 ? PR.pos[2][p] : 0.};
+    double xi[3];
+    get_xipos<DIM>(g, PR.elem[p], pos, xi);
+    PR.ncpos[0][p] = xi[0]; PR.ncpos[1][p] = xi[1]; PR.ncpos[2][p] = xi[2];
+    if (SHAPE_IS_CPDI(SHAPE) && !cpdi_setup<DIM, SHAPE>(g, PR, p)) { atomicCAS(&flags->cpdiLeft, 0, PR.orig[p] + 1); return; }
+    const double mp = PR.mp[p];
+    const double vol = mp / m.p[0];             // GetUnscaledVolume; F = I, so this is the volume for the gradient too
+    const double vx = PR.vel[0][p], vy = PR.vel[1][p], vz = DIM == 3 ? PR.vel[2][p] : 0.;
+    double d[3] = {pos[0], pos[1], pos[2]};
+    if (byDisplacements) {
+        const size_t q = (size_t)PR.orig[p];
+        d[0] -= origpos[q]; d[1] -= origpos[norig + q];
+        if (DIM == 3) d[2] -= origpos[2 * norig + q];
+    }
+    particle_nodes<DIM, SHAPE, true>(g, PR, p, [&](int nd, double S, double gx, double gy, double gz) {
+        const double fnmp = S * mp;
+        atomAdd(&N.pk[0][nd], vx * fnmp);
+        atomAdd(&N.pk[1][nd], vy * fnmp);
+        if (DIM == 3) atomAdd(&N.pk[2][nd], vz * fnmp);
+        atomAdd(&N.mass[nd], fnmp);
+        atomicAdd(&C.rcnt[nd], 1);
+        atomAdd(&C.cvol[nd], S * vol);
+        atomAdd(&C.cdisp[0][nd], d[0] * fnmp);
+        atomAdd(&C.cdisp[1][nd], d[1] * fnmp);
+        if (DIM == 3) atomAdd(&C.cdisp[2][nd], d[2] * fnmp);
+        if (needGradient) {
+            atomAdd(&C.cgrad[0][nd], gx * vol);
+            atomAdd(&C.cgrad[1][nd], gy * vol);
+            if (DIM == 3) atomAdd(&C.cgrad[2][nd], gz * vol);
+        }
+    });
 }
 
 // symmetry-plane bits of NodalPoint::fixedDirection (32 x, 64 y, 128 z) zero a vector's components (CrackVelocityField::AdjustForSymmetry)
@@ -782,21 +836,123 @@ __global__ void k_material_contact(Grid g, Nodes N, ContactNodes C, ContactParam
     const int nn = g.nnodes;
     if (i >= nn) return;
     int act[MPM_MAX_FIELDS];
-    int numMats = 0;
+    int numMats = 0, rigidFld = -1, numberMaterials = 0;
+    bool multiRigid = false;
     double Pc[3] = {0., 0., 0.}, Mc = 0.;
     for (int f = 0; f < cp.nf; f++) {
         const int v = f * nn + i;
-        if (N.cnt[v] > 0) {
+        if (cp.rigidMask >> f & 1) {
+            if (C.rcnt[v] > 0) { numberMaterials++; if (rigidFld >= 0) multiRigid = true; else rigidFld = f; }
+        } else if (N.cnt[v] > 0) {
             Pc[0] += N.pk[0][v]; Pc[1] += N.pk[1][v]; Pc[2] += N.pk[2][v];
             Mc += N.mass[v];
             act[numMats++] = f;
+            numberMaterials++;
         }
     }
-    if (numMats <= 1) return;
+    if (numberMaterials <= 1) return;
     int sd = 0;
     if (bcOfNode) { const int u = bcOfNode[i]; if (u >= 0) sd = B.symdir[u]; }
     const bool postUpdate = callType == CALL_UPDATE_MOMENTUM;
     const bool useGrad = cp.normalMethod != NORMALS_SPECIFIED;
+    double xn[3];
+    {   // node coordinates (power-law position cutoff only)
+        const int iz = g.dim == 3 ? i / g.zplane : 0, r = i - iz * g.zplane, iy = r / g.yplane, ix = r - iy * g.yplane;
+        xn[0] = g.xpts[ix]; xn[1] = g.ypts[iy]; xn[2] = g.dim == 3 ? g.zpts[iz] : 0.;
+    }
+    if (rigidFld >= 0) {
+        // CrackVelocityFieldMulti::RigidMaterialContactOnCVF (:676-955): every nonrigid material of the node against the rigid
+        // material (the one of largest contact volume when there are several); only the nonrigid momenta change
+        double rigidVolume = C.cvol[rigidFld * nn + i];
+        if (multiRigid)
+            for (int f = rigidFld + 1; f < cp.nf; f++)
+                if ((cp.rigidMask >> f & 1) && C.rcnt[f * nn + i] > 0) {
+                    const double tv = C.cvol[f * nn + i];
+                    if (tv > rigidVolume) { rigidVolume = tv; rigidFld = f; }
+                }
+        const int vr = rigidFld * nn + i;
+        const double actualRigidVolume = N.mass[vr];
+        double rvel[3];
+        { const double s = 1. / actualRigidVolume; rvel[0] = N.pk[0][vr] * s; rvel[1] = N.pk[1][vr] * s; rvel[2] = N.pk[2][vr] * s; }
+        for (int mi = 0; mi < numMats; mi++) {
+            const int fi = act[mi], vi = fi * nn + i;
+            const int law = cp.lawKind[fi * cp.nf + rigidFld];
+            const double massi = N.mass[vi], mred = massi, voli = C.cvol[vi];
+            double delPi[3] = {N.pk[0][vi] * -1., N.pk[1][vi] * -1., N.pk[2][vi] * -1.};
+            delPi[0] += rvel[0] * massi; delPi[1] += rvel[1] * massi; delPi[2] += rvel[2] * massi;
+            adjust_for_symmetry(sd, delPi);
+            if (law != LAW_IGNORE) {
+                double gradj[3] = {0., 0., 0.}, normi[3] = {0., 0., 0.}, norm[3] = {0., 0., 0.};
+                if (useGrad) {
+                    gradj[0] = C.cgrad[0][vr] * -1.; gradj[1] = C.cgrad[1][vr] * -1.; gradj[2] = C.cgrad[2][vr] * -1.;
+                    adjust_for_symmetry(sd, gradj);
+                    normi[0] = C.cgrad[0][vi]; normi[1] = C.cgrad[1][vi]; normi[2] = C.cgrad[2][vi];
+                    adjust_for_symmetry(sd, normi);
+                }
+                const double jBias = cp.rigidBias;
+                switch (cp.normalMethod) {      // GetNormalVector with j = the rigid field (:960-1071)
+                case NORMALS_MAXG: {
+                    const double magi = sqrt(normi[0] * normi[0] + normi[1] * normi[1] + normi[2] * normi[2]);
+                    const double magj = sqrt(gradj[0] * gradj[0] + gradj[1] * gradj[1] + gradj[2] * gradj[2]);
+                    if (magi >= jBias * magj) { const double s = 1. / magi; norm[0] = normi[0] * s; norm[1] = normi[1] * s; norm[2] = normi[2] * s; }
+                    else { const double s = 1. / magj; norm[0] = gradj[0] * s; norm[1] = gradj[1] * s; norm[2] = gradj[2] * s; }
+                    break;
+                }
+                case NORMALS_MAXV: {
+                    if (voli >= rigidVolume) { norm[0] = normi[0]; norm[1] = normi[1]; norm[2] = normi[2]; }
+                    else { norm[0] = gradj[0]; norm[1] = gradj[1]; norm[2] = gradj[2]; }
+                    const double s = 1. / sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
+                    norm[0] *= s; norm[1] *= s; norm[2] *= s;
+                    break;
+                }
+                case NORMALS_AVGG: {
+                    norm[0] = normi[0] + gradj[0]; norm[1] = normi[1] + gradj[1]; norm[2] = normi[2] + gradj[2];
+                    const double magi = norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2];
+                    const double vRatio = (voli + rigidVolume) / rigidVolume;
+                    const double magj = gradj[0] * gradj[0] + gradj[1] * gradj[1] + gradj[2] * gradj[2];
+                    if (magi >= jBias * magj * vRatio * vRatio) { const double s = 1. / sqrt(magi); norm[0] *= s; norm[1] *= s; norm[2] *= s; }
+                    else { const double s = 1. / sqrt(magj); norm[0] = gradj[0] * s; norm[1] = gradj[1] * s; norm[2] = gradj[2] * s; }
+                    break;
+                }
+                case NORMALS_OWNG: {
+                    const double s = 1. / sqrt(normi[0] * normi[0] + normi[1] * normi[1] + normi[2] * normi[2]);
+                    norm[0] = normi[0] * s; norm[1] = normi[1] * s; norm[2] = normi[2] * s;
+                    break;
+                }
+                default: {
+                    norm[0] = cp.normal[0]; norm[1] = cp.normal[1]; norm[2] = cp.normal[2];
+                    if (adjust_for_symmetry(sd, norm)) {
+                        const double s = 1. / sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
+                        norm[0] *= s; norm[1] *= s; norm[2] *= s;
+                    }
+                    break;
+                }
+                }
+                if (norm[0] != norm[0] || norm[1] != norm[1] || norm[2] != norm[2]) continue;
+                const double dotn = delPi[0] * norm[0] + delPi[1] * norm[1] + delPi[2] * norm[2];
+                double dispRigid[3], dispi[3];
+                { const double s = 1. / actualRigidVolume; dispRigid[0] = C.cdisp[0][vr] * s; dispRigid[1] = C.cdisp[1][vr] * s; dispRigid[2] = C.cdisp[2][vr] * s; }
+                adjust_for_symmetry(sd, dispRigid);
+                { const double s = 1. / massi; dispi[0] = C.cdisp[0][vi] * s; dispi[1] = C.cdisp[1][vi] * s; dispi[2] = C.cdisp[2][vi] * s; }
+                adjust_for_symmetry(sd, dispi);
+                const double deln = material_separation(g, cp, dispRigid[0] * norm[0] + dispRigid[1] * norm[1] + dispRigid[2] * norm[2],
+                                                        dispi[0] * norm[0] + dispi[1] * norm[1] + dispi[2] * norm[2], norm, xn);
+                double delFi[3];
+                if (postUpdate) { delFi[0] = N.ftot[0][vi] * -1.; delFi[1] = N.ftot[1][vi] * -1.; delFi[2] = N.ftot[2][vi] * -1.; }
+                if (!frictional_delta_momentum(law, cp.lawFriction[fi * cp.nf + rigidFld], cp.lawStatic[fi * cp.nf + rigidFld], delPi, norm, dotn, deln, mred, dt,
+                                               postUpdate ? delFi : (const double *)0)) continue;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double pk = N.pk[c][vi] + delPi[c];
+                N.pk[c][vi] = pk;
+                if (callType == CALL_UPDATE_MOMENTUM) { N.ftot[c][vi] += delPi[c] * (1. / dt); C.rforce[c][vr] += delPi[c]; }    // + AddContactForce on the rigid field
+                else if (callType == CALL_MASS_MOMENTUM) N.pkc[c][vi] = pk;
+            }
+        }
+        return;
+    }
+    if (numMats <= 1) return;
     const bool doingPairs = numMats == 2 && cp.normalMethod != NORMALS_OWNG;
     const int miMax = doingPairs ? numMats - 1 : numMats;
     // centre-of-mass displacement (or position) and total contact volume of the nonrigid materials
@@ -808,11 +964,6 @@ __global__ void k_material_contact(Grid g, Nodes N, ContactNodes C, ContactParam
     }
     adjust_for_symmetry(sd, dispc);
     { const double s = 1. / Mc; dispc[0] *= s; dispc[1] *= s; dispc[2] *= s; }
-    double xn[3];
-    {   // node coordinates (power-law position cutoff only)
-        const int iz = g.dim == 3 ? i / g.zplane : 0, r = i - iz * g.zplane, iy = r / g.yplane, ix = r - iy * g.yplane;
-        xn[0] = g.xpts[ix]; xn[1] = g.ypts[iy]; xn[2] = g.dim == 3 ? g.zpts[iz] : 0.;
-    }
     for (int mi = 0; mi < miMax; mi++) {
         const int fi = act[mi], vi = fi * nn + i;
         const double massi = N.mass[vi];

@@ -20,7 +20,8 @@ enum { SHAPE_LINEAR = 0, SHAPE_UGIMP = 1, SHAPE_B2GIMP = 5, SHAPE_B2SPLINE = 6, 
 #define SHAPE_IS_QCPDI(S) ((S) == SHAPE_QCPDI || (S) == SHAPE_QCPDI_MERGED)
 #define SHAPE_IS_CPDI(S) ((S) == SHAPE_LCPDI || (S) == SHAPE_LCPDI_MERGED || (S) == SHAPE_B2CPDI || SHAPE_IS_QCPDI(S))
 #define SHAPE_IS_MERGED(S) ((S) == SHAPE_LCPDI_MERGED || (S) == SHAPE_QCPDI_MERGED)
-enum { MAT_NONE = 0, MAT_ISOTROPIC = 1, MAT_MOONEY = 8, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28 };
+enum { MAT_NONE = 0, MAT_ISOTROPIC = 1, MAT_MOONEY = 8, MAT_ISOPLASTICITY = 9, MAT_RIGIDBC = 11, MAT_NEOHOOKEAN = 28,
+       MAT_RIGIDCONTACT = 35 };     // RigidMaterial in contact mode (SetDirection 8, RIGID_MULTIMATERIAL_MODE): multimaterial mode only
 
 // BC pass types (reference NodalVelBC.cpp:321-380)
 enum { PASS_MASS_MOMENTUM = 0, PASS_GRID_FORCES = 1, PASS_UPDATE_MOMENTUM = 2, PASS_UPDATE_STRAINS_LAST = 3,
@@ -100,6 +101,10 @@ struct ContactNodes {
     double *cvol;            // [nf*nnodes] contactInfo->cvolume
     double *cgrad[3];        // volume gradient (terms[volumeGradientIndex])
     double *cdisp[3];        // mass-weighted displacement (contactByDisplacements) or position
+    double *rforce[3];       // [nf*nnodes] a rigid field's ftot: the momentum changes its contact gave the other materials, CUMULATIVE over
+                             // the steps (MatVelocityField::Zero leaves it alone; the reference clears it when a contact-force quantity is read)
+    int *rcnt;               // [nf*nnodes] rigid contact particles seen by a RIGID material's field (its numberPoints; Nodes::cnt stays
+                             // 0 there, so every node kernel of the nonrigid fields passes a rigid field by)
 };
 // ---- conduction (ConductionTask, the first transport task) ------------------------------------
 // NodalPoint::gCond (TransportField): one value per NODE (not per material velocity field)
@@ -115,6 +120,8 @@ struct ContactParams {
     int normalMethod;        // mpmgrid.materialNormalMethod (0..4)
     int byDisplacements;     // mpmgrid.contactByDisplacements
     int cubic;               // 3D cubic / 2D square cells (MeshInfo::GetPerpendicularDistance short cut)
+    int rigidMask;           // bit f: field f belongs to a rigid contact material
+    double rigidBias;        // mpmgrid.rigidGradientBias, squared as MeshInfo::MaterialOutput leaves it
     double positionCutoff;   // mpmgrid.positionCutoff
     double normal[3];        // SPECIFIED_NORMAL
     int lawKind[MPM_MAX_FIELDS * MPM_MAX_FIELDS];

@@ -352,13 +352,14 @@ class GpuTask : public MPMTask
     void UpdateRigidVelocities(void)
     {
         if (!gRigidFunctions) return;
-        const int nr = nmpms - nmpmsRC;
+        // (rigid contact particles [nmpmsRB, nmpmsRC): SetRigidContactVelTask.cpp:38-46; rigid-BC particles after them)
+        const int nr = nmpms - nmpmsNR;
         std::vector<double> v(3 * (size_t)nr);
-        for (int p = nmpmsRC; p < nmpms; p++) {
+        for (int p = nmpmsNR; p < nmpms; p++) {
             MPMBase *m = mpm[p];
             bool hasDir[3];
             ((RigidMaterial *)theMaterials[m->MatID()])->GetVectorSetting(&m->vel, hasDir, mtime, &m->pos);
-            const int j = p - nmpmsRC;
+            const int j = p - nmpmsNR;
             v[j] = m->vel.x; v[nr + j] = m->vel.y; v[2 * (size_t)nr + j] = m->vel.z;
         }
         each_ctx([&](mpmgpu_ctx *c) { return mpmgpu_update_rigid_velocities(c, nr, v.data()); }, "GpuTask(rigid velocities)");
@@ -366,7 +367,7 @@ class GpuTask : public MPMTask
     void AfterStep(void)
     {
         if (gRigidFunctions)        // keep the host copy of the rigid positions current for the next evaluation
-            for (int p = nmpmsRC; p < nmpms; p++) mpm[p]->MovePosition(timestep);
+            for (int p = nmpmsNR; p < nmpms; p++) mpm[p]->MovePosition(timestep);
         gHostStale = true;
         {   // particles pushed back into the grid: the reference warns once per particle and aborts at the <LeaveLimit>
             // threshold (ResetElementsTask.cpp:71-95); same warning object, same exception
@@ -498,6 +499,13 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         if (lb->ptNum - 1 >= nmpmsNR) return "load BCs on rigid particles";
     }
     if (firstTractionPt != NULL) return "particle traction BCs (MatPtTractionBC)";
+    // global quantities the reference reads from its nodes or BC objects, which the replaced tasks no longer fill
+    for (GlobalQuantity *gq = firstGlobal; gq != NULL; gq = gq->GetNextGlobal()) {
+        const int q = gq->quantity;
+        if (q == TOT_FCONX || q == TOT_FCONY || q == TOT_FCONZ || q == TOT_REACTX || q == TOT_REACTY || q == TOT_REACTZ || q == GRID_KINE_ENERGY ||
+            q == INTERFACE_ENERGY || q == FRICTION_WORK)
+            return "global quantities read from the grid (contact / reaction forces, grid kinetic energy, interface energy, friction work)";
+    }
     // damping that changes during the run (functions of time, feedback on the kinetic energy: BodyForce.cpp:167-230)
     if (bodyFrc.useFeedback || bodyFrc.usePFeedback || bodyFrc.gridfunction != NULL || bodyFrc.pgridfunction != NULL)
         return "time-dependent or feedback damping";
@@ -521,7 +529,8 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     if (fabs(fmobj->restartScaling) > 1.e-6) return "time-step restarts (<RestartScaling>)";
     if (fmobj->deleteLeavingParticles) return "deleting particles that leave the grid (<LeaveLimit> < 0)";
     if (warnings.GetMaxIssues(fmobj->warnParticleDeleted) >= 2) return "deleting nan particles (<DeleteLimit> > 1)";
-    if (nmpmsRC != nmpmsNR) return "rigid contact or rigid block particles present";
+    if (nmpmsRB != nmpmsNR) return "rigid block particles present";
+    if (nmpmsRC != nmpmsRB && !fmobj->multiMaterialMode) return "rigid contact particles outside multimaterial mode";
     if (nmpms != nmpmsNR && MaterialBase::extrapolateRigidBCs) return "rigid BCs by extrapolation";
     if (fmobj->np != PLANE_STRAIN_MPM && fmobj->np != PLANE_STRESS_MPM && fmobj->np != THREED_MPM) return "analysis type";
     if (ElementBase::useGimp != POINT_GIMP && ElementBase::useGimp != UNIFORM_GIMP && ElementBase::useGimp != LINEAR_CPDI &&
@@ -545,7 +554,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
             break;
         case 11: {
             RigidMaterial *rm = (RigidMaterial *)mb;
-            if (!rm->IsRigidBC()) return "rigid contact material";
+            if (rm->IsRigidBlock()) return "rigid block material";
             if (rm->Vfunction != NULL || rm->useControlVelocity) return "rigid material with value function or control velocity";
             if (rm->setTemperature || rm->setConcentration) return "rigid material that sets temperature or concentration";
             if (rm->function != NULL) gRigidFunctions = true;
@@ -688,6 +697,9 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         } else if (mb->MaterialID() == CONTACTLAW || mb->MaterialID() == COULOMBFRICTIONLAW) {
             m.kind = MPMGPU_MAT_NONE; m.n_history = 0;          // keeps the particles' material numbers in place
             memset(m.p, 0, sizeof m.p);
+        } else if (((RigidMaterial *)mb)->IsRigidContact()) {       // rigid contact particles: their own velocity field (multimaterial mode)
+            m.kind = MPMGPU_MAT_RIGIDCONTACT; m.n_history = 0;
+            m.p[0] = mb->rho;
         } else {                                     // rigid BC particles: directions they control
             m.kind = MPMGPU_MAT_RIGIDBC; m.n_history = 0;
             m.p[8] = ((RigidMaterial *)mb)->setDirection;
@@ -708,6 +720,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         mm.position_cutoff = mpmgrid.positionCutoff;
         mm.contact_normal[0] = mpmgrid.contactNormal.x; mm.contact_normal[1] = mpmgrid.contactNormal.y; mm.contact_normal[2] = mpmgrid.contactNormal.z;
         mm.law_kind = mmKind.data(); mm.law_friction = mmFriction.data(); mm.law_static = mmStatic.data();
+        mm.rigid_gradient_bias = mpmgrid.rigidGradientBias;         // (squared by MeshInfo::MaterialOutput already)
         if (mpmgpu_set_multimaterial(gCtx, &mm) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     }
 

@@ -10,6 +10,7 @@ import numpy as np
 NPARAMS = 32
 MAX_HISTORY = 4            # MPMGPU_MAX_HISTORY
 ISOTROPIC, MOONEY, ISOPLASTICITY, RIGIDBC, NEOHOOKEAN = 1, 8, 9, 11, 28
+RIGIDCONTACT = 35           # MPMGPU_MAT_RIGIDCONTACT: RigidMaterial (MaterialID 11) with SetDirection 8, multimaterial mode only
 NOT_A_PARTICLE_MATERIAL = 0      # MPMGPU_MAT_NONE: keeps the place of a contact law in the materials list (ContactLaw, MaterialID 60-63)
 CONTACT_LAW, COULOMB_FRICTION_LAW = 60, 61        # Materials/ContactLaw.hpp:14 (ignore contact), Materials/CoulombFriction.hpp:14
 PLANE_STRAIN_MPM, PLANE_STRESS_MPM, THREED_MPM = 10, 11, 12
@@ -132,6 +133,12 @@ def rigid_bc(direction_bits, mirrored=0):
     p[8] = float(direction_bits)
     p[9] = float(mirrored)
     return dict(kind=RIGIDBC, n_history=0, p=p, rho=1.0, wave_speed=0.0)
+
+
+def rigid_contact():
+    """RigidMaterial in contact mode (<SetDirection>8</SetDirection>, RIGID_MULTIMATERIAL_MODE): its particles keep their own
+    velocity field, against which the other materials of a node make contact (multimaterial mode)."""
+    return dict(kind=RIGIDCONTACT, n_history=0, p=_base(1.0, DEFAULT_CV, None), rho=1.0, wave_speed=0.0)
 
 
 def neohookean(G, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None, av=None):

@@ -328,6 +328,10 @@ def from_reference_dump(z, snapshot="p0"):
                 raise NotImplementedError("hardening law %d" % law)
         elif mid in (M.CONTACT_LAW, M.COULOMB_FRICTION_LAW) and "mm/nfields" in z:
             m = M.contact_law_placeholder()
+        elif mid == M.RIGIDBC and int(q[8]) == 8:
+            if q[10] != 0 or q[11] != 0:
+                raise NotImplementedError("rigid contact material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")
+            m = M.rigid_contact()
         elif mid == M.RIGIDBC:
             if q[10] != 0 or q[11] != 0:
                 raise NotImplementedError("rigid material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")
@@ -370,7 +374,8 @@ def from_reference_dump(z, snapshot="p0"):
         pr.multimaterial = dict(n_fields=nf, field_of_material=np.where(field < 0, 0, field).astype(np.int32),
                                 normal_method=int(z["mm/normal_method"]), by_displacements=int(z["mm/by_displacements"]),
                                 position_cutoff=float(z["mm/position_cutoff"]), contact_normal=np.asarray(z["mm/contact_normal"], float),
-                                law_kind=kind, law_friction=fric, law_static=stat)
+                                law_kind=kind, law_friction=fric, law_static=stat,
+                                rigid_gradient_bias=float(z["mm/rigid_gradient_bias"]) if "mm/rigid_gradient_bias" in z else 1.0)
         pr.origpos = np.asarray(z[s + "/origpos"], float) if (s + "/origpos") in z else None
     nb = z["velbcs/node"].shape[0]
     pr.bc_node = z["velbcs/node"].astype(np.int32)

@@ -329,6 +329,7 @@ void ref_get_multimaterial(int *out, int *field, double *law, double *normal)
     out[3] = fmobj->multiMaterialMode ? 1 : 0;
     normal[0] = mpmgrid.contactNormal.x; normal[1] = mpmgrid.contactNormal.y; normal[2] = mpmgrid.contactNormal.z;
     normal[3] = mpmgrid.positionCutoff;
+    normal[4] = mpmgrid.rigidGradientBias;          // already squared by MeshInfo::MaterialOutput
     for (int i = 0; i < nmat; i++) field[i] = theMaterials[i]->GetField();
     for (int i = 0; i < nmat; i++)
         for (int j = 0; j < nmat; j++) {

@@ -106,12 +106,12 @@ class RefRun:
         out = np.zeros(8, np.int32)
         field = np.zeros(nm, np.int32)
         law = np.zeros((nm, nm, 4))
-        normal = np.zeros(4)
+        normal = np.zeros(5)
         self.lib.ref_get_multimaterial(_ip(out), _ip(field), _dp(law), _dp(normal))
         if not out[3]:
             return None
         return dict(nfields=nf, normal_method=int(out[0]), by_displacements=int(out[1]), field=field, law=law,
-                    position_cutoff=float(normal[3]), contact_normal=normal[:3].copy())
+                    position_cutoff=float(normal[3]), contact_normal=normal[:3].copy(), rigid_gradient_bias=float(normal[4]))
 
     def conduction(self):
         """Conduction settings (None when the task is off): kcond per material, counts of the BCs this repo does not build."""

@@ -42,7 +42,8 @@ struct EmuSim {
     ContactNodes C;
     ContactParams cp;
     std::vector<double> cpool, origpos;
-    std::vector<int> foff, fieldOfMat;
+    std::vector<int> foff, fieldOfMat, foffR, rcnt;
+    std::vector<double> rforce;
     // conduction (capi.cu: ctx->conduction, T)
     bool conduction = false;
     TransportNodes T;
@@ -157,9 +158,12 @@ void apply_bcs(EmuSim *S, int pass, int adjustSym)
 }
 
 // capi.cu::contact_extrapolation / material_contact
-void contact_extrapolation(EmuSim *S)
+void contact_extrapolation(EmuSim *S, bool rigidToo = false)
 {
     if (!S->multimaterial) return;
+    if (rigidToo && S->cp.rigidMask && S->PR.n > 0)
+        DISPATCH(k_p2g_rigid_contact, S->PR.n, S->g, S->PR, S->mats.data(), S->N, S->C, S->origpos.data(), (size_t)S->n, S->cp.byDisplacements,
+                 S->cp.normalMethod != NORMALS_SPECIFIED ? 1 : 0, &S->flags);
     DISPATCH(k_p2g_contact_terms, S->P.nNR, S->g, S->P, S->mats.data(), S->C, S->origpos.data(), (size_t)S->n, S->cp.byDisplacements,
              S->cp.normalMethod != NORMALS_SPECIFIED ? 1 : 0);
 }
@@ -202,12 +206,13 @@ void run_task(EmuSim *S, int t)
         std::fill(S->ncnt.begin(), S->ncnt.end(), 0);
         std::fill(S->cpool.begin(), S->cpool.end(), 0.);
         std::fill(S->tpool.begin(), S->tpool.end(), 0.);
+        std::fill(S->rcnt.begin(), S->rcnt.end(), 0);
         DISPATCH(k_init_particles, S->P.n, S->g, S->P, &S->flags);
         break;
     case 1:
         DISPATCH(k_p2g_mass_momentum, S->P.nNR, S->g, S->P, S->N);
         if (S->conduction) DISPATCH(k_p2g_temperature, S->P.nNR, S->g, S->P, S->mats.data(), S->T);
-        contact_extrapolation(S);
+        contact_extrapolation(S, true);
         break;
     case 2: {
         EMU_LAUNCH(k_copy_momenta, nblk(nn, 256), 256, nn, S->N);
@@ -250,8 +255,8 @@ void run_task(EmuSim *S, int t)
     case 8:
         if (S->sp.method == METHOD_USF) break;
         if (!S->sp.skipPost) {
-            EMU_LAUNCH(k_rezero_momenta, nblk(nn, 256), 256, nn, S->N);
-            if (S->multimaterial) EMU_LAUNCH(k_zero_contact_terms, nblk(nn, 256), 256, nn, S->C);
+            if (S->multimaterial) EMU_LAUNCH(k_rezero_fields_task6, nblk(nn, 256), 256, S->g.nnodes, S->nf, S->cp.rigidMask, S->N, S->C, S->sp.dt);
+            else EMU_LAUNCH(k_rezero_momenta, nblk(nn, 256), 256, nn, S->N);
             DISPATCH(k_p2g_momentum_last, S->P.nNR, S->g, S->P, S->N);
             contact_extrapolation(S);
             material_contact(S, CALL_UPDATE_STRAINS_LAST);
@@ -346,7 +351,8 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
 
 // capi.cu::mpmgpu_set_multimaterial: nf fields per node (field-major node arrays), contact extrapolations, particle field offsets
 extern "C" void emu_set_multimaterial(void *h, int nf, const int *fieldOfMat, int normalMethod, int byDisplacements, double positionCutoff,
-                                      const double *normal, const int *lawKind, const double *lawFriction, const double *lawStatic, const double *origpos)
+                                      const double *normal, const int *lawKind, const double *lawFriction, const double *lawStatic, const double *origpos,
+                                      double rigidBias)
 {
     EmuSim *S = (EmuSim *)h;
     S->multimaterial = true; S->nf = nf;
@@ -365,6 +371,15 @@ extern "C" void emu_set_multimaterial(void *h, int nf, const int *fieldOfMat, in
     cp.cubic = dbleEqual(S->g.gx, S->g.gy) && (S->dim == 2 || dbleEqual(S->g.gx, S->g.gz)) ? 1 : 0;
     for (int i = 0; i < nf * nf; i++) { cp.lawKind[i] = (i / nf == i % nf) ? LAW_IGNORE : lawKind[i]; cp.lawFriction[i] = lawFriction[i]; cp.lawStatic[i] = lawStatic[i]; }
     S->fieldOfMat.assign(fieldOfMat, fieldOfMat + S->mats.size());
+    cp.rigidBias = rigidBias > 0. ? rigidBias : 1.;
+    for (size_t m = 0; m < S->mats.size(); m++) if (S->mats[m].kind == MAT_RIGIDCONTACT) { cp.rigidMask |= 1 << S->fieldOfMat[m]; S->mats[m].p[8] = 0.; S->mats[m].p[9] = 0.; }
+    S->rcnt.assign(nv, 0);
+    S->C.rcnt = S->rcnt.data();
+    S->rforce.assign(nv * 3, 0.);
+    for (int c = 0; c < 3; c++) S->C.rforce[c] = S->rforce.data() + (size_t)c * nv;
+    S->foffR.assign(S->PR.n ? S->PR.n : 1, 0);
+    for (int p = 0; p < S->PR.n; p++) S->foffR[p] = S->fieldOfMat[S->PR.mat[p]] * S->g.nnodes;
+    S->PR.foff = S->foffR.data();
     S->foff.assign(S->P.n ? S->P.n : 1, 0);
     for (int p = 0; p < S->P.n; p++) S->foff[p] = S->fieldOfMat[S->P.mat[p]] * S->g.nnodes;
     S->P.foff = S->foff.data();
@@ -495,8 +510,9 @@ extern "C" void emu_get_nodes(void *h, int *cnt, double *mass, double *pk, doubl
     EmuSim *S = (EmuSim *)h;
     const size_t nn = (size_t)S->nvn;
     for (size_t i = 0; i < nn; i++) {
-        cnt[i] = S->N.cnt[i]; mass[i] = S->N.mass[i];
-        for (int c = 0; c < 3; c++) { pk[c * nn + i] = S->N.pk[c][i]; ftot[c * nn + i] = S->N.ftot[c][i]; vk[c * nn + i] = S->N.vk[c][i]; pkc[c * nn + i] = S->N.pkc[c][i]; }
+        cnt[i] = S->N.cnt[i] + (S->multimaterial ? S->C.rcnt[i] : 0); mass[i] = S->N.mass[i];
+        const bool rigidField = S->multimaterial && (S->cp.rigidMask >> (i / (size_t)S->g.nnodes) & 1);
+        for (int c = 0; c < 3; c++) { pk[c * nn + i] = S->N.pk[c][i]; ftot[c * nn + i] = rigidField ? S->C.rforce[c][i] : S->N.ftot[c][i]; vk[c * nn + i] = S->N.vk[c][i]; pkc[c * nn + i] = S->N.pkc[c][i]; }
     }
 }
 

@@ -163,6 +163,12 @@ CASES = {
     "mm3d_two_blocks_avgg_position": (inputs.blocks3d_contact(inputs.multimaterial(2, 0.4, 0.9), gimp=None, materials=2), (1, 2, 40), 2),
     "mm3d_two_blocks_maxg_stick_b2gimp": (inputs.blocks3d_contact(inputs.multimaterial(0, -1.0), gimp="B2GIMP", materials=2), (1, 2, 40), 2),
     "mm3d_two_blocks_maxv_friction_ugimp": (inputs.blocks3d_contact(inputs.multimaterial(1, 0.25), materials=2), (1, 2, 40), 2),
+    # rigid contact materials (RigidMaterial with SetDirection 8): their particles keep their own field and velocity; every
+    # other material of a node makes contact with it (RigidMaterialContactOnCVF)
+    "mm2d_rigid_plate_maxg_friction": (inputs.rigid_contact_plate(inputs.disks2d(analysis=10, vel=3000.0, vmax=11.0, gap=0.0,
+                                                                  extra_header=inputs.multimaterial(0, 0.3, None, ' RigidBias="10"'))), (1, 2, 60), 2),
+    "mm3d_rigid_block_avgg_position_usl": (inputs.blocks3d_contact(inputs.multimaterial(2, None, 0.8), method=3, materials=2, rigid_b=True), (1, 2, 40), 2),
+    "mm3d_rigid_block_maxv_stick_lcpdi": (inputs.blocks3d_contact(inputs.multimaterial(1, -1.0), gimp="lCPDI", materials=2, rigid_b=True), (1, 2, 40), 2),
     # heat conduction: bodies of different temperature, conductivity and heat capacity in contact;
     # one velocity field, then material velocity fields with frictional contact in 3D (transport stays on the node)
     "cond2d_disks_usavg": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=0.0)),

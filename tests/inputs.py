@@ -210,7 +210,18 @@ def conduction(xml, temps, kcond, cp, stress_free=300.0):
     return xml.replace("</JANFEAInput>", "<Thermal><Conduction/></Thermal></JANFEAInput>")
 
 
-def blocks3d_contact(header, gimp="uGIMP", method=2, materials=3):
+def rigid_contact_plate(xml):
+    """disks2d with the second disk turned into a plate of RIGID CONTACT particles (RigidMaterial, SetDirection 8) that moves
+    against the first disk at an angle."""
+    a, b = xml.split('<Body matname="Disk 2"')
+    vx = b.split('vx="')[1].split('"')[0]
+    b = b.replace('vx="%s" vy="0"' % vx, 'vx="-2000.0" vy="700"', 1).replace('<Oval xmin="0.0" xmax="12.0" ymin="-6.0" ymax="6.0"/>', '<Rect xmin="0.0" xmax="2.0" ymin="-8.0" ymax="8.0"/>', 1)
+    xml = a + '<Body matname="Disk 2"' + b
+    head, tail = xml.split('<Material Type="1" Name="Disk 2">')
+    return head + '<Material Type="11" Name="Disk 2"><SetDirection>8</SetDirection></Material>' + tail.split("</Material>", 1)[1]
+
+
+def blocks3d_contact(header, gimp="uGIMP", method=2, materials=3, rigid_b=False):
     """Three (or two) 3D blocks of different materials flying into each other inside a 12 x 10 x 10 grid (A and B touch from the start, so the first steps already carry contact): nodes seen by two
     and by three materials (the lumped branch of MaterialContactOnCVFLumped)."""
     gimp_tag = '<GIMP type="%s"/>' % gimp if gimp else ""
@@ -243,4 +254,6 @@ def blocks3d_contact(header, gimp="uGIMP", method=2, materials=3):
   <Material Type="9" Name="B"><rho>2.0</rho><E>400</E><nu>0.33</nu><alpha>20</alpha><Hardening>Linear</Hardening><yield>8</yield><Ep>40</Ep></Material>
   %s
 </JANFEAInput>
-""" % (method, gimp_tag, header, third, third_mat)
+""".replace('<Material Type="9" Name="B"><rho>2.0</rho><E>400</E><nu>0.33</nu><alpha>20</alpha><Hardening>Linear</Hardening><yield>8</yield><Ep>40</Ep></Material>',
+             '<Material Type="11" Name="B"><SetDirection>8</SetDirection></Material>' if rigid_b else
+             '<Material Type="9" Name="B"><rho>2.0</rho><E>400</E><nu>0.33</nu><alpha>20</alpha><Hardening>Linear</Hardening><yield>8</yield><Ep>40</Ep></Material>') % (method, gimp_tag, header, third, third_mat)

@@ -105,7 +105,7 @@ class EmuSim:
             self._mm = [c(mm["field_of_material"], dtype=np.int32), c(mm["contact_normal"], dtype=np.float64), c(np.asarray(mm["law_kind"]).reshape(-1), dtype=np.int32),
                         c(np.asarray(mm["law_friction"]).reshape(-1), dtype=np.float64), c(np.asarray(mm["law_static"]).reshape(-1), dtype=np.float64), orig]
             lib.emu_set_multimaterial(self.h, nf, _ip(self._mm[0]), int(mm["normal_method"]), int(mm["by_displacements"]), d(mm["position_cutoff"]),
-                                      _dp(self._mm[1]), _ip(self._mm[2]), _dp(self._mm[3]), _dp(self._mm[4]), _dp(self._mm[5]))
+                                      _dp(self._mm[1]), _ip(self._mm[2]), _dp(self._mm[3]), _dp(self._mm[4]), _dp(self._mm[5]), d(mm.get("rigid_gradient_bias", 1.0)))
             self.nnodes *= nf
             self.n_fields = nf
 

@@ -51,6 +51,11 @@ CASES = {
     "blocks3d_multimaterial_position": (inputs.blocks3d_contact(inputs.multimaterial(0, 0.25, 0.8), materials=2)
                                         .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
                                         .replace('max="1.0"', 'max="0.03"'), None, "res/blk."),
+    # a plate of rigid contact particles (RigidMaterial, SetDirection 8) whose velocity follows a setting function pushes a disk
+    "disks2d_rigid_contact_plate": (inputs.rigid_contact_plate(inputs.disks2d(analysis=10, vel=3000.0, vmax=11.0, gap=0.0, maxtime=0.6, archive_ms=0.15,
+                                                               extra_header=inputs.multimaterial(0, 0.3, None, ' RigidBias="10"')))
+                                    .replace("<SetDirection>8</SetDirection>", "<SetDirection>8</SetDirection><SettingFunction>-2000*(1+0.3*sin(20*t))</SettingFunction>"
+                                                                               "<SettingFunction2>700</SettingFunction2>"), None, "res/disks."),
     # heat conduction between two disks of different temperature, conductivity and heat capacity; the archives carry the
     # particle temperature
     "disks2d_conduction": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=0.0, maxtime=0.6, archive_ms=0.15)),

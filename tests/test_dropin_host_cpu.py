@@ -65,6 +65,9 @@ CASES = {
                         "nodal temperature BCs"),
     "diffusion": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</MPMHeader>", '<Diffusion reference="0"/></MPMHeader>'),
                   "transport tasks other than conduction"),
+    # global quantities the reference reads from its nodes / BC objects would be silently zero: the replaced tasks no longer fill them
+    "reaction force quantity": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
+        "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="reactionz"/></MPMHeader>'), "global quantities read from the grid"),
     "more exponential terms": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material=inputs.neohookean_material(),
                                               extra_header="<DefGradTerms>3</DefGradTerms>"), "<DefGradTerms> other than the default"),
 }
