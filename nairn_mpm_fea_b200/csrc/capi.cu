@@ -628,7 +628,11 @@ static int alloc_rigid(mpmgpu_ctx *ctx, size_t cap)
         bind_particles(ctx->PR, ctx->rigidPool, ctx->rigidIntPool, capPad);
         ctx->rigidCap = capPad;
         const size_t nn = (size_t)ctx->g.nnodes;
-        for (int d = 0; d < 3; d++) { CK(dalloc(ctx, &ctx->R.owner[d], nn)); ctx->R.vel[d] = ctx->PR.vel[d]; }
+        for (int d = 0; d < 3; d++) {
+            CK(dalloc(ctx, &ctx->R.owner[d], nn));
+            CK(cudaMemsetAsync(ctx->R.owner[d], 0x7f, nn * sizeof(int), ctx->stream));        // RIGID_NONE until the projection task claims dofs
+            ctx->R.vel[d] = ctx->PR.vel[d];
+        }
         unsigned char *fb = NULL;
         CK(dalloc(ctx, &fb, nn));
         if (ctx->hFixedBits.size() == nn) CK(cudaMemcpyAsync(fb, ctx->hFixedBits.data(), nn, cudaMemcpyHostToDevice, ctx->stream));
@@ -706,7 +710,10 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     if (chk.notRigid != 0x7fffffff) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle %d (after n_nonrigid) is not a rigid-BC material", chk.notRigid);
     if (chk.rigidEarly != 0x7fffffff)
         return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: rigid particle %d before n_nonrigid=%d (the reference reorders them to the end, NairnMPM.cpp:1121-1150)", chk.rigidEarly, nNR);
-    ctx->R.on = nR > 0 ? 1 : 0;
+    // (rigid CONTACT particles ride in the rigid set too but make no velocity BCs)
+    int nRigidBC = 0;
+    for (int p = nNR; p < n; p++) if (ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1].kind == MAT_RIGIDBC) nRigidBC++;
+    ctx->R.on = nRigidBC > 0 ? 1 : 0;
     ctx->R.mirrored = 0;
     for (int p = nNR; p < n; p++) if (ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1].p[9] != 0.) ctx->R.mirrored = 1;
     ctx->R.mat = ctx->PR.mat; ctx->R.mats = ctx->dMats;

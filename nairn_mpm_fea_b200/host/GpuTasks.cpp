@@ -414,6 +414,7 @@ class GpuTask : public MPMTask
             // the PeriodicXPIC custom task changes the order between steps (Custom_Tasks/PeriodicXPIC.cpp:161-240)
             check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(Initialize)");
             UpdateParticleLoads();
+            if (nmpmsRC != nmpmsRB) UpdateRigidVelocities();        // rigid contact particles: SetRigidContactVelTask runs before the extrapolation
             check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)");
             break;
         case G_RIGIDBC:
