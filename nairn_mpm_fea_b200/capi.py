@@ -268,6 +268,7 @@ class MpmGpu:
             keep[k] = _c32(pt.get(k))
             setattr(v, k, _i(keep[k]))
         self.n = n
+        self.thermal = bool(getattr(self, "conduction", False)) or pt.get("temperature") is not None
         self._check(self.lib.mpmgpu_upload_particles(self.ctx, C.byref(v)))
 
     def set_multimaterial(self, mm):
@@ -350,7 +351,7 @@ class MpmGpu:
         for k in ("pos", "vel", "sp", "pressure", "ep", "wrot", "eplast", "energies", "history", "acc"):
             setattr(v, k, _d(out[k]))
         v.in_elem, v.crossings = _i(out["in_elem"]), _i(out["crossings"])
-        if getattr(self, "conduction", False):
+        if getattr(self, "thermal", False):
             out["temperature"] = np.zeros(n)
             v.temperature = _d(out["temperature"])
             mask |= F_TEMPERATURE

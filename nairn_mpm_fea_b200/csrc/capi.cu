@@ -93,6 +93,7 @@ struct mpmgpu_ctx {
     std::vector<int> hFieldOfMat;
     // conduction (mpmgpu_set_conduction): nodal transport field, particle temperature + gradient
     bool conduction = false;
+    bool thermal = false;               // particle temperatures can change (conduction, or a start off the stress-free temperature): the laws get dT
     TransportNodes T;
     double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
     // CUDA graphs of one whole step (mpmgpu_step): keyed by a byte signature of everything the step's launches capture by value
@@ -417,10 +418,9 @@ extern "C" int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kc
     if (ctx->sp.xpicOrder > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: XPIC/FMPM of order > 1 with transport (XPICExtrapolationTaskTO) is not built");
     for (int i = 0; i < nmat; i++) {
         const Material &m = ctx->hMats[i];
-        // thermal expansion: the device laws carry no residual strains (materials.cuh), so a temperature change must not strain
-        const bool cte = (m.kind == MAT_ISOTROPIC && (m.p[17] != 0. || m.p[18] != 0. || m.p[19] != 0.)) ||
-                         ((m.kind == MAT_NEOHOOKEAN || m.kind == MAT_MOONEY || m.kind == MAT_ISOPLASTICITY) && m.p[12] != 0.);
-        if (cte) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: material %d has a thermal expansion coefficient; thermal strains are not built (conduction runs for materials with zero expansion)", i + 1);
+        // thermal strains are in the device laws (materials.cuh) except in IsotropicMat's large-rotation form
+        const bool cte = m.kind == MAT_ISOTROPIC && m.p[7] != 0. && (m.p[17] != 0. || m.p[18] != 0. || m.p[19] != 0.);
+        if (cte) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: material %d: thermal expansion with <largeRotation> on IsotropicMat is not built", i + 1);
         if (m.kind != MAT_NONE && m.kind != MAT_RIGIDBC && !(m.p[1] > 0.)) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: material %d has no heat capacity", i + 1);
     }
     cudaSetDevice(ctx->cfg.device);
@@ -729,11 +729,19 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
             if (nR) CK(cudaMemcpyAsync(ctx->archOrigin + (size_t)c * n + nNR, ctx->PR.pos[c], (size_t)nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
-    if (ctx->conduction) {
-        if (ctx->globalIds) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: conduction with caller-global particle ids (slab mode) is not built");
-        if (!ctx->tempPool) { CK(dalloc(ctx, &ctx->tempPool, ctx->cap * 4)); CK(cudaMemsetAsync(ctx->tempPool, 0, ctx->cap * 4 * sizeof(double), ctx->stream)); }
+    ctx->thermal = ctx->conduction || h->temperature != NULL;
+    if (ctx->thermal) {
+        if (ctx->globalIds) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle temperatures / conduction with caller-global particle ids (slab mode) are not built");
+        if (!ctx->conduction)
+            for (int i = 0; i < ctx->nmat; i++) {
+                const Material &m = ctx->hMats[i];
+                if (m.kind == MAT_ISOTROPIC && m.p[7] != 0. && (m.p[17] != 0. || m.p[18] != 0. || m.p[19] != 0.))
+                    return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: material %d: thermal expansion with <largeRotation> on IsotropicMat is not built", i + 1);
+            }
+        if (!ctx->tempPool) { CK(dalloc(ctx, &ctx->tempPool, ctx->cap * 5)); CK(cudaMemsetAsync(ctx->tempPool, 0, ctx->cap * 5 * sizeof(double), ctx->stream)); }
         ctx->P.temp = ctx->tempPool;
         for (int c = 0; c < 3; c++) ctx->P.tgrad[c] = ctx->tempPool + (size_t)(c + 1) * ctx->cap;
+        ctx->P.dTr = ctx->tempPool + (size_t)4 * ctx->cap;
         if (nNR) {
             // pTemperature; without the array every particle starts at the temperature of its last strain update (energies[5])
             if (h->temperature) { if ((rc = up_field(ctx, &ctx->P.temp, h->temperature, 1, n, 0, nNR))) return rc; }
@@ -774,7 +782,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         if (ctx->hasReflectedBCs) ok = false;   // symmetry-plane BCs read the momentum of the node across the plane: per-task kernels
         if (ctx->R.mirrored) ok = false;        // a mirrored rigid BC reads a neighbour node's momentum between the node updates: per-task kernels
         if (ctx->multimaterial) ok = false;     // material velocity fields + contact: per-task kernels
-        if (ctx->conduction) ok = false;        // transport tasks: per-task kernels
+        if (ctx->conduction || ctx->thermal) ok = false;        // transport tasks, temperature changes handed to the laws: per-task kernels
         if (ctx->cfg.kernel_path == 1) ok = false;
         if (ctx->cfg.kernel_path == 2 && !ok)
             return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) needs 3D uGIMP, lp<=1, no mirrored rigid BCs and no large-rotation or Mooney materials");
@@ -1133,8 +1141,10 @@ static int strain_update(mpmgpu_ctx *ctx, double strainTime, bool postUpdate = f
         if (!postUpdate || !ctx->sp.skipPost) { int rc = xpic_extrapolation(ctx, 0); if (rc) return rc; }
     } else
     LAUNCH(k_grid_velocity, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N);
-    if (ctx->largeRotation) DISPATCH_DIM_SHAPE(k_update_strains_lr, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
-    else DISPATCH_DIM_SHAPE(k_update_strains, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime);
+    // MPMBase::ScaledResidualStrains: the two passes of USAVG share the step's temperature change
+    const double dTscale = ctx->sp.method == METHOD_USAVG ? (postUpdate ? 1.0 - ctx->sp.fractionUSF : ctx->sp.fractionUSF) : 1.0;
+    if (ctx->largeRotation) DISPATCH_DIM_SHAPE(k_update_strains_lr, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime, dTscale);
+    else DISPATCH_DIM_SHAPE(k_update_strains, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, strainTime, dTscale);
     return MPMGPU_OK;
 }
 
@@ -1175,6 +1185,7 @@ static int t_update_particles(mpmgpu_ctx *ctx)
     if (!ctx->sp.usingFMPM) m = -m;
     DISPATCH_DIM_SHAPE(k_update_particles, ctx->P.nNR, ctx->g, ctx->P, ctx->N, ctx->dMats, ctx->sp, m);
     if (ctx->conduction) DISPATCH_DIM_SHAPE_VALUES(k_update_temperature, ctx->P.nNR, ctx->g, ctx->P, ctx->dMats, ctx->T, ctx->sp.dt);
+    else if (ctx->thermal) LAUNCH(k_update_temperature_offsets, nblocks(ctx->P.nNR, 256), 256, ctx->P.nNR, ctx->P);      // UpdateParticlesTask.cpp:246-251
     return move_rigid(ctx);
 }
 
@@ -1697,7 +1708,7 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
         }
         if ((mask & MPMGPU_F_HISTORY) && (rc = down_field(ctx, P.hist, PR.hist, h->history, MPM_MAX_HISTORY, n, dtmp))) break;
         if ((mask & MPMGPU_F_ACC) && (rc = down_field(ctx, P.acc, PR.acc, h->acc, 3, n, dtmp))) break;
-        if ((mask & MPMGPU_F_TEMPERATURE) && h->temperature && ctx->conduction) {
+        if ((mask & MPMGPU_F_TEMPERATURE) && h->temperature && ctx->thermal) {
             // pTemperature of the nonrigid particles (rigid-BC particles: the temperature of energies[5])
             double *const t1[1] = {P.temp}, *const t1R[1] = {PR.prevT};
             if ((rc = down_field(ctx, t1, t1R, h->temperature, 1, n, dtmp))) break;

@@ -297,6 +297,7 @@ __device__ __forceinline__ void load_pstate(const Particles &P, int p, PState &s
     s.pressure = P.pressure[p];
     s.work = P.work[p]; s.res = P.res[p]; s.heat = P.heat[p]; s.entropy = P.entropy[p]; s.plast = P.plast[p];
     s.prevT = P.prevT[p];
+    s.dT = 0.;
 #pragma unroll
     for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = P.hist[i][p];
 }
@@ -314,9 +315,11 @@ __device__ __forceinline__ void store_pstate(const Particles &P, int p, const PS
 }
 
 // ---- tasks 4 and 9b: FullStrainUpdate (UpdateStrainsFirstTask.cpp:101-168, MatPoint3D.cpp:45-93) ----
+// dTscale: share of the step's temperature change this pass answers to (MPMBase::ScaledResidualStrains, MPMBase.cpp:346-360:
+// fractionUSF / 1 - fractionUSF for the two passes of USAVG, 1 otherwise)
 template <int DIM, int SHAPE, bool LRLAW>
 __device__ __forceinline__ void update_strains_body(const Grid &g, const Particles &P, const Nodes &N, const Material *mats,
-                                                    double strainTime)
+                                                    double strainTime, double dTscale)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
@@ -335,6 +338,7 @@ __device__ __forceinline__ void update_strains_body(const Grid &g, const Particl
     for (int i = 0; i < 9; i++) dv[i] *= strainTime;
     PState s;
     load_pstate(P, p, s);
+    if (P.dTr) s.dT = P.dTr[p] * dTscale;
     if (LRLAW) constitutive_law_lr<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
     else constitutive_law<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
     store_pstate(P, p, s);
@@ -342,17 +346,17 @@ __device__ __forceinline__ void update_strains_body(const Grid &g, const Particl
 
 template <int DIM, int SHAPE>
 __global__ void __launch_bounds__(TASK_THREADS) k_update_strains(Grid g, Particles P, Nodes N, const Material *mats,
-                                                                 double strainTime)
+                                                                 double strainTime, double dTscale)
 {
-    update_strains_body<DIM, SHAPE, false>(g, P, N, mats, strainTime);
+    update_strains_body<DIM, SHAPE, false>(g, P, N, mats, strainTime, dTscale);
 }
 
 // the same task when some material asks for the large-rotation hypoelastic update (Elastic::useLargeRotation)
 template <int DIM, int SHAPE>
 __global__ void __launch_bounds__(TASK_THREADS) k_update_strains_lr(Grid g, Particles P, Nodes N, const Material *mats,
-                                                                    double strainTime)
+                                                                    double strainTime, double dTscale)
 {
-    update_strains_body<DIM, SHAPE, true>(g, P, N, mats, strainTime);
+    update_strains_body<DIM, SHAPE, true>(g, P, N, mats, strainTime, dTscale);
 }
 
 // ---- task 5: GridForcesTask (GridForcesTask.cpp:55-117, MatPoint3D.cpp:248-252) ---------------
@@ -1078,6 +1082,17 @@ __global__ void k_material_contact(Grid g, Nodes N, ContactNodes C, ContactParam
     }
 }
 
+// Without a transport task the particle update still hands the laws a temperature change: the difference between the particle's
+// temperature and the one its last strain update saw (UpdateParticlesTask.cpp:246-251) -- nonzero once, after a start off the
+// stress-free temperature.
+__global__ void k_update_temperature_offsets(int n, Particles P)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    P.dTr[p] = P.temp[p] - P.prevT[p];
+    P.prevT[p] = P.temp[p];
+}
+
 // =================================================================================================================
 // Conduction: the first transport task on the same scatter/gather skeleton (Custom_Tasks/ConductionTask.cpp,
 // TransportTask.cpp).  One scalar per node and particle; isothermal energy mode;
@@ -1179,6 +1194,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_update_temperature(Grid g, Par
     const double prev = P.prevT[p];
     const double dTcond = value - prev;
     P.prevT[p] = value;
+    P.dTr[p] = dTcond;                  // res.dT of the next strain updates (mpmptr->dTrans = res, UpdateParticlesTask.cpp:261)
     P.temp[p] += dt * rate;
     const double cv = mats[P.mat[p]].p[1];
     P.heat[p] += cv * dTcond;

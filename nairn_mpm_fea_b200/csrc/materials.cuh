@@ -15,6 +15,9 @@ struct PState {
     double work, res, heat, entropy, plast;
     double prevT;       // pPreviousTemperature
     double hist[MPM_MAX_HISTORY];
+    double dT;          // temperature change this strain update answers to (ResidualStrains::dT, already scaled for the pass:
+                        // MPMBase::ScaledResidualStrains); 0 unless the particle temperatures change (conduction, a start off the
+                        // stress-free temperature)
 };
 
 enum { XX = 0, YY = 1, ZZ = 2, YZ = 3, XZ = 4, XY = 5 };
@@ -115,20 +118,22 @@ __device__ __forceinline__ void isotropic_law(PState &s, const double du[9], int
         const double dgamxy = du[1] + du[3], dgamxz = du[2] + du[6], dgamyz = du[5] + du[7];
         const double dwrotxy = du[3] - du[1], dwrotxz = du[6] - du[2], dwrotyz = du[7] - du[5];
         const double dVoverV = dvxx + dvyy + dvzz;
+        const double eres = q[19] * s.dT;                         // CTE3 dT (:307)
+        const double dvxxeff = dvxx - eres, dvyyeff = dvyy - eres, dvzzeff = dvzz - eres;
         double st0[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) st0[i] = s.sp[i];
         double delsp[6];
-        delsp[XX] = q[8] * dvxx + q[9] * dvyy + q[10] * dvzz;     // C11 C12 C13
-        delsp[YY] = q[9] * dvxx + q[11] * dvyy + q[12] * dvzz;    // C12 C22 C23
-        delsp[ZZ] = q[10] * dvxx + q[12] * dvyy + q[13] * dvzz;   // C13 C23 C33
+        delsp[XX] = q[8] * dvxxeff + q[9] * dvyyeff + q[10] * dvzzeff;     // C11 C12 C13
+        delsp[YY] = q[9] * dvxxeff + q[11] * dvyyeff + q[12] * dvzzeff;    // C12 C22 C23
+        delsp[ZZ] = q[10] * dvxxeff + q[12] * dvyyeff + q[13] * dvzzeff;   // C13 C23 C33
         delsp[YZ] = q[14] * dgamyz;                               // C44
         delsp[XZ] = q[15] * dgamxz;                               // C55
         delsp[XY] = q[16] * dgamxy;                               // C66
         hypo3d(s.sp, dwrotxy, dwrotxz, dwrotyz, delsp);
         s.work += 0.5 * ((st0[XX] + s.sp[XX]) * dvxx + (st0[YY] + s.sp[YY]) * dvyy + (st0[ZZ] + s.sp[ZZ]) * dvzz +
                          (st0[YZ] + s.sp[YZ]) * dgamyz + (st0[XZ] + s.sp[XZ]) * dgamxz + (st0[XY] + s.sp[XY]) * dgamxy);
-        // residual energy increment is 0.5*(trace sum)*eres with eres = 0
+        s.res += 0.5 * (st0[XX] + s.sp[XX] + st0[YY] + s.sp[YY] + st0[ZZ] + s.sp[ZZ]) * eres;
         double dTq0 = -gamma0 * s.prevT * dVoverV;
         increment_heat_energy(s, Cv, dTq0, 0.);
     } else {
@@ -136,24 +141,30 @@ __device__ __forceinline__ void isotropic_law(PState &s, const double du[9], int
         const double dgam = du[1] + du[3];
         const double dwrotxy = du[3] - du[1];
         double dVoverV = dvxx + dvyy;
+        const double eres = q[17] * s.dT, ezzres = q[19] * s.dT;      // CTE1 (reduced in plane strain) and CTE3 (:198-199); doopse = 0
+        const double dvxxeff = dvxx - eres, dvyyeff = dvyy - eres;
         double st0[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) st0[i] = s.sp[i];
-        const double c1 = q[8] * dvxx + q[9] * dvyy;      // C[1][1] C[1][2]
-        const double c2 = q[9] * dvxx + q[11] * dvyy;     // C[1][2] C[2][2]
+        const double c1 = q[8] * dvxxeff + q[9] * dvyyeff;      // C[1][1] C[1][2]
+        const double c2 = q[9] * dvxxeff + q[11] * dvyyeff;     // C[1][2] C[2][2]
         const double c3 = q[16] * dgam;                   // C[3][3]
         hypo2d(s.sp, dwrotxy, c1, c2, c3);
         double workEnergy = 0.5 * ((st0[XX] + s.sp[XX]) * dvxx + (st0[YY] + s.sp[YY]) * dvyy + (st0[XY] + s.sp[XY]) * dgam);
+        double resEnergy = 0.5 * (st0[XX] + s.sp[XX] + st0[YY] + s.sp[YY]) * ezzres;
         if (np == NP_PLANE_STRAIN) {
-            s.sp[ZZ] += q[21] * dvxx + q[22] * dvyy;      // C[4][1] C[4][2]; (doopse - ezzres) = 0
+            s.sp[ZZ] += q[21] * (dvxx - ezzres) + q[22] * (dvyy - ezzres) + q[23] * (0. - ezzres);      // C[4][1] C[4][2] C[4][4] (:241)
+            resEnergy += 0.5 * (st0[ZZ] + s.sp[ZZ]) * ezzres;
         } else {
             // plane stress: out-of-plane strain increment (MoreIsotropicMat.cpp:249-258)
-            double dezz = q[21] * dvxx + q[22] * dvyy;
+            double dezz = q[21] * (dvxx - ezzres) + q[22] * (dvyy - ezzres) + ezzres;
             s.F[8] += dezz * s.F[8];                      // MPMBase::IncrementDeformationGradientZZ: ep.zz += dezz*(1+ep.zz) (MPMBase.cpp:637-639)
             workEnergy += 0.5 * (st0[ZZ] + s.sp[ZZ]) * dezz;
+            resEnergy += 0.5 * (st0[ZZ] + s.sp[ZZ]) * ezzres;
             dVoverV += dezz;
         }
         s.work += workEnergy;
+        s.res += resEnergy;
         double dTq0 = -gamma0 * s.prevT * dVoverV;
         increment_heat_energy(s, Cv, dTq0, 0.);
     }
@@ -391,7 +402,7 @@ __device__ __forceinline__ void neohookean_law(PState &s, const double du[9], do
         detDf = ezz * (d00 * d11 - d10 * d01);
     }
     double Jres = s.hist[1];
-    const double dJres = 1.;
+    const double dJres = s.dT != 0. ? exp(3. * m.p[12] * s.dT) : 1.;        // HyperElastic::GetIncrementalResJ (HyperElastic.cpp:89-95): exp(3 CTE1 dT)
     Jres *= dJres;
     s.hist[1] = Jres;
     const double resStretch = pow(Jres, 1. / 3.);
@@ -513,7 +524,7 @@ __device__ __forceinline__ void mooney_law(PState &s, const double du[9], double
         detDf = ezz * (d00 * d11 - d10 * d01);
     }
     double Jres = s.hist[1];
-    const double dJres = 1.;
+    const double dJres = s.dT != 0. ? exp(3. * m.p[12] * s.dT) : 1.;        // HyperElastic::GetIncrementalResJ (HyperElastic.cpp:89-95): exp(3 CTE1 dT)
     Jres *= dJres;
     s.hist[1] = Jres;
     if (DIM == 2 && np == NP_PLANE_STRESS) {
@@ -811,15 +822,16 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
     // plane stress terms (IsoPlasticity::GetCopyOfMechanicalProps :551-556)
     const bool planeStress = DIM == 2 && np == NP_PLANE_STRESS;
     const double psRed = 1. / (Kred / (2. * Gred) + 2. / 3.), psLr2G = (Kred / (2. * Gred) - 1. / 3.) * psRed, psKred = Kred * psRed;
-    const double delV = planeStress ? psRed * (de[0] + de[4]) : de[0] + de[4] + de[8];          // :171-174 (eres = 0)
+    const double eres = m.p[12] * s.dT;         // CTE3 dT (:133)
+    const double delV = planeStress ? psRed * (de[0] + de[4] - 2. * eres) : de[0] + de[4] + de[8] - 3. * eres;          // :147-156, :165-174
     const double P0 = s.pressure;
     const double dgxy = de[1] + de[3];
     double dgxz = 0., dgyz = 0.;
     if (DIM == 3) { dgxz = de[2] + de[6]; dgyz = de[5] + de[7]; }
-    const double dexxr = de[0], deyyr = de[4], dezzr = de[8];
+    const double dexxr = de[0] - eres, deyyr = de[4] - eres, dezzr = de[8] - eres;
     // UpdatePressure (:462-492)
     double dP = -Kred * delV;
-    const double dVoverV = delV;
+    const double dVoverV = delV + 3. * eres;
     double dispEnergy = 0.;
     if (dVoverV < 0. && m.p[3] != 0.) {         // artificial viscosity (:474-479)
         const double QAVred = artificial_viscosity(dVoverV / delTime, sqrt(Kred), m);
@@ -829,6 +841,7 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
     s.pressure += dP;
     double Pfinal = s.pressure;
     s.work += -Pfinal * dVoverV;
+    s.res += -3. * Pfinal * eres;
     double dTq0 = -gamma0 * s.prevT * dVoverV;
     // rotate plastic strain and prior stress (:218-268)
     double *ep = s.eplast, *sp = s.sp;
@@ -882,7 +895,7 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
         if (DIM == 3) s.work += sp[XX] * de[0] + sp[YY] * de[4] + sp[ZZ] * de[8] + sp[YZ] * dgyz + sp[XZ] * dgxz + sp[XY] * dgxy;
         else {
             if (planeStress) {          // zz deformation (:315-320), MPMBase::IncrementDeformationGradientZZ
-                const double dezz = -psLr2G * (dexxr + deyyr);
+                const double dezz = -psLr2G * (dexxr + deyyr) + eres;
                 s.F[8] += dezz * s.F[8];
             }
             s.work += sp[XX] * de[0] + sp[YY] * de[4] + sp[XY] * dgxy;
@@ -930,10 +943,11 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
         const double dPps = -n1 / 3. - Pfinal;
         s.pressure += dPps;
         const double dezzp = lambdak * dfds[ZZ];
-        const double dVtot = delV + psRed * dezzp;
+        const double dVtot = delV + 3. * eres + psRed * dezzp;
         s.work += -Pfinal * psRed * dezzp - dPps * dVtot;
+        s.res += -3. * dPps * eres;
         Pfinal = s.pressure;
-        dezzTotal = -psLr2G * (dexxr + deyyr - lambdak * (dfds[XX] + dfds[YY])) + dezzp;
+        dezzTotal = -psLr2G * (dexxr + deyyr - lambdak * (dfds[XX] + dfds[YY])) + dezzp + eres;
         s.F[8] += dezzTotal * s.F[8];
         dTq0 -= gamma0 * s.prevT * dezzp;
         spPS[0] = sxx + Pfinal; spPS[1] = syy + Pfinal; spPS[2] = Pfinal; spPS[3] = txy;

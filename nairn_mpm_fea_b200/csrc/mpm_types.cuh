@@ -85,6 +85,9 @@ struct Particles {
     // conduction (mpmgpu_set_conduction): pTemperature and the temperature gradient of the step (MPMBase::pTemp), NULL = off
     double *temp;
     double *tgrad[3];
+    // ResidualStrains::dT of the step (MPMBase::dTrans.dT, set by the particle update and used by the next strain updates), NULL =
+    // the particle temperatures never change
+    double *dTr;
     // multimaterial mode: node-index offset of the particle's material velocity field (field * nnodes), NULL = one field
     const int *foff;
 };

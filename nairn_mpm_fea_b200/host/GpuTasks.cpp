@@ -82,6 +82,7 @@ long long gLeftGridWarned = 0;     // first-time grid leavers already handed to 
 bool gCustomTasksReadParticles = false;     // (the only custom task the adapter admits, PeriodicXPIC, touches bodyFrc alone)
 std::vector<int> gLoadPts;          // particles with load BCs (MatPtLoadBC), 0-based, each once
 bool gLoadsSent = false;
+bool gThermal = false;              // particle temperatures live on the device (conduction, or a start off the stress-free temperature)
 bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
 void check(int rc, const char *where, mpmgpu_ctx *ctx = NULL)
@@ -141,12 +142,12 @@ void DownloadToHost(void)
     h.pos = pos.data(); h.vel = vel.data(); h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data();
     h.eplast = epl.data(); h.energies = en.data(); h.history = hist.data(); h.acc = acc.data(); h.in_elem = elem.data(); h.crossings = cross.data();
     std::vector<double> temp;
-    if (ConductionTask::active) { temp.resize(n); h.temperature = temp.data(); }
-    check(mpmgpu_download_particles(gCtx, &h, MPMGPU_F_ALL | (ConductionTask::active ? MPMGPU_F_TEMPERATURE : 0)), "GpuTasks::DownloadToHost");
+    if (gThermal) { temp.resize(n); h.temperature = temp.data(); }
+    check(mpmgpu_download_particles(gCtx, &h, MPMGPU_F_ALL | (gThermal ? MPMGPU_F_TEMPERATURE : 0)), "GpuTasks::DownloadToHost");
     for (int p = 0; p < n; p++) {
         MPMBase *m = mpm[p];
         AssignParticle(m, n, p, pos.data(), vel.data(), acc.data(), sp.data(), pr.data(), ep.data(), wrot.data(), epl.data(), en.data(), hist.data(), elem.data(), cross.data());
-        if (ConductionTask::active) { m->pTemperature = temp[p]; m->pPreviousTemperature = en[5 * n + p]; }
+        if (gThermal) { m->pTemperature = temp[p]; m->pPreviousTemperature = en[5 * n + p]; }
     }
     gHostStale = false;
 }
@@ -519,10 +520,11 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     // a particle temperature other than the one its previous strain update saw gives a thermal strain increment
     // res.dT = pTemperature - pPreviousTemperature in the first particle update (UpdateParticlesTask.cpp:252-256);
     // the device has no residual strains (eres = 0)
-    // (with conduction the particle temperatures are state of the transport task; materials with thermal expansion are then
-    // refused by mpmgpu_set_conduction)
-    for (int p = 0; p < nmpmsNR && !ConductionTask::active; p++)
-        if (mpm[p]->pTemperature != mpm[p]->pPreviousTemperature) return "particle temperatures that differ from the stress-free temperature (thermal strains)";
+    // (particle temperatures travel to the device -- mpmgpu_particles.temperature -- whenever they matter: with conduction they are
+    // state of the transport task; without it a start off the stress-free temperature gives the first particle update a thermal
+    // strain increment res.dT = pTemperature - pPreviousTemperature, UpdateParticlesTask.cpp:246-251, which the device laws carry)
+    bool temperatureOffsets = false;
+    for (int p = 0; p < nmpmsNR && !temperatureOffsets; p++) temperatureOffsets = mpm[p]->pTemperature != mpm[p]->pPreviousTemperature;
     // custom tasks run on the host particles between the step tasks; only the one that just switches the XPIC/FMPM order is safe
     for (CustomTask *ct = theTasks; ct != NULL; ct = ct->nextTask)
         if (strcmp(ct->TaskName(), "Periodic XPIC Implementation") != 0) return "custom tasks other than PeriodicXPIC";
@@ -761,7 +763,8 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data(); h.eplast = epl.data(); h.energies = en.data();
     h.pfext = anyFext ? pf.data() : NULL; h.crossings = cross.data(); h.history = hist.data();
     std::vector<double> temp0;
-    if (ConductionTask::active) {
+    gThermal = ConductionTask::active || temperatureOffsets;
+    if (gThermal) {
         temp0.resize(n);
         for (int p = 0; p < n; p++) temp0[p] = mpm[p]->pTemperature;
         h.temperature = temp0.data();

@@ -354,6 +354,10 @@ def from_reference_dump(z, snapshot="p0"):
                 raise NotImplementedError("conduction with " + k)
         pr.conduction = dict(kcond=np.asarray(z["conduction/kcond"], float))
         pr.particles["temperature"] = np.asarray(z[s + "/temperature"], float)
+    elif (s + "/temperature") in z and np.any(np.asarray(z[s + "/temperature"]) != np.asarray(z[s + "/energies"])[5]):
+        # no transport task, but particles that start off the temperature of their last strain update: the first particle
+        # update hands the laws that difference (UpdateParticlesTask.cpp:246-251)
+        pr.particles["temperature"] = np.asarray(z[s + "/temperature"], float)
     if "mm/nfields" in z:
         # multimaterial mode: the reference's table is by material pair; the device wants it by velocity-field pair
         nf = int(z["mm/nfields"])

@@ -518,6 +518,9 @@ int ref_hardening_terms(int mat, double alpint, double dalpha, double delTime, d
 
 // The reference's own MPMConstitutiveLaw applied to every non-rigid particle with a caller-given du[p][9] (row-major): the law alone,
 // on the state the particles are in.  Lets tests compare another implementation of a law with the reference at the law level.
+static double g_law_dT = 0.;        // ResidualStrains::dT handed to the laws by ref_constitutive_law_all
+void ref_set_law_dT(double dT) { g_law_dT = dT; }
+
 int ref_constitutive_law_all(const double *du, double delTime)
 {
     static char *matBuf = NULL, *altBuf = NULL;
@@ -529,7 +532,7 @@ int ref_constitutive_law_all(const double *du, double delTime)
             void *props = matRef->GetCopyOfMechanicalProps(mptr, fmobj->np, (void *)matBuf, (void *)altBuf, 0);
             const double *d = du + (size_t)9 * p;
             ResidualStrains res;
-            res.dT = 0.; res.dC = 0.; res.doopse = 0.;
+            res.dT = g_law_dT; res.dC = 0.; res.doopse = 0.;
             if (fmobj->IsThreeD()) {
                 Matrix3 dm(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8]);
                 matRef->MPMConstitutiveLaw(mptr, dm, delTime, fmobj->np, props, &res, 0);

@@ -94,9 +94,12 @@ class RefRun:
                                    _dp(o["wrot"]), _dp(o["eplast"]), _dp(o["energies"]), _dp(o["hist"]),
                                    C.c_int(nhist), _dp(o["pFext"]), _dp(o["origpos"]), _ip(o["crossings"]),
                                    _dp(o["ncpos"]), _dp(o["acc"]))
-        if self.lib.ref_conduction_on():
-            out.update(temperature=np.zeros(n), tgrad=np.zeros((3, n)))
-            self.lib.ref_get_temperatures(_dp(out["temperature"]), _dp(out["tgrad"]))
+        # pTemperature always (a start off the stress-free temperature strains the particles also without conduction);
+        # the temperature gradient only exists with the conduction task
+        out.update(temperature=np.zeros(n), tgrad=np.zeros((3, n)))
+        self.lib.ref_get_temperatures(_dp(out["temperature"]), _dp(out["tgrad"]))
+        if not self.lib.ref_conduction_on():
+            del out["tgrad"]
         return out
 
     def multimaterial(self):

@@ -4,6 +4,10 @@
 #include "materials.cuh"
 #include <string.h>
 
+// temperature change handed to the laws (ResidualStrains::dT of the strain update)
+static double g_dT = 0.;
+extern "C" void devlaws_set_dT(double dT) { g_dT = dT; }
+
 // state arrays are [component][n] as in mpmgpu_particles; F is [9][n] row-major components; du is [n][9]
 extern "C" int devlaws_batch(int dim, int np, int kind, int nhist, const double *params, int n,
                              double *F, double *sp, double *pressure, double *eplast, double *energies /* work res heat entropy plast prevT */,
@@ -14,6 +18,7 @@ extern "C" int devlaws_batch(int dim, int np, int kind, int nhist, const double 
     memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
     for (int p = 0; p < n; p++) {
         PState s;
+        s.dT = g_dT;
         for (int i = 0; i < 9; i++) s.F[i] = F[(size_t)i * n + p];
         for (int i = 0; i < 6; i++) { s.sp[i] = sp[(size_t)i * n + p]; s.eplast[i] = eplast[(size_t)i * n + p]; }
         s.pressure = pressure[p];
@@ -40,6 +45,7 @@ extern "C" int devlaws_plain_one(int dim, int np, int kind, const double *params
     m.kind = kind; m.nhist = 0;
     memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
     PState s;
+    s.dT = g_dT;
     for (int i = 0; i < 9; i++) s.F[i] = F[i];
     for (int i = 0; i < 6; i++) { s.sp[i] = sp[i]; s.eplast[i] = eplast[i]; }
     s.pressure = *pressure;

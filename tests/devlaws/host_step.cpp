@@ -45,7 +45,7 @@ struct EmuSim {
     std::vector<int> foff, fieldOfMat, foffR, rcnt;
     std::vector<double> rforce;
     // conduction (capi.cu: ctx->conduction, T)
-    bool conduction = false;
+    bool conduction = false, thermal = false;
     TransportNodes T;
     std::vector<double> tpool, kcond, temps;
 };
@@ -192,8 +192,9 @@ void strain_update(EmuSim *S, double strainTime, bool postUpdate)
         if (!postUpdate || !S->sp.skipPost) xpic_extrapolation(S, 0);
     } else
         EMU_LAUNCH(k_grid_velocity, nblk(S->nvn, 256), 256, S->nvn, S->N);
-    if (S->largeRotation) DISPATCH(k_update_strains_lr, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime);
-    else DISPATCH(k_update_strains, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime);
+    const double dTscale = S->sp.method == METHOD_USAVG ? (postUpdate ? 1.0 - S->sp.fractionUSF : S->sp.fractionUSF) : 1.0;
+    if (S->largeRotation) DISPATCH(k_update_strains_lr, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime, dTscale);
+    else DISPATCH(k_update_strains, S->P.nNR, S->g, S->P, S->N, S->mats.data(), strainTime, dTscale);
 }
 
 // task numbers as in capi.cu: 0 initialization ... 9 reset elements
@@ -246,6 +247,7 @@ void run_task(EmuSim *S, int t)
         if (!S->sp.usingFMPM) m = -m;
         DISPATCH(k_update_particles, S->P.nNR, S->g, S->P, S->N, S->mats.data(), S->sp, m);
         if (S->conduction) DISPATCH(k_update_temperature, S->P.nNR, S->g, S->P, S->mats.data(), S->T, S->sp.dt);
+        else if (S->thermal) EMU_LAUNCH(k_update_temperature_offsets, nblk(S->P.nNR, 256), 256, S->P.nNR, S->P);
         if (S->PR.n > 0) {
             if (S->dim == 3) EMU_LAUNCH(k_move_rigid<3>, nblk(S->PR.n, 128), 128, S->PR, S->sp.dt);
             else EMU_LAUNCH(k_move_rigid<2>, nblk(S->PR.n, 128), 128, S->PR, S->sp.dt);
@@ -387,25 +389,30 @@ extern "C" void emu_set_multimaterial(void *h, int nf, const int *fieldOfMat, in
 }
 
 // capi.cu::mpmgpu_set_conduction + the temperature part of mpmgpu_upload_particles
+// kcond NULL: particle temperatures without conduction (a start off the stress-free temperature)
 extern "C" void emu_set_conduction(void *h, const double *kcond, const double *temperature)
 {
     EmuSim *S = (EmuSim *)h;
-    S->conduction = true;
+    S->conduction = kcond != NULL;
+    S->thermal = true;
     const size_t nn = (size_t)S->g.nnodes;
-    S->tpool.assign(nn * 3, 0.);
-    S->kcond.assign(kcond, kcond + S->mats.size());
-    S->T.gT = S->tpool.data(); S->T.gVCT = S->tpool.data() + nn; S->T.gQ = S->tpool.data() + 2 * nn; S->T.kcond = S->kcond.data();
+    if (kcond) {
+        S->tpool.assign(nn * 3, 0.);
+        S->kcond.assign(kcond, kcond + S->mats.size());
+        S->T.gT = S->tpool.data(); S->T.gVCT = S->tpool.data() + nn; S->T.gQ = S->tpool.data() + 2 * nn; S->T.kcond = S->kcond.data();
+    }
     const size_t C = S->P.n ? (size_t)S->P.n : 1;
-    S->temps.assign(C * 4, 0.);
+    S->temps.assign(C * 5, 0.);
     for (int p = 0; p < S->P.n; p++) S->temps[p] = temperature[p];
     S->P.temp = S->temps.data();
     for (int c = 0; c < 3; c++) S->P.tgrad[c] = S->temps.data() + (size_t)(c + 1) * C;
+    S->P.dTr = S->temps.data() + 4 * C;
 }
 
 extern "C" void emu_get_transport(void *h, double *gT, double *gVCT, double *gQ, double *temperature)
 {
     EmuSim *S = (EmuSim *)h;
-    for (int i = 0; i < S->g.nnodes; i++) { gT[i] = S->T.gT[i]; gVCT[i] = S->T.gVCT[i]; gQ[i] = S->T.gQ[i]; }
+    for (int i = 0; i < S->g.nnodes && S->conduction; i++) { gT[i] = S->T.gT[i]; gVCT[i] = S->T.gVCT[i]; gQ[i] = S->T.gQ[i]; }
     for (int p = 0; p < S->n; p++) temperature[p] = p < S->P.n ? S->P.temp[p] : S->PR.prevT[p - S->P.n];
 }
 

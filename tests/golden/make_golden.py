@@ -179,6 +179,27 @@ CASES = {
                                                      (250.0, 420.0), (900.0, 3000.0), (1200.0, 700.0)), (1, 2, 60), 2),
     "cond3d_blocks_multimaterial": (inputs.conduction(inputs.blocks3d_contact(inputs.multimaterial(2, 0.3), materials=2).replace("<alpha>20</alpha>", "<alpha>0</alpha>"),
                                                       (400.0, 280.0), (5000.0, 1500.0), (600.0, 900.0)), (1, 2, 40), 2),
+    # thermal strains in the laws: conduction with expanding materials, and bodies that start off the stress-free temperature
+    # (one temperature jump handed to the laws by the first particle update) -- every law and analysis type that carries the terms
+    "th2d_cond_iso_planestrain": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=60.0)),
+                                                    (380.0, 290.0), (2000.0, 500.0), (800.0, 1500.0)), (1, 2, 40), 2),
+    "th2d_cond_isoplastic_neo_planestress": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=11, vel=3000.0, vmax=11.0, gap=0.0, alpha=60.0))
+                                                               .replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha>',
+                                                                        '<Material Type="9" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep>')
+                                                               .replace('<Material Type="1" Name="Disk 2"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha>',
+                                                                        '<Material Type="28" Name="Disk 2"><rho>1.5</rho><G>0.4</G><K>1.0</K><alpha>60</alpha>'),
+                                                               (390.0, 280.0), (2000.0, 500.0), (800.0, 1500.0)), (1, 2, 40), 2),
+    "th3d_offset_iso": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-3.0e3, vx=1.0e3, extra_header="<StressFreeTemp>300</StressFreeTemp>")
+                        .replace("<alpha>0</alpha>", "<alpha>80</alpha>").replace('<Body ', '<Body temp="340" ', 1), (1, 2, 40), 2, 0.3, 2000.0),
+    "th3d_offset_isoplastic_usl": (inputs.block3d(ncell=3, margin=3, method=3, material=inputs.isoplastic_material(yld=5.0), vz=-2.0e4,
+                                                  extra_header="<StressFreeTemp>300</StressFreeTemp>").replace('<Body ', '<Body temp="420" ', 1), (1, 2, 40), 2, 0.3, 2000.0),
+    "th3d_offset_neohookean": (inputs.block3d(ncell=3, margin=3, material=inputs.neohookean_material(), vz=-6.0e3, extra_header="<StressFreeTemp>300</StressFreeTemp>")
+                               .replace('<Body ', '<Body temp="260" ', 1), (1, 2, 40), 2, 0.3, 2000.0),
+    "th2d_offset_mooney_iso_planestress": (inputs.oblique_disks(inputs.disks2d(analysis=11, vel=3000.0, vmax=11.0, gap=0.0, alpha=60.0, extra_header="<StressFreeTemp>300</StressFreeTemp>"))
+                                           .replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha></Material>',
+                                                    inputs.mooney_material(0.3, 0.1, 1.0, 1, name="Disk 1", rho=1.5))
+                                           .replace('<Body matname="Disk 1"', '<Body temp="350" matname="Disk 1"').replace('<Body matname="Disk 2"', '<Body temp="270" matname="Disk 2"'),
+                                           (1, 2, 40), 2),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

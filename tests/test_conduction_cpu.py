@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from nairn_mpm_fea_b200.problem import from_reference_dump
-from tests.parity import COND_CASES, check_multimaterial_run, check_multimaterial_tasks, load_golden
+from tests.parity import COND_CASES, THERMAL_COND_CASES, THERMAL_OFFSET_CASES, check_multimaterial_run, check_multimaterial_tasks, load_golden
 from tests.test_device_step_cpu import EmuSim, lib  # noqa: F401
 
 
@@ -31,6 +31,23 @@ def test_device_source_whole_runs_match_reference(lib, case):  # noqa: F811
     t0, t1 = z["p0/temperature"], z["p%d/temperature" % last]
     assert np.max(np.abs(t1 - t0)) > 1.0, "no heat moved"
     assert np.max(np.abs(got["temperature"] - t1)) <= 1e-9 * np.max(np.abs(t1))
+    sim.close()
+
+
+@pytest.mark.parametrize("case", THERMAL_COND_CASES + THERMAL_OFFSET_CASES)
+def test_thermal_strains_match_reference(lib, case):  # noqa: F811
+    """The temperature change of a step reaches the laws as ResidualStrains::dT (scaled per pass in USAVG): IsotropicMat (3D,
+    plane strain, plane stress), IsoPlasticity (3D USL and plane stress, yielding), Neohookean (3D, plane stress) and Mooney
+    (plane stress) with thermal expansion -- under conduction, and after a start off the stress-free temperature without any
+    transport task.  Every task of two steps and the whole run; the residual energy is part of the compared energies."""
+    z = load_golden(case)
+    sim = EmuSim(lib, from_reference_dump(z))
+    check_multimaterial_tasks(sim, z, case, require="transport_value" if case in THERMAL_COND_CASES else "mass")
+    sim.close()
+    sim = EmuSim(lib, from_reference_dump(z))
+    check_multimaterial_run(sim, z, case)
+    last = max(int(k[1:].split("/")[0]) for k in z if k.startswith("p") and k.endswith("/energies"))
+    assert np.max(np.abs(z["p%d/energies" % last][1])) > 0.0, "no residual energy: the case does not exercise thermal strains"
     sim.close()
 
 

@@ -4,7 +4,7 @@ velocity field and with material velocity fields + contact; conservation of heat
 import numpy as np
 import pytest
 
-from tests.parity import COND_CASES, check_multimaterial_run, check_multimaterial_tasks, load_golden
+from tests.parity import COND_CASES, THERMAL_COND_CASES, THERMAL_OFFSET_CASES, check_multimaterial_run, check_multimaterial_tasks, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +32,19 @@ def test_whole_runs(case):
     sim.close()
 
 
+@pytest.mark.parametrize("case", THERMAL_COND_CASES + THERMAL_OFFSET_CASES)
+def test_thermal_strains_match_reference(case):
+    """Thermal strains in the laws (conduction with expanding materials; a start off the stress-free temperature): every task of
+    two steps and the whole run against the reference, residual energy included."""
+    z = load_golden(case)
+    sim, _ = make_sim(z)
+    check_multimaterial_tasks(sim, z, case, require="transport_value" if case in THERMAL_COND_CASES else "mass")
+    sim.close()
+    sim, _ = make_sim(z)
+    check_multimaterial_run(sim, z, case)
+    sim.close()
+
+
 def test_insulated_bodies_keep_their_heat():
     """sum_p mp Cv T_p changes only by round-off: conduction moves heat between particles, the grid update conserves it
     (FLIP update: dT_p = dt sum_i S_ip rate_i, and sum_p mp Cv S_ip = gVCT_i)."""
@@ -53,7 +66,8 @@ def test_refusals():
     from nairn_mpm_fea_b200.problem import from_reference_dump
     z = load_golden("cond2d_disks_usavg")
     prob = from_reference_dump(z)
-    prob.materials[0]["p"][17] = 6.0e-5           # a thermal expansion coefficient: thermal strains are not built
+    prob.materials[0]["p"][17] = 6.0e-5           # thermal expansion on the large-rotation IsotropicMat is the one combination not built
+    prob.materials[0]["p"][7] = 1.0
     with pytest.raises(MpmGpuError, match="thermal expansion"):
         MpmGpu(prob, device=0)
     prob = from_reference_dump(z)

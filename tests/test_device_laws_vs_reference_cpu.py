@@ -37,8 +37,9 @@ sys.path.insert(0, %(root)r)
 import numpy as np
 from oracle import refharness
 from nairn_mpm_fea_b200.problem import from_reference_dump
-xml_path, nsteps, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+xml_path, nsteps, out, law_dT = sys.argv[1], int(sys.argv[2]), sys.argv[3], float(sys.argv[4])
 r = refharness.RefRun(xml_path, 1)
+r.lib.ref_set_law_dT(C.c_double(law_dT))           # the temperature change the law call sees (ResidualStrains::dT)
 r.step(nsteps)
 ids = np.zeros(16, np.int32); params = np.zeros((16, 32))
 nm = r.lib.ref_get_materials(ids.ctypes.data_as(C.POINTER(C.c_int)), params.ctypes.data_as(C.POINTER(C.c_double)))
@@ -60,9 +61,15 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+# temperature change handed to both laws: every material here has <alpha> != 0, so the thermal-strain terms are part of what is
+# compared.  IsotropicMat's large-rotation form is the one law without them on the device (refused with expansion + temperature change).
+LAW_DT = 2.5
+
+
 @pytest.mark.parametrize("analysis", ["3d", "planestrain", "planestress"])
 @pytest.mark.parametrize("law", sorted(MATERIALS))
 def test_device_law_equals_the_references_own_law_on_the_same_input(law, analysis):
+    law_dT = 0.0 if law == "isotropic_lr" else LAW_DT
     from oracle import refharness
     if not refharness.available():
         pytest.skip("oracle/_ref not built")
@@ -79,12 +86,13 @@ def test_device_law_equals_the_references_own_law_on_the_same_input(law, analysi
     d = tempfile.mkdtemp(prefix="lawref_")
     open(os.path.join(d, "in.fmcmd"), "w").write(xml)
     out = os.path.join(d, "law.npz")
-    p = subprocess.run([sys.executable, "-c", _WORKER % dict(root=ROOT), os.path.join(d, "in.fmcmd"), str(nsteps), out], cwd=d, capture_output=True, text=True)
+    p = subprocess.run([sys.executable, "-c", _WORKER % dict(root=ROOT), os.path.join(d, "in.fmcmd"), str(nsteps), out, repr(law_dT)], cwd=d, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-1500:]
     z = dict(np.load(out))
     if not os.path.exists(LIBDEV):
         pytest.skip("tests/devlaws not built (run tests/test_device_laws_cpu.py first)")
     dev = C.CDLL(LIBDEV)
+    dev.devlaws_set_dT(C.c_double(law_dT))
     prob = from_reference_dump({"mat_ids": z["mat_ids"], "mat_params": z["mat_params"], **_fake_dump(z)})
     np_, dt, nNR = int(z["np_"]), float(z["dt"]), int(z["nNR"])
     checked = 0

@@ -22,7 +22,7 @@ DEV = os.path.join(HERE, "devlaws")
 LIB = os.path.join(DEV, "_build", "libdevstep.so")
 
 # (the multimaterial goldens mm* and the conduction goldens cond* have their own checks: tests/test_multimaterial_cpu.py, tests/test_conduction_cpu.py)
-CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and not f.startswith(("mm", "cond")))
+CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and not f.startswith(("mm", "cond", "th")))
 TASK_INDEX = {"initialization": 0, "mass_and_momentum": 1, "post_extrapolation": 2, "update_strains_first": 3, "grid_forces": 4,
               "post_forces": 5, "update_momenta": 6, "update_particles": 7, "update_strains_last": 8, "reset_elements": 9,
               "project_rigid_bcs": 10}
@@ -95,9 +95,13 @@ class EmuSim:
         self.n_fields = 0
         self.conduction = getattr(prob, "conduction", None) is not None
         self.real_nodes = self.nnodes
+        self.thermal = self.conduction or pt.get("temperature") is not None
         if self.conduction:
             self._cond = [c(prob.conduction["kcond"], dtype=np.float64), c(pt["temperature"], dtype=np.float64)]
             lib.emu_set_conduction(self.h, _dp(self._cond[0]), _dp(self._cond[1]))
+        elif self.thermal:
+            self._cond = [c(pt["temperature"], dtype=np.float64)]
+            lib.emu_set_conduction(self.h, None, _dp(self._cond[0]))
         mm = getattr(prob, "multimaterial", None)
         if mm is not None:
             nf = int(mm["n_fields"])
@@ -125,7 +129,7 @@ class EmuSim:
                  in_elem=np.zeros(n, np.int32), crossings=np.zeros(n, np.int32))
         self.lib.emu_get_particles(self.h, _dp(o["pos"]), _dp(o["vel"]), _dp(o["sp"]), _dp(o["pressure"]), _dp(o["ep"]), _dp(o["wrot"]),
                                    _dp(o["eplast"]), _dp(o["energies"]), _dp(o["history"]), _dp(o["acc"]), _ip(o["in_elem"]), _ip(o["crossings"]))
-        if self.conduction:
+        if self.thermal:
             o["temperature"] = np.zeros(n)
             t = [np.zeros(self.real_nodes) for _ in range(3)]
             self.lib.emu_get_transport(self.h, _dp(t[0]), _dp(t[1]), _dp(t[2]), _dp(o["temperature"]))

@@ -56,9 +56,14 @@ CASES = {
                                                                extra_header=inputs.multimaterial(0, 0.3, None, ' RigidBias="10"')))
                                     .replace("<SetDirection>8</SetDirection>", "<SetDirection>8</SetDirection><SettingFunction>-2000*(1+0.3*sin(20*t))</SettingFunction>"
                                                                                "<SettingFunction2>700</SettingFunction2>"), None, "res/disks."),
+    # a block that starts 60 K above its stress-free temperature (thermal expansion, no transport task) and yields
+    "block3d_thermal_offset_isoplastic": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, material=inputs.isoplastic_material(yld=5.0), vz=-2.0e4,
+                                                         extra_header="<StressFreeTemp>300</StressFreeTemp>").replace('<Body ', '<Body temp="360" ', 1)
+                                          .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+                                          .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYYNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
     # heat conduction between two disks of different temperature, conductivity and heat capacity; the archives carry the
     # particle temperature
-    "disks2d_conduction": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=0.0, maxtime=0.6, archive_ms=0.15)),
+    "disks2d_conduction": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=60.0, maxtime=0.6, archive_ms=0.15)),
                                              (380.0, 290.0), (2000.0, 500.0), (800.0, 1500.0))
                            .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/disks."),
     # config 4 family: IsoPlasticity bar on a plate of rigid-BC particles
