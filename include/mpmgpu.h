@@ -169,7 +169,10 @@ typedef struct mpmgpu_particles {
                                    particles and downloads come back in DEVICE order with ids filled in;
                                    when NULL particles are identified by their upload index and downloads come
                                    back in upload order. */
-    double *temperature;/* [n]     MPMBase::pTemperature; used with conduction only (mpmgpu_set_conduction); NULL on upload = energies[5] */
+    double *temperature;/* [n]     MPMBase::pTemperature.  Upload: give it with conduction (mpmgpu_set_conduction) and whenever particles start
+                                   off the temperature of their last strain update (energies[5]): the first particle update then hands the
+                                   laws dT = temperature - energies[5] (thermal strains, UpdateParticlesTask.cpp:246-251).  NULL = energies[5].
+                                   Giving it switches the run to the per-task kernels. */
 } mpmgpu_particles;
 
 /* download masks */
@@ -183,7 +186,7 @@ typedef struct mpmgpu_particles {
 #define MPMGPU_F_ELEM     0x080   /* in_elem + crossings */
 #define MPMGPU_F_ACC      0x100
 #define MPMGPU_F_ALL      0x1ff
-#define MPMGPU_F_TEMPERATURE 0x200 /* pTemperature (conduction only; not part of MPMGPU_F_ALL) */
+#define MPMGPU_F_TEMPERATURE 0x200 /* pTemperature (runs that uploaded temperatures or use conduction; not part of MPMGPU_F_ALL) */
 
 /* Host view of the node accumulators (debug / global quantities / parity tests).
  * Arrays are nnodes long (vectors [3][nnodes]), reference node order; NULL = skip. */
@@ -246,9 +249,10 @@ int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm);
  * temperature, heat energy and entropy of the conducted heat; the laws see the grid-extrapolated temperature as their
  * previous temperature.  kcond[m] = conductivity / rho of material m in the host's units (TransportProperties::kCondTensor,
  * isotropic: MaterialBaseMPM.cpp:320-326; ignored for rigid-BC materials).  Built: isothermal energy mode, insulated boundaries,
- * any number of materials (also in multimaterial mode: transport values live on the node, not on a velocity field).  Refused:
- * materials with thermal expansion (the device laws carry no residual strains), XPIC/FMPM order > 1, slab mode; temperature and
- * heat-flux BCs, adiabatic coupling and contact heating are the adapter's to refuse.  Per-task kernels.  Call after
+ * any number of materials (also in multimaterial mode: transport values live on the node, not on a velocity field), thermal
+ * expansion (the temperature change of a step reaches the laws as ResidualStrains::dT).  Refused: thermal expansion on the
+ * large-rotation IsotropicMat, XPIC/FMPM order > 1, slab mode; temperature and heat-flux BCs, adiabatic coupling and contact
+ * heating are the adapter's to refuse.  Per-task kernels.  Call after
  * mpmgpu_set_materials and before mpmgpu_upload_particles. */
 int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kcond);
 int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
