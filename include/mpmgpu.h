@@ -249,12 +249,19 @@ int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm);
  * temperature, heat energy and entropy of the conducted heat; the laws see the grid-extrapolated temperature as their
  * previous temperature.  kcond[m] = conductivity / rho of material m in the host's units (TransportProperties::kCondTensor,
  * isotropic: MaterialBaseMPM.cpp:320-326; ignored for rigid-BC materials).  Built: isothermal energy mode, insulated boundaries,
- * any number of materials (also in multimaterial mode: transport values live on the node, not on a velocity field), thermal
- * expansion (the temperature change of a step reaches the laws as ResidualStrains::dT).  Refused: thermal expansion on the
- * large-rotation IsotropicMat, XPIC/FMPM order > 1, slab mode; temperature and heat-flux BCs, adiabatic coupling and contact
- * heating are the adapter's to refuse.  Per-task kernels.  Call after
+ * any number of materials (also in multimaterial mode: transport values live on the node, not on a velocity field), nodal
+ * temperature BCs (mpmgpu_set_temperature_bcs), thermal expansion (the temperature change of a step reaches the laws as ResidualStrains::dT).  Refused: thermal expansion on the
+ * large-rotation IsotropicMat, XPIC/FMPM order > 1, slab mode; heat-flux BCs, adiabatic coupling and contact heating are the
+ * adapter's to refuse.  Per-task kernels.  Call after
  * mpmgpu_set_materials and before mpmgpu_upload_particles. */
 int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kcond);
+/* Nodal temperature BCs (NodalTempBC list, firstTempBC ...; <TempBC> in <GridBCs>) in the host's list order: node[i] 1-based,
+ * value[i] = BCValue at this step's time, active[i] = GetNodeNum(time) != 0 (NULL: all active).  Before the temperature gradients
+ * are taken the BC nodes hold the sum of their BC values and get their own value back afterwards (TransportTask::ImposeValueBCs /
+ * RestoreValueBCs, TransportTask.cpp:167-222); after the grid update the nodal value becomes that sum and the rate what takes it
+ * there (ImposeValueGridBCs :316-404).  The heat the BCs feed in (NodalValueBC::qreaction, a global-quantity input) is not
+ * tracked.  Call after mpmgpu_set_conduction; call again whenever values change. */
+int mpmgpu_set_temperature_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *value, const int *active);
 int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
 /* timestep, strainTimestepFirst, strainTimestepLast (NairnMPM.cpp:1207-1240) */
 int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dt_strain_first, double dt_strain_last);

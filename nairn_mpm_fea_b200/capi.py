@@ -26,7 +26,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
-           "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
+           "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_set_temperature_bcs", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
@@ -112,6 +112,7 @@ def load_library(path=None):
     lib.mpmgpu_upload_particles.argtypes = [vp, C.POINTER(ParticlesView)]
     lib.mpmgpu_set_multimaterial.argtypes = [vp, C.POINTER(MultiMaterial)]
     lib.mpmgpu_set_conduction.argtypes = [vp, C.c_int, _dp]
+    lib.mpmgpu_set_temperature_bcs.argtypes = [vp, C.c_int, _ip, _dp, _ip]
     lib.mpmgpu_set_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.mpmgpu_set_xpic.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
@@ -229,6 +230,8 @@ class MpmGpu:
         if self.conduction:
             k = _c64(prob.conduction["kcond"])
             self._check(self.lib.mpmgpu_set_conduction(self.ctx, len(prob.materials), _d(k)))
+            if prob.conduction.get("tbc_node") is not None:
+                self.set_temperature_bcs(prob.conduction["tbc_node"], prob.conduction["tbc_value"])
         self.set_velocity_bcs(prob.bc_node, prob.bc_norm, prob.bc_value, prob.bc_active, prob.bc_symdir)
         if getattr(prob, "bc_reflected", None) is not None:
             self.set_velocity_bc_reflections(prob.bc_reflected, prob.bc_ratio)
@@ -288,6 +291,11 @@ class MpmGpu:
         self._check(self.lib.mpmgpu_set_multimaterial(self.ctx, C.byref(v)))
         self.nnodes = self.prob.nnodes * nf          # node arrays are field-major from now on
         self.n_fields = nf
+
+    def set_temperature_bcs(self, node, value, active=None):
+        """Nodal temperature BCs in list order (1-based nodes, values at this step's time); call again when values change."""
+        node, value, active = _c32(node), _c64(value), _c32(active)
+        self._check(self.lib.mpmgpu_set_temperature_bcs(self.ctx, 0 if node is None else len(node), _i(node), _d(value), _i(active)))
 
     def set_velocity_bcs(self, node, norm, value, active=None, symdir=None):
         n = 0 if node is None else len(node)

@@ -96,6 +96,10 @@ struct mpmgpu_ctx {
     bool thermal = false;               // particle temperatures can change (conduction, or a start off the stress-free temperature): the laws get dT
     TransportNodes T;
     double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
+    TempBCs Q;                          // nodal temperature BCs (mpmgpu_set_temperature_bcs)
+    int tbcEntries = 0, tbcCap = 0;
+    std::vector<int> tbcOrder;          // entry e on device = host list index tbcOrder[e]
+    int *dTbcNode = NULL, *dTbcStart = NULL, *dTbcActive = NULL; double *dTbcValue = NULL, *dTbcSaved = NULL;
     // CUDA graphs of one whole step (mpmgpu_step): keyed by a byte signature of everything the step's launches capture by value
     // (particle / node / BC structs with their device pointers, step parameters, mode flags); a setter that changes any of it,
     // or a physical sort that swaps the particle pools, simply selects or creates another graph.  MPMGPU_GRAPHS=0 switches it off.
@@ -217,7 +221,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->nBCEntries = 0;
     memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R);
     ctx->rigidPool = NULL; ctx->rigidIntPool = NULL; ctx->rigidCap = 0;
-    memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B); memset(&ctx->C, 0, sizeof ctx->C); memset(&ctx->cp, 0, sizeof ctx->cp); memset(&ctx->T, 0, sizeof ctx->T);
+    memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B); memset(&ctx->C, 0, sizeof ctx->C); memset(&ctx->cp, 0, sizeof ctx->cp); memset(&ctx->T, 0, sizeof ctx->T); memset(&ctx->Q, 0, sizeof ctx->Q);
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
     memset(&ctx->hFlags, 0, sizeof ctx->hFlags);
     tiled_state_init(ctx->tiled);
@@ -432,6 +436,43 @@ extern "C" int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kc
     CK(cudaMemcpy(ctx->dKcond, kcond, nmat * sizeof(double), cudaMemcpyHostToDevice));
     ctx->T.kcond = ctx->dKcond;
     ctx->conduction = true;
+    return MPMGPU_OK;
+}
+
+// Nodal temperature BCs in the host's list order (firstTempBC ...): node[i] 1-based, value[i] = BCValue at this step's time,
+// active[i] = GetNodeNum(time) != 0.  Call again (same or another list) whenever values change.
+extern "C" int mpmgpu_set_temperature_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *value, const int *active)
+{
+    if (!ctx || n < 0 || (n > 0 && (!node || !value))) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_temperature_bcs: bad arguments");
+    if (!ctx->conduction) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_temperature_bcs: call mpmgpu_set_conduction first");
+    cudaSetDevice(ctx->cfg.device);
+    if (n == 0) { ctx->Q.nUnique = 0; ctx->tbcEntries = 0; return MPMGPU_OK; }
+    for (int i = 0; i < n; i++)
+        if (node[i] < 1 || node[i] > ctx->g.nnodes) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_temperature_bcs: BC %d on node %d of %d", i, node[i], ctx->g.nnodes);
+    // group by node, list order kept inside a node (the reference walks its list: zero all, then add all)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return node[a] < node[b]; });
+    std::vector<int> un, st, ac(n); std::vector<double> va(n);
+    for (int e = 0; e < n; e++) {
+        const int i = order[e];
+        if (e == 0 || node[i] != node[order[e - 1]]) { un.push_back(node[i] - 1); st.push_back(e); }
+        va[e] = value[i]; ac[e] = active ? active[i] : 1;
+    }
+    st.push_back(n);
+    if (n > ctx->tbcCap) {
+        CK(dalloc(ctx, &ctx->dTbcNode, (size_t)n)); CK(dalloc(ctx, &ctx->dTbcStart, (size_t)n + 1)); CK(dalloc(ctx, &ctx->dTbcActive, (size_t)n));
+        CK(dalloc(ctx, &ctx->dTbcValue, (size_t)n)); CK(dalloc(ctx, &ctx->dTbcSaved, (size_t)n));
+        ctx->tbcCap = n;
+    }
+    CK(cudaMemcpyAsync(ctx->dTbcNode, un.data(), un.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTbcStart, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTbcActive, ac.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTbcValue, va.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->Q.nUnique = (int)un.size(); ctx->Q.node = ctx->dTbcNode; ctx->Q.start = ctx->dTbcStart; ctx->Q.value = ctx->dTbcValue;
+    ctx->Q.active = ctx->dTbcActive; ctx->Q.saved = ctx->dTbcSaved;
+    ctx->tbcEntries = n;
     return MPMGPU_OK;
 }
 
@@ -1083,6 +1124,8 @@ static int t_initialization(mpmgpu_ctx *ctx)
 {
     const Grid &g = ctx->g;
     (void)g;
+    // (before the point counts of the previous step are cleared: the transport field is zeroed on the nodes that were active)
+    if (ctx->conduction) LAUNCH(k_transport_zero_active, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->nf, ctx->N, ctx->T);
     size_t nnPad = ctx->nodePad;
     // MatVelocityField::Zero: mass, pk, ftot, vk[0], vk[pkCopy] (+XPIC vectors), numberPoints
     CK(cudaMemsetAsync(ctx->nodePool, 0, nnPad * 22 * sizeof(double), ctx->stream));
@@ -1093,9 +1136,7 @@ static int t_initialization(mpmgpu_ctx *ctx)
         CK(cudaMemsetAsync(ctx->C.rcnt, 0, nnPad * sizeof(int), ctx->stream));
         ctx->launches += 2;
     }
-    if (ctx->conduction) {      // TransportField zeroed with the node (NodalPoint::InitializeForTimeStep)
-        CK(cudaMemsetAsync(ctx->transportPool, 0, (((size_t)ctx->g.nnodes + 31) & ~(size_t)31) * 3 * sizeof(double), ctx->stream)); ctx->launches++;
-    }
+
     DISPATCH_DIM_SHAPE(k_init_particles, ctx->P.n, ctx->g, ctx->P, ctx->dFlags);
     return MPMGPU_OK;
 }
@@ -1116,7 +1157,9 @@ static int t_post_extrapolation(mpmgpu_ctx *ctx)
     { int rc = apply_bcs(ctx, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2); if (rc) return rc; }
     if (ctx->conduction) {      // TransportTask::GetTransportValues + TransportBCsAndGradients (PostExtrapolationTask.cpp:88,160)
         LAUNCH(k_transport_nodal_value, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->nf, ctx->N, ctx->T);
+        if (ctx->Q.nUnique > 0) LAUNCH(k_temp_bcs_impose, nblocks(ctx->Q.nUnique, 128), 128, ctx->Q, ctx->T, 0);
         DISPATCH_DIM_SHAPE(k_transport_gradients, ctx->P.nNR, ctx->g, ctx->P, ctx->T);
+        if (ctx->Q.nUnique > 0) LAUNCH(k_temp_bcs_impose, nblocks(ctx->Q.nUnique, 128), 128, ctx->Q, ctx->T, 1);
     }
     return MPMGPU_OK;
 }
@@ -1173,7 +1216,9 @@ static int t_update_momenta(mpmgpu_ctx *ctx)
     LAUNCH(k_update_momenta, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N, ctx->sp.dt);
     if (ctx->conduction) LAUNCH(k_transport_update, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->nf, ctx->N, ctx->T, ctx->sp.dt);    // UpdateMomentaTask.cpp:55
     { int rc = material_contact(ctx, CALL_UPDATE_MOMENTUM); if (rc) return rc; }
-    if (ctx->sp.xpicOrder <= 1) return apply_bcs(ctx, PASS_UPDATE_MOMENTUM, 0);      // NodalVelBC.cpp:367-375
+    if (ctx->sp.xpicOrder <= 1) { int rc = apply_bcs(ctx, PASS_UPDATE_MOMENTUM, 0); if (rc) return rc; }      // NodalVelBC.cpp:367-375
+    // TransportTask::TransportGridBCs (UpdateMomentaTask.cpp:61)
+    if (ctx->conduction && ctx->Q.nUnique > 0) LAUNCH(k_temp_bcs_grid, nblocks(ctx->Q.nUnique, 128), 128, ctx->Q, ctx->T, ctx->sp.dt);
     return MPMGPU_OK;
 }
 
@@ -1546,8 +1591,8 @@ static void step_signature(const mpmgpu_ctx *ctx, std::string &sig)
     auto add = [&](const void *p, size_t n) { sig.append((const char *)p, n); };
     add(&ctx->g, sizeof ctx->g); add(&ctx->P, sizeof ctx->P); add(&ctx->PR, sizeof ctx->PR); add(&ctx->N, sizeof ctx->N);
     add(&ctx->B, sizeof ctx->B); add(&ctx->R, sizeof ctx->R); add(&ctx->sp, sizeof ctx->sp); add(&ctx->tiled.FN, sizeof ctx->tiled.FN);
-    add(&ctx->C, sizeof ctx->C); add(&ctx->cp, sizeof ctx->cp); add(&ctx->T, sizeof ctx->T);
-    const long long misc[16] = {ctx->tiled.enabled, ctx->tiled.stateKind, ctx->tiled.usePipe, ctx->hasFext, ctx->hasBCs, ctx->largeRotation, ctx->multimaterial,
+    add(&ctx->C, sizeof ctx->C); add(&ctx->cp, sizeof ctx->cp); add(&ctx->T, sizeof ctx->T); add(&ctx->Q, sizeof ctx->Q);
+    const long long misc[17] = {ctx->thermal, ctx->tiled.enabled, ctx->tiled.stateKind, ctx->tiled.usePipe, ctx->hasFext, ctx->hasBCs, ctx->largeRotation, ctx->multimaterial,
                                 ctx->conduction, ctx->nf, ctx->nvn, ctx->cpdiMerge, ctx->cpdiMergeValues, (long long)(size_t)ctx->dMats, (long long)(size_t)ctx->archOrigin,
                                 (long long)(size_t)ctx->nodePool, (long long)(size_t)ctx->stream};
     add(misc, sizeof misc);

@@ -1123,6 +1123,18 @@ __device__ __forceinline__ bool node_has_particles(const Nodes &N, int i, int nn
     return false;
 }
 
+// task 1: the reference zeroes the transport field of the nodes on its ACTIVE list only -- the nodes that had particles in the
+// previous step (InitializationTask.cpp:52-56 -> NodalPoint::InitializeForTimeStep).  A temperature-BC node without particles
+// therefore keeps the value and rate its BC wrote (ImposeValueGridBCs runs on every BC node), and when particles reach it later
+// the extrapolation starts from those stale numbers.  Kept: it is what the reference computes.  N.cnt still holds the previous
+// step's point counts when this runs.
+__global__ void k_transport_zero_active(int nnodes, int nf, Nodes N, TransportNodes T)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes || !node_has_particles(N, i, nnodes, nf)) return;
+    T.gT[i] = 0.; T.gVCT[i] = 0.; T.gQ[i] = 0.;
+}
+
 // task 3: TransportTask::GetTransportNodalValue (TransportTask.cpp:152-161)
 __global__ void k_transport_nodal_value(int nnodes, int nf, Nodes N, TransportNodes T)
 {
@@ -1144,6 +1156,40 @@ __global__ void __launch_bounds__(TASK_THREADS) k_transport_gradients(Grid g, Pa
         if (DIM == 3) tg[2] += gz * Ti;
     });
     P.tgrad[0][p] = tg[0]; P.tgrad[1][p] = tg[1]; P.tgrad[2][p] = tg[2];
+}
+
+// task 3: TransportTask::ImposeValueBCs(copyFirst) before the gradients and RestoreValueBCs after them (TransportTask.cpp:167-222,
+// called from TransportBCsAndGradients :550-565): on a node with active temperature BCs the gradients see the sum of the BC values
+__global__ void k_temp_bcs_impose(TempBCs Q, TransportNodes T, int restore)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= Q.nUnique) return;
+    const int nd = Q.node[u];
+    bool any = false;
+    double sum = 0.;
+    for (int e = Q.start[u]; e < Q.start[u + 1]; e++) if (Q.active[e]) { any = true; sum += Q.value[e]; }
+    if (!any) return;
+    if (restore) T.gT[nd] = Q.saved[u];
+    else { Q.saved[u] = T.gT[nd]; T.gT[nd] = sum; }
+}
+
+// task 7: TransportTask::ImposeValueGridBCs in the momentum update (TransportTask.cpp:316-404): the nodal value becomes the sum of
+// the BC values and the rate what takes it there, so that the particles' FLIP update sees a consistent pair
+__global__ void k_temp_bcs_grid(TempBCs Q, TransportNodes T, double dt)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= Q.nUnique) return;
+    const int nd = Q.node[u];
+    bool first = true;
+    double gT = T.gT[nd], gQ = T.gQ[nd];
+    for (int e = Q.start[u]; e < Q.start[u + 1]; e++) {
+        if (!Q.active[e]) continue;
+        if (first) { gQ += -gT / dt; gT = 0.; first = false; }
+        const double bcT = Q.value[e];
+        gT += bcT;
+        gQ += bcT / dt;
+    }
+    if (!first) { T.gT[nd] = gT; T.gQ[nd] = gQ; }
 }
 
 // task 5: ConductionTask::AddForces -> MatPoint3D::FCond / MatPoint2D::FCond (MatPoint3D.cpp:280-287, MatPoint2D.cpp:272-278)

@@ -118,6 +118,16 @@ struct TransportNodes {
     const double *kcond;     // [nmat] conductivity / rho of every material (TransportProperties::kCondTensor, isotropic)
 };
 
+// nodal temperature BCs (NodalTempBC list), grouped by node; entries keep the host's list order inside a node
+struct TempBCs {
+    int nUnique;
+    const int *node;         // [nUnique] 0-based node
+    const int *start;        // [nUnique+1] range into value/active
+    const double *value;     // [nEntries] BCValue at this step's time
+    const int *active;       // [nEntries] GetNodeNum(time) != 0
+    double *saved;           // [nUnique] the no-BC nodal value between ImposeValueBCs and RestoreValueBCs
+};
+
 struct ContactParams {
     int nf;                  // material velocity fields per node (maxMaterialFields)
     int normalMethod;        // mpmgrid.materialNormalMethod (0..4)

@@ -82,6 +82,8 @@ long long gLeftGridWarned = 0;     // first-time grid leavers already handed to 
 bool gCustomTasksReadParticles = false;     // (the only custom task the adapter admits, PeriodicXPIC, touches bodyFrc alone)
 std::vector<int> gLoadPts;          // particles with load BCs (MatPtLoadBC), 0-based, each once
 bool gLoadsSent = false;
+std::vector<NodalTempBC *> gTempBCs;    // nodal temperature BCs in list order (conduction)
+bool gTempBCsVary = false, gTempBCsSent = false;
 bool gThermal = false;              // particle temperatures live on the device (conduction, or a start off the stress-free temperature)
 bool gFusedStep = false;            // -fused: the whole step runs in the first task (mpmgpu_step, fused kernels); the other tasks are empty
 
@@ -337,6 +339,19 @@ class GpuTask : public MPMTask
         for (size_t i = 0; i < gBCs.size(); i++) { a[i] = gBCs[i]->GetNodeNum(mtime) > 0; v[i] = a[i] ? gBCs[i]->BCValue(mtime) : 0.; }
         each_ctx([&](mpmgpu_ctx *c) { return mpmgpu_update_velocity_bc_values(c, (int)v.size(), v.data(), a.data()); }, "GpuTask(BC values)");
     }
+    // nodal temperature BCs at this step's time (TransportTask::ImposeValueBCs / ImposeValueGridBCs read BCValue(mtime))
+    void UpdateTemperatureBCs(void)
+    {
+        if (gTempBCs.empty() || (gTempBCsSent && !gTempBCsVary)) return;
+        std::vector<int> node(gTempBCs.size()), act(gTempBCs.size()); std::vector<double> val(gTempBCs.size());
+        for (size_t i = 0; i < gTempBCs.size(); i++) {
+            node[i] = gTempBCs[i]->GetNodeNum();
+            act[i] = gTempBCs[i]->GetNodeNum(mtime) != 0 ? 1 : 0;
+            val[i] = act[i] ? gTempBCs[i]->BCValue(mtime) : 0.;
+        }
+        check(mpmgpu_set_temperature_bcs(gCtx, (int)node.size(), node.data(), val.data(), act.data()), "GpuTask(temperature BCs)");
+        gTempBCsSent = true;
+    }
     // MatPtLoadBC::SetParticleFext (InitializationTask.cpp:91) by the reference's own BC objects on mpm[]->pFext; the forces of the
     // loaded particles go to the device
     void UpdateParticleLoads(void)
@@ -395,6 +410,7 @@ class GpuTask : public MPMTask
                 UpdateBCValues();
                 UpdateRigidVelocities();
                 UpdateParticleLoads();
+                UpdateTemperatureBCs();
                 if (!gSlabs.empty()) {
                     // every slab steps at the same time: the halo and migrant exchanges inside mpmgpu_slab_step are NCCL calls that
                     // wait for the neighbours
@@ -415,6 +431,7 @@ class GpuTask : public MPMTask
             // the PeriodicXPIC custom task changes the order between steps (Custom_Tasks/PeriodicXPIC.cpp:161-240)
             check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(Initialize)");
             UpdateParticleLoads();
+            UpdateTemperatureBCs();
             if (nmpmsRC != nmpmsRB) UpdateRigidVelocities();        // rigid contact particles: SetRigidContactVelTask runs before the extrapolation
             check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)");
             break;
@@ -484,7 +501,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         // heat conduction runs on the device (mpmgpu_set_conduction); every other transport task and every option of the
         // conduction task the device does not have stays refused
         if (transportTasks != conduction || conduction->GetNextTransportTask() != NULL) return "transport tasks other than conduction (diffusion, poroelasticity, ...)";
-        if (firstTempBC != NULL || firstRigidTempBC != NULL) return "nodal temperature BCs";
+        if (firstRigidTempBC != NULL) return "temperature BCs set by rigid particles";
         if (firstHeatFluxPt != NULL) return "particle heat-flux BCs";
         if (ConductionTask::crackTipHeating || ConductionTask::crackContactHeating || ConductionTask::matContactHeating) return "crack-tip or contact heating";
         if (TransportTask::hasXPICOption) return "XPIC/FMPM options for transport tasks";
@@ -840,6 +857,11 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         for (size_t r = 0; r < gSlabs.size(); r++) if (rcs[r] != MPMGPU_OK) return mpmgpu_last_error(gSlabs[r]);
     }
 
+    if (ConductionTask::active)
+        for (NodalTempBC *bc = firstTempBC; bc != NULL; bc = (NodalTempBC *)bc->GetNextObject()) {
+            gTempBCs.push_back(bc);
+            if (bc->style != CONSTANT_VALUE || bc->GetBCFirstTime() > 0.) gTempBCsVary = true;
+        }
     // swap the CPU task objects for GPU ones, keeping order and names (custom-task runner stays)
     MPMTask *prev = NULL;
     for (MPMTask *t = firstMPMTask; t != NULL;) {

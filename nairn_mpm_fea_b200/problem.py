@@ -349,10 +349,13 @@ def from_reference_dump(z, snapshot="p0"):
     if np.any(z[s + "/pFext"] != 0.0):
         pr.particles["pfext"] = z[s + "/pFext"]
     if "conduction/kcond" in z:
-        for k in ("adiabatic", "n_temp_bcs", "n_flux_bcs", "contact_heating"):
+        for k in ("adiabatic", "n_flux_bcs", "contact_heating"):
             if int(z["conduction/" + k]):
                 raise NotImplementedError("conduction with " + k)
         pr.conduction = dict(kcond=np.asarray(z["conduction/kcond"], float))
+        if "conduction/tbc_node" in z:      # nodal temperature BCs (constant values in the goldens; a host re-evaluates others every step)
+            pr.conduction["tbc_node"] = np.asarray(z["conduction/tbc_node"], np.int32)
+            pr.conduction["tbc_value"] = np.asarray(z["conduction/tbc_value"], float)
         pr.particles["temperature"] = np.asarray(z[s + "/temperature"], float)
     elif (s + "/temperature") in z and np.any(np.asarray(z[s + "/temperature"]) != np.asarray(z[s + "/energies"])[5]):
         # no transport task, but particles that start off the temperature of their last strain update: the first particle

@@ -365,6 +365,17 @@ void ref_get_conduction(int *out, double *kcond)
 
 int ref_conduction_on(void) { return ConductionTask::active ? 1 : 0; }
 
+// nodal temperature BCs in list order: node (1-based, 0 when not active at mtime) and value at mtime
+int ref_get_temp_bcs(int *node, double *value)
+{
+    int n = 0;
+    for (NodalTempBC *b = firstTempBC; b != NULL; b = (NodalTempBC *)b->GetNextObject()) {
+        if (node) { node[n] = b->GetNodeNum(); value[n] = b->GetNodeNum(mtime) != 0 ? b->BCValue(mtime) : 0.; }
+        n++;
+    }
+    return n;
+}
+
 // pTemperature [n] and the particle's temperature gradient of the step [3][n]
 void ref_get_temperatures(double *T, double *grad)
 {

@@ -123,7 +123,12 @@ class RefRun:
         self.lib.ref_get_conduction(_ip(out), _dp(k))
         if not out[0]:
             return None
-        return dict(kcond=k, adiabatic=int(out[1]), n_temp_bcs=int(out[2]), n_flux_bcs=int(out[3]), contact_heating=int(out[4]))
+        d = dict(kcond=k, adiabatic=int(out[1]), n_temp_bcs=int(out[2]), n_flux_bcs=int(out[3]), contact_heating=int(out[4]))
+        nb = self.lib.ref_get_temp_bcs(None, None)
+        if nb:
+            d["tbc_node"], d["tbc_value"] = np.zeros(nb, np.int32), np.zeros(nb)
+            self.lib.ref_get_temp_bcs(_ip(d["tbc_node"]), _dp(d["tbc_value"]))
+        return d
 
     def _transport(self, o):
         if self.lib.ref_conduction_on():

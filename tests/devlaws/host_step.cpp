@@ -48,6 +48,8 @@ struct EmuSim {
     bool conduction = false, thermal = false;
     TransportNodes T;
     std::vector<double> tpool, kcond, temps;
+    TempBCs Q;
+    std::vector<int> tbcNode, tbcStart, tbcActive; std::vector<double> tbcValue, tbcSaved;
 };
 
 struct HostArrays {
@@ -203,10 +205,10 @@ void run_task(EmuSim *S, int t)
     const int nn = S->nvn;
     switch (t) {
     case 0:
+        if (S->conduction) EMU_LAUNCH(k_transport_zero_active, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->nf, S->N, S->T);
         std::fill(S->npool.begin(), S->npool.end(), 0.);
         std::fill(S->ncnt.begin(), S->ncnt.end(), 0);
         std::fill(S->cpool.begin(), S->cpool.end(), 0.);
-        std::fill(S->tpool.begin(), S->tpool.end(), 0.);
         std::fill(S->rcnt.begin(), S->rcnt.end(), 0);
         DISPATCH(k_init_particles, S->P.n, S->g, S->P, &S->flags);
         break;
@@ -222,7 +224,9 @@ void run_task(EmuSim *S, int t)
         apply_bcs(S, PASS_MASS_MOMENTUM, hasUSF ? 1 : 2);
         if (S->conduction) {
             EMU_LAUNCH(k_transport_nodal_value, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->nf, S->N, S->T);
+            if (S->Q.nUnique > 0) EMU_LAUNCH(k_temp_bcs_impose, nblk(S->Q.nUnique, 128), 128, S->Q, S->T, 0);
             DISPATCH(k_transport_gradients, S->P.nNR, S->g, S->P, S->T);
+            if (S->Q.nUnique > 0) EMU_LAUNCH(k_temp_bcs_impose, nblk(S->Q.nUnique, 128), 128, S->Q, S->T, 1);
         }
         break;
     }
@@ -239,6 +243,7 @@ void run_task(EmuSim *S, int t)
         if (S->conduction) EMU_LAUNCH(k_transport_update, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->nf, S->N, S->T, S->sp.dt);
         material_contact(S, CALL_UPDATE_MOMENTUM);
         if (S->sp.xpicOrder <= 1) apply_bcs(S, PASS_UPDATE_MOMENTUM, 0);
+        if (S->conduction && S->Q.nUnique > 0) EMU_LAUNCH(k_temp_bcs_grid, nblk(S->Q.nUnique, 128), 128, S->Q, S->T, S->sp.dt);
         break;
     case 7: {
         if (S->sp.xpicOrder > 1) xpic_extrapolation(S, 1);
@@ -347,7 +352,7 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     R.mat = S->PR.mat; R.mats = S->mats.data();
     R.stride[0] = 1; R.stride[1] = g.yplane; R.stride[2] = g.zplane; R.nnodes = g.nnodes;
     bind_nodes(S, (size_t)g.nnodes);
-    memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp);
+    memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp); memset(&S->Q, 0, sizeof S->Q);
     return S;
 }
 
@@ -407,6 +412,24 @@ extern "C" void emu_set_conduction(void *h, const double *kcond, const double *t
     S->P.temp = S->temps.data();
     for (int c = 0; c < 3; c++) S->P.tgrad[c] = S->temps.data() + (size_t)(c + 1) * C;
     S->P.dTr = S->temps.data() + 4 * C;
+}
+
+// capi.cu::mpmgpu_set_temperature_bcs: grouped by node, list order kept inside a node
+extern "C" void emu_set_temperature_bcs(void *h, int n, const int *node, const double *value)
+{
+    EmuSim *S = (EmuSim *)h;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return node[a] < node[b]; });
+    S->tbcNode.clear(); S->tbcStart.clear(); S->tbcActive.assign(n, 1); S->tbcValue.assign(n, 0.); S->tbcSaved.assign(n ? n : 1, 0.);
+    for (int e = 0; e < n; e++) {
+        const int i = order[e];
+        if (e == 0 || node[i] != node[order[e - 1]]) { S->tbcNode.push_back(node[i] - 1); S->tbcStart.push_back(e); }
+        S->tbcValue[e] = value[i];
+    }
+    S->tbcStart.push_back(n);
+    S->Q.nUnique = (int)S->tbcNode.size(); S->Q.node = S->tbcNode.data(); S->Q.start = S->tbcStart.data(); S->Q.value = S->tbcValue.data();
+    S->Q.active = S->tbcActive.data(); S->Q.saved = S->tbcSaved.data();
 }
 
 extern "C" void emu_get_transport(void *h, double *gT, double *gVCT, double *gQ, double *temperature)

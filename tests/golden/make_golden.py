@@ -179,6 +179,13 @@ CASES = {
                                                      (250.0, 420.0), (900.0, 3000.0), (1200.0, 700.0)), (1, 2, 60), 2),
     "cond3d_blocks_multimaterial": (inputs.conduction(inputs.blocks3d_contact(inputs.multimaterial(2, 0.3), materials=2).replace("<alpha>20</alpha>", "<alpha>0</alpha>"),
                                                       (400.0, 280.0), (5000.0, 1500.0), (600.0, 900.0)), (1, 2, 40), 2),
+    # nodal temperature BCs: the bottom plane of the grid is held at 450 K and a strip on one side at 250 K (two BCs overlap on
+    # the corner nodes); the block expands as it heats
+    "cond3d_block_temperature_bcs": (inputs.conduction(inputs.block3d(ncell=4, margin=3, E=100.0, vz=-2.0e3, vx=1.0e3).replace("<alpha>0</alpha>", "<alpha>50</alpha>"),
+                                                       (300.0,), (4000.0,), (700.0,))
+                                     .replace("</GridBCs>", '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="4.01"><TempBC value="450"/></BCBox>'
+                                                            '<BCBox xmin="-1" xmax="4.01" ymin="-1" ymax="20" zmin="-1" zmax="20"><TempBC value="250"/></BCBox></GridBCs>'),
+                                     (1, 2, 40), 2, 0.3, 1500.0),
     # thermal strains in the laws: conduction with expanding materials, and bodies that start off the stress-free temperature
     # (one temperature jump handed to the laws by the first particle update) -- every law and analysis type that carries the terms
     "th2d_cond_iso_planestrain": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=60.0)),

@@ -61,6 +61,13 @@ CASES = {
                                                          extra_header="<StressFreeTemp>300</StressFreeTemp>").replace('<Body ', '<Body temp="360" ', 1)
                                           .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
                                           .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYYNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
+    # conduction with nodal temperature BCs: a constant one on the bottom plane and a ramp that starts late on one side
+    "block3d_conduction_temperature_bcs": (inputs.conduction(inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=-2.0e3, vx=1.0e3).replace("<alpha>0</alpha>", "<alpha>50</alpha>"),
+                                                             (300.0,), (4000.0,), (700.0,))
+                                           .replace("</GridBCs>", '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="4.01"><TempBC value="450"/></BCBox>'
+                                                                  '<BCBox xmin="-1" xmax="4.01" ymin="-1" ymax="20" zmin="-1" zmax="20"><TempBC style="2" value="20000" time="0.005"/></BCBox></GridBCs>')
+                                           .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+                                           .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
     # heat conduction between two disks of different temperature, conductivity and heat capacity; the archives carry the
     # particle temperature
     "disks2d_conduction": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=60.0, maxtime=0.6, archive_ms=0.15)),

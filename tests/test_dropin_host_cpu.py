@@ -62,9 +62,10 @@ CASES = {
     "multimaterial fmpm2": (inputs.oblique_disks(inputs.disks2d(analysis=10, maxtime=0.5, extra_header=inputs.multimaterial(2, 0.3)))
                             .replace("</JANFEAInput>", inputs.periodic_xpic(2, True, 1) + "</JANFEAInput>"), "order > 1 in multimaterial mode"),
     # conduction runs on the device (tests/test_dropin_gpu.py); its BCs, other transport tasks and thermal expansion do not
-    "temperature BCs": (inputs.conduction(inputs.block3d(ncell=3, margin=2, maxtime=0.003), (350.0,), (2000.0,), (800.0,))
-                        .replace("</JANFEAInput>", '<GridBCs><BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="2.01"><TempBC value="400"/></BCBox></GridBCs></JANFEAInput>'),
-                        "nodal temperature BCs"),
+    # (nodal temperature BCs run on the device: tests/test_dropin_gpu.py)
+    "heat flux BCs": (inputs.conduction(inputs.block3d(ncell=3, margin=2, maxtime=0.003), (350.0,), (2000.0,), (800.0,))
+                      .replace("</GridBCs>", '</GridBCs><ParticleBCs><BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="4" zmax="20"><HeatFluxBC dir="1" face="1" style="1" value="100"/></BCBox></ParticleBCs>'),
+                      "particle heat-flux BCs"),
     "diffusion": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</MPMHeader>", '<Diffusion reference="0"/></MPMHeader>'),
                   "transport tasks other than conduction"),
     # global quantities the reference reads from its nodes / BC objects would be silently zero: the replaced tasks no longer fill them
