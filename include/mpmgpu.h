@@ -251,10 +251,15 @@ int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm);
  * isotropic: MaterialBaseMPM.cpp:320-326; ignored for rigid-BC materials).  Built: isothermal energy mode, insulated boundaries,
  * any number of materials (also in multimaterial mode: transport values live on the node, not on a velocity field), nodal
  * temperature BCs (mpmgpu_set_temperature_bcs), thermal expansion (the temperature change of a step reaches the laws as ResidualStrains::dT).  Refused: thermal expansion on the
- * large-rotation IsotropicMat, XPIC/FMPM order > 1, slab mode; heat-flux BCs, adiabatic coupling and contact heating are the
- * adapter's to refuse.  Per-task kernels.  Call after
+ * large-rotation IsotropicMat, XPIC/FMPM order > 1, slab mode; heat-flux BCs and contact heating are the adapter's to refuse.  Per-task kernels.  Call after
  * mpmgpu_set_materials and before mpmgpu_upload_particles. */
 int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kcond);
+/* <EnergyCoupling/> (ConductionTask::adiabatic): MaterialBase::IncrementHeatEnergy buffers dTq0 + dPhi/Cv as a temperature rise on
+ * the particle instead of releasing it as heat (MaterialBaseMPM.cpp:982-1006); the next particle update adds the buffer to the
+ * particle's temperatures and, with conduction, to the dT the laws see (UpdateParticlesTask.cpp:229-235) -- plastic work heats the
+ * material (thermal softening in Johnson-Cook hardening).  With or without conduction; per-task kernels.  Before
+ * mpmgpu_upload_particles. */
+int mpmgpu_set_energy_coupling(mpmgpu_ctx *ctx, int adiabatic);
 /* Nodal temperature BCs (NodalTempBC list, firstTempBC ...; <TempBC> in <GridBCs>) in the host's list order: node[i] 1-based,
  * value[i] = BCValue at this step's time, active[i] = GetNodeNum(time) != 0 (NULL: all active).  Before the temperature gradients
  * are taken the BC nodes hold the sum of their BC values and get their own value back afterwards (TransportTask::ImposeValueBCs /

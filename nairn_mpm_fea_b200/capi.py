@@ -26,7 +26,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
-           "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_set_temperature_bcs", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
+           "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_set_energy_coupling", "mpmgpu_set_temperature_bcs", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
@@ -226,6 +226,9 @@ class MpmGpu:
         mm = getattr(prob, "multimaterial", None)
         if mm is not None:
             self.set_multimaterial(mm)
+        self.adiabatic = bool(getattr(prob, "adiabatic", False))
+        if self.adiabatic:
+            self._check(self.lib.mpmgpu_set_energy_coupling(self.ctx, 1))
         self.conduction = getattr(prob, "conduction", None) is not None
         if self.conduction:
             k = _c64(prob.conduction["kcond"])
@@ -271,7 +274,7 @@ class MpmGpu:
             keep[k] = _c32(pt.get(k))
             setattr(v, k, _i(keep[k]))
         self.n = n
-        self.thermal = bool(getattr(self, "conduction", False)) or pt.get("temperature") is not None
+        self.thermal = bool(getattr(self, "conduction", False)) or bool(getattr(self, "adiabatic", False)) or pt.get("temperature") is not None
         self._check(self.lib.mpmgpu_upload_particles(self.ctx, C.byref(v)))
 
     def set_multimaterial(self, mm):

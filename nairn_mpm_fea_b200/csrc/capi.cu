@@ -93,6 +93,7 @@ struct mpmgpu_ctx {
     std::vector<int> hFieldOfMat;
     // conduction (mpmgpu_set_conduction): nodal transport field, particle temperature + gradient
     bool conduction = false;
+    bool adiabatic = false;             // <EnergyCoupling/> (mpmgpu_set_energy_coupling): the laws buffer a temperature rise instead of releasing heat
     bool thermal = false;               // particle temperatures can change (conduction, or a start off the stress-free temperature): the laws get dT
     TransportNodes T;
     double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
@@ -439,6 +440,18 @@ extern "C" int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kc
     return MPMGPU_OK;
 }
 
+// <EnergyCoupling/>: ConductionTask::adiabatic.  Before mpmgpu_upload_particles.
+extern "C" int mpmgpu_set_energy_coupling(mpmgpu_ctx *ctx, int adiabatic)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_energy_coupling: call before mpmgpu_upload_particles");
+    if (adiabatic && ctx->tiled.slab.on) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_energy_coupling: not available in slab mode");
+    if (adiabatic && ctx->cfg.kernel_path == 2) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_energy_coupling: adiabatic coupling runs on the per-task kernels (kernel_path 2 asked for the fused path)");
+    ctx->adiabatic = adiabatic != 0;
+    ctx->sp.adiabatic = ctx->adiabatic ? 1 : 0;
+    return MPMGPU_OK;
+}
+
 // Nodal temperature BCs in the host's list order (firstTempBC ...): node[i] 1-based, value[i] = BCValue at this step's time,
 // active[i] = GetNodeNum(time) != 0.  Call again (same or another list) whenever values change.
 extern "C" int mpmgpu_set_temperature_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *value, const int *active)
@@ -770,7 +783,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
             if (nR) CK(cudaMemcpyAsync(ctx->archOrigin + (size_t)c * n + nNR, ctx->PR.pos[c], (size_t)nR * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
-    ctx->thermal = ctx->conduction || h->temperature != NULL;
+    ctx->thermal = ctx->conduction || ctx->adiabatic || h->temperature != NULL;
     if (ctx->thermal) {
         if (ctx->globalIds) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: particle temperatures / conduction with caller-global particle ids (slab mode) are not built");
         if (!ctx->conduction)
@@ -779,10 +792,12 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
                 if (m.kind == MAT_ISOTROPIC && m.p[7] != 0. && (m.p[17] != 0. || m.p[18] != 0. || m.p[19] != 0.))
                     return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: material %d: thermal expansion with <largeRotation> on IsotropicMat is not built", i + 1);
             }
-        if (!ctx->tempPool) { CK(dalloc(ctx, &ctx->tempPool, ctx->cap * 5)); CK(cudaMemsetAsync(ctx->tempPool, 0, ctx->cap * 5 * sizeof(double), ctx->stream)); }
+        if (!ctx->tempPool) { CK(dalloc(ctx, &ctx->tempPool, ctx->cap * 6)); CK(cudaMemsetAsync(ctx->tempPool, 0, ctx->cap * 6 * sizeof(double), ctx->stream)); }
         ctx->P.temp = ctx->tempPool;
         for (int c = 0; c < 3; c++) ctx->P.tgrad[c] = ctx->tempPool + (size_t)(c + 1) * ctx->cap;
         ctx->P.dTr = ctx->tempPool + (size_t)4 * ctx->cap;
+        ctx->P.dTad = ctx->adiabatic ? ctx->tempPool + (size_t)5 * ctx->cap : NULL;
+        if (ctx->adiabatic && nNR) CK(cudaMemsetAsync(ctx->P.dTad, 0, (size_t)nNR * sizeof(double), ctx->stream));
         if (nNR) {
             // pTemperature; without the array every particle starts at the temperature of its last strain update (energies[5])
             if (h->temperature) { if ((rc = up_field(ctx, &ctx->P.temp, h->temperature, 1, n, 0, nNR))) return rc; }

@@ -370,7 +370,7 @@ __device__ __forceinline__ void load_state(const Particles &P, int p, PState &s)
         s.pressure = 0.; s.res = 0.; s.plast = 0.;
         s.work = P.work[p]; s.heat = P.heat[p]; s.entropy = P.entropy[p];
         s.prevT = P.prevT[p];
-        s.dT = 0.;
+        s.dT = 0.; s.dTad = 0.; s.adiabatic = 0;
 #pragma unroll
         for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = 0.;
     }

@@ -297,7 +297,7 @@ __device__ __forceinline__ void load_pstate(const Particles &P, int p, PState &s
     s.pressure = P.pressure[p];
     s.work = P.work[p]; s.res = P.res[p]; s.heat = P.heat[p]; s.entropy = P.entropy[p]; s.plast = P.plast[p];
     s.prevT = P.prevT[p];
-    s.dT = 0.;
+    s.dT = 0.; s.dTad = 0.; s.adiabatic = 0;
 #pragma unroll
     for (int i = 0; i < MPM_MAX_HISTORY; i++) s.hist[i] = P.hist[i][p];
 }
@@ -339,9 +339,11 @@ __device__ __forceinline__ void update_strains_body(const Grid &g, const Particl
     PState s;
     load_pstate(P, p, s);
     if (P.dTr) s.dT = P.dTr[p] * dTscale;
+    if (P.dTad) s.adiabatic = 1;
     if (LRLAW) constitutive_law_lr<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
     else constitutive_law<DIM>(s, dv, strainTime, g.np, mats[P.mat[p]]);
     store_pstate(P, p, s);
+    if (P.dTad) P.dTad[p] += s.dTad;          // MPMBase::Add_dTad
 }
 
 template <int DIM, int SHAPE>
@@ -1085,10 +1087,13 @@ __global__ void k_material_contact(Grid g, Nodes N, ContactNodes C, ContactParam
 // Without a transport task the particle update still hands the laws a temperature change: the difference between the particle's
 // temperature and the one its last strain update saw (UpdateParticlesTask.cpp:246-251) -- nonzero once, after a start off the
 // stress-free temperature.
+// With <EnergyCoupling/> the buffered adiabatic rise moves both temperatures first (:229-235); without conduction the difference
+// taken afterwards does not see it.
 __global__ void k_update_temperature_offsets(int n, Particles P)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    if (P.dTad) { const double dTad = P.dTad[p]; P.dTad[p] = 0.; P.temp[p] += dTad; P.prevT[p] += dTad; }
     P.dTr[p] = P.temp[p] - P.prevT[p];
     P.prevT[p] = P.temp[p];
 }
@@ -1239,10 +1244,16 @@ __global__ void __launch_bounds__(TASK_THREADS) k_update_temperature(Grid g, Par
     });
     const double prev = P.prevT[p];
     const double dTcond = value - prev;
-    P.prevT[p] = value;
-    P.dTr[p] = dTcond;                  // res.dT of the next strain updates (mpmptr->dTrans = res, UpdateParticlesTask.cpp:261)
-    P.temp[p] += dt * rate;
+    double prevNew = value, dTres = dTcond, Tp = P.temp[p] + dt * rate;
+    if (P.dTad) {           // <EnergyCoupling/>: the adiabatic rise the laws buffered moves both temperatures and res.dT, not dTcond (:229-235)
+        const double dTad = P.dTad[p];
+        P.dTad[p] = 0.;
+        Tp += dTad; prevNew += dTad; dTres += dTad;
+    }
+    P.prevT[p] = prevNew;
+    P.dTr[p] = dTres;                   // res.dT of the next strain updates (mpmptr->dTrans = res, UpdateParticlesTask.cpp:261)
+    P.temp[p] = Tp;
     const double cv = mats[P.mat[p]].p[1];
     P.heat[p] += cv * dTcond;
-    P.entropy[p] += cv * log(value / (value - dTcond));
+    P.entropy[p] += cv * log(prevNew / (prevNew - dTcond));
 }

@@ -15,6 +15,8 @@ struct PState {
     double work, res, heat, entropy, plast;
     double prevT;       // pPreviousTemperature
     double hist[MPM_MAX_HISTORY];
+    double dTad;        // adiabatic mode: temperature rise this law call adds to the particle's buffer (MPMBase::buffer_dTad)
+    int adiabatic;      // ConductionTask::adiabatic (<EnergyCoupling/>): heat stays on the particle as a temperature rise
     double dT;          // temperature change this strain update answers to (ResidualStrains::dT, already scaled for the pass:
                         // MPMBase::ScaledResidualStrains); 0 unless the particle temperatures change (conduction, a start off the
                         // stress-free temperature)
@@ -37,10 +39,17 @@ __device__ __forceinline__ double mat3_det(const double m[9])
     return m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[6] * m[5]) + m[2] * (m[3] * m[7] - m[6] * m[4]);
 }
 
-// MaterialBase::IncrementHeatEnergy, isothermal branch (Materials/MaterialBaseMPM.cpp:982-1006;
-// ConductionTask::adiabatic is false unless <EnergyCoupling/> -- transport is out of scope)
+// MaterialBase::IncrementHeatEnergy (Materials/MaterialBaseMPM.cpp:982-1006): isothermal -- the heat leaves, the temperature
+// stays -- or, with <EnergyCoupling/> (ConductionTask::adiabatic), adiabatic -- dTq0 + dPhi/Cv is buffered as a temperature rise that
+// the next particle update applies, and only the dissipated part makes entropy
 __device__ __forceinline__ void increment_heat_energy(PState &s, double Cv, double dTq0, double dPhi)
 {
+    if (s.adiabatic) {
+        const double dTphi = dPhi / Cv;
+        s.dTad += dTq0 + dTphi;
+        s.entropy += Cv * log((s.prevT + dTphi) / s.prevT);      // MPMBase::AddEntropy(Cv, T1, T2)
+        return;
+    }
     double baseHeat = -Cv * dTq0;
     s.heat += baseHeat - dPhi;
     s.entropy += baseHeat / s.prevT;

@@ -88,6 +88,7 @@ struct Particles {
     // ResidualStrains::dT of the step (MPMBase::dTrans.dT, set by the particle update and used by the next strain updates), NULL =
     // the particle temperatures never change
     double *dTr;
+    double *dTad;            // adiabatic mode (<EnergyCoupling/>): MPMBase::buffer_dTad, the temperature rise the laws have buffered this step
     // multimaterial mode: node-index offset of the particle's material velocity field (field * nnodes), NULL = one field
     const int *foff;
 };
@@ -156,6 +157,7 @@ struct StepParams {
     int method, skipPost;
     int xpicOrder, usingFMPM;
     int hasGravity;
+    int adiabatic;           // ConductionTask::adiabatic
 };
 
 // velocity BCs grouped by node (entries keep the host's list order within a node)

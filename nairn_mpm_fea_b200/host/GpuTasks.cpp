@@ -531,12 +531,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     // grid body forces that are functions of position and time are added to the grid force by PostForcesTask
     // (BodyForce::GetGridBodyForce, BodyForce.cpp:97-117); the device applies constant gravity only
     if (bodyFrc.hasGridBodyForce) return "grid body force functions (<BodyXForce> ...)";
-    // <EnergyCoupling>: IncrementHeatEnergy takes the adiabatic branch (temperature rise from dissipated energy,
-    // MaterialBaseMPM.cpp:982-1006, UpdateParticlesTask.cpp:228-235); the device laws are isothermal
-    if (ConductionTask::adiabatic) return "adiabatic energy coupling (<EnergyCoupling>)";
-    // a particle temperature other than the one its previous strain update saw gives a thermal strain increment
-    // res.dT = pTemperature - pPreviousTemperature in the first particle update (UpdateParticlesTask.cpp:252-256);
-    // the device has no residual strains (eres = 0)
+    // (<EnergyCoupling/>, ConductionTask::adiabatic, runs on the device: mpmgpu_set_energy_coupling)
     // (particle temperatures travel to the device -- mpmgpu_particles.temperature -- whenever they matter: with conduction they are
     // state of the transport task; without it a start off the stress-free temperature gives the first particle update a thermal
     // strain increment res.dT = pTemperature - pPreviousTemperature, UpdateParticlesTask.cpp:246-251, which the device laws carry)
@@ -727,6 +722,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         }
     }
     ALL_CTX(mpmgpu_set_materials(ctx_, nmat, mats.data()));
+    if (ConductionTask::adiabatic && mpmgpu_set_energy_coupling(gCtx, 1) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
     if (ConductionTask::active) {
         std::vector<double> kc(nmat, 0.);
         for (int i = 0; i < nmat; i++) kc[i] = theMaterials[i]->kCond;          // conductivity / rho (MaterialBaseMPM.cpp:233)
@@ -780,7 +776,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     h.sp = sp.data(); h.pressure = pr.data(); h.ep = ep.data(); h.wrot = wrot.data(); h.eplast = epl.data(); h.energies = en.data();
     h.pfext = anyFext ? pf.data() : NULL; h.crossings = cross.data(); h.history = hist.data();
     std::vector<double> temp0;
-    gThermal = ConductionTask::active || temperatureOffsets;
+    gThermal = ConductionTask::active || ConductionTask::adiabatic || temperatureOffsets;
     if (gThermal) {
         temp0.resize(n);
         for (int p = 0; p < n; p++) temp0[p] = mpm[p]->pTemperature;

@@ -50,6 +50,7 @@ class Problem:
         self.origpos = None             # [3][n] MPMBase::origpos when it differs from the uploaded positions
         # <Thermal><Conduction/>: None, or dict(kcond [nmat] = conductivity / rho); particles["temperature"] = pTemperature
         self.conduction = None
+        self.adiabatic = False          # <EnergyCoupling/> (ConductionTask::adiabatic)
         self.particles = {}
 
     @property
@@ -348,8 +349,9 @@ def from_reference_dump(z, snapshot="p0"):
                         n_nonrigid=int(info["nmpmsNR"]))
     if np.any(z[s + "/pFext"] != 0.0):
         pr.particles["pfext"] = z[s + "/pFext"]
+    pr.adiabatic = bool(info.get("adiabatic", 0))
     if "conduction/kcond" in z:
-        for k in ("adiabatic", "n_flux_bcs", "contact_heating"):
+        for k in ("n_flux_bcs", "contact_heating"):
             if int(z["conduction/" + k]):
                 raise NotImplementedError("conduction with " + k)
         pr.conduction = dict(kcond=np.asarray(z["conduction/kcond"], float))

@@ -18,7 +18,7 @@ extern "C" int devlaws_batch(int dim, int np, int kind, int nhist, const double 
     memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
     for (int p = 0; p < n; p++) {
         PState s;
-        s.dT = g_dT;
+        s.dT = g_dT; s.dTad = 0.; s.adiabatic = 0;
         for (int i = 0; i < 9; i++) s.F[i] = F[(size_t)i * n + p];
         for (int i = 0; i < 6; i++) { s.sp[i] = sp[(size_t)i * n + p]; s.eplast[i] = eplast[(size_t)i * n + p]; }
         s.pressure = pressure[p];
@@ -45,7 +45,7 @@ extern "C" int devlaws_plain_one(int dim, int np, int kind, const double *params
     m.kind = kind; m.nhist = 0;
     memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
     PState s;
-    s.dT = g_dT;
+    s.dT = g_dT; s.dTad = 0.; s.adiabatic = 0;
     for (int i = 0; i < 9; i++) s.F[i] = F[i];
     for (int i = 0; i < 6; i++) { s.sp[i] = sp[i]; s.eplast[i] = eplast[i]; }
     s.pressure = *pressure;

@@ -407,12 +407,15 @@ extern "C" void emu_set_conduction(void *h, const double *kcond, const double *t
         S->T.gT = S->tpool.data(); S->T.gVCT = S->tpool.data() + nn; S->T.gQ = S->tpool.data() + 2 * nn; S->T.kcond = S->kcond.data();
     }
     const size_t C = S->P.n ? (size_t)S->P.n : 1;
-    S->temps.assign(C * 5, 0.);
+    S->temps.assign(C * 6, 0.);
     for (int p = 0; p < S->P.n; p++) S->temps[p] = temperature[p];
     S->P.temp = S->temps.data();
     for (int c = 0; c < 3; c++) S->P.tgrad[c] = S->temps.data() + (size_t)(c + 1) * C;
     S->P.dTr = S->temps.data() + 4 * C;
+    S->P.dTad = S->sp.adiabatic ? S->temps.data() + 5 * C : NULL;
 }
+
+extern "C" void emu_set_energy_coupling(void *h, int adiabatic) { ((EmuSim *)h)->sp.adiabatic = adiabatic; }
 
 // capi.cu::mpmgpu_set_temperature_bcs: grouped by node, list order kept inside a node
 extern "C" void emu_set_temperature_bcs(void *h, int n, const int *node, const double *value)

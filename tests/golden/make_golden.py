@@ -207,6 +207,16 @@ CASES = {
                                                     inputs.mooney_material(0.3, 0.1, 1.0, 1, name="Disk 1", rho=1.5))
                                            .replace('<Body matname="Disk 1"', '<Body temp="350" matname="Disk 1"').replace('<Body matname="Disk 2"', '<Body temp="270" matname="Disk 2"'),
                                            (1, 2, 40), 2),
+    # <EnergyCoupling/>: adiabatic mode -- plastic work and the thermoelastic effect heat the particles (Johnson-Cook softening
+    # feels it), without a transport task and together with conduction
+    "th3d_adiabatic_johnsoncook": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_hardening_material("JohnsonCook", Djc=0.01), vz=-6.0e4, vx=5.0e3,
+                                                  extra_header="<StressFreeTemp>300</StressFreeTemp>").replace("</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>"),
+                                   (1, 2, 60), 2, 0.3, 3000.0),
+    "th2d_adiabatic_conduction_isoplastic": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=4000.0, vmax=11.0, gap=0.0, alpha=60.0))
+                                                               .replace('<Material Type="1" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60.0</alpha>',
+                                                                        '<Material Type="9" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep>'),
+                                                               (320.0, 290.0), (2000.0, 500.0), (800.0, 1500.0)).replace("<Conduction/>", "<Conduction/><EnergyCoupling/>"),
+                                             (1, 2, 40), 2),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

@@ -48,7 +48,7 @@ def lib():
                         src, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.emu_create.restype = C.c_void_p
-    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_conduction", "emu_get_transport", "emu_set_temperature_bcs", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
+    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_conduction", "emu_get_transport", "emu_set_temperature_bcs", "emu_set_energy_coupling", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
         getattr(lib, f).argtypes = None
     return lib
 
@@ -95,7 +95,10 @@ class EmuSim:
         self.n_fields = 0
         self.conduction = getattr(prob, "conduction", None) is not None
         self.real_nodes = self.nnodes
-        self.thermal = self.conduction or pt.get("temperature") is not None
+        adiabatic = bool(getattr(prob, "adiabatic", False))
+        if adiabatic:
+            lib.emu_set_energy_coupling(self.h, 1)
+        self.thermal = self.conduction or adiabatic or pt.get("temperature") is not None
         if self.conduction:
             self._cond = [c(prob.conduction["kcond"], dtype=np.float64), c(pt["temperature"], dtype=np.float64)]
             lib.emu_set_conduction(self.h, _dp(self._cond[0]), _dp(self._cond[1]))
@@ -103,7 +106,7 @@ class EmuSim:
                 self._cond += [c(prob.conduction["tbc_node"], dtype=np.int32), c(prob.conduction["tbc_value"], dtype=np.float64)]
                 lib.emu_set_temperature_bcs(self.h, len(self._cond[2]), _ip(self._cond[2]), _dp(self._cond[3]))
         elif self.thermal:
-            self._cond = [c(pt["temperature"], dtype=np.float64)]
+            self._cond = [c(pt["temperature"] if pt.get("temperature") is not None else keep["energies"][5], dtype=np.float64)]
             lib.emu_set_conduction(self.h, None, _dp(self._cond[0]))
         mm = getattr(prob, "multimaterial", None)
         if mm is not None:

@@ -45,8 +45,7 @@ CASES = {
     # temperature rise, or a thermal strain from particles that start away from the stress-free temperature
     "grid body force function": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
         "</JANFEAInput>", "<Gravity><GridBodyXForce>10*x</GridBodyXForce></Gravity></JANFEAInput>"), "grid body force functions"),
-    "adiabatic coupling": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
-        "</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>"), "adiabatic energy coupling"),
+    # (adiabatic coupling, <EnergyCoupling/>, runs on the device: tests/test_dropin_gpu.py)
     # (particles that start off the stress-free temperature run on the device since the laws carry thermal strains: tests/test_dropin_gpu.py)
     "thermal expansion with large rotation": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, extra_header="<StressFreeTemp>300</StressFreeTemp>")
                                               .replace("<alpha>0</alpha>", "<alpha>50</alpha><largeRotation>1</largeRotation>").replace('<Body ', '<Body temp="350" ', 1),
