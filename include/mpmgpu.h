@@ -268,6 +268,17 @@ int mpmgpu_set_energy_coupling(mpmgpu_ctx *ctx, int adiabatic);
  * tracked.  Call after mpmgpu_set_conduction; call again whenever values change. */
 int mpmgpu_set_temperature_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *value, const int *active);
 int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
+/* Reaction forces of the velocity BCs (NodalVelBC::freaction, the input of the "reactionx/y/z" global quantities:
+ * GlobalQuantity.cpp:971-986 -> NodalVelBC::TotalReactionForce, NodalVelBC.cpp:246-252).  Each BC's freaction starts from zero in
+ * the grid-forces pass and collects the force that pass adds to the node's material fields, -(ftot.n + pk.n/dt) n for the zeroing
+ * and m v/dt n for the imposed value (MatVelocityField.cpp:504-524, :563-569), plus with XPIC/FMPM order > 1 the lumped
+ * -m dv*.n/dt n of the particle-update pass (:529-536).  mpmgpu_track_reactions(ctx, 1) turns the bookkeeping on (after
+ * mpmgpu_set_materials; not in slab mode).  mpmgpu_download_reactions: bc_reaction[3*i..] = freaction of entry i of the list given
+ * to mpmgpu_set_velocity_bcs (n = its length; the host sums by bcID), rigid_reaction[3*m..] = the summed freaction of the BCs made
+ * by the rigid-BC particles of material m (0-based; their bcID is the material number, ProjectRigidBCsTask.cpp:241).  Either may
+ * be NULL.  The values are those of the last completed step. */
+int mpmgpu_track_reactions(mpmgpu_ctx *ctx, int on);
+int mpmgpu_download_reactions(mpmgpu_ctx *ctx, int n, double *bc_reaction, double *rigid_reaction);
 /* timestep, strainTimestepFirst, strainTimestepLast (NairnMPM.cpp:1207-1240) */
 int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dt_strain_first, double dt_strain_last);
 /* XPIC/FMPM order can change per step (Custom_Tasks/PeriodicXPIC.cpp:161-240) */

@@ -26,7 +26,8 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
-           "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_set_energy_coupling", "mpmgpu_set_temperature_bcs", "mpmgpu_upload_particles", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
+           "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_set_energy_coupling", "mpmgpu_set_temperature_bcs", "mpmgpu_upload_particles",
+           "mpmgpu_track_reactions", "mpmgpu_download_reactions", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
@@ -113,6 +114,8 @@ def load_library(path=None):
     lib.mpmgpu_set_multimaterial.argtypes = [vp, C.POINTER(MultiMaterial)]
     lib.mpmgpu_set_conduction.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_set_temperature_bcs.argtypes = [vp, C.c_int, _ip, _dp, _ip]
+    lib.mpmgpu_track_reactions.argtypes = [vp, C.c_int]
+    lib.mpmgpu_download_reactions.argtypes = [vp, C.c_int, _dp, _dp]
     lib.mpmgpu_set_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.mpmgpu_set_xpic.argtypes = [vp, C.c_int, C.c_int]
     lib.mpmgpu_set_velocity_bcs.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
@@ -305,6 +308,18 @@ class MpmGpu:
         node, norm, value = _c32(node), _c64(norm), _c64(value)
         active, symdir = _c32(active), _c32(symdir)
         self._check(self.lib.mpmgpu_set_velocity_bcs(self.ctx, n, _i(node), _d(norm), _d(value), _i(active), _i(symdir)))
+
+    def track_reactions(self, on=True):
+        """Keep the reaction force of every velocity BC (NodalVelBC::freaction); read them with reactions()."""
+        self._check(self.lib.mpmgpu_track_reactions(self.ctx, 1 if on else 0))
+
+    def reactions(self):
+        """(bc [n,3] in the order of the velocity-BC list, rigid [nmat,3] per rigid-BC material) of the last step."""
+        n = 0 if self.prob.bc_node is None else len(self.prob.bc_node)
+        bc = np.zeros((n, 3))
+        rigid = np.zeros((len(self.prob.materials), 3))
+        self._check(self.lib.mpmgpu_download_reactions(self.ctx, n, _d(bc), _d(rigid)))
+        return bc, rigid
 
     def set_velocity_bc_reflections(self, reflected_node, ratio):
         """Symmetry-plane BCs: per BC of the list the 1-based node it reflects (<= 0: plain BC) and the cell-size ratio."""

@@ -41,6 +41,10 @@ struct mpmgpu_ctx {
     StepParams sp;
     VelBCs B;
     int nBCEntries;
+    bool trackReactions = false;        // mpmgpu_track_reactions: B.reaction / R.reaction are kept
+    double *dReaction = NULL;           // [3*reactionCap] grid BC entries (device order)
+    size_t reactionCap = 0;
+    double *dRigidReaction = NULL;      // [3*nmat]
     std::vector<int> bcOrder;           // entry e on device = host list index bcOrder[e]
     Material *dMats;
     int nmat;
@@ -440,6 +444,67 @@ extern "C" int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kc
     return MPMGPU_OK;
 }
 
+// Reaction forces of the velocity BCs (NodalVelBC::freaction): buffers for the BC list set now and for the rigid materials.
+static int reaction_buffers(mpmgpu_ctx *ctx)
+{
+    if (!ctx->trackReactions) { ctx->B.reaction = NULL; ctx->R.reaction = NULL; ctx->tiled.FN.R.reaction = NULL; return MPMGPU_OK; }
+    if ((size_t)ctx->nBCEntries > ctx->reactionCap) {
+        CK(dalloc(ctx, &ctx->dReaction, 3 * (size_t)ctx->nBCEntries));
+        ctx->reactionCap = (size_t)ctx->nBCEntries;
+    }
+    if (ctx->nBCEntries > 0) CK(cudaMemsetAsync(ctx->dReaction, 0, 3 * (size_t)ctx->nBCEntries * sizeof(double), ctx->stream));
+    if (!ctx->dRigidReaction && ctx->nmat > 0) {
+        CK(dalloc(ctx, &ctx->dRigidReaction, 3 * (size_t)ctx->nmat));
+        CK(cudaMemsetAsync(ctx->dRigidReaction, 0, 3 * (size_t)ctx->nmat * sizeof(double), ctx->stream));
+    }
+    ctx->B.reaction = ctx->nBCEntries > 0 ? ctx->dReaction : NULL;
+    ctx->R.reaction = ctx->dRigidReaction;
+    ctx->tiled.FN.R.reaction = ctx->dRigidReaction;
+    return MPMGPU_OK;
+}
+
+// every BC's freaction starts from zero in the grid-forces pass (NodalVelBC::ZeroVelocityBC, NodalVelBC.cpp:190); the rigid-particle
+// BCs are made anew each step
+static int reactions_zero(mpmgpu_ctx *ctx)
+{
+    if (!ctx->trackReactions) return MPMGPU_OK;
+    if (ctx->B.reaction) CK(cudaMemsetAsync(ctx->B.reaction, 0, 3 * (size_t)ctx->nBCEntries * sizeof(double), ctx->stream));
+    if (ctx->R.reaction) CK(cudaMemsetAsync(ctx->R.reaction, 0, 3 * (size_t)ctx->nmat * sizeof(double), ctx->stream));
+    return MPMGPU_OK;
+}
+
+extern "C" int mpmgpu_track_reactions(mpmgpu_ctx *ctx, int on)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (on && ctx->tiled.slab.on) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_track_reactions: not available in slab mode (halo nodes would count twice)");
+    if (on && ctx->nmat <= 0) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_track_reactions: call after mpmgpu_set_materials");
+    cudaSetDevice(ctx->cfg.device);
+    ctx->trackReactions = on != 0;
+    return reaction_buffers(ctx);
+}
+
+extern "C" int mpmgpu_download_reactions(mpmgpu_ctx *ctx, int n, double *bc_reaction, double *rigid_reaction)
+{
+    if (!ctx) return MPMGPU_EINVAL;
+    if (!ctx->trackReactions) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_download_reactions: mpmgpu_track_reactions was not called");
+    if (bc_reaction && n != ctx->nBCEntries) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_download_reactions: n=%d but %d BCs are set", n, ctx->nBCEntries);
+    cudaSetDevice(ctx->cfg.device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (bc_reaction && n > 0) {
+        std::vector<double> dev(3 * (size_t)n);
+        CK(cudaMemcpy(dev.data(), ctx->dReaction, dev.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int e = 0; e < n; e++) {
+            const int i = ctx->bcOrder[e];
+            for (int d = 0; d < 3; d++) bc_reaction[3 * (size_t)i + d] = dev[3 * (size_t)e + d];
+        }
+    }
+    if (rigid_reaction) {
+        if (ctx->dRigidReaction) CK(cudaMemcpy(rigid_reaction, ctx->dRigidReaction, 3 * (size_t)ctx->nmat * sizeof(double), cudaMemcpyDeviceToHost));
+        else for (int i = 0; i < 3 * ctx->nmat; i++) rigid_reaction[i] = 0.;
+    }
+    return MPMGPU_OK;
+}
+
 // <EnergyCoupling/>: ConductionTask::adiabatic.  Before mpmgpu_upload_particles.
 extern "C" int mpmgpu_set_energy_coupling(mpmgpu_ctx *ctx, int adiabatic)
 {
@@ -772,6 +837,7 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
     for (int p = nNR; p < n; p++) if (ctx->hMats[(h->matnum ? h->matnum[p] : 1) - 1].p[9] != 0.) ctx->R.mirrored = 1;
     ctx->R.mat = ctx->PR.mat; ctx->R.mats = ctx->dMats;
     ctx->R.stride[0] = 1; ctx->R.stride[1] = ctx->g.yplane; ctx->R.stride[2] = ctx->g.zplane; ctx->R.nnodes = ctx->g.nnodes;
+    ctx->R.reaction = ctx->trackReactions ? ctx->dRigidReaction : NULL;
     ctx->tiled.FN.R = ctx->R;
     if (!ctx->globalIds && !ctx->archOriginFromCaller) {
         // "original position" column of the archive records (ArchiveData.cpp:868-872): the positions at upload unless the caller
@@ -891,7 +957,7 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
         }
         if (ctx->R.fixedBits) cudaMemcpy((void *)ctx->R.fixedBits, ctx->hFixedBits.data(), ctx->hFixedBits.size(), cudaMemcpyHostToDevice);
     }
-    if (n == 0) { ctx->B.nUnique = 0; ctx->tiled.FN.bcOfNode = NULL; return MPMGPU_OK; }
+    if (n == 0) { ctx->B.nUnique = 0; ctx->tiled.FN.bcOfNode = NULL; return reaction_buffers(ctx); }
     if (!node || !norm || !value) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: null arrays");
     for (int i = 0; i < n; i++)
         if (node[i] < 1 || node[i] > ctx->g.nnodes) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_velocity_bcs: BC %d on node %d of %d", i, node[i], ctx->g.nnodes);
@@ -930,7 +996,7 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
         CK(cudaMemcpy(dof, of.data(), (size_t)ctx->g.nnodes * sizeof(int), cudaMemcpyHostToDevice));
         ctx->tiled.FN.bcOfNode = dof;
     }
-    return MPMGPU_OK;
+    return reaction_buffers(ctx);
 }
 
 // Symmetry-plane BCs (<Horiz symmin=...>, Generators.cpp:2178-2190): entry i of the list set by mpmgpu_set_velocity_bcs
@@ -1223,6 +1289,8 @@ static int t_grid_forces(mpmgpu_ctx *ctx)
 static int t_post_forces(mpmgpu_ctx *ctx)
 {
     LAUNCH(k_post_forces, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N, ctx->sp);
+    int rc = reactions_zero(ctx);
+    if (rc) return rc;
     return apply_bcs(ctx, PASS_GRID_FORCES, 0);
 }
 
@@ -1525,6 +1593,7 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_begin(ctx);
         if (t.slab.on && (rc = halo_add(ctx, 1))) return rc;
         // (with order > 1 the re-zeroing of pk for task 9a waits until v* has been formed from it)
+        if ((rc = reactions_zero(ctx))) return rc;
         LAUNCH(k_n2_forces_momenta, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp, (reextrap && !highOrder) ? 1 : 0);
         if (highOrder) {                                       // UpdateParticlesTask.cpp:66-71
             if ((rc = xpic_fused(ctx, 1))) return rc;
@@ -1999,6 +2068,7 @@ extern "C" int mpmgpu_slab_configure(mpmgpu_ctx *ctx, int cell_lo, int cell_hi, 
     if (ctx->cfg.shape != MPMGPU_UNIFORM_GIMP || ctx->cfg.kernel_path == 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: slab mode runs on the fused 3D uGIMP path");
     if (cell_lo < 0 || cell_hi > ctx->g.depth || cell_hi - cell_lo < 3) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: slab [%d,%d) of %d cell planes (need >= 3)", cell_lo, cell_hi, ctx->g.depth);
     if ((has_lower && cell_lo < 2) || (has_upper && cell_hi > ctx->g.depth - 2)) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: interior faces must be >= 2 planes from the grid edge");
+    if (ctx->trackReactions) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_slab_configure: reaction forces (mpmgpu_track_reactions) are not kept in slab mode");
     cudaSetDevice(ctx->cfg.device);
     TiledState &t = ctx->tiled;
     t.slab.on = 1; t.slab.cellLo = cell_lo; t.slab.cellHi = cell_hi;

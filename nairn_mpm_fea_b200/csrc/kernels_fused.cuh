@@ -1034,6 +1034,11 @@ __global__ void k_nx_finish(int n0, int nnodes, Nodes N, FusedNodes FN, VelBCs B
             const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
             const double dotn = d[0] * nx + d[1] * ny + d[2] * nz;
             d[0] += nx * (-dotn); d[1] += ny * (-dotn); d[2] += nz * (-dotn);
+            if (particleUpdate && B.reaction) {      // lumped-mass addition to the BC's freaction (MatVelocityField.cpp:532-536)
+                const double s = -mass * dotn / dt;
+                const double r[3] = {nx * s, ny * s, nz * s};
+                add_reaction(B.reaction + 3 * e, r);
+            }
             if (addReaction) {
                 const double s = -mass * dotn / dt;
                 ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
@@ -1046,6 +1051,7 @@ __global__ void k_nx_finish(int n0, int nnodes, Nodes N, FusedNodes FN, VelBCs B
             if (FN.R.owner[c][i] == RIGID_NONE) continue;
             const double dotn = d[c];
             d[c] += -dotn;
+            if (particleUpdate && FN.R.reaction && dotn != 0.) atomicAdd(FN.R.reaction + 3 * FN.R.mat[FN.R.owner[c][i]] + c, -mass * dotn / dt);
             if (addReaction) ft[c] += -mass * dotn / dt;
         }
     }

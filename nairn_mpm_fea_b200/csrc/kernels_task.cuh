@@ -89,13 +89,15 @@ __global__ void k_copy_momenta(int nnodes, Nodes N)
 
 // ---- grid velocity BCs (NodalVelBC.cpp:321-400, MatVelocityField.cpp:490-575) ----------------
 // zero pass of one BC with unit direction n (ZeroVelocityBC / SetFtotDirection / ZeroMomentumBC)
-__device__ __forceinline__ void bc_zero(int pass, double dt, double nx, double ny, double nz, double pk[3], double ft[3])
+// react (grid-forces pass only): where the force the BC adds is summed too (NodalVelBC::freaction, MatVelocityField.cpp:519-524,:563-569)
+__device__ __forceinline__ void bc_zero(int pass, double dt, double nx, double ny, double nz, double pk[3], double ft[3], double *react = nullptr)
 {
     if (pass == PASS_GRID_FORCES) {
         double dotf = ft[0] * nx + ft[1] * ny + ft[2] * nz;
         double dotp = pk[0] * nx + pk[1] * ny + pk[2] * nz;
         double s = -dotf - dotp / dt;
         ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        if (react) { react[0] += nx * s; react[1] += ny * s; react[2] += nz * s; }
     } else {
         double dotn = pk[0] * nx + pk[1] * ny + pk[2] * nz;
         pk[0] += nx * (-dotn); pk[1] += ny * (-dotn); pk[2] += nz * (-dotn);
@@ -107,11 +109,12 @@ __device__ __forceinline__ void bc_zero(int pass, double dt, double nx, double n
 }
 
 // add pass (AddVelocityBC / AddFtotDirection / AddMomentumBC)
-__device__ __forceinline__ void bc_add(int pass, double dt, double mass, double vel, double nx, double ny, double nz, double pk[3], double ft[3])
+__device__ __forceinline__ void bc_add(int pass, double dt, double mass, double vel, double nx, double ny, double nz, double pk[3], double ft[3], double *react = nullptr)
 {
     if (pass == PASS_GRID_FORCES) {
         double s = mass * vel / dt;
         ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
+        if (react) { react[0] += nx * s; react[1] += ny * s; react[2] += nz * s; }
     } else {
         double pvel = mass * vel;
         pk[0] += nx * pvel; pk[1] += ny * pvel; pk[2] += nz * pvel;
@@ -120,6 +123,14 @@ __device__ __forceinline__ void bc_add(int pass, double dt, double mass, double 
             ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
         }
     }
+}
+
+// one BC's share of the reaction force; the material fields of a node (multimaterial mode) add into the same entry
+__device__ __forceinline__ void add_reaction(double *dst, const double r[3])
+{
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+        if (r[d] != 0.) atomicAdd(dst + d, r[d]);
 }
 
 // BC application for one node: its entries are walked in list order, first the zero pass over all of
@@ -131,9 +142,12 @@ __device__ __forceinline__ void bc_add(int pass, double dt, double mass, double 
 __device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, double dt, double mass, double pk[3], double ft[3], const Nodes *N = nullptr, int off = 0)
 {
     const int e0 = B.start[u], e1 = B.start[u + 1];
+    const bool track = B.reaction != nullptr && pass == PASS_GRID_FORCES;
     for (int e = e0; e < e1; e++) {
         if (!B.active[e]) continue;
-        bc_zero(pass, dt, B.norm[3 * e], B.norm[3 * e + 1], B.norm[3 * e + 2], pk, ft);
+        double r[3] = {0., 0., 0.};
+        bc_zero(pass, dt, B.norm[3 * e], B.norm[3 * e + 1], B.norm[3 * e + 2], pk, ft, track ? r : nullptr);
+        if (track) add_reaction(B.reaction + 3 * e, r);
     }
     for (int e = e0; e < e1; e++) {
         if (!B.active[e]) continue;
@@ -146,7 +160,9 @@ __device__ __forceinline__ void node_bcs(const VelBCs &B, int u, int pass, doubl
                 v = v + B.reflRatio[e] * (v - dotn / N->mass[r]);
             }
         }
-        bc_add(pass, dt, mass, v, nx, ny, nz, pk, ft);
+        double r[3] = {0., 0., 0.};
+        bc_add(pass, dt, mass, v, nx, ny, nz, pk, ft, track ? r : nullptr);
+        if (track) add_reaction(B.reaction + 3 * e, r);
     }
 }
 
@@ -163,16 +179,23 @@ __device__ __forceinline__ bool node_rigid_bcs(const RigidBCs &R, int nd, int pa
 #pragma unroll
     for (int d = 0; d < 3; d++) { o[d] = R.owner[d][nd]; any |= o[d] != RIGID_NONE; }
     if (!any) return false;
+    const bool track = R.reaction != nullptr && pass == PASS_GRID_FORCES;
+    double r[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
 #pragma unroll
     for (int d = 0; d < 3; d++)
-        if (o[d] != RIGID_NONE) bc_zero(pass, dt, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft);
+        if (o[d] != RIGID_NONE) bc_zero(pass, dt, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft, track ? r[d] : nullptr);
 #pragma unroll
     for (int d = 0; d < 3; d++)
         if (o[d] != RIGID_NONE) {
             double v = R.vel[d][o[d]];
             if (MIRROR) { bool skip; v = rigid_bc_velocity(R, *N, nd, d, o[d], skip); if (skip) continue; }
-            bc_add(pass, dt, mass, v, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft);
+            bc_add(pass, dt, mass, v, d == 0 ? 1. : 0., d == 1 ? 1. : 0., d == 2 ? 1. : 0., pk, ft, track ? r[d] : nullptr);
         }
+    if (track) {        // the BC's ID is its rigid particle's material (ProjectRigidBCsTask.cpp:241)
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            if (o[d] != RIGID_NONE) add_reaction(R.reaction + 3 * R.mat[o[d]], r[d]);
+    }
     return true;
 }
 
@@ -527,6 +550,11 @@ __global__ void k_xpic_finish(int nnodes, Nodes N, VelBCs B, const int *bcOfNode
             const double nx = B.norm[3 * e], ny = B.norm[3 * e + 1], nz = B.norm[3 * e + 2];
             const double dotn = d[0] * nx + d[1] * ny + d[2] * nz;
             d[0] += nx * (-dotn); d[1] += ny * (-dotn); d[2] += nz * (-dotn);
+            if (particleUpdate && B.reaction) {     // lumped-mass addition to freaction (MatVelocityField.cpp:532-536)
+                const double s = -mass * dotn / dt;
+                const double r[3] = {nx * s, ny * s, nz * s};
+                add_reaction(B.reaction + 3 * e, r);
+            }
             if (particleUpdate && !usingFMPM) {
                 const double s = -mass * dotn / dt;
                 ft[0] += nx * s; ft[1] += ny * s; ft[2] += nz * s;
@@ -541,6 +569,7 @@ __global__ void k_xpic_finish(int nnodes, Nodes N, VelBCs B, const int *bcOfNode
             if (R.owner[c][i] == RIGID_NONE) continue;
             const double dotn = d[c];
             d[c] += -dotn;
+            if (particleUpdate && R.reaction && dotn != 0.) atomicAdd(R.reaction + 3 * R.mat[R.owner[c][i]] + c, -mass * dotn / dt);
             if (particleUpdate && !usingFMPM) N.ftot[c][i] += -mass * dotn / dt;
         }
     }

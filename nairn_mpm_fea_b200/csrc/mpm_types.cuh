@@ -171,6 +171,7 @@ struct VelBCs {
     const int *active;       // [nEntries]
     const int *refl;         // [nEntries] 0-based node whose velocity a symmetry-plane BC reflects, -1 = plain BC; NULL = none at all
     const double *reflRatio; // [nEntries] cell-size ratio across the plane (NodalVelBC::reflectRatio)
+    double *reaction;        // [3*nEntries] NodalVelBC::freaction of each entry, summed over the material fields; NULL = not tracked
 };
 
 // Velocity BCs made by rigid-BC particles (ProjectRigidBCsTask.cpp:39-158): per node and direction the
@@ -186,6 +187,7 @@ struct RigidBCs {
     const Material *mats;
     int stride[3];           // node spacing along x, y, z
     int nnodes;
+    double *reaction;        // [3*nmat] freaction of the rigid-particle BCs summed per rigid material (their bcID); NULL = not tracked
 };
 
 struct StatusFlags {         // device -> host error reporting (ResetElementsTask.cpp:71-151)

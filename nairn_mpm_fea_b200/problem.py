@@ -393,6 +393,7 @@ def from_reference_dump(z, snapshot="p0"):
     pr.bc_active = np.ones(nb, np.int32)
     pr.bc_symdir = np.zeros(nb, np.int32)
     pr.bc_style = z["velbcs/style"]
+    pr.bc_id = z["velbcs/id"].astype(np.int32) if "velbcs/id" in z else np.zeros(nb, np.int32)        # BoundaryCondition::bcID
     pr.bc_ftime = z["velbcs/ftime"]
     if "velbcs/reflected" in z and np.any(z["velbcs/reflected"] > 0):
         # symmetry planes (<Horiz symmin=...>): the plane's nodes carry the symmetry bits of NodalPoint::fixedDirection

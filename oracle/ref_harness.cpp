@@ -414,6 +414,22 @@ void ref_get_velbcs(int *node, int *dir, int *style, double *norm, double *value
     }
 }
 
+// per BC: bcID (BoundaryCondition::GetID; the "id" attribute of the BC's XML block, the material number for rigid-particle BCs)
+void ref_get_velbc_ids(int *ids)
+{
+    int k = 0;
+    for (NodalVelBC *bc = firstVelocityBC; bc != NULL; bc = (NodalVelBC *)bc->GetNextObject(), k++) ids[k] = bc->GetID();
+}
+
+// what the "reactionx/y/z" global quantities read (GlobalQuantity.cpp:971-986): the summed freaction of the BCs with ID ids[k], all when 0
+void ref_reaction_forces(int nids, const int *ids, double *out)
+{
+    for (int k = 0; k < nids; k++) {
+        Vector f = NodalVelBC::TotalReactionForce(ids[k]);
+        out[3 * k] = f.x; out[3 * k + 1] = f.y; out[3 * k + 2] = f.z;
+    }
+}
+
 // per BC: NodalVelBC::reflectedNode (1-based node across a symmetry plane, -1 none) and reflectRatio
 void ref_get_velbc_reflections(int *reflected, double *ratio)
 {

@@ -182,12 +182,20 @@ class RefRun:
         n = self.lib.ref_num_velbcs()
         o = dict(node=np.zeros(n, np.int32), dir=np.zeros(n, np.int32), style=np.zeros(n, np.int32),
                  norm=np.zeros((n, 3)), value=np.zeros(n), ftime=np.zeros(n), offset=np.zeros(n),
-                 currentValue=np.zeros(n), reflected=np.full(n, -1, np.int32), ratio=np.ones(n))
+                 currentValue=np.zeros(n), reflected=np.full(n, -1, np.int32), ratio=np.ones(n), id=np.zeros(n, np.int32))
         if n:
             self.lib.ref_get_velbcs(_ip(o["node"]), _ip(o["dir"]), _ip(o["style"]), _dp(o["norm"]),
                                     _dp(o["value"]), _dp(o["ftime"]), _dp(o["offset"]), _dp(o["currentValue"]))
             self.lib.ref_get_velbc_reflections(_ip(o["reflected"]), _dp(o["ratio"]))
+            self.lib.ref_get_velbc_ids(_ip(o["id"]))
         return o
+
+    def reactions(self, ids):
+        """NodalVelBC::TotalReactionForce for each BC id (0 = every BC; rigid-particle BCs carry their material number)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.zeros((len(ids), 3))
+        self.lib.ref_reaction_forces(len(ids), _ip(ids), _dp(out))
+        return out
 
     def materials(self):
         nm = self.info["nmat"]
@@ -223,7 +231,10 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
     _flatten("info", r.info, out)
     out["node_coords"] = r.node_coords()
     out["element_extents"] = r.element_extents()
-    _flatten("velbcs", r.velbcs(), out)
+    vb = r.velbcs()
+    _flatten("velbcs", vb, out)
+    react_ids = np.array(sorted(set([0] + [int(i) for i in vb["id"]] + list(range(1, r.info["nmat"] + 1)))), np.int32)
+    out["reaction_ids"] = react_ids
     ids, par = r.materials()
     out["mat_ids"], out["mat_params"] = ids, par
     mm = r.multimaterial()
@@ -249,6 +260,7 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
             _flatten("s%d/t%d/nodes" % (s + 1, i), r.nodes(), out)
             _flatten("s%d/t%d/p" % (s + 1, i), r.particles(), out)
         done += 1
+        out["reaction%d" % done] = r.reactions(react_ids)
         if done in snaps:
             _flatten("p%d" % done, r.particles(), out)
             _flatten("n%d" % done, r.nodes(), out)
@@ -260,6 +272,7 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
                 done += 1
             _flatten("p%d" % done, r.particles(), out)
             _flatten("n%d" % done, r.nodes(), out)
+            out["reaction%d" % done] = r.reactions(react_ids)
     out["xpic_by_step"] = np.array(xpic, dtype=np.int32).reshape(-1, 2)
     _flatten("info_end", r.get_info(), out)
     r.close()

@@ -33,6 +33,7 @@ struct EmuSim {
     std::vector<int> bcNode, bcStart, bcSym, bcActive, bcOfNode;
     std::vector<double> bcNorm, bcValue, bcRatio;
     std::vector<int> bcRefl, bcOrder;
+    std::vector<double> bcReact, rigidReact;      // capi.cu: dReaction, dRigidReaction (always kept here)
     int dim, shape, n;
     bool largeRotation;
     long long mstep;
@@ -237,7 +238,11 @@ void run_task(EmuSim *S, int t)
         DISPATCH(k_p2g_forces, S->P.nNR, S->g, S->P, S->N, 0);
         if (S->conduction) DISPATCH(k_p2g_conduction, S->P.nNR, S->g, S->P, S->T);
         break;
-    case 5: EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp); apply_bcs(S, PASS_GRID_FORCES, 0); break;
+    case 5:
+        EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp);
+        std::fill(S->bcReact.begin(), S->bcReact.end(), 0.); std::fill(S->rigidReact.begin(), S->rigidReact.end(), 0.);     // capi.cu: reactions_zero
+        apply_bcs(S, PASS_GRID_FORCES, 0);
+        break;
     case 6:
         EMU_LAUNCH(k_update_momenta, nblk(nn, 256), 256, nn, S->N, S->sp.dt);
         if (S->conduction) EMU_LAUNCH(k_transport_update, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->nf, S->N, S->T, S->sp.dt);
@@ -351,6 +356,9 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     for (int p = nNR; p < n; p++) if (S->mats[matnum[p] - 1].p[9] != 0.) R.mirrored = 1;
     R.mat = S->PR.mat; R.mats = S->mats.data();
     R.stride[0] = 1; R.stride[1] = g.yplane; R.stride[2] = g.zplane; R.nnodes = g.nnodes;
+    S->rigidReact.assign(3 * S->mats.size(), 0.);
+    R.reaction = S->rigidReact.data();
+    S->B.reaction = NULL;
     bind_nodes(S, (size_t)g.nnodes);
     memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp); memset(&S->Q, 0, sizeof S->Q);
     return S;
@@ -481,6 +489,8 @@ extern "C" void emu_set_bcs(void *h, int n, const int *node, const double *norm,
     S->B.nUnique = (int)S->bcNode.size(); S->B.node = S->bcNode.data(); S->B.start = S->bcStart.data(); S->B.symdir = S->bcSym.data();
     S->B.active = S->bcActive.data(); S->B.norm = S->bcNorm.data(); S->B.value = S->bcValue.data();
     S->B.refl = NULL; S->B.reflRatio = NULL;
+    S->bcReact.assign(3 * (size_t)n, 0.);
+    S->B.reaction = S->bcReact.data();
     S->bcOrder = order;
     S->bcOfNode.assign((size_t)S->g.nnodes, -1);
     for (int u = 0; u < S->B.nUnique; u++) S->bcOfNode[S->bcNode[u]] = u;
@@ -493,6 +503,15 @@ extern "C" void emu_set_bc_reflections(void *h, int n, const int *reflected, con
     S->bcRefl.assign(n, -1); S->bcRatio.assign(n, 1.);
     for (int e = 0; e < n; e++) { const int i = S->bcOrder[e]; S->bcRefl[e] = reflected[i] > 0 ? reflected[i] - 1 : -1; S->bcRatio[e] = ratio[i]; }
     S->B.refl = S->bcRefl.data(); S->B.reflRatio = S->bcRatio.data();
+}
+
+// capi.cu::mpmgpu_download_reactions
+extern "C" void emu_get_reactions(void *h, double *bc, double *rigid)
+{
+    EmuSim *S = (EmuSim *)h;
+    for (size_t e = 0; e < S->bcOrder.size() && bc; e++)
+        for (int c = 0; c < 3; c++) bc[3 * (size_t)S->bcOrder[e] + c] = S->bcReact[3 * e + c];
+    for (size_t i = 0; i < S->rigidReact.size() && rigid; i++) rigid[i] = S->rigidReact[i];
 }
 
 extern "C" void emu_set_xpic(void *h, int order, int usingFMPM) { EmuSim *S = (EmuSim *)h; S->sp.xpicOrder = order; S->sp.usingFMPM = usingFMPM; }

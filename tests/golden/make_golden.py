@@ -217,6 +217,15 @@ CASES = {
                                                                         '<Material Type="9" Name="Disk 1"><rho>1.5</rho><E>1.0</E><nu>0.33</nu><alpha>60</alpha><Hardening>Linear</Hardening><yield>0.02</yield><Ep>0.1</Ep>'),
                                                                (320.0, 290.0), (2000.0, 500.0), (800.0, 1500.0)).replace("<Conduction/>", "<Conduction/><EnergyCoupling/>"),
                                              (1, 2, 40), 2),
+    # reaction forces of the velocity BCs (NodalVelBC::freaction summed by bcID: "reaction<step>" beside "reaction_ids")
+    "react3d_walls_ugimp": (inputs.reaction_walls3d(E=100.0, vz=-3.0e3, vx=2.0e3, vy=-1.0e3, gravity=(0.0, 0.0, -5.0e5)), (1, 2, 40), 2, 0.3, 1000.0),
+    "react3d_walls_lcpdi_usl": (inputs.reaction_walls3d(ncell=3, E=100.0, gimp="lCPDI", method=3, vz=-3.0e3, vx=2.0e3, vy=-1.0e3), (1, 2, 30), 2),
+    "react3d_rigid_piston_fmpm2": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=0.0, rigid=("piston", 7, (1.0e3, -5.0e2, -6.0e3)),
+                                                  custom_tasks=inputs.periodic_xpic(2, True, 1)), (1, 2, 30), 2, 0.3, 1000.0),
+    "react3d_rigid_wall_xpic2": (inputs.block3d(ncell=3, margin=3, E=100.0, vz=-5.0e3, vx=1.0e3, bc=False, rigid=("wall", 4, (0.0, 0.0, 0.0)),
+                                                custom_tasks=inputs.periodic_xpic(2, False, 1)), (1, 2, 30), 2, 0.3, 1000.0),
+    "react2d_multimaterial_wall": (inputs.grid_bcs(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=4000.0, vmax=11.0, gap=0.0, extra_header=inputs.multimaterial(2, 0.3))),
+                                                   [('<BCLine x1="0" y1="-11" x2="0" y2="11" tolerance="1.1">', 'dir="1" vel="0" id="-4"')]), (1, 2, 40), 2),
     "block3d_ugimp_usavg": (inputs.block3d(ncell=4, margin=2), (1, 10, 100), 1),
     "block3d_fast_crossings": (inputs.block3d(ncell=4, margin=3, E=10.0, vx=2.0e4, vy=1.0e4, vz=-1.5e4), (1, 40), 1),
     "block3d_gravity_damping": (inputs.block3d(ncell=3, margin=2, vz=-500.0, gravity=(0.0, 0.0, -9.8e6),

@@ -257,3 +257,24 @@ def blocks3d_contact(header, gimp="uGIMP", method=2, materials=3, rigid_b=False)
 """.replace('<Material Type="9" Name="B"><rho>2.0</rho><E>400</E><nu>0.33</nu><alpha>20</alpha><Hardening>Linear</Hardening><yield>8</yield><Ep>40</Ep></Material>',
              '<Material Type="11" Name="B"><SetDirection>8</SetDirection></Material>' if rigid_b else
              '<Material Type="9" Name="B"><rho>2.0</rho><E>400</E><nu>0.33</nu><alpha>20</alpha><Hardening>Linear</Hardening><yield>8</yield><Ep>40</Ep></Material>') % (method, gimp_tag, header, third, third_mat)
+
+
+def grid_bcs(xml, blocks):
+    """Append a <GridBCs> element made of (shape element, DisBC attributes) pairs, e.g.
+    ('<BCBox xmin="0" .../>'-style opening tag without the slash, 'dir="3" vel="0" id="-1"')."""
+    body = "".join("%s<DisBC %s/></%s>" % (shape, bc, shape[1:].split()[0].rstrip(">")) for shape, bc in blocks)
+    return xml.replace("</MaterialPoints>", "</MaterialPoints><GridBCs>%s</GridBCs>" % body, 1)
+
+
+def reaction_walls3d(ncell=4, margin=3, **kw):
+    """block3d held by four sets of velocity BCs with their own ids (the "reactionx/y/z" global quantities sum NodalVelBC::freaction
+    by id): the bottom plane (z, id -1), the +x face the block moves into (x, id -2), the top plane pushed down at constant
+    velocity (z, id -3) and the -y face with a skewed xy condition (id -4)."""
+    n, lo, hi = ncell + 2 * margin, margin, margin + ncell
+    box = '<BCBox xmin="%g" xmax="%g" ymin="%g" ymax="%g" zmin="%g" zmax="%g">'
+    return grid_bcs(block3d(ncell=ncell, margin=margin, bc=False, **kw), [
+        (box % (-1, n + 1, -1, n + 1, -1, lo + 0.01), 'dir="3" vel="0" id="-1"'),
+        (box % (hi - 0.01, n + 1, -1, n + 1, -1, n + 1), 'dir="1" vel="0" id="-2"'),
+        (box % (-1, n + 1, -1, n + 1, hi - 0.01, n + 1), 'dir="3" vel="-800" id="-3"'),
+        (box % (-1, n + 1, -1, lo + 0.01, lo + 0.99, hi - 0.99), 'dir="12" angle="20" vel="0" id="-4"'),
+    ])

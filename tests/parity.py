@@ -271,3 +271,53 @@ def check_multimaterial_run(sim, z, case):
     nf = int(z["mm/nfields"]) if "mm/nfields" in z else 1
     cnt = nodes["number_points"].reshape(nf, -1) > 0
     return int(np.sum(cnt.sum(axis=0) > 1))
+
+
+# reaction forces of the velocity BCs: goldens with "reaction<step>" = NodalVelBC::TotalReactionForce(id) for id in "reaction_ids"
+REACTION_CASES = ["react3d_walls_ugimp", "react3d_walls_lcpdi_usl", "react3d_rigid_piston_fmpm2", "react3d_rigid_wall_xpic2", "react2d_multimaterial_wall"]
+
+
+def reaction_totals(prob, ids, bc, rigid):
+    """What GlobalQuantity's reactionx/y/z would read (GlobalQuantity.cpp:971-986): the BCs' freaction summed by bcID; 0 takes
+    every BC, rigid-particle BCs carry their material number (ProjectRigidBCsTask.cpp:241)."""
+    out = np.zeros((len(ids), 3))
+    for k, i in enumerate(ids):
+        if i == 0:
+            out[k] = bc.sum(axis=0) + rigid.sum(axis=0)
+        elif i < 0:
+            out[k] = bc[prob.bc_id == i].sum(axis=0) if len(bc) else 0.0
+        else:
+            out[k] = rigid[i - 1]
+    return out
+
+
+def check_reactions(sim, prob, z, step, tol):
+    """The reaction totals after `step` steps against the reference's, to tol of the largest total of that step."""
+    ref = z["reaction%d" % step]
+    bc, rigid = sim.reactions()
+    got = reaction_totals(prob, [int(i) for i in z["reaction_ids"]], bc, rigid)
+    scale = max(np.abs(ref).max(), np.abs(bc).sum(axis=0).max() if len(bc) else 0.0)
+    assert scale > 0.0
+    err = np.abs(got - ref).max() / scale
+    assert err < tol, "reaction forces after step %d: rel err %.3g\n got %s\n ref %s" % (step, err, got, ref)
+    return err
+
+
+def check_reaction_run(sim, prob, z, case):
+    """Whole steps with the reaction totals checked after every step the golden holds them for."""
+    have = sorted(int(k[8:]) for k in z if k.startswith("reaction") and k != "reaction_ids")
+    assert have and have[-1] > 2
+    done = 0
+    for s in have:
+        while done < s:
+            x = xpic_for_step(z, done + 1)
+            if x:
+                sim.set_xpic(*x)
+            sim.step(1)
+            done += 1
+        check_reactions(sim, prob, z, s, TOL_1STEP if s <= 2 else TOL_100STEP)
+        if ("p%d/pos" % s) in z:
+            got = sim.download()
+            errs, bad = compare_particles(got, z, "p%d" % s, TOL_1STEP if s <= 2 else TOL_100STEP, scale_prefix="p2" if s == 1 else None)
+            assert not bad, "%s after %d steps: %s" % (case, s, bad)
+            assert np.array_equal(got["in_elem"], z["p%d/inElem" % s])
