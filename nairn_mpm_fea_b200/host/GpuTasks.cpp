@@ -76,6 +76,13 @@ std::vector<mpmgpu_ctx *> gSlabs;
 int gNumGpus = 1;
 bool gHostStale = false;            // device is ahead of mpm[]
 std::vector<NodalVelBC *> gBCs;     // host BC list in list order
+// "reactionx/y/z" global quantities (GlobalQuantity.cpp:971-986) read NodalVelBC::freaction of the host's BC objects: when one is
+// asked for, the device keeps every BC's reaction force (mpmgpu_track_reactions) and SyncReactionsToHost writes them into the
+// objects before the reference's own code sums them by ID.  The BCs rigid particles would make (ProjectRigidBCsTask, not run on
+// the host any more) are stood in for by one carrier object per rigid-BC material at the end of the list, holding the material's
+// summed reaction under its ID (= material number, ProjectRigidBCsTask.cpp:241).
+bool gTrackReactions = false;
+std::vector<NodalVelBC *> gRigidCarriers;       // by material index, NULL for the others
 bool gBCsVary = false;
 bool gRigidFunctions = false;       // some rigid-BC material sets its velocity by functions of time and position
 long long gLeftGridWarned = 0;     // first-time grid leavers already handed to the reference's MPMWarnings
@@ -132,8 +139,19 @@ void DownloadSlabsToHost(void)
 }
 
 // device -> mpm[] (MPMBase fields; SetDeformationGradient is implicit: ep + wrot are downloaded)
+void SyncReactionsToHost(void)
+{
+    if (!gTrackReactions) return;
+    std::vector<double> bc(3 * gBCs.size() + 3), rigid(3 * (size_t)nmat);
+    check(mpmgpu_download_reactions(gCtx, (int)gBCs.size(), bc.data(), rigid.data()), "GpuTasks::SyncReactionsToHost");
+    for (size_t i = 0; i < gBCs.size(); i++) gBCs[i]->freaction = MakeVector(bc[3 * i], bc[3 * i + 1], bc[3 * i + 2]);
+    for (int m = 0; m < nmat; m++)
+        if (gRigidCarriers[m] != NULL) gRigidCarriers[m]->freaction = MakeVector(rigid[3 * m], rigid[3 * m + 1], rigid[3 * m + 2]);
+}
+
 void DownloadToHost(void)
 {
+    SyncReactionsToHost();
     if (!gHostStale) return;
     if (!gSlabs.empty()) { DownloadSlabsToHost(); gHostStale = false; return; }
     const int n = nmpms;
@@ -233,6 +251,8 @@ bool QuantityFromSums(GlobalQuantity *g, const std::vector<double> &sums, double
 // quantities that do not read the particles (step number, times, grid damping values ...): the reference's own code serves
 bool QuantityIsParticleFree(int q)
 {
+    // (reaction forces: the reference's code reads the BC objects SyncReactionsToHost has just filled)
+    if (gTrackReactions && (q == TOT_REACTX || q == TOT_REACTY || q == TOT_REACTZ)) return true;
     return q == STEP_NUMBER || q == CPU_TIME || q == ELAPSED_TIME || q == GRID_ALPHA || q == PARTICLE_ALPHA;
 }
 
@@ -252,6 +272,7 @@ void GlobalArchiveFromDevice(double atime)
     if (archiver->globalFile == NULL) return;
     std::vector<double> sums((size_t)nmat * MPMGPU_GS_NSUMS, 0.);
     check(mpmgpu_global_sums(gCtx, sums.data()), "GpuTasks::GlobalArchive");
+    SyncReactionsToHost();
     archiver->lastArchived.clear();
     archiver->lastArchivedStep = fmobj->mstep;
     for (GlobalQuantity *g = firstGlobal; g != NULL;) {
@@ -521,9 +542,12 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     // global quantities the reference reads from its nodes or BC objects, which the replaced tasks no longer fill
     for (GlobalQuantity *gq = firstGlobal; gq != NULL; gq = gq->GetNextGlobal()) {
         const int q = gq->quantity;
-        if (q == TOT_FCONX || q == TOT_FCONY || q == TOT_FCONZ || q == TOT_REACTX || q == TOT_REACTY || q == TOT_REACTZ || q == GRID_KINE_ENERGY ||
-            q == INTERFACE_ENERGY || q == FRICTION_WORK)
-            return "global quantities read from the grid (contact / reaction forces, grid kinetic energy, interface energy, friction work)";
+        if (q == TOT_FCONX || q == TOT_FCONY || q == TOT_FCONZ || q == GRID_KINE_ENERGY || q == INTERFACE_ENERGY || q == FRICTION_WORK)
+            return "global quantities read from the grid (contact forces, grid kinetic energy, interface energy, friction work)";
+        if (q == TOT_REACTX || q == TOT_REACTY || q == TOT_REACTZ) {
+            if (ngpus > 1) return "reaction-force global quantities with -gpus N (the slabs do not keep them)";
+            gTrackReactions = true;
+        }
     }
     // damping that changes during the run (functions of time, feedback on the kinetic energy: BodyForce.cpp:167-230)
     if (bodyFrc.useFeedback || bodyFrc.usePFeedback || bodyFrc.gridfunction != NULL || bodyFrc.pgridfunction != NULL)
@@ -837,6 +861,23 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         // would mirror at run time (SetMirroredVelBC) are handled by the device's rigid-BC projection instead
         brefl.push_back(bc->reflectedNode); bratio.push_back(bc->reflectRatio);
         if (bc->reflectedNode >= 0) anyReflected = true;
+    }
+    if (gTrackReactions) {
+        if (mpmgpu_track_reactions(gCtx, 1) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+        // carriers for the reactions of the rigid-particle BCs, linked after the grid BCs (where ProjectRigidBCsTask would put its own)
+        gRigidCarriers.assign((size_t)nmat, (NodalVelBC *)NULL);
+        BoundaryCondition *last = gBCs.empty() ? NULL : gBCs.back();
+        for (int m = 0; m < nmat; m++) {
+            if (!theMaterials[m]->IsRigidBC()) continue;
+            const int keep = nd[1]->fixedDirection;         // (the constructor marks the node's dof as fixed: undone, this BC fixes nothing)
+            NodalVelBC *c = new NodalVelBC(1, X_DIRECTION, CONSTANT_VALUE, 0., 0., 0., 0.);
+            nd[1]->fixedDirection = keep;
+            c->SetID(m + 1);
+            if (last != NULL) last->SetNextObject(c); else firstVelocityBC = c;
+            if (firstRigidVelocityBC == NULL) firstRigidVelocityBC = c;
+            last = c;
+            gRigidCarriers[m] = c;
+        }
     }
     ALL_CTX(mpmgpu_set_velocity_bcs(ctx_, (int)bnode.size(), bnode.data(), bnorm.data(), bval.data(), bact.data(), bsym.data()));
     if (anyReflected) ALL_CTX(mpmgpu_set_velocity_bc_reflections(ctx_, (int)bnode.size(), brefl.data(), bratio.data()));

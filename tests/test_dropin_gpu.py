@@ -194,3 +194,32 @@ def test_device_packed_archives_equal_the_host_writers():
         assert len(rd) == len(rh)
         for x, y in zip(rd, rh):
             assert abs(float(x) - float(y)) <= 2e-6 * max(abs(float(y)), 1e-300) + 1e-30, (rd, rh)
+
+
+@pytest.mark.parametrize("mode", ["tasks", "fused", "fused_hostoutput"])
+def test_reaction_force_global_quantities_match_reference(mode):
+    """"reactionx/y/z" global quantities (GlobalQuantity.cpp:971-986) by BC id: the bottom plane's grid BCs (id -1), the BCs a
+    rigid piston makes (id = its material number, 2) and all of them (0).  The device keeps NodalVelBC::freaction per BC
+    (mpmgpu_track_reactions); the adapter writes them into the host's BC objects and the reference's own code sums them."""
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("oracle/_ref/NairnMPM or host/_build/NairnMPM_gpu not built")
+    xml = (inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=0.0, rigid=("piston", 7, (1.0e3, -5.0e2, -6.0e3)))
+           .replace('<DisBC dir="3" vel="0"/>', '<DisBC dir="3" vel="0" id="-1"/>')
+           .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"
+                    "<GlobalArchiveTime units=\"ms\">0.002</GlobalArchiveTime><GlobalArchive type=\"reactionz\" material=\"-1\"/>"
+                    "<GlobalArchive type=\"reactionz\" material=\"2\"/><GlobalArchive type=\"reactionx\" material=\"2\"/>"
+                    "<GlobalArchive type=\"reactiony\"/><GlobalArchive type=\"reactionz\"/><GlobalArchive type=\"Kinetic Energy\"/>"))
+    assert 'id="-1"' in xml
+    dref, out_ref = run(REF, xml, ("-np", "4"))
+    extra = {"tasks": (), "fused": ("-fused",), "fused_hostoutput": ("-fused", "-hostoutput")}[mode]
+    dgpu, out_gpu = run(GPU, xml, extra)
+    assert "GPU TASKS" in out_gpu
+    rows_r = [ln.split("\t") for ln in open(os.path.join(dref, "res/blk.global")).read().splitlines() if not ln.startswith("#")]
+    rows_g = [ln.split("\t") for ln in open(os.path.join(dgpu, "res/blk.global")).read().splitlines() if not ln.startswith("#")]
+    assert len(rows_r) == len(rows_g) and len(rows_r) >= 10
+    cols = np.array([[float(x) for x in r] for r in rows_r])
+    assert np.all(np.abs(cols[:, 1:6]).max(axis=0) > 0), "a reaction column is zero throughout: the input does not exercise it"
+    for rr, rg in zip(rows_r, rows_g):
+        assert len(rr) == len(rg) == 7
+        for j, (x, y) in enumerate(zip(rr, rg)):
+            assert abs(float(x) - float(y)) <= 5e-6 * max(np.abs(cols[:, j]).max(), 1e-300), (rr, rg)

@@ -68,8 +68,11 @@ CASES = {
     "diffusion": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</MPMHeader>", '<Diffusion reference="0"/></MPMHeader>'),
                   "transport tasks other than conduction"),
     # global quantities the reference reads from its nodes / BC objects would be silently zero: the replaced tasks no longer fill them
-    "reaction force quantity": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
-        "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="reactionz"/></MPMHeader>'), "global quantities read from the grid"),
+    # (reaction forces are kept on the device: tests/test_dropin_gpu.py)
+    "contact force quantity": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
+        "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="contactz"/></MPMHeader>'), "global quantities read from the grid"),
+    "reaction force quantity on several GPUs": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
+        "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="reactionz"/></MPMHeader>'), "reaction-force global quantities with -gpus N"),
     "more exponential terms": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material=inputs.neohookean_material(),
                                               extra_header="<DefGradTerms>3</DefGradTerms>"), "<DefGradTerms> other than the default"),
 }
@@ -87,7 +90,7 @@ def test_ineligible_inputs_are_refused_with_the_reason(case):
     if not os.path.exists(GPU):
         pytest.skip("host/_build/NairnMPM_gpu not built")
     xml, reason = CASES[case]
-    p = run(xml)
+    p = run(xml, ("-gpus", "2") if "several GPUs" in case else ())
     assert p.returncode == 2, (p.returncode, p.stderr[-500:], p.stdout[-300:])
     if reason is None:          # refused by the library after mpmgpu_create: needs the device (tests/test_dropin_gpu.py); here it stops at "no CUDA device"
         assert "cannot run this input on libmpmgpu" in p.stderr
