@@ -133,6 +133,9 @@ typedef struct mpmgpu_config {
  *                   6 Nonlinear2 yldred (1 + beta alpha^n)   [17] beta [18] n
  *                   3 JohnsonCook  [17] Bred [18] n [19] C [20] ep0 [21] D [22] n2 [23] Tm [24] m [25] reference temperature
  *                                  [26] edotMin [27] eminTerm  (JohnsonCook.cpp:106-127)
+ *                   4 SCGL  min(yldred (1 + beta alpha)^n, yldMaxred) Gratio, Gratio = max(0, 1 + GPpred P + GTp (T - Tref)) also
+ *                           scales Gred  [17] beta [18] n [19] yldMaxred [20] GPpred [21] GTp [25] reference temperature
+ *                           (SCGLHardening.cpp:72-91, :138-198; IsoPlasticity.cpp:548-549)
  *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)  [9] mirrored (-1, 0, +1)
  */
 typedef struct mpmgpu_material {

@@ -327,6 +327,11 @@ extern "C" int mpmgpu_set_materials(mpmgpu_ctx *ctx, int nmat, const mpmgpu_mate
         if (mats[i].n_history < 0 || mats[i].n_history > MPM_MAX_HISTORY) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: %d history doubles (max %d)", mats[i].n_history, MPM_MAX_HISTORY);
         ctx->hMats[i].kind = k; ctx->hMats[i].nhist = mats[i].n_history;
         memcpy(ctx->hMats[i].p, mats[i].p, sizeof(double) * MPM_MAT_NPARAMS);
+        if (k == MAT_ISOPLASTICITY) {
+            const int law = (int)mats[i].p[16];
+            if (law != 0 && law != HARD_LINEAR && law != HARD_NONLINEAR && law != HARD_JOHNSONCOOK && law != HARD_SCGL && law != HARD_NONLINEAR2)
+                return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: hardening law %d is not supported (1 Linear, 2 Nonlinear, 3 JohnsonCook, 4 SCGL, 6 Nonlinear2)", law);
+        }
         if (mats[i].p[3] != 0. && k != MAT_NEOHOOKEAN && k != MAT_ISOPLASTICITY && k != MAT_MOONEY)
             return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_materials: material kind %d does not support artificial viscosity (MaterialBase::SupportsArtificialViscosity)", k);
         // MeshInfo::GetAverageCellSize for equal elements (MeshInfo.cpp:1517-1523): a grid constant the law needs
@@ -1434,6 +1439,7 @@ static int sort_particles(mpmgpu_ctx *ctx)
     // heat 37 entropy 38 plast 39 prevT 40 hist 41-44 pfext 45-47 acc 48-50 | ints: elem mat cross orig key.
     // ncpos, key (F1 rewrites them right after the sort) and acc (F3 writes it before anyone reads it) never move; with
     // IsotropicMat only, eplast, the plastic energy and the history are zero in both pools; likewise pfext without particle loads.
+    static_assert(MPM_MAX_HISTORY == 4 && NPD == 51, "the field positions below follow bind_particles with 4 history variables");
     unsigned long long live = (1ull << NPD) - 1ull;
     live &= ~(7ull << 10); live &= ~(7ull << 48);
     if (t.stateKind == SK_ELASTIC) { live &= ~(63ull << 29); live &= ~(1ull << 39); live &= ~(15ull << 41); }

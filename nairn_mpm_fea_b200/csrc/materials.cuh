@@ -627,18 +627,25 @@ __device__ __forceinline__ void mooney_law(PState &s, const double du[9], double
 //   Nonlinear2 (6, Materials/Nonlinear2Hardening.cpp): yield = yldred (1 + beta alpha^n)        [17] beta [18] n
 //   JohnsonCook (3, Materials/JohnsonCook.cpp): (yldred + Bred alpha^n)(1 + C ln(epdot/ep0) [+ D ln^n2])(1 - T*^m)
 //        [17] Bred [18] n [19] C [20] ep0 [21] D [22] n2 [23] Tm [24] m [25] reference temperature [26] edotMin [27] eminTerm
+//   SCGL (4, Materials/SCGLHardening.cpp): yield = min(yldred (1 + beta alpha)^n, yldMaxred) Gratio with the shear modulus ratio
+//        Gratio = 1 + GPpred P + GTp (T - Tref) >= 0 of the particle's pressure and temperature, which also scales Gred
+//        [17] beta [18] n [19] yldMaxred [20] GPpred [21] GTp [25] reference temperature
 // alphaMax [14] and yldredMin [15] keep their meaning for the two power laws.
-enum { HARD_LINEAR = 1, HARD_NONLINEAR = 2, HARD_JOHNSONCOOK = 3, HARD_NONLINEAR2 = 6 };
+enum { HARD_LINEAR = 1, HARD_NONLINEAR = 2, HARD_JOHNSONCOOK = 3, HARD_SCGL = 4, HARD_NONLINEAR2 = 6 };
 #define MPM_TWOTHIRDS 0.6666666666666667
 #define MPM_SQRT_EIGHT27THS 0.5443310539518174
 
 struct HardAlpha { double alpint, dalpha; };      // HardeningAlpha (Materials/HardeningLawBase.hpp)
-struct HardProps { int law; double TjcTerm, hmlgTemp; };       // JCProperties (JohnsonCook::GetCopyOfHardeningProps :130-152)
+struct HardProps { int law; double TjcTerm, hmlgTemp, Gratio; };       // JCProperties (JohnsonCook::GetCopyOfHardeningProps :130-152), SCGLProperties
 
-__device__ __forceinline__ HardProps hard_props(const Material &m, double prevT)
+__device__ __forceinline__ HardProps hard_props(const Material &m, double prevT, double pressure)
 {
     HardProps h;
-    h.law = (int)m.p[16]; h.TjcTerm = 1.; h.hmlgTemp = 0.;
+    h.law = (int)m.p[16]; h.TjcTerm = 1.; h.hmlgTemp = 0.; h.Gratio = 1.;
+    if (h.law == HARD_SCGL) {        // SCGLHardening::GetShearRatio with J = 1 (SCGLHardening.cpp:141-152, IsoPlasticity.cpp:548)
+        h.Gratio = 1. + m.p[20] * pressure + m.p[21] * (prevT - m.p[25]);
+        if (h.Gratio < 0.) h.Gratio = 0.;
+    }
     if (h.law == HARD_JOHNSONCOOK) {
         h.hmlgTemp = (prevT - m.p[25]) / (m.p[23] - m.p[25]);
         if (h.hmlgTemp > 1.) h.TjcTerm = 0.;
@@ -677,6 +684,7 @@ __device__ __forceinline__ void jc_rate_terms(const Material &m, double delTime,
 __device__ __forceinline__ double hard_yield(const Material &m, const HardProps &h, double delTime, const HardAlpha &a)
 {
     const double yldred = m.p[10];
+    if (h.law == HARD_SCGL) return fmin(yldred * pow(1. + m.p[17] * a.alpint, m.p[18]), m.p[19]) * h.Gratio;        // SCGLHardening.cpp:160-164
     if (h.law == HARD_NONLINEAR) return a.alpint < m.p[14] ? yldred * pow(1. + m.p[17] * a.alpint, m.p[18]) : m.p[15];
     if (h.law == HARD_NONLINEAR2) return a.alpint < m.p[14] ? yldred * (1. + m.p[17] * pow(a.alpint, m.p[18])) : m.p[15];
     if (h.hmlgTemp >= 1.) return 0.;
@@ -691,6 +699,11 @@ __device__ __forceinline__ double hard_yield(const Material &m, const HardProps 
 __device__ __forceinline__ double hard_kprime(const Material &m, const HardProps &h, double delTime, const HardAlpha &a)
 {
     const double yldred = m.p[10];
+    if (h.law == HARD_SCGL) {        // SCGLHardening.cpp:170-181
+        if (yldred * pow(1. + m.p[17] * a.alpint, m.p[18]) >= m.p[19]) return 0.;
+        const double bfactor = dble_equal(m.p[18], 1.) ? m.p[17] : m.p[17] * m.p[18] * pow(1. + m.p[17] * a.alpint, m.p[18] - 1.);
+        return MPM_TWOTHIRDS * (yldred * h.Gratio) * bfactor;
+    }
     if (h.law == HARD_NONLINEAR) return a.alpint < m.p[14] ? MPM_TWOTHIRDS * yldred * m.p[17] * m.p[18] * pow(1. + m.p[17] * a.alpint, m.p[18] - 1) : 0.;
     if (h.law == HARD_NONLINEAR2) return a.alpint < m.p[14] ? MPM_TWOTHIRDS * yldred * m.p[17] * m.p[18] * pow(a.alpint, m.p[18] - 1.) : 0.;
     if (h.hmlgTemp >= 1.) return 0.;
@@ -708,6 +721,11 @@ __device__ __forceinline__ double hard_kprime(const Material &m, const HardProps
 __device__ __forceinline__ double hard_k2prime(const Material &m, const HardProps &h, double fnp1, double delTime, const HardAlpha &a)
 {
     const double yldred = m.p[10];
+    if (h.law == HARD_SCGL) {        // SCGLHardening.cpp:184-192
+        if (yldred * pow(1. + m.p[17] * a.alpint, m.p[18]) >= m.p[19]) return 0.;
+        const double factor = yldred * h.Gratio;
+        return MPM_SQRT_EIGHT27THS * factor * factor * m.p[17] * m.p[18] * pow(1. + m.p[17] * a.alpint, 2. * m.p[18] - 1) * fnp1;
+    }
     if (h.law == HARD_NONLINEAR)
         return a.alpint < m.p[14] ? MPM_SQRT_EIGHT27THS * yldred * yldred * m.p[17] * m.p[18] * pow(1. + m.p[17] * a.alpint, 2. * m.p[18] - 1) * fnp1 : 0.;
     if (h.law == HARD_NONLINEAR2) {
@@ -731,6 +749,7 @@ __device__ __forceinline__ double hard_k2prime(const Material &m, const HardProp
 // K(alpha) - K(0) for the dissipated energy (HardeningLawBase.cpp:110-113; JohnsonCook.cpp:230-238)
 __device__ __forceinline__ double hard_yield_increment(const Material &m, const HardProps &h, double delTime, const HardAlpha &a)
 {
+    if (h.law == HARD_SCGL) return (fmin(m.p[10] * pow(1. + m.p[17] * a.alpint, m.p[18]), m.p[19]) - m.p[10]) * h.Gratio;      // SCGLHardening.cpp:195-198
     if (h.law != HARD_JOHNSONCOOK) return hard_yield(m, h, delTime, a) - m.p[10];
     if (h.hmlgTemp >= 1.) return 0.;
     const double ep = a.dalpha / (delTime * m.p[20]);
@@ -820,8 +839,9 @@ __device__ __forceinline__ void isoplasticity_law(PState &s, const double du[9],
 {
     // GENERAL: a hardening law other than Linear (slot 16): numerical return by the bracketed Newton's method of HardeningLawBase
     HardProps hp;
-    if (GENERAL) hp = hard_props(m, s.prevT);
-    const double Gred = m.p[8], Kred = m.p[9], yldred = m.p[10], Epred = m.p[11];
+    if (GENERAL) hp = hard_props(m, s.prevT, s.pressure);
+    // (the shear modulus follows the hardening law's ratio: IsoPlasticity::GetCopyOfMechanicalProps :548-549)
+    const double Gred = GENERAL ? m.p[8] * hp.Gratio : m.p[8], Kred = m.p[9], yldred = m.p[10], Epred = m.p[11];
     const double gamma0 = m.p[13], Cv = m.p[1], alphaMax = m.p[14], yldredMin = m.p[15];
     // large rotation (:140-158): the strain increment in the current configuration replaces du, state n-1 is rotated by dR
     double deLR[9], dR[9];

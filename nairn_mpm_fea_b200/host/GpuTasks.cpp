@@ -38,6 +38,7 @@
 #include "Materials/NonlinearHardening.hpp"
 #include "Materials/Nonlinear2Hardening.hpp"
 #include "Materials/JohnsonCook.hpp"
+#include "Materials/SCGLHardening.hpp"
 #include "Global_Quantities/ThermalRamp.hpp"
 #include "Materials/RigidMaterial.hpp"
 #include "Boundary_Conditions/NodalVelBC.hpp"
@@ -587,8 +588,9 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         case 8: if (((Mooney *)mb)->rubber) return "Mooney with the IdealRubber option"; break;
         case 9:
             {   HardeningLawBase *hl = ((IsoPlasticity *)mb)->plasticLaw;
-                if (dynamic_cast<LinearHardening *>(hl) == NULL && dynamic_cast<NonlinearHardening *>(hl) == NULL && dynamic_cast<JohnsonCook *>(hl) == NULL)
-                    return "IsoPlasticity hardening law other than Linear, Nonlinear, Nonlinear2 and JohnsonCook";
+                if (dynamic_cast<LinearHardening *>(hl) == NULL && dynamic_cast<NonlinearHardening *>(hl) == NULL && dynamic_cast<JohnsonCook *>(hl) == NULL &&
+                    hl->lawID != SCGLHARDENING_ID)
+                    return "IsoPlasticity hardening law other than Linear, Nonlinear, Nonlinear2, JohnsonCook and SCGL";
             }
             break;
         case 11: {
@@ -727,6 +729,10 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
             else if (nh != NULL) {      // Nonlinear (2) and its subclass Nonlinear2 (6): NonlinearHardening.cpp:49-60, Nonlinear2Hardening.cpp:28-39
                 m.p[16] = dynamic_cast<Nonlinear2Hardening *>(hl) != NULL ? 6. : 2.;
                 m.p[17] = nh->beta; m.p[18] = nh->npow; m.p[14] = nh->alphaMax;
+            } else if (hl->lawID == SCGLHARDENING_ID) {        // SCGL (4): SCGLHardening.cpp:72-91, :138-198
+                SCGLHardening *sc = (SCGLHardening *)hl;
+                m.p[16] = 4.;
+                m.p[17] = sc->beta; m.p[18] = sc->nhard; m.p[19] = sc->yldMaxred; m.p[20] = sc->GPpred; m.p[21] = sc->GTp; m.p[25] = thermal.reference;
             } else {                    // Johnson-Cook (3): JohnsonCook.cpp:106-127
                 m.p[16] = 3.;
                 m.p[17] = jc->Bred; m.p[18] = jc->njc; m.p[19] = jc->Cjc; m.p[20] = jc->ep0jc; m.p[21] = jc->Djc; m.p[22] = jc->n2jc;

@@ -165,7 +165,7 @@ def mooney(G1, G2, K, rho, aI=0.0, Cv=DEFAULT_CV, UofJOption=0, pdamping=None, a
                 init_history=[1.0, 1.0], init_eplast=[1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
 
 
-HARD_LINEAR, HARD_NONLINEAR, HARD_JOHNSONCOOK, HARD_NONLINEAR2 = 1, 2, 3, 6        # MaterialBase::SetHardeningLaw ids
+HARD_LINEAR, HARD_NONLINEAR, HARD_JOHNSONCOOK, HARD_SCGL, HARD_NONLINEAR2 = 1, 2, 3, 4, 6        # MaterialBase::SetHardeningLaw ids
 
 
 def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np_=THREED_MPM, pdamping=None, yld_min=0.0, av=None,
@@ -174,7 +174,9 @@ def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np
     LinearHardening (LinearHardening.cpp:55-80; the default) or, through `hardening`,
       ("nonlinear", beta, n)   yield (1 + beta alpha)^n        NonlinearHardening.cpp:49-60
       ("nonlinear2", beta, n)  yield (1 + beta alpha^n)        Nonlinear2Hardening.cpp:28-39
-      ("johnsoncook", dict(B=, n=, C=, ep0=, D=0, n2=1, Tm=, m=, Tref=))  JohnsonCook.cpp:106-127 (yld is A; B in the units of yld)."""
+      ("johnsoncook", dict(B=, n=, C=, ep0=, D=0, n2=1, Tm=, m=, Tref=))  JohnsonCook.cpp:106-127 (yld is A; B in the units of yld)
+      ("scgl", dict(beta=, n=, yld_max=, GPp=, GTp=, Tref=))  SCGLHardening.cpp:72-91: min(yld (1 + beta alpha)^n, yld_max) times the
+                   shear-modulus ratio 1 + GPp P + GTp (T - Tref), which also scales G (yld_max in the units of yld, GPp per unit of P)."""
     iso = isotropic(E, nu, rho, aI, Cv, np_, pdamping)
     p = _base(rho, Cv, pdamping, av, large_rotation)
     C66, C33 = iso["C66"], iso["C33"]
@@ -210,6 +212,12 @@ def isoplasticity(E, nu, rho, yld, Ep=None, Khard=0.0, aI=0.0, Cv=DEFAULT_CV, np
             p[16] = HARD_JOHNSONCOOK
             p[17], p[18], p[19], p[20], p[21], p[22] = j["B"] / rho, j["n"], C, j["ep0"], j.get("D", 0.0), j.get("n2", 1.0)
             p[23], p[24], p[25], p[26], p[27] = j["Tm"], j["m"], j.get("Tref", 0.0), edot_min, 1.0 + C * float(np.log(edot_min))
+            p[11] = 0.0
+            p[14] = 1.0e50
+        elif law == "scgl":
+            j = hardening[1]
+            p[16] = HARD_SCGL
+            p[17], p[18], p[19], p[20], p[21], p[25] = j["beta"], j["n"], j["yld_max"] / rho, j["GPp"] * rho, j["GTp"], j.get("Tref", 0.0)
             p[11] = 0.0
             p[14] = 1.0e50
         else:

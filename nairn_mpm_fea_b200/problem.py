@@ -325,6 +325,9 @@ def from_reference_dump(z, snapshot="p0"):
                 m = M.isoplasticity(q[8], q[9], q[0], q[15], None, 0.0, q[11] * 1.0e6, q[1], pr.np, pd, q[20] * q[0], av, large_rotation=lr,
                                     hardening=("johnsoncook", dict(B=q[24] * q[0], n=q[25], C=q[26], ep0=q[27], D=q[28], n2=q[29], Tm=q[30],
                                                                    m=q[31], Tref=q[16])))
+            elif law == M.HARD_SCGL:
+                m = M.isoplasticity(q[8], q[9], q[0], q[15], None, 0.0, q[11] * 1.0e6, q[1], pr.np, pd, q[20] * q[0], av, large_rotation=lr,
+                                    hardening=("scgl", dict(beta=q[24], n=q[25], yld_max=q[26] * q[0], GPp=q[27] / q[0], GTp=q[28], Tref=q[16])))
             else:
                 raise NotImplementedError("hardening law %d" % law)
         elif mid in (M.CONTACT_LAW, M.COULOMB_FRICTION_LAW) and "mm/nfields" in z:

@@ -35,6 +35,7 @@
 #include "Materials/NonlinearHardening.hpp"
 #include "Materials/Nonlinear2Hardening.hpp"
 #include "Materials/JohnsonCook.hpp"
+#include "Materials/SCGLHardening.hpp"
 #include "Global_Quantities/ThermalRamp.hpp"
 #include "Materials/Mooney.hpp"
 #include "Materials/IsoPlasticity.hpp"
@@ -445,7 +446,8 @@ void ref_get_velbc_reflections(int *reflected, double *ratio)
 //  neo(28):     8 G 9 K 10 Lame 11 Gsp 12 Ksp 13 Lamesp 14 UofJOption 15 CTE1 16 gamma0(as used)
 //  mooney(8):   8 G1 9 G2 10 K 11 G1sp 12 G2sp 13 Ksp 14 UofJOption 15 CTE1 16 gamma0 17 IdealRubber
 //  isoplas(9):  8 E 9 nu 10 G 11 CTE3 12 gamma0 13 Gred 14 Kred 15 yield 16 Ep 17 yldred 18 Epred 19 alphaMax 20 yldredMin 21 beta
-//               22 useLargeRotation 23 hardening law id (1 Linear, 2 Nonlinear, 6 Nonlinear2, 3 JohnsonCook)
+//               22 useLargeRotation 23 hardening law id (1 Linear, 2 Nonlinear, 6 Nonlinear2, 3 JohnsonCook, 4 SCGL)
+//               SCGL: 24 beta 25 nhard 26 yldMaxred 27 GPpred 28 GTp (16 thermal.reference)
 //               Nonlinear/Nonlinear2: 24 beta 25 npow (19 alphaMax);  JohnsonCook: 24 Bred 25 njc 26 Cjc 27 ep0jc 28 Djc 29 n2jc 30 Tmjc 31 mjc
 //               16 thermal.reference
 int ref_get_materials(int *ids, double *params)
@@ -494,6 +496,9 @@ int ref_get_materials(int *ids, double *params)
                              NonlinearHardening *nh = dynamic_cast<NonlinearHardening *>(h);
                              JohnsonCook *jc = dynamic_cast<JohnsonCook *>(h);
                              if (nh != NULL) { q[23] = n2h != NULL ? 6. : 2.; q[24] = nh->beta; q[25] = nh->npow; q[19] = nh->alphaMax; }
+                             SCGLHardening *sc = h->lawID == SCGLHARDENING_ID ? (SCGLHardening *)h : NULL;     // (SLMaterial, id 5, derives from it: not exported)
+                             if (sc != NULL) { q[23] = 4.; q[24] = sc->beta; q[25] = sc->nhard; q[26] = sc->yldMaxred; q[27] = sc->GPpred; q[28] = sc->GTp;
+                                               q[16] = thermal.reference; }
                              if (jc != NULL) { q[23] = 3.; q[24] = jc->Bred; q[25] = jc->njc; q[26] = jc->Cjc; q[27] = jc->ep0jc; q[28] = jc->Djc;
                                                q[29] = jc->n2jc; q[30] = jc->Tmjc; q[31] = jc->mjc; q[16] = thermal.reference; } }
         }
@@ -536,6 +541,7 @@ int ref_hardening_terms(int mat, double alpint, double dalpha, double delTime, d
     a.alpint = alpint; a.dalpha = dalpha;
     char buffer[256];
     void *props = h->GetCopyOfHardeningProps(mpm[0], fmobj->np, (void *)buffer, 0);
+    h->GetShearRatio(mpm[0], mpm[0]->GetPressure(), 1., props, 0);          // (fills SCGLProperties::Gratio, as IsoPlasticity::GetCopyOfMechanicalProps does)
     out[0] = h->GetYield(mpm[0], fmobj->np, delTime, &a, props);
     out[1] = h->GetKPrime(mpm[0], fmobj->np, delTime, &a, props);
     out[2] = h->GetK2Prime(mpm[0], fnp1, delTime, &a, props);

@@ -265,12 +265,12 @@ extern "C" int devshape_find_element(int dim, int np, int horiz, int vert, int d
 }
 
 // the hardening-law terms of the device source alone: out = {yield, K', K2'(fnp1), yield increment}
-extern "C" int devlaws_hardening_terms(const double *params, double prevT, double alpint, double dalpha, double delTime, double fnp1, double *out)
+extern "C" int devlaws_hardening_terms(const double *params, double prevT, double alpint, double dalpha, double delTime, double fnp1, double *out, double pressure)
 {
     Material m;
     m.kind = MAT_ISOPLASTICITY; m.nhist = 1;
     memcpy(m.p, params, sizeof(double) * MPM_MAT_NPARAMS);
-    const HardProps h = hard_props(m, prevT);
+    const HardProps h = hard_props(m, prevT, pressure);
     HardAlpha a;
     a.alpint = alpint; a.dalpha = dalpha;
     out[0] = hard_yield(m, h, delTime, a);

@@ -140,6 +140,12 @@ CASES = {
     "disks2d_nonlinear2_planestress": (inputs.disks2d(analysis=11, gimp=None, vel=3000.0)
                                        .replace(DISK1, inputs.isoplastic_hardening_material("Nonlinear2", rho=1.5, E=1.0, yld=0.02, name="Disk 1")), (1, 20), 1),
     # quadratic B-spline shape functions: B2SPLINE and its GIMP form B2GIMP (3D incl. rigid-BC particles, 2D)
+    # SCGL hardening: shear modulus and yield stress follow the particle's pressure (and temperature: th3d_offset_scgl); yieldMax out of
+    # reach (on the cap the reference's own return solver is decided by rounding noise: tests/test_device_laws_vs_reference_cpu.py)
+    "block3d_scgl": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_hardening_material("SCGL", yieldMax=400.0, GPpG0=4.0e-4), vz=-4.0e4, vx=5.0e3,
+                                    extra_header="<StressFreeTemp>300</StressFreeTemp>"), (1, 60), 1, 0.3, 3000.0),
+    "disks2d_scgl_planestrain": (inputs.disks2d(analysis=10, vel=3000.0, extra_header="<StressFreeTemp>300</StressFreeTemp>")
+                                 .replace(DISK2, inputs.isoplastic_hardening_material("SCGL", rho=1.5, E=1.0, yld=0.02, yieldMax=0.4, name="Disk 2")), (1, 100), 1),
     "block3d_b2spline": (inputs.block3d(ncell=3, margin=3, E=100.0, gimp="B2SPLINE", vz=-6.0e3, vx=3.0e3), (1, 30), 1, 0.3, 3000.0),
     "block3d_b2gimp": (inputs.block3d(ncell=3, margin=3, E=100.0, gimp="B2GIMP", vz=-6.0e3, vx=3.0e3, custom_tasks=inputs.periodic_xpic(2, True, 1)), (1, 2, 30), 2, 0.3, 3000.0),
     "block3d_b2gimp_rigid_wall": (inputs.block3d(ncell=3, margin=3, gimp="B2GIMP", material=inputs.isoplastic_material(), vz=-4.0e4, bc=False,
@@ -200,6 +206,8 @@ CASES = {
                         .replace("<alpha>0</alpha>", "<alpha>80</alpha>").replace('<Body ', '<Body temp="340" ', 1), (1, 2, 40), 2, 0.3, 2000.0),
     "th3d_offset_isoplastic_usl": (inputs.block3d(ncell=3, margin=3, method=3, material=inputs.isoplastic_material(yld=5.0), vz=-2.0e4,
                                                   extra_header="<StressFreeTemp>300</StressFreeTemp>").replace('<Body ', '<Body temp="420" ', 1), (1, 2, 40), 2, 0.3, 2000.0),
+    "th3d_offset_scgl": (inputs.block3d(ncell=3, margin=3, material=inputs.isoplastic_hardening_material("SCGL", yieldMax=400.0, GPpG0=4.0e-4, GTpG0=-1.0e-3), vz=-4.0e4,
+                                        vx=5.0e3, extra_header="<StressFreeTemp>300</StressFreeTemp>").replace('<Body ', '<Body temp="380" ', 1), (1, 2, 40), 2, 0.3, 3000.0),
     "th3d_offset_neohookean": (inputs.block3d(ncell=3, margin=3, material=inputs.neohookean_material(), vz=-6.0e3, extra_header="<StressFreeTemp>300</StressFreeTemp>")
                                .replace('<Body ', '<Body temp="260" ', 1), (1, 2, 40), 2, 0.3, 2000.0),
     "th2d_offset_mooney_iso_planestress": (inputs.oblique_disks(inputs.disks2d(analysis=11, vel=3000.0, vmax=11.0, gap=0.0, alpha=60.0, extra_header="<StressFreeTemp>300</StressFreeTemp>"))

@@ -154,8 +154,11 @@ def isoplastic_material(rho=2.0, E=2000.0, nu=0.33, yld=20.0, Ep=100.0, av=None)
 
 
 def isoplastic_hardening_material(law, rho=2.0, E=2000.0, nu=0.33, yld=20.0, name="Blk", **k):
-    """IsoPlasticity with <Hardening>Nonlinear|Nonlinear2|JohnsonCook</Hardening> and that law's own properties."""
-    if law in ("Nonlinear", "Nonlinear2"):
+    """IsoPlasticity with <Hardening>Nonlinear|Nonlinear2|JohnsonCook|SCGL</Hardening> and that law's own properties."""
+    if law == "SCGL":       # SCGLHardening.cpp:38-69: pressure- and temperature-dependent shear modulus, capped power-law yield
+        props = ("<yield>%r</yield><betahard>%r</betahard><nhard>%r</nhard><yieldMax>%r</yieldMax><GPpG0>%r</GPpG0><GTpG0>%r</GTpG0>"
+                 % (yld, k.get("betahard", 8.0), k.get("nhard", 0.4), k.get("yieldMax", 1.6 * yld), k.get("GPpG0", 0.5 / E), k.get("GTpG0", -2.2e-4)))
+    elif law in ("Nonlinear", "Nonlinear2"):
         props = "<yield>%r</yield><Khard>%r</Khard><nhard>%r</nhard>" % (yld, k.get("Khard", 8.0), k.get("nhard", 0.4))
         if k.get("yieldMin") is not None:
             props += "<yieldMin>%r</yieldMin>" % k["yieldMin"]

@@ -56,6 +56,11 @@ CASES = {
                                                                extra_header=inputs.multimaterial(0, 0.3, None, ' RigidBias="10"')))
                                     .replace("<SetDirection>8</SetDirection>", "<SetDirection>8</SetDirection><SettingFunction>-2000*(1+0.3*sin(20*t))</SettingFunction>"
                                                                                "<SettingFunction2>700</SettingFunction2>"), None, "res/disks."),
+    # SCGL hardening (pressure- and temperature-dependent shear modulus) on a block that starts 80 K above the stress-free temperature
+    "block3d_scgl_thermal_offset": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, material=inputs.isoplastic_hardening_material("SCGL", yieldMax=400.0, GPpG0=4.0e-4, GTpG0=-1.0e-3),
+                                                   vz=-4.0e4, vx=5.0e3, extra_header="<StressFreeTemp>300</StressFreeTemp>").replace('<Body ', '<Body temp="380" ', 1)
+                                    .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+                                    .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYYNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
     # adiabatic coupling: a Johnson-Cook block heats itself by plastic work (thermal softening), no transport task
     "block3d_adiabatic_johnsoncook": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, material=inputs.isoplastic_hardening_material("JohnsonCook", Djc=0.01), vz=-4.0e4,
                                                      extra_header="<StressFreeTemp>300</StressFreeTemp>").replace("</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>")

@@ -29,7 +29,7 @@ CASES = {
     "unsupported material": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="2" Name="Blk"><rho>1</rho><EA>1000</EA>'
                                             '<ET>500</ET><GA>300</GA><nuT>0.3</nuT><nuA>0.25</nuA><alphaA>0</alphaA><alphaT>0</alphaT></Material>'), "material type"),
     "other hardening law": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="9" Name="Blk"><rho>8.9</rho><E>100000</E><nu>0.33</nu>'
-                                           '<alpha>20</alpha><Hardening>SCGL</Hardening><yield>120</yield><GPpG0>0.01</GPpG0><betahard>36</betahard><nhard>0.45</nhard>'
+                                           '<alpha>20</alpha><Hardening>SL</Hardening><yield>120</yield><GPpG0>0.01</GPpG0><betahard>36</betahard><nhard>0.45</nhard>'
                                            '<yieldMax>640</yieldMax></Material>'), "hardening law other than"),
     "ideal rubber": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material='<Material Type="8" Name="Blk"><rho>1</rho><G1>30</G1><G2>0</G2><K>100</K>'
                                     '<alpha>0</alpha><IdealRubber/></Material>'), "IdealRubber"),
