@@ -137,6 +137,9 @@ typedef struct mpmgpu_config {
  *                           scales Gred  [17] beta [18] n [19] yldMaxred [20] GPpred [21] GTp [25] reference temperature
  *                           (SCGLHardening.cpp:72-91, :138-198; IsoPlasticity.cpp:548-549)
  *  RIGIDBC:         [8] direction bits (1 x, 2 y, 4 z: RigidMaterial setDirection)  [9] mirrored (-1, 0, +1)
+ *                   [10] != 0: sets the temperature (RigidMaterial::setTemperature): with conduction the first such particle to reach a
+ *                   node without a grid temperature BC holds it at its own temperature (mpmgpu_particles.temperature of the rigid
+ *                   particle; ProjectRigidBCsTask.cpp:118-125)
  */
 typedef struct mpmgpu_material {
     int kind;

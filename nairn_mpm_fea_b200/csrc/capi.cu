@@ -101,6 +101,10 @@ struct mpmgpu_ctx {
     bool thermal = false;               // particle temperatures can change (conduction, or a start off the stress-free temperature): the laws get dT
     TransportNodes T;
     double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
+    bool rigidTemp = false;             // some rigid-BC material sets the temperature: R.ownerT / R.ptemp / R.savedT are allocated
+    double *rigidTempPool = NULL;       // pTemperature of the rigid particles
+    unsigned char *dFixedTemp = NULL;   // nodes with a grid temperature BC
+    std::vector<unsigned char> hFixedTemp;
     TempBCs Q;                          // nodal temperature BCs (mpmgpu_set_temperature_bcs)
     int tbcEntries = 0, tbcCap = 0;
     std::vector<int> tbcOrder;          // entry e on device = host list index tbcOrder[e]
@@ -529,9 +533,20 @@ extern "C" int mpmgpu_set_temperature_bcs(mpmgpu_ctx *ctx, int n, const int *nod
     if (!ctx || n < 0 || (n > 0 && (!node || !value))) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_temperature_bcs: bad arguments");
     if (!ctx->conduction) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_temperature_bcs: call mpmgpu_set_conduction first");
     cudaSetDevice(ctx->cfg.device);
-    if (n == 0) { ctx->Q.nUnique = 0; ctx->tbcEntries = 0; return MPMGPU_OK; }
     for (int i = 0; i < n; i++)
         if (node[i] < 1 || node[i] > ctx->g.nnodes) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_temperature_bcs: BC %d on node %d of %d", i, node[i], ctx->g.nnodes);
+    {   // nodes whose temperature a grid BC holds (active or not: NodalTempBC's constructor sets the node's TEMP_DIRECTION bit): rigid
+        // particles make no BC there (ProjectRigidBCsTask.cpp:202)
+        std::vector<unsigned char> fixed((size_t)ctx->g.nnodes, 0);
+        for (int i = 0; i < n; i++) fixed[node[i] - 1] = 1;
+        if (fixed != ctx->hFixedTemp) {
+            if (!ctx->dFixedTemp) CK(dalloc(ctx, &ctx->dFixedTemp, (size_t)ctx->g.nnodes));
+            CK(cudaMemcpy(ctx->dFixedTemp, fixed.data(), fixed.size(), cudaMemcpyHostToDevice));
+            ctx->hFixedTemp.swap(fixed);
+        }
+        ctx->R.fixedT = ctx->dFixedTemp;
+    }
+    if (n == 0) { ctx->Q.nUnique = 0; ctx->tbcEntries = 0; return MPMGPU_OK; }
     // group by node, list order kept inside a node (the reference walks its list: zero all, then add all)
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
@@ -869,6 +884,22 @@ extern "C" int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *
         ctx->P.dTr = ctx->tempPool + (size_t)4 * ctx->cap;
         ctx->P.dTad = ctx->adiabatic ? ctx->tempPool + (size_t)5 * ctx->cap : NULL;
         if (ctx->adiabatic && nNR) CK(cudaMemsetAsync(ctx->P.dTad, 0, (size_t)nNR * sizeof(double), ctx->stream));
+        ctx->rigidTemp = false;
+        if (ctx->conduction && nR)
+            for (int i = 0; i < ctx->nmat; i++) if (ctx->hMats[i].kind == MAT_RIGIDBC && ctx->hMats[i].p[10] != 0.) ctx->rigidTemp = true;
+        if (ctx->rigidTemp) {           // rigid particles that hold the nodes they touch at their own temperature
+            if (!h->temperature) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_upload_particles: a rigid material sets the temperature: mpmgpu_particles.temperature is needed");
+            const size_t nn = (size_t)ctx->g.nnodes;
+            if (!ctx->rigidTempPool) {
+                CK(dalloc(ctx, &ctx->rigidTempPool, ctx->rigidCap));
+                CK(dalloc(ctx, &ctx->R.ownerT, nn)); CK(dalloc(ctx, &ctx->R.savedT, nn));
+                CK(cudaMemsetAsync(ctx->R.ownerT, 0x7f, nn * sizeof(int), ctx->stream));
+            }
+            ctx->PR.temp = ctx->rigidTempPool;
+            if ((rc = up_field(ctx, &ctx->PR.temp, h->temperature, 1, n, nNR, nR))) return rc;
+            ctx->R.ptemp = ctx->PR.temp;
+            ctx->R.fixedT = ctx->dFixedTemp;
+        } else { ctx->R.ownerT = NULL; ctx->R.ptemp = NULL; ctx->R.savedT = NULL; }
         if (nNR) {
             // pTemperature; without the array every particle starts at the temperature of its last strain update (energies[5])
             if (h->temperature) { if ((rc = up_field(ctx, &ctx->P.temp, h->temperature, 1, n, 0, nNR))) return rc; }
@@ -1185,6 +1216,7 @@ static int t_project_rigid_bcs(mpmgpu_ctx *ctx)
 {
     if (!ctx->R.on) return MPMGPU_OK;
     for (int d = 0; d < 3; d++) CK(cudaMemsetAsync(ctx->R.owner[d], 0x7f, (size_t)ctx->g.nnodes * sizeof(int), ctx->stream));
+    if (ctx->R.ownerT) CK(cudaMemsetAsync(ctx->R.ownerT, 0x7f, (size_t)ctx->g.nnodes * sizeof(int), ctx->stream));
     ctx->launches += 3;
     DISPATCH_DIM_SHAPE(k_project_rigid_bcs, ctx->PR.n, ctx->g, ctx->PR, ctx->dMats, ctx->R, ctx->dFlags);
     return MPMGPU_OK;
@@ -1244,8 +1276,10 @@ static int t_post_extrapolation(mpmgpu_ctx *ctx)
     if (ctx->conduction) {      // TransportTask::GetTransportValues + TransportBCsAndGradients (PostExtrapolationTask.cpp:88,160)
         LAUNCH(k_transport_nodal_value, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->nf, ctx->N, ctx->T);
         if (ctx->Q.nUnique > 0) LAUNCH(k_temp_bcs_impose, nblocks(ctx->Q.nUnique, 128), 128, ctx->Q, ctx->T, 0);
+        if (ctx->R.ownerT) LAUNCH(k_rigid_temp_bcs_impose, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->R, ctx->T, 0);
         DISPATCH_DIM_SHAPE(k_transport_gradients, ctx->P.nNR, ctx->g, ctx->P, ctx->T);
         if (ctx->Q.nUnique > 0) LAUNCH(k_temp_bcs_impose, nblocks(ctx->Q.nUnique, 128), 128, ctx->Q, ctx->T, 1);
+        if (ctx->R.ownerT) LAUNCH(k_rigid_temp_bcs_impose, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->R, ctx->T, 1);
     }
     return MPMGPU_OK;
 }
@@ -1307,6 +1341,7 @@ static int t_update_momenta(mpmgpu_ctx *ctx)
     if (ctx->sp.xpicOrder <= 1) { int rc = apply_bcs(ctx, PASS_UPDATE_MOMENTUM, 0); if (rc) return rc; }      // NodalVelBC.cpp:367-375
     // TransportTask::TransportGridBCs (UpdateMomentaTask.cpp:61)
     if (ctx->conduction && ctx->Q.nUnique > 0) LAUNCH(k_temp_bcs_grid, nblocks(ctx->Q.nUnique, 128), 128, ctx->Q, ctx->T, ctx->sp.dt);
+    if (ctx->conduction && ctx->R.ownerT) LAUNCH(k_rigid_temp_bcs_grid, nblocks(ctx->g.nnodes, 256), 256, ctx->g.nnodes, ctx->R, ctx->T, ctx->sp.dt);
     return MPMGPU_OK;
 }
 
@@ -1845,7 +1880,7 @@ extern "C" int mpmgpu_download_particles(mpmgpu_ctx *ctx, mpmgpu_particles *h, u
         if ((mask & MPMGPU_F_ACC) && (rc = down_field(ctx, P.acc, PR.acc, h->acc, 3, n, dtmp))) break;
         if ((mask & MPMGPU_F_TEMPERATURE) && h->temperature && ctx->thermal) {
             // pTemperature of the nonrigid particles (rigid-BC particles: the temperature of energies[5])
-            double *const t1[1] = {P.temp}, *const t1R[1] = {PR.prevT};
+            double *const t1[1] = {P.temp}, *const t1R[1] = {ctx->rigidTemp ? PR.temp : PR.prevT};
             if ((rc = down_field(ctx, t1, t1R, h->temperature, 1, n, dtmp))) break;
         }
         if (mask & MPMGPU_F_ELEM) {

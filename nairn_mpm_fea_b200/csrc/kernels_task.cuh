@@ -269,11 +269,13 @@ __global__ void __launch_bounds__(TASK_THREADS) k_project_rigid_bcs(Grid g, Part
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= PR.n) return;
     const int dirs = (int)mats[PR.mat[p]].p[8];      // RigidMaterial::setDirection: x=1, y=2, z=4
+    const bool setsT = R.ownerT != nullptr && mats[PR.mat[p]].p[10] != 0.;      // RigidMaterial::RigidTemperature
     auto claim = [&](int nd, double, double, double, double) {
         const int fixed = R.fixedBits ? R.fixedBits[nd] : 0;
 #pragma unroll
         for (int d = 0; d < DIM; d++)
             if ((dirs >> d & 1) && !(fixed >> d & 1)) atomicMin(&R.owner[d][nd], p);
+        if (setsT && !(R.fixedT && R.fixedT[nd])) atomicMin(&R.ownerT[nd], p);
     };
     if (SHAPE_IS_CPDI(SHAPE)) {
         // the nodes of the particle domain's corners (the reference's InitializationTask finds them for rigid particles too)
@@ -1224,6 +1226,30 @@ __global__ void k_temp_bcs_grid(TempBCs Q, TransportNodes T, double dt)
         gQ += bcT / dt;
     }
     if (!first) { T.gT[nd] = gT; T.gQ[nd] = gQ; }
+}
+
+// the same two steps for the temperature BCs rigid particles made this step (they follow the grid BCs in the reference's list and sit
+// on nodes without one: ProjectRigidBCsTask.cpp:202; one BC per node)
+__global__ void k_rigid_temp_bcs_impose(int nnodes, RigidBCs R, TransportNodes T, int restore)
+{
+    const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= nnodes) return;
+    const int o = R.ownerT[nd];
+    if (o == RIGID_NONE) return;
+    if (restore) T.gT[nd] = R.savedT[nd];
+    else { R.savedT[nd] = T.gT[nd]; T.gT[nd] = R.ptemp[o]; }
+}
+
+__global__ void k_rigid_temp_bcs_grid(int nnodes, RigidBCs R, TransportNodes T, double dt)
+{
+    const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= nnodes) return;
+    const int o = R.ownerT[nd];
+    if (o == RIGID_NONE) return;
+    const double bcT = R.ptemp[o];
+    double gQ = T.gQ[nd] + -T.gT[nd] / dt;
+    gQ += bcT / dt;
+    T.gT[nd] = bcT; T.gQ[nd] = gQ;
 }
 
 // task 5: ConductionTask::AddForces -> MatPoint3D::FCond / MatPoint2D::FCond (MatPoint3D.cpp:280-287, MatPoint2D.cpp:272-278)

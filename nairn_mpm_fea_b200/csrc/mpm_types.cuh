@@ -188,6 +188,12 @@ struct RigidBCs {
     int stride[3];           // node spacing along x, y, z
     int nnodes;
     double *reaction;        // [3*nmat] freaction of the rigid-particle BCs summed per rigid material (their bcID); NULL = not tracked
+    // temperature BCs made by rigid particles whose material sets the temperature (RigidMaterial::setTemperature,
+    // ProjectRigidBCsTask.cpp:118-125): the first such particle to reach a node without a grid temperature BC holds it at its own
+    int *ownerT;             // [nnodes] claiming rigid particle, RIGID_NONE when free; NULL = no rigid temperature BCs
+    const double *ptemp;     // rigid particles' pTemperature
+    const unsigned char *fixedT;      // [nnodes] 1 = the node has a grid temperature BC (NodalPoint::fixedDirection & TEMP_DIRECTION), or NULL
+    double *savedT;          // [nnodes] the node's own value while the BC value stands in for the gradients
 };
 
 struct StatusFlags {         // device -> host error reporting (ResetElementsTask.cpp:71-151)

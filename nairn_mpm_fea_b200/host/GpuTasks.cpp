@@ -597,7 +597,9 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
             RigidMaterial *rm = (RigidMaterial *)mb;
             if (rm->IsRigidBlock()) return "rigid block material";
             if (rm->Vfunction != NULL || rm->useControlVelocity) return "rigid material with value function or control velocity";
-            if (rm->setTemperature || rm->setConcentration) return "rigid material that sets temperature or concentration";
+            if (rm->setConcentration) return "rigid material that sets concentration";
+            // (setTemperature: with conduction the device projects these particles' temperatures onto the nodes they touch; the value
+            // function that would change the particle temperature in time was refused above)
             if (rm->function != NULL) gRigidFunctions = true;
             break;
         }
@@ -749,6 +751,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
             m.kind = MPMGPU_MAT_RIGIDBC; m.n_history = 0;
             m.p[8] = ((RigidMaterial *)mb)->setDirection;
             m.p[9] = ((RigidMaterial *)mb)->mirrored;
+            m.p[10] = ((RigidMaterial *)mb)->setTemperature ? 1. : 0.;
         }
     }
     ALL_CTX(mpmgpu_set_materials(ctx_, nmat, mats.data()));

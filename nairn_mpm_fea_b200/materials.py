@@ -126,12 +126,14 @@ def contact_law_placeholder():
     return dict(kind=NOT_A_PARTICLE_MATERIAL, n_history=0, p=np.zeros(NPARAMS), rho=0.0, wave_speed=0.0)
 
 
-def rigid_bc(direction_bits, mirrored=0):
+def rigid_bc(direction_bits, mirrored=0, sets_temperature=False):
     """RigidMaterial as moving velocity BC (MaterialID 11, Materials/RigidMaterial.hpp).  mirrored = -1 / +1: the BC nodes
-    reflect the velocity of the body at the minimum / maximum edge (NodalVelBC::SetMirroredVelBC)."""
+    reflect the velocity of the body at the minimum / maximum edge (NodalVelBC::SetMirroredVelBC).  sets_temperature
+    (<SetTemperature/>): with conduction the nodes its particles touch are held at the particles' temperature."""
     p = _base(1.0, DEFAULT_CV, None)
     p[8] = float(direction_bits)
     p[9] = float(mirrored)
+    p[10] = 1.0 if sets_temperature else 0.0
     return dict(kind=RIGIDBC, n_history=0, p=p, rho=1.0, wave_speed=0.0)
 
 

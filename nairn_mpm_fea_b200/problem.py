@@ -337,9 +337,9 @@ def from_reference_dump(z, snapshot="p0"):
                 raise NotImplementedError("rigid contact material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")
             m = M.rigid_contact()
         elif mid == M.RIGIDBC:
-            if q[10] != 0 or q[11] != 0:
-                raise NotImplementedError("rigid material with setting functions (host-evaluated: update_rigid_velocities) / temperature or concentration")
-            m = M.rigid_bc(int(q[8]), int(q[9]))
+            if q[10] != 0 or int(q[11]) & 2 or (len(q) > 12 and q[12] != 0):
+                raise NotImplementedError("rigid material with setting functions (host-evaluated: update_rigid_velocities) / concentration")
+            m = M.rigid_bc(int(q[8]), int(q[9]), sets_temperature=bool(int(q[11]) & 1))
         else:
             raise NotImplementedError("material id %d" % mid)
         pr.materials.append(m)

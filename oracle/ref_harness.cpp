@@ -481,7 +481,8 @@ int ref_get_materials(int *ids, double *params)
             RigidMaterial *rm = (RigidMaterial *)m;
             q[8] = rm->setDirection; q[9] = rm->mirrored;
             q[10] = (rm->function != NULL || rm->function2 != NULL || rm->function3 != NULL) ? 1. : 0.;
-            q[11] = (rm->setTemperature || rm->setConcentration) ? 1. : 0.;
+            q[11] = (rm->setTemperature ? 1. : 0.) + (rm->setConcentration ? 2. : 0.);
+            q[12] = rm->Vfunction != NULL ? 1. : 0.;
         }
         else if (ids[i] == 9) {
             IsoPlasticity *pm = (IsoPlasticity *)m;

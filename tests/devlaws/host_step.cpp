@@ -51,6 +51,8 @@ struct EmuSim {
     std::vector<double> tpool, kcond, temps;
     TempBCs Q;
     std::vector<int> tbcNode, tbcStart, tbcActive; std::vector<double> tbcValue, tbcSaved;
+    // temperature BCs of rigid particles (capi.cu: rigidTemp, R.ownerT / ptemp / fixedT / savedT)
+    std::vector<int> ownerT; std::vector<double> rigidTemps, savedT; std::vector<unsigned char> fixedTemp;
 };
 
 struct HostArrays {
@@ -226,8 +228,10 @@ void run_task(EmuSim *S, int t)
         if (S->conduction) {
             EMU_LAUNCH(k_transport_nodal_value, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->nf, S->N, S->T);
             if (S->Q.nUnique > 0) EMU_LAUNCH(k_temp_bcs_impose, nblk(S->Q.nUnique, 128), 128, S->Q, S->T, 0);
+            if (S->R.ownerT) EMU_LAUNCH(k_rigid_temp_bcs_impose, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->R, S->T, 0);
             DISPATCH(k_transport_gradients, S->P.nNR, S->g, S->P, S->T);
             if (S->Q.nUnique > 0) EMU_LAUNCH(k_temp_bcs_impose, nblk(S->Q.nUnique, 128), 128, S->Q, S->T, 1);
+            if (S->R.ownerT) EMU_LAUNCH(k_rigid_temp_bcs_impose, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->R, S->T, 1);
         }
         break;
     }
@@ -249,6 +253,7 @@ void run_task(EmuSim *S, int t)
         material_contact(S, CALL_UPDATE_MOMENTUM);
         if (S->sp.xpicOrder <= 1) apply_bcs(S, PASS_UPDATE_MOMENTUM, 0);
         if (S->conduction && S->Q.nUnique > 0) EMU_LAUNCH(k_temp_bcs_grid, nblk(S->Q.nUnique, 128), 128, S->Q, S->T, S->sp.dt);
+        if (S->conduction && S->R.ownerT) EMU_LAUNCH(k_rigid_temp_bcs_grid, nblk(S->g.nnodes, 256), 256, S->g.nnodes, S->R, S->T, S->sp.dt);
         break;
     case 7: {
         if (S->sp.xpicOrder > 1) xpic_extrapolation(S, 1);
@@ -288,6 +293,7 @@ void run_task(EmuSim *S, int t)
     case 10:            // ProjectRigidBCsTask: between mass/momentum and post-extrapolation (capi.cu::t_project_rigid_bcs)
         if (!S->R.on) break;
         std::fill(S->owner.begin(), S->owner.end(), RIGID_NONE);
+        std::fill(S->ownerT.begin(), S->ownerT.end(), RIGID_NONE);
         DISPATCH(k_project_rigid_bcs, S->PR.n, S->g, S->PR, S->mats.data(), S->R, &S->flags);
         break;
     }
@@ -421,6 +427,16 @@ extern "C" void emu_set_conduction(void *h, const double *kcond, const double *t
     for (int c = 0; c < 3; c++) S->P.tgrad[c] = S->temps.data() + (size_t)(c + 1) * C;
     S->P.dTr = S->temps.data() + 4 * C;
     S->P.dTad = S->sp.adiabatic ? S->temps.data() + 5 * C : NULL;
+    // rigid particles of a material that sets the temperature (capi.cu::mpmgpu_upload_particles: rigidTemp)
+    bool rigidTemp = false;
+    for (size_t i = 0; i < S->mats.size() && kcond && S->PR.n > 0; i++) if (S->mats[i].kind == MAT_RIGIDBC && S->mats[i].p[10] != 0.) rigidTemp = true;
+    if (rigidTemp) {
+        S->rigidTemps.assign(temperature + S->P.n, temperature + S->n);
+        S->ownerT.assign(nn, RIGID_NONE); S->savedT.assign(nn, 0.);
+        if (S->fixedTemp.size() != nn) S->fixedTemp.assign(nn, 0);
+        S->PR.temp = S->rigidTemps.data();
+        S->R.ownerT = S->ownerT.data(); S->R.ptemp = S->rigidTemps.data(); S->R.savedT = S->savedT.data(); S->R.fixedT = S->fixedTemp.data();
+    }
 }
 
 extern "C" void emu_set_energy_coupling(void *h, int adiabatic) { ((EmuSim *)h)->sp.adiabatic = adiabatic; }
@@ -429,6 +445,9 @@ extern "C" void emu_set_energy_coupling(void *h, int adiabatic) { ((EmuSim *)h)-
 extern "C" void emu_set_temperature_bcs(void *h, int n, const int *node, const double *value)
 {
     EmuSim *S = (EmuSim *)h;
+    S->fixedTemp.assign((size_t)S->g.nnodes, 0);
+    for (int i = 0; i < n; i++) S->fixedTemp[node[i] - 1] = 1;
+    S->R.fixedT = S->fixedTemp.data();
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return node[a] < node[b]; });
@@ -447,7 +466,7 @@ extern "C" void emu_get_transport(void *h, double *gT, double *gVCT, double *gQ,
 {
     EmuSim *S = (EmuSim *)h;
     for (int i = 0; i < S->g.nnodes && S->conduction; i++) { gT[i] = S->T.gT[i]; gVCT[i] = S->T.gVCT[i]; gQ[i] = S->T.gQ[i]; }
-    for (int p = 0; p < S->n; p++) temperature[p] = p < S->P.n ? S->P.temp[p] : S->PR.prevT[p - S->P.n];
+    for (int p = 0; p < S->n; p++) temperature[p] = p < S->P.n ? S->P.temp[p] : (S->R.ownerT ? S->PR.temp[p - S->P.n] : S->PR.prevT[p - S->P.n]);
 }
 
 extern "C" void emu_get_contact(void *h, double *cvol, double *cgrad, double *cdisp)

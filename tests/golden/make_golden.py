@@ -192,6 +192,17 @@ CASES = {
                                      .replace("</GridBCs>", '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="4.01"><TempBC value="450"/></BCBox>'
                                                             '<BCBox xmin="-1" xmax="4.01" ymin="-1" ymax="20" zmin="-1" zmax="20"><TempBC value="250"/></BCBox></GridBCs>'),
                                      (1, 2, 40), 2, 0.3, 1500.0),
+    # temperature BCs made by rigid particles (<SetTemperature/>): a hot piston pressing on a block whose bottom plane and one side carry
+    # grid temperature BCs (the side's nodes under the piston stay with the grid BC), and a heater plate that controls nothing else
+    "cond3d_rigid_hot_piston": (inputs.conduction(inputs.block3d(ncell=3, margin=3, E=100.0, vz=0.0, rigid=("piston", 4, (0.0, 0.0, -3.0e3)))
+                                                  .replace("<SetDirection>4</SetDirection>", "<SetDirection>4</SetDirection><SetTemperature/>"),
+                                                  (300.0, 600.0), (4000.0,), (700.0,))
+                                .replace("</GridBCs>", '<BCBox xmin="-1" xmax="10" ymin="-1" ymax="10" zmin="-1" zmax="3.01"><TempBC value="350"/></BCBox>'
+                                                       '<BCBox xmin="-1" xmax="3.01" ymin="-1" ymax="10" zmin="-1" zmax="10"><TempBC value="320"/></BCBox></GridBCs>'),
+                                (1, 2, 40), 2, 0.3, 1000.0),
+    "cond3d_rigid_heater_lcpdi_usl": (inputs.conduction(inputs.block3d(ncell=3, margin=3, E=100.0, gimp="lCPDI", method=3, vz=-2.0e3, vx=1.0e3, rigid=("wall", 0, (0.0, 0.0, 0.0)))
+                                                        .replace("<SetDirection>0</SetDirection>", "<SetDirection>0</SetDirection><SetTemperature/>"),
+                                                        (300.0, 500.0), (4000.0,), (700.0,)), (1, 2, 40), 2),
     # thermal strains in the laws: conduction with expanding materials, and bodies that start off the stress-free temperature
     # (one temperature jump handed to the laws by the first particle update) -- every law and analysis type that carries the terms
     "th2d_cond_iso_planestrain": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=60.0)),
