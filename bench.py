@@ -224,6 +224,9 @@ def host_state_bytes(pt):
     return n
 
 
+_JSON_LINES = []          # what rank 0 prints at the very end (see main)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -412,7 +415,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        _JSON_LINES.append(json.dumps(line))
 
 
 def sim_kernel_path_name(k):
@@ -540,7 +543,7 @@ def run_reference_arm(args):
     d = time_reference(args.cpu_ncell, args.steps, warm=args.warmup)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if d is None or "error" in d:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built or failed: %s" % (d or {}).get("error", "")}))
+        _JSON_LINES.append(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built or failed: %s" % (d or {}).get("error", "")}))
         return
     v = d["n"] * d["steps"] / d["run_s"]
     sample = ("reference NairnMPM (oracle/_ref) on the bench block input (same jittered start and velocity field) at %d^3 cells = %d particles (bounded sample of the "
@@ -551,7 +554,7 @@ def run_reference_arm(args):
             "config": {"workload": "%s (CPU sample: %d^3 cells)" % (args.workload, args.cpu_ncell)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": d["cores"], "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    _JSON_LINES.append(json.dumps(line))
 
 
 def main():
@@ -573,10 +576,23 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_ours(args)
+    # stdout carries the ONE JSON line and nothing else: whatever libraries write to file descriptor 1 meanwhile (NCCL prints its
+    # version banner there when NCCL_DEBUG asks for it) goes to stderr; the line itself is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _JSON_LINES:
+        sys.stdout.write("\n".join(_JSON_LINES) + "\n")
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
