@@ -274,6 +274,16 @@ int mpmgpu_set_energy_coupling(mpmgpu_ctx *ctx, int adiabatic);
  * tracked.  Call after mpmgpu_set_conduction; call again whenever values change. */
 int mpmgpu_set_temperature_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *value, const int *active);
 int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
+/* Particle traction BCs (MatPtTractionBC list, firstTractionPt ...; <TractionBC> in <ParticleBCs>): entry i loads face[i] of the
+ * domain of particle particle[i] (0-based host index, non-rigid) in direction[i] -- 1 x, 2 y, 3 z (3D), 11 normal to the deformed
+ * face, 12 along it (2D) -- with the stress value[i] = BCValue at this step's time.  Faces: 2D 1 bottom, 2 right, 3 top, 4 left;
+ * 3D 1 -y, 2 +x, 3 +y, 4 -x, 5 -z, 6 +z.  In the post-forces task (PostForcesTask.cpp:51) each of the face's corners (2 or 4,
+ * MatPoint2D/3D::GetSurfaceInfo: the deformed domain for the CPDI shapes, the undeformed one weighted with the deformed face size
+ * for the others) hands direction x area/corners x value x N_i to the nodes of its element that carry the particle's material
+ * (MatPtTractionBC::AddMPFluxBC, MatPtTractionBC.cpp:64-226).  Not built: axisymmetric, <ExactTractions>, B-spline shapes, slab mode.
+ * Call after mpmgpu_upload_particles; mpmgpu_update_particle_traction_values hands over new values of the same list. */
+int mpmgpu_set_particle_tractions(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const int *direction, const double *value);
+int mpmgpu_update_particle_traction_values(mpmgpu_ctx *ctx, int n, const double *value);
 /* Reaction forces of the velocity BCs (NodalVelBC::freaction, the input of the "reactionx/y/z" global quantities:
  * GlobalQuantity.cpp:971-986 -> NodalVelBC::TotalReactionForce, NodalVelBC.cpp:246-252).  Each BC's freaction starts from zero in
  * the grid-forces pass and collects the force that pass adds to the node's material fields, -(ftot.n + pk.n/dt) n for the zeroing

@@ -101,6 +101,10 @@ struct mpmgpu_ctx {
     bool thermal = false;               // particle temperatures can change (conduction, or a start off the stress-free temperature): the laws get dT
     TransportNodes T;
     double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
+    TractionBCs TB;                     // particle traction BCs (mpmgpu_set_particle_tractions)
+    int *dTracStart = NULL, *dTracFace = NULL, *dTracDir = NULL; double *dTracValue = NULL;
+    int tracCap = 0, tracStartLen = 0;
+    std::vector<int> tracOrder;         // entry e on device = list index tracOrder[e]
     bool rigidTemp = false;             // some rigid-BC material sets the temperature: R.ownerT / R.ptemp / R.savedT are allocated
     double *rigidTempPool = NULL;       // pTemperature of the rigid particles
     unsigned char *dFixedTemp = NULL;   // nodes with a grid temperature BC
@@ -228,7 +232,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
     ctx->cpElemPool = NULL; ctx->cpXiPool = NULL; ctx->cpWgPool = NULL;
     ctx->nBCEntries = 0;
-    memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R);
+    memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R); memset(&ctx->TB, 0, sizeof ctx->TB);
     ctx->rigidPool = NULL; ctx->rigidIntPool = NULL; ctx->rigidCap = 0;
     memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B); memset(&ctx->C, 0, sizeof ctx->C); memset(&ctx->cp, 0, sizeof ctx->cp); memset(&ctx->T, 0, sizeof ctx->T); memset(&ctx->Q, 0, sizeof ctx->Q);
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
@@ -1103,6 +1107,71 @@ extern "C" int mpmgpu_update_particle_loads(mpmgpu_ctx *ctx, int n_loaded, const
     return MPMGPU_OK;
 }
 
+// Particle traction BCs (MatPtTractionBC list, firstTractionPt ...): entry i loads face[i] of particle particle[i] (0-based host
+// index of a non-rigid particle) in direction direction[i] with the stress value[i] = BCValue at this step's time.
+extern "C" int mpmgpu_set_particle_tractions(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const int *direction, const double *value)
+{
+    if (!ctx || n < 0 || (n > 0 && (!particle || !face || !direction || !value))) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: bad argument");
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_particle_tractions: upload the particles first");
+    if (ctx->globalIds || ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_particle_tractions: not available in slab mode");
+    if (ctx->cfg.shape == MPMGPU_BSPLINE || ctx->cfg.shape == MPMGPU_BSPLINE_GIMP || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI)
+        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: traction BCs with the B-spline shape functions are not built");
+    cudaSetDevice(ctx->cfg.device);
+    const int nNR = ctx->P.n;
+    if (n == 0) { ctx->TB.n = 0; ctx->tracOrder.clear(); return MPMGPU_OK; }
+    const int nfaces = ctx->dim == 3 ? 6 : 4;
+    for (int i = 0; i < n; i++) {
+        if (particle[i] < 0 || particle[i] >= nNR) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: entry %d is particle %d of %d non-rigid particles", i, particle[i], nNR);
+        if (face[i] < 1 || face[i] > nfaces) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: entry %d has face %d (1..%d)", i, face[i], nfaces);
+        const int d = direction[i];
+        if (!(d == 1 || d == 2 || (d == 3 && ctx->dim == 3) || d == 11 || (d == 12 && ctx->dim == 2)))
+            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: entry %d has direction %d (1 x, 2 y, 3 z in 3D, 11 normal, 12 tangent in 2D)", i, d);
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return particle[a] < particle[b]; });
+    std::vector<int> st((size_t)nNR + 1, 0), fa(n), di(n);
+    std::vector<double> va(n);
+    for (int e = 0; e < n; e++) { const int i = order[e]; st[particle[i] + 1]++; fa[e] = face[i]; di[e] = direction[i]; va[e] = value[i]; }
+    for (int i = 0; i < nNR; i++) st[i + 1] += st[i];
+    if (ctx->tracStartLen < nNR + 1) { CK(dalloc(ctx, &ctx->dTracStart, (size_t)nNR + 1)); ctx->tracStartLen = nNR + 1; }
+    if (ctx->tracCap < n) {
+        CK(dalloc(ctx, &ctx->dTracFace, (size_t)n)); CK(dalloc(ctx, &ctx->dTracDir, (size_t)n)); CK(dalloc(ctx, &ctx->dTracValue, (size_t)n));
+        ctx->tracCap = n;
+    }
+    CK(cudaMemcpyAsync(ctx->dTracStart, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTracFace, fa.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTracDir, di.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTracValue, va.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->TB.n = n; ctx->TB.start = ctx->dTracStart; ctx->TB.face = ctx->dTracFace; ctx->TB.dir = ctx->dTracDir; ctx->TB.value = ctx->dTracValue;
+    ctx->tracOrder.swap(order);
+    return MPMGPU_OK;
+}
+
+// the values of the same list at a new time (BCs that vary)
+extern "C" int mpmgpu_update_particle_traction_values(mpmgpu_ctx *ctx, int n, const double *value)
+{
+    if (!ctx || !value || n != ctx->TB.n) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_particle_traction_values: n=%d but %d traction BCs are set", n, ctx ? ctx->TB.n : 0);
+    if (n == 0) return MPMGPU_OK;
+    cudaSetDevice(ctx->cfg.device);
+    std::vector<double> va(n);
+    for (int e = 0; e < n; e++) va[e] = value[ctx->tracOrder[e]];
+    CK(cudaMemcpyAsync(ctx->dTracValue, va.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
+static int particle_tractions(mpmgpu_ctx *ctx)
+{
+    if (ctx->TB.n <= 0 || ctx->P.nNR <= 0) return MPMGPU_OK;
+    const int cpdi = ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 1 : 0;
+    const double thick = ctx->cfg.thickness > 0. ? ctx->cfg.thickness : 1.;
+    if (ctx->dim == 3) LAUNCH((k_particle_tractions<3>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, ctx->TB, cpdi, thick, ctx->nf, ctx->dFlags);
+    else LAUNCH((k_particle_tractions<2>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, ctx->TB, cpdi, thick, ctx->nf, ctx->dFlags);
+    return MPMGPU_OK;
+}
+
 // Rigid-BC particles whose material has setting functions: the host evaluates them each step
 // (RigidMaterial::GetVectorSetting, Materials/RigidMaterial.cpp:376-531) and hands over the velocities
 extern "C" int mpmgpu_update_rigid_velocities(mpmgpu_ctx *ctx, int n_rigid, const double *vel)
@@ -1327,8 +1396,10 @@ static int t_grid_forces(mpmgpu_ctx *ctx)
 
 static int t_post_forces(mpmgpu_ctx *ctx)
 {
+    int rc = particle_tractions(ctx);          // PostForcesTask.cpp:51, before the body forces
+    if (rc) return rc;
     LAUNCH(k_post_forces, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N, ctx->sp);
-    int rc = reactions_zero(ctx);
+    rc = reactions_zero(ctx);
     if (rc) return rc;
     return apply_bcs(ctx, PASS_GRID_FORCES, 0);
 }
@@ -1634,6 +1705,7 @@ static int fused_phase(mpmgpu_ctx *ctx, int phase)
         prof_begin(ctx);
         if (t.slab.on && (rc = halo_add(ctx, 1))) return rc;
         // (with order > 1 the re-zeroing of pk for task 9a waits until v* has been formed from it)
+        if ((rc = particle_tractions(ctx))) return rc;
         if ((rc = reactions_zero(ctx))) return rc;
         LAUNCH(k_n2_forces_momenta, ngrid, 256, n0, ncount, ctx->N, t.FN, ctx->B, sp, (reextrap && !highOrder) ? 1 : 0);
         if (highOrder) {                                       // UpdateParticlesTask.cpp:66-71

@@ -410,6 +410,112 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_forces(Grid g, Particles P
     });
 }
 
+// ---- task 6a: particle traction BCs (PostForcesTask.cpp:51 -> MatPtTractionBC::AddMPFluxBC, MatPtTractionBC.cpp:64-226) ----
+// One thread per particle; its traction entries load one face of its domain each.  The face's corners (2 in 2D, 4 in 3D) come from
+// MatPoint2D/3D::GetSurfaceInfo (MatPoint2D.cpp, MatPoint3D.cpp): semi-side vectors F.lp for the CPDI shapes, the undeformed ones for
+// the others with the weight taken from the deformed face all the same; every corner hands wtNorm * value * N_i(corner) to the
+// nodes of its element (plain element shape functions, ElementBase::GetShapeFunctionsForTractions) that carry non-rigid particles
+// and the particle's material field.  wtNorm = direction x (face area / corners).
+template <int DIM>
+__global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Particles P, Nodes N, TractionBCs TB, int cpdi, double thickness, int nf, StatusFlags *flags)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nNR) return;
+    const int o = P.orig[p];
+    const int e0 = TB.start[o], e1 = TB.start[o + 1];
+    if (e0 == e1) return;
+    const int el = P.elem[p];
+    const ElemIJK c0 = elem_ijk(g, el);
+    const double psx = (g.xpts[c0.i + 1] - g.xpts[c0.i]) * (0.5 * P.lp[0][p]), psy = (g.ypts[c0.j + 1] - g.ypts[c0.j]) * (0.5 * P.lp[1][p]);
+    const double psz = DIM == 3 ? (g.zpts[c0.k + 1] - g.zpts[c0.k]) * (0.5 * P.lp[2][p]) : 0.;
+    double F[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = P.F[i][p];
+    // deformed semi-side vectors (GetSemiSideVectors)
+    const double d1[3] = {F[0] * psx, F[3] * psx, DIM == 3 ? F[6] * psx : 0.};
+    const double d2[3] = {F[1] * psy, F[4] * psy, DIM == 3 ? F[7] * psy : 0.};
+    const double d3[3] = {DIM == 3 ? F[2] * psz : 0., DIM == 3 ? F[5] * psz : 0., DIM == 3 ? F[8] * psz : 0.};
+    const double pos[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
+    const int off = nf > 1 ? P.foff[p] : 0;
+    for (int e = e0; e < e1; e++) {
+        const int face = TB.face[e], dof = TB.dir[e];
+        const double tmag = TB.value[e];
+        double r1[3] = {d1[0], d1[1], d1[2]}, r2[3] = {d2[0], d2[1], d2[2]}, r3[3] = {d3[0], d3[1], d3[2]};
+        double uSize = -1.;
+        if (!cpdi) {        // undeformed edge for the extrapolation, deformed size for the weight
+            if (DIM == 3) {
+                const double *a = (face == 2 || face == 4) ? r2 : r1, *b = (face == 1 || face == 3 || face == 2 || face == 4) ? r3 : r2;
+                const double Ap[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+                uSize = sqrt(Ap[0] * Ap[0] + Ap[1] * Ap[1] + Ap[2] * Ap[2]);
+            } else {
+                const double *a = (face == 1 || face == 3) ? r1 : r2;
+                uSize = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            }
+            r1[0] = psx; r1[1] = 0.; r1[2] = 0.; r2[0] = 0.; r2[1] = psy; r2[2] = 0.; r3[0] = 0.; r3[1] = 0.; r3[2] = psz;
+        }
+        // corners c[0..NCF-1] of the face and one more point off the face (signs of r1, r2, r3)
+        const int NCF = DIM == 3 ? 4 : 2;
+        double sgn[5][3];
+        if (DIM == 3) {
+            const double S3[6][5][3] = {
+                {{-1, -1, -1}, {1, -1, -1}, {1, -1, 1}, {-1, -1, 1}, {-1, 1, -1}},
+                {{1, -1, -1}, {1, 1, -1}, {1, 1, 1}, {1, -1, 1}, {-1, -1, -1}},
+                {{1, 1, -1}, {-1, 1, -1}, {-1, 1, 1}, {1, 1, 1}, {1, -1, -1}},
+                {{-1, 1, -1}, {-1, -1, -1}, {-1, -1, 1}, {-1, 1, 1}, {1, 1, -1}},
+                {{1, -1, -1}, {-1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {1, -1, 1}},
+                {{-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}, {-1, -1, -1}}};
+            const int f = face >= 1 && face <= 5 ? face - 1 : 5;
+            for (int i = 0; i < 5; i++) for (int d = 0; d < 3; d++) sgn[i][d] = S3[f][i][d];
+        } else {
+            const double S2[4][3][2] = {{{-1, -1}, {1, -1}, {-1, 1}}, {{1, -1}, {1, 1}, {-1, -1}}, {{1, 1}, {-1, 1}, {1, -1}}, {{-1, 1}, {-1, -1}, {1, 1}}};
+            const int f = face >= 1 && face <= 3 ? face - 1 : 3;
+            for (int i = 0; i < 3; i++) { sgn[i][0] = S2[f][i][0]; sgn[i][1] = S2[f][i][1]; sgn[i][2] = 0.; }
+            for (int d = 0; d < 3; d++) { sgn[3][d] = 0.; sgn[4][d] = 0.; }
+        }
+        double c[4][3];
+        for (int i = 0; i < NCF; i++)
+            for (int d = 0; d < 3; d++) c[i][d] = pos[d] + sgn[i][0] * r1[d] + sgn[i][1] * r2[d] + sgn[i][2] * r3[d];
+        // edge radii and the weighted direction
+        double ra[3], rb[3];
+        for (int d = 0; d < 3; d++) { ra[d] = 0.5 * (c[1][d] - c[0][d]); rb[d] = DIM == 3 ? 0.5 * (c[3][d] - c[0][d]) : 0.; }
+        double wt[3] = {0., 0., 0.};
+        if (DIM == 3) {
+            double Ap[3] = {ra[1] * rb[2] - ra[2] * rb[1], ra[2] * rb[0] - ra[0] * rb[2], ra[0] * rb[1] - ra[1] * rb[0]};
+            const double faceWt = uSize < 0. ? sqrt(Ap[0] * Ap[0] + Ap[1] * Ap[1] + Ap[2] * Ap[2]) : uSize;
+            if (dof == 1) wt[0] = faceWt;
+            else if (dof == 2) wt[1] = faceWt;
+            else if (dof == 11) {
+                if (uSize > 0.) { const double sc = uSize / sqrt(Ap[0] * Ap[0] + Ap[1] * Ap[1] + Ap[2] * Ap[2]); Ap[0] *= sc; Ap[1] *= sc; Ap[2] *= sc; }
+                wt[0] = Ap[0]; wt[1] = Ap[1]; wt[2] = Ap[2];
+            } else wt[2] = faceWt;
+        } else {
+            double faceWt = uSize < 0. ? sqrt(ra[0] * ra[0] + ra[1] * ra[1]) : uSize;
+            faceWt *= thickness;
+            if (dof == 1) wt[0] = faceWt;
+            else if (dof == 2) wt[1] = faceWt;
+            else if (dof == 11) { const double ex = ra[1], ey = -ra[0], en = sqrt(ex * ex + ey * ey); wt[0] = ex * faceWt / en; wt[1] = ey * faceWt / en; }
+            else if (dof == 12) { const double ex = ra[0], ey = ra[1], en = sqrt(ex * ex + ey * ey); wt[0] = ex * faceWt / en; wt[1] = ey * faceWt / en; }
+            else wt[2] = faceWt;
+        }
+        const double lpz[3] = {0., 0., 0.};
+        for (int i = 0; i < NCF; i++) {
+            const int ce = find_element_from_point<DIM>(g, c[i]);
+            if (ce <= 0) { atomicCAS(&flags->cpdiLeft, 0, o + 1); continue; }     // "A Traction edge node has left the grid"
+            double xi[3];
+            get_xipos<DIM>(g, ce, c[i], xi);
+            for_each_node<DIM, SHAPE_LINEAR, false>(g, ce, xi, lpz, [&](int nd, double S, double, double, double) {
+                bool any = false;       // NodalPoint::NodeHasNonrigidParticles, then the particle's own field (AddTractionTask3)
+                for (int f = 0; f < nf; f++) any |= N.cnt[nd + f * g.nnodes] > 0;
+                if (!any || N.cnt[nd + off] <= 0) return;
+                const double s = tmag * S;
+                if (wt[0] != 0.) atomAdd(&N.ftot[0][nd + off], wt[0] * s);
+                if (wt[1] != 0.) atomAdd(&N.ftot[1][nd + off], wt[1] * s);
+                if (DIM == 3 && wt[2] != 0.) atomAdd(&N.ftot[2][nd + off], wt[2] * s);
+            });
+        }
+    }
+}
+
 // ---- task 6: PostForcesTask node pass (PostForcesTask.cpp:46-94) -------------------------------
 __global__ void k_post_forces(int nnodes, Nodes N, StepParams sp)
 {

@@ -196,6 +196,15 @@ struct RigidBCs {
     double *savedT;          // [nnodes] the node's own value while the BC value stands in for the gradients
 };
 
+// Particle traction BCs (MatPtTractionBC): a stress on one face of a particle's domain, handed to the nodes around the face's corners
+struct TractionBCs {
+    int n;                   // entries
+    const int *start;        // [nParticles+1] entries of host particle i (CSR; the reference walks its list, sums commute)
+    const int *face;         // [n] 1..4 (2D: bottom, right, top, left), 1..6 (3D: -y, +x, +y, -x, -z, +z)
+    const int *dir;          // [n] 1 x, 2 y, 3 z, 11 normal, 12 tangent (2D)
+    const double *value;     // [n] BCValue at this step's time (stress)
+};
+
 struct StatusFlags {         // device -> host error reporting (ResetElementsTask.cpp:71-151)
     unsigned long long crossings;
     unsigned long long leftGrid;

@@ -88,6 +88,8 @@ bool gBCsVary = false;
 bool gRigidFunctions = false;       // some rigid-BC material sets its velocity by functions of time and position
 long long gLeftGridWarned = 0;     // first-time grid leavers already handed to the reference's MPMWarnings
 bool gCustomTasksReadParticles = false;     // (the only custom task the adapter admits, PeriodicXPIC, touches bodyFrc alone)
+std::vector<MatPtTractionBC *> gTractions;      // particle traction BCs in list order
+bool gTractionsVary = false;
 std::vector<int> gLoadPts;          // particles with load BCs (MatPtLoadBC), 0-based, each once
 bool gLoadsSent = false;
 std::vector<NodalTempBC *> gTempBCs;    // nodal temperature BCs in list order (conduction)
@@ -386,6 +388,14 @@ class GpuTask : public MPMTask
         check(mpmgpu_update_particle_loads(gCtx, (int)nl, gLoadsSent ? NULL : gLoadPts.data(), f.data()), "GpuTask(particle loads)");
         gLoadsSent = true;
     }
+    // MatPtTractionBC values at this step's time (MatPtTractionBC::AddMPFluxBC reads BCValue(bctime), MatPtTractionBC.cpp:68)
+    void UpdateTractionValues(void)
+    {
+        if (gTractions.empty() || !gTractionsVary) return;
+        std::vector<double> v(gTractions.size());
+        for (size_t i = 0; i < gTractions.size(); i++) v[i] = gTractions[i]->BCValue(mtime);
+        check(mpmgpu_update_particle_traction_values(gCtx, (int)v.size(), v.data()), "GpuTask(traction values)");
+    }
     // RigidMaterial::GetVectorSetting evaluated by the reference's own Expression objects (ProjectRigidBCsTask.cpp:75-93)
     void UpdateRigidVelocities(void)
     {
@@ -432,6 +442,8 @@ class GpuTask : public MPMTask
                 UpdateBCValues();
                 UpdateRigidVelocities();
                 UpdateParticleLoads();
+            UpdateTractionValues();
+                UpdateTractionValues();
                 UpdateTemperatureBCs();
                 if (!gSlabs.empty()) {
                     // every slab steps at the same time: the halo and migrant exchanges inside mpmgpu_slab_step are NCCL calls that
@@ -453,6 +465,7 @@ class GpuTask : public MPMTask
             // the PeriodicXPIC custom task changes the order between steps (Custom_Tasks/PeriodicXPIC.cpp:161-240)
             check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(Initialize)");
             UpdateParticleLoads();
+            UpdateTractionValues();
             UpdateTemperatureBCs();
             if (nmpmsRC != nmpmsRB) UpdateRigidVelocities();        // rigid contact particles: SetRigidContactVelTask runs before the extrapolation
             check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)");
@@ -539,7 +552,13 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         if (lb->style == FUNCTION_VALUE) return "particle load BCs set by a function";
         if (lb->ptNum - 1 >= nmpmsNR) return "load BCs on rigid particles";
     }
-    if (firstTractionPt != NULL) return "particle traction BCs (MatPtTractionBC)";
+    // particle traction BCs run on the device (mpmgpu_set_particle_tractions); the host re-evaluates values that depend on time only
+    for (MatPtLoadBC *lb = firstTractionPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
+        if (lb->style == FUNCTION_VALUE) return "particle traction BCs set by a function";
+        if (lb->ptNum - 1 >= nmpmsNR) return "traction BCs on rigid particles";
+        if (fmobj->exactTractions) return "<ExactTractions>";
+        if (ngpus > 1) return "particle traction BCs with -gpus N";
+    }
     // global quantities the reference reads from its nodes or BC objects, which the replaced tasks no longer fill
     for (GlobalQuantity *gq = firstGlobal; gq != NULL; gq = gq->GetNextGlobal()) {
         const int q = gq->quantity;
@@ -890,6 +909,16 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     }
     ALL_CTX(mpmgpu_set_velocity_bcs(ctx_, (int)bnode.size(), bnode.data(), bnorm.data(), bval.data(), bact.data(), bsym.data()));
     if (anyReflected) ALL_CTX(mpmgpu_set_velocity_bc_reflections(ctx_, (int)bnode.size(), brefl.data(), bratio.data()));
+    if (firstTractionPt != NULL) {      // MatPtTractionBC list in list order
+        std::vector<int> tp, tf, td; std::vector<double> tv;
+        for (MatPtLoadBC *lb = firstTractionPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
+            MatPtTractionBC *tb = (MatPtTractionBC *)lb;
+            gTractions.push_back(tb);
+            tp.push_back(tb->ptNum - 1); tf.push_back(tb->face); td.push_back(tb->direction); tv.push_back(tb->BCValue(mtime));
+            if (tb->style != CONSTANT_VALUE || tb->GetBCFirstTime() > 0.) gTractionsVary = true;
+        }
+        if (mpmgpu_set_particle_tractions(gCtx, (int)tp.size(), tp.data(), tf.data(), td.data(), tv.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    }
     if (!gSlabs.empty()) {
         // the slabs join the two NCCL communicators of the run (collective: one thread per GPU)
         char ids[256];

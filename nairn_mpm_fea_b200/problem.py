@@ -396,6 +396,8 @@ def from_reference_dump(z, snapshot="p0"):
     pr.bc_active = np.ones(nb, np.int32)
     pr.bc_symdir = np.zeros(nb, np.int32)
     pr.bc_style = z["velbcs/style"]
+    if "tractions/particle" in z:       # MatPtTractionBC list (constant-style values; others are the host's to re-evaluate)
+        pr.tractions = {k: np.asarray(z["tractions/" + k]) for k in ("particle", "face", "direction", "value")}
     pr.bc_id = z["velbcs/id"].astype(np.int32) if "velbcs/id" in z else np.zeros(nb, np.int32)        # BoundaryCondition::bcID
     pr.bc_ftime = z["velbcs/ftime"]
     if "velbcs/reflected" in z and np.any(z["velbcs/reflected"] > 0):

@@ -35,6 +35,7 @@
 #include "Materials/NonlinearHardening.hpp"
 #include "Materials/Nonlinear2Hardening.hpp"
 #include "Materials/JohnsonCook.hpp"
+#include "Boundary_Conditions/MatPtTractionBC.hpp"
 #include "Materials/SCGLHardening.hpp"
 #include "Global_Quantities/ThermalRamp.hpp"
 #include "Materials/Mooney.hpp"
@@ -412,6 +413,22 @@ void ref_get_velbcs(int *node, int *dir, int *style, double *norm, double *value
         norm[3 * k] = bc->norm.x; norm[3 * k + 1] = bc->norm.y; norm[3 * k + 2] = bc->norm.z;
         value[k] = bc->value; ftime[k] = bc->ftime; offset[k] = bc->offset;
         currentValue[k] = bc->currentValue;
+    }
+}
+
+// particle traction BCs (MatPtTractionBC list): 1-based particle, face, direction, style, BCValue at the current time
+int ref_num_tractions(void)
+{
+    int k = 0;
+    for (MatPtLoadBC *bc = firstTractionPt; bc != NULL; bc = (MatPtLoadBC *)bc->GetNextObject()) k++;
+    return k;
+}
+void ref_get_tractions(int *particle, int *face, int *direction, int *style, double *value)
+{
+    int k = 0;
+    for (MatPtLoadBC *b = firstTractionPt; b != NULL; b = (MatPtLoadBC *)b->GetNextObject(), k++) {
+        MatPtTractionBC *bc = (MatPtTractionBC *)b;
+        particle[k] = bc->ptNum; face[k] = bc->face; direction[k] = bc->direction; style[k] = bc->style; value[k] = bc->BCValue(mtime);
     }
 }
 

@@ -51,6 +51,8 @@ struct EmuSim {
     std::vector<double> tpool, kcond, temps;
     TempBCs Q;
     std::vector<int> tbcNode, tbcStart, tbcActive; std::vector<double> tbcValue, tbcSaved;
+    // particle traction BCs (capi.cu: TB)
+    TractionBCs TB; std::vector<int> trStart, trFace, trDir; std::vector<double> trValue; double thickness = 1.;
     // temperature BCs of rigid particles (capi.cu: rigidTemp, R.ownerT / ptemp / fixedT / savedT)
     std::vector<int> ownerT; std::vector<double> rigidTemps, savedT; std::vector<unsigned char> fixedTemp;
 };
@@ -243,6 +245,11 @@ void run_task(EmuSim *S, int t)
         if (S->conduction) DISPATCH(k_p2g_conduction, S->P.nNR, S->g, S->P, S->T);
         break;
     case 5:
+        if (S->TB.n > 0) {      // capi.cu: particle_tractions
+            const int cpdi = SHAPE_IS_CPDI(S->shape) ? 1 : 0;
+            if (S->dim == 3) EMU_LAUNCH((k_particle_tractions<3>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->TB, cpdi, S->thickness, S->nf, &S->flags);
+            else EMU_LAUNCH((k_particle_tractions<2>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->TB, cpdi, S->thickness, S->nf, &S->flags);
+        }
         EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp);
         std::fill(S->bcReact.begin(), S->bcReact.end(), 0.); std::fill(S->rigidReact.begin(), S->rigidReact.end(), 0.);     // capi.cu: reactions_zero
         apply_bcs(S, PASS_GRID_FORCES, 0);
@@ -366,7 +373,7 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     R.reaction = S->rigidReact.data();
     S->B.reaction = NULL;
     bind_nodes(S, (size_t)g.nnodes);
-    memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp); memset(&S->Q, 0, sizeof S->Q);
+    memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp); memset(&S->Q, 0, sizeof S->Q); memset(&S->TB, 0, sizeof S->TB);
     return S;
 }
 
@@ -522,6 +529,20 @@ extern "C" void emu_set_bc_reflections(void *h, int n, const int *reflected, con
     S->bcRefl.assign(n, -1); S->bcRatio.assign(n, 1.);
     for (int e = 0; e < n; e++) { const int i = S->bcOrder[e]; S->bcRefl[e] = reflected[i] > 0 ? reflected[i] - 1 : -1; S->bcRatio[e] = ratio[i]; }
     S->B.refl = S->bcRefl.data(); S->B.reflRatio = S->bcRatio.data();
+}
+
+// capi.cu::mpmgpu_set_particle_tractions (0-based particles)
+extern "C" void emu_set_tractions(void *h, int n, const int *particle, const int *face, const int *direction, const double *value, double thickness)
+{
+    EmuSim *S = (EmuSim *)h;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return particle[a] < particle[b]; });
+    S->trStart.assign((size_t)S->P.n + 1, 0); S->trFace.resize(n); S->trDir.resize(n); S->trValue.resize(n);
+    for (int e = 0; e < n; e++) { const int i = order[e]; S->trStart[particle[i] + 1]++; S->trFace[e] = face[i]; S->trDir[e] = direction[i]; S->trValue[e] = value[i]; }
+    for (int i = 0; i < S->P.n; i++) S->trStart[i + 1] += S->trStart[i];
+    S->TB.n = n; S->TB.start = S->trStart.data(); S->TB.face = S->trFace.data(); S->TB.dir = S->trDir.data(); S->TB.value = S->trValue.data();
+    S->thickness = thickness;
 }
 
 // capi.cu::mpmgpu_download_reactions

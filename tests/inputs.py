@@ -281,3 +281,10 @@ def reaction_walls3d(ncell=4, margin=3, **kw):
         (box % (-1, n + 1, -1, n + 1, hi - 0.01, n + 1), 'dir="3" vel="-800" id="-3"'),
         (box % (-1, n + 1, -1, lo + 0.01, lo + 0.99, hi - 0.99), 'dir="12" angle="20" vel="0" id="-4"'),
     ])
+
+
+def particle_bcs(xml, blocks):
+    """Append a <ParticleBCs> element made of (shape opening tag, BC element) pairs, e.g.
+    ('<BCBox xmin="0" ...>', '<TractionBC dir="11" face="6" style="1" stress="-5"/>')."""
+    body = "".join("%s%s</%s>" % (shape, bc, shape[1:].split()[0].rstrip(">")) for shape, bc in blocks)
+    return xml.replace("</MaterialPoints>", "</MaterialPoints><ParticleBCs>%s</ParticleBCs>" % body, 1)

@@ -212,7 +212,7 @@ def compare_nodes(got, ref, prefix, tol, scale_prefix=None):
 
 
 # ---- multimaterial mode (goldens mm*): shared by the CPU run of the device source and the GPU run through the C ABI ----------
-MM_CASES = ["mm2d_friction_avgg", "mm2d_frictionless_maxg_position", "mm2d_stick_maxv_linear_usl", "mm2d_ignore_lcpdi_usf",
+MM_CASES = ["trac2d_multimaterial_lcpdi_planestress", "mm2d_friction_avgg", "mm2d_frictionless_maxg_position", "mm2d_stick_maxv_linear_usl", "mm2d_ignore_lcpdi_usf",
             "mm2d_friction_sn_powerlaw", "mm3d_two_blocks_avgg_position", "mm3d_two_blocks_maxg_stick_b2gimp",
             "mm3d_two_blocks_maxv_friction_ugimp", "mm2d_rigid_plate_maxg_friction", "mm3d_rigid_block_avgg_position_usl",
             "mm3d_rigid_block_maxv_stick_lcpdi"]

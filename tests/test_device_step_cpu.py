@@ -22,7 +22,7 @@ DEV = os.path.join(HERE, "devlaws")
 LIB = os.path.join(DEV, "_build", "libdevstep.so")
 
 # (the multimaterial goldens mm* and the conduction goldens cond* have their own checks: tests/test_multimaterial_cpu.py, tests/test_conduction_cpu.py)
-CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and not f.startswith(("mm", "cond", "th", "react2d_multimaterial")))
+CASES = sorted(os.path.basename(f)[:-4] for f in os.listdir(os.path.join(HERE, "golden")) if f.endswith(".npz") and not f.startswith(("mm", "cond", "th", "react2d_multimaterial", "trac2d_multimaterial")))
 TASK_INDEX = {"initialization": 0, "mass_and_momentum": 1, "post_extrapolation": 2, "update_strains_first": 3, "grid_forces": 4,
               "post_forces": 5, "update_momenta": 6, "update_particles": 7, "update_strains_last": 8, "reset_elements": 9,
               "project_rigid_bcs": 10}
@@ -48,7 +48,7 @@ def lib():
                         src, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.emu_create.restype = C.c_void_p
-    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_conduction", "emu_get_transport", "emu_set_temperature_bcs", "emu_set_energy_coupling", "emu_get_reactions", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
+    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_conduction", "emu_get_transport", "emu_set_temperature_bcs", "emu_set_energy_coupling", "emu_get_reactions", "emu_set_tractions", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
         getattr(lib, f).argtypes = None
     return lib
 
@@ -118,6 +118,15 @@ class EmuSim:
                                       _dp(self._mm[1]), _ip(self._mm[2]), _dp(self._mm[3]), _dp(self._mm[4]), _dp(self._mm[5]), d(mm.get("rigid_gradient_bias", 1.0)))
             self.nnodes *= nf
             self.n_fields = nf
+        self._set_tractions()
+
+    def _set_tractions(self):
+        tr = getattr(self.prob, "tractions", None)
+        if tr is None or not len(tr["particle"]):
+            return
+        c = np.ascontiguousarray
+        self._tr = [c(tr["particle"], dtype=np.int32), c(tr["face"], dtype=np.int32), c(tr["direction"], dtype=np.int32), c(tr["value"], dtype=np.float64)]
+        self.lib.emu_set_tractions(self.h, len(self._tr[0]), _ip(self._tr[0]), _ip(self._tr[1]), _ip(self._tr[2]), _dp(self._tr[3]), C.c_double(float(self.prob.thickness)))
 
     def set_xpic(self, order, fmpm):
         self.lib.emu_set_xpic(self.h, int(order), int(fmpm))
