@@ -442,7 +442,6 @@ class GpuTask : public MPMTask
                 UpdateBCValues();
                 UpdateRigidVelocities();
                 UpdateParticleLoads();
-            UpdateTractionValues();
                 UpdateTractionValues();
                 UpdateTemperatureBCs();
                 if (!gSlabs.empty()) {
