@@ -284,6 +284,14 @@ int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
  * Call after mpmgpu_upload_particles; mpmgpu_update_particle_traction_values hands over new values of the same list. */
 int mpmgpu_set_particle_tractions(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const int *direction, const double *value);
 int mpmgpu_update_particle_traction_values(mpmgpu_ctx *ctx, int n, const double *value);
+/* Particle heat-flux BCs (MatPtHeatFluxBC list, firstHeatFluxPt ...; <HeatFluxBC dir="1"> in <ParticleBCs>: external flux): the same
+ * walk over a face's corners at the end of the post-forces task (TransportTask::TransportForceBCs, PostForcesTask.cpp:97); value[i]
+ * (energy per time and area at this step's time) x face area / corners x N_i goes into the conduction rate of every node around the
+ * corner that carries non-rigid particles (MatPtHeatFluxBC::AddMPFluxBC, MatPtHeatFluxBC.cpp:64-160; TransportTask::AddFluxCondition).
+ * Silent and coupled (dir="2", a function of the particle temperature) fluxes are the adapter's to refuse.  After
+ * mpmgpu_set_conduction and mpmgpu_upload_particles. */
+int mpmgpu_set_particle_heat_fluxes(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const double *value);
+int mpmgpu_update_particle_heat_flux_values(mpmgpu_ctx *ctx, int n, const double *value);
 /* Reaction forces of the velocity BCs (NodalVelBC::freaction, the input of the "reactionx/y/z" global quantities:
  * GlobalQuantity.cpp:971-986 -> NodalVelBC::TotalReactionForce, NodalVelBC.cpp:246-252).  Each BC's freaction starts from zero in
  * the grid-forces pass and collects the force that pass adds to the node's material fields, -(ftot.n + pk.n/dt) n for the zeroing

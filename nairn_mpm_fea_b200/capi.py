@@ -27,7 +27,8 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
            "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_set_energy_coupling", "mpmgpu_set_temperature_bcs", "mpmgpu_upload_particles",
-           "mpmgpu_track_reactions", "mpmgpu_download_reactions", "mpmgpu_set_particle_tractions", "mpmgpu_update_particle_traction_values", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
+           "mpmgpu_track_reactions", "mpmgpu_download_reactions", "mpmgpu_set_particle_tractions", "mpmgpu_update_particle_traction_values",
+           "mpmgpu_set_particle_heat_fluxes", "mpmgpu_update_particle_heat_flux_values", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
     "mpmgpu_download_particles", "mpmgpu_download_nodes", "mpmgpu_synchronize", "mpmgpu_get_status",
@@ -116,6 +117,8 @@ def load_library(path=None):
     lib.mpmgpu_set_temperature_bcs.argtypes = [vp, C.c_int, _ip, _dp, _ip]
     lib.mpmgpu_set_particle_tractions.argtypes = [vp, C.c_int, _ip, _ip, _ip, _dp]
     lib.mpmgpu_update_particle_traction_values.argtypes = [vp, C.c_int, _dp]
+    lib.mpmgpu_set_particle_heat_fluxes.argtypes = [vp, C.c_int, _ip, _ip, _dp]
+    lib.mpmgpu_update_particle_heat_flux_values.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_track_reactions.argtypes = [vp, C.c_int]
     lib.mpmgpu_download_reactions.argtypes = [vp, C.c_int, _dp, _dp]
     lib.mpmgpu_set_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
@@ -250,6 +253,9 @@ class MpmGpu:
             tr = getattr(prob, "tractions", None)
             if tr is not None and len(tr["particle"]):
                 self.set_particle_tractions(tr["particle"], tr["face"], tr["direction"], tr["value"])
+            hf = getattr(prob, "heat_fluxes", None)
+            if hf is not None and len(hf["particle"]):
+                self.set_particle_heat_fluxes(hf["particle"], hf["face"], hf["value"])
 
     # -- plumbing -----------------------------------------------------------------------------
     def _check(self, rc):
@@ -318,6 +324,11 @@ class MpmGpu:
         """Traction BCs in list order: 0-based particle, face, direction (1, 2, 3, 11 normal, 12 tangent), stress at this step's time."""
         particle, face, direction, value = _c32(particle), _c32(face), _c32(direction), _c64(value)
         self._check(self.lib.mpmgpu_set_particle_tractions(self.ctx, len(particle), _i(particle), _i(face), _i(direction), _d(value)))
+
+    def set_particle_heat_fluxes(self, particle, face, value):
+        """External heat-flux BCs in list order: 0-based particle, face, flux at this step's time (conduction must be on)."""
+        particle, face, value = _c32(particle), _c32(face), _c64(value)
+        self._check(self.lib.mpmgpu_set_particle_heat_fluxes(self.ctx, len(particle), _i(particle), _i(face), _d(value)))
 
     def update_particle_traction_values(self, value):
         value = _c64(value)

@@ -101,10 +101,12 @@ struct mpmgpu_ctx {
     bool thermal = false;               // particle temperatures can change (conduction, or a start off the stress-free temperature): the laws get dT
     TransportNodes T;
     double *transportPool = NULL, *dKcond = NULL, *tempPool = NULL;
-    TractionBCs TB;                     // particle traction BCs (mpmgpu_set_particle_tractions)
-    int *dTracStart = NULL, *dTracFace = NULL, *dTracDir = NULL; double *dTracValue = NULL;
-    int tracCap = 0, tracStartLen = 0;
-    std::vector<int> tracOrder;         // entry e on device = list index tracOrder[e]
+    struct FaceBCs {                    // particle BCs on a face of the particle domain: tractions, heat fluxes
+        TractionBCs TB;
+        int *dStart = NULL, *dFace = NULL, *dDir = NULL; double *dValue = NULL;
+        int cap = 0, startLen = 0;
+        std::vector<int> order;         // entry e on device = list index order[e]
+    } trac, flux;
     bool rigidTemp = false;             // some rigid-BC material sets the temperature: R.ownerT / R.ptemp / R.savedT are allocated
     double *rigidTempPool = NULL;       // pTemperature of the rigid particles
     unsigned char *dFixedTemp = NULL;   // nodes with a grid temperature BC
@@ -232,7 +234,7 @@ extern "C" int mpmgpu_create(const mpmgpu_config *cfg, mpmgpu_ctx **out)
     ctx->particlePool = NULL; ctx->particleIntPool = NULL; ctx->nodePool = NULL;
     ctx->cpElemPool = NULL; ctx->cpXiPool = NULL; ctx->cpWgPool = NULL;
     ctx->nBCEntries = 0;
-    memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R); memset(&ctx->TB, 0, sizeof ctx->TB);
+    memset(&ctx->P, 0, sizeof ctx->P); memset(&ctx->PR, 0, sizeof ctx->PR); memset(&ctx->R, 0, sizeof ctx->R); memset(&ctx->trac.TB, 0, sizeof ctx->trac.TB); memset(&ctx->flux.TB, 0, sizeof ctx->flux.TB);
     ctx->rigidPool = NULL; ctx->rigidIntPool = NULL; ctx->rigidCap = 0;
     memset(&ctx->N, 0, sizeof ctx->N); memset(&ctx->B, 0, sizeof ctx->B); memset(&ctx->C, 0, sizeof ctx->C); memset(&ctx->cp, 0, sizeof ctx->cp); memset(&ctx->T, 0, sizeof ctx->T); memset(&ctx->Q, 0, sizeof ctx->Q);
     memset(ctx->taskMs, 0, sizeof ctx->taskMs); memset(ctx->taskCalls, 0, sizeof ctx->taskCalls);
@@ -1107,70 +1109,93 @@ extern "C" int mpmgpu_update_particle_loads(mpmgpu_ctx *ctx, int n_loaded, const
     return MPMGPU_OK;
 }
 
-// Particle traction BCs (MatPtTractionBC list, firstTractionPt ...): entry i loads face[i] of particle particle[i] (0-based host
-// index of a non-rigid particle) in direction direction[i] with the stress value[i] = BCValue at this step's time.
-extern "C" int mpmgpu_set_particle_tractions(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const int *direction, const double *value)
+// Particle BCs on a face of the particle domain, in the host's list order: tractions (MatPtTractionBC list, firstTractionPt ...:
+// stress value[i] in direction[i]) and heat fluxes (MatPtHeatFluxBC list, firstHeatFluxPt ...: external flux value[i]).  particle[i] is
+// the 0-based host index of a non-rigid particle, value[i] = BCValue at this step's time.
+static int set_face_bcs(mpmgpu_ctx *ctx, mpmgpu_ctx::FaceBCs &S, const char *who, int n, const int *particle, const int *face, const int *direction, const double *value)
 {
-    if (!ctx || n < 0 || (n > 0 && (!particle || !face || !direction || !value))) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: bad argument");
-    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_particle_tractions: upload the particles first");
-    if (ctx->globalIds || ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_particle_tractions: not available in slab mode");
+    if (!ctx || n < 0 || (n > 0 && (!particle || !face || !value))) return fail(ctx, MPMGPU_EINVAL, "%s: bad argument", who);
+    if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "%s: upload the particles first", who);
+    if (ctx->globalIds || ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "%s: not available in slab mode", who);
     if (ctx->cfg.shape == MPMGPU_BSPLINE || ctx->cfg.shape == MPMGPU_BSPLINE_GIMP || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI)
-        return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: traction BCs with the B-spline shape functions are not built");
+        return fail(ctx, MPMGPU_EINVAL, "%s: face BCs with the B-spline shape functions are not built", who);
     cudaSetDevice(ctx->cfg.device);
     const int nNR = ctx->P.n;
-    if (n == 0) { ctx->TB.n = 0; ctx->tracOrder.clear(); return MPMGPU_OK; }
+    if (n == 0) { S.TB.n = 0; S.order.clear(); return MPMGPU_OK; }
     const int nfaces = ctx->dim == 3 ? 6 : 4;
     for (int i = 0; i < n; i++) {
-        if (particle[i] < 0 || particle[i] >= nNR) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: entry %d is particle %d of %d non-rigid particles", i, particle[i], nNR);
-        if (face[i] < 1 || face[i] > nfaces) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: entry %d has face %d (1..%d)", i, face[i], nfaces);
-        const int d = direction[i];
+        if (particle[i] < 0 || particle[i] >= nNR) return fail(ctx, MPMGPU_EINVAL, "%s: entry %d is particle %d of %d non-rigid particles", who, i, particle[i], nNR);
+        if (face[i] < 1 || face[i] > nfaces) return fail(ctx, MPMGPU_EINVAL, "%s: entry %d has face %d (1..%d)", who, i, face[i], nfaces);
+        const int d = direction ? direction[i] : 1;
         if (!(d == 1 || d == 2 || (d == 3 && ctx->dim == 3) || d == 11 || (d == 12 && ctx->dim == 2)))
-            return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: entry %d has direction %d (1 x, 2 y, 3 z in 3D, 11 normal, 12 tangent in 2D)", i, d);
+            return fail(ctx, MPMGPU_EINVAL, "%s: entry %d has direction %d (1 x, 2 y, 3 z in 3D, 11 normal, 12 tangent in 2D)", who, i, d);
     }
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return particle[a] < particle[b]; });
     std::vector<int> st((size_t)nNR + 1, 0), fa(n), di(n);
     std::vector<double> va(n);
-    for (int e = 0; e < n; e++) { const int i = order[e]; st[particle[i] + 1]++; fa[e] = face[i]; di[e] = direction[i]; va[e] = value[i]; }
+    for (int e = 0; e < n; e++) { const int i = order[e]; st[particle[i] + 1]++; fa[e] = face[i]; di[e] = direction ? direction[i] : 1; va[e] = value[i]; }
     for (int i = 0; i < nNR; i++) st[i + 1] += st[i];
-    if (ctx->tracStartLen < nNR + 1) { CK(dalloc(ctx, &ctx->dTracStart, (size_t)nNR + 1)); ctx->tracStartLen = nNR + 1; }
-    if (ctx->tracCap < n) {
-        CK(dalloc(ctx, &ctx->dTracFace, (size_t)n)); CK(dalloc(ctx, &ctx->dTracDir, (size_t)n)); CK(dalloc(ctx, &ctx->dTracValue, (size_t)n));
-        ctx->tracCap = n;
+    if (S.startLen < nNR + 1) { CK(dalloc(ctx, &S.dStart, (size_t)nNR + 1)); S.startLen = nNR + 1; }
+    if (S.cap < n) {
+        CK(dalloc(ctx, &S.dFace, (size_t)n)); CK(dalloc(ctx, &S.dDir, (size_t)n)); CK(dalloc(ctx, &S.dValue, (size_t)n));
+        S.cap = n;
     }
-    CK(cudaMemcpyAsync(ctx->dTracStart, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dTracFace, fa.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dTracDir, di.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dTracValue, va.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(S.dStart, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(S.dFace, fa.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(S.dDir, di.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(S.dValue, va.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->TB.n = n; ctx->TB.start = ctx->dTracStart; ctx->TB.face = ctx->dTracFace; ctx->TB.dir = ctx->dTracDir; ctx->TB.value = ctx->dTracValue;
-    ctx->tracOrder.swap(order);
+    S.TB.n = n; S.TB.start = S.dStart; S.TB.face = S.dFace; S.TB.dir = S.dDir; S.TB.value = S.dValue;
+    S.order.swap(order);
     return MPMGPU_OK;
 }
 
 // the values of the same list at a new time (BCs that vary)
-extern "C" int mpmgpu_update_particle_traction_values(mpmgpu_ctx *ctx, int n, const double *value)
+static int update_face_bc_values(mpmgpu_ctx *ctx, mpmgpu_ctx::FaceBCs &S, const char *who, int n, const double *value)
 {
-    if (!ctx || !value || n != ctx->TB.n) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_particle_traction_values: n=%d but %d traction BCs are set", n, ctx ? ctx->TB.n : 0);
+    if (!ctx || !value || n != S.TB.n) return fail(ctx, MPMGPU_EINVAL, "%s: n=%d but %d BCs are set", who, n, ctx ? S.TB.n : 0);
     if (n == 0) return MPMGPU_OK;
     cudaSetDevice(ctx->cfg.device);
     std::vector<double> va(n);
-    for (int e = 0; e < n; e++) va[e] = value[ctx->tracOrder[e]];
-    CK(cudaMemcpyAsync(ctx->dTracValue, va.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    for (int e = 0; e < n; e++) va[e] = value[S.order[e]];
+    CK(cudaMemcpyAsync(S.dValue, va.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return MPMGPU_OK;
 }
 
-static int particle_tractions(mpmgpu_ctx *ctx)
+extern "C" int mpmgpu_set_particle_tractions(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const int *direction, const double *value)
 {
-    if (ctx->TB.n <= 0 || ctx->P.nNR <= 0) return MPMGPU_OK;
+    if (ctx && n > 0 && !direction) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_particle_tractions: bad argument");
+    return set_face_bcs(ctx, ctx->trac, "mpmgpu_set_particle_tractions", n, particle, face, direction, value);
+}
+extern "C" int mpmgpu_update_particle_traction_values(mpmgpu_ctx *ctx, int n, const double *value)
+{
+    return update_face_bc_values(ctx, ctx->trac, "mpmgpu_update_particle_traction_values", n, value);
+}
+extern "C" int mpmgpu_set_particle_heat_fluxes(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const double *value)
+{
+    if (ctx && !ctx->conduction) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_particle_heat_fluxes: call mpmgpu_set_conduction first");
+    return set_face_bcs(ctx, ctx->flux, "mpmgpu_set_particle_heat_fluxes", n, particle, face, NULL, value);
+}
+extern "C" int mpmgpu_update_particle_heat_flux_values(mpmgpu_ctx *ctx, int n, const double *value)
+{
+    return update_face_bc_values(ctx, ctx->flux, "mpmgpu_update_particle_heat_flux_values", n, value);
+}
+
+static int face_bc_launch(mpmgpu_ctx *ctx, const TractionBCs &TB, double *fluxQ)
+{
+    if (TB.n <= 0 || ctx->P.nNR <= 0) return MPMGPU_OK;
     const int cpdi = ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 1 : 0;
     const double thick = ctx->cfg.thickness > 0. ? ctx->cfg.thickness : 1.;
-    if (ctx->dim == 3) LAUNCH((k_particle_tractions<3>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, ctx->TB, cpdi, thick, ctx->nf, ctx->dFlags);
-    else LAUNCH((k_particle_tractions<2>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, ctx->TB, cpdi, thick, ctx->nf, ctx->dFlags);
+    if (ctx->dim == 3) LAUNCH((k_particle_tractions<3>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, TB, cpdi, thick, ctx->nf, ctx->dFlags, fluxQ);
+    else LAUNCH((k_particle_tractions<2>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, TB, cpdi, thick, ctx->nf, ctx->dFlags, fluxQ);
     return MPMGPU_OK;
 }
+static int particle_tractions(mpmgpu_ctx *ctx) { return face_bc_launch(ctx, ctx->trac.TB, NULL); }
+// TransportTask::TransportForceBCs at the end of the post-forces task (PostForcesTask.cpp:97)
+static int particle_heat_fluxes(mpmgpu_ctx *ctx) { return ctx->conduction ? face_bc_launch(ctx, ctx->flux.TB, ctx->T.gQ) : MPMGPU_OK; }
 
 // Rigid-BC particles whose material has setting functions: the host evaluates them each step
 // (RigidMaterial::GetVectorSetting, Materials/RigidMaterial.cpp:376-531) and hands over the velocities
@@ -1401,7 +1426,8 @@ static int t_post_forces(mpmgpu_ctx *ctx)
     LAUNCH(k_post_forces, nblocks(ctx->nvn, 256), 256, ctx->nvn, ctx->N, ctx->sp);
     rc = reactions_zero(ctx);
     if (rc) return rc;
-    return apply_bcs(ctx, PASS_GRID_FORCES, 0);
+    if ((rc = apply_bcs(ctx, PASS_GRID_FORCES, 0))) return rc;
+    return particle_heat_fluxes(ctx);
 }
 
 static int t_update_momenta(mpmgpu_ctx *ctx)

@@ -416,8 +416,12 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_forces(Grid g, Particles P
 // the others with the weight taken from the deformed face all the same; every corner hands wtNorm * value * N_i(corner) to the
 // nodes of its element (plain element shape functions, ElementBase::GetShapeFunctionsForTractions) that carry non-rigid particles
 // and the particle's material field.  wtNorm = direction x (face area / corners).
+// fluxQ != NULL: the same walk for particle heat-flux BCs (MatPtHeatFluxBC::AddMPFluxBC, MatPtHeatFluxBC.cpp:64-160, external flux): the
+// value is a scalar flux, the direction argument of GetSurfaceInfo is x only to carry the face weight, and value x weight x N_i goes
+// into the transport rate gQ of every node with non-rigid particles (TransportTask::AddFluxCondition, TransportTask.cpp:302-308).
 template <int DIM>
-__global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Particles P, Nodes N, TractionBCs TB, int cpdi, double thickness, int nf, StatusFlags *flags)
+__global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Particles P, Nodes N, TractionBCs TB, int cpdi, double thickness, int nf, StatusFlags *flags,
+                                                                     double *fluxQ = nullptr)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Par
     const double pos[3] = {P.pos[0][p], P.pos[1][p], DIM == 3 ? P.pos[2][p] : 0.};
     const int off = nf > 1 ? P.foff[p] : 0;
     for (int e = e0; e < e1; e++) {
-        const int face = TB.face[e], dof = TB.dir[e];
+        const int face = TB.face[e], dof = fluxQ ? 1 : TB.dir[e];
         const double tmag = TB.value[e];
         double r1[3] = {d1[0], d1[1], d1[2]}, r2[3] = {d2[0], d2[1], d2[2]}, r3[3] = {d3[0], d3[1], d3[2]};
         double uSize = -1.;
@@ -506,6 +510,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Par
             for_each_node<DIM, SHAPE_LINEAR, false>(g, ce, xi, lpz, [&](int nd, double S, double, double, double) {
                 bool any = false;       // NodalPoint::NodeHasNonrigidParticles, then the particle's own field (AddTractionTask3)
                 for (int f = 0; f < nf; f++) any |= N.cnt[nd + f * g.nnodes] > 0;
+                if (fluxQ) { if (any) atomAdd(&fluxQ[nd], (tmag * wt[0]) * S); return; }
                 if (!any || N.cnt[nd + off] <= 0) return;
                 const double s = tmag * S;
                 if (wt[0] != 0.) atomAdd(&N.ftot[0][nd + off], wt[0] * s);

@@ -90,6 +90,8 @@ long long gLeftGridWarned = 0;     // first-time grid leavers already handed to 
 bool gCustomTasksReadParticles = false;     // (the only custom task the adapter admits, PeriodicXPIC, touches bodyFrc alone)
 std::vector<MatPtTractionBC *> gTractions;      // particle traction BCs in list order
 bool gTractionsVary = false;
+std::vector<MatPtHeatFluxBC *> gHeatFluxes;     // particle heat-flux BCs in list order (conduction)
+bool gHeatFluxesVary = false;
 std::vector<int> gLoadPts;          // particles with load BCs (MatPtLoadBC), 0-based, each once
 bool gLoadsSent = false;
 std::vector<NodalTempBC *> gTempBCs;    // nodal temperature BCs in list order (conduction)
@@ -396,6 +398,13 @@ class GpuTask : public MPMTask
         for (size_t i = 0; i < gTractions.size(); i++) v[i] = gTractions[i]->BCValue(mtime);
         check(mpmgpu_update_particle_traction_values(gCtx, (int)v.size(), v.data()), "GpuTask(traction values)");
     }
+    void UpdateHeatFluxValues(void)
+    {
+        if (gHeatFluxes.empty() || !gHeatFluxesVary) return;
+        std::vector<double> v(gHeatFluxes.size());
+        for (size_t i = 0; i < gHeatFluxes.size(); i++) v[i] = gHeatFluxes[i]->BCValue(mtime);
+        check(mpmgpu_update_particle_heat_flux_values(gCtx, (int)v.size(), v.data()), "GpuTask(heat flux values)");
+    }
     // RigidMaterial::GetVectorSetting evaluated by the reference's own Expression objects (ProjectRigidBCsTask.cpp:75-93)
     void UpdateRigidVelocities(void)
     {
@@ -443,6 +452,7 @@ class GpuTask : public MPMTask
                 UpdateRigidVelocities();
                 UpdateParticleLoads();
                 UpdateTractionValues();
+                UpdateHeatFluxValues();
                 UpdateTemperatureBCs();
                 if (!gSlabs.empty()) {
                     // every slab steps at the same time: the halo and migrant exchanges inside mpmgpu_slab_step are NCCL calls that
@@ -465,6 +475,7 @@ class GpuTask : public MPMTask
             check(mpmgpu_set_xpic(gCtx, bodyFrc.GetXPICOrder(), bodyFrc.UsingFMPM() ? 1 : 0), "GpuTask(Initialize)");
             UpdateParticleLoads();
             UpdateTractionValues();
+            UpdateHeatFluxValues();
             UpdateTemperatureBCs();
             if (nmpmsRC != nmpmsRB) UpdateRigidVelocities();        // rigid contact particles: SetRigidContactVelTask runs before the extrapolation
             check(mpmgpu_task_initialization(gCtx), "GpuTask(Initialize)");
@@ -536,7 +547,11 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         // conduction task the device does not have stays refused
         if (transportTasks != conduction || conduction->GetNextTransportTask() != NULL) return "transport tasks other than conduction (diffusion, poroelasticity, ...)";
         if (firstRigidTempBC != NULL) return "temperature BCs set by rigid particles";
-        if (firstHeatFluxPt != NULL) return "particle heat-flux BCs";
+        // particle heat-flux BCs run on the device when they are external fluxes the host can evaluate (mpmgpu_set_particle_heat_fluxes)
+        for (MatPtLoadBC *lb = firstHeatFluxPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
+            if (lb->style == SILENT || lb->style == FUNCTION_VALUE || lb->direction != EXTERNAL_FLUX) return "particle heat-flux BCs that are silent, coupled or set by a function";
+            if (lb->ptNum - 1 >= nmpmsNR) return "heat-flux BCs on rigid particles";
+        }
         if (ConductionTask::crackTipHeating || ConductionTask::crackContactHeating || ConductionTask::matContactHeating) return "crack-tip or contact heating";
         if (TransportTask::hasXPICOption) return "XPIC/FMPM options for transport tasks";
         if (bodyFrc.GetXPICOrder() > 1) return "XPIC/FMPM of order > 1 with transport tasks";
@@ -908,6 +923,16 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     }
     ALL_CTX(mpmgpu_set_velocity_bcs(ctx_, (int)bnode.size(), bnode.data(), bnorm.data(), bval.data(), bact.data(), bsym.data()));
     if (anyReflected) ALL_CTX(mpmgpu_set_velocity_bc_reflections(ctx_, (int)bnode.size(), brefl.data(), bratio.data()));
+    if (ConductionTask::active && firstHeatFluxPt != NULL) {      // MatPtHeatFluxBC list in list order
+        std::vector<int> tp, tf; std::vector<double> tv;
+        for (MatPtLoadBC *lb = firstHeatFluxPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
+            MatPtHeatFluxBC *hb = (MatPtHeatFluxBC *)lb;
+            gHeatFluxes.push_back(hb);
+            tp.push_back(hb->ptNum - 1); tf.push_back(hb->face); tv.push_back(hb->BCValue(mtime));
+            if (hb->style != CONSTANT_VALUE || hb->GetBCFirstTime() > 0.) gHeatFluxesVary = true;
+        }
+        if (mpmgpu_set_particle_heat_fluxes(gCtx, (int)tp.size(), tp.data(), tf.data(), tv.data()) != MPMGPU_OK) return mpmgpu_last_error(gCtx);
+    }
     if (firstTractionPt != NULL) {      // MatPtTractionBC list in list order
         std::vector<int> tp, tf, td; std::vector<double> tv;
         for (MatPtLoadBC *lb = firstTractionPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {

@@ -354,9 +354,10 @@ def from_reference_dump(z, snapshot="p0"):
         pr.particles["pfext"] = z[s + "/pFext"]
     pr.adiabatic = bool(info.get("adiabatic", 0))
     if "conduction/kcond" in z:
-        for k in ("n_flux_bcs", "contact_heating"):
-            if int(z["conduction/" + k]):
-                raise NotImplementedError("conduction with " + k)
+        if int(z["conduction/contact_heating"]):
+            raise NotImplementedError("conduction with contact_heating")
+        if int(z["conduction/n_flux_bcs"]) and "heatflux/particle" not in z:
+            raise NotImplementedError("conduction with heat-flux BCs the dump does not list")
         pr.conduction = dict(kcond=np.asarray(z["conduction/kcond"], float))
         if "conduction/tbc_node" in z:      # nodal temperature BCs (constant values in the goldens; a host re-evaluates others every step)
             pr.conduction["tbc_node"] = np.asarray(z["conduction/tbc_node"], np.int32)
@@ -396,6 +397,10 @@ def from_reference_dump(z, snapshot="p0"):
     pr.bc_active = np.ones(nb, np.int32)
     pr.bc_symdir = np.zeros(nb, np.int32)
     pr.bc_style = z["velbcs/style"]
+    if "heatflux/particle" in z:        # MatPtHeatFluxBC list (external fluxes of constant style)
+        if np.any(z["heatflux/direction"] != 1) or np.any(z["heatflux/style"] == 5):
+            raise NotImplementedError("coupled or silent heat-flux BCs")
+        pr.heat_fluxes = {k: np.asarray(z["heatflux/" + k]) for k in ("particle", "face", "value")}
     if "tractions/particle" in z:       # MatPtTractionBC list (constant-style values; others are the host's to re-evaluate)
         pr.tractions = {k: np.asarray(z["tractions/" + k]) for k in ("particle", "face", "direction", "value")}
     pr.bc_id = z["velbcs/id"].astype(np.int32) if "velbcs/id" in z else np.zeros(nb, np.int32)        # BoundaryCondition::bcID

@@ -432,6 +432,22 @@ void ref_get_tractions(int *particle, int *face, int *direction, int *style, dou
     }
 }
 
+// particle heat-flux BCs (MatPtHeatFluxBC list): 1-based particle, face, direction (1 external, 2 coupled), style, BCValue now
+int ref_num_heat_fluxes(void)
+{
+    int k = 0;
+    for (MatPtLoadBC *bc = firstHeatFluxPt; bc != NULL; bc = (MatPtLoadBC *)bc->GetNextObject()) k++;
+    return k;
+}
+void ref_get_heat_fluxes(int *particle, int *face, int *direction, int *style, double *value)
+{
+    int k = 0;
+    for (MatPtLoadBC *b = firstHeatFluxPt; b != NULL; b = (MatPtLoadBC *)b->GetNextObject(), k++) {
+        MatPtHeatFluxBC *bc = (MatPtHeatFluxBC *)b;
+        particle[k] = bc->ptNum; face[k] = bc->face; direction[k] = bc->direction; style[k] = bc->style; value[k] = bc->BCValue(mtime);
+    }
+}
+
 // per BC: bcID (BoundaryCondition::GetID; the "id" attribute of the BC's XML block, the material number for rigid-particle BCs)
 void ref_get_velbc_ids(int *ids)
 {

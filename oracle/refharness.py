@@ -200,6 +200,16 @@ class RefRun:
         o["particle"] -= 1
         return o
 
+    def heat_fluxes(self):
+        """MatPtHeatFluxBC list: 0-based particle, face, direction (1 external), style, BCValue at the current time (None when empty)."""
+        n = self.lib.ref_num_heat_fluxes()
+        if n == 0:
+            return None
+        o = dict(particle=np.zeros(n, np.int32), face=np.zeros(n, np.int32), direction=np.zeros(n, np.int32), style=np.zeros(n, np.int32), value=np.zeros(n))
+        self.lib.ref_get_heat_fluxes(_ip(o["particle"]), _ip(o["face"]), _ip(o["direction"]), _ip(o["style"]), _dp(o["value"]))
+        o["particle"] -= 1
+        return o
+
     def reactions(self, ids):
         """NodalVelBC::TotalReactionForce for each BC id (0 = every BC; rigid-particle BCs carry their material number)."""
         ids = np.ascontiguousarray(ids, np.int32)
@@ -256,6 +266,9 @@ def _worker(xml, out_npz, nprocs, snaps, per_task_steps, jitter_amp=0.0, vel_amp
     trac = r.tractions()
     if trac is not None:
         _flatten("tractions", trac, out)
+    hflux = r.heat_fluxes()
+    if hflux is not None:
+        _flatten("heatflux", hflux, out)
     names = r.task_names()
     out["task_names"] = np.array(names)
     _flatten("p0", r.particles(), out)

@@ -53,6 +53,7 @@ struct EmuSim {
     std::vector<int> tbcNode, tbcStart, tbcActive; std::vector<double> tbcValue, tbcSaved;
     // particle traction BCs (capi.cu: TB)
     TractionBCs TB; std::vector<int> trStart, trFace, trDir; std::vector<double> trValue; double thickness = 1.;
+    TractionBCs HF; std::vector<int> hfStart, hfFace, hfDir; std::vector<double> hfValue;      // heat fluxes (capi.cu: flux)
     // temperature BCs of rigid particles (capi.cu: rigidTemp, R.ownerT / ptemp / fixedT / savedT)
     std::vector<int> ownerT; std::vector<double> rigidTemps, savedT; std::vector<unsigned char> fixedTemp;
 };
@@ -253,6 +254,11 @@ void run_task(EmuSim *S, int t)
         EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp);
         std::fill(S->bcReact.begin(), S->bcReact.end(), 0.); std::fill(S->rigidReact.begin(), S->rigidReact.end(), 0.);     // capi.cu: reactions_zero
         apply_bcs(S, PASS_GRID_FORCES, 0);
+        if (S->conduction && S->HF.n > 0) {      // capi.cu: particle_heat_fluxes
+            const int cpdi = SHAPE_IS_CPDI(S->shape) ? 1 : 0;
+            if (S->dim == 3) EMU_LAUNCH((k_particle_tractions<3>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->HF, cpdi, S->thickness, S->nf, &S->flags, S->T.gQ);
+            else EMU_LAUNCH((k_particle_tractions<2>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->HF, cpdi, S->thickness, S->nf, &S->flags, S->T.gQ);
+        }
         break;
     case 6:
         EMU_LAUNCH(k_update_momenta, nblk(nn, 256), 256, nn, S->N, S->sp.dt);
@@ -373,7 +379,7 @@ extern "C" void *emu_create(int np, int horiz, int vert, int depth, const double
     R.reaction = S->rigidReact.data();
     S->B.reaction = NULL;
     bind_nodes(S, (size_t)g.nnodes);
-    memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp); memset(&S->Q, 0, sizeof S->Q); memset(&S->TB, 0, sizeof S->TB);
+    memset(&S->C, 0, sizeof S->C); memset(&S->cp, 0, sizeof S->cp); memset(&S->Q, 0, sizeof S->Q); memset(&S->TB, 0, sizeof S->TB); memset(&S->HF, 0, sizeof S->HF);
     return S;
 }
 
@@ -542,6 +548,20 @@ extern "C" void emu_set_tractions(void *h, int n, const int *particle, const int
     for (int e = 0; e < n; e++) { const int i = order[e]; S->trStart[particle[i] + 1]++; S->trFace[e] = face[i]; S->trDir[e] = direction[i]; S->trValue[e] = value[i]; }
     for (int i = 0; i < S->P.n; i++) S->trStart[i + 1] += S->trStart[i];
     S->TB.n = n; S->TB.start = S->trStart.data(); S->TB.face = S->trFace.data(); S->TB.dir = S->trDir.data(); S->TB.value = S->trValue.data();
+    S->thickness = thickness;
+}
+
+// capi.cu::mpmgpu_set_particle_heat_fluxes
+extern "C" void emu_set_heat_fluxes(void *h, int n, const int *particle, const int *face, const double *value, double thickness)
+{
+    EmuSim *S = (EmuSim *)h;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return particle[a] < particle[b]; });
+    S->hfStart.assign((size_t)S->P.n + 1, 0); S->hfFace.resize(n); S->hfDir.assign(n, 1); S->hfValue.resize(n);
+    for (int e = 0; e < n; e++) { const int i = order[e]; S->hfStart[particle[i] + 1]++; S->hfFace[e] = face[i]; S->hfValue[e] = value[i]; }
+    for (int i = 0; i < S->P.n; i++) S->hfStart[i + 1] += S->hfStart[i];
+    S->HF.n = n; S->HF.start = S->hfStart.data(); S->HF.face = S->hfFace.data(); S->HF.dir = S->hfDir.data(); S->HF.value = S->hfValue.data();
     S->thickness = thickness;
 }
 

@@ -203,6 +203,14 @@ CASES = {
     "cond3d_rigid_heater_lcpdi_usl": (inputs.conduction(inputs.block3d(ncell=3, margin=3, E=100.0, gimp="lCPDI", method=3, vz=-2.0e3, vx=1.0e3, rigid=("wall", 0, (0.0, 0.0, 0.0)))
                                                         .replace("<SetDirection>0</SetDirection>", "<SetDirection>0</SetDirection><SetTemperature/>"),
                                                         (300.0, 500.0), (4000.0,), (700.0,)), (1, 2, 40), 2),
+    # particle heat-flux BCs (MatPtHeatFluxBC, external flux): heat fed into the top face of a moving block (uGIMP: undeformed corners)
+    # and into one side of a disk (lCPDI, plane stress: deformed corners, thickness)
+    "cond3d_heat_flux_ugimp": (inputs.particle_bcs(inputs.conduction(inputs.block3d(ncell=3, margin=3, E=100.0, vz=-2.0e3, vx=1.0e3), (300.0,), (4000.0,), (700.0,)), [
+        ('<BCBox xmin="-1" xmax="10" ymin="-1" ymax="10" zmin="5.5" zmax="10">', '<HeatFluxBC dir="1" face="6" style="1" value="5e7"/>'),
+        ('<BCBox xmin="5.5" xmax="10" ymin="-1" ymax="10" zmin="-1" zmax="10">', '<HeatFluxBC dir="1" face="2" style="1" value="-2e7"/>')]), (1, 2, 40), 2, 0.3, 1000.0),
+    "cond2d_heat_flux_lcpdi_planestress": (inputs.particle_bcs(inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=11, gimp="lCPDI", vel=2000.0, vmax=11.0, gap=0.0, alpha=0.0)),
+                                                                                 (380.0, 290.0), (2000.0, 500.0), (800.0, 1500.0)), [
+        ('<BCLine x1="-12" y1="-11" x2="-12" y2="11" tolerance="3">', '<HeatFluxBC dir="1" face="4" style="1" value="3e5"/>')]), (1, 2, 40), 2),
     # thermal strains in the laws: conduction with expanding materials, and bodies that start off the stress-free temperature
     # (one temperature jump handed to the laws by the first particle update) -- every law and analysis type that carries the terms
     "th2d_cond_iso_planestrain": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, vel=2000.0, vmax=11.0, gap=0.0, alpha=60.0)),

@@ -48,7 +48,7 @@ def lib():
                         src, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.emu_create.restype = C.c_void_p
-    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_conduction", "emu_get_transport", "emu_set_temperature_bcs", "emu_set_energy_coupling", "emu_get_reactions", "emu_set_tractions", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
+    for f in ("emu_set_multimaterial", "emu_get_contact", "emu_set_conduction", "emu_get_transport", "emu_set_temperature_bcs", "emu_set_energy_coupling", "emu_get_reactions", "emu_set_tractions", "emu_set_heat_fluxes", "emu_set_bcs", "emu_set_bc_reflections", "emu_set_xpic", "emu_task", "emu_step", "emu_flags", "emu_get_particles", "emu_get_nodes", "emu_get_device_state", "emu_destroy"):
         getattr(lib, f).argtypes = None
     return lib
 
@@ -119,6 +119,7 @@ class EmuSim:
             self.nnodes *= nf
             self.n_fields = nf
         self._set_tractions()
+        self._set_heat_fluxes()
 
     def _set_tractions(self):
         tr = getattr(self.prob, "tractions", None)
@@ -127,6 +128,14 @@ class EmuSim:
         c = np.ascontiguousarray
         self._tr = [c(tr["particle"], dtype=np.int32), c(tr["face"], dtype=np.int32), c(tr["direction"], dtype=np.int32), c(tr["value"], dtype=np.float64)]
         self.lib.emu_set_tractions(self.h, len(self._tr[0]), _ip(self._tr[0]), _ip(self._tr[1]), _ip(self._tr[2]), _dp(self._tr[3]), C.c_double(float(self.prob.thickness)))
+
+    def _set_heat_fluxes(self):
+        hf = getattr(self.prob, "heat_fluxes", None)
+        if hf is None or not len(hf["particle"]):
+            return
+        c = np.ascontiguousarray
+        self._hf = [c(hf["particle"], dtype=np.int32), c(hf["face"], dtype=np.int32), c(hf["value"], dtype=np.float64)]
+        self.lib.emu_set_heat_fluxes(self.h, len(self._hf[0]), _ip(self._hf[0]), _ip(self._hf[1]), _dp(self._hf[2]), C.c_double(float(self.prob.thickness)))
 
     def set_xpic(self, order, fmpm):
         self.lib.emu_set_xpic(self.h, int(order), int(fmpm))

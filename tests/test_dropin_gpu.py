@@ -77,6 +77,12 @@ CASES = {
     "disks2d_traction_lcpdi": (inputs.particle_bcs(inputs.oblique_disks(inputs.disks2d(analysis=10, gimp="lCPDI", vel=1000.0, vmax=11.0, gap=0.0, maxtime=0.6, archive_ms=0.15)), [
         ('<BCLine x1="-12" y1="-11" x2="-12" y2="11" tolerance="3">', '<TractionBC dir="11" face="4" style="1" stress="-0.005"/>'),
         ('<BCLine x1="-20" y1="6" x2="20" y2="6" tolerance="2">', '<TractionBC dir="12" face="3" style="2" stress="0.01"/>')]), None, "res/disks."),
+    # conduction with a heat flux that ramps up on the top face of the block and a constant one leaving through a side
+    "block3d_conduction_heat_flux": (inputs.particle_bcs(inputs.conduction(inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=-2.0e3, vx=1.0e3), (300.0,), (4000.0,), (700.0,)), [
+        ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="6.5" zmax="20">', '<HeatFluxBC dir="1" face="6" style="2" value="4e9"/>'),
+        ('<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20">', '<HeatFluxBC dir="1" face="2" style="1" value="-2e7"/>')])
+                                     .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+                                     .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
     # adiabatic coupling: a Johnson-Cook block heats itself by plastic work (thermal softening), no transport task
     "block3d_adiabatic_johnsoncook": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, material=inputs.isoplastic_hardening_material("JohnsonCook", Djc=0.01), vz=-4.0e4,
                                                      extra_header="<StressFreeTemp>300</StressFreeTemp>").replace("</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>")

@@ -63,8 +63,8 @@ CASES = {
     # conduction runs on the device (tests/test_dropin_gpu.py); its BCs, other transport tasks and thermal expansion do not
     # (nodal temperature BCs run on the device: tests/test_dropin_gpu.py)
     "heat flux BCs": (inputs.conduction(inputs.block3d(ncell=3, margin=2, maxtime=0.003), (350.0,), (2000.0,), (800.0,))
-                      .replace("</GridBCs>", '</GridBCs><ParticleBCs><BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="4" zmax="20"><HeatFluxBC dir="1" face="1" style="1" value="100"/></BCBox></ParticleBCs>'),
-                      "particle heat-flux BCs"),
+                      .replace("</GridBCs>", '</GridBCs><ParticleBCs><BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="4" zmax="20"><HeatFluxBC dir="2" face="1" style="6" function="10*(t-300)"/></BCBox></ParticleBCs>'),
+                      "particle heat-flux BCs that are silent, coupled or set by a function"),
     "diffusion": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</MPMHeader>", '<Diffusion reference="0"/></MPMHeader>'),
                   "transport tasks other than conduction"),
     # global quantities the reference reads from its nodes / BC objects would be silently zero: the replaced tasks no longer fill them
