@@ -302,6 +302,12 @@ int mpmgpu_update_particle_heat_flux_values(mpmgpu_ctx *ctx, int n, const double
  * by the rigid-BC particles of material m (0-based; their bcID is the material number, ProjectRigidBCsTask.cpp:241).  Either may
  * be NULL.  The values are those of the last completed step. */
 int mpmgpu_track_reactions(mpmgpu_ctx *ctx, int on);
+/* Contact forces on rigid contact materials (the "contactx/y/z" global quantities, GlobalQuantity.cpp:905-968 ->
+ * NodalPoint::AddGetContactForce, NodalPointMPM.cpp:1458-1472): force[3*f..] = the summed force row of rigid material field f over
+ * the nodes where it is active now -- the momentum its contacts gave the other materials since the last clearing
+ * (MatVelocityField::AddContactForce); 0 for non-rigid fields; n_fields x 3 doubles.  clear != 0 zeroes the rows that were read, as
+ * the reference does outside VTK archiving.  The caller scales by 1/(steps since the last clearing x timestep).  Multimaterial mode. */
+int mpmgpu_contact_forces(mpmgpu_ctx *ctx, int clear, double *force);
 int mpmgpu_download_reactions(mpmgpu_ctx *ctx, int n, double *bc_reaction, double *rigid_reaction);
 /* timestep, strainTimestepFirst, strainTimestepLast (NairnMPM.cpp:1207-1240) */
 int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dt_strain_first, double dt_strain_last);

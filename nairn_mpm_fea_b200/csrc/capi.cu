@@ -488,6 +488,27 @@ static int reactions_zero(mpmgpu_ctx *ctx)
     return MPMGPU_OK;
 }
 
+static int stage_buffer(mpmgpu_ctx *ctx, size_t ndoubles, double **out);
+
+// Contact forces on the rigid contact materials: force[3*f..] = sum over the nodes where rigid material field f is active of the
+// momentum its contacts gave the other materials since the last clearing (a rigid field's ftot, MatVelocityField::AddContactForce);
+// 0 for the other fields.  The caller divides by (steps since the last clearing) x timestep.
+extern "C" int mpmgpu_contact_forces(mpmgpu_ctx *ctx, int clear, double *force)
+{
+    if (!ctx || !force) return MPMGPU_EINVAL;
+    if (!ctx->multimaterial) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_contact_forces: not in multimaterial mode");
+    cudaSetDevice(ctx->cfg.device);
+    double *tmp = NULL;
+    int rc = stage_buffer(ctx, (size_t)3 * MPM_MAX_FIELDS, &tmp);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(tmp, 0, 3 * MPM_MAX_FIELDS * sizeof(double), ctx->stream));
+    if (ctx->cp.rigidMask)
+        LAUNCH(k_contact_force_sum, nblocks((long long)ctx->g.nnodes * ctx->nf, 256), 256, ctx->g.nnodes, ctx->nf, (unsigned)ctx->cp.rigidMask, ctx->C, clear ? 1 : 0, tmp);
+    CK(cudaMemcpyAsync(force, tmp, (size_t)3 * ctx->nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
 extern "C" int mpmgpu_track_reactions(mpmgpu_ctx *ctx, int on)
 {
     if (!ctx) return MPMGPU_EINVAL;
@@ -1815,6 +1836,9 @@ static void step_signature(const mpmgpu_ctx *ctx, std::string &sig)
     add(&ctx->g, sizeof ctx->g); add(&ctx->P, sizeof ctx->P); add(&ctx->PR, sizeof ctx->PR); add(&ctx->N, sizeof ctx->N);
     add(&ctx->B, sizeof ctx->B); add(&ctx->R, sizeof ctx->R); add(&ctx->sp, sizeof ctx->sp); add(&ctx->tiled.FN, sizeof ctx->tiled.FN);
     add(&ctx->C, sizeof ctx->C); add(&ctx->cp, sizeof ctx->cp); add(&ctx->T, sizeof ctx->T); add(&ctx->Q, sizeof ctx->Q);
+    add(&ctx->trac.TB, sizeof ctx->trac.TB); add(&ctx->flux.TB, sizeof ctx->flux.TB);
+    const long long more[3] = {ctx->trackReactions, ctx->nBCEntries, ctx->nmat};        // (sizes of the memset nodes of reactions_zero)
+    add(more, sizeof more);
     const long long misc[17] = {ctx->thermal, ctx->tiled.enabled, ctx->tiled.stateKind, ctx->tiled.usePipe, ctx->hasFext, ctx->hasBCs, ctx->largeRotation, ctx->multimaterial,
                                 ctx->conduction, ctx->nf, ctx->nvn, ctx->cpdiMerge, ctx->cpdiMergeValues, (long long)(size_t)ctx->dMats, (long long)(size_t)ctx->archOrigin,
                                 (long long)(size_t)ctx->nodePool, (long long)(size_t)ctx->stream};

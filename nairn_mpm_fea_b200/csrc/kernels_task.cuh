@@ -410,6 +410,23 @@ __global__ void __launch_bounds__(TASK_THREADS) k_p2g_forces(Grid g, Particles P
     });
 }
 
+// Contact force quantities (GlobalQuantity.cpp:905-968 -> NodalPoint::AddGetContactForce -> CrackVelocityFieldMulti::
+// SumAndClearRigidContactForces :1712-1728): the summed force row of every rigid material field over the nodes where that field is
+// active now, cleared after reading
+__global__ void k_contact_force_sum(int nnodes, int nf, unsigned rigidMask, ContactNodes C, int clear, double *out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nnodes * nf) return;
+    const int f = t / nnodes;
+    if (!(rigidMask >> f & 1) || C.rcnt[t] <= 0) return;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double v = C.rforce[c][t];
+        if (v != 0.) atomicAdd(out + 3 * f + c, v);
+        if (clear) C.rforce[c][t] = 0.;
+    }
+}
+
 // ---- task 6a: particle traction BCs (PostForcesTask.cpp:51 -> MatPtTractionBC::AddMPFluxBC, MatPtTractionBC.cpp:64-226) ----
 // One thread per particle; its traction entries load one face of its domain each.  The face's corners (2 in 2D, 4 in 3D) come from
 // MatPoint2D/3D::GetSurfaceInfo (MatPoint2D.cpp, MatPoint3D.cpp): semi-side vectors F.lp for the CPDI shapes, the undeformed ones for

@@ -253,6 +253,34 @@ bool QuantityFromSums(GlobalQuantity *g, const std::vector<double> &sums, double
     return false;
 }
 
+// "contactx/y/z": GlobalQuantity.cpp:905-968 with the node loop (NodalPoint::AddGetContactForce) replaced by the device's sum over
+// the rigid material fields; the bookkeeping of the steps since the forces were last cleared is the archiver's own
+bool gContactQuantities = false;
+bool QuantityFromContact(GlobalQuantity *g, double &value)
+{
+    const int q = g->quantity;
+    if (q != TOT_FCONX && q != TOT_FCONY && q != TOT_FCONZ) return false;
+    if (!gContactQuantities) return false;
+    Vector ftotal = MakeVector(0., 0., 0.);
+    if (fmobj->mstep != 0) {
+        const int totalSteps = archiver->GetArchiveContactStepInterval();
+        Vector *forces = archiver->GetLastContactForcePtr();
+        if (totalSteps > 0) {
+            std::vector<double> f(3 * (size_t)maxMaterialFields, 0.);
+            check(mpmgpu_contact_forces(gCtx, 1, f.data()), "GpuTasks::contact forces");
+            // NodalPoint::AddGetContactForce: scale = -Scaling(1.e-6) * stepScale / timestep with stepScale = -1/totalSteps
+            const double scale = UnitsController::Scaling(1.e-6) / ((double)totalSteps * timestep);
+            for (int im = 0; im < maxMaterialFields; im++) forces[im] = MakeVector(f[3 * im] * scale, f[3 * im + 1] * scale, f[3 * im + 2] * scale);
+        }
+        for (int im = 0; im < maxMaterialFields; im++) {
+            if (g->whichMat == 0) AddVector(&ftotal, &forces[im]);
+            else if (g->whichMat == MaterialBase::GetFieldMatID(im) + 1) { AddVector(&ftotal, &forces[im]); break; }
+        }
+    }
+    value = q == TOT_FCONX ? ftotal.x : (q == TOT_FCONY ? ftotal.y : ftotal.z);
+    return true;
+}
+
 // quantities that do not read the particles (step number, times, grid damping values ...): the reference's own code serves
 bool QuantityIsParticleFree(int q)
 {
@@ -266,6 +294,7 @@ bool GlobalsCoveredByDevice(void)
     std::vector<double> zero((size_t)nmat * MPMGPU_GS_NSUMS, 0.);
     for (GlobalQuantity *g = firstGlobal; g != NULL; g = g->GetNextGlobal()) {
         double v;
+        if (gContactQuantities && (g->quantity == TOT_FCONX || g->quantity == TOT_FCONY || g->quantity == TOT_FCONZ)) continue;
         if (!QuantityIsParticleFree(g->quantity) && !QuantityFromSums(g, zero, v)) return false;
     }
     return true;
@@ -282,7 +311,8 @@ void GlobalArchiveFromDevice(double atime)
     archiver->lastArchivedStep = fmobj->mstep;
     for (GlobalQuantity *g = firstGlobal; g != NULL;) {
         double v;
-        if (QuantityIsParticleFree(g->quantity)) g = g->AppendQuantity(archiver->lastArchived);
+        if (QuantityFromContact(g, v)) { archiver->lastArchived.push_back(v); g = g->GetNextGlobal(); }
+        else if (QuantityIsParticleFree(g->quantity)) g = g->AppendQuantity(archiver->lastArchived);
         else { QuantityFromSums(g, sums, v); archiver->lastArchived.push_back(v); g = g->GetNextGlobal(); }
     }
     char fline[1000], numStr[100];
@@ -299,6 +329,16 @@ void GlobalArchiveFromDevice(double atime)
 // Returns false when the reference has to do it itself from a downloaded mpm[].
 bool OutputFromDevice(double atime)
 {
+    if (gDeviceOutput && gContactQuantities && atime > fmobj->maxtime) {
+        // last step: the reference writes the global row itself (ArchiveData.cpp:733), and its contact-force quantities would sum host
+        // nodes nobody filled.  Read the forces from the device now: that leaves them in the archiver's own array and moves its
+        // step mark, so the reference's code finds zero steps since the last reading and uses what is stored (GlobalQuantity.cpp:931-958)
+        for (GlobalQuantity *g = firstGlobal; g != NULL; g = g->GetNextGlobal()) {
+            double v;
+            if (QuantityFromContact(g, v)) break;
+        }
+        return false;
+    }
     if (!gDeviceOutput || atime > fmobj->maxtime) return false;         // last step: archived unconditionally by the reference
     const bool globalByTime = firstGlobal != NULL && archiver->globalTime >= 0.;
     const bool globalDue = globalByTime && atime > archiver->nextGlobalTime;
@@ -576,13 +616,21 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     // global quantities the reference reads from its nodes or BC objects, which the replaced tasks no longer fill
     for (GlobalQuantity *gq = firstGlobal; gq != NULL; gq = gq->GetNextGlobal()) {
         const int q = gq->quantity;
-        if (q == TOT_FCONX || q == TOT_FCONY || q == TOT_FCONZ || q == GRID_KINE_ENERGY || q == INTERFACE_ENERGY || q == FRICTION_WORK)
-            return "global quantities read from the grid (contact forces, grid kinetic energy, interface energy, friction work)";
+        if (q == GRID_KINE_ENERGY || q == INTERFACE_ENERGY || q == FRICTION_WORK)
+            return "global quantities read from the grid (grid kinetic energy, interface energy, friction work)";
+        if (q == TOT_FCONX || q == TOT_FCONY || q == TOT_FCONZ) {
+            if (!fmobj->multiMaterialMode) return "contact-force global quantities outside multimaterial mode";
+            if (ngpus > 1 || !gDeviceOutput) return "contact-force global quantities with -gpus N or -hostoutput (they are summed on the device)";
+            if (archiver->globalTime < 0.) return "contact-force global quantities archived with the particle archives";
+            gContactQuantities = true;
+        }
         if (q == TOT_REACTX || q == TOT_REACTY || q == TOT_REACTZ) {
             if (ngpus > 1) return "reaction-force global quantities with -gpus N (the slabs do not keep them)";
             gTrackReactions = true;
         }
     }
+    if (gContactQuantities && !GlobalsCoveredByDevice())
+        return "contact-force global quantities next to a quantity the device does not sum (the host's nodes carry no contact forces)";
     // damping that changes during the run (functions of time, feedback on the kinetic energy: BodyForce.cpp:167-230)
     if (bodyFrc.useFeedback || bodyFrc.usePFeedback || bodyFrc.gridfunction != NULL || bodyFrc.pgridfunction != NULL)
         return "time-dependent or feedback damping";
@@ -990,6 +1038,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         for (int r = 0; r < gNumGpus; r++) std::cout << " [" << slabLo[r] << "," << slabHi[r] << "):" << slabSel[r].size();
         std::cout << " particles (rigid-BC particles on every slab)" << std::endl;
     }
+    if (gContactQuantities && !gDeviceOutput) return "contact-force global quantities when the archives have to be written by the host";
     return NULL;
 }
 

@@ -250,3 +250,27 @@ def test_reaction_force_global_quantities_match_reference(mode):
         assert len(rr) == len(rg) == 7
         for j, (x, y) in enumerate(zip(rr, rg)):
             assert abs(float(x) - float(y)) <= 5e-6 * max(np.abs(cols[:, j]).max(), 1e-300), (rr, rg)
+
+
+@pytest.mark.parametrize("mode", ["tasks", "fused"])
+def test_contact_force_global_quantities_match_reference(mode):
+    """"contactx/y" global quantities (GlobalQuantity.cpp:905-968): the force a plate of rigid contact particles exerts on a disk, by
+    material and in total, averaged over the steps since the last global archive and cleared after reading.  The device sums the
+    rigid field's force row over its active nodes (mpmgpu_contact_forces); the adapter keeps the reference's own step bookkeeping."""
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("oracle/_ref/NairnMPM or host/_build/NairnMPM_gpu not built")
+    xml = (inputs.rigid_contact_plate(inputs.disks2d(analysis=10, vel=3000.0, vmax=11.0, gap=0.0, maxtime=0.6, archive_ms=0.3, extra_header=inputs.multimaterial(0, 0.3)))
+           .replace("</MPMHeader>", "<GlobalArchiveTime units=\"ms\">0.02</GlobalArchiveTime><GlobalArchive type=\"contactx\" material=\"2\"/>"
+                    "<GlobalArchive type=\"contacty\" material=\"2\"/><GlobalArchive type=\"contactx\"/><GlobalArchive type=\"Kinetic Energy\"/></MPMHeader>"))
+    dref, out_ref = run(REF, xml, ("-np", "4"))
+    dgpu, out_gpu = run(GPU, xml, ("-fused",) if mode == "fused" else ())
+    assert "GPU TASKS" in out_gpu
+    rows_r = [ln.split("\t") for ln in open(os.path.join(dref, "res/disks.global")).read().splitlines() if not ln.startswith("#")]
+    rows_g = [ln.split("\t") for ln in open(os.path.join(dgpu, "res/disks.global")).read().splitlines() if not ln.startswith("#")]
+    assert len(rows_r) == len(rows_g) and len(rows_r) >= 10, (len(rows_r), len(rows_g))
+    cols = np.array([[float(x) for x in r] for r in rows_r])
+    assert np.all(np.abs(cols[:, 1:4]).max(axis=0) > 0), "a contact-force column is zero throughout: the input does not exercise it"
+    for rr, rg in zip(rows_r, rows_g):
+        assert len(rr) == len(rg) == 5
+        for j, (x, y) in enumerate(zip(rr, rg)):
+            assert abs(float(x) - float(y)) <= 5e-6 * max(np.abs(cols[:, j]).max(), 1e-300), (rr, rg)
