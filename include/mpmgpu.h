@@ -257,7 +257,7 @@ int mpmgpu_set_multimaterial(mpmgpu_ctx *ctx, const mpmgpu_multimaterial *mm);
  * isotropic: MaterialBaseMPM.cpp:320-326; ignored for rigid-BC materials).  Built: isothermal energy mode, insulated boundaries,
  * any number of materials (also in multimaterial mode: transport values live on the node, not on a velocity field), nodal
  * temperature BCs (mpmgpu_set_temperature_bcs), thermal expansion (the temperature change of a step reaches the laws as ResidualStrains::dT).  Refused: thermal expansion on the
- * large-rotation IsotropicMat, XPIC/FMPM order > 1, slab mode; heat-flux BCs and contact heating are the adapter's to refuse.  Per-task kernels.  Call after
+ * large-rotation IsotropicMat, slab mode; silent / coupled heat-flux BCs, the transport task's own XPIC option and contact heating are the adapter's to refuse (a mechanical XPIC/FMPM order > 1 leaves the transport update FLIP, as in the reference).  Per-task kernels.  Call after
  * mpmgpu_set_materials and before mpmgpu_upload_particles. */
 int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kcond);
 /* <EnergyCoupling/> (ConductionTask::adiabatic): MaterialBase::IncrementHeatEnergy buffers dTq0 + dPhi/Cv as a temperature rise on

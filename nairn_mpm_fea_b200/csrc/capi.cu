@@ -439,7 +439,8 @@ extern "C" int mpmgpu_set_conduction(mpmgpu_ctx *ctx, int nmat, const double *kc
     if (ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_set_conduction: call before mpmgpu_upload_particles");
     if (ctx->tiled.slab.on) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: not available in slab mode");
     if (ctx->cfg.kernel_path == 2) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: transport tasks run on the per-task kernels (kernel_path 2 asked for the fused path)");
-    if (ctx->sp.xpicOrder > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_conduction: XPIC/FMPM of order > 1 with transport (XPICExtrapolationTaskTO) is not built");
+    // (a mechanical XPIC/FMPM order > 1 leaves the transport update as it is -- FLIP -- unless the transport task has its own XPIC
+    // option, XPICExtrapolationTaskTO, which is the adapter's to refuse: UpdateParticlesTask.cpp:85-97)
     for (int i = 0; i < nmat; i++) {
         const Material &m = ctx->hMats[i];
         // thermal strains are in the device laws (materials.cuh) except in IsotropicMat's large-rotation form
@@ -996,7 +997,6 @@ extern "C" int mpmgpu_set_time_step(mpmgpu_ctx *ctx, double dt, double dtFirst, 
 extern "C" int mpmgpu_set_xpic(mpmgpu_ctx *ctx, int order, int usingFMPM)
 {
     if (ctx && ctx->multimaterial && order > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: XPIC/FMPM of order > 1 with material contact is not built");
-    if (ctx && ctx->conduction && order > 1) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: XPIC/FMPM of order > 1 with transport is not built");
     if (!ctx) return MPMGPU_EINVAL;
     if (order < 0) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_set_xpic: order %d", order);
     ctx->sp.xpicOrder = order; ctx->sp.usingFMPM = usingFMPM;

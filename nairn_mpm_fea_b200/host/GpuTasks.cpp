@@ -594,7 +594,7 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         }
         if (ConductionTask::crackTipHeating || ConductionTask::crackContactHeating || ConductionTask::matContactHeating) return "crack-tip or contact heating";
         if (TransportTask::hasXPICOption) return "XPIC/FMPM options for transport tasks";
-        if (bodyFrc.GetXPICOrder() > 1) return "XPIC/FMPM of order > 1 with transport tasks";
+        // (a mechanical XPIC/FMPM order > 1 does not touch the transport update: UpdateParticlesTask.cpp:85-97)
     }
     // everything the replaced CPU tasks would do on the side must be absent, or the run would silently differ:
     // particle loads / tractions are re-evaluated every step by InitializationTask and GridForcesTask

@@ -203,6 +203,14 @@ CASES = {
     "cond3d_rigid_heater_lcpdi_usl": (inputs.conduction(inputs.block3d(ncell=3, margin=3, E=100.0, gimp="lCPDI", method=3, vz=-2.0e3, vx=1.0e3, rigid=("wall", 0, (0.0, 0.0, 0.0)))
                                                         .replace("<SetDirection>0</SetDirection>", "<SetDirection>0</SetDirection><SetTemperature/>"),
                                                         (300.0, 500.0), (4000.0,), (700.0,)), (1, 2, 40), 2),
+    # conduction under a mechanical FMPM(2) / XPIC(2) update (the transport update itself stays FLIP: no transport XPIC option)
+    "cond3d_block_fmpm2_temperature_bcs": (inputs.conduction(inputs.block3d(ncell=3, margin=3, E=100.0, vz=-2.0e3, vx=1.0e3, custom_tasks=inputs.periodic_xpic(2, True, 1))
+                                                             .replace("<alpha>0</alpha>", "<alpha>50</alpha>"), (300.0,), (4000.0,), (700.0,))
+                                           .replace("</GridBCs>", '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="3.01"><TempBC value="450"/></BCBox></GridBCs>'),
+                                           (1, 2, 40), 2, 0.3, 1500.0),
+    "cond2d_disks_xpic2_usl": (inputs.conduction(inputs.oblique_disks(inputs.disks2d(analysis=10, method=3, vel=2000.0, vmax=11.0, gap=0.0, alpha=60.0))
+                                                 .replace("</JANFEAInput>", inputs.periodic_xpic(2, False, 1) + "</JANFEAInput>"),
+                                                 (380.0, 290.0), (2000.0, 500.0), (800.0, 1500.0)), (1, 2, 40), 2),
     # particle heat-flux BCs (MatPtHeatFluxBC, external flux): heat fed into the top face of a moving block (uGIMP: undeformed corners)
     # and into one side of a disk (lCPDI, plane stress: deformed corners, thickness)
     "cond3d_heat_flux_ugimp": (inputs.particle_bcs(inputs.conduction(inputs.block3d(ncell=3, margin=3, E=100.0, vz=-2.0e3, vx=1.0e3), (300.0,), (4000.0,), (700.0,)), [

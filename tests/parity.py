@@ -218,7 +218,7 @@ MM_CASES = ["trac2d_multimaterial_lcpdi_planestress", "mm2d_friction_avgg", "mm2
             "mm3d_rigid_block_maxv_stick_lcpdi"]
 
 
-COND_CASES = ["cond3d_heat_flux_ugimp", "cond2d_heat_flux_lcpdi_planestress", "cond3d_rigid_hot_piston", "cond3d_rigid_heater_lcpdi_usl", "cond2d_disks_usavg", "cond2d_disks_lcpdi_usl_neo", "cond3d_blocks_multimaterial", "cond3d_block_temperature_bcs"]
+COND_CASES = ["cond3d_block_fmpm2_temperature_bcs", "cond2d_disks_xpic2_usl", "cond3d_heat_flux_ugimp", "cond2d_heat_flux_lcpdi_planestress", "cond3d_rigid_hot_piston", "cond3d_rigid_heater_lcpdi_usl", "cond2d_disks_usavg", "cond2d_disks_lcpdi_usl_neo", "cond3d_blocks_multimaterial", "cond3d_block_temperature_bcs"]
 # thermal strains: conduction with expanding materials (th*_cond_*), bodies that start off the stress-free temperature (th*_offset_*)
 THERMAL_COND_CASES = ["th2d_cond_iso_planestrain", "th2d_cond_isoplastic_neo_planestress", "th2d_adiabatic_conduction_isoplastic"]
 THERMAL_OFFSET_CASES = ["th3d_offset_scgl", "th3d_offset_iso", "th3d_offset_isoplastic_usl", "th3d_offset_neohookean", "th2d_offset_mooney_iso_planestress",

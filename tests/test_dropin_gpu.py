@@ -83,6 +83,12 @@ CASES = {
         ('<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20">', '<HeatFluxBC dir="1" face="2" style="1" value="-2e7"/>')])
                                      .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
                                      .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
+    # conduction under a mechanical FMPM(2) update scheduled by PeriodicXPIC
+    "block3d_conduction_fmpm2": (inputs.conduction(inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=-2.0e3, vx=1.0e3, custom_tasks=inputs.periodic_xpic(2, True, 1))
+                                                   .replace("<alpha>0</alpha>", "<alpha>50</alpha>"), (300.0,), (4000.0,), (700.0,))
+                                 .replace("</GridBCs>", '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="3.01"><TempBC value="450"/></BCBox></GridBCs>')
+                                 .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+                                 .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
     # adiabatic coupling: a Johnson-Cook block heats itself by plastic work (thermal softening), no transport task
     "block3d_adiabatic_johnsoncook": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, material=inputs.isoplastic_hardening_material("JohnsonCook", Djc=0.01), vz=-4.0e4,
                                                      extra_header="<StressFreeTemp>300</StressFreeTemp>").replace("</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>")
