@@ -73,7 +73,4 @@ def test_refusals():
     prob = from_reference_dump(z)
     with pytest.raises(MpmGpuError, match="per-task"):
         MpmGpu(prob, device=0, kernel_path=2)
-    prob = from_reference_dump(z)
-    prob.xpic_order, prob.using_fmpm = 2, True
-    with pytest.raises(MpmGpuError, match="order > 1"):
-        MpmGpu(prob, device=0)
+    # (a mechanical FMPM(2) update with conduction runs: goldens cond3d_block_fmpm2_temperature_bcs, cond2d_disks_xpic2_usl)
