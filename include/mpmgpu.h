@@ -273,6 +273,10 @@ int mpmgpu_set_energy_coupling(mpmgpu_ctx *ctx, int adiabatic);
  * there (ImposeValueGridBCs :316-404).  The heat the BCs feed in (NodalValueBC::qreaction, a global-quantity input) is not
  * tracked.  Call after mpmgpu_set_conduction; call again whenever values change. */
 int mpmgpu_set_temperature_bcs(mpmgpu_ctx *ctx, int n, const int *node, const double *value, const int *active);
+/* Rigid particles of a material that sets the temperature (material slot 10) through a value function of time and position
+ * (RigidMaterial::GetValueSetting, which ProjectRigidBCsTask.cpp:118-121 evaluates for every particle every step): the host does that
+ * and hands over pTemperature of all rigid particles, host order, before the step. */
+int mpmgpu_update_rigid_temperatures(mpmgpu_ctx *ctx, int n_rigid, const double *temperature);
 int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
 /* Particle traction BCs (MatPtTractionBC list, firstTractionPt ...; <TractionBC> in <ParticleBCs>): entry i loads face[i] of the
  * domain of particle particle[i] (0-based host index, non-rigid) in direction[i] -- 1 x, 2 y, 3 z (3D), 11 normal to the deformed

@@ -27,7 +27,7 @@ TASKS = ["initialization", "mass_and_momentum", "post_extrapolation", "update_st
 # every symbol include/mpmgpu.h declares (tests check the library exports all of them)
 EXPORTS = ["mpmgpu_abi_version", "mpmgpu_create", "mpmgpu_destroy", "mpmgpu_last_error", "mpmgpu_set_materials",
            "mpmgpu_set_multimaterial", "mpmgpu_set_conduction", "mpmgpu_set_energy_coupling", "mpmgpu_set_temperature_bcs", "mpmgpu_upload_particles",
-           "mpmgpu_track_reactions", "mpmgpu_download_reactions", "mpmgpu_contact_forces", "mpmgpu_set_particle_tractions", "mpmgpu_update_particle_traction_values",
+           "mpmgpu_track_reactions", "mpmgpu_download_reactions", "mpmgpu_contact_forces", "mpmgpu_update_rigid_temperatures", "mpmgpu_set_particle_tractions", "mpmgpu_update_particle_traction_values",
            "mpmgpu_set_particle_heat_fluxes", "mpmgpu_update_particle_heat_flux_values", "mpmgpu_set_time_step", "mpmgpu_set_xpic", "mpmgpu_set_velocity_bcs",
            "mpmgpu_update_velocity_bc_values", "mpmgpu_set_velocity_bc_reflections", "mpmgpu_update_particle_loads", "mpmgpu_update_rigid_velocities", "mpmgpu_step", "mpmgpu_set_poll_interval"] + ["mpmgpu_task_" + t for t in TASKS] + [
     "mpmgpu_task_project_rigid_bcs",
@@ -120,6 +120,7 @@ def load_library(path=None):
     lib.mpmgpu_set_particle_heat_fluxes.argtypes = [vp, C.c_int, _ip, _ip, _dp]
     lib.mpmgpu_update_particle_heat_flux_values.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_contact_forces.argtypes = [vp, C.c_int, _dp]
+    lib.mpmgpu_update_rigid_temperatures.argtypes = [vp, C.c_int, _dp]
     lib.mpmgpu_track_reactions.argtypes = [vp, C.c_int]
     lib.mpmgpu_download_reactions.argtypes = [vp, C.c_int, _dp, _dp]
     lib.mpmgpu_set_time_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]

@@ -1232,6 +1232,20 @@ extern "C" int mpmgpu_update_rigid_velocities(mpmgpu_ctx *ctx, int n_rigid, cons
     return MPMGPU_OK;
 }
 
+// Rigid particles whose material sets the temperature by a value function (RigidMaterial::GetValueSetting, evaluated by the host each
+// step as ProjectRigidBCsTask.cpp:120 does): pTemperature of every rigid particle in host order
+extern "C" int mpmgpu_update_rigid_temperatures(mpmgpu_ctx *ctx, int n_rigid, const double *temperature)
+{
+    if (!ctx || !temperature) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_rigid_temperatures: null argument");
+    if (!ctx->uploaded || n_rigid != ctx->PR.n) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_rigid_temperatures: %d temperatures for %d rigid particles", n_rigid, ctx ? ctx->PR.n : 0);
+    if (!ctx->rigidTemp) return fail(ctx, MPMGPU_ESTATE, "mpmgpu_update_rigid_temperatures: no rigid material sets the temperature (material slot 10) or conduction is off");
+    if (n_rigid == 0) return MPMGPU_OK;
+    cudaSetDevice(ctx->cfg.device);
+    CK(cudaMemcpyAsync(ctx->PR.temp, temperature, (size_t)n_rigid * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MPMGPU_OK;
+}
+
 extern "C" int mpmgpu_update_velocity_bc_values(mpmgpu_ctx *ctx, int n, const double *value, const int *active)
 {
     if (!ctx || n != ctx->nBCEntries) return fail(ctx, MPMGPU_EINVAL, "mpmgpu_update_velocity_bc_values: n=%d but %d BCs are set", n, ctx ? ctx->nBCEntries : 0);

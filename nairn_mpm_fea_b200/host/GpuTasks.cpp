@@ -86,6 +86,7 @@ bool gTrackReactions = false;
 std::vector<NodalVelBC *> gRigidCarriers;       // by material index, NULL for the others
 bool gBCsVary = false;
 bool gRigidFunctions = false;       // some rigid-BC material sets its velocity by functions of time and position
+bool gRigidValueFunctions = false;  // ... or its temperature by a value function (RigidMaterial::GetValueSetting)
 long long gLeftGridWarned = 0;     // first-time grid leavers already handed to the reference's MPMWarnings
 bool gCustomTasksReadParticles = false;     // (the only custom task the adapter admits, PeriodicXPIC, touches bodyFrc alone)
 std::vector<MatPtTractionBC *> gTractions;      // particle traction BCs in list order
@@ -460,6 +461,17 @@ class GpuTask : public MPMTask
             v[j] = m->vel.x; v[nr + j] = m->vel.y; v[2 * (size_t)nr + j] = m->vel.z;
         }
         each_ctx([&](mpmgpu_ctx *c) { return mpmgpu_update_rigid_velocities(c, nr, v.data()); }, "GpuTask(rigid velocities)");
+        if (gRigidValueFunctions) {     // ProjectRigidBCsTask.cpp:118-125: the value function sets the particle's temperature, which its BCs impose
+            std::vector<double> t((size_t)nr);
+            for (int p = nmpmsNR; p < nmpms; p++) {
+                MPMBase *m = mpm[p];
+                RigidMaterial *rm = (RigidMaterial *)theMaterials[m->MatID()];
+                double rvalue;
+                if (rm->RigidTemperature() && rm->GetValueSetting(&rvalue, mtime, &m->pos)) m->pTemperature = rvalue;
+                t[p - nmpmsNR] = m->pTemperature;
+            }
+            check(mpmgpu_update_rigid_temperatures(gCtx, nr, t.data()), "GpuTask(rigid temperatures)");
+        }
     }
     void AfterStep(void)
     {
@@ -677,7 +689,11 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         case 11: {
             RigidMaterial *rm = (RigidMaterial *)mb;
             if (rm->IsRigidBlock()) return "rigid block material";
-            if (rm->Vfunction != NULL || rm->useControlVelocity) return "rigid material with value function or control velocity";
+            if (rm->useControlVelocity) return "rigid material with control velocity";
+            if (rm->Vfunction != NULL) {        // the value function of a temperature-setting material is evaluated by the host every step
+                if (!rm->setTemperature || rm->setConcentration || !ConductionTask::active || ngpus > 1) return "rigid material with a value function (other than a temperature with conduction)";
+                gRigidFunctions = true; gRigidValueFunctions = true;
+            }
             if (rm->setConcentration) return "rigid material that sets concentration";
             // (setTemperature: with conduction the device projects these particles' temperatures onto the nodes they touch; the value
             // function that would change the particle temperature in time was refused above)

@@ -89,6 +89,12 @@ CASES = {
                                  .replace("</GridBCs>", '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="3.01"><TempBC value="450"/></BCBox></GridBCs>')
                                  .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
                                  .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
+    # ... and with the piston's temperature set by a value function of time and position (evaluated by the host every step)
+    "block3d_conduction_rigid_piston_value_function": (inputs.conduction(inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=0.0, rigid=("piston", 4, (0.0, 0.0, -3.0e3)))
+                                                                         .replace("<SetDirection>4</SetDirection>", "<SetDirection>4</SetDirection><SetTemperature/><ValueFunction>500+6000*t+10*x</ValueFunction>"),
+                                                                         (300.0, 600.0), (4000.0,), (700.0,))
+                                                       .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
+                                                       .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
     # adiabatic coupling: a Johnson-Cook block heats itself by plastic work (thermal softening), no transport task
     "block3d_adiabatic_johnsoncook": (inputs.block3d(ncell=4, margin=3, maxtime=0.03, material=inputs.isoplastic_hardening_material("JohnsonCook", Djc=0.01), vz=-4.0e4,
                                                      extra_header="<StressFreeTemp>300</StressFreeTemp>").replace("</JANFEAInput>", "<Thermal><EnergyCoupling/></Thermal></JANFEAInput>")
