@@ -43,6 +43,7 @@
 #include "Materials/RigidMaterial.hpp"
 #include "Boundary_Conditions/NodalVelBC.hpp"
 #include "Boundary_Conditions/MatPtLoadBC.hpp"
+#include "Read_XML/Expression.hpp"
 #include "Boundary_Conditions/MatPtTractionBC.hpp"
 #include "Boundary_Conditions/MatPtHeatFluxBC.hpp"
 #include "Boundary_Conditions/NodalTempBC.hpp"
@@ -571,6 +572,10 @@ int TaskCode(const char *name)
 } // namespace
 
 // Returns NULL when installed, else the reason the run stays on the CPU tasks.
+// a particle BC's function may read the particle's position and rotation (MatPtLoadBC::GetPositionVars), which live on the device
+// between archives: the host can evaluate it only when it reads the time alone (Expression::IsPositionIndependent)
+static bool TimeOnlyFunction(MatPtLoadBC *lb) { return lb->function != NULL && lb->function->IsPositionIndependent(); }
+
 const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
 {
     gNumGpus = ngpus < 1 ? 1 : ngpus;
@@ -601,7 +606,8 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
         if (firstRigidTempBC != NULL) return "temperature BCs set by rigid particles";
         // particle heat-flux BCs run on the device when they are external fluxes the host can evaluate (mpmgpu_set_particle_heat_fluxes)
         for (MatPtLoadBC *lb = firstHeatFluxPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
-            if (lb->style == SILENT || lb->style == FUNCTION_VALUE || lb->direction != EXTERNAL_FLUX) return "particle heat-flux BCs that are silent, coupled or set by a function";
+            if (lb->style == SILENT || lb->direction != EXTERNAL_FLUX || (lb->style == FUNCTION_VALUE && !TimeOnlyFunction(lb)))
+                return "particle heat-flux BCs that are silent, coupled or set by a function of position";
             if (lb->ptNum - 1 >= nmpmsNR) return "heat-flux BCs on rigid particles";
         }
         if (ConductionTask::crackTipHeating || ConductionTask::crackContactHeating || ConductionTask::matContactHeating) return "crack-tip or contact heating";
@@ -615,12 +621,12 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     // position and rotation) would need the current particle state on the host
     for (MatPtLoadBC *lb = firstLoadedPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
         if (lb->style == SILENT) return "silent particle load BCs";
-        if (lb->style == FUNCTION_VALUE) return "particle load BCs set by a function";
+        if (lb->style == FUNCTION_VALUE && !TimeOnlyFunction(lb)) return "particle load BCs set by a function of position";
         if (lb->ptNum - 1 >= nmpmsNR) return "load BCs on rigid particles";
     }
     // particle traction BCs run on the device (mpmgpu_set_particle_tractions); the host re-evaluates values that depend on time only
     for (MatPtLoadBC *lb = firstTractionPt; lb != NULL; lb = (MatPtLoadBC *)lb->GetNextObject()) {
-        if (lb->style == FUNCTION_VALUE) return "particle traction BCs set by a function";
+        if (lb->style == FUNCTION_VALUE && !TimeOnlyFunction(lb)) return "particle traction BCs set by a function of position";
         if (lb->ptNum - 1 >= nmpmsNR) return "traction BCs on rigid particles";
         if (fmobj->exactTractions) return "<ExactTractions>";
         if (ngpus > 1) return "particle traction BCs with -gpus N";

@@ -43,6 +43,7 @@ CASES = {
                                         '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="6.5" zmax="20"><LoadBC dir="3" style="1" load="-0.5"/></BCBox>'
                                         '<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20"><LoadBC dir="1" style="2" load="40" time="0.005"/></BCBox>'
                                         '<BCBox xmin="-1" xmax="20" ymin="-1" ymax="3.5" zmin="-1" zmax="20"><LoadBC dir="2" style="3" load="0.3" time="300"/></BCBox>'
+                                        '<BCBox xmin="-1" xmax="3.5" ymin="-1" ymax="20" zmin="-1" zmax="20"><LoadBC dir="1" style="6" function="0.4*sin(300*t)"/></BCBox>'
                                         "</ParticleBCs>")
                                .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
     # multimaterial mode: the two disks keep their own velocity fields and meet with Coulomb friction
@@ -72,7 +73,8 @@ CASES = {
     # particle traction BCs: a pressure that ramps up on the top face (normal to the deformed face) and a constant shear on one side
     "block3d_traction_pressure_ramp": (inputs.particle_bcs(inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=0.0), [
         ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="6.5" zmax="20">', '<TractionBC dir="11" face="6" style="2" stress="-400"/>'),
-        ('<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20">', '<TractionBC dir="3" face="2" style="1" stress="2"/>')])
+        ('<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20">', '<TractionBC dir="3" face="2" style="1" stress="2"/>'),
+        ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="3.5" zmin="-1" zmax="20">', '<TractionBC dir="2" face="1" style="6" function="3*sin(200*t)"/>')])
                                        .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"), None, "res/blk."),
     "disks2d_traction_lcpdi": (inputs.particle_bcs(inputs.oblique_disks(inputs.disks2d(analysis=10, gimp="lCPDI", vel=1000.0, vmax=11.0, gap=0.0, maxtime=0.6, archive_ms=0.15)), [
         ('<BCLine x1="-12" y1="-11" x2="-12" y2="11" tolerance="3">', '<TractionBC dir="11" face="4" style="1" stress="-0.005"/>'),
@@ -80,7 +82,8 @@ CASES = {
     # conduction with a heat flux that ramps up on the top face of the block and a constant one leaving through a side
     "block3d_conduction_heat_flux": (inputs.particle_bcs(inputs.conduction(inputs.block3d(ncell=4, margin=3, maxtime=0.03, E=100.0, vz=-2.0e3, vx=1.0e3), (300.0,), (4000.0,), (700.0,)), [
         ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="6.5" zmax="20">', '<HeatFluxBC dir="1" face="6" style="2" value="4e9"/>'),
-        ('<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20">', '<HeatFluxBC dir="1" face="2" style="1" value="-2e7"/>')])
+        ('<BCBox xmin="6.5" xmax="20" ymin="-1" ymax="20" zmin="-1" zmax="20">', '<HeatFluxBC dir="1" face="2" style="1" value="-2e7"/>'),
+        ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="3.5" zmin="-1" zmax="20">', '<HeatFluxBC dir="1" face="1" style="6" function="1e7*(1-cos(300*t))"/>')])
                                      .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>")
                                      .replace("<MPMArchiveOrder>iYYYYNNNNNNNYNNNNY</MPMArchiveOrder>", "<MPMArchiveOrder>iYYYYNNYNNNNYNNNNY</MPMArchiveOrder>"), None, "res/blk."),
     # conduction under a mechanical FMPM(2) update scheduled by PeriodicXPIC

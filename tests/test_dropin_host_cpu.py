@@ -64,13 +64,13 @@ CASES = {
     # (nodal temperature BCs run on the device: tests/test_dropin_gpu.py)
     "heat flux BCs": (inputs.conduction(inputs.block3d(ncell=3, margin=2, maxtime=0.003), (350.0,), (2000.0,), (800.0,))
                       .replace("</GridBCs>", '</GridBCs><ParticleBCs><BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="4" zmax="20"><HeatFluxBC dir="2" face="1" style="6" function="10*(t-300)"/></BCBox></ParticleBCs>'),
-                      "particle heat-flux BCs that are silent, coupled or set by a function"),
+                      "particle heat-flux BCs that are silent, coupled or set by a function of position"),
     "diffusion": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace("</MPMHeader>", '<Diffusion reference="0"/></MPMHeader>'),
                   "transport tasks other than conduction"),
     # global quantities the reference reads from its nodes / BC objects would be silently zero: the replaced tasks no longer fill them
     # (reaction forces are kept on the device: tests/test_dropin_gpu.py)
     "traction function": (inputs.particle_bcs(inputs.block3d(ncell=3, margin=2, maxtime=0.003), [
-        ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="4" zmax="20">', '<TractionBC dir="11" face="6" style="6" function="-5*t"/>')]), "particle traction BCs set by a function"),
+        ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="4" zmax="20">', '<TractionBC dir="11" face="6" style="6" function="-5*t*(1+x)"/>')]), "particle traction BCs set by a function of position"),
     "contact force quantity without multimaterial mode": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
         "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="contactz"/></MPMHeader>'), "contact-force global quantities outside multimaterial mode"),
     "grid kinetic energy quantity": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
