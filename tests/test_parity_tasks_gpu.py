@@ -59,7 +59,7 @@ def test_each_task_of_step_one(case):
 
 @pytest.mark.parametrize("case,kernel_path,sort_interval",
                          [(c, 1, 0) for c in CASES] + [(c, 2, 0) for c in FUSED_CASES] +
-                         [("block3d_jitter", 2, 1), ("block3d_fast_crossings", 2, 3)])
+                         [("block3d_jitter", 2, 1), ("block3d_fast_crossings", 2, 3), ("trac3d_pressure_shear_ugimp", 2, 1)])
 def test_whole_steps(case, kernel_path, sort_interval):
     """kernel_path 1 = per-task kernels, 2 = fused dual-cell path (with its periodic physical sort)."""
     z = load_golden(case)
