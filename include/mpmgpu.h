@@ -284,7 +284,7 @@ int mpmgpu_upload_particles(mpmgpu_ctx *ctx, const mpmgpu_particles *host);
  * 3D 1 -y, 2 +x, 3 +y, 4 -x, 5 -z, 6 +z.  In the post-forces task (PostForcesTask.cpp:51) each of the face's corners (2 or 4,
  * MatPoint2D/3D::GetSurfaceInfo: the deformed domain for the CPDI shapes, the undeformed one weighted with the deformed face size
  * for the others) hands direction x area/corners x value x N_i to the nodes of its element that carry the particle's material
- * (MatPtTractionBC::AddMPFluxBC, MatPtTractionBC.cpp:64-226).  Not built: axisymmetric, <ExactTractions>, B-spline shapes, slab mode.
+ * (MatPtTractionBC::AddMPFluxBC, MatPtTractionBC.cpp:64-226).  With the B-spline shapes the corner's weights are the quadratic splines of its element (ElementBase::GetShapeFunctionsForTractions).  Not built: axisymmetric, <ExactTractions>, slab mode.
  * Call after mpmgpu_upload_particles; mpmgpu_update_particle_traction_values hands over new values of the same list. */
 int mpmgpu_set_particle_tractions(mpmgpu_ctx *ctx, int n, const int *particle, const int *face, const int *direction, const double *value);
 int mpmgpu_update_particle_traction_values(mpmgpu_ctx *ctx, int n, const double *value);

@@ -1138,8 +1138,6 @@ static int set_face_bcs(mpmgpu_ctx *ctx, mpmgpu_ctx::FaceBCs &S, const char *who
     if (!ctx || n < 0 || (n > 0 && (!particle || !face || !value))) return fail(ctx, MPMGPU_EINVAL, "%s: bad argument", who);
     if (!ctx->uploaded) return fail(ctx, MPMGPU_ESTATE, "%s: upload the particles first", who);
     if (ctx->globalIds || ctx->tiled.slab.on) return fail(ctx, MPMGPU_ESTATE, "%s: not available in slab mode", who);
-    if (ctx->cfg.shape == MPMGPU_BSPLINE || ctx->cfg.shape == MPMGPU_BSPLINE_GIMP || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI)
-        return fail(ctx, MPMGPU_EINVAL, "%s: face BCs with the B-spline shape functions are not built", who);
     cudaSetDevice(ctx->cfg.device);
     const int nNR = ctx->P.n;
     if (n == 0) { S.TB.n = 0; S.order.clear(); return MPMGPU_OK; }
@@ -1208,10 +1206,11 @@ extern "C" int mpmgpu_update_particle_heat_flux_values(mpmgpu_ctx *ctx, int n, c
 static int face_bc_launch(mpmgpu_ctx *ctx, const TractionBCs &TB, double *fluxQ)
 {
     if (TB.n <= 0 || ctx->P.nNR <= 0) return MPMGPU_OK;
-    const int cpdi = ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI ? 1 : 0;
+    const int cpdi = ctx->cfg.shape == MPMGPU_LINEAR_CPDI || ctx->cfg.shape == MPMGPU_QUADRATIC_CPDI || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI ? 1 : 0;
+    const int spline = ctx->cfg.shape == MPMGPU_BSPLINE || ctx->cfg.shape == MPMGPU_BSPLINE_GIMP || ctx->cfg.shape == MPMGPU_BSPLINE_CPDI ? 1 : 0;
     const double thick = ctx->cfg.thickness > 0. ? ctx->cfg.thickness : 1.;
-    if (ctx->dim == 3) LAUNCH((k_particle_tractions<3>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, TB, cpdi, thick, ctx->nf, ctx->dFlags, fluxQ);
-    else LAUNCH((k_particle_tractions<2>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, TB, cpdi, thick, ctx->nf, ctx->dFlags, fluxQ);
+    if (ctx->dim == 3) LAUNCH((k_particle_tractions<3>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, TB, cpdi, thick, ctx->nf, ctx->dFlags, fluxQ, spline);
+    else LAUNCH((k_particle_tractions<2>), nblocks(ctx->P.nNR, TASK_THREADS), TASK_THREADS, ctx->g, ctx->P, ctx->N, TB, cpdi, thick, ctx->nf, ctx->dFlags, fluxQ, spline);
     return MPMGPU_OK;
 }
 static int particle_tractions(mpmgpu_ctx *ctx) { return face_bc_launch(ctx, ctx->trac.TB, NULL); }

@@ -436,9 +436,11 @@ __global__ void k_contact_force_sum(int nnodes, int nf, unsigned rigidMask, Cont
 // fluxQ != NULL: the same walk for particle heat-flux BCs (MatPtHeatFluxBC::AddMPFluxBC, MatPtHeatFluxBC.cpp:64-160, external flux): the
 // value is a scalar flux, the direction argument of GetSurfaceInfo is x only to carry the face weight, and value x weight x N_i goes
 // into the transport rate gQ of every node with non-rigid particles (TransportTask::AddFluxCondition, TransportTask.cpp:302-308).
+// spline: the quadratic B-spline shape functions of the corner's element stand in for the plain element ones (B2SPLINE, B2GIMP, B2CPDI:
+// ElementBase::GetShapeFunctionsForTractions, MoreMPMElementBase.cpp:91-107).
 template <int DIM>
 __global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Particles P, Nodes N, TractionBCs TB, int cpdi, double thickness, int nf, StatusFlags *flags,
-                                                                     double *fluxQ = nullptr)
+                                                                     double *fluxQ = nullptr, int spline = 0)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nNR) return;
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Par
             if (ce <= 0) { atomicCAS(&flags->cpdiLeft, 0, o + 1); continue; }     // "A Traction edge node has left the grid"
             double xi[3];
             get_xipos<DIM>(g, ce, c[i], xi);
-            for_each_node<DIM, SHAPE_LINEAR, false>(g, ce, xi, lpz, [&](int nd, double S, double, double, double) {
+            auto hand = [&](int nd, double S, double, double, double) {
                 bool any = false;       // NodalPoint::NodeHasNonrigidParticles, then the particle's own field (AddTractionTask3)
                 for (int f = 0; f < nf; f++) any |= N.cnt[nd + f * g.nnodes] > 0;
                 if (fluxQ) { if (any) atomAdd(&fluxQ[nd], (tmag * wt[0]) * S); return; }
@@ -533,7 +535,9 @@ __global__ void __launch_bounds__(TASK_THREADS) k_particle_tractions(Grid g, Par
                 if (wt[0] != 0.) atomAdd(&N.ftot[0][nd + off], wt[0] * s);
                 if (wt[1] != 0.) atomAdd(&N.ftot[1][nd + off], wt[1] * s);
                 if (DIM == 3 && wt[2] != 0.) atomAdd(&N.ftot[2][nd + off], wt[2] * s);
-            });
+            };
+            if (spline) for_each_node<DIM, SHAPE_B2SPLINE, false>(g, ce, xi, lpz, hand);
+            else for_each_node<DIM, SHAPE_LINEAR, false>(g, ce, xi, lpz, hand);
         }
     }
 }

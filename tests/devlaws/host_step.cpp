@@ -248,16 +248,18 @@ void run_task(EmuSim *S, int t)
     case 5:
         if (S->TB.n > 0) {      // capi.cu: particle_tractions
             const int cpdi = SHAPE_IS_CPDI(S->shape) ? 1 : 0;
-            if (S->dim == 3) EMU_LAUNCH((k_particle_tractions<3>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->TB, cpdi, S->thickness, S->nf, &S->flags);
-            else EMU_LAUNCH((k_particle_tractions<2>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->TB, cpdi, S->thickness, S->nf, &S->flags);
+            const int spline = S->shape == SHAPE_B2SPLINE || S->shape == SHAPE_B2GIMP || S->shape == SHAPE_B2CPDI ? 1 : 0;
+            if (S->dim == 3) EMU_LAUNCH((k_particle_tractions<3>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->TB, cpdi, S->thickness, S->nf, &S->flags, (double *)NULL, spline);
+            else EMU_LAUNCH((k_particle_tractions<2>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->TB, cpdi, S->thickness, S->nf, &S->flags, (double *)NULL, spline);
         }
         EMU_LAUNCH(k_post_forces, nblk(nn, 256), 256, nn, S->N, S->sp);
         std::fill(S->bcReact.begin(), S->bcReact.end(), 0.); std::fill(S->rigidReact.begin(), S->rigidReact.end(), 0.);     // capi.cu: reactions_zero
         apply_bcs(S, PASS_GRID_FORCES, 0);
         if (S->conduction && S->HF.n > 0) {      // capi.cu: particle_heat_fluxes
             const int cpdi = SHAPE_IS_CPDI(S->shape) ? 1 : 0;
-            if (S->dim == 3) EMU_LAUNCH((k_particle_tractions<3>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->HF, cpdi, S->thickness, S->nf, &S->flags, S->T.gQ);
-            else EMU_LAUNCH((k_particle_tractions<2>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->HF, cpdi, S->thickness, S->nf, &S->flags, S->T.gQ);
+            const int spline = S->shape == SHAPE_B2SPLINE || S->shape == SHAPE_B2GIMP || S->shape == SHAPE_B2CPDI ? 1 : 0;
+            if (S->dim == 3) EMU_LAUNCH((k_particle_tractions<3>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->HF, cpdi, S->thickness, S->nf, &S->flags, S->T.gQ, spline);
+            else EMU_LAUNCH((k_particle_tractions<2>), nblk(S->P.nNR, TASK_THREADS), TASK_THREADS, S->g, S->P, S->N, S->HF, cpdi, S->thickness, S->nf, &S->flags, S->T.gQ, spline);
         }
         break;
     case 6:

@@ -268,6 +268,12 @@ CASES = {
     "trac2d_multimaterial_lcpdi_planestress": (inputs.particle_bcs(inputs.oblique_disks(inputs.disks2d(analysis=11, gimp="lCPDI", vel=2000.0, vmax=11.0, gap=0.0, extra_header=inputs.multimaterial(2, 0.3))), [
         ('<BCLine x1="-12" y1="-11" x2="-12" y2="11" tolerance="3">', '<TractionBC dir="11" face="4" style="1" stress="-0.05"/>'),
         ('<BCLine x1="0" y1="-11" x2="0" y2="11" tolerance="3">', '<TractionBC dir="2" face="1" style="1" stress="0.03"/>')]), (1, 2, 40), 2),
+    "trac3d_pressure_b2gimp": (inputs.particle_bcs(inputs.block3d(ncell=3, margin=3, E=100.0, gimp="B2GIMP", vz=-2.0e3, vx=1.0e3), [
+        ('<BCBox xmin="-1" xmax="10" ymin="-1" ymax="10" zmin="5.5" zmax="10">', '<TractionBC dir="11" face="6" style="1" stress="-8"/>'),
+        ('<BCBox xmin="5.5" xmax="10" ymin="-1" ymax="10" zmin="-1" zmax="10">', '<TractionBC dir="3" face="2" style="1" stress="3"/>')]), (1, 2, 30), 2, 0.3, 1000.0),
+    "trac2d_disks_b2cpdi": (inputs.particle_bcs(inputs.oblique_disks(inputs.disks2d(analysis=10, gimp="B2CPDI", vel=1000.0, vmax=11.0, gap=0.0)), [
+        ('<BCLine x1="-12" y1="-11" x2="-12" y2="11" tolerance="3">', '<TractionBC dir="11" face="4" style="1" stress="-0.005"/>'),
+        ('<BCLine x1="-20" y1="6" x2="20" y2="6" tolerance="2">', '<TractionBC dir="12" face="3" style="1" stress="0.003"/>')]), (1, 2, 30), 2),
     # reaction forces of the velocity BCs (NodalVelBC::freaction summed by bcID: "reaction<step>" beside "reaction_ids")
     "react3d_walls_ugimp": (inputs.reaction_walls3d(E=100.0, vz=-3.0e3, vx=2.0e3, vy=-1.0e3, gravity=(0.0, 0.0, -5.0e5)), (1, 2, 40), 2, 0.3, 1000.0),
     "react3d_walls_lcpdi_usl": (inputs.reaction_walls3d(ncell=3, E=100.0, gimp="lCPDI", method=3, vz=-3.0e3, vx=2.0e3, vy=-1.0e3), (1, 2, 30), 2),

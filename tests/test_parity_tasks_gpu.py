@@ -13,14 +13,14 @@ from tests.parity import (TASK_MAP, TOL_1STEP, TOL_100STEP, compare_nodes, compa
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["trac3d_pressure_shear_ugimp", "trac3d_pressure_lcpdi_usl", "trac2d_disks_normal_tangent", "block3d_scgl", "disks2d_scgl_planestrain", "disks2d_symmetry_planes", "disks2d_rigid_plate", "block3d_rigid_mirrored", "block3d_lcpdi_rigid_wall", "disks2d_isoplastic_planestress", "block3d_pic", "block3d_fmpm1", "block3d_usavg_minus", "block3d_usavg_minus_xpic2", "block3d_usl_minus_fmpm2", "block3d_usf_fmpm2",
+CASES = ["trac3d_pressure_b2gimp", "trac2d_disks_b2cpdi", "trac3d_pressure_shear_ugimp", "trac3d_pressure_lcpdi_usl", "trac2d_disks_normal_tangent", "block3d_scgl", "disks2d_scgl_planestrain", "disks2d_symmetry_planes", "disks2d_rigid_plate", "block3d_rigid_mirrored", "block3d_lcpdi_rigid_wall", "disks2d_isoplastic_planestress", "block3d_pic", "block3d_fmpm1", "block3d_usavg_minus", "block3d_usavg_minus_xpic2", "block3d_usl_minus_fmpm2", "block3d_usf_fmpm2",
          "block3d_neohookean_av", "block3d_isoplastic_av", "block3d_rigid_wall", "block3d_rigid_piston", "block3d_rigid_linear_xpic2", "block3d_lcpdi_neo_xpic2", "block3d_lcpdi_rcrit", "disks2d_lcpdi", "disks2d_qcpdi", "block3d_xpic3", "block3d_fmpm2", "disks2d_fmpm3_neo", "block3d_neohookean", "block3d_neohookean_uj1", "block3d_isoplastic", "disks2d_neohookean", "disks2d_isoplastic",
          "disks2d_ugimp_planestrain", "disks2d_linear_planestress", "block3d_jitter", "block3d_ugimp_usavg", "block3d_fast_crossings", "block3d_gravity_damping", "block3d_linear_usl",
          "block3d_ugimp_usf"]
 
 
 # the fused path: 3D uGIMP, any of the materials, FLIP/PIC and XPIC(k)/FMPM(k), rigid-BC particles
-FUSED_CASES = [c for c in CASES if "linear" not in c and "2d" not in c and "cpdi" not in c and "mirrored" not in c and "scgl" not in c]
+FUSED_CASES = [c for c in CASES if "linear" not in c and "2d" not in c and "cpdi" not in c and "mirrored" not in c and "scgl" not in c and "b2" not in c]
 
 
 def make_sim(z, kernel_path=1, sort_interval=0):
