@@ -41,6 +41,8 @@ struct mpmgpu_ctx {
     StepParams sp;
     VelBCs B;
     int nBCEntries;
+    int *dBcNode = NULL, *dBcStart = NULL, *dBcSym = NULL, *dBcActive = NULL, *dBcOfNode = NULL; double *dBcNorm = NULL, *dBcValue = NULL;
+    int bcCapUnique = 0, bcCapEntries = 0;
     bool trackReactions = false;        // mpmgpu_track_reactions: B.reaction / R.reaction are kept
     double *dReaction = NULL;           // [3*reactionCap] grid BC entries (device order)
     size_t reactionCap = 0;
@@ -1040,9 +1042,17 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
     st.push_back(n);
     ctx->bcOrder = order;
     int nu = (int)un.size();
-    int *dn, *ds, *dsd, *da; double *dnm, *dva;
-    CK(dalloc(ctx, &dn, nu)); CK(dalloc(ctx, &ds, nu + 1)); CK(dalloc(ctx, &dsd, nu)); CK(dalloc(ctx, &da, n));
-    CK(dalloc(ctx, &dnm, 3 * (size_t)n)); CK(dalloc(ctx, &dva, n));
+    // (buffers are kept between calls and grow on demand: a host may hand the list over every step)
+    if (nu > ctx->bcCapUnique) {
+        CK(dalloc(ctx, &ctx->dBcNode, nu)); CK(dalloc(ctx, &ctx->dBcStart, nu + 1)); CK(dalloc(ctx, &ctx->dBcSym, nu));
+        ctx->bcCapUnique = nu;
+    }
+    if (n > ctx->bcCapEntries) {
+        CK(dalloc(ctx, &ctx->dBcActive, n)); CK(dalloc(ctx, &ctx->dBcNorm, 3 * (size_t)n)); CK(dalloc(ctx, &ctx->dBcValue, n));
+        ctx->bcCapEntries = n;
+    }
+    int *dn = ctx->dBcNode, *ds = ctx->dBcStart, *dsd = ctx->dBcSym, *da = ctx->dBcActive; double *dnm = ctx->dBcNorm, *dva = ctx->dBcValue;
+    CK(cudaStreamSynchronize(ctx->stream));        // a step in flight may still read the old contents
     CK(cudaMemcpy(dn, un.data(), nu * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ds, st.data(), (nu + 1) * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dsd, sd.data(), nu * sizeof(int), cudaMemcpyHostToDevice));
@@ -1054,10 +1064,9 @@ extern "C" int mpmgpu_set_velocity_bcs(mpmgpu_ctx *ctx, int n, const int *node, 
     {   // node -> BC group lookup for the fused node sweeps
         std::vector<int> of(ctx->g.nnodes, -1);
         for (int u = 0; u < nu; u++) of[un[u]] = u;
-        int *dof;
-        CK(dalloc(ctx, &dof, (size_t)ctx->g.nnodes));
-        CK(cudaMemcpy(dof, of.data(), (size_t)ctx->g.nnodes * sizeof(int), cudaMemcpyHostToDevice));
-        ctx->tiled.FN.bcOfNode = dof;
+        if (!ctx->dBcOfNode) CK(dalloc(ctx, &ctx->dBcOfNode, (size_t)ctx->g.nnodes));
+        CK(cudaMemcpy(ctx->dBcOfNode, of.data(), (size_t)ctx->g.nnodes * sizeof(int), cudaMemcpyHostToDevice));
+        ctx->tiled.FN.bcOfNode = ctx->dBcOfNode;
     }
     return reaction_buffers(ctx);
 }
