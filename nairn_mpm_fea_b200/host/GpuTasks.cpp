@@ -146,8 +146,28 @@ void DownloadSlabsToHost(void)
 }
 
 // device -> mpm[] (MPMBase fields; SetDeformationGradient is implicit: ep + wrot are downloaded)
+// "Grid Kinetic Energy" (GlobalQuantity.cpp:1145-1151) sums 0.5 |pk|^2 / mass over the host's nodes: in single-material mode the
+// mass, momentum and point count of every node are copied into the host's MatVelocityField objects before a global archive
+bool gGridKineticEnergy = false;
+void SyncNodesToHost(void)
+{
+    if (!gGridKineticEnergy) return;
+    const size_t nn = (size_t)nnodes;
+    std::vector<int> cnt(nn); std::vector<double> mass(nn), pk(3 * nn);
+    mpmgpu_nodes h;
+    memset(&h, 0, sizeof h);
+    h.nnodes = nnodes; h.number_points = cnt.data(); h.mass = mass.data(); h.pk = pk.data();
+    check(mpmgpu_download_nodes(gCtx, &h), "GpuTasks::SyncNodesToHost");
+    for (size_t i = 0; i < nn; i++) {
+        MatVelocityField *m = nd[i + 1]->cvf[0]->mvf[0];
+        nd[i + 1]->cvf[0]->numberPoints = cnt[i];         // (CrackVelocityField::ActiveField reads the crack field's own count)
+        m->numberPoints = cnt[i]; m->mass = mass[i]; m->pk = MakeVector(pk[i], pk[nn + i], pk[2 * nn + i]);
+    }
+}
+
 void SyncReactionsToHost(void)
 {
+    SyncNodesToHost();
     if (!gTrackReactions) return;
     std::vector<double> bc(3 * gBCs.size() + 3), rigid(3 * (size_t)nmat);
     check(mpmgpu_download_reactions(gCtx, (int)gBCs.size(), bc.data(), rigid.data()), "GpuTasks::SyncReactionsToHost");
@@ -288,6 +308,7 @@ bool QuantityIsParticleFree(int q)
 {
     // (reaction forces: the reference's code reads the BC objects SyncReactionsToHost has just filled)
     if (gTrackReactions && (q == TOT_REACTX || q == TOT_REACTY || q == TOT_REACTZ)) return true;
+    if (gGridKineticEnergy && q == GRID_KINE_ENERGY) return true;       // (the host's nodes hold the device's values: SyncNodesToHost)
     return q == STEP_NUMBER || q == CPU_TIME || q == ELAPSED_TIME || q == GRID_ALPHA || q == PARTICLE_ALPHA;
 }
 
@@ -634,8 +655,12 @@ const char *GpuTasks_Install(int device, bool fusedStep, int ngpus)
     // global quantities the reference reads from its nodes or BC objects, which the replaced tasks no longer fill
     for (GlobalQuantity *gq = firstGlobal; gq != NULL; gq = gq->GetNextGlobal()) {
         const int q = gq->quantity;
-        if (q == GRID_KINE_ENERGY || q == INTERFACE_ENERGY || q == FRICTION_WORK)
-            return "global quantities read from the grid (grid kinetic energy, interface energy, friction work)";
+        if (q == INTERFACE_ENERGY || q == FRICTION_WORK)
+            return "global quantities read from the grid (interface energy, friction work)";
+        if (q == GRID_KINE_ENERGY) {
+            if (fmobj->multiMaterialMode || ngpus > 1) return "grid kinetic energy in multimaterial mode or with -gpus N";
+            gGridKineticEnergy = true;
+        }
         if (q == TOT_FCONX || q == TOT_FCONY || q == TOT_FCONZ) {
             if (!fmobj->multiMaterialMode) return "contact-force global quantities outside multimaterial mode";
             if (ngpus > 1 || !gDeviceOutput) return "contact-force global quantities with -gpus N or -hostoutput (they are summed on the device)";

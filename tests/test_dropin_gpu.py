@@ -250,7 +250,8 @@ def test_reaction_force_global_quantities_match_reference(mode):
            .replace("<ArchiveTime units=\"ms\">1000</ArchiveTime>", "<ArchiveTime units=\"ms\">0.01</ArchiveTime>"
                     "<GlobalArchiveTime units=\"ms\">0.002</GlobalArchiveTime><GlobalArchive type=\"reactionz\" material=\"-1\"/>"
                     "<GlobalArchive type=\"reactionz\" material=\"2\"/><GlobalArchive type=\"reactionx\" material=\"2\"/>"
-                    "<GlobalArchive type=\"reactiony\"/><GlobalArchive type=\"reactionz\"/><GlobalArchive type=\"Kinetic Energy\"/>"))
+                    "<GlobalArchive type=\"reactiony\"/><GlobalArchive type=\"reactionz\"/><GlobalArchive type=\"Kinetic Energy\"/>"
+                    "<GlobalArchive type=\"Grid Kinetic Energy\"/>"))        # (0.5 |pk|^2 / m over the host's nodes, which the adapter fills from the device)
     assert 'id="-1"' in xml
     dref, out_ref = run(REF, xml, ("-np", "4"))
     extra = {"tasks": (), "fused": ("-fused",), "fused_hostoutput": ("-fused", "-hostoutput")}[mode]
@@ -260,9 +261,9 @@ def test_reaction_force_global_quantities_match_reference(mode):
     rows_g = [ln.split("\t") for ln in open(os.path.join(dgpu, "res/blk.global")).read().splitlines() if not ln.startswith("#")]
     assert len(rows_r) == len(rows_g) and len(rows_r) >= 10
     cols = np.array([[float(x) for x in r] for r in rows_r])
-    assert np.all(np.abs(cols[:, 1:6]).max(axis=0) > 0), "a reaction column is zero throughout: the input does not exercise it"
+    assert np.all(np.abs(cols[:, 1:8]).max(axis=0) > 0), "a reaction or energy column is zero throughout: the input does not exercise it"
     for rr, rg in zip(rows_r, rows_g):
-        assert len(rr) == len(rg) == 7
+        assert len(rr) == len(rg) == 8
         for j, (x, y) in enumerate(zip(rr, rg)):
             assert abs(float(x) - float(y)) <= 5e-6 * max(np.abs(cols[:, j]).max(), 1e-300), (rr, rg)
 

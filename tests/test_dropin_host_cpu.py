@@ -73,8 +73,8 @@ CASES = {
         ('<BCBox xmin="-1" xmax="20" ymin="-1" ymax="20" zmin="4" zmax="20">', '<TractionBC dir="11" face="6" style="6" function="-5*t*(1+x)"/>')]), "particle traction BCs set by a function of position"),
     "contact force quantity without multimaterial mode": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
         "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="contactz"/></MPMHeader>'), "contact-force global quantities outside multimaterial mode"),
-    "grid kinetic energy quantity": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
-        "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="Grid Kinetic Energy"/></MPMHeader>'), "global quantities read from the grid"),
+    "grid kinetic energy quantity on several GPUs": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
+        "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="Grid Kinetic Energy"/></MPMHeader>'), "grid kinetic energy in multimaterial mode or with -gpus N"),
     "reaction force quantity on several GPUs": (inputs.block3d(ncell=3, margin=2, maxtime=0.003).replace(
         "</MPMHeader>", '<GlobalArchiveTime units="ms">0.001</GlobalArchiveTime><GlobalArchive type="reactionz"/></MPMHeader>'), "reaction-force global quantities with -gpus N"),
     "more exponential terms": (inputs.block3d(ncell=3, margin=2, maxtime=0.003, material=inputs.neohookean_material(),
