@@ -42,7 +42,8 @@ struct mpmgpu_ctx {
     VelBCs B;
     int nBCEntries;
     int *dBcNode = NULL, *dBcStart = NULL, *dBcSym = NULL, *dBcActive = NULL, *dBcOfNode = NULL; double *dBcNorm = NULL, *dBcValue = NULL;
-    int bcCapUnique = 0, bcCapEntries = 0;
+    int bcCapUnique = 0, bcCapEntries = 0, bcCapRefl = 0;
+    int *dBcRefl = NULL; double *dBcReflRatio = NULL;
     bool trackReactions = false;        // mpmgpu_track_reactions: B.reaction / R.reaction are kept
     double *dReaction = NULL;           // [3*reactionCap] grid BC entries (device order)
     size_t reactionCap = 0;
@@ -1089,8 +1090,9 @@ extern "C" int mpmgpu_set_velocity_bc_reflections(mpmgpu_ctx *ctx, int n, const 
     }
     if (!any) { ctx->B.refl = NULL; ctx->B.reflRatio = NULL; return MPMGPU_OK; }
     if (ctx->cfg.kernel_path == 2) return fail(ctx, MPMGPU_EINVAL, "kernel_path=2 (fused) cannot apply reflected (symmetry-plane) velocity BCs");
-    int *dre; double *dra;
-    CK(dalloc(ctx, &dre, n)); CK(dalloc(ctx, &dra, n));
+    if (n > ctx->bcCapRefl) { CK(dalloc(ctx, &ctx->dBcRefl, n)); CK(dalloc(ctx, &ctx->dBcReflRatio, n)); ctx->bcCapRefl = n; }
+    int *dre = ctx->dBcRefl; double *dra = ctx->dBcReflRatio;
+    CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(dre, re.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dra, ra.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     ctx->B.refl = dre; ctx->B.reflRatio = dra;
